@@ -1,0 +1,144 @@
+"""Pin the CPU oracle against outputs of the live reference (tests/golden/*.npz).
+
+The reference has no tests of its own; these vectors were produced by
+tests/golden/make_golden.py importing /root/reference in the build container.
+"""
+import numpy as np
+import pytest
+
+from lstm_ode_bci_b200 import synth
+from oracle import lstm_oracle, ode_oracle, torch_port
+
+LSTM_CASES = ["lstm_tiny.npz", "lstm_h128_t64.npz", "lstm_h128.npz", "lstm_h256.npz"]
+
+
+def _lstm_inputs(g):
+    if "x" in g:
+        params = {k[6:]: v for k, v in g.items() if k.startswith("param:")}
+        return params, g["x"]
+    params = synth.make_lstm_params(int(g["seed_w"]), int(g["C"]), int(g["H"]), int(g["L"]),
+                                    logit_gain=float(g["gain"]))
+    x = synth.make_windows(int(g["seed_x"]), int(g["B"]), int(g["T"]), int(g["C"]),
+                           structured=bool(g["structured"]))
+    return params, x
+
+
+@pytest.mark.parametrize("name", LSTM_CASES)
+def test_numpy_oracle_matches_reference_forward(golden, name):
+    g = golden(name)
+    params, x = _lstm_inputs(g)
+    if name == "lstm_h256.npz":
+        x = x[:2]
+    logits, attn = lstm_oracle.forward(params, x, dtype=np.float64)
+    n = len(x)
+    # reference ran fp32; float64 oracle differs only by the reference's own rounding
+    assert np.abs(logits - g["logits"][:n]).max() < 2e-6
+    assert np.abs(attn - g["attention"][:n]).max() < 2e-7
+    assert np.abs(lstm_oracle.softmax_probs(logits) - g["probs"][:n]).max() < 1e-6
+    assert np.allclose(attn.sum(axis=1), 1.0, atol=1e-12)
+
+
+@pytest.mark.parametrize("name", ["lstm_tiny.npz", "lstm_h128_t64.npz"])
+def test_torch_port_matches_reference_forward(golden, name):
+    import torch
+    g = golden(name)
+    params, x = _lstm_inputs(g)
+    m = torch_port.build_port(params).eval()
+    with torch.no_grad():
+        logits, attn = m(torch.from_numpy(x), return_attention=True)
+    assert np.abs(logits.numpy() - g["logits"]).max() < 1e-6
+    assert np.abs(attn.numpy() - g["attention"]).max() < 1e-7
+    # state-dict key ABI
+    assert list(m.state_dict().keys()) == list(synth.lstm_param_shapes(
+        int(g["C"]), int(g["H"]), int(g["L"])).keys())
+
+
+@pytest.mark.parametrize("name", ["lstm_grad_tiny.npz", "lstm_grad_h128.npz"])
+def test_torch_port_matches_reference_gradients(golden, name):
+    g = golden(name)
+    params = synth.make_lstm_params(int(g["seed_w"]), int(g["C"]), int(g["H"]), int(g["L"]), logit_gain=float(g["gain"]))
+    x = synth.make_windows(int(g["seed_x"]), int(g["B"]), int(g["T"]), int(g["C"]))
+    m = torch_port.build_port(params, dropout=0.0)
+    loss, grads, dx, _ = torch_port.loss_and_grads(m, x, g["y"], g["class_weight"])
+    assert abs(loss - float(g["loss"])) < 1e-6
+    for k, gr in grads.items():
+        ref_norm = float(g["gnorm:" + k])
+        assert abs(np.linalg.norm(gr.astype(np.float64)) - ref_norm) <= 1e-5 * max(ref_norm, 1e-3), k
+        assert np.allclose(gr.reshape(-1)[:16], g["ghead:" + k], rtol=1e-4, atol=1e-7), k
+    assert abs(np.linalg.norm(dx) - float(g["dx_norm"])) < 1e-5 * float(g["dx_norm"])
+
+
+def test_coupling_and_initial_state_match_reference(golden):
+    g = golden("ode_ref06.npz")
+    k = ode_oracle.modulate_rates(g["base"], g["alpha"], g["p_closed"], g["p_open"])
+    assert np.array_equal(k, g["rates"])          # bit-exact, incl. float32 promotion + floor
+    assert np.array_equal(ode_oracle.initial_state_06(g["p_open"], g["p_closed"]), g["y0"])
+    # alpha = 0 leaves the rates untouched (above the floor)
+    k0 = ode_oracle.modulate_rates(g["base"], 0.0, g["p_closed"], g["p_open"])
+    assert np.array_equal(k0, np.maximum(0.001, g["base"].astype(np.float32).astype(np.float64)))
+
+
+def test_exact_and_rk4_match_reference_lsoda(golden):
+    g = golden("ode_ref06.npz")
+    ex = ode_oracle.exact_solution(ode_oracle.STYLE_REF06, g["y0"], g["rates"], 20.0, 20)
+    assert np.abs(ex - g["traj"]).max() < 2e-7            # LSODA @1.49e-8 vs closed form
+    # RK4 truncation: err <= 0.01 (h*lam)^4 with lam = largest total outflow rate; rates in
+    # this fixture reach lam = 0.95 (all six swept inside the fit bounds), so 8 sub-steps per
+    # output interval are needed for <= 1e-6 (4 give 6e-6, 1 gives 4e-3).
+    r8 = ode_oracle.rk4(ode_oracle.STYLE_REF06, g["y0"], g["rates"], 20.0, 20, substeps=8)
+    assert np.abs(r8 - ex).max() < 4e-7
+    assert np.abs(r8 - g["traj"]).max() < 5e-7
+    assert np.abs(r8.sum(axis=2) - 1).max() < 1e-15
+    k = g["rates"]
+    lam = np.maximum(np.maximum(k[0] + k[1], k[2] + k[3]), k[4] + k[5])
+    for s in (2, 4, 16):
+        e = np.abs(ode_oracle.rk4(ode_oracle.STYLE_REF06, g["y0"], k, 20.0, 20, s) - ex).max(axis=(1, 2))
+        assert (e <= 0.0105 * (20.0 / 19 / s * lam) ** 4 + 1e-12).all()
+
+
+def test_rk45_restatement_matches_reference_solve_ivp(golden):
+    g = golden("ode_ref05.npz")
+    out, stats = ode_oracle.rk45_scipy(ode_oracle.STYLE_REF06, g["y0"], g["rates"], 20.0, 20, return_stats=True)
+    assert np.abs(out - g["traj_rk45"]).max() < 1e-13     # same algorithm, same decisions
+    assert all(s["accepted"] >= 3 for s in stats)
+    ex = ode_oracle.exact_solution(ode_oracle.STYLE_REF06, g["y0"][:8], g["rates"][:, :8], 50.0, 100)
+    assert np.abs(ex - g["traj_odeint_100"]).max() < 2e-7
+
+
+def test_forecast_style_matches_reference_08(golden):
+    g = golden("ode_ref08.npz")
+    y0 = ode_oracle.prob_to_state_08(g["p_closed"])
+    assert np.abs(y0 - g["y0"]).max() < 1e-15
+    n = len(y0)
+    rates = np.where((np.arange(n) % 2 == 0)[None, :], g["rates_default"][:, None], g["rates_fit"][:, None])
+    ex = ode_oracle.exact_solution(ode_oracle.STYLE_REF08, y0, rates, 20.0, 21)
+    assert np.abs(ex - g["traj"]).max() < 2e-7
+    r4 = ode_oracle.rk4(ode_oracle.STYLE_REF08, y0, rates, 20.0, 21, substeps=8)
+    assert np.abs(r4 - g["traj"]).max() < 3e-7
+    # multistep_forecast read-out (08:252-289)
+    probs = g["series_probs"]
+    m = len(probs) - 20
+    y0s = ode_oracle.prob_to_state_08(probs[:m, 1])
+    tr = ode_oracle.exact_solution(ode_oracle.STYLE_REF08, y0s, g["rates_default"], 20.0, 21)
+    pred = ode_oracle.forecast_readout_08(tr, (5, 10, 20))
+    assert np.abs(pred - g["fc_pred"]).max() < 2e-7
+    actual = np.stack([probs[h:h + m, 1] for h in (5, 10, 20)], axis=1)
+    assert np.array_equal(actual, g["fc_actual"])
+
+
+def test_pipeline_matches_reference_predict_batch(golden):
+    g = golden("pipeline_h128.npz")
+    gl = golden("lstm_h128.npz")
+    params, x = _lstm_inputs(gl)
+    probs, attn = torch_port.forward_probs(torch_port.build_port(params), x, batch_size=3)
+    assert np.abs(probs - g["probs"]).max() < 1e-6
+    k = ode_oracle.modulate_rates(ode_oracle.rates_to_array(synth.DEFAULT_RATES), 0.5, g["probs"][:, 1], g["probs"][:, 0])
+    y0 = ode_oracle.initial_state_06(g["probs"][:, 0], g["probs"][:, 1])
+    tr = ode_oracle.exact_solution(ode_oracle.STYLE_REF06, y0, k, 20.0, 20)
+    assert np.abs(tr - g["traj"]).max() < 2e-7
+    assert np.array_equal(ode_oracle.final_prediction_06(tr), g["preds"])
+    assert np.abs(tr[:, -1] - g["three_state"]).max() < 2e-7
+    assert np.array_equal(ode_oracle.three_state_class_10(tr[:, -1]), g["cls"])
+    # predict_trajectory(X[:1], forecast_steps=10): t = linspace(0,10,10) (06:299-301)
+    tr1 = ode_oracle.exact_solution(ode_oracle.STYLE_REF06, y0[:1], k[:, :1], 10.0, 10)
+    assert np.abs(tr1[0] - g["single_traj"]).max() < 2e-7
