@@ -1,0 +1,202 @@
+/*
+ * bci_b200.h -- C ABI of the B200-native hot path of LSTM-ODE-BCI.
+ *
+ * The reference (khurrameycon/LSTM-ODE-BCI) is pure Python and has no FFI of its own; its
+ * de-facto boundary for this path is the Python call contract of three objects
+ * (SURVEY.md §8 b).  Each entry point below names the reference call it replaces
+ * (file:line under the reference tree).  INTEGRATION.md shows the ctypes stub a reference
+ * maintainer would add to bind them.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative BCI_E* code otherwise;
+ *     bci_last_error() returns a thread-local message for the last failure.
+ *   - all data pointers are DEVICE pointers owned by the caller unless a name ends in
+ *     `_host`; the library allocates only the per-handle packed weight copies.
+ *   - `stream` is a cudaStream_t passed as void*; calls are asynchronous on it.
+ *   - one handle may be used by one stream at a time (thread-compatible, not thread-safe).
+ *   - no C++/torch types cross this boundary.
+ */
+#ifndef BCI_B200_H
+#define BCI_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BCI_ABI_VERSION 1
+#define BCI_MAX_LAYERS 4
+
+enum {
+  BCI_OK = 0,
+  BCI_EINVAL = -1,      /* bad argument / unsupported configuration */
+  BCI_ECUDA = -2,       /* CUDA runtime / driver error */
+  BCI_ENOMEM = -3,      /* workspace too small or allocation failed */
+  BCI_ESTATE = -4,      /* call order violated (e.g. forward before load_weights) */
+  BCI_EUNSUPPORTED = -5 /* device is not sm_100 */
+};
+
+enum { BCI_PRECISION_FP32 = 0, BCI_PRECISION_BF16 = 1 };
+
+int bci_abi_version(void);
+const char* bci_last_error(void);
+/* Device capability probe: writes SM count, returns BCI_EUNSUPPORTED unless CC 10.x. */
+int bci_device_check(int device, int* sm_count);
+
+/* ------------------------------------------------------------------------------------------
+ * BiLSTM + attention pooling  (EnhancedLSTMModel, 04_lstm_model.py:153-222)
+ * ---------------------------------------------------------------------------------------- */
+typedef struct bci_lstm_s* bci_lstm_t;
+
+typedef struct {
+  int32_t input_size;    /* C: EEG channels (61)                     04:163 input_size        */
+  int32_t hidden_size;   /* H: 128 or 256                            04:163,876-877           */
+  int32_t num_layers;    /* 1..BCI_MAX_LAYERS (3)                    04:163                   */
+  int32_t num_classes;   /* 2                                        04:164                   */
+  int32_t bidirectional; /* must be 1 (ablation variants are SURVEY §8 f)                     */
+  int32_t precision;     /* BCI_PRECISION_*                                                   */
+} bci_lstm_config;
+
+/* Device pointers to fp32 parameters in the reference state-dict layout:
+ * PyTorch (out,in) row-major, gate row order i,f,g,o.  [layer][0]=forward, [layer][1]=reverse. */
+typedef struct {
+  const float* input_proj_w;  /* input_proj.0.weight (H,C)   */
+  const float* input_proj_b;  /* input_proj.0.bias   (H)     */
+  const float* input_ln_w;    /* input_proj.1.weight (H)     */
+  const float* input_ln_b;    /* input_proj.1.bias   (H)     */
+  const float* w_ih[BCI_MAX_LAYERS][2]; /* lstm.weight_ih_l{k}[_reverse] (4H, H or 2H) */
+  const float* w_hh[BCI_MAX_LAYERS][2]; /* lstm.weight_hh_l{k}[_reverse] (4H, H)       */
+  const float* b_ih[BCI_MAX_LAYERS][2]; /* lstm.bias_ih_l{k}[_reverse]   (4H)          */
+  const float* b_hh[BCI_MAX_LAYERS][2]; /* lstm.bias_hh_l{k}[_reverse]   (4H)          */
+  const float* ln_w;          /* layer_norm.weight (2H) */
+  const float* ln_b;          /* layer_norm.bias   (2H) */
+  const float* attn_w1;       /* attention.attention.0.weight (H,2H) */
+  const float* attn_b1;       /* attention.attention.0.bias   (H)    */
+  const float* attn_w2;       /* attention.attention.2.weight (1,H)  */
+  const float* attn_b2;       /* attention.attention.2.bias   (1)    */
+  const float* cls_w0;        /* classifier.0.weight (H,2H)   */
+  const float* cls_b0;        /* classifier.0.bias   (H)      */
+  const float* cls_w3;        /* classifier.3.weight (H/2,H)  */
+  const float* cls_b3;        /* classifier.3.bias   (H/2)    */
+  const float* cls_w6;        /* classifier.6.weight (classes,H/2) */
+  const float* cls_b6;        /* classifier.6.bias   (classes)     */
+} bci_lstm_weights;
+
+/* replaces EnhancedLSTMModel.__init__ (04:163-204): allocates the packed weight store. */
+int bci_lstm_create(const bci_lstm_config* cfg, bci_lstm_t* out);
+int bci_lstm_destroy(bci_lstm_t h);
+
+/* replaces load_state_dict / .to(device) (06:416-430): repacks the fp32 parameters into the
+ * kernels' layouts (transposed fp32 copies; bf16 swizzle-ready copies in BF16 precision).
+ * Re-callable after every optimizer step. */
+int bci_lstm_load_weights(bci_lstm_t h, const bci_lstm_weights* w, void* stream);
+
+/* bytes of caller-provided scratch needed by forward (train=0) or forward+backward (train=1) */
+int bci_lstm_workspace_bytes(bci_lstm_t h, int32_t batch, int32_t seq_len, int32_t train, size_t* bytes);
+
+/* replaces EnhancedLSTMModel.forward(x, return_attention) (04:206-222) followed by the callers'
+ * softmax(dim=1) (04:613, 06:232,351, 08:207, 10:231).
+ *   x      (B,T,C) fp32 contiguous, batch-first
+ *   logits (B,classes) fp32            required
+ *   probs  (B,classes) fp32            optional (NULL to skip); column 0 = P(open), 1 = P(closed)
+ *   attn   (B,T) fp32                  optional
+ *   train  0: eval (dropout off).  1: additionally keeps the activations bci_lstm_backward needs
+ *          in the workspace; dropout probabilities are taken from `dropout` (0 = none; the four
+ *          sites of 04:177,186,199,202 use dropout/2, dropout, dropout, dropout). */
+int bci_lstm_forward(bci_lstm_t h, const float* x, int32_t batch, int32_t seq_len, int32_t train,
+                     float dropout, uint64_t seed, float* logits, float* probs, float* attn,
+                     void* workspace, size_t workspace_bytes, void* stream);
+
+/* Gradient pointers, same layout/shape as bci_lstm_weights; every pointer must be non-NULL.
+ * Gradients are OVERWRITTEN (not accumulated). */
+typedef struct {
+  float* input_proj_w; float* input_proj_b; float* input_ln_w; float* input_ln_b;
+  float* w_ih[BCI_MAX_LAYERS][2]; float* w_hh[BCI_MAX_LAYERS][2];
+  float* b_ih[BCI_MAX_LAYERS][2]; float* b_hh[BCI_MAX_LAYERS][2];
+  float* ln_w; float* ln_b; float* attn_w1; float* attn_b1; float* attn_w2; float* attn_b2;
+  float* cls_w0; float* cls_b0; float* cls_w3; float* cls_b3; float* cls_w6; float* cls_b6;
+} bci_lstm_grads;
+
+/* replaces loss.backward() through the model (04:490-494; 07:242-258 for dx): BPTT from
+ * dlogits (B,classes).  Must follow a train=1 forward on the same workspace.  dx (B,T,C)
+ * optional. */
+int bci_lstm_backward(bci_lstm_t h, const float* x, const float* dlogits, int32_t batch, int32_t seq_len,
+                      float* dx, const bci_lstm_grads* grads, void* workspace, size_t workspace_bytes,
+                      void* stream);
+
+/* replaces clip_grad_norm_ + AdamW.step on a flat fp32 bucket (04:497-507, 04:438): p, g, m, v
+ * are flat arrays of n floats; `grad_scale` multiplies g first (1/world_size after an NCCL
+ * sum all-reduce, 1/loss_scale for AMP); if max_norm > 0 the scaled gradient is clipped to that
+ * global L2 norm.  `norm_scratch` is 2 floats of device scratch; the pre-clip norm is left in
+ * norm_scratch[1]. */
+int bci_adamw_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1,
+                   float beta2, float eps, float weight_decay, int32_t step, float grad_scale,
+                   float max_norm, float* norm_scratch, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Three-state A/P/F ODE ensemble with probabilistic rate coupling
+ * ---------------------------------------------------------------------------------------- */
+enum { BCI_ODE_RK4 = 0, BCI_ODE_RK45 = 1 };
+/* REF06: clamp max(0,.) in the RHS, y0 /= sum(y0), t = linspace(0,t_end,n_points), then
+ *        clip[0,1] + row renormalisation   (CognitiveStateODE.solve, 06:174-180 == 05:137-169)
+ * REF08: raw RHS, y0 as given, no post-processing (predict_trajectory, 08:149-153; pass
+ *        t_end = n_steps*dt and n_points = n_steps+1) */
+enum { BCI_ODE_STYLE_REF06 = 0, BCI_ODE_STYLE_REF08 = 1 };
+/* where the initial state comes from */
+enum {
+  BCI_Y0_GIVEN = 0,          /* y0 (3,N) SoA                                               */
+  BCI_Y0_FROM_PROBS_06 = 1,  /* thresholds on P(closed)/P(open): 06:377-382 == 10:250-255   */
+  BCI_Y0_FROM_PCLOSED_08 = 2 /* prob_to_ode_state(P(closed)): 08:215-234                    */
+};
+enum { BCI_OUT_F32 = 0, BCI_OUT_F64 = 1 };
+
+typedef struct {
+  int32_t mode;        /* BCI_ODE_RK4 | BCI_ODE_RK45 */
+  int32_t style;       /* BCI_ODE_STYLE_* */
+  int32_t y0_mode;     /* BCI_Y0_* */
+  int32_t coupling;    /* 1: modulate_ode_rates (06:236-264): k_af,k_pf *= 1+alpha*P(closed);
+                          k_fa,k_pa *= 1+alpha*P(open); all six floored at 0.001.  0: rates used as is */
+  int64_t n;           /* trajectories */
+  float base_rates[6]; /* k_ap,k_af,k_pa,k_pf,k_fa,k_fp used when rates == NULL */
+  float alpha;         /* coupling strength used when alpha_arr == NULL (06:204) */
+  const float* rates;     /* optional (6,N) SoA per-trajectory base rates */
+  const float* alpha_arr; /* optional (N) */
+  const float* p_open;    /* (N), required if coupling or BCI_Y0_FROM_PROBS_06 */
+  const float* p_closed;  /* (N), required if coupling or y0_mode != GIVEN */
+  const float* y0;        /* (3,N) SoA, required if BCI_Y0_GIVEN */
+  double t_end;
+  int32_t n_points;    /* >= 2 */
+  int32_t substeps;    /* RK4: equal steps per output interval; 0 = per trajectory so that
+                          0.01*(h*lambda)^4 <= 2e-7 (lambda = largest total outflow rate) */
+  double rtol, atol;   /* RK45: scipy.solve_ivp defaults 1e-3 / 1e-6 (05:158-163) */
+  int32_t out_dtype;   /* BCI_OUT_F32 | BCI_OUT_F64: element type of traj / final_state */
+  void* traj;          /* optional (N,n_points,3) */
+  void* final_state;   /* optional (N,3): last row of the trajectory (10:271-273) */
+  int32_t* n_steps;    /* optional (N): RK45 accepted+rejected steps / RK4 steps taken */
+} bci_ode_args;
+
+/* replaces the per-sample host loop of predict_batch step 2 (06:372-401),
+ * get_three_state_probabilities step 2 (10:245-273), multistep_forecast (08:264-282) and
+ * CognitiveStateODE.solve / predict_trajectory themselves: one launch, one thread per trajectory. */
+int bci_ode_solve(const bci_ode_args* args, void* stream);
+
+/* replaces the read-outs that follow the solve:
+ *   pred06[i]  = traj_last[i].F > 0.5                          (06:396-401)
+ *   cls10[i]   = 2 if F > .5 else 0 if A > .5 else 1           (10:282-288)
+ * from final_state (N,3) fp32; either output may be NULL. */
+int bci_ode_classify(const float* final_state, int64_t n, int32_t* pred06, int32_t* cls10, void* stream);
+/* forecast read-out clip(F_h + 0.5 P_h, 0, 1) at `n_h` horizons (08:273-279) from traj
+ * (N,n_points,3) fp32 -> out (N,n_h) fp32.  horizons_host is a HOST array. */
+int bci_ode_forecast_readout(const float* traj, int64_t n, int32_t n_points, const int32_t* horizons_host,
+                             int32_t n_h, float* out, void* stream);
+
+/* Micro-benchmark used by bench.py for the FP32 roofline denominator (SURVEY.md §8 d: the FP32
+ * FMA peak is not in MEASURED_PEAKS.json): launches a dependent-FMA kernel, returns TFLOP/s. */
+int bci_fp32_peak_probe(double* tflops, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BCI_B200_H */

@@ -1,0 +1,136 @@
+// extern "C" entry points of libbci_b200.so (see include/bci_b200.h).
+#include "lstm_handle.cuh"
+#include <cstring>
+#include <cstdlib>
+#include <new>
+
+namespace bci {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int lstm_pack_f32(bci_lstm_s* h, cudaStream_t st);
+size_t lstm_store_bytes_f32(const bci_lstm_config& c);
+void lstm_carve_f32(bci_lstm_s* h, char* base);
+int lstm_forward_train(bci_lstm_s* h, const float* x, int batch, int T, float dropout, uint64_t seed, float* logits,
+                       float* probs, float* attn, void* ws, size_t ws_bytes, cudaStream_t st);
+size_t lstm_workspace_train(const bci_lstm_config& c, int batch, int T);
+int lstm_backward_impl(bci_lstm_s* h, const float* x, const float* dlogits, int batch, int T, float* dx,
+                       const bci_lstm_grads* grads, void* ws, size_t ws_bytes, cudaStream_t st);
+
+}  // namespace bci
+
+using namespace bci;
+
+extern "C" int bci_abi_version(void) { return BCI_ABI_VERSION; }
+extern "C" const char* bci_last_error(void) { return g_err; }
+
+extern "C" int bci_device_check(int device, int* sm) {
+  int n = 0;
+  BCI_CUDA_OK(cudaGetDeviceCount(&n));
+  BCI_REQUIRE(device >= 0 && device < n, BCI_EINVAL, "bci_device_check: device %d of %d", device, n);
+  int major = 0, minor = 0, sms = 0;
+  BCI_CUDA_OK(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device));
+  BCI_CUDA_OK(cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, device));
+  BCI_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+  if (sm) *sm = sms;
+  BCI_REQUIRE(major == 10, BCI_EUNSUPPORTED, "bci_b200 is built for sm_100a only; device %d is sm_%d%d", device, major, minor);
+  return BCI_OK;
+}
+
+extern "C" int bci_lstm_create(const bci_lstm_config* cfg, bci_lstm_t* out) {
+  BCI_REQUIRE(cfg && out, BCI_EINVAL, "bci_lstm_create: NULL argument");
+  BCI_REQUIRE(cfg->hidden_size == 128 || cfg->hidden_size == 256, BCI_EINVAL,
+              "bci_lstm_create: hidden_size must be 128 or 256 (got %d)", cfg->hidden_size);
+  BCI_REQUIRE(cfg->input_size >= 1 && cfg->input_size <= 64, BCI_EINVAL, "bci_lstm_create: input_size must be 1..64 (got %d)",
+              cfg->input_size);
+  BCI_REQUIRE(cfg->num_layers >= 1 && cfg->num_layers <= BCI_MAX_LAYERS, BCI_EINVAL, "bci_lstm_create: num_layers must be 1..%d",
+              BCI_MAX_LAYERS);
+  BCI_REQUIRE(cfg->num_classes >= 1 && cfg->num_classes <= 8, BCI_EINVAL, "bci_lstm_create: num_classes must be 1..8");
+  BCI_REQUIRE(cfg->bidirectional == 1, BCI_EINVAL, "bci_lstm_create: only bidirectional=1 is supported");
+  BCI_REQUIRE(cfg->precision == BCI_PRECISION_FP32 || cfg->precision == BCI_PRECISION_BF16, BCI_EINVAL,
+              "bci_lstm_create: bad precision %d", cfg->precision);
+  bci_lstm_s* h = new (std::nothrow) bci_lstm_s();
+  BCI_REQUIRE(h, BCI_ENOMEM, "bci_lstm_create: host allocation failed");
+  std::memset(h, 0, sizeof(*h));
+  h->cfg = *cfg;
+  cudaError_t e = cudaGetDevice(&h->device);
+  if (e != cudaSuccess) { delete h; set_error("cudaGetDevice failed: %s", cudaGetErrorString(e)); return BCI_ECUDA; }
+  const size_t f32_bytes = lstm_store_bytes_f32(*cfg);
+  const size_t bf_bytes = lstm_store_bytes_bf16(*cfg);
+  h->store_bytes = f32_bytes + bf_bytes;
+  e = cudaMalloc(&h->store, h->store_bytes);
+  if (e != cudaSuccess) { delete h; set_error("cudaMalloc(%zu) for packed weights failed: %s", f32_bytes + bf_bytes, cudaGetErrorString(e)); return BCI_ENOMEM; }
+  lstm_carve_f32(h, (char*)h->store);
+  lstm_carve_bf16(h, (char*)h->store + f32_bytes);
+  *out = h;
+  return BCI_OK;
+}
+
+extern "C" int bci_lstm_destroy(bci_lstm_t h) {
+  if (!h) return BCI_OK;
+  if (h->store) cudaFree(h->store);
+  delete h;
+  return BCI_OK;
+}
+
+extern "C" int bci_lstm_load_weights(bci_lstm_t h, const bci_lstm_weights* w, void* stream) {
+  BCI_REQUIRE(h && w, BCI_EINVAL, "bci_lstm_load_weights: NULL argument");
+  const bci_lstm_config& c = h->cfg;
+  const void* must[] = {w->input_proj_w, w->input_proj_b, w->input_ln_w, w->input_ln_b, w->ln_w, w->ln_b, w->attn_w1, w->attn_b1,
+                        w->attn_w2, w->attn_b2, w->cls_w0, w->cls_b0, w->cls_w3, w->cls_b3, w->cls_w6, w->cls_b6};
+  for (const void* p : must) BCI_REQUIRE(p, BCI_EINVAL, "bci_lstm_load_weights: a required weight pointer is NULL");
+  for (int l = 0; l < c.num_layers; ++l)
+    for (int d = 0; d < 2; ++d)
+      BCI_REQUIRE(w->w_ih[l][d] && w->w_hh[l][d] && w->b_ih[l][d] && w->b_hh[l][d], BCI_EINVAL,
+                  "bci_lstm_load_weights: LSTM weight pointer NULL (layer %d dir %d)", l, d);
+  h->raw = *w;
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = lstm_pack_f32(h, st);
+  if (rc) return rc;
+  if (c.precision == BCI_PRECISION_BF16) {
+    rc = lstm_pack_bf16(h, st);
+    if (rc) return rc;
+  }
+  h->loaded = true;
+  return BCI_OK;
+}
+
+extern "C" int bci_lstm_workspace_bytes(bci_lstm_t h, int32_t batch, int32_t seq_len, int32_t train, size_t* bytes) {
+  BCI_REQUIRE(h && bytes, BCI_EINVAL, "bci_lstm_workspace_bytes: NULL argument");
+  BCI_REQUIRE(batch >= 0 && seq_len >= 1, BCI_EINVAL, "bci_lstm_workspace_bytes: bad shape (%d,%d)", batch, seq_len);
+  if (train) *bytes = lstm_workspace_train(h->cfg, batch, seq_len);
+  else *bytes = h->cfg.precision == BCI_PRECISION_BF16 ? lstm_workspace_bf16(h->cfg, batch, seq_len)
+                                                        : lstm_workspace_fp32(h->cfg, batch, seq_len);
+  return BCI_OK;
+}
+
+extern "C" int bci_lstm_forward(bci_lstm_t h, const float* x, int32_t batch, int32_t seq_len, int32_t train, float dropout,
+                                uint64_t seed, float* logits, float* probs, float* attn, void* workspace,
+                                size_t workspace_bytes, void* stream) {
+  BCI_REQUIRE(h, BCI_EINVAL, "bci_lstm_forward: NULL handle");
+  BCI_REQUIRE(h->loaded, BCI_ESTATE, "bci_lstm_forward: call bci_lstm_load_weights first");
+  BCI_REQUIRE(batch >= 0 && seq_len >= 1 && seq_len <= 65536, BCI_EINVAL, "bci_lstm_forward: bad shape (%d,%d)", batch, seq_len);
+  if (batch == 0) return BCI_OK;
+  BCI_REQUIRE(x && logits, BCI_EINVAL, "bci_lstm_forward: x and logits are required");
+  BCI_REQUIRE(workspace, BCI_ENOMEM, "bci_lstm_forward: workspace is NULL");
+  BCI_REQUIRE(dropout >= 0.f && dropout < 1.f, BCI_EINVAL, "bci_lstm_forward: dropout must be in [0,1)");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (train) return lstm_forward_train(h, x, batch, seq_len, dropout, seed, logits, probs, attn, workspace, workspace_bytes, st);
+  if (h->cfg.precision == BCI_PRECISION_BF16)
+    return lstm_forward_bf16(h, x, batch, seq_len, logits, probs, attn, workspace, workspace_bytes, st);
+  return lstm_forward_fp32(h, x, batch, seq_len, logits, probs, attn, workspace, workspace_bytes, st);
+}
+
+extern "C" int bci_lstm_backward(bci_lstm_t h, const float* x, const float* dlogits, int32_t batch, int32_t seq_len, float* dx,
+                                 const bci_lstm_grads* grads, void* workspace, size_t workspace_bytes, void* stream) {
+  BCI_REQUIRE(h && x && dlogits && grads && workspace, BCI_EINVAL, "bci_lstm_backward: NULL argument");
+  BCI_REQUIRE(h->loaded, BCI_ESTATE, "bci_lstm_backward: call bci_lstm_load_weights first");
+  return lstm_backward_impl(h, x, dlogits, batch, seq_len, dx, grads, workspace, workspace_bytes, (cudaStream_t)stream);
+}

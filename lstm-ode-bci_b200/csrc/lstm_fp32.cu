@@ -1,0 +1,339 @@
+// fp32 (parity) mode of the BiLSTM forward: CUDA-core FMA everywhere, accurate expf/tanhf, so
+// logits/probabilities match the reference's fp32 path to <= 1e-5 (north_star).  Tensor cores
+// (10-bit TF32 / 8-bit bf16 mantissas) cannot meet that bound over 3 x 256 dependent steps; the
+// tcgen05 path lives in lstm_bf16.cu.
+//
+//   K2  proj_gemm_f32 : G[T*Bc][8H] = in[T*Bc][K] . W_ih^T (both directions) + (b_ih + b_hh)
+//   K3  lstm_rec_f32  : persistent over the whole sequence per (window tile, direction):
+//                       gates = G_t + h W_hh^T, sigma/tanh, cell update, h -> smem for step t+1
+// Reference: nn.LSTM inside EnhancedLSTMModel (04_lstm_model.py:181-188,211).
+#include "lstm_shared_kernels.cuh"
+
+namespace bci {
+
+// ---------------------------------------------------------------------------------------------
+// K2: SGEMM with bias, C[M][N] = A[M][K] Bt[K][N] + bias[N].  128x128x16 tiles, 8x8 per thread,
+// register-prefetched global loads, conflict-free split fragments.
+// ---------------------------------------------------------------------------------------------
+constexpr int GM = 128, GN = 128, GK = 16, GEMM_THREADS = 256;
+
+__global__ void __launch_bounds__(GEMM_THREADS)
+proj_gemm_f32(const float* __restrict__ A, const float* __restrict__ Bt, const float* __restrict__ bias,
+              float* __restrict__ C, int M, int N, int K) {
+  __shared__ __align__(16) float As[2][GK][GM + 4];
+  __shared__ __align__(16) float Bs[2][GK][GN];
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;
+  const int m0 = blockIdx.y * GM, n0 = blockIdx.x * GN;
+  // global load mapping: A tile 128 rows x 16 k: thread loads 2 float4 along k
+  const int a_row = tid >> 2, a_kq = (tid & 3) * 4;  // rows a_row and a_row+64
+  const int b_row = tid >> 5, b_nq = (tid & 31) * 4; // k rows b_row and b_row+8
+  float4 ra[2], rb[2];
+  auto load_tiles = [&](int k0) {
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int m = m0 + a_row + i * 64;
+      ra[i] = (m < M) ? *reinterpret_cast<const float4*>(A + (long long)m * K + k0 + a_kq) : make_float4(0.f, 0.f, 0.f, 0.f);
+      rb[i] = *reinterpret_cast<const float4*>(Bt + (long long)(k0 + b_row + i * 8) * N + n0 + b_nq);
+    }
+  };
+  auto store_tiles = [&](int buf) {
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int m = a_row + i * 64;
+      As[buf][a_kq + 0][m] = ra[i].x; As[buf][a_kq + 1][m] = ra[i].y;
+      As[buf][a_kq + 2][m] = ra[i].z; As[buf][a_kq + 3][m] = ra[i].w;
+      *reinterpret_cast<float4*>(&Bs[buf][b_row + i * 8][b_nq]) = rb[i];
+    }
+  };
+  float acc[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+
+  load_tiles(0);
+  store_tiles(0);
+  __syncthreads();
+  const int nk = K / GK;
+  for (int kt = 0; kt < nk; ++kt) {
+    const int buf = kt & 1;
+    if (kt + 1 < nk) load_tiles((kt + 1) * GK);
+#pragma unroll
+    for (int k = 0; k < GK; ++k) {
+      const float4 a0 = *reinterpret_cast<const float4*>(&As[buf][k][ty * 4]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&As[buf][k][64 + ty * 4]);
+      const float4 b0 = *reinterpret_cast<const float4*>(&Bs[buf][k][tx * 4]);
+      const float4 b1 = *reinterpret_cast<const float4*>(&Bs[buf][k][64 + tx * 4]);
+      const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    if (kt + 1 < nk) {
+      store_tiles(buf ^ 1);
+      __syncthreads();
+    }
+  }
+  // epilogue: rows {ty*4+i, 64+ty*4+i}, cols {tx*4.., 64+tx*4..}
+  const float4 bia0 = *reinterpret_cast<const float4*>(bias + n0 + tx * 4);
+  const float4 bia1 = *reinterpret_cast<const float4*>(bias + n0 + 64 + tx * 4);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int m = m0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
+    if (m < M) {
+      float4 o0 = make_float4(acc[i][0] + bia0.x, acc[i][1] + bia0.y, acc[i][2] + bia0.z, acc[i][3] + bia0.w);
+      float4 o1 = make_float4(acc[i][4] + bia1.x, acc[i][5] + bia1.y, acc[i][6] + bia1.z, acc[i][7] + bia1.w);
+      *reinterpret_cast<float4*>(C + (long long)m * N + n0 + tx * 4) = o0;
+      *reinterpret_cast<float4*>(C + (long long)m * N + n0 + 64 + tx * 4) = o1;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K3: recurrence.  grid = (window tiles, 2 directions); 256 threads; thread = (hidden unit j,
+// group of 16 windows).  h_{t-1} lives transposed in shared memory ([k][window], broadcast
+// float4 reads); W_hh^T (gate-interleaved, [k][4H]) streams through L1/L2 as coalesced float4;
+// the cell state stays in registers for the whole sequence.
+// ---------------------------------------------------------------------------------------------
+constexpr int REC_THREADS = 256;
+constexpr int REC_WPT = 16;  // windows per thread
+
+template <int H>
+__global__ void __launch_bounds__(REC_THREADS, 2)
+lstm_rec_f32(const float* __restrict__ G,      // [T][Bc][2][H][4]
+             const float* __restrict__ whh_f,  // [H][H][4] forward direction
+             const float* __restrict__ whh_r,  // reverse direction
+             float* __restrict__ out,          // [T][Bc][2H]
+             float* __restrict__ gates_save,   // optional [T][Bc][2][H][4] post-activation (train)
+             float* __restrict__ c_save,       // optional [T][Bc][2][H] (train)
+             int Bc, int T) {
+  constexpr int GROUPS = REC_THREADS / H;
+  constexpr int MT = GROUPS * REC_WPT;
+  constexpr int HS = MT + 4;  // padded row: conflict-free float4 stores, 16 B aligned
+  __shared__ __align__(16) float hs[2][H][HS];
+  const int tid = threadIdx.x;
+  const int j = tid % H, grp = tid / H;
+  const int dir = blockIdx.y;
+  const int b_base = blockIdx.x * MT + grp * REC_WPT;
+  const float4* __restrict__ W = reinterpret_cast<const float4*>(dir ? whh_r : whh_f);
+
+  for (int i = tid; i < 2 * H * HS; i += REC_THREADS) (&hs[0][0][0])[i] = 0.f;
+  float c[REC_WPT];
+#pragma unroll
+  for (int w = 0; w < REC_WPT; ++w) c[w] = 0.f;
+  __syncthreads();
+
+  int cur = 0;
+  for (int s = 0; s < T; ++s) {
+    const int t = dir ? (T - 1 - s) : s;
+    float4 acc[REC_WPT];
+    const float4* Gt = reinterpret_cast<const float4*>(G) + (((long long)t * Bc) * 2 + dir) * H + j;
+#pragma unroll
+    for (int w = 0; w < REC_WPT; ++w) {
+      const int b = b_base + w;
+      acc[w] = (b < Bc) ? __ldg(Gt + (long long)b * 2 * H) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    const float* hcur = &hs[cur][0][grp * REC_WPT];
+#pragma unroll 2
+    for (int k = 0; k < H; ++k) {
+      const float4 w4 = __ldg(W + (long long)k * H + j);
+      const float4* hp = reinterpret_cast<const float4*>(hcur + k * HS);
+#pragma unroll
+      for (int q = 0; q < REC_WPT / 4; ++q) {
+        const float4 h4 = hp[q];
+        const float hv[4] = {h4.x, h4.y, h4.z, h4.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          float4& a = acc[q * 4 + e];
+          a.x = fmaf(hv[e], w4.x, a.x); a.y = fmaf(hv[e], w4.y, a.y);
+          a.z = fmaf(hv[e], w4.z, a.z); a.w = fmaf(hv[e], w4.w, a.w);
+        }
+      }
+    }
+    float4* hnext = reinterpret_cast<float4*>(&hs[cur ^ 1][j][grp * REC_WPT]);
+    float hq[4];
+#pragma unroll
+    for (int w = 0; w < REC_WPT; ++w) {
+      const float ig = sigmoid_acc(acc[w].x), fg = sigmoid_acc(acc[w].y);
+      const float gg = tanhf(acc[w].z), og = sigmoid_acc(acc[w].w);
+      c[w] = fmaf(fg, c[w], ig * gg);
+      const float hv = og * tanhf(c[w]);
+      hq[w & 3] = hv;
+      if ((w & 3) == 3) hnext[w >> 2] = make_float4(hq[0], hq[1], hq[2], hq[3]);
+      const int b = b_base + w;
+      if (b < Bc) {
+        const long long row = (long long)t * Bc + b;
+        out[row * (2 * H) + dir * H + j] = hv;
+        if (gates_save) {
+          reinterpret_cast<float4*>(gates_save)[(row * 2 + dir) * H + j] = make_float4(ig, fg, gg, og);
+          c_save[(row * 2 + dir) * H + j] = c[w];
+        }
+      }
+    }
+    __syncthreads();
+    cur ^= 1;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// weight packing (runs at bci_lstm_load_weights)
+// ---------------------------------------------------------------------------------------------
+__global__ void transpose_kernel(const float* __restrict__ src, float* __restrict__ dst, int rows, int cols) {
+  // dst[c][r] = src[r][c]
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)rows * cols) return;
+  const int r = (int)(i / cols), c = (int)(i - (long long)r * cols);
+  dst[(long long)c * rows + r] = src[i];
+}
+
+// src (4H, K) gate-major rows (i,f,g,o blocks) -> dst [K][ld] at column col0 + unit*4 + gate
+__global__ void pack_gates_t_kernel(const float* __restrict__ src, float* __restrict__ dst, int H, int K, int ld, int col0) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)4 * H * K) return;
+  const int row = (int)(i / K), k = (int)(i - (long long)row * K);
+  const int gate = row / H, unit = row - gate * H;
+  dst[(long long)k * ld + col0 + unit * 4 + gate] = src[i];
+}
+
+__global__ void pack_bias_kernel(const float* __restrict__ bih, const float* __restrict__ bhh, float* __restrict__ dst, int H, int col0) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 4 * H) return;
+  const int gate = i / H, unit = i - gate * H;
+  dst[col0 + unit * 4 + gate] = bih[i] + bhh[i];
+}
+
+__global__ void copy_kernel(const float* __restrict__ src, float* __restrict__ dst, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = src[i];
+}
+
+static inline unsigned nblk(long long n) { return (unsigned)ceil_div64(n, 256); }
+
+int lstm_pack_f32(bci_lstm_s* h, cudaStream_t st) {
+  const bci_lstm_config& c = h->cfg;
+  const bci_lstm_weights& w = h->raw;
+  PackedF32& p = h->f32;
+  const int H = c.hidden_size, C = c.input_size, D = 2 * H;
+  transpose_kernel<<<nblk((long long)H * C), 256, 0, st>>>(w.input_proj_w, p.w0t, H, C);
+  copy_kernel<<<nblk(H), 256, 0, st>>>(w.input_proj_b, p.b0, H);
+  copy_kernel<<<nblk(H), 256, 0, st>>>(w.input_ln_w, p.ln0w, H);
+  copy_kernel<<<nblk(H), 256, 0, st>>>(w.input_ln_b, p.ln0b, H);
+  for (int l = 0; l < c.num_layers; ++l) {
+    const int K = layer_in_width(c, l);
+    for (int d = 0; d < 2; ++d) {
+      pack_gates_t_kernel<<<nblk((long long)4 * H * K), 256, 0, st>>>(w.w_ih[l][d], p.wih_t[l], H, K, 8 * H, d * 4 * H);
+      pack_gates_t_kernel<<<nblk((long long)4 * H * H), 256, 0, st>>>(w.w_hh[l][d], p.whh_t[l][d], H, H, 4 * H, 0);
+      pack_bias_kernel<<<nblk(4 * H), 256, 0, st>>>(w.b_ih[l][d], w.b_hh[l][d], p.bias[l], H, d * 4 * H);
+    }
+  }
+  copy_kernel<<<nblk(D), 256, 0, st>>>(w.ln_w, p.lnw, D);
+  copy_kernel<<<nblk(D), 256, 0, st>>>(w.ln_b, p.lnb, D);
+  transpose_kernel<<<nblk((long long)H * D), 256, 0, st>>>(w.attn_w1, p.aw1t, H, D);
+  copy_kernel<<<nblk(H), 256, 0, st>>>(w.attn_b1, p.ab1, H);
+  copy_kernel<<<nblk(H), 256, 0, st>>>(w.attn_w2, p.aw2, H);
+  copy_kernel<<<1, 256, 0, st>>>(w.attn_b2, p.ab2, 1);
+  transpose_kernel<<<nblk((long long)H * D), 256, 0, st>>>(w.cls_w0, p.c0t, H, D);
+  copy_kernel<<<nblk(H), 256, 0, st>>>(w.cls_b0, p.cb0, H);
+  transpose_kernel<<<nblk((long long)(H / 2) * H), 256, 0, st>>>(w.cls_w3, p.c3t, H / 2, H);
+  copy_kernel<<<nblk(H / 2), 256, 0, st>>>(w.cls_b3, p.cb3, H / 2);
+  copy_kernel<<<nblk(c.num_classes * (H / 2)), 256, 0, st>>>(w.cls_w6, p.c6, c.num_classes * (H / 2));
+  copy_kernel<<<1, 256, 0, st>>>(w.cls_b6, p.cb6, c.num_classes);
+  BCI_LAUNCH_OK();
+  return BCI_OK;
+}
+
+size_t lstm_store_bytes_f32(const bci_lstm_config& c) {
+  const size_t H = c.hidden_size, C = c.input_size, D = 2 * H;
+  size_t n = C * H + 3 * H;
+  for (int l = 0; l < c.num_layers; ++l) n += (size_t)layer_in_width(c, l) * 8 * H + 8 * H + 2 * H * 4 * H;
+  n += 2 * D + D * H + H + H + 4 + D * H + H + H * (H / 2) + H / 2 + (size_t)c.num_classes * (H / 2) + c.num_classes + 64;
+  return align_up(n * sizeof(float) + 256 * 64, 256);
+}
+
+void lstm_carve_f32(bci_lstm_s* h, char* base) {
+  const bci_lstm_config& c = h->cfg;
+  const size_t H = c.hidden_size, C = c.input_size, D = 2 * H;
+  size_t off = 0;
+  auto take = [&](size_t n) { float* p = reinterpret_cast<float*>(base + off); off += align_up(n * sizeof(float), 256); return p; };
+  PackedF32& p = h->f32;
+  p.w0t = take(C * H); p.b0 = take(H); p.ln0w = take(H); p.ln0b = take(H);
+  for (int l = 0; l < c.num_layers; ++l) {
+    p.wih_t[l] = take((size_t)layer_in_width(c, l) * 8 * H);
+    p.bias[l] = take(8 * H);
+    p.whh_t[l][0] = take(H * 4 * H);
+    p.whh_t[l][1] = take(H * 4 * H);
+  }
+  p.lnw = take(D); p.lnb = take(D); p.aw1t = take(D * H); p.ab1 = take(H); p.aw2 = take(H); p.ab2 = take(4);
+  p.c0t = take(D * H); p.cb0 = take(H); p.c3t = take(H * (H / 2)); p.cb3 = take(H / 2);
+  p.c6 = take((size_t)c.num_classes * (H / 2)); p.cb6 = take(c.num_classes);
+}
+
+// ---------------------------------------------------------------------------------------------
+// host orchestration
+// ---------------------------------------------------------------------------------------------
+static size_t chunk_bytes_f32(const bci_lstm_config& c, int Bc, int T) {
+  const size_t H = c.hidden_size, rows = (size_t)Bc * T;
+  return align_up(rows * H * 4, 256) + align_up(rows * 8 * H * 4, 256) + 2 * align_up(rows * 2 * H * 4, 256) +
+         align_up((size_t)Bc * T * 4, 256);
+}
+
+size_t lstm_workspace_fp32(const bci_lstm_config& c, int batch, int T) {
+  const int Bc = batch < max_chunk(c, 0) ? batch : max_chunk(c, 0);
+  return chunk_bytes_f32(c, Bc > 0 ? Bc : 1, T);
+}
+
+template <int H>
+static int forward_chunk_f32(bci_lstm_s* h, const float* x, int Bc, int T, float* logits, float* probs, float* attn,
+                             char* ws, cudaStream_t st) {
+  const bci_lstm_config& c = h->cfg;
+  const size_t rows = (size_t)Bc * T;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { char* p = ws + off; off += align_up(bytes, 256); return p; };
+  float* z = reinterpret_cast<float*>(take(rows * H * 4));
+  float* g = reinterpret_cast<float*>(take(rows * 8 * H * 4));
+  float* o0 = reinterpret_cast<float*>(take(rows * 2 * H * 4));
+  float* o1 = reinterpret_cast<float*>(take(rows * 2 * H * 4));
+  float* scores = reinterpret_cast<float*>(take(rows * 4));
+  int rc = launch_input_proj<H, float>(h, x, Bc, T, z, st);
+  if (rc) return rc;
+  const float* in = z;
+  float* outs[2] = {o0, o1};
+  constexpr int MT = (REC_THREADS / H) * REC_WPT;
+  for (int l = 0; l < c.num_layers; ++l) {
+    const int K = layer_in_width(c, l);
+    const int M = (int)rows, N = 8 * H;
+    dim3 gg(N / GN, ceil_div(M, GM));
+    proj_gemm_f32<<<gg, GEMM_THREADS, 0, st>>>(in, h->f32.wih_t[l], h->f32.bias[l], g, M, N, K);
+    BCI_LAUNCH_OK();
+    float* o = outs[l & 1];
+    dim3 gr(ceil_div(Bc, MT), 2);
+    lstm_rec_f32<H><<<gr, REC_THREADS, 0, st>>>(g, h->f32.whh_t[l][0], h->f32.whh_t[l][1], o, nullptr, nullptr, Bc, T);
+    BCI_LAUNCH_OK();
+    in = o;
+  }
+  return launch_pool_head<H, float>(h, in, Bc, T, logits, probs, attn, scores, st);
+}
+
+int lstm_forward_fp32(bci_lstm_s* h, const float* x, int batch, int T, float* logits, float* probs, float* attn,
+                      void* ws, size_t ws_bytes, cudaStream_t st) {
+  const bci_lstm_config& c = h->cfg;
+  const int chunk = batch < max_chunk(c, 0) ? batch : max_chunk(c, 0);
+  BCI_REQUIRE(ws_bytes >= chunk_bytes_f32(c, chunk, T), BCI_ENOMEM, "bci_lstm_forward: workspace %zu < %zu bytes", ws_bytes,
+              chunk_bytes_f32(c, chunk, T));
+  for (int b0 = 0; b0 < batch; b0 += chunk) {
+    const int Bc = (batch - b0) < chunk ? (batch - b0) : chunk;
+    const float* xb = x + (size_t)b0 * T * c.input_size;
+    float* lg = logits + (size_t)b0 * c.num_classes;
+    float* pr = probs ? probs + (size_t)b0 * c.num_classes : nullptr;
+    float* at = attn ? attn + (size_t)b0 * T : nullptr;
+    int rc = c.hidden_size == 128 ? forward_chunk_f32<128>(h, xb, Bc, T, lg, pr, at, (char*)ws, st)
+                                  : forward_chunk_f32<256>(h, xb, Bc, T, lg, pr, at, (char*)ws, st);
+    if (rc) return rc;
+  }
+  return BCI_OK;
+}
+
+}  // namespace bci

@@ -1,0 +1,89 @@
+// Handle + packed-weight layout shared by the LSTM translation units.
+#pragma once
+#include "common.cuh"
+#include <cuda_bf16.h>
+
+namespace bci {
+
+// Packed fp32 weights (all device pointers into one allocation owned by the handle).
+// Gate-interleaved column order everywhere: column n = dir*4H + unit*4 + gate (gate = i,f,g,o)
+// so that one thread owning hidden unit `unit` reads its four gates as one float4.
+struct PackedF32 {
+  float* w0t;    // [C][H]      input_proj.0.weight^T
+  float* b0;     // [H]
+  float* ln0w;   // [H]
+  float* ln0b;   // [H]
+  float* wih_t[BCI_MAX_LAYERS];     // [K_l][8H]   both directions, gate-interleaved
+  float* bias[BCI_MAX_LAYERS];      // [8H]        b_ih + b_hh, same order
+  float* whh_t[BCI_MAX_LAYERS][2];  // [H][4H]     per direction, gate-interleaved
+  float* lnw;    // [2H]
+  float* lnb;    // [2H]
+  float* aw1t;   // [2H][H]     attention.0.weight^T
+  float* ab1;    // [H]
+  float* aw2;    // [H]
+  float* ab2;    // [1]
+  float* c0t;    // [2H][H]     classifier.0.weight^T
+  float* cb0;    // [H]
+  float* c3t;    // [H][H/2]    classifier.3.weight^T
+  float* cb3;    // [H/2]
+  float* c6;     // [classes][H/2]
+  float* cb6;    // [classes]
+};
+
+// bf16 operand copies for the tcgen05 path (K-major rows, PyTorch (out,in) orientation kept):
+//   wih_bf[l]    [8H][K_l]  row n' = dir*4H + perm(unit,gate)   (B operand of the projection GEMM)
+//   whh_bf[l][d] [4H][H]    row n' = perm(unit,gate)            (B operand of the recurrence MMA)
+//   bias_p[l]    [8H] fp32 in the same permuted order
+// perm(unit,gate) = (unit/8)*32 + gate*8 + unit%8: a 32-column TMEM slab holds i,f,g,o of 8 units.
+struct PackedBF16 {
+  __nv_bfloat16* wih_bf[BCI_MAX_LAYERS];
+  __nv_bfloat16* whh_bf[BCI_MAX_LAYERS][2];
+  float* bias_p[BCI_MAX_LAYERS];
+};
+
+}  // namespace bci
+
+struct bci_lstm_s {
+  bci_lstm_config cfg;
+  int device;
+  bool loaded;
+  void* store;         // one cudaMalloc
+  size_t store_bytes;
+  bci::PackedF32 f32;
+  bci::PackedBF16 bf16;
+  // raw (unpacked) weight pointers of the last load_weights (caller-owned; used by backward)
+  bci_lstm_weights raw;
+};
+
+namespace bci {
+
+inline int layer_in_width(const bci_lstm_config& c, int l) { return l == 0 ? c.hidden_size : 2 * c.hidden_size; }
+
+// chunking policy: windows processed per internal pass (bounds the workspace)
+inline int max_chunk(const bci_lstm_config& c, int train) {
+  if (c.precision == BCI_PRECISION_BF16) return train ? 2048 : 16384;
+  const int base = train ? 512 : 2048;
+  return c.hidden_size > 128 ? base / 2 : base;
+}
+
+struct FwdWorkspace {
+  // fp32 path
+  float* z;       // [T][Bc][H]
+  float* g;       // [T][Bc][8H]
+  float* out[2];  // [T][Bc][2H] ping-pong
+  size_t total;
+};
+
+// fp32 forward entry points (lstm_fp32.cu)
+int lstm_forward_fp32(bci_lstm_s* h, const float* x, int batch, int T, float* logits, float* probs, float* attn,
+                      void* ws, size_t ws_bytes, cudaStream_t st);
+size_t lstm_workspace_fp32(const bci_lstm_config& c, int batch, int T);
+// bf16 / tcgen05 forward (lstm_bf16.cu)
+int lstm_forward_bf16(bci_lstm_s* h, const float* x, int batch, int T, float* logits, float* probs, float* attn,
+                      void* ws, size_t ws_bytes, cudaStream_t st);
+size_t lstm_workspace_bf16(const bci_lstm_config& c, int batch, int T);
+int lstm_pack_bf16(bci_lstm_s* h, cudaStream_t st);
+size_t lstm_store_bytes_bf16(const bci_lstm_config& c);
+void lstm_carve_bf16(bci_lstm_s* h, char* base);
+
+}  // namespace bci

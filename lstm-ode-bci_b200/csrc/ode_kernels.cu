@@ -1,0 +1,512 @@
+// Three-state A/P/F ODE ensemble with probabilistic rate coupling -- one thread per trajectory.
+//
+// Replaces the serial host loops of the reference (06_lstm_ode_integration.py:372-401,
+// 10_three_state_probabilities.py:245-273, 08_forecasting.py:264-282) and the solver calls
+// inside them (CognitiveStateODE.solve 06:174-180; predict_trajectory 08:149-153).
+//
+// RK4 (fp32, FP32-pipe bound): classical Runge-Kutta with S equal sub-steps per output
+// interval; the state update is Kahan-compensated so that fp32 rounding does not accumulate
+// over the 19*S steps (plain fp32 drifts to ~9e-7).  Per-trajectory inputs are
+// read as coalesced structure-of-arrays; the (N,n,3) output is staged through shared memory
+// (odd row stride => conflict free) and written back as one contiguous, fully coalesced
+// stream per block.
+//
+// RK45 (fp64): Dormand-Prince 5(4) with scipy.integrate.solve_ivp's controller restated
+// (scipy/integrate/_ivp/rk.py, common.py, ivp.py): select_initial_step, RMS error norm with
+// scale = atol + max(|y|,|y_new|)*rtol, SAFETY 0.9, factor range [0.2,10], exponent -1/5, no
+// growth after a rejection, quartic dense output evaluated at the t_eval grid.  Step
+// accept/reject decisions are discontinuous, so the whole controller runs in fp64 per thread.
+#include "common.cuh"
+#include <math_constants.h>
+
+namespace bci {
+
+constexpr int ODE_BLOCK = 128;
+constexpr int ODE_CHUNK_POINTS = 20;  // output points staged in smem per flush
+
+struct OdeParams {
+  int style, y0_mode, coupling;
+  long long n;
+  float base[6];
+  float alpha;
+  const float* rates;
+  const float* alpha_arr;
+  const float* p_open;
+  const float* p_closed;
+  const float* y0;
+  double t_end;
+  int n_points;
+  int substeps;
+  double rtol, atol;
+  void* traj;
+  void* final_state;
+  int* n_steps;
+};
+
+// ---- per-trajectory setup shared by both integrators -------------------------------------
+// Coupling in fp32 with one rounding per operation (no FMA contraction): the reference
+// evaluates params[k] * (1 + alpha * p) on float32 numpy scalars (06:249-258; NumPy>=2
+// promotion), so this is bit-faithful to it.
+__device__ __forceinline__ void load_rates(const OdeParams& P, long long i, float k[6], float& po, float& pc) {
+  if (P.rates) {
+#pragma unroll
+    for (int r = 0; r < 6; ++r) k[r] = __ldg(P.rates + (long long)r * P.n + i);
+  } else {
+#pragma unroll
+    for (int r = 0; r < 6; ++r) k[r] = P.base[r];
+  }
+  po = P.p_open ? __ldg(P.p_open + i) : 0.f;
+  pc = P.p_closed ? __ldg(P.p_closed + i) : 0.f;
+  if (P.coupling) {
+    const float a = P.alpha_arr ? __ldg(P.alpha_arr + i) : P.alpha;
+    const float fat = __fadd_rn(1.0f, __fmul_rn(a, pc));
+    const float rec = __fadd_rn(1.0f, __fmul_rn(a, po));
+    k[1] = __fmul_rn(k[1], fat);  // k_af   Active  -> Fatigued
+    k[3] = __fmul_rn(k[3], fat);  // k_pf   Passive -> Fatigued
+    k[4] = __fmul_rn(k[4], rec);  // k_fa   Fatigued -> Active
+    k[2] = __fmul_rn(k[2], rec);  // k_pa   Passive -> Active
+#pragma unroll
+    for (int r = 0; r < 6; ++r) k[r] = fmaxf(0.001f, k[r]);  // 06:261-262
+  }
+}
+
+// Initial state.  06-style constants are the fp64 literals of 06:377-382 (normalised by their
+// sum in fp64 as solve() does, 06:176); 08-style follows prob_to_ode_state (08:215-234) in
+// fp32 with unfused operations, matching the float32 evaluation in the reference.
+__device__ __forceinline__ void initial_state(const OdeParams& P, long long i, float po, float pc, double y[3]) {
+  if (P.y0_mode == BCI_Y0_FROM_PROBS_06) {
+    if (pc > 0.6f)      { y[0] = 0.2;  y[1] = 0.2;  y[2] = 0.6; }
+    else if (po > 0.6f) { y[0] = 0.6;  y[1] = 0.2;  y[2] = 0.2; }
+    else                { y[0] = 0.33; y[1] = 0.34; y[2] = 0.33; }
+  } else if (P.y0_mode == BCI_Y0_FROM_PCLOSED_08) {
+    const float a = __fsub_rn(1.0f, pc);
+    const bool hi = pc > 0.5f;
+    const float f = __fmul_rn(pc, hi ? 0.6f : 0.3f);
+    const float p = __fmul_rn(pc, hi ? 0.4f : 0.3f);
+    const float tot = __fadd_rn(__fadd_rn(a, p), f);
+    y[0] = (double)__fdiv_rn(a, tot);
+    y[1] = (double)__fdiv_rn(p, tot);
+    y[2] = (double)__fdiv_rn(f, tot);
+  } else {
+    y[0] = (double)__ldg(P.y0 + i);
+    y[1] = (double)__ldg(P.y0 + P.n + i);
+    y[2] = (double)__ldg(P.y0 + 2 * P.n + i);
+  }
+  if (P.style == BCI_ODE_STYLE_REF06) {  // 06:176  y0 / sum(y0)
+    const double s = (y[0] + y[1]) + y[2];
+    y[0] /= s; y[1] /= s; y[2] /= s;
+  }
+}
+
+// clip[0,1] + renormalise (06:178-179)
+template <typename T>
+__device__ __forceinline__ void post06(T& a, T& p, T& f) {
+  a = a < T(0) ? T(0) : (a > T(1) ? T(1) : a);
+  p = p < T(0) ? T(0) : (p > T(1) ? T(1) : p);
+  f = f < T(0) ? T(0) : (f > T(1) ? T(1) : f);
+  const T s = (a + p) + f;
+  a /= s; p /= s; f /= s;
+}
+
+// ---- RK4, fp32 ---------------------------------------------------------------------------
+template <bool CLAMP>
+__device__ __forceinline__ void rhs32(const float k[6], float A, float P, float F, float& dA, float& dP, float& dF) {
+  if (CLAMP) { A = fmaxf(A, 0.f); P = fmaxf(P, 0.f); F = fmaxf(F, 0.f); }
+  // dA = -k_ap A - k_af A + k_pa P + k_fa F ; dP = k_ap A - k_pa P - k_pf P + k_fp F ;
+  // dF = k_af A + k_pf P - k_fa F - k_fp F            (05_ode_model.py:129-133)
+  dA = fmaf(k[4], F, fmaf(k[2], P, fmaf(-k[1], A, -k[0] * A)));
+  dP = fmaf(k[5], F, fmaf(-k[3], P, fmaf(-k[2], P, k[0] * A)));
+  dF = fmaf(-k[5], F, fmaf(-k[4], F, fmaf(k[3], P, k[1] * A)));
+}
+
+template <bool CLAMP, typename OutT>
+__global__ void __launch_bounds__(ODE_BLOCK)
+ode_rk4_kernel(const OdeParams P) {
+  extern __shared__ float stage[];  // [ODE_BLOCK][row_stride]
+  const int tid = threadIdx.x;
+  const long long base_i = (long long)blockIdx.x * ODE_BLOCK;
+  const long long i = base_i + tid;
+  const bool live = i < P.n;
+  const int n3 = P.n_points * 3;
+  const int chunk_pts = P.n_points < ODE_CHUNK_POINTS ? P.n_points : ODE_CHUNK_POINTS;
+  const int row_stride = (chunk_pts * 3) | 1;
+  const bool want_traj = P.traj != nullptr;
+  const int rows_here = (int)((P.n - base_i) < ODE_BLOCK ? (P.n - base_i) : ODE_BLOCK);
+
+  float k[6] = {0, 0, 0, 0, 0, 0};
+  float A = 0.f, Pp = 0.f, F = 0.f;
+  int S = 1;
+  float h = 0.f;
+  if (live) {
+    float po, pc;
+    load_rates(P, i, k, po, pc);
+    double y[3];
+    initial_state(P, i, po, pc, y);
+    A = (float)y[0]; Pp = (float)y[1]; F = (float)y[2];
+    const double dt_out = P.t_end / (double)(P.n_points - 1);
+    S = P.substeps;
+    if (S <= 0) {  // per-trajectory: 0.01 (h lam)^4 <= 2e-7  <=>  h lam <= 0.0669
+      const float lam = fmaxf(fmaxf(k[0] + k[1], k[2] + k[3]), k[4] + k[5]);
+      S = (int)ceil(dt_out * (double)lam / 0.0669);
+      S = S < 1 ? 1 : (S > 4096 ? 4096 : S);
+    }
+    h = (float)(dt_out / (double)S);
+  }
+  const float hh = 0.5f * h, h6 = h * (1.0f / 6.0f);
+  float cA = 0.f, cP = 0.f, cF = 0.f;  // Kahan compensation of the state
+
+  int pt = 0;  // next output point index
+  while (pt < P.n_points) {
+    const int pts = (P.n_points - pt) < chunk_pts ? (P.n_points - pt) : chunk_pts;
+    for (int q = 0; q < pts; ++q, ++pt) {
+      if (live && pt > 0) {
+        for (int s = 0; s < S; ++s) {
+          float a1, p1, f1, a2, p2, f2, a3, p3, f3, a4, p4, f4;
+          rhs32<CLAMP>(k, A, Pp, F, a1, p1, f1);
+          rhs32<CLAMP>(k, fmaf(hh, a1, A), fmaf(hh, p1, Pp), fmaf(hh, f1, F), a2, p2, f2);
+          rhs32<CLAMP>(k, fmaf(hh, a2, A), fmaf(hh, p2, Pp), fmaf(hh, f2, F), a3, p3, f3);
+          rhs32<CLAMP>(k, fmaf(h, a3, A), fmaf(h, p3, Pp), fmaf(h, f3, F), a4, p4, f4);
+          // y += h/6 (k1 + 2 k2 + 2 k3 + k4), compensated
+          const float dAa = fmaf(h6, (a1 + a4) + 2.0f * (a2 + a3), -cA);
+          const float dPp = fmaf(h6, (p1 + p4) + 2.0f * (p2 + p3), -cP);
+          const float dFf = fmaf(h6, (f1 + f4) + 2.0f * (f2 + f3), -cF);
+          const float nA = A + dAa, nP = Pp + dPp, nF = F + dFf;
+          cA = (nA - A) - dAa; cP = (nP - Pp) - dPp; cF = (nF - F) - dFf;
+          A = nA; Pp = nP; F = nF;
+        }
+      }
+      if (want_traj) {
+        float oa = A, op = Pp, of = F;
+        if (CLAMP) post06(oa, op, of);
+        float* row = stage + tid * row_stride + q * 3;
+        row[0] = oa; row[1] = op; row[2] = of;
+      }
+    }
+    if (want_traj) {
+      __syncthreads();
+      // flush [rows_here][pts*3] -> traj[(base_i+r)*n3 + (pt-pts)*3 + c]
+      const int w = pts * 3;
+      const int col0 = (pt - pts) * 3;
+      OutT* out = reinterpret_cast<OutT*>(P.traj);
+      if (w == n3) {  // whole rows staged: one contiguous range, fully coalesced
+        const int total = rows_here * w;
+        OutT* dst = out + base_i * n3;
+        for (int e = tid; e < total; e += ODE_BLOCK) {
+          const int r = e / w, c = e - r * w;
+          dst[e] = (OutT)stage[r * row_stride + c];
+        }
+      } else {
+        const int total = rows_here * w;
+        for (int e = tid; e < total; e += ODE_BLOCK) {
+          const int r = e / w, c = e - r * w;
+          out[(base_i + r) * n3 + col0 + c] = (OutT)stage[r * row_stride + c];
+        }
+      }
+      __syncthreads();
+    }
+  }
+  if (live) {
+    if (P.final_state) {
+      float oa = A, op = Pp, of = F;
+      if (CLAMP) post06(oa, op, of);
+      OutT* fs = reinterpret_cast<OutT*>(P.final_state) + i * 3;
+      fs[0] = (OutT)oa; fs[1] = (OutT)op; fs[2] = (OutT)of;
+    }
+    if (P.n_steps) P.n_steps[i] = S * (P.n_points - 1);
+  }
+}
+
+// ---- RK45 (scipy-exact Dormand-Prince), fp64 -----------------------------------------------
+template <bool CLAMP>
+__device__ __forceinline__ void rhs64(const double k[6], double A, double P, double F, double d[3]) {
+  if (CLAMP) { A = fmax(A, 0.0); P = fmax(P, 0.0); F = fmax(F, 0.0); }
+  // same left-to-right evaluation order as the Python expressions (no contraction)
+  d[0] = __dadd_rn(__dadd_rn(__dsub_rn(__dmul_rn(-k[0], A), __dmul_rn(k[1], A)), __dmul_rn(k[2], P)), __dmul_rn(k[4], F));
+  d[1] = __dadd_rn(__dsub_rn(__dsub_rn(__dmul_rn(k[0], A), __dmul_rn(k[2], P)), __dmul_rn(k[3], P)), __dmul_rn(k[5], F));
+  d[2] = __dsub_rn(__dsub_rn(__dadd_rn(__dmul_rn(k[1], A), __dmul_rn(k[3], P)), __dmul_rn(k[4], F)), __dmul_rn(k[5], F));
+}
+
+__device__ __forceinline__ double rms3(double a, double b, double c) {
+  return sqrt(a * a + b * b + c * c) / sqrt(3.0);
+}
+
+template <bool CLAMP, typename OutT>
+__global__ void __launch_bounds__(ODE_BLOCK)
+ode_rk45_kernel(const OdeParams P) {
+  const long long i = (long long)blockIdx.x * ODE_BLOCK + threadIdx.x;
+  if (i >= P.n) return;
+  // Butcher tableau (rk.py RK45)
+  const double A21 = 1.0 / 5;
+  const double A31 = 3.0 / 40, A32 = 9.0 / 40;
+  const double A41 = 44.0 / 45, A42 = -56.0 / 15, A43 = 32.0 / 9;
+  const double A51 = 19372.0 / 6561, A52 = -25360.0 / 2187, A53 = 64448.0 / 6561, A54 = -212.0 / 729;
+  const double A61 = 9017.0 / 3168, A62 = -355.0 / 33, A63 = 46732.0 / 5247, A64 = 49.0 / 176, A65 = -5103.0 / 18656;
+  const double B1 = 35.0 / 384, B3 = 500.0 / 1113, B4 = 125.0 / 192, B5 = -2187.0 / 6784, B6 = 11.0 / 84;
+  const double E1 = -71.0 / 57600, E3 = 71.0 / 16695, E4 = -71.0 / 1920, E5 = 17253.0 / 339200, E6 = -22.0 / 525, E7 = 1.0 / 40;
+  const double P1[4] = {1.0, -8048581381.0 / 2820520608.0, 8663915743.0 / 2820520608.0, -12715105075.0 / 11282082432.0};
+  const double P3[4] = {0.0, 131558114200.0 / 32700410799.0, -68118460800.0 / 10900136933.0, 87487479700.0 / 32700410799.0};
+  const double P4[4] = {0.0, -1754552775.0 / 470086768.0, 14199869525.0 / 1410260304.0, -10690763975.0 / 1880347072.0};
+  const double P5[4] = {0.0, 127303824393.0 / 49829197408.0, -318862633887.0 / 49829197408.0, 701980252875.0 / 199316789632.0};
+  const double P6[4] = {0.0, -282668133.0 / 205662961.0, 2019193451.0 / 616988883.0, -1453857185.0 / 822651844.0};
+  const double P7[4] = {0.0, 40617522.0 / 29380423.0, -110615467.0 / 29380423.0, 69997945.0 / 29380423.0};
+
+  float kf[6], po, pc;
+  load_rates(P, i, kf, po, pc);
+  double k[6];
+#pragma unroll
+  for (int r = 0; r < 6; ++r) k[r] = (double)kf[r];
+  double y[3];
+  initial_state(P, i, po, pc, y);
+
+  const double rtol = P.rtol, atol = P.atol, t_end = P.t_end;
+  const int n_points = P.n_points;
+  const double dt_out = t_end / (double)(n_points - 1);  // np.linspace step
+  OutT* traj = reinterpret_cast<OutT*>(P.traj);
+  const long long n3 = (long long)n_points * 3;
+
+  double f0[3];
+  rhs64<CLAMP>(k, y[0], y[1], y[2], f0);
+  // select_initial_step (common.py)
+  double h_abs;
+  {
+    double sc[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) sc[c] = atol + fabs(y[c]) * rtol;
+    const double d0 = rms3(y[0] / sc[0], y[1] / sc[1], y[2] / sc[2]);
+    const double d1 = rms3(f0[0] / sc[0], f0[1] / sc[1], f0[2] / sc[2]);
+    double h0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * d0 / d1;
+    h0 = fmin(h0, t_end);
+    double f1[3];
+    rhs64<CLAMP>(k, y[0] + h0 * f0[0], y[1] + h0 * f0[1], y[2] + h0 * f0[2], f1);
+    const double d2 = rms3((f1[0] - f0[0]) / sc[0], (f1[1] - f0[1]) / sc[1], (f1[2] - f0[2]) / sc[2]) / h0;
+    double h1;
+    if (d1 <= 1e-15 && d2 <= 1e-15) h1 = fmax(1e-6, h0 * 1e-3);
+    else h1 = pow(0.01 / fmax(d1, d2), 1.0 / 5.0);
+    h_abs = fmin(fmin(100.0 * h0, h1), t_end);
+  }
+
+  double t = 0.0;
+  int ti = 0, steps = 0;
+  double last[3] = {y[0], y[1], y[2]};
+  while (t < t_end && steps < 100000) {
+    const double min_step = 10.0 * fabs(nextafter(t, (double)CUDART_INF) - t);
+    if (h_abs < min_step) h_abs = min_step;
+    bool rejected = false;
+    double K[7][3], y_new[3], t_new, h;
+    while (true) {
+      ++steps;
+      t_new = t + h_abs;
+      if (t_new - t_end > 0.0) t_new = t_end;
+      h = t_new - t;
+      h_abs = fabs(h);
+#pragma unroll
+      for (int c = 0; c < 3; ++c) K[0][c] = f0[c];
+      // stage s: dy = dot(K[:s].T, a[:s]) * h ; K[s] = f(y + dy)       (rk_step)
+      double ys[3];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) ys[c] = y[c] + (K[0][c] * A21) * h;
+      rhs64<CLAMP>(k, ys[0], ys[1], ys[2], K[1]);
+#pragma unroll
+      for (int c = 0; c < 3; ++c) ys[c] = y[c] + (K[0][c] * A31 + K[1][c] * A32) * h;
+      rhs64<CLAMP>(k, ys[0], ys[1], ys[2], K[2]);
+#pragma unroll
+      for (int c = 0; c < 3; ++c) ys[c] = y[c] + (K[0][c] * A41 + K[1][c] * A42 + K[2][c] * A43) * h;
+      rhs64<CLAMP>(k, ys[0], ys[1], ys[2], K[3]);
+#pragma unroll
+      for (int c = 0; c < 3; ++c) ys[c] = y[c] + (K[0][c] * A51 + K[1][c] * A52 + K[2][c] * A53 + K[3][c] * A54) * h;
+      rhs64<CLAMP>(k, ys[0], ys[1], ys[2], K[4]);
+#pragma unroll
+      for (int c = 0; c < 3; ++c) ys[c] = y[c] + (K[0][c] * A61 + K[1][c] * A62 + K[2][c] * A63 + K[3][c] * A64 + K[4][c] * A65) * h;
+      rhs64<CLAMP>(k, ys[0], ys[1], ys[2], K[5]);
+#pragma unroll
+      for (int c = 0; c < 3; ++c)
+        y_new[c] = y[c] + h * (K[0][c] * B1 + K[2][c] * B3 + K[3][c] * B4 + K[4][c] * B5 + K[5][c] * B6);
+      rhs64<CLAMP>(k, y_new[0], y_new[1], y_new[2], K[6]);
+      double e[3];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const double sc = atol + fmax(fabs(y[c]), fabs(y_new[c])) * rtol;
+        const double err = (K[0][c] * E1 + K[2][c] * E3 + K[3][c] * E4 + K[4][c] * E5 + K[5][c] * E6 + K[6][c] * E7) * h;
+        e[c] = err / sc;
+      }
+      const double err_norm = rms3(e[0], e[1], e[2]);
+      if (err_norm < 1.0) {
+        double factor = (err_norm == 0.0) ? 10.0 : fmin(10.0, 0.9 * pow(err_norm, -0.2));
+        if (rejected) factor = fmin(1.0, factor);
+        h_abs *= factor;
+        break;
+      }
+      h_abs *= fmax(0.2, 0.9 * pow(err_norm, -0.2));
+      rejected = true;
+      if (steps >= 100000) break;
+    }
+    // dense output for every t_eval[ti] <= t_new   (ivp.py: searchsorted side='right')
+    while (ti < n_points) {
+      const double te = (ti == n_points - 1) ? t_end : (double)ti * dt_out;
+      if (te > t_new) break;
+      const double x = (te - t) / h;
+      const double x2 = x * x, x3 = x2 * x, x4 = x3 * x;
+      double o[3];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const double q0 = K[0][c] * P1[0];
+        const double q1 = K[0][c] * P1[1] + K[2][c] * P3[1] + K[3][c] * P4[1] + K[4][c] * P5[1] + K[5][c] * P6[1] + K[6][c] * P7[1];
+        const double q2 = K[0][c] * P1[2] + K[2][c] * P3[2] + K[3][c] * P4[2] + K[4][c] * P5[2] + K[5][c] * P6[2] + K[6][c] * P7[2];
+        const double q3 = K[0][c] * P1[3] + K[2][c] * P3[3] + K[3][c] * P4[3] + K[4][c] * P5[3] + K[5][c] * P6[3] + K[6][c] * P7[3];
+        o[c] = h * (q0 * x + q1 * x2 + q2 * x3 + q3 * x4) + y[c];
+      }
+      if (CLAMP) post06(o[0], o[1], o[2]);
+      if (traj) {
+        OutT* dst = traj + i * n3 + (long long)ti * 3;
+        dst[0] = (OutT)o[0]; dst[1] = (OutT)o[1]; dst[2] = (OutT)o[2];
+      }
+      last[0] = o[0]; last[1] = o[1]; last[2] = o[2];
+      ++ti;
+    }
+    t = t_new;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) { y[c] = y_new[c]; f0[c] = K[6][c]; }
+  }
+  if (P.final_state) {
+    OutT* fs = reinterpret_cast<OutT*>(P.final_state) + i * 3;
+    fs[0] = (OutT)last[0]; fs[1] = (OutT)last[1]; fs[2] = (OutT)last[2];
+  }
+  if (P.n_steps) P.n_steps[i] = steps;
+}
+
+// ---- read-outs ------------------------------------------------------------------------------
+__global__ void ode_classify_kernel(const float* __restrict__ fs, long long n, int* pred06, int* cls10) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float a = fs[i * 3 + 0], f = fs[i * 3 + 2];
+  if (pred06) pred06[i] = f > 0.5f ? 1 : 0;
+  if (cls10) cls10[i] = f > 0.5f ? 2 : (a > 0.5f ? 0 : 1);
+}
+
+struct Horizons { int h[16]; int n; };
+__global__ void ode_readout_kernel(const float* __restrict__ traj, long long n, int n_points, Horizons H, float* out) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n * H.n) return;
+  const long long i = e / H.n;
+  const int j = (int)(e - i * H.n);
+  const float* row = traj + (i * n_points + H.h[j]) * 3;
+  // trajectory[h, 2] + trajectory[h, 1] * 0.5, clipped to [0,1]   (08:275-278)
+  const float v = __fadd_rn(row[2], __fmul_rn(row[1], 0.5f));
+  out[e] = fminf(fmaxf(v, 0.f), 1.f);
+}
+
+// ---- FP32 FMA peak probe -------------------------------------------------------------------
+__global__ void __launch_bounds__(256) fma_probe_kernel(float* out, int iters) {
+  float a0 = threadIdx.x * 1e-3f, a1 = a0 + 1.f, a2 = a0 + 2.f, a3 = a0 + 3.f;
+  float a4 = a0 + 4.f, a5 = a0 + 5.f, a6 = a0 + 6.f, a7 = a0 + 7.f;
+  const float m = 0.999f, c = 1e-3f;
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+      a0 = fmaf(a0, m, c); a1 = fmaf(a1, m, c); a2 = fmaf(a2, m, c); a3 = fmaf(a3, m, c);
+      a4 = fmaf(a4, m, c); a5 = fmaf(a5, m, c); a6 = fmaf(a6, m, c); a7 = fmaf(a7, m, c);
+    }
+  }
+  out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+}
+
+}  // namespace bci
+
+using namespace bci;
+
+template <bool CLAMP, typename OutT>
+static int launch_ode(const OdeParams& P, int mode, cudaStream_t st) {
+  const unsigned grid = (unsigned)ceil_div64(P.n, ODE_BLOCK);
+  if (mode == BCI_ODE_RK4) {
+    const int chunk_pts = P.n_points < ODE_CHUNK_POINTS ? P.n_points : ODE_CHUNK_POINTS;
+    const size_t smem = P.traj ? (size_t)ODE_BLOCK * ((chunk_pts * 3) | 1) * sizeof(float) : 0;
+    ode_rk4_kernel<CLAMP, OutT><<<grid, ODE_BLOCK, smem, st>>>(P);
+  } else {
+    ode_rk45_kernel<CLAMP, OutT><<<grid, ODE_BLOCK, 0, st>>>(P);
+  }
+  BCI_LAUNCH_OK();
+  return BCI_OK;
+}
+
+extern "C" int bci_ode_solve(const bci_ode_args* a, void* stream) {
+  BCI_REQUIRE(a != nullptr, BCI_EINVAL, "bci_ode_solve: args is NULL");
+  BCI_REQUIRE(a->mode == BCI_ODE_RK4 || a->mode == BCI_ODE_RK45, BCI_EINVAL, "bci_ode_solve: bad mode %d", a->mode);
+  BCI_REQUIRE(a->style == BCI_ODE_STYLE_REF06 || a->style == BCI_ODE_STYLE_REF08, BCI_EINVAL, "bci_ode_solve: bad style %d", a->style);
+  BCI_REQUIRE(a->y0_mode >= BCI_Y0_GIVEN && a->y0_mode <= BCI_Y0_FROM_PCLOSED_08, BCI_EINVAL, "bci_ode_solve: bad y0_mode %d", a->y0_mode);
+  BCI_REQUIRE(a->n >= 0, BCI_EINVAL, "bci_ode_solve: negative n");
+  BCI_REQUIRE(a->n_points >= 2, BCI_EINVAL, "bci_ode_solve: n_points must be >= 2 (got %d)", a->n_points);
+  BCI_REQUIRE(a->t_end > 0.0, BCI_EINVAL, "bci_ode_solve: t_end must be > 0");
+  BCI_REQUIRE(a->substeps >= 0, BCI_EINVAL, "bci_ode_solve: substeps must be >= 0");
+  BCI_REQUIRE(a->out_dtype == BCI_OUT_F32 || a->out_dtype == BCI_OUT_F64, BCI_EINVAL, "bci_ode_solve: bad out_dtype");
+  BCI_REQUIRE(!(a->coupling) || (a->p_open && a->p_closed), BCI_EINVAL, "bci_ode_solve: coupling needs p_open and p_closed");
+  BCI_REQUIRE(a->y0_mode != BCI_Y0_GIVEN || a->y0, BCI_EINVAL, "bci_ode_solve: y0 is NULL with BCI_Y0_GIVEN");
+  BCI_REQUIRE(a->y0_mode != BCI_Y0_FROM_PROBS_06 || (a->p_open && a->p_closed), BCI_EINVAL, "bci_ode_solve: y0 from probs needs p_open/p_closed");
+  BCI_REQUIRE(a->y0_mode != BCI_Y0_FROM_PCLOSED_08 || a->p_closed, BCI_EINVAL, "bci_ode_solve: y0 from p_closed needs p_closed");
+  BCI_REQUIRE(a->mode != BCI_ODE_RK45 || (a->rtol > 0.0 && a->atol > 0.0), BCI_EINVAL, "bci_ode_solve: RK45 needs rtol, atol > 0");
+  BCI_REQUIRE(a->traj || a->final_state, BCI_EINVAL, "bci_ode_solve: no output requested");
+  if (a->n == 0) return BCI_OK;
+  OdeParams P;
+  P.style = a->style; P.y0_mode = a->y0_mode; P.coupling = a->coupling; P.n = a->n;
+  for (int r = 0; r < 6; ++r) P.base[r] = a->base_rates[r];
+  P.alpha = a->alpha; P.rates = a->rates; P.alpha_arr = a->alpha_arr;
+  P.p_open = a->p_open; P.p_closed = a->p_closed; P.y0 = a->y0;
+  P.t_end = a->t_end; P.n_points = a->n_points; P.substeps = a->substeps;
+  P.rtol = a->rtol; P.atol = a->atol; P.traj = a->traj; P.final_state = a->final_state; P.n_steps = a->n_steps;
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool clamp = a->style == BCI_ODE_STYLE_REF06;
+  if (a->out_dtype == BCI_OUT_F32) return clamp ? launch_ode<true, float>(P, a->mode, st) : launch_ode<false, float>(P, a->mode, st);
+  return clamp ? launch_ode<true, double>(P, a->mode, st) : launch_ode<false, double>(P, a->mode, st);
+}
+
+extern "C" int bci_ode_classify(const float* fs, int64_t n, int32_t* pred06, int32_t* cls10, void* stream) {
+  BCI_REQUIRE(fs && n >= 0, BCI_EINVAL, "bci_ode_classify: bad arguments");
+  if (n == 0) return BCI_OK;
+  ode_classify_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, (cudaStream_t)stream>>>(fs, n, pred06, cls10);
+  BCI_LAUNCH_OK();
+  return BCI_OK;
+}
+
+extern "C" int bci_ode_forecast_readout(const float* traj, int64_t n, int32_t n_points, const int32_t* hz, int32_t n_h,
+                                        float* out, void* stream) {
+  BCI_REQUIRE(traj && out && hz && n >= 0, BCI_EINVAL, "bci_ode_forecast_readout: bad arguments");
+  BCI_REQUIRE(n_h >= 1 && n_h <= 16, BCI_EINVAL, "bci_ode_forecast_readout: 1..16 horizons supported");
+  Horizons H;
+  H.n = n_h;
+  for (int j = 0; j < n_h; ++j) {
+    BCI_REQUIRE(hz[j] >= 0 && hz[j] < n_points, BCI_EINVAL, "bci_ode_forecast_readout: horizon %d outside trajectory", hz[j]);
+    H.h[j] = hz[j];
+  }
+  if (n == 0) return BCI_OK;
+  ode_readout_kernel<<<(unsigned)ceil_div64(n * n_h, 256), 256, 0, (cudaStream_t)stream>>>(traj, n, n_points, H, out);
+  BCI_LAUNCH_OK();
+  return BCI_OK;
+}
+
+extern "C" int bci_fp32_peak_probe(double* tflops, void* stream) {
+  BCI_REQUIRE(tflops, BCI_EINVAL, "bci_fp32_peak_probe: NULL output");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int blocks = sm_count() * 8, threads = 256, iters = 2048;
+  float* buf = nullptr;
+  BCI_CUDA_OK(cudaMalloc(&buf, (size_t)blocks * threads * sizeof(float)));
+  cudaEvent_t e0, e1;
+  BCI_CUDA_OK(cudaEventCreate(&e0));
+  BCI_CUDA_OK(cudaEventCreate(&e1));
+  double best = 0.0;
+  for (int rep = 0; rep < 5; ++rep) {
+    cudaEventRecord(e0, st);
+    fma_probe_kernel<<<blocks, threads, 0, st>>>(buf, iters);
+    cudaEventRecord(e1, st);
+    cudaEventSynchronize(e1);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    const double flop = 2.0 * 8 * 16 * (double)iters * blocks * threads;
+    const double tf = flop / (ms * 1e-3) / 1e12;
+    if (rep > 0 && tf > best) best = tf;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(buf);
+  BCI_CUDA_OK(cudaGetLastError());
+  *tflops = best;
+  return BCI_OK;
+}

@@ -1,0 +1,246 @@
+"""Host-side mirrors of the reference's LSTM -> coupling -> ODE callers.
+
+  LSTMODEIntegration           06_lstm_ode_integration.py:183-406
+  get_three_state_probabilities 10_three_state_probabilities.py:204-290
+  prob_to_ode_state / predict_trajectory / multistep_forecast / rolling_forecast_evaluation
+                               08_forecasting.py:149-153,215-289,346-392
+
+Same names, arguments, return shapes/dtypes; but the per-sample host loops of the reference
+(06:372-401, 10:245-273, 08:264-282) become ONE ODE-ensemble launch, and the LSTM
+probabilities never leave the device between the two stages.
+"""
+import numpy as np
+import torch
+
+from . import _native as N
+from . import ops
+from .ode import CognitiveStateODE, solve_ensemble, _dev
+from .synth import RATE_ORDER
+
+
+def _lstm_probs_device(lstm_model, X, batch_size, want_attn, device):
+    """Batched device inference; X numpy (host) or tensor.  Host batches go through pinned staging
+    buffers on a copy stream, double-buffered against compute (the reference copies each batch
+    synchronously, 06:346)."""
+    dev = _dev(device)
+    lstm_model.eval()
+    n = len(X)
+    probs = torch.empty((n, lstm_model.num_classes), device=dev, dtype=torch.float32)
+    attn = None
+    if isinstance(X, torch.Tensor) and X.is_cuda:
+        with torch.no_grad():
+            for i in range(0, n, batch_size):
+                xb = X[i:i + batch_size]
+                if want_attn:
+                    p, a = lstm_model.predict_proba(xb, return_attention=True)
+                    if attn is None:
+                        attn = torch.empty((n, a.shape[1]), device=dev, dtype=torch.float32)
+                    attn[i:i + len(xb)] = a
+                else:
+                    p = lstm_model.predict_proba(xb)
+                probs[i:i + len(xb)] = p
+        return probs, attn
+    Xh = torch.as_tensor(X)
+    if Xh.dtype != torch.float32:
+        Xh = Xh.float()
+    T, Cc = Xh.shape[1], Xh.shape[2]
+    copy_stream = torch.cuda.Stream(device=dev)
+    main = torch.cuda.current_stream(dev)
+    nb = min(batch_size, max(n, 1))
+    pinned = [torch.empty((nb, T, Cc), dtype=torch.float32).pin_memory() for _ in range(2)]
+    staged = [torch.empty((nb, T, Cc), dtype=torch.float32, device=dev) for _ in range(2)]
+    ready = [torch.cuda.Event() for _ in range(2)]
+    consumed = [torch.cuda.Event() for _ in range(2)]
+
+    def stage(slot, i):
+        m = min(batch_size, n - i)
+        consumed[slot].synchronize()            # pinned buffer free again (host side)
+        pinned[slot][:m].copy_(Xh[i:i + m])
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(consumed[slot])
+            staged[slot][:m].copy_(pinned[slot][:m], non_blocking=True)
+            ready[slot].record(copy_stream)
+        return m
+
+    with torch.no_grad():
+        starts = list(range(0, n, batch_size))
+        for s in range(2):
+            consumed[s].record(main)
+        sizes = {}
+        if starts:
+            sizes[0] = stage(0, starts[0])
+        for k, i in enumerate(starts):
+            slot = k & 1
+            if k + 1 < len(starts):
+                sizes[k + 1] = stage((k + 1) & 1, starts[k + 1])
+            main.wait_event(ready[slot])
+            m = sizes[k]
+            xb = staged[slot][:m]
+            if want_attn:
+                p, a = lstm_model.predict_proba(xb, return_attention=True)
+                if attn is None:
+                    attn = torch.empty((n, a.shape[1]), device=dev, dtype=torch.float32)
+                attn[i:i + m] = a
+            else:
+                p = lstm_model.predict_proba(xb)
+            probs[i:i + m] = p
+            consumed[slot].record(main)
+    return probs, attn
+
+
+class LSTMODEIntegration:
+    """Drop-in for 06_lstm_ode_integration.py:183-406."""
+
+    def __init__(self, lstm_model, ode_model, coupling_strength=0.5, device=None, substeps=8):
+        self.lstm_model = lstm_model
+        self.ode_model = ode_model
+        self.coupling_strength = coupling_strength
+        self.base_params = ode_model.params.copy()
+        self.device = device
+        self.substeps = substeps
+
+    def get_lstm_probabilities(self, X):
+        """(probs (B,2) [P(open),P(closed)], attention (B,T)) as numpy (06:216-234)."""
+        probs, attn = _lstm_probs_device(self.lstm_model, X, max(len(X), 1), True, self.device)
+        return probs.cpu().numpy(), attn.cpu().numpy()
+
+    def modulate_ode_rates(self, p_closed, p_open):
+        """06:236-264 for one sample (host dict, as the reference returns); the batched path applies the
+        same float32 arithmetic inside the ODE kernel."""
+        a = np.float32(self.coupling_strength)
+        pc, po = np.float32(p_closed), np.float32(p_open)
+        prm = self.base_params.copy()
+        fat = np.float32(1) + a * pc
+        rec = np.float32(1) + a * po
+        prm["k_af"] = np.float32(prm["k_af"]) * fat
+        prm["k_pf"] = np.float32(prm["k_pf"]) * fat
+        prm["k_fa"] = np.float32(prm["k_fa"]) * rec
+        prm["k_pa"] = np.float32(prm["k_pa"]) * rec
+        return {k: max(0.001, float(v)) for k, v in prm.items()}
+
+    def _solve(self, probs_dev, forecast_steps, y0=None):
+        n = probs_dev.shape[0]
+        p_open = probs_dev[:, 0].contiguous()
+        p_closed = probs_dev[:, 1].contiguous()
+        return solve_ensemble(n, p_open=p_open, p_closed=p_closed, base_rates=self.base_params,
+                              alpha=self.coupling_strength, y0=y0, y0_mode="given" if y0 is not None else "probs06",
+                              coupling=True, style="ref06", mode="rk4", t_end=float(forecast_steps),
+                              n_points=int(forecast_steps), substeps=self.substeps, device=self.device)
+
+    def predict_trajectory(self, X, initial_state=None, forecast_steps=10):
+        """(trajectory (steps,3) f64, probs (1,2), attention (1,T)) -- 06:266-306."""
+        probs, attn = _lstm_probs_device(self.lstm_model, X, max(len(X), 1), True, self.device)
+        y0 = None
+        if initial_state is not None:
+            y0 = torch.tensor(np.asarray(initial_state, dtype=np.float64).reshape(3, 1), dtype=torch.float32)
+        traj, _, _ = self._solve(probs[:1], forecast_steps, y0)
+        return traj[0].double().cpu().numpy(), probs.cpu().numpy(), attn.cpu().numpy()
+
+    def predict_batch(self, X_batch, forecast_steps=20, batch_size=512, show_progress=True):
+        """(trajectories (N,steps,3) f64, probs (N,2) f32, predictions (N,) int) -- 06:308-406."""
+        probs, _ = _lstm_probs_device(self.lstm_model, X_batch, batch_size, False, self.device)
+        traj, final, _ = self._solve(probs, forecast_steps)
+        pred, _ = ops.ode_classify(final, True, False)
+        return traj.double().cpu().numpy(), probs.cpu().numpy(), pred.cpu().numpy().astype(np.int64)
+
+    def predict_batch_device(self, X_dev, forecast_steps=20, batch_size=4096, want_traj=True):
+        """Same computation with every tensor left on the device (used by the sharded pipeline)."""
+        probs, _ = _lstm_probs_device(self.lstm_model, X_dev, batch_size, False, self.device)
+        n = probs.shape[0]
+        traj, final, _ = solve_ensemble(n, p_open=probs[:, 0].contiguous(), p_closed=probs[:, 1].contiguous(),
+                                        base_rates=self.base_params, alpha=self.coupling_strength, y0_mode="probs06",
+                                        coupling=True, style="ref06", mode="rk4", t_end=float(forecast_steps),
+                                        n_points=int(forecast_steps), substeps=self.substeps, want_traj=want_traj,
+                                        device=self.device)
+        pred, cls = ops.ode_classify(final, True, True)
+        return traj, probs, final, pred, cls
+
+
+def get_three_state_probabilities(lstm_model, ode_model, X, batch_size=512, device=None, substeps=8):
+    """10:204-290 -> (lstm_probs (N,2) f32, three_state (N,3) f64, predictions (N,))."""
+    probs, _ = _lstm_probs_device(lstm_model, X, batch_size, False, device)
+    n = probs.shape[0]
+    _, final, _ = solve_ensemble(n, p_open=probs[:, 0].contiguous(), p_closed=probs[:, 1].contiguous(),
+                                 base_rates=ode_model.params, alpha=0.5, y0_mode="probs06", coupling=True,
+                                 style="ref06", mode="rk4", t_end=20.0, n_points=20, substeps=substeps,
+                                 want_traj=False, device=device)
+    _, cls = ops.ode_classify(final, False, True)
+    return probs.cpu().numpy(), final.double().cpu().numpy(), cls.cpu().numpy().astype(np.int64)
+
+
+# ---- 08_forecasting.py mirrors ----------------------------------------------------------------
+def get_lstm_probabilities(lstm_model, X_data, batch_size=256, device=None):
+    """08:198-212 -> (N,2) numpy."""
+    probs, _ = _lstm_probs_device(lstm_model, X_data, batch_size, False, device)
+    return probs.cpu().numpy()
+
+
+def prob_to_ode_state(prob_closed):
+    """08:215-234 for one probability (host scalar helper; float32 arithmetic when given a float32,
+    as NumPy >= 2 evaluates the reference).  The batched path derives y0 inside the ODE kernel."""
+    p = prob_closed
+    wt = np.float32 if isinstance(p, np.float32) else np.float64
+    p = wt(p)
+    A = wt(1.0) - p
+    if p > 0.5:
+        F, P = p * wt(0.6), p * wt(0.4)
+    else:
+        F, P = p * wt(0.3), p * wt(0.3)
+    total = A + P + F
+    return np.array([A / total, P / total, F / total])
+
+
+def predict_trajectory(initial_state, params, n_steps, dt=1.0, device=None, substeps=8):
+    """08:149-153 -> (n_steps+1, 3) float64: raw rates, no clamp, no renormalisation."""
+    y0 = torch.tensor(np.asarray(initial_state, dtype=np.float64).reshape(3, 1), dtype=torch.float32)
+    traj, _, _ = solve_ensemble(1, base_rates=params, y0=y0, y0_mode="given", coupling=False, style="ref08",
+                                mode="rk4", t_end=float(n_steps) * float(dt), n_points=int(n_steps) + 1,
+                                substeps=substeps, f64=True, device=device)
+    return traj[0].cpu().numpy()
+
+
+def _forecast_device(p_closed_dev, ode_params, max_horizon, horizons, device, substeps):
+    n = p_closed_dev.shape[0]
+    traj, _, _ = solve_ensemble(n, p_closed=p_closed_dev, base_rates=ode_params, y0_mode="pclosed08", coupling=False,
+                                style="ref08", mode="rk4", t_end=float(max_horizon), n_points=int(max_horizon) + 1,
+                                substeps=substeps, device=device)
+    return ops.ode_forecast_readout(traj, horizons)
+
+
+def multistep_forecast(probs, ode_params, horizons=[5, 10, 20], device=None, substeps=8):
+    """08:252-289 -> {h: {'predictions': (N-maxh,), 'actuals': (N-maxh,)}}."""
+    dev = _dev(device)
+    probs_t = torch.as_tensor(probs, dtype=torch.float32).to(dev)
+    max_h = max(horizons)
+    m = len(probs_t) - max_h
+    results = {h: {"predictions": np.zeros(0), "actuals": np.zeros(0)} for h in horizons}
+    if m <= 0:
+        return results
+    pred = _forecast_device(probs_t[:m, 1].contiguous(), ode_params, max_h, list(horizons), dev, substeps).cpu().numpy()
+    pc = probs_t[:, 1].cpu().numpy()
+    for j, h in enumerate(horizons):
+        results[h]["predictions"] = pred[:, j].astype(np.float64)
+        results[h]["actuals"] = pc[h:h + m]
+    return results
+
+
+def rolling_forecast_evaluation(probs, ode_params, window_size=50, horizon=10, device=None, substeps=8):
+    """08:346-392 -> pandas DataFrame[window, accuracy, mae]."""
+    import pandas as pd
+    dev = _dev(device)
+    probs_t = torch.as_tensor(probs, dtype=torch.float32).to(dev)
+    n = len(probs_t)
+    n_windows = (n - window_size - horizon) // window_size
+    rows = []
+    if n_windows <= 0:
+        return pd.DataFrame(rows)
+    last = min(n_windows * window_size, n - horizon)
+    pred = _forecast_device(probs_t[:last, 1].contiguous(), ode_params, horizon, [horizon], dev, substeps)[:, 0].cpu().numpy()
+    pc = probs_t[:, 1].cpu().numpy()
+    for w in range(n_windows):
+        s, e = w * window_size, min((w + 1) * window_size, n - horizon)
+        if e <= s:
+            continue
+        p, a = pred[s:e], pc[s + horizon:e + horizon]
+        rows.append({"window": w, "accuracy": np.mean((p > 0.5) == (a > 0.5)), "mae": np.mean(np.abs(p - a))})
+    return pd.DataFrame(rows)

@@ -1,0 +1,114 @@
+"""Host-side mirror of the reference's BiLSTM-attention classifier.
+
+`EnhancedLSTMModel` keeps the reference's constructor signature, `.forward(x, return_attention)`
+contract, train/eval switches and -- most importantly -- its state-dict key names and shapes
+(04_lstm_model.py:163-204), so a checkpoint written by 04_lstm_model.py:921-933
+loads unchanged (`load_state_dict`) and the 06/08/10 scripts can use this class in place of
+their own copy.  The module tree below exists only to hold parameters under those names; all
+arithmetic is the CUDA path behind `bci::lstm_attn_forward`.
+"""
+import torch
+from torch import nn
+
+from . import _native as N
+from . import ops
+
+
+class _Pool(nn.Module):
+    def __init__(self, width):
+        super().__init__()
+        self.attention = nn.Sequential(nn.Linear(width, width // 2), nn.Tanh(), nn.Linear(width // 2, 1))
+
+
+class EnhancedLSTMModel(nn.Module):
+    """Drop-in for the reference class of the same name (04_lstm_model.py:153-222).
+
+    precision: "fp32" (parity mode, CUDA-core FMA, <=1e-5 on logits/probabilities) or "bf16"
+    (tcgen05 tensor-core mode).  Under `torch.autocast("cuda")` -- which the reference enables on
+    GPUs (04:486-490, 06:348-351) -- "auto" selects bf16, otherwise fp32.
+    """
+
+    def __init__(self, input_size=14, hidden_size=128, num_layers=3, num_classes=2, dropout=0.4,
+                 bidirectional=True, num_heads=4, precision="auto"):
+        super().__init__()
+        if not bidirectional:
+            raise N.BciError(-1, "only bidirectional=True is built (ablation variants: SURVEY.md §8 f)")
+        self.hidden_size, self.num_layers, self.bidirectional = hidden_size, num_layers, bidirectional
+        self.num_directions = 2
+        self.input_size, self.num_classes, self.dropout_p = input_size, num_classes, dropout
+        self.precision = precision
+        d = 2 * hidden_size
+        self.input_proj = nn.Sequential(nn.Linear(input_size, hidden_size), nn.LayerNorm(hidden_size),
+                                        nn.GELU(), nn.Dropout(dropout / 2))
+        self.lstm = nn.LSTM(hidden_size, hidden_size, num_layers, batch_first=True,
+                            dropout=dropout if num_layers > 1 else 0, bidirectional=True)
+        self.layer_norm = nn.LayerNorm(d)
+        self.attention = _Pool(d)
+        self.classifier = nn.Sequential(nn.Linear(d, hidden_size), nn.GELU(), nn.Dropout(dropout),
+                                        nn.Linear(hidden_size, hidden_size // 2), nn.GELU(), nn.Dropout(dropout),
+                                        nn.Linear(hidden_size // 2, num_classes))
+        self._engines = {}       # precision -> handle id
+        self._loaded = {}        # precision -> tuple of parameter versions/ptrs at last load
+
+    # -- engine management -------------------------------------------------------------------
+    def _precision_now(self):
+        if self.precision == "auto":
+            return "bf16" if torch.is_autocast_enabled("cuda") else "fp32"
+        return self.precision
+
+    def _signature(self):
+        return tuple((p.data_ptr(), p._version) for p in self.parameters())
+
+    def _engine(self, prec):
+        if prec not in ("fp32", "bf16"):
+            raise N.BciError(-1, "precision must be fp32, bf16 or auto")
+        hid = self._engines.get(prec)
+        if hid is None:
+            hid = ops.lstm_create(self.input_size, self.hidden_size, self.num_layers, self.num_classes,
+                                  N.PRECISION_BF16 if prec == "bf16" else N.PRECISION_FP32)
+            self._engines[prec] = hid
+        sig = self._signature()
+        if self._loaded.get(prec) != sig:
+            ops.lstm_load_weights(hid, {k: v for k, v in self.state_dict().items()})
+            self._loaded[prec] = sig
+        return hid
+
+    def __del__(self):
+        try:
+            for hid in self._engines.values():
+                ops.lstm_destroy(hid)
+        except Exception:
+            pass
+
+    # -- the reference's forward contract ----------------------------------------------------
+    def forward(self, x, return_attention=False):
+        if not x.is_cuda:
+            raise N.BciError(-1, "EnhancedLSTMModel (bci_b200) runs on CUDA tensors only; move the model and "
+                                 "input with .to('cuda') -- there is no CPU fallback")
+        x = x.float()
+        if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters())) \
+                and self.training:
+            from .train import lstm_attn_autograd
+            return lstm_attn_autograd(self, x, return_attention)
+        hid = self._engine(self._precision_now())
+        logits, _probs, attn = ops.lstm_attn_forward(x, hid, bool(return_attention))
+        return (logits, attn) if return_attention else logits
+
+    @torch.no_grad()
+    def predict_proba(self, x, return_attention=False):
+        """logits -> softmax fused in the head kernel: columns [P(open), P(closed)] (06:223,232)."""
+        hid = self._engine(self._precision_now())
+        _logits, probs, attn = ops.lstm_attn_forward(x.float(), hid, bool(return_attention))
+        return (probs, attn) if return_attention else probs
+
+
+def from_params(params, precision="fp32", device="cuda", dropout=0.4):
+    """Build a CUDA model from a {state-dict key: ndarray/tensor} dict."""
+    H, Cc = params["input_proj.0.weight"].shape
+    layers = 0
+    while f"lstm.weight_hh_l{layers}" in params:
+        layers += 1
+    classes = params["classifier.6.weight"].shape[0]
+    m = EnhancedLSTMModel(Cc, H, layers, classes, dropout, True, precision=precision)
+    m.load_state_dict({k: torch.as_tensor(v).float() for k, v in params.items()}, strict=True)
+    return m.to(device).eval()

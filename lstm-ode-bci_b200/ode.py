@@ -1,0 +1,103 @@
+"""Host-side mirror of the reference's three-state ODE model (05_ode_model.py:58-346,
+copies at 06:146-180, 10:117-151; functional form 08:132-153).
+
+`CognitiveStateODE` keeps the reference's object contract -- a mutable `.params` dict that
+callers reassign per sample (06:296,304,386,404) and `solve(initial_state, t_span, n_points
+[, method]) -> (t, solution)` returning float64 numpy -- but integrates on the GPU.  The batched
+entry point `solve_ensemble` is what the pipeline mirrors use: one launch for N trajectories.
+"""
+import numpy as np
+import torch
+
+from . import _native as N
+from . import ops
+from .synth import DEFAULT_RATES, RATE_ORDER
+
+
+def _dev(device):
+    d = torch.device(device if device is not None else "cuda")
+    if d.type != "cuda":
+        raise N.BciError(-1, "bci_b200 ODE solver runs on CUDA only (no CPU fallback)")
+    return torch.device("cuda", d.index if d.index is not None else torch.cuda.current_device())
+
+
+def _as_dev(a, dev, shape=None):
+    if a is None:
+        return None
+    t = torch.as_tensor(a)
+    if not t.is_cuda:
+        t = t.to(dev, non_blocking=True)
+    t = t.to(torch.float32)
+    return t.contiguous()
+
+
+def solve_ensemble(n, *, p_open=None, p_closed=None, rates=None, base_rates=None, alpha=0.5, alpha_arr=None,
+                   y0=None, y0_mode="given", coupling=False, style="ref06", mode="rk4", t_end=20.0,
+                   n_points=20, substeps=8, rtol=1e-3, atol=1e-6, want_traj=True, want_steps=False,
+                   f64=False, device=None):
+    """N independent coupled trajectories in one launch (tensors stay on the device).
+
+    rates      (6,N) per-trajectory base rates (k_ap,k_af,k_pa,k_pf,k_fa,k_fp) or None -> base_rates dict/list
+    y0         (3,N) SoA initial states when y0_mode == "given"
+    y0_mode    "given" | "probs06" (06:377-382) | "pclosed08" (08:215-234)
+    style      "ref06": clamp + normalise + clip/renorm (06:174-180) | "ref08": raw (08:149-153)
+    mode       "rk4" (fp32, `substeps` per output interval; 0 = automatic) | "rk45" (scipy-exact, fp64)
+    Returns (traj (N,n_points,3) or empty, final_state (N,3), n_steps (N) or empty) CUDA tensors.
+    """
+    dev = _dev(device)
+    if base_rates is None:
+        base_rates = DEFAULT_RATES
+    if isinstance(base_rates, dict):
+        base_rates = [float(base_rates[k]) for k in RATE_ORDER]
+    y0m = {"given": N.Y0_GIVEN, "probs06": N.Y0_FROM_PROBS_06, "pclosed08": N.Y0_FROM_PCLOSED_08}[y0_mode]
+    return ops.ode_ensemble(_as_dev(p_open, dev), _as_dev(p_closed, dev), _as_dev(rates, dev), _as_dev(alpha_arr, dev),
+                            _as_dev(y0, dev), [float(v) for v in base_rates], float(alpha), int(n),
+                            {"rk4": N.ODE_RK4, "rk45": N.ODE_RK45}[mode],
+                            {"ref06": N.STYLE_REF06, "ref08": N.STYLE_REF08}[style], y0m, bool(coupling),
+                            float(t_end), int(n_points), int(substeps), float(rtol), float(atol),
+                            bool(want_traj), bool(want_steps), bool(f64), dev.index)
+
+
+class CognitiveStateODE:
+    """Drop-in for the reference class (05_ode_model.py:58; 06:146; 10:117)."""
+
+    def __init__(self, params=None, device=None, substeps=0):
+        self.params = dict(DEFAULT_RATES) if params is None else params
+        self.state_names = ["Active", "Passive", "Fatigued"]
+        self.state_labels = ["A", "P", "F"]
+        self.device = device
+        self.substeps = substeps  # RK4 sub-steps per output interval; 0 = automatic (<= 2e-7 truncation)
+
+    def ode_system(self, y, t, params=None):
+        """Right-hand side (05:101-135), host scalar version kept for API completeness."""
+        p = self.params if params is None else params
+        A, P, F = max(0, y[0]), max(0, y[1]), max(0, y[2])
+        return [-p["k_ap"] * A - p["k_af"] * A + p["k_pa"] * P + p["k_fa"] * F,
+                p["k_ap"] * A - p["k_pa"] * P - p["k_pf"] * P + p["k_fp"] * F,
+                p["k_af"] * A + p["k_pf"] * P - p["k_fa"] * F - p["k_fp"] * F]
+
+    def solve(self, initial_state, t_span, n_points=100, method="odeint"):
+        """(t, solution[n_points,3]) float64.  method 'odeint' -> fixed-step RK4 on the GPU accurate
+        to the reference's LSODA within 1e-6; 'solve_ivp' -> scipy-exact RK45 (05:137-169)."""
+        t0, t1 = float(t_span[0]), float(t_span[1])
+        t = np.linspace(t0, t1, n_points)
+        y0 = torch.tensor(np.asarray(initial_state, dtype=np.float64).reshape(3, 1), dtype=torch.float32)
+        mode = "rk4" if method == "odeint" else "rk45"
+        # constant-rate autonomous system: integrating over [t0,t1] == over [0,t1-t0]
+        traj, _, _ = solve_ensemble(1, base_rates=self.params, y0=y0, y0_mode="given", coupling=False, style="ref06",
+                                    mode=mode, t_end=t1 - t0, n_points=n_points, substeps=self.substeps,
+                                    f64=True, device=self.device)
+        return t, traj[0].cpu().numpy()
+
+    def get_transition_matrix(self):
+        p = self.params
+        return np.array([[-(p["k_ap"] + p["k_af"]), p["k_ap"], p["k_af"]],
+                         [p["k_pa"], -(p["k_pa"] + p["k_pf"]), p["k_pf"]],
+                         [p["k_fa"], p["k_fp"], -(p["k_fa"] + p["k_fp"])]])
+
+    def get_steady_state(self):
+        """05:198-221: solve to t=1000 with 1000 points and take the last state."""
+        _, sol = self.solve([0.33, 0.33, 0.34], (0, 1000), 1000)
+        return {"Active": sol[-1][0], "Passive": sol[-1][1], "Fatigued": sol[-1][2]}
+
+

@@ -1,0 +1,93 @@
+"""GPU parity of the BiLSTM + attention-pooling forward (through the C ABI / custom op).
+fp32 mode tolerance (north_star): max-abs <= 1e-5 on logits and P(open)/P(closed); attention <= 1e-6.
+bf16 (tcgen05) mode tolerance, stated separately: logits <= 3e-2 * gain-scale, probabilities <= 1e-2,
+attention <= 2e-3 (calibrated against the reference's own autocast-vs-fp32 gap)."""
+import numpy as np
+import pytest
+import torch
+
+from lstm_ode_bci_b200 import lstm, synth
+from oracle import lstm_oracle, torch_port
+
+pytestmark = pytest.mark.gpu
+
+
+def _inputs(g):
+    if "x" in g:
+        return {k[6:]: v for k, v in g.items() if k.startswith("param:")}, g["x"]
+    params = synth.make_lstm_params(int(g["seed_w"]), int(g["C"]), int(g["H"]), int(g["L"]), logit_gain=float(g["gain"]))
+    x = synth.make_windows(int(g["seed_x"]), int(g["B"]), int(g["T"]), int(g["C"]), structured=bool(g["structured"]))
+    return params, x
+
+
+@pytest.mark.parametrize("name", ["lstm_h128.npz", "lstm_h128_t64.npz", "lstm_h256.npz"])
+def test_fp32_forward_matches_reference_golden(golden, name):
+    g = golden(name)
+    params, x = _inputs(g)
+    m = lstm.from_params(params, precision="fp32")
+    with torch.no_grad():
+        logits, attn = m(torch.from_numpy(x).cuda(), return_attention=True)
+        probs = m.predict_proba(torch.from_numpy(x).cuda())
+    assert np.abs(logits.cpu().numpy() - g["logits"]).max() <= 1e-5
+    assert np.abs(probs.cpu().numpy() - g["probs"]).max() <= 1e-5
+    assert np.abs(attn.cpu().numpy() - g["attention"]).max() <= 1e-6
+    assert np.abs(attn.sum(dim=1).cpu().numpy() - 1).max() <= 1e-5
+
+
+@pytest.mark.parametrize("H,B,T", [(128, 32, 256), (128, 1, 256), (128, 33, 40), (256, 17, 64), (128, 70, 7)])
+def test_fp32_forward_matches_oracle(H, B, T):
+    """config 1 (B=32 x 256 x 61) plus ragged tiles, odd sequence lengths and H=256."""
+    params = synth.make_lstm_params(100 + H + B, 61, H, 3, logit_gain=6.0)
+    x = synth.make_windows(200 + B, B, T, 61, structured=True)
+    port = torch_port.build_port(params).eval()
+    with torch.no_grad():
+        want_logits, want_attn = port(torch.from_numpy(x), return_attention=True)
+        want_probs = torch.softmax(want_logits, dim=1)
+    m = lstm.from_params(params, precision="fp32")
+    with torch.no_grad():
+        logits, attn = m(torch.from_numpy(x).cuda(), return_attention=True)
+        probs = m.predict_proba(torch.from_numpy(x).cuda())
+    assert np.abs(logits.cpu().numpy() - want_logits.numpy()).max() <= 1e-5
+    assert np.abs(probs.cpu().numpy() - want_probs.numpy()).max() <= 1e-5
+    assert np.abs(attn.cpu().numpy() - want_attn.numpy()).max() <= 1e-6
+    if B <= 2:  # independent float64 numpy restatement as a second witness
+        lg64, at64 = lstm_oracle.forward(params, x)
+        assert np.abs(logits.cpu().numpy() - lg64).max() <= 1e-5
+        assert np.abs(attn.cpu().numpy() - at64).max() <= 1e-6
+
+
+def test_fp32_chunked_batch_equals_unchunked():
+    """batch larger than the internal chunk (2048 windows) == concatenation of smaller calls; windows are
+    independent (SURVEY.md §8 e)."""
+    params = synth.make_lstm_params(5, 61, 128, 3, logit_gain=6.0)
+    m = lstm.from_params(params, precision="fp32")
+    x = torch.from_numpy(synth.make_windows(6, 2100, 16, 61)).cuda()
+    with torch.no_grad():
+        full = m(x)
+        parts = torch.cat([m(x[:1000]), m(x[1000:])])
+    assert torch.equal(full, parts)
+    assert m(x[:0]).shape == (0, 2)
+
+
+def test_weights_reload_after_update():
+    params = synth.make_lstm_params(9, 61, 128, 3)
+    m = lstm.from_params(params, precision="fp32")
+    x = torch.from_numpy(synth.make_windows(3, 4, 32, 61)).cuda()
+    with torch.no_grad():
+        a = m(x).clone()
+        m.classifier[6].bias.add_(1.0)          # in-place update bumps the version -> repack
+        b = m(x)
+    assert np.allclose((b - a).cpu().numpy(), 1.0, atol=1e-6)
+
+
+def test_state_dict_roundtrip_with_port():
+    """A checkpoint of the reference layout loads unchanged (SURVEY.md §5 checkpoint row)."""
+    params = synth.make_lstm_params(11, 61, 128, 3)
+    port = torch_port.build_port(params)
+    m = lstm.EnhancedLSTMModel(61, 128, 3, 2).cuda().eval()
+    m.load_state_dict(port.state_dict(), strict=True)
+    x = synth.make_windows(4, 3, 48, 61)
+    with torch.no_grad():
+        want = port.eval()(torch.from_numpy(x))
+        got = m(torch.from_numpy(x).cuda())
+    assert np.abs(got.cpu().numpy() - want.numpy()).max() <= 1e-5

@@ -1,0 +1,45 @@
+"""GPU parity of the callers: predict_batch (06:308-406), predict_trajectory (06:266-306),
+get_three_state_probabilities (10:204-290) against the live-reference golden vectors."""
+import numpy as np
+import pytest
+import torch
+
+from lstm_ode_bci_b200 import integration, lstm, ode, patch, synth
+
+pytestmark = pytest.mark.gpu
+
+
+def test_predict_batch_matches_reference(golden):
+    g = golden("pipeline_h128.npz")
+    gl = golden("lstm_h128.npz")
+    params = synth.make_lstm_params(int(gl["seed_w"]), 61, 128, 3, logit_gain=float(gl["gain"]))
+    x = synth.make_windows(int(gl["seed_x"]), int(gl["B"]), 256, 61, structured=bool(gl["structured"]))
+    m = lstm.from_params(params, precision="fp32")
+    integ = integration.LSTMODEIntegration(m, ode.CognitiveStateODE(), coupling_strength=0.5)
+    traj, probs, preds = integ.predict_batch(x, forecast_steps=20, batch_size=3, show_progress=False)
+    assert traj.shape == (8, 20, 3) and traj.dtype == np.float64
+    assert probs.shape == (8, 2) and probs.dtype == np.float32 and preds.shape == (8,)
+    assert np.abs(probs - g["probs"]).max() <= 1e-5
+    assert np.abs(traj - g["traj"]).max() <= 1e-6
+    assert np.array_equal(preds, g["preds"])
+    assert integ.ode_model.params == integ.base_params          # params restored (06:404)
+    tr1, pr1, at1 = integ.predict_trajectory(x[:1], forecast_steps=10)
+    assert np.abs(tr1 - g["single_traj"]).max() <= 1e-6
+    assert np.abs(pr1 - g["single_probs"]).max() <= 1e-5
+    assert np.abs(at1 - g["single_attn"]).max() <= 1e-6
+    lp, three, cls = integration.get_three_state_probabilities(m, ode.CognitiveStateODE(), x, batch_size=4)
+    assert np.abs(lp - g["lstm_probs10"]).max() <= 1e-5
+    assert np.abs(three - g["three_state"]).max() <= 1e-6
+    assert np.array_equal(cls, g["cls"])
+    # device-resident variant agrees with the host-facing one
+    trd, prd, fin, pred, cls_d = integ.predict_batch_device(torch.from_numpy(x).cuda())
+    assert np.abs(trd.cpu().numpy() - traj).max() <= 1e-6 and np.array_equal(pred.cpu().numpy(), preds)
+
+
+def test_patch_reference_swaps_by_name():
+    import types
+    fake = types.SimpleNamespace(EnhancedLSTMModel=object, CognitiveStateODE=object, predict_trajectory=object,
+                                 prob_to_ode_state=object, multistep_forecast=object, get_lstm_probabilities=object)
+    done = patch.patch_reference(fake)
+    assert fake.EnhancedLSTMModel is lstm.EnhancedLSTMModel and fake.CognitiveStateODE is ode.CognitiveStateODE
+    assert fake.predict_trajectory is integration.predict_trajectory and "multistep_forecast" in done
