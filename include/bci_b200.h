@@ -93,6 +93,17 @@ int bci_lstm_destroy(bci_lstm_t h);
  * Re-callable after every optimizer step. */
 int bci_lstm_load_weights(bci_lstm_t h, const bci_lstm_weights* w, void* stream);
 
+/* Optional per-phase device timing for bench.py's roofline (SURVEY.md §8 d).  When enabled, forward
+ * records CUDA events on the caller's stream between its phases; bci_lstm_get_profile synchronises
+ * those events and returns the accumulated milliseconds and launch counts per phase since the last
+ * call, then resets them.  Phases: 0 input projection (K1), 1 W_ih projection GEMM (K2),
+ * 2 recurrence (K3), 3 LayerNorm+attention pooling+head (K4/K5). */
+#define BCI_PROF_PHASES 4
+int bci_lstm_set_profiling(bci_lstm_t h, int32_t enable);
+int bci_lstm_get_profile(bci_lstm_t h, float ms[BCI_PROF_PHASES], int32_t launches[BCI_PROF_PHASES]);
+/* Number of kernels this library has launched in this process (bench.py's gpu_launches claim). */
+int64_t bci_launch_count(void);
+
 /* bytes of caller-provided scratch needed by forward (train=0) or forward+backward (train=1) */
 int bci_lstm_workspace_bytes(bci_lstm_t h, int32_t batch, int32_t seq_len, int32_t train, size_t* bytes);
 
@@ -195,6 +206,18 @@ int bci_ode_forecast_readout(const float* traj, int64_t n, int32_t n_points, con
 /* Micro-benchmark used by bench.py for the FP32 roofline denominator (SURVEY.md §8 d: the FP32
  * FMA peak is not in MEASURED_PEAKS.json): launches a dependent-FMA kernel, returns TFLOP/s. */
 int bci_fp32_peak_probe(double* tflops, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Diagnostics: the two tensor-core kernels of the bf16 path, callable in isolation so the GPU unit
+ * tests can check each against a plain matmul / a step-by-step recurrence.
+ *   proj_gemm: C[M][N] (bf16) = A[M][K] (bf16) . W[N][K]^T (bf16) + bias[N] (fp32);  N % 256 == 0, K % 64 == 0
+ *   rec:       G [T][Bc][1024] bf16 (dir*512 + permuted gate column, bias included), whh_* [512][128] bf16
+ *              permuted rows (perm(unit,gate) = (unit/8)*32 + gate*8 + unit%8) -> out [T][Bc][256] bf16
+ * ---------------------------------------------------------------------------------------- */
+int bci_selftest_proj_gemm_bf16(const void* A, const void* W, const float* bias, void* C, int32_t M, int32_t N,
+                                int32_t K, void* stream);
+int bci_selftest_rec_bf16(const void* G, const void* whh_f, const void* whh_r, void* out, int32_t Bc, int32_t T,
+                          void* stream);
 
 #ifdef __cplusplus
 }

@@ -65,6 +65,9 @@ SIGNATURES = {
     "bci_lstm_create": (C.c_int, [C.POINTER(LstmConfig), C.POINTER(C.c_void_p)]),
     "bci_lstm_destroy": (C.c_int, [C.c_void_p]),
     "bci_lstm_load_weights": (C.c_int, [C.c_void_p, C.POINTER(LstmWeights), C.c_void_p]),
+    "bci_lstm_set_profiling": (C.c_int, [C.c_void_p, C.c_int32]),
+    "bci_lstm_get_profile": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_int32)]),
+    "bci_launch_count": (C.c_int64, []),
     "bci_lstm_workspace_bytes": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_size_t)]),
     "bci_lstm_forward": (C.c_int, [C.c_void_p, _FP, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_uint64,
                                    _FP, _FP, _FP, _FP, C.c_size_t, C.c_void_p]),
@@ -75,6 +78,8 @@ SIGNATURES = {
     "bci_ode_solve": (C.c_int, [C.POINTER(OdeArgs), C.c_void_p]),
     "bci_ode_classify": (C.c_int, [_FP, C.c_int64, _FP, _FP, C.c_void_p]),
     "bci_ode_forecast_readout": (C.c_int, [_FP, C.c_int64, C.c_int32, C.POINTER(C.c_int32), C.c_int32, _FP, C.c_void_p]),
+    "bci_selftest_proj_gemm_bf16": (C.c_int, [_FP, _FP, _FP, _FP, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
+    "bci_selftest_rec_bf16": (C.c_int, [_FP, _FP, _FP, _FP, C.c_int32, C.c_int32, C.c_void_p]),
     "bci_fp32_peak_probe": (C.c_int, [C.POINTER(C.c_double), C.c_void_p]),
 }
 

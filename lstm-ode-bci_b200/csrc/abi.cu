@@ -8,6 +8,9 @@ namespace bci {
 
 static thread_local char g_err[512] = "";
 
+static long long g_launches = 0;
+void note_launch() { __atomic_add_fetch(&g_launches, 1, __ATOMIC_RELAXED); }
+
 void set_error(const char* fmt, ...) {
   va_list ap;
   va_start(ap, fmt);
@@ -30,6 +33,31 @@ using namespace bci;
 
 extern "C" int bci_abi_version(void) { return BCI_ABI_VERSION; }
 extern "C" const char* bci_last_error(void) { return g_err; }
+
+extern "C" int64_t bci_launch_count(void) { return __atomic_load_n(&g_launches, __ATOMIC_RELAXED); }
+
+extern "C" int bci_lstm_set_profiling(bci_lstm_t h, int32_t enable) {
+  BCI_REQUIRE(h, BCI_EINVAL, "bci_lstm_set_profiling: NULL handle");
+  h->prof.enabled = enable != 0;
+  h->prof.n = 0;
+  return BCI_OK;
+}
+
+extern "C" int bci_lstm_get_profile(bci_lstm_t h, float ms[BCI_PROF_PHASES], int32_t launches[BCI_PROF_PHASES]) {
+  BCI_REQUIRE(h && ms && launches, BCI_EINVAL, "bci_lstm_get_profile: NULL argument");
+  for (int i = 0; i < BCI_PROF_PHASES; ++i) { ms[i] = 0.f; launches[i] = 0; }
+  Profiler& p = h->prof;
+  if (p.n > 0) BCI_CUDA_OK(cudaEventSynchronize(p.ev[p.n - 1]));
+  for (int i = 1; i < p.n; ++i) {
+    if (p.phase[i] < 0) continue;
+    float t = 0.f;
+    BCI_CUDA_OK(cudaEventElapsedTime(&t, p.ev[i - 1], p.ev[i]));
+    ms[p.phase[i]] += t;
+    launches[p.phase[i]] += 1;
+  }
+  p.n = 0;
+  return BCI_OK;
+}
 
 extern "C" int bci_device_check(int device, int* sm) {
   int n = 0;
@@ -76,6 +104,7 @@ extern "C" int bci_lstm_create(const bci_lstm_config* cfg, bci_lstm_t* out) {
 extern "C" int bci_lstm_destroy(bci_lstm_t h) {
   if (!h) return BCI_OK;
   if (h->store) cudaFree(h->store);
+  if (h->prof.created) for (int i = 0; i < Profiler::MAX_EV; ++i) cudaEventDestroy(h->prof.ev[i]);
   delete h;
   return BCI_OK;
 }

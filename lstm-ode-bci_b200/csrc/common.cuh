@@ -10,6 +10,7 @@
 namespace bci {
 
 void set_error(const char* fmt, ...);
+void note_launch();  // counts kernel launches (bci_launch_count)
 
 #define BCI_CUDA_OK(expr)                                                             \
   do {                                                                                \
@@ -35,6 +36,7 @@ void set_error(const char* fmt, ...);
       ::bci::set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e), __FILE__, __LINE__); \
       return BCI_ECUDA;                                                                \
     }                                                                                  \
+    ::bci::note_launch();                                                              \
   } while (0)
 
 inline int sm_count() {

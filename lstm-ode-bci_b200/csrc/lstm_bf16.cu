@@ -1,0 +1,524 @@
+// bf16 tensor-core mode of the BiLSTM forward (H = 128), hand-written for sm_100a.
+//
+//   K2  proj_gemm_bf16 : G = in . W_ih^T + b for all T steps and both directions -- a persistent,
+//       warp-specialised tcgen05 GEMM: TMA (cp.async.bulk.tensor, SWIZZLE_128B) feeds a 4-stage
+//       smem ring, one thread issues tcgen05.mma (M128 x N256 x K16, bf16 -> fp32 in TMEM), the
+//       accumulator is double-buffered in TMEM (2 x 256 columns) so the epilogue warps (tcgen05.ld
+//       -> +bias -> bf16 -> global) of tile i overlap the MMAs of tile i+1.
+//   K3  lstm_rec_bf16  : the serial recurrence, one CTA per (128-window tile, direction), resident
+//       for the whole sequence: W_hh (512x128 bf16, 128 KB) stays in shared memory in UMMA layout,
+//       each step issues h_{t-1} . W_hh^T as 16 tcgen05.mma into the 512 TMEM columns, eight epilogue
+//       warps read their gate slabs back (tcgen05.ld), add the projected input G_t, apply
+//       sigma/tanh (MUFU tanh.approx), update the fp32 cell state held in registers for all 256
+//       steps, and write h_t as bf16 straight into the swizzled A-operand buffer of the next step.
+//       Gate columns are permuted (unit/8, gate, unit%8) so one 32-column TMEM slab carries i,f,g,o
+//       of 8 hidden units and the cell update is thread-local.  The two N=256 halves are committed
+//       to separate mbarriers, so half of the epilogue starts while the second half of the MMAs runs.
+//
+// Reference semantics: nn.LSTM inside EnhancedLSTMModel (04_lstm_model.py:181-188,211); on CUDA the
+// reference itself runs this under autocast (04:486-490, 06:348-351).
+#include "lstm_shared_kernels.cuh"
+#include "sm100_prims.cuh"
+#include <cuda.h>
+
+namespace bci {
+using namespace sm100;
+
+// ---------------------------------------------------------------------------------------------
+// weight packing for the tensor-core path
+// ---------------------------------------------------------------------------------------------
+__host__ __device__ constexpr int gate_perm(int unit, int gate) { return (unit >> 3) * 32 + gate * 8 + (unit & 7); }
+
+// src (4H, K) gate-major rows -> dst bf16 [row0 + perm(unit,gate)][K]
+__global__ void pack_rows_perm_bf16(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int H, int K, int row0) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)4 * H * K) return;
+  const int row = (int)(i / K), k = (int)(i - (long long)row * K);
+  const int gate = row / H, unit = row - gate * H;
+  dst[(long long)(row0 + gate_perm(unit, gate)) * K + k] = __float2bfloat16_rn(src[i]);
+}
+__global__ void pack_bias_perm(const float* __restrict__ bih, const float* __restrict__ bhh, float* __restrict__ dst, int H, int col0) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 4 * H) return;
+  const int gate = i / H, unit = i - gate * H;
+  dst[col0 + gate_perm(unit, gate)] = bih[i] + bhh[i];
+}
+
+size_t lstm_store_bytes_bf16(const bci_lstm_config& c) {
+  if (c.precision != BCI_PRECISION_BF16) return 0;
+  const size_t H = c.hidden_size;
+  size_t n = 0;
+  for (int l = 0; l < c.num_layers; ++l)
+    n += align_up((size_t)8 * H * layer_in_width(c, l) * 2, 256) + 2 * align_up(4 * H * H * 2, 256) + align_up(8 * H * 4, 256);
+  return n + 1024;
+}
+
+void lstm_carve_bf16(bci_lstm_s* h, char* base) {
+  const bci_lstm_config& c = h->cfg;
+  if (c.precision != BCI_PRECISION_BF16) return;
+  const size_t H = c.hidden_size;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { char* p = base + off; off += align_up(bytes, 256); return p; };
+  for (int l = 0; l < c.num_layers; ++l) {
+    h->bf16.wih_bf[l] = reinterpret_cast<__nv_bfloat16*>(take((size_t)8 * H * layer_in_width(c, l) * 2));
+    h->bf16.whh_bf[l][0] = reinterpret_cast<__nv_bfloat16*>(take(4 * H * H * 2));
+    h->bf16.whh_bf[l][1] = reinterpret_cast<__nv_bfloat16*>(take(4 * H * H * 2));
+    h->bf16.bias_p[l] = reinterpret_cast<float*>(take(8 * H * 4));
+  }
+}
+
+int lstm_pack_bf16(bci_lstm_s* h, cudaStream_t st) {
+  const bci_lstm_config& c = h->cfg;
+  const bci_lstm_weights& w = h->raw;
+  const int H = c.hidden_size;
+  BCI_REQUIRE(H == 128, BCI_EINVAL, "bf16 (tcgen05) mode is built for hidden_size=128; use fp32 precision for H=%d", H);
+  for (int l = 0; l < c.num_layers; ++l) {
+    const int K = layer_in_width(c, l);
+    for (int d = 0; d < 2; ++d) {
+      pack_rows_perm_bf16<<<(unsigned)ceil_div64((long long)4 * H * K, 256), 256, 0, st>>>(w.w_ih[l][d], h->bf16.wih_bf[l], H, K, d * 4 * H);
+      pack_rows_perm_bf16<<<(unsigned)ceil_div64((long long)4 * H * H, 256), 256, 0, st>>>(w.w_hh[l][d], h->bf16.whh_bf[l][d], H, H, 0);
+      pack_bias_perm<<<ceil_div(4 * H, 256), 256, 0, st>>>(w.b_ih[l][d], w.b_hh[l][d], h->bf16.bias_p[l], H, d * 4 * H);
+    }
+  }
+  BCI_LAUNCH_OK();
+  return BCI_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K2: persistent TMA + tcgen05 GEMM.  C[M][N] (bf16) = A[M][K] (bf16) . W[N][K]^T (bf16) + bias[N]
+// ---------------------------------------------------------------------------------------------
+constexpr int GB_BM = 128, GB_BN = 256, GB_BK = 64, GB_STAGES = 4;
+constexpr int GB_THREADS = 192;  // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-5: epilogue
+constexpr uint32_t GB_A_BYTES = GB_BM * GB_BK * 2, GB_B_BYTES = GB_BN * GB_BK * 2;
+constexpr uint32_t GB_STAGE_BYTES = GB_A_BYTES + GB_B_BYTES;
+constexpr size_t GB_SMEM = 1024 /*align slack*/ + (size_t)GB_STAGES * GB_STAGE_BYTES + 2 * GB_BN * sizeof(float) + 256;
+
+__global__ void __launch_bounds__(GB_THREADS, 1)
+proj_gemm_bf16(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const float* __restrict__ bias, __nv_bfloat16* __restrict__ C, int M, int N, int K) {
+  extern __shared__ uint8_t gb_smem_raw[];
+  const uint32_t raw = smem_u32(gb_smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* gen = gb_smem_raw + (base - raw);  // generic pointer to the aligned base
+  const uint32_t sA = base, sB = base + GB_STAGES * GB_A_BYTES;
+  float* bias_s = reinterpret_cast<float*>(gen + GB_STAGES * GB_STAGE_BYTES);  // [2][256]
+  uint8_t* ctl = gen + GB_STAGES * GB_STAGE_BYTES + 2 * GB_BN * sizeof(float);
+  const uint32_t bar0 = smem_u32(ctl);
+  auto full_bar = [&](int s) { return bar0 + 8u * s; };
+  auto empty_bar = [&](int s) { return bar0 + 8u * (GB_STAGES + s); };
+  auto tfull_bar = [&](int a) { return bar0 + 8u * (2 * GB_STAGES + a); };
+  auto tempty_bar = [&](int a) { return bar0 + 8u * (2 * GB_STAGES + 2 + a); };
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ctl + 8 * (2 * GB_STAGES + 4));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_blocks = N / GB_BN, m_blocks = (M + GB_BM - 1) / GB_BM;
+  const int num_tiles = n_blocks * m_blocks, k_blocks = K / GB_BK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < GB_STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 128); }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(smem_u32(tmem_slot), 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m0 = (tile / n_blocks) * GB_BM, n0 = (tile % n_blocks) * GB_BN;
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          mbar_arrive_expect_tx(full_bar(stage), GB_STAGE_BYTES);
+          tma_load_2d(sA + stage * GB_A_BYTES, &tmA, kb * GB_BK, m0, full_bar(stage));
+          tma_load_2d(sB + stage * GB_B_BYTES, &tmB, kb * GB_BK, n0, full_bar(stage));
+          if (++stage == GB_STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(GB_BM, GB_BN);
+      int stage = 0; uint32_t phase = 0; int acc = 0; uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)acc * GB_BN;
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+#pragma unroll
+          for (int kk = 0; kk < GB_BK / 16; ++kk) {
+            const uint64_t da = umma_desc_sw128(sA + stage * GB_A_BYTES + kk * 32);
+            const uint64_t db = umma_desc_sw128(sB + stage * GB_B_BYTES + kk * 32);
+            umma_bf16(d_tmem, da, db, idesc, (kb | kk) != 0 ? 1u : 0u);
+          }
+          umma_commit(empty_bar(stage));  // frees the smem slot when these MMAs retire
+          if (++stage == GB_STAGES) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit(tfull_bar(acc));
+        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      }
+    }
+  } else {
+    // epilogue: 4 warps, warp w owns TMEM lane quarter (w % 4)
+    const int quarter = warp & 3;
+    const int et = (warp - 2) * 32 + lane;  // 0..127
+    int acc = 0; uint32_t acc_phase = 0; int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int m0 = (tile / n_blocks) * GB_BM, n0 = (tile % n_blocks) * GB_BN;
+      float* bs = bias_s + (it & 1) * GB_BN;
+      bs[et] = __ldg(bias + n0 + et);
+      bs[et + 128] = __ldg(bias + n0 + 128 + et);
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      const int row = m0 + quarter * 32 + lane;
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)acc * GB_BN;
+      __nv_bfloat16* crow = C + (long long)row * N + n0;
+#pragma unroll 1
+      for (int ch = 0; ch < GB_BN / 32; ++ch) {
+        uint32_t r[32];
+        tmem_ld32(taddr + ch * 32, r);
+        tmem_ld_wait();
+        uint32_t o[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const float v0 = __uint_as_float(r[2 * j]) + bs[ch * 32 + 2 * j];
+          const float v1 = __uint_as_float(r[2 * j + 1]) + bs[ch * 32 + 2 * j + 1];
+          __nv_bfloat162 p = __floats2bfloat162_rn(v0, v1);
+          o[j] = *reinterpret_cast<uint32_t*>(&p);
+        }
+        if (row < M) {
+          uint4* dst = reinterpret_cast<uint4*>(crow + ch * 32);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) dst[q] = make_uint4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(tempty_bar(acc));
+      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// driver entry point for tensor-map encoding, fetched through the runtime (no libcuda link dependency)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// 2D bf16 row-major [rows][cols] tensor, box = box_rows x 64 columns, 128-byte swizzle
+static int make_tmap_bf16(CUtensorMap* tm, const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+  EncodeTiledFn enc = get_encode_fn();
+  BCI_REQUIRE(enc, BCI_ECUDA, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {cols * 2};
+  cuuint32_t box[2] = {64, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  BCI_REQUIRE(r == CUDA_SUCCESS, BCI_ECUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  return BCI_OK;
+}
+
+int launch_proj_gemm_bf16(const __nv_bfloat16* A, const __nv_bfloat16* W, const float* bias, __nv_bfloat16* C, int M, int N,
+                          int K, cudaStream_t st) {
+  BCI_REQUIRE(N % GB_BN == 0 && K % GB_BK == 0 && M > 0, BCI_EINVAL, "proj_gemm_bf16: unsupported shape M=%d N=%d K=%d", M, N, K);
+  CUtensorMap tmA, tmB;
+  int rc = make_tmap_bf16(&tmA, A, (uint64_t)M, (uint64_t)K, GB_BM);
+  if (rc) return rc;
+  rc = make_tmap_bf16(&tmB, W, (uint64_t)N, (uint64_t)K, GB_BN);
+  if (rc) return rc;
+  static bool attr = false;
+  if (!attr) {
+    BCI_CUDA_OK(cudaFuncSetAttribute(proj_gemm_bf16, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GB_SMEM));
+    attr = true;
+  }
+  const int tiles = (N / GB_BN) * ceil_div(M, GB_BM);
+  const int grid = tiles < sm_count() ? tiles : sm_count();
+  proj_gemm_bf16<<<grid, GB_THREADS, GB_SMEM, st>>>(tmA, tmB, bias, C, M, N, K);
+  BCI_LAUNCH_OK();
+  return BCI_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K3: persistent tcgen05 recurrence (H = 128)
+// ---------------------------------------------------------------------------------------------
+constexpr int RB_H = 128, RB_M = 128, RB_N = 4 * RB_H;  // 512 gate columns per direction
+constexpr int RB_EPI_WARPS = 8, RB_THREADS = (RB_EPI_WARPS + 1) * 32;
+constexpr uint32_t RB_W_BYTES = RB_N * RB_H * 2;   // 131072: two K-atoms of [512][64]
+constexpr uint32_t RB_W_ATOM = RB_N * 128;         // 65536
+constexpr uint32_t RB_H_BYTES = RB_M * RB_H * 2;   // 32768: two K-atoms of [128][64]
+constexpr uint32_t RB_H_ATOM = RB_M * 128;         // 16384
+constexpr size_t RB_SMEM = 1024 + RB_W_BYTES + RB_H_BYTES + 64;
+
+__device__ __forceinline__ float tanh_fast(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float sigmoid_fast(float x) { return fmaf(0.5f, tanh_fast(0.5f * x), 0.5f); }
+
+__global__ void __launch_bounds__(RB_THREADS, 1)
+lstm_rec_bf16(const __nv_bfloat16* __restrict__ G,      // [T][Bc][1024]  (dir*512 + permuted gate column), bias included
+              const __nv_bfloat16* __restrict__ whh_f,  // [512][128] permuted rows, forward
+              const __nv_bfloat16* __restrict__ whh_r,  // reverse
+              __nv_bfloat16* __restrict__ out,          // [T][Bc][256]
+              int Bc, int T) {
+  extern __shared__ uint8_t rb_smem_raw[];
+  const uint32_t raw = smem_u32(rb_smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* gen = rb_smem_raw + (base - raw);
+  const uint32_t sW = base, sH = base + RB_W_BYTES;
+  uint8_t* genW = gen;
+  uint8_t* genH = gen + RB_W_BYTES;
+  uint8_t* ctl = gen + RB_W_BYTES + RB_H_BYTES;
+  const uint32_t bar_half0 = smem_u32(ctl), bar_half1 = bar_half0 + 8, bar_h = bar_half0 + 16;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ctl + 24);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int dir = blockIdx.y;
+  const int b0 = blockIdx.x * RB_M;
+
+  // stage W_hh into the SW128 K-major UMMA layout; zero h_{-1}
+  {
+    const uint4* src = reinterpret_cast<const uint4*>(dir ? whh_r : whh_f);  // 16 chunks of 16 B per row
+    for (int q = tid; q < RB_N * 16; q += RB_THREADS) {
+      const uint32_t row = q >> 4, cc = q & 15, atom = cc >> 3, c = cc & 7;
+      *reinterpret_cast<uint4*>(genW + atom * RB_W_ATOM + sw128_chunk_off(row, c)) = __ldg(src + q);
+    }
+    for (int q = tid; q < (int)(RB_H_BYTES / 16); q += RB_THREADS) reinterpret_cast<uint4*>(genH)[q] = make_uint4(0, 0, 0, 0);
+  }
+  if (tid == 0) {
+    mbar_init(bar_half0, 1);
+    mbar_init(bar_half1, 1);
+    mbar_init(bar_h, RB_EPI_WARPS * 32);
+    fence_mbar_init();
+  }
+  if (warp == RB_EPI_WARPS) {
+    tmem_alloc(smem_u32(tmem_slot), 512);
+    tmem_relinquish();
+  }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == RB_EPI_WARPS) {
+    // ---------------- MMA issuer ----------------
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(RB_M, 256);
+      for (int s = 0; s < T; ++s) {
+        if (s > 0) {
+          mbar_wait(bar_h, (uint32_t)((s - 1) & 1));  // h_{s-1} written, TMEM drained
+          tc_fence_after();
+        }
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+#pragma unroll
+          for (int k = 0; k < RB_H / 16; ++k) {
+            const uint32_t atom = k >> 2, kk = k & 3;
+            const uint64_t da = umma_desc_sw128(sH + atom * RB_H_ATOM + kk * 32);
+            const uint64_t db = umma_desc_sw128(sW + atom * RB_W_ATOM + half * (256 * 128) + kk * 32);
+            umma_bf16(tmem_base + half * 256, da, db, idesc, k != 0 ? 1u : 0u);
+          }
+          umma_commit(half == 0 ? bar_half0 : bar_half1);
+        }
+      }
+    }
+  } else {
+    // ---------------- epilogue: thread = (window row, half of the hidden units) ----------------
+    const int quarter = warp & 3, half = warp >> 2;
+    const int r = quarter * 32 + lane;  // window row inside the tile == TMEM lane
+    const int b = b0 + r;
+    const bool live = b < Bc;
+    const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)half * 256;
+    const uint32_t my_bar = half == 0 ? bar_half0 : bar_half1;
+    float c[64];
+#pragma unroll
+    for (int i = 0; i < 64; ++i) c[i] = 0.f;
+    uint8_t* hrow = genH + half * RB_H_ATOM;  // units [64*half, 64*half+64) live in K-atom `half`
+
+    for (int s = 0; s < T; ++s) {
+      const int t = dir ? (T - 1 - s) : s;
+      const long long grow = (long long)t * Bc + (live ? b : 0);
+      const uint4* gp = reinterpret_cast<const uint4*>(G + grow * 1024 + dir * 512 + half * 256);
+      __nv_bfloat16* op = out + grow * 256 + dir * 128 + half * 64;
+      uint4 gq[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) gq[q] = __ldg(gp + q);  // slab 0, issued before waiting on the MMA
+      mbar_wait(my_bar, (uint32_t)(s & 1));
+      tc_fence_after();
+#pragma unroll
+      for (int sl = 0; sl < 8; ++sl) {  // fully unrolled: c[] must stay in registers
+        uint32_t acc[32];
+        tmem_ld32(taddr + sl * 32, acc);
+        uint4 gn[4];
+        if (sl < 7) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) gn[q] = __ldg(gp + (sl + 1) * 4 + q);
+        }
+        tmem_ld_wait();
+        const uint32_t* gw = reinterpret_cast<const uint32_t*>(gq);  // 16 words = 32 bf16: [gate][unit%8]
+        uint32_t hp[4];
+#pragma unroll
+        for (int u2 = 0; u2 < 4; ++u2) {
+          float hv[2];
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int u = u2 * 2 + e;
+            // bf16 -> fp32: element u of gate g sits in word (g*8+u)/2, low or high half
+            auto gval = [&](int g) {
+              const uint32_t w = gw[(g * 8 + u) >> 1];
+              return __uint_as_float((u & 1) ? (w & 0xFFFF0000u) : (w << 16));
+            };
+            const float ig = sigmoid_fast(__uint_as_float(acc[0 * 8 + u]) + gval(0));
+            const float fg = sigmoid_fast(__uint_as_float(acc[1 * 8 + u]) + gval(1));
+            const float gg = tanh_fast(__uint_as_float(acc[2 * 8 + u]) + gval(2));
+            const float og = sigmoid_fast(__uint_as_float(acc[3 * 8 + u]) + gval(3));
+            float& cc = c[sl * 8 + u];
+            cc = fmaf(fg, cc, ig * gg);
+            hv[e] = og * tanh_fast(cc);
+          }
+          __nv_bfloat162 p = __floats2bfloat162_rn(hv[0], hv[1]);
+          hp[u2] = *reinterpret_cast<uint32_t*>(&p);
+        }
+        const uint4 hvec = make_uint4(hp[0], hp[1], hp[2], hp[3]);
+        // units 64*half + 8*sl .. +7  ->  chunk sl of row r in K-atom `half`
+        *reinterpret_cast<uint4*>(hrow + sw128_chunk_off((uint32_t)r, (uint32_t)sl)) = hvec;
+        if (live) *reinterpret_cast<uint4*>(op + sl * 8) = hvec;
+        if (sl < 7) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) gq[q] = gn[q];
+        }
+      }
+      fence_proxy_async_smem();  // h_t (generic-proxy stores) -> visible to the next step's tcgen05.mma
+      tc_fence_before();         // order this thread's TMEM reads before the barrier
+      mbar_arrive(bar_h);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == RB_EPI_WARPS) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+int launch_rec_bf16(const __nv_bfloat16* G, const __nv_bfloat16* whh_f, const __nv_bfloat16* whh_r, __nv_bfloat16* out, int Bc,
+                    int T, cudaStream_t st) {
+  static bool attr = false;
+  if (!attr) {
+    BCI_CUDA_OK(cudaFuncSetAttribute(lstm_rec_bf16, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RB_SMEM));
+    attr = true;
+  }
+  dim3 grid(ceil_div(Bc, RB_M), 2);
+  lstm_rec_bf16<<<grid, RB_THREADS, RB_SMEM, st>>>(G, whh_f, whh_r, out, Bc, T);
+  BCI_LAUNCH_OK();
+  return BCI_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// host orchestration
+// ---------------------------------------------------------------------------------------------
+static size_t chunk_bytes_bf16(const bci_lstm_config& c, int Bc, int T) {
+  const size_t H = c.hidden_size, rows = (size_t)Bc * T;
+  return align_up(rows * H * 2, 1024) + align_up(rows * 8 * H * 2, 1024) + 2 * align_up(rows * 2 * H * 2, 1024) +
+         align_up(rows * 4, 1024);
+}
+
+size_t lstm_workspace_bf16(const bci_lstm_config& c, int batch, int T) {
+  const int Bc = batch < max_chunk(c, 0) ? batch : max_chunk(c, 0);
+  return chunk_bytes_bf16(c, Bc > 0 ? Bc : 1, T);
+}
+
+static int forward_chunk_bf16(bci_lstm_s* h, const float* x, int Bc, int T, float* logits, float* probs, float* attn, char* ws,
+                              cudaStream_t st) {
+  constexpr int H = 128;
+  const bci_lstm_config& c = h->cfg;
+  const size_t rows = (size_t)Bc * T;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { char* p = ws + off; off += align_up(bytes, 1024); return p; };
+  __nv_bfloat16* z = reinterpret_cast<__nv_bfloat16*>(take(rows * H * 2));
+  __nv_bfloat16* g = reinterpret_cast<__nv_bfloat16*>(take(rows * 8 * H * 2));
+  __nv_bfloat16* o0 = reinterpret_cast<__nv_bfloat16*>(take(rows * 2 * H * 2));
+  __nv_bfloat16* o1 = reinterpret_cast<__nv_bfloat16*>(take(rows * 2 * H * 2));
+  float* scores = reinterpret_cast<float*>(take(rows * 4));
+  h->prof.mark(-1, st);
+  int rc = launch_input_proj<H, __nv_bfloat16>(h, x, Bc, T, z, st);
+  if (rc) return rc;
+  h->prof.mark(0, st);
+  const __nv_bfloat16* in = z;
+  __nv_bfloat16* outs[2] = {o0, o1};
+  for (int l = 0; l < c.num_layers; ++l) {
+    rc = launch_proj_gemm_bf16(in, h->bf16.wih_bf[l], h->bf16.bias_p[l], g, (int)rows, 8 * H, layer_in_width(c, l), st);
+    if (rc) return rc;
+    h->prof.mark(1, st);
+    __nv_bfloat16* o = outs[l & 1];
+    rc = launch_rec_bf16(g, h->bf16.whh_bf[l][0], h->bf16.whh_bf[l][1], o, Bc, T, st);
+    if (rc) return rc;
+    h->prof.mark(2, st);
+    in = o;
+  }
+  rc = launch_pool_head<H, __nv_bfloat16>(h, in, Bc, T, logits, probs, attn, scores, st);
+  h->prof.mark(3, st);
+  return rc;
+}
+
+int lstm_forward_bf16(bci_lstm_s* h, const float* x, int batch, int T, float* logits, float* probs, float* attn, void* ws,
+                      size_t ws_bytes, cudaStream_t st) {
+  const bci_lstm_config& c = h->cfg;
+  BCI_REQUIRE(c.hidden_size == 128, BCI_EINVAL, "bf16 mode supports hidden_size=128 only");
+  BCI_REQUIRE(((uintptr_t)ws & 1023) == 0, BCI_EINVAL, "bci_lstm_forward: workspace must be 1024-byte aligned");
+  const int chunk = batch < max_chunk(c, 0) ? batch : max_chunk(c, 0);
+  BCI_REQUIRE(ws_bytes >= chunk_bytes_bf16(c, chunk, T), BCI_ENOMEM, "bci_lstm_forward: workspace %zu < %zu bytes", ws_bytes,
+              chunk_bytes_bf16(c, chunk, T));
+  for (int b0 = 0; b0 < batch; b0 += chunk) {
+    const int Bc = (batch - b0) < chunk ? (batch - b0) : chunk;
+    int rc = forward_chunk_bf16(h, x + (size_t)b0 * T * c.input_size, Bc, T, logits + (size_t)b0 * c.num_classes,
+                                probs ? probs + (size_t)b0 * c.num_classes : nullptr, attn ? attn + (size_t)b0 * T : nullptr,
+                                (char*)ws, st);
+    if (rc) return rc;
+  }
+  return BCI_OK;
+}
+
+}  // namespace bci
+
+// ---- diagnostics exported for the GPU unit tests (tests/test_gpu_tensorcore.py) ---------------------
+extern "C" int bci_selftest_proj_gemm_bf16(const void* A, const void* W, const float* bias, void* C, int32_t M, int32_t N,
+                                           int32_t K, void* stream) {
+  return bci::launch_proj_gemm_bf16((const __nv_bfloat16*)A, (const __nv_bfloat16*)W, bias, (__nv_bfloat16*)C, M, N, K,
+                                    (cudaStream_t)stream);
+}
+extern "C" int bci_selftest_rec_bf16(const void* G, const void* whh_f, const void* whh_r, void* out, int32_t Bc, int32_t T,
+                                     void* stream) {
+  return bci::launch_rec_bf16((const __nv_bfloat16*)G, (const __nv_bfloat16*)whh_f, (const __nv_bfloat16*)whh_r,
+                              (__nv_bfloat16*)out, Bc, T, (cudaStream_t)stream);
+}

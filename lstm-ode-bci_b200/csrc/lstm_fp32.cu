@@ -297,8 +297,10 @@ static int forward_chunk_f32(bci_lstm_s* h, const float* x, int Bc, int T, float
   float* o0 = reinterpret_cast<float*>(take(rows * 2 * H * 4));
   float* o1 = reinterpret_cast<float*>(take(rows * 2 * H * 4));
   float* scores = reinterpret_cast<float*>(take(rows * 4));
+  h->prof.mark(-1, st);
   int rc = launch_input_proj<H, float>(h, x, Bc, T, z, st);
   if (rc) return rc;
+  h->prof.mark(0, st);
   const float* in = z;
   float* outs[2] = {o0, o1};
   constexpr int MT = (REC_THREADS / H) * REC_WPT;
@@ -308,13 +310,17 @@ static int forward_chunk_f32(bci_lstm_s* h, const float* x, int Bc, int T, float
     dim3 gg(N / GN, ceil_div(M, GM));
     proj_gemm_f32<<<gg, GEMM_THREADS, 0, st>>>(in, h->f32.wih_t[l], h->f32.bias[l], g, M, N, K);
     BCI_LAUNCH_OK();
+    h->prof.mark(1, st);
     float* o = outs[l & 1];
     dim3 gr(ceil_div(Bc, MT), 2);
     lstm_rec_f32<H><<<gr, REC_THREADS, 0, st>>>(g, h->f32.whh_t[l][0], h->f32.whh_t[l][1], o, nullptr, nullptr, Bc, T);
     BCI_LAUNCH_OK();
+    h->prof.mark(2, st);
     in = o;
   }
-  return launch_pool_head<H, float>(h, in, Bc, T, logits, probs, attn, scores, st);
+  rc = launch_pool_head<H, float>(h, in, Bc, T, logits, probs, attn, scores, st);
+  h->prof.mark(3, st);
+  return rc;
 }
 
 int lstm_forward_fp32(bci_lstm_s* h, const float* x, int batch, int T, float* logits, float* probs, float* attn,

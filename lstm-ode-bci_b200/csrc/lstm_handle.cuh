@@ -43,6 +43,24 @@ struct PackedBF16 {
 
 }  // namespace bci
 
+namespace bci {
+struct Profiler {
+  static constexpr int MAX_EV = 2048;
+  bool enabled = false;
+  int n = 0;
+  cudaEvent_t ev[MAX_EV];
+  int phase[MAX_EV];      // phase that ENDS at ev[i] (-1 for the opening event of a forward)
+  bool created = false;
+  // record the end of `ph` (or the start marker with ph = -1)
+  void mark(int ph, cudaStream_t st) {
+    if (!enabled || n >= MAX_EV) return;
+    if (!created) { for (int i = 0; i < MAX_EV; ++i) cudaEventCreate(&ev[i]); created = true; }
+    cudaEventRecord(ev[n], st);
+    phase[n++] = ph;
+  }
+};
+}  // namespace bci
+
 struct bci_lstm_s {
   bci_lstm_config cfg;
   int device;
@@ -53,6 +71,7 @@ struct bci_lstm_s {
   bci::PackedBF16 bf16;
   // raw (unpacked) weight pointers of the last load_weights (caller-owned; used by backward)
   bci_lstm_weights raw;
+  bci::Profiler prof;
 };
 
 namespace bci {

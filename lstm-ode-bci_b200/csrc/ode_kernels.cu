@@ -438,13 +438,13 @@ extern "C" int bci_ode_solve(const bci_ode_args* a, void* stream) {
   BCI_REQUIRE(a->t_end > 0.0, BCI_EINVAL, "bci_ode_solve: t_end must be > 0");
   BCI_REQUIRE(a->substeps >= 0, BCI_EINVAL, "bci_ode_solve: substeps must be >= 0");
   BCI_REQUIRE(a->out_dtype == BCI_OUT_F32 || a->out_dtype == BCI_OUT_F64, BCI_EINVAL, "bci_ode_solve: bad out_dtype");
+  if (a->n == 0) return BCI_OK;  // empty ensemble: nothing to read or write (pointers may be NULL)
   BCI_REQUIRE(!(a->coupling) || (a->p_open && a->p_closed), BCI_EINVAL, "bci_ode_solve: coupling needs p_open and p_closed");
   BCI_REQUIRE(a->y0_mode != BCI_Y0_GIVEN || a->y0, BCI_EINVAL, "bci_ode_solve: y0 is NULL with BCI_Y0_GIVEN");
   BCI_REQUIRE(a->y0_mode != BCI_Y0_FROM_PROBS_06 || (a->p_open && a->p_closed), BCI_EINVAL, "bci_ode_solve: y0 from probs needs p_open/p_closed");
   BCI_REQUIRE(a->y0_mode != BCI_Y0_FROM_PCLOSED_08 || a->p_closed, BCI_EINVAL, "bci_ode_solve: y0 from p_closed needs p_closed");
   BCI_REQUIRE(a->mode != BCI_ODE_RK45 || (a->rtol > 0.0 && a->atol > 0.0), BCI_EINVAL, "bci_ode_solve: RK45 needs rtol, atol > 0");
   BCI_REQUIRE(a->traj || a->final_state, BCI_EINVAL, "bci_ode_solve: no output requested");
-  if (a->n == 0) return BCI_OK;
   OdeParams P;
   P.style = a->style; P.y0_mode = a->y0_mode; P.coupling = a->coupling; P.n = a->n;
   for (int r = 0; r < 6; ++r) P.base[r] = a->base_rates[r];

@@ -98,6 +98,25 @@ def lstm_load_weights(hid, state):
     h.keepalive = tensors  # backward reads the raw weights; keep them alive with the handle
 
 
+PHASES = ("input_proj", "proj_gemm", "recurrence", "pool_head")
+
+
+def lstm_set_profiling(hid, enable):
+    N.check(N.lib().bci_lstm_set_profiling(_handles[hid].ptr, int(bool(enable))))
+
+
+def lstm_get_profile(hid):
+    """{phase: (milliseconds, launches)} accumulated since the last call (synchronises)."""
+    ms = (C.c_float * 4)()
+    ln = (C.c_int32 * 4)()
+    N.check(N.lib().bci_lstm_get_profile(_handles[hid].ptr, ms, ln))
+    return {PHASES[i]: (float(ms[i]), int(ln[i])) for i in range(4)}
+
+
+def launch_count():
+    return int(N.lib().bci_launch_count())
+
+
 def lstm_workspace_bytes(hid, batch, seq_len, train):
     h = _handles[hid]
     n = C.c_size_t(0)
