@@ -1,0 +1,325 @@
+#!/usr/bin/env python
+"""bench.py -- BiLSTM 256x61 windows/s (+ ODE trajectories/s) on N B200s, one process per GPU.
+
+    python bench.py --gpus 1 --steps K --warmup W            # this framework (CUDA, sm_100a)
+    python bench.py --impl reference ...                     # the reference's CPU path (torch port) on host cores
+    torchrun --nproc-per-node N bench.py --gpus N ...        # N > 1 (driver launches it this way)
+
+A step = one pass of the hot path (EnhancedLSTMModel.forward + softmax -> P(open)/P(closed),
+04_lstm_model.py:206-222, 06:351) over one batch of synthetic windows per GPU.  Workload at every N:
+BASELINE.json configs[1] (inference sweep point: 18944 = 148 SMs x 128 windows per GPU, bf16 tensor-core
+mode), weak scaling (per-GPU batch fixed; windows are independent -> no data-path collective).
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FLOP_PER_WINDOW = 557_793_536          # SURVEY.md §8 d (H=128, T=256, C=61, 3 layers, forward)
+FLOP_PHASE = {"input_proj": 3_997_696, "proj_gemm": 335_544_320, "recurrence": 201_326_592,
+              "pool_head": 16_842_752 + 82_176}
+ODE_SUBSTEPS = 8
+ODE_FLOP_PER_TRAJ = 12 + 19 * ODE_SUBSTEPS * 123 + 20 * 11      # SURVEY.md §8 d: 18 928 at S=8
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"],
+                "bf16_tflops_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons every 200 ms while the timed region runs."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = sorted(float(r[1]) for r in self.rows if len(r) >= 8 and r[1].replace(".", "").isdigit())
+        mx = [float(r[2]) for r in self.rows if len(r) >= 8 and r[2].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 8 for i in range(4) if r[4 + i].lower().startswith("active")})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def cpu_lstm_baseline(budget_s=20.0, sample=128):
+    """Reference CPU path (torch port of the reference module, all host threads) on a bounded sample."""
+    import torch
+    from lstm_ode_bci_b200 import synth
+    from oracle import torch_port
+    torch.set_num_threads(os.cpu_count() or 1)
+    params = synth.make_lstm_params(42, 61, 128, 3)
+    port = torch_port.build_port(params).eval()
+    x = torch.from_numpy(synth.make_windows(7, sample, 256, 61))
+    with torch.no_grad():
+        port(x[:8])
+        t0 = time.perf_counter()
+        port(x)
+        one = time.perf_counter() - t0
+        reps = max(1, min(10, int(budget_s / max(one, 1e-3)) - 1))
+        best = one
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            port(x)
+            best = min(best, time.perf_counter() - t0)
+    return {"value": sample / best, "unit": "windows/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{sample} windows x 256 x 61 fp32, best of {reps + 1} (oracle/torch_port.py = torch CPU path of the reference module)"}
+
+
+def cpu_ode_baseline(n=1500):
+    from lstm_ode_bci_b200 import synth
+    from oracle import ode_oracle
+    sw = synth.make_ode_sweep(42, n)
+    t0 = time.perf_counter()
+    ode_oracle.reference_style_loop(sw["p_open"], sw["p_closed"], dict(synth.DEFAULT_RATES), 0.5, 20)
+    dt = time.perf_counter() - t0
+    return {"value": n / dt, "unit": "trajectories/s", "cores": 1, "kind": "port",
+            "sample": f"{n} trajectories, per-sample scipy.odeint loop as 06:372-401 (serial by construction)"}
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    steps, warm = args.steps, args.warmup
+    import torch
+    from lstm_ode_bci_b200 import synth
+    from oracle import torch_port
+    torch.set_num_threads(os.cpu_count() or 1)
+    sample = args.ref_sample
+    port = torch_port.build_port(synth.make_lstm_params(42, 61, 128, 3)).eval()
+    x = torch.from_numpy(synth.make_windows(7, sample, 256, 61))
+    with torch.no_grad():
+        for _ in range(warm):
+            torch.softmax(port(x), 1)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            torch.softmax(port(x), 1)
+        dt = time.perf_counter() - t0
+    v = sample * steps / dt
+    cores = torch.get_num_threads()
+    line = {"impl": "reference", "metric": "bilstm_windows_per_s", "value": v, "unit": "windows/s", "n_gpus": args.gpus,
+            "steps": steps, "warmup": warm, "ms_per_step": dt / steps * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args, world),
+            "cpu_baseline": {"value": v, "unit": "windows/s", "cores": cores, "kind": "port",
+                             "sample": f"{sample} windows per step (bounded sample of the per-GPU batch), torch CPU path of the reference module"},
+            "e2e": {"value": v, "unit": "windows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, world):
+    return {"workload": "BASELINE configs[1]: BiLSTM(3x128,T=256,C=61)+attention pooling inference -> P(open)/P(closed)",
+            "windows_per_gpu": args.batch, "global_windows_per_step": args.batch * world, "hidden": 128, "layers": 3,
+            "seq_len": 256, "channels": 61, "precision_mode": args.precision,
+            "l2_policy": "inputs larger than L2 (%.2f GB per step per GPU)" % (args.batch * 256 * 61 * 4 / 1e9),
+            "parallelism": f"window-sharded x{world}, no data-path collective"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=18944, help="windows per GPU per step (148 SMs x 128)")
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--ode-n", type=int, default=1 << 24)
+    ap.add_argument("--ref-sample", type=int, default=128)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-ode", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        return run_reference(args, rank, world)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from lstm_ode_bci_b200 import _native, integration, lstm, ode, ops, synth
+
+    torch.cuda.set_device(local)
+    _native.require_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    peaks = load_peaks()
+    B, K, W = args.batch, args.steps, args.warmup
+    params = synth.make_lstm_params(42, 61, 128, 3)
+    model = lstm.from_params(params, precision=args.precision, device=f"cuda:{local}")
+    gen = torch.Generator(device="cuda").manual_seed(42 + rank)
+    x = torch.randn((B, 256, 61), device="cuda", generator=gen)           # N(0,1): z-scored EEG (02:134-152)
+    hid = model._engine(args.precision)
+
+    # ---- device-resident throughput (value) --------------------------------------------------
+    for _ in range(W):
+        model.predict_proba(x)
+    ops.lstm_set_profiling(hid, True)
+    ops.lstm_get_profile(hid)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    l0 = ops.launch_count()
+    e0.record()
+    for _ in range(K):
+        probs = model.predict_proba(x)
+    e1.record()
+    barrier()
+    launches = ops.launch_count() - l0
+    ms = max_over_ranks(e0.elapsed_time(e1))
+    prof = ops.lstm_get_profile(hid)
+    ops.lstm_set_profiling(hid, False)
+    clocks = sampler.stop() if rank == 0 else None
+    value = world * B * K / (ms * 1e-3)
+
+    # ---- end to end through the public API with HOST buffers ---------------------------------
+    x_host = torch.empty((B, 256, 61), dtype=torch.float32).pin_memory()
+    x_host.copy_(x)
+    def e2e_step():
+        p, _ = integration._lstm_probs_device(model, x_host, 4096, False, f"cuda:{local}")
+        return p.cpu()
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    e2e_steps = max(2, min(K, 5))
+    for _ in range(e2e_steps):
+        ph = e2e_step()
+    barrier()
+    e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
+    e2e = {"value": world * B * e2e_steps / (e2e_ms * 1e-3), "unit": "windows/s",
+           "h2d_bytes_per_step": int(x_host.numel() * 4), "d2h_bytes_per_step": int(ph.numel() * 4),
+           "api": "integration get_lstm_probabilities path: pinned host windows -> chunked H2D on a copy stream "
+                  "overlapped with compute -> probs D2H", "steps": e2e_steps}
+
+    # ---- roofline of the dominant kernel ------------------------------------------------------
+    dom = max(prof, key=lambda k: prof[k][0])
+    dom_ms, dom_launches = prof[dom]
+    per_launch_flop = FLOP_PHASE[dom] * B * K / max(dom_launches, 1)
+    achieved = FLOP_PHASE[dom] * B * K / (dom_ms * 1e-3) / 1e12 if dom_ms > 0 else 0.0
+    peak_tf = peaks["bf16_tflops_sustained"] if args.precision == "bf16" else None
+    roof = {"bound": "tensor", "kernel": dom, "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
+            "frac": (achieved / peak_tf) if peak_tf else None, "traffic": None,
+            "peak_source": "bf16_tflops_sustained of %s (kernel timed inside a long step)" % peaks["source"],
+            "flop_per_launch": per_launch_flop, "avg_launch_ms": dom_ms / max(dom_launches, 1),
+            "phase_ms_per_step": {k: v[0] / K for k, v in prof.items()},
+            "phase_share": {k: v[0] / max(sum(p[0] for p in prof.values()), 1e-9) for k, v in prof.items()},
+            "whole_path": {"achieved": value / world * FLOP_PER_WINDOW / 1e12, "unit": "TFLOP/s per GPU",
+                           "frac_of_bf16_burst": value / world * FLOP_PER_WINDOW / 1e12 / peaks["bf16_tflops"],
+                           "frac_of_bf16_sustained": value / world * FLOP_PER_WINDOW / 1e12 / peaks["bf16_tflops_sustained"]}}
+    if args.precision == "fp32":
+        fp32_peak = ops.fp32_peak_probe()
+        roof.update({"bound": "fp32", "peak": fp32_peak, "frac": achieved / fp32_peak,
+                     "peak_source": "FP32 FMA micro-benchmark measured in this run (bci_fp32_peak_probe)"})
+
+    line = {"metric": "bilstm_windows_per_s", "value": value, "unit": "windows/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": args.precision if args.precision != "fp32" else "f32", "data": "synthetic",
+            "config": workload_config(args, world), "e2e": e2e, "gpu_launches": int(launches), "roofline": roof,
+            "clocks": clocks}
+
+    # ---- ODE ensemble (second half of the metric: trajectories/s) -----------------------------
+    if not args.no_ode:
+        n = args.ode_n
+        sw = synth.make_ode_sweep(42 + rank, n)
+        dev = {k: torch.from_numpy(v).cuda() for k, v in sw.items()}
+        def ode_step(want_traj=True, mode="rk4"):
+            return ode.solve_ensemble(n, p_open=dev["p_open"], p_closed=dev["p_closed"], rates=dev["rates"],
+                                      alpha_arr=dev["alpha"], y0_mode="probs06", coupling=True, style="ref06", mode=mode,
+                                      t_end=20.0, n_points=20, substeps=ODE_SUBSTEPS, want_traj=want_traj)
+        def time_ode(**kw):
+            for _ in range(3):
+                ode_step(**kw)
+            barrier()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(5):
+                ode_step(**kw)
+            b.record()
+            barrier()
+            return max_over_ranks(a.elapsed_time(b)) / 5
+        t_traj, t_final, t_rk45 = time_ode(want_traj=True), time_ode(want_traj=False), time_ode(want_traj=True, mode="rk45")
+        fp32_peak = ops.fp32_peak_probe()
+        bytes_traj = n * (36 + 240 + 12)
+        line["ode"] = {
+            "metric": "ode_trajectories_per_s", "unit": "trajectories/s", "n_per_gpu": n, "substeps": ODE_SUBSTEPS,
+            "rk4_full_trajectory": {"value": world * n / (t_traj * 1e-3), "ms": t_traj,
+                                    "roofline": {"bound": "fp32", "achieved": n * ODE_FLOP_PER_TRAJ / (t_traj * 1e-3) / 1e12,
+                                                 "peak": fp32_peak, "unit": "TFLOP/s",
+                                                 "frac": n * ODE_FLOP_PER_TRAJ / (t_traj * 1e-3) / 1e12 / fp32_peak,
+                                                 "hbm_gbs": bytes_traj / (t_traj * 1e-3) / 1e9,
+                                                 "hbm_frac": bytes_traj / (t_traj * 1e-3) / 1e9 / peaks["hbm_gbs"]}},
+            "rk4_final_state_only": {"value": world * n / (t_final * 1e-3), "ms": t_final,
+                                     "roofline": {"bound": "fp32", "achieved": n * ODE_FLOP_PER_TRAJ / (t_final * 1e-3) / 1e12,
+                                                  "peak": fp32_peak, "unit": "TFLOP/s",
+                                                  "frac": n * ODE_FLOP_PER_TRAJ / (t_final * 1e-3) / 1e12 / fp32_peak}},
+            "rk45_full_trajectory": {"value": world * n / (t_rk45 * 1e-3), "ms": t_rk45, "rtol": 1e-3, "atol": 1e-6},
+            "flop_per_trajectory": ODE_FLOP_PER_TRAJ, "fp32_peak_source": "FMA micro-benchmark in this run"}
+        del dev
+
+    if rank == 0 and not args.no_cpu_baseline and world == 1:
+        line["cpu_baseline"] = cpu_lstm_baseline()
+        if not args.no_ode:
+            line["ode"]["cpu_baseline"] = cpu_ode_baseline()
+    elif rank == 0:
+        line["cpu_baseline"] = None
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -27,21 +27,30 @@ using namespace sm100;
 // ---------------------------------------------------------------------------------------------
 // weight packing for the tensor-core path
 // ---------------------------------------------------------------------------------------------
-__host__ __device__ constexpr int gate_perm(int unit, int gate) { return (unit >> 3) * 32 + gate * 8 + (unit & 7); }
+// Two column orders for the 512 gate pre-activations of one direction (H = 128):
+//   perm_T : TMEM / W_hh row order   half*256 + slab*32 + gate*8 + u      (unit = half*64 + slab*8 + u)
+//            -> thread (row, half) reads slab `slab` of its half as one 32-column tcgen05.ld
+//   perm_G : memory order of G       slab*64 + half*32 + gate*8 + u
+//            -> slab `slab` of BOTH halves is one contiguous 128-byte row segment = one TMA box
+__host__ __device__ constexpr int perm_T(int unit, int gate) { return (unit >> 3) * 32 + gate * 8 + (unit & 7); }
+__host__ __device__ constexpr int perm_G(int unit, int gate) {
+  return ((unit >> 3) & 7) * 64 + (unit >> 6) * 32 + gate * 8 + (unit & 7);
+}
 
-// src (4H, K) gate-major rows -> dst bf16 [row0 + perm(unit,gate)][K]
-__global__ void pack_rows_perm_bf16(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int H, int K, int row0) {
+// src (4H, K) gate-major rows -> dst bf16 [row0 + perm(unit,gate)][K];  order 0 = perm_T, 1 = perm_G
+__global__ void pack_rows_perm_bf16(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int H, int K, int row0, int order) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (long long)4 * H * K) return;
   const int row = (int)(i / K), k = (int)(i - (long long)row * K);
   const int gate = row / H, unit = row - gate * H;
-  dst[(long long)(row0 + gate_perm(unit, gate)) * K + k] = __float2bfloat16_rn(src[i]);
+  const int pr = order ? perm_G(unit, gate) : perm_T(unit, gate);
+  dst[(long long)(row0 + pr) * K + k] = __float2bfloat16_rn(src[i]);
 }
 __global__ void pack_bias_perm(const float* __restrict__ bih, const float* __restrict__ bhh, float* __restrict__ dst, int H, int col0) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= 4 * H) return;
   const int gate = i / H, unit = i - gate * H;
-  dst[col0 + gate_perm(unit, gate)] = bih[i] + bhh[i];
+  dst[col0 + perm_G(unit, gate)] = bih[i] + bhh[i];
 }
 
 size_t lstm_store_bytes_bf16(const bci_lstm_config& c) {
@@ -75,8 +84,8 @@ int lstm_pack_bf16(bci_lstm_s* h, cudaStream_t st) {
   for (int l = 0; l < c.num_layers; ++l) {
     const int K = layer_in_width(c, l);
     for (int d = 0; d < 2; ++d) {
-      pack_rows_perm_bf16<<<(unsigned)ceil_div64((long long)4 * H * K, 256), 256, 0, st>>>(w.w_ih[l][d], h->bf16.wih_bf[l], H, K, d * 4 * H);
-      pack_rows_perm_bf16<<<(unsigned)ceil_div64((long long)4 * H * H, 256), 256, 0, st>>>(w.w_hh[l][d], h->bf16.whh_bf[l][d], H, H, 0);
+      pack_rows_perm_bf16<<<(unsigned)ceil_div64((long long)4 * H * K, 256), 256, 0, st>>>(w.w_ih[l][d], h->bf16.wih_bf[l], H, K, d * 4 * H, 1);
+      pack_rows_perm_bf16<<<(unsigned)ceil_div64((long long)4 * H * H, 256), 256, 0, st>>>(w.w_hh[l][d], h->bf16.whh_bf[l][d], H, H, 0, 0);
       pack_bias_perm<<<ceil_div(4 * H, 256), 256, 0, st>>>(w.b_ih[l][d], w.b_hh[l][d], h->bf16.bias_p[l], H, d * 4 * H);
     }
   }
@@ -86,44 +95,63 @@ int lstm_pack_bf16(bci_lstm_s* h, cudaStream_t st) {
 
 // ---------------------------------------------------------------------------------------------
 // K2: persistent TMA + tcgen05 GEMM.  C[M][N] (bf16) = A[M][K] (bf16) . W[N][K]^T (bf16) + bias[N]
+// Each CTA owns ONE 256-column block of W for its whole life (W block resident in smem, loaded once
+// by TMA) and streams 128-row A tiles through a 4-stage ring, so per output tile only A (K*256 B)
+// and C cross L2 -- the first version re-fetched the W block per tile and was L2-bound (ncu:
+// lts throughput 72 %, tensor pipe 26 %).
 // ---------------------------------------------------------------------------------------------
-constexpr int GB_BM = 128, GB_BN = 256, GB_BK = 64, GB_STAGES = 4;
+constexpr int GB_BM = 128, GB_BN = 256, GB_BK = 64, GB_MAX_STAGES = 8, GB_MAX_K = 256;
 constexpr int GB_THREADS = 192;  // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-5: epilogue
-constexpr uint32_t GB_A_BYTES = GB_BM * GB_BK * 2, GB_B_BYTES = GB_BN * GB_BK * 2;
-constexpr uint32_t GB_STAGE_BYTES = GB_A_BYTES + GB_B_BYTES;
-constexpr size_t GB_SMEM = 1024 /*align slack*/ + (size_t)GB_STAGES * GB_STAGE_BYTES + 2 * GB_BN * sizeof(float) + 256;
+constexpr uint32_t GB_A_BYTES = GB_BM * GB_BK * 2, GB_B_ATOM = GB_BN * GB_BK * 2;
+constexpr uint32_t GB_C_BYTES = GB_BM * 128 * 2;  // staging for half a C tile: two [128][64] bf16 SW128 atoms
+// smem: [W block: k_blocks x 32 KB][A ring: stages x 16 KB][C staging 32 KB][bias 1 KB][barriers]
+static inline int gb_stages(int K) { return K <= 128 ? 8 : 4; }
+static inline size_t gb_smem(int K) {
+  return 1024 + (size_t)(K / GB_BK) * GB_B_ATOM + (size_t)gb_stages(K) * GB_A_BYTES + GB_C_BYTES + GB_BN * sizeof(float) + 256;
+}
 
 __global__ void __launch_bounds__(GB_THREADS, 1)
 proj_gemm_bf16(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-               const float* __restrict__ bias, __nv_bfloat16* __restrict__ C, int M, int N, int K) {
+               const __grid_constant__ CUtensorMap tmC, const float* __restrict__ bias, int M, int N, int K, int GB_STAGES) {
   extern __shared__ uint8_t gb_smem_raw[];
   const uint32_t raw = smem_u32(gb_smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t* gen = gb_smem_raw + (base - raw);  // generic pointer to the aligned base
-  const uint32_t sA = base, sB = base + GB_STAGES * GB_A_BYTES;
-  float* bias_s = reinterpret_cast<float*>(gen + GB_STAGES * GB_STAGE_BYTES);  // [2][256]
-  uint8_t* ctl = gen + GB_STAGES * GB_STAGE_BYTES + 2 * GB_BN * sizeof(float);
+  const uint32_t b_bytes = (uint32_t)(K / GB_BK) * GB_B_ATOM;
+  const uint32_t sB = base, sA = base + b_bytes, sC = sA + GB_STAGES * GB_A_BYTES;
+  uint8_t* genC = gen + b_bytes + GB_STAGES * GB_A_BYTES;
+  float* bias_s = reinterpret_cast<float*>(genC + GB_C_BYTES);  // [256]
+  uint8_t* ctl = genC + GB_C_BYTES + GB_BN * sizeof(float);
   const uint32_t bar0 = smem_u32(ctl);
   auto full_bar = [&](int s) { return bar0 + 8u * s; };
-  auto empty_bar = [&](int s) { return bar0 + 8u * (GB_STAGES + s); };
-  auto tfull_bar = [&](int a) { return bar0 + 8u * (2 * GB_STAGES + a); };
-  auto tempty_bar = [&](int a) { return bar0 + 8u * (2 * GB_STAGES + 2 + a); };
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ctl + 8 * (2 * GB_STAGES + 4));
+  auto empty_bar = [&](int s) { return bar0 + 8u * (GB_MAX_STAGES + s); };
+  auto tfull_bar = [&](int a) { return bar0 + 8u * (2 * GB_MAX_STAGES + a); };
+  auto tempty_bar = [&](int a) { return bar0 + 8u * (2 * GB_MAX_STAGES + 2 + a); };
+  const uint32_t bfull_bar = bar0 + 8u * (2 * GB_MAX_STAGES + 4);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ctl + 8 * (2 * GB_MAX_STAGES + 5));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n_blocks = N / GB_BN, m_blocks = (M + GB_BM - 1) / GB_BM;
-  const int num_tiles = n_blocks * m_blocks, k_blocks = K / GB_BK;
+  const int n_blocks = N / GB_BN, m_blocks = (M + GB_BM - 1) / GB_BM, k_blocks = K / GB_BK;
+  const int n_blk = blockIdx.x % n_blocks, n0 = n_blk * GB_BN;
+  const int m_first = blockIdx.x / n_blocks, m_step = gridDim.x / n_blocks;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmC);
     for (int s = 0; s < GB_STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 128); }
+    mbar_init(bfull_bar, 1);
     fence_mbar_init();
   }
   if (warp == 1) {
     tmem_alloc(smem_u32(tmem_slot), 512);
     tmem_relinquish();
+  }
+  if (warp >= 2) {
+    const int et = (warp - 2) * 32 + lane;
+    bias_s[et] = __ldg(bias + n0 + et);
+    bias_s[et + 128] = __ldg(bias + n0 + 128 + et);
   }
   tc_fence_before();
   __syncthreads();
@@ -132,14 +160,14 @@ proj_gemm_bf16(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   if (warp == 0) {
     if (lane == 0) {
+      mbar_arrive_expect_tx(bfull_bar, (uint32_t)k_blocks * GB_B_ATOM);
+      for (int kb = 0; kb < k_blocks; ++kb) tma_load_2d(sB + kb * GB_B_ATOM, &tmB, kb * GB_BK, n0, bfull_bar);
       int stage = 0; uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m0 = (tile / n_blocks) * GB_BM, n0 = (tile % n_blocks) * GB_BN;
+      for (int mb = m_first; mb < m_blocks; mb += m_step) {
         for (int kb = 0; kb < k_blocks; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
-          mbar_arrive_expect_tx(full_bar(stage), GB_STAGE_BYTES);
-          tma_load_2d(sA + stage * GB_A_BYTES, &tmA, kb * GB_BK, m0, full_bar(stage));
-          tma_load_2d(sB + stage * GB_B_BYTES, &tmB, kb * GB_BK, n0, full_bar(stage));
+          mbar_arrive_expect_tx(full_bar(stage), GB_A_BYTES);
+          tma_load_2d(sA + stage * GB_A_BYTES, &tmA, kb * GB_BK, mb * GB_BM, full_bar(stage));
           if (++stage == GB_STAGES) { stage = 0; phase ^= 1u; }
         }
       }
@@ -148,7 +176,8 @@ proj_gemm_bf16(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_bf16(GB_BM, GB_BN);
       int stage = 0; uint32_t phase = 0; int acc = 0; uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      mbar_wait(bfull_bar, 0);
+      for (int mb = m_first; mb < m_blocks; mb += m_step) {
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)acc * GB_BN;
@@ -158,10 +187,10 @@ proj_gemm_bf16(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
           for (int kk = 0; kk < GB_BK / 16; ++kk) {
             const uint64_t da = umma_desc_sw128(sA + stage * GB_A_BYTES + kk * 32);
-            const uint64_t db = umma_desc_sw128(sB + stage * GB_B_BYTES + kk * 32);
+            const uint64_t db = umma_desc_sw128(sB + kb * GB_B_ATOM + kk * 32);
             umma_bf16(d_tmem, da, db, idesc, (kb | kk) != 0 ? 1u : 0u);
           }
-          umma_commit(empty_bar(stage));  // frees the smem slot when these MMAs retire
+          umma_commit(empty_bar(stage));  // frees the A slot when these MMAs retire
           if (++stage == GB_STAGES) { stage = 0; phase ^= 1u; }
         }
         umma_commit(tfull_bar(acc));
@@ -169,44 +198,61 @@ proj_gemm_bf16(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
   } else {
-    // epilogue: 4 warps, warp w owns TMEM lane quarter (w % 4)
+    // epilogue: 4 warps, warp w owns TMEM lane quarter (w % 4).  Each half tile (128 x 128) is converted
+    // to bf16 into a swizzled smem staging buffer and written with two TMA stores (full 128-byte lines);
+    // per-lane 16-byte global stores to 32 different rows cost 32 L1 wavefronts per instruction.
     const int quarter = warp & 3;
-    const int et = (warp - 2) * 32 + lane;  // 0..127
-    int acc = 0; uint32_t acc_phase = 0; int it = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-      const int m0 = (tile / n_blocks) * GB_BM, n0 = (tile % n_blocks) * GB_BN;
-      float* bs = bias_s + (it & 1) * GB_BN;
-      bs[et] = __ldg(bias + n0 + et);
-      bs[et + 128] = __ldg(bias + n0 + 128 + et);
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+    const int rt = quarter * 32 + lane;  // row inside the tile
+    const bool issuer = (warp == 2 && lane == 0);
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int mb = m_first; mb < m_blocks; mb += m_step) {
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
-      const int row = m0 + quarter * 32 + lane;
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)acc * GB_BN;
-      __nv_bfloat16* crow = C + (long long)row * N + n0;
-#pragma unroll 1
+      uint32_t r[2][32];
+      tmem_ld32(taddr, r[0]);
+#pragma unroll
       for (int ch = 0; ch < GB_BN / 32; ++ch) {
-        uint32_t r[32];
-        tmem_ld32(taddr + ch * 32, r);
+        if ((ch & 3) == 0) {
+          // staging buffer must have been drained by the previous half's TMA stores
+          if (issuer) tma_store_wait_read();
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+        }
         tmem_ld_wait();
+        if (ch + 1 < GB_BN / 32) tmem_ld32(taddr + (ch + 1) * 32, r[(ch + 1) & 1]);  // next slab in flight
+        const uint32_t* rc = r[ch & 1];
         uint32_t o[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
-          const float v0 = __uint_as_float(r[2 * j]) + bs[ch * 32 + 2 * j];
-          const float v1 = __uint_as_float(r[2 * j + 1]) + bs[ch * 32 + 2 * j + 1];
+          const float v0 = __uint_as_float(rc[2 * j]) + bias_s[ch * 32 + 2 * j];
+          const float v1 = __uint_as_float(rc[2 * j + 1]) + bias_s[ch * 32 + 2 * j + 1];
           __nv_bfloat162 p = __floats2bfloat162_rn(v0, v1);
           o[j] = *reinterpret_cast<uint32_t*>(&p);
         }
-        if (row < M) {
-          uint4* dst = reinterpret_cast<uint4*>(crow + ch * 32);
+        // 32 columns = 4 chunks of 16 B; atom (ch>>1)&1 of the half tile, chunk (ch&1)*4+q of row rt
+        uint8_t* catom = genC + ((ch >> 1) & 1) * (GB_BM * 128);
 #pragma unroll
-          for (int q = 0; q < 4; ++q) dst[q] = make_uint4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
+        for (int q = 0; q < 4; ++q)
+          *reinterpret_cast<uint4*>(catom + sw128_chunk_off((uint32_t)rt, (uint32_t)((ch & 1) * 4 + q))) =
+              make_uint4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
+        if ((ch & 3) == 3) {
+          if (ch == GB_BN / 32 - 1) {  // all TMEM reads of this accumulator are done
+            tc_fence_before();
+            mbar_arrive(tempty_bar(acc));
+          }
+          fence_proxy_async_smem();
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          if (issuer) {
+            const int c0 = n0 + (ch >> 2) * 128;
+            tma_store_2d(&tmC, sC, c0, mb * GB_BM);
+            tma_store_2d(&tmC, sC + GB_BM * 128, c0 + 64, mb * GB_BM);
+            tma_store_commit();
+          }
         }
       }
-      tc_fence_before();
-      mbar_arrive(tempty_bar(acc));
       if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
     }
+    if (issuer) tma_store_wait_all();
   }
   tc_fence_before();
   __syncthreads();
@@ -231,13 +277,13 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-// 2D bf16 row-major [rows][cols] tensor, box = box_rows x 64 columns, 128-byte swizzle
-static int make_tmap_bf16(CUtensorMap* tm, const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+// 2D bf16 row-major [rows][cols] tensor, box = box_rows x box_cols (64 columns = 128 B), 128-byte swizzle
+static int make_tmap_bf16(CUtensorMap* tm, const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_cols, uint32_t box_rows) {
   EncodeTiledFn enc = get_encode_fn();
   BCI_REQUIRE(enc, BCI_ECUDA, "cuTensorMapEncodeTiled entry point not available");
   cuuint64_t dims[2] = {cols, rows};
   cuuint64_t strides[1] = {cols * 2};
-  cuuint32_t box[2] = {64, box_rows};
+  cuuint32_t box[2] = {box_cols, box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -246,36 +292,67 @@ static int make_tmap_bf16(CUtensorMap* tm, const void* ptr, uint64_t rows, uint6
   return BCI_OK;
 }
 
+// 3D bf16 tensor [d2][d1][cols] (row-major), box = 1 x box_rows x box_cols, 128-byte swizzle; rows beyond d1 are
+// clipped on store, so a partial last window tile cannot spill into the next time step.
+static int make_tmap_bf16_3d(CUtensorMap* tm, const void* ptr, uint64_t d2, uint64_t d1, uint64_t cols, uint32_t box_cols,
+                             uint32_t box_rows) {
+  EncodeTiledFn enc = get_encode_fn();
+  BCI_REQUIRE(enc, BCI_ECUDA, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[3] = {cols, d1, d2};
+  cuuint64_t strides[2] = {cols * 2, d1 * cols * 2};
+  cuuint32_t box[3] = {box_cols, box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  BCI_REQUIRE(r == CUDA_SUCCESS, BCI_ECUDA, "cuTensorMapEncodeTiled(3D) failed with CUresult %d", (int)r);
+  return BCI_OK;
+}
+
 int launch_proj_gemm_bf16(const __nv_bfloat16* A, const __nv_bfloat16* W, const float* bias, __nv_bfloat16* C, int M, int N,
                           int K, cudaStream_t st) {
-  BCI_REQUIRE(N % GB_BN == 0 && K % GB_BK == 0 && M > 0, BCI_EINVAL, "proj_gemm_bf16: unsupported shape M=%d N=%d K=%d", M, N, K);
+  CUtensorMap tmC;
+  {
+    int rc0 = make_tmap_bf16(&tmC, C, (uint64_t)M, (uint64_t)N, 64, GB_BM);
+    if (rc0) return rc0;
+  }
+  BCI_REQUIRE(N % GB_BN == 0 && K % GB_BK == 0 && K <= GB_MAX_K && M > 0 && N / GB_BN <= sm_count(), BCI_EINVAL,
+              "proj_gemm_bf16: unsupported shape M=%d N=%d K=%d", M, N, K);
   CUtensorMap tmA, tmB;
-  int rc = make_tmap_bf16(&tmA, A, (uint64_t)M, (uint64_t)K, GB_BM);
+  int rc = make_tmap_bf16(&tmA, A, (uint64_t)M, (uint64_t)K, 64, GB_BM);
   if (rc) return rc;
-  rc = make_tmap_bf16(&tmB, W, (uint64_t)N, (uint64_t)K, GB_BN);
+  rc = make_tmap_bf16(&tmB, W, (uint64_t)N, (uint64_t)K, 64, GB_BN);
   if (rc) return rc;
   static bool attr = false;
   if (!attr) {
-    BCI_CUDA_OK(cudaFuncSetAttribute(proj_gemm_bf16, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GB_SMEM));
+    BCI_CUDA_OK(cudaFuncSetAttribute(proj_gemm_bf16, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gb_smem(GB_MAX_K)));
     attr = true;
   }
-  const int tiles = (N / GB_BN) * ceil_div(M, GB_BM);
-  const int grid = tiles < sm_count() ? tiles : sm_count();
-  proj_gemm_bf16<<<grid, GB_THREADS, GB_SMEM, st>>>(tmA, tmB, bias, C, M, N, K);
+  const int n_blocks = N / GB_BN, m_blocks = ceil_div(M, GB_BM);
+  int per_n = sm_count() / n_blocks;
+  if (per_n > m_blocks) per_n = m_blocks;
+  const int grid = per_n * n_blocks;
+  proj_gemm_bf16<<<grid, GB_THREADS, gb_smem(K), st>>>(tmA, tmB, tmC, bias, M, N, K, gb_stages(K));
   BCI_LAUNCH_OK();
   return BCI_OK;
 }
 
 // ---------------------------------------------------------------------------------------------
 // K3: persistent tcgen05 recurrence (H = 128)
+// warps 0-7: epilogue (thread = window row x half of the hidden units); warp 8: MMA issuer + TMEM
+// owner; warp 9: TMA producer streaming G_t through a 4-slot smem ring (one slot = slab `sl` of both
+// halves for the 128 rows = 16 KB, SWIZZLE_128B).  The first version loaded G with per-thread LDGs
+// one slab ahead and spent 62 % of its stall samples on long-scoreboard waits (ncu, profiles/).
 // ---------------------------------------------------------------------------------------------
 constexpr int RB_H = 128, RB_M = 128, RB_N = 4 * RB_H;  // 512 gate columns per direction
-constexpr int RB_EPI_WARPS = 8, RB_THREADS = (RB_EPI_WARPS + 1) * 32;
+constexpr int RB_EPI_WARPS = 8, RB_THREADS = (RB_EPI_WARPS + 2) * 32;
 constexpr uint32_t RB_W_BYTES = RB_N * RB_H * 2;   // 131072: two K-atoms of [512][64]
 constexpr uint32_t RB_W_ATOM = RB_N * 128;         // 65536
 constexpr uint32_t RB_H_BYTES = RB_M * RB_H * 2;   // 32768: two K-atoms of [128][64]
 constexpr uint32_t RB_H_ATOM = RB_M * 128;         // 16384
-constexpr size_t RB_SMEM = 1024 + RB_W_BYTES + RB_H_BYTES + 64;
+constexpr int RB_G_SLOTS = 4;
+constexpr uint32_t RB_G_SLOT = RB_M * 128;         // 16384: [128 rows][64 bf16]
+constexpr size_t RB_SMEM = 1024 + RB_W_BYTES + RB_H_BYTES + RB_G_SLOTS * RB_G_SLOT + 128;
 
 __device__ __forceinline__ float tanh_fast(float x) {
   float y;
@@ -285,21 +362,25 @@ __device__ __forceinline__ float tanh_fast(float x) {
 __device__ __forceinline__ float sigmoid_fast(float x) { return fmaf(0.5f, tanh_fast(0.5f * x), 0.5f); }
 
 __global__ void __launch_bounds__(RB_THREADS, 1)
-lstm_rec_bf16(const __nv_bfloat16* __restrict__ G,      // [T][Bc][1024]  (dir*512 + permuted gate column), bias included
-              const __nv_bfloat16* __restrict__ whh_f,  // [512][128] permuted rows, forward
-              const __nv_bfloat16* __restrict__ whh_r,  // reverse
-              __nv_bfloat16* __restrict__ out,          // [T][Bc][256]
+lstm_rec_bf16(const __grid_constant__ CUtensorMap tmG,    // G viewed as [T*Bc][1024] bf16, box 64 cols x 128 rows
+              const __grid_constant__ CUtensorMap tmOut,  // out [T][Bc][256] bf16 (3D), box 64 cols x 128 rows x 1
+              const __nv_bfloat16* __restrict__ whh_f,    // [512][128] rows in perm_T order, forward
+              const __nv_bfloat16* __restrict__ whh_r,    // reverse
               int Bc, int T) {
   extern __shared__ uint8_t rb_smem_raw[];
   const uint32_t raw = smem_u32(rb_smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t* gen = rb_smem_raw + (base - raw);
-  const uint32_t sW = base, sH = base + RB_W_BYTES;
+  const uint32_t sW = base, sH = base + RB_W_BYTES, sG = sH + RB_H_BYTES;
   uint8_t* genW = gen;
   uint8_t* genH = gen + RB_W_BYTES;
-  uint8_t* ctl = gen + RB_W_BYTES + RB_H_BYTES;
+  uint8_t* genG = genH + RB_H_BYTES;
+  uint8_t* ctl = genG + RB_G_SLOTS * RB_G_SLOT;
   const uint32_t bar_half0 = smem_u32(ctl), bar_half1 = bar_half0 + 8, bar_h = bar_half0 + 16;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ctl + 24);
+  auto gfull = [&](int i) { return bar_half0 + 24u + 8u * i; };
+  auto gempty = [&](int i) { return bar_half0 + 24u + 8u * (RB_G_SLOTS + i); };
+  const uint32_t bar_hfree = bar_half0 + 24u + 16u * RB_G_SLOTS;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ctl + 32 + 16 * RB_G_SLOTS);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int dir = blockIdx.y;
@@ -318,7 +399,11 @@ lstm_rec_bf16(const __nv_bfloat16* __restrict__ G,      // [T][Bc][1024]  (dir*5
     mbar_init(bar_half0, 1);
     mbar_init(bar_half1, 1);
     mbar_init(bar_h, RB_EPI_WARPS * 32);
+    for (int i = 0; i < RB_G_SLOTS; ++i) { mbar_init(gfull(i), 1); mbar_init(gempty(i), RB_EPI_WARPS); }
+    mbar_init(bar_hfree, 1);
     fence_mbar_init();
+    tma_prefetch_desc(&tmG);
+    tma_prefetch_desc(&tmOut);
   }
   if (warp == RB_EPI_WARPS) {
     tmem_alloc(smem_u32(tmem_slot), 512);
@@ -330,34 +415,62 @@ lstm_rec_bf16(const __nv_bfloat16* __restrict__ G,      // [T][Bc][1024]  (dir*5
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == RB_EPI_WARPS) {
-    // ---------------- MMA issuer ----------------
+  if (warp == RB_EPI_WARPS + 1) {
+    // ---------------- TMA producer: G_t slabs, runs up to RB_G_SLOTS slabs ahead ----------------
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int s = 0; s < T; ++s) {
+        const int t = dir ? (T - 1 - s) : s;
+        const int row0 = t * Bc + b0;
+#pragma unroll 1
+        for (int sl = 0; sl < 8; ++sl, ++it) {
+          const int slot = it & (RB_G_SLOTS - 1);
+          mbar_wait(gempty(slot), ((it / RB_G_SLOTS) & 1u) ^ 1u);
+          mbar_arrive_expect_tx(gfull(slot), RB_G_SLOT);
+          tma_load_2d(sG + slot * RB_G_SLOT, &tmG, dir * 512 + sl * 64, row0, gfull(slot));
+        }
+      }
+    }
+  } else if (warp == RB_EPI_WARPS) {
+    // ---------------- MMA issuer (also streams h_t to global with TMA stores) ----------------
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_bf16(RB_M, 256);
-      for (int s = 0; s < T; ++s) {
+      for (int s = 0; s <= T; ++s) {
         if (s > 0) {
           mbar_wait(bar_h, (uint32_t)((s - 1) & 1));  // h_{s-1} written, TMEM drained
           tc_fence_after();
         }
+        if (s < T) {
 #pragma unroll
-        for (int half = 0; half < 2; ++half) {
+          for (int half = 0; half < 2; ++half) {
 #pragma unroll
-          for (int k = 0; k < RB_H / 16; ++k) {
-            const uint32_t atom = k >> 2, kk = k & 3;
-            const uint64_t da = umma_desc_sw128(sH + atom * RB_H_ATOM + kk * 32);
-            const uint64_t db = umma_desc_sw128(sW + atom * RB_W_ATOM + half * (256 * 128) + kk * 32);
-            umma_bf16(tmem_base + half * 256, da, db, idesc, k != 0 ? 1u : 0u);
+            for (int k = 0; k < RB_H / 16; ++k) {
+              const uint32_t atom = k >> 2, kk = k & 3;
+              const uint64_t da = umma_desc_sw128(sH + atom * RB_H_ATOM + kk * 32);
+              const uint64_t db = umma_desc_sw128(sW + atom * RB_W_ATOM + half * (256 * 128) + kk * 32);
+              umma_bf16(tmem_base + half * 256, da, db, idesc, k != 0 ? 1u : 0u);
+            }
+            umma_commit(half == 0 ? bar_half0 : bar_half1);
           }
-          umma_commit(half == 0 ? bar_half0 : bar_half1);
+        }
+        if (s > 0) {
+          // h_{s-1} sits in the A-operand buffer as two [128 x 64] SW128 atoms == two TMA store boxes;
+          // the store is issued behind the MMAs (off the critical path) and the epilogue may only
+          // overwrite the buffer once the TMA engine has finished reading it (bar_hfree).
+          const int tp = dir ? (T - s) : (s - 1);
+          tma_store_3d(&tmOut, sH, dir * 128, b0, tp);
+          tma_store_3d(&tmOut, sH + RB_H_ATOM, dir * 128 + 64, b0, tp);
+          tma_store_commit();
+          tma_store_wait_read();
+          mbar_arrive(bar_hfree);
         }
       }
+      tma_store_wait_all();
     }
   } else {
     // ---------------- epilogue: thread = (window row, half of the hidden units) ----------------
     const int quarter = warp & 3, half = warp >> 2;
     const int r = quarter * 32 + lane;  // window row inside the tile == TMEM lane
-    const int b = b0 + r;
-    const bool live = b < Bc;
     const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)half * 256;
     const uint32_t my_bar = half == 0 ? bar_half0 : bar_half1;
     float c[64];
@@ -366,24 +479,21 @@ lstm_rec_bf16(const __nv_bfloat16* __restrict__ G,      // [T][Bc][1024]  (dir*5
     uint8_t* hrow = genH + half * RB_H_ATOM;  // units [64*half, 64*half+64) live in K-atom `half`
 
     for (int s = 0; s < T; ++s) {
-      const int t = dir ? (T - 1 - s) : s;
-      const long long grow = (long long)t * Bc + (live ? b : 0);
-      const uint4* gp = reinterpret_cast<const uint4*>(G + grow * 1024 + dir * 512 + half * 256);
-      __nv_bfloat16* op = out + grow * 256 + dir * 128 + half * 64;
-      uint4 gq[4];
-#pragma unroll
-      for (int q = 0; q < 4; ++q) gq[q] = __ldg(gp + q);  // slab 0, issued before waiting on the MMA
       mbar_wait(my_bar, (uint32_t)(s & 1));
       tc_fence_after();
 #pragma unroll
       for (int sl = 0; sl < 8; ++sl) {  // fully unrolled: c[] must stay in registers
         uint32_t acc[32];
         tmem_ld32(taddr + sl * 32, acc);
-        uint4 gn[4];
-        if (sl < 7) {
+        // G slab: ring slot sl % 4, phase flips every 4 slabs (8 slabs per step => same pattern every step)
+        const int slot = sl & (RB_G_SLOTS - 1);
+        mbar_wait(gfull(slot), (uint32_t)((sl / RB_G_SLOTS) & 1));
+        uint4 gq[4];
+        const uint8_t* gs = genG + slot * RB_G_SLOT;
 #pragma unroll
-          for (int q = 0; q < 4; ++q) gn[q] = __ldg(gp + (sl + 1) * 4 + q);
-        }
+        for (int q = 0; q < 4; ++q) gq[q] = *reinterpret_cast<const uint4*>(gs + sw128_chunk_off((uint32_t)r, (uint32_t)(half * 4 + q)));
+        __syncwarp();
+        if (lane == 0) mbar_arrive(gempty(slot));
         tmem_ld_wait();
         const uint32_t* gw = reinterpret_cast<const uint32_t*>(gq);  // 16 words = 32 bf16: [gate][unit%8]
         uint32_t hp[4];
@@ -410,13 +520,9 @@ lstm_rec_bf16(const __nv_bfloat16* __restrict__ G,      // [T][Bc][1024]  (dir*5
           hp[u2] = *reinterpret_cast<uint32_t*>(&p);
         }
         const uint4 hvec = make_uint4(hp[0], hp[1], hp[2], hp[3]);
+        if (sl == 0 && s > 0) mbar_wait(bar_hfree, (uint32_t)((s - 1) & 1));  // TMA store of h_{s-1} has drained the buffer
         // units 64*half + 8*sl .. +7  ->  chunk sl of row r in K-atom `half`
         *reinterpret_cast<uint4*>(hrow + sw128_chunk_off((uint32_t)r, (uint32_t)sl)) = hvec;
-        if (live) *reinterpret_cast<uint4*>(op + sl * 8) = hvec;
-        if (sl < 7) {
-#pragma unroll
-          for (int q = 0; q < 4; ++q) gq[q] = gn[q];
-        }
       }
       fence_proxy_async_smem();  // h_t (generic-proxy stores) -> visible to the next step's tcgen05.mma
       tc_fence_before();         // order this thread's TMEM reads before the barrier
@@ -438,8 +544,13 @@ int launch_rec_bf16(const __nv_bfloat16* G, const __nv_bfloat16* whh_f, const __
     BCI_CUDA_OK(cudaFuncSetAttribute(lstm_rec_bf16, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RB_SMEM));
     attr = true;
   }
+  CUtensorMap tmG, tmOut;
+  int rc = make_tmap_bf16(&tmG, G, (uint64_t)T * (uint64_t)Bc, 1024, 64, RB_M);
+  if (rc) return rc;
+  rc = make_tmap_bf16_3d(&tmOut, out, (uint64_t)T, (uint64_t)Bc, 256, 64, RB_M);
+  if (rc) return rc;
   dim3 grid(ceil_div(Bc, RB_M), 2);
-  lstm_rec_bf16<<<grid, RB_THREADS, RB_SMEM, st>>>(G, whh_f, whh_r, out, Bc, T);
+  lstm_rec_bf16<<<grid, RB_THREADS, RB_SMEM, st>>>(tmG, tmOut, whh_f, whh_r, Bc, T);
   BCI_LAUNCH_OK();
   return BCI_OK;
 }

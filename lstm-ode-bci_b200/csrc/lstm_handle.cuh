@@ -80,7 +80,8 @@ inline int layer_in_width(const bci_lstm_config& c, int l) { return l == 0 ? c.h
 
 // chunking policy: windows processed per internal pass (bounds the workspace)
 inline int max_chunk(const bci_lstm_config& c, int train) {
-  if (c.precision == BCI_PRECISION_BF16) return train ? 2048 : 16384;
+  // bf16 inference: 74 x 128 windows = exactly one wave of (tile, direction) CTAs of the recurrence on 148 SMs
+  if (c.precision == BCI_PRECISION_BF16) return train ? 2048 : 74 * 128;
   const int base = train ? 512 : 2048;
   return c.hidden_size > 128 ? base / 2 : base;
 }

@@ -47,18 +47,23 @@ def _lstm_probs_device(lstm_model, X, batch_size, want_attn, device):
     copy_stream = torch.cuda.Stream(device=dev)
     main = torch.cuda.current_stream(dev)
     nb = min(batch_size, max(n, 1))
-    pinned = [torch.empty((nb, T, Cc), dtype=torch.float32).pin_memory() for _ in range(2)]
+    src_pinned = Xh.is_pinned() and Xh.is_contiguous()     # caller already staged: DMA straight from it
+    pinned = None if src_pinned else [torch.empty((nb, T, Cc), dtype=torch.float32).pin_memory() for _ in range(2)]
     staged = [torch.empty((nb, T, Cc), dtype=torch.float32, device=dev) for _ in range(2)]
     ready = [torch.cuda.Event() for _ in range(2)]
     consumed = [torch.cuda.Event() for _ in range(2)]
 
     def stage(slot, i):
         m = min(batch_size, n - i)
-        consumed[slot].synchronize()            # pinned buffer free again (host side)
-        pinned[slot][:m].copy_(Xh[i:i + m])
+        if src_pinned:
+            src = Xh[i:i + m]
+        else:
+            consumed[slot].synchronize()        # pinned staging buffer free again (host side)
+            pinned[slot][:m].copy_(Xh[i:i + m])
+            src = pinned[slot][:m]
         with torch.cuda.stream(copy_stream):
             copy_stream.wait_event(consumed[slot])
-            staged[slot][:m].copy_(pinned[slot][:m], non_blocking=True)
+            staged[slot][:m].copy_(src, non_blocking=True)
             ready[slot].record(copy_stream)
         return m
 

@@ -1,0 +1,13 @@
+"""One bf16 forward over a single wave of window tiles (profiling target for ncu)."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from lstm_ode_bci_b200 import lstm, synth
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 9472
+prec = sys.argv[2] if len(sys.argv) > 2 else "bf16"
+m = lstm.from_params(synth.make_lstm_params(42, 61, 128, 3), precision=prec)
+x = torch.randn(B, 256, 61, device="cuda")
+for _ in range(2):
+    p = m.predict_proba(x)
+torch.cuda.synchronize()
+print("ok", float(p.sum()))

@@ -27,7 +27,7 @@ def _p(t):
     return C.c_void_p(t.data_ptr())
 
 
-@pytest.mark.parametrize("M,Nn,K", [(128, 256, 64), (128, 256, 128), (1000, 1024, 128), (4173, 1024, 256), (77, 512, 512)])
+@pytest.mark.parametrize("M,Nn,K", [(128, 256, 64), (128, 256, 128), (1000, 1024, 128), (4173, 1024, 256), (77, 512, 256), (300, 2048, 64)])
 def test_proj_gemm_tcgen05_matches_matmul(M, Nn, K):
     g = torch.Generator(device="cuda").manual_seed(M + K)
     A = (torch.randn(M, K, device="cuda", generator=g) * 0.7).to(torch.bfloat16)
@@ -44,11 +44,13 @@ def test_proj_gemm_tcgen05_matches_matmul(M, Nn, K):
     assert bool((err <= tol).all()), float((err - tol).max())
 
 
-def _perm(H=128):
-    idx = np.empty(4 * H, dtype=np.int64)        # idx[natural row gate*H+unit] = permuted row
+def _perm(H=128, order="T"):
+    """idx[natural row gate*H+unit] = permuted row; see include/bci_b200.h (perm_T / perm_G)."""
+    idx = np.empty(4 * H, dtype=np.int64)
     for gate in range(4):
         for unit in range(H):
-            idx[gate * H + unit] = (unit // 8) * 32 + gate * 8 + unit % 8
+            half, slab, u = unit // 64, (unit // 8) % 8, unit % 8
+            idx[gate * H + unit] = (half * 256 + slab * 32 if order == "T" else slab * 64 + half * 32) + gate * 8 + u
     return idx
 
 
@@ -58,20 +60,21 @@ def test_recurrence_tcgen05_matches_stepwise(Bc, T):
     g = torch.Generator(device="cuda").manual_seed(Bc * 131 + T)
     whh = [(torch.rand(4 * H, H, device="cuda", generator=g) * 2 - 1) / np.sqrt(H) for _ in range(2)]
     Gn = torch.randn(T, Bc, 2, 4 * H, device="cuda", generator=g) * 1.5       # natural gate order i,f,g,o
-    perm = torch.from_numpy(_perm(H)).cuda()
+    perm = torch.from_numpy(_perm(H, "T")).cuda()
+    perm_g = torch.from_numpy(_perm(H, "G")).cuda()
     whh_p = []
     for d in range(2):
         wp = torch.empty_like(whh[d])
         wp[perm] = whh[d]
         whh_p.append(wp.to(torch.bfloat16).contiguous())
     Gp = torch.empty_like(Gn)
-    Gp[:, :, :, perm] = Gn
+    Gp[:, :, :, perm_g] = Gn
     Gp = Gp.reshape(T, Bc, 8 * H).to(torch.bfloat16).contiguous()
     out = torch.full((T, Bc, 2 * H), float("nan"), device="cuda", dtype=torch.bfloat16)
     N.check(N.lib().bci_selftest_rec_bf16(_p(Gp), _p(whh_p[0]), _p(whh_p[1]), _p(out), Bc, T, _stream()))
     torch.cuda.synchronize()
     # step-by-step emulation with the same roundings (bf16 G, bf16 weights, bf16 h fed back; fp32 c)
-    Gq = Gp.float().reshape(T, Bc, 2, 4 * H)[:, :, :, perm]                   # back to natural order
+    Gq = Gp.float().reshape(T, Bc, 2, 4 * H)[:, :, :, perm_g]                 # back to natural order
     want = torch.empty(T, Bc, 2 * H, device="cuda")
     for d in range(2):
         w = whh[d].to(torch.bfloat16).float()
