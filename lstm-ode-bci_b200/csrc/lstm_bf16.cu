@@ -19,7 +19,7 @@
 // reference itself runs this under autocast (04:486-490, 06:348-351).
 #include "lstm_shared_kernels.cuh"
 #include "sm100_prims.cuh"
-#include <cuda.h>
+#include "tmap.cuh"
 
 namespace bci {
 using namespace sm100;
@@ -59,6 +59,7 @@ size_t lstm_store_bytes_bf16(const bci_lstm_config& c) {
   size_t n = 0;
   for (int l = 0; l < c.num_layers; ++l)
     n += align_up((size_t)8 * H * layer_in_width(c, l) * 2, 256) + 2 * align_up(4 * H * H * 2, 256) + align_up(8 * H * 4, 256);
+  n += align_up(H * 2 * H * 2, 256) + align_up(H * sizeof(float4), 256);  // attention W1' (bf16) + per-unit params
   return n + 1024;
 }
 
@@ -74,6 +75,8 @@ void lstm_carve_bf16(bci_lstm_s* h, char* base) {
     h->bf16.whh_bf[l][1] = reinterpret_cast<__nv_bfloat16*>(take(4 * H * H * 2));
     h->bf16.bias_p[l] = reinterpret_cast<float*>(take(8 * H * 4));
   }
+  h->bf16.aw1_bf = reinterpret_cast<__nv_bfloat16*>(take(H * 2 * H * 2));
+  h->bf16.apar = reinterpret_cast<float4*>(take(H * sizeof(float4)));
 }
 
 int lstm_pack_bf16(bci_lstm_s* h, cudaStream_t st) {
@@ -89,6 +92,8 @@ int lstm_pack_bf16(bci_lstm_s* h, cudaStream_t st) {
       pack_bias_perm<<<ceil_div(4 * H, 256), 256, 0, st>>>(w.b_ih[l][d], w.b_hh[l][d], h->bf16.bias_p[l], H, d * 4 * H);
     }
   }
+  int rc = pack_pool_bf16(h, st);
+  if (rc) return rc;
   BCI_LAUNCH_OK();
   return BCI_OK;
 }
@@ -262,53 +267,6 @@ proj_gemm_bf16(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
 }
 
-// driver entry point for tensor-map encoding, fetched through the runtime (no libcuda link dependency)
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-static EncodeTiledFn get_encode_fn() {
-  static EncodeTiledFn fn = nullptr;
-  if (!fn) {
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<EncodeTiledFn>(p);
-  }
-  return fn;
-}
-
-// 2D bf16 row-major [rows][cols] tensor, box = box_rows x box_cols (64 columns = 128 B), 128-byte swizzle
-static int make_tmap_bf16(CUtensorMap* tm, const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_cols, uint32_t box_rows) {
-  EncodeTiledFn enc = get_encode_fn();
-  BCI_REQUIRE(enc, BCI_ECUDA, "cuTensorMapEncodeTiled entry point not available");
-  cuuint64_t dims[2] = {cols, rows};
-  cuuint64_t strides[1] = {cols * 2};
-  cuuint32_t box[2] = {box_cols, box_rows};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  BCI_REQUIRE(r == CUDA_SUCCESS, BCI_ECUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
-  return BCI_OK;
-}
-
-// 3D bf16 tensor [d2][d1][cols] (row-major), box = 1 x box_rows x box_cols, 128-byte swizzle; rows beyond d1 are
-// clipped on store, so a partial last window tile cannot spill into the next time step.
-static int make_tmap_bf16_3d(CUtensorMap* tm, const void* ptr, uint64_t d2, uint64_t d1, uint64_t cols, uint32_t box_cols,
-                             uint32_t box_rows) {
-  EncodeTiledFn enc = get_encode_fn();
-  BCI_REQUIRE(enc, BCI_ECUDA, "cuTensorMapEncodeTiled entry point not available");
-  cuuint64_t dims[3] = {cols, d1, d2};
-  cuuint64_t strides[2] = {cols * 2, d1 * cols * 2};
-  cuuint32_t box[3] = {box_cols, box_rows, 1};
-  cuuint32_t estr[3] = {1, 1, 1};
-  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  BCI_REQUIRE(r == CUDA_SUCCESS, BCI_ECUDA, "cuTensorMapEncodeTiled(3D) failed with CUresult %d", (int)r);
-  return BCI_OK;
-}
-
 int launch_proj_gemm_bf16(const __nv_bfloat16* A, const __nv_bfloat16* W, const float* bias, __nv_bfloat16* C, int M, int N,
                           int K, cudaStream_t st) {
   CUtensorMap tmC;
@@ -361,11 +319,13 @@ __device__ __forceinline__ float tanh_fast(float x) {
 }
 __device__ __forceinline__ float sigmoid_fast(float x) { return fmaf(0.5f, tanh_fast(0.5f * x), 0.5f); }
 
+template <bool STATS>
 __global__ void __launch_bounds__(RB_THREADS, 1)
 lstm_rec_bf16(const __grid_constant__ CUtensorMap tmG,    // G viewed as [T*Bc][1024] bf16, box 64 cols x 128 rows
               const __grid_constant__ CUtensorMap tmOut,  // out [T][Bc][256] bf16 (3D), box 64 cols x 128 rows x 1
               const __nv_bfloat16* __restrict__ whh_f,    // [512][128] rows in perm_T order, forward
               const __nv_bfloat16* __restrict__ whh_r,    // reverse
+              float2* __restrict__ stats,                 // STATS: [T*Bc][dir][half] (sum, sum of squares) of h over 64 units
               int Bc, int T) {
   extern __shared__ uint8_t rb_smem_raw[];
   const uint32_t raw = smem_u32(rb_smem_raw);
@@ -481,6 +441,7 @@ lstm_rec_bf16(const __grid_constant__ CUtensorMap tmG,    // G viewed as [T*Bc][
     for (int s = 0; s < T; ++s) {
       mbar_wait(my_bar, (uint32_t)(s & 1));
       tc_fence_after();
+      float ssum = 0.f, ssq = 0.f;
 #pragma unroll
       for (int sl = 0; sl < 8; ++sl) {  // fully unrolled: c[] must stay in registers
         uint32_t acc[32];
@@ -515,6 +476,7 @@ lstm_rec_bf16(const __grid_constant__ CUtensorMap tmG,    // G viewed as [T*Bc][
             float& cc = c[sl * 8 + u];
             cc = fmaf(fg, cc, ig * gg);
             hv[e] = og * tanh_fast(cc);
+            if (STATS) { ssum += hv[e]; ssq = fmaf(hv[e], hv[e], ssq); }
           }
           __nv_bfloat162 p = __floats2bfloat162_rn(hv[0], hv[1]);
           hp[u2] = *reinterpret_cast<uint32_t*>(&p);
@@ -527,6 +489,11 @@ lstm_rec_bf16(const __grid_constant__ CUtensorMap tmG,    // G viewed as [T*Bc][
       fence_proxy_async_smem();  // h_t (generic-proxy stores) -> visible to the next step's tcgen05.mma
       tc_fence_before();         // order this thread's TMEM reads before the barrier
       mbar_arrive(bar_h);
+      if (STATS) {
+        // partial LayerNorm statistics of the last layer's output row (consumed by attn_score_bf16 / attn_pool_finish)
+        const int t = dir ? (T - 1 - s) : s;
+        if (b0 + r < Bc) stats[((long long)t * Bc + b0 + r) * 4 + dir * 2 + half] = make_float2(ssum, ssq);
+      }
     }
   }
   tc_fence_before();
@@ -537,11 +504,12 @@ lstm_rec_bf16(const __grid_constant__ CUtensorMap tmG,    // G viewed as [T*Bc][
   }
 }
 
-int launch_rec_bf16(const __nv_bfloat16* G, const __nv_bfloat16* whh_f, const __nv_bfloat16* whh_r, __nv_bfloat16* out, int Bc,
-                    int T, cudaStream_t st) {
+int launch_rec_bf16(const __nv_bfloat16* G, const __nv_bfloat16* whh_f, const __nv_bfloat16* whh_r, __nv_bfloat16* out,
+                    float2* stats, int Bc, int T, cudaStream_t st) {
   static bool attr = false;
   if (!attr) {
-    BCI_CUDA_OK(cudaFuncSetAttribute(lstm_rec_bf16, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RB_SMEM));
+    BCI_CUDA_OK(cudaFuncSetAttribute(lstm_rec_bf16<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RB_SMEM));
+    BCI_CUDA_OK(cudaFuncSetAttribute(lstm_rec_bf16<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RB_SMEM));
     attr = true;
   }
   CUtensorMap tmG, tmOut;
@@ -550,7 +518,8 @@ int launch_rec_bf16(const __nv_bfloat16* G, const __nv_bfloat16* whh_f, const __
   rc = make_tmap_bf16_3d(&tmOut, out, (uint64_t)T, (uint64_t)Bc, 256, 64, RB_M);
   if (rc) return rc;
   dim3 grid(ceil_div(Bc, RB_M), 2);
-  lstm_rec_bf16<<<grid, RB_THREADS, RB_SMEM, st>>>(tmG, tmOut, whh_f, whh_r, Bc, T);
+  if (stats) lstm_rec_bf16<true><<<grid, RB_THREADS, RB_SMEM, st>>>(tmG, tmOut, whh_f, whh_r, stats, Bc, T);
+  else lstm_rec_bf16<false><<<grid, RB_THREADS, RB_SMEM, st>>>(tmG, tmOut, whh_f, whh_r, nullptr, Bc, T);
   BCI_LAUNCH_OK();
   return BCI_OK;
 }
@@ -561,7 +530,7 @@ int launch_rec_bf16(const __nv_bfloat16* G, const __nv_bfloat16* whh_f, const __
 static size_t chunk_bytes_bf16(const bci_lstm_config& c, int Bc, int T) {
   const size_t H = c.hidden_size, rows = (size_t)Bc * T;
   return align_up(rows * H * 2, 1024) + align_up(rows * 8 * H * 2, 1024) + 2 * align_up(rows * 2 * H * 2, 1024) +
-         align_up(rows * 4, 1024);
+         align_up(rows * 4, 1024) + align_up(rows * 4 * sizeof(float2), 1024);
 }
 
 size_t lstm_workspace_bf16(const bci_lstm_config& c, int batch, int T) {
@@ -581,6 +550,7 @@ static int forward_chunk_bf16(bci_lstm_s* h, const float* x, int Bc, int T, floa
   __nv_bfloat16* o0 = reinterpret_cast<__nv_bfloat16*>(take(rows * 2 * H * 2));
   __nv_bfloat16* o1 = reinterpret_cast<__nv_bfloat16*>(take(rows * 2 * H * 2));
   float* scores = reinterpret_cast<float*>(take(rows * 4));
+  float2* stats = reinterpret_cast<float2*>(take(rows * 4 * sizeof(float2)));
   h->prof.mark(-1, st);
   int rc = launch_input_proj<H, __nv_bfloat16>(h, x, Bc, T, z, st);
   if (rc) return rc;
@@ -592,12 +562,12 @@ static int forward_chunk_bf16(bci_lstm_s* h, const float* x, int Bc, int T, floa
     if (rc) return rc;
     h->prof.mark(1, st);
     __nv_bfloat16* o = outs[l & 1];
-    rc = launch_rec_bf16(g, h->bf16.whh_bf[l][0], h->bf16.whh_bf[l][1], o, Bc, T, st);
+    rc = launch_rec_bf16(g, h->bf16.whh_bf[l][0], h->bf16.whh_bf[l][1], o, l == c.num_layers - 1 ? stats : nullptr, Bc, T, st);
     if (rc) return rc;
     h->prof.mark(2, st);
     in = o;
   }
-  rc = launch_pool_head<H, __nv_bfloat16>(h, in, Bc, T, logits, probs, attn, scores, st);
+  rc = launch_pool_bf16(h, in, stats, scores, Bc, T, logits, probs, attn, st);
   h->prof.mark(3, st);
   return rc;
 }
@@ -631,5 +601,5 @@ extern "C" int bci_selftest_proj_gemm_bf16(const void* A, const void* W, const f
 extern "C" int bci_selftest_rec_bf16(const void* G, const void* whh_f, const void* whh_r, void* out, int32_t Bc, int32_t T,
                                      void* stream) {
   return bci::launch_rec_bf16((const __nv_bfloat16*)G, (const __nv_bfloat16*)whh_f, (const __nv_bfloat16*)whh_r,
-                              (__nv_bfloat16*)out, Bc, T, (cudaStream_t)stream);
+                              (__nv_bfloat16*)out, nullptr, Bc, T, (cudaStream_t)stream);
 }

@@ -1,0 +1,347 @@
+// bf16 mode of K4/K5: LayerNorm + additive-attention pooling + classifier (04_lstm_model.py:112-128,
+// 192-204,212-218) with the score GEMM on tcgen05 and the sequence read from HBM exactly twice.
+//
+// LayerNorm is folded into the GEMM instead of being materialised:
+//     y = (x - mean) rstd w + b                          (per row x of the last LSTM layer, 2H = 256 wide)
+//     W1 y + b1 = rstd (x . W1' - mean s) + c            W1' = W1 diag(w),  s_j = sum_d W1'_jd,  c_j = b1_j + sum_d b_d W1_jd
+//     ctx = sum_t a_t y_t = w (sum_t beta_t x_t - sum_t beta_t mean_t) + b          beta_t = a_t rstd_t   (sum_t a_t = 1)
+// so both passes run on the raw bf16 rows.  Row sums / sums of squares come from the recurrence
+// epilogue of the last layer (lstm_rec_bf16<STATS>), four partials per row.
+//
+//   attn_score_bf16   : persistent TMA + tcgen05 GEMM [T*Bc,256] x [256,128]; W1' resident in smem; the epilogue
+//                       warps turn each 128-wide accumulator row into one score: sum_j w2_j tanh(rstd (acc_j - mean s_j) + c_j)
+//   attn_pool_finish  : one CTA per window: softmax over T (block shuffles), beta-weighted row sum (coalesced
+//                       bf16x2 stream), affine, classifier MLP, softmax -> logits / probs / attention.
+#include "lstm_shared_kernels.cuh"
+#include "sm100_prims.cuh"
+#include "tmap.cuh"
+
+namespace bci {
+using namespace sm100;
+
+// ---- packing ---------------------------------------------------------------------------------
+__global__ void pack_attn_w1_kernel(const float* __restrict__ w1, const float* __restrict__ lnw, __nv_bfloat16* __restrict__ dst, int H, int D) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= H * D) return;
+  dst[i] = __float2bfloat16_rn(w1[i] * lnw[i % D]);
+}
+__global__ void pack_attn_par_kernel(const float* __restrict__ w1, const __nv_bfloat16* __restrict__ w1p, const float* __restrict__ lnb,
+                                     const float* __restrict__ b1, const float* __restrict__ w2, float4* __restrict__ par, int H, int D) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= H) return;
+  float s = 0.f, c = b1[j];
+  for (int d = 0; d < D; ++d) {
+    s += __bfloat162float(w1p[j * D + d]);
+    c = fmaf(lnb[d], w1[j * D + d], c);
+  }
+  par[j] = make_float4(s, c, w2[j], 0.f);
+}
+
+int pack_pool_bf16(bci_lstm_s* h, cudaStream_t st) {
+  const int H = h->cfg.hidden_size, D = 2 * H;
+  const bci_lstm_weights& w = h->raw;
+  pack_attn_w1_kernel<<<ceil_div(H * D, 256), 256, 0, st>>>(w.attn_w1, w.ln_w, h->bf16.aw1_bf, H, D);
+  pack_attn_par_kernel<<<ceil_div(H, 128), 128, 0, st>>>(w.attn_w1, h->bf16.aw1_bf, w.ln_b, w.attn_b1, w.attn_w2, h->bf16.apar, H, D);
+  BCI_LAUNCH_OK();
+  return BCI_OK;
+}
+
+// ---- scores on tensor cores ----------------------------------------------------------------------
+constexpr int SC_BM = 128, SC_N = 128, SC_K = 256, SC_BK = 64, SC_STAGES = 8, SC_THREADS = 192;
+constexpr uint32_t SC_A_BYTES = SC_BM * SC_BK * 2;  // 16 KB
+constexpr uint32_t SC_B_ATOM = SC_N * SC_BK * 2;    // 16 KB
+constexpr uint32_t SC_B_BYTES = (SC_K / SC_BK) * SC_B_ATOM;
+constexpr size_t SC_SMEM = 1024 + SC_B_BYTES + (size_t)SC_STAGES * SC_A_BYTES + SC_N * sizeof(float4) + 256;
+
+__device__ __forceinline__ float tanh_mufu(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+__global__ void __launch_bounds__(SC_THREADS, 1)
+attn_score_bf16(const __grid_constant__ CUtensorMap tmA,   // seq [M][256] bf16, box 64 x 128
+                const __grid_constant__ CUtensorMap tmB,   // W1' [128][256] bf16, box 64 x 128
+                const float4* __restrict__ par,            // [128] {s_j, c_j, w2_j, 0}
+                const float2* __restrict__ stats,          // [M][4] partial (sum, sumsq)
+                float b2, float* __restrict__ scores, int M) {
+  extern __shared__ uint8_t sc_smem_raw[];
+  const uint32_t raw = smem_u32(sc_smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* gen = sc_smem_raw + (base - raw);
+  const uint32_t sB = base, sA = base + SC_B_BYTES;
+  float4* par_s = reinterpret_cast<float4*>(gen + SC_B_BYTES + SC_STAGES * SC_A_BYTES);
+  uint8_t* ctl = reinterpret_cast<uint8_t*>(par_s + SC_N);
+  const uint32_t bar0 = smem_u32(ctl);
+  auto full_bar = [&](int s) { return bar0 + 8u * s; };
+  auto empty_bar = [&](int s) { return bar0 + 8u * (SC_STAGES + s); };
+  auto tfull_bar = [&](int a) { return bar0 + 8u * (2 * SC_STAGES + a); };
+  auto tempty_bar = [&](int a) { return bar0 + 8u * (2 * SC_STAGES + 2 + a); };
+  const uint32_t bfull_bar = bar0 + 8u * (2 * SC_STAGES + 4);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ctl + 8 * (2 * SC_STAGES + 5));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tiles = (M + SC_BM - 1) / SC_BM;
+  constexpr int k_blocks = SC_K / SC_BK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < SC_STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 128); }
+    mbar_init(bfull_bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(smem_u32(tmem_slot), 256);
+    tmem_relinquish();
+  }
+  if (warp >= 2) par_s[(warp - 2) * 32 + lane] = __ldg(par + (warp - 2) * 32 + lane);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_arrive_expect_tx(bfull_bar, SC_B_BYTES);
+      for (int kb = 0; kb < k_blocks; ++kb) tma_load_2d(sB + kb * SC_B_ATOM, &tmB, kb * SC_BK, 0, bfull_bar);
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          mbar_arrive_expect_tx(full_bar(stage), SC_A_BYTES);
+          tma_load_2d(sA + stage * SC_A_BYTES, &tmA, kb * SC_BK, tile * SC_BM, full_bar(stage));
+          if (++stage == SC_STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(SC_BM, SC_N);
+      int stage = 0; uint32_t phase = 0; int acc = 0; uint32_t acc_phase = 0;
+      mbar_wait(bfull_bar, 0);
+      for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)acc * SC_N;
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+#pragma unroll
+          for (int kk = 0; kk < SC_BK / 16; ++kk)
+            umma_bf16(d_tmem, umma_desc_sw128(sA + stage * SC_A_BYTES + kk * 32), umma_desc_sw128(sB + kb * SC_B_ATOM + kk * 32),
+                      idesc, (kb | kk) != 0 ? 1u : 0u);
+          umma_commit(empty_bar(stage));
+          if (++stage == SC_STAGES) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit(tfull_bar(acc));
+        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      }
+    }
+  } else {
+    const int quarter = warp & 3;
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+      const int gr = tile * SC_BM + quarter * 32 + lane;
+      float rs = 0.f, mp = 0.f;
+      if (gr < M) {
+        const float4* sp = reinterpret_cast<const float4*>(stats + (long long)gr * 4);
+        const float4 p0 = __ldg(sp), p1 = __ldg(sp + 1);  // (sum,sq) x 4 partials
+        const float sum = (p0.x + p0.z) + (p1.x + p1.z), sq = (p0.y + p0.w) + (p1.y + p1.w);
+        const float mean = sum * (1.0f / SC_K);
+        const float var = fmaxf(sq * (1.0f / SC_K) - mean * mean, 0.f);
+        rs = 1.0f / sqrtf(var + 1e-5f);
+        mp = -rs * mean;
+      }
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)acc * SC_N;
+      uint32_t r[2][32];
+      tmem_ld32(taddr, r[0]);
+      float score = 0.f;
+#pragma unroll
+      for (int ch = 0; ch < SC_N / 32; ++ch) {
+        tmem_ld_wait();
+        if (ch + 1 < SC_N / 32) tmem_ld32(taddr + (ch + 1) * 32, r[(ch + 1) & 1]);
+        const uint32_t* rc = r[ch & 1];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const float4 p = par_s[ch * 32 + j];
+          const float pre = fmaf(rs, __uint_as_float(rc[j]), fmaf(mp, p.x, p.y));
+          score = fmaf(p.z, tanh_mufu(pre), score);
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(tempty_bar(acc));
+      if (gr < M) scores[gr] = score + b2;
+      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 256);
+  }
+}
+
+// ---- softmax over time, weighted sum, head -------------------------------------------------------
+constexpr int PF_THREADS = 256;
+
+__device__ __forceinline__ float block_reduce(float v, float* red, bool is_max) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  v = is_max ? warp_max(v) : warp_sum(v);
+  __syncthreads();
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  float r = red[0];
+#pragma unroll
+  for (int w = 1; w < PF_THREADS / 32; ++w) r = is_max ? fmaxf(r, red[w]) : r + red[w];
+  return r;
+}
+
+__global__ void __launch_bounds__(PF_THREADS)
+attn_pool_finish_bf16(const __nv_bfloat16* __restrict__ seq,  // [T][Bc][256]
+                      const float* __restrict__ scores,       // [T][Bc]
+                      const float2* __restrict__ stats,       // [T*Bc][4]
+                      int Bc, int T, int classes,
+                      const float* __restrict__ lnw, const float* __restrict__ lnb,
+                      const float* __restrict__ c0t, const float* __restrict__ cb0,
+                      const float* __restrict__ c3t, const float* __restrict__ cb3,
+                      const float* __restrict__ c6, const float* __restrict__ cb6,
+                      float* __restrict__ logits, float* __restrict__ probs, float* __restrict__ attn) {
+  constexpr int H = 128, D = 256;
+  extern __shared__ __align__(16) float pf_smem[];
+  float* beta = pf_smem;          // [T]  raw scores first, then beta_t = a_t * rstd_t
+  float* bmean = beta + T;        // [T]  row means
+  float* ctx_s = bmean + T;       // [2][D]
+  float* h1_s = ctx_s + 2 * D;    // [H]
+  float* h2_s = h1_s + H;         // [H/2]
+  float* red = h2_s + H / 2;      // [8] + logits[8]
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+  float lmax = -INFINITY;
+  for (int t = tid; t < T; t += PF_THREADS) {
+    const long long row = (long long)t * Bc + b;
+    const float s = __ldg(scores + row);
+    const float4* sp = reinterpret_cast<const float4*>(stats + row * 4);
+    const float4 p0 = __ldg(sp), p1 = __ldg(sp + 1);
+    beta[t] = s;
+    bmean[t] = ((p0.x + p0.z) + (p1.x + p1.z)) * (1.0f / D);
+    lmax = fmaxf(lmax, s);
+  }
+  const float m = block_reduce(lmax, red, true);
+  float lsum = 0.f;
+  for (int t = tid; t < T; t += PF_THREADS) lsum += expf(beta[t] - m);
+  const float inv_l = 1.0f / block_reduce(lsum, red, false);
+  float lgam = 0.f;
+  for (int t = tid; t < T; t += PF_THREADS) {
+    const long long row = (long long)t * Bc + b;
+    const float a = expf(beta[t] - m) * inv_l;
+    if (attn) attn[(long long)b * T + t] = a;
+    const float4* sp = reinterpret_cast<const float4*>(stats + row * 4);
+    const float4 p0 = __ldg(sp), p1 = __ldg(sp + 1);
+    const float sq = (p0.y + p0.w) + (p1.y + p1.w);
+    const float mean = bmean[t];
+    const float var = fmaxf(sq * (1.0f / D) - mean * mean, 0.f);
+    const float bt = a / sqrtf(var + 1e-5f);
+    beta[t] = bt;
+    lgam = fmaf(bt, mean, lgam);
+  }
+  const float gamma = block_reduce(lgam, red, false);  // also makes beta[] visible to all threads
+
+  // beta-weighted sum of the raw rows: thread (g, p) owns features 2p, 2p+1 over time steps t = g mod 2
+  const int g = tid >> 7, p = tid & 127;
+  float a0 = 0.f, a1 = 0.f;
+  const __nv_bfloat162* col = reinterpret_cast<const __nv_bfloat162*>(seq) + (long long)b * (D / 2) + p;
+  const long long tstride = (long long)Bc * (D / 2);
+  int t = g;
+  for (; t + 14 < T; t += 16) {
+    __nv_bfloat162 v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) v[u] = col[(long long)(t + 2 * u) * tstride];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const float2 f = __bfloat1622float2(v[u]);
+      const float bt = beta[t + 2 * u];
+      a0 = fmaf(bt, f.x, a0);
+      a1 = fmaf(bt, f.y, a1);
+    }
+  }
+  for (; t < T; t += 2) {
+    const float2 f = __bfloat1622float2(col[(long long)t * tstride]);
+    a0 = fmaf(beta[t], f.x, a0);
+    a1 = fmaf(beta[t], f.y, a1);
+  }
+  ctx_s[g * D + 2 * p] = a0;
+  ctx_s[g * D + 2 * p + 1] = a1;
+  __syncthreads();
+  {
+    const float raw = ctx_s[tid] + ctx_s[D + tid];
+    const float cv = fmaf(lnw[tid], raw - gamma, lnb[tid]);
+    __syncthreads();
+    ctx_s[tid] = cv;
+  }
+  __syncthreads();
+  // classifier: Linear(2H,H) GELU Linear(H,H/2) GELU Linear(H/2,classes); softmax
+  if (tid < H) {
+    float a = cb0[tid];
+    for (int d = 0; d < D; ++d) a = fmaf(ctx_s[d], __ldg(c0t + (long long)d * H + tid), a);
+    h1_s[tid] = gelu_erf(a);
+  }
+  __syncthreads();
+  if (tid < H / 2) {
+    float a = cb3[tid];
+    for (int k = 0; k < H; ++k) a = fmaf(h1_s[k], __ldg(c3t + k * (H / 2) + tid), a);
+    h2_s[tid] = gelu_erf(a);
+  }
+  __syncthreads();
+  for (int c = warp; c < classes; c += PF_THREADS / 32) {
+    float a = 0.f;
+    for (int k = lane; k < H / 2; k += 32) a = fmaf(h2_s[k], __ldg(c6 + c * (H / 2) + k), a);
+    a = warp_sum(a) + cb6[c];
+    if (lane == 0) { logits[(long long)b * classes + c] = a; red[8 + c] = a; }
+  }
+  if (probs) {
+    __syncthreads();
+    if (tid == 0) {
+      float mx = -INFINITY;
+      for (int c = 0; c < classes; ++c) mx = fmaxf(mx, red[8 + c]);
+      float den = 0.f;
+      for (int c = 0; c < classes; ++c) den += expf(red[8 + c] - mx);
+      for (int c = 0; c < classes; ++c) probs[(long long)b * classes + c] = expf(red[8 + c] - mx) / den;
+    }
+  }
+}
+
+int launch_pool_bf16(bci_lstm_s* h, const __nv_bfloat16* seq, const float2* stats, float* scores, int Bc, int T, float* logits,
+                     float* probs, float* attn, cudaStream_t st) {
+  const int M = Bc * T;
+  CUtensorMap tmA, tmB;
+  int rc = make_tmap_bf16(&tmA, seq, (uint64_t)M, 256, 64, SC_BM);
+  if (rc) return rc;
+  rc = make_tmap_bf16(&tmB, h->bf16.aw1_bf, 128, 256, 64, SC_N);
+  if (rc) return rc;
+  static bool attr = false;
+  if (!attr) {
+    BCI_CUDA_OK(cudaFuncSetAttribute(attn_score_bf16, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SC_SMEM));
+    attr = true;
+  }
+  // attention.attention.2.bias shifts every score of a window by the same constant and softmax over T is
+  // shift invariant, so it cannot change any output (attention weights, context, logits): not applied.
+  const float b2 = 0.f;
+  const int tiles = ceil_div(M, SC_BM);
+  const int grid = tiles < sm_count() ? tiles : sm_count();
+  attn_score_bf16<<<grid, SC_THREADS, SC_SMEM, st>>>(tmA, tmB, h->bf16.apar, stats, b2, scores, M);
+  BCI_LAUNCH_OK();
+  const PackedF32& p = h->f32;
+  const size_t smem = (size_t)(2 * T + 2 * 256 + 128 + 64 + 16) * sizeof(float);
+  BCI_REQUIRE(smem <= 48 * 1024, BCI_EINVAL, "bf16 pooling supports seq_len <= 5900 (got %d)", T);
+  attn_pool_finish_bf16<<<Bc, PF_THREADS, smem, st>>>(seq, scores, stats, Bc, T, h->cfg.num_classes, p.lnw, p.lnb, p.c0t, p.cb0,
+                                                       p.c3t, p.cb3, p.c6, p.cb6, logits, probs, attn);
+  BCI_LAUNCH_OK();
+  return BCI_OK;
+}
+
+}  // namespace bci

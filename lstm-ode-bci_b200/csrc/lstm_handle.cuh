@@ -39,6 +39,10 @@ struct PackedBF16 {
   __nv_bfloat16* wih_bf[BCI_MAX_LAYERS];
   __nv_bfloat16* whh_bf[BCI_MAX_LAYERS][2];
   float* bias_p[BCI_MAX_LAYERS];
+  // attention scores on tensor cores with LayerNorm folded in (lstm_bf16_pool.cu):
+  //   aw1_bf [H][2H] = bf16(W1[j][d] * ln_w[d]);  apar[j] = {s_j = sum_d aw1_bf[j][d], c_j = b1_j + sum_d ln_b[d] W1[j][d], w2_j, 0}
+  __nv_bfloat16* aw1_bf;
+  float4* apar;
 };
 
 }  // namespace bci
@@ -105,5 +109,8 @@ size_t lstm_workspace_bf16(const bci_lstm_config& c, int batch, int T);
 int lstm_pack_bf16(bci_lstm_s* h, cudaStream_t st);
 size_t lstm_store_bytes_bf16(const bci_lstm_config& c);
 void lstm_carve_bf16(bci_lstm_s* h, char* base);
+int pack_pool_bf16(bci_lstm_s* h, cudaStream_t st);
+int launch_pool_bf16(bci_lstm_s* h, const __nv_bfloat16* seq, const float2* stats, float* scores, int Bc, int T, float* logits,
+                     float* probs, float* attn, cudaStream_t st);
 
 }  // namespace bci
