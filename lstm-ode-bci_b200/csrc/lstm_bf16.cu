@@ -60,6 +60,7 @@ size_t lstm_store_bytes_bf16(const bci_lstm_config& c) {
   for (int l = 0; l < c.num_layers; ++l)
     n += align_up((size_t)8 * H * layer_in_width(c, l) * 2, 256) + 2 * align_up(4 * H * H * 2, 256) + align_up(8 * H * 4, 256);
   n += align_up(H * 2 * H * 2, 256) + align_up(H * sizeof(float4), 256);  // attention W1' (bf16) + per-unit params
+  n += align_up(H * 64 * 2, 256) + align_up(H * sizeof(float4), 256);     // input projection W0 (bf16, K padded) + params
   return n + 1024;
 }
 
@@ -77,6 +78,8 @@ void lstm_carve_bf16(bci_lstm_s* h, char* base) {
   }
   h->bf16.aw1_bf = reinterpret_cast<__nv_bfloat16*>(take(H * 2 * H * 2));
   h->bf16.apar = reinterpret_cast<float4*>(take(H * sizeof(float4)));
+  h->bf16.w0_bf = reinterpret_cast<__nv_bfloat16*>(take(H * 64 * 2));
+  h->bf16.par0 = reinterpret_cast<float4*>(take(H * sizeof(float4)));
 }
 
 int lstm_pack_bf16(bci_lstm_s* h, cudaStream_t st) {
@@ -93,6 +96,8 @@ int lstm_pack_bf16(bci_lstm_s* h, cudaStream_t st) {
     }
   }
   int rc = pack_pool_bf16(h, st);
+  if (rc) return rc;
+  rc = pack_inproj_bf16(h, st);
   if (rc) return rc;
   BCI_LAUNCH_OK();
   return BCI_OK;
@@ -552,7 +557,8 @@ static int forward_chunk_bf16(bci_lstm_s* h, const float* x, int Bc, int T, floa
   float* scores = reinterpret_cast<float*>(take(rows * 4));
   float2* stats = reinterpret_cast<float2*>(take(rows * 4 * sizeof(float2)));
   h->prof.mark(-1, st);
-  int rc = launch_input_proj<H, __nv_bfloat16>(h, x, Bc, T, z, st);
+  // tensor-core input projection needs whole 128-row tiles inside one window; other lengths use the CUDA-core kernel
+  int rc = (T % 128 == 0) ? launch_input_proj_bf16(h, x, Bc, T, z, st) : launch_input_proj<H, __nv_bfloat16>(h, x, Bc, T, z, st);
   if (rc) return rc;
   h->prof.mark(0, st);
   const __nv_bfloat16* in = z;

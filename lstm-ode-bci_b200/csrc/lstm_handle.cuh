@@ -43,6 +43,10 @@ struct PackedBF16 {
   //   aw1_bf [H][2H] = bf16(W1[j][d] * ln_w[d]);  apar[j] = {s_j = sum_d aw1_bf[j][d], c_j = b1_j + sum_d ln_b[d] W1[j][d], w2_j, 0}
   __nv_bfloat16* aw1_bf;
   float4* apar;
+  // input projection on tensor cores (lstm_bf16_inproj.cu): w0_bf [H][64] = bf16(input_proj.0.weight), K zero-padded
+  // from C to 64; par0[j] = {b0_j, ln_w_j, ln_b_j, 0}
+  __nv_bfloat16* w0_bf;
+  float4* par0;
 };
 
 }  // namespace bci
@@ -110,6 +114,8 @@ int lstm_pack_bf16(bci_lstm_s* h, cudaStream_t st);
 size_t lstm_store_bytes_bf16(const bci_lstm_config& c);
 void lstm_carve_bf16(bci_lstm_s* h, char* base);
 int pack_pool_bf16(bci_lstm_s* h, cudaStream_t st);
+int pack_inproj_bf16(bci_lstm_s* h, cudaStream_t st);
+int launch_input_proj_bf16(bci_lstm_s* h, const float* x, int Bc, int T, __nv_bfloat16* z, cudaStream_t st);
 int launch_pool_bf16(bci_lstm_s* h, const __nv_bfloat16* seq, const float2* stats, float* scores, int Bc, int T, float* logits,
                      float* probs, float* attn, cudaStream_t st);
 

@@ -93,7 +93,7 @@ def test_recurrence_tcgen05_matches_stepwise(Bc, T):
     assert float((got - want).abs().max()) <= 1.5e-2      # bf16 output rounding (4e-3) + tanh.approx, compounding over T
 
 
-@pytest.mark.parametrize("B,T", [(8, 256), (130, 64)])
+@pytest.mark.parametrize("B,T", [(8, 256), (130, 64), (37, 128)])
 def test_bf16_forward_close_to_fp32_oracle(B, T):
     params = synth.make_lstm_params(42, 61, 128, 3, logit_gain=12.0)
     x = synth.make_windows(7, B, T, 61, structured=True)
