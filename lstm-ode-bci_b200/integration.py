@@ -18,16 +18,92 @@ from .ode import CognitiveStateODE, solve_ensemble, _dev
 from .synth import RATE_ORDER
 
 
+def stream_lstm_probs(lstm_model, host_batches, device=None, chunk=9472, want_attn=False):
+    """Pipelined inference over a stream of HOST batches (the reference copies each batch synchronously, 06:346).
+
+    host_batches: iterable of CPU float32 tensors / numpy arrays (n_i, T, C).  Pinned tensors are DMA-ed in
+    place; pageable ones go through pinned staging buffers.  Yields, in order, (probs, attention-or-None) as
+    CUDA tensors enqueued on the current stream (use them on that stream, or synchronise).  The H2D copy of batch i+1 (copy stream, `chunk`-window
+    pieces) overlaps the kernels of batch i (current stream); `chunk` defaults to one full wave of recurrence CTAs."""
+    dev = _dev(device)
+    lstm_model.eval()
+    copy_stream = torch.cuda.Stream(device=dev)
+    main = torch.cuda.current_stream(dev)
+    slots = [dict(buf=None, free=None, pin=None) for _ in range(2)]
+
+    def submit(k, xb):
+        sl = slots[k & 1]
+        xh = torch.as_tensor(xb)
+        if xh.dtype != torch.float32:
+            xh = xh.float()
+        n = xh.shape[0]
+        if sl["buf"] is None or sl["buf"].shape[0] < n or sl["buf"].shape[1:] != xh.shape[1:]:
+            sl["buf"] = torch.empty(tuple(xh.shape), dtype=torch.float32, device=dev)
+        if sl["free"] is not None:
+            copy_stream.wait_event(sl["free"])           # kernels of the batch that last used this buffer are done
+        direct = xh.is_pinned() and xh.is_contiguous()
+        if not direct:
+            if sl["pin"] is None or sl["pin"].shape[0] < n or sl["pin"].shape[1:] != xh.shape[1:]:
+                sl["pin"] = torch.empty(tuple(xh.shape), dtype=torch.float32).pin_memory()
+            if sl["free"] is not None:
+                sl["free"].synchronize()
+        events = []
+        for i in range(0, n, chunk):
+            m = min(chunk, n - i)
+            src = xh[i:i + m]
+            if not direct:
+                sl["pin"][i:i + m].copy_(src)
+                src = sl["pin"][i:i + m]
+            with torch.cuda.stream(copy_stream):
+                sl["buf"][i:i + m].copy_(src, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(copy_stream)
+            events.append((i, m, ev))
+        return sl, n, events
+
+    def compute(sl, n, events):
+        probs = torch.empty((n, lstm_model.num_classes), device=dev, dtype=torch.float32)
+        attn = None
+        with torch.no_grad():
+            for i, m, ev in events:
+                main.wait_event(ev)
+                xb = sl["buf"][i:i + m]
+                if want_attn:
+                    p, a = lstm_model.predict_proba(xb, return_attention=True)
+                    if attn is None:
+                        attn = torch.empty((n, a.shape[1]), device=dev, dtype=torch.float32)
+                    attn[i:i + m] = a
+                else:
+                    p = lstm_model.predict_proba(xb)
+                probs[i:i + m] = p
+        sl["free"] = torch.cuda.Event()
+        sl["free"].record(main)
+        return probs, attn
+
+    it = iter(host_batches)
+    k = 0
+    try:
+        pending = submit(k, next(it))
+    except StopIteration:
+        return
+    while pending is not None:
+        try:
+            nxt = submit(k + 1, next(it))                 # queue the next batch's copies before computing this one
+        except StopIteration:
+            nxt = None
+        yield compute(*pending)
+        pending = nxt
+        k += 1
+
+
 def _lstm_probs_device(lstm_model, X, batch_size, want_attn, device):
-    """Batched device inference; X numpy (host) or tensor.  Host batches go through pinned staging
-    buffers on a copy stream, double-buffered against compute (the reference copies each batch
-    synchronously, 06:346)."""
+    """All-window inference returning device tensors; X numpy/CPU tensor (pipelined H2D) or CUDA tensor."""
     dev = _dev(device)
     lstm_model.eval()
     n = len(X)
-    probs = torch.empty((n, lstm_model.num_classes), device=dev, dtype=torch.float32)
-    attn = None
     if isinstance(X, torch.Tensor) and X.is_cuda:
+        probs = torch.empty((n, lstm_model.num_classes), device=dev, dtype=torch.float32)
+        attn = None
         with torch.no_grad():
             for i in range(0, n, batch_size):
                 xb = X[i:i + batch_size]
@@ -40,56 +116,10 @@ def _lstm_probs_device(lstm_model, X, batch_size, want_attn, device):
                     p = lstm_model.predict_proba(xb)
                 probs[i:i + len(xb)] = p
         return probs, attn
-    Xh = torch.as_tensor(X)
-    if Xh.dtype != torch.float32:
-        Xh = Xh.float()
-    T, Cc = Xh.shape[1], Xh.shape[2]
-    copy_stream = torch.cuda.Stream(device=dev)
-    main = torch.cuda.current_stream(dev)
-    nb = min(batch_size, max(n, 1))
-    src_pinned = Xh.is_pinned() and Xh.is_contiguous()     # caller already staged: DMA straight from it
-    pinned = None if src_pinned else [torch.empty((nb, T, Cc), dtype=torch.float32).pin_memory() for _ in range(2)]
-    staged = [torch.empty((nb, T, Cc), dtype=torch.float32, device=dev) for _ in range(2)]
-    ready = [torch.cuda.Event() for _ in range(2)]
-    consumed = [torch.cuda.Event() for _ in range(2)]
-
-    def stage(slot, i):
-        m = min(batch_size, n - i)
-        if src_pinned:
-            src = Xh[i:i + m]
-        else:
-            consumed[slot].synchronize()        # pinned staging buffer free again (host side)
-            pinned[slot][:m].copy_(Xh[i:i + m])
-            src = pinned[slot][:m]
-        with torch.cuda.stream(copy_stream):
-            copy_stream.wait_event(consumed[slot])
-            staged[slot][:m].copy_(src, non_blocking=True)
-            ready[slot].record(copy_stream)
-        return m
-
-    with torch.no_grad():
-        starts = list(range(0, n, batch_size))
-        for s in range(2):
-            consumed[s].record(main)
-        sizes = {}
-        if starts:
-            sizes[0] = stage(0, starts[0])
-        for k, i in enumerate(starts):
-            slot = k & 1
-            if k + 1 < len(starts):
-                sizes[k + 1] = stage((k + 1) & 1, starts[k + 1])
-            main.wait_event(ready[slot])
-            m = sizes[k]
-            xb = staged[slot][:m]
-            if want_attn:
-                p, a = lstm_model.predict_proba(xb, return_attention=True)
-                if attn is None:
-                    attn = torch.empty((n, a.shape[1]), device=dev, dtype=torch.float32)
-                attn[i:i + m] = a
-            else:
-                p = lstm_model.predict_proba(xb)
-            probs[i:i + m] = p
-            consumed[slot].record(main)
+    if n == 0:
+        return (torch.empty((0, lstm_model.num_classes), device=dev),
+                torch.empty((0, 0), device=dev) if want_attn else None)
+    (probs, attn), = list(stream_lstm_probs(lstm_model, [X], dev, chunk=max(int(batch_size), 1), want_attn=want_attn))
     return probs, attn
 
 
