@@ -107,16 +107,30 @@ __device__ __forceinline__ void post06(T& a, T& p, T& f) {
   const T s = (a + p) + f;
   a /= s; p /= s; f /= s;
 }
+// fp32 fast path of the same post-processing: one IEEE reciprocal + three multiplies (<= 1 ulp per component,
+// |A+P+F-1| stays <= ~1.2e-7) instead of three ~10-instruction divisions per output point
+__device__ __forceinline__ void post06_rcp(float& a, float& p, float& f) {
+  a = fminf(fmaxf(a, 0.f), 1.f);
+  p = fminf(fmaxf(p, 0.f), 1.f);
+  f = fminf(fmaxf(f, 0.f), 1.f);
+  const float inv = __frcp_rn((a + p) + f);
+  a *= inv; p *= inv; f *= inv;
+}
 
 // ---- RK4, fp32 ---------------------------------------------------------------------------
+// Step-scaled generator: the nine coefficients of h*Q^T are formed once per trajectory, so one RHS
+// evaluation is 3 FMUL + 6 FFMA (the reference's dA = -k_ap A - k_af A + k_pa P + k_fa F groups as
+// -(k_ap + k_af) A + ..., 05_ode_model.py:129-133) and every Runge-Kutta combination uses immediate
+// constants (0.5, 2, 1/6).  The first version spent 98 issue slots per step (78 FP + 12 FMNMX + 8
+// loop) and was issue-bound at 54 % of the FMA peak; this form needs 66 + 12.
+struct HQ { float aa, ap, af, pa, pp, pf, fa, fp, ff; };  // row = derivative component, col = state
+
 template <bool CLAMP>
-__device__ __forceinline__ void rhs32(const float k[6], float A, float P, float F, float& dA, float& dP, float& dF) {
+__device__ __forceinline__ void rhs_h(const HQ& q, float A, float P, float F, float& dA, float& dP, float& dF) {
   if (CLAMP) { A = fmaxf(A, 0.f); P = fmaxf(P, 0.f); F = fmaxf(F, 0.f); }
-  // dA = -k_ap A - k_af A + k_pa P + k_fa F ; dP = k_ap A - k_pa P - k_pf P + k_fp F ;
-  // dF = k_af A + k_pf P - k_fa F - k_fp F            (05_ode_model.py:129-133)
-  dA = fmaf(k[4], F, fmaf(k[2], P, fmaf(-k[1], A, -k[0] * A)));
-  dP = fmaf(k[5], F, fmaf(-k[3], P, fmaf(-k[2], P, k[0] * A)));
-  dF = fmaf(-k[5], F, fmaf(-k[4], F, fmaf(k[3], P, k[1] * A)));
+  dA = fmaf(q.af, F, fmaf(q.ap, P, q.aa * A));
+  dP = fmaf(q.pf, F, fmaf(q.pa, A, q.pp * P));
+  dF = fmaf(q.fp, P, fmaf(q.fa, A, q.ff * F));
 }
 
 template <bool CLAMP, typename OutT>
@@ -152,24 +166,28 @@ ode_rk4_kernel(const OdeParams P) {
     }
     h = (float)(dt_out / (double)S);
   }
-  const float hh = 0.5f * h, h6 = h * (1.0f / 6.0f);
+  HQ q;
+  q.aa = -h * (k[0] + k[1]); q.ap = h * k[2];           q.af = h * k[4];
+  q.pa = h * k[0];           q.pp = -h * (k[2] + k[3]); q.pf = h * k[5];
+  q.fa = h * k[1];           q.fp = h * k[3];           q.ff = -h * (k[4] + k[5]);
   float cA = 0.f, cP = 0.f, cF = 0.f;  // Kahan compensation of the state
 
   int pt = 0;  // next output point index
   while (pt < P.n_points) {
     const int pts = (P.n_points - pt) < chunk_pts ? (P.n_points - pt) : chunk_pts;
-    for (int q = 0; q < pts; ++q, ++pt) {
+    for (int qq = 0; qq < pts; ++qq, ++pt) {
       if (live && pt > 0) {
+#pragma unroll 2
         for (int s = 0; s < S; ++s) {
-          float a1, p1, f1, a2, p2, f2, a3, p3, f3, a4, p4, f4;
-          rhs32<CLAMP>(k, A, Pp, F, a1, p1, f1);
-          rhs32<CLAMP>(k, fmaf(hh, a1, A), fmaf(hh, p1, Pp), fmaf(hh, f1, F), a2, p2, f2);
-          rhs32<CLAMP>(k, fmaf(hh, a2, A), fmaf(hh, p2, Pp), fmaf(hh, f2, F), a3, p3, f3);
-          rhs32<CLAMP>(k, fmaf(h, a3, A), fmaf(h, p3, Pp), fmaf(h, f3, F), a4, p4, f4);
-          // y += h/6 (k1 + 2 k2 + 2 k3 + k4), compensated
-          const float dAa = fmaf(h6, (a1 + a4) + 2.0f * (a2 + a3), -cA);
-          const float dPp = fmaf(h6, (p1 + p4) + 2.0f * (p2 + p3), -cP);
-          const float dFf = fmaf(h6, (f1 + f4) + 2.0f * (f2 + f3), -cF);
+          float a1, p1, f1, a2, p2, f2, a3, p3, f3, a4, p4, f4;  // h * k_i
+          rhs_h<CLAMP>(q, A, Pp, F, a1, p1, f1);
+          rhs_h<CLAMP>(q, fmaf(0.5f, a1, A), fmaf(0.5f, p1, Pp), fmaf(0.5f, f1, F), a2, p2, f2);
+          rhs_h<CLAMP>(q, fmaf(0.5f, a2, A), fmaf(0.5f, p2, Pp), fmaf(0.5f, f2, F), a3, p3, f3);
+          rhs_h<CLAMP>(q, A + a3, Pp + p3, F + f3, a4, p4, f4);
+          // y += (k1 + 2 k2 + 2 k3 + k4) / 6, compensated
+          const float dAa = fmaf(fmaf(2.0f, a2 + a3, a1 + a4), 1.0f / 6.0f, -cA);
+          const float dPp = fmaf(fmaf(2.0f, p2 + p3, p1 + p4), 1.0f / 6.0f, -cP);
+          const float dFf = fmaf(fmaf(2.0f, f2 + f3, f1 + f4), 1.0f / 6.0f, -cF);
           const float nA = A + dAa, nP = Pp + dPp, nF = F + dFf;
           cA = (nA - A) - dAa; cP = (nP - Pp) - dPp; cF = (nF - F) - dFf;
           A = nA; Pp = nP; F = nF;
@@ -177,8 +195,8 @@ ode_rk4_kernel(const OdeParams P) {
       }
       if (want_traj) {
         float oa = A, op = Pp, of = F;
-        if (CLAMP) post06(oa, op, of);
-        float* row = stage + tid * row_stride + q * 3;
+        if (CLAMP) post06_rcp(oa, op, of);
+        float* row = stage + tid * row_stride + qq * 3;
         row[0] = oa; row[1] = op; row[2] = of;
       }
     }
@@ -191,9 +209,20 @@ ode_rk4_kernel(const OdeParams P) {
       if (w == n3) {  // whole rows staged: one contiguous range, fully coalesced
         const int total = rows_here * w;
         OutT* dst = out + base_i * n3;
-        for (int e = tid; e < total; e += ODE_BLOCK) {
-          const int r = e / w, c = e - r * w;
-          dst[e] = (OutT)stage[r * row_stride + c];
+        if (sizeof(OutT) == 4 && (w & 3) == 0 && rows_here == ODE_BLOCK) {
+          // 16-byte stores: 4 consecutive outputs never straddle a staged row because w % 4 == 0
+          float4* dst4 = reinterpret_cast<float4*>(dst);
+          for (int e4 = tid; e4 < total / 4; e4 += ODE_BLOCK) {
+            const int e = e4 * 4;
+            const int r = e / w, c = e - r * w;
+            const float* sp = stage + r * row_stride + c;
+            dst4[e4] = make_float4(sp[0], sp[1], sp[2], sp[3]);
+          }
+        } else {
+          for (int e = tid; e < total; e += ODE_BLOCK) {
+            const int r = e / w, c = e - r * w;
+            dst[e] = (OutT)stage[r * row_stride + c];
+          }
         }
       } else {
         const int total = rows_here * w;
@@ -208,7 +237,7 @@ ode_rk4_kernel(const OdeParams P) {
   if (live) {
     if (P.final_state) {
       float oa = A, op = Pp, of = F;
-      if (CLAMP) post06(oa, op, of);
+      if (CLAMP) post06_rcp(oa, op, of);  // same arithmetic as the trajectory rows: final_state == traj[:, -1] bit for bit
       OutT* fs = reinterpret_cast<OutT*>(P.final_state) + i * 3;
       fs[0] = (OutT)oa; fs[1] = (OutT)op; fs[2] = (OutT)of;
     }

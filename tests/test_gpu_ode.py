@@ -127,8 +127,8 @@ def test_large_ensemble_properties():
     dev = {k: torch.tensor(v).cuda() for k, v in sw.items()}
     traj, final, _ = ode.solve_ensemble(n, p_open=dev["p_open"], p_closed=dev["p_closed"], rates=dev["rates"],
                                         alpha_arr=dev["alpha"], y0_mode="probs06", coupling=True, substeps=8)
-    s = traj.sum(dim=2)
-    assert float((s - 1).abs().max()) <= 2e-7                     # A+P+F = 1
+    s = traj.double().sum(dim=2)                                  # fp64 sum: measure the outputs, not the summation
+    assert float((s - 1).abs().max()) <= 2e-7                     # A+P+F = 1 to fp32 output rounding
     assert float(traj.min()) >= 0.0 and float(traj.max()) <= 1.0
     assert torch.equal(final, traj[:, -1])
     # alpha = 0  <=>  no coupling at all
