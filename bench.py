@@ -163,6 +163,8 @@ def main():
     ap.add_argument("--ref-sample", type=int, default=128)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ode", action="store_true")
+    ap.add_argument("--no-train", action="store_true")
+    ap.add_argument("--train-batch", type=int, default=512)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -318,6 +320,33 @@ def main():
             "rk45_full_trajectory": {"value": world * n / (t_rk45 * 1e-3), "ms": t_rk45, "rtol": 1e-3, "atol": 1e-6},
             "flop_per_trajectory": ODE_FLOP_PER_TRAJ, "fp32_peak_source": "FMA micro-benchmark in this run"}
         del dev
+
+    # ---- training step (BASELINE configs[2]): fwd + BPTT + NCCL all-reduce + clip + AdamW, 512 windows per GPU -----
+    if not args.no_train:
+        from lstm_ode_bci_b200 import train
+        tb = args.train_batch
+        tmodel = lstm.from_params(params, precision="fp32", device=f"cuda:{local}", dropout=0.4).train()
+        trainer = train.FusedTrainer(tmodel, lr=3e-4, weight_decay=1e-4, max_norm=1.0, class_weight=[0.8, 1.2])
+        xt = x[:tb].contiguous()
+        yt = (torch.arange(tb, device="cuda") % 2)
+        for i in range(2):
+            trainer.step(xt, yt, seed=i)
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        tsteps = 3
+        for i in range(tsteps):
+            loss_t, norm_t = trainer.step(xt, yt, seed=10 + i)
+        b.record()
+        barrier()
+        tms = max_over_ranks(a.elapsed_time(b)) / tsteps
+        line["train_step"] = {"metric": "train_windows_per_s", "value": world * tb / (tms * 1e-3), "unit": "windows/s",
+                              "ms_per_step": tms, "windows_per_gpu": tb, "precision": "fp32", "dropout": 0.4,
+                              "optimizer": "AdamW(3e-4, wd 1e-4) + clip 1.0, fused; gradients all-reduced over NCCL" if world > 1
+                              else "AdamW(3e-4, wd 1e-4) + clip 1.0, fused",
+                              "flop_per_window": 3 * FLOP_PER_WINDOW, "achieved_tflops_per_gpu": tb * 3 * FLOP_PER_WINDOW / (tms * 1e-3) / 1e12,
+                              "loss": float(loss_t), "grad_norm": float(norm_t)}
+        del trainer, tmodel
 
     if rank == 0 and not args.no_cpu_baseline and world == 1:
         line["cpu_baseline"] = cpu_lstm_baseline()

@@ -178,6 +178,27 @@ lstm_rec_f32(const float* __restrict__ G,      // [T][Bc][2][H][4]
   }
 }
 
+int launch_proj_gemm_f32(const float* A, const float* Bt, const float* bias, float* C, int M, int N, int K, cudaStream_t st) {
+  BCI_REQUIRE(N % GN == 0 && K % GK == 0, BCI_EINVAL, "proj_gemm_f32: N %% 128 and K %% 16 required (N=%d K=%d)", N, K);
+  dim3 gg(N / GN, ceil_div(M, GM));
+  proj_gemm_f32<<<gg, GEMM_THREADS, 0, st>>>(A, Bt, bias, C, M, N, K);
+  BCI_LAUNCH_OK();
+  return BCI_OK;
+}
+
+int launch_rec_f32(int H, const float* G, const float* whh_f, const float* whh_r, float* out, float* gates, float* csave, int Bc,
+                   int T, cudaStream_t st) {
+  if (H == 128) {
+    constexpr int MT = (REC_THREADS / 128) * REC_WPT;
+    lstm_rec_f32<128><<<dim3(ceil_div(Bc, MT), 2), REC_THREADS, 0, st>>>(G, whh_f, whh_r, out, gates, csave, Bc, T);
+  } else {
+    constexpr int MT = (REC_THREADS / 256) * REC_WPT;
+    lstm_rec_f32<256><<<dim3(ceil_div(Bc, MT), 2), REC_THREADS, 0, st>>>(G, whh_f, whh_r, out, gates, csave, Bc, T);
+  }
+  BCI_LAUNCH_OK();
+  return BCI_OK;
+}
+
 // ---------------------------------------------------------------------------------------------
 // weight packing (runs at bci_lstm_load_weights)
 // ---------------------------------------------------------------------------------------------
@@ -196,6 +217,15 @@ __global__ void pack_gates_t_kernel(const float* __restrict__ src, float* __rest
   const int row = (int)(i / K), k = (int)(i - (long long)row * K);
   const int gate = row / H, unit = row - gate * H;
   dst[(long long)k * ld + col0 + unit * 4 + gate] = src[i];
+}
+
+// src (4H, K) gate-major rows -> dst [row0 + unit*4 + gate][K]
+__global__ void pack_gates_rows_kernel(const float* __restrict__ src, float* __restrict__ dst, int H, int K, int row0) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)4 * H * K) return;
+  const int row = (int)(i / K), k = (int)(i - (long long)row * K);
+  const int gate = row / H, unit = row - gate * H;
+  dst[(long long)(row0 + unit * 4 + gate) * K + k] = src[i];
 }
 
 __global__ void pack_bias_kernel(const float* __restrict__ bih, const float* __restrict__ bhh, float* __restrict__ dst, int H, int col0) {
@@ -227,6 +257,8 @@ int lstm_pack_f32(bci_lstm_s* h, cudaStream_t st) {
       pack_gates_t_kernel<<<nblk((long long)4 * H * K), 256, 0, st>>>(w.w_ih[l][d], p.wih_t[l], H, K, 8 * H, d * 4 * H);
       pack_gates_t_kernel<<<nblk((long long)4 * H * H), 256, 0, st>>>(w.w_hh[l][d], p.whh_t[l][d], H, H, 4 * H, 0);
       pack_bias_kernel<<<nblk(4 * H), 256, 0, st>>>(w.b_ih[l][d], w.b_hh[l][d], p.bias[l], H, d * 4 * H);
+      pack_gates_rows_kernel<<<nblk((long long)4 * H * K), 256, 0, st>>>(w.w_ih[l][d], p.wih_b[l], H, K, d * 4 * H);
+      pack_gates_rows_kernel<<<nblk((long long)4 * H * H), 256, 0, st>>>(w.w_hh[l][d], p.whh_b[l][d], H, H, 0);
     }
   }
   copy_kernel<<<nblk(D), 256, 0, st>>>(w.ln_w, p.lnw, D);
@@ -248,7 +280,7 @@ int lstm_pack_f32(bci_lstm_s* h, cudaStream_t st) {
 size_t lstm_store_bytes_f32(const bci_lstm_config& c) {
   const size_t H = c.hidden_size, C = c.input_size, D = 2 * H;
   size_t n = C * H + 3 * H;
-  for (int l = 0; l < c.num_layers; ++l) n += (size_t)layer_in_width(c, l) * 8 * H + 8 * H + 2 * H * 4 * H;
+  for (int l = 0; l < c.num_layers; ++l) n += 2 * ((size_t)layer_in_width(c, l) * 8 * H + 2 * H * 4 * H) + 8 * H;
   n += 2 * D + D * H + H + H + 4 + D * H + H + H * (H / 2) + H / 2 + (size_t)c.num_classes * (H / 2) + c.num_classes + 64;
   return align_up(n * sizeof(float) + 256 * 64, 256);
 }
@@ -265,6 +297,9 @@ void lstm_carve_f32(bci_lstm_s* h, char* base) {
     p.bias[l] = take(8 * H);
     p.whh_t[l][0] = take(H * 4 * H);
     p.whh_t[l][1] = take(H * 4 * H);
+    p.wih_b[l] = take((size_t)layer_in_width(c, l) * 8 * H);
+    p.whh_b[l][0] = take(H * 4 * H);
+    p.whh_b[l][1] = take(H * 4 * H);
   }
   p.lnw = take(D); p.lnb = take(D); p.aw1t = take(D * H); p.ab1 = take(H); p.aw2 = take(H); p.ab2 = take(4);
   p.c0t = take(D * H); p.cb0 = take(H); p.c3t = take(H * (H / 2)); p.cb3 = take(H / 2);

@@ -16,6 +16,9 @@ struct PackedF32 {
   float* wih_t[BCI_MAX_LAYERS];     // [K_l][8H]   both directions, gate-interleaved
   float* bias[BCI_MAX_LAYERS];      // [8H]        b_ih + b_hh, same order
   float* whh_t[BCI_MAX_LAYERS][2];  // [H][4H]     per direction, gate-interleaved
+  // row-major copies with gate-interleaved ROWS (n = dir*4H + unit*4 + gate), used by the backward pass:
+  float* wih_b[BCI_MAX_LAYERS];     // [8H][K_l]   din = dG . wih_b
+  float* whh_b[BCI_MAX_LAYERS][2];  // [4H][H]     dh_{t-1} = dG_t . whh_b
   float* lnw;    // [2H]
   float* lnb;    // [2H]
   float* aw1t;   // [2H][H]     attention.0.weight^T
@@ -106,6 +109,9 @@ struct FwdWorkspace {
 int lstm_forward_fp32(bci_lstm_s* h, const float* x, int batch, int T, float* logits, float* probs, float* attn,
                       void* ws, size_t ws_bytes, cudaStream_t st);
 size_t lstm_workspace_fp32(const bci_lstm_config& c, int batch, int T);
+int launch_proj_gemm_f32(const float* A, const float* Bt, const float* bias, float* C, int M, int N, int K, cudaStream_t st);
+int launch_rec_f32(int H, const float* G, const float* whh_f, const float* whh_r, float* out, float* gates, float* csave, int Bc,
+                   int T, cudaStream_t st);
 // bf16 / tcgen05 forward (lstm_bf16.cu)
 int lstm_forward_bf16(bci_lstm_s* h, const float* x, int batch, int T, float* logits, float* probs, float* attn,
                       void* ws, size_t ws_bytes, cudaStream_t st);

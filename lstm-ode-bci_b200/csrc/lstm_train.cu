@@ -1,0 +1,866 @@
+// Training step of the BiLSTM-attention classifier in fp32: forward with saved activations, full
+// backward (BPTT through 3 x 2 LSTM directions, attention pooling, LayerNorms, heads) and a fused
+// clip + AdamW update.  Replaces loss.backward() / clip_grad_norm_ / AdamW.step of the reference's
+// train loop (04_lstm_model.py:482-507; plain variant 09_sensitivity_analysis.py:297-303) and the
+// backward-to-input used by the attribution script (07_explainability.py:242-258).
+//
+// Structure: every dense contraction is one of two generic fp32 GEMMs over the flattened row space
+// M = T*Bc (NN: data gradients / projections, TN with split-K + atomics: weight gradients); the serial
+// parts are lstm_rec_f32 (forward, saving gate activations and cell states) and lstm_bptt_f32 (its
+// mirror: dh_{t-1} = dG_t . W_hh with the same thread = (hidden unit, 16 windows) mapping); everything
+// row-local (LayerNorm, GELU, softmax over T, head MLP) is small fused kernels.  Dropout (four sites,
+// 04:177,186,199,202) uses a stateless hash of (seed, site, element index) so the backward pass
+// regenerates the masks instead of storing them.
+#include "lstm_shared_kernels.cuh"
+
+namespace bci {
+
+// ---- stateless dropout -------------------------------------------------------------------------
+__device__ __forceinline__ float drop_scale(uint64_t seed, uint32_t site, uint64_t idx, float p) {
+  if (p <= 0.f) return 1.f;
+  uint64_t z = seed + 0x9E3779B97F4A7C15ull * (idx + 1) + ((uint64_t)site << 56);
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z ^= z >> 31;
+  const float u = (float)(uint32_t)(z >> 40) * (1.0f / 16777216.0f);
+  return u < p ? 0.f : 1.0f / (1.0f - p);
+}
+__device__ __forceinline__ float gelu_grad(float x) {
+  // d/dx [0.5 x (1 + erf(x/sqrt2))] = Phi(x) + x phi(x)
+  const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
+  return cdf + x * 0.3989422804014327f * expf(-0.5f * x * x);
+}
+
+// ---- generic GEMMs (bounds-checked, 64x64x16 tiles, 4x4 per thread) -----------------------------
+constexpr int TG = 64, TGK = 16, TG_THREADS = 256;
+
+// C[M][N] (ldc) = (accumulate ? C : 0) + A[M][K] (lda) . Bt[K][N] (ldb) + bias[N]
+__global__ void __launch_bounds__(TG_THREADS)
+gemm_nn_f32(const float* __restrict__ A, int lda, const float* __restrict__ Bt, int ldb, float* __restrict__ C, int ldc, int M, int N,
+            int K, const float* __restrict__ bias, int accumulate) {
+  __shared__ float As[TGK][TG + 1];
+  __shared__ float Bs[TGK][TG + 1];
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int m0 = blockIdx.y * TG, n0 = blockIdx.x * TG;
+  float acc[4][4] = {};
+  for (int k0 = 0; k0 < K; k0 += TGK) {
+    for (int e = tid; e < TG * TGK; e += TG_THREADS) {
+      const int m = e / TGK, k = e % TGK;  // A: k fastest (row-major rows)
+      As[k][m] = (m0 + m < M && k0 + k < K) ? A[(long long)(m0 + m) * lda + k0 + k] : 0.f;
+      const int kk = e / TG, n = e % TG;   // Bt: n fastest
+      Bs[kk][n] = (k0 + kk < K && n0 + n < N) ? Bt[(long long)(k0 + kk) * ldb + n0 + n] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < TGK; ++k) {
+      float a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { a[i] = As[k][ty * 4 + i]; b[i] = Bs[k][tx * 4 + i]; }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int m = m0 + ty * 4 + i;
+    if (m >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tx * 4 + j;
+      if (n >= N) continue;
+      float v = acc[i][j] + (bias ? bias[n] : 0.f);
+      float* c = C + (long long)m * ldc + n;
+      *c = accumulate ? *c + v : v;
+    }
+  }
+}
+
+// C[P][Q] (ldc) += sum_{r < R} A[r][p] (lda) * B[r][q] (ldb); grid.z splits R; C must be zeroed first
+__global__ void __launch_bounds__(TG_THREADS)
+gemm_tn_f32(const float* __restrict__ A, int lda, const float* __restrict__ B, int ldb, float* __restrict__ C, int ldc, long long R,
+            int P, int Q) {
+  __shared__ float As[TGK][TG + 1];
+  __shared__ float Bs[TGK][TG + 1];
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int p0 = blockIdx.y * TG, q0 = blockIdx.x * TG;
+  const long long per = (R + gridDim.z - 1) / gridDim.z;
+  const long long r_begin = per * blockIdx.z, r_end = (r_begin + per < R) ? r_begin + per : R;
+  float acc[4][4] = {};
+  for (long long r0 = r_begin; r0 < r_end; r0 += TGK) {
+    for (int e = tid; e < TG * TGK; e += TG_THREADS) {
+      const int rr = e / TG, c = e % TG;
+      const long long r = r0 + rr;
+      As[rr][c] = (r < r_end && p0 + c < P) ? A[r * lda + p0 + c] : 0.f;
+      Bs[rr][c] = (r < r_end && q0 + c < Q) ? B[r * ldb + q0 + c] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < TGK; ++k) {
+      float a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { a[i] = As[k][ty * 4 + i]; b[i] = Bs[k][tx * 4 + i]; }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int p = p0 + ty * 4 + i, q = q0 + tx * 4 + j;
+      if (p < P && q < Q) atomicAdd(C + (long long)p * ldc + q, acc[i][j]);
+    }
+}
+
+// out[n] += sum_r A[r][n]   (column sums, atomics per block)
+__global__ void colsum_kernel(const float* __restrict__ A, int lda, long long R, int N, float* __restrict__ out) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  const long long per = (R + gridDim.y - 1) / gridDim.y;
+  const long long r0 = per * blockIdx.y, r1 = (r0 + per < R) ? r0 + per : R;
+  float s = 0.f;
+  for (long long r = r0; r < r1; ++r) s += A[r * lda + n];
+  atomicAdd(out + n, s);
+}
+
+static int gemm_nn(const float* A, int lda, const float* Bt, int ldb, float* C, int ldc, int M, int N, int K, const float* bias,
+                   int accumulate, cudaStream_t st) {
+  dim3 g(ceil_div(N, TG), ceil_div(M, TG));
+  gemm_nn_f32<<<g, TG_THREADS, 0, st>>>(A, lda, Bt, ldb, C, ldc, M, N, K, bias, accumulate);
+  BCI_LAUNCH_OK();
+  return BCI_OK;
+}
+static int gemm_tn(const float* A, int lda, const float* B, int ldb, float* C, int ldc, long long R, int P, int Q, cudaStream_t st) {
+  if (R <= 0) return BCI_OK;
+  const int tiles = ceil_div(P, TG) * ceil_div(Q, TG);
+  int splits = (4 * sm_count() + tiles - 1) / tiles;
+  const long long max_splits = (R + 255) / 256;
+  if (splits > max_splits) splits = (int)max_splits;
+  if (splits < 1) splits = 1;
+  if (splits > 65535) splits = 65535;
+  dim3 g(ceil_div(Q, TG), ceil_div(P, TG), splits);
+  gemm_tn_f32<<<g, TG_THREADS, 0, st>>>(A, lda, B, ldb, C, ldc, R, P, Q);
+  BCI_LAUNCH_OK();
+  return BCI_OK;
+}
+static int colsum(const float* A, int lda, long long R, int N, float* out, cudaStream_t st) {
+  int ys = (int)((R + 1023) / 1024);
+  if (ys > 1024) ys = 1024;
+  if (ys < 1) ys = 1;
+  colsum_kernel<<<dim3(ceil_div(N, 128), ys), 128, 0, st>>>(A, lda, R, N, out);
+  BCI_LAUNCH_OK();
+  return BCI_OK;
+}
+
+// ---- row-local forward kernels -----------------------------------------------------------------
+// K1 (train): one warp per (t,b) row.  Saves xT (time-major copy of x), xhat0 (normalised pre-activation), rstd0 and
+// z = dropout(GELU(LN(.))).  x (Bc,T,C) batch-first.
+template <int H>
+__global__ void __launch_bounds__(256)
+inproj_train_fwd(const float* __restrict__ x, int Bc, int T, int C, const float* __restrict__ w0t, const float* __restrict__ b0,
+                 const float* __restrict__ lnw, const float* __restrict__ lnb, float* __restrict__ xT, float* __restrict__ xhat,
+                 float* __restrict__ rstd_out, float* __restrict__ z, float p_drop, uint64_t seed) {
+  constexpr int NV = H / 32;
+  const int lane = threadIdx.x & 31;
+  const long long rows = (long long)Bc * T;
+  const long long wstride = (long long)gridDim.x * 8;
+  for (long long r = (long long)blockIdx.x * 8 + (threadIdx.x >> 5); r < rows; r += wstride) {
+    const int t = (int)(r / Bc), b = (int)(r - (long long)t * Bc);  // r is the TIME-MAJOR row index
+    const float* xr = x + ((long long)b * T + t) * C;
+    float acc[NV];
+#pragma unroll
+    for (int v = 0; v < NV; ++v) acc[v] = b0[v * 32 + lane];
+    for (int c = 0; c < C; ++c) {
+      const float xv = xr[c];
+      if (lane == 0) xT[r * C + c] = xv;
+#pragma unroll
+      for (int v = 0; v < NV; ++v) acc[v] = fmaf(xv, w0t[c * H + v * 32 + lane], acc[v]);
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int v = 0; v < NV; ++v) s += acc[v];
+    const float mean = warp_sum(s) * (1.0f / H);
+    float q2 = 0.f;
+#pragma unroll
+    for (int v = 0; v < NV; ++v) { const float d = acc[v] - mean; q2 = fmaf(d, d, q2); }
+    const float rstd = 1.0f / sqrtf(warp_sum(q2) * (1.0f / H) + 1e-5f);
+    if (lane == 0) rstd_out[r] = rstd;
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      const int j = v * 32 + lane;
+      const float xh = (acc[v] - mean) * rstd;
+      xhat[r * H + j] = xh;
+      const float y = fmaf(xh, lnw[j], lnb[j]);
+      z[r * H + j] = gelu_erf(y) * drop_scale(seed, 0, (uint64_t)r * H + j, p_drop);
+    }
+  }
+}
+
+// dv = LayerNorm-backward(dz * mask * gelu'(y)); accumulates dlnw/dlnb.  One warp per row.
+template <int H>
+__global__ void __launch_bounds__(256)
+inproj_bwd_rows(const float* __restrict__ dz, const float* __restrict__ xhat, const float* __restrict__ rstd_in,
+                const float* __restrict__ lnw, const float* __restrict__ lnb, long long rows, float* __restrict__ dv,
+                float* __restrict__ dlnw, float* __restrict__ dlnb, float p_drop, uint64_t seed) {
+  constexpr int NV = H / 32;
+  const int lane = threadIdx.x & 31;
+  const long long wstride = (long long)gridDim.x * 8;
+  float gw[NV] = {}, gb[NV] = {};
+  for (long long r = (long long)blockIdx.x * 8 + (threadIdx.x >> 5); r < rows; r += wstride) {
+    float dy[NV], xh[NV];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      const int j = v * 32 + lane;
+      xh[v] = xhat[r * H + j];
+      const float y = fmaf(xh[v], lnw[j], lnb[j]);
+      dy[v] = dz[r * H + j] * drop_scale(seed, 0, (uint64_t)r * H + j, p_drop) * gelu_grad(y);
+      gw[v] = fmaf(dy[v], xh[v], gw[v]);
+      gb[v] += dy[v];
+      const float dyw = dy[v] * lnw[j];
+      s1 += dyw;
+      s2 = fmaf(dyw, xh[v], s2);
+    }
+    s1 = warp_sum(s1) * (1.0f / H);
+    s2 = warp_sum(s2) * (1.0f / H);
+    const float rstd = rstd_in[r];
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      const int j = v * 32 + lane;
+      dv[r * H + j] = rstd * (dy[v] * lnw[j] - s1 - xh[v] * s2);
+    }
+  }
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    atomicAdd(dlnw + v * 32 + lane, gw[v]);
+    atomicAdd(dlnb + v * 32 + lane, gb[v]);
+  }
+}
+
+// final LayerNorm forward over rows of width D: xhat, rstd, Y = xhat*w + b
+template <int D>
+__global__ void __launch_bounds__(256)
+ln_rows_fwd(const float* __restrict__ x, long long rows, const float* __restrict__ w, const float* __restrict__ b, float* __restrict__ xhat,
+            float* __restrict__ rstd_out, float* __restrict__ y) {
+  constexpr int NV = D / 32;
+  const int lane = threadIdx.x & 31;
+  const long long wstride = (long long)gridDim.x * 8;
+  for (long long r = (long long)blockIdx.x * 8 + (threadIdx.x >> 5); r < rows; r += wstride) {
+    float v[NV];
+    float s = 0.f;
+#pragma unroll
+    for (int e = 0; e < NV; ++e) { v[e] = x[r * D + e * 32 + lane]; s += v[e]; }
+    const float mean = warp_sum(s) * (1.0f / D);
+    float q2 = 0.f;
+#pragma unroll
+    for (int e = 0; e < NV; ++e) { const float d = v[e] - mean; q2 = fmaf(d, d, q2); }
+    const float rstd = 1.0f / sqrtf(warp_sum(q2) * (1.0f / D) + 1e-5f);
+    if (lane == 0) rstd_out[r] = rstd;
+#pragma unroll
+    for (int e = 0; e < NV; ++e) {
+      const int d = e * 32 + lane;
+      const float xh = (v[e] - mean) * rstd;
+      xhat[r * D + d] = xh;
+      y[r * D + d] = fmaf(xh, w[d], b[d]);
+    }
+  }
+}
+
+// dx = LayerNorm-backward(dy) (dy already includes both the pooled-context and the score paths)
+template <int D>
+__global__ void __launch_bounds__(256)
+ln_rows_bwd(const float* __restrict__ dy, const float* __restrict__ xhat, const float* __restrict__ rstd_in, const float* __restrict__ w,
+            long long rows, float* __restrict__ dx, float* __restrict__ dw, float* __restrict__ db) {
+  constexpr int NV = D / 32;
+  const int lane = threadIdx.x & 31;
+  const long long wstride = (long long)gridDim.x * 8;
+  float gw[NV] = {}, gb[NV] = {};
+  for (long long r = (long long)blockIdx.x * 8 + (threadIdx.x >> 5); r < rows; r += wstride) {
+    float g[NV], xh[NV];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int e = 0; e < NV; ++e) {
+      const int d = e * 32 + lane;
+      g[e] = dy[r * D + d];
+      xh[e] = xhat[r * D + d];
+      gw[e] = fmaf(g[e], xh[e], gw[e]);
+      gb[e] += g[e];
+      const float gwv = g[e] * w[d];
+      s1 += gwv;
+      s2 = fmaf(gwv, xh[e], s2);
+    }
+    s1 = warp_sum(s1) * (1.0f / D);
+    s2 = warp_sum(s2) * (1.0f / D);
+    const float rstd = rstd_in[r];
+#pragma unroll
+    for (int e = 0; e < NV; ++e) {
+      const int d = e * 32 + lane;
+      dx[r * D + d] = rstd * (g[e] * w[d] - s1 - xh[e] * s2);
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < NV; ++e) {
+    atomicAdd(dw + e * 32 + lane, gw[e]);
+    atomicAdd(db + e * 32 + lane, gb[e]);
+  }
+}
+
+// ---- attention pooling (train): one CTA per window -------------------------------------------------
+// forward: s_t = b2 + sum_j w2_j tanh(PRE[t][b][j]); a = softmax_T(s); ctx = sum_t a_t Y[t][b][:]
+template <int H>
+__global__ void __launch_bounds__(256)
+attn_train_fwd(const float* __restrict__ pre, const float* __restrict__ y, int Bc, int T, const float* __restrict__ w2,
+               const float* __restrict__ b2, float* __restrict__ attn, float* __restrict__ ctx) {
+  constexpr int D = 2 * H;
+  extern __shared__ float at_smem[];  // [T] scores -> weights
+  __shared__ float red[8];
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int t = warp; t < T; t += 8) {
+    const float* pr = pre + ((long long)t * Bc + b) * H;
+    float s = 0.f;
+    for (int j = lane; j < H; j += 32) s = fmaf(w2[j], tanhf(pr[j]), s);
+    s = warp_sum(s);
+    if (lane == 0) at_smem[t] = s + b2[0];
+  }
+  __syncthreads();
+  float m = -INFINITY;
+  for (int t = tid; t < T; t += 256) m = fmaxf(m, at_smem[t]);
+  m = warp_max(m);
+  if (lane == 0) red[warp] = m;
+  __syncthreads();
+  m = red[0];
+  for (int w = 1; w < 8; ++w) m = fmaxf(m, red[w]);
+  __syncthreads();
+  float l = 0.f;
+  for (int t = tid; t < T; t += 256) { const float e = expf(at_smem[t] - m); at_smem[t] = e; l += e; }
+  l = warp_sum(l);
+  if (lane == 0) red[warp] = l;
+  __syncthreads();
+  l = 0.f;
+  for (int w = 0; w < 8; ++w) l += red[w];
+  const float inv = 1.0f / l;
+  for (int t = tid; t < T; t += 256) { const float a = at_smem[t] * inv; at_smem[t] = a; attn[(long long)b * T + t] = a; }
+  __syncthreads();
+  for (int d = tid; d < D; d += 256) {
+    float c = 0.f;
+    for (int t = 0; t < T; ++t) c = fmaf(at_smem[t], y[((long long)t * Bc + b) * D + d], c);
+    ctx[(long long)b * D + d] = c;
+  }
+}
+
+// backward: from dctx -> dY (context path only), dPRE (in place over pre), dw2, db2
+template <int H>
+__global__ void __launch_bounds__(256)
+attn_train_bwd(float* __restrict__ pre, const float* __restrict__ y, const float* __restrict__ attn, const float* __restrict__ dctx,
+               int Bc, int T, const float* __restrict__ w2, float* __restrict__ dY, float* __restrict__ dw2, float* __restrict__ db2) {
+  constexpr int D = 2 * H;
+  extern __shared__ float ab_smem[];  // [T] da -> ds ; [D] dctx
+  float* ds = ab_smem;
+  float* dc = ab_smem + T;
+  __shared__ float red[8];
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int d = tid; d < D; d += 256) dc[d] = dctx[(long long)b * D + d];
+  __syncthreads();
+  // da_t = dctx . Y_t ; dY_t = a_t * dctx
+  for (int t = warp; t < T; t += 8) {
+    const long long row = (long long)t * Bc + b;
+    const float a = attn[(long long)b * T + t];
+    float s = 0.f;
+    for (int d = lane; d < D; d += 32) {
+      s = fmaf(dc[d], y[row * D + d], s);
+      dY[row * D + d] = a * dc[d];
+    }
+    s = warp_sum(s);
+    if (lane == 0) ds[t] = s;
+  }
+  __syncthreads();
+  float dot = 0.f;
+  for (int t = tid; t < T; t += 256) dot = fmaf(attn[(long long)b * T + t], ds[t], dot);
+  dot = warp_sum(dot);
+  if (lane == 0) red[warp] = dot;
+  __syncthreads();
+  dot = 0.f;
+  for (int w = 0; w < 8; ++w) dot += red[w];
+  __syncthreads();
+  float sb2 = 0.f;
+  for (int t = tid; t < T; t += 256) { const float v = attn[(long long)b * T + t] * (ds[t] - dot); ds[t] = v; sb2 += v; }
+  sb2 = warp_sum(sb2);
+  if (lane == 0) red[warp] = sb2;
+  __syncthreads();
+  if (tid == 0) { float s = 0.f; for (int w = 0; w < 8; ++w) s += red[w]; atomicAdd(db2, s); }
+  // dPRE[t][j] = ds_t w2_j (1 - u^2), u = tanh(pre);  dw2_j += sum_t ds_t u
+  for (int j = tid; j < H; j += 256) {
+    const float w = w2[j];
+    float g = 0.f;
+    for (int t = 0; t < T; ++t) {
+      float* pp = pre + ((long long)t * Bc + b) * H + j;
+      const float u = tanhf(*pp);
+      g = fmaf(ds[t], u, g);
+      *pp = ds[t] * w * (1.0f - u * u);
+    }
+    atomicAdd(dw2 + j, g);
+  }
+}
+
+// ---- classifier head (train): one CTA per window ------------------------------------------------------
+template <int H>
+__global__ void __launch_bounds__(H)
+head_train_fwd(const float* __restrict__ ctx, int classes, const float* __restrict__ c0t, const float* __restrict__ cb0,
+               const float* __restrict__ c3t, const float* __restrict__ cb3, const float* __restrict__ c6, const float* __restrict__ cb6,
+               float* __restrict__ pre1, float* __restrict__ h1d, float* __restrict__ pre2, float* __restrict__ h2d,
+               float* __restrict__ logits, float* __restrict__ probs, float p_drop, uint64_t seed) {
+  constexpr int D = 2 * H;
+  __shared__ float cs[D], h1[H], h2[H / 2], lg[8];
+  const int b = blockIdx.x, tid = threadIdx.x;
+  for (int d = tid; d < D; d += H) cs[d] = ctx[(long long)b * D + d];
+  __syncthreads();
+  if (tid < H) {
+    float a = cb0[tid];
+    for (int d = 0; d < D; ++d) a = fmaf(cs[d], c0t[(long long)d * H + tid], a);
+    pre1[(long long)b * H + tid] = a;
+    const float v = gelu_erf(a) * drop_scale(seed, 2, (uint64_t)b * H + tid, p_drop);
+    h1[tid] = v;
+    h1d[(long long)b * H + tid] = v;
+  }
+  __syncthreads();
+  if (tid < H / 2) {
+    float a = cb3[tid];
+    for (int k = 0; k < H; ++k) a = fmaf(h1[k], c3t[k * (H / 2) + tid], a);
+    pre2[(long long)b * (H / 2) + tid] = a;
+    const float v = gelu_erf(a) * drop_scale(seed, 3, (uint64_t)b * (H / 2) + tid, p_drop);
+    h2[tid] = v;
+    h2d[(long long)b * (H / 2) + tid] = v;
+  }
+  __syncthreads();
+  if (tid < classes) {
+    float a = cb6[tid];
+    for (int k = 0; k < H / 2; ++k) a = fmaf(h2[k], c6[tid * (H / 2) + k], a);
+    logits[(long long)b * classes + tid] = a;
+    lg[tid] = a;
+  }
+  __syncthreads();
+  if (probs && tid == 0) {
+    float mx = -INFINITY, den = 0.f;
+    for (int c = 0; c < classes; ++c) mx = fmaxf(mx, lg[c]);
+    for (int c = 0; c < classes; ++c) den += expf(lg[c] - mx);
+    for (int c = 0; c < classes; ++c) probs[(long long)b * classes + c] = expf(lg[c] - mx) / den;
+  }
+}
+
+// dlogits -> dpre2, dpre1, dctx (weight gradients are TN GEMMs over the batch afterwards)
+template <int H>
+__global__ void __launch_bounds__(H)
+head_train_bwd(const float* __restrict__ dlogits, int classes, const float* __restrict__ pre1, const float* __restrict__ pre2,
+               const float* __restrict__ w6 /*[cls][H/2]*/, const float* __restrict__ w3 /*[H/2][H]*/, const float* __restrict__ w0 /*[H][2H]*/,
+               float* __restrict__ dpre1, float* __restrict__ dpre2, float* __restrict__ dctx, float p_drop, uint64_t seed) {
+  constexpr int D = 2 * H;
+  __shared__ float dl[8], d2[H / 2], d1[H];
+  const int b = blockIdx.x, tid = threadIdx.x;
+  if (tid < classes) dl[tid] = dlogits[(long long)b * classes + tid];
+  __syncthreads();
+  if (tid < H / 2) {
+    float g = 0.f;
+    for (int c = 0; c < classes; ++c) g = fmaf(dl[c], w6[c * (H / 2) + tid], g);
+    g *= drop_scale(seed, 3, (uint64_t)b * (H / 2) + tid, p_drop) * gelu_grad(pre2[(long long)b * (H / 2) + tid]);
+    d2[tid] = g;
+    dpre2[(long long)b * (H / 2) + tid] = g;
+  }
+  __syncthreads();
+  if (tid < H) {
+    float g = 0.f;
+    for (int k = 0; k < H / 2; ++k) g = fmaf(d2[k], w3[k * H + tid], g);
+    g *= drop_scale(seed, 2, (uint64_t)b * H + tid, p_drop) * gelu_grad(pre1[(long long)b * H + tid]);
+    d1[tid] = g;
+    dpre1[(long long)b * H + tid] = g;
+  }
+  __syncthreads();
+  for (int d = tid; d < D; d += H) {
+    float g = 0.f;
+    for (int j = 0; j < H; ++j) g = fmaf(d1[j], w0[j * D + d], g);
+    dctx[(long long)b * D + d] = g;
+  }
+}
+
+// ---- BPTT through one LSTM layer ---------------------------------------------------------------------------
+// grid = (window tiles, 2 directions), 256 threads, thread = (hidden unit j, group of 16 windows): the mirror of
+// lstm_rec_f32.  Walks the direction's time order backwards; dG_t (gate-interleaved) goes to global for the weight /
+// input GEMMs and, transposed, to shared memory for dh_{t-1} = dG_t . W_hh.
+constexpr int BP_THREADS = 256, BP_WPT = 16;
+
+template <int H>
+__global__ void __launch_bounds__(BP_THREADS, 1)
+lstm_bptt_f32(const float* __restrict__ dout,    // [T][Bc][2H]  grad wrt the layer output
+              const float* __restrict__ gates,   // [T][Bc][2][H][4] post-activation i,f,g,o
+              const float* __restrict__ csave,   // [T][Bc][2][H]
+              const float* __restrict__ whh_bf,  // [4H][H] gate-interleaved rows, forward direction
+              const float* __restrict__ whh_br,  // reverse direction
+              float* __restrict__ dG,            // [T][Bc][2][H][4]
+              int Bc, int T) {
+  constexpr int GROUPS = BP_THREADS / H, MT = GROUPS * BP_WPT, GS = MT + 4;
+  extern __shared__ __align__(16) float bp_smem[];  // [4H][GS]
+  const int tid = threadIdx.x, j = tid % H, grp = tid / H;
+  const int dir = blockIdx.y;
+  const int b_base = blockIdx.x * MT + grp * BP_WPT;
+  const float* __restrict__ W = dir ? whh_br : whh_bf;
+  float dh_rec[BP_WPT], dc[BP_WPT];
+#pragma unroll
+  for (int w = 0; w < BP_WPT; ++w) { dh_rec[w] = 0.f; dc[w] = 0.f; }
+
+  for (int s = T - 1; s >= 0; --s) {
+    const int t = dir ? (T - 1 - s) : s;               // time index of forward step s
+    const int tp = dir ? (t + 1) : (t - 1);            // time index of forward step s-1 (previous state)
+    float* dgs = bp_smem + (j * 4) * GS + grp * BP_WPT;
+#pragma unroll
+    for (int w = 0; w < BP_WPT; ++w) {
+      const int b = b_base + w;
+      float4 dg = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (b < Bc) {
+        const long long row = (long long)t * Bc + b;
+        const float4 g = reinterpret_cast<const float4*>(gates)[(row * 2 + dir) * H + j];
+        const float c = csave[(row * 2 + dir) * H + j];
+        const float cprev = (s > 0) ? csave[(((long long)tp * Bc + b) * 2 + dir) * H + j] : 0.f;
+        const float dh = dout[row * (2 * H) + dir * H + j] + dh_rec[w];
+        const float tc = tanhf(c);
+        const float dct = fmaf(dh * g.w, 1.0f - tc * tc, dc[w]);
+        dg.x = dct * g.z * g.x * (1.0f - g.x);          // d pre_i
+        dg.y = dct * cprev * g.y * (1.0f - g.y);        // d pre_f
+        dg.z = dct * g.x * (1.0f - g.z * g.z);          // d pre_g
+        dg.w = dh * tc * g.w * (1.0f - g.w);            // d pre_o
+        dc[w] = dct * g.y;
+        reinterpret_cast<float4*>(dG)[(row * 2 + dir) * H + j] = dg;
+      }
+      dgs[0 * GS + w] = dg.x; dgs[1 * GS + w] = dg.y; dgs[2 * GS + w] = dg.z; dgs[3 * GS + w] = dg.w;
+    }
+    __syncthreads();
+    // dh_rec[w] (unit j) = sum_n dG[w][n] * W_hh_b[n][j]
+    float acc[BP_WPT];
+#pragma unroll
+    for (int w = 0; w < BP_WPT; ++w) acc[w] = 0.f;
+    const float* gsrc = bp_smem + grp * BP_WPT;
+#pragma unroll 4
+    for (int n = 0; n < 4 * H; ++n) {
+      const float wv = __ldg(W + (long long)n * H + j);
+      const float4* gp = reinterpret_cast<const float4*>(gsrc + n * GS);
+#pragma unroll
+      for (int q = 0; q < BP_WPT / 4; ++q) {
+        const float4 g4 = gp[q];
+        acc[q * 4 + 0] = fmaf(g4.x, wv, acc[q * 4 + 0]);
+        acc[q * 4 + 1] = fmaf(g4.y, wv, acc[q * 4 + 1]);
+        acc[q * 4 + 2] = fmaf(g4.z, wv, acc[q * 4 + 2]);
+        acc[q * 4 + 3] = fmaf(g4.w, wv, acc[q * 4 + 3]);
+      }
+    }
+#pragma unroll
+    for (int w = 0; w < BP_WPT; ++w) dh_rec[w] = acc[w];
+    __syncthreads();
+  }
+}
+
+// ---- small elementwise helpers ---------------------------------------------------------------------------------
+__global__ void scale_mask_kernel(const float* __restrict__ src, float* __restrict__ dst, long long n, float p, uint64_t seed, uint32_t site) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = src[i] * drop_scale(seed, site, (uint64_t)i, p);
+}
+// interleaved rows (n = unit*4 + gate, optionally + dir*4H) -> reference gate-major rows; dst (4H, K)
+__global__ void unpack_gate_rows_kernel(const float* __restrict__ src, float* __restrict__ dst, int H, int K, int row0) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)4 * H * K) return;
+  const int row = (int)(i / K), k = (int)(i - (long long)row * K);
+  const int gate = row / H, unit = row - gate * H;
+  dst[i] = src[(long long)(row0 + unit * 4 + gate) * K + k];
+}
+__global__ void unpack_bias_kernel(const float* __restrict__ src, float* __restrict__ d_ih, float* __restrict__ d_hh, int H, int row0) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 4 * H) return;
+  const int gate = i / H, unit = i - gate * H;
+  const float v = src[row0 + unit * 4 + gate];
+  d_ih[i] = v;
+  d_hh[i] = v;
+}
+// dxT [T][Bc][C] -> dx (Bc,T,C)
+__global__ void untranspose_x_kernel(const float* __restrict__ src, float* __restrict__ dst, int Bc, int T, int C) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)Bc * T * C) return;
+  const int c = (int)(i % C);
+  const long long bt = i / C;
+  const int t = (int)(bt % T), b = (int)(bt / T);
+  dst[i] = src[((long long)t * Bc + b) * C + c];
+}
+
+// ---- workspace -------------------------------------------------------------------------------------------------------
+struct TrainWs {
+  float *xT, *xhat0, *rstd0, *z;
+  float *gates[BCI_MAX_LAYERS], *cst[BCI_MAX_LAYERS], *out[BCI_MAX_LAYERS], *outd[BCI_MAX_LAYERS];
+  float *G;                 // forward: projected inputs; backward: dG
+  float *xhatF, *rstdF, *Y, *PRE, *attn, *ctx, *pre1, *h1d, *pre2, *h2d;
+  float *dA, *dB;           // [M][2H] gradient ping-pong
+  float *dctx, *dpre1, *dpre2, *tmpW, *hdr;
+  size_t total;
+};
+struct TrainHeader { float dropout; uint32_t valid; uint64_t seed; int batch, T; };
+
+static void carve_train(const bci_lstm_config& c, int B, int T, float p_drop, char* base, TrainWs& w) {
+  const size_t H = c.hidden_size, D = 2 * H, C = c.input_size, M = (size_t)B * T;
+  size_t off = 0;
+  auto take = [&](size_t n) { float* p = reinterpret_cast<float*>(base + off); off += align_up(n * sizeof(float), 256); return p; };
+  w.hdr = take(64);
+  w.xT = take(M * C); w.xhat0 = take(M * H); w.rstd0 = take(M); w.z = take(M * H);
+  for (int l = 0; l < c.num_layers; ++l) {
+    w.gates[l] = take(M * 8 * H); w.cst[l] = take(M * 2 * H); w.out[l] = take(M * D);
+    w.outd[l] = (p_drop > 0.f && l < c.num_layers - 1) ? take(M * D) : w.out[l];
+  }
+  w.G = take(M * 8 * H);
+  w.xhatF = take(M * D); w.rstdF = take(M); w.Y = take(M * D); w.PRE = take(M * H);
+  w.attn = take((size_t)B * T); w.ctx = take(B * D); w.pre1 = take(B * H); w.h1d = take(B * H);
+  w.pre2 = take(B * (H / 2)); w.h2d = take(B * (H / 2));
+  w.dA = take(M * D); w.dB = take(M * D);
+  w.dctx = take(B * D); w.dpre1 = take(B * H); w.dpre2 = take(B * (H / 2));
+  w.tmpW = take(8 * H * D + 1024);
+  w.total = off;
+}
+
+size_t lstm_workspace_train(const bci_lstm_config& c, int batch, int T) {
+  TrainWs w;
+  carve_train(c, batch > 0 ? batch : 1, T, 0.5f, nullptr, w);  // worst case: dropout copies present
+  return w.total;
+}
+
+template <int H>
+static int forward_train_t(bci_lstm_s* h, const float* x, int B, int T, float p_drop, uint64_t seed, float* logits, float* probs,
+                           float* attn, TrainWs& w, cudaStream_t st) {
+  const bci_lstm_config& c = h->cfg;
+  const PackedF32& p = h->f32;
+  constexpr int D = 2 * H;
+  const int C = c.input_size;
+  const long long M = (long long)B * T;
+  const int rb = (int)((M + 7) / 8 < 4096 ? (M + 7) / 8 : 4096);
+  inproj_train_fwd<H><<<rb, 256, 0, st>>>(x, B, T, C, p.w0t, p.b0, p.ln0w, p.ln0b, w.xT, w.xhat0, w.rstd0, w.z, p_drop * 0.5f, seed);
+  BCI_LAUNCH_OK();
+  const float* in = w.z;
+  for (int l = 0; l < c.num_layers; ++l) {
+    int rc = launch_proj_gemm_f32(in, p.wih_t[l], p.bias[l], w.G, (int)M, 8 * H, layer_in_width(c, l), st);
+    if (rc) return rc;
+    rc = launch_rec_f32(H, w.G, p.whh_t[l][0], p.whh_t[l][1], w.out[l], w.gates[l], w.cst[l], B, T, st);
+    if (rc) return rc;
+    if (w.outd[l] != w.out[l]) {
+      scale_mask_kernel<<<(unsigned)ceil_div64(M * D, 256), 256, 0, st>>>(w.out[l], w.outd[l], M * D, p_drop, seed, 16 + l);
+      BCI_LAUNCH_OK();
+    }
+    in = w.outd[l];
+  }
+  const float* seq = w.out[c.num_layers - 1];
+  ln_rows_fwd<D><<<rb, 256, 0, st>>>(seq, M, p.lnw, p.lnb, w.xhatF, w.rstdF, w.Y);
+  BCI_LAUNCH_OK();
+  int rc = launch_proj_gemm_f32(w.Y, p.aw1t, p.ab1, w.PRE, (int)M, H, D, st);
+  if (rc) return rc;
+  attn_train_fwd<H><<<B, 256, T * sizeof(float), st>>>(w.PRE, w.Y, B, T, p.aw2, p.ab2, w.attn, w.ctx);
+  BCI_LAUNCH_OK();
+  if (attn) BCI_CUDA_OK(cudaMemcpyAsync(attn, w.attn, (size_t)B * T * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  head_train_fwd<H><<<B, H, 0, st>>>(w.ctx, c.num_classes, p.c0t, p.cb0, p.c3t, p.cb3, p.c6, p.cb6, w.pre1, w.h1d, w.pre2, w.h2d,
+                                       logits, probs, p_drop, seed);
+  BCI_LAUNCH_OK();
+  return BCI_OK;
+}
+
+int lstm_forward_train(bci_lstm_s* h, const float* x, int batch, int T, float dropout, uint64_t seed, float* logits, float* probs,
+                       float* attn, void* ws, size_t ws_bytes, cudaStream_t st) {
+  const bci_lstm_config& c = h->cfg;
+  BCI_REQUIRE(batch <= 4 * max_chunk(c, 1), BCI_EINVAL, "bci_lstm_forward(train=1): batch %d exceeds the training limit %d", batch,
+              4 * max_chunk(c, 1));
+  TrainWs w;
+  carve_train(c, batch, T, dropout, (char*)ws, w);
+  BCI_REQUIRE(ws_bytes >= w.total, BCI_ENOMEM, "bci_lstm_forward(train=1): workspace %zu < %zu bytes", ws_bytes, w.total);
+  BCI_REQUIRE(T * sizeof(float) + 2 * c.hidden_size * sizeof(float) <= 40 * 1024, BCI_EINVAL, "training supports seq_len <= 8192");
+  TrainHeader hd{dropout, 0xB200C0DEu, seed, batch, T};
+  BCI_CUDA_OK(cudaMemcpyAsync(w.hdr, &hd, sizeof(hd), cudaMemcpyHostToDevice, st));
+  return c.hidden_size == 128 ? forward_train_t<128>(h, x, batch, T, dropout, seed, logits, probs, attn, w, st)
+                              : forward_train_t<256>(h, x, batch, T, dropout, seed, logits, probs, attn, w, st);
+}
+
+template <int H>
+static int backward_t(bci_lstm_s* h, const float* dlogits, int B, int T, float p_drop, uint64_t seed, float* dx, const bci_lstm_grads* g,
+                      TrainWs& w, cudaStream_t st) {
+  const bci_lstm_config& c = h->cfg;
+  const PackedF32& p = h->f32;
+  const bci_lstm_weights& raw = h->raw;
+  constexpr int D = 2 * H;
+  const int C = c.input_size, L = c.num_layers, cls = c.num_classes;
+  const long long M = (long long)B * T;
+  const int rb = (int)((M + 7) / 8 < 4096 ? (M + 7) / 8 : 4096);
+  auto zero = [&](float* ptr, size_t n) { return cudaMemsetAsync(ptr, 0, n * sizeof(float), st); };
+  int rc;
+  // ---- head ----
+  head_train_bwd<H><<<B, H, 0, st>>>(dlogits, cls, w.pre1, w.pre2, raw.cls_w6, raw.cls_w3, raw.cls_w0, w.dpre1, w.dpre2, w.dctx,
+                                       p_drop, seed);
+  BCI_LAUNCH_OK();
+  BCI_CUDA_OK(zero(g->cls_w6, (size_t)cls * (H / 2))); BCI_CUDA_OK(zero(g->cls_b6, cls));
+  BCI_CUDA_OK(zero(g->cls_w3, (size_t)(H / 2) * H));   BCI_CUDA_OK(zero(g->cls_b3, H / 2));
+  BCI_CUDA_OK(zero(g->cls_w0, (size_t)H * D));         BCI_CUDA_OK(zero(g->cls_b0, H));
+  if ((rc = gemm_tn(dlogits, cls, w.h2d, H / 2, g->cls_w6, H / 2, B, cls, H / 2, st))) return rc;
+  if ((rc = colsum(dlogits, cls, B, cls, g->cls_b6, st))) return rc;
+  if ((rc = gemm_tn(w.dpre2, H / 2, w.h1d, H, g->cls_w3, H, B, H / 2, H, st))) return rc;
+  if ((rc = colsum(w.dpre2, H / 2, B, H / 2, g->cls_b3, st))) return rc;
+  if ((rc = gemm_tn(w.dpre1, H, w.ctx, D, g->cls_w0, D, B, H, D, st))) return rc;
+  if ((rc = colsum(w.dpre1, H, B, H, g->cls_b0, st))) return rc;
+  // ---- attention pooling ----
+  BCI_CUDA_OK(zero(g->attn_w2, H)); BCI_CUDA_OK(zero(g->attn_b2, 1));
+  BCI_CUDA_OK(zero(g->attn_w1, (size_t)H * D)); BCI_CUDA_OK(zero(g->attn_b1, H));
+  BCI_CUDA_OK(zero(g->ln_w, D)); BCI_CUDA_OK(zero(g->ln_b, D));
+  attn_train_bwd<H><<<B, 256, (T + D) * sizeof(float), st>>>(w.PRE, w.Y, w.attn, w.dctx, B, T, p.aw2, w.dA /*dY*/, g->attn_w2, g->attn_b2);
+  BCI_LAUNCH_OK();
+  // dY += dPRE . W1 ; dW1 = dPRE^T Y ; db1 = colsum(dPRE)
+  if ((rc = gemm_nn(w.PRE, H, raw.attn_w1, D, w.dA, D, (int)M, D, H, nullptr, 1, st))) return rc;
+  if ((rc = gemm_tn(w.PRE, H, w.Y, D, g->attn_w1, D, M, H, D, st))) return rc;
+  if ((rc = colsum(w.PRE, H, M, H, g->attn_b1, st))) return rc;
+  // final LayerNorm backward: dA (dY) -> dB (grad wrt the last LSTM layer's output)
+  ln_rows_bwd<D><<<rb, 256, 0, st>>>(w.dA, w.xhatF, w.rstdF, p.lnw, M, w.dB, g->ln_w, g->ln_b);
+  BCI_LAUNCH_OK();
+  float* dcur = w.dB;   // grad wrt out[l]
+  float* dnext = w.dA;  // scratch for grad wrt the layer input
+  // ---- LSTM layers, top down ----
+  static bool attr = false;
+  constexpr int MT = (BP_THREADS / H) * BP_WPT;
+  const size_t bp_smem = (size_t)4 * H * (MT + 4) * sizeof(float);
+  if (!attr) {
+    BCI_CUDA_OK(cudaFuncSetAttribute(lstm_bptt_f32<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bp_smem));
+    attr = true;
+  }
+  for (int l = L - 1; l >= 0; --l) {
+    const int K = layer_in_width(c, l);
+    const float* in = (l == 0) ? w.z : w.outd[l - 1];
+    lstm_bptt_f32<H><<<dim3(ceil_div(B, MT), 2), BP_THREADS, bp_smem, st>>>(dcur, w.gates[l], w.cst[l], p.whh_b[l][0], p.whh_b[l][1], w.G, B, T);
+    BCI_LAUNCH_OK();
+    // dW_ih (both directions at once, interleaved rows) = dG^T . in
+    BCI_CUDA_OK(zero(w.tmpW, (size_t)8 * H * K));
+    if ((rc = gemm_tn(w.G, 8 * H, in, K, w.tmpW, K, M, 8 * H, K, st))) return rc;
+    for (int d = 0; d < 2; ++d) {
+      unpack_gate_rows_kernel<<<(unsigned)ceil_div64((long long)4 * H * K, 256), 256, 0, st>>>(w.tmpW, g->w_ih[l][d], H, K, d * 4 * H);
+      BCI_LAUNCH_OK();
+    }
+    // dW_hh[d] = dG[:, d]^T . h_prev, h_prev(t) = out[t-1] (forward) / out[t+1] (reverse): a row shift by Bc rows
+    for (int d = 0; d < 2; ++d) {
+      BCI_CUDA_OK(zero(w.tmpW, (size_t)4 * H * H));
+      const long long R = M - B;
+      const float* Ad = w.G + d * 4 * H + (d == 0 ? (long long)B * 8 * H : 0);
+      const float* Bd = w.out[l] + d * H + (d == 0 ? 0 : (long long)B * D);
+      if ((rc = gemm_tn(Ad, 8 * H, Bd, D, w.tmpW, H, R, 4 * H, H, st))) return rc;
+      unpack_gate_rows_kernel<<<(unsigned)ceil_div64((long long)4 * H * H, 256), 256, 0, st>>>(w.tmpW, g->w_hh[l][d], H, H, 0);
+      BCI_LAUNCH_OK();
+    }
+    // biases
+    BCI_CUDA_OK(zero(w.tmpW, (size_t)8 * H));
+    if ((rc = colsum(w.G, 8 * H, M, 8 * H, w.tmpW, st))) return rc;
+    for (int d = 0; d < 2; ++d) {
+      unpack_bias_kernel<<<ceil_div(4 * H, 256), 256, 0, st>>>(w.tmpW, g->b_ih[l][d], g->b_hh[l][d], H, d * 4 * H);
+      BCI_LAUNCH_OK();
+    }
+    // grad wrt the layer input: dnext [M][K] = dG . wih_b
+    if ((rc = gemm_nn(w.G, 8 * H, p.wih_b[l], K, dnext, K, (int)M, K, 8 * H, nullptr, 0, st))) return rc;
+    if (l > 0 && w.outd[l - 1] != w.out[l - 1]) {
+      scale_mask_kernel<<<(unsigned)ceil_div64(M * K, 256), 256, 0, st>>>(dnext, dnext, M * K, p_drop, seed, 16 + (l - 1));
+      BCI_LAUNCH_OK();
+    }
+    float* tsw = dcur; dcur = dnext; dnext = tsw;
+  }
+  // ---- input projection: dcur = dz [M][H] ----
+  BCI_CUDA_OK(zero(g->input_ln_w, H)); BCI_CUDA_OK(zero(g->input_ln_b, H));
+  BCI_CUDA_OK(zero(g->input_proj_w, (size_t)H * C)); BCI_CUDA_OK(zero(g->input_proj_b, H));
+  inproj_bwd_rows<H><<<rb, 256, 0, st>>>(dcur, w.xhat0, w.rstd0, p.ln0w, p.ln0b, M, dnext /*dv*/, g->input_ln_w, g->input_ln_b,
+                                         p_drop * 0.5f, seed);
+  BCI_LAUNCH_OK();
+  if ((rc = gemm_tn(dnext, H, w.xT, C, g->input_proj_w, C, M, H, C, st))) return rc;
+  if ((rc = colsum(dnext, H, M, H, g->input_proj_b, st))) return rc;
+  if (dx) {
+    // dxT [M][C] = dv . W0 (H x C); reuse dcur as scratch
+    if ((rc = gemm_nn(dnext, H, raw.input_proj_w, C, dcur, C, (int)M, C, H, nullptr, 0, st))) return rc;
+    untranspose_x_kernel<<<(unsigned)ceil_div64(M * C, 256), 256, 0, st>>>(dcur, dx, B, T, C);
+    BCI_LAUNCH_OK();
+  }
+  return BCI_OK;
+}
+
+int lstm_backward_impl(bci_lstm_s* h, const float* x, const float* dlogits, int batch, int T, float* dx, const bci_lstm_grads* g,
+                       void* ws, size_t ws_bytes, cudaStream_t st) {
+  (void)x;
+  const bci_lstm_config& c = h->cfg;
+  // the forward left its configuration in the workspace header
+  TrainHeader hd;
+  BCI_CUDA_OK(cudaMemcpyAsync(&hd, ws, sizeof(hd), cudaMemcpyDeviceToHost, st));
+  BCI_CUDA_OK(cudaStreamSynchronize(st));
+  BCI_REQUIRE(hd.valid == 0xB200C0DEu && hd.batch == batch && hd.T == T, BCI_ESTATE,
+              "bci_lstm_backward: workspace does not hold a train=1 forward of this shape");
+  TrainWs w;
+  carve_train(c, batch, T, hd.dropout, (char*)ws, w);
+  BCI_REQUIRE(ws_bytes >= w.total, BCI_ENOMEM, "bci_lstm_backward: workspace %zu < %zu bytes", ws_bytes, w.total);
+  const float* const* gp = reinterpret_cast<const float* const*>(g);
+  for (size_t i = 0; i < sizeof(bci_lstm_grads) / sizeof(float*); ++i) {
+    const size_t lay = 4, per = BCI_MAX_LAYERS * 2;
+    // layer arrays: only the first num_layers entries are required
+    if (i >= lay && i < lay + 4 * per) {
+      const size_t li = ((i - lay) % per) / 2;
+      if ((int)li >= c.num_layers) continue;
+    }
+    BCI_REQUIRE(gp[i] != nullptr, BCI_EINVAL, "bci_lstm_backward: gradient pointer %zu is NULL", i);
+  }
+  return c.hidden_size == 128 ? backward_t<128>(h, dlogits, batch, T, hd.dropout, hd.seed, dx, g, w, st)
+                              : backward_t<256>(h, dlogits, batch, T, hd.dropout, hd.seed, dx, g, w, st);
+}
+
+// ---- fused clip + AdamW ---------------------------------------------------------------------------------------------
+__global__ void sumsq_kernel(const float* __restrict__ g, long long n, float* __restrict__ out) {
+  float s = 0.f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) s = fmaf(g[i], g[i], s);
+  s = warp_sum(s);
+  __shared__ float red[8];
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w];
+    atomicAdd(out, t);
+  }
+}
+__global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, long long n,
+                             float lr, float b1, float b2, float eps, float wd, float bc1, float bc2, float grad_scale, float max_norm,
+                             float* __restrict__ norm_scratch) {
+  // torch.nn.utils.clip_grad_norm_: coef = max_norm / (total_norm + 1e-6), clamped to 1; AdamW (decoupled decay) as torch.optim.AdamW
+  const float total = sqrtf(norm_scratch[0]) * fabsf(grad_scale);
+  float coef = grad_scale;
+  if (max_norm > 0.f) coef *= fminf(1.0f, max_norm / (total + 1e-6f));
+  if (blockIdx.x == 0 && threadIdx.x == 0) norm_scratch[1] = total;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float gi = g[i] * coef;
+    float pi = p[i] * (1.0f - lr * wd);
+    const float mi = fmaf(b1, m[i], (1.0f - b1) * gi);
+    const float vi = fmaf(b2, v[i], (1.0f - b2) * gi * gi);
+    m[i] = mi;
+    v[i] = vi;
+    const float denom = sqrtf(vi) / sqrtf(bc2) + eps;
+    pi -= (lr / bc1) * (mi / denom);
+    p[i] = pi;
+  }
+}
+
+}  // namespace bci
+
+extern "C" int bci_adamw_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
+                              float weight_decay, int32_t step, float grad_scale, float max_norm, float* norm_scratch, void* stream) {
+  using namespace bci;
+  BCI_REQUIRE(p && g && m && v && norm_scratch && n >= 0 && step >= 1, BCI_EINVAL, "bci_adamw_step: bad arguments");
+  if (n == 0) return BCI_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  BCI_CUDA_OK(cudaMemsetAsync(norm_scratch, 0, 2 * sizeof(float), st));
+  const int blocks = (int)((n + 1023) / 1024 < 4 * sm_count() ? (n + 1023) / 1024 : 4 * sm_count());
+  sumsq_kernel<<<blocks, 256, 0, st>>>(g, n, norm_scratch);
+  BCI_LAUNCH_OK();
+  const float bc1 = 1.0f - powf(beta1, (float)step), bc2 = 1.0f - powf(beta2, (float)step);
+  adamw_kernel<<<blocks, 256, 0, st>>>(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, bc1, bc2, grad_scale, max_norm, norm_scratch);
+  BCI_LAUNCH_OK();
+  return BCI_OK;
+}

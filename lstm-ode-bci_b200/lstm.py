@@ -86,8 +86,7 @@ class EnhancedLSTMModel(nn.Module):
             raise N.BciError(-1, "EnhancedLSTMModel (bci_b200) runs on CUDA tensors only; move the model and "
                                  "input with .to('cuda') -- there is no CPU fallback")
         x = x.float()
-        if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters())) \
-                and self.training:
+        if torch.is_grad_enabled() and (x.requires_grad or (self.training and any(p.requires_grad for p in self.parameters()))):
             from .train import lstm_attn_autograd
             return lstm_attn_autograd(self, x, return_attention)
         hid = self._engine(self._precision_now())
