@@ -20,6 +20,7 @@
 #include "lstm_shared_kernels.cuh"
 #include "sm100_prims.cuh"
 #include "tmap.cuh"
+#include <cuda_fp16.h>
 
 namespace bci {
 using namespace sm100;
@@ -44,13 +45,15 @@ __global__ void pack_rows_perm_bf16(const float* __restrict__ src, __nv_bfloat16
   const int row = (int)(i / K), k = (int)(i - (long long)row * K);
   const int gate = row / H, unit = row - gate * H;
   const int pr = order ? perm_G(unit, gate) : perm_T(unit, gate);
-  dst[(long long)(row0 + pr) * K + k] = __float2bfloat16_rn(src[i]);
+  // sigmoid(x) = 0.5 + 0.5 tanh(x/2): the 1/2 is folded into the i,f,o rows here (exact in binary floating point)
+  const float sc = (gate == 2) ? 1.0f : 0.5f;
+  dst[(long long)(row0 + pr) * K + k] = __float2bfloat16_rn(sc * src[i]);
 }
 __global__ void pack_bias_perm(const float* __restrict__ bih, const float* __restrict__ bhh, float* __restrict__ dst, int H, int col0) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= 4 * H) return;
   const int gate = i / H, unit = i - gate * H;
-  dst[col0 + perm_G(unit, gate)] = bih[i] + bhh[i];
+  dst[col0 + perm_G(unit, gate)] = ((gate == 2) ? 1.0f : 0.5f) * (bih[i] + bhh[i]);
 }
 
 size_t lstm_store_bytes_bf16(const bci_lstm_config& c) {
@@ -322,16 +325,24 @@ __device__ __forceinline__ float tanh_fast(float x) {
   asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-__device__ __forceinline__ float sigmoid_fast(float x) { return fmaf(0.5f, tanh_fast(0.5f * x), 0.5f); }
+// x already carries the 1/2 of sigmoid(2x') = 0.5 + 0.5 tanh(x') (folded into the weights at pack time)
+__device__ __forceinline__ float sigmoid_half_arg(float xh) { return fmaf(0.5f, tanh_fast(xh), 0.5f); }
+// two activations per MUFU op: tanh.approx.f16x2 (max rel. error 2^-10.99, below the bf16 rounding of h)
+__device__ __forceinline__ __half2 tanh2_f16(float a, float b) {
+  __half2 x = __floats2half2_rn(a, b);
+  uint32_t xi = *reinterpret_cast<uint32_t*>(&x), yi;
+  asm("tanh.approx.f16x2 %0, %1;" : "=r"(yi) : "r"(xi));
+  return *reinterpret_cast<__half2*>(&yi);
+}
 
-template <bool STATS>
+template <bool STATS, bool F16ACT>
 __global__ void __launch_bounds__(RB_THREADS, 1)
 lstm_rec_bf16(const __grid_constant__ CUtensorMap tmG,    // G viewed as [T*Bc][1024] bf16, box 64 cols x 128 rows
               const __grid_constant__ CUtensorMap tmOut,  // out [T][Bc][256] bf16 (3D), box 64 cols x 128 rows x 1
               const __nv_bfloat16* __restrict__ whh_f,    // [512][128] rows in perm_T order, forward
               const __nv_bfloat16* __restrict__ whh_r,    // reverse
               float2* __restrict__ stats,                 // STATS: [T*Bc][dir][half] (sum, sum of squares) of h over 64 units
-              int Bc, int T) {
+              int Bc, int T, int dbg) {
   extern __shared__ uint8_t rb_smem_raw[];
   const uint32_t raw = smem_u32(rb_smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
@@ -382,13 +393,24 @@ lstm_rec_bf16(const __grid_constant__ CUtensorMap tmG,    // G viewed as [T*Bc][
 
   if (warp == RB_EPI_WARPS + 1) {
     // ---------------- TMA producer: G_t slabs, runs up to RB_G_SLOTS slabs ahead ----------------
-    if (lane == 0) {
+    if (lane == 0 && !(dbg & 1)) {
+      // The smem ring holds only 4 slabs (64 KB = half a step), less than the DRAM latency-bandwidth product at full
+      // rate, so every slab is first pulled into L2 RB_PF steps ahead (cp.async.bulk.prefetch) and the ring loads
+      // become L2 hits.
+      constexpr int RB_PF = 2;
+      for (int sp = 0; sp < RB_PF && sp < T; ++sp) {
+        const int tpf = dir ? (T - 1 - sp) : sp;
+        for (int sl = 0; sl < 8; ++sl) tma_prefetch_l2_2d(&tmG, dir * 512 + sl * 64, tpf * Bc + b0);
+      }
       uint32_t it = 0;
       for (int s = 0; s < T; ++s) {
         const int t = dir ? (T - 1 - s) : s;
         const int row0 = t * Bc + b0;
+        const int spf = s + RB_PF;
+        const int rowpf = (dir ? (T - 1 - spf) : spf) * Bc + b0;
 #pragma unroll 1
         for (int sl = 0; sl < 8; ++sl, ++it) {
+          if (spf < T) tma_prefetch_l2_2d(&tmG, dir * 512 + sl * 64, rowpf);
           const int slot = it & (RB_G_SLOTS - 1);
           mbar_wait(gempty(slot), ((it / RB_G_SLOTS) & 1u) ^ 1u);
           mbar_arrive_expect_tx(gfull(slot), RB_G_SLOT);
@@ -409,7 +431,7 @@ lstm_rec_bf16(const __grid_constant__ CUtensorMap tmG,    // G viewed as [T*Bc][
 #pragma unroll
           for (int half = 0; half < 2; ++half) {
 #pragma unroll
-            for (int k = 0; k < RB_H / 16; ++k) {
+            for (int k = 0; k < ((dbg & 4) ? 1 : RB_H / 16); ++k) {
               const uint32_t atom = k >> 2, kk = k & 3;
               const uint64_t da = umma_desc_sw128(sH + atom * RB_H_ATOM + kk * 32);
               const uint64_t db = umma_desc_sw128(sW + atom * RB_W_ATOM + half * (256 * 128) + kk * 32);
@@ -418,7 +440,9 @@ lstm_rec_bf16(const __grid_constant__ CUtensorMap tmG,    // G viewed as [T*Bc][
             umma_commit(half == 0 ? bar_half0 : bar_half1);
           }
         }
-        if (s > 0) {
+        if (s > 0 && (dbg & 2)) {
+          mbar_arrive(bar_hfree);
+        } else if (s > 0) {
           // h_{s-1} sits in the A-operand buffer as two [128 x 64] SW128 atoms == two TMA store boxes;
           // the store is issued behind the MMAs (off the critical path) and the epilogue may only
           // overwrite the buffer once the TMA engine has finished reading it (bar_hfree).
@@ -453,35 +477,61 @@ lstm_rec_bf16(const __grid_constant__ CUtensorMap tmG,    // G viewed as [T*Bc][
         tmem_ld32(taddr + sl * 32, acc);
         // G slab: ring slot sl % 4, phase flips every 4 slabs (8 slabs per step => same pattern every step)
         const int slot = sl & (RB_G_SLOTS - 1);
-        mbar_wait(gfull(slot), (uint32_t)((sl / RB_G_SLOTS) & 1));
         uint4 gq[4];
-        const uint8_t* gs = genG + slot * RB_G_SLOT;
+        if (!(dbg & 1)) {
+          mbar_wait(gfull(slot), (uint32_t)((sl / RB_G_SLOTS) & 1));
+          const uint8_t* gs = genG + slot * RB_G_SLOT;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) gq[q] = *reinterpret_cast<const uint4*>(gs + sw128_chunk_off((uint32_t)r, (uint32_t)(half * 4 + q)));
-        __syncwarp();
-        if (lane == 0) mbar_arrive(gempty(slot));
+          for (int q = 0; q < 4; ++q) gq[q] = *reinterpret_cast<const uint4*>(gs + sw128_chunk_off((uint32_t)r, (uint32_t)(half * 4 + q)));
+          __syncwarp();
+          if (lane == 0) mbar_arrive(gempty(slot));
+        } else {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) gq[q] = make_uint4(0x3c003c00u, 0x3c003c00u, 0x3c003c00u, 0x3c003c00u);
+        }
         tmem_ld_wait();
         const uint32_t* gw = reinterpret_cast<const uint32_t*>(gq);  // 16 words = 32 bf16: [gate][unit%8]
         uint32_t hp[4];
 #pragma unroll
         for (int u2 = 0; u2 < 4; ++u2) {
           float hv[2];
+          // bf16 -> fp32: element u of gate g sits in word (g*8+u)/2, low or high half
+          auto gval = [&](int g, int u) {
+            const uint32_t w = gw[(g * 8 + u) >> 1];
+            return __uint_as_float((u & 1) ? (w & 0xFFFF0000u) : (w << 16));
+          };
+          if (F16ACT) {
+            const int u0 = u2 * 2, u1 = u2 * 2 + 1;
+            const __half2 half_h2 = __float2half2_rn(0.5f);
+            const float2 ig = __half22float2(__hfma2(tanh2_f16(__uint_as_float(acc[0 * 8 + u0]) + gval(0, u0),
+                                                               __uint_as_float(acc[0 * 8 + u1]) + gval(0, u1)), half_h2, half_h2));
+            const float2 fg = __half22float2(__hfma2(tanh2_f16(__uint_as_float(acc[1 * 8 + u0]) + gval(1, u0),
+                                                               __uint_as_float(acc[1 * 8 + u1]) + gval(1, u1)), half_h2, half_h2));
+            const float2 gg = __half22float2(tanh2_f16(__uint_as_float(acc[2 * 8 + u0]) + gval(2, u0),
+                                                       __uint_as_float(acc[2 * 8 + u1]) + gval(2, u1)));
+            const float2 og = __half22float2(__hfma2(tanh2_f16(__uint_as_float(acc[3 * 8 + u0]) + gval(3, u0),
+                                                               __uint_as_float(acc[3 * 8 + u1]) + gval(3, u1)), half_h2, half_h2));
+            float& c0 = c[sl * 8 + u0];
+            float& c1 = c[sl * 8 + u1];
+            c0 = fmaf(fg.x, c0, ig.x * gg.x);
+            c1 = fmaf(fg.y, c1, ig.y * gg.y);
+            const float2 tc = __half22float2(tanh2_f16(c0, c1));
+            hv[0] = og.x * tc.x;
+            hv[1] = og.y * tc.y;
+            if (STATS) { ssum += hv[0] + hv[1]; ssq = fmaf(hv[0], hv[0], fmaf(hv[1], hv[1], ssq)); }
+          } else {
 #pragma unroll
-          for (int e = 0; e < 2; ++e) {
-            const int u = u2 * 2 + e;
-            // bf16 -> fp32: element u of gate g sits in word (g*8+u)/2, low or high half
-            auto gval = [&](int g) {
-              const uint32_t w = gw[(g * 8 + u) >> 1];
-              return __uint_as_float((u & 1) ? (w & 0xFFFF0000u) : (w << 16));
-            };
-            const float ig = sigmoid_fast(__uint_as_float(acc[0 * 8 + u]) + gval(0));
-            const float fg = sigmoid_fast(__uint_as_float(acc[1 * 8 + u]) + gval(1));
-            const float gg = tanh_fast(__uint_as_float(acc[2 * 8 + u]) + gval(2));
-            const float og = sigmoid_fast(__uint_as_float(acc[3 * 8 + u]) + gval(3));
-            float& cc = c[sl * 8 + u];
-            cc = fmaf(fg, cc, ig * gg);
-            hv[e] = og * tanh_fast(cc);
-            if (STATS) { ssum += hv[e]; ssq = fmaf(hv[e], hv[e], ssq); }
+            for (int e = 0; e < 2; ++e) {
+              const int u = u2 * 2 + e;
+              const float ig = sigmoid_half_arg(__uint_as_float(acc[0 * 8 + u]) + gval(0, u));
+              const float fg = sigmoid_half_arg(__uint_as_float(acc[1 * 8 + u]) + gval(1, u));
+              const float gg = tanh_fast(__uint_as_float(acc[2 * 8 + u]) + gval(2, u));
+              const float og = sigmoid_half_arg(__uint_as_float(acc[3 * 8 + u]) + gval(3, u));
+              float& cc = c[sl * 8 + u];
+              cc = fmaf(fg, cc, ig * gg);
+              hv[e] = og * tanh_fast(cc);
+              if (STATS) { ssum += hv[e]; ssq = fmaf(hv[e], hv[e], ssq); }
+            }
           }
           __nv_bfloat162 p = __floats2bfloat162_rn(hv[0], hv[1]);
           hp[u2] = *reinterpret_cast<uint32_t*>(&p);
@@ -509,12 +559,30 @@ lstm_rec_bf16(const __grid_constant__ CUtensorMap tmG,    // G viewed as [T*Bc][
   }
 }
 
+// activation variant of the recurrence epilogue: 1 = tanh.approx.f16x2 (two activations per MUFU op), 0 = tanh.approx.f32.
+// Chosen per process by BCI_REC_ACT (default f16x2, see DESIGN.md for the measured accuracy of both).
+static int rec_act_mode() {
+  static int mode = -1;
+  if (mode < 0) {
+    const char* e = getenv("BCI_REC_ACT");
+    mode = (e && e[0] == 'f' && e[1] == '3') ? 0 : 1;  // "f32" -> 0
+  }
+  return mode;
+}
+static int rec_dbg() {  // timing experiments only (results are wrong when set): 1 = no G traffic, 2 = no h TMA store, 4 = no MMA
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("BCI_REC_DBG"); v = e ? atoi(e) : 0; }
+  return v;
+}
+
 int launch_rec_bf16(const __nv_bfloat16* G, const __nv_bfloat16* whh_f, const __nv_bfloat16* whh_r, __nv_bfloat16* out,
                     float2* stats, int Bc, int T, cudaStream_t st) {
   static bool attr = false;
   if (!attr) {
-    BCI_CUDA_OK(cudaFuncSetAttribute(lstm_rec_bf16<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RB_SMEM));
-    BCI_CUDA_OK(cudaFuncSetAttribute(lstm_rec_bf16<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RB_SMEM));
+    BCI_CUDA_OK(cudaFuncSetAttribute(lstm_rec_bf16<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RB_SMEM));
+    BCI_CUDA_OK(cudaFuncSetAttribute(lstm_rec_bf16<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RB_SMEM));
+    BCI_CUDA_OK(cudaFuncSetAttribute(lstm_rec_bf16<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RB_SMEM));
+    BCI_CUDA_OK(cudaFuncSetAttribute(lstm_rec_bf16<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RB_SMEM));
     attr = true;
   }
   CUtensorMap tmG, tmOut;
@@ -523,8 +591,13 @@ int launch_rec_bf16(const __nv_bfloat16* G, const __nv_bfloat16* whh_f, const __
   rc = make_tmap_bf16_3d(&tmOut, out, (uint64_t)T, (uint64_t)Bc, 256, 64, RB_M);
   if (rc) return rc;
   dim3 grid(ceil_div(Bc, RB_M), 2);
-  if (stats) lstm_rec_bf16<true><<<grid, RB_THREADS, RB_SMEM, st>>>(tmG, tmOut, whh_f, whh_r, stats, Bc, T);
-  else lstm_rec_bf16<false><<<grid, RB_THREADS, RB_SMEM, st>>>(tmG, tmOut, whh_f, whh_r, nullptr, Bc, T);
+  if (rec_act_mode()) {
+    if (stats) lstm_rec_bf16<true, true><<<grid, RB_THREADS, RB_SMEM, st>>>(tmG, tmOut, whh_f, whh_r, stats, Bc, T, rec_dbg());
+    else lstm_rec_bf16<false, true><<<grid, RB_THREADS, RB_SMEM, st>>>(tmG, tmOut, whh_f, whh_r, nullptr, Bc, T, rec_dbg());
+  } else {
+    if (stats) lstm_rec_bf16<true, false><<<grid, RB_THREADS, RB_SMEM, st>>>(tmG, tmOut, whh_f, whh_r, stats, Bc, T, rec_dbg());
+    else lstm_rec_bf16<false, false><<<grid, RB_THREADS, RB_SMEM, st>>>(tmG, tmOut, whh_f, whh_r, nullptr, Bc, T, rec_dbg());
+  }
   BCI_LAUNCH_OK();
   return BCI_OK;
 }

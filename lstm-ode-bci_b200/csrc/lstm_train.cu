@@ -354,10 +354,11 @@ attn_train_fwd(const float* __restrict__ pre, const float* __restrict__ y, int B
   }
 }
 
-// backward: from dctx -> dY (context path only), dPRE (in place over pre), dw2, db2
+// backward: from dctx -> dY (context path only), dPRE, dw2, db2.  `pre` is left intact so the same saved forward can be
+// back-propagated repeatedly (07_explainability.py:252 calls backward(retain_graph=True) once per sample).
 template <int H>
 __global__ void __launch_bounds__(256)
-attn_train_bwd(float* __restrict__ pre, const float* __restrict__ y, const float* __restrict__ attn, const float* __restrict__ dctx,
+attn_train_bwd(const float* __restrict__ pre, float* __restrict__ dpre, const float* __restrict__ y, const float* __restrict__ attn, const float* __restrict__ dctx,
                int Bc, int T, const float* __restrict__ w2, float* __restrict__ dY, float* __restrict__ dw2, float* __restrict__ db2) {
   constexpr int D = 2 * H;
   extern __shared__ float ab_smem[];  // [T] da -> ds ; [D] dctx
@@ -399,10 +400,10 @@ attn_train_bwd(float* __restrict__ pre, const float* __restrict__ y, const float
     const float w = w2[j];
     float g = 0.f;
     for (int t = 0; t < T; ++t) {
-      float* pp = pre + ((long long)t * Bc + b) * H + j;
-      const float u = tanhf(*pp);
+      const long long o = ((long long)t * Bc + b) * H + j;
+      const float u = tanhf(pre[o]);
       g = fmaf(ds[t], u, g);
-      *pp = ds[t] * w * (1.0f - u * u);
+      dpre[o] = ds[t] * w * (1.0f - u * u);
     }
     atomicAdd(dw2 + j, g);
   }
@@ -712,12 +713,13 @@ static int backward_t(bci_lstm_s* h, const float* dlogits, int B, int T, float p
   BCI_CUDA_OK(zero(g->attn_w2, H)); BCI_CUDA_OK(zero(g->attn_b2, 1));
   BCI_CUDA_OK(zero(g->attn_w1, (size_t)H * D)); BCI_CUDA_OK(zero(g->attn_b1, H));
   BCI_CUDA_OK(zero(g->ln_w, D)); BCI_CUDA_OK(zero(g->ln_b, D));
-  attn_train_bwd<H><<<B, 256, (T + D) * sizeof(float), st>>>(w.PRE, w.Y, w.attn, w.dctx, B, T, p.aw2, w.dA /*dY*/, g->attn_w2, g->attn_b2);
+  float* dPRE = w.dB;  // [M][H] lives in dB until the LayerNorm backward below overwrites it (no longer needed then)
+  attn_train_bwd<H><<<B, 256, (T + D) * sizeof(float), st>>>(w.PRE, dPRE, w.Y, w.attn, w.dctx, B, T, p.aw2, w.dA /*dY*/, g->attn_w2, g->attn_b2);
   BCI_LAUNCH_OK();
   // dY += dPRE . W1 ; dW1 = dPRE^T Y ; db1 = colsum(dPRE)
-  if ((rc = gemm_nn(w.PRE, H, raw.attn_w1, D, w.dA, D, (int)M, D, H, nullptr, 1, st))) return rc;
-  if ((rc = gemm_tn(w.PRE, H, w.Y, D, g->attn_w1, D, M, H, D, st))) return rc;
-  if ((rc = colsum(w.PRE, H, M, H, g->attn_b1, st))) return rc;
+  if ((rc = gemm_nn(dPRE, H, raw.attn_w1, D, w.dA, D, (int)M, D, H, nullptr, 1, st))) return rc;
+  if ((rc = gemm_tn(dPRE, H, w.Y, D, g->attn_w1, D, M, H, D, st))) return rc;
+  if ((rc = colsum(dPRE, H, M, H, g->attn_b1, st))) return rc;
   // final LayerNorm backward: dA (dY) -> dB (grad wrt the last LSTM layer's output)
   ln_rows_bwd<D><<<rb, 256, 0, st>>>(w.dA, w.xhatF, w.rstdF, p.lnw, M, w.dB, g->ln_w, g->ln_b);
   BCI_LAUNCH_OK();

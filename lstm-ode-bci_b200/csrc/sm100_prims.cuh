@@ -48,6 +48,11 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst_smem, const void* tmap,
       ::"r"(dst_smem), "l"(tmap), "r"(bar), "r"(c0), "r"(c1) : "memory");
 }
 
+// pull a 2D tile into L2 only (no smem destination, no barrier): hides DRAM latency ahead of a shallow smem ring
+__device__ __forceinline__ void tma_prefetch_l2_2d(const void* tmap, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(tmap), "r"(c0), "r"(c1) : "memory");
+}
+
 // smem tile -> global (bulk async group); OOB parts of the box are clipped by the tensor map
 __device__ __forceinline__ void tma_store_2d(const void* tmap, uint32_t src_smem, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"

@@ -89,6 +89,47 @@ class CognitiveStateODE:
                                     f64=True, device=self.device)
         return t, traj[0].cpu().numpy()
 
+    FIT_BOUNDS = [(0.01, 0.5), (0.001, 0.2), (0.02, 0.5), (0.01, 0.3), (0.01, 0.3), (0.02, 0.4)]   # 05:287-294
+
+    def population_loss(self, param_matrix, observed_proportions, time_points, substeps=0):
+        """Objective of fit_to_data (05:259-283) for a whole population at once: param_matrix (6,S) -> (S,) float64.
+        One ODE-ensemble launch integrates all S candidates; MSE + 1e-3 |k|^2 is reduced on the device."""
+        obs = torch.as_tensor(np.asarray(observed_proportions, dtype=np.float64))
+        S = param_matrix.shape[1]
+        dev = _dev(self.device)
+        y0 = obs[0].to(torch.float32).reshape(3, 1).repeat(1, S)
+        rates = torch.as_tensor(np.ascontiguousarray(param_matrix), dtype=torch.float32)
+        traj, _, _ = solve_ensemble(S, rates=rates, y0=y0, y0_mode="given", coupling=False, style="ref06", mode="rk4",
+                                    t_end=float(time_points[-1] - time_points[0]), n_points=len(time_points),
+                                    substeps=substeps, f64=True, device=dev)
+        mse = ((traj - obs.to(dev)[None]) ** 2).mean(dim=(1, 2))
+        reg = 0.001 * (rates.to(dev).double() ** 2).sum(dim=0)
+        return (mse + reg).cpu().numpy()
+
+    def fit_to_data(self, observed_proportions, time_points, method="differential_evolution"):
+        """05:244-322 (SURVEY.md §8 f rank 2).  Same bounds, seed, maxiter, tol, polish and return value; the differential
+        evolution evaluates each generation's population in one GPU launch (scipy `vectorized=True`, deferred updating)
+        instead of one odeint call per candidate, so the optimiser's path differs from the reference's immediate-updating
+        run while converging to the same minimum of the same objective."""
+        from scipy.optimize import differential_evolution, minimize
+        observed = np.asarray(observed_proportions, dtype=np.float64)
+        tp = np.asarray(time_points, dtype=np.float64)
+
+        def pop_loss(x):
+            x = np.asarray(x, dtype=np.float64)
+            return self.population_loss(x.reshape(6, -1), observed, tp) if x.ndim == 2 else \
+                float(self.population_loss(x.reshape(6, 1), observed, tp)[0])
+
+        if method == "differential_evolution":
+            result = differential_evolution(pop_loss, self.FIT_BOUNDS, seed=42, maxiter=1000, tol=1e-7, polish=True,
+                                            vectorized=True, updating="deferred")
+        else:
+            result = minimize(pop_loss, [0.1, 0.02, 0.15, 0.08, 0.05, 0.1], bounds=self.FIT_BOUNDS, method="L-BFGS-B",
+                              options={"maxiter": 1000})
+        fitted = {k: float(result.x[i]) for i, k in enumerate(RATE_ORDER)}
+        self.params = fitted
+        return fitted, float(result.fun)
+
     def get_transition_matrix(self):
         p = self.params
         return np.array([[-(p["k_ap"] + p["k_af"]), p["k_ap"], p["k_af"]],

@@ -52,7 +52,7 @@ class _LstmAttnFn(torch.autograd.Function):
         dl = dlogits.contiguous().float()
         N.check(N.lib().bci_lstm_backward(h.ptr, ops._ptr(ctx.x), ops._ptr(dl), B, T, ops._ptr(dx), C.byref(gs),
                                           ops._ptr(ctx.ws), ctx.nbytes, ops._stream()))
-        ctx.ws = None
+        # the workspace is kept: backward(retain_graph=True) may be called again on the same forward (07:252)
         return (None, dx, None, None, None) + tuple(grads[k] for k in names)
 
 

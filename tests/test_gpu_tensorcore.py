@@ -62,22 +62,26 @@ def test_recurrence_tcgen05_matches_stepwise(Bc, T):
     Gn = torch.randn(T, Bc, 2, 4 * H, device="cuda", generator=g) * 1.5       # natural gate order i,f,g,o
     perm = torch.from_numpy(_perm(H, "T")).cuda()
     perm_g = torch.from_numpy(_perm(H, "G")).cuda()
+    # the kernel expects the 1/2 of sigmoid(x) = 0.5 + 0.5 tanh(x/2) folded into the i,f,o rows / columns
+    gate_scale = torch.ones(4 * H, device="cuda")
+    gate_scale[:2 * H] = 0.5
+    gate_scale[3 * H:] = 0.5
     whh_p = []
     for d in range(2):
         wp = torch.empty_like(whh[d])
-        wp[perm] = whh[d]
+        wp[perm] = whh[d] * gate_scale[:, None]
         whh_p.append(wp.to(torch.bfloat16).contiguous())
     Gp = torch.empty_like(Gn)
-    Gp[:, :, :, perm_g] = Gn
+    Gp[:, :, :, perm_g] = Gn * gate_scale
     Gp = Gp.reshape(T, Bc, 8 * H).to(torch.bfloat16).contiguous()
     out = torch.full((T, Bc, 2 * H), float("nan"), device="cuda", dtype=torch.bfloat16)
     N.check(N.lib().bci_selftest_rec_bf16(_p(Gp), _p(whh_p[0]), _p(whh_p[1]), _p(out), Bc, T, _stream()))
     torch.cuda.synchronize()
     # step-by-step emulation with the same roundings (bf16 G, bf16 weights, bf16 h fed back; fp32 c)
-    Gq = Gp.float().reshape(T, Bc, 2, 4 * H)[:, :, :, perm_g]                 # back to natural order
+    Gq = Gp.float().reshape(T, Bc, 2, 4 * H)[:, :, :, perm_g] / gate_scale   # back to natural order and scale
     want = torch.empty(T, Bc, 2 * H, device="cuda")
     for d in range(2):
-        w = whh[d].to(torch.bfloat16).float()
+        w = (whh[d] * gate_scale[:, None]).to(torch.bfloat16).float() / gate_scale[:, None]
         h = torch.zeros(Bc, H, device="cuda")
         c = torch.zeros(Bc, H, device="cuda")
         for s in range(T):
