@@ -114,9 +114,9 @@ int lstm_pack_bf16(bci_lstm_s* h, cudaStream_t st) {
 // lts throughput 72 %, tensor pipe 26 %).
 // ---------------------------------------------------------------------------------------------
 constexpr int GB_BM = 128, GB_BN = 256, GB_BK = 64, GB_MAX_STAGES = 8, GB_MAX_K = 256;
-constexpr int GB_THREADS = 192;  // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-5: epilogue
+constexpr int GB_THREADS = 320;  // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-9: epilogue (2 groups of 4)
 constexpr uint32_t GB_A_BYTES = GB_BM * GB_BK * 2, GB_B_ATOM = GB_BN * GB_BK * 2;
-constexpr uint32_t GB_C_BYTES = GB_BM * 128 * 2;  // staging for half a C tile: two [128][64] bf16 SW128 atoms
+constexpr uint32_t GB_C_BYTES = GB_BM * 128 * 2;  // C staging: one [128][64] bf16 SW128 atom per epilogue group
 // smem: [W block: k_blocks x 32 KB][A ring: stages x 16 KB][C staging 32 KB][bias 1 KB][barriers]
 static inline int gb_stages(int K) { return K <= 128 ? 8 : 4; }
 static inline size_t gb_smem(int K) {
@@ -153,7 +153,7 @@ proj_gemm_bf16(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     tma_prefetch_desc(&tmB);
     tma_prefetch_desc(&tmC);
     for (int s = 0; s < GB_STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 128); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 256); }
     mbar_init(bfull_bar, 1);
     fence_mbar_init();
   }
@@ -162,9 +162,8 @@ proj_gemm_bf16(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     tmem_relinquish();
   }
   if (warp >= 2) {
-    const int et = (warp - 2) * 32 + lane;
+    const int et = (warp - 2) * 32 + lane;  // 0..255
     bias_s[et] = __ldg(bias + n0 + et);
-    bias_s[et + 128] = __ldg(bias + n0 + 128 + et);
   }
   tc_fence_before();
   __syncthreads();
@@ -211,54 +210,54 @@ proj_gemm_bf16(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
   } else {
-    // epilogue: 4 warps, warp w owns TMEM lane quarter (w % 4).  Each half tile (128 x 128) is converted
-    // to bf16 into a swizzled smem staging buffer and written with two TMA stores (full 128-byte lines);
-    // per-lane 16-byte global stores to 32 different rows cost 32 L1 wavefronts per instruction.
+    // epilogue: 8 warps = 2 groups of 4; warp w owns TMEM lane quarter (w % 4), group g owns columns [128 g, 128 g + 128)
+    // of the tile and its own 16 KB staging atom.  Each 64-column pass is converted to bf16 into the swizzled staging
+    // atom and written with one TMA store (full 128-byte lines); per-lane 16-byte global stores to 32 different rows
+    // would cost 32 L1 wavefronts per instruction.
     const int quarter = warp & 3;
+    const int grp = (warp - 2) >> 2;
     const int rt = quarter * 32 + lane;  // row inside the tile
-    const bool issuer = (warp == 2 && lane == 0);
+    const bool issuer = (((warp - 2) & 3) == 0 && lane == 0);
+    uint8_t* cst = genC + grp * (GB_BM * 128);
+    const uint32_t cst_s = sC + grp * (GB_BM * 128);
     int acc = 0; uint32_t acc_phase = 0;
     for (int mb = m_first; mb < m_blocks; mb += m_step) {
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)acc * GB_BN;
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)acc * GB_BN + grp * 128;
       uint32_t r[2][32];
       tmem_ld32(taddr, r[0]);
 #pragma unroll
-      for (int ch = 0; ch < GB_BN / 32; ++ch) {
-        if ((ch & 3) == 0) {
-          // staging buffer must have been drained by the previous half's TMA stores
+      for (int ch = 0; ch < 4; ++ch) {
+        if ((ch & 1) == 0) {
+          // the group's staging atom must have been drained by its previous TMA store
           if (issuer) tma_store_wait_read();
-          asm volatile("bar.sync 1, 128;" ::: "memory");
+          asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
         }
         tmem_ld_wait();
-        if (ch + 1 < GB_BN / 32) tmem_ld32(taddr + (ch + 1) * 32, r[(ch + 1) & 1]);  // next slab in flight
+        if (ch + 1 < 4) tmem_ld32(taddr + (ch + 1) * 32, r[(ch + 1) & 1]);  // next slab in flight
         const uint32_t* rc = r[ch & 1];
         uint32_t o[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
-          const float v0 = __uint_as_float(rc[2 * j]) + bias_s[ch * 32 + 2 * j];
-          const float v1 = __uint_as_float(rc[2 * j + 1]) + bias_s[ch * 32 + 2 * j + 1];
+          const float v0 = __uint_as_float(rc[2 * j]) + bias_s[grp * 128 + ch * 32 + 2 * j];
+          const float v1 = __uint_as_float(rc[2 * j + 1]) + bias_s[grp * 128 + ch * 32 + 2 * j + 1];
           __nv_bfloat162 p = __floats2bfloat162_rn(v0, v1);
           o[j] = *reinterpret_cast<uint32_t*>(&p);
         }
-        // 32 columns = 4 chunks of 16 B; atom (ch>>1)&1 of the half tile, chunk (ch&1)*4+q of row rt
-        uint8_t* catom = genC + ((ch >> 1) & 1) * (GB_BM * 128);
 #pragma unroll
         for (int q = 0; q < 4; ++q)
-          *reinterpret_cast<uint4*>(catom + sw128_chunk_off((uint32_t)rt, (uint32_t)((ch & 1) * 4 + q))) =
+          *reinterpret_cast<uint4*>(cst + sw128_chunk_off((uint32_t)rt, (uint32_t)((ch & 1) * 4 + q))) =
               make_uint4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
-        if ((ch & 3) == 3) {
-          if (ch == GB_BN / 32 - 1) {  // all TMEM reads of this accumulator are done
+        if ((ch & 1) == 1) {
+          if (ch == 3) {  // all TMEM reads of this accumulator (by this thread) are done
             tc_fence_before();
             mbar_arrive(tempty_bar(acc));
           }
           fence_proxy_async_smem();
-          asm volatile("bar.sync 1, 128;" ::: "memory");
+          asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
           if (issuer) {
-            const int c0 = n0 + (ch >> 2) * 128;
-            tma_store_2d(&tmC, sC, c0, mb * GB_BM);
-            tma_store_2d(&tmC, sC + GB_BM * 128, c0 + 64, mb * GB_BM);
+            tma_store_2d(&tmC, cst_s, n0 + grp * 128 + (ch >> 1) * 64, mb * GB_BM);
             tma_store_commit();
           }
         }
@@ -394,23 +393,12 @@ lstm_rec_bf16(const __grid_constant__ CUtensorMap tmG,    // G viewed as [T*Bc][
   if (warp == RB_EPI_WARPS + 1) {
     // ---------------- TMA producer: G_t slabs, runs up to RB_G_SLOTS slabs ahead ----------------
     if (lane == 0 && !(dbg & 1)) {
-      // The smem ring holds only 4 slabs (64 KB = half a step), less than the DRAM latency-bandwidth product at full
-      // rate, so every slab is first pulled into L2 RB_PF steps ahead (cp.async.bulk.prefetch) and the ring loads
-      // become L2 hits.
-      constexpr int RB_PF = 2;
-      for (int sp = 0; sp < RB_PF && sp < T; ++sp) {
-        const int tpf = dir ? (T - 1 - sp) : sp;
-        for (int sl = 0; sl < 8; ++sl) tma_prefetch_l2_2d(&tmG, dir * 512 + sl * 64, tpf * Bc + b0);
-      }
       uint32_t it = 0;
       for (int s = 0; s < T; ++s) {
         const int t = dir ? (T - 1 - s) : s;
         const int row0 = t * Bc + b0;
-        const int spf = s + RB_PF;
-        const int rowpf = (dir ? (T - 1 - spf) : spf) * Bc + b0;
 #pragma unroll 1
         for (int sl = 0; sl < 8; ++sl, ++it) {
-          if (spf < T) tma_prefetch_l2_2d(&tmG, dir * 512 + sl * 64, rowpf);
           const int slot = it & (RB_G_SLOTS - 1);
           mbar_wait(gempty(slot), ((it / RB_G_SLOTS) & 1u) ^ 1u);
           mbar_arrive_expect_tx(gfull(slot), RB_G_SLOT);
@@ -559,13 +547,14 @@ lstm_rec_bf16(const __grid_constant__ CUtensorMap tmG,    // G viewed as [T*Bc][
   }
 }
 
-// activation variant of the recurrence epilogue: 1 = tanh.approx.f16x2 (two activations per MUFU op), 0 = tanh.approx.f32.
-// Chosen per process by BCI_REC_ACT (default f16x2, see DESIGN.md for the measured accuracy of both).
+// activation variant of the recurrence epilogue: 0 = tanh.approx.f32 (default), 1 = tanh.approx.f16x2 (BCI_REC_ACT=f16).
+// The packed form was tried to halve the MUFU load, but ptxas splits it into two MUFU.TANH.F16 (same MUFU count, measured
+// no faster, slightly less accurate) -- kept only as an experiment switch.
 static int rec_act_mode() {
   static int mode = -1;
   if (mode < 0) {
     const char* e = getenv("BCI_REC_ACT");
-    mode = (e && e[0] == 'f' && e[1] == '3') ? 0 : 1;  // "f32" -> 0
+    mode = (e && e[0] == 'f' && e[1] == '1') ? 1 : 0;  // "f16" -> 1; default tanh.approx.f32
   }
   return mode;
 }

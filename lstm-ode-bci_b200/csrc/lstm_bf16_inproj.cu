@@ -39,12 +39,25 @@ int pack_inproj_bf16(bci_lstm_s* h, cudaStream_t st) {
   return BCI_OK;
 }
 
-constexpr int IP_M = 128, IP_N = 128, IP_K = 64, IP_THREADS = 320;
+constexpr int IP_M = 128, IP_N = 128, IP_K = 64, IP_THREADS = 448;  // producer, MMA, 4 converter warps, 8 epilogue warps
 constexpr uint32_t IP_A_BYTES = IP_M * 128;       // 16 KB, one SW128 atom
 constexpr uint32_t IP_B_BYTES = IP_N * 128;       // 16 KB
 constexpr uint32_t IP_OUT_BYTES = 2 * IP_M * 128; // two [128][64] bf16 atoms
 constexpr uint32_t IP_RAW_MAX = IP_M * 64 * 4;    // 32 KB per raw buffer (C <= 64)
-constexpr size_t IP_SMEM = 1024 + 2 * IP_RAW_MAX + 2 * IP_A_BYTES + IP_B_BYTES + IP_OUT_BYTES + IP_N * sizeof(float4) + 256;
+constexpr size_t IP_SMEM = 1024 + 2 * IP_RAW_MAX + 2 * IP_A_BYTES + IP_B_BYTES + IP_OUT_BYTES + IP_N * sizeof(float4) + 2 * IP_M * sizeof(float2) + 256;
+
+// erf-GELU with a branch-free erf (Abramowitz-Stegun 7.1.26, |err| <= 1.5e-7 -- four orders below the bf16 rounding of
+// the output): 2 MUFU (rcp, ex2) + ~10 FMA instead of erff's divergent ~30-instruction paths.
+__device__ __forceinline__ float gelu_erf_fast(float y) {
+  const float x = fabsf(y) * 0.70710678118654752440f;
+  const float t = __fdividef(1.0f, fmaf(0.3275911f, x, 1.0f));
+  float p = fmaf(1.061405429f, t, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  const float e = 1.0f - p * t * exp2f(-1.4426950408889634f * x * x);  // erf(|y|/sqrt2)
+  return 0.5f * y * (1.0f + copysignf(e, y));
+}
 
 __device__ __forceinline__ void bulk_copy_g2s(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -67,7 +80,8 @@ input_proj_bf16(const float* __restrict__ x,              // (Bc,T,C) fp32
   uint8_t* genO = gen + 2 * IP_A_BYTES + IP_B_BYTES;
   const float* genR = reinterpret_cast<const float*>(genO + IP_OUT_BYTES);
   float4* par_s = reinterpret_cast<float4*>(gen + 2 * IP_A_BYTES + IP_B_BYTES + IP_OUT_BYTES + 2 * IP_RAW_MAX);
-  uint8_t* ctl = reinterpret_cast<uint8_t*>(par_s + IP_N);
+  float2* part_s = reinterpret_cast<float2*>(par_s + IP_N);  // [2 column halves][128 rows] partial (sum, sumsq)
+  uint8_t* ctl = reinterpret_cast<uint8_t*>(part_s + 2 * IP_M);
   const uint32_t bar0 = smem_u32(ctl);
   auto raw_full = [&](int i) { return bar0 + 8u * i; };
   auto raw_empty = [&](int i) { return bar0 + 8u * (2 + i); };
@@ -89,7 +103,7 @@ input_proj_bf16(const float* __restrict__ x,              // (Bc,T,C) fp32
     for (int i = 0; i < 2; ++i) {
       mbar_init(raw_full(i), 1); mbar_init(raw_empty(i), 128);
       mbar_init(a_full(i), 128); mbar_init(a_empty(i), 1);
-      mbar_init(t_full(i), 1);   mbar_init(t_empty(i), 128);
+      mbar_init(t_full(i), 1);   mbar_init(t_empty(i), 256);
     }
     mbar_init(b_full, 1);
     fence_mbar_init();
@@ -98,7 +112,7 @@ input_proj_bf16(const float* __restrict__ x,              // (Bc,T,C) fp32
     tmem_alloc(smem_u32(tmem_slot), 256);
     tmem_relinquish();
   }
-  if (warp >= 6) par_s[(warp - 6) * 32 + lane] = __ldg(par + (warp - 6) * 32 + lane);
+  if (warp >= 6 && warp < 10) par_s[(warp - 6) * 32 + lane] = __ldg(par + (warp - 6) * 32 + lane);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -166,63 +180,63 @@ input_proj_bf16(const float* __restrict__ x,              // (Bc,T,C) fp32
       mbar_arrive(raw_empty(s));
     }
   } else {
-    // ---------------- epilogue: bias + LayerNorm + GELU, one thread per row ----------------
-    const int quarter = warp & 3;           // warps 6..9 -> quarters 2,3,0,1
+    // ---------------- epilogue: bias + LayerNorm + GELU; 8 warps, two threads per row (column halves) ----------------
+    const int quarter = warp & 3;            // TMEM lane quarter of this warp
+    const int grp = (warp - 6) >> 2;         // column half: columns [64 grp, 64 grp + 64) == staging atom grp
     const int r = quarter * 32 + lane;
-    const bool issuer = (warp == 6 && lane == 0);
+    const bool issuer = (((warp - 6) & 3) == 0 && lane == 0);
+    uint8_t* oatom = genO + grp * (IP_M * 128);
     int it = 0;
     for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
       const int s = it & 1;
       mbar_wait(t_full(s), (it >> 1) & 1u);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)s * IP_N;
-      // pass 1: row mean / variance of v = acc + b0
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)s * IP_N + grp * 64;
+      // the row's 64 accumulator columns of this half stay in registers for both passes
+      uint32_t a[2][32];
+      tmem_ld32(taddr, a[0]);
+      tmem_ld32(taddr + 32, a[1]);
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(t_empty(s));               // TMEM accumulator free again
       float sum = 0.f, sq = 0.f;
-      uint32_t a[32];
 #pragma unroll
-      for (int ch = 0; ch < 4; ++ch) {
-        tmem_ld32(taddr + ch * 32, a);
-        tmem_ld_wait();
+      for (int ch = 0; ch < 2; ++ch)
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
-          const float v = __uint_as_float(a[j]) + par_s[ch * 32 + j].x;
+          const float v = __uint_as_float(a[ch][j]) + par_s[grp * 64 + ch * 32 + j].x;
+          a[ch][j] = __float_as_uint(v);
           sum += v;
           sq = fmaf(v, v, sq);
         }
-      }
-      const float mean = sum * (1.0f / IP_N);
-      const float rstd = 1.0f / sqrtf(fmaxf(sq * (1.0f / IP_N) - mean * mean, 0.f) + 1e-5f);
-      // staging buffer free? (previous tile's TMA stores have finished reading it)
+      part_s[grp * IP_M + r] = make_float2(sum, sq);
+      // staging atom free? (this group's previous TMA store has finished reading it)
       if (issuer) tma_store_wait_read();
-      asm volatile("bar.sync 2, 128;" ::: "memory");
-      // pass 2: normalise, GELU, pack to bf16 into the swizzled staging tile
+      asm volatile("bar.sync 2, 256;" ::: "memory");   // partial sums of both halves visible; staging free
+      const float2 other = part_s[(grp ^ 1) * IP_M + r];
+      const float mean = (sum + other.x) * (1.0f / IP_N);
+      const float rstd = 1.0f / sqrtf(fmaxf((sq + other.y) * (1.0f / IP_N) - mean * mean, 0.f) + 1e-5f);
 #pragma unroll
-      for (int ch = 0; ch < 4; ++ch) {
-        tmem_ld32(taddr + ch * 32, a);
-        tmem_ld_wait();
+      for (int ch = 0; ch < 2; ++ch) {
         uint32_t o[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
-          const float4 p0 = par_s[ch * 32 + 2 * j], p1 = par_s[ch * 32 + 2 * j + 1];
-          const float y0 = fmaf((__uint_as_float(a[2 * j]) + p0.x - mean) * rstd, p0.y, p0.z);
-          const float y1 = fmaf((__uint_as_float(a[2 * j + 1]) + p1.x - mean) * rstd, p1.y, p1.z);
-          __nv_bfloat162 pk = __floats2bfloat162_rn(gelu_erf(y0), gelu_erf(y1));
+          const float4 p0 = par_s[grp * 64 + ch * 32 + 2 * j], p1 = par_s[grp * 64 + ch * 32 + 2 * j + 1];
+          const float y0 = fmaf((__uint_as_float(a[ch][2 * j]) - mean) * rstd, p0.y, p0.z);
+          const float y1 = fmaf((__uint_as_float(a[ch][2 * j + 1]) - mean) * rstd, p1.y, p1.z);
+          __nv_bfloat162 pk = __floats2bfloat162_rn(gelu_erf_fast(y0), gelu_erf_fast(y1));
           o[j] = *reinterpret_cast<uint32_t*>(&pk);
         }
-        uint8_t* oatom = genO + (ch >> 1) * (IP_M * 128);
 #pragma unroll
         for (int q = 0; q < 4; ++q)
-          *reinterpret_cast<uint4*>(oatom + sw128_chunk_off((uint32_t)r, (uint32_t)((ch & 1) * 4 + q))) =
+          *reinterpret_cast<uint4*>(oatom + sw128_chunk_off((uint32_t)r, (uint32_t)(ch * 4 + q))) =
               make_uint4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
       }
-      tc_fence_before();
-      mbar_arrive(t_empty(s));
       fence_proxy_async_smem();
-      asm volatile("bar.sync 2, 128;" ::: "memory");
+      asm volatile("bar.sync 2, 256;" ::: "memory");   // both atoms written (also protects part_s for the next tile)
       if (issuer) {
         const int b = tile / tiles_per_win, t0 = (tile - b * tiles_per_win) * IP_M;
-        tma_store_3d(&tmZ, sO, 0, b, t0);
-        tma_store_3d(&tmZ, sO + IP_M * 128, 64, b, t0);
+        tma_store_3d(&tmZ, sO + grp * (IP_M * 128), grp * 64, b, t0);
         tma_store_commit();
       }
     }
