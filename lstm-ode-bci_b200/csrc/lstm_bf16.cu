@@ -602,7 +602,7 @@ static size_t chunk_bytes_bf16(const bci_lstm_config& c, int Bc, int T) {
 
 size_t lstm_workspace_bf16(const bci_lstm_config& c, int batch, int T) {
   const int Bc = batch < max_chunk(c, 0) ? batch : max_chunk(c, 0);
-  return chunk_bytes_bf16(c, Bc > 0 ? Bc : 1, T);
+  return chunk_bytes_bf16(c, Bc > 0 ? Bc : 1, T) + 1024;  // + slack: the TMA-addressed buffers are aligned to 1 KB internally
 }
 
 static int forward_chunk_bf16(bci_lstm_s* h, const float* x, int Bc, int T, float* logits, float* probs, float* attn, char* ws,
@@ -644,15 +644,15 @@ int lstm_forward_bf16(bci_lstm_s* h, const float* x, int batch, int T, float* lo
                       size_t ws_bytes, cudaStream_t st) {
   const bci_lstm_config& c = h->cfg;
   BCI_REQUIRE(c.hidden_size == 128, BCI_EINVAL, "bf16 mode supports hidden_size=128 only");
-  BCI_REQUIRE(((uintptr_t)ws & 1023) == 0, BCI_EINVAL, "bci_lstm_forward: workspace must be 1024-byte aligned");
   const int chunk = batch < max_chunk(c, 0) ? batch : max_chunk(c, 0);
-  BCI_REQUIRE(ws_bytes >= chunk_bytes_bf16(c, chunk, T), BCI_ENOMEM, "bci_lstm_forward: workspace %zu < %zu bytes", ws_bytes,
-              chunk_bytes_bf16(c, chunk, T));
+  char* ws_al = reinterpret_cast<char*>(((uintptr_t)ws + 1023) & ~(uintptr_t)1023);
+  BCI_REQUIRE(ws_bytes >= chunk_bytes_bf16(c, chunk, T) + (size_t)(ws_al - (char*)ws), BCI_ENOMEM,
+              "bci_lstm_forward: workspace %zu < %zu bytes", ws_bytes, chunk_bytes_bf16(c, chunk, T) + 1024);
   for (int b0 = 0; b0 < batch; b0 += chunk) {
     const int Bc = (batch - b0) < chunk ? (batch - b0) : chunk;
     int rc = forward_chunk_bf16(h, x + (size_t)b0 * T * c.input_size, Bc, T, logits + (size_t)b0 * c.num_classes,
                                 probs ? probs + (size_t)b0 * c.num_classes : nullptr, attn ? attn + (size_t)b0 * T : nullptr,
-                                (char*)ws, st);
+                                ws_al, st);
     if (rc) return rc;
   }
   return BCI_OK;

@@ -178,7 +178,7 @@ class LSTMODEIntegration:
         pred, _ = ops.ode_classify(final, True, False)
         return traj.double().cpu().numpy(), probs.cpu().numpy(), pred.cpu().numpy().astype(np.int64)
 
-    def predict_batch_device(self, X_dev, forecast_steps=20, batch_size=4096, want_traj=True):
+    def predict_batch_device(self, X_dev, forecast_steps=20, batch_size=9472, want_traj=True):
         """Same computation with every tensor left on the device (used by the sharded pipeline)."""
         probs, _ = _lstm_probs_device(self.lstm_model, X_dev, batch_size, False, self.device)
         n = probs.shape[0]

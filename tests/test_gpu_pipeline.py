@@ -43,3 +43,24 @@ def test_patch_reference_swaps_by_name():
     done = patch.patch_reference(fake)
     assert fake.EnhancedLSTMModel is lstm.EnhancedLSTMModel and fake.CognitiveStateODE is ode.CognitiveStateODE
     assert fake.predict_trajectory is integration.predict_trajectory and "multistep_forecast" in done
+
+
+def test_config5_pipeline_single_rank_matches_unsharded_mirrors():
+    """Config 5 (08-style forecast after 06-style coupling) through parallel.forecast_pipeline_sharded on one rank ==
+    the plain mirrors run back to back."""
+    from lstm_ode_bci_b200 import parallel
+    params = synth.make_lstm_params(3, 61, 128, 3, logit_gain=20.0)
+    x = synth.make_windows(5, 70, 128, 61, structured=True)
+    m = lstm.from_params(params, precision="fp32")
+    integ = integration.LSTMODEIntegration(m, ode.CognitiveStateODE(), coupling_strength=0.5)
+    xd = torch.from_numpy(x).cuda()
+    res = parallel.forecast_pipeline_sharded(integ, xd, len(x), horizons=(5, 10, 20))
+    traj, probs, preds = integ.predict_batch(x, forecast_steps=20, batch_size=32, show_progress=False)
+    assert np.abs(res["probs"].cpu().numpy() - probs).max() <= 1e-6
+    assert np.abs(res["traj"].cpu().numpy() - traj).max() <= 1e-6
+    fc = integration.multistep_forecast(probs, integ.base_params, horizons=[5, 10, 20])
+    got = res["forecast"].cpu().numpy()
+    b, e = res["forecast_range"]
+    assert (b, e) == (0, len(x) - 20)
+    for j, h in enumerate((5, 10, 20)):
+        assert np.abs(got[:, j] - fc[h]["predictions"]).max() <= 1e-6
