@@ -211,7 +211,8 @@ int bci_fp32_peak_probe(double* tflops, void* stream);
  * Diagnostics: the two tensor-core kernels of the bf16 path, callable in isolation so the GPU unit
  * tests can check each against a plain matmul / a step-by-step recurrence.
  *   proj_gemm: C[M][N] (bf16) = A[M][K] (bf16) . W[N][K]^T (bf16) + bias[N] (fp32);  N % 256 == 0, K % 64 == 0
- *   rec:       G [T][Bc][1024] bf16, column dir*512 + perm_G(unit,gate) (bias included);
+ *   rec:       G bf16 in the blocked streaming layout [row/128][dir*64 + perm_G/8][row%128][perm_G%8], row = t*Bc + b,
+ *              padded to whole 128-row blocks (bias included, i/f/o pre-activations pre-scaled by 1/2);
  *              whh_* [512][128] bf16 with rows in perm_T(unit,gate) order -> out [T][Bc][256] bf16, where for
  *              unit = half*64 + slab*8 + u:  perm_T = half*256 + slab*32 + gate*8 + u,
  *                                            perm_G = slab*64 + half*32 + gate*8 + u

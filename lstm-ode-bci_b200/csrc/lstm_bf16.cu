@@ -123,9 +123,16 @@ static inline size_t gb_smem(int K) {
   return 1024 + (size_t)(K / GB_BK) * GB_B_ATOM + (size_t)gb_stages(K) * GB_A_BYTES + GB_C_BYTES + GB_BN * sizeof(float) + 256;
 }
 
+// BLOCKED = false: C row-major [M][N] through a tensor map.
+// BLOCKED = true : C in the recurrence's streaming layout  [m_block = row/128][n/8 (16-byte chunk)][row%128][8 bf16]
+//                  (N = 1024: 256 KB per m_block).  A 64-column pass of the epilogue is then 8 chunks x 2 KB = one contiguous
+//                  16 KB block: staged as [chunk][row] (conflict-free 16-byte stores) and written with one 1-D bulk store;
+//                  the recurrence reads it back with fully coalesced 16-byte loads (lane = row).
+template <bool BLOCKED>
 __global__ void __launch_bounds__(GB_THREADS, 1)
 proj_gemm_bf16(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-               const __grid_constant__ CUtensorMap tmC, const float* __restrict__ bias, int M, int N, int K, int GB_STAGES) {
+               const __grid_constant__ CUtensorMap tmC, __nv_bfloat16* __restrict__ Cblk, const float* __restrict__ bias, int M,
+               int N, int K, int GB_STAGES) {
   extern __shared__ uint8_t gb_smem_raw[];
   const uint32_t raw = smem_u32(gb_smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
@@ -246,9 +253,11 @@ proj_gemm_bf16(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           o[j] = *reinterpret_cast<uint32_t*>(&p);
         }
 #pragma unroll
-        for (int q = 0; q < 4; ++q)
-          *reinterpret_cast<uint4*>(cst + sw128_chunk_off((uint32_t)rt, (uint32_t)((ch & 1) * 4 + q))) =
-              make_uint4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
+        for (int q = 0; q < 4; ++q) {
+          const uint32_t cidx = (uint32_t)((ch & 1) * 4 + q);  // 16-byte chunk inside the 64-column pass
+          uint8_t* dstp = BLOCKED ? cst + cidx * 2048u + (uint32_t)rt * 16u : cst + sw128_chunk_off((uint32_t)rt, cidx);
+          *reinterpret_cast<uint4*>(dstp) = make_uint4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
+        }
         if ((ch & 1) == 1) {
           if (ch == 3) {  // all TMEM reads of this accumulator (by this thread) are done
             tc_fence_before();
@@ -257,7 +266,9 @@ proj_gemm_bf16(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           fence_proxy_async_smem();
           asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
           if (issuer) {
-            tma_store_2d(&tmC, cst_s, n0 + grp * 128 + (ch >> 1) * 64, mb * GB_BM);
+            const int col = n0 + grp * 128 + (ch >> 1) * 64;
+            if (BLOCKED) bulk_store_s2g(Cblk + ((size_t)mb * N + (size_t)col) * GB_BM, cst_s, 16384u);
+            else tma_store_2d(&tmC, cst_s, col, mb * GB_BM);
             tma_store_commit();
           }
         }
@@ -275,9 +286,10 @@ proj_gemm_bf16(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 }
 
 int launch_proj_gemm_bf16(const __nv_bfloat16* A, const __nv_bfloat16* W, const float* bias, __nv_bfloat16* C, int M, int N,
-                          int K, cudaStream_t st) {
+                          int K, bool blocked, cudaStream_t st) {
   CUtensorMap tmC;
   {
+    // (for the blocked layout the map is unused; encode a valid one over the same buffer anyway)
     int rc0 = make_tmap_bf16(&tmC, C, (uint64_t)M, (uint64_t)N, 64, GB_BM);
     if (rc0) return rc0;
   }
@@ -290,24 +302,30 @@ int launch_proj_gemm_bf16(const __nv_bfloat16* A, const __nv_bfloat16* W, const 
   if (rc) return rc;
   static bool attr = false;
   if (!attr) {
-    BCI_CUDA_OK(cudaFuncSetAttribute(proj_gemm_bf16, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gb_smem(GB_MAX_K)));
+    BCI_CUDA_OK(cudaFuncSetAttribute(proj_gemm_bf16<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gb_smem(GB_MAX_K)));
+    BCI_CUDA_OK(cudaFuncSetAttribute(proj_gemm_bf16<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gb_smem(GB_MAX_K)));
     attr = true;
   }
   const int n_blocks = N / GB_BN, m_blocks = ceil_div(M, GB_BM);
   int per_n = sm_count() / n_blocks;
   if (per_n > m_blocks) per_n = m_blocks;
   const int grid = per_n * n_blocks;
-  proj_gemm_bf16<<<grid, GB_THREADS, gb_smem(K), st>>>(tmA, tmB, tmC, bias, M, N, K, gb_stages(K));
+  if (blocked) proj_gemm_bf16<true><<<grid, GB_THREADS, gb_smem(K), st>>>(tmA, tmB, tmC, C, bias, M, N, K, gb_stages(K));
+  else proj_gemm_bf16<false><<<grid, GB_THREADS, gb_smem(K), st>>>(tmA, tmB, tmC, C, bias, M, N, K, gb_stages(K));
   BCI_LAUNCH_OK();
   return BCI_OK;
 }
 
 // ---------------------------------------------------------------------------------------------
 // K3: persistent tcgen05 recurrence (H = 128)
-// warps 0-7: epilogue (thread = window row x half of the hidden units); warp 8: MMA issuer + TMEM
-// owner; warp 9: TMA producer streaming G_t through a 4-slot smem ring (one slot = slab `sl` of both
-// halves for the 128 rows = 16 KB, SWIZZLE_128B).  The first version loaded G with per-thread LDGs
-// one slab ahead and spent 62 % of its stall samples on long-scoreboard waits (ncu, profiles/).
+// warps 0-7: epilogue (thread = window row x half of the hidden units); warp 8: MMA issuer + TMEM owner + TMA stores of
+// h_t; warp 9: L2 prefetcher for the next step's G block.
+// G arrives in the blocked streaming layout written by proj_gemm_bf16<true>: for a fixed 16-byte chunk (8 units of one
+// gate) the 128 rows of an m-block are contiguous, so the per-thread loads of a warp (lane = row) coalesce into 512-byte
+// requests.  History (profiles/): v1 per-thread loads from row-major G: 62 % long-scoreboard stalls (32 L1 wavefronts
+// per load); v2 G through a 4-slot TMA smem ring: smem bandwidth became the limiter (MMA operands 192 KB + G 256 KB + h
+// 64 KB per step against 128 B/clk); v3 (this): no G traffic through smem, h double-buffered so the TMA store of h_{t-1}
+// never delays the epilogue of step t.
 // ---------------------------------------------------------------------------------------------
 constexpr int RB_H = 128, RB_M = 128, RB_N = 4 * RB_H;  // 512 gate columns per direction
 constexpr int RB_EPI_WARPS = 8, RB_THREADS = (RB_EPI_WARPS + 2) * 32;
@@ -315,9 +333,7 @@ constexpr uint32_t RB_W_BYTES = RB_N * RB_H * 2;   // 131072: two K-atoms of [51
 constexpr uint32_t RB_W_ATOM = RB_N * 128;         // 65536
 constexpr uint32_t RB_H_BYTES = RB_M * RB_H * 2;   // 32768: two K-atoms of [128][64]
 constexpr uint32_t RB_H_ATOM = RB_M * 128;         // 16384
-constexpr int RB_G_SLOTS = 4;
-constexpr uint32_t RB_G_SLOT = RB_M * 128;         // 16384: [128 rows][64 bf16]
-constexpr size_t RB_SMEM = 1024 + RB_W_BYTES + RB_H_BYTES + RB_G_SLOTS * RB_G_SLOT + 128;
+constexpr size_t RB_SMEM = 1024 + RB_W_BYTES + 2 * RB_H_BYTES + 128;
 
 __device__ __forceinline__ float tanh_fast(float x) {
   float y;
@@ -336,7 +352,7 @@ __device__ __forceinline__ __half2 tanh2_f16(float a, float b) {
 
 template <bool STATS, bool F16ACT>
 __global__ void __launch_bounds__(RB_THREADS, 1)
-lstm_rec_bf16(const __grid_constant__ CUtensorMap tmG,    // G viewed as [T*Bc][1024] bf16, box 64 cols x 128 rows
+lstm_rec_bf16(const __nv_bfloat16* __restrict__ G,        // blocked: [row/128][dir*64 + chunk][row%128][8], bias included
               const __grid_constant__ CUtensorMap tmOut,  // out [T][Bc][256] bf16 (3D), box 64 cols x 128 rows x 1
               const __nv_bfloat16* __restrict__ whh_f,    // [512][128] rows in perm_T order, forward
               const __nv_bfloat16* __restrict__ whh_r,    // reverse
@@ -346,38 +362,32 @@ lstm_rec_bf16(const __grid_constant__ CUtensorMap tmG,    // G viewed as [T*Bc][
   const uint32_t raw = smem_u32(rb_smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t* gen = rb_smem_raw + (base - raw);
-  const uint32_t sW = base, sH = base + RB_W_BYTES, sG = sH + RB_H_BYTES;
+  const uint32_t sW = base, sH = base + RB_W_BYTES;       // sH: two h buffers of RB_H_BYTES
   uint8_t* genW = gen;
   uint8_t* genH = gen + RB_W_BYTES;
-  uint8_t* genG = genH + RB_H_BYTES;
-  uint8_t* ctl = genG + RB_G_SLOTS * RB_G_SLOT;
-  const uint32_t bar_half0 = smem_u32(ctl), bar_half1 = bar_half0 + 8, bar_h = bar_half0 + 16;
-  auto gfull = [&](int i) { return bar_half0 + 24u + 8u * i; };
-  auto gempty = [&](int i) { return bar_half0 + 24u + 8u * (RB_G_SLOTS + i); };
-  const uint32_t bar_hfree = bar_half0 + 24u + 16u * RB_G_SLOTS;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ctl + 32 + 16 * RB_G_SLOTS);
+  uint8_t* ctl = genH + 2 * RB_H_BYTES;
+  const uint32_t bar_half0 = smem_u32(ctl), bar_half1 = bar_half0 + 8, bar_h = bar_half0 + 16, bar_hfree = bar_half0 + 24;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ctl + 32);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int dir = blockIdx.y;
   const int b0 = blockIdx.x * RB_M;
 
-  // stage W_hh into the SW128 K-major UMMA layout; zero h_{-1}
+  // stage W_hh into the SW128 K-major UMMA layout; zero both h buffers (h_{-1} = 0 lives in buffer 1)
   {
     const uint4* src = reinterpret_cast<const uint4*>(dir ? whh_r : whh_f);  // 16 chunks of 16 B per row
     for (int q = tid; q < RB_N * 16; q += RB_THREADS) {
       const uint32_t row = q >> 4, cc = q & 15, atom = cc >> 3, c = cc & 7;
       *reinterpret_cast<uint4*>(genW + atom * RB_W_ATOM + sw128_chunk_off(row, c)) = __ldg(src + q);
     }
-    for (int q = tid; q < (int)(RB_H_BYTES / 16); q += RB_THREADS) reinterpret_cast<uint4*>(genH)[q] = make_uint4(0, 0, 0, 0);
+    for (int q = tid; q < (int)(2 * RB_H_BYTES / 16); q += RB_THREADS) reinterpret_cast<uint4*>(genH)[q] = make_uint4(0, 0, 0, 0);
   }
   if (tid == 0) {
     mbar_init(bar_half0, 1);
     mbar_init(bar_half1, 1);
     mbar_init(bar_h, RB_EPI_WARPS * 32);
-    for (int i = 0; i < RB_G_SLOTS; ++i) { mbar_init(gfull(i), 1); mbar_init(gempty(i), RB_EPI_WARPS); }
     mbar_init(bar_hfree, 1);
     fence_mbar_init();
-    tma_prefetch_desc(&tmG);
     tma_prefetch_desc(&tmOut);
   }
   if (warp == RB_EPI_WARPS) {
@@ -390,20 +400,24 @@ lstm_rec_bf16(const __grid_constant__ CUtensorMap tmG,    // G viewed as [T*Bc][
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  // byte address of chunk 0 of (row, dir) in the blocked G layout
+  auto g_row_ptr = [&](long long row) {
+    return reinterpret_cast<const uint8_t*>(G) + (((row >> 7) * 2 + dir) * 64) * 2048ll + (row & 127) * 16ll;
+  };
+
   if (warp == RB_EPI_WARPS + 1) {
-    // ---------------- TMA producer: G_t slabs, runs up to RB_G_SLOTS slabs ahead ----------------
-    if (lane == 0 && !(dbg & 1)) {
-      uint32_t it = 0;
+    // ---------------- L2 prefetcher: the G block of the NEXT step (128 rows x 512 columns = 128 KB per direction) ----------------
+    if (!(dbg & 1)) {
       for (int s = 0; s < T; ++s) {
-        const int t = dir ? (T - 1 - s) : s;
-        const int row0 = t * Bc + b0;
-#pragma unroll 1
-        for (int sl = 0; sl < 8; ++sl, ++it) {
-          const int slot = it & (RB_G_SLOTS - 1);
-          mbar_wait(gempty(slot), ((it / RB_G_SLOTS) & 1u) ^ 1u);
-          mbar_arrive_expect_tx(gfull(slot), RB_G_SLOT);
-          tma_load_2d(sG + slot * RB_G_SLOT, &tmG, dir * 512 + sl * 64, row0, gfull(slot));
-        }
+        const int sn = s + 1;
+        if (sn >= T) break;
+        const long long row0 = (long long)(dir ? (T - 1 - sn) : sn) * Bc + b0;
+        // the tile's rows live in one m-block when Bc % 128 == 0, else in two consecutive ones
+        const uint8_t* blk0 = reinterpret_cast<const uint8_t*>(G) + (((row0 >> 7) * 2 + dir) * 64) * 2048ll;
+        if (lane < 8) bulk_prefetch_l2(blk0 + lane * 16384, 16384u);
+        if ((row0 & 127) != 0 && lane >= 8 && lane < 16) bulk_prefetch_l2(blk0 + 2 * 64 * 2048ll + (lane - 8) * 16384, 16384u);
+        // pace: one step of prefetch per step of compute (bar_h completes once per step)
+        mbar_wait(bar_h, (uint32_t)(s & 1));
       }
     }
   } else if (warp == RB_EPI_WARPS) {
@@ -415,30 +429,31 @@ lstm_rec_bf16(const __grid_constant__ CUtensorMap tmG,    // G viewed as [T*Bc][
           mbar_wait(bar_h, (uint32_t)((s - 1) & 1));  // h_{s-1} written, TMEM drained
           tc_fence_after();
         }
+        const uint32_t hprev = sH + (uint32_t)((s + 1) & 1) * RB_H_BYTES;  // h_{s-1} lives in buffer (s-1)&1
         if (s < T) {
 #pragma unroll
           for (int half = 0; half < 2; ++half) {
 #pragma unroll
             for (int k = 0; k < ((dbg & 4) ? 1 : RB_H / 16); ++k) {
               const uint32_t atom = k >> 2, kk = k & 3;
-              const uint64_t da = umma_desc_sw128(sH + atom * RB_H_ATOM + kk * 32);
+              const uint64_t da = umma_desc_sw128(hprev + atom * RB_H_ATOM + kk * 32);
               const uint64_t db = umma_desc_sw128(sW + atom * RB_W_ATOM + half * (256 * 128) + kk * 32);
               umma_bf16(tmem_base + half * 256, da, db, idesc, k != 0 ? 1u : 0u);
             }
             umma_commit(half == 0 ? bar_half0 : bar_half1);
           }
         }
-        if (s > 0 && (dbg & 2)) {
-          mbar_arrive(bar_hfree);
-        } else if (s > 0) {
-          // h_{s-1} sits in the A-operand buffer as two [128 x 64] SW128 atoms == two TMA store boxes;
-          // the store is issued behind the MMAs (off the critical path) and the epilogue may only
-          // overwrite the buffer once the TMA engine has finished reading it (bar_hfree).
-          const int tp = dir ? (T - s) : (s - 1);
-          tma_store_3d(&tmOut, sH, dir * 128, b0, tp);
-          tma_store_3d(&tmOut, sH + RB_H_ATOM, dir * 128 + 64, b0, tp);
-          tma_store_commit();
-          tma_store_wait_read();
+        if (s > 0) {
+          // h_{s-1} sits in its operand buffer as two [128 x 64] SW128 atoms == two TMA store boxes.  The other buffer
+          // (being written by the epilogue of step s) was last read by the store issued one iteration ago: allow one
+          // store group in flight and release that buffer.
+          if (!(dbg & 2)) {
+            const int tp = dir ? (T - s) : (s - 1);
+            tma_store_3d(&tmOut, hprev, dir * 128, b0, tp);
+            tma_store_3d(&tmOut, hprev + RB_H_ATOM, dir * 128 + 64, b0, tp);
+            tma_store_commit();
+            asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+          }
           mbar_arrive(bar_hfree);
         }
       }
@@ -448,14 +463,31 @@ lstm_rec_bf16(const __grid_constant__ CUtensorMap tmG,    // G viewed as [T*Bc][
     // ---------------- epilogue: thread = (window row, half of the hidden units) ----------------
     const int quarter = warp & 3, half = warp >> 2;
     const int r = quarter * 32 + lane;  // window row inside the tile == TMEM lane
+    const bool live = b0 + r < Bc;
     const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)half * 256;
     const uint32_t my_bar = half == 0 ? bar_half0 : bar_half1;
     float c[64];
 #pragma unroll
     for (int i = 0; i < 64; ++i) c[i] = 0.f;
-    uint8_t* hrow = genH + half * RB_H_ATOM;  // units [64*half, 64*half+64) live in K-atom `half`
 
     for (int s = 0; s < T; ++s) {
+      const int t = dir ? (T - 1 - s) : s;
+      // chunk (sl*8 + half*4 + gate) of this thread's row: gates i,f,g,o of units 64*half + 8*sl .. +7
+      const uint8_t* gp = g_row_ptr((long long)t * Bc + (live ? b0 + r : b0)) + (half * 4) * 2048;
+      // G slabs are loaded two slabs ahead (gbuf[sl % 3]); slabs 0 and 1 are issued before waiting on the MMA
+      uint4 gbuf[3][4];
+      if (!(dbg & 1)) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) gbuf[0][q] = ldg_stream_v4(gp + q * 2048);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) gbuf[1][q] = ldg_stream_v4(gp + (8 + q) * 2048);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+          for (int q = 0; q < 4; ++q) gbuf[i][q] = make_uint4(0x3c003c00u, 0x3c003c00u, 0x3c003c00u, 0x3c003c00u);
+      }
+      uint8_t* hrow = genH + (uint32_t)(s & 1) * RB_H_BYTES + half * RB_H_ATOM;  // h_s -> buffer s&1, K-atom `half`
       mbar_wait(my_bar, (uint32_t)(s & 1));
       tc_fence_after();
       float ssum = 0.f, ssq = 0.f;
@@ -463,29 +495,19 @@ lstm_rec_bf16(const __grid_constant__ CUtensorMap tmG,    // G viewed as [T*Bc][
       for (int sl = 0; sl < 8; ++sl) {  // fully unrolled: c[] must stay in registers
         uint32_t acc[32];
         tmem_ld32(taddr + sl * 32, acc);
-        // G slab: ring slot sl % 4, phase flips every 4 slabs (8 slabs per step => same pattern every step)
-        const int slot = sl & (RB_G_SLOTS - 1);
-        uint4 gq[4];
-        if (!(dbg & 1)) {
-          mbar_wait(gfull(slot), (uint32_t)((sl / RB_G_SLOTS) & 1));
-          const uint8_t* gs = genG + slot * RB_G_SLOT;
+        if (sl < 6 && !(dbg & 1)) {
 #pragma unroll
-          for (int q = 0; q < 4; ++q) gq[q] = *reinterpret_cast<const uint4*>(gs + sw128_chunk_off((uint32_t)r, (uint32_t)(half * 4 + q)));
-          __syncwarp();
-          if (lane == 0) mbar_arrive(gempty(slot));
-        } else {
-#pragma unroll
-          for (int q = 0; q < 4; ++q) gq[q] = make_uint4(0x3c003c00u, 0x3c003c00u, 0x3c003c00u, 0x3c003c00u);
+          for (int q = 0; q < 4; ++q) gbuf[(sl + 2) % 3][q] = ldg_stream_v4(gp + ((sl + 2) * 8 + q) * 2048);
         }
         tmem_ld_wait();
-        const uint32_t* gw = reinterpret_cast<const uint32_t*>(gq);  // 16 words = 32 bf16: [gate][unit%8]
+        // gbuf[sl % 3][g] = 8 bf16 of gate g (units u = 0..7): element u sits in word u/2, low or high half
+        const uint32_t* gw = reinterpret_cast<const uint32_t*>(gbuf[sl % 3]);
         uint32_t hp[4];
 #pragma unroll
         for (int u2 = 0; u2 < 4; ++u2) {
           float hv[2];
-          // bf16 -> fp32: element u of gate g sits in word (g*8+u)/2, low or high half
           auto gval = [&](int g, int u) {
-            const uint32_t w = gw[(g * 8 + u) >> 1];
+            const uint32_t w = gw[g * 4 + (u >> 1)];
             return __uint_as_float((u & 1) ? (w & 0xFFFF0000u) : (w << 16));
           };
           if (F16ACT) {
@@ -525,7 +547,8 @@ lstm_rec_bf16(const __grid_constant__ CUtensorMap tmG,    // G viewed as [T*Bc][
           hp[u2] = *reinterpret_cast<uint32_t*>(&p);
         }
         const uint4 hvec = make_uint4(hp[0], hp[1], hp[2], hp[3]);
-        if (sl == 0 && s > 0) mbar_wait(bar_hfree, (uint32_t)((s - 1) & 1));  // TMA store of h_{s-1} has drained the buffer
+        // buffer s&1 was last read by the TMA store of h_{s-2}; the MMA thread's arrival of iteration s certifies it is done
+        if (sl == 0 && s > 0) mbar_wait(bar_hfree, (uint32_t)((s - 1) & 1));
         // units 64*half + 8*sl .. +7  ->  chunk sl of row r in K-atom `half`
         *reinterpret_cast<uint4*>(hrow + sw128_chunk_off((uint32_t)r, (uint32_t)sl)) = hvec;
       }
@@ -534,8 +557,7 @@ lstm_rec_bf16(const __grid_constant__ CUtensorMap tmG,    // G viewed as [T*Bc][
       mbar_arrive(bar_h);
       if (STATS) {
         // partial LayerNorm statistics of the last layer's output row (consumed by attn_score_bf16 / attn_pool_finish)
-        const int t = dir ? (T - 1 - s) : s;
-        if (b0 + r < Bc) stats[((long long)t * Bc + b0 + r) * 4 + dir * 2 + half] = make_float2(ssum, ssq);
+        if (live) stats[((long long)t * Bc + b0 + r) * 4 + dir * 2 + half] = make_float2(ssum, ssq);
       }
     }
   }
@@ -574,18 +596,16 @@ int launch_rec_bf16(const __nv_bfloat16* G, const __nv_bfloat16* whh_f, const __
     BCI_CUDA_OK(cudaFuncSetAttribute(lstm_rec_bf16<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RB_SMEM));
     attr = true;
   }
-  CUtensorMap tmG, tmOut;
-  int rc = make_tmap_bf16(&tmG, G, (uint64_t)T * (uint64_t)Bc, 1024, 64, RB_M);
-  if (rc) return rc;
-  rc = make_tmap_bf16_3d(&tmOut, out, (uint64_t)T, (uint64_t)Bc, 256, 64, RB_M);
+  CUtensorMap tmOut;
+  int rc = make_tmap_bf16_3d(&tmOut, out, (uint64_t)T, (uint64_t)Bc, 256, 64, RB_M);
   if (rc) return rc;
   dim3 grid(ceil_div(Bc, RB_M), 2);
   if (rec_act_mode()) {
-    if (stats) lstm_rec_bf16<true, true><<<grid, RB_THREADS, RB_SMEM, st>>>(tmG, tmOut, whh_f, whh_r, stats, Bc, T, rec_dbg());
-    else lstm_rec_bf16<false, true><<<grid, RB_THREADS, RB_SMEM, st>>>(tmG, tmOut, whh_f, whh_r, nullptr, Bc, T, rec_dbg());
+    if (stats) lstm_rec_bf16<true, true><<<grid, RB_THREADS, RB_SMEM, st>>>(G, tmOut, whh_f, whh_r, stats, Bc, T, rec_dbg());
+    else lstm_rec_bf16<false, true><<<grid, RB_THREADS, RB_SMEM, st>>>(G, tmOut, whh_f, whh_r, nullptr, Bc, T, rec_dbg());
   } else {
-    if (stats) lstm_rec_bf16<true, false><<<grid, RB_THREADS, RB_SMEM, st>>>(tmG, tmOut, whh_f, whh_r, stats, Bc, T, rec_dbg());
-    else lstm_rec_bf16<false, false><<<grid, RB_THREADS, RB_SMEM, st>>>(tmG, tmOut, whh_f, whh_r, nullptr, Bc, T, rec_dbg());
+    if (stats) lstm_rec_bf16<true, false><<<grid, RB_THREADS, RB_SMEM, st>>>(G, tmOut, whh_f, whh_r, stats, Bc, T, rec_dbg());
+    else lstm_rec_bf16<false, false><<<grid, RB_THREADS, RB_SMEM, st>>>(G, tmOut, whh_f, whh_r, nullptr, Bc, T, rec_dbg());
   }
   BCI_LAUNCH_OK();
   return BCI_OK;
@@ -596,7 +616,8 @@ int launch_rec_bf16(const __nv_bfloat16* G, const __nv_bfloat16* whh_f, const __
 // ---------------------------------------------------------------------------------------------
 static size_t chunk_bytes_bf16(const bci_lstm_config& c, int Bc, int T) {
   const size_t H = c.hidden_size, rows = (size_t)Bc * T;
-  return align_up(rows * H * 2, 1024) + align_up(rows * 8 * H * 2, 1024) + 2 * align_up(rows * 2 * H * 2, 1024) +
+  const size_t rows_pad = (rows + 127) / 128 * 128;  // G is stored in whole 128-row blocks
+  return align_up(rows * H * 2, 1024) + align_up(rows_pad * 8 * H * 2, 1024) + 2 * align_up(rows * 2 * H * 2, 1024) +
          align_up(rows * 4, 1024) + align_up(rows * 4 * sizeof(float2), 1024);
 }
 
@@ -613,7 +634,7 @@ static int forward_chunk_bf16(bci_lstm_s* h, const float* x, int Bc, int T, floa
   size_t off = 0;
   auto take = [&](size_t bytes) { char* p = ws + off; off += align_up(bytes, 1024); return p; };
   __nv_bfloat16* z = reinterpret_cast<__nv_bfloat16*>(take(rows * H * 2));
-  __nv_bfloat16* g = reinterpret_cast<__nv_bfloat16*>(take(rows * 8 * H * 2));
+  __nv_bfloat16* g = reinterpret_cast<__nv_bfloat16*>(take((rows + 127) / 128 * 128 * 8 * H * 2));
   __nv_bfloat16* o0 = reinterpret_cast<__nv_bfloat16*>(take(rows * 2 * H * 2));
   __nv_bfloat16* o1 = reinterpret_cast<__nv_bfloat16*>(take(rows * 2 * H * 2));
   float* scores = reinterpret_cast<float*>(take(rows * 4));
@@ -626,7 +647,7 @@ static int forward_chunk_bf16(bci_lstm_s* h, const float* x, int Bc, int T, floa
   const __nv_bfloat16* in = z;
   __nv_bfloat16* outs[2] = {o0, o1};
   for (int l = 0; l < c.num_layers; ++l) {
-    rc = launch_proj_gemm_bf16(in, h->bf16.wih_bf[l], h->bf16.bias_p[l], g, (int)rows, 8 * H, layer_in_width(c, l), st);
+    rc = launch_proj_gemm_bf16(in, h->bf16.wih_bf[l], h->bf16.bias_p[l], g, (int)rows, 8 * H, layer_in_width(c, l), true, st);
     if (rc) return rc;
     h->prof.mark(1, st);
     __nv_bfloat16* o = outs[l & 1];
@@ -663,7 +684,7 @@ int lstm_forward_bf16(bci_lstm_s* h, const float* x, int batch, int T, float* lo
 // ---- diagnostics exported for the GPU unit tests (tests/test_gpu_tensorcore.py) ---------------------
 extern "C" int bci_selftest_proj_gemm_bf16(const void* A, const void* W, const float* bias, void* C, int32_t M, int32_t N,
                                            int32_t K, void* stream) {
-  return bci::launch_proj_gemm_bf16((const __nv_bfloat16*)A, (const __nv_bfloat16*)W, bias, (__nv_bfloat16*)C, M, N, K,
+  return bci::launch_proj_gemm_bf16((const __nv_bfloat16*)A, (const __nv_bfloat16*)W, bias, (__nv_bfloat16*)C, M, N, K, false,
                                     (cudaStream_t)stream);
 }
 extern "C" int bci_selftest_rec_bf16(const void* G, const void* whh_f, const void* whh_r, void* out, int32_t Bc, int32_t T,

@@ -74,8 +74,14 @@ def test_recurrence_tcgen05_matches_stepwise(Bc, T):
     Gp = torch.empty_like(Gn)
     Gp[:, :, :, perm_g] = Gn * gate_scale
     Gp = Gp.reshape(T, Bc, 8 * H).to(torch.bfloat16).contiguous()
+    # blocked streaming layout expected by the kernel: [row/128][dir*64 + chunk][row%128][8]
+    M = T * Bc
+    Mp = (M + 127) // 128 * 128
+    flat = torch.zeros(Mp, 8 * H, device="cuda", dtype=torch.bfloat16)
+    flat[:M] = Gp.reshape(M, 8 * H)
+    Gblk = flat.reshape(Mp // 128, 128, 128, 8).permute(0, 2, 1, 3).contiguous()
     out = torch.full((T, Bc, 2 * H), float("nan"), device="cuda", dtype=torch.bfloat16)
-    N.check(N.lib().bci_selftest_rec_bf16(_p(Gp), _p(whh_p[0]), _p(whh_p[1]), _p(out), Bc, T, _stream()))
+    N.check(N.lib().bci_selftest_rec_bf16(_p(Gblk), _p(whh_p[0]), _p(whh_p[1]), _p(out), Bc, T, _stream()))
     torch.cuda.synchronize()
     # step-by-step emulation with the same roundings (bf16 G, bf16 weights, bf16 h fed back; fp32 c)
     Gq = Gp.float().reshape(T, Bc, 2, 4 * H)[:, :, :, perm_g] / gate_scale   # back to natural order and scale
