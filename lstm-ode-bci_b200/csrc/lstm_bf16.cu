@@ -350,6 +350,8 @@ __device__ __forceinline__ __half2 tanh2_f16(float a, float b) {
   return *reinterpret_cast<__half2*>(&yi);
 }
 
+// 10 warps put 3 on one SM sub-partition (16 K registers each): 3 x 32 x 168 is the per-thread ceiling, hence the few
+// spilled words ptxas reports; 200 registers per thread compile but do not launch.
 template <bool STATS, bool F16ACT>
 __global__ void __launch_bounds__(RB_THREADS, 1)
 lstm_rec_bf16(const __nv_bfloat16* __restrict__ G,        // blocked: [row/128][dir*64 + chunk][row%128][8], bias included
