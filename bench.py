@@ -29,6 +29,12 @@ ODE_SUBSTEPS = 8
 ODE_FLOP_PER_TRAJ = 12 + 19 * ODE_SUBSTEPS * 123 + 20 * 11      # SURVEY.md §8 d: 18 928 at S=8
 
 
+def load_traffic():
+    """ncu-measured DRAM bytes per launch (profiles/r1_traffic.json); None if the file is absent."""
+    p = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    return json.load(open(p)) if os.path.exists(p) else None
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -271,6 +277,11 @@ def main():
             "whole_path": {"achieved": value / world * FLOP_PER_WINDOW / 1e12, "unit": "TFLOP/s per GPU",
                            "frac_of_bf16_burst": value / world * FLOP_PER_WINDOW / 1e12 / peaks["bf16_tflops"],
                            "frac_of_bf16_sustained": value / world * FLOP_PER_WINDOW / 1e12 / peaks["bf16_tflops_sustained"]}}
+    traffic = load_traffic()
+    if traffic and args.precision == "bf16" and dom in traffic and (B % traffic["windows_per_launch"] == 0):
+        roof["traffic"] = traffic[dom]["bytes_per_launch"]
+        roof["traffic_unit"] = "bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum, %d-window launch); algorithmic %d" % (
+            traffic["windows_per_launch"], traffic[dom]["algorithmic_bytes_per_launch"])
     if args.precision == "fp32":
         fp32_peak = ops.fp32_peak_probe()
         roof.update({"bound": "fp32", "peak": fp32_peak, "frac": achieved / fp32_peak,
@@ -311,6 +322,7 @@ def main():
                                     "roofline": {"bound": "fp32", "achieved": n * ODE_FLOP_PER_TRAJ / (t_traj * 1e-3) / 1e12,
                                                  "peak": fp32_peak, "unit": "TFLOP/s",
                                                  "frac": n * ODE_FLOP_PER_TRAJ / (t_traj * 1e-3) / 1e12 / fp32_peak,
+                                                 "traffic": (traffic or {}).get("ode_rk4", {}).get("bytes_per_launch") if n == 1 << 24 else None,
                                                  "hbm_gbs": bytes_traj / (t_traj * 1e-3) / 1e9,
                                                  "hbm_frac": bytes_traj / (t_traj * 1e-3) / 1e9 / peaks["hbm_gbs"]}},
             "rk4_final_state_only": {"value": world * n / (t_final * 1e-3), "ms": t_final,

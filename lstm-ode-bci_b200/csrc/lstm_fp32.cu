@@ -19,7 +19,7 @@ constexpr int GM = 128, GN = 128, GK = 16, GEMM_THREADS = 256;
 
 __global__ void __launch_bounds__(GEMM_THREADS)
 proj_gemm_f32(const float* __restrict__ A, const float* __restrict__ Bt, const float* __restrict__ bias,
-              float* __restrict__ C, int M, int N, int K) {
+              float* __restrict__ C, int M, int N, int K, int accumulate) {
   __shared__ __align__(16) float As[2][GK][GM + 4];
   __shared__ __align__(16) float Bs[2][GK][GN];
   const int tid = threadIdx.x;
@@ -78,16 +78,18 @@ proj_gemm_f32(const float* __restrict__ A, const float* __restrict__ Bt, const f
     }
   }
   // epilogue: rows {ty*4+i, 64+ty*4+i}, cols {tx*4.., 64+tx*4..}
-  const float4 bia0 = *reinterpret_cast<const float4*>(bias + n0 + tx * 4);
-  const float4 bia1 = *reinterpret_cast<const float4*>(bias + n0 + 64 + tx * 4);
+  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  const float4 bia0 = bias ? *reinterpret_cast<const float4*>(bias + n0 + tx * 4) : zero4;
+  const float4 bia1 = bias ? *reinterpret_cast<const float4*>(bias + n0 + 64 + tx * 4) : zero4;
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const int m = m0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
     if (m < M) {
-      float4 o0 = make_float4(acc[i][0] + bia0.x, acc[i][1] + bia0.y, acc[i][2] + bia0.z, acc[i][3] + bia0.w);
-      float4 o1 = make_float4(acc[i][4] + bia1.x, acc[i][5] + bia1.y, acc[i][6] + bia1.z, acc[i][7] + bia1.w);
-      *reinterpret_cast<float4*>(C + (long long)m * N + n0 + tx * 4) = o0;
-      *reinterpret_cast<float4*>(C + (long long)m * N + n0 + 64 + tx * 4) = o1;
+      float4* c0 = reinterpret_cast<float4*>(C + (long long)m * N + n0 + tx * 4);
+      float4* c1 = reinterpret_cast<float4*>(C + (long long)m * N + n0 + 64 + tx * 4);
+      const float4 p0 = accumulate ? *c0 : zero4, p1 = accumulate ? *c1 : zero4;
+      *c0 = make_float4(acc[i][0] + bia0.x + p0.x, acc[i][1] + bia0.y + p0.y, acc[i][2] + bia0.z + p0.z, acc[i][3] + bia0.w + p0.w);
+      *c1 = make_float4(acc[i][4] + bia1.x + p1.x, acc[i][5] + bia1.y + p1.y, acc[i][6] + bia1.z + p1.z, acc[i][7] + bia1.w + p1.w);
     }
   }
 }
@@ -99,9 +101,9 @@ proj_gemm_f32(const float* __restrict__ A, const float* __restrict__ Bt, const f
 // the cell state stays in registers for the whole sequence.
 // ---------------------------------------------------------------------------------------------
 constexpr int REC_THREADS = 256;
-constexpr int REC_WPT = 16;  // windows per thread
+constexpr int REC_WPT = 16;  // windows per thread (inference tiles); small training batches use 8 to fill more SMs
 
-template <int H>
+template <int H, int REC_WPT = 16>
 __global__ void __launch_bounds__(REC_THREADS, 2)
 lstm_rec_f32(const float* __restrict__ G,      // [T][Bc][2][H][4]
              const float* __restrict__ whh_f,  // [H][H][4] forward direction
@@ -178,22 +180,26 @@ lstm_rec_f32(const float* __restrict__ G,      // [T][Bc][2][H][4]
   }
 }
 
-int launch_proj_gemm_f32(const float* A, const float* Bt, const float* bias, float* C, int M, int N, int K, cudaStream_t st) {
+int launch_proj_gemm_f32(const float* A, const float* Bt, const float* bias, float* C, int M, int N, int K, cudaStream_t st,
+                         int accumulate) {
   BCI_REQUIRE(N % GN == 0 && K % GK == 0, BCI_EINVAL, "proj_gemm_f32: N %% 128 and K %% 16 required (N=%d K=%d)", N, K);
   dim3 gg(N / GN, ceil_div(M, GM));
-  proj_gemm_f32<<<gg, GEMM_THREADS, 0, st>>>(A, Bt, bias, C, M, N, K);
+  proj_gemm_f32<<<gg, GEMM_THREADS, 0, st>>>(A, Bt, bias, C, M, N, K, accumulate);
   BCI_LAUNCH_OK();
   return BCI_OK;
 }
 
 int launch_rec_f32(int H, const float* G, const float* whh_f, const float* whh_r, float* out, float* gates, float* csave, int Bc,
                    int T, cudaStream_t st) {
+  // tiles of 16 windows per thread unless that leaves most SMs idle (training batches): then 8
+  const int groups = REC_THREADS / H;
+  const bool small = 2 * ceil_div(Bc, groups * 16) < sm_count();
   if (H == 128) {
-    constexpr int MT = (REC_THREADS / 128) * REC_WPT;
-    lstm_rec_f32<128><<<dim3(ceil_div(Bc, MT), 2), REC_THREADS, 0, st>>>(G, whh_f, whh_r, out, gates, csave, Bc, T);
+    if (small) lstm_rec_f32<128, 8><<<dim3(ceil_div(Bc, 2 * 8), 2), REC_THREADS, 0, st>>>(G, whh_f, whh_r, out, gates, csave, Bc, T);
+    else lstm_rec_f32<128, 16><<<dim3(ceil_div(Bc, 2 * 16), 2), REC_THREADS, 0, st>>>(G, whh_f, whh_r, out, gates, csave, Bc, T);
   } else {
-    constexpr int MT = (REC_THREADS / 256) * REC_WPT;
-    lstm_rec_f32<256><<<dim3(ceil_div(Bc, MT), 2), REC_THREADS, 0, st>>>(G, whh_f, whh_r, out, gates, csave, Bc, T);
+    if (small) lstm_rec_f32<256, 8><<<dim3(ceil_div(Bc, 8), 2), REC_THREADS, 0, st>>>(G, whh_f, whh_r, out, gates, csave, Bc, T);
+    else lstm_rec_f32<256, 16><<<dim3(ceil_div(Bc, 16), 2), REC_THREADS, 0, st>>>(G, whh_f, whh_r, out, gates, csave, Bc, T);
   }
   BCI_LAUNCH_OK();
   return BCI_OK;
@@ -343,12 +349,12 @@ static int forward_chunk_f32(bci_lstm_s* h, const float* x, int Bc, int T, float
     const int K = layer_in_width(c, l);
     const int M = (int)rows, N = 8 * H;
     dim3 gg(N / GN, ceil_div(M, GM));
-    proj_gemm_f32<<<gg, GEMM_THREADS, 0, st>>>(in, h->f32.wih_t[l], h->f32.bias[l], g, M, N, K);
+    proj_gemm_f32<<<gg, GEMM_THREADS, 0, st>>>(in, h->f32.wih_t[l], h->f32.bias[l], g, M, N, K, 0);
     BCI_LAUNCH_OK();
     h->prof.mark(1, st);
     float* o = outs[l & 1];
     dim3 gr(ceil_div(Bc, MT), 2);
-    lstm_rec_f32<H><<<gr, REC_THREADS, 0, st>>>(g, h->f32.whh_t[l][0], h->f32.whh_t[l][1], o, nullptr, nullptr, Bc, T);
+    lstm_rec_f32<H, REC_WPT><<<gr, REC_THREADS, 0, st>>>(g, h->f32.whh_t[l][0], h->f32.whh_t[l][1], o, nullptr, nullptr, Bc, T);
     BCI_LAUNCH_OK();
     h->prof.mark(2, st);
     in = o;

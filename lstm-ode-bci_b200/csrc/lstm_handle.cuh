@@ -109,7 +109,8 @@ struct FwdWorkspace {
 int lstm_forward_fp32(bci_lstm_s* h, const float* x, int batch, int T, float* logits, float* probs, float* attn,
                       void* ws, size_t ws_bytes, cudaStream_t st);
 size_t lstm_workspace_fp32(const bci_lstm_config& c, int batch, int T);
-int launch_proj_gemm_f32(const float* A, const float* Bt, const float* bias, float* C, int M, int N, int K, cudaStream_t st);
+int launch_proj_gemm_f32(const float* A, const float* Bt, const float* bias, float* C, int M, int N, int K, cudaStream_t st,
+                         int accumulate = 0);
 int launch_rec_f32(int H, const float* G, const float* whh_f, const float* whh_r, float* out, float* gates, float* csave, int Bc,
                    int T, cudaStream_t st);
 // bf16 / tcgen05 forward (lstm_bf16.cu)

@@ -118,6 +118,77 @@ gemm_tn_f32(const float* __restrict__ A, int lda, const float* __restrict__ B, i
     }
 }
 
+// Fast path of the same contraction for P % 128 == 0, Q % 128 == 0, lda/ldb % 4 == 0: 128x128x16 tiles, 8x8 per thread,
+// 16-byte loads (both operands are row-major in the reduction index, so tiles go to smem without a transpose).
+__global__ void __launch_bounds__(256)
+gemm_tn_f32_fast(const float* __restrict__ A, int lda, const float* __restrict__ B, int ldb, float* __restrict__ C, int ldc, long long R) {
+  __shared__ __align__(16) float As[2][16][128];
+  __shared__ __align__(16) float Bs[2][16][128];
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int p0 = blockIdx.y * 128, q0 = blockIdx.x * 128;
+  const long long per = ((R + gridDim.z - 1) / gridDim.z + 15) / 16 * 16;
+  const long long r_begin = per * blockIdx.z, r_end = (r_begin + per < R) ? r_begin + per : R;
+  if (r_begin >= r_end) return;
+  const int lr = tid >> 5, lc = (tid & 31) * 4;  // rows lr, lr+8 of the 16-row slab; 4 consecutive columns
+  float4 ra[2], rb[2];
+  auto load = [&](long long r0) {
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const long long r = r0 + lr + i * 8;
+      const bool ok = r < r_end;
+      ra[i] = ok ? *reinterpret_cast<const float4*>(A + r * lda + p0 + lc) : make_float4(0.f, 0.f, 0.f, 0.f);
+      rb[i] = ok ? *reinterpret_cast<const float4*>(B + r * ldb + q0 + lc) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  };
+  auto store = [&](int buf) {
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      *reinterpret_cast<float4*>(&As[buf][lr + i * 8][lc]) = ra[i];
+      *reinterpret_cast<float4*>(&Bs[buf][lr + i * 8][lc]) = rb[i];
+    }
+  };
+  float acc[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+  load(r_begin);
+  store(0);
+  __syncthreads();
+  int buf = 0;
+  for (long long r0 = r_begin; r0 < r_end; r0 += 16) {
+    const bool more = r0 + 16 < r_end;
+    if (more) load(r0 + 16);
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      const float4 a0 = *reinterpret_cast<const float4*>(&As[buf][k][ty * 4]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&As[buf][k][64 + ty * 4]);
+      const float4 b0 = *reinterpret_cast<const float4*>(&Bs[buf][k][tx * 4]);
+      const float4 b1 = *reinterpret_cast<const float4*>(&Bs[buf][k][64 + tx * 4]);
+      const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    if (more) {
+      store(buf ^ 1);
+      __syncthreads();
+      buf ^= 1;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int p = p0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int q = q0 + (j < 4 ? tx * 4 + j : 64 + tx * 4 + (j - 4));
+      atomicAdd(C + (long long)p * ldc + q, acc[i][j]);
+    }
+  }
+}
+
 // out[n] += sum_r A[r][n]   (column sums, atomics per block)
 __global__ void colsum_kernel(const float* __restrict__ A, int lda, long long R, int N, float* __restrict__ out) {
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
@@ -131,6 +202,9 @@ __global__ void colsum_kernel(const float* __restrict__ A, int lda, long long R,
 
 static int gemm_nn(const float* A, int lda, const float* Bt, int ldb, float* C, int ldc, int M, int N, int K, const float* bias,
                    int accumulate, cudaStream_t st) {
+  if (N % 128 == 0 && K % 16 == 0 && lda == K && ldb == N && ldc == N && ((uintptr_t)A & 15) == 0 && ((uintptr_t)Bt & 15) == 0 &&
+      ((uintptr_t)C & 15) == 0)
+    return launch_proj_gemm_f32(A, Bt, bias, C, M, N, K, st, accumulate);
   dim3 g(ceil_div(N, TG), ceil_div(M, TG));
   gemm_nn_f32<<<g, TG_THREADS, 0, st>>>(A, lda, Bt, ldb, C, ldc, M, N, K, bias, accumulate);
   BCI_LAUNCH_OK();
@@ -138,6 +212,15 @@ static int gemm_nn(const float* A, int lda, const float* Bt, int ldb, float* C, 
 }
 static int gemm_tn(const float* A, int lda, const float* B, int ldb, float* C, int ldc, long long R, int P, int Q, cudaStream_t st) {
   if (R <= 0) return BCI_OK;
+  if (P % 128 == 0 && Q % 128 == 0 && lda % 4 == 0 && ldb % 4 == 0 && R >= 1024 && ((uintptr_t)A & 15) == 0 && ((uintptr_t)B & 15) == 0) {
+    const int tiles = (P / 128) * (Q / 128);
+    long long splits = (2 * sm_count() + tiles - 1) / tiles;
+    if (splits > R / 256) splits = R / 256;
+    if (splits < 1) splits = 1;
+    gemm_tn_f32_fast<<<dim3(Q / 128, P / 128, (unsigned)splits), 256, 0, st>>>(A, lda, B, ldb, C, ldc, R);
+    BCI_LAUNCH_OK();
+    return BCI_OK;
+  }
   const int tiles = ceil_div(P, TG) * ceil_div(Q, TG);
   int splits = (4 * sm_count() + tiles - 1) / tiles;
   const long long max_splits = (R + 255) / 256;
@@ -492,9 +575,9 @@ head_train_bwd(const float* __restrict__ dlogits, int classes, const float* __re
 // grid = (window tiles, 2 directions), 256 threads, thread = (hidden unit j, group of 16 windows): the mirror of
 // lstm_rec_f32.  Walks the direction's time order backwards; dG_t (gate-interleaved) goes to global for the weight /
 // input GEMMs and, transposed, to shared memory for dh_{t-1} = dG_t . W_hh.
-constexpr int BP_THREADS = 256, BP_WPT = 16;
+constexpr int BP_THREADS = 256;
 
-template <int H>
+template <int H, int BP_WPT>
 __global__ void __launch_bounds__(BP_THREADS, 1)
 lstm_bptt_f32(const float* __restrict__ dout,    // [T][Bc][2H]  grad wrt the layer output
               const float* __restrict__ gates,   // [T][Bc][2][H][4] post-activation i,f,g,o
@@ -726,17 +809,25 @@ static int backward_t(bci_lstm_s* h, const float* dlogits, int B, int T, float p
   float* dcur = w.dB;   // grad wrt out[l]
   float* dnext = w.dA;  // scratch for grad wrt the layer input
   // ---- LSTM layers, top down ----
-  static bool attr = false;
-  constexpr int MT = (BP_THREADS / H) * BP_WPT;
+  // 16 windows per thread unless that leaves most SMs idle (typical training batches): then 8
+  const bool small = 2 * ceil_div(B, (BP_THREADS / H) * 16) < sm_count();
+  const int MT = (BP_THREADS / H) * (small ? 8 : 16);
   const size_t bp_smem = (size_t)4 * H * (MT + 4) * sizeof(float);
+  static bool attr = false;
   if (!attr) {
-    BCI_CUDA_OK(cudaFuncSetAttribute(lstm_bptt_f32<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bp_smem));
+    BCI_CUDA_OK(cudaFuncSetAttribute(lstm_bptt_f32<H, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)((size_t)4 * H * ((BP_THREADS / H) * 16 + 4) * sizeof(float))));
+    BCI_CUDA_OK(cudaFuncSetAttribute(lstm_bptt_f32<H, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)((size_t)4 * H * ((BP_THREADS / H) * 8 + 4) * sizeof(float))));
     attr = true;
   }
   for (int l = L - 1; l >= 0; --l) {
     const int K = layer_in_width(c, l);
     const float* in = (l == 0) ? w.z : w.outd[l - 1];
-    lstm_bptt_f32<H><<<dim3(ceil_div(B, MT), 2), BP_THREADS, bp_smem, st>>>(dcur, w.gates[l], w.cst[l], p.whh_b[l][0], p.whh_b[l][1], w.G, B, T);
+    if (small)
+      lstm_bptt_f32<H, 8><<<dim3(ceil_div(B, MT), 2), BP_THREADS, bp_smem, st>>>(dcur, w.gates[l], w.cst[l], p.whh_b[l][0], p.whh_b[l][1], w.G, B, T);
+    else
+      lstm_bptt_f32<H, 16><<<dim3(ceil_div(B, MT), 2), BP_THREADS, bp_smem, st>>>(dcur, w.gates[l], w.cst[l], p.whh_b[l][0], p.whh_b[l][1], w.G, B, T);
     BCI_LAUNCH_OK();
     // dW_ih (both directions at once, interleaved rows) = dG^T . in
     BCI_CUDA_OK(zero(w.tmpW, (size_t)8 * H * K));
