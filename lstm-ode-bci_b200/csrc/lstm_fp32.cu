@@ -139,19 +139,27 @@ lstm_rec_f32(const float* __restrict__ G,      // [T][Bc][2][H][4]
       acc[w] = (b < Bc) ? __ldg(Gt + (long long)b * 2 * H) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
     const float* hcur = &hs[cur][0][grp * REC_WPT];
-#pragma unroll 2
-    for (int k = 0; k < H; ++k) {
-      const float4 w4 = __ldg(W + (long long)k * H + j);
-      const float4* hp = reinterpret_cast<const float4*>(hcur + k * HS);
+    // W_hh^T streams from L2 (it does not fit beside h in one SM's smem in fp32): 8 independent 16-byte loads are issued
+    // per thread before they are consumed, otherwise each k iteration exposes a full L2 round trip (the first version,
+    // unrolled by 2, spent ~36 k cycles per step on exactly that).
+    for (int k0 = 0; k0 < H; k0 += 8) {
+      float4 w8[8];
 #pragma unroll
-      for (int q = 0; q < REC_WPT / 4; ++q) {
-        const float4 h4 = hp[q];
-        const float hv[4] = {h4.x, h4.y, h4.z, h4.w};
+      for (int kk = 0; kk < 8; ++kk) w8[kk] = __ldg(W + (long long)(k0 + kk) * H + j);
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          float4& a = acc[q * 4 + e];
-          a.x = fmaf(hv[e], w4.x, a.x); a.y = fmaf(hv[e], w4.y, a.y);
-          a.z = fmaf(hv[e], w4.z, a.z); a.w = fmaf(hv[e], w4.w, a.w);
+      for (int kk = 0; kk < 8; ++kk) {
+        const float4 w4 = w8[kk];
+        const float4* hp = reinterpret_cast<const float4*>(hcur + (k0 + kk) * HS);
+#pragma unroll
+        for (int q = 0; q < REC_WPT / 4; ++q) {
+          const float4 h4 = hp[q];
+          const float hv[4] = {h4.x, h4.y, h4.z, h4.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            float4& a = acc[q * 4 + e];
+            a.x = fmaf(hv[e], w4.x, a.x); a.y = fmaf(hv[e], w4.y, a.y);
+            a.z = fmaf(hv[e], w4.z, a.z); a.w = fmaf(hv[e], w4.w, a.w);
+          }
         }
       }
     }

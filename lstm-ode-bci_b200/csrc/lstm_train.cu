@@ -627,17 +627,22 @@ lstm_bptt_f32(const float* __restrict__ dout,    // [T][Bc][2H]  grad wrt the la
 #pragma unroll
     for (int w = 0; w < BP_WPT; ++w) acc[w] = 0.f;
     const float* gsrc = bp_smem + grp * BP_WPT;
-#pragma unroll 4
-    for (int n = 0; n < 4 * H; ++n) {
-      const float wv = __ldg(W + (long long)n * H + j);
-      const float4* gp = reinterpret_cast<const float4*>(gsrc + n * GS);
+    // 16 independent weight loads in flight per thread (see lstm_rec_f32: the L2 round trip must not be paid per row)
+    for (int n0 = 0; n0 < 4 * H; n0 += 16) {
+      float wv[16];
 #pragma unroll
-      for (int q = 0; q < BP_WPT / 4; ++q) {
-        const float4 g4 = gp[q];
-        acc[q * 4 + 0] = fmaf(g4.x, wv, acc[q * 4 + 0]);
-        acc[q * 4 + 1] = fmaf(g4.y, wv, acc[q * 4 + 1]);
-        acc[q * 4 + 2] = fmaf(g4.z, wv, acc[q * 4 + 2]);
-        acc[q * 4 + 3] = fmaf(g4.w, wv, acc[q * 4 + 3]);
+      for (int nn = 0; nn < 16; ++nn) wv[nn] = __ldg(W + (long long)(n0 + nn) * H + j);
+#pragma unroll
+      for (int nn = 0; nn < 16; ++nn) {
+        const float4* gp = reinterpret_cast<const float4*>(gsrc + (n0 + nn) * GS);
+#pragma unroll
+        for (int q = 0; q < BP_WPT / 4; ++q) {
+          const float4 g4 = gp[q];
+          acc[q * 4 + 0] = fmaf(g4.x, wv[nn], acc[q * 4 + 0]);
+          acc[q * 4 + 1] = fmaf(g4.y, wv[nn], acc[q * 4 + 1]);
+          acc[q * 4 + 2] = fmaf(g4.z, wv[nn], acc[q * 4 + 2]);
+          acc[q * 4 + 3] = fmaf(g4.w, wv[nn], acc[q * 4 + 3]);
+        }
       }
     }
 #pragma unroll
