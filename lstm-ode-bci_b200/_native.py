@@ -91,8 +91,16 @@ def lib():
     global _lib
     if _lib is None:
         if not os.path.exists(LIB_PATH):
-            raise BciError(-2, "libbci_b200.so not found at %s -- run `python -m lstm_ode_bci_b200.build` "
-                               "(or __graft_entry__.build()); there is no CPU fallback" % LIB_PATH)
+            # a fresh checkout: try the in-tree nvcc build once (this is the build step, not a fallback -- without a
+            # working CUDA toolchain the import fails loudly)
+            try:
+                from . import build as _build
+                import sys
+                print("[bci_b200] libbci_b200.so missing; building it in-tree with nvcc ...", file=sys.stderr)
+                _build.build()
+            except Exception as e:
+                raise BciError(-2, "libbci_b200.so not found at %s and the in-tree build failed (%s) -- run `python -m "
+                                   "lstm_ode_bci_b200.build` (or __graft_entry__.build()); there is no CPU fallback" % (LIB_PATH, e))
         l = C.CDLL(LIB_PATH)
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(l, name)
