@@ -119,7 +119,7 @@ def cpu_ode_baseline(n=1500):
             "sample": f"{n} trajectories, per-sample scipy.odeint loop as 06:372-401 (serial by construction)"}
 
 
-def run_reference(args, rank, world):
+def run_reference(args, rank, world, json_out):
     if rank != 0:
         return
     steps, warm = args.steps, args.warmup
@@ -146,7 +146,7 @@ def run_reference(args, rank, world):
             "cpu_baseline": {"value": v, "unit": "windows/s", "cores": cores, "kind": "port",
                              "sample": f"{sample} windows per step (bounded sample of the per-GPU batch), torch CPU path of the reference module"},
             "e2e": {"value": v, "unit": "windows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=json_out, flush=True)
 
 
 def workload_config(args, world):
@@ -157,7 +157,17 @@ def workload_config(args, world):
             "parallelism": f"window-sharded x{world}, no data-path collective"}
 
 
+def _claim_stdout():
+    """Keep the real stdout for the ONE JSON line; anything a library prints to fd 1 (NCCL's version banner, ...) is
+    redirected to stderr."""
+    sys.stdout.flush()
+    real = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    return real
+
+
 def main():
+    json_out = _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -178,7 +188,7 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
-        return run_reference(args, rank, world)
+        return run_reference(args, rank, world, json_out)
 
     import numpy as np
     import torch
@@ -367,7 +377,7 @@ def main():
     elif rank == 0:
         line["cpu_baseline"] = None
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=json_out, flush=True)
     if world > 1:
         dist.destroy_process_group()
 
