@@ -147,6 +147,31 @@ int bci_adamw_step(float* p, const float* g, float* m, float* v, int64_t n, floa
                    float max_norm, float* norm_scratch, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Data-parallel optimizer step over peer memory (BASELINE config 3; SURVEY.md §8 b `bci_fused_step`, §8 e).
+ * The reference trains on one device (04:482-507); this is its loop body for N ranks: the gradient
+ * all-reduce is fused into the load phase of the clip + AdamW kernels -- each rank reads every peer's
+ * gradient bucket directly over NVLink (CUDA IPC peer pointers, system-scope flags), sums in rank order and
+ * updates its replica.  Results are bit-identical on all ranks.
+ *   1. every rank: bci_comm_create -> bci_comm_export (BCI_COMM_HANDLE_BYTES host bytes)
+ *   2. exchange the handles (torch.distributed all_gather_object / any host channel), rank order
+ *   3. every rank: bci_comm_connect(all handles)
+ *   4. per step: write local gradients into bci_comm_bucket (e.g. bci_lstm_backward with grads pointing into
+ *      it), then bci_fused_step on the same stream.  All ranks must call it the same number of times.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct bci_comm_s* bci_comm_t;
+#define BCI_COMM_HANDLE_BYTES 128
+int bci_comm_create(int32_t rank, int32_t world, int64_t n_floats, bci_comm_t* out);
+int bci_comm_export(bci_comm_t c, void* handle_host);
+int bci_comm_connect(bci_comm_t c, const void* handles_host /* world x BCI_COMM_HANDLE_BYTES */);
+/* device pointer of this rank's gradient bucket (n_floats fp32, owned by the communicator) */
+int bci_comm_bucket(bci_comm_t c, float** bucket, int64_t* n_floats);
+int bci_comm_destroy(bci_comm_t c);
+/* replaces all-reduce(mean) + clip_grad_norm_(max_norm) + AdamW.step (04:497-507) on flat p/m/v of n_floats;
+ * norm_out (optional, 2 device floats): [0] squared norm of the summed gradient, [1] pre-clip norm of the mean */
+int bci_fused_step(bci_comm_t c, float* p, float* m, float* v, float lr, float beta1, float beta2, float eps,
+                   float weight_decay, int32_t step, float max_norm, float* norm_out, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Three-state A/P/F ODE ensemble with probabilistic rate coupling
  * ---------------------------------------------------------------------------------------- */
 enum { BCI_ODE_RK4 = 0, BCI_ODE_RK45 = 1 };

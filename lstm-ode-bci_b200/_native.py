@@ -15,6 +15,7 @@ ODE_RK4, ODE_RK45 = 0, 1
 STYLE_REF06, STYLE_REF08 = 0, 1
 Y0_GIVEN, Y0_FROM_PROBS_06, Y0_FROM_PCLOSED_08 = 0, 1, 2
 OUT_F32, OUT_F64 = 0, 1
+COMM_HANDLE_BYTES = 128
 
 _ERR_NAMES = {-1: "BCI_EINVAL", -2: "BCI_ECUDA", -3: "BCI_ENOMEM", -4: "BCI_ESTATE", -5: "BCI_EUNSUPPORTED"}
 
@@ -75,6 +76,13 @@ SIGNATURES = {
                                     _FP, C.c_size_t, C.c_void_p]),
     "bci_adamw_step": (C.c_int, [_FP, _FP, _FP, _FP, C.c_int64, C.c_float, C.c_float, C.c_float, C.c_float,
                                  C.c_float, C.c_int32, C.c_float, C.c_float, _FP, C.c_void_p]),
+    "bci_comm_create": (C.c_int, [C.c_int32, C.c_int32, C.c_int64, C.POINTER(C.c_void_p)]),
+    "bci_comm_export": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "bci_comm_connect": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "bci_comm_bucket": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]),
+    "bci_comm_destroy": (C.c_int, [C.c_void_p]),
+    "bci_fused_step": (C.c_int, [C.c_void_p, _FP, _FP, _FP, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float,
+                                 C.c_int32, C.c_float, _FP, C.c_void_p]),
     "bci_ode_solve": (C.c_int, [C.POINTER(OdeArgs), C.c_void_p]),
     "bci_ode_classify": (C.c_int, [_FP, C.c_int64, _FP, _FP, C.c_void_p]),
     "bci_ode_forecast_readout": (C.c_int, [_FP, C.c_int64, C.c_int32, C.POINTER(C.c_int32), C.c_int32, _FP, C.c_void_p]),

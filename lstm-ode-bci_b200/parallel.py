@@ -2,6 +2,8 @@
 shards and never exchange data on the hot path; the only collectives are the gradient all-reduce of the
 training step (train.FusedTrainer) and the final result gather below.  Works on any torch.distributed backend
 (nccl on the GPUs; the CPU tests run it over gloo)."""
+import ctypes as C
+
 import torch
 import torch.distributed as dist
 
@@ -54,3 +56,53 @@ def forecast_pipeline_sharded(integration, X_local, n_total, horizons=(5, 10, 20
         prm = ode_params if ode_params is not None else integration.base_params
         fc = _forecast_device(all_probs[b:e, 1].contiguous(), prm, max(horizons), list(horizons), X_local.device, integration.substeps)
     return {"traj": traj, "final": final, "pred": pred, "cls": cls, "probs": all_probs, "forecast": fc, "forecast_range": (b, e)}
+
+
+class _DevArray:
+    """Zero-copy torch view of a raw device allocation owned by the C library (via __cuda_array_interface__)."""
+
+    def __init__(self, ptr, n):
+        self.__cuda_array_interface__ = {"shape": (int(n),), "typestr": "<f4", "data": (int(ptr), False), "version": 3}
+
+
+class P2PComm:
+    """Peer-memory communicator of the fused optimizer step (`bci_fused_step`, csrc/comm_p2p.cu).
+
+    Each rank's gradient bucket is allocated by the library and exported as a CUDA IPC handle; the handles travel
+    through torch.distributed (any backend) once at construction.  After that a training step involves no NCCL
+    call: the reduction happens inside the optimizer kernels over NVLink peer loads.  GPU only (no CPU path)."""
+
+    def __init__(self, n_floats, group=None, device=None):
+        from . import _native as N
+        self._N = N
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.n = int(n_floats)
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.ptr = C.c_void_p(0)
+        with torch.cuda.device(self.device):
+            N.check(N.lib().bci_comm_create(self.rank, self.world, self.n, C.byref(self.ptr)))
+            if self.world > 1:
+                blob = C.create_string_buffer(N.COMM_HANDLE_BYTES)
+                N.check(N.lib().bci_comm_export(self.ptr, blob))
+                blobs = [None] * self.world
+                dist.all_gather_object(blobs, bytes(blob.raw), group=group)
+                N.check(N.lib().bci_comm_connect(self.ptr, C.create_string_buffer(b"".join(blobs), N.COMM_HANDLE_BYTES * self.world)))
+            bp, bn = C.c_void_p(0), C.c_int64(0)
+            N.check(N.lib().bci_comm_bucket(self.ptr, C.byref(bp), C.byref(bn)))
+        self.bucket = torch.as_tensor(_DevArray(bp.value, bn.value), device=self.device)
+        if self.world > 1:
+            dist.barrier(group=group)      # every rank has opened every handle before anyone steps
+
+    def fused_step(self, p, m, v, lr, betas, eps, weight_decay, step, max_norm, norm_out=None):
+        N = self._N
+        from .ops import _ptr, _stream
+        N.check(N.lib().bci_fused_step(self.ptr, _ptr(p), _ptr(m), _ptr(v), lr, betas[0], betas[1], eps, weight_decay,
+                                       int(step), max_norm, _ptr(norm_out), _stream()))
+
+    def close(self):
+        if self.ptr:
+            torch.cuda.synchronize(self.device)
+            self.bucket = None
+            self._N.lib().bci_comm_destroy(self.ptr)
+            self.ptr = C.c_void_p(0)

@@ -6,8 +6,10 @@
                        loss.backward(); clip_grad_norm_; optimizer.step()) runs unchanged, and so does the
                        backward-to-input of 07_explainability.py:242-258.
   FusedTrainer         config 3 of BASELINE.json: per-GPU batch, weighted cross-entropy, flat fp32 gradient
-                       bucket, one NCCL all-reduce (torch.distributed) per step, then clip + AdamW fused in
-                       bci_adamw_step.  Windows are independent, so data parallelism over ranks is exact.
+                       bucket; collective="p2p" (default on >1 GPU ranks): the all-reduce is fused into the clip +
+                       AdamW kernels over NVLink peer memory (bci_fused_step, csrc/comm_p2p.cu); collective="nccl":
+                       one torch.distributed all-reduce per step, then bci_adamw_step.  Windows are independent, so
+                       data parallelism over ranks is exact.
 """
 import ctypes as C
 
@@ -74,7 +76,7 @@ class FusedTrainer:
     launch each."""
 
     def __init__(self, model, lr=3e-4, weight_decay=1e-4, betas=(0.9, 0.999), eps=1e-8, max_norm=1.0, class_weight=None,
-                 process_group=None):
+                 process_group=None, collective="auto"):
         self.model = model
         self.lr, self.wd, self.betas, self.eps, self.max_norm = lr, weight_decay, betas, eps, max_norm
         self.pg = process_group
@@ -82,8 +84,21 @@ class FusedTrainer:
         ps = [p for _, p in model.named_parameters()]
         dev = ps[0].device
         n = sum(p.numel() for p in ps)
+        import torch.distributed as dist
+        world = dist.get_world_size(process_group) if (dist.is_available() and dist.is_initialized()) else 1
+        if collective == "auto":
+            collective = "p2p" if world > 1 else "none"
+        if collective not in ("p2p", "nccl", "none"):
+            raise N.BciError(-1, "collective must be auto, p2p, nccl or none")
+        self.collective, self.world = collective, world
         self.flat = torch.empty(n, device=dev, dtype=torch.float32)
-        self.grad = torch.zeros(n, device=dev, dtype=torch.float32)
+        self.comm = None
+        if collective == "p2p":
+            from .parallel import P2PComm
+            self.comm = P2PComm(n, group=process_group, device=dev)
+            self.grad = self.comm.bucket                      # backward writes straight into the peer-visible bucket
+        else:
+            self.grad = torch.zeros(n, device=dev, dtype=torch.float32)
         self.m = torch.zeros(n, device=dev, dtype=torch.float32)
         self.v = torch.zeros(n, device=dev, dtype=torch.float32)
         self.norm = torch.zeros(2, device=dev, dtype=torch.float32)
@@ -123,11 +138,15 @@ class FusedTrainer:
         gs = _grad_struct(model, self.grad_views)
         N.check(N.lib().bci_lstm_backward(h.ptr, ops._ptr(xc), ops._ptr(dlogits.contiguous()), B, T, C.c_void_p(0), C.byref(gs),
                                           ops._ptr(ws), nbytes, ops._stream()))
-        scale = 1.0
-        if self.pg is not None or (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
-            dist.all_reduce(self.grad, op=dist.ReduceOp.SUM, group=self.pg)      # NCCL over NVLink on GPUs
-            scale = 1.0 / dist.get_world_size(self.pg)
         self.step_count += 1
+        if self.comm is not None:
+            self.comm.fused_step(self.flat, self.m, self.v, self.lr, self.betas, self.eps, self.wd, self.step_count,
+                                 self.max_norm, self.norm)
+            return loss.detach(), self.norm[1]
+        scale = 1.0
+        if self.collective == "nccl" and self.world > 1:
+            dist.all_reduce(self.grad, op=dist.ReduceOp.SUM, group=self.pg)      # NCCL over NVLink on GPUs
+            scale = 1.0 / self.world
         N.check(N.lib().bci_adamw_step(ops._ptr(self.flat), ops._ptr(self.grad), ops._ptr(self.m), ops._ptr(self.v),
                                        self.flat.numel(), self.lr, self.betas[0], self.betas[1], self.eps, self.wd,
                                        self.step_count, scale, self.max_norm, ops._ptr(self.norm), ops._stream()))
