@@ -228,6 +228,34 @@ int bci_ode_classify(const float* final_state, int64_t n, int32_t* pred06, int32
 int bci_ode_forecast_readout(const float* traj, int64_t n, int32_t n_points, const int32_t* horizons_host,
                              int32_t n_h, float* out, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Raw recording -> model windows (SURVEY.md §8 f row 4; 02_preprocessing.py:114-180)
+ * ---------------------------------------------------------------------------------------- */
+typedef struct {
+  int32_t n_recordings;  /* R equally long recordings processed in one call                        */
+  int32_t n_channels;    /* C (61)                                                                  */
+  int64_t n_samples;     /* samples per recording (150 000 = 300 s x 500 Hz)                        */
+  int32_t in_dtype;      /* BCI_OUT_F64 (mne's raw.get_data(), 02:200) or BCI_OUT_F32               */
+  int32_t order;         /* len(a) - 1 == len(b) - 1; butter(4, ..., 'band') -> 8   (02:128-130)    */
+  const double* b_host;  /* HOST: numerator   (order + 1)                                           */
+  const double* a_host;  /* HOST: denominator (order + 1)                                           */
+  const double* zi_host; /* HOST: scipy.signal.lfilter_zi(b, a) (order)                             */
+  int32_t padlen;        /* filtfilt edge padding; scipy default 3 * max(len(a), len(b)) = 27       */
+  int32_t seq_len;       /* SEQUENCE_LENGTH 256 (02:50)                                             */
+  int32_t step;          /* int(seq_len * (1 - overlap)) = 128 (02:51,170)                          */
+  const double* mean_in; /* optional DEVICE (C): reuse normalisation parameters (02:207-210) ...    */
+  const double* std_in;  /* ... together with std_in; NULL = per-recording statistics (02:212)      */
+} bci_preproc_args;
+
+int bci_preprocess_workspace_bytes(const bci_preproc_args* a, size_t* bytes);
+/* replaces bandpass_filter + normalize_data + create_sequences (02:114-180) for a batch of recordings:
+ *   raw      (R, C, n_samples) DEVICE, in_dtype
+ *   windows  (R * n_seq, seq_len, C) fp32, n_seq = (n_samples - seq_len) / step + 1   -- the LSTM's input layout
+ *   mean_out, std_out (R, C) fp64: the statistics used (02:145-151; std floored at 1e-10)
+ *   filtered optional (R, C, n_samples) fp64: the band-passed signal before normalisation */
+int bci_preprocess(const bci_preproc_args* a, const void* raw, float* windows, double* mean_out, double* std_out,
+                   double* filtered, void* workspace, size_t workspace_bytes, void* stream);
+
 /* Micro-benchmark used by bench.py for the FP32 roofline denominator (SURVEY.md §8 d: the FP32
  * FMA peak is not in MEASURED_PEAKS.json): launches a dependent-FMA kernel, returns TFLOP/s. */
 int bci_fp32_peak_probe(double* tflops, void* stream);

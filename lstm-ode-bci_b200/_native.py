@@ -58,6 +58,13 @@ class OdeArgs(C.Structure):
                 ("traj", _FP), ("final_state", _FP), ("n_steps", _FP)]
 
 
+class PreprocArgs(C.Structure):
+    _fields_ = [("n_recordings", C.c_int32), ("n_channels", C.c_int32), ("n_samples", C.c_int64), ("in_dtype", C.c_int32),
+                ("order", C.c_int32), ("b_host", C.POINTER(C.c_double)), ("a_host", C.POINTER(C.c_double)),
+                ("zi_host", C.POINTER(C.c_double)), ("padlen", C.c_int32), ("seq_len", C.c_int32), ("step", C.c_int32),
+                ("mean_in", _FP), ("std_in", _FP)]
+
+
 # name -> (restype, argtypes); every symbol include/bci_b200.h declares
 SIGNATURES = {
     "bci_abi_version": (C.c_int, []),
@@ -83,6 +90,8 @@ SIGNATURES = {
     "bci_comm_destroy": (C.c_int, [C.c_void_p]),
     "bci_fused_step": (C.c_int, [C.c_void_p, _FP, _FP, _FP, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float,
                                  C.c_int32, C.c_float, _FP, C.c_void_p]),
+    "bci_preprocess_workspace_bytes": (C.c_int, [C.POINTER(PreprocArgs), C.POINTER(C.c_size_t)]),
+    "bci_preprocess": (C.c_int, [C.POINTER(PreprocArgs), _FP, _FP, _FP, _FP, _FP, _FP, C.c_size_t, C.c_void_p]),
     "bci_ode_solve": (C.c_int, [C.POINTER(OdeArgs), C.c_void_p]),
     "bci_ode_classify": (C.c_int, [_FP, C.c_int64, _FP, _FP, C.c_void_p]),
     "bci_ode_forecast_readout": (C.c_int, [_FP, C.c_int64, C.c_int32, C.POINTER(C.c_int32), C.c_int32, _FP, C.c_void_p]),

@@ -101,3 +101,19 @@ def make_ode_sweep(seed, n):
     p_closed = rng.uniform(0.0, 1.0, size=n).astype(np.float32)
     p_open = (np.float32(1.0) - p_closed).astype(np.float32)
     return {"rates": rates, "alpha": np.ascontiguousarray(alpha), "p_open": p_open, "p_closed": p_closed}
+
+
+def make_raw_eeg(seed, recordings, channels=61, samples=150000, fs=500.0, dtype=np.float64):
+    """Raw-recording stand-in for mne's raw.get_data() (02_preprocessing.py:200): volts-scale (R, C, n) with a slow drift
+    (below the 1 Hz corner), 50 Hz mains (above the 45 Hz corner), a 10 Hz alpha rhythm and broadband noise, a different
+    DC offset and gain per channel, so the band-pass, the z-score and the windowing all have something to do."""
+    rng = np.random.default_rng(seed)
+    t = np.arange(samples, dtype=np.float64) / fs
+    x = 8e-6 * rng.standard_normal((recordings, channels, samples))
+    gain = rng.uniform(0.5, 2.0, size=(recordings, channels, 1))
+    dc = 1e-4 * rng.standard_normal((recordings, channels, 1))
+    ph = rng.uniform(0, 2 * np.pi, size=(recordings, channels, 3, 1))
+    x += 2e-5 * np.sin(2 * np.pi * 0.2 * t + ph[:, :, 0])
+    x += 1e-5 * np.sin(2 * np.pi * 50.0 * t + ph[:, :, 1])
+    x += 1.2e-5 * np.sin(2 * np.pi * 10.0 * t + ph[:, :, 2])
+    return np.ascontiguousarray((gain * x + dc).astype(dtype))

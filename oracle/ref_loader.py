@@ -20,6 +20,8 @@ import types
 REFERENCE_ROOT = os.environ.get("BCI_REFERENCE_ROOT", "/root/reference")
 
 _FILES = {
+    "ref02": "02_preprocessing.py",
+    "ref09": "09_sensitivity_analysis.py",
     "ref04": "04_lstm_model.py",
     "ref05": "05_ode_model.py",
     "ref06": "06_lstm_ode_integration.py",
@@ -33,7 +35,7 @@ def reference_available():
 
 
 def _install_plot_stubs():
-    for name in ("matplotlib", "matplotlib.pyplot", "matplotlib.gridspec", "matplotlib.patches", "seaborn"):
+    for name in ("matplotlib", "matplotlib.pyplot", "matplotlib.gridspec", "matplotlib.patches", "seaborn", "mne"):
         if name not in sys.modules:
             try:
                 importlib.import_module(name)
@@ -53,6 +55,9 @@ def _install_plot_stubs():
         plt.style = types.SimpleNamespace(use=lambda *a, **k: None)
     if not hasattr(plt, "rcParams"):
         plt.rcParams = {}
+    mne = sys.modules["mne"]
+    if not hasattr(mne, "set_log_level"):
+        mne.set_log_level = lambda *a, **k: None
     sns = sys.modules["seaborn"]
     for fn in ("set_style", "set_palette", "set_theme", "set_context"):
         if not hasattr(sns, fn):
@@ -63,7 +68,7 @@ _cache = {}
 
 
 def load(name):
-    """name in {ref04, ref05, ref06, ref08, ref10}; returns the imported module."""
+    """name in {ref02, ref04, ref05, ref06, ref08, ref09, ref10}; returns the imported module."""
     if name in _cache:
         return _cache[name]
     if not reference_available():

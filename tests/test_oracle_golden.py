@@ -142,3 +142,35 @@ def test_pipeline_matches_reference_predict_batch(golden):
     # predict_trajectory(X[:1], forecast_steps=10): t = linspace(0,10,10) (06:299-301)
     tr1 = ode_oracle.exact_solution(ode_oracle.STYLE_REF06, y0[:1], k[:, :1], 10.0, 10)
     assert np.abs(tr1[0] - g["single_traj"]).max() < 2e-7
+
+
+# ---- preprocessing (SURVEY.md §8 f row 4): oracle vs the live reference's 02_preprocessing.py outputs -------------------
+def test_preproc_oracle_matches_reference_golden(golden):
+    from oracle import preproc_oracle as po
+    from lstm_ode_bci_b200 import synth
+    g = golden("preproc_ref02.npz")
+    seed, C, n = int(g["seed"]), int(g["C"]), int(g["n"])
+    raw = synth.make_raw_eeg(seed, 1, C, n)[0]
+    filt = po.bandpass_filter(raw, 1.0, 45.0, 500, 4)
+    assert np.abs(filt[::7] - g["filtered"]).max() <= 1e-12 * np.abs(g["filtered"]).max()
+    X, y, prm = po.preprocess_recording(raw, 1)
+    assert X.shape == (int(g["n_seq"]), 256, C) and np.array_equal(y, g["y"])
+    assert np.abs(np.asarray(prm["mean"]) - g["mean"]).max() <= 1e-18 and np.abs(np.asarray(prm["std"]) / g["std"] - 1).max() <= 1e-12
+    assert np.abs(X.astype(np.float32)[:, :, ::5] - g["X"]).max() <= 1e-6
+    raw2 = synth.make_raw_eeg(seed + 1, 1, C, n)[0]
+    X2, _, _ = po.preprocess_recording(raw2, 0, prm)
+    assert np.abs(X2.astype(np.float32)[::3, :, ::9] - g["X2"]).max() <= 1e-6
+
+
+def test_preproc_recursion_restatement_matches_scipy():
+    """The plain-numpy DF2T recursion (what the CUDA kernel implements) == scipy.signal.filtfilt on a short signal."""
+    from scipy.signal import filtfilt
+    from oracle import preproc_oracle as po
+    rng = np.random.default_rng(3)
+    x = rng.standard_normal((3, 400)) + 5.0
+    b, a = po.butter_band(1.0, 45.0, 500, 4)
+    want = filtfilt(b, a, x, axis=1)
+    got = po.filtfilt_restated(b, a, x, use_numpy_recursion=True)
+    assert np.abs(got - want).max() <= 1e-9 * np.abs(want).max()
+    with pytest.raises(ValueError):
+        po.filtfilt_restated(b, a, x[:, :27])
