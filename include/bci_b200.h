@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define BCI_ABI_VERSION 1
+#define BCI_ABI_VERSION 2
 #define BCI_MAX_LAYERS 4
 
 enum {
@@ -55,12 +55,18 @@ typedef struct {
   int32_t hidden_size;   /* H: 128 or 256                            04:163,876-877           */
   int32_t num_layers;    /* 1..BCI_MAX_LAYERS (3)                    04:163                   */
   int32_t num_classes;   /* 2                                        04:164                   */
-  int32_t bidirectional; /* must be 1 (ablation variants are SURVEY §8 f)                     */
-  int32_t precision;     /* BCI_PRECISION_*                                                   */
+  int32_t bidirectional; /* 1 (04:164) or 0 (AblationLSTMModel, 09:176-240)                   */
+  int32_t precision;     /* BCI_PRECISION_*; BF16 requires the full model (bidirectional, attention,
+                            LayerNorm, hidden_size 128)                                       */
+  int32_t use_attention; /* 1: attention pooling (04:112-128); 0: mean over time (09:232-234) */
+  int32_t use_layer_norm;/* 1: LayerNorm in input_proj and after the LSTM; 0: nn.Identity (09:191,210) */
 } bci_lstm_config;
 
 /* Device pointers to fp32 parameters in the reference state-dict layout:
- * PyTorch (out,in) row-major, gate row order i,f,g,o.  [layer][0]=forward, [layer][1]=reverse. */
+ * PyTorch (out,in) row-major, gate row order i,f,g,o.  [layer][0]=forward, [layer][1]=reverse.
+ * With D = H * (bidirectional ? 2 : 1): w_ih of layers >= 1 is (4H, D), ln_* (D), attn_w1 (D/2, D),
+ * attn_b1 (D/2), attn_w2 (1, D/2), cls_w0 (H, D).  Pointers of absent modules (reverse direction when
+ * unidirectional, attn_* without attention, *ln_* without LayerNorm) are ignored and may be NULL. */
 typedef struct {
   const float* input_proj_w;  /* input_proj.0.weight (H,C)   */
   const float* input_proj_b;  /* input_proj.0.bias   (H)     */
@@ -120,8 +126,8 @@ int bci_lstm_forward(bci_lstm_t h, const float* x, int32_t batch, int32_t seq_le
                      float dropout, uint64_t seed, float* logits, float* probs, float* attn,
                      void* workspace, size_t workspace_bytes, void* stream);
 
-/* Gradient pointers, same layout/shape as bci_lstm_weights; every pointer must be non-NULL.
- * Gradients are OVERWRITTEN (not accumulated). */
+/* Gradient pointers, same layout/shape as bci_lstm_weights; every pointer of a module the configuration has
+ * must be non-NULL.  Gradients are OVERWRITTEN (not accumulated). */
 typedef struct {
   float* input_proj_w; float* input_proj_b; float* input_ln_w; float* input_ln_b;
   float* w_ih[BCI_MAX_LAYERS][2]; float* w_hh[BCI_MAX_LAYERS][2];

@@ -28,7 +28,8 @@ class BciError(RuntimeError):
 
 class LstmConfig(C.Structure):
     _fields_ = [("input_size", C.c_int32), ("hidden_size", C.c_int32), ("num_layers", C.c_int32),
-                ("num_classes", C.c_int32), ("bidirectional", C.c_int32), ("precision", C.c_int32)]
+                ("num_classes", C.c_int32), ("bidirectional", C.c_int32), ("precision", C.c_int32),
+                ("use_attention", C.c_int32), ("use_layer_norm", C.c_int32)]
 
 
 _FP = C.c_void_p  # device pointers travel as integers
@@ -123,7 +124,7 @@ def lib():
             fn = getattr(l, name)
             fn.restype = res
             fn.argtypes = args
-        if l.bci_abi_version() != 1:
+        if l.bci_abi_version() != 2:
             raise BciError(-1, "ABI version mismatch")
         _lib = l
     return _lib

@@ -81,9 +81,13 @@ extern "C" int bci_lstm_create(const bci_lstm_config* cfg, bci_lstm_t* out) {
   BCI_REQUIRE(cfg->num_layers >= 1 && cfg->num_layers <= BCI_MAX_LAYERS, BCI_EINVAL, "bci_lstm_create: num_layers must be 1..%d",
               BCI_MAX_LAYERS);
   BCI_REQUIRE(cfg->num_classes >= 1 && cfg->num_classes <= 8, BCI_EINVAL, "bci_lstm_create: num_classes must be 1..8");
-  BCI_REQUIRE(cfg->bidirectional == 1, BCI_EINVAL, "bci_lstm_create: only bidirectional=1 is supported");
+  BCI_REQUIRE((cfg->bidirectional | 1) == 1 && (cfg->use_attention | 1) == 1 && (cfg->use_layer_norm | 1) == 1, BCI_EINVAL,
+              "bci_lstm_create: bidirectional, use_attention and use_layer_norm must be 0 or 1");
   BCI_REQUIRE(cfg->precision == BCI_PRECISION_FP32 || cfg->precision == BCI_PRECISION_BF16, BCI_EINVAL,
               "bci_lstm_create: bad precision %d", cfg->precision);
+  BCI_REQUIRE(cfg->precision == BCI_PRECISION_FP32 || (cfg->bidirectional && cfg->use_attention && cfg->use_layer_norm), BCI_EINVAL,
+              "bci_lstm_create: the bf16 (tcgen05) mode is built for the full model only (bidirectional, attention pooling, "
+              "LayerNorm); the ablation variants of 09_sensitivity_analysis.py run in fp32 precision");
   bci_lstm_s* h = new (std::nothrow) bci_lstm_s();
   BCI_REQUIRE(h, BCI_ENOMEM, "bci_lstm_create: host allocation failed");
   std::memset(h, 0, sizeof(*h));
@@ -112,11 +116,14 @@ extern "C" int bci_lstm_destroy(bci_lstm_t h) {
 extern "C" int bci_lstm_load_weights(bci_lstm_t h, const bci_lstm_weights* w, void* stream) {
   BCI_REQUIRE(h && w, BCI_EINVAL, "bci_lstm_load_weights: NULL argument");
   const bci_lstm_config& c = h->cfg;
-  const void* must[] = {w->input_proj_w, w->input_proj_b, w->input_ln_w, w->input_ln_b, w->ln_w, w->ln_b, w->attn_w1, w->attn_b1,
-                        w->attn_w2, w->attn_b2, w->cls_w0, w->cls_b0, w->cls_w3, w->cls_b3, w->cls_w6, w->cls_b6};
+  const void* must[] = {w->input_proj_w, w->input_proj_b, w->cls_w0, w->cls_b0, w->cls_w3, w->cls_b3, w->cls_w6, w->cls_b6};
   for (const void* p : must) BCI_REQUIRE(p, BCI_EINVAL, "bci_lstm_load_weights: a required weight pointer is NULL");
+  if (c.use_layer_norm)
+    BCI_REQUIRE(w->input_ln_w && w->input_ln_b && w->ln_w && w->ln_b, BCI_EINVAL, "bci_lstm_load_weights: a LayerNorm pointer is NULL");
+  if (c.use_attention)
+    BCI_REQUIRE(w->attn_w1 && w->attn_b1 && w->attn_w2 && w->attn_b2, BCI_EINVAL, "bci_lstm_load_weights: an attention pointer is NULL");
   for (int l = 0; l < c.num_layers; ++l)
-    for (int d = 0; d < 2; ++d)
+    for (int d = 0; d < num_dirs(c); ++d)
       BCI_REQUIRE(w->w_ih[l][d] && w->w_hh[l][d] && w->b_ih[l][d] && w->b_hh[l][d], BCI_EINVAL,
                   "bci_lstm_load_weights: LSTM weight pointer NULL (layer %d dir %d)", l, d);
   h->raw = *w;

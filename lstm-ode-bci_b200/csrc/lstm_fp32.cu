@@ -105,13 +105,13 @@ constexpr int REC_WPT = 16;  // windows per thread (inference tiles); small trai
 
 template <int H, int REC_WPT = 16>
 __global__ void __launch_bounds__(REC_THREADS, 2)
-lstm_rec_f32(const float* __restrict__ G,      // [T][Bc][2][H][4]
+lstm_rec_f32(const float* __restrict__ G,      // [T][Bc][ND][H][4]
              const float* __restrict__ whh_f,  // [H][H][4] forward direction
              const float* __restrict__ whh_r,  // reverse direction
-             float* __restrict__ out,          // [T][Bc][2H]
-             float* __restrict__ gates_save,   // optional [T][Bc][2][H][4] post-activation (train)
-             float* __restrict__ c_save,       // optional [T][Bc][2][H] (train)
-             int Bc, int T) {
+             float* __restrict__ out,          // [T][Bc][ND*H]
+             float* __restrict__ gates_save,   // optional [T][Bc][ND][H][4] post-activation (train)
+             float* __restrict__ c_save,       // optional [T][Bc][ND][H] (train)
+             int Bc, int T, int ND) {
   constexpr int GROUPS = REC_THREADS / H;
   constexpr int MT = GROUPS * REC_WPT;
   constexpr int HS = MT + 4;  // padded row: conflict-free float4 stores, 16 B aligned
@@ -132,11 +132,11 @@ lstm_rec_f32(const float* __restrict__ G,      // [T][Bc][2][H][4]
   for (int s = 0; s < T; ++s) {
     const int t = dir ? (T - 1 - s) : s;
     float4 acc[REC_WPT];
-    const float4* Gt = reinterpret_cast<const float4*>(G) + (((long long)t * Bc) * 2 + dir) * H + j;
+    const float4* Gt = reinterpret_cast<const float4*>(G) + (((long long)t * Bc) * ND + dir) * H + j;
 #pragma unroll
     for (int w = 0; w < REC_WPT; ++w) {
       const int b = b_base + w;
-      acc[w] = (b < Bc) ? __ldg(Gt + (long long)b * 2 * H) : make_float4(0.f, 0.f, 0.f, 0.f);
+      acc[w] = (b < Bc) ? __ldg(Gt + (long long)b * ND * H) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
     const float* hcur = &hs[cur][0][grp * REC_WPT];
     // W_hh^T streams from L2 (it does not fit beside h in one SM's smem in fp32): 8 independent 16-byte loads are issued
@@ -176,10 +176,10 @@ lstm_rec_f32(const float* __restrict__ G,      // [T][Bc][2][H][4]
       const int b = b_base + w;
       if (b < Bc) {
         const long long row = (long long)t * Bc + b;
-        out[row * (2 * H) + dir * H + j] = hv;
+        out[row * (ND * H) + dir * H + j] = hv;
         if (gates_save) {
-          reinterpret_cast<float4*>(gates_save)[(row * 2 + dir) * H + j] = make_float4(ig, fg, gg, og);
-          c_save[(row * 2 + dir) * H + j] = c[w];
+          reinterpret_cast<float4*>(gates_save)[(row * ND + dir) * H + j] = make_float4(ig, fg, gg, og);
+          c_save[(row * ND + dir) * H + j] = c[w];
         }
       }
     }
@@ -197,17 +197,17 @@ int launch_proj_gemm_f32(const float* A, const float* Bt, const float* bias, flo
   return BCI_OK;
 }
 
-int launch_rec_f32(int H, const float* G, const float* whh_f, const float* whh_r, float* out, float* gates, float* csave, int Bc,
-                   int T, cudaStream_t st) {
+int launch_rec_f32(int H, int ND, const float* G, const float* whh_f, const float* whh_r, float* out, float* gates, float* csave,
+                   int Bc, int T, cudaStream_t st) {
   // tiles of 16 windows per thread unless that leaves most SMs idle (training batches): then 8
   const int groups = REC_THREADS / H;
-  const bool small = 2 * ceil_div(Bc, groups * 16) < sm_count();
+  const bool small = ND * ceil_div(Bc, groups * 16) < sm_count();
   if (H == 128) {
-    if (small) lstm_rec_f32<128, 8><<<dim3(ceil_div(Bc, 2 * 8), 2), REC_THREADS, 0, st>>>(G, whh_f, whh_r, out, gates, csave, Bc, T);
-    else lstm_rec_f32<128, 16><<<dim3(ceil_div(Bc, 2 * 16), 2), REC_THREADS, 0, st>>>(G, whh_f, whh_r, out, gates, csave, Bc, T);
+    if (small) lstm_rec_f32<128, 8><<<dim3(ceil_div(Bc, 2 * 8), ND), REC_THREADS, 0, st>>>(G, whh_f, whh_r, out, gates, csave, Bc, T, ND);
+    else lstm_rec_f32<128, 16><<<dim3(ceil_div(Bc, 2 * 16), ND), REC_THREADS, 0, st>>>(G, whh_f, whh_r, out, gates, csave, Bc, T, ND);
   } else {
-    if (small) lstm_rec_f32<256, 8><<<dim3(ceil_div(Bc, 8), 2), REC_THREADS, 0, st>>>(G, whh_f, whh_r, out, gates, csave, Bc, T);
-    else lstm_rec_f32<256, 16><<<dim3(ceil_div(Bc, 16), 2), REC_THREADS, 0, st>>>(G, whh_f, whh_r, out, gates, csave, Bc, T);
+    if (small) lstm_rec_f32<256, 8><<<dim3(ceil_div(Bc, 8), ND), REC_THREADS, 0, st>>>(G, whh_f, whh_r, out, gates, csave, Bc, T, ND);
+    else lstm_rec_f32<256, 16><<<dim3(ceil_div(Bc, 16), ND), REC_THREADS, 0, st>>>(G, whh_f, whh_r, out, gates, csave, Bc, T, ND);
   }
   BCI_LAUNCH_OK();
   return BCI_OK;
@@ -260,27 +260,33 @@ int lstm_pack_f32(bci_lstm_s* h, cudaStream_t st) {
   const bci_lstm_config& c = h->cfg;
   const bci_lstm_weights& w = h->raw;
   PackedF32& p = h->f32;
-  const int H = c.hidden_size, C = c.input_size, D = 2 * H;
+  const int H = c.hidden_size, C = c.input_size, ND = num_dirs(c), D = ND * H, AH = D / 2;
   transpose_kernel<<<nblk((long long)H * C), 256, 0, st>>>(w.input_proj_w, p.w0t, H, C);
   copy_kernel<<<nblk(H), 256, 0, st>>>(w.input_proj_b, p.b0, H);
-  copy_kernel<<<nblk(H), 256, 0, st>>>(w.input_ln_w, p.ln0w, H);
-  copy_kernel<<<nblk(H), 256, 0, st>>>(w.input_ln_b, p.ln0b, H);
+  if (c.use_layer_norm) {
+    copy_kernel<<<nblk(H), 256, 0, st>>>(w.input_ln_w, p.ln0w, H);
+    copy_kernel<<<nblk(H), 256, 0, st>>>(w.input_ln_b, p.ln0b, H);
+  }
   for (int l = 0; l < c.num_layers; ++l) {
     const int K = layer_in_width(c, l);
-    for (int d = 0; d < 2; ++d) {
-      pack_gates_t_kernel<<<nblk((long long)4 * H * K), 256, 0, st>>>(w.w_ih[l][d], p.wih_t[l], H, K, 8 * H, d * 4 * H);
+    for (int d = 0; d < ND; ++d) {
+      pack_gates_t_kernel<<<nblk((long long)4 * H * K), 256, 0, st>>>(w.w_ih[l][d], p.wih_t[l], H, K, ND * 4 * H, d * 4 * H);
       pack_gates_t_kernel<<<nblk((long long)4 * H * H), 256, 0, st>>>(w.w_hh[l][d], p.whh_t[l][d], H, H, 4 * H, 0);
       pack_bias_kernel<<<nblk(4 * H), 256, 0, st>>>(w.b_ih[l][d], w.b_hh[l][d], p.bias[l], H, d * 4 * H);
       pack_gates_rows_kernel<<<nblk((long long)4 * H * K), 256, 0, st>>>(w.w_ih[l][d], p.wih_b[l], H, K, d * 4 * H);
       pack_gates_rows_kernel<<<nblk((long long)4 * H * H), 256, 0, st>>>(w.w_hh[l][d], p.whh_b[l][d], H, H, 0);
     }
   }
-  copy_kernel<<<nblk(D), 256, 0, st>>>(w.ln_w, p.lnw, D);
-  copy_kernel<<<nblk(D), 256, 0, st>>>(w.ln_b, p.lnb, D);
-  transpose_kernel<<<nblk((long long)H * D), 256, 0, st>>>(w.attn_w1, p.aw1t, H, D);
-  copy_kernel<<<nblk(H), 256, 0, st>>>(w.attn_b1, p.ab1, H);
-  copy_kernel<<<nblk(H), 256, 0, st>>>(w.attn_w2, p.aw2, H);
-  copy_kernel<<<1, 256, 0, st>>>(w.attn_b2, p.ab2, 1);
+  if (c.use_layer_norm) {
+    copy_kernel<<<nblk(D), 256, 0, st>>>(w.ln_w, p.lnw, D);
+    copy_kernel<<<nblk(D), 256, 0, st>>>(w.ln_b, p.lnb, D);
+  }
+  if (c.use_attention) {
+    transpose_kernel<<<nblk((long long)AH * D), 256, 0, st>>>(w.attn_w1, p.aw1t, AH, D);
+    copy_kernel<<<nblk(AH), 256, 0, st>>>(w.attn_b1, p.ab1, AH);
+    copy_kernel<<<nblk(AH), 256, 0, st>>>(w.attn_w2, p.aw2, AH);
+    copy_kernel<<<1, 256, 0, st>>>(w.attn_b2, p.ab2, 1);
+  }
   transpose_kernel<<<nblk((long long)H * D), 256, 0, st>>>(w.cls_w0, p.c0t, H, D);
   copy_kernel<<<nblk(H), 256, 0, st>>>(w.cls_b0, p.cb0, H);
   transpose_kernel<<<nblk((long long)(H / 2) * H), 256, 0, st>>>(w.cls_w3, p.c3t, H / 2, H);
@@ -324,8 +330,8 @@ void lstm_carve_f32(bci_lstm_s* h, char* base) {
 // host orchestration
 // ---------------------------------------------------------------------------------------------
 static size_t chunk_bytes_f32(const bci_lstm_config& c, int Bc, int T) {
-  const size_t H = c.hidden_size, rows = (size_t)Bc * T;
-  return align_up(rows * H * 4, 256) + align_up(rows * 8 * H * 4, 256) + 2 * align_up(rows * 2 * H * 4, 256) +
+  const size_t H = c.hidden_size, D = feat_width(c), rows = (size_t)Bc * T;
+  return align_up(rows * H * 4, 256) + align_up(rows * 4 * D * 4, 256) + 2 * align_up(rows * D * 4, 256) +
          align_up((size_t)Bc * T * 4, 256);
 }
 
@@ -334,17 +340,18 @@ size_t lstm_workspace_fp32(const bci_lstm_config& c, int batch, int T) {
   return chunk_bytes_f32(c, Bc > 0 ? Bc : 1, T);
 }
 
-template <int H>
+template <int H, int ND>
 static int forward_chunk_f32(bci_lstm_s* h, const float* x, int Bc, int T, float* logits, float* probs, float* attn,
                              char* ws, cudaStream_t st) {
   const bci_lstm_config& c = h->cfg;
   const size_t rows = (size_t)Bc * T;
+  constexpr int D = ND * H;
   size_t off = 0;
   auto take = [&](size_t bytes) { char* p = ws + off; off += align_up(bytes, 256); return p; };
   float* z = reinterpret_cast<float*>(take(rows * H * 4));
-  float* g = reinterpret_cast<float*>(take(rows * 8 * H * 4));
-  float* o0 = reinterpret_cast<float*>(take(rows * 2 * H * 4));
-  float* o1 = reinterpret_cast<float*>(take(rows * 2 * H * 4));
+  float* g = reinterpret_cast<float*>(take(rows * 4 * D * 4));
+  float* o0 = reinterpret_cast<float*>(take(rows * D * 4));
+  float* o1 = reinterpret_cast<float*>(take(rows * D * 4));
   float* scores = reinterpret_cast<float*>(take(rows * 4));
   h->prof.mark(-1, st);
   int rc = launch_input_proj<H, float>(h, x, Bc, T, z, st);
@@ -355,19 +362,19 @@ static int forward_chunk_f32(bci_lstm_s* h, const float* x, int Bc, int T, float
   constexpr int MT = (REC_THREADS / H) * REC_WPT;
   for (int l = 0; l < c.num_layers; ++l) {
     const int K = layer_in_width(c, l);
-    const int M = (int)rows, N = 8 * H;
+    const int M = (int)rows, N = 4 * D;
     dim3 gg(N / GN, ceil_div(M, GM));
     proj_gemm_f32<<<gg, GEMM_THREADS, 0, st>>>(in, h->f32.wih_t[l], h->f32.bias[l], g, M, N, K, 0);
     BCI_LAUNCH_OK();
     h->prof.mark(1, st);
     float* o = outs[l & 1];
-    dim3 gr(ceil_div(Bc, MT), 2);
-    lstm_rec_f32<H, REC_WPT><<<gr, REC_THREADS, 0, st>>>(g, h->f32.whh_t[l][0], h->f32.whh_t[l][1], o, nullptr, nullptr, Bc, T);
+    dim3 gr(ceil_div(Bc, MT), ND);
+    lstm_rec_f32<H, REC_WPT><<<gr, REC_THREADS, 0, st>>>(g, h->f32.whh_t[l][0], h->f32.whh_t[l][1], o, nullptr, nullptr, Bc, T, ND);
     BCI_LAUNCH_OK();
     h->prof.mark(2, st);
     in = o;
   }
-  rc = launch_pool_head<H, float>(h, in, Bc, T, logits, probs, attn, scores, st);
+  rc = launch_pool_head<H, ND, float>(h, in, Bc, T, logits, probs, attn, scores, st);
   h->prof.mark(3, st);
   return rc;
 }
@@ -384,8 +391,13 @@ int lstm_forward_fp32(bci_lstm_s* h, const float* x, int batch, int T, float* lo
     float* lg = logits + (size_t)b0 * c.num_classes;
     float* pr = probs ? probs + (size_t)b0 * c.num_classes : nullptr;
     float* at = attn ? attn + (size_t)b0 * T : nullptr;
-    int rc = c.hidden_size == 128 ? forward_chunk_f32<128>(h, xb, Bc, T, lg, pr, at, (char*)ws, st)
-                                  : forward_chunk_f32<256>(h, xb, Bc, T, lg, pr, at, (char*)ws, st);
+    int rc;
+    if (c.bidirectional)
+      rc = c.hidden_size == 128 ? forward_chunk_f32<128, 2>(h, xb, Bc, T, lg, pr, at, (char*)ws, st)
+                                : forward_chunk_f32<256, 2>(h, xb, Bc, T, lg, pr, at, (char*)ws, st);
+    else
+      rc = c.hidden_size == 128 ? forward_chunk_f32<128, 1>(h, xb, Bc, T, lg, pr, at, (char*)ws, st)
+                                : forward_chunk_f32<256, 1>(h, xb, Bc, T, lg, pr, at, (char*)ws, st);
     if (rc) return rc;
   }
   return BCI_OK;

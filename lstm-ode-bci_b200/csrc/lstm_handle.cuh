@@ -13,19 +13,19 @@ struct PackedF32 {
   float* b0;     // [H]
   float* ln0w;   // [H]
   float* ln0b;   // [H]
-  float* wih_t[BCI_MAX_LAYERS];     // [K_l][8H]   both directions, gate-interleaved
-  float* bias[BCI_MAX_LAYERS];      // [8H]        b_ih + b_hh, same order
+  float* wih_t[BCI_MAX_LAYERS];     // [K_l][ND*4H] all directions, gate-interleaved (ND = 1 or 2 directions)
+  float* bias[BCI_MAX_LAYERS];      // [ND*4H]     b_ih + b_hh, same order
   float* whh_t[BCI_MAX_LAYERS][2];  // [H][4H]     per direction, gate-interleaved
   // row-major copies with gate-interleaved ROWS (n = dir*4H + unit*4 + gate), used by the backward pass:
-  float* wih_b[BCI_MAX_LAYERS];     // [8H][K_l]   din = dG . wih_b
+  float* wih_b[BCI_MAX_LAYERS];     // [ND*4H][K_l] din = dG . wih_b
   float* whh_b[BCI_MAX_LAYERS][2];  // [4H][H]     dh_{t-1} = dG_t . whh_b
-  float* lnw;    // [2H]
-  float* lnb;    // [2H]
-  float* aw1t;   // [2H][H]     attention.0.weight^T
-  float* ab1;    // [H]
-  float* aw2;    // [H]
+  float* lnw;    // [D]         D = ND*H
+  float* lnb;    // [D]
+  float* aw1t;   // [D][D/2]    attention.0.weight^T
+  float* ab1;    // [D/2]
+  float* aw2;    // [D/2]
   float* ab2;    // [1]
-  float* c0t;    // [2H][H]     classifier.0.weight^T
+  float* c0t;    // [D][H]      classifier.0.weight^T
   float* cb0;    // [H]
   float* c3t;    // [H][H/2]    classifier.3.weight^T
   float* cb3;    // [H/2]
@@ -87,7 +87,10 @@ struct bci_lstm_s {
 
 namespace bci {
 
-inline int layer_in_width(const bci_lstm_config& c, int l) { return l == 0 ? c.hidden_size : 2 * c.hidden_size; }
+inline int num_dirs(const bci_lstm_config& c) { return c.bidirectional ? 2 : 1; }
+inline int feat_width(const bci_lstm_config& c) { return num_dirs(c) * c.hidden_size; }          // D: LSTM output width
+inline int attn_width(const bci_lstm_config& c) { return feat_width(c) / 2; }                    // attention hidden width
+inline int layer_in_width(const bci_lstm_config& c, int l) { return l == 0 ? c.hidden_size : feat_width(c); }
 
 // chunking policy: windows processed per internal pass (bounds the workspace)
 inline int max_chunk(const bci_lstm_config& c, int train) {
@@ -111,8 +114,8 @@ int lstm_forward_fp32(bci_lstm_s* h, const float* x, int batch, int T, float* lo
 size_t lstm_workspace_fp32(const bci_lstm_config& c, int batch, int T);
 int launch_proj_gemm_f32(const float* A, const float* Bt, const float* bias, float* C, int M, int N, int K, cudaStream_t st,
                          int accumulate = 0);
-int launch_rec_f32(int H, const float* G, const float* whh_f, const float* whh_r, float* out, float* gates, float* csave, int Bc,
-                   int T, cudaStream_t st);
+int launch_rec_f32(int H, int ND, const float* G, const float* whh_f, const float* whh_r, float* out, float* gates, float* csave,
+                   int Bc, int T, cudaStream_t st);
 // bf16 / tcgen05 forward (lstm_bf16.cu)
 int lstm_forward_bf16(bci_lstm_s* h, const float* x, int batch, int T, float* logits, float* probs, float* attn,
                       void* ws, size_t ws_bytes, cudaStream_t st);

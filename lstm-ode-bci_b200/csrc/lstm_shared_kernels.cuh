@@ -25,7 +25,7 @@ template <int H, typename OutT>
 __global__ void __launch_bounds__(K1_THREADS)
 input_proj_kernel(const float* __restrict__ x, int Bc, int T, int C, const float* __restrict__ w0t,
                   const float* __restrict__ b0, const float* __restrict__ lnw, const float* __restrict__ lnb,
-                  OutT* __restrict__ z) {
+                  OutT* __restrict__ z, int use_ln) {
   extern __shared__ __align__(16) float k1_smem[];  // [C][H]
   constexpr int NV = H / 32;          // outputs per lane (4 or 8)
   constexpr int NQ = NV / 4;          // float4 groups per lane
@@ -41,7 +41,7 @@ input_proj_kernel(const float* __restrict__ x, int Bc, int T, int C, const float
 #pragma unroll
     for (int v = 0; v < 4; ++v) {
       const int j = q * 128 + lane * 4 + v;
-      bias[q * 4 + v] = b0[j]; gw[q * 4 + v] = lnw[j]; gb[q * 4 + v] = lnb[j];
+      bias[q * 4 + v] = b0[j]; gw[q * 4 + v] = use_ln ? lnw[j] : 1.f; gb[q * 4 + v] = use_ln ? lnb[j] : 0.f;
     }
   for (long long r = (long long)blockIdx.x * (K1_THREADS / 32) + warp; r < rows; r += wstride) {
     const int b = (int)(r / T), t = (int)(r - (long long)b * T);
@@ -65,17 +65,18 @@ input_proj_kernel(const float* __restrict__ x, int Bc, int T, int C, const float
     float s = 0.f;
 #pragma unroll
     for (int v = 0; v < NV; ++v) s += acc[v];
-    const float mean = warp_sum(s) * (1.0f / H);
+    float mean = warp_sum(s) * (1.0f / H);
     float q2 = 0.f;
 #pragma unroll
     for (int v = 0; v < NV; ++v) { const float d = acc[v] - mean; q2 = fmaf(d, d, q2); }
-    const float rstd = 1.0f / sqrtf(warp_sum(q2) * (1.0f / H) + 1e-5f);
+    float rstd = 1.0f / sqrtf(warp_sum(q2) * (1.0f / H) + 1e-5f);
+    if (!use_ln) { mean = 0.f; rstd = 1.f; }  // nn.Identity instead of LayerNorm (09:191)
     OutT* zr = z + ((long long)t * Bc + b) * H;
 #pragma unroll
     for (int q = 0; q < NQ; ++q)
 #pragma unroll
       for (int v = 0; v < 4; ++v) {
-        const float y = (acc[q * 4 + v] - mean) * rstd * gw[q * 4 + v] + gb[q * 4 + v];
+        const float y = use_ln ? (acc[q * 4 + v] - mean) * rstd * gw[q * 4 + v] + gb[q * 4 + v] : acc[q * 4 + v];
         zr[q * 128 + lane * 4 + v] = from_f32<OutT>(gelu_erf(y));
       }
   }
@@ -90,19 +91,22 @@ input_proj_kernel(const float* __restrict__ x, int Bc, int T, int C, const float
 // ---------------------------------------------------------------------------------------------
 constexpr int K4_THREADS = 256;
 
-template <int H>
+template <int H, int ND>
 struct PoolCfg {
-  static constexpr int D = 2 * H;
-  static constexpr int GROUPS = K4_THREADS / H;  // 2 (H=128) or 1 (H=256)
+  static constexpr int D = ND * H;               // LSTM output width
+  static constexpr int AH = D / 2;               // attention hidden width (04:115: hidden_size // 2 of the 2H-wide input)
+  static constexpr int GROUPS = K4_THREADS / AH; // row groups of the score GEMM: 1, 2 or 4
   static constexpr int RPT = 16;                 // rows (timesteps) per thread in the score GEMM
-  static constexpr int TC = GROUPS * RPT;        // timesteps per chunk: 32 or 16
+  static constexpr int TC = GROUPS * RPT;        // timesteps per chunk: 16, 32 or 64
   static constexpr int YS_STRIDE = TC + 4;       // padded, keeps float4 alignment
-  static constexpr int WARPS_PER_GROUP = H / 32;
+  static constexpr int WARPS_PER_GROUP = AH / 32;
   // smem floats: ys_t[D][YS_STRIDE] + red[TC][WARPS_PER_GROUP] + chunk_s[TC] + ctx[D] + h1[H] + h2[H/2] + misc
   static constexpr int SMEM_FLOATS = D * YS_STRIDE + TC * WARPS_PER_GROUP + TC + D + H + H / 2 + 8;
 };
 
-template <int H, typename InT>
+// use_ln = 0: nn.Identity instead of the final LayerNorm (09:210); use_attn = 0: mean over time instead of attention
+// pooling (09:232-234) -- constant scores make the online softmax below exactly that mean.
+template <int H, int ND, typename InT>
 __global__ void __launch_bounds__(K4_THREADS)
 attn_pool_head_kernel(const InT* __restrict__ seq,  // [T][Bc][2H]
                       int Bc, int T, int classes,
@@ -115,10 +119,10 @@ attn_pool_head_kernel(const InT* __restrict__ seq,  // [T][Bc][2H]
                       float* __restrict__ logits,   // [Bc][classes]
                       float* __restrict__ probs,    // [Bc][classes] or null
                       float* __restrict__ attn,     // [Bc][T] or null
-                      float* __restrict__ scores_ws // [Bc][T] scratch for raw scores (needed iff attn)
-) {
-  using Cfg = PoolCfg<H>;
-  constexpr int D = Cfg::D, TC = Cfg::TC, RPT = Cfg::RPT, YS = Cfg::YS_STRIDE, WPG = Cfg::WARPS_PER_GROUP;
+                      float* __restrict__ scores_ws, // [Bc][T] scratch for raw scores (needed iff attn)
+                      int use_ln, int use_attn) {
+  using Cfg = PoolCfg<H, ND>;
+  constexpr int D = Cfg::D, AH = Cfg::AH, TC = Cfg::TC, RPT = Cfg::RPT, YS = Cfg::YS_STRIDE, WPG = Cfg::WARPS_PER_GROUP;
   extern __shared__ __align__(16) float k4_smem[];
   float* ys_t = k4_smem;                 // [D][YS]   LayerNorm-ed chunk, transposed
   float* red = ys_t + D * YS;            // [TC][WPG] partial scores per warp
@@ -130,17 +134,17 @@ attn_pool_head_kernel(const InT* __restrict__ seq,  // [T][Bc][2H]
 
   const int b = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int j = tid % H;                 // hidden unit of the score GEMM
-  const int grp = tid / H;               // row group
-  const int wig = (tid % H) >> 5;        // warp index inside the group
-  constexpr int DPT = D / K4_THREADS;    // ctx features per thread (1 or 2)
+  const int j = tid % AH;                // hidden unit of the score GEMM
+  const int grp = tid / AH;              // row group
+  const int wig = (tid % AH) >> 5;       // warp index inside the group
+  constexpr int DPT = (D + K4_THREADS - 1) / K4_THREADS;  // ctx features per thread (1 or 2; threads >= D idle for D = 128)
   constexpr int EPL = D / 32;            // elements per lane in the LN pass (8 or 16)
 
   float m_run = -INFINITY, l_run = 0.f;
   float ctx[DPT];
 #pragma unroll
   for (int q = 0; q < DPT; ++q) ctx[q] = 0.f;
-  const float b1 = ab1[j], w2 = aw2[j], b2 = ab2[0];
+  const float b1 = use_attn ? ab1[j] : 0.f, w2 = use_attn ? aw2[j] : 0.f, b2 = use_attn ? ab2[0] : 0.f;
 
   for (int t0 = 0; t0 < T; t0 += TC) {
     const int rows = min(TC, T - t0);
@@ -160,7 +164,7 @@ attn_pool_head_kernel(const InT* __restrict__ seq,  // [T][Bc][2H]
 #pragma unroll
         for (int e = 0; e < EPL; ++e) {
           const int d = e * 32 + lane;
-          ys_t[d * YS + r] = (v[e] - mean) * rstd * lnw[d] + lnb[d];
+          ys_t[d * YS + r] = use_ln ? (v[e] - mean) * rstd * lnw[d] + lnb[d] : v[e];
         }
       } else {
 #pragma unroll
@@ -173,9 +177,10 @@ attn_pool_head_kernel(const InT* __restrict__ seq,  // [T][Bc][2H]
 #pragma unroll
     for (int r = 0; r < RPT; ++r) acc[r] = b1;
     const float* yrow = ys_t + grp * RPT;
+    if (use_attn) {
 #pragma unroll 4
     for (int d = 0; d < D; ++d) {
-      const float w = __ldg(aw1t + (long long)d * H + j);
+      const float w = __ldg(aw1t + (long long)d * AH + j);
       const float4* yp = reinterpret_cast<const float4*>(yrow + d * YS);
 #pragma unroll
       for (int q = 0; q < RPT / 4; ++q) {
@@ -185,6 +190,7 @@ attn_pool_head_kernel(const InT* __restrict__ seq,  // [T][Bc][2H]
         acc[q * 4 + 2] = fmaf(y4.z, w, acc[q * 4 + 2]);
         acc[q * 4 + 3] = fmaf(y4.w, w, acc[q * 4 + 3]);
       }
+    }
     }
 #pragma unroll
     for (int r = 0; r < RPT; ++r) {
@@ -217,8 +223,10 @@ attn_pool_head_kernel(const InT* __restrict__ seq,  // [T][Bc][2H]
       l_run += (p0 + p1) + (p2 + p3);
 #pragma unroll
       for (int q = 0; q < DPT; ++q) {
-        const float4 y4 = *reinterpret_cast<const float4*>(ys_t + (q * K4_THREADS + tid) * YS + r);
-        ctx[q] = fmaf(p3, y4.w, fmaf(p2, y4.z, fmaf(p1, y4.y, fmaf(p0, y4.x, ctx[q]))));
+        if (q * K4_THREADS + tid < D) {
+          const float4 y4 = *reinterpret_cast<const float4*>(ys_t + (q * K4_THREADS + tid) * YS + r);
+          ctx[q] = fmaf(p3, y4.w, fmaf(p2, y4.z, fmaf(p1, y4.y, fmaf(p0, y4.x, ctx[q]))));
+        }
       }
     }
     m_run = m_new;
@@ -226,7 +234,8 @@ attn_pool_head_kernel(const InT* __restrict__ seq,  // [T][Bc][2H]
   }
   const float inv_l = 1.0f / l_run;
 #pragma unroll
-  for (int q = 0; q < DPT; ++q) ctx_s[q * K4_THREADS + tid] = ctx[q] * inv_l;
+  for (int q = 0; q < DPT; ++q)
+    if (q * K4_THREADS + tid < D) ctx_s[q * K4_THREADS + tid] = ctx[q] * inv_l;
   if (attn) {
     for (int t = tid; t < T; t += K4_THREADS)
       attn[(long long)b * T + t] = expf(scores_ws[(long long)b * T + t] - m_run) * inv_l;
@@ -265,20 +274,21 @@ attn_pool_head_kernel(const InT* __restrict__ seq,  // [T][Bc][2H]
   }
 }
 
-template <int H, typename InT>
+template <int H, int ND, typename InT>
 inline int launch_pool_head(const bci_lstm_s* h, const InT* seq, int Bc, int T, float* logits, float* probs, float* attn,
                             float* scores_ws, cudaStream_t st) {
-  using Cfg = PoolCfg<H>;
+  using Cfg = PoolCfg<H, ND>;
   const size_t smem = Cfg::SMEM_FLOATS * sizeof(float);
   static bool attr_set = false;
   if (!attr_set) {
-    BCI_CUDA_OK(cudaFuncSetAttribute(attn_pool_head_kernel<H, InT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    BCI_CUDA_OK(cudaFuncSetAttribute(attn_pool_head_kernel<H, ND, InT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;
   }
   const PackedF32& p = h->f32;
-  attn_pool_head_kernel<H, InT><<<Bc, K4_THREADS, smem, st>>>(seq, Bc, T, h->cfg.num_classes, p.lnw, p.lnb, p.aw1t, p.ab1,
-                                                               p.aw2, p.ab2, p.c0t, p.cb0, p.c3t, p.cb3, p.c6, p.cb6,
-                                                               logits, probs, attn, scores_ws);
+  attn_pool_head_kernel<H, ND, InT><<<Bc, K4_THREADS, smem, st>>>(seq, Bc, T, h->cfg.num_classes, p.lnw, p.lnb, p.aw1t, p.ab1,
+                                                                   p.aw2, p.ab2, p.c0t, p.cb0, p.c3t, p.cb3, p.c6, p.cb6,
+                                                                   logits, probs, attn, scores_ws, h->cfg.use_layer_norm,
+                                                                   h->cfg.use_attention);
   BCI_LAUNCH_OK();
   return BCI_OK;
 }
@@ -297,7 +307,8 @@ inline int launch_input_proj(const bci_lstm_s* h, const float* x, int Bc, int T,
   const long long cap = (long long)sm_count() * 4;
   if (blocks > cap) blocks = cap;
   const PackedF32& p = h->f32;
-  input_proj_kernel<H, OutT><<<(unsigned)blocks, K1_THREADS, smem, st>>>(x, Bc, T, C, p.w0t, p.b0, p.ln0w, p.ln0b, z);
+  input_proj_kernel<H, OutT><<<(unsigned)blocks, K1_THREADS, smem, st>>>(x, Bc, T, C, p.w0t, p.b0, p.ln0w, p.ln0b, z,
+                                                                         h->cfg.use_layer_norm);
   BCI_LAUNCH_OK();
   return BCI_OK;
 }

@@ -248,7 +248,7 @@ template <int H>
 __global__ void __launch_bounds__(256)
 inproj_train_fwd(const float* __restrict__ x, int Bc, int T, int C, const float* __restrict__ w0t, const float* __restrict__ b0,
                  const float* __restrict__ lnw, const float* __restrict__ lnb, float* __restrict__ xT, float* __restrict__ xhat,
-                 float* __restrict__ rstd_out, float* __restrict__ z, float p_drop, uint64_t seed) {
+                 float* __restrict__ rstd_out, float* __restrict__ z, float p_drop, uint64_t seed, int use_ln) {
   constexpr int NV = H / 32;
   const int lane = threadIdx.x & 31;
   const long long rows = (long long)Bc * T;
@@ -277,9 +277,10 @@ inproj_train_fwd(const float* __restrict__ x, int Bc, int T, int C, const float*
 #pragma unroll
     for (int v = 0; v < NV; ++v) {
       const int j = v * 32 + lane;
-      const float xh = (acc[v] - mean) * rstd;
+      // without LayerNorm (09:191) xhat holds the raw pre-activation and y = xhat
+      const float xh = use_ln ? (acc[v] - mean) * rstd : acc[v];
       xhat[r * H + j] = xh;
-      const float y = fmaf(xh, lnw[j], lnb[j]);
+      const float y = use_ln ? fmaf(xh, lnw[j], lnb[j]) : xh;
       z[r * H + j] = gelu_erf(y) * drop_scale(seed, 0, (uint64_t)r * H + j, p_drop);
     }
   }
@@ -290,11 +291,20 @@ template <int H>
 __global__ void __launch_bounds__(256)
 inproj_bwd_rows(const float* __restrict__ dz, const float* __restrict__ xhat, const float* __restrict__ rstd_in,
                 const float* __restrict__ lnw, const float* __restrict__ lnb, long long rows, float* __restrict__ dv,
-                float* __restrict__ dlnw, float* __restrict__ dlnb, float p_drop, uint64_t seed) {
+                float* __restrict__ dlnw, float* __restrict__ dlnb, float p_drop, uint64_t seed, int use_ln) {
   constexpr int NV = H / 32;
   const int lane = threadIdx.x & 31;
   const long long wstride = (long long)gridDim.x * 8;
   float gw[NV] = {}, gb[NV] = {};
+  if (!use_ln) {  // dv = dz * mask * gelu'(pre-activation)
+    for (long long r = (long long)blockIdx.x * 8 + (threadIdx.x >> 5); r < rows; r += wstride)
+#pragma unroll
+      for (int v = 0; v < NV; ++v) {
+        const int j = v * 32 + lane;
+        dv[r * H + j] = dz[r * H + j] * drop_scale(seed, 0, (uint64_t)r * H + j, p_drop) * gelu_grad(xhat[r * H + j]);
+      }
+    return;
+  }
   for (long long r = (long long)blockIdx.x * 8 + (threadIdx.x >> 5); r < rows; r += wstride) {
     float dy[NV], xh[NV];
     float s1 = 0.f, s2 = 0.f;
@@ -330,7 +340,7 @@ inproj_bwd_rows(const float* __restrict__ dz, const float* __restrict__ xhat, co
 template <int D>
 __global__ void __launch_bounds__(256)
 ln_rows_fwd(const float* __restrict__ x, long long rows, const float* __restrict__ w, const float* __restrict__ b, float* __restrict__ xhat,
-            float* __restrict__ rstd_out, float* __restrict__ y) {
+            float* __restrict__ rstd_out, float* __restrict__ y, int use_ln) {
   constexpr int NV = D / 32;
   const int lane = threadIdx.x & 31;
   const long long wstride = (long long)gridDim.x * 8;
@@ -348,9 +358,9 @@ ln_rows_fwd(const float* __restrict__ x, long long rows, const float* __restrict
 #pragma unroll
     for (int e = 0; e < NV; ++e) {
       const int d = e * 32 + lane;
-      const float xh = (v[e] - mean) * rstd;
+      const float xh = use_ln ? (v[e] - mean) * rstd : v[e];   // nn.Identity (09:210): Y = out
       xhat[r * D + d] = xh;
-      y[r * D + d] = fmaf(xh, w[d], b[d]);
+      y[r * D + d] = use_ln ? fmaf(xh, w[d], b[d]) : xh;
     }
   }
 }
@@ -359,11 +369,17 @@ ln_rows_fwd(const float* __restrict__ x, long long rows, const float* __restrict
 template <int D>
 __global__ void __launch_bounds__(256)
 ln_rows_bwd(const float* __restrict__ dy, const float* __restrict__ xhat, const float* __restrict__ rstd_in, const float* __restrict__ w,
-            long long rows, float* __restrict__ dx, float* __restrict__ dw, float* __restrict__ db) {
+            long long rows, float* __restrict__ dx, float* __restrict__ dw, float* __restrict__ db, int use_ln) {
   constexpr int NV = D / 32;
   const int lane = threadIdx.x & 31;
   const long long wstride = (long long)gridDim.x * 8;
   float gw[NV] = {}, gb[NV] = {};
+  if (!use_ln) {
+    for (long long r = (long long)blockIdx.x * 8 + (threadIdx.x >> 5); r < rows; r += wstride)
+#pragma unroll
+      for (int e = 0; e < NV; ++e) dx[r * D + e * 32 + lane] = dy[r * D + e * 32 + lane];
+    return;
+  }
   for (long long r = (long long)blockIdx.x * 8 + (threadIdx.x >> 5); r < rows; r += wstride) {
     float g[NV], xh[NV];
     float s1 = 0.f, s2 = 0.f;
@@ -396,20 +412,21 @@ ln_rows_bwd(const float* __restrict__ dy, const float* __restrict__ xhat, const 
 
 // ---- attention pooling (train): one CTA per window -------------------------------------------------
 // forward: s_t = b2 + sum_j w2_j tanh(PRE[t][b][j]); a = softmax_T(s); ctx = sum_t a_t Y[t][b][:]
-template <int H>
+// D = LSTM output width, AH = D/2 = attention hidden width; pre == nullptr: mean pooling (09:232-234, a_t = 1/T)
 __global__ void __launch_bounds__(256)
-attn_train_fwd(const float* __restrict__ pre, const float* __restrict__ y, int Bc, int T, const float* __restrict__ w2,
+attn_train_fwd(const float* __restrict__ pre, const float* __restrict__ y, int Bc, int T, int D, int AH, const float* __restrict__ w2,
                const float* __restrict__ b2, float* __restrict__ attn, float* __restrict__ ctx) {
-  constexpr int D = 2 * H;
   extern __shared__ float at_smem[];  // [T] scores -> weights
   __shared__ float red[8];
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   for (int t = warp; t < T; t += 8) {
-    const float* pr = pre + ((long long)t * Bc + b) * H;
     float s = 0.f;
-    for (int j = lane; j < H; j += 32) s = fmaf(w2[j], tanhf(pr[j]), s);
-    s = warp_sum(s);
-    if (lane == 0) at_smem[t] = s + b2[0];
+    if (pre) {
+      const float* pr = pre + ((long long)t * Bc + b) * AH;
+      for (int j = lane; j < AH; j += 32) s = fmaf(w2[j], tanhf(pr[j]), s);
+      s = warp_sum(s) + b2[0];
+    }
+    if (lane == 0) at_smem[t] = s;
   }
   __syncthreads();
   float m = -INFINITY;
@@ -439,11 +456,9 @@ attn_train_fwd(const float* __restrict__ pre, const float* __restrict__ y, int B
 
 // backward: from dctx -> dY (context path only), dPRE, dw2, db2.  `pre` is left intact so the same saved forward can be
 // back-propagated repeatedly (07_explainability.py:252 calls backward(retain_graph=True) once per sample).
-template <int H>
 __global__ void __launch_bounds__(256)
 attn_train_bwd(const float* __restrict__ pre, float* __restrict__ dpre, const float* __restrict__ y, const float* __restrict__ attn, const float* __restrict__ dctx,
-               int Bc, int T, const float* __restrict__ w2, float* __restrict__ dY, float* __restrict__ dw2, float* __restrict__ db2) {
-  constexpr int D = 2 * H;
+               int Bc, int T, int D, int AH, const float* __restrict__ w2, float* __restrict__ dY, float* __restrict__ dw2, float* __restrict__ db2) {
   extern __shared__ float ab_smem[];  // [T] da -> ds ; [D] dctx
   float* ds = ab_smem;
   float* dc = ab_smem + T;
@@ -463,6 +478,7 @@ attn_train_bwd(const float* __restrict__ pre, float* __restrict__ dpre, const fl
     s = warp_sum(s);
     if (lane == 0) ds[t] = s;
   }
+  if (!pre) return;  // mean pooling: a_t = 1/T is a constant, dY = dctx / T is all there is
   __syncthreads();
   float dot = 0.f;
   for (int t = tid; t < T; t += 256) dot = fmaf(attn[(long long)b * T + t], ds[t], dot);
@@ -479,11 +495,11 @@ attn_train_bwd(const float* __restrict__ pre, float* __restrict__ dpre, const fl
   __syncthreads();
   if (tid == 0) { float s = 0.f; for (int w = 0; w < 8; ++w) s += red[w]; atomicAdd(db2, s); }
   // dPRE[t][j] = ds_t w2_j (1 - u^2), u = tanh(pre);  dw2_j += sum_t ds_t u
-  for (int j = tid; j < H; j += 256) {
+  for (int j = tid; j < AH; j += 256) {
     const float w = w2[j];
     float g = 0.f;
     for (int t = 0; t < T; ++t) {
-      const long long o = ((long long)t * Bc + b) * H + j;
+      const long long o = ((long long)t * Bc + b) * AH + j;
       const float u = tanhf(pre[o]);
       g = fmaf(ds[t], u, g);
       dpre[o] = ds[t] * w * (1.0f - u * u);
@@ -498,9 +514,8 @@ __global__ void __launch_bounds__(H)
 head_train_fwd(const float* __restrict__ ctx, int classes, const float* __restrict__ c0t, const float* __restrict__ cb0,
                const float* __restrict__ c3t, const float* __restrict__ cb3, const float* __restrict__ c6, const float* __restrict__ cb6,
                float* __restrict__ pre1, float* __restrict__ h1d, float* __restrict__ pre2, float* __restrict__ h2d,
-               float* __restrict__ logits, float* __restrict__ probs, float p_drop, uint64_t seed) {
-  constexpr int D = 2 * H;
-  __shared__ float cs[D], h1[H], h2[H / 2], lg[8];
+               float* __restrict__ logits, float* __restrict__ probs, float p_drop, uint64_t seed, int D) {
+  __shared__ float cs[2 * H], h1[H], h2[H / 2], lg[8];
   const int b = blockIdx.x, tid = threadIdx.x;
   for (int d = tid; d < D; d += H) cs[d] = ctx[(long long)b * D + d];
   __syncthreads();
@@ -542,8 +557,7 @@ template <int H>
 __global__ void __launch_bounds__(H)
 head_train_bwd(const float* __restrict__ dlogits, int classes, const float* __restrict__ pre1, const float* __restrict__ pre2,
                const float* __restrict__ w6 /*[cls][H/2]*/, const float* __restrict__ w3 /*[H/2][H]*/, const float* __restrict__ w0 /*[H][2H]*/,
-               float* __restrict__ dpre1, float* __restrict__ dpre2, float* __restrict__ dctx, float p_drop, uint64_t seed) {
-  constexpr int D = 2 * H;
+               float* __restrict__ dpre1, float* __restrict__ dpre2, float* __restrict__ dctx, float p_drop, uint64_t seed, int D) {
   __shared__ float dl[8], d2[H / 2], d1[H];
   const int b = blockIdx.x, tid = threadIdx.x;
   if (tid < classes) dl[tid] = dlogits[(long long)b * classes + tid];
@@ -579,13 +593,13 @@ constexpr int BP_THREADS = 256;
 
 template <int H, int BP_WPT>
 __global__ void __launch_bounds__(BP_THREADS, 1)
-lstm_bptt_f32(const float* __restrict__ dout,    // [T][Bc][2H]  grad wrt the layer output
-              const float* __restrict__ gates,   // [T][Bc][2][H][4] post-activation i,f,g,o
-              const float* __restrict__ csave,   // [T][Bc][2][H]
+lstm_bptt_f32(const float* __restrict__ dout,    // [T][Bc][ND*H]  grad wrt the layer output
+              const float* __restrict__ gates,   // [T][Bc][ND][H][4] post-activation i,f,g,o
+              const float* __restrict__ csave,   // [T][Bc][ND][H]
               const float* __restrict__ whh_bf,  // [4H][H] gate-interleaved rows, forward direction
               const float* __restrict__ whh_br,  // reverse direction
-              float* __restrict__ dG,            // [T][Bc][2][H][4]
-              int Bc, int T) {
+              float* __restrict__ dG,            // [T][Bc][ND][H][4]
+              int Bc, int T, int ND) {
   constexpr int GROUPS = BP_THREADS / H, MT = GROUPS * BP_WPT, GS = MT + 4;
   extern __shared__ __align__(16) float bp_smem[];  // [4H][GS]
   const int tid = threadIdx.x, j = tid % H, grp = tid / H;
@@ -606,10 +620,10 @@ lstm_bptt_f32(const float* __restrict__ dout,    // [T][Bc][2H]  grad wrt the la
       float4 dg = make_float4(0.f, 0.f, 0.f, 0.f);
       if (b < Bc) {
         const long long row = (long long)t * Bc + b;
-        const float4 g = reinterpret_cast<const float4*>(gates)[(row * 2 + dir) * H + j];
-        const float c = csave[(row * 2 + dir) * H + j];
-        const float cprev = (s > 0) ? csave[(((long long)tp * Bc + b) * 2 + dir) * H + j] : 0.f;
-        const float dh = dout[row * (2 * H) + dir * H + j] + dh_rec[w];
+        const float4 g = reinterpret_cast<const float4*>(gates)[(row * ND + dir) * H + j];
+        const float c = csave[(row * ND + dir) * H + j];
+        const float cprev = (s > 0) ? csave[(((long long)tp * Bc + b) * ND + dir) * H + j] : 0.f;
+        const float dh = dout[row * (ND * H) + dir * H + j] + dh_rec[w];
         const float tc = tanhf(c);
         const float dct = fmaf(dh * g.w, 1.0f - tc * tc, dc[w]);
         dg.x = dct * g.z * g.x * (1.0f - g.x);          // d pre_i
@@ -617,7 +631,7 @@ lstm_bptt_f32(const float* __restrict__ dout,    // [T][Bc][2H]  grad wrt the la
         dg.z = dct * g.x * (1.0f - g.z * g.z);          // d pre_g
         dg.w = dh * tc * g.w * (1.0f - g.w);            // d pre_o
         dc[w] = dct * g.y;
-        reinterpret_cast<float4*>(dG)[(row * 2 + dir) * H + j] = dg;
+        reinterpret_cast<float4*>(dG)[(row * ND + dir) * H + j] = dg;
       }
       dgs[0 * GS + w] = dg.x; dgs[1 * GS + w] = dg.y; dgs[2 * GS + w] = dg.z; dgs[3 * GS + w] = dg.w;
     }
@@ -695,22 +709,22 @@ struct TrainWs {
 struct TrainHeader { float dropout; uint32_t valid; uint64_t seed; int batch, T; };
 
 static void carve_train(const bci_lstm_config& c, int B, int T, float p_drop, char* base, TrainWs& w) {
-  const size_t H = c.hidden_size, D = 2 * H, C = c.input_size, M = (size_t)B * T;
+  const size_t H = c.hidden_size, D = feat_width(c), C = c.input_size, M = (size_t)B * T;
   size_t off = 0;
   auto take = [&](size_t n) { float* p = reinterpret_cast<float*>(base + off); off += align_up(n * sizeof(float), 256); return p; };
   w.hdr = take(64);
   w.xT = take(M * C); w.xhat0 = take(M * H); w.rstd0 = take(M); w.z = take(M * H);
   for (int l = 0; l < c.num_layers; ++l) {
-    w.gates[l] = take(M * 8 * H); w.cst[l] = take(M * 2 * H); w.out[l] = take(M * D);
+    w.gates[l] = take(M * 4 * D); w.cst[l] = take(M * D); w.out[l] = take(M * D);
     w.outd[l] = (p_drop > 0.f && l < c.num_layers - 1) ? take(M * D) : w.out[l];
   }
-  w.G = take(M * 8 * H);
-  w.xhatF = take(M * D); w.rstdF = take(M); w.Y = take(M * D); w.PRE = take(M * H);
+  w.G = take(M * 4 * D);
+  w.xhatF = take(M * D); w.rstdF = take(M); w.Y = take(M * D); w.PRE = take(M * (D / 2));
   w.attn = take((size_t)B * T); w.ctx = take(B * D); w.pre1 = take(B * H); w.h1d = take(B * H);
   w.pre2 = take(B * (H / 2)); w.h2d = take(B * (H / 2));
   w.dA = take(M * D); w.dB = take(M * D);
   w.dctx = take(B * D); w.dpre1 = take(B * H); w.dpre2 = take(B * (H / 2));
-  w.tmpW = take(8 * H * D + 1024);
+  w.tmpW = take(4 * D * (D > H ? D : H) + 1024);
   w.total = off;
 }
 
@@ -720,22 +734,22 @@ size_t lstm_workspace_train(const bci_lstm_config& c, int batch, int T) {
   return w.total;
 }
 
-template <int H>
+template <int H, int ND>
 static int forward_train_t(bci_lstm_s* h, const float* x, int B, int T, float p_drop, uint64_t seed, float* logits, float* probs,
                            float* attn, TrainWs& w, cudaStream_t st) {
   const bci_lstm_config& c = h->cfg;
   const PackedF32& p = h->f32;
-  constexpr int D = 2 * H;
-  const int C = c.input_size;
+  constexpr int D = ND * H, AH = D / 2;
+  const int C = c.input_size, use_ln = c.use_layer_norm;
   const long long M = (long long)B * T;
   const int rb = (int)((M + 7) / 8 < 4096 ? (M + 7) / 8 : 4096);
-  inproj_train_fwd<H><<<rb, 256, 0, st>>>(x, B, T, C, p.w0t, p.b0, p.ln0w, p.ln0b, w.xT, w.xhat0, w.rstd0, w.z, p_drop * 0.5f, seed);
+  inproj_train_fwd<H><<<rb, 256, 0, st>>>(x, B, T, C, p.w0t, p.b0, p.ln0w, p.ln0b, w.xT, w.xhat0, w.rstd0, w.z, p_drop * 0.5f, seed, use_ln);
   BCI_LAUNCH_OK();
   const float* in = w.z;
   for (int l = 0; l < c.num_layers; ++l) {
-    int rc = launch_proj_gemm_f32(in, p.wih_t[l], p.bias[l], w.G, (int)M, 8 * H, layer_in_width(c, l), st);
+    int rc = launch_proj_gemm_f32(in, p.wih_t[l], p.bias[l], w.G, (int)M, 4 * D, layer_in_width(c, l), st);
     if (rc) return rc;
-    rc = launch_rec_f32(H, w.G, p.whh_t[l][0], p.whh_t[l][1], w.out[l], w.gates[l], w.cst[l], B, T, st);
+    rc = launch_rec_f32(H, ND, w.G, p.whh_t[l][0], p.whh_t[l][1], w.out[l], w.gates[l], w.cst[l], B, T, st);
     if (rc) return rc;
     if (w.outd[l] != w.out[l]) {
       scale_mask_kernel<<<(unsigned)ceil_div64(M * D, 256), 256, 0, st>>>(w.out[l], w.outd[l], M * D, p_drop, seed, 16 + l);
@@ -744,15 +758,18 @@ static int forward_train_t(bci_lstm_s* h, const float* x, int B, int T, float p_
     in = w.outd[l];
   }
   const float* seq = w.out[c.num_layers - 1];
-  ln_rows_fwd<D><<<rb, 256, 0, st>>>(seq, M, p.lnw, p.lnb, w.xhatF, w.rstdF, w.Y);
+  ln_rows_fwd<D><<<rb, 256, 0, st>>>(seq, M, p.lnw, p.lnb, w.xhatF, w.rstdF, w.Y, use_ln);
   BCI_LAUNCH_OK();
-  int rc = launch_proj_gemm_f32(w.Y, p.aw1t, p.ab1, w.PRE, (int)M, H, D, st);
-  if (rc) return rc;
-  attn_train_fwd<H><<<B, 256, T * sizeof(float), st>>>(w.PRE, w.Y, B, T, p.aw2, p.ab2, w.attn, w.ctx);
+  int rc = BCI_OK;
+  if (c.use_attention) {
+    rc = gemm_nn(w.Y, D, p.aw1t, AH, w.PRE, AH, (int)M, AH, D, p.ab1, 0, st);
+    if (rc) return rc;
+  }
+  attn_train_fwd<<<B, 256, T * sizeof(float), st>>>(c.use_attention ? w.PRE : nullptr, w.Y, B, T, D, AH, p.aw2, p.ab2, w.attn, w.ctx);
   BCI_LAUNCH_OK();
   if (attn) BCI_CUDA_OK(cudaMemcpyAsync(attn, w.attn, (size_t)B * T * sizeof(float), cudaMemcpyDeviceToDevice, st));
   head_train_fwd<H><<<B, H, 0, st>>>(w.ctx, c.num_classes, p.c0t, p.cb0, p.c3t, p.cb3, p.c6, p.cb6, w.pre1, w.h1d, w.pre2, w.h2d,
-                                       logits, probs, p_drop, seed);
+                                       logits, probs, p_drop, seed, D);
   BCI_LAUNCH_OK();
   return BCI_OK;
 }
@@ -768,25 +785,28 @@ int lstm_forward_train(bci_lstm_s* h, const float* x, int batch, int T, float dr
   BCI_REQUIRE(T * sizeof(float) + 2 * c.hidden_size * sizeof(float) <= 40 * 1024, BCI_EINVAL, "training supports seq_len <= 8192");
   TrainHeader hd{dropout, 0xB200C0DEu, seed, batch, T};
   BCI_CUDA_OK(cudaMemcpyAsync(w.hdr, &hd, sizeof(hd), cudaMemcpyHostToDevice, st));
-  return c.hidden_size == 128 ? forward_train_t<128>(h, x, batch, T, dropout, seed, logits, probs, attn, w, st)
-                              : forward_train_t<256>(h, x, batch, T, dropout, seed, logits, probs, attn, w, st);
+  if (c.bidirectional)
+    return c.hidden_size == 128 ? forward_train_t<128, 2>(h, x, batch, T, dropout, seed, logits, probs, attn, w, st)
+                                : forward_train_t<256, 2>(h, x, batch, T, dropout, seed, logits, probs, attn, w, st);
+  return c.hidden_size == 128 ? forward_train_t<128, 1>(h, x, batch, T, dropout, seed, logits, probs, attn, w, st)
+                              : forward_train_t<256, 1>(h, x, batch, T, dropout, seed, logits, probs, attn, w, st);
 }
 
-template <int H>
+template <int H, int ND>
 static int backward_t(bci_lstm_s* h, const float* dlogits, int B, int T, float p_drop, uint64_t seed, float* dx, const bci_lstm_grads* g,
                       TrainWs& w, cudaStream_t st) {
   const bci_lstm_config& c = h->cfg;
   const PackedF32& p = h->f32;
   const bci_lstm_weights& raw = h->raw;
-  constexpr int D = 2 * H;
-  const int C = c.input_size, L = c.num_layers, cls = c.num_classes;
+  constexpr int D = ND * H, AH = D / 2, G4 = 4 * D;  // G4: gate columns of all directions
+  const int C = c.input_size, L = c.num_layers, cls = c.num_classes, use_ln = c.use_layer_norm;
   const long long M = (long long)B * T;
   const int rb = (int)((M + 7) / 8 < 4096 ? (M + 7) / 8 : 4096);
   auto zero = [&](float* ptr, size_t n) { return cudaMemsetAsync(ptr, 0, n * sizeof(float), st); };
   int rc;
   // ---- head ----
   head_train_bwd<H><<<B, H, 0, st>>>(dlogits, cls, w.pre1, w.pre2, raw.cls_w6, raw.cls_w3, raw.cls_w0, w.dpre1, w.dpre2, w.dctx,
-                                       p_drop, seed);
+                                       p_drop, seed, D);
   BCI_LAUNCH_OK();
   BCI_CUDA_OK(zero(g->cls_w6, (size_t)cls * (H / 2))); BCI_CUDA_OK(zero(g->cls_b6, cls));
   BCI_CUDA_OK(zero(g->cls_w3, (size_t)(H / 2) * H));   BCI_CUDA_OK(zero(g->cls_b3, H / 2));
@@ -798,24 +818,29 @@ static int backward_t(bci_lstm_s* h, const float* dlogits, int B, int T, float p
   if ((rc = gemm_tn(w.dpre1, H, w.ctx, D, g->cls_w0, D, B, H, D, st))) return rc;
   if ((rc = colsum(w.dpre1, H, B, H, g->cls_b0, st))) return rc;
   // ---- attention pooling ----
-  BCI_CUDA_OK(zero(g->attn_w2, H)); BCI_CUDA_OK(zero(g->attn_b2, 1));
-  BCI_CUDA_OK(zero(g->attn_w1, (size_t)H * D)); BCI_CUDA_OK(zero(g->attn_b1, H));
-  BCI_CUDA_OK(zero(g->ln_w, D)); BCI_CUDA_OK(zero(g->ln_b, D));
-  float* dPRE = w.dB;  // [M][H] lives in dB until the LayerNorm backward below overwrites it (no longer needed then)
-  attn_train_bwd<H><<<B, 256, (T + D) * sizeof(float), st>>>(w.PRE, dPRE, w.Y, w.attn, w.dctx, B, T, p.aw2, w.dA /*dY*/, g->attn_w2, g->attn_b2);
+  float* dPRE = w.dB;  // [M][AH] lives in dB until the LayerNorm backward below overwrites it (no longer needed then)
+  if (c.use_attention) {
+    BCI_CUDA_OK(zero(g->attn_w2, AH)); BCI_CUDA_OK(zero(g->attn_b2, 1));
+    BCI_CUDA_OK(zero(g->attn_w1, (size_t)AH * D)); BCI_CUDA_OK(zero(g->attn_b1, AH));
+  }
+  if (use_ln) { BCI_CUDA_OK(zero(g->ln_w, D)); BCI_CUDA_OK(zero(g->ln_b, D)); }
+  attn_train_bwd<<<B, 256, (T + D) * sizeof(float), st>>>(c.use_attention ? w.PRE : nullptr, dPRE, w.Y, w.attn, w.dctx, B, T, D, AH, p.aw2,
+                                                          w.dA /*dY*/, g->attn_w2, g->attn_b2);
   BCI_LAUNCH_OK();
-  // dY += dPRE . W1 ; dW1 = dPRE^T Y ; db1 = colsum(dPRE)
-  if ((rc = gemm_nn(dPRE, H, raw.attn_w1, D, w.dA, D, (int)M, D, H, nullptr, 1, st))) return rc;
-  if ((rc = gemm_tn(dPRE, H, w.Y, D, g->attn_w1, D, M, H, D, st))) return rc;
-  if ((rc = colsum(dPRE, H, M, H, g->attn_b1, st))) return rc;
+  if (c.use_attention) {
+    // dY += dPRE . W1 ; dW1 = dPRE^T Y ; db1 = colsum(dPRE)
+    if ((rc = gemm_nn(dPRE, AH, raw.attn_w1, D, w.dA, D, (int)M, D, AH, nullptr, 1, st))) return rc;
+    if ((rc = gemm_tn(dPRE, AH, w.Y, D, g->attn_w1, D, M, AH, D, st))) return rc;
+    if ((rc = colsum(dPRE, AH, M, AH, g->attn_b1, st))) return rc;
+  }
   // final LayerNorm backward: dA (dY) -> dB (grad wrt the last LSTM layer's output)
-  ln_rows_bwd<D><<<rb, 256, 0, st>>>(w.dA, w.xhatF, w.rstdF, p.lnw, M, w.dB, g->ln_w, g->ln_b);
+  ln_rows_bwd<D><<<rb, 256, 0, st>>>(w.dA, w.xhatF, w.rstdF, p.lnw, M, w.dB, g->ln_w, g->ln_b, use_ln);
   BCI_LAUNCH_OK();
   float* dcur = w.dB;   // grad wrt out[l]
   float* dnext = w.dA;  // scratch for grad wrt the layer input
   // ---- LSTM layers, top down ----
   // 16 windows per thread unless that leaves most SMs idle (typical training batches): then 8
-  const bool small = 2 * ceil_div(B, (BP_THREADS / H) * 16) < sm_count();
+  const bool small = ND * ceil_div(B, (BP_THREADS / H) * 16) < sm_count();
   const int MT = (BP_THREADS / H) * (small ? 8 : 16);
   const size_t bp_smem = (size_t)4 * H * (MT + 4) * sizeof(float);
   static bool attr = false;
@@ -830,36 +855,36 @@ static int backward_t(bci_lstm_s* h, const float* dlogits, int B, int T, float p
     const int K = layer_in_width(c, l);
     const float* in = (l == 0) ? w.z : w.outd[l - 1];
     if (small)
-      lstm_bptt_f32<H, 8><<<dim3(ceil_div(B, MT), 2), BP_THREADS, bp_smem, st>>>(dcur, w.gates[l], w.cst[l], p.whh_b[l][0], p.whh_b[l][1], w.G, B, T);
+      lstm_bptt_f32<H, 8><<<dim3(ceil_div(B, MT), ND), BP_THREADS, bp_smem, st>>>(dcur, w.gates[l], w.cst[l], p.whh_b[l][0], p.whh_b[l][1], w.G, B, T, ND);
     else
-      lstm_bptt_f32<H, 16><<<dim3(ceil_div(B, MT), 2), BP_THREADS, bp_smem, st>>>(dcur, w.gates[l], w.cst[l], p.whh_b[l][0], p.whh_b[l][1], w.G, B, T);
+      lstm_bptt_f32<H, 16><<<dim3(ceil_div(B, MT), ND), BP_THREADS, bp_smem, st>>>(dcur, w.gates[l], w.cst[l], p.whh_b[l][0], p.whh_b[l][1], w.G, B, T, ND);
     BCI_LAUNCH_OK();
-    // dW_ih (both directions at once, interleaved rows) = dG^T . in
-    BCI_CUDA_OK(zero(w.tmpW, (size_t)8 * H * K));
-    if ((rc = gemm_tn(w.G, 8 * H, in, K, w.tmpW, K, M, 8 * H, K, st))) return rc;
-    for (int d = 0; d < 2; ++d) {
+    // dW_ih (all directions at once, interleaved rows) = dG^T . in
+    BCI_CUDA_OK(zero(w.tmpW, (size_t)G4 * K));
+    if ((rc = gemm_tn(w.G, G4, in, K, w.tmpW, K, M, G4, K, st))) return rc;
+    for (int d = 0; d < ND; ++d) {
       unpack_gate_rows_kernel<<<(unsigned)ceil_div64((long long)4 * H * K, 256), 256, 0, st>>>(w.tmpW, g->w_ih[l][d], H, K, d * 4 * H);
       BCI_LAUNCH_OK();
     }
     // dW_hh[d] = dG[:, d]^T . h_prev, h_prev(t) = out[t-1] (forward) / out[t+1] (reverse): a row shift by Bc rows
-    for (int d = 0; d < 2; ++d) {
+    for (int d = 0; d < ND; ++d) {
       BCI_CUDA_OK(zero(w.tmpW, (size_t)4 * H * H));
       const long long R = M - B;
-      const float* Ad = w.G + d * 4 * H + (d == 0 ? (long long)B * 8 * H : 0);
+      const float* Ad = w.G + d * 4 * H + (d == 0 ? (long long)B * G4 : 0);
       const float* Bd = w.out[l] + d * H + (d == 0 ? 0 : (long long)B * D);
-      if ((rc = gemm_tn(Ad, 8 * H, Bd, D, w.tmpW, H, R, 4 * H, H, st))) return rc;
+      if ((rc = gemm_tn(Ad, G4, Bd, D, w.tmpW, H, R, 4 * H, H, st))) return rc;
       unpack_gate_rows_kernel<<<(unsigned)ceil_div64((long long)4 * H * H, 256), 256, 0, st>>>(w.tmpW, g->w_hh[l][d], H, H, 0);
       BCI_LAUNCH_OK();
     }
     // biases
-    BCI_CUDA_OK(zero(w.tmpW, (size_t)8 * H));
-    if ((rc = colsum(w.G, 8 * H, M, 8 * H, w.tmpW, st))) return rc;
-    for (int d = 0; d < 2; ++d) {
+    BCI_CUDA_OK(zero(w.tmpW, (size_t)G4));
+    if ((rc = colsum(w.G, G4, M, G4, w.tmpW, st))) return rc;
+    for (int d = 0; d < ND; ++d) {
       unpack_bias_kernel<<<ceil_div(4 * H, 256), 256, 0, st>>>(w.tmpW, g->b_ih[l][d], g->b_hh[l][d], H, d * 4 * H);
       BCI_LAUNCH_OK();
     }
     // grad wrt the layer input: dnext [M][K] = dG . wih_b
-    if ((rc = gemm_nn(w.G, 8 * H, p.wih_b[l], K, dnext, K, (int)M, K, 8 * H, nullptr, 0, st))) return rc;
+    if ((rc = gemm_nn(w.G, G4, p.wih_b[l], K, dnext, K, (int)M, K, G4, nullptr, 0, st))) return rc;
     if (l > 0 && w.outd[l - 1] != w.out[l - 1]) {
       scale_mask_kernel<<<(unsigned)ceil_div64(M * K, 256), 256, 0, st>>>(dnext, dnext, M * K, p_drop, seed, 16 + (l - 1));
       BCI_LAUNCH_OK();
@@ -867,10 +892,10 @@ static int backward_t(bci_lstm_s* h, const float* dlogits, int B, int T, float p
     float* tsw = dcur; dcur = dnext; dnext = tsw;
   }
   // ---- input projection: dcur = dz [M][H] ----
-  BCI_CUDA_OK(zero(g->input_ln_w, H)); BCI_CUDA_OK(zero(g->input_ln_b, H));
+  if (use_ln) { BCI_CUDA_OK(zero(g->input_ln_w, H)); BCI_CUDA_OK(zero(g->input_ln_b, H)); }
   BCI_CUDA_OK(zero(g->input_proj_w, (size_t)H * C)); BCI_CUDA_OK(zero(g->input_proj_b, H));
   inproj_bwd_rows<H><<<rb, 256, 0, st>>>(dcur, w.xhat0, w.rstd0, p.ln0w, p.ln0b, M, dnext /*dv*/, g->input_ln_w, g->input_ln_b,
-                                         p_drop * 0.5f, seed);
+                                         p_drop * 0.5f, seed, use_ln);
   BCI_LAUNCH_OK();
   if ((rc = gemm_tn(dnext, H, w.xT, C, g->input_proj_w, C, M, H, C, st))) return rc;
   if ((rc = colsum(dnext, H, M, H, g->input_proj_b, st))) return rc;
@@ -896,18 +921,22 @@ int lstm_backward_impl(bci_lstm_s* h, const float* x, const float* dlogits, int 
   TrainWs w;
   carve_train(c, batch, T, hd.dropout, (char*)ws, w);
   BCI_REQUIRE(ws_bytes >= w.total, BCI_ENOMEM, "bci_lstm_backward: workspace %zu < %zu bytes", ws_bytes, w.total);
-  const float* const* gp = reinterpret_cast<const float* const*>(g);
-  for (size_t i = 0; i < sizeof(bci_lstm_grads) / sizeof(float*); ++i) {
-    const size_t lay = 4, per = BCI_MAX_LAYERS * 2;
-    // layer arrays: only the first num_layers entries are required
-    if (i >= lay && i < lay + 4 * per) {
-      const size_t li = ((i - lay) % per) / 2;
-      if ((int)li >= c.num_layers) continue;
-    }
-    BCI_REQUIRE(gp[i] != nullptr, BCI_EINVAL, "bci_lstm_backward: gradient pointer %zu is NULL", i);
-  }
-  return c.hidden_size == 128 ? backward_t<128>(h, dlogits, batch, T, hd.dropout, hd.seed, dx, g, w, st)
-                              : backward_t<256>(h, dlogits, batch, T, hd.dropout, hd.seed, dx, g, w, st);
+  // every module the configuration has needs its gradient pointers
+  BCI_REQUIRE(g->input_proj_w && g->input_proj_b && g->cls_w0 && g->cls_b0 && g->cls_w3 && g->cls_b3 && g->cls_w6 && g->cls_b6,
+              BCI_EINVAL, "bci_lstm_backward: a projection / classifier gradient pointer is NULL");
+  if (c.use_layer_norm)
+    BCI_REQUIRE(g->input_ln_w && g->input_ln_b && g->ln_w && g->ln_b, BCI_EINVAL, "bci_lstm_backward: a LayerNorm gradient pointer is NULL");
+  if (c.use_attention)
+    BCI_REQUIRE(g->attn_w1 && g->attn_b1 && g->attn_w2 && g->attn_b2, BCI_EINVAL, "bci_lstm_backward: an attention gradient pointer is NULL");
+  for (int l = 0; l < c.num_layers; ++l)
+    for (int d = 0; d < num_dirs(c); ++d)
+      BCI_REQUIRE(g->w_ih[l][d] && g->w_hh[l][d] && g->b_ih[l][d] && g->b_hh[l][d], BCI_EINVAL,
+                  "bci_lstm_backward: LSTM gradient pointer NULL (layer %d dir %d)", l, d);
+  if (c.bidirectional)
+    return c.hidden_size == 128 ? backward_t<128, 2>(h, dlogits, batch, T, hd.dropout, hd.seed, dx, g, w, st)
+                                : backward_t<256, 2>(h, dlogits, batch, T, hd.dropout, hd.seed, dx, g, w, st);
+  return c.hidden_size == 128 ? backward_t<128, 1>(h, dlogits, batch, T, hd.dropout, hd.seed, dx, g, w, st)
+                              : backward_t<256, 1>(h, dlogits, batch, T, hd.dropout, hd.seed, dx, g, w, st);
 }
 
 // ---- fused clip + AdamW ---------------------------------------------------------------------------------------------

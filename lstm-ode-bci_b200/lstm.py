@@ -26,34 +26,41 @@ class EnhancedLSTMModel(nn.Module):
     precision: "fp32" (parity mode, CUDA-core FMA, <=1e-5 on logits/probabilities) or "bf16"
     (tcgen05 tensor-core mode).  Under `torch.autocast("cuda")` -- which the reference enables on
     GPUs (04:486-490, 06:348-351) -- "auto" selects bf16, otherwise fp32.
+
+    `use_attention` / `use_layer_norm` / `bidirectional=False` are the ablation switches of
+    09_sensitivity_analysis.py:176-240 (see AblationLSTMModel below); those variants run in fp32 precision.
     """
 
     def __init__(self, input_size=14, hidden_size=128, num_layers=3, num_classes=2, dropout=0.4,
-                 bidirectional=True, num_heads=4, precision="auto"):
+                 bidirectional=True, num_heads=4, precision="auto", use_attention=True, use_layer_norm=True):
         super().__init__()
-        if not bidirectional:
-            raise N.BciError(-1, "only bidirectional=True is built (ablation variants: SURVEY.md §8 f)")
-        self.hidden_size, self.num_layers, self.bidirectional = hidden_size, num_layers, bidirectional
-        self.num_directions = 2
+        self.hidden_size, self.num_layers, self.bidirectional = hidden_size, num_layers, bool(bidirectional)
+        self.use_attention, self.use_layer_norm = bool(use_attention), bool(use_layer_norm)
+        self.num_directions = 2 if bidirectional else 1
         self.input_size, self.num_classes, self.dropout_p = input_size, num_classes, dropout
         self.precision = precision
-        d = 2 * hidden_size
-        self.input_proj = nn.Sequential(nn.Linear(input_size, hidden_size), nn.LayerNorm(hidden_size),
+        d = self.num_directions * hidden_size
+        self.input_proj = nn.Sequential(nn.Linear(input_size, hidden_size),
+                                        nn.LayerNorm(hidden_size) if use_layer_norm else nn.Identity(),
                                         nn.GELU(), nn.Dropout(dropout / 2))
         self.lstm = nn.LSTM(hidden_size, hidden_size, num_layers, batch_first=True,
-                            dropout=dropout if num_layers > 1 else 0, bidirectional=True)
-        self.layer_norm = nn.LayerNorm(d)
-        self.attention = _Pool(d)
+                            dropout=dropout if num_layers > 1 else 0, bidirectional=self.bidirectional)
+        self.layer_norm = nn.LayerNorm(d) if use_layer_norm else nn.Identity()
+        self.attention = _Pool(d) if use_attention else None
         self.classifier = nn.Sequential(nn.Linear(d, hidden_size), nn.GELU(), nn.Dropout(dropout),
                                         nn.Linear(hidden_size, hidden_size // 2), nn.GELU(), nn.Dropout(dropout),
                                         nn.Linear(hidden_size // 2, num_classes))
         self._engines = {}       # precision -> handle id
         self._loaded = {}        # precision -> tuple of parameter versions/ptrs at last load
 
+    @property
+    def is_full_model(self):
+        return self.bidirectional and self.use_attention and self.use_layer_norm
+
     # -- engine management -------------------------------------------------------------------
     def _precision_now(self):
         if self.precision == "auto":
-            return "bf16" if torch.is_autocast_enabled("cuda") else "fp32"
+            return "bf16" if (torch.is_autocast_enabled("cuda") and self.is_full_model and self.hidden_size == 128) else "fp32"
         return self.precision
 
     def _signature(self):
@@ -65,7 +72,8 @@ class EnhancedLSTMModel(nn.Module):
         hid = self._engines.get(prec)
         if hid is None:
             hid = ops.lstm_create(self.input_size, self.hidden_size, self.num_layers, self.num_classes,
-                                  N.PRECISION_BF16 if prec == "bf16" else N.PRECISION_FP32)
+                                  N.PRECISION_BF16 if prec == "bf16" else N.PRECISION_FP32, self.bidirectional,
+                                  self.use_attention, self.use_layer_norm)
             self._engines[prec] = hid
         sig = self._signature()
         if self._loaded.get(prec) != sig:
@@ -101,13 +109,30 @@ class EnhancedLSTMModel(nn.Module):
         return (probs, attn) if return_attention else probs
 
 
+class AblationLSTMModel(EnhancedLSTMModel):
+    """Drop-in for 09_sensitivity_analysis.py:176-240: same constructor (defaults included), `forward(x) -> logits` only.
+    The six configurations of run_architecture_ablation (09:330-378) -- full, no attention (mean pooling), unidirectional,
+    1 and 2 layers, minimal -- and use_layer_norm=False all map onto switches of the same CUDA op; training goes through
+    the same autograd bridge, so quick_train_evaluate (09:265-327) runs unchanged."""
+
+    def __init__(self, input_size=61, hidden_size=256, num_layers=3, num_classes=2, dropout=0.4, bidirectional=True,
+                 use_attention=True, use_layer_norm=True, precision="fp32"):
+        super().__init__(input_size, hidden_size, num_layers, num_classes, dropout, bidirectional, precision=precision,
+                         use_attention=use_attention, use_layer_norm=use_layer_norm)
+
+    def forward(self, x):
+        return super().forward(x, return_attention=False)
+
+
 def from_params(params, precision="fp32", device="cuda", dropout=0.4):
-    """Build a CUDA model from a {state-dict key: ndarray/tensor} dict."""
+    """Build a CUDA model from a {state-dict key: ndarray/tensor} dict (variant switches inferred from the keys)."""
     H, Cc = params["input_proj.0.weight"].shape
     layers = 0
     while f"lstm.weight_hh_l{layers}" in params:
         layers += 1
     classes = params["classifier.6.weight"].shape[0]
-    m = EnhancedLSTMModel(Cc, H, layers, classes, dropout, True, precision=precision)
+    m = EnhancedLSTMModel(Cc, H, layers, classes, dropout, "lstm.weight_hh_l0_reverse" in params, precision=precision,
+                          use_attention="attention.attention.0.weight" in params,
+                          use_layer_norm="layer_norm.weight" in params)
     m.load_state_dict({k: torch.as_tensor(v).float() for k, v in params.items()}, strict=True)
     return m.to(device).eval()

@@ -48,8 +48,10 @@ class _Handle:
             self.ptr = C.c_void_p(0)
 
 
-def lstm_create(input_size, hidden_size, num_layers, num_classes, precision):
-    cfg = N.LstmConfig(int(input_size), int(hidden_size), int(num_layers), int(num_classes), 1, int(precision))
+def lstm_create(input_size, hidden_size, num_layers, num_classes, precision, bidirectional=True, use_attention=True,
+                use_layer_norm=True):
+    cfg = N.LstmConfig(int(input_size), int(hidden_size), int(num_layers), int(num_classes), int(bool(bidirectional)),
+                       int(precision), int(bool(use_attention)), int(bool(use_layer_norm)))
     h = _Handle(cfg)
     with _handles_lock:
         hid = _next_handle[0]
@@ -78,11 +80,14 @@ _KEYMAP = [
 
 
 def fill_pointer_struct(struct, tensors, num_layers):
-    """tensors: {state-dict key: contiguous fp32 CUDA tensor} (SURVEY.md §8 a1 names)."""
+    """tensors: {state-dict key: contiguous fp32 CUDA tensor} (SURVEY.md §8 a1 names).  Keys of modules an ablation
+    variant does not have (LayerNorms, attention, the reverse direction: 09:176-240) are left NULL."""
     for field, key in _KEYMAP:
-        setattr(struct, field, tensors[key].data_ptr())
+        setattr(struct, field, tensors[key].data_ptr() if key in tensors else None)
     for l in range(num_layers):
         for d, suf in enumerate(("", "_reverse")):
+            if f"lstm.weight_ih_l{l}{suf}" not in tensors:
+                continue
             struct.w_ih[l][d] = tensors[f"lstm.weight_ih_l{l}{suf}"].data_ptr()
             struct.w_hh[l][d] = tensors[f"lstm.weight_hh_l{l}{suf}"].data_ptr()
             struct.b_ih[l][d] = tensors[f"lstm.bias_ih_l{l}{suf}"].data_ptr()

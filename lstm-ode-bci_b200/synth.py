@@ -15,14 +15,17 @@ RATE_ORDER = ("k_ap", "k_af", "k_pa", "k_pf", "k_fa", "k_fp")
 ALPHA_GRID = (0.0, 0.25, 0.5, 0.75, 1.0)  # 06_lstm_ode_integration.py:531
 
 
-def lstm_param_shapes(input_size=61, hidden=128, layers=3, classes=2, bidirectional=True):
-    """Ordered {state_dict key: shape} of EnhancedLSTMModel (04_lstm_model.py:163-204)."""
+def lstm_param_shapes(input_size=61, hidden=128, layers=3, classes=2, bidirectional=True, use_attention=True,
+                      use_layer_norm=True):
+    """Ordered {state_dict key: shape} of EnhancedLSTMModel (04_lstm_model.py:163-204) and, with the switches, of
+    AblationLSTMModel (09_sensitivity_analysis.py:176-240: Identity / no attention module / one direction)."""
     H, D = hidden, (2 if bidirectional else 1)
     s = {}
     s["input_proj.0.weight"] = (H, input_size)
     s["input_proj.0.bias"] = (H,)
-    s["input_proj.1.weight"] = (H,)
-    s["input_proj.1.bias"] = (H,)
+    if use_layer_norm:
+        s["input_proj.1.weight"] = (H,)
+        s["input_proj.1.bias"] = (H,)
     for l in range(layers):
         k_in = H if l == 0 else D * H
         for suf in ([""] + (["_reverse"] if bidirectional else [])):
@@ -30,12 +33,14 @@ def lstm_param_shapes(input_size=61, hidden=128, layers=3, classes=2, bidirectio
             s[f"lstm.weight_hh_l{l}{suf}"] = (4 * H, H)
             s[f"lstm.bias_ih_l{l}{suf}"] = (4 * H,)
             s[f"lstm.bias_hh_l{l}{suf}"] = (4 * H,)
-    s["layer_norm.weight"] = (D * H,)
-    s["layer_norm.bias"] = (D * H,)
-    s["attention.attention.0.weight"] = (D * H // 2, D * H)
-    s["attention.attention.0.bias"] = (D * H // 2,)
-    s["attention.attention.2.weight"] = (1, D * H // 2)
-    s["attention.attention.2.bias"] = (1,)
+    if use_layer_norm:
+        s["layer_norm.weight"] = (D * H,)
+        s["layer_norm.bias"] = (D * H,)
+    if use_attention:
+        s["attention.attention.0.weight"] = (D * H // 2, D * H)
+        s["attention.attention.0.bias"] = (D * H // 2,)
+        s["attention.attention.2.weight"] = (1, D * H // 2)
+        s["attention.attention.2.bias"] = (1,)
     s["classifier.0.weight"] = (H, D * H)
     s["classifier.0.bias"] = (H,)
     s["classifier.3.weight"] = (H // 2, H)
@@ -46,14 +51,15 @@ def lstm_param_shapes(input_size=61, hidden=128, layers=3, classes=2, bidirectio
 
 
 def make_lstm_params(seed=42, input_size=61, hidden=128, layers=3, classes=2,
-                     bidirectional=True, logit_gain=1.0):
+                     bidirectional=True, logit_gain=1.0, use_attention=True, use_layer_norm=True):
     """fp32 parameters with torch-like init ranges (U(-1/sqrt(fan), 1/sqrt(fan)); LN weight
     ~1, bias ~0 perturbed so the affine terms are exercised).  `logit_gain` scales the last
     classifier layer so P(open)/P(closed) spread past the 0.6 thresholds of
     06_lstm_ode_integration.py:377-382 (default init gives P ~ 0.5, SURVEY.md §8 d)."""
     rng = np.random.default_rng(seed)
     out = {}
-    for name, shape in lstm_param_shapes(input_size, hidden, layers, classes, bidirectional).items():
+    shapes = lstm_param_shapes(input_size, hidden, layers, classes, bidirectional, use_attention, use_layer_norm)
+    for name, shape in shapes.items():
         if name in ("input_proj.1.weight", "layer_norm.weight"):
             a = 1.0 + 0.1 * rng.standard_normal(shape)
         elif name in ("input_proj.1.bias", "layer_norm.bias"):
@@ -64,8 +70,7 @@ def make_lstm_params(seed=42, input_size=61, hidden=128, layers=3, classes=2,
             elif name.endswith("weight"):
                 bound = 1.0 / math.sqrt(shape[-1])
             else:  # Linear bias: fan_in of the matching weight
-                wshape = lstm_param_shapes(input_size, hidden, layers, classes, bidirectional)[
-                    name[:-4] + "weight"]
+                wshape = shapes[name[:-4] + "weight"]
                 bound = 1.0 / math.sqrt(wshape[-1])
             a = rng.uniform(-bound, bound, size=shape)
         out[name] = np.ascontiguousarray(a, dtype=np.float32)

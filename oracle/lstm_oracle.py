@@ -44,7 +44,8 @@ def _layer_norm(x, w, b, eps=1e-5):
 def input_projection(p, x):
     """04_lstm_model.py:173-178,208 (eval: dropout is identity)."""
     z = x @ p["input_proj.0.weight"].T + p["input_proj.0.bias"]
-    z = _layer_norm(z, p["input_proj.1.weight"], p["input_proj.1.bias"])
+    if "input_proj.1.weight" in p:  # nn.Identity in the use_layer_norm=False ablation (09:191)
+        z = _layer_norm(z, p["input_proj.1.weight"], p["input_proj.1.bias"])
     return _gelu(z)
 
 
@@ -126,8 +127,13 @@ def forward(params, x, dtype=np.float64, return_intermediates=False):
     _, layers, bidir = infer_config(p)
     z = input_projection(p, x)
     out = lstm_stack(p, z, layers, bidir)
-    y = _layer_norm(out, p["layer_norm.weight"], p["layer_norm.bias"])
-    ctx, attn = attention_pool(p, y)
+    # ablation variants (09_sensitivity_analysis.py:176-240): Identity instead of LayerNorm (09:210), mean over time
+    # instead of attention pooling (09:229-234)
+    y = _layer_norm(out, p["layer_norm.weight"], p["layer_norm.bias"]) if "layer_norm.weight" in p else out
+    if "attention.attention.0.weight" in p:
+        ctx, attn = attention_pool(p, y)
+    else:
+        ctx, attn = y.mean(axis=1), np.full(y.shape[:2], 1.0 / y.shape[1], dtype=y.dtype)
     logits = classifier(p, ctx)
     if return_intermediates:
         return logits, attn, {"z": z, "lstm_out": out, "y": y, "ctx": ctx}

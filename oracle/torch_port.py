@@ -42,21 +42,29 @@ class _Pool(nn.Module):
 
 
 class BiLSTMAttnPort(nn.Module):
+    """EnhancedLSTMModel (04:153-222); with use_attention / use_layer_norm / bidirectional switched off it is
+    AblationLSTMModel (09_sensitivity_analysis.py:176-240)."""
+
     def __init__(self, input_size=61, hidden_size=128, num_layers=3, num_classes=2,
-                 dropout=0.4, bidirectional=True):
+                 dropout=0.4, bidirectional=True, use_attention=True, use_layer_norm=True):
         super().__init__()
         d = 2 if bidirectional else 1
-        self.input_proj = nn.Sequential(nn.Linear(input_size, hidden_size), nn.LayerNorm(hidden_size),
+        self.input_proj = nn.Sequential(nn.Linear(input_size, hidden_size),
+                                        nn.LayerNorm(hidden_size) if use_layer_norm else nn.Identity(),
                                         nn.GELU(), nn.Dropout(dropout / 2))
         self.lstm = nn.LSTM(hidden_size, hidden_size, num_layers, batch_first=True,
                             dropout=dropout if num_layers > 1 else 0.0, bidirectional=bidirectional)
-        self.layer_norm = nn.LayerNorm(d * hidden_size)
-        self.attention = _Pool(d * hidden_size)
+        self.layer_norm = nn.LayerNorm(d * hidden_size) if use_layer_norm else nn.Identity()
+        self.attention = _Pool(d * hidden_size) if use_attention else None
         self.classifier = _mlp([d * hidden_size, hidden_size, hidden_size // 2, num_classes], nn.GELU, dropout)
 
     def forward(self, x, return_attention=False):
         seq, _ = self.lstm(self.input_proj(x))
-        ctx, attn = self.attention(self.layer_norm(seq))
+        y = self.layer_norm(seq)
+        if self.attention is not None:
+            ctx, attn = self.attention(y)
+        else:
+            ctx, attn = torch.mean(y, dim=1), torch.full(y.shape[:2], 1.0 / y.shape[1])
         logits = self.classifier(ctx)
         return (logits, attn) if return_attention else logits
 
@@ -70,7 +78,8 @@ def build_port(params, dropout=0.4):
         layers += 1
     bidir = "lstm.weight_hh_l0_reverse" in params
     classes = params["classifier.6.weight"].shape[0]
-    m = BiLSTMAttnPort(C, H, layers, classes, dropout, bidir)
+    m = BiLSTMAttnPort(C, H, layers, classes, dropout, bidir, "attention.attention.0.weight" in params,
+                       "layer_norm.weight" in params)
     m.load_state_dict({k: torch.from_numpy(np.array(v, dtype=np.float32)) for k, v in params.items()}, strict=True)
     return m
 

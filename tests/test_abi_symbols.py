@@ -34,7 +34,7 @@ def test_ctypes_mirror_matches_header(libpath):
     from lstm_ode_bci_b200 import _native
     assert sorted(_native.SIGNATURES) == _declared()
     lib = _native.lib()
-    assert lib.bci_abi_version() == 1
+    assert lib.bci_abi_version() == 2
     for name in _native.SIGNATURES:
         assert getattr(lib, name) is not None
 

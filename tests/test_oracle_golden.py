@@ -174,3 +174,32 @@ def test_preproc_recursion_restatement_matches_scipy():
     assert np.abs(got - want).max() <= 1e-9 * np.abs(want).max()
     with pytest.raises(ValueError):
         po.filtfilt_restated(b, a, x[:, :27])
+
+
+# ---- ablation variants (SURVEY.md §8 f row 3): oracle / port vs the live reference's AblationLSTMModel -----------------
+ABLATION_TAGS = ["full", "noattn", "unidir", "layers1", "layers2", "minimal256", "unidir256", "noln", "noln_unidir_mean"]
+
+
+def ablation_case(g, tag):
+    from lstm_ode_bci_b200 import synth
+    sw, sx, H, L, bidir, att, ln, B, T, C = (int(v) for v in g[tag + ":cfg"])
+    params = synth.make_lstm_params(sw, C, H, L, bidirectional=bool(bidir), logit_gain=4.0, use_attention=bool(att), use_layer_norm=bool(ln))
+    x = synth.make_windows(sx, B, T, C)
+    y = (np.arange(B) % 2).astype(np.int64)
+    return params, x, y
+
+
+@pytest.mark.parametrize("tag", ABLATION_TAGS)
+def test_ablation_oracles_match_reference_golden(golden, tag):
+    from oracle import lstm_oracle, torch_port
+    g = golden("ablation_ref09.npz")
+    params, x, y = ablation_case(g, tag)
+    logits, attn = lstm_oracle.forward(params, x)
+    assert np.abs(logits - g[tag + ":logits"]).max() <= 2e-6
+    assert np.abs(attn.sum(axis=1) - 1).max() <= 1e-12
+    port = torch_port.build_port(params, dropout=0.0)
+    loss, grads, dx, lg = torch_port.loss_and_grads(port, x, y)
+    assert np.abs(lg - g[tag + ":logits"]).max() <= 1e-6 and abs(loss - float(g[tag + ":loss"])) <= 1e-6
+    for k, gr in grads.items():
+        assert abs(np.linalg.norm(gr.astype(np.float64)) - float(g[tag + ":gnorm:" + k])) <= 1e-5 * max(float(g[tag + ":gnorm:" + k]), 1e-3), k
+    assert abs(np.linalg.norm(dx.astype(np.float64)) - float(g[tag + ":dx_norm"])) <= 1e-5 * float(g[tag + ":dx_norm"])
