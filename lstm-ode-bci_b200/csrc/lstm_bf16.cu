@@ -49,11 +49,30 @@ __global__ void pack_rows_perm_bf16(const float* __restrict__ src, __nv_bfloat16
   const float sc = (gate == 2) ? 1.0f : 0.5f;
   dst[(long long)(row0 + pr) * K + k] = __float2bfloat16_rn(sc * src[i]);
 }
-__global__ void pack_bias_perm(const float* __restrict__ bih, const float* __restrict__ bhh, float* __restrict__ dst, int H, int col0) {
+__global__ void pack_bias_perm(const float* __restrict__ bih, const float* __restrict__ bhh, float* __restrict__ dst, int H, int col0,
+                               int order) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= 4 * H) return;
   const int gate = i / H, unit = i - gate * H;
-  dst[col0 + perm_G(unit, gate)] = ((gate == 2) ? 1.0f : 0.5f) * (bih[i] + bhh[i]);
+  dst[col0 + (order ? perm_G(unit, gate) : perm_T(unit, gate))] = ((gate == 2) ? 1.0f : 0.5f) * (bih[i] + bhh[i]);
+}
+
+// ---- which recurrence path the bf16 forward uses -----------------------------------------------------------------------
+//   fused : lstm_fused_bf16 (4-CTA clusters, W_ih + W_hh resident, G never materialised)          [default when it fits]
+//   split : proj_gemm_bf16 (K2) -> G in HBM -> lstm_rec_bf16 (K3)                                  [BCI_BF16_PATH=split]
+static int bf16_path_fused() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("BCI_BF16_PATH");
+    if (e && e[0] == 's') v = 0;
+    else v = fused_max_clusters() > 0 ? 1 : 0;
+  }
+  return v;
+}
+int bf16_chunk_windows() {
+  // split: 74 x 128 windows = exactly one wave of (tile, direction) CTAs of the recurrence on 148 SMs.
+  // fused: every cluster runs two work items (both directions of one tile pair) per chunk: 2 tiles per co-resident cluster.
+  return bf16_path_fused() ? fused_max_clusters() * 2 * 128 : 74 * 128;
 }
 
 size_t lstm_store_bytes_bf16(const bci_lstm_config& c) {
@@ -61,7 +80,7 @@ size_t lstm_store_bytes_bf16(const bci_lstm_config& c) {
   const size_t H = c.hidden_size;
   size_t n = 0;
   for (int l = 0; l < c.num_layers; ++l)
-    n += align_up((size_t)8 * H * layer_in_width(c, l) * 2, 256) + 2 * align_up(4 * H * H * 2, 256) + align_up(8 * H * 4, 256);
+    n += 2 * align_up((size_t)8 * H * layer_in_width(c, l) * 2, 256) + 2 * align_up(4 * H * H * 2, 256) + 2 * align_up(8 * H * 4, 256);
   n += align_up(H * 2 * H * 2, 256) + align_up(H * sizeof(float4), 256);  // attention W1' (bf16) + per-unit params
   n += align_up(H * 64 * 2, 256) + align_up(H * sizeof(float4), 256);     // input projection W0 (bf16, K padded) + params
   return n + 1024;
@@ -78,6 +97,8 @@ void lstm_carve_bf16(bci_lstm_s* h, char* base) {
     h->bf16.whh_bf[l][0] = reinterpret_cast<__nv_bfloat16*>(take(4 * H * H * 2));
     h->bf16.whh_bf[l][1] = reinterpret_cast<__nv_bfloat16*>(take(4 * H * H * 2));
     h->bf16.bias_p[l] = reinterpret_cast<float*>(take(8 * H * 4));
+    h->bf16.wih_t_bf[l] = reinterpret_cast<__nv_bfloat16*>(take((size_t)8 * H * layer_in_width(c, l) * 2));
+    h->bf16.bias_t[l] = reinterpret_cast<float*>(take(8 * H * 4));
   }
   h->bf16.aw1_bf = reinterpret_cast<__nv_bfloat16*>(take(H * 2 * H * 2));
   h->bf16.apar = reinterpret_cast<float4*>(take(H * sizeof(float4)));
@@ -95,7 +116,9 @@ int lstm_pack_bf16(bci_lstm_s* h, cudaStream_t st) {
     for (int d = 0; d < 2; ++d) {
       pack_rows_perm_bf16<<<(unsigned)ceil_div64((long long)4 * H * K, 256), 256, 0, st>>>(w.w_ih[l][d], h->bf16.wih_bf[l], H, K, d * 4 * H, 1);
       pack_rows_perm_bf16<<<(unsigned)ceil_div64((long long)4 * H * H, 256), 256, 0, st>>>(w.w_hh[l][d], h->bf16.whh_bf[l][d], H, H, 0, 0);
-      pack_bias_perm<<<ceil_div(4 * H, 256), 256, 0, st>>>(w.b_ih[l][d], w.b_hh[l][d], h->bf16.bias_p[l], H, d * 4 * H);
+      pack_bias_perm<<<ceil_div(4 * H, 256), 256, 0, st>>>(w.b_ih[l][d], w.b_hh[l][d], h->bf16.bias_p[l], H, d * 4 * H, 1);
+      pack_rows_perm_bf16<<<(unsigned)ceil_div64((long long)4 * H * K, 256), 256, 0, st>>>(w.w_ih[l][d], h->bf16.wih_t_bf[l], H, K, d * 4 * H, 0);
+      pack_bias_perm<<<ceil_div(4 * H, 256), 256, 0, st>>>(w.b_ih[l][d], w.b_hh[l][d], h->bf16.bias_t[l], H, d * 4 * H, 0);
     }
   }
   int rc = pack_pool_bf16(h, st);
@@ -358,7 +381,7 @@ lstm_rec_bf16(const __nv_bfloat16* __restrict__ G,        // blocked: [row/128][
               const __grid_constant__ CUtensorMap tmOut,  // out [T][Bc][256] bf16 (3D), box 64 cols x 128 rows x 1
               const __nv_bfloat16* __restrict__ whh_f,    // [512][128] rows in perm_T order, forward
               const __nv_bfloat16* __restrict__ whh_r,    // reverse
-              float2* __restrict__ stats,                 // STATS: [T*Bc][dir][half] (sum, sum of squares) of h over 64 units
+              float2* __restrict__ stats,                 // STATS: [T*Bc][dir][half][2] (sum, sum of squares) of h over 32 units
               int Bc, int T, int dbg) {
   extern __shared__ uint8_t rb_smem_raw[];
   const uint32_t raw = smem_u32(rb_smem_raw);
@@ -492,9 +515,10 @@ lstm_rec_bf16(const __nv_bfloat16* __restrict__ G,        // blocked: [row/128][
       uint8_t* hrow = genH + (uint32_t)(s & 1) * RB_H_BYTES + half * RB_H_ATOM;  // h_s -> buffer s&1, K-atom `half`
       mbar_wait(my_bar, (uint32_t)(s & 1));
       tc_fence_after();
-      float ssum = 0.f, ssq = 0.f;
+      float ssum = 0.f, ssq = 0.f, ssum_lo = 0.f, ssq_lo = 0.f;
 #pragma unroll
       for (int sl = 0; sl < 8; ++sl) {  // fully unrolled: c[] must stay in registers
+        if (STATS && sl == 4) { ssum_lo = ssum; ssq_lo = ssq; ssum = 0.f; ssq = 0.f; }  // 32-unit partials (shared layout with the fused kernel)
         uint32_t acc[32];
         tmem_ld32(taddr + sl * 32, acc);
         if (sl < 6 && !(dbg & 1)) {
@@ -559,7 +583,8 @@ lstm_rec_bf16(const __nv_bfloat16* __restrict__ G,        // blocked: [row/128][
       mbar_arrive(bar_h);
       if (STATS) {
         // partial LayerNorm statistics of the last layer's output row (consumed by attn_score_bf16 / attn_pool_finish)
-        if (live) stats[((long long)t * Bc + b0 + r) * 4 + dir * 2 + half] = make_float2(ssum, ssq);
+        if (live)
+          *reinterpret_cast<float4*>(stats + ((long long)t * Bc + b0 + r) * 8 + dir * 4 + half * 2) = make_float4(ssum_lo, ssq_lo, ssum, ssq);
       }
     }
   }
@@ -618,9 +643,10 @@ int launch_rec_bf16(const __nv_bfloat16* G, const __nv_bfloat16* whh_f, const __
 // ---------------------------------------------------------------------------------------------
 static size_t chunk_bytes_bf16(const bci_lstm_config& c, int Bc, int T) {
   const size_t H = c.hidden_size, rows = (size_t)Bc * T;
-  const size_t rows_pad = (rows + 127) / 128 * 128;  // G is stored in whole 128-row blocks
-  return align_up(rows * H * 2, 1024) + align_up(rows_pad * 8 * H * 2, 1024) + 2 * align_up(rows * 2 * H * 2, 1024) +
-         align_up(rows * 4, 1024) + align_up(rows * 4 * sizeof(float2), 1024);
+  const size_t rows_pad = (rows + 127) / 128 * 128;  // G is stored in whole 128-row blocks (split path only)
+  const size_t g_bytes = bf16_path_fused() ? 0 : align_up(rows_pad * 8 * H * 2, 1024);
+  return align_up(rows * H * 2, 1024) + g_bytes + 2 * align_up(rows * 2 * H * 2, 1024) +
+         align_up(rows * 4, 1024) + align_up(rows * 8 * sizeof(float2), 1024);
 }
 
 size_t lstm_workspace_bf16(const bci_lstm_config& c, int batch, int T) {
@@ -636,11 +662,12 @@ static int forward_chunk_bf16(bci_lstm_s* h, const float* x, int Bc, int T, floa
   size_t off = 0;
   auto take = [&](size_t bytes) { char* p = ws + off; off += align_up(bytes, 1024); return p; };
   __nv_bfloat16* z = reinterpret_cast<__nv_bfloat16*>(take(rows * H * 2));
-  __nv_bfloat16* g = reinterpret_cast<__nv_bfloat16*>(take((rows + 127) / 128 * 128 * 8 * H * 2));
+  const bool fused = bf16_path_fused() != 0;
+  __nv_bfloat16* g = fused ? nullptr : reinterpret_cast<__nv_bfloat16*>(take((rows + 127) / 128 * 128 * 8 * H * 2));
   __nv_bfloat16* o0 = reinterpret_cast<__nv_bfloat16*>(take(rows * 2 * H * 2));
   __nv_bfloat16* o1 = reinterpret_cast<__nv_bfloat16*>(take(rows * 2 * H * 2));
   float* scores = reinterpret_cast<float*>(take(rows * 4));
-  float2* stats = reinterpret_cast<float2*>(take(rows * 4 * sizeof(float2)));
+  float2* stats = reinterpret_cast<float2*>(take(rows * 8 * sizeof(float2)));
   h->prof.mark(-1, st);
   // tensor-core input projection needs whole 128-row tiles inside one window; other lengths use the CUDA-core kernel
   int rc = (T % 128 == 0) ? launch_input_proj_bf16(h, x, Bc, T, z, st) : launch_input_proj<H, __nv_bfloat16>(h, x, Bc, T, z, st);
@@ -649,12 +676,20 @@ static int forward_chunk_bf16(bci_lstm_s* h, const float* x, int Bc, int T, floa
   const __nv_bfloat16* in = z;
   __nv_bfloat16* outs[2] = {o0, o1};
   for (int l = 0; l < c.num_layers; ++l) {
-    rc = launch_proj_gemm_bf16(in, h->bf16.wih_bf[l], h->bf16.bias_p[l], g, (int)rows, 8 * H, layer_in_width(c, l), true, st);
-    if (rc) return rc;
-    h->prof.mark(1, st);
     __nv_bfloat16* o = outs[l & 1];
-    rc = launch_rec_bf16(g, h->bf16.whh_bf[l][0], h->bf16.whh_bf[l][1], o, l == c.num_layers - 1 ? stats : nullptr, Bc, T, st);
-    if (rc) return rc;
+    float2* st_l = l == c.num_layers - 1 ? stats : nullptr;
+    if (fused) {
+      // projection and recurrence in one cluster kernel (phase 2 of the profile; phase 1 stays empty)
+      rc = launch_fused_rec_bf16(in, h->bf16.wih_t_bf[l], h->bf16.whh_bf[l][0], h->bf16.whh_bf[l][1], h->bf16.bias_t[l], o, st_l, Bc, T,
+                                 layer_in_width(c, l), st);
+      if (rc) return rc;
+    } else {
+      rc = launch_proj_gemm_bf16(in, h->bf16.wih_bf[l], h->bf16.bias_p[l], g, (int)rows, 8 * H, layer_in_width(c, l), true, st);
+      if (rc) return rc;
+      h->prof.mark(1, st);
+      rc = launch_rec_bf16(g, h->bf16.whh_bf[l][0], h->bf16.whh_bf[l][1], o, st_l, Bc, T, st);
+      if (rc) return rc;
+    }
     h->prof.mark(2, st);
     in = o;
   }

@@ -1,0 +1,346 @@
+// Fused projection + recurrence of one bidirectional LSTM layer (bf16 mode, H = 128) on a 4-CTA cluster.
+//
+// The two-kernel path (lstm_bf16.cu: K2 proj_gemm_bf16 -> G in HBM -> K3 lstm_rec_bf16) is bound by the 512 KB per window per
+// layer of G it writes and reads back (ncu: K2 DRAM 69 %, K3 DRAM 58 %).  Here G never exists: per step the gate
+// pre-activations  [in_t | h_{t-1}] . [W_ih | W_hh]^T  are accumulated in TMEM by one chain of tcgen05 MMAs, with BOTH weight
+// matrices of the direction (384 KB bf16 for a 256-wide input) resident in the shared memory of four SMs:
+//
+//   cluster rank r = 2 p + s      p = gate-column half (hidden units [64 p, 64 p + 64), all four gates: 256 columns)
+//                                 s = window tile of the cluster's tile pair (128 windows each) = position in the CTA pair
+//   pair p = CTAs (p,0),(p,1)     one tcgen05.mma.cta_group::2 (M = 256: both tiles, N = 256, K = 16) per K slice; each CTA keeps
+//                                 128 of the pair's 256 weight rows (96 KB), supplies its own tile's A operand ([in_t | h_{t-1}])
+//                                 and receives its own 128 x 256 accumulator in its TMEM (2 x 256 columns, double-buffered)
+//   per step                      MMA_hh(t) (needs h_{t-1}) -> commit (multicast to the pair) -> 8 epilogue warps per CTA:
+//                                 tcgen05.ld, + bias, sigma/tanh (MUFU), cell update (fp32 registers), h_t (bf16) written into the
+//                                 A-operand buffer of step t+1 -- locally AND, through distributed shared memory
+//                                 (st.shared::cluster), into the CTA (1-p, s) that computes the other half of the gates for the
+//                                 same windows -> release-arrives (cluster scope) on the h_full mbarriers of both pair leaders.
+//                                 MMA_ih(t+1) = in_{t+1} . W_ih^T does not depend on h and is issued into the other accumulator
+//                                 while the epilogue of step t runs; in_t tiles arrive through a 4-slot TMA ring.
+//   h_t -> HBM                    each CTA TMA-stores its own 64-unit atom of h_t (its K-atom of the operand buffer).
+//
+// Reference semantics: nn.LSTM inside EnhancedLSTMModel (04_lstm_model.py:181-188,211).
+#include "lstm_shared_kernels.cuh"
+#include "sm100_prims.cuh"
+#include "tmap.cuh"
+
+namespace bci {
+using namespace sm100;
+
+constexpr int FR_M = 128;                       // windows per tile
+constexpr int FR_EPI_WARPS = 8;
+constexpr int FR_THREADS = (FR_EPI_WARPS + 3) * 32;  // + MMA issuer, TMA producer, h store warp
+constexpr uint32_t FR_ATOM = 128 * 128;         // [128 rows][64 bf16] SW128 atom
+constexpr int FR_STAGES = 4;
+constexpr int FR_W_ATOMS = 6;                   // up to 4 K-atoms of W_ih (input width 256) + 2 of W_hh
+constexpr uint32_t FR_OFF_H = FR_W_ATOMS * FR_ATOM;              // two h buffers x two atoms
+constexpr uint32_t FR_OFF_RING = FR_OFF_H + 4 * FR_ATOM;
+constexpr uint32_t FR_OFF_BIAS = FR_OFF_RING + FR_STAGES * FR_ATOM;  // 256 floats
+constexpr uint32_t FR_OFF_CTL = FR_OFF_BIAS + 1024;
+constexpr size_t FR_SMEM = 1024 + FR_OFF_CTL + 256;
+
+__device__ __forceinline__ float fr_tanh(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// work item w (0 .. 2*tile_pairs): direction = w / tile_pairs, tile pair = w % tile_pairs
+template <bool STATS>
+__global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(FR_THREADS, 1)
+lstm_fused_bf16(const __grid_constant__ CUtensorMap tmIn,   // in  [T][Bc][Kin] bf16, box 64 x 128 x 1
+                const __grid_constant__ CUtensorMap tmOut,  // out [T][Bc][256] bf16, box 64 x 128 x 1
+                const __nv_bfloat16* __restrict__ wih,      // [2][512][Kin] rows in perm_T order (i,f,o rows pre-scaled by 1/2)
+                const __nv_bfloat16* __restrict__ whh_f,    // [512][128] perm_T rows, forward
+                const __nv_bfloat16* __restrict__ whh_r,    // reverse
+                const float* __restrict__ bias,             // [2][512] perm_T order, pre-scaled like the rows
+                float2* __restrict__ stats,                 // STATS: [T*Bc][8] (sum, sumsq) of h over 32 units: [dir][p][ch]
+                int Bc, int T, int Kin, int tile_pairs) {
+  extern __shared__ uint8_t fr_smem_raw[];
+  const uint32_t raw = smem_u32(fr_smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* gen = fr_smem_raw + (base - raw);
+  const uint32_t sW = base, sH = base + FR_OFF_H, sRing = base + FR_OFF_RING;
+  uint8_t* genH = gen + FR_OFF_H;
+  float* bias_s = reinterpret_cast<float*>(gen + FR_OFF_BIAS);
+  uint8_t* ctl = gen + FR_OFF_CTL;
+  const uint32_t bar0 = smem_u32(ctl);
+  auto in_full = [&](int s) { return bar0 + 8u * s; };            // leader: 1 arrival (expect_tx), bytes of both CTAs
+  auto in_empty = [&](int s) { return bar0 + 8u * (4 + s); };     // every CTA: multicast commit
+  auto acc_full = [&](int a) { return bar0 + 8u * (8 + a); };     // every CTA: multicast commit
+  auto h_full = [&](int b) { return bar0 + 8u * (10 + b); };      // leader: 8 warps x 4 CTAs
+  auto h_local = [&](int b) { return bar0 + 8u * (12 + b); };     // every CTA: its own 8 epilogue warps
+  auto st_free = [&](int b) { return bar0 + 8u * (14 + b); };     // every CTA: the h store warp
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ctl + 8 * 16);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int p = (int)(rank >> 1), s = (int)(rank & 1);
+  const bool leader = (s == 0);
+  const int nk = Kin / 64;  // K-atoms of the input part
+
+  if (tid == 0) {
+    for (int i = 0; i < FR_STAGES; ++i) { mbar_init(in_full(i), 1); mbar_init(in_empty(i), 1); }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(acc_full(i), 1);
+      mbar_init(h_full(i), 4 * FR_EPI_WARPS);
+      mbar_init(h_local(i), FR_EPI_WARPS);
+      mbar_init(st_free(i), 1);
+    }
+    fence_mbar_init();
+    tma_prefetch_desc(&tmIn);
+    tma_prefetch_desc(&tmOut);
+  }
+  if (warp == FR_EPI_WARPS) {
+    tmem_alloc_2sm(smem_u32(tmem_slot), 512);
+    tmem_relinquish_2sm();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  cluster_sync_all();  // every CTA's barriers are initialised before anyone signals them
+
+  const int n_work = 2 * tile_pairs;
+  const int n_clusters = (int)cluster_nclusters_x();
+  // running step counter over all work items of this cluster (mbarrier parities are functions of it)
+  int g0 = 0;
+  for (int w = (int)cluster_id_x(); w < n_work; w += n_clusters, g0 += T) {
+    const int dir = w / tile_pairs, tp = w - dir * tile_pairs;
+    const int b0 = (2 * tp + s) * FR_M;  // first window of this CTA's tile
+
+    // ---- (re)load this CTA's weight rows: perm_T rows [256 p + 128 s, +128) of direction `dir` ----
+    if (g0 > 0) cluster_sync_all();  // all MMAs of the previous item retired (its last h_full was waited on below)
+    {
+      const int row0 = 256 * p + 128 * s;
+      const uint4* src_ih = reinterpret_cast<const uint4*>(wih + ((size_t)dir * 512 + row0) * Kin);
+      const int cpr = Kin / 8;  // 16-byte chunks per row
+      for (int q = tid; q < 128 * cpr; q += FR_THREADS) {
+        const uint32_t row = q / cpr, cc = q - row * cpr, atom = cc >> 3, c = cc & 7;
+        *reinterpret_cast<uint4*>(gen + atom * FR_ATOM + sw128_chunk_off(row, c)) = __ldg(src_ih + q);
+      }
+      const uint4* src_hh = reinterpret_cast<const uint4*>((dir ? whh_r : whh_f) + (size_t)row0 * 128);
+      for (int q = tid; q < 128 * 16; q += FR_THREADS) {
+        const uint32_t row = q >> 4, cc = q & 15, atom = cc >> 3, c = cc & 7;
+        *reinterpret_cast<uint4*>(gen + (nk + atom) * FR_ATOM + sw128_chunk_off(row, c)) = __ldg(src_hh + q);
+      }
+      // bias of the pair's 256 gate columns (every CTA of the pair needs all of them for its own rows)
+      for (int q = tid; q < 256; q += FR_THREADS) bias_s[q] = __ldg(bias + dir * 512 + 256 * p + q);
+    }
+    fence_proxy_async_all();
+    __syncthreads();
+    cluster_sync_all();
+
+    if (warp == FR_EPI_WARPS + 1) {
+      // ---------------- TMA producer: this CTA's in_t tile, K-atom by K-atom, through the ring ----------------
+      if (lane == 0) {
+        int k_total = (g0 / T) * T * nk;  // ring slots consumed before this item (same count in every CTA)
+        for (int st = 0; st < T; ++st) {
+          const int t = dir ? (T - 1 - st) : st;
+          for (int k = 0; k < nk; ++k, ++k_total) {
+            const int stage = k_total % FR_STAGES;
+            const uint32_t ph = (uint32_t)((k_total / FR_STAGES) & 1);
+            mbar_wait(in_empty(stage), ph ^ 1u);
+            if (leader) mbar_arrive_expect_tx(in_full(stage), 2 * FR_ATOM);
+            tma_load_3d_2sm(sRing + stage * FR_ATOM, &tmIn, k * 64, b0, t, mapa_u32(in_full(stage), rank & ~1u));
+          }
+        }
+      }
+    } else if (warp == FR_EPI_WARPS) {
+      // ---------------- MMA issuer (pair leader only) ----------------
+      if (leader && lane == 0) {
+        constexpr uint32_t idesc = umma_idesc_bf16(256, 256);
+        const uint16_t pair_mask = (uint16_t)(3u << (2 * p));
+        int k_total = (g0 / T) * T * nk;
+        auto issue_ih = [&](int acc) {
+          for (int k = 0; k < nk; ++k, ++k_total) {
+            const int stage = k_total % FR_STAGES;
+            mbar_wait(in_full(stage), (uint32_t)((k_total / FR_STAGES) & 1));
+            tc_fence_after();
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+              const uint64_t da = umma_desc_sw128(sRing + stage * FR_ATOM + kk * 32);
+              const uint64_t db = umma_desc_sw128(sW + k * FR_ATOM + kk * 32);
+              umma_bf16_2sm(tmem_base + acc * 256, da, db, idesc, (k | kk) != 0 ? 1u : 0u);
+            }
+            umma_commit_2sm_mc(in_empty(stage), pair_mask);  // frees the slot in both CTAs when these MMAs retire
+          }
+        };
+        issue_ih(g0 & 1);
+        for (int st = 0; st < T; ++st) {
+          const int g = g0 + st;
+          if (g > 0) {
+            // h_{g-1} complete in both CTAs of the pair, accumulator (g-1)&1 drained by both epilogues
+            mbar_wait_cluster(h_full((g - 1) & 1), (uint32_t)(((g - 1) >> 1) & 1));
+            tc_fence_after();
+          }
+          if (st > 0) {
+            const uint32_t hprev = sH + (uint32_t)((g - 1) & 1) * 2 * FR_ATOM;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              const uint32_t atom = k >> 2, kk = k & 3;
+              const uint64_t da = umma_desc_sw128(hprev + atom * FR_ATOM + kk * 32);
+              const uint64_t db = umma_desc_sw128(sW + (nk + atom) * FR_ATOM + kk * 32);
+              umma_bf16_2sm(tmem_base + (g & 1) * 256, da, db, idesc, 1u);
+            }
+          }
+          umma_commit_2sm_mc(acc_full(g & 1), pair_mask);
+          if (st + 1 < T) issue_ih((g + 1) & 1);
+        }
+        // the item's last epilogue must finish before the weights are replaced / the kernel ends
+        mbar_wait_cluster(h_full((g0 + T - 1) & 1), (uint32_t)(((g0 + T - 1) >> 1) & 1));
+      }
+    } else if (warp == FR_EPI_WARPS + 2) {
+      // ---------------- h store warp: this CTA's 64-unit atom of h_t -> out[t] ----------------
+      if (lane == 0) {
+        for (int st = 0; st < T; ++st) {
+          const int g = g0 + st;
+          const int t = dir ? (T - 1 - st) : st;
+          mbar_wait(h_local(g & 1), (uint32_t)((g >> 1) & 1));
+          tma_store_3d(&tmOut, sH + (uint32_t)(g & 1) * 2 * FR_ATOM + p * FR_ATOM, dir * 128 + 64 * p, b0, t);
+          tma_store_commit();
+          asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+          if (st > 0) mbar_arrive(st_free((g - 1) & 1));
+        }
+        tma_store_wait_all();
+        mbar_arrive(st_free((g0 + T - 1) & 1));
+      }
+    } else {
+      // ---------------- epilogue: thread = (window row, 32 of the CTA's 64 hidden units) ----------------
+      const int quarter = warp & 3, ch = warp >> 2;
+      const int r = quarter * 32 + lane;
+      const bool live = b0 + r < Bc;
+      const uint32_t taddr0 = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)ch * 128;
+      const uint32_t partner = (uint32_t)(2 * (1 - p) + s);  // same windows, other half of the gates
+      const uint32_t hf_own = mapa_u32(h_full(0), (uint32_t)(2 * p)), hf_oth = mapa_u32(h_full(0), (uint32_t)(2 * (1 - p)));
+      const float4* bias4 = reinterpret_cast<const float4*>(bias_s) + ch * 32;
+      float c[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) c[i] = 0.f;
+
+      for (int st = 0; st < T; ++st) {
+        const int g = g0 + st, buf = g & 1;
+        const int t = dir ? (T - 1 - st) : st;
+        uint8_t* hloc = genH + (uint32_t)buf * 2 * FR_ATOM + p * FR_ATOM;
+        const uint32_t hrem = mapa_u32(sH + (uint32_t)buf * 2 * FR_ATOM + p * FR_ATOM, partner);
+        mbar_wait(acc_full(buf), (uint32_t)((g >> 1) & 1));
+        tc_fence_after();
+        float ssum = 0.f, ssq = 0.f;
+        uint32_t acc[2][32];
+        tmem_ld32(taddr0 + buf * 256, acc[0]);
+#pragma unroll
+        for (int sl = 0; sl < 4; ++sl) {
+          tmem_ld_wait();
+          if (sl + 1 < 4) tmem_ld32(taddr0 + buf * 256 + (sl + 1) * 32, acc[(sl + 1) & 1]);
+          const uint32_t* a = acc[sl & 1];
+          float4 bq[8];  // bias of the slab's 32 columns (gate*8 + u): warp-uniform 16-byte loads
+#pragma unroll
+          for (int q = 0; q < 8; ++q) bq[q] = bias4[sl * 8 + q];
+          auto bval = [&](int gate, int u) {
+            const float4& v = bq[gate * 2 + (u >> 2)];
+            return (u & 3) == 0 ? v.x : (u & 3) == 1 ? v.y : (u & 3) == 2 ? v.z : v.w;
+          };
+          uint32_t hp[4];
+#pragma unroll
+          for (int u2 = 0; u2 < 4; ++u2) {
+            float hv[2];
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const int u = u2 * 2 + e;
+              const float ig = fmaf(0.5f, fr_tanh(__uint_as_float(a[0 * 8 + u]) + bval(0, u)), 0.5f);
+              const float fg = fmaf(0.5f, fr_tanh(__uint_as_float(a[1 * 8 + u]) + bval(1, u)), 0.5f);
+              const float gg = fr_tanh(__uint_as_float(a[2 * 8 + u]) + bval(2, u));
+              const float og = fmaf(0.5f, fr_tanh(__uint_as_float(a[3 * 8 + u]) + bval(3, u)), 0.5f);
+              float& cc = c[sl * 8 + u];
+              cc = fmaf(fg, cc, ig * gg);
+              hv[e] = og * fr_tanh(cc);
+              if (STATS) { ssum += hv[e]; ssq = fmaf(hv[e], hv[e], ssq); }
+            }
+            __nv_bfloat162 pk = __floats2bfloat162_rn(hv[0], hv[1]);
+            hp[u2] = *reinterpret_cast<uint32_t*>(&pk);
+          }
+          const uint4 hvec = make_uint4(hp[0], hp[1], hp[2], hp[3]);
+          // buffer `buf` was last read by the TMA store of h_{g-2}
+          if (sl == 0 && g >= 2) mbar_wait(st_free(buf), (uint32_t)(((g >> 1) - 1) & 1));
+          const uint32_t off = sw128_chunk_off((uint32_t)r, (uint32_t)(ch * 4 + sl));
+          *reinterpret_cast<uint4*>(hloc + off) = hvec;
+          st_cluster_v4(hrem + off, hvec);
+        }
+        fence_proxy_async_all();  // generic-proxy stores (local + remote) -> visible to tcgen05.mma / TMA
+        tc_fence_before();        // order this thread's TMEM reads before the arrives
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(h_local(buf));
+          mbar_arrive_cluster(hf_own + 8u * buf);
+          mbar_arrive_cluster(hf_oth + 8u * buf);
+        }
+        if (STATS) {
+          if (live) stats[((long long)t * Bc + b0 + r) * 8 + dir * 4 + p * 2 + ch] = make_float2(ssum, ssq);
+        }
+      }
+    }
+    __syncthreads();
+  }
+  tc_fence_before();
+  cluster_sync_all();  // no CTA leaves while a peer may still write into its shared memory / wait on its MMAs
+  if (warp == FR_EPI_WARPS) {
+    tc_fence_after();
+    tmem_dealloc_2sm(tmem_base, 512);
+  }
+}
+
+static int fused_setup(int* max_clusters_out) {
+  static int state = 0, max_clusters = 0;  // 0 = not tried, 1 = ok, -1 = unavailable
+  if (state == 0) {
+    state = -1;
+    BCI_CUDA_OK(cudaFuncSetAttribute(lstm_fused_bf16<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FR_SMEM));
+    BCI_CUDA_OK(cudaFuncSetAttribute(lstm_fused_bf16<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FR_SMEM));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(4 * sm_count(), 1, 1);
+    cfg.blockDim = dim3(FR_THREADS, 1, 1);
+    cfg.dynamicSmemBytes = FR_SMEM;
+    cudaLaunchAttribute la[1];
+    la[0].id = cudaLaunchAttributeClusterDimension;
+    la[0].val.clusterDim.x = 4; la[0].val.clusterDim.y = 1; la[0].val.clusterDim.z = 1;
+    cfg.attrs = la; cfg.numAttrs = 1;
+    BCI_CUDA_OK(cudaOccupancyMaxActiveClusters(&max_clusters, lstm_fused_bf16<false>, &cfg));
+    BCI_REQUIRE(max_clusters > 0, BCI_ECUDA, "fused recurrence: no 4-CTA cluster fits on this device");
+    state = 1;
+  }
+  if (max_clusters_out) *max_clusters_out = max_clusters;
+  return state == 1 ? BCI_OK : BCI_ECUDA;
+}
+
+int fused_max_clusters() {
+  int n = 0;
+  return fused_setup(&n) == BCI_OK ? n : 0;
+}
+
+int launch_fused_rec_bf16(const __nv_bfloat16* in, const __nv_bfloat16* wih, const __nv_bfloat16* whh_f, const __nv_bfloat16* whh_r,
+                          const float* bias, __nv_bfloat16* out, float2* stats, int Bc, int T, int Kin, cudaStream_t st) {
+  BCI_REQUIRE(Kin == 128 || Kin == 256, BCI_EINVAL, "fused recurrence: input width must be 128 or 256 (got %d)", Kin);
+  int max_clusters = 0;
+  int rc0 = fused_setup(&max_clusters);
+  if (rc0) return rc0;
+  CUtensorMap tmIn, tmOut;
+  int rc = make_tmap_bf16_3d(&tmIn, in, (uint64_t)T, (uint64_t)Bc, (uint64_t)Kin, 64, FR_M);
+  if (rc) return rc;
+  rc = make_tmap_bf16_3d(&tmOut, out, (uint64_t)T, (uint64_t)Bc, 256, 64, FR_M);
+  if (rc) return rc;
+  const int tiles = ceil_div(Bc, FR_M), tile_pairs = (tiles + 1) / 2;
+  int clusters = 2 * tile_pairs < max_clusters ? 2 * tile_pairs : max_clusters;
+  if (stats) lstm_fused_bf16<true><<<4 * clusters, FR_THREADS, FR_SMEM, st>>>(tmIn, tmOut, wih, whh_f, whh_r, bias, stats, Bc, T, Kin, tile_pairs);
+  else lstm_fused_bf16<false><<<4 * clusters, FR_THREADS, FR_SMEM, st>>>(tmIn, tmOut, wih, whh_f, whh_r, bias, nullptr, Bc, T, Kin, tile_pairs);
+  BCI_LAUNCH_OK();
+  return BCI_OK;
+}
+
+}  // namespace bci
+
+// diagnostics: one fused layer in isolation (tests/test_gpu_tensorcore.py)
+extern "C" int bci_selftest_fused_rec_bf16(const void* in, const void* wih, const void* whh_f, const void* whh_r, const float* bias,
+                                           void* out, void* stats, int32_t Bc, int32_t T, int32_t Kin, void* stream) {
+  return bci::launch_fused_rec_bf16((const __nv_bfloat16*)in, (const __nv_bfloat16*)wih, (const __nv_bfloat16*)whh_f,
+                                    (const __nv_bfloat16*)whh_r, bias, (__nv_bfloat16*)out, (float2*)stats, Bc, T, Kin,
+                                    (cudaStream_t)stream);
+}

@@ -63,7 +63,7 @@ __global__ void __launch_bounds__(SC_THREADS, 1)
 attn_score_bf16(const __grid_constant__ CUtensorMap tmA,   // seq [M][256] bf16, box 64 x 128
                 const __grid_constant__ CUtensorMap tmB,   // W1' [128][256] bf16, box 64 x 128
                 const float4* __restrict__ par,            // [128] {s_j, c_j, w2_j, 0}
-                const float2* __restrict__ stats,          // [M][4] partial (sum, sumsq)
+                const float2* __restrict__ stats,          // [M][8] partial (sum, sumsq) over 32 units each
                 float b2, float* __restrict__ scores, int M) {
   extern __shared__ uint8_t sc_smem_raw[];
   const uint32_t raw = smem_u32(sc_smem_raw);
@@ -146,9 +146,10 @@ attn_score_bf16(const __grid_constant__ CUtensorMap tmA,   // seq [M][256] bf16,
       const int gr = tile * SC_BM + quarter * 32 + lane;
       float rs = 0.f, mp = 0.f;
       if (gr < M) {
-        const float4* sp = reinterpret_cast<const float4*>(stats + (long long)gr * 4);
-        const float4 p0 = __ldg(sp), p1 = __ldg(sp + 1);  // (sum,sq) x 4 partials
-        const float sum = (p0.x + p0.z) + (p1.x + p1.z), sq = (p0.y + p0.w) + (p1.y + p1.w);
+        const float4* sp = reinterpret_cast<const float4*>(stats + (long long)gr * 8);
+        const float4 p0 = __ldg(sp), p1 = __ldg(sp + 1), p2 = __ldg(sp + 2), p3 = __ldg(sp + 3);  // (sum,sq) x 8 partials
+        const float sum = ((p0.x + p0.z) + (p1.x + p1.z)) + ((p2.x + p2.z) + (p3.x + p3.z));
+        const float sq = ((p0.y + p0.w) + (p1.y + p1.w)) + ((p2.y + p2.w) + (p3.y + p3.w));
         const float mean = sum * (1.0f / SC_K);
         const float var = fmaxf(sq * (1.0f / SC_K) - mean * mean, 0.f);
         rs = 1.0f / sqrtf(var + 1e-5f);
@@ -204,7 +205,7 @@ __device__ __forceinline__ float block_reduce(float v, float* red, bool is_max) 
 __global__ void __launch_bounds__(PF_THREADS)
 attn_pool_finish_bf16(const __nv_bfloat16* __restrict__ seq,  // [T][Bc][256]
                       const float* __restrict__ scores,       // [T][Bc]
-                      const float2* __restrict__ stats,       // [T*Bc][4]
+                      const float2* __restrict__ stats,       // [T*Bc][8]
                       int Bc, int T, int classes,
                       const float* __restrict__ lnw, const float* __restrict__ lnb,
                       const float* __restrict__ c0t, const float* __restrict__ cb0,
@@ -225,10 +226,10 @@ attn_pool_finish_bf16(const __nv_bfloat16* __restrict__ seq,  // [T][Bc][256]
   for (int t = tid; t < T; t += PF_THREADS) {
     const long long row = (long long)t * Bc + b;
     const float s = __ldg(scores + row);
-    const float4* sp = reinterpret_cast<const float4*>(stats + row * 4);
-    const float4 p0 = __ldg(sp), p1 = __ldg(sp + 1);
+    const float4* sp = reinterpret_cast<const float4*>(stats + row * 8);
+    const float4 p0 = __ldg(sp), p1 = __ldg(sp + 1), p2 = __ldg(sp + 2), p3 = __ldg(sp + 3);
     beta[t] = s;
-    bmean[t] = ((p0.x + p0.z) + (p1.x + p1.z)) * (1.0f / D);
+    bmean[t] = (((p0.x + p0.z) + (p1.x + p1.z)) + ((p2.x + p2.z) + (p3.x + p3.z))) * (1.0f / D);
     lmax = fmaxf(lmax, s);
   }
   const float m = block_reduce(lmax, red, true);
@@ -240,9 +241,9 @@ attn_pool_finish_bf16(const __nv_bfloat16* __restrict__ seq,  // [T][Bc][256]
     const long long row = (long long)t * Bc + b;
     const float a = expf(beta[t] - m) * inv_l;
     if (attn) attn[(long long)b * T + t] = a;
-    const float4* sp = reinterpret_cast<const float4*>(stats + row * 4);
-    const float4 p0 = __ldg(sp), p1 = __ldg(sp + 1);
-    const float sq = (p0.y + p0.w) + (p1.y + p1.w);
+    const float4* sp = reinterpret_cast<const float4*>(stats + row * 8);
+    const float4 p0 = __ldg(sp), p1 = __ldg(sp + 1), p2 = __ldg(sp + 2), p3 = __ldg(sp + 3);
+    const float sq = ((p0.y + p0.w) + (p1.y + p1.w)) + ((p2.y + p2.w) + (p3.y + p3.w));
     const float mean = bmean[t];
     const float var = fmaxf(sq * (1.0f / D) - mean * mean, 0.f);
     const float bt = a / sqrtf(var + 1e-5f);

@@ -42,6 +42,9 @@ struct PackedBF16 {
   __nv_bfloat16* wih_bf[BCI_MAX_LAYERS];
   __nv_bfloat16* whh_bf[BCI_MAX_LAYERS][2];
   float* bias_p[BCI_MAX_LAYERS];
+  // fused cluster kernel (lstm_bf16_fused.cu): W_ih rows and biases in the SAME perm_T order as whh_bf
+  __nv_bfloat16* wih_t_bf[BCI_MAX_LAYERS];  // [2][4H][K_l]
+  float* bias_t[BCI_MAX_LAYERS];            // [2][4H]
   // attention scores on tensor cores with LayerNorm folded in (lstm_bf16_pool.cu):
   //   aw1_bf [H][2H] = bf16(W1[j][d] * ln_w[d]);  apar[j] = {s_j = sum_d aw1_bf[j][d], c_j = b1_j + sum_d ln_b[d] W1[j][d], w2_j, 0}
   __nv_bfloat16* aw1_bf;
@@ -93,9 +96,9 @@ inline int attn_width(const bci_lstm_config& c) { return feat_width(c) / 2; }   
 inline int layer_in_width(const bci_lstm_config& c, int l) { return l == 0 ? c.hidden_size : feat_width(c); }
 
 // chunking policy: windows processed per internal pass (bounds the workspace)
+int bf16_chunk_windows();  // lstm_bf16.cu: depends on the recurrence path in use (split K2+K3 or fused cluster kernel)
 inline int max_chunk(const bci_lstm_config& c, int train) {
-  // bf16 inference: 74 x 128 windows = exactly one wave of (tile, direction) CTAs of the recurrence on 148 SMs
-  if (c.precision == BCI_PRECISION_BF16) return train ? 2048 : 74 * 128;
+  if (c.precision == BCI_PRECISION_BF16) return train ? 2048 : bf16_chunk_windows();
   const int base = train ? 512 : 2048;
   return c.hidden_size > 128 ? base / 2 : base;
 }
@@ -128,5 +131,8 @@ int pack_inproj_bf16(bci_lstm_s* h, cudaStream_t st);
 int launch_input_proj_bf16(bci_lstm_s* h, const float* x, int Bc, int T, __nv_bfloat16* z, cudaStream_t st);
 int launch_pool_bf16(bci_lstm_s* h, const __nv_bfloat16* seq, const float2* stats, float* scores, int Bc, int T, float* logits,
                      float* probs, float* attn, cudaStream_t st);
+int launch_fused_rec_bf16(const __nv_bfloat16* in, const __nv_bfloat16* wih, const __nv_bfloat16* whh_f, const __nv_bfloat16* whh_r,
+                          const float* bias, __nv_bfloat16* out, float2* stats, int Bc, int T, int Kin, cudaStream_t st);
+int fused_max_clusters();  // co-resident 4-CTA clusters of the fused kernel on this device (0 if it cannot run)
 
 }  // namespace bci

@@ -132,3 +132,55 @@ def test_bf16_rejects_h256():
     m = lstm.from_params(params, precision="bf16")
     with pytest.raises(N.BciError):
         m(torch.zeros(1, 8, 61, device="cuda"))
+
+
+@pytest.mark.parametrize("Bc,T,Kin", [(256, 3, 128), (256, 6, 256), (200, 9, 256), (5, 17, 128), (700, 5, 256)])
+def test_fused_cluster_recurrence_matches_stepwise(Bc, T, Kin):
+    """lstm_fused_bf16 (4-CTA cluster, cta_group::2 MMAs, h exchanged through DSMEM): projection + recurrence of one layer
+    against a step-by-step emulation with the same roundings (bf16 inputs / weights / h fed back, fp32 gates and cell)."""
+    H = 128
+    g = torch.Generator(device="cuda").manual_seed(Bc * 7 + T * 3 + Kin)
+    wih = [(torch.rand(4 * H, Kin, device="cuda", generator=g) * 2 - 1) / np.sqrt(H) for _ in range(2)]
+    whh = [(torch.rand(4 * H, H, device="cuda", generator=g) * 2 - 1) / np.sqrt(H) for _ in range(2)]
+    b = [(torch.rand(4 * H, device="cuda", generator=g) * 2 - 1) * 0.3 for _ in range(2)]
+    x = (torch.randn(T, Bc, Kin, device="cuda", generator=g) * 0.8).to(torch.bfloat16).contiguous()
+    perm = torch.from_numpy(_perm(H, "T")).cuda()
+    gate_scale = torch.ones(4 * H, device="cuda")
+    gate_scale[:2 * H] = 0.5
+    gate_scale[3 * H:] = 0.5
+    wih_p = torch.empty(2, 4 * H, Kin, device="cuda")
+    whh_p, bias_p = [], torch.empty(2, 4 * H, device="cuda")
+    for d in range(2):
+        wih_p[d][perm] = wih[d] * gate_scale[:, None]
+        wp = torch.empty_like(whh[d])
+        wp[perm] = whh[d] * gate_scale[:, None]
+        whh_p.append(wp.to(torch.bfloat16).contiguous())
+        bias_p[d][perm] = b[d] * gate_scale
+    wih_p = wih_p.to(torch.bfloat16).contiguous()
+    bias_p = bias_p.contiguous()
+    out = torch.full((T, Bc, 2 * H), float("nan"), device="cuda", dtype=torch.bfloat16)
+    stats = torch.full((T * Bc, 8, 2), float("nan"), device="cuda")
+    N.check(N.lib().bci_selftest_fused_rec_bf16(_p(x), _p(wih_p), _p(whh_p[0]), _p(whh_p[1]), _p(bias_p), _p(out), _p(stats),
+                                                Bc, T, Kin, _stream()))
+    torch.cuda.synchronize()
+    want = torch.empty(T, Bc, 2 * H, device="cuda")
+    for d in range(2):
+        wi = (wih[d] * gate_scale[:, None]).to(torch.bfloat16).float() / gate_scale[:, None]
+        wh = (whh[d] * gate_scale[:, None]).to(torch.bfloat16).float() / gate_scale[:, None]
+        h = torch.zeros(Bc, H, device="cuda")
+        c = torch.zeros(Bc, H, device="cuda")
+        for s in range(T):
+            t = T - 1 - s if d else s
+            pre = x[t].float() @ wi.T + h @ wh.T + b[d]
+            i, f, gg, o = pre[:, :H].sigmoid(), pre[:, H:2 * H].sigmoid(), pre[:, 2 * H:3 * H].tanh(), pre[:, 3 * H:].sigmoid()
+            c = f * c + i * gg
+            hf = o * c.tanh()
+            want[t, :, d * H:(d + 1) * H] = hf
+            h = hf.to(torch.bfloat16).float()
+    got = out.float()
+    assert torch.isfinite(got).all()
+    assert float((got - want).abs().max()) <= 1.5e-2
+    # LayerNorm partial statistics: 8 partials per row = [dir][32-unit group]
+    ssum = want.reshape(T * Bc, 8, 32).sum(-1)
+    ssq = (want.reshape(T * Bc, 8, 32) ** 2).sum(-1)
+    assert float((stats[:, :, 0] - ssum).abs().max()) <= 5e-2 and float((stats[:, :, 1] - ssq).abs().max()) <= 5e-2
