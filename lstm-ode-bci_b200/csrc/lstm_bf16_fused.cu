@@ -12,9 +12,14 @@
 //                                 and receives its own 128 x 256 accumulator in its TMEM (2 x 256 columns, double-buffered)
 //   per step                      MMA_hh(t) (needs h_{t-1}) -> commit (multicast to the pair) -> 8 epilogue warps per CTA:
 //                                 tcgen05.ld, + bias, sigma/tanh (MUFU), cell update (fp32 registers), h_t (bf16) written into the
-//                                 A-operand buffer of step t+1 -- locally AND, through distributed shared memory
-//                                 (st.shared::cluster), into the CTA (1-p, s) that computes the other half of the gates for the
-//                                 same windows -> release-arrives (cluster scope) on the h_full mbarriers of both pair leaders.
+//                                 A-operand buffer of step t+1 (this CTA's 64-unit K-atom, 16 KB contiguous).  When the atom is
+//                                 complete one thread sends it through distributed shared memory to the CTA (1-p, s) that computes
+//                                 the other half of the gates for the same windows: one cp.async.bulk shared::cta ->
+//                                 shared::cluster whose bytes complete an mbarrier in the destination CTA.  (The first version
+//                                 used per-thread st.shared::cluster + fence.proxy.async + release arrives: 2 300 of 6 800 cycles
+//                                 per step were those fences waiting on the ~20 B/clk remote-store path; see profiles/.)
+//                                 The pair leader issues MMA_hh(t+1) once both CTAs of its pair hold the complete h_t: its own two
+//                                 barriers (local atom written, incoming atom landed) and one relay arrive from its peer.
 //                                 MMA_ih(t+1) = in_{t+1} . W_ih^T does not depend on h and is issued into the other accumulator
 //                                 while the epilogue of step t runs; in_t tiles arrive through a 4-slot TMA ring.
 //   h_t -> HBM                    each CTA TMA-stores its own 64-unit atom of h_t (its K-atom of the operand buffer).
@@ -55,8 +60,13 @@ lstm_fused_bf16(const __grid_constant__ CUtensorMap tmIn,   // in  [T][Bc][Kin] 
                 const __nv_bfloat16* __restrict__ whh_r,    // reverse
                 const float* __restrict__ bias,             // [2][512] perm_T order, pre-scaled like the rows
                 float2* __restrict__ stats,                 // STATS: [T*Bc][8] (sum, sumsq) of h over 32 units: [dir][p][ch]
-                int Bc, int T, int Kin, int tile_pairs) {
+                int Bc, int T, int Kin, int tile_pairs,
+                long long* __restrict__ tl) {               // optional timeline (BCI_FUSED_TIMELINE): cluster 0, rank 0, 8 stamps x step
   extern __shared__ uint8_t fr_smem_raw[];
+  const bool tl_on = tl != nullptr && blockIdx.x < 4;  // ranks 0 (leader) and 1 (its peer) of cluster 0; globaltimer is common to SMs
+  auto stamp = [&](int st, int slot) {
+    if (tl_on && st < 64) { long long c; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(c)); tl[(blockIdx.x * 64 + st) * 8 + slot] = c; }
+  };
   const uint32_t raw = smem_u32(fr_smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t* gen = fr_smem_raw + (base - raw);
@@ -68,10 +78,11 @@ lstm_fused_bf16(const __grid_constant__ CUtensorMap tmIn,   // in  [T][Bc][Kin] 
   auto in_full = [&](int s) { return bar0 + 8u * s; };            // leader: 1 arrival (expect_tx), bytes of both CTAs
   auto in_empty = [&](int s) { return bar0 + 8u * (4 + s); };     // every CTA: multicast commit
   auto acc_full = [&](int a) { return bar0 + 8u * (8 + a); };     // every CTA: multicast commit
-  auto h_full = [&](int b) { return bar0 + 8u * (10 + b); };      // leader: 8 warps x 4 CTAs
+  auto h_in = [&](int b) { return bar0 + 8u * (10 + b); };        // every CTA: incoming K-atom (expect_tx by the local store warp)
+  auto peer_ready = [&](int b) { return bar0 + 8u * (16 + b); };  // leader: the peer CTA holds the complete h (relay arrive)
   auto h_local = [&](int b) { return bar0 + 8u * (12 + b); };     // every CTA: its own 8 epilogue warps
   auto st_free = [&](int b) { return bar0 + 8u * (14 + b); };     // every CTA: the h store warp
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ctl + 8 * 16);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ctl + 8 * 18);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t rank = cluster_ctarank();
@@ -83,7 +94,8 @@ lstm_fused_bf16(const __grid_constant__ CUtensorMap tmIn,   // in  [T][Bc][Kin] 
     for (int i = 0; i < FR_STAGES; ++i) { mbar_init(in_full(i), 1); mbar_init(in_empty(i), 1); }
     for (int i = 0; i < 2; ++i) {
       mbar_init(acc_full(i), 1);
-      mbar_init(h_full(i), 4 * FR_EPI_WARPS);
+      mbar_init(h_in(i), 1);
+      mbar_init(peer_ready(i), 1);
       mbar_init(h_local(i), FR_EPI_WARPS);
       mbar_init(st_free(i), 1);
     }
@@ -137,6 +149,12 @@ lstm_fused_bf16(const __grid_constant__ CUtensorMap tmIn,   // in  [T][Bc][Kin] 
         int k_total = (g0 / T) * T * nk;  // ring slots consumed before this item (same count in every CTA)
         for (int st = 0; st < T; ++st) {
           const int t = dir ? (T - 1 - st) : st;
+          // the ring holds one step (4 slots): pull the tile of step st+2 into L2 now so that its smem loads, which can only be
+          // issued once the MMAs of step st+1 have freed the slots, are L2 hits (one of the two CTAs sharing the tile does it)
+          if (p == 0 && st + 2 < T) {
+            const int t2 = dir ? (T - 3 - st) : st + 2;
+            for (int k = 0; k < nk; ++k) tma_prefetch_l2_3d(&tmIn, k * 64, b0, t2);
+          }
           for (int k = 0; k < nk; ++k, ++k_total) {
             const int stage = k_total % FR_STAGES;
             const uint32_t ph = (uint32_t)((k_total / FR_STAGES) & 1);
@@ -171,9 +189,15 @@ lstm_fused_bf16(const __grid_constant__ CUtensorMap tmIn,   // in  [T][Bc][Kin] 
           const int g = g0 + st;
           if (g > 0) {
             // h_{g-1} complete in both CTAs of the pair, accumulator (g-1)&1 drained by both epilogues
-            mbar_wait_cluster(h_full((g - 1) & 1), (uint32_t)(((g - 1) >> 1) & 1));
+            const int hb = (g - 1) & 1;
+            const uint32_t hp = (uint32_t)(((g - 1) >> 1) & 1);
+            mbar_wait(h_local(hb), hp);
+            mbar_wait(h_in(hb), hp);
+            stamp(st, 7);  // leader: own incoming atom landed
+            mbar_wait_cluster(peer_ready(hb), hp);
             tc_fence_after();
           }
+          stamp(st, 0);  // h_{t-1} complete, MMA_hh about to be issued
           if (st > 0) {
             const uint32_t hprev = sH + (uint32_t)((g - 1) & 1) * 2 * FR_ATOM;
 #pragma unroll
@@ -185,19 +209,48 @@ lstm_fused_bf16(const __grid_constant__ CUtensorMap tmIn,   // in  [T][Bc][Kin] 
             }
           }
           umma_commit_2sm_mc(acc_full(g & 1), pair_mask);
+          stamp(st, 1);  // MMA_hh issued + committed
           if (st + 1 < T) issue_ih((g + 1) & 1);
+          stamp(st, 2);  // MMA_ih(t+1) issued
         }
         // the item's last epilogue must finish before the weights are replaced / the kernel ends
-        mbar_wait_cluster(h_full((g0 + T - 1) & 1), (uint32_t)(((g0 + T - 1) >> 1) & 1));
+        {
+          const int hb = (g0 + T - 1) & 1;
+          const uint32_t hp = (uint32_t)(((g0 + T - 1) >> 1) & 1);
+          mbar_wait(h_local(hb), hp);
+          mbar_wait(h_in(hb), hp);
+          mbar_wait_cluster(peer_ready(hb), hp);
+        }
+      } else if (!leader && lane == 0) {
+        // ---------------- relay (peer CTA of the pair): tell the leader when this CTA holds the complete h_g ----------------
+        const uint32_t pr = mapa_u32(peer_ready(0), rank & ~1u);
+        for (int st = 0; st < T; ++st) {
+          const int g = g0 + st, hb = g & 1;
+          const uint32_t hp = (uint32_t)((g >> 1) & 1);
+          mbar_wait(h_local(hb), hp);
+          mbar_wait(h_in(hb), hp);
+          stamp(st, 0);  // relay: incoming atom landed
+          // RELAXED arrive: this thread has written nothing the leader needs -- the data sits in this CTA's shared memory
+          // (written by the bulk copy, whose completion the h_in wait above observed, and by the local epilogue warps, who
+          // fenced generic->async before arriving on h_local); a release arrive here costs a MEMBAR.GPU = 640 ns per step
+          // (measured, profiles/r1_fused_timeline.md) on the critical path of every step.
+          mbar_arrive_cluster_relaxed(pr + 8u * hb);
+          stamp(st, 1);  // relay: arrive done
+        }
       }
     } else if (warp == FR_EPI_WARPS + 2) {
       // ---------------- h store warp: this CTA's 64-unit atom of h_t -> out[t] ----------------
       if (lane == 0) {
+        const uint32_t partner = (uint32_t)(2 * (1 - p) + s);  // same windows, other half of the gates
         for (int st = 0; st < T; ++st) {
           const int g = g0 + st;
           const int t = dir ? (T - 1 - st) : st;
+          const uint32_t atom = sH + (uint32_t)(g & 1) * 2 * FR_ATOM + p * FR_ATOM;
+          mbar_arrive_expect_tx(h_in(g & 1), FR_ATOM);  // the partner's atom of h_g will land in this CTA
           mbar_wait(h_local(g & 1), (uint32_t)((g >> 1) & 1));
-          tma_store_3d(&tmOut, sH + (uint32_t)(g & 1) * 2 * FR_ATOM + p * FR_ATOM, dir * 128 + 64 * p, b0, t);
+          stamp(st, 5);  // store warp: local atom complete
+          bulk_copy_s2s_cluster(mapa_u32(atom, partner), atom, FR_ATOM, mapa_u32(h_in(g & 1), partner));
+          tma_store_3d(&tmOut, atom, dir * 128 + 64 * p, b0, t);
           tma_store_commit();
           asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
           if (st > 0) mbar_arrive(st_free((g - 1) & 1));
@@ -211,8 +264,6 @@ lstm_fused_bf16(const __grid_constant__ CUtensorMap tmIn,   // in  [T][Bc][Kin] 
       const int r = quarter * 32 + lane;
       const bool live = b0 + r < Bc;
       const uint32_t taddr0 = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)ch * 128;
-      const uint32_t partner = (uint32_t)(2 * (1 - p) + s);  // same windows, other half of the gates
-      const uint32_t hf_own = mapa_u32(h_full(0), (uint32_t)(2 * p)), hf_oth = mapa_u32(h_full(0), (uint32_t)(2 * (1 - p)));
       const float4* bias4 = reinterpret_cast<const float4*>(bias_s) + ch * 32;
       float c[32];
 #pragma unroll
@@ -222,9 +273,9 @@ lstm_fused_bf16(const __grid_constant__ CUtensorMap tmIn,   // in  [T][Bc][Kin] 
         const int g = g0 + st, buf = g & 1;
         const int t = dir ? (T - 1 - st) : st;
         uint8_t* hloc = genH + (uint32_t)buf * 2 * FR_ATOM + p * FR_ATOM;
-        const uint32_t hrem = mapa_u32(sH + (uint32_t)buf * 2 * FR_ATOM + p * FR_ATOM, partner);
         mbar_wait(acc_full(buf), (uint32_t)((g >> 1) & 1));
         tc_fence_after();
+        if (tid == 0) stamp(st, 3);  // accumulator ready
         float ssum = 0.f, ssq = 0.f;
         uint32_t acc[2][32];
         tmem_ld32(taddr0 + buf * 256, acc[0]);
@@ -264,16 +315,13 @@ lstm_fused_bf16(const __grid_constant__ CUtensorMap tmIn,   // in  [T][Bc][Kin] 
           if (sl == 0 && g >= 2) mbar_wait(st_free(buf), (uint32_t)(((g >> 1) - 1) & 1));
           const uint32_t off = sw128_chunk_off((uint32_t)r, (uint32_t)(ch * 4 + sl));
           *reinterpret_cast<uint4*>(hloc + off) = hvec;
-          st_cluster_v4(hrem + off, hvec);
         }
-        fence_proxy_async_all();  // generic-proxy stores (local + remote) -> visible to tcgen05.mma / TMA
-        tc_fence_before();        // order this thread's TMEM reads before the arrives
+        if (tid == 0) stamp(st, 4);  // math + stores issued
+        fence_proxy_async_smem();  // generic-proxy stores -> visible to tcgen05.mma / the bulk copies
+        tc_fence_before();         // order this thread's TMEM reads before the arrive
         __syncwarp();
-        if (lane == 0) {
-          mbar_arrive(h_local(buf));
-          mbar_arrive_cluster(hf_own + 8u * buf);
-          mbar_arrive_cluster(hf_oth + 8u * buf);
-        }
+        if (lane == 0) mbar_arrive(h_local(buf));
+        if (tid == 0) stamp(st, 6);  // arrives done
         if (STATS) {
           if (live) stats[((long long)t * Bc + b0 + r) * 8 + dir * 4 + p * 2 + ch] = make_float2(ssum, ssq);
         }
@@ -329,8 +377,26 @@ int launch_fused_rec_bf16(const __nv_bfloat16* in, const __nv_bfloat16* wih, con
   if (rc) return rc;
   const int tiles = ceil_div(Bc, FR_M), tile_pairs = (tiles + 1) / 2;
   int clusters = 2 * tile_pairs < max_clusters ? 2 * tile_pairs : max_clusters;
-  if (stats) lstm_fused_bf16<true><<<4 * clusters, FR_THREADS, FR_SMEM, st>>>(tmIn, tmOut, wih, whh_f, whh_r, bias, stats, Bc, T, Kin, tile_pairs);
-  else lstm_fused_bf16<false><<<4 * clusters, FR_THREADS, FR_SMEM, st>>>(tmIn, tmOut, wih, whh_f, whh_r, bias, nullptr, Bc, T, Kin, tile_pairs);
+  // BCI_FUSED_TIMELINE=<path>: clock64 stamps of the first 64 steps of cluster 0 / rank 0 are written to <path> (debug only)
+  static const char* tl_path = getenv("BCI_FUSED_TIMELINE");
+  static long long* tl_dev = nullptr;
+  if (tl_path && !tl_dev) { BCI_CUDA_OK(cudaMalloc(&tl_dev, 4 * 64 * 8 * sizeof(long long))); }
+  if (tl_dev) BCI_CUDA_OK(cudaMemsetAsync(tl_dev, 0, 4 * 64 * 8 * sizeof(long long), st));
+  if (stats) lstm_fused_bf16<true><<<4 * clusters, FR_THREADS, FR_SMEM, st>>>(tmIn, tmOut, wih, whh_f, whh_r, bias, stats, Bc, T, Kin, tile_pairs, tl_dev);
+  else lstm_fused_bf16<false><<<4 * clusters, FR_THREADS, FR_SMEM, st>>>(tmIn, tmOut, wih, whh_f, whh_r, bias, nullptr, Bc, T, Kin, tile_pairs, tl_dev);
+  if (tl_dev) {
+    long long host[4 * 64 * 8];
+    BCI_CUDA_OK(cudaMemcpyAsync(host, tl_dev, sizeof(host), cudaMemcpyDeviceToHost, st));
+    BCI_CUDA_OK(cudaStreamSynchronize(st));
+    FILE* f = fopen(tl_path, "w");
+    if (f) {
+      for (int i = 0; i < 256; ++i) {
+        for (int j = 0; j < 8; ++j) fprintf(f, "%lld ", host[i * 8 + j] ? host[i * 8 + j] - host[0] : 0ll);
+        fprintf(f, "\n");
+      }
+      fclose(f);
+    }
+  }
   BCI_LAUNCH_OK();
   return BCI_OK;
 }

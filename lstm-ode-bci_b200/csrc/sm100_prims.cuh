@@ -53,6 +53,10 @@ __device__ __forceinline__ void tma_prefetch_l2_2d(const void* tmap, int c0, int
   asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(tmap), "r"(c0), "r"(c1) : "memory");
 }
 
+__device__ __forceinline__ void tma_prefetch_l2_3d(const void* tmap, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"(tmap), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+
 // smem tile -> global (bulk async group); OOB parts of the box are clipped by the tensor map
 __device__ __forceinline__ void tma_store_2d(const void* tmap, uint32_t src_smem, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
@@ -155,6 +159,12 @@ __device__ __forceinline__ void st_cluster_v4(uint32_t cluster_addr, const uint4
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
+// relaxed arrive on an mbarrier of any CTA of the cluster: pair it with ONE fence_acq_rel_cluster() in front of several arrives
+// (a release-arrive each costs a full MEMBAR.GPU + ERRBAR)
+__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void fence_acq_rel_cluster() { asm volatile("fence.acq_rel.cluster;" ::: "memory"); }
 // wait on a LOCAL mbarrier whose arrivals come from other CTAs of the cluster
 __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
   uint32_t ok;
@@ -165,6 +175,12 @@ __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity)
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
   } while (!ok);
+}
+// contiguous block of THIS CTA's shared memory -> shared memory of another CTA of the cluster (both shared::cluster addresses
+// except the source); `bytes` are counted on the mbarrier `dst_bar` of the DESTINATION CTA when they have landed
+__device__ __forceinline__ void bulk_copy_s2s_cluster(uint32_t dst_cluster, uint32_t src_cta, uint32_t bytes, uint32_t dst_bar_cluster) {
+  asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst_cluster), "r"(src_cta), "r"(bytes), "r"(dst_bar_cluster) : "memory");
 }
 // generic-proxy writes (local or remote shared memory) -> visible to the async proxy (tcgen05.mma / TMA reads)
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
