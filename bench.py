@@ -7,8 +7,9 @@
 
 A step = one pass of the hot path (EnhancedLSTMModel.forward + softmax -> P(open)/P(closed),
 04_lstm_model.py:206-222, 06:351) over one batch of synthetic windows per GPU.  Workload at every N:
-BASELINE.json configs[1] (inference sweep point: 18944 = 148 SMs x 128 windows per GPU, bf16 tensor-core
-mode), weak scaling (per-GPU batch fixed; windows are independent -> no data-path collective).
+BASELINE.json configs[1] (inference sweep point: one or two full waves of the recurrence kernel per GPU --
+16 896 windows = 33 four-CTA clusters x 4 tiles x 128 for the fused bf16 path on a 148-SM B200 -- bf16
+tensor-core mode), weak scaling (per-GPU batch fixed; windows are independent -> no data-path collective).
 Prints ONE JSON line on rank 0.
 """
 import argparse
@@ -25,6 +26,8 @@ sys.path.insert(0, ROOT)
 FLOP_PER_WINDOW = 557_793_536          # SURVEY.md §8 d (H=128, T=256, C=61, 3 layers, forward)
 FLOP_PHASE = {"input_proj": 3_997_696, "proj_gemm": 335_544_320, "recurrence": 201_326_592,
               "pool_head": 16_842_752 + 82_176}
+# fused bf16 path (csrc/lstm_bf16_fused.cu): projection and recurrence are ONE kernel, reported under "recurrence"
+FLOP_PHASE_FUSED = dict(FLOP_PHASE, proj_gemm=0, recurrence=335_544_320 + 201_326_592)
 ODE_SUBSTEPS = 8
 ODE_FLOP_PER_TRAJ = 12 + 19 * ODE_SUBSTEPS * 123 + 20 * 11      # SURVEY.md §8 d: 18 928 at S=8
 
@@ -126,6 +129,8 @@ def run_reference(args, rank, world, json_out):
     import torch
     from lstm_ode_bci_b200 import synth
     from oracle import torch_port
+    if args.batch <= 0:
+        args.batch = 16896      # the b200 arm's default per-GPU batch on a 148-SM B200 (bci_lstm_chunk_windows, fused bf16 path)
     torch.set_num_threads(os.cpu_count() or 1)
     sample = args.ref_sample
     port = torch_port.build_port(synth.make_lstm_params(42, 61, 128, 3)).eval()
@@ -173,7 +178,9 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--batch", type=int, default=18944, help="windows per GPU per step (148 SMs x 128)")
+    ap.add_argument("--batch", type=int, default=0,
+                    help="windows per GPU per step; 0 = the smallest multiple >= 16384 of the forward's internal pass size "
+                         "(bci_lstm_chunk_windows: 16896 for the fused bf16 path on 148 SMs)")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--ode-n", type=int, default=1 << 24)
     ap.add_argument("--ref-sample", type=int, default=128)
@@ -214,12 +221,16 @@ def main():
         return float(t.item())
 
     peaks = load_peaks()
-    B, K, W = args.batch, args.steps, args.warmup
+    K, W = args.steps, args.warmup
     params = synth.make_lstm_params(42, 61, 128, 3)
     model = lstm.from_params(params, precision=args.precision, device=f"cuda:{local}")
+    hid = model._engine(args.precision)
+    chunk = ops.lstm_chunk_windows(hid)
+    if args.batch <= 0:
+        args.batch = chunk * max(1, -(-16384 // chunk))
+    B = args.batch
     gen = torch.Generator(device="cuda").manual_seed(42 + rank)
     x = torch.randn((B, 256, 61), device="cuda", generator=gen)           # N(0,1): z-scored EEG (02:134-152)
-    hid = model._engine(args.precision)
 
     # ---- device-resident throughput (value) --------------------------------------------------
     for _ in range(W):
@@ -273,12 +284,17 @@ def main():
            "steps": e2e_steps, "h2d_gbs": x_host.numel() * 4 * e2e_steps / (e2e_ms * 1e-3) / 1e9}
 
     # ---- roofline of the dominant kernel ------------------------------------------------------
+    fused = args.precision == "bf16" and prof["proj_gemm"][1] == 0
+    flop_phase = FLOP_PHASE_FUSED if fused else FLOP_PHASE
     dom = max(prof, key=lambda k: prof[k][0])
     dom_ms, dom_launches = prof[dom]
-    per_launch_flop = FLOP_PHASE[dom] * B * K / max(dom_launches, 1)
-    achieved = FLOP_PHASE[dom] * B * K / (dom_ms * 1e-3) / 1e12 if dom_ms > 0 else 0.0
+    per_launch_flop = flop_phase[dom] * B * K / max(dom_launches, 1)
+    achieved = flop_phase[dom] * B * K / (dom_ms * 1e-3) / 1e12 if dom_ms > 0 else 0.0
     peak_tf = peaks["bf16_tflops_sustained"] if args.precision == "bf16" else None
-    roof = {"bound": "tensor", "kernel": dom, "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
+    kernel_name = {"recurrence": "lstm_fused_bf16 (projection + recurrence, 4-CTA clusters)" if fused else "lstm_rec_bf16",
+                   "proj_gemm": "proj_gemm_bf16", "input_proj": "input_proj_bf16", "pool_head": "attn_score_bf16 + attn_pool_finish_bf16"}
+    roof = {"bound": "tensor", "kernel": dom, "kernel_name": kernel_name.get(dom, dom) if args.precision == "bf16" else dom,
+            "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
             "frac": (achieved / peak_tf) if peak_tf else None, "traffic": None,
             "peak_source": "bf16_tflops_sustained of %s (kernel timed inside a long step)" % peaks["source"],
             "flop_per_launch": per_launch_flop, "avg_launch_ms": dom_ms / max(dom_launches, 1),
@@ -288,10 +304,13 @@ def main():
                            "frac_of_bf16_burst": value / world * FLOP_PER_WINDOW / 1e12 / peaks["bf16_tflops"],
                            "frac_of_bf16_sustained": value / world * FLOP_PER_WINDOW / 1e12 / peaks["bf16_tflops_sustained"]}}
     traffic = load_traffic()
-    if traffic and args.precision == "bf16" and dom in traffic and (B % traffic["windows_per_launch"] == 0):
-        roof["traffic"] = traffic[dom]["bytes_per_launch"]
-        roof["traffic_unit"] = "bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum, %d-window launch); algorithmic %d" % (
-            traffic["windows_per_launch"], traffic[dom]["algorithmic_bytes_per_launch"])
+    tkey = "recurrence_fused" if (fused and dom == "recurrence") else dom
+    if traffic and args.precision == "bf16" and tkey in traffic:
+        wpl = traffic[tkey].get("windows_per_launch", traffic.get("windows_per_launch"))
+        if wpl and B % wpl == 0:
+            roof["traffic"] = traffic[tkey]["bytes_per_launch"]
+            roof["traffic_unit"] = "bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum, %d-window launch); algorithmic %d" % (
+                wpl, traffic[tkey]["algorithmic_bytes_per_launch"])
     if args.precision == "fp32":
         fp32_peak = ops.fp32_peak_probe()
         roof.update({"bound": "fp32", "peak": fp32_peak, "frac": achieved / fp32_peak,
@@ -364,7 +383,8 @@ def main():
         tms = max_over_ranks(a.elapsed_time(b)) / tsteps
         line["train_step"] = {"metric": "train_windows_per_s", "value": world * tb / (tms * 1e-3), "unit": "windows/s",
                               "ms_per_step": tms, "windows_per_gpu": tb, "precision": "fp32", "dropout": 0.4,
-                              "optimizer": "AdamW(3e-4, wd 1e-4) + clip 1.0, fused; gradients all-reduced over NCCL" if world > 1
+                              "optimizer": "AdamW(3e-4, wd 1e-4) + clip 1.0 with the gradient all-reduce fused into the optimizer kernels "
+                                           "over NVLink peer memory (bci_fused_step)" if world > 1
                               else "AdamW(3e-4, wd 1e-4) + clip 1.0, fused",
                               "flop_per_window": 3 * FLOP_PER_WINDOW, "achieved_tflops_per_gpu": tb * 3 * FLOP_PER_WINDOW / (tms * 1e-3) / 1e12,
                               "loss": float(loss_t), "grad_norm": float(norm_t)}

@@ -110,6 +110,11 @@ int bci_lstm_get_profile(bci_lstm_t h, float ms[BCI_PROF_PHASES], int32_t launch
 /* Number of kernels this library has launched in this process (bench.py's gpu_launches claim). */
 int64_t bci_launch_count(void);
 
+/* windows processed per internal pass of the inference forward (one full wave of the recurrence kernel on this device:
+ * 16 896 = 33 clusters x 4 tiles x 128 for the fused bf16 path on a 148-SM B200); batches that are multiples of it leave no
+ * SM idle.  bench.py sizes its step with it. */
+int bci_lstm_chunk_windows(bci_lstm_t h, int32_t* windows);
+
 /* bytes of caller-provided scratch needed by forward (train=0) or forward+backward (train=1) */
 int bci_lstm_workspace_bytes(bci_lstm_t h, int32_t batch, int32_t seq_len, int32_t train, size_t* bytes);
 

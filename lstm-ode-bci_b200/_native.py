@@ -77,6 +77,7 @@ SIGNATURES = {
     "bci_lstm_set_profiling": (C.c_int, [C.c_void_p, C.c_int32]),
     "bci_lstm_get_profile": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_int32)]),
     "bci_launch_count": (C.c_int64, []),
+    "bci_lstm_chunk_windows": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32)]),
     "bci_lstm_workspace_bytes": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_size_t)]),
     "bci_lstm_forward": (C.c_int, [C.c_void_p, _FP, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_uint64,
                                    _FP, _FP, _FP, _FP, C.c_size_t, C.c_void_p]),

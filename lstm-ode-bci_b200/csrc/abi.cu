@@ -138,6 +138,12 @@ extern "C" int bci_lstm_load_weights(bci_lstm_t h, const bci_lstm_weights* w, vo
   return BCI_OK;
 }
 
+extern "C" int bci_lstm_chunk_windows(bci_lstm_t h, int32_t* windows) {
+  BCI_REQUIRE(h && windows, BCI_EINVAL, "bci_lstm_chunk_windows: NULL argument");
+  *windows = max_chunk(h->cfg, 0);
+  return BCI_OK;
+}
+
 extern "C" int bci_lstm_workspace_bytes(bci_lstm_t h, int32_t batch, int32_t seq_len, int32_t train, size_t* bytes) {
   BCI_REQUIRE(h && bytes, BCI_EINVAL, "bci_lstm_workspace_bytes: NULL argument");
   BCI_REQUIRE(batch >= 0 && seq_len >= 1, BCI_EINVAL, "bci_lstm_workspace_bytes: bad shape (%d,%d)", batch, seq_len);

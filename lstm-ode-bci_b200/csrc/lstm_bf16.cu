@@ -71,8 +71,8 @@ static int bf16_path_fused() {
 }
 int bf16_chunk_windows() {
   // split: 74 x 128 windows = exactly one wave of (tile, direction) CTAs of the recurrence on 148 SMs.
-  // fused: every cluster runs two work items (both directions of one tile pair) per chunk: 2 tiles per co-resident cluster.
-  return bf16_path_fused() ? fused_max_clusters() * 2 * 128 : 74 * 128;
+  // fused: every cluster runs two work items (both directions of one tile quad) per chunk: 4 tiles per co-resident cluster.
+  return bf16_path_fused() ? fused_max_clusters() * 4 * 128 : 74 * 128;
 }
 
 size_t lstm_store_bytes_bf16(const bci_lstm_config& c) {

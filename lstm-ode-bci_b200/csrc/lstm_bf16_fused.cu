@@ -6,23 +6,24 @@
 // matrices of the direction (384 KB bf16 for a 256-wide input) resident in the shared memory of four SMs:
 //
 //   cluster rank r = 2 p + s      p = gate-column half (hidden units [64 p, 64 p + 64), all four gates: 256 columns)
-//                                 s = window tile of the cluster's tile pair (128 windows each) = position in the CTA pair
-//   pair p = CTAs (p,0),(p,1)     one tcgen05.mma.cta_group::2 (M = 256: both tiles, N = 256, K = 16) per K slice; each CTA keeps
-//                                 128 of the pair's 256 weight rows (96 KB), supplies its own tile's A operand ([in_t | h_{t-1}])
-//                                 and receives its own 128 x 256 accumulator in its TMEM (2 x 256 columns, double-buffered)
-//   per step                      MMA_hh(t) (needs h_{t-1}) -> commit (multicast to the pair) -> 8 epilogue warps per CTA:
-//                                 tcgen05.ld, + bias, sigma/tanh (MUFU), cell update (fp32 registers), h_t (bf16) written into the
-//                                 A-operand buffer of step t+1 (this CTA's 64-unit K-atom, 16 KB contiguous).  When the atom is
-//                                 complete one thread sends it through distributed shared memory to the CTA (1-p, s) that computes
-//                                 the other half of the gates for the same windows: one cp.async.bulk shared::cta ->
-//                                 shared::cluster whose bytes complete an mbarrier in the destination CTA.  (The first version
-//                                 used per-thread st.shared::cluster + fence.proxy.async + release arrives: 2 300 of 6 800 cycles
-//                                 per step were those fences waiting on the ~20 B/clk remote-store path; see profiles/.)
-//                                 The pair leader issues MMA_hh(t+1) once both CTAs of its pair hold the complete h_t: its own two
-//                                 barriers (local atom written, incoming atom landed) and one relay arrive from its peer.
-//                                 MMA_ih(t+1) = in_{t+1} . W_ih^T does not depend on h and is issued into the other accumulator
-//                                 while the epilogue of step t runs; in_t tiles arrive through a 4-slot TMA ring.
-//   h_t -> HBM                    each CTA TMA-stores its own 64-unit atom of h_t (its K-atom of the operand buffer).
+//                                 s = window-tile column of the cluster's tile quad = position in the CTA pair
+//   pair p = CTAs (p,0),(p,1)     one tcgen05.mma.cta_group::2 (M = 256, N = 256, K = 16) per K slice; each CTA keeps 128 of the
+//                                 pair's 256 weight rows (96 KB), supplies its own tiles' A operand ([in_t | h_{t-1}]) and
+//                                 receives its own 128 x 256 accumulators in its TMEM
+//   two tiles per CTA (q = 0,1)   PING-PONG: while the 8 epilogue warps work on tile q (tcgen05.ld, + bias, sigma/tanh on the
+//                                 MUFU, cell update in fp32 registers, h_t -> bf16 operand buffer), the tensor pipe runs
+//                                 MMA_ih + MMA_hh of tile 1-q and the h exchange of tile 1-q is in flight.  Both pipes stay busy:
+//                                 per tile-step 3 072 tensor cycles against ~3 300 epilogue cycles.  (One tile per CTA left
+//                                 MMA latency + exchange, ~1 350 ns of 3 200 ns per step, exposed: profiles/r1_fused_timeline.md.)
+//   h exchange (DSMEM)            each CTA computes h_t for its 64 units = one K-atom (16 KB contiguous) of the operand buffer of
+//                                 step t+1.  When the atom is complete one thread sends it to the CTA (1-p, s) that computes the
+//                                 other gates of the same windows: a single cp.async.bulk shared::cta -> shared::cluster whose
+//                                 bytes complete an mbarrier there (per-thread st.shared::cluster + proxy/cluster fences cost
+//                                 2 300 cycles per step in the first version).  The pair leader issues MMA_hh once both CTAs of
+//                                 its pair hold the complete h: two local barriers plus RELAXED relay arrives from its peer.
+//   buffers                       W 6 atoms (96 KB) + h 2 tiles x 2 atoms (64 KB, single-buffered: the ping-pong schedule separates
+//                                 readers and writers) + 4-slot TMA ring for in_t (64 KB) + bias; TMEM 2 tiles x 256 columns.
+//   h_t -> HBM                    each CTA TMA-stores its own 64-unit atom of h_t.
 //
 // Reference semantics: nn.LSTM inside EnhancedLSTMModel (04_lstm_model.py:181-188,211).
 #include "lstm_shared_kernels.cuh"
@@ -34,11 +35,11 @@ using namespace sm100;
 
 constexpr int FR_M = 128;                       // windows per tile
 constexpr int FR_EPI_WARPS = 8;
-constexpr int FR_THREADS = (FR_EPI_WARPS + 3) * 32;  // + MMA issuer, TMA producer, h store warp
+constexpr int FR_THREADS = (FR_EPI_WARPS + 3) * 32;  // + MMA issuer / relay, TMA producer, h store warp
 constexpr uint32_t FR_ATOM = 128 * 128;         // [128 rows][64 bf16] SW128 atom
 constexpr int FR_STAGES = 4;
 constexpr int FR_W_ATOMS = 6;                   // up to 4 K-atoms of W_ih (input width 256) + 2 of W_hh
-constexpr uint32_t FR_OFF_H = FR_W_ATOMS * FR_ATOM;              // two h buffers x two atoms
+constexpr uint32_t FR_OFF_H = FR_W_ATOMS * FR_ATOM;              // h of tile 0 and tile 1, two atoms each
 constexpr uint32_t FR_OFF_RING = FR_OFF_H + 4 * FR_ATOM;
 constexpr uint32_t FR_OFF_BIAS = FR_OFF_RING + FR_STAGES * FR_ATOM;  // 256 floats
 constexpr uint32_t FR_OFF_CTL = FR_OFF_BIAS + 1024;
@@ -50,7 +51,7 @@ __device__ __forceinline__ float fr_tanh(float x) {
   return y;
 }
 
-// work item w (0 .. 2*tile_pairs): direction = w / tile_pairs, tile pair = w % tile_pairs
+// work item w (0 .. 2*tile_quads): direction = w / tile_quads, tile quad = w % tile_quads; CTA (p, s) owns tiles 4 quad + 2 q + s
 template <bool STATS>
 __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(FR_THREADS, 1)
 lstm_fused_bf16(const __grid_constant__ CUtensorMap tmIn,   // in  [T][Bc][Kin] bf16, box 64 x 128 x 1
@@ -60,10 +61,10 @@ lstm_fused_bf16(const __grid_constant__ CUtensorMap tmIn,   // in  [T][Bc][Kin] 
                 const __nv_bfloat16* __restrict__ whh_r,    // reverse
                 const float* __restrict__ bias,             // [2][512] perm_T order, pre-scaled like the rows
                 float2* __restrict__ stats,                 // STATS: [T*Bc][8] (sum, sumsq) of h over 32 units: [dir][p][ch]
-                int Bc, int T, int Kin, int tile_pairs,
-                long long* __restrict__ tl) {               // optional timeline (BCI_FUSED_TIMELINE): cluster 0, rank 0, 8 stamps x step
+                int Bc, int T, int Kin, int tile_quads,
+                long long* __restrict__ tl) {               // optional timeline (BCI_FUSED_TIMELINE): cluster 0, 8 stamps x step x rank
   extern __shared__ uint8_t fr_smem_raw[];
-  const bool tl_on = tl != nullptr && blockIdx.x < 4;  // ranks 0 (leader) and 1 (its peer) of cluster 0; globaltimer is common to SMs
+  const bool tl_on = tl != nullptr && blockIdx.x < 4;
   auto stamp = [&](int st, int slot) {
     if (tl_on && st < 64) { long long c; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(c)); tl[(blockIdx.x * 64 + st) * 8 + slot] = c; }
   };
@@ -75,29 +76,35 @@ lstm_fused_bf16(const __grid_constant__ CUtensorMap tmIn,   // in  [T][Bc][Kin] 
   float* bias_s = reinterpret_cast<float*>(gen + FR_OFF_BIAS);
   uint8_t* ctl = gen + FR_OFF_CTL;
   const uint32_t bar0 = smem_u32(ctl);
-  auto in_full = [&](int s) { return bar0 + 8u * s; };            // leader: 1 arrival (expect_tx), bytes of both CTAs
-  auto in_empty = [&](int s) { return bar0 + 8u * (4 + s); };     // every CTA: multicast commit
-  auto acc_full = [&](int a) { return bar0 + 8u * (8 + a); };     // every CTA: multicast commit
-  auto h_in = [&](int b) { return bar0 + 8u * (10 + b); };        // every CTA: incoming K-atom (expect_tx by the local store warp)
-  auto peer_ready = [&](int b) { return bar0 + 8u * (16 + b); };  // leader: the peer CTA holds the complete h (relay arrive)
-  auto h_local = [&](int b) { return bar0 + 8u * (12 + b); };     // every CTA: its own 8 epilogue warps
-  auto st_free = [&](int b) { return bar0 + 8u * (14 + b); };     // every CTA: the h store warp
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ctl + 8 * 18);
+  // per-tile barriers complete once per step g: parity g & 1
+  auto in_full = [&](int i) { return bar0 + 8u * i; };            // leader: 1 arrival (expect_tx), bytes of both CTAs
+  auto in_empty = [&](int i) { return bar0 + 8u * (4 + i); };     // every CTA: multicast commit
+  auto acc_full = [&](int q) { return bar0 + 8u * (8 + q); };     // every CTA: multicast commit (tile q's accumulator is ready)
+  auto h_local = [&](int q) { return bar0 + 8u * (10 + q); };     // every CTA: its 8 epilogue warps wrote h (and drained TMEM)
+  auto h_in = [&](int q) { return bar0 + 8u * (12 + q); };        // every CTA: the partner's atom landed (expect_tx by the store warp)
+  auto st_free = [&](int q) { return bar0 + 8u * (14 + q); };     // every CTA: TMA store of the local atom finished reading it
+  auto peer_local = [&](int q) { return bar0 + 8u * (16 + q); };  // leader: relay of the peer's h_local
+  auto peer_in = [&](int q) { return bar0 + 8u * (18 + q); };     // leader: relay of the peer's h_in
+  auto copy_done = [&](int q) { return bar0 + 8u * (20 + q); };   // every CTA: ack -- my outgoing atom landed at the partner
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ctl + 8 * 22);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t rank = cluster_ctarank();
   const int p = (int)(rank >> 1), s = (int)(rank & 1);
   const bool leader = (s == 0);
+  const uint32_t partner = (uint32_t)(2 * (1 - p) + s);  // same windows, other half of the gates
   const int nk = Kin / 64;  // K-atoms of the input part
 
   if (tid == 0) {
     for (int i = 0; i < FR_STAGES; ++i) { mbar_init(in_full(i), 1); mbar_init(in_empty(i), 1); }
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(acc_full(i), 1);
-      mbar_init(h_in(i), 1);
-      mbar_init(peer_ready(i), 1);
-      mbar_init(h_local(i), FR_EPI_WARPS);
-      mbar_init(st_free(i), 1);
+    for (int q = 0; q < 2; ++q) {
+      mbar_init(acc_full(q), 1);
+      mbar_init(h_local(q), FR_EPI_WARPS);
+      mbar_init(h_in(q), 1);
+      mbar_init(st_free(q), 1);
+      mbar_init(peer_local(q), 1);
+      mbar_init(peer_in(q), 1);
+      mbar_init(copy_done(q), 1);
     }
     fence_mbar_init();
     tma_prefetch_desc(&tmIn);
@@ -113,217 +120,232 @@ lstm_fused_bf16(const __grid_constant__ CUtensorMap tmIn,   // in  [T][Bc][Kin] 
   const uint32_t tmem_base = *tmem_slot;
   cluster_sync_all();  // every CTA's barriers are initialised before anyone signals them
 
-  const int n_work = 2 * tile_pairs;
+  const int n_work = 2 * tile_quads;
   const int n_clusters = (int)cluster_nclusters_x();
   // running step counter over all work items of this cluster (mbarrier parities are functions of it)
   int g0 = 0;
   for (int w = (int)cluster_id_x(); w < n_work; w += n_clusters, g0 += T) {
-    const int dir = w / tile_pairs, tp = w - dir * tile_pairs;
-    const int b0 = (2 * tp + s) * FR_M;  // first window of this CTA's tile
+    const int dir = w / tile_quads, tq = w - dir * tile_quads;
+    const int b0q[2] = {(4 * tq + s) * FR_M, (4 * tq + 2 + s) * FR_M};  // first window of this CTA's tiles q = 0, 1
 
     // ---- (re)load this CTA's weight rows: perm_T rows [256 p + 128 s, +128) of direction `dir` ----
-    if (g0 > 0) cluster_sync_all();  // all MMAs of the previous item retired (its last h_full was waited on below)
+    if (g0 > 0) cluster_sync_all();  // every role finished the previous item (its last step was waited on below)
     {
       const int row0 = 256 * p + 128 * s;
       const uint4* src_ih = reinterpret_cast<const uint4*>(wih + ((size_t)dir * 512 + row0) * Kin);
       const int cpr = Kin / 8;  // 16-byte chunks per row
-      for (int q = tid; q < 128 * cpr; q += FR_THREADS) {
-        const uint32_t row = q / cpr, cc = q - row * cpr, atom = cc >> 3, c = cc & 7;
-        *reinterpret_cast<uint4*>(gen + atom * FR_ATOM + sw128_chunk_off(row, c)) = __ldg(src_ih + q);
+      for (int i = tid; i < 128 * cpr; i += FR_THREADS) {
+        const uint32_t row = i / cpr, cc = i - row * cpr, atom = cc >> 3, c = cc & 7;
+        *reinterpret_cast<uint4*>(gen + atom * FR_ATOM + sw128_chunk_off(row, c)) = __ldg(src_ih + i);
       }
       const uint4* src_hh = reinterpret_cast<const uint4*>((dir ? whh_r : whh_f) + (size_t)row0 * 128);
-      for (int q = tid; q < 128 * 16; q += FR_THREADS) {
-        const uint32_t row = q >> 4, cc = q & 15, atom = cc >> 3, c = cc & 7;
-        *reinterpret_cast<uint4*>(gen + (nk + atom) * FR_ATOM + sw128_chunk_off(row, c)) = __ldg(src_hh + q);
+      for (int i = tid; i < 128 * 16; i += FR_THREADS) {
+        const uint32_t row = i >> 4, cc = i & 15, atom = cc >> 3, c = cc & 7;
+        *reinterpret_cast<uint4*>(gen + (nk + atom) * FR_ATOM + sw128_chunk_off(row, c)) = __ldg(src_hh + i);
       }
       // bias of the pair's 256 gate columns (every CTA of the pair needs all of them for its own rows)
-      for (int q = tid; q < 256; q += FR_THREADS) bias_s[q] = __ldg(bias + dir * 512 + 256 * p + q);
+      for (int i = tid; i < 256; i += FR_THREADS) bias_s[i] = __ldg(bias + dir * 512 + 256 * p + i);
     }
     fence_proxy_async_all();
     __syncthreads();
     cluster_sync_all();
 
     if (warp == FR_EPI_WARPS + 1) {
-      // ---------------- TMA producer: this CTA's in_t tile, K-atom by K-atom, through the ring ----------------
+      // ---------------- TMA producer: in_t of tile 0, then tile 1, K-atom by K-atom, through the ring ----------------
       if (lane == 0) {
-        int k_total = (g0 / T) * T * nk;  // ring slots consumed before this item (same count in every CTA)
+        int k_total = g0 * 2 * nk;  // ring slots consumed before this item (same count in every CTA)
+        const uint32_t lead_full0 = mapa_u32(in_full(0), rank & ~1u);
         for (int st = 0; st < T; ++st) {
           const int t = dir ? (T - 1 - st) : st;
-          // the ring holds one step (4 slots): pull the tile of step st+2 into L2 now so that its smem loads, which can only be
-          // issued once the MMAs of step st+1 have freed the slots, are L2 hits (one of the two CTAs sharing the tile does it)
+          // the ring holds one tile-step: pull the tiles of step st+2 into L2 now so that their smem loads, which can only be
+          // issued once earlier MMAs have freed the slots, are L2 hits (one of the two CTAs sharing the tiles does it)
           if (p == 0 && st + 2 < T) {
             const int t2 = dir ? (T - 3 - st) : st + 2;
-            for (int k = 0; k < nk; ++k) tma_prefetch_l2_3d(&tmIn, k * 64, b0, t2);
+            for (int q = 0; q < 2; ++q)
+              for (int k = 0; k < nk; ++k) tma_prefetch_l2_3d(&tmIn, k * 64, b0q[q], t2);
           }
-          for (int k = 0; k < nk; ++k, ++k_total) {
-            const int stage = k_total % FR_STAGES;
-            const uint32_t ph = (uint32_t)((k_total / FR_STAGES) & 1);
-            mbar_wait(in_empty(stage), ph ^ 1u);
-            if (leader) mbar_arrive_expect_tx(in_full(stage), 2 * FR_ATOM);
-            tma_load_3d_2sm(sRing + stage * FR_ATOM, &tmIn, k * 64, b0, t, mapa_u32(in_full(stage), rank & ~1u));
+          for (int q = 0; q < 2; ++q) {
+            for (int k = 0; k < nk; ++k, ++k_total) {
+              const int stage = k_total % FR_STAGES;
+              const uint32_t ph = (uint32_t)((k_total / FR_STAGES) & 1);
+              mbar_wait(in_empty(stage), ph ^ 1u);
+              if (leader) mbar_arrive_expect_tx(in_full(stage), 2 * FR_ATOM);
+              tma_load_3d_2sm(sRing + stage * FR_ATOM, &tmIn, k * 64, b0q[q], t, lead_full0 + 8u * stage);
+            }
           }
         }
       }
     } else if (warp == FR_EPI_WARPS) {
-      // ---------------- MMA issuer (pair leader only) ----------------
       if (leader && lane == 0) {
+        // ---------------- MMA issuer (pair leader) ----------------
         constexpr uint32_t idesc = umma_idesc_bf16(256, 256);
         const uint16_t pair_mask = (uint16_t)(3u << (2 * p));
-        int k_total = (g0 / T) * T * nk;
-        auto issue_ih = [&](int acc) {
-          for (int k = 0; k < nk; ++k, ++k_total) {
-            const int stage = k_total % FR_STAGES;
-            mbar_wait(in_full(stage), (uint32_t)((k_total / FR_STAGES) & 1));
-            tc_fence_after();
-#pragma unroll
-            for (int kk = 0; kk < 4; ++kk) {
-              const uint64_t da = umma_desc_sw128(sRing + stage * FR_ATOM + kk * 32);
-              const uint64_t db = umma_desc_sw128(sW + k * FR_ATOM + kk * 32);
-              umma_bf16_2sm(tmem_base + acc * 256, da, db, idesc, (k | kk) != 0 ? 1u : 0u);
-            }
-            umma_commit_2sm_mc(in_empty(stage), pair_mask);  // frees the slot in both CTAs when these MMAs retire
-          }
+        const uint32_t ack0 = mapa_u32(copy_done(0), partner);
+        int k_total = g0 * 2 * nk;
+        // accumulator of tile q drained by both CTAs of the pair (their epilogues of step gp)
+        auto wait_drained = [&](int q, int gp) {
+          mbar_wait(h_local(q), (uint32_t)(gp & 1));
+          mbar_wait_cluster(peer_local(q), (uint32_t)(gp & 1));
+          tc_fence_after();
         };
-        issue_ih(g0 & 1);
+        // h of step gp complete in both CTAs of the pair
+        auto wait_exchanged = [&](int q, int gp) {
+          mbar_wait(h_in(q), (uint32_t)(gp & 1));
+          mbar_arrive_cluster_relaxed(ack0 + 8u * q);  // tell the sender its outgoing copy has landed
+          mbar_wait_cluster(peer_in(q), (uint32_t)(gp & 1));
+          tc_fence_after();
+        };
         for (int st = 0; st < T; ++st) {
           const int g = g0 + st;
-          if (g > 0) {
-            // h_{g-1} complete in both CTAs of the pair, accumulator (g-1)&1 drained by both epilogues
-            const int hb = (g - 1) & 1;
-            const uint32_t hp = (uint32_t)(((g - 1) >> 1) & 1);
-            mbar_wait(h_local(hb), hp);
-            mbar_wait(h_in(hb), hp);
-            stamp(st, 7);  // leader: own incoming atom landed
-            mbar_wait_cluster(peer_ready(hb), hp);
-            tc_fence_after();
-          }
-          stamp(st, 0);  // h_{t-1} complete, MMA_hh about to be issued
-          if (st > 0) {
-            const uint32_t hprev = sH + (uint32_t)((g - 1) & 1) * 2 * FR_ATOM;
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
-              const uint32_t atom = k >> 2, kk = k & 3;
-              const uint64_t da = umma_desc_sw128(hprev + atom * FR_ATOM + kk * 32);
-              const uint64_t db = umma_desc_sw128(sW + (nk + atom) * FR_ATOM + kk * 32);
-              umma_bf16_2sm(tmem_base + (g & 1) * 256, da, db, idesc, 1u);
+          for (int q = 0; q < 2; ++q) {
+            if (st > 0) wait_drained(q, g - 1);
+            if (q == 0) stamp(st, 0);
+            // ---- MMA_ih: acc_q = in_t(tile q) . W_ih^T ----
+            for (int k = 0; k < nk; ++k, ++k_total) {
+              const int stage = k_total % FR_STAGES;
+              mbar_wait(in_full(stage), (uint32_t)((k_total / FR_STAGES) & 1));
+              tc_fence_after();
+#pragma unroll
+              for (int kk = 0; kk < 4; ++kk) {
+                const uint64_t da = umma_desc_sw128(sRing + stage * FR_ATOM + kk * 32);
+                const uint64_t db = umma_desc_sw128(sW + k * FR_ATOM + kk * 32);
+                umma_bf16_2sm(tmem_base + q * 256, da, db, idesc, (k | kk) != 0 ? 1u : 0u);
+              }
+              umma_commit_2sm_mc(in_empty(stage), pair_mask);  // frees the slot in both CTAs when these MMAs retire
             }
+            if (q == 0) stamp(st, 1);
+            // ---- MMA_hh: acc_q += h_{t-1}(tile q) . W_hh^T ----
+            if (st > 0) {
+              wait_exchanged(q, g - 1);
+              if (q == 0) stamp(st, 2);
+              const uint32_t hq = sH + (uint32_t)q * 2 * FR_ATOM;
+#pragma unroll
+              for (int k = 0; k < 8; ++k) {
+                const uint32_t atom = k >> 2, kk = k & 3;
+                const uint64_t da = umma_desc_sw128(hq + atom * FR_ATOM + kk * 32);
+                const uint64_t db = umma_desc_sw128(sW + (nk + atom) * FR_ATOM + kk * 32);
+                umma_bf16_2sm(tmem_base + q * 256, da, db, idesc, 1u);
+              }
+            }
+            umma_commit_2sm_mc(acc_full(q), pair_mask);
           }
-          umma_commit_2sm_mc(acc_full(g & 1), pair_mask);
-          stamp(st, 1);  // MMA_hh issued + committed
-          if (st + 1 < T) issue_ih((g + 1) & 1);
-          stamp(st, 2);  // MMA_ih(t+1) issued
         }
-        // the item's last epilogue must finish before the weights are replaced / the kernel ends
-        {
-          const int hb = (g0 + T - 1) & 1;
-          const uint32_t hp = (uint32_t)(((g0 + T - 1) >> 1) & 1);
-          mbar_wait(h_local(hb), hp);
-          mbar_wait(h_in(hb), hp);
-          mbar_wait_cluster(peer_ready(hb), hp);
+        // the item's last step must be complete everywhere before the weights are replaced / the kernel ends
+        for (int q = 0; q < 2; ++q) {
+          wait_drained(q, g0 + T - 1);
+          wait_exchanged(q, g0 + T - 1);
         }
       } else if (!leader && lane == 0) {
-        // ---------------- relay (peer CTA of the pair): tell the leader when this CTA holds the complete h_g ----------------
-        const uint32_t pr = mapa_u32(peer_ready(0), rank & ~1u);
+        // ---------------- relay (peer CTA of the pair) ----------------
+        // RELAXED arrives: this thread has written nothing the leader needs -- the data sits in this CTA's shared memory (written
+        // by the bulk copy, whose completion the h_in wait observes, and by the local epilogue warps, who fenced generic->async
+        // before arriving on h_local); a release arrive costs a MEMBAR.GPU = 640 ns per step (measured) on the critical path.
+        const uint32_t pl0 = mapa_u32(peer_local(0), rank & ~1u), pi0 = mapa_u32(peer_in(0), rank & ~1u);
+        const uint32_t ack0 = mapa_u32(copy_done(0), partner);
         for (int st = 0; st < T; ++st) {
-          const int g = g0 + st, hb = g & 1;
-          const uint32_t hp = (uint32_t)((g >> 1) & 1);
-          mbar_wait(h_local(hb), hp);
-          mbar_wait(h_in(hb), hp);
-          stamp(st, 0);  // relay: incoming atom landed
-          // RELAXED arrive: this thread has written nothing the leader needs -- the data sits in this CTA's shared memory
-          // (written by the bulk copy, whose completion the h_in wait above observed, and by the local epilogue warps, who
-          // fenced generic->async before arriving on h_local); a release arrive here costs a MEMBAR.GPU = 640 ns per step
-          // (measured, profiles/r1_fused_timeline.md) on the critical path of every step.
-          mbar_arrive_cluster_relaxed(pr + 8u * hb);
-          stamp(st, 1);  // relay: arrive done
+          const int g = g0 + st;
+          for (int q = 0; q < 2; ++q) {
+            mbar_wait(h_local(q), (uint32_t)(g & 1));
+            mbar_arrive_cluster_relaxed(pl0 + 8u * q);
+            mbar_wait(h_in(q), (uint32_t)(g & 1));
+            mbar_arrive_cluster_relaxed(pi0 + 8u * q);
+            mbar_arrive_cluster_relaxed(ack0 + 8u * q);
+          }
         }
       }
     } else if (warp == FR_EPI_WARPS + 2) {
-      // ---------------- h store warp: this CTA's 64-unit atom of h_t -> out[t] ----------------
+      // ---------------- h store warp: this CTA's 64-unit atom of h_t -> partner CTA (DSMEM) and -> out[t] ----------------
       if (lane == 0) {
-        const uint32_t partner = (uint32_t)(2 * (1 - p) + s);  // same windows, other half of the gates
         for (int st = 0; st < T; ++st) {
           const int g = g0 + st;
           const int t = dir ? (T - 1 - st) : st;
-          const uint32_t atom = sH + (uint32_t)(g & 1) * 2 * FR_ATOM + p * FR_ATOM;
-          mbar_arrive_expect_tx(h_in(g & 1), FR_ATOM);  // the partner's atom of h_g will land in this CTA
-          mbar_wait(h_local(g & 1), (uint32_t)((g >> 1) & 1));
-          stamp(st, 5);  // store warp: local atom complete
-          bulk_copy_s2s_cluster(mapa_u32(atom, partner), atom, FR_ATOM, mapa_u32(h_in(g & 1), partner));
-          tma_store_3d(&tmOut, atom, dir * 128 + 64 * p, b0, t);
-          tma_store_commit();
-          asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-          if (st > 0) mbar_arrive(st_free((g - 1) & 1));
+          for (int q = 0; q < 2; ++q) {
+            const uint32_t atom = sH + (uint32_t)q * 2 * FR_ATOM + p * FR_ATOM;
+            mbar_arrive_expect_tx(h_in(q), FR_ATOM);  // the partner's atom of h_g (tile q) will land in this CTA
+            mbar_wait(h_local(q), (uint32_t)(g & 1));
+            if (q == 0) stamp(st, 5);
+            bulk_copy_s2s_cluster(mapa_u32(atom, partner), atom, FR_ATOM, mapa_u32(h_in(q), partner));
+            tma_store_3d(&tmOut, atom, dir * 128 + 64 * p, b0q[q], t);
+            tma_store_commit();
+            asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");  // the PREVIOUS store has finished reading its atom
+            if (st > 0 || q > 0) mbar_arrive(st_free(q ^ 1));
+          }
         }
         tma_store_wait_all();
-        mbar_arrive(st_free((g0 + T - 1) & 1));
+        mbar_arrive(st_free(1));
       }
     } else {
-      // ---------------- epilogue: thread = (window row, 32 of the CTA's 64 hidden units) ----------------
+      // ---------------- epilogue: thread = (window row, 32 of the CTA's 64 hidden units), tiles q = 0, 1 alternately ----------------
       const int quarter = warp & 3, ch = warp >> 2;
       const int r = quarter * 32 + lane;
-      const bool live = b0 + r < Bc;
       const uint32_t taddr0 = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)ch * 128;
       const float4* bias4 = reinterpret_cast<const float4*>(bias_s) + ch * 32;
-      float c[32];
+      float c[2][32];
 #pragma unroll
-      for (int i = 0; i < 32; ++i) c[i] = 0.f;
+      for (int q = 0; q < 2; ++q)
+#pragma unroll
+        for (int i = 0; i < 32; ++i) c[q][i] = 0.f;
 
       for (int st = 0; st < T; ++st) {
-        const int g = g0 + st, buf = g & 1;
+        const int g = g0 + st;
         const int t = dir ? (T - 1 - st) : st;
-        uint8_t* hloc = genH + (uint32_t)buf * 2 * FR_ATOM + p * FR_ATOM;
-        mbar_wait(acc_full(buf), (uint32_t)((g >> 1) & 1));
-        tc_fence_after();
-        if (tid == 0) stamp(st, 3);  // accumulator ready
-        float ssum = 0.f, ssq = 0.f;
-        uint32_t acc[2][32];
-        tmem_ld32(taddr0 + buf * 256, acc[0]);
 #pragma unroll
-        for (int sl = 0; sl < 4; ++sl) {
-          tmem_ld_wait();
-          if (sl + 1 < 4) tmem_ld32(taddr0 + buf * 256 + (sl + 1) * 32, acc[(sl + 1) & 1]);
-          const uint32_t* a = acc[sl & 1];
-          float4 bq[8];  // bias of the slab's 32 columns (gate*8 + u): warp-uniform 16-byte loads
+        for (int q = 0; q < 2; ++q) {
+          uint8_t* hloc = genH + (uint32_t)q * 2 * FR_ATOM + p * FR_ATOM;
+          mbar_wait(acc_full(q), (uint32_t)(g & 1));
+          tc_fence_after();
+          if (tid == 0 && q == 0) stamp(st, 3);  // accumulator ready
+          float ssum = 0.f, ssq = 0.f;
+          uint32_t acc[2][32];
+          tmem_ld32(taddr0 + q * 256, acc[0]);
 #pragma unroll
-          for (int q = 0; q < 8; ++q) bq[q] = bias4[sl * 8 + q];
-          auto bval = [&](int gate, int u) {
-            const float4& v = bq[gate * 2 + (u >> 2)];
-            return (u & 3) == 0 ? v.x : (u & 3) == 1 ? v.y : (u & 3) == 2 ? v.z : v.w;
-          };
-          uint32_t hp[4];
+          for (int sl = 0; sl < 4; ++sl) {
+            tmem_ld_wait();
+            if (sl + 1 < 4) tmem_ld32(taddr0 + q * 256 + (sl + 1) * 32, acc[(sl + 1) & 1]);
+            const uint32_t* a = acc[sl & 1];
+            float4 bq[8];  // bias of the slab's 32 columns (gate*8 + u): warp-uniform 16-byte loads
 #pragma unroll
-          for (int u2 = 0; u2 < 4; ++u2) {
-            float hv[2];
+            for (int i = 0; i < 8; ++i) bq[i] = bias4[sl * 8 + i];
+            auto bval = [&](int gate, int u) {
+              const float4& v = bq[gate * 2 + (u >> 2)];
+              return (u & 3) == 0 ? v.x : (u & 3) == 1 ? v.y : (u & 3) == 2 ? v.z : v.w;
+            };
+            uint32_t hp[4];
 #pragma unroll
-            for (int e = 0; e < 2; ++e) {
-              const int u = u2 * 2 + e;
-              const float ig = fmaf(0.5f, fr_tanh(__uint_as_float(a[0 * 8 + u]) + bval(0, u)), 0.5f);
-              const float fg = fmaf(0.5f, fr_tanh(__uint_as_float(a[1 * 8 + u]) + bval(1, u)), 0.5f);
-              const float gg = fr_tanh(__uint_as_float(a[2 * 8 + u]) + bval(2, u));
-              const float og = fmaf(0.5f, fr_tanh(__uint_as_float(a[3 * 8 + u]) + bval(3, u)), 0.5f);
-              float& cc = c[sl * 8 + u];
-              cc = fmaf(fg, cc, ig * gg);
-              hv[e] = og * fr_tanh(cc);
-              if (STATS) { ssum += hv[e]; ssq = fmaf(hv[e], hv[e], ssq); }
+            for (int u2 = 0; u2 < 4; ++u2) {
+              float hv[2];
+#pragma unroll
+              for (int e = 0; e < 2; ++e) {
+                const int u = u2 * 2 + e;
+                const float ig = fmaf(0.5f, fr_tanh(__uint_as_float(a[0 * 8 + u]) + bval(0, u)), 0.5f);
+                const float fg = fmaf(0.5f, fr_tanh(__uint_as_float(a[1 * 8 + u]) + bval(1, u)), 0.5f);
+                const float gg = fr_tanh(__uint_as_float(a[2 * 8 + u]) + bval(2, u));
+                const float og = fmaf(0.5f, fr_tanh(__uint_as_float(a[3 * 8 + u]) + bval(3, u)), 0.5f);
+                float& cc = c[q][sl * 8 + u];
+                cc = fmaf(fg, cc, ig * gg);
+                hv[e] = og * fr_tanh(cc);
+                if (STATS) { ssum += hv[e]; ssq = fmaf(hv[e], hv[e], ssq); }
+              }
+              __nv_bfloat162 pk = __floats2bfloat162_rn(hv[0], hv[1]);
+              hp[u2] = *reinterpret_cast<uint32_t*>(&pk);
             }
-            __nv_bfloat162 pk = __floats2bfloat162_rn(hv[0], hv[1]);
-            hp[u2] = *reinterpret_cast<uint32_t*>(&pk);
+            const uint4 hvec = make_uint4(hp[0], hp[1], hp[2], hp[3]);
+            // the local atom still held h_{g-1}: its TMA store and its copy to the partner must have finished reading it
+            if (sl == 0 && g > 0) {
+              mbar_wait(st_free(q), (uint32_t)((g - 1) & 1));
+              mbar_wait_cluster(copy_done(q), (uint32_t)((g - 1) & 1));
+            }
+            *reinterpret_cast<uint4*>(hloc + sw128_chunk_off((uint32_t)r, (uint32_t)(ch * 4 + sl))) = hvec;
           }
-          const uint4 hvec = make_uint4(hp[0], hp[1], hp[2], hp[3]);
-          // buffer `buf` was last read by the TMA store of h_{g-2}
-          if (sl == 0 && g >= 2) mbar_wait(st_free(buf), (uint32_t)(((g >> 1) - 1) & 1));
-          const uint32_t off = sw128_chunk_off((uint32_t)r, (uint32_t)(ch * 4 + sl));
-          *reinterpret_cast<uint4*>(hloc + off) = hvec;
-        }
-        if (tid == 0) stamp(st, 4);  // math + stores issued
-        fence_proxy_async_smem();  // generic-proxy stores -> visible to tcgen05.mma / the bulk copies
-        tc_fence_before();         // order this thread's TMEM reads before the arrive
-        __syncwarp();
-        if (lane == 0) mbar_arrive(h_local(buf));
-        if (tid == 0) stamp(st, 6);  // arrives done
-        if (STATS) {
-          if (live) stats[((long long)t * Bc + b0 + r) * 8 + dir * 4 + p * 2 + ch] = make_float2(ssum, ssq);
+          if (tid == 0 && q == 0) stamp(st, 4);  // math + stores issued
+          fence_proxy_async_smem();  // generic-proxy stores -> visible to tcgen05.mma / the bulk copies
+          tc_fence_before();         // order this thread's TMEM reads before the arrive
+          __syncwarp();
+          if (lane == 0) mbar_arrive(h_local(q));
+          if (STATS) {
+            if (b0q[q] + r < Bc) stats[((long long)t * Bc + b0q[q] + r) * 8 + dir * 4 + p * 2 + ch] = make_float2(ssum, ssq);
+          }
         }
       }
     }
@@ -375,15 +397,15 @@ int launch_fused_rec_bf16(const __nv_bfloat16* in, const __nv_bfloat16* wih, con
   if (rc) return rc;
   rc = make_tmap_bf16_3d(&tmOut, out, (uint64_t)T, (uint64_t)Bc, 256, 64, FR_M);
   if (rc) return rc;
-  const int tiles = ceil_div(Bc, FR_M), tile_pairs = (tiles + 1) / 2;
-  int clusters = 2 * tile_pairs < max_clusters ? 2 * tile_pairs : max_clusters;
+  const int tiles = ceil_div(Bc, FR_M), tile_quads = (tiles + 3) / 4;
+  int clusters = 2 * tile_quads < max_clusters ? 2 * tile_quads : max_clusters;
   // BCI_FUSED_TIMELINE=<path>: clock64 stamps of the first 64 steps of cluster 0 / rank 0 are written to <path> (debug only)
   static const char* tl_path = getenv("BCI_FUSED_TIMELINE");
   static long long* tl_dev = nullptr;
   if (tl_path && !tl_dev) { BCI_CUDA_OK(cudaMalloc(&tl_dev, 4 * 64 * 8 * sizeof(long long))); }
   if (tl_dev) BCI_CUDA_OK(cudaMemsetAsync(tl_dev, 0, 4 * 64 * 8 * sizeof(long long), st));
-  if (stats) lstm_fused_bf16<true><<<4 * clusters, FR_THREADS, FR_SMEM, st>>>(tmIn, tmOut, wih, whh_f, whh_r, bias, stats, Bc, T, Kin, tile_pairs, tl_dev);
-  else lstm_fused_bf16<false><<<4 * clusters, FR_THREADS, FR_SMEM, st>>>(tmIn, tmOut, wih, whh_f, whh_r, bias, nullptr, Bc, T, Kin, tile_pairs, tl_dev);
+  if (stats) lstm_fused_bf16<true><<<4 * clusters, FR_THREADS, FR_SMEM, st>>>(tmIn, tmOut, wih, whh_f, whh_r, bias, stats, Bc, T, Kin, tile_quads, tl_dev);
+  else lstm_fused_bf16<false><<<4 * clusters, FR_THREADS, FR_SMEM, st>>>(tmIn, tmOut, wih, whh_f, whh_r, bias, nullptr, Bc, T, Kin, tile_quads, tl_dev);
   if (tl_dev) {
     long long host[4 * 64 * 8];
     BCI_CUDA_OK(cudaMemcpyAsync(host, tl_dev, sizeof(host), cudaMemcpyDeviceToHost, st));

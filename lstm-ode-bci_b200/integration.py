@@ -18,7 +18,7 @@ from .ode import CognitiveStateODE, solve_ensemble, _dev
 from .synth import RATE_ORDER
 
 
-def stream_lstm_probs(lstm_model, host_batches, device=None, chunk=9472, want_attn=False):
+def stream_lstm_probs(lstm_model, host_batches, device=None, chunk=None, want_attn=False):
     """Pipelined inference over a stream of HOST batches (the reference copies each batch synchronously, 06:346).
 
     host_batches: iterable of CPU float32 tensors / numpy arrays (n_i, T, C).  Pinned tensors are DMA-ed in
@@ -27,6 +27,8 @@ def stream_lstm_probs(lstm_model, host_batches, device=None, chunk=9472, want_at
     pieces) overlaps the kernels of batch i (current stream); `chunk` defaults to one full wave of recurrence CTAs."""
     dev = _dev(device)
     lstm_model.eval()
+    if chunk is None:
+        chunk = ops.lstm_chunk_windows(lstm_model._engine(lstm_model._precision_now()))
     copy_stream = torch.cuda.Stream(device=dev)
     main = torch.cuda.current_stream(dev)
     slots = [dict(buf=None, free=None, pin=None) for _ in range(2)]

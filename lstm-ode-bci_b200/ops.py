@@ -122,6 +122,13 @@ def launch_count():
     return int(N.lib().bci_launch_count())
 
 
+def lstm_chunk_windows(hid):
+    """Windows per internal pass of the inference forward (one full wave of the recurrence kernel on this device)."""
+    n = C.c_int32(0)
+    N.check(N.lib().bci_lstm_chunk_windows(_handles[hid].ptr, C.byref(n)))
+    return n.value
+
+
 def lstm_workspace_bytes(hid, batch, seq_len, train):
     h = _handles[hid]
     n = C.c_size_t(0)
