@@ -61,9 +61,18 @@ lstm_fused_bf16(const __grid_constant__ CUtensorMap tmIn,   // in  [T][Bc][Kin] 
                 const __nv_bfloat16* __restrict__ whh_r,    // reverse
                 const float* __restrict__ bias,             // [2][512] perm_T order, pre-scaled like the rows
                 float2* __restrict__ stats,                 // STATS: [T*Bc][8] (sum, sumsq) of h over 32 units: [dir][p][ch]
-                int Bc, int T, int Kin, int tile_quads,
+                int Bc, int T, int Kin, int tile_quads, int jitter,  // jitter: 0 or a power of two (max sleep in ns)
                 long long* __restrict__ tl) {               // optional timeline (BCI_FUSED_TIMELINE): cluster 0, 8 stamps x step x rank
   extern __shared__ uint8_t fr_smem_raw[];
+  // BCI_FUSED_JITTER (tests only): every role sleeps a pseudo-random time at its synchronisation points, to shake out ordering
+  // assumptions that only hold at the natural timing
+  uint32_t jit_state = jitter ? (uint32_t)(blockIdx.x * 7919u + threadIdx.x * 104729u + 12345u) : 0u;
+  auto jit = [&]() {
+    if (jitter) {
+      jit_state = jit_state * 1664525u + 1013904223u;
+      __nanosleep((jit_state >> 20) & (uint32_t)(jitter - 1));
+    }
+  };
   const bool tl_on = tl != nullptr && blockIdx.x < 4;
   auto stamp = [&](int st, int slot) {
     if (tl_on && st < 64) { long long c; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(c)); tl[(blockIdx.x * 64 + st) * 8 + slot] = c; }
@@ -86,7 +95,9 @@ lstm_fused_bf16(const __grid_constant__ CUtensorMap tmIn,   // in  [T][Bc][Kin] 
   auto peer_local = [&](int q) { return bar0 + 8u * (16 + q); };  // leader: relay of the peer's h_local
   auto peer_in = [&](int q) { return bar0 + 8u * (18 + q); };     // leader: relay of the peer's h_in
   auto copy_done = [&](int q) { return bar0 + 8u * (20 + q); };   // every CTA: ack -- my outgoing atom landed at the partner
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ctl + 8 * 22);
+  auto recv_ready = [&](int q) { return bar0 + 8u * (22 + q); };  // every CTA: the partner's MMA_hh(g) retired: its copy of h_{g-1}
+                                                                   // may be overwritten by my atom of h_g (h is single-buffered)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ctl + 8 * 24);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t rank = cluster_ctarank();
@@ -105,8 +116,13 @@ lstm_fused_bf16(const __grid_constant__ CUtensorMap tmIn,   // in  [T][Bc][Kin] 
       mbar_init(peer_local(q), 1);
       mbar_init(peer_in(q), 1);
       mbar_init(copy_done(q), 1);
+      mbar_init(recv_ready(q), 1);
     }
     fence_mbar_init();
+    // h_in is armed for the first step here and re-armed by its (single) waiter after every completed phase: arming it from
+    // the store warp let a second expect_tx arrive land on a phase whose bytes were still in flight (arrival-count
+    // underflow -> launch failure as soon as the partner CTA ran a little late; found with BCI_FUSED_JITTER and under ncu)
+    for (int q = 0; q < 2; ++q) mbar_arrive_expect_tx(h_in(q), FR_ATOM);
     tma_prefetch_desc(&tmIn);
     tma_prefetch_desc(&tmOut);
   }
@@ -168,6 +184,7 @@ lstm_fused_bf16(const __grid_constant__ CUtensorMap tmIn,   // in  [T][Bc][Kin] 
             for (int k = 0; k < nk; ++k, ++k_total) {
               const int stage = k_total % FR_STAGES;
               const uint32_t ph = (uint32_t)((k_total / FR_STAGES) & 1);
+              jit();
               mbar_wait(in_empty(stage), ph ^ 1u);
               if (leader) mbar_arrive_expect_tx(in_full(stage), 2 * FR_ATOM);
               tma_load_3d_2sm(sRing + stage * FR_ATOM, &tmIn, k * 64, b0q[q], t, lead_full0 + 8u * stage);
@@ -184,13 +201,16 @@ lstm_fused_bf16(const __grid_constant__ CUtensorMap tmIn,   // in  [T][Bc][Kin] 
         int k_total = g0 * 2 * nk;
         // accumulator of tile q drained by both CTAs of the pair (their epilogues of step gp)
         auto wait_drained = [&](int q, int gp) {
+          jit();
           mbar_wait(h_local(q), (uint32_t)(gp & 1));
           mbar_wait_cluster(peer_local(q), (uint32_t)(gp & 1));
           tc_fence_after();
         };
         // h of step gp complete in both CTAs of the pair
         auto wait_exchanged = [&](int q, int gp) {
+          jit();
           mbar_wait(h_in(q), (uint32_t)(gp & 1));
+          mbar_arrive_expect_tx(h_in(q), FR_ATOM);     // re-arm for the next step's incoming atom
           mbar_arrive_cluster_relaxed(ack0 + 8u * q);  // tell the sender its outgoing copy has landed
           mbar_wait_cluster(peer_in(q), (uint32_t)(gp & 1));
           tc_fence_after();
@@ -246,9 +266,12 @@ lstm_fused_bf16(const __grid_constant__ CUtensorMap tmIn,   // in  [T][Bc][Kin] 
         for (int st = 0; st < T; ++st) {
           const int g = g0 + st;
           for (int q = 0; q < 2; ++q) {
+            jit();
             mbar_wait(h_local(q), (uint32_t)(g & 1));
             mbar_arrive_cluster_relaxed(pl0 + 8u * q);
+            jit();
             mbar_wait(h_in(q), (uint32_t)(g & 1));
+            mbar_arrive_expect_tx(h_in(q), FR_ATOM);  // re-arm for the next step's incoming atom
             mbar_arrive_cluster_relaxed(pi0 + 8u * q);
             mbar_arrive_cluster_relaxed(ack0 + 8u * q);
           }
@@ -262,9 +285,10 @@ lstm_fused_bf16(const __grid_constant__ CUtensorMap tmIn,   // in  [T][Bc][Kin] 
           const int t = dir ? (T - 1 - st) : st;
           for (int q = 0; q < 2; ++q) {
             const uint32_t atom = sH + (uint32_t)q * 2 * FR_ATOM + p * FR_ATOM;
-            mbar_arrive_expect_tx(h_in(q), FR_ATOM);  // the partner's atom of h_g (tile q) will land in this CTA
+            jit();
             mbar_wait(h_local(q), (uint32_t)(g & 1));
             if (q == 0) stamp(st, 5);
+            mbar_wait_cluster(recv_ready(q), (uint32_t)(g & 1));  // the partner pair has finished reading h_{g-1} of this tile
             bulk_copy_s2s_cluster(mapa_u32(atom, partner), atom, FR_ATOM, mapa_u32(h_in(q), partner));
             tma_store_3d(&tmOut, atom, dir * 128 + 64 * p, b0q[q], t);
             tma_store_commit();
@@ -293,8 +317,12 @@ lstm_fused_bf16(const __grid_constant__ CUtensorMap tmIn,   // in  [T][Bc][Kin] 
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
           uint8_t* hloc = genH + (uint32_t)q * 2 * FR_ATOM + p * FR_ATOM;
+          if (lane == 0) jit();
+          __syncwarp();
           mbar_wait(acc_full(q), (uint32_t)(g & 1));
           tc_fence_after();
+          // MMA_hh(g) of this pair has retired: the partner may now send its atom of h_g into this CTA's (single) h buffer
+          if (tid == 0) mbar_arrive_cluster_relaxed(mapa_u32(recv_ready(q), partner));
           if (tid == 0 && q == 0) stamp(st, 3);  // accumulator ready
           float ssum = 0.f, ssq = 0.f;
           uint32_t acc[2][32];
@@ -404,8 +432,9 @@ int launch_fused_rec_bf16(const __nv_bfloat16* in, const __nv_bfloat16* wih, con
   static long long* tl_dev = nullptr;
   if (tl_path && !tl_dev) { BCI_CUDA_OK(cudaMalloc(&tl_dev, 4 * 64 * 8 * sizeof(long long))); }
   if (tl_dev) BCI_CUDA_OK(cudaMemsetAsync(tl_dev, 0, 4 * 64 * 8 * sizeof(long long), st));
-  if (stats) lstm_fused_bf16<true><<<4 * clusters, FR_THREADS, FR_SMEM, st>>>(tmIn, tmOut, wih, whh_f, whh_r, bias, stats, Bc, T, Kin, tile_quads, tl_dev);
-  else lstm_fused_bf16<false><<<4 * clusters, FR_THREADS, FR_SMEM, st>>>(tmIn, tmOut, wih, whh_f, whh_r, bias, nullptr, Bc, T, Kin, tile_quads, tl_dev);
+  static const int jitter = [] { const char* e = getenv("BCI_FUSED_JITTER"); int v = e ? atoi(e) : 0; return (v > 0 && (v & (v - 1)) == 0) ? v : 0; }();
+  if (stats) lstm_fused_bf16<true><<<4 * clusters, FR_THREADS, FR_SMEM, st>>>(tmIn, tmOut, wih, whh_f, whh_r, bias, stats, Bc, T, Kin, tile_quads, jitter, tl_dev);
+  else lstm_fused_bf16<false><<<4 * clusters, FR_THREADS, FR_SMEM, st>>>(tmIn, tmOut, wih, whh_f, whh_r, bias, nullptr, Bc, T, Kin, tile_quads, jitter, tl_dev);
   if (tl_dev) {
     long long host[4 * 64 * 8];
     BCI_CUDA_OK(cudaMemcpyAsync(host, tl_dev, sizeof(host), cudaMemcpyDeviceToHost, st));

@@ -184,3 +184,23 @@ def test_fused_cluster_recurrence_matches_stepwise(Bc, T, Kin):
     ssum = want.reshape(T * Bc, 8, 32).sum(-1)
     ssq = (want.reshape(T * Bc, 8, 32) ** 2).sum(-1)
     assert float((stats[:, :, 0] - ssum).abs().max()) <= 5e-2 and float((stats[:, :, 1] - ssq).abs().max()) <= 5e-2
+
+
+def test_fused_kernel_is_robust_to_timing_jitter():
+    """The cluster kernel's cross-CTA protocol (mbarriers, DSMEM copies, relays) must not depend on the natural timing:
+    with BCI_FUSED_JITTER every role sleeps a pseudo-random time (up to 4 us) at its synchronisation points.  An earlier
+    version re-armed an mbarrier too early and only failed (launch failure) under such perturbation or under ncu."""
+    import os, subprocess, sys
+    code = (
+        "import numpy as np, torch\n"
+        "from lstm_ode_bci_b200 import lstm, synth\n"
+        "p = synth.make_lstm_params(42, 61, 128, 3, logit_gain=12.0)\n"
+        "x = torch.from_numpy(synth.make_windows(7, 700, 256, 61, structured=True)).cuda()\n"
+        "a = lstm.from_params(p, precision='bf16').predict_proba(x).cpu().numpy()\n"
+        "b = lstm.from_params(p, precision='fp32').predict_proba(x[:64]).cpu().numpy()\n"
+        "assert np.isfinite(a).all() and np.abs(a[:64] - b).max() <= 1e-2, np.abs(a[:64] - b).max()\n"
+        "print('jitter ok')\n")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, BCI_FUSED_JITTER="4096", PYTHONPATH=root)
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "jitter ok" in r.stdout, r.stderr[-2000:]
