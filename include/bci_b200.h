@@ -288,7 +288,7 @@ int bci_selftest_rec_bf16(const void* G, const void* whh_f, const void* whh_r, v
 /* fused projection + recurrence of one layer on a 4-CTA cluster (csrc/lstm_bf16_fused.cu):
  *   in [T][Bc][Kin] bf16 (Kin = 128 or 256); wih [2][512][Kin], whh_* [512][128] bf16 with rows in perm_T order (i,f,o rows
  *   pre-scaled by 1/2); bias [2][512] fp32 in the same order and scaling -> out [T][Bc][256] bf16; stats optional
- *   [T*Bc][8] float2 partial (sum, sum of squares) of h over 32 units, index dir*4 + unit/32 */
+ *   [T][8][Bc] float2 partial (sum, sum of squares) of h over 32 units, slot = dir*4 + unit/32 */
 int bci_selftest_fused_rec_bf16(const void* in, const void* wih, const void* whh_f, const void* whh_r, const float* bias,
                                 void* out, void* stats, int32_t Bc, int32_t T, int32_t Kin, void* stream);
 

@@ -381,7 +381,7 @@ lstm_rec_bf16(const __nv_bfloat16* __restrict__ G,        // blocked: [row/128][
               const __grid_constant__ CUtensorMap tmOut,  // out [T][Bc][256] bf16 (3D), box 64 cols x 128 rows x 1
               const __nv_bfloat16* __restrict__ whh_f,    // [512][128] rows in perm_T order, forward
               const __nv_bfloat16* __restrict__ whh_r,    // reverse
-              float2* __restrict__ stats,                 // STATS: [T*Bc][dir][half][2] (sum, sum of squares) of h over 32 units
+              float2* __restrict__ stats,                 // STATS: [T][dir*4 + half*2 + k][Bc] (sum, sum of squares) of h over 32 units
               int Bc, int T, int dbg) {
   extern __shared__ uint8_t rb_smem_raw[];
   const uint32_t raw = smem_u32(rb_smem_raw);
@@ -583,8 +583,11 @@ lstm_rec_bf16(const __nv_bfloat16* __restrict__ G,        // blocked: [row/128][
       mbar_arrive(bar_h);
       if (STATS) {
         // partial LayerNorm statistics of the last layer's output row (consumed by attn_score_bf16 / attn_pool_finish)
-        if (live)
-          *reinterpret_cast<float4*>(stats + ((long long)t * Bc + b0 + r) * 8 + dir * 4 + half * 2) = make_float4(ssum_lo, ssq_lo, ssum, ssq);
+        if (live) {  // [T][8][Bc]: a warp's 32 windows are 256 contiguous bytes per slot (full sectors, no DRAM read-modify-write)
+          float2* sp = stats + ((long long)t * 8 + dir * 4 + half * 2) * Bc + b0 + r;
+          sp[0] = make_float2(ssum_lo, ssq_lo);
+          sp[Bc] = make_float2(ssum, ssq);
+        }
       }
     }
   }

@@ -60,7 +60,7 @@ lstm_fused_bf16(const __grid_constant__ CUtensorMap tmIn,   // in  [T][Bc][Kin] 
                 const __nv_bfloat16* __restrict__ whh_f,    // [512][128] perm_T rows, forward
                 const __nv_bfloat16* __restrict__ whh_r,    // reverse
                 const float* __restrict__ bias,             // [2][512] perm_T order, pre-scaled like the rows
-                float2* __restrict__ stats,                 // STATS: [T*Bc][8] (sum, sumsq) of h over 32 units: [dir][p][ch]
+                float2* __restrict__ stats,                 // STATS: [T][8][Bc] (sum, sumsq) of h over 32 units, slot = dir*4 + p*2 + ch
                 int Bc, int T, int Kin, int tile_quads, int jitter,  // jitter: 0 or a power of two (max sleep in ns)
                 long long* __restrict__ tl) {               // optional timeline (BCI_FUSED_TIMELINE): cluster 0, 8 stamps x step x rank
   extern __shared__ uint8_t fr_smem_raw[];
@@ -372,7 +372,9 @@ lstm_fused_bf16(const __grid_constant__ CUtensorMap tmIn,   // in  [T][Bc][Kin] 
           __syncwarp();
           if (lane == 0) mbar_arrive(h_local(q));
           if (STATS) {
-            if (b0q[q] + r < Bc) stats[((long long)t * Bc + b0q[q] + r) * 8 + dir * 4 + p * 2 + ch] = make_float2(ssum, ssq);
+            // [T][8][Bc]: the warp's 32 windows are 256 contiguous bytes (the row-major [row][8] layout of the first version made
+            // every 8-byte store a partial sector: ncu showed 2.3 GB of DRAM read-modify-write reads and a 35 % slower kernel)
+            if (b0q[q] + r < Bc) stats[((long long)t * 8 + dir * 4 + p * 2 + ch) * Bc + b0q[q] + r] = make_float2(ssum, ssq);
           }
         }
       }

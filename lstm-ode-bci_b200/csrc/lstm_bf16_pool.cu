@@ -63,8 +63,9 @@ __global__ void __launch_bounds__(SC_THREADS, 1)
 attn_score_bf16(const __grid_constant__ CUtensorMap tmA,   // seq [M][256] bf16, box 64 x 128
                 const __grid_constant__ CUtensorMap tmB,   // W1' [128][256] bf16, box 64 x 128
                 const float4* __restrict__ par,            // [128] {s_j, c_j, w2_j, 0}
-                const float2* __restrict__ stats,          // [M][8] partial (sum, sumsq) over 32 units each
-                float b2, float* __restrict__ scores, int M) {
+                float2* __restrict__ stats,                // [T][8][Bc] partial (sum, sumsq) over 32 units each; slot 0 of every
+                                                           // row is REPLACED by (mean, rstd) for attn_pool_finish_bf16
+                float b2, float* __restrict__ scores, int M, int Bc) {
   extern __shared__ uint8_t sc_smem_raw[];
   const uint32_t raw = smem_u32(sc_smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
@@ -146,14 +147,17 @@ attn_score_bf16(const __grid_constant__ CUtensorMap tmA,   // seq [M][256] bf16,
       const int gr = tile * SC_BM + quarter * 32 + lane;
       float rs = 0.f, mp = 0.f;
       if (gr < M) {
-        const float4* sp = reinterpret_cast<const float4*>(stats + (long long)gr * 8);
-        const float4 p0 = __ldg(sp), p1 = __ldg(sp + 1), p2 = __ldg(sp + 2), p3 = __ldg(sp + 3);  // (sum,sq) x 8 partials
-        const float sum = ((p0.x + p0.z) + (p1.x + p1.z)) + ((p2.x + p2.z) + (p3.x + p3.z));
-        const float sq = ((p0.y + p0.w) + (p1.y + p1.w)) + ((p2.y + p2.w) + (p3.y + p3.w));
+        // slot-major layout: the 32 lanes (consecutive windows of one time step) read 256 contiguous bytes per slot
+        const int tt = gr / Bc, bb = gr - tt * Bc;
+        float2* sp = stats + ((long long)tt * 8) * Bc + bb;
+        float sum = 0.f, sq = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { const float2 v = sp[(long long)k * Bc]; sum += v.x; sq += v.y; }
         const float mean = sum * (1.0f / SC_K);
         const float var = fmaxf(sq * (1.0f / SC_K) - mean * mean, 0.f);
         rs = 1.0f / sqrtf(var + 1e-5f);
         mp = -rs * mean;
+        sp[0] = make_float2(mean, rs);  // only this thread ever reads this row's partials
       }
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
@@ -205,7 +209,7 @@ __device__ __forceinline__ float block_reduce(float v, float* red, bool is_max) 
 __global__ void __launch_bounds__(PF_THREADS)
 attn_pool_finish_bf16(const __nv_bfloat16* __restrict__ seq,  // [T][Bc][256]
                       const float* __restrict__ scores,       // [T][Bc]
-                      const float2* __restrict__ stats,       // [T*Bc][8]
+                      const float2* __restrict__ stats,       // [T][8][Bc]: slot 0 = (mean, rstd) written by attn_score_bf16
                       int Bc, int T, int classes,
                       const float* __restrict__ lnw, const float* __restrict__ lnb,
                       const float* __restrict__ c0t, const float* __restrict__ cb0,
@@ -226,10 +230,8 @@ attn_pool_finish_bf16(const __nv_bfloat16* __restrict__ seq,  // [T][Bc][256]
   for (int t = tid; t < T; t += PF_THREADS) {
     const long long row = (long long)t * Bc + b;
     const float s = __ldg(scores + row);
-    const float4* sp = reinterpret_cast<const float4*>(stats + row * 8);
-    const float4 p0 = __ldg(sp), p1 = __ldg(sp + 1), p2 = __ldg(sp + 2), p3 = __ldg(sp + 3);
     beta[t] = s;
-    bmean[t] = (((p0.x + p0.z) + (p1.x + p1.z)) + ((p2.x + p2.z) + (p3.x + p3.z))) * (1.0f / D);
+    bmean[t] = stats[((long long)t * 8) * Bc + b].x;
     lmax = fmaxf(lmax, s);
   }
   const float m = block_reduce(lmax, red, true);
@@ -241,12 +243,8 @@ attn_pool_finish_bf16(const __nv_bfloat16* __restrict__ seq,  // [T][Bc][256]
     const long long row = (long long)t * Bc + b;
     const float a = expf(beta[t] - m) * inv_l;
     if (attn) attn[(long long)b * T + t] = a;
-    const float4* sp = reinterpret_cast<const float4*>(stats + row * 8);
-    const float4 p0 = __ldg(sp), p1 = __ldg(sp + 1), p2 = __ldg(sp + 2), p3 = __ldg(sp + 3);
-    const float sq = ((p0.y + p0.w) + (p1.y + p1.w)) + ((p2.y + p2.w) + (p3.y + p3.w));
     const float mean = bmean[t];
-    const float var = fmaxf(sq * (1.0f / D) - mean * mean, 0.f);
-    const float bt = a / sqrtf(var + 1e-5f);
+    const float bt = a * stats[((long long)t * 8) * Bc + b].y;
     beta[t] = bt;
     lgam = fmaf(bt, mean, lgam);
   }
@@ -316,7 +314,7 @@ attn_pool_finish_bf16(const __nv_bfloat16* __restrict__ seq,  // [T][Bc][256]
   }
 }
 
-int launch_pool_bf16(bci_lstm_s* h, const __nv_bfloat16* seq, const float2* stats, float* scores, int Bc, int T, float* logits,
+int launch_pool_bf16(bci_lstm_s* h, const __nv_bfloat16* seq, float2* stats, float* scores, int Bc, int T, float* logits,
                      float* probs, float* attn, cudaStream_t st) {
   const int M = Bc * T;
   CUtensorMap tmA, tmB;
@@ -334,7 +332,7 @@ int launch_pool_bf16(bci_lstm_s* h, const __nv_bfloat16* seq, const float2* stat
   const float b2 = 0.f;
   const int tiles = ceil_div(M, SC_BM);
   const int grid = tiles < sm_count() ? tiles : sm_count();
-  attn_score_bf16<<<grid, SC_THREADS, SC_SMEM, st>>>(tmA, tmB, h->bf16.apar, stats, b2, scores, M);
+  attn_score_bf16<<<grid, SC_THREADS, SC_SMEM, st>>>(tmA, tmB, h->bf16.apar, stats, b2, scores, M, Bc);
   BCI_LAUNCH_OK();
   const PackedF32& p = h->f32;
   const size_t smem = (size_t)(2 * T + 2 * 256 + 128 + 64 + 16) * sizeof(float);

@@ -129,7 +129,7 @@ void lstm_carve_bf16(bci_lstm_s* h, char* base);
 int pack_pool_bf16(bci_lstm_s* h, cudaStream_t st);
 int pack_inproj_bf16(bci_lstm_s* h, cudaStream_t st);
 int launch_input_proj_bf16(bci_lstm_s* h, const float* x, int Bc, int T, __nv_bfloat16* z, cudaStream_t st);
-int launch_pool_bf16(bci_lstm_s* h, const __nv_bfloat16* seq, const float2* stats, float* scores, int Bc, int T, float* logits,
+int launch_pool_bf16(bci_lstm_s* h, const __nv_bfloat16* seq, float2* stats, float* scores, int Bc, int T, float* logits,
                      float* probs, float* attn, cudaStream_t st);
 int launch_fused_rec_bf16(const __nv_bfloat16* in, const __nv_bfloat16* wih, const __nv_bfloat16* whh_f, const __nv_bfloat16* whh_r,
                           const float* bias, __nv_bfloat16* out, float2* stats, int Bc, int T, int Kin, cudaStream_t st);

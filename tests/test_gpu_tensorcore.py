@@ -159,7 +159,7 @@ def test_fused_cluster_recurrence_matches_stepwise(Bc, T, Kin):
     wih_p = wih_p.to(torch.bfloat16).contiguous()
     bias_p = bias_p.contiguous()
     out = torch.full((T, Bc, 2 * H), float("nan"), device="cuda", dtype=torch.bfloat16)
-    stats = torch.full((T * Bc, 8, 2), float("nan"), device="cuda")
+    stats = torch.full((T, 8, Bc, 2), float("nan"), device="cuda")
     N.check(N.lib().bci_selftest_fused_rec_bf16(_p(x), _p(wih_p), _p(whh_p[0]), _p(whh_p[1]), _p(bias_p), _p(out), _p(stats),
                                                 Bc, T, Kin, _stream()))
     torch.cuda.synchronize()
@@ -180,10 +180,10 @@ def test_fused_cluster_recurrence_matches_stepwise(Bc, T, Kin):
     got = out.float()
     assert torch.isfinite(got).all()
     assert float((got - want).abs().max()) <= 1.5e-2
-    # LayerNorm partial statistics: 8 partials per row = [dir][32-unit group]
-    ssum = want.reshape(T * Bc, 8, 32).sum(-1)
-    ssq = (want.reshape(T * Bc, 8, 32) ** 2).sum(-1)
-    assert float((stats[:, :, 0] - ssum).abs().max()) <= 5e-2 and float((stats[:, :, 1] - ssq).abs().max()) <= 5e-2
+    # LayerNorm partial statistics: 8 partials per row = [dir][32-unit group], stored slot-major [T][8][Bc]
+    ssum = want.reshape(T, Bc, 8, 32).sum(-1).permute(0, 2, 1)
+    ssq = (want.reshape(T, Bc, 8, 32) ** 2).sum(-1).permute(0, 2, 1)
+    assert float((stats[..., 0] - ssum).abs().max()) <= 5e-2 and float((stats[..., 1] - ssq).abs().max()) <= 5e-2
 
 
 def test_fused_kernel_is_robust_to_timing_jitter():
