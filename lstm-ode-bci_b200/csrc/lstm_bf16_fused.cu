@@ -97,7 +97,9 @@ lstm_fused_bf16(const __grid_constant__ CUtensorMap tmIn,   // in  [T][Bc][Kin] 
   auto copy_done = [&](int q) { return bar0 + 8u * (20 + q); };   // every CTA: ack -- my outgoing atom landed at the partner
   auto recv_ready = [&](int q) { return bar0 + 8u * (22 + q); };  // every CTA: the partner's MMA_hh(g) retired: its copy of h_{g-1}
                                                                    // may be overwritten by my atom of h_g (h is single-buffered)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ctl + 8 * 24);
+  auto acc_free = [&](int q) { return bar0 + 8u * (24 + q); };    // every CTA: its 8 epilogue warps have read the whole accumulator
+  auto peer_free = [&](int q) { return bar0 + 8u * (26 + q); };   // leader: relay of the peer's acc_free
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ctl + 8 * 28);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t rank = cluster_ctarank();
@@ -117,6 +119,8 @@ lstm_fused_bf16(const __grid_constant__ CUtensorMap tmIn,   // in  [T][Bc][Kin] 
       mbar_init(peer_in(q), 1);
       mbar_init(copy_done(q), 1);
       mbar_init(recv_ready(q), 1);
+      mbar_init(acc_free(q), FR_EPI_WARPS);
+      mbar_init(peer_free(q), 1);
     }
     fence_mbar_init();
     // h_in is armed for the first step here and re-armed by its (single) waiter after every completed phase: arming it from
@@ -199,16 +203,20 @@ lstm_fused_bf16(const __grid_constant__ CUtensorMap tmIn,   // in  [T][Bc][Kin] 
         const uint16_t pair_mask = (uint16_t)(3u << (2 * p));
         const uint32_t ack0 = mapa_u32(copy_done(0), partner);
         int k_total = g0 * 2 * nk;
-        // accumulator of tile q drained by both CTAs of the pair (their epilogues of step gp)
+        // accumulator of tile q drained by both CTAs of the pair: signalled after the LAST tcgen05.ld of their epilogues of
+        // step gp, i.e. ~1/4 of an epilogue before h is complete, so MMA_ih of the next step starts that much earlier (with the
+        // single-buffered accumulator, waiting for the whole epilogue left the epilogue warps idle ~0.3 us per tile-step)
         auto wait_drained = [&](int q, int gp) {
+          jit();
+          mbar_wait(acc_free(q), (uint32_t)(gp & 1));
+          mbar_wait_cluster(peer_free(q), (uint32_t)(gp & 1));
+          tc_fence_after();
+        };
+        // h of step gp complete in both CTAs of the pair (both K-atoms: written locally and landed from the partner)
+        auto wait_exchanged = [&](int q, int gp) {
           jit();
           mbar_wait(h_local(q), (uint32_t)(gp & 1));
           mbar_wait_cluster(peer_local(q), (uint32_t)(gp & 1));
-          tc_fence_after();
-        };
-        // h of step gp complete in both CTAs of the pair
-        auto wait_exchanged = [&](int q, int gp) {
-          jit();
           mbar_wait(h_in(q), (uint32_t)(gp & 1));
           mbar_arrive_expect_tx(h_in(q), FR_ATOM);     // re-arm for the next step's incoming atom
           mbar_arrive_cluster_relaxed(ack0 + 8u * q);  // tell the sender its outgoing copy has landed
@@ -262,11 +270,14 @@ lstm_fused_bf16(const __grid_constant__ CUtensorMap tmIn,   // in  [T][Bc][Kin] 
         // by the bulk copy, whose completion the h_in wait observes, and by the local epilogue warps, who fenced generic->async
         // before arriving on h_local); a release arrive costs a MEMBAR.GPU = 640 ns per step (measured) on the critical path.
         const uint32_t pl0 = mapa_u32(peer_local(0), rank & ~1u), pi0 = mapa_u32(peer_in(0), rank & ~1u);
+        const uint32_t pf0 = mapa_u32(peer_free(0), rank & ~1u);
         const uint32_t ack0 = mapa_u32(copy_done(0), partner);
         for (int st = 0; st < T; ++st) {
           const int g = g0 + st;
           for (int q = 0; q < 2; ++q) {
             jit();
+            mbar_wait(acc_free(q), (uint32_t)(g & 1));
+            mbar_arrive_cluster_relaxed(pf0 + 8u * q);
             mbar_wait(h_local(q), (uint32_t)(g & 1));
             mbar_arrive_cluster_relaxed(pl0 + 8u * q);
             jit();
@@ -331,6 +342,11 @@ lstm_fused_bf16(const __grid_constant__ CUtensorMap tmIn,   // in  [T][Bc][Kin] 
           for (int sl = 0; sl < 4; ++sl) {
             tmem_ld_wait();
             if (sl + 1 < 4) tmem_ld32(taddr0 + q * 256 + (sl + 1) * 32, acc[(sl + 1) & 1]);
+            if (sl == 3) {  // the accumulator is in registers: MMA_ih of the next step may overwrite it
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(acc_free(q));
+            }
             const uint32_t* a = acc[sl & 1];
             float4 bq[8];  // bias of the slab's 32 columns (gate*8 + u): warp-uniform 16-byte loads
 #pragma unroll
