@@ -134,7 +134,10 @@ def test_bf16_rejects_h256():
         m(torch.zeros(1, 8, 61, device="cuda"))
 
 
-@pytest.mark.parametrize("Bc,T,Kin", [(256, 3, 128), (256, 6, 256), (200, 9, 256), (5, 17, 128), (700, 5, 256)])
+# (1, 1): one window, one step; (513, 2): 5 tiles = 2 tile quads, the second mostly empty; (20480, 3): 40 quads x 2 directions = 80
+# work items on 33 resident clusters -> up to 3 items per cluster (persistent loop, weight reload between items)
+@pytest.mark.parametrize("Bc,T,Kin", [(256, 3, 128), (256, 6, 256), (200, 9, 256), (5, 17, 128), (700, 5, 256), (1, 1, 256),
+                                      (513, 2, 128), (20480, 3, 256)])
 def test_fused_cluster_recurrence_matches_stepwise(Bc, T, Kin):
     """lstm_fused_bf16 (4-CTA cluster, cta_group::2 MMAs, h exchanged through DSMEM): projection + recurrence of one layer
     against a step-by-step emulation with the same roundings (bf16 inputs / weights / h fed back, fp32 gates and cell)."""
