@@ -188,6 +188,8 @@ def main():
     ap.add_argument("--no-ode", action="store_true")
     ap.add_argument("--no-train", action="store_true")
     ap.add_argument("--train-batch", type=int, default=512)
+    ap.add_argument("--no-extras", action="store_true", help="skip the preprocessing / ablation-variant measurements")
+    ap.add_argument("--preproc-recordings", type=int, default=36)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -389,6 +391,53 @@ def main():
                               "flop_per_window": 3 * FLOP_PER_WINDOW, "achieved_tflops_per_gpu": tb * 3 * FLOP_PER_WINDOW / (tms * 1e-3) / 1e12,
                               "loss": float(loss_t), "grad_norm": float(norm_t)}
         del trainer, tmodel
+
+    # ---- SURVEY §8 f rows 3-4: preprocessing of raw recordings and one ablation variant (measured, not part of `value`) ----
+    if not args.no_extras:
+        from lstm_ode_bci_b200 import preprocessing as pp
+        R, Cc, n = args.preproc_recordings, 61, 150000
+        raw = torch.randn((R, Cc, n), device="cuda", generator=gen) * 1e-5 + 1e-4      # fp32 stand-in for mne's raw.get_data()
+        b_, a_, zi_, padlen = pp.design_bandpass()
+        for _ in range(2):
+            out = pp.preprocess_recordings(raw, b_, a_, zi_, padlen)
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(3):
+            out = pp.preprocess_recordings(raw, b_, a_, zi_, padlen)
+        b.record()
+        barrier()
+        pms = max_over_ranks(a.elapsed_time(b)) / 3
+        nwin = int(out["X"].shape[0])
+        # the recursion is FP64-pipe bound: 33 unfused operations (17 mul + 16 add/sub, scipy's evaluation order) per sample and
+        # pass; the chunk-parallel form adds 8192 warm-up samples per 16384-sample chunk.  Peak = measured DFMA issue rate.
+        fp64_peak = ops.fp64_peak_probe()                  # TFLOP/s counting 2 flop per DFMA
+        useful_ops = R * Cc * (n + 54) * 2 * 33.0
+        pbytes = R * Cc * n * (4 + 8 + 8 + 8 + 8 + 8)
+        line["preprocess"] = {"metric": "preprocessed_windows_per_s", "value": world * nwin / (pms * 1e-3), "unit": "windows/s",
+                              "ms": pms, "recordings_per_gpu": R, "samples_per_recording": n, "channels": Cc, "windows_per_gpu": nwin,
+                              "roofline": {"bound": "fp64", "achieved": useful_ops / (pms * 1e-3) / 1e12, "peak": fp64_peak / 2.0,
+                                           "unit": "T fp64 instr/s (useful filter operations vs measured DFMA issue rate)",
+                                           "frac": useful_ops / (pms * 1e-3) / 1e12 / (fp64_peak / 2.0),
+                                           "hbm_gbs": pbytes / (pms * 1e-3) / 1e9, "hbm_frac": pbytes / (pms * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                                           "note": "whole call (filter passes + statistics + windowing); warm-up work (x1.5) not counted as useful"}}
+        del raw, out
+        abl = lstm.AblationLSTMModel(input_size=61, hidden_size=256, num_layers=1, bidirectional=False, use_attention=False).cuda().eval()
+        xa = x[:2048]
+        with torch.no_grad():
+            for _ in range(2):
+                abl(xa)
+            barrier()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(3):
+                abl(xa)
+            b.record()
+        barrier()
+        ams = max_over_ranks(a.elapsed_time(b)) / 3
+        line["ablation_minimal"] = {"metric": "windows_per_s", "value": world * 2048 / (ams * 1e-3), "unit": "windows/s", "ms": ams,
+                                    "config": "09:342-349 'Minimal': H=256, 1 layer, unidirectional, mean pooling, fp32", "windows_per_gpu": 2048}
+        del abl
 
     if rank == 0 and not args.no_cpu_baseline and world == 1:
         line["cpu_baseline"] = cpu_lstm_baseline()

@@ -270,6 +270,8 @@ int bci_preprocess(const bci_preproc_args* a, const void* raw, float* windows, d
 /* Micro-benchmark used by bench.py for the FP32 roofline denominator (SURVEY.md §8 d: the FP32
  * FMA peak is not in MEASURED_PEAKS.json): launches a dependent-FMA kernel, returns TFLOP/s. */
 int bci_fp32_peak_probe(double* tflops, void* stream);
+/* the same for the FP64 pipe (roofline denominator of the preprocessing recursion) */
+int bci_fp64_peak_probe(double* tflops, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Diagnostics: the two tensor-core kernels of the bf16 path, callable in isolation so the GPU unit

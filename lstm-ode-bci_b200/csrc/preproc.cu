@@ -9,12 +9,11 @@
 // initial state zi * ext[0] (zi = lfilter_zi(b, a): the steady state of a unit step), runs it again over the reversed
 // output with zi * y[-1], reverses and trims the padding.
 //
-// Layout: one thread per (recording, channel) row walks its samples serially in fp64 (the recursion is inherently
-// sequential per row; a batch of recordings supplies the parallelism: 60 subjects x 3 sessions x 2 tasks x 61 channels =
-// 21 960 rows), loading 8 samples ahead so one L2 round trip is paid per 8 recursion steps.  The forward pass writes the
-// extended signal to the workspace, the backward pass overwrites it in place and accumulates the row's sum / sum of
-// squares; a second kernel normalises, transposes through shared memory and writes every sample into all windows that
-// contain it (coalesced 4-byte stores, C contiguous floats per time step).
+// Layout: one thread per (recording, channel, chunk of 16 384 samples) walks its samples serially in fp64 with 8 192 samples of
+// warm-up (see filtfilt_chunk_kernel); the forward pass writes the extended signal to the workspace, the backward pass reads
+// it and writes a second buffer plus per-chunk sum / sum of squares; a last kernel normalises, transposes through shared
+// memory and writes every sample into all windows that contain it (coalesced 4-byte stores, C contiguous floats per step).
+// Bound: the FP64 pipe (33 unfused operations per sample and pass); bci_fp64_peak_probe measures its peak.
 #include "common.cuh"
 
 namespace bci {
@@ -47,63 +46,123 @@ __device__ __forceinline__ double df2t_step(const FiltCoef& c, double (&z)[ORD],
   return y;
 }
 
-template <typename InT, int ORD>
+// Time-parallel form of the recursion.  A row is cut into chunks of PP_CHUNK output samples; every chunk is one thread that
+// first runs PP_WARM samples of warm-up from a zero state (outputs discarded), except where the chunk reaches the start of the
+// pass, which begins exactly as scipy does (state zi * first sample).  The filter's slowest pole (Butterworth band-pass, 1 Hz
+// corner at 500 Hz) has |p| = 0.9952 per sample, so after 8192 samples the influence of the unknown state has decayed by
+// e^-39: the chunked result equals the serial one to rounding (1e-16 of the signal), far inside the 1e-9 parity bound, while
+// a batch of R recordings exposes R x 61 x n/PP_CHUNK threads instead of R x 61 (the fp64 pipe issues one warp instruction per
+// 8 cycles per SM sub-partition on B200; a single warp per 32 rows left 130 of 148 SMs idle).
+constexpr int PP_CHUNK = 16384, PP_WARM = 8192;
+
+// pass = 0: forward over the odd-extended input -> yf (rows x m);  pass = 1: backward over yf -> yb (rows x m), plus per-chunk
+// (sum, sumsq) of the kept samples [p, p+n)
+template <typename InT, int ORD, int PASS>
 __global__ void __launch_bounds__(128)
-filtfilt_rows_kernel(const InT* __restrict__ raw, long long n, int rows, int p, const FiltCoef c,
-                     double* __restrict__ ybuf /* rows x (n + 2p) */, double* __restrict__ sums /* rows x 2 */) {
-  const int row = blockIdx.x * blockDim.x + threadIdx.x;
-  if (row >= rows) return;
-  const InT* x = raw + (long long)row * n;
+filtfilt_chunk_kernel(const InT* __restrict__ raw, long long n, int rows, int p, const FiltCoef c, const double* __restrict__ yf,
+                      double* __restrict__ yout, int chunks, double* __restrict__ partial /* rows x chunks x 2 */) {
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= (long long)rows * chunks) return;
+  // consecutive threads = consecutive rows of the same chunk index: the 32 lanes of a warp walk 32 different rows in step
+  const int ck = (int)(gid / rows), row = (int)(gid - (long long)ck * rows);
   const long long m = n + 2 * (long long)p;
-  double* y = ybuf + (long long)row * m;
+  const InT* x = raw + (long long)row * n;
+  const double* src = yf + (long long)row * m;
+  double* dst = yout + (long long)row * m;
   double z[ORD];
-  // ---- forward over the extended signal ----
-  const double x0 = ext_sample(x, n, p, 0);
+  if (PASS == 0) {
+    const long long s0 = (long long)ck * PP_CHUNK, e0 = (s0 + PP_CHUNK < m) ? s0 + PP_CHUNK : m;
+    long long i = s0 - PP_WARM;
+    if (i <= 0) {
+      i = 0;
+      const double x0 = ext_sample(x, n, p, 0);
 #pragma unroll
-  for (int j = 0; j < ORD; ++j) z[j] = __dmul_rn(c.zi[j], x0);
-  long long i = 0;
-  for (; i < p; ++i) y[i] = df2t_step<ORD>(c, z, ext_sample(x, n, p, i));
-  const long long mid_end = p + n;
-  for (; i + 8 <= mid_end; i += 8) {
-    double xv[8];
+      for (int j = 0; j < ORD; ++j) z[j] = __dmul_rn(c.zi[j], x0);
+    } else {
 #pragma unroll
-    for (int k = 0; k < 8; ++k) xv[k] = (double)x[i - p + k];
-#pragma unroll
-    for (int k = 0; k < 8; ++k) y[i + k] = df2t_step<ORD>(c, z, xv[k]);
-  }
-  for (; i < m; ++i) y[i] = df2t_step<ORD>(c, z, ext_sample(x, n, p, i));
-  // ---- backward, in place ----
-  const double yl = y[m - 1];
-#pragma unroll
-  for (int j = 0; j < ORD; ++j) z[j] = __dmul_rn(c.zi[j], yl);
-  double s = 0.0, ss = 0.0;
-  i = m - 1;
-  for (; i >= mid_end; --i) y[i] = df2t_step<ORD>(c, z, y[i]);
-  for (; i - 7 >= p; i -= 8) {
-    double yv[8];
-#pragma unroll
-    for (int k = 0; k < 8; ++k) yv[k] = y[i - k];
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const double o = df2t_step<ORD>(c, z, yv[k]);
-      y[i - k] = o;
-      s += o;
-      ss = fma(o, o, ss);
+      for (int j = 0; j < ORD; ++j) z[j] = 0.0;
     }
+    // edges of the extended signal go through ext_sample one by one; the interior [p, p+n) is read in batches of 8, the next
+    // batch loaded before the current one is consumed, so one memory round trip is paid per 8 recursion steps (every lane walks
+    // its own row: the loads of a warp are 32 different sectors)
+    auto run = [&](long long from, long long to, bool keep) {
+      long long k = from;
+      for (; k < to && k < p; ++k) { const double o = df2t_step<ORD>(c, z, ext_sample(x, n, p, k)); if (keep) dst[k] = o; }
+      const long long in_end = (to < p + n) ? to : p + n;
+      if (k + 8 <= in_end) {
+        double cur[8], nxt[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) cur[u] = (double)x[k - p + u];
+        for (; k + 16 <= in_end; k += 8) {
+#pragma unroll
+          for (int u = 0; u < 8; ++u) nxt[u] = (double)x[k - p + 8 + u];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) { const double o = df2t_step<ORD>(c, z, cur[u]); if (keep) dst[k + u] = o; }
+#pragma unroll
+          for (int u = 0; u < 8; ++u) cur[u] = nxt[u];
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) { const double o = df2t_step<ORD>(c, z, cur[u]); if (keep) dst[k + u] = o; }
+        k += 8;
+      }
+      for (; k < to; ++k) { const double o = df2t_step<ORD>(c, z, ext_sample(x, n, p, k)); if (keep) dst[k] = o; }
+    };
+    run(i, s0, false);
+    run(s0, e0, true);
+  } else {
+    // backward: chunk ck covers [s0, e0) counted from the END of the extended signal
+    const long long hi = m - (long long)ck * PP_CHUNK;              // exclusive upper index
+    const long long lo = (hi - PP_CHUNK > 0) ? hi - PP_CHUNK : 0;   // inclusive lower index
+    long long i = hi - 1 + PP_WARM;
+    if (i >= m - 1) {
+      i = m - 1;
+      const double yl = src[m - 1];
+#pragma unroll
+      for (int j = 0; j < ORD; ++j) z[j] = __dmul_rn(c.zi[j], yl);
+    } else {
+#pragma unroll
+      for (int j = 0; j < ORD; ++j) z[j] = 0.0;
+    }
+    double sm = 0.0, ss = 0.0;
+    // descending batches of 8 with the next batch in flight (see the forward pass)
+    auto run = [&](long long from, long long to, bool keep) {  // processes from, from-1, ..., to (inclusive), from >= to
+      long long k = from;
+      if (k - 7 >= to) {
+        double cur[8], nxt[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) cur[u] = src[k - u];
+        for (; k - 15 >= to; k -= 8) {
+#pragma unroll
+          for (int u = 0; u < 8; ++u) nxt[u] = src[k - 8 - u];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const double o = df2t_step<ORD>(c, z, cur[u]);
+            if (keep) { dst[k - u] = o; if (k - u >= p && k - u < p + n) { sm += o; ss = fma(o, o, ss); } }
+          }
+#pragma unroll
+          for (int u = 0; u < 8; ++u) cur[u] = nxt[u];
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const double o = df2t_step<ORD>(c, z, cur[u]);
+          if (keep) { dst[k - u] = o; if (k - u >= p && k - u < p + n) { sm += o; ss = fma(o, o, ss); } }
+        }
+        k -= 8;
+      }
+      for (; k >= to; --k) {
+        const double o = df2t_step<ORD>(c, z, src[k]);
+        if (keep) { dst[k] = o; if (k >= p && k < p + n) { sm += o; ss = fma(o, o, ss); } }
+      }
+    };
+    if (i >= hi) run(i, hi, false);
+    if (hi - 1 >= lo) run(hi - 1, lo, true);
+    partial[((long long)row * chunks + ck) * 2] = sm;
+    partial[((long long)row * chunks + ck) * 2 + 1] = ss;
   }
-  for (; i >= p; --i) {
-    const double o = df2t_step<ORD>(c, z, y[i]);
-    y[i] = o;
-    s += o;
-    ss = fma(o, o, ss);
-  }
-  // (the left padding is never read again)
-  sums[2 * row] = s;
-  sums[2 * row + 1] = ss;
 }
 
 // mean / std per row from the sums (np.mean, np.std ddof=0, std floored at 1e-10: 02:145-151) unless given
-__global__ void rowstats_kernel(const double* __restrict__ sums, long long n, int rows, const double* __restrict__ mean_in,
+__global__ void rowstats_kernel(const double* __restrict__ partial, int chunks, long long n, int rows, const double* __restrict__ mean_in,
                                 const double* __restrict__ std_in, int C, double* __restrict__ mean_out, double* __restrict__ std_out) {
   const int row = blockIdx.x * blockDim.x + threadIdx.x;
   if (row >= rows) return;
@@ -112,8 +171,10 @@ __global__ void rowstats_kernel(const double* __restrict__ sums, long long n, in
     mu = mean_in[row % C];
     sd = std_in[row % C];
   } else {
-    mu = sums[2 * row] / (double)n;
-    double var = sums[2 * row + 1] / (double)n - mu * mu;
+    double s1 = 0.0, s2 = 0.0;  // fixed order: deterministic
+    for (int k = 0; k < chunks; ++k) { s1 += partial[((long long)row * chunks + k) * 2]; s2 += partial[((long long)row * chunks + k) * 2 + 1]; }
+    mu = s1 / (double)n;
+    double var = s2 / (double)n - mu * mu;
     if (var < 0.0) var = 0.0;
     sd = sqrt(var);
     if (sd < 1e-10) sd = 1e-10;
@@ -162,23 +223,48 @@ zscore_window_kernel(const double* __restrict__ ybuf, long long n, int p, int C,
   }
 }
 
+template <typename InT, int ORD>
+static int launch_filtfilt_ord(const InT* raw, long long n, int rows, int p, const FiltCoef& c, double* yf, double* yb, int chunks,
+                               double* partial, cudaStream_t st) {
+  const long long threads = (long long)rows * chunks;
+  const unsigned blocks = (unsigned)ceil_div64(threads, 128);
+  filtfilt_chunk_kernel<InT, ORD, 0><<<blocks, 128, 0, st>>>(raw, n, rows, p, c, nullptr, yf, chunks, partial);
+  BCI_LAUNCH_OK();
+  filtfilt_chunk_kernel<InT, ORD, 1><<<blocks, 128, 0, st>>>(raw, n, rows, p, c, yf, yb, chunks, partial);
+  BCI_LAUNCH_OK();
+  return BCI_OK;
+}
+
 template <typename InT>
-static int launch_filtfilt(const InT* raw, long long n, int rows, int p, const FiltCoef& c, int order, double* ybuf, double* sums,
-                           cudaStream_t st) {
-  const int blocks = ceil_div(rows, 128);
+static int launch_filtfilt(const InT* raw, long long n, int rows, int p, const FiltCoef& c, int order, double* yf, double* yb, int chunks,
+                           double* partial, cudaStream_t st) {
   switch (order) {
-    case 2: filtfilt_rows_kernel<InT, 2><<<blocks, 128, 0, st>>>(raw, n, rows, p, c, ybuf, sums); break;
-    case 4: filtfilt_rows_kernel<InT, 4><<<blocks, 128, 0, st>>>(raw, n, rows, p, c, ybuf, sums); break;
-    case 6: filtfilt_rows_kernel<InT, 6><<<blocks, 128, 0, st>>>(raw, n, rows, p, c, ybuf, sums); break;
-    case 8: filtfilt_rows_kernel<InT, 8><<<blocks, 128, 0, st>>>(raw, n, rows, p, c, ybuf, sums); break;
-    case 12: filtfilt_rows_kernel<InT, 12><<<blocks, 128, 0, st>>>(raw, n, rows, p, c, ybuf, sums); break;
-    case 16: filtfilt_rows_kernel<InT, 16><<<blocks, 128, 0, st>>>(raw, n, rows, p, c, ybuf, sums); break;
+    case 2: return launch_filtfilt_ord<InT, 2>(raw, n, rows, p, c, yf, yb, chunks, partial, st);
+    case 4: return launch_filtfilt_ord<InT, 4>(raw, n, rows, p, c, yf, yb, chunks, partial, st);
+    case 6: return launch_filtfilt_ord<InT, 6>(raw, n, rows, p, c, yf, yb, chunks, partial, st);
+    case 8: return launch_filtfilt_ord<InT, 8>(raw, n, rows, p, c, yf, yb, chunks, partial, st);
+    case 12: return launch_filtfilt_ord<InT, 12>(raw, n, rows, p, c, yf, yb, chunks, partial, st);
+    case 16: return launch_filtfilt_ord<InT, 16>(raw, n, rows, p, c, yf, yb, chunks, partial, st);
     default:
       set_error("bci_preprocess: filter order %d not built (2,4,6,8,12,16; butter(N,'band') has order 2N)", order);
       return BCI_EINVAL;
   }
-  BCI_LAUNCH_OK();
-  return BCI_OK;
+}
+
+static inline int pp_chunks(long long m) { return (int)((m + PP_CHUNK - 1) / PP_CHUNK); }
+
+// dependent-free DFMA stream: the FP64 pipe's peak, the roofline denominator of the filter kernels
+__global__ void __launch_bounds__(256) dfma_probe_kernel(double* out, int iters) {
+  double a0 = threadIdx.x * 1e-3, a1 = a0 + 1., a2 = a0 + 2., a3 = a0 + 3., a4 = a0 + 4., a5 = a0 + 5., a6 = a0 + 6., a7 = a0 + 7.;
+  const double mm = 0.999, cc = 1e-3;
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      a0 = fma(a0, mm, cc); a1 = fma(a1, mm, cc); a2 = fma(a2, mm, cc); a3 = fma(a3, mm, cc);
+      a4 = fma(a4, mm, cc); a5 = fma(a5, mm, cc); a6 = fma(a6, mm, cc); a7 = fma(a7, mm, cc);
+    }
+  }
+  out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
 }
 
 }  // namespace bci
@@ -188,7 +274,9 @@ using namespace bci;
 extern "C" int bci_preprocess_workspace_bytes(const bci_preproc_args* a, size_t* bytes) {
   BCI_REQUIRE(a && bytes, BCI_EINVAL, "bci_preprocess_workspace_bytes: NULL argument");
   const size_t rows = (size_t)a->n_recordings * a->n_channels;
-  *bytes = align_up(rows * (size_t)(a->n_samples + 2 * (int64_t)a->padlen) * 8, 256) + align_up(rows * 16, 256);
+  const size_t m = (size_t)(a->n_samples + 2 * (int64_t)a->padlen);
+  // forward output, backward output (the passes are chunk-parallel, so the backward pass cannot work in place), chunk partials
+  *bytes = 2 * align_up(rows * m * 8, 256) + align_up(rows * (size_t)pp_chunks((long long)m) * 16, 256);
   return BCI_OK;
 }
 
@@ -216,12 +304,14 @@ extern "C" int bci_preprocess(const bci_preproc_args* a, const void* raw, float*
     c.a[i] = i <= a->order ? a->a_host[i] / a0 : 0.0;
   }
   for (int i = 0; i < PP_MAX_ORDER; ++i) c.zi[i] = i < a->order ? a->zi_host[i] : 0.0;
-  double* ybuf = reinterpret_cast<double*>(workspace);
-  double* sums = reinterpret_cast<double*>((char*)workspace + align_up((size_t)rows * m * 8, 256));
-  int rc = a->in_dtype == BCI_OUT_F64 ? launch_filtfilt<double>((const double*)raw, n, rows, a->padlen, c, a->order, ybuf, sums, st)
-                                      : launch_filtfilt<float>((const float*)raw, n, rows, a->padlen, c, a->order, ybuf, sums, st);
+  const int chunks = pp_chunks(m);
+  double* yf = reinterpret_cast<double*>(workspace);
+  double* ybuf = reinterpret_cast<double*>((char*)workspace + align_up((size_t)rows * m * 8, 256));
+  double* sums = reinterpret_cast<double*>((char*)workspace + 2 * align_up((size_t)rows * m * 8, 256));
+  int rc = a->in_dtype == BCI_OUT_F64 ? launch_filtfilt<double>((const double*)raw, n, rows, a->padlen, c, a->order, yf, ybuf, chunks, sums, st)
+                                      : launch_filtfilt<float>((const float*)raw, n, rows, a->padlen, c, a->order, yf, ybuf, chunks, sums, st);
   if (rc) return rc;
-  rowstats_kernel<<<ceil_div(rows, 128), 128, 0, st>>>(sums, n, rows, a->mean_in, a->std_in, a->n_channels, mean_out, std_out);
+  rowstats_kernel<<<ceil_div(rows, 128), 128, 0, st>>>(sums, chunks, n, rows, a->mean_in, a->std_in, a->n_channels, mean_out, std_out);
   BCI_LAUNCH_OK();
   const long long n_seq = (n - a->seq_len) / a->step + 1;
   const size_t smem = (size_t)WIN_TILE * (a->n_channels + 1) * sizeof(float);
@@ -234,5 +324,33 @@ extern "C" int bci_preprocess(const bci_preproc_args* a, const void* raw, float*
   zscore_window_kernel<<<grid, 256, smem, st>>>(ybuf, n, a->padlen, a->n_channels, a->seq_len, a->step, n_seq, mean_out, std_out,
                                                 windows, filtered);
   BCI_LAUNCH_OK();
+  return BCI_OK;
+}
+
+extern "C" int bci_fp64_peak_probe(double* tflops, void* stream) {
+  BCI_REQUIRE(tflops, BCI_EINVAL, "bci_fp64_peak_probe: NULL output");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int blocks = sm_count() * 8, threads = 256, iters = 2048;
+  double* buf = nullptr;
+  BCI_CUDA_OK(cudaMalloc(&buf, (size_t)blocks * threads * sizeof(double)));
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  double best = 0.0;
+  for (int rep = 0; rep < 3; ++rep) {
+    cudaEventRecord(e0, st);
+    dfma_probe_kernel<<<blocks, threads, 0, st>>>(buf, iters);
+    cudaEventRecord(e1, st);
+    cudaEventSynchronize(e1);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    const double tf = 2.0 * 8 * 8 * (double)iters * blocks * threads / (ms * 1e-3) / 1e12;
+    if (rep > 0 && tf > best) best = tf;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(buf);
+  BCI_CUDA_OK(cudaGetLastError());
+  *tflops = best;
   return BCI_OK;
 }

@@ -245,3 +245,9 @@ def fp32_peak_probe():
     v = C.c_double(0.0)
     N.check(N.lib().bci_fp32_peak_probe(C.byref(v), _stream()))
     return v.value
+
+
+def fp64_peak_probe():
+    v = C.c_double(0.0)
+    N.check(N.lib().bci_fp64_peak_probe(C.byref(v), _stream()))
+    return v.value
