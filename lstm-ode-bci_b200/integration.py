@@ -103,6 +103,8 @@ def _lstm_probs_device(lstm_model, X, batch_size, want_attn, device):
     dev = _dev(device)
     lstm_model.eval()
     n = len(X)
+    if batch_size is None:  # one full wave of the recurrence kernel (the reference's 512, 06:308, only bounds ITS memory use)
+        batch_size = ops.lstm_chunk_windows(lstm_model._engine(lstm_model._precision_now()))
     if isinstance(X, torch.Tensor) and X.is_cuda:
         probs = torch.empty((n, lstm_model.num_classes), device=dev, dtype=torch.float32)
         attn = None
@@ -180,7 +182,7 @@ class LSTMODEIntegration:
         pred, _ = ops.ode_classify(final, True, False)
         return traj.double().cpu().numpy(), probs.cpu().numpy(), pred.cpu().numpy().astype(np.int64)
 
-    def predict_batch_device(self, X_dev, forecast_steps=20, batch_size=9472, want_traj=True):
+    def predict_batch_device(self, X_dev, forecast_steps=20, batch_size=None, want_traj=True):
         """Same computation with every tensor left on the device (used by the sharded pipeline)."""
         probs, _ = _lstm_probs_device(self.lstm_model, X_dev, batch_size, False, self.device)
         n = probs.shape[0]
