@@ -206,6 +206,11 @@ __device__ __forceinline__ float block_reduce(float v, float* red, bool is_max) 
   return r;
 }
 
+// PF_WPC windows per CTA: the classifier weights (128 KB + 32 KB fp32) are read once per PF_WPC windows instead of once per
+// window (the first version moved as many bytes of weights through L1 as of sequence data), and the sequence is read with
+// 16-byte loads, one warp per time step (512 contiguous bytes), 4 steps in flight per warp.
+constexpr int PF_WPC = 4;
+
 __global__ void __launch_bounds__(PF_THREADS)
 attn_pool_finish_bf16(const __nv_bfloat16* __restrict__ seq,  // [T][Bc][256]
                       const float* __restrict__ scores,       // [T][Bc]
@@ -216,100 +221,121 @@ attn_pool_finish_bf16(const __nv_bfloat16* __restrict__ seq,  // [T][Bc][256]
                       const float* __restrict__ c3t, const float* __restrict__ cb3,
                       const float* __restrict__ c6, const float* __restrict__ cb6,
                       float* __restrict__ logits, float* __restrict__ probs, float* __restrict__ attn) {
-  constexpr int H = 128, D = 256;
+  constexpr int H = 128, D = 256, NW = PF_THREADS / 32;
   extern __shared__ __align__(16) float pf_smem[];
-  float* beta = pf_smem;          // [T]  raw scores first, then beta_t = a_t * rstd_t
-  float* bmean = beta + T;        // [T]  row means
-  float* ctx_s = bmean + T;       // [2][D]
-  float* h1_s = ctx_s + 2 * D;    // [H]
-  float* h2_s = h1_s + H;         // [H/2]
-  float* red = h2_s + H / 2;      // [8] + logits[8]
-  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  float* beta = pf_smem;                 // [T]  raw scores first, then beta_t = a_t * rstd_t
+  float* bmean = beta + T;               // [T]  row means
+  float* part = bmean + T;               // [NW][D] per-warp partial sums
+  float* ctx_s = part + NW * D;          // [PF_WPC][D]
+  float* h1_s = ctx_s + PF_WPC * D;      // [PF_WPC][H]
+  float* h2_s = h1_s + PF_WPC * H;       // [PF_WPC][H/2]
+  float* red = h2_s + PF_WPC * (H / 2);  // [8] + logits [PF_WPC][8]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int b_first = blockIdx.x * PF_WPC;
+  const int nwin = (Bc - b_first) < PF_WPC ? (Bc - b_first) : PF_WPC;
 
-  float lmax = -INFINITY;
-  for (int t = tid; t < T; t += PF_THREADS) {
-    const long long row = (long long)t * Bc + b;
-    const float s = __ldg(scores + row);
-    beta[t] = s;
-    bmean[t] = stats[((long long)t * 8) * Bc + b].x;
-    lmax = fmaxf(lmax, s);
-  }
-  const float m = block_reduce(lmax, red, true);
-  float lsum = 0.f;
-  for (int t = tid; t < T; t += PF_THREADS) lsum += expf(beta[t] - m);
-  const float inv_l = 1.0f / block_reduce(lsum, red, false);
-  float lgam = 0.f;
-  for (int t = tid; t < T; t += PF_THREADS) {
-    const long long row = (long long)t * Bc + b;
-    const float a = expf(beta[t] - m) * inv_l;
-    if (attn) attn[(long long)b * T + t] = a;
-    const float mean = bmean[t];
-    const float bt = a * stats[((long long)t * 8) * Bc + b].y;
-    beta[t] = bt;
-    lgam = fmaf(bt, mean, lgam);
-  }
-  const float gamma = block_reduce(lgam, red, false);  // also makes beta[] visible to all threads
-
-  // beta-weighted sum of the raw rows: thread (g, p) owns features 2p, 2p+1 over time steps t = g mod 2
-  const int g = tid >> 7, p = tid & 127;
-  float a0 = 0.f, a1 = 0.f;
-  const __nv_bfloat162* col = reinterpret_cast<const __nv_bfloat162*>(seq) + (long long)b * (D / 2) + p;
-  const long long tstride = (long long)Bc * (D / 2);
-  int t = g;
-  for (; t + 14 < T; t += 16) {
-    __nv_bfloat162 v[8];
-#pragma unroll
-    for (int u = 0; u < 8; ++u) v[u] = col[(long long)(t + 2 * u) * tstride];
-#pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      const float2 f = __bfloat1622float2(v[u]);
-      const float bt = beta[t + 2 * u];
-      a0 = fmaf(bt, f.x, a0);
-      a1 = fmaf(bt, f.y, a1);
+  for (int w = 0; w < nwin; ++w) {
+    const int b = b_first + w;
+    float lmax = -INFINITY;
+    for (int t = tid; t < T; t += PF_THREADS) {
+      const float s = __ldg(scores + (long long)t * Bc + b);
+      beta[t] = s;
+      bmean[t] = stats[((long long)t * 8) * Bc + b].x;
+      lmax = fmaxf(lmax, s);
     }
-  }
-  for (; t < T; t += 2) {
-    const float2 f = __bfloat1622float2(col[(long long)t * tstride]);
-    a0 = fmaf(beta[t], f.x, a0);
-    a1 = fmaf(beta[t], f.y, a1);
-  }
-  ctx_s[g * D + 2 * p] = a0;
-  ctx_s[g * D + 2 * p + 1] = a1;
-  __syncthreads();
-  {
-    const float raw = ctx_s[tid] + ctx_s[D + tid];
-    const float cv = fmaf(lnw[tid], raw - gamma, lnb[tid]);
+    const float m = block_reduce(lmax, red, true);
+    float lsum = 0.f;
+    for (int t = tid; t < T; t += PF_THREADS) lsum += expf(beta[t] - m);
+    const float inv_l = 1.0f / block_reduce(lsum, red, false);
+    float lgam = 0.f;
+    for (int t = tid; t < T; t += PF_THREADS) {
+      const float a = expf(beta[t] - m) * inv_l;
+      if (attn) attn[(long long)b * T + t] = a;
+      const float mean = bmean[t];
+      const float bt = a * stats[((long long)t * 8) * Bc + b].y;
+      beta[t] = bt;
+      lgam = fmaf(bt, mean, lgam);
+    }
+    const float gamma = block_reduce(lgam, red, false);  // also makes beta[] visible to all threads
+
+    // beta-weighted sum of the raw rows: warp = time step (mod NW), lane = 8 consecutive features (one 16-byte load)
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+    const uint4* rowp = reinterpret_cast<const uint4*>(seq) + (long long)b * (D / 8) + lane;
+    const long long tstride = (long long)Bc * (D / 8);
+    auto fma8 = [&](const uint4& v, float bt) {
+      const uint32_t wv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        acc[2 * i] = fmaf(bt, __uint_as_float(wv[i] << 16), acc[2 * i]);
+        acc[2 * i + 1] = fmaf(bt, __uint_as_float(wv[i] & 0xFFFF0000u), acc[2 * i + 1]);
+      }
+    };
+    int t = warp;
+    for (; t + 3 * NW < T; t += 4 * NW) {
+      uint4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[u] = ldg_stream_v4(rowp + (long long)(t + u * NW) * tstride);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) fma8(v[u], beta[t + u * NW]);
+    }
+    for (; t < T; t += NW) fma8(ldg_stream_v4(rowp + (long long)t * tstride), beta[t]);
+#pragma unroll
+    for (int i = 0; i < 8; i += 4)
+      *reinterpret_cast<float4*>(part + warp * D + lane * 8 + i) = make_float4(acc[i], acc[i + 1], acc[i + 2], acc[i + 3]);
     __syncthreads();
-    ctx_s[tid] = cv;
+    {
+      float raw = 0.f;
+#pragma unroll
+      for (int k = 0; k < NW; ++k) raw += part[k * D + tid];
+      ctx_s[w * D + tid] = fmaf(lnw[tid], raw - gamma, lnb[tid]);
+    }
+    __syncthreads();
   }
-  __syncthreads();
-  // classifier: Linear(2H,H) GELU Linear(H,H/2) GELU Linear(H/2,classes); softmax
+  // classifier for the CTA's windows at once: Linear(2H,H) GELU Linear(H,H/2) GELU Linear(H/2,classes); softmax
   if (tid < H) {
-    float a = cb0[tid];
-    for (int d = 0; d < D; ++d) a = fmaf(ctx_s[d], __ldg(c0t + (long long)d * H + tid), a);
-    h1_s[tid] = gelu_erf(a);
+    float a[PF_WPC];
+#pragma unroll
+    for (int w = 0; w < PF_WPC; ++w) a[w] = cb0[tid];
+    for (int d = 0; d < D; ++d) {
+      const float wt = __ldg(c0t + (long long)d * H + tid);
+#pragma unroll
+      for (int w = 0; w < PF_WPC; ++w) a[w] = fmaf(ctx_s[w * D + d], wt, a[w]);
+    }
+#pragma unroll
+    for (int w = 0; w < PF_WPC; ++w) h1_s[w * H + tid] = gelu_erf(a[w]);
   }
   __syncthreads();
   if (tid < H / 2) {
-    float a = cb3[tid];
-    for (int k = 0; k < H; ++k) a = fmaf(h1_s[k], __ldg(c3t + k * (H / 2) + tid), a);
-    h2_s[tid] = gelu_erf(a);
+    float a[PF_WPC];
+#pragma unroll
+    for (int w = 0; w < PF_WPC; ++w) a[w] = cb3[tid];
+    for (int k = 0; k < H; ++k) {
+      const float wt = __ldg(c3t + k * (H / 2) + tid);
+#pragma unroll
+      for (int w = 0; w < PF_WPC; ++w) a[w] = fmaf(h1_s[w * H + k], wt, a[w]);
+    }
+#pragma unroll
+    for (int w = 0; w < PF_WPC; ++w) h2_s[w * (H / 2) + tid] = gelu_erf(a[w]);
   }
   __syncthreads();
-  for (int c = warp; c < classes; c += PF_THREADS / 32) {
+  for (int i = warp; i < nwin * classes; i += NW) {
+    const int w = i / classes, c = i - w * classes;
     float a = 0.f;
-    for (int k = lane; k < H / 2; k += 32) a = fmaf(h2_s[k], __ldg(c6 + c * (H / 2) + k), a);
+    for (int k = lane; k < H / 2; k += 32) a = fmaf(h2_s[w * (H / 2) + k], __ldg(c6 + c * (H / 2) + k), a);
     a = warp_sum(a) + cb6[c];
-    if (lane == 0) { logits[(long long)b * classes + c] = a; red[8 + c] = a; }
+    if (lane == 0) { logits[(long long)(b_first + w) * classes + c] = a; red[8 + w * 8 + c] = a; }
   }
   if (probs) {
     __syncthreads();
-    if (tid == 0) {
+    if (tid < nwin) {
+      const float* lg = red + 8 + tid * 8;
       float mx = -INFINITY;
-      for (int c = 0; c < classes; ++c) mx = fmaxf(mx, red[8 + c]);
+      for (int c = 0; c < classes; ++c) mx = fmaxf(mx, lg[c]);
       float den = 0.f;
-      for (int c = 0; c < classes; ++c) den += expf(red[8 + c] - mx);
-      for (int c = 0; c < classes; ++c) probs[(long long)b * classes + c] = expf(red[8 + c] - mx) / den;
+      for (int c = 0; c < classes; ++c) den += expf(lg[c] - mx);
+      for (int c = 0; c < classes; ++c) probs[(long long)(b_first + tid) * classes + c] = expf(lg[c] - mx) / den;
     }
   }
 }
@@ -335,9 +361,9 @@ int launch_pool_bf16(bci_lstm_s* h, const __nv_bfloat16* seq, float2* stats, flo
   attn_score_bf16<<<grid, SC_THREADS, SC_SMEM, st>>>(tmA, tmB, h->bf16.apar, stats, b2, scores, M, Bc);
   BCI_LAUNCH_OK();
   const PackedF32& p = h->f32;
-  const size_t smem = (size_t)(2 * T + 2 * 256 + 128 + 64 + 16) * sizeof(float);
-  BCI_REQUIRE(smem <= 48 * 1024, BCI_EINVAL, "bf16 pooling supports seq_len <= 5900 (got %d)", T);
-  attn_pool_finish_bf16<<<Bc, PF_THREADS, smem, st>>>(seq, scores, stats, Bc, T, h->cfg.num_classes, p.lnw, p.lnb, p.c0t, p.cb0,
+  const size_t smem = (size_t)(2 * T + (PF_THREADS / 32) * 256 + PF_WPC * (256 + 128 + 64) + 8 + PF_WPC * 8) * sizeof(float);
+  BCI_REQUIRE(smem <= 48 * 1024, BCI_EINVAL, "bf16 pooling supports seq_len <= 4000 (got %d)", T);
+  attn_pool_finish_bf16<<<ceil_div(Bc, PF_WPC), PF_THREADS, smem, st>>>(seq, scores, stats, Bc, T, h->cfg.num_classes, p.lnw, p.lnb, p.c0t, p.cb0,
                                                        p.c3t, p.cb3, p.c6, p.cb6, logits, probs, attn);
   BCI_LAUNCH_OK();
   return BCI_OK;
