@@ -136,14 +136,17 @@ int lstm_pack_bf16(bci_lstm_s* h, cudaStream_t st) {
 // and C cross L2 -- the first version re-fetched the W block per tile and was L2-bound (ncu:
 // lts throughput 72 %, tensor pipe 26 %).
 // ---------------------------------------------------------------------------------------------
-constexpr int GB_BM = 128, GB_BN = 256, GB_BK = 64, GB_MAX_STAGES = 8, GB_MAX_K = 256;
+constexpr int GB_BM = 128, GB_BK = 64, GB_MAX_STAGES = 8;
+// BN = 256 (K <= 256) is the H = 128 configuration; BN = 128 keeps a 128-column W block of up to K = 512 resident (H = 256:
+// layers 1-2 have a 512-wide input)
+template <int BN> struct GbCfg { static constexpr int MAX_K = BN == 256 ? 256 : 512; };
 constexpr int GB_THREADS = 320;  // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-9: epilogue (2 groups of 4)
-constexpr uint32_t GB_A_BYTES = GB_BM * GB_BK * 2, GB_B_ATOM = GB_BN * GB_BK * 2;
+constexpr uint32_t GB_A_BYTES = GB_BM * GB_BK * 2;
 constexpr uint32_t GB_C_BYTES = GB_BM * 128 * 2;  // C staging: one [128][64] bf16 SW128 atom per epilogue group
-// smem: [W block: k_blocks x 32 KB][A ring: stages x 16 KB][C staging 32 KB][bias 1 KB][barriers]
+// smem: [W block: k_blocks x BN x 128 B][A ring: stages x 16 KB][C staging 32 KB][bias][barriers]
 static inline int gb_stages(int K) { return K <= 128 ? 8 : 4; }
-static inline size_t gb_smem(int K) {
-  return 1024 + (size_t)(K / GB_BK) * GB_B_ATOM + (size_t)gb_stages(K) * GB_A_BYTES + GB_C_BYTES + GB_BN * sizeof(float) + 256;
+static inline size_t gb_smem(int K, int BN) {
+  return 1024 + (size_t)(K / GB_BK) * (size_t)(BN * GB_BK * 2) + (size_t)gb_stages(K) * GB_A_BYTES + GB_C_BYTES + 256 * sizeof(float) + 256;
 }
 
 // BLOCKED = false: C row-major [M][N] through a tensor map.
@@ -151,7 +154,7 @@ static inline size_t gb_smem(int K) {
 //                  (N = 1024: 256 KB per m_block).  A 64-column pass of the epilogue is then 8 chunks x 2 KB = one contiguous
 //                  16 KB block: staged as [chunk][row] (conflict-free 16-byte stores) and written with one 1-D bulk store;
 //                  the recurrence reads it back with fully coalesced 16-byte loads (lane = row).
-template <bool BLOCKED>
+template <bool BLOCKED, int GB_BN>
 __global__ void __launch_bounds__(GB_THREADS, 1)
 proj_gemm_bf16(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmC, __nv_bfloat16* __restrict__ Cblk, const float* __restrict__ bias, int M,
@@ -160,11 +163,14 @@ proj_gemm_bf16(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint32_t raw = smem_u32(gb_smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t* gen = gb_smem_raw + (base - raw);  // generic pointer to the aligned base
+  constexpr uint32_t GB_B_ATOM = GB_BN * GB_BK * 2;
+  constexpr int GCOLS = GB_BN / 2;      // columns per epilogue group
+  constexpr int PASSES = GCOLS / 64;    // 64-column staging passes per group (2 for BN = 256, 1 for BN = 128)
   const uint32_t b_bytes = (uint32_t)(K / GB_BK) * GB_B_ATOM;
   const uint32_t sB = base, sA = base + b_bytes, sC = sA + GB_STAGES * GB_A_BYTES;
   uint8_t* genC = gen + b_bytes + GB_STAGES * GB_A_BYTES;
-  float* bias_s = reinterpret_cast<float*>(genC + GB_C_BYTES);  // [256]
-  uint8_t* ctl = genC + GB_C_BYTES + GB_BN * sizeof(float);
+  float* bias_s = reinterpret_cast<float*>(genC + GB_C_BYTES);  // [BN]
+  uint8_t* ctl = genC + GB_C_BYTES + 256 * sizeof(float);
   const uint32_t bar0 = smem_u32(ctl);
   auto full_bar = [&](int s) { return bar0 + 8u * s; };
   auto empty_bar = [&](int s) { return bar0 + 8u * (GB_MAX_STAGES + s); };
@@ -193,7 +199,7 @@ proj_gemm_bf16(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
   if (warp >= 2) {
     const int et = (warp - 2) * 32 + lane;  // 0..255
-    bias_s[et] = __ldg(bias + n0 + et);
+    if (et < GB_BN) bias_s[et] = __ldg(bias + n0 + et);
   }
   tc_fence_before();
   __syncthreads();
@@ -254,24 +260,24 @@ proj_gemm_bf16(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     for (int mb = m_first; mb < m_blocks; mb += m_step) {
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)acc * GB_BN + grp * 128;
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)acc * GB_BN + grp * GCOLS;
       uint32_t r[2][32];
       tmem_ld32(taddr, r[0]);
 #pragma unroll
-      for (int ch = 0; ch < 4; ++ch) {
+      for (int ch = 0; ch < 2 * PASSES; ++ch) {
         if ((ch & 1) == 0) {
           // the group's staging atom must have been drained by its previous TMA store
           if (issuer) tma_store_wait_read();
           asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
         }
         tmem_ld_wait();
-        if (ch + 1 < 4) tmem_ld32(taddr + (ch + 1) * 32, r[(ch + 1) & 1]);  // next slab in flight
+        if (ch + 1 < 2 * PASSES) tmem_ld32(taddr + (ch + 1) * 32, r[(ch + 1) & 1]);  // next slab in flight
         const uint32_t* rc = r[ch & 1];
         uint32_t o[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
-          const float v0 = __uint_as_float(rc[2 * j]) + bias_s[grp * 128 + ch * 32 + 2 * j];
-          const float v1 = __uint_as_float(rc[2 * j + 1]) + bias_s[grp * 128 + ch * 32 + 2 * j + 1];
+          const float v0 = __uint_as_float(rc[2 * j]) + bias_s[grp * GCOLS + ch * 32 + 2 * j];
+          const float v1 = __uint_as_float(rc[2 * j + 1]) + bias_s[grp * GCOLS + ch * 32 + 2 * j + 1];
           __nv_bfloat162 p = __floats2bfloat162_rn(v0, v1);
           o[j] = *reinterpret_cast<uint32_t*>(&p);
         }
@@ -282,14 +288,14 @@ proj_gemm_bf16(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           *reinterpret_cast<uint4*>(dstp) = make_uint4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
         }
         if ((ch & 1) == 1) {
-          if (ch == 3) {  // all TMEM reads of this accumulator (by this thread) are done
+          if (ch == 2 * PASSES - 1) {  // all TMEM reads of this accumulator (by this thread) are done
             tc_fence_before();
             mbar_arrive(tempty_bar(acc));
           }
           fence_proxy_async_smem();
           asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
           if (issuer) {
-            const int col = n0 + grp * 128 + (ch >> 1) * 64;
+            const int col = n0 + grp * GCOLS + (ch >> 1) * 64;
             if (BLOCKED) bulk_store_s2g(Cblk + ((size_t)mb * N + (size_t)col) * GB_BM, cst_s, 16384u);
             else tma_store_2d(&tmC, cst_s, col, mb * GB_BM);
             tma_store_commit();
@@ -308,35 +314,42 @@ proj_gemm_bf16(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
 }
 
-int launch_proj_gemm_bf16(const __nv_bfloat16* A, const __nv_bfloat16* W, const float* bias, __nv_bfloat16* C, int M, int N,
-                          int K, bool blocked, cudaStream_t st) {
+template <int BN>
+static int launch_proj_gemm_bn(const __nv_bfloat16* A, const __nv_bfloat16* W, const float* bias, __nv_bfloat16* C, int M, int N,
+                               int K, bool blocked, cudaStream_t st) {
   CUtensorMap tmC;
   {
     // (for the blocked layout the map is unused; encode a valid one over the same buffer anyway)
     int rc0 = make_tmap_bf16(&tmC, C, (uint64_t)M, (uint64_t)N, 64, GB_BM);
     if (rc0) return rc0;
   }
-  BCI_REQUIRE(N % GB_BN == 0 && K % GB_BK == 0 && K <= GB_MAX_K && M > 0 && N / GB_BN <= sm_count(), BCI_EINVAL,
+  BCI_REQUIRE(N % BN == 0 && K % GB_BK == 0 && K <= GbCfg<BN>::MAX_K && M > 0 && N / BN <= sm_count(), BCI_EINVAL,
               "proj_gemm_bf16: unsupported shape M=%d N=%d K=%d", M, N, K);
   CUtensorMap tmA, tmB;
   int rc = make_tmap_bf16(&tmA, A, (uint64_t)M, (uint64_t)K, 64, GB_BM);
   if (rc) return rc;
-  rc = make_tmap_bf16(&tmB, W, (uint64_t)N, (uint64_t)K, 64, GB_BN);
+  rc = make_tmap_bf16(&tmB, W, (uint64_t)N, (uint64_t)K, 64, BN);
   if (rc) return rc;
   static bool attr = false;
   if (!attr) {
-    BCI_CUDA_OK(cudaFuncSetAttribute(proj_gemm_bf16<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gb_smem(GB_MAX_K)));
-    BCI_CUDA_OK(cudaFuncSetAttribute(proj_gemm_bf16<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gb_smem(GB_MAX_K)));
+    BCI_CUDA_OK(cudaFuncSetAttribute(proj_gemm_bf16<false, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gb_smem(GbCfg<BN>::MAX_K, BN)));
+    BCI_CUDA_OK(cudaFuncSetAttribute(proj_gemm_bf16<true, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gb_smem(GbCfg<BN>::MAX_K, BN)));
     attr = true;
   }
-  const int n_blocks = N / GB_BN, m_blocks = ceil_div(M, GB_BM);
+  const int n_blocks = N / BN, m_blocks = ceil_div(M, GB_BM);
   int per_n = sm_count() / n_blocks;
   if (per_n > m_blocks) per_n = m_blocks;
   const int grid = per_n * n_blocks;
-  if (blocked) proj_gemm_bf16<true><<<grid, GB_THREADS, gb_smem(K), st>>>(tmA, tmB, tmC, C, bias, M, N, K, gb_stages(K));
-  else proj_gemm_bf16<false><<<grid, GB_THREADS, gb_smem(K), st>>>(tmA, tmB, tmC, C, bias, M, N, K, gb_stages(K));
+  if (blocked) proj_gemm_bf16<true, BN><<<grid, GB_THREADS, gb_smem(K, BN), st>>>(tmA, tmB, tmC, C, bias, M, N, K, gb_stages(K));
+  else proj_gemm_bf16<false, BN><<<grid, GB_THREADS, gb_smem(K, BN), st>>>(tmA, tmB, tmC, C, bias, M, N, K, gb_stages(K));
   BCI_LAUNCH_OK();
   return BCI_OK;
+}
+
+int launch_proj_gemm_bf16(const __nv_bfloat16* A, const __nv_bfloat16* W, const float* bias, __nv_bfloat16* C, int M, int N,
+                          int K, bool blocked, cudaStream_t st) {
+  if (K <= 256 && N % 256 == 0) return launch_proj_gemm_bn<256>(A, W, bias, C, M, N, K, blocked, st);
+  return launch_proj_gemm_bn<128>(A, W, bias, C, M, N, K, blocked, st);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -27,7 +27,9 @@ def _p(t):
     return C.c_void_p(t.data_ptr())
 
 
-@pytest.mark.parametrize("M,Nn,K", [(128, 256, 64), (128, 256, 128), (1000, 1024, 128), (4173, 1024, 256), (77, 512, 256), (300, 2048, 64)])
+# K = 512 / N % 256 != 0 select the 128-column W-block variant (H = 256 layers 1-2)
+@pytest.mark.parametrize("M,Nn,K", [(128, 256, 64), (128, 256, 128), (1000, 1024, 128), (4173, 1024, 256), (77, 512, 256), (300, 2048, 64),
+                                    (300, 2048, 512), (1000, 1024, 384), (129, 128, 256), (2500, 2048, 256)])
 def test_proj_gemm_tcgen05_matches_matmul(M, Nn, K):
     g = torch.Generator(device="cuda").manual_seed(M + K)
     A = (torch.randn(M, K, device="cuda", generator=g) * 0.7).to(torch.bfloat16)
