@@ -291,6 +291,10 @@ int bci_selftest_rec_bf16(const void* G, const void* whh_f, const void* whh_r, v
  *   in [T][Bc][Kin] bf16 (Kin = 128 or 256); wih [2][512][Kin], whh_* [512][128] bf16 with rows in perm_T order (i,f,o rows
  *   pre-scaled by 1/2); bias [2][512] fp32 in the same order and scaling -> out [T][Bc][256] bf16; stats optional
  *   [T][8][Bc] float2 partial (sum, sum of squares) of h over 32 units, slot = dir*4 + unit/32 */
+/* H = 256 cluster recurrence (csrc/lstm_bf16_h256.cu): G bf16 in the blocked streaming layout [row/128][256 chunks][row%128][8] with
+ * columns dir*1024 + perm_256(unit, gate) = (unit/128)*512 + ((unit/64)%2)*256 + ((unit/8)%8)*32 + gate*8 + unit%8 (bias included,
+ * i/f/o pre-scaled by 1/2); whh [2][1024][256] bf16 rows in the same order -> out [T][Bc][512] bf16 */
+int bci_selftest_rec256_bf16(const void* G, const void* whh, void* out, int32_t Bc, int32_t T, void* stream);
 int bci_selftest_fused_rec_bf16(const void* in, const void* wih, const void* whh_f, const void* whh_r, const float* bias,
                                 void* out, void* stats, int32_t Bc, int32_t T, int32_t Kin, void* stream);
 

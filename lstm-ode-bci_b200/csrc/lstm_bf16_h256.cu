@@ -1,0 +1,349 @@
+// bf16 tensor-core mode for hidden_size = 256 -- the size of the reference's trained checkpoint on 61 channels
+// (04_lstm_model.py:876-877: hidden_size = 256 if n_channels > 30).
+//
+// W_hh of one direction is 1024 x 256 bf16 = 512 KB and W_ih of layers 1-2 another 1 MB: the fully fused kernel of
+// lstm_bf16_fused.cu (both matrices resident in a 4-CTA cluster) would need 16 SMs per cluster.  This first H = 256 version is
+// the hybrid: the time-parallel projection G = in . W_ih^T + b is the tcgen05 GEMM of lstm_bf16.cu (128-column W blocks, K up
+// to 512, blocked streaming layout), and the recurrence runs on a 4-CTA cluster that keeps W_hh resident:
+//
+//   cluster rank r = 2 p + s    p = half of the hidden units ([128 p, 128 p + 128): 512 gate columns), s = window tile
+//   pair p = CTAs (p,0),(p,1)   tcgen05.mma.cta_group::2, M = 256 (both tiles) x N = 256 x K = 16, two N blocks: each CTA keeps
+//                               2 x 128 of the pair's 512 W_hh rows (128 KB) and its tile's h (4 K-atoms, 64 KB, single-buffered);
+//                               the 128 x 512 fp32 accumulator fills the CTA's TMEM
+//   per step                    MMA_hh -> commit (multicast to the pair) -> 8 epilogue warps (thread = window row x 64 units):
+//                               tcgen05.ld + G_t (coalesced 16-byte streaming loads, two slabs ahead) -> sigma/tanh -> fp32 cell
+//                               state in registers -> h_t (bf16) into the operand buffer; the CTA's two atoms (32 KB) go to the
+//                               CTA (1-p, s) with one DSMEM bulk copy; handshakes as in lstm_bf16_fused.cu (recv_ready, h_in
+//                               re-armed by its waiter, relaxed relays).  One tile per CTA: TMEM is full, so MMA latency and
+//                               the exchange are exposed here -- the price of H = 256 until the 16-SM design exists.
+//
+// Gate column order ("perm_256"): R = p*512 + nb*256 + slab*32 + gate*8 + u  for unit = 128 p + 64 nb + 8 slab + u, used for the
+// rows of W_hh and W_ih, the bias and G's columns (a 16-byte chunk of G = 8 units of one gate; the four gates of a slab are
+// four consecutive chunks).
+#include "lstm_shared_kernels.cuh"
+#include "sm100_prims.cuh"
+#include "tmap.cuh"
+
+namespace bci {
+using namespace sm100;
+
+__host__ __device__ constexpr int perm_256(int unit, int gate) {
+  return (unit >> 7) * 512 + ((unit >> 6) & 1) * 256 + ((unit >> 3) & 7) * 32 + gate * 8 + (unit & 7);
+}
+
+// src (4H, K) gate-major rows -> dst bf16 [row0 + perm_256(unit, gate)][K], i/f/o rows pre-scaled by 1/2 (sigmoid via tanh)
+__global__ void pack_rows_perm256_bf16(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int K, int row0) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)1024 * K) return;
+  const int row = (int)(i / K), k = (int)(i - (long long)row * K);
+  const int gate = row >> 8, unit = row & 255;
+  const float sc = (gate == 2) ? 1.0f : 0.5f;
+  dst[(long long)(row0 + perm_256(unit, gate)) * K + k] = __float2bfloat16_rn(sc * src[i]);
+}
+__global__ void pack_bias_perm256(const float* __restrict__ bih, const float* __restrict__ bhh, float* __restrict__ dst, int col0) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 1024) return;
+  const int gate = i >> 8, unit = i & 255;
+  dst[col0 + perm_256(unit, gate)] = ((gate == 2) ? 1.0f : 0.5f) * (bih[i] + bhh[i]);
+}
+
+constexpr int HR_M = 128, HR_EPI_WARPS = 8;
+constexpr int HR_THREADS = (HR_EPI_WARPS + 3) * 32;  // + MMA issuer / relay, h store warp, G prefetcher
+constexpr uint32_t HR_ATOM = 128 * 128;              // [128 rows][64 bf16] SW128 atom
+constexpr uint32_t HR_OFF_H = 8 * HR_ATOM;           // W: 2 N blocks x 4 K-atoms
+constexpr uint32_t HR_OFF_CTL = HR_OFF_H + 4 * HR_ATOM;
+constexpr size_t HR_SMEM = 1024 + HR_OFF_CTL + 256;
+
+__device__ __forceinline__ float hr_tanh(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// work item w (0 .. 2*tile_pairs): direction = w / tile_pairs, tile pair = w % tile_pairs; CTA (p, s) owns tile 2 pair + s
+__global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(HR_THREADS, 1)
+lstm_rec256_bf16(const __nv_bfloat16* __restrict__ G,        // blocked: [row/128][256 chunks][row%128][8], columns dir*1024 + perm_256
+                 const __grid_constant__ CUtensorMap tmOut,  // out [T][Bc][512] bf16, box 64 x 128 x 1
+                 const __nv_bfloat16* __restrict__ whh,      // [2][1024][256] rows in perm_256 order (i,f,o pre-scaled by 1/2)
+                 int Bc, int T, int tile_pairs, int jitter) {
+  extern __shared__ uint8_t hr_smem_raw[];
+  uint32_t jit_state = jitter ? (uint32_t)(blockIdx.x * 7919u + threadIdx.x * 104729u + 12345u) : 0u;
+  auto jit = [&]() {
+    if (jitter) {
+      jit_state = jit_state * 1664525u + 1013904223u;
+      __nanosleep((jit_state >> 20) & (uint32_t)(jitter - 1));
+    }
+  };
+  const uint32_t raw = smem_u32(hr_smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* gen = hr_smem_raw + (base - raw);
+  const uint32_t sW = base, sH = base + HR_OFF_H;
+  uint8_t* genH = gen + HR_OFF_H;
+  uint8_t* ctl = gen + HR_OFF_CTL;
+  const uint32_t bar0 = smem_u32(ctl);
+  // every barrier completes once per step g: parity g & 1
+  const uint32_t acc_full = bar0, h_local = bar0 + 8, h_in = bar0 + 16, st_free = bar0 + 24, peer_local = bar0 + 32,
+                 peer_in = bar0 + 40, copy_done = bar0 + 48, recv_ready = bar0 + 56;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ctl + 64);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int p = (int)(rank >> 1), s = (int)(rank & 1);
+  const bool leader = (s == 0);
+  const uint32_t partner = (uint32_t)(2 * (1 - p) + s);
+
+  if (tid == 0) {
+    mbar_init(acc_full, 1);
+    mbar_init(h_local, HR_EPI_WARPS);
+    mbar_init(h_in, 1);
+    mbar_init(st_free, 1);
+    mbar_init(peer_local, 1);
+    mbar_init(peer_in, 1);
+    mbar_init(copy_done, 1);
+    mbar_init(recv_ready, 1);
+    fence_mbar_init();
+    mbar_arrive_expect_tx(h_in, 2 * HR_ATOM);  // armed for the first step; re-armed by its single waiter afterwards
+    tma_prefetch_desc(&tmOut);
+  }
+  if (warp == HR_EPI_WARPS) {
+    tmem_alloc_2sm(smem_u32(tmem_slot), 512);
+    tmem_relinquish_2sm();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  cluster_sync_all();
+
+  const int n_work = 2 * tile_pairs;
+  const int n_clusters = (int)cluster_nclusters_x();
+  int g0 = 0;
+  for (int w = (int)cluster_id_x(); w < n_work; w += n_clusters, g0 += T) {
+    const int dir = w / tile_pairs, tp = w - dir * tile_pairs;
+    const int b0 = (2 * tp + s) * HR_M;
+
+    if (g0 > 0) cluster_sync_all();
+    {
+      // this CTA's W_hh rows: for N block nb, rows [p*512 + nb*256 + 128 s, +128); h_{-1} = 0
+      for (int i = tid; i < 2 * 128 * 32; i += HR_THREADS) {
+        const uint32_t nb = i >> 12, rem = i & 4095, row = rem >> 5, cc = rem & 31, atom = cc >> 3, c = cc & 7;
+        const uint4* src = reinterpret_cast<const uint4*>(whh + ((size_t)dir * 1024 + p * 512 + nb * 256 + 128 * s + row) * 256);
+        *reinterpret_cast<uint4*>(gen + (nb * 4 + atom) * HR_ATOM + sw128_chunk_off(row, c)) = __ldg(src + cc);
+      }
+      for (int i = tid; i < (int)(4 * HR_ATOM / 16); i += HR_THREADS) reinterpret_cast<uint4*>(genH)[i] = make_uint4(0, 0, 0, 0);
+    }
+    fence_proxy_async_all();
+    __syncthreads();
+    cluster_sync_all();
+
+    // chunk 0 of (row, dir) in the blocked G layout: 256 chunks of 2 KB per 128-row block
+    auto g_block = [&](long long row) { return reinterpret_cast<const uint8_t*>(G) + (row >> 7) * (256ll * 2048); };
+
+    if (warp == HR_EPI_WARPS + 2) {
+      // ---------------- L2 prefetcher: this CTA's part of the NEXT step's G block (64 chunks of 2 KB = 128 KB) ----------------
+      for (int st = 0; st + 1 < T; ++st) {
+        const int sn = st + 1;
+        const long long row0 = (long long)(dir ? (T - 1 - sn) : sn) * Bc + b0;
+        const uint8_t* blk = g_block(row0) + (long long)(dir * 128 + p * 64) * 2048;
+        if (lane < 8) bulk_prefetch_l2(blk + lane * 16384, 16384u);
+        if ((row0 & 127) != 0 && lane >= 8 && lane < 16) bulk_prefetch_l2(blk + 256ll * 2048 + (lane - 8) * 16384, 16384u);
+        // pace: one step of prefetch per step of compute.  Nothing depends on this warp, so it may fall behind and see the
+        // barrier two phases later (same parity): bounded polling instead of a wait that could then never return
+        for (int polls = 0; polls < 50000 && !mbar_try_wait(h_local, (uint32_t)((g0 + st) & 1)); ++polls) { }
+      }
+    } else if (warp == HR_EPI_WARPS) {
+      if (leader && lane == 0) {
+        // ---------------- MMA issuer (pair leader) ----------------
+        constexpr uint32_t idesc = umma_idesc_bf16(256, 256);
+        const uint16_t pair_mask = (uint16_t)(3u << (2 * p));
+        const uint32_t ack = mapa_u32(copy_done, partner);
+        auto wait_h = [&](int gp) {  // h of step gp complete in both CTAs of the pair, accumulator drained
+          jit();
+          mbar_wait(h_local, (uint32_t)(gp & 1));
+          mbar_wait_cluster(peer_local, (uint32_t)(gp & 1));
+          mbar_wait(h_in, (uint32_t)(gp & 1));
+          mbar_arrive_expect_tx(h_in, 2 * HR_ATOM);
+          mbar_arrive_cluster_relaxed(ack);
+          mbar_wait_cluster(peer_in, (uint32_t)(gp & 1));
+          tc_fence_after();
+        };
+        for (int st = 0; st < T; ++st) {
+          const int g = g0 + st;
+          if (st > 0) wait_h(g - 1);
+#pragma unroll
+          for (int nb = 0; nb < 2; ++nb) {
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+              const uint32_t atom = k >> 2, kk = k & 3;
+              const uint64_t da = umma_desc_sw128(sH + atom * HR_ATOM + kk * 32);
+              const uint64_t db = umma_desc_sw128(sW + (nb * 4 + atom) * HR_ATOM + kk * 32);
+              umma_bf16_2sm(tmem_base + nb * 256, da, db, idesc, k != 0 ? 1u : 0u);
+            }
+          }
+          umma_commit_2sm_mc(acc_full, pair_mask);
+        }
+        wait_h(g0 + T - 1);
+      } else if (!leader && lane == 0) {
+        // ---------------- relay (peer CTA of the pair): relaxed arrives, see lstm_bf16_fused.cu ----------------
+        const uint32_t pl = mapa_u32(peer_local, rank & ~1u), pi = mapa_u32(peer_in, rank & ~1u);
+        const uint32_t ack = mapa_u32(copy_done, partner);
+        for (int st = 0; st < T; ++st) {
+          const int g = g0 + st;
+          jit();
+          mbar_wait(h_local, (uint32_t)(g & 1));
+          mbar_arrive_cluster_relaxed(pl);
+          mbar_wait(h_in, (uint32_t)(g & 1));
+          mbar_arrive_expect_tx(h_in, 2 * HR_ATOM);
+          mbar_arrive_cluster_relaxed(pi);
+          mbar_arrive_cluster_relaxed(ack);
+        }
+      }
+    } else if (warp == HR_EPI_WARPS + 1) {
+      // ---------------- h store warp: this CTA's two K-atoms of h_t -> partner CTA (DSMEM) and -> out[t] ----------------
+      if (lane == 0) {
+        const uint32_t atoms = sH + 2 * p * HR_ATOM;
+        for (int st = 0; st < T; ++st) {
+          const int g = g0 + st;
+          const int t = dir ? (T - 1 - st) : st;
+          jit();
+          mbar_wait(h_local, (uint32_t)(g & 1));
+          mbar_wait_cluster(recv_ready, (uint32_t)(g & 1));  // the partner pair's MMA of this step has retired
+          bulk_copy_s2s_cluster(mapa_u32(atoms, partner), atoms, 2 * HR_ATOM, mapa_u32(h_in, partner));
+          tma_store_3d(&tmOut, atoms, dir * 256 + 128 * p, b0, t);
+          tma_store_3d(&tmOut, atoms + HR_ATOM, dir * 256 + 128 * p + 64, b0, t);
+          tma_store_commit();
+          tma_store_wait_read();
+          mbar_arrive(st_free);
+        }
+        tma_store_wait_all();
+      }
+    } else {
+      // ---------------- epilogue: thread = (window row, 64 of the CTA's 128 hidden units) ----------------
+      const int quarter = warp & 3, ch = warp >> 2;
+      const int r = quarter * 32 + lane;
+      const bool live = b0 + r < Bc;
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)ch * 256;
+      uint8_t* hrow = genH + (2 * p + ch) * HR_ATOM;  // this thread's 64 units = K-atom 2p + ch
+      const uint32_t rr = mapa_u32(recv_ready, partner);
+      float c[64];
+#pragma unroll
+      for (int i = 0; i < 64; ++i) c[i] = 0.f;
+
+      for (int st = 0; st < T; ++st) {
+        const int g = g0 + st;
+        const int t = dir ? (T - 1 - st) : st;
+        const long long row = (long long)t * Bc + (live ? b0 + r : b0);
+        // chunks (sl*4 + gate) of this thread's 64 units: units 128 p + 64 ch + 8 sl .. +7
+        const uint8_t* gp = g_block(row) + (long long)(dir * 128 + p * 64 + ch * 32) * 2048 + (row & 127) * 16ll;
+        uint4 gbuf[3][4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) gbuf[0][q] = ldg_stream_v4(gp + q * 2048);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) gbuf[1][q] = ldg_stream_v4(gp + (4 + q) * 2048);
+        if (lane == 0) jit();
+        __syncwarp();
+        mbar_wait(acc_full, (uint32_t)(g & 1));
+        tc_fence_after();
+        if (tid == 0) mbar_arrive_cluster_relaxed(rr);  // MMA of this step retired: the partner may send its atoms of h_g
+#pragma unroll
+        for (int sl = 0; sl < 8; ++sl) {
+          uint32_t acc[32];
+          tmem_ld32(taddr + sl * 32, acc);
+          if (sl < 6) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) gbuf[(sl + 2) % 3][q] = ldg_stream_v4(gp + ((sl + 2) * 4 + q) * 2048);
+          }
+          tmem_ld_wait();
+          const uint32_t* gw = reinterpret_cast<const uint32_t*>(gbuf[sl % 3]);
+          auto gval = [&](int gate, int u) {
+            const uint32_t wv = gw[gate * 4 + (u >> 1)];
+            return __uint_as_float((u & 1) ? (wv & 0xFFFF0000u) : (wv << 16));
+          };
+          uint32_t hp[4];
+#pragma unroll
+          for (int u2 = 0; u2 < 4; ++u2) {
+            float hv[2];
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const int u = u2 * 2 + e;
+              const float ig = fmaf(0.5f, hr_tanh(__uint_as_float(acc[0 * 8 + u]) + gval(0, u)), 0.5f);
+              const float fg = fmaf(0.5f, hr_tanh(__uint_as_float(acc[1 * 8 + u]) + gval(1, u)), 0.5f);
+              const float gg = hr_tanh(__uint_as_float(acc[2 * 8 + u]) + gval(2, u));
+              const float og = fmaf(0.5f, hr_tanh(__uint_as_float(acc[3 * 8 + u]) + gval(3, u)), 0.5f);
+              float& cc = c[sl * 8 + u];
+              cc = fmaf(fg, cc, ig * gg);
+              hv[e] = og * hr_tanh(cc);
+            }
+            __nv_bfloat162 pk = __floats2bfloat162_rn(hv[0], hv[1]);
+            hp[u2] = *reinterpret_cast<uint32_t*>(&pk);
+          }
+          // the local atoms still hold h_{g-1}: their TMA store and their copy to the partner must have finished reading them
+          if (sl == 0 && g > 0) {
+            mbar_wait(st_free, (uint32_t)((g - 1) & 1));
+            mbar_wait_cluster(copy_done, (uint32_t)((g - 1) & 1));
+          }
+          *reinterpret_cast<uint4*>(hrow + sw128_chunk_off((uint32_t)r, (uint32_t)sl)) = make_uint4(hp[0], hp[1], hp[2], hp[3]);
+        }
+        fence_proxy_async_smem();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(h_local);
+      }
+    }
+    __syncthreads();
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == HR_EPI_WARPS) {
+    tc_fence_after();
+    tmem_dealloc_2sm(tmem_base, 512);
+  }
+}
+
+static int h256_setup(int* max_clusters_out) {
+  static int state = 0, max_clusters = 0;
+  if (state == 0) {
+    state = -1;
+    BCI_CUDA_OK(cudaFuncSetAttribute(lstm_rec256_bf16, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HR_SMEM));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(4 * sm_count(), 1, 1);
+    cfg.blockDim = dim3(HR_THREADS, 1, 1);
+    cfg.dynamicSmemBytes = HR_SMEM;
+    cudaLaunchAttribute la[1];
+    la[0].id = cudaLaunchAttributeClusterDimension;
+    la[0].val.clusterDim.x = 4; la[0].val.clusterDim.y = 1; la[0].val.clusterDim.z = 1;
+    cfg.attrs = la; cfg.numAttrs = 1;
+    BCI_CUDA_OK(cudaOccupancyMaxActiveClusters(&max_clusters, lstm_rec256_bf16, &cfg));
+    BCI_REQUIRE(max_clusters > 0, BCI_ECUDA, "H=256 recurrence: no 4-CTA cluster fits on this device");
+    state = 1;
+  }
+  if (max_clusters_out) *max_clusters_out = max_clusters;
+  return state == 1 ? BCI_OK : BCI_ECUDA;
+}
+
+int h256_max_clusters() {
+  int n = 0;
+  return h256_setup(&n) == BCI_OK ? n : 0;
+}
+
+int launch_rec256_bf16(const __nv_bfloat16* G, const __nv_bfloat16* whh, __nv_bfloat16* out, int Bc, int T, cudaStream_t st) {
+  int max_clusters = 0;
+  int rc = h256_setup(&max_clusters);
+  if (rc) return rc;
+  CUtensorMap tmOut;
+  rc = make_tmap_bf16_3d(&tmOut, out, (uint64_t)T, (uint64_t)Bc, 512, 64, HR_M);
+  if (rc) return rc;
+  const int tiles = ceil_div(Bc, HR_M), tile_pairs = (tiles + 1) / 2;
+  const int clusters = 2 * tile_pairs < max_clusters ? 2 * tile_pairs : max_clusters;
+  static const int jitter = [] { const char* e = getenv("BCI_FUSED_JITTER"); int v = e ? atoi(e) : 0; return (v > 0 && (v & (v - 1)) == 0) ? v : 0; }();
+  lstm_rec256_bf16<<<4 * clusters, HR_THREADS, HR_SMEM, st>>>(G, tmOut, whh, Bc, T, tile_pairs, jitter);
+  BCI_LAUNCH_OK();
+  return BCI_OK;
+}
+
+}  // namespace bci
+
+// diagnostics (tests/test_gpu_tensorcore.py): the H = 256 cluster recurrence in isolation
+extern "C" int bci_selftest_rec256_bf16(const void* G, const void* whh, void* out, int32_t Bc, int32_t T, void* stream) {
+  return bci::launch_rec256_bf16((const __nv_bfloat16*)G, (const __nv_bfloat16*)whh, (__nv_bfloat16*)out, Bc, T, (cudaStream_t)stream);
+}

@@ -209,3 +209,57 @@ def test_fused_kernel_is_robust_to_timing_jitter():
     env = dict(os.environ, BCI_FUSED_JITTER="4096", PYTHONPATH=root)
     r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "jitter ok" in r.stdout, r.stderr[-2000:]
+
+
+def _perm256():
+    idx = np.empty(1024, dtype=np.int64)
+    for gate in range(4):
+        for unit in range(256):
+            idx[gate * 256 + unit] = (unit // 128) * 512 + ((unit // 64) % 2) * 256 + ((unit // 8) % 8) * 32 + gate * 8 + unit % 8
+    return idx
+
+
+@pytest.mark.parametrize("Bc,T", [(256, 4), (200, 9), (5, 33), (700, 3)])
+def test_recurrence_h256_cluster_matches_stepwise(Bc, T):
+    """lstm_rec256_bf16 (4-CTA cluster, W_hh resident, h exchanged through DSMEM) against a step-by-step emulation with the
+    same roundings (bf16 G, bf16 weights, bf16 h fed back; fp32 c)."""
+    H = 256
+    g = torch.Generator(device="cuda").manual_seed(Bc * 131 + T + 256)
+    whh = [(torch.rand(4 * H, H, device="cuda", generator=g) * 2 - 1) / np.sqrt(H) for _ in range(2)]
+    Gn = torch.randn(T, Bc, 2, 4 * H, device="cuda", generator=g) * 1.5
+    perm = torch.from_numpy(_perm256()).cuda()
+    gate_scale = torch.ones(4 * H, device="cuda")
+    gate_scale[:2 * H] = 0.5
+    gate_scale[3 * H:] = 0.5
+    whh_p = torch.empty(2, 4 * H, H, device="cuda")
+    for d in range(2):
+        whh_p[d][perm] = whh[d] * gate_scale[:, None]
+    whh_p = whh_p.to(torch.bfloat16).contiguous()
+    Gp = torch.empty_like(Gn)
+    Gp[:, :, :, perm] = Gn * gate_scale
+    Gp = Gp.reshape(T, Bc, 8 * H).to(torch.bfloat16).contiguous()
+    M = T * Bc
+    Mp = (M + 127) // 128 * 128
+    flat = torch.zeros(Mp, 8 * H, device="cuda", dtype=torch.bfloat16)
+    flat[:M] = Gp.reshape(M, 8 * H)
+    Gblk = flat.reshape(Mp // 128, 128, 256, 8).permute(0, 2, 1, 3).contiguous()
+    out = torch.full((T, Bc, 2 * H), float("nan"), device="cuda", dtype=torch.bfloat16)
+    N.check(N.lib().bci_selftest_rec256_bf16(_p(Gblk), _p(whh_p), _p(out), Bc, T, _stream()))
+    torch.cuda.synchronize()
+    Gq = Gp.float().reshape(T, Bc, 2, 4 * H)[:, :, :, perm] / gate_scale
+    want = torch.empty(T, Bc, 2 * H, device="cuda")
+    for d in range(2):
+        w = (whh[d] * gate_scale[:, None]).to(torch.bfloat16).float() / gate_scale[:, None]
+        h = torch.zeros(Bc, H, device="cuda")
+        c = torch.zeros(Bc, H, device="cuda")
+        for s in range(T):
+            t = T - 1 - s if d else s
+            pre = Gq[t, :, d] + h @ w.T
+            i, f, gg, o = pre[:, :H].sigmoid(), pre[:, H:2 * H].sigmoid(), pre[:, 2 * H:3 * H].tanh(), pre[:, 3 * H:].sigmoid()
+            c = f * c + i * gg
+            hf = o * c.tanh()
+            want[t, :, d * H:(d + 1) * H] = hf
+            h = hf.to(torch.bfloat16).float()
+    got = out.float()
+    assert torch.isfinite(got).all()
+    assert float((got - want).abs().max()) <= 1.5e-2
