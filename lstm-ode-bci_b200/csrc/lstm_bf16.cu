@@ -75,10 +75,19 @@ int bf16_chunk_windows() {
   return bf16_path_fused() ? fused_max_clusters() * 4 * 128 : 74 * 128;
 }
 
+size_t lstm_workspace_h256(const bci_lstm_config& c, int batch, int T);
+int lstm_forward_h256(bci_lstm_s* h, const float* x, int batch, int T, float* logits, float* probs, float* attn, void* ws,
+                      size_t ws_bytes, cudaStream_t st);
+
 size_t lstm_store_bytes_bf16(const bci_lstm_config& c) {
   if (c.precision != BCI_PRECISION_BF16) return 0;
   const size_t H = c.hidden_size;
   size_t n = 0;
+  if (H == 256) {
+    for (int l = 0; l < c.num_layers; ++l)
+      n += align_up((size_t)2048 * layer_in_width(c, l) * 2, 256) + align_up((size_t)2048 * 256 * 2, 256) + align_up(2048 * 4, 256);
+    return n + 1024;
+  }
   for (int l = 0; l < c.num_layers; ++l)
     n += 2 * align_up((size_t)8 * H * layer_in_width(c, l) * 2, 256) + 2 * align_up(4 * H * H * 2, 256) + 2 * align_up(8 * H * 4, 256);
   n += align_up(H * 2 * H * 2, 256) + align_up(H * sizeof(float4), 256);  // attention W1' (bf16) + per-unit params
@@ -92,6 +101,14 @@ void lstm_carve_bf16(bci_lstm_s* h, char* base) {
   const size_t H = c.hidden_size;
   size_t off = 0;
   auto take = [&](size_t bytes) { char* p = base + off; off += align_up(bytes, 256); return p; };
+  if (H == 256) {
+    for (int l = 0; l < c.num_layers; ++l) {
+      h->bf16.wih256[l] = reinterpret_cast<__nv_bfloat16*>(take((size_t)2048 * layer_in_width(c, l) * 2));
+      h->bf16.whh256[l] = reinterpret_cast<__nv_bfloat16*>(take((size_t)2048 * 256 * 2));
+      h->bf16.bias256[l] = reinterpret_cast<float*>(take(2048 * 4));
+    }
+    return;
+  }
   for (int l = 0; l < c.num_layers; ++l) {
     h->bf16.wih_bf[l] = reinterpret_cast<__nv_bfloat16*>(take((size_t)8 * H * layer_in_width(c, l) * 2));
     h->bf16.whh_bf[l][0] = reinterpret_cast<__nv_bfloat16*>(take(4 * H * H * 2));
@@ -110,7 +127,8 @@ int lstm_pack_bf16(bci_lstm_s* h, cudaStream_t st) {
   const bci_lstm_config& c = h->cfg;
   const bci_lstm_weights& w = h->raw;
   const int H = c.hidden_size;
-  BCI_REQUIRE(H == 128, BCI_EINVAL, "bf16 (tcgen05) mode is built for hidden_size=128; use fp32 precision for H=%d", H);
+  if (H == 256) return pack_h256_bf16(h, st);
+  BCI_REQUIRE(H == 128, BCI_EINVAL, "bf16 (tcgen05) mode is built for hidden_size 128 and 256 (got %d)", H);
   for (int l = 0; l < c.num_layers; ++l) {
     const int K = layer_in_width(c, l);
     for (int d = 0; d < 2; ++d) {
@@ -666,6 +684,7 @@ static size_t chunk_bytes_bf16(const bci_lstm_config& c, int Bc, int T) {
 }
 
 size_t lstm_workspace_bf16(const bci_lstm_config& c, int batch, int T) {
+  if (c.hidden_size == 256) return lstm_workspace_h256(c, batch, T);
   const int Bc = batch < max_chunk(c, 0) ? batch : max_chunk(c, 0);
   return chunk_bytes_bf16(c, Bc > 0 ? Bc : 1, T) + 1024;  // + slack: the TMA-addressed buffers are aligned to 1 KB internally
 }
@@ -717,7 +736,8 @@ static int forward_chunk_bf16(bci_lstm_s* h, const float* x, int Bc, int T, floa
 int lstm_forward_bf16(bci_lstm_s* h, const float* x, int batch, int T, float* logits, float* probs, float* attn, void* ws,
                       size_t ws_bytes, cudaStream_t st) {
   const bci_lstm_config& c = h->cfg;
-  BCI_REQUIRE(c.hidden_size == 128, BCI_EINVAL, "bf16 mode supports hidden_size=128 only");
+  if (c.hidden_size == 256) return lstm_forward_h256(h, x, batch, T, logits, probs, attn, ws, ws_bytes, st);
+  BCI_REQUIRE(c.hidden_size == 128, BCI_EINVAL, "bf16 mode supports hidden_size 128 and 256");
   const int chunk = batch < max_chunk(c, 0) ? batch : max_chunk(c, 0);
   char* ws_al = reinterpret_cast<char*>(((uintptr_t)ws + 1023) & ~(uintptr_t)1023);
   BCI_REQUIRE(ws_bytes >= chunk_bytes_bf16(c, chunk, T) + (size_t)(ws_al - (char*)ws), BCI_ENOMEM,

@@ -341,6 +341,73 @@ int launch_rec256_bf16(const __nv_bfloat16* G, const __nv_bfloat16* whh, __nv_bf
   return BCI_OK;
 }
 
+int pack_h256_bf16(bci_lstm_s* h, cudaStream_t st) {
+  const bci_lstm_config& c = h->cfg;
+  const bci_lstm_weights& w = h->raw;
+  for (int l = 0; l < c.num_layers; ++l) {
+    const int K = layer_in_width(c, l);
+    for (int d = 0; d < 2; ++d) {
+      pack_rows_perm256_bf16<<<(unsigned)ceil_div64((long long)1024 * K, 256), 256, 0, st>>>(w.w_ih[l][d], h->bf16.wih256[l], K, d * 1024);
+      pack_rows_perm256_bf16<<<(unsigned)ceil_div64((long long)1024 * 256, 256), 256, 0, st>>>(w.w_hh[l][d], h->bf16.whh256[l], 256, d * 1024);
+      pack_bias_perm256<<<4, 256, 0, st>>>(w.b_ih[l][d], w.b_hh[l][d], h->bf16.bias256[l], d * 1024);
+    }
+  }
+  BCI_LAUNCH_OK();
+  return BCI_OK;
+}
+
+static size_t chunk_bytes_h256(const bci_lstm_config& c, int Bc, int T) {
+  const size_t rows = (size_t)Bc * T, rows_pad = (rows + 127) / 128 * 128;
+  return align_up(rows * 256 * 2, 1024) + align_up(rows_pad * 2048 * 2, 1024) + 2 * align_up(rows * 512 * 2, 1024) + align_up(rows * 4, 1024);
+}
+
+size_t lstm_workspace_h256(const bci_lstm_config& c, int batch, int T) {
+  const int Bc = batch < max_chunk(c, 0) ? batch : max_chunk(c, 0);
+  return chunk_bytes_h256(c, Bc > 0 ? Bc : 1, T) + 1024;
+}
+
+// K1 and K4/K5 are the generic CUDA-core kernels (bf16 activations); the three LSTM layers run on tensor cores
+int lstm_forward_h256(bci_lstm_s* h, const float* x, int batch, int T, float* logits, float* probs, float* attn, void* ws,
+                      size_t ws_bytes, cudaStream_t st) {
+  const bci_lstm_config& c = h->cfg;
+  const int chunk = batch < max_chunk(c, 0) ? batch : max_chunk(c, 0);
+  char* ws_al = reinterpret_cast<char*>(((uintptr_t)ws + 1023) & ~(uintptr_t)1023);
+  BCI_REQUIRE(ws_bytes >= chunk_bytes_h256(c, chunk, T) + (size_t)(ws_al - (char*)ws), BCI_ENOMEM,
+              "bci_lstm_forward: workspace %zu < %zu bytes", ws_bytes, chunk_bytes_h256(c, chunk, T) + 1024);
+  for (int b0 = 0; b0 < batch; b0 += chunk) {
+    const int Bc = (batch - b0) < chunk ? (batch - b0) : chunk;
+    const size_t rows = (size_t)Bc * T;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { char* p = ws_al + off; off += align_up(bytes, 1024); return p; };
+    __nv_bfloat16* z = reinterpret_cast<__nv_bfloat16*>(take(rows * 256 * 2));
+    __nv_bfloat16* g = reinterpret_cast<__nv_bfloat16*>(take((rows + 127) / 128 * 128 * 2048 * 2));
+    __nv_bfloat16* o0 = reinterpret_cast<__nv_bfloat16*>(take(rows * 512 * 2));
+    __nv_bfloat16* o1 = reinterpret_cast<__nv_bfloat16*>(take(rows * 512 * 2));
+    float* scores = reinterpret_cast<float*>(take(rows * 4));
+    h->prof.mark(-1, st);
+    int rc = launch_input_proj<256, __nv_bfloat16>(h, x + (size_t)b0 * T * c.input_size, Bc, T, z, st);
+    if (rc) return rc;
+    h->prof.mark(0, st);
+    const __nv_bfloat16* in = z;
+    __nv_bfloat16* outs[2] = {o0, o1};
+    for (int l = 0; l < c.num_layers; ++l) {
+      rc = launch_proj_gemm_bf16(in, h->bf16.wih256[l], h->bf16.bias256[l], g, (int)rows, 2048, layer_in_width(c, l), true, st);
+      if (rc) return rc;
+      h->prof.mark(1, st);
+      rc = launch_rec256_bf16(g, h->bf16.whh256[l], outs[l & 1], Bc, T, st);
+      if (rc) return rc;
+      h->prof.mark(2, st);
+      in = outs[l & 1];
+    }
+    rc = launch_pool_head<256, 2, __nv_bfloat16>(h, in, Bc, T, logits + (size_t)b0 * c.num_classes,
+                                                  probs ? probs + (size_t)b0 * c.num_classes : nullptr,
+                                                  attn ? attn + (size_t)b0 * T : nullptr, scores, st);
+    if (rc) return rc;
+    h->prof.mark(3, st);
+  }
+  return BCI_OK;
+}
+
 }  // namespace bci
 
 // diagnostics (tests/test_gpu_tensorcore.py): the H = 256 cluster recurrence in isolation

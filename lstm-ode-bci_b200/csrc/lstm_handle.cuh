@@ -45,6 +45,10 @@ struct PackedBF16 {
   // fused cluster kernel (lstm_bf16_fused.cu): W_ih rows and biases in the SAME perm_T order as whh_bf
   __nv_bfloat16* wih_t_bf[BCI_MAX_LAYERS];  // [2][4H][K_l]
   float* bias_t[BCI_MAX_LAYERS];            // [2][4H]
+  // H = 256 (lstm_bf16_h256.cu): rows / columns in perm_256 order
+  __nv_bfloat16* wih256[BCI_MAX_LAYERS];    // [2*1024][K_l]  B operand of the projection GEMM
+  __nv_bfloat16* whh256[BCI_MAX_LAYERS];    // [2][1024][256] resident operand of the cluster recurrence
+  float* bias256[BCI_MAX_LAYERS];           // [2*1024]
   // attention scores on tensor cores with LayerNorm folded in (lstm_bf16_pool.cu):
   //   aw1_bf [H][2H] = bf16(W1[j][d] * ln_w[d]);  apar[j] = {s_j = sum_d aw1_bf[j][d], c_j = b1_j + sum_d ln_b[d] W1[j][d], w2_j, 0}
   __nv_bfloat16* aw1_bf;
@@ -97,8 +101,10 @@ inline int layer_in_width(const bci_lstm_config& c, int l) { return l == 0 ? c.h
 
 // chunking policy: windows processed per internal pass (bounds the workspace)
 int bf16_chunk_windows();  // lstm_bf16.cu: depends on the recurrence path in use (split K2+K3 or fused cluster kernel)
+int h256_max_clusters();   // lstm_bf16_h256.cu: co-resident 4-CTA clusters of the H = 256 recurrence
 inline int max_chunk(const bci_lstm_config& c, int train) {
-  if (c.precision == BCI_PRECISION_BF16) return train ? 2048 : bf16_chunk_windows();
+  if (c.precision == BCI_PRECISION_BF16)
+    return train ? 2048 : (c.hidden_size == 256 ? h256_max_clusters() * 2 * 128 : bf16_chunk_windows());
   const int base = train ? 512 : 2048;
   return c.hidden_size > 128 ? base / 2 : base;
 }
@@ -134,5 +140,10 @@ int launch_pool_bf16(bci_lstm_s* h, const __nv_bfloat16* seq, float2* stats, flo
 int launch_fused_rec_bf16(const __nv_bfloat16* in, const __nv_bfloat16* wih, const __nv_bfloat16* whh_f, const __nv_bfloat16* whh_r,
                           const float* bias, __nv_bfloat16* out, float2* stats, int Bc, int T, int Kin, cudaStream_t st);
 int fused_max_clusters();  // co-resident 4-CTA clusters of the fused kernel on this device (0 if it cannot run)
+// H = 256 bf16 path (lstm_bf16_h256.cu)
+int launch_rec256_bf16(const __nv_bfloat16* G, const __nv_bfloat16* whh, __nv_bfloat16* out, int Bc, int T, cudaStream_t st);
+int pack_h256_bf16(bci_lstm_s* h, cudaStream_t st);
+int launch_proj_gemm_bf16(const __nv_bfloat16* A, const __nv_bfloat16* W, const float* bias, __nv_bfloat16* C, int M, int N, int K,
+                          bool blocked, cudaStream_t st);
 
 }  // namespace bci

@@ -60,7 +60,7 @@ class EnhancedLSTMModel(nn.Module):
     # -- engine management -------------------------------------------------------------------
     def _precision_now(self):
         if self.precision == "auto":
-            return "bf16" if (torch.is_autocast_enabled("cuda") and self.is_full_model and self.hidden_size == 128) else "fp32"
+            return "bf16" if (torch.is_autocast_enabled("cuda") and self.is_full_model and self.hidden_size in (128, 256)) else "fp32"
         return self.precision
 
     def _signature(self):

@@ -129,8 +129,29 @@ def test_bf16_forward_close_to_fp32_oracle(B, T):
     assert np.abs(p32 - want_probs).max() <= 1e-5
 
 
-def test_bf16_rejects_h256():
-    params = synth.make_lstm_params(1, 61, 256, 3)
+@pytest.mark.parametrize("B,T", [(8, 256), (300, 64)])
+def test_bf16_h256_forward_close_to_fp32_oracle(B, T):
+    """hidden_size = 256 (the reference's trained checkpoint on 61 channels, 04:876-877) in bf16 mode: tcgen05 projection GEMM +
+    the cluster recurrence of lstm_bf16_h256.cu; same stated bf16 tolerance as H = 128."""
+    params = synth.make_lstm_params(44, 61, 256, 3, logit_gain=12.0)
+    x = synth.make_windows(9, B, T, 61, structured=True)
+    port = torch_port.build_port(params).eval()
+    with torch.no_grad():
+        want_logits, want_attn = port(torch.from_numpy(x), return_attention=True)
+        want_probs = torch.softmax(want_logits, 1).numpy()
+    m = lstm.from_params(params, precision="bf16")
+    with torch.no_grad():
+        logits, attn = m(torch.from_numpy(x).cuda(), return_attention=True)
+        probs = m.predict_proba(torch.from_numpy(x).cuda())
+    dl = np.abs(logits.cpu().numpy() - want_logits.numpy()).max()
+    dp = np.abs(probs.cpu().numpy() - want_probs).max()
+    da = np.abs(attn.cpu().numpy() - want_attn.numpy()).max()
+    print(f"bf16 H=256 vs fp32 oracle: dlogit {dl:.3e} dprob {dp:.3e} dattn {da:.3e}")
+    assert dl <= 12.0 * 3e-2 and dp <= 1e-2 and da <= 2e-3
+
+
+def test_bf16_rejects_ablation_variants_and_other_sizes():
+    params = synth.make_lstm_params(1, 61, 128, 2, bidirectional=False)
     m = lstm.from_params(params, precision="bf16")
     with pytest.raises(N.BciError):
         m(torch.zeros(1, 8, 61, device="cuda"))
