@@ -435,6 +435,25 @@ def main():
             b.record()
         barrier()
         ams = max_over_ranks(a.elapsed_time(b)) / 3
+        # hidden_size 256 = the reference's trained checkpoint on 61 channels (04:876-877): bf16 tensor-core mode
+        m256 = lstm.from_params(synth.make_lstm_params(44, 61, 256, 3), precision="bf16", device=f"cuda:{local}")
+        b256 = ops.lstm_chunk_windows(m256._engine("bf16"))
+        x256 = x[:b256]
+        for _ in range(2):
+            m256.predict_proba(x256)
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(3):
+            m256.predict_proba(x256)
+        b.record()
+        barrier()
+        hms = max_over_ranks(a.elapsed_time(b)) / 3
+        line["h256_bf16"] = {"metric": "windows_per_s", "value": world * int(x256.shape[0]) / (hms * 1e-3), "unit": "windows/s", "ms": hms,
+                             "windows_per_gpu": int(x256.shape[0]), "flop_per_window": 2_223_047_168,
+                             "tflops_per_gpu": int(x256.shape[0]) * 2.223047168e9 / (hms * 1e-3) / 1e12,
+                             "config": "EnhancedLSTMModel(61, hidden 256, 3 layers): projection GEMM + cluster recurrence (lstm_bf16_h256.cu)"}
+        del m256
         line["ablation_minimal"] = {"metric": "windows_per_s", "value": world * 2048 / (ams * 1e-3), "unit": "windows/s", "ms": ams,
                                     "config": "09:342-349 'Minimal': H=256, 1 layer, unidirectional, mean pooling, fp32", "windows_per_gpu": 2048}
         del abl

@@ -86,6 +86,7 @@ size_t lstm_store_bytes_bf16(const bci_lstm_config& c) {
   if (H == 256) {
     for (int l = 0; l < c.num_layers; ++l)
       n += align_up((size_t)2048 * layer_in_width(c, l) * 2, 256) + align_up((size_t)2048 * 256 * 2, 256) + align_up(2048 * 4, 256);
+    n += align_up((size_t)256 * 512 * 2, 256) + align_up(256 * sizeof(float4), 256) + align_up(256 * 4, 256);  // attention W1', params, zeros
     return n + 1024;
   }
   for (int l = 0; l < c.num_layers; ++l)
@@ -107,6 +108,9 @@ void lstm_carve_bf16(bci_lstm_s* h, char* base) {
       h->bf16.whh256[l] = reinterpret_cast<__nv_bfloat16*>(take((size_t)2048 * 256 * 2));
       h->bf16.bias256[l] = reinterpret_cast<float*>(take(2048 * 4));
     }
+    h->bf16.aw1_bf = reinterpret_cast<__nv_bfloat16*>(take((size_t)256 * 512 * 2));
+    h->bf16.apar = reinterpret_cast<float4*>(take(256 * sizeof(float4)));
+    h->bf16.zero_bias = reinterpret_cast<float*>(take(256 * 4));
     return;
   }
   for (int l = 0; l < c.num_layers; ++l) {

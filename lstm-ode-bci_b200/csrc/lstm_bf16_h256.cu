@@ -141,12 +141,14 @@ lstm_rec256_bf16(const __nv_bfloat16* __restrict__ G,        // blocked: [row/12
 
     if (warp == HR_EPI_WARPS + 2) {
       // ---------------- L2 prefetcher: this CTA's part of the NEXT step's G block (64 chunks of 2 KB = 128 KB) ----------------
-      for (int st = 0; st + 1 < T; ++st) {
+      const long long n_blocks = ((long long)T * Bc + 127) >> 7;  // G is allocated in whole 128-row blocks
+      for (int st = 0; st + 1 < T && b0 < Bc; ++st) {
         const int sn = st + 1;
         const long long row0 = (long long)(dir ? (T - 1 - sn) : sn) * Bc + b0;
         const uint8_t* blk = g_block(row0) + (long long)(dir * 128 + p * 64) * 2048;
         if (lane < 8) bulk_prefetch_l2(blk + lane * 16384, 16384u);
-        if ((row0 & 127) != 0 && lane >= 8 && lane < 16) bulk_prefetch_l2(blk + 256ll * 2048 + (lane - 8) * 16384, 16384u);
+        if ((row0 & 127) != 0 && (row0 >> 7) + 1 < n_blocks && lane >= 8 && lane < 16)
+          bulk_prefetch_l2(blk + 256ll * 2048 + (lane - 8) * 16384, 16384u);
         // pace: one step of prefetch per step of compute.  Nothing depends on this warp, so it may fall behind and see the
         // barrier two phases later (same parity): bounded polling instead of a wait that could then never return
         for (int polls = 0; polls < 50000 && !mbar_try_wait(h_local, (uint32_t)((g0 + st) & 1)); ++polls) { }
@@ -232,7 +234,8 @@ lstm_rec256_bf16(const __nv_bfloat16* __restrict__ G,        // blocked: [row/12
       for (int st = 0; st < T; ++st) {
         const int g = g0 + st;
         const int t = dir ? (T - 1 - st) : st;
-        const long long row = (long long)t * Bc + (live ? b0 + r : b0);
+        // rows of windows beyond the batch (partial or absent tiles) read a valid row instead; their results are never stored
+        const long long row = (long long)t * Bc + (live ? b0 + r : (b0 < Bc ? b0 : 0));
         // chunks (sl*4 + gate) of this thread's 64 units: units 128 p + 64 ch + 8 sl .. +7
         const uint8_t* gp = g_block(row) + (long long)(dir * 128 + p * 64 + ch * 32) * 2048 + (row & 127) * 16ll;
         uint4 gbuf[3][4];
@@ -353,12 +356,14 @@ int pack_h256_bf16(bci_lstm_s* h, cudaStream_t st) {
     }
   }
   BCI_LAUNCH_OK();
-  return BCI_OK;
+  return pack_pool256_bf16(h, st);
 }
 
 static size_t chunk_bytes_h256(const bci_lstm_config& c, int Bc, int T) {
   const size_t rows = (size_t)Bc * T, rows_pad = (rows + 127) / 128 * 128;
-  return align_up(rows * 256 * 2, 1024) + align_up(rows_pad * 2048 * 2, 1024) + 2 * align_up(rows * 512 * 2, 1024) + align_up(rows * 4, 1024);
+  // z, G (also reused as the [rows][256] bf16 score pre-activations after the last layer), two outputs, scores, row statistics
+  return align_up(rows * 256 * 2, 1024) + align_up(rows_pad * 2048 * 2, 1024) + 2 * align_up(rows * 512 * 2, 1024) + align_up(rows * 4, 1024) +
+         align_up(rows * 8, 1024);
 }
 
 size_t lstm_workspace_h256(const bci_lstm_config& c, int batch, int T) {
@@ -366,7 +371,7 @@ size_t lstm_workspace_h256(const bci_lstm_config& c, int batch, int T) {
   return chunk_bytes_h256(c, Bc > 0 ? Bc : 1, T) + 1024;
 }
 
-// K1 and K4/K5 are the generic CUDA-core kernels (bf16 activations); the three LSTM layers run on tensor cores
+// K1 is the generic CUDA-core kernel (bf16 output); the three LSTM layers and the attention scores run on tensor cores
 int lstm_forward_h256(bci_lstm_s* h, const float* x, int batch, int T, float* logits, float* probs, float* attn, void* ws,
                       size_t ws_bytes, cudaStream_t st) {
   const bci_lstm_config& c = h->cfg;
@@ -384,6 +389,7 @@ int lstm_forward_h256(bci_lstm_s* h, const float* x, int batch, int T, float* lo
     __nv_bfloat16* o0 = reinterpret_cast<__nv_bfloat16*>(take(rows * 512 * 2));
     __nv_bfloat16* o1 = reinterpret_cast<__nv_bfloat16*>(take(rows * 512 * 2));
     float* scores = reinterpret_cast<float*>(take(rows * 4));
+    float2* rowstat = reinterpret_cast<float2*>(take(rows * 8));
     h->prof.mark(-1, st);
     int rc = launch_input_proj<256, __nv_bfloat16>(h, x + (size_t)b0 * T * c.input_size, Bc, T, z, st);
     if (rc) return rc;
@@ -399,9 +405,9 @@ int lstm_forward_h256(bci_lstm_s* h, const float* x, int batch, int T, float* lo
       h->prof.mark(2, st);
       in = outs[l & 1];
     }
-    rc = launch_pool_head<256, 2, __nv_bfloat16>(h, in, Bc, T, logits + (size_t)b0 * c.num_classes,
-                                                  probs ? probs + (size_t)b0 * c.num_classes : nullptr,
-                                                  attn ? attn + (size_t)b0 * T : nullptr, scores, st);
+    // pooling: score GEMM on tensor cores (G's buffer is free now and holds the bf16 pre-activations), LayerNorm folded in
+    rc = launch_pool256_bf16(h, in, g, rowstat, scores, Bc, T, logits + (size_t)b0 * c.num_classes,
+                             probs ? probs + (size_t)b0 * c.num_classes : nullptr, attn ? attn + (size_t)b0 * T : nullptr, st);
     if (rc) return rc;
     h->prof.mark(3, st);
   }

@@ -211,17 +211,20 @@ __device__ __forceinline__ float block_reduce(float v, float* red, bool is_max) 
 // 16-byte loads, one warp per time step (512 contiguous bytes), 4 steps in flight per warp.
 constexpr int PF_WPC = 4;
 
+// D = LSTM output width (256 for hidden_size 128, 512 for 256); rowstat[t * rs_tstride + b] = (mean, rstd) of row (t, b)
+template <int D>
 __global__ void __launch_bounds__(PF_THREADS)
-attn_pool_finish_bf16(const __nv_bfloat16* __restrict__ seq,  // [T][Bc][256]
+attn_pool_finish_bf16(const __nv_bfloat16* __restrict__ seq,  // [T][Bc][D]
                       const float* __restrict__ scores,       // [T][Bc]
-                      const float2* __restrict__ stats,       // [T][8][Bc]: slot 0 = (mean, rstd) written by attn_score_bf16
+                      const float2* __restrict__ stats,       // H=128: [T][8][Bc], slot 0 = (mean, rstd) written by attn_score_bf16
+                      long long rs_tstride,
                       int Bc, int T, int classes,
                       const float* __restrict__ lnw, const float* __restrict__ lnb,
                       const float* __restrict__ c0t, const float* __restrict__ cb0,
                       const float* __restrict__ c3t, const float* __restrict__ cb3,
                       const float* __restrict__ c6, const float* __restrict__ cb6,
                       float* __restrict__ logits, float* __restrict__ probs, float* __restrict__ attn) {
-  constexpr int H = 128, D = 256, NW = PF_THREADS / 32;
+  constexpr int H = D / 2, NW = PF_THREADS / 32, CPL = D / 256;  // CPL: 16-byte chunks per lane and row
   extern __shared__ __align__(16) float pf_smem[];
   float* beta = pf_smem;                 // [T]  raw scores first, then beta_t = a_t * rstd_t
   float* bmean = beta + T;               // [T]  row means
@@ -240,7 +243,7 @@ attn_pool_finish_bf16(const __nv_bfloat16* __restrict__ seq,  // [T][Bc][256]
     for (int t = tid; t < T; t += PF_THREADS) {
       const float s = __ldg(scores + (long long)t * Bc + b);
       beta[t] = s;
-      bmean[t] = stats[((long long)t * 8) * Bc + b].x;
+      bmean[t] = stats[(long long)t * rs_tstride + b].x;
       lmax = fmaxf(lmax, s);
     }
     const float m = block_reduce(lmax, red, true);
@@ -252,44 +255,56 @@ attn_pool_finish_bf16(const __nv_bfloat16* __restrict__ seq,  // [T][Bc][256]
       const float a = expf(beta[t] - m) * inv_l;
       if (attn) attn[(long long)b * T + t] = a;
       const float mean = bmean[t];
-      const float bt = a * stats[((long long)t * 8) * Bc + b].y;
+      const float bt = a * stats[(long long)t * rs_tstride + b].y;
       beta[t] = bt;
       lgam = fmaf(bt, mean, lgam);
     }
     const float gamma = block_reduce(lgam, red, false);  // also makes beta[] visible to all threads
 
     // beta-weighted sum of the raw rows: warp = time step (mod NW), lane = 8 consecutive features (one 16-byte load)
-    float acc[8];
+    float acc[8 * CPL];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+    for (int i = 0; i < 8 * CPL; ++i) acc[i] = 0.f;
     const uint4* rowp = reinterpret_cast<const uint4*>(seq) + (long long)b * (D / 8) + lane;
     const long long tstride = (long long)Bc * (D / 8);
-    auto fma8 = [&](const uint4& v, float bt) {
+    auto fma8 = [&](const uint4& v, float bt, int cp) {
       const uint32_t wv[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        acc[2 * i] = fmaf(bt, __uint_as_float(wv[i] << 16), acc[2 * i]);
-        acc[2 * i + 1] = fmaf(bt, __uint_as_float(wv[i] & 0xFFFF0000u), acc[2 * i + 1]);
+        acc[cp * 8 + 2 * i] = fmaf(bt, __uint_as_float(wv[i] << 16), acc[cp * 8 + 2 * i]);
+        acc[cp * 8 + 2 * i + 1] = fmaf(bt, __uint_as_float(wv[i] & 0xFFFF0000u), acc[cp * 8 + 2 * i + 1]);
       }
     };
+    constexpr int UN = 4 / CPL;  // time steps in flight per warp (4 x 16-byte loads per lane either way)
     int t = warp;
-    for (; t + 3 * NW < T; t += 4 * NW) {
-      uint4 v[4];
+    for (; t + (UN - 1) * NW < T; t += UN * NW) {
+      uint4 v[UN][CPL];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) v[u] = ldg_stream_v4(rowp + (long long)(t + u * NW) * tstride);
+      for (int u = 0; u < UN; ++u)
 #pragma unroll
-      for (int u = 0; u < 4; ++u) fma8(v[u], beta[t + u * NW]);
+        for (int cp = 0; cp < CPL; ++cp) v[u][cp] = ldg_stream_v4(rowp + (long long)(t + u * NW) * tstride + cp * 32);
+#pragma unroll
+      for (int u = 0; u < UN; ++u)
+#pragma unroll
+        for (int cp = 0; cp < CPL; ++cp) fma8(v[u][cp], beta[t + u * NW], cp);
     }
-    for (; t < T; t += NW) fma8(ldg_stream_v4(rowp + (long long)t * tstride), beta[t]);
+    for (; t < T; t += NW)
 #pragma unroll
-    for (int i = 0; i < 8; i += 4)
-      *reinterpret_cast<float4*>(part + warp * D + lane * 8 + i) = make_float4(acc[i], acc[i + 1], acc[i + 2], acc[i + 3]);
+      for (int cp = 0; cp < CPL; ++cp) fma8(ldg_stream_v4(rowp + (long long)t * tstride + cp * 32), beta[t], cp);
+#pragma unroll
+    for (int cp = 0; cp < CPL; ++cp)
+#pragma unroll
+      for (int i = 0; i < 8; i += 4)
+        *reinterpret_cast<float4*>(part + warp * D + (cp * 32 + lane) * 8 + i) =
+            make_float4(acc[cp * 8 + i], acc[cp * 8 + i + 1], acc[cp * 8 + i + 2], acc[cp * 8 + i + 3]);
     __syncthreads();
-    {
+#pragma unroll
+    for (int f = 0; f < CPL; ++f) {
+      const int d = f * PF_THREADS + tid;
       float raw = 0.f;
 #pragma unroll
-      for (int k = 0; k < NW; ++k) raw += part[k * D + tid];
-      ctx_s[w * D + tid] = fmaf(lnw[tid], raw - gamma, lnb[tid]);
+      for (int k = 0; k < NW; ++k) raw += part[k * D + d];
+      ctx_s[w * D + d] = fmaf(lnw[d], raw - gamma, lnb[d]);
     }
     __syncthreads();
   }
@@ -340,6 +355,84 @@ attn_pool_finish_bf16(const __nv_bfloat16* __restrict__ seq,  // [T][Bc][256]
   }
 }
 
+static inline size_t pool_finish_smem(int D, int T) {
+  return (size_t)(2 * T + (PF_THREADS / 32) * D + PF_WPC * (D + D / 2 + D / 4) + 8 + PF_WPC * 8) * sizeof(float);
+}
+
+// ---- H = 256: scores from a plain tcgen05 GEMM ------------------------------------------------------------------------------
+// PRE_raw = X . W1'^T is computed by proj_gemm_bf16 (N = 256, K = 512, bf16 output, zero bias) on the raw rows; this kernel (one
+// warp per row) computes the row's LayerNorm statistics from X, folds them in -- pre_j = rstd (PRE_raw_j - mean s_j) + c_j --
+// and reduces  sum_j w2_j tanh(pre_j)  to the row's score; (mean, rstd) are kept for the finish kernel.
+__global__ void __launch_bounds__(256)
+attn_score256_kernel(const __nv_bfloat16* __restrict__ seq,   // [M][512]
+                     const __nv_bfloat16* __restrict__ pre,   // [M][256]
+                     const float4* __restrict__ par,          // [256] {s_j, c_j, w2_j, 0}
+                     float* __restrict__ scores, float2* __restrict__ rowstat, long long M) {
+  const int lane = threadIdx.x & 31;
+  const long long wstride = (long long)gridDim.x * 8;
+  float4 pj[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) pj[i] = __ldg(par + lane * 8 + i);
+  for (long long r = (long long)blockIdx.x * 8 + (threadIdx.x >> 5); r < M; r += wstride) {
+    const uint4* xr = reinterpret_cast<const uint4*>(seq + r * 512);
+    const uint4 x0 = ldg_stream_v4(xr + lane), x1 = ldg_stream_v4(xr + 32 + lane);
+    const uint4 pr = ldg_stream_v4(reinterpret_cast<const uint4*>(pre + r * 256) + lane);
+    float sm = 0.f, sq = 0.f;
+    const uint32_t xw[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float a = __uint_as_float(xw[i] << 16), b = __uint_as_float(xw[i] & 0xFFFF0000u);
+      sm += a + b;
+      sq = fmaf(a, a, fmaf(b, b, sq));
+    }
+    sm = warp_sum(sm);
+    sq = warp_sum(sq);
+    const float mean = sm * (1.0f / 512.0f);
+    const float rs = 1.0f / sqrtf(fmaxf(sq * (1.0f / 512.0f) - mean * mean, 0.f) + 1e-5f);
+    const uint32_t pw[4] = {pr.x, pr.y, pr.z, pr.w};
+    float sc = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float a = __uint_as_float((i & 1) ? (pw[i >> 1] & 0xFFFF0000u) : (pw[i >> 1] << 16));
+      sc = fmaf(pj[i].z, tanh_mufu(fmaf(rs, a - mean * pj[i].x, pj[i].y)), sc);
+    }
+    sc = warp_sum(sc);
+    if (lane == 0) {
+      scores[r] = sc;
+      rowstat[r] = make_float2(mean, rs);
+    }
+  }
+}
+
+int pack_pool256_bf16(bci_lstm_s* h, cudaStream_t st) {
+  const bci_lstm_weights& w = h->raw;
+  pack_attn_w1_kernel<<<ceil_div(256 * 512, 256), 256, 0, st>>>(w.attn_w1, w.ln_w, h->bf16.aw1_bf, 256, 512);
+  pack_attn_par_kernel<<<2, 128, 0, st>>>(w.attn_w1, h->bf16.aw1_bf, w.ln_b, w.attn_b1, w.attn_w2, h->bf16.apar, 256, 512);
+  BCI_CUDA_OK(cudaMemsetAsync(h->bf16.zero_bias, 0, 256 * sizeof(float), st));
+  BCI_LAUNCH_OK();
+  return BCI_OK;
+}
+
+// seq [T][Bc][512] -> logits / probs / attention; pre [M][256] bf16 and rowstat [M] are workspace
+int launch_pool256_bf16(bci_lstm_s* h, const __nv_bfloat16* seq, __nv_bfloat16* pre, float2* rowstat, float* scores, int Bc, int T,
+                        float* logits, float* probs, float* attn, cudaStream_t st) {
+  const long long M = (long long)Bc * T;
+  int rc = launch_proj_gemm_bf16(seq, h->bf16.aw1_bf, h->bf16.zero_bias, pre, (int)M, 256, 512, false, st);
+  if (rc) return rc;
+  long long blocks = (M + 7) / 8;
+  if (blocks > 148ll * 16) blocks = 148ll * 16;
+  attn_score256_kernel<<<(unsigned)blocks, 256, 0, st>>>(seq, pre, h->bf16.apar, scores, rowstat, M);
+  BCI_LAUNCH_OK();
+  const PackedF32& p = h->f32;
+  const size_t smem = pool_finish_smem(512, T);
+  BCI_REQUIRE(smem <= 48 * 1024, BCI_EINVAL, "bf16 pooling (H=256) supports seq_len <= 2500 (got %d)", T);
+  attn_pool_finish_bf16<512><<<ceil_div(Bc, PF_WPC), PF_THREADS, smem, st>>>(seq, scores, rowstat, (long long)Bc, Bc, T, h->cfg.num_classes,
+                                                                            p.lnw, p.lnb, p.c0t, p.cb0, p.c3t, p.cb3, p.c6, p.cb6, logits,
+                                                                            probs, attn);
+  BCI_LAUNCH_OK();
+  return BCI_OK;
+}
+
 int launch_pool_bf16(bci_lstm_s* h, const __nv_bfloat16* seq, float2* stats, float* scores, int Bc, int T, float* logits,
                      float* probs, float* attn, cudaStream_t st) {
   const int M = Bc * T;
@@ -361,9 +454,9 @@ int launch_pool_bf16(bci_lstm_s* h, const __nv_bfloat16* seq, float2* stats, flo
   attn_score_bf16<<<grid, SC_THREADS, SC_SMEM, st>>>(tmA, tmB, h->bf16.apar, stats, b2, scores, M, Bc);
   BCI_LAUNCH_OK();
   const PackedF32& p = h->f32;
-  const size_t smem = (size_t)(2 * T + (PF_THREADS / 32) * 256 + PF_WPC * (256 + 128 + 64) + 8 + PF_WPC * 8) * sizeof(float);
+  const size_t smem = pool_finish_smem(256, T);
   BCI_REQUIRE(smem <= 48 * 1024, BCI_EINVAL, "bf16 pooling supports seq_len <= 4000 (got %d)", T);
-  attn_pool_finish_bf16<<<ceil_div(Bc, PF_WPC), PF_THREADS, smem, st>>>(seq, scores, stats, Bc, T, h->cfg.num_classes, p.lnw, p.lnb, p.c0t, p.cb0,
+  attn_pool_finish_bf16<256><<<ceil_div(Bc, PF_WPC), PF_THREADS, smem, st>>>(seq, scores, stats, 8ll * Bc, Bc, T, h->cfg.num_classes, p.lnw, p.lnb, p.c0t, p.cb0,
                                                        p.c3t, p.cb3, p.c6, p.cb6, logits, probs, attn);
   BCI_LAUNCH_OK();
   return BCI_OK;

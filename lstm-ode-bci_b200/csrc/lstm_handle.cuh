@@ -49,6 +49,7 @@ struct PackedBF16 {
   __nv_bfloat16* wih256[BCI_MAX_LAYERS];    // [2*1024][K_l]  B operand of the projection GEMM
   __nv_bfloat16* whh256[BCI_MAX_LAYERS];    // [2][1024][256] resident operand of the cluster recurrence
   float* bias256[BCI_MAX_LAYERS];           // [2*1024]
+  float* zero_bias;                         // [256] zeros (bias operand of the H = 256 score GEMM)
   // attention scores on tensor cores with LayerNorm folded in (lstm_bf16_pool.cu):
   //   aw1_bf [H][2H] = bf16(W1[j][d] * ln_w[d]);  apar[j] = {s_j = sum_d aw1_bf[j][d], c_j = b1_j + sum_d ln_b[d] W1[j][d], w2_j, 0}
   __nv_bfloat16* aw1_bf;
@@ -143,6 +144,9 @@ int fused_max_clusters();  // co-resident 4-CTA clusters of the fused kernel on 
 // H = 256 bf16 path (lstm_bf16_h256.cu)
 int launch_rec256_bf16(const __nv_bfloat16* G, const __nv_bfloat16* whh, __nv_bfloat16* out, int Bc, int T, cudaStream_t st);
 int pack_h256_bf16(bci_lstm_s* h, cudaStream_t st);
+int pack_pool256_bf16(bci_lstm_s* h, cudaStream_t st);
+int launch_pool256_bf16(bci_lstm_s* h, const __nv_bfloat16* seq, __nv_bfloat16* pre, float2* rowstat, float* scores, int Bc, int T,
+                        float* logits, float* probs, float* attn, cudaStream_t st);
 int launch_proj_gemm_bf16(const __nv_bfloat16* A, const __nv_bfloat16* W, const float* bias, __nv_bfloat16* C, int M, int N, int K,
                           bool blocked, cudaStream_t st);
 
