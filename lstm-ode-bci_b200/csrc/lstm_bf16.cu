@@ -87,6 +87,7 @@ size_t lstm_store_bytes_bf16(const bci_lstm_config& c) {
     for (int l = 0; l < c.num_layers; ++l)
       n += align_up((size_t)2048 * layer_in_width(c, l) * 2, 256) + align_up((size_t)2048 * 256 * 2, 256) + align_up(2048 * 4, 256);
     n += align_up((size_t)256 * 512 * 2, 256) + align_up(256 * sizeof(float4), 256) + align_up(256 * 4, 256);  // attention W1', params, zeros
+    n += align_up((size_t)256 * 64 * 2, 256);                                                                  // input projection W0 (bf16, K padded)
     return n + 1024;
   }
   for (int l = 0; l < c.num_layers; ++l)
@@ -111,6 +112,7 @@ void lstm_carve_bf16(bci_lstm_s* h, char* base) {
     h->bf16.aw1_bf = reinterpret_cast<__nv_bfloat16*>(take((size_t)256 * 512 * 2));
     h->bf16.apar = reinterpret_cast<float4*>(take(256 * sizeof(float4)));
     h->bf16.zero_bias = reinterpret_cast<float*>(take(256 * 4));
+    h->bf16.w0_bf = reinterpret_cast<__nv_bfloat16*>(take((size_t)256 * 64 * 2));
     return;
   }
   for (int l = 0; l < c.num_layers; ++l) {

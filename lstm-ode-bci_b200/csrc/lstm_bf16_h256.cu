@@ -344,6 +344,84 @@ int launch_rec256_bf16(const __nv_bfloat16* G, const __nv_bfloat16* whh, __nv_bf
   return BCI_OK;
 }
 
+// ---- K1 for H = 256: x (B,T,C) fp32 -> bf16 rows [T][Bc][64] -> tcgen05 GEMM (+ b0) -> LayerNorm + GELU row kernel ----------------
+__global__ void x_to_bf16_rows(const float* __restrict__ x, int Bc, int T, int C, __nv_bfloat16* __restrict__ xr) {
+  // one thread per (row, pair of channels); rows are time-major r = t*Bc + b, K padded from C to 64 with zeros
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long rows = (long long)Bc * T;
+  if (i >= rows * 32) return;
+  const long long r = i >> 5;
+  const int k = (int)(i & 31) * 2;
+  const int t = (int)(r / Bc), b = (int)(r - (long long)t * Bc);
+  const float* src = x + ((long long)b * T + t) * C;
+  const float v0 = k < C ? src[k] : 0.f, v1 = (k + 1) < C ? src[k + 1] : 0.f;
+  reinterpret_cast<__nv_bfloat162*>(xr)[i] = __floats2bfloat162_rn(v0, v1);
+}
+
+// z = GELU(LayerNorm(pre)) in place over bf16 rows of 256 (one warp per row, 8 columns per lane); tanh-form GELU as in the
+// H = 128 kernel (lstm_bf16_inproj.cu)
+__global__ void __launch_bounds__(256)
+ln_gelu_rows256(__nv_bfloat16* __restrict__ z, long long rows, const float* __restrict__ lnw, const float* __restrict__ lnb) {
+  const int lane = threadIdx.x & 31;
+  float gw[8], gb[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { gw[i] = lnw[lane * 8 + i]; gb[i] = lnb[lane * 8 + i]; }
+  const long long wstride = (long long)gridDim.x * 8;
+  for (long long r = (long long)blockIdx.x * 8 + (threadIdx.x >> 5); r < rows; r += wstride) {
+    uint4* p = reinterpret_cast<uint4*>(z + r * 256) + lane;
+    const uint4 v = *p;
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    float f[8];
+    float sm = 0.f, sq = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      f[2 * i] = __uint_as_float(w[i] << 16);
+      f[2 * i + 1] = __uint_as_float(w[i] & 0xFFFF0000u);
+      sm += f[2 * i] + f[2 * i + 1];
+      sq = fmaf(f[2 * i], f[2 * i], fmaf(f[2 * i + 1], f[2 * i + 1], sq));
+    }
+    sm = warp_sum(sm);
+    sq = warp_sum(sq);
+    const float mean = sm * (1.0f / 256.0f);
+    const float rstd = 1.0f / sqrtf(fmaxf(sq * (1.0f / 256.0f) - mean * mean, 0.f) + 1e-5f);
+    uint32_t o[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float y[2];
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const float yy = fmaf((f[2 * i + e] - mean) * rstd, gw[2 * i + e], gb[2 * i + e]);
+        const float u = yy * fmaf(0.0356774081f, yy * yy, 0.7978845608f);
+        const float hy = 0.5f * yy;
+        y[e] = fmaf(hy, hr_tanh(u), hy);
+      }
+      __nv_bfloat162 pk = __floats2bfloat162_rn(y[0], y[1]);
+      o[i] = *reinterpret_cast<uint32_t*>(&pk);
+    }
+    *p = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+__global__ void pack_w0_256(const float* __restrict__ w0, __nv_bfloat16* __restrict__ dst, int C) {  // (256, C) -> [256][64] bf16, K zero-padded
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 256 * 64) return;
+  const int j = i >> 6, k = i & 63;
+  dst[i] = __float2bfloat16_rn(k < C ? w0[j * C + k] : 0.f);
+}
+
+static int launch_input_proj256(bci_lstm_s* h, const float* x, int Bc, int T, __nv_bfloat16* xr, __nv_bfloat16* z, cudaStream_t st) {
+  const long long rows = (long long)Bc * T;
+  x_to_bf16_rows<<<(unsigned)ceil_div64(rows * 32, 256), 256, 0, st>>>(x, Bc, T, h->cfg.input_size, xr);
+  BCI_LAUNCH_OK();
+  int rc = launch_proj_gemm_bf16(xr, h->bf16.w0_bf, h->f32.b0, z, (int)rows, 256, 64, false, st);
+  if (rc) return rc;
+  long long blocks = (rows + 7) / 8;
+  if (blocks > 148ll * 16) blocks = 148ll * 16;
+  ln_gelu_rows256<<<(unsigned)blocks, 256, 0, st>>>(z, rows, h->f32.ln0w, h->f32.ln0b);
+  BCI_LAUNCH_OK();
+  return BCI_OK;
+}
+
 int pack_h256_bf16(bci_lstm_s* h, cudaStream_t st) {
   const bci_lstm_config& c = h->cfg;
   const bci_lstm_weights& w = h->raw;
@@ -355,6 +433,7 @@ int pack_h256_bf16(bci_lstm_s* h, cudaStream_t st) {
       pack_bias_perm256<<<4, 256, 0, st>>>(w.b_ih[l][d], w.b_hh[l][d], h->bf16.bias256[l], d * 1024);
     }
   }
+  pack_w0_256<<<64, 256, 0, st>>>(w.input_proj_w, h->bf16.w0_bf, c.input_size);
   BCI_LAUNCH_OK();
   return pack_pool256_bf16(h, st);
 }
@@ -371,7 +450,7 @@ size_t lstm_workspace_h256(const bci_lstm_config& c, int batch, int T) {
   return chunk_bytes_h256(c, Bc > 0 ? Bc : 1, T) + 1024;
 }
 
-// K1 is the generic CUDA-core kernel (bf16 output); the three LSTM layers and the attention scores run on tensor cores
+// every contraction runs on tensor cores: K1 = bf16 row conversion + proj_gemm_bf16 (K = 64) + LayerNorm/GELU row kernel
 int lstm_forward_h256(bci_lstm_s* h, const float* x, int batch, int T, float* logits, float* probs, float* attn, void* ws,
                       size_t ws_bytes, cudaStream_t st) {
   const bci_lstm_config& c = h->cfg;
@@ -391,7 +470,8 @@ int lstm_forward_h256(bci_lstm_s* h, const float* x, int batch, int T, float* lo
     float* scores = reinterpret_cast<float*>(take(rows * 4));
     float2* rowstat = reinterpret_cast<float2*>(take(rows * 8));
     h->prof.mark(-1, st);
-    int rc = launch_input_proj<256, __nv_bfloat16>(h, x + (size_t)b0 * T * c.input_size, Bc, T, z, st);
+    // (x as bf16 rows is staged in the second output buffer, which is not written before layer 1)
+    int rc = launch_input_proj256(h, x + (size_t)b0 * T * c.input_size, Bc, T, o1, z, st);
     if (rc) return rc;
     h->prof.mark(0, st);
     const __nv_bfloat16* in = z;
