@@ -82,9 +82,13 @@ lstm_rec256_bf16(const __nv_bfloat16* __restrict__ G,        // blocked: [row/12
   uint8_t* ctl = gen + HR_OFF_CTL;
   const uint32_t bar0 = smem_u32(ctl);
   // every barrier completes once per step g: parity g & 1
-  const uint32_t acc_full = bar0, h_local = bar0 + 8, h_in = bar0 + 16, st_free = bar0 + 24, peer_local = bar0 + 32,
-                 peer_in = bar0 + 40, copy_done = bar0 + 48, recv_ready = bar0 + 56;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ctl + 64);
+  // acc_full[nb] / h_local[ch]: the two N blocks (= the two 64-unit column halves) are committed and consumed separately, so the
+  // epilogue warps of block 0 start while the MMAs of block 1 run, and the first K-atom of h_t is on its way to the partner
+  // while the second is still being computed
+  const uint32_t acc_full0 = bar0, h_local0 = bar0 + 8, h_in = bar0 + 16, st_free = bar0 + 24, peer_local = bar0 + 32,
+                 peer_in = bar0 + 40, copy_done = bar0 + 48, recv_ready = bar0 + 56, acc_full1 = bar0 + 64, h_local1 = bar0 + 72,
+                 loc_free = bar0 + 80;  // the MMAs that read this CTA's OWN two atoms of h_{t-1} have retired
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ctl + 88);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t rank = cluster_ctarank();
@@ -93,8 +97,11 @@ lstm_rec256_bf16(const __nv_bfloat16* __restrict__ G,        // blocked: [row/12
   const uint32_t partner = (uint32_t)(2 * (1 - p) + s);
 
   if (tid == 0) {
-    mbar_init(acc_full, 1);
-    mbar_init(h_local, HR_EPI_WARPS);
+    mbar_init(acc_full0, 1);
+    mbar_init(acc_full1, 1);
+    mbar_init(loc_free, 1);
+    mbar_init(h_local0, HR_EPI_WARPS / 2);
+    mbar_init(h_local1, HR_EPI_WARPS / 2);
     mbar_init(h_in, 1);
     mbar_init(st_free, 1);
     mbar_init(peer_local, 1);
@@ -151,7 +158,7 @@ lstm_rec256_bf16(const __nv_bfloat16* __restrict__ G,        // blocked: [row/12
           bulk_prefetch_l2(blk + 256ll * 2048 + (lane - 8) * 16384, 16384u);
         // pace: one step of prefetch per step of compute.  Nothing depends on this warp, so it may fall behind and see the
         // barrier two phases later (same parity): bounded polling instead of a wait that could then never return
-        for (int polls = 0; polls < 50000 && !mbar_try_wait(h_local, (uint32_t)((g0 + st) & 1)); ++polls) { }
+        for (int polls = 0; polls < 50000 && !mbar_try_wait(h_local1, (uint32_t)((g0 + st) & 1)); ++polls) { }
       }
     } else if (warp == HR_EPI_WARPS) {
       if (leader && lane == 0) {
@@ -161,7 +168,8 @@ lstm_rec256_bf16(const __nv_bfloat16* __restrict__ G,        // blocked: [row/12
         const uint32_t ack = mapa_u32(copy_done, partner);
         auto wait_h = [&](int gp) {  // h of step gp complete in both CTAs of the pair, accumulator drained
           jit();
-          mbar_wait(h_local, (uint32_t)(gp & 1));
+          mbar_wait(h_local0, (uint32_t)(gp & 1));
+          mbar_wait(h_local1, (uint32_t)(gp & 1));
           mbar_wait_cluster(peer_local, (uint32_t)(gp & 1));
           mbar_wait(h_in, (uint32_t)(gp & 1));
           mbar_arrive_expect_tx(h_in, 2 * HR_ATOM);
@@ -172,17 +180,21 @@ lstm_rec256_bf16(const __nv_bfloat16* __restrict__ G,        // blocked: [row/12
         for (int st = 0; st < T; ++st) {
           const int g = g0 + st;
           if (st > 0) wait_h(g - 1);
+          // h is single-buffered and the epilogue warps of N block 0 start (and overwrite this pair's own atoms 2p, 2p+1 with
+          // h_t) while N block 1 is still being multiplied: block 1 therefore consumes the pair's own atoms FIRST and commits
+          // `loc_free` once those K slices have retired; the other pair's atoms are only replaced after recv_ready (all MMAs done)
 #pragma unroll
           for (int nb = 0; nb < 2; ++nb) {
 #pragma unroll
             for (int k = 0; k < 16; ++k) {
-              const uint32_t atom = k >> 2, kk = k & 3;
+              const uint32_t atom = (uint32_t)(((k >> 2) + 2 * p) & 3), kk = k & 3;
               const uint64_t da = umma_desc_sw128(sH + atom * HR_ATOM + kk * 32);
               const uint64_t db = umma_desc_sw128(sW + (nb * 4 + atom) * HR_ATOM + kk * 32);
               umma_bf16_2sm(tmem_base + nb * 256, da, db, idesc, k != 0 ? 1u : 0u);
+              if (nb == 1 && k == 7) umma_commit_2sm_mc(loc_free, pair_mask);
             }
+            umma_commit_2sm_mc(nb == 0 ? acc_full0 : acc_full1, pair_mask);
           }
-          umma_commit_2sm_mc(acc_full, pair_mask);
         }
         wait_h(g0 + T - 1);
       } else if (!leader && lane == 0) {
@@ -192,7 +204,8 @@ lstm_rec256_bf16(const __nv_bfloat16* __restrict__ G,        // blocked: [row/12
         for (int st = 0; st < T; ++st) {
           const int g = g0 + st;
           jit();
-          mbar_wait(h_local, (uint32_t)(g & 1));
+          mbar_wait(h_local0, (uint32_t)(g & 1));
+          mbar_wait(h_local1, (uint32_t)(g & 1));
           mbar_arrive_cluster_relaxed(pl);
           mbar_wait(h_in, (uint32_t)(g & 1));
           mbar_arrive_expect_tx(h_in, 2 * HR_ATOM);
@@ -208,10 +221,12 @@ lstm_rec256_bf16(const __nv_bfloat16* __restrict__ G,        // blocked: [row/12
           const int g = g0 + st;
           const int t = dir ? (T - 1 - st) : st;
           jit();
-          mbar_wait(h_local, (uint32_t)(g & 1));
-          mbar_wait_cluster(recv_ready, (uint32_t)(g & 1));  // the partner pair's MMA of this step has retired
-          bulk_copy_s2s_cluster(mapa_u32(atoms, partner), atoms, 2 * HR_ATOM, mapa_u32(h_in, partner));
+          mbar_wait(h_local0, (uint32_t)(g & 1));
+          mbar_wait_cluster(recv_ready, (uint32_t)(g & 1));  // the partner pair's MMAs of this step (both N blocks) have retired
+          bulk_copy_s2s_cluster(mapa_u32(atoms, partner), atoms, HR_ATOM, mapa_u32(h_in, partner));
           tma_store_3d(&tmOut, atoms, dir * 256 + 128 * p, b0, t);
+          mbar_wait(h_local1, (uint32_t)(g & 1));
+          bulk_copy_s2s_cluster(mapa_u32(atoms + HR_ATOM, partner), atoms + HR_ATOM, HR_ATOM, mapa_u32(h_in, partner));
           tma_store_3d(&tmOut, atoms + HR_ATOM, dir * 256 + 128 * p + 64, b0, t);
           tma_store_commit();
           tma_store_wait_read();
@@ -245,9 +260,10 @@ lstm_rec256_bf16(const __nv_bfloat16* __restrict__ G,        // blocked: [row/12
         for (int q = 0; q < 4; ++q) gbuf[1][q] = ldg_stream_v4(gp + (4 + q) * 2048);
         if (lane == 0) jit();
         __syncwarp();
-        mbar_wait(acc_full, (uint32_t)(g & 1));
+        mbar_wait(ch == 0 ? acc_full0 : acc_full1, (uint32_t)(g & 1));
         tc_fence_after();
-        if (tid == 0) mbar_arrive_cluster_relaxed(rr);  // MMA of this step retired: the partner may send its atoms of h_g
+        // all MMAs of this step (the second N block is committed last) retired: the partner may send its atoms of h_g
+        if (warp == 4 && lane == 0) mbar_arrive_cluster_relaxed(rr);
 #pragma unroll
         for (int sl = 0; sl < 8; ++sl) {
           uint32_t acc[32];
@@ -281,16 +297,19 @@ lstm_rec256_bf16(const __nv_bfloat16* __restrict__ G,        // blocked: [row/12
             hp[u2] = *reinterpret_cast<uint32_t*>(&pk);
           }
           // the local atoms still hold h_{g-1}: their TMA store and their copy to the partner must have finished reading them
-          if (sl == 0 && g > 0) {
-            mbar_wait(st_free, (uint32_t)((g - 1) & 1));
-            mbar_wait_cluster(copy_done, (uint32_t)((g - 1) & 1));
+          if (sl == 0) {
+            if (g > 0) {
+              mbar_wait(st_free, (uint32_t)((g - 1) & 1));
+              mbar_wait_cluster(copy_done, (uint32_t)((g - 1) & 1));
+            }
+            mbar_wait(loc_free, (uint32_t)(g & 1));  // (N block 0's warps run ahead of N block 1's MMAs)
           }
           *reinterpret_cast<uint4*>(hrow + sw128_chunk_off((uint32_t)r, (uint32_t)sl)) = make_uint4(hp[0], hp[1], hp[2], hp[3]);
         }
         fence_proxy_async_smem();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(h_local);
+        if (lane == 0) mbar_arrive(ch == 0 ? h_local0 : h_local1);
       }
     }
     __syncthreads();
