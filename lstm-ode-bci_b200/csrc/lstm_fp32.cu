@@ -103,8 +103,11 @@ proj_gemm_f32(const float* __restrict__ A, const float* __restrict__ Bt, const f
 constexpr int REC_THREADS = 256;
 constexpr int REC_WPT = 16;  // windows per thread (inference tiles); small training batches use 8 to fill more SMs
 
-template <int H, int REC_WPT = 16>
-__global__ void __launch_bounds__(REC_THREADS, 2)
+// PF = W_hh rows (float4 each) in flight per thread.  Large batches run two CTAs per SM and are FMA-bound: PF = 8 (128-register
+// budget).  Small (training) batches cannot fill the machine: there the L2 round trips of the weight stream are the step time,
+// so the <.., 8, 32> variant runs one CTA per SM with 32 loads in flight (4 round trips per step instead of 16).
+template <int H, int REC_WPT = 16, int PF = 8>
+__global__ void __launch_bounds__(REC_THREADS, PF > 8 ? 1 : 2)
 lstm_rec_f32(const float* __restrict__ G,      // [T][Bc][ND][H][4]
              const float* __restrict__ whh_f,  // [H][H][4] forward direction
              const float* __restrict__ whh_r,  // reverse direction
@@ -142,12 +145,12 @@ lstm_rec_f32(const float* __restrict__ G,      // [T][Bc][ND][H][4]
     // W_hh^T streams from L2 (it does not fit beside h in one SM's smem in fp32): 8 independent 16-byte loads are issued
     // per thread before they are consumed, otherwise each k iteration exposes a full L2 round trip (the first version,
     // unrolled by 2, spent ~36 k cycles per step on exactly that).
-    for (int k0 = 0; k0 < H; k0 += 8) {
-      float4 w8[8];
+    for (int k0 = 0; k0 < H; k0 += PF) {
+      float4 w8[PF];
 #pragma unroll
-      for (int kk = 0; kk < 8; ++kk) w8[kk] = __ldg(W + (long long)(k0 + kk) * H + j);
+      for (int kk = 0; kk < PF; ++kk) w8[kk] = __ldg(W + (long long)(k0 + kk) * H + j);
 #pragma unroll
-      for (int kk = 0; kk < 8; ++kk) {
+      for (int kk = 0; kk < PF; ++kk) {
         const float4 w4 = w8[kk];
         const float4* hp = reinterpret_cast<const float4*>(hcur + (k0 + kk) * HS);
 #pragma unroll
@@ -202,11 +205,14 @@ int launch_rec_f32(int H, int ND, const float* G, const float* whh_f, const floa
   // tiles of 16 windows per thread unless that leaves most SMs idle (training batches): then 8
   const int groups = REC_THREADS / H;
   const bool small = ND * ceil_div(Bc, groups * 16) < sm_count();
+  const bool tiny = ND * ceil_div(Bc, groups * 8) < sm_count();  // even 8-window groups leave SMs idle (training: 512 windows)
   if (H == 128) {
-    if (small) lstm_rec_f32<128, 8><<<dim3(ceil_div(Bc, 2 * 8), ND), REC_THREADS, 0, st>>>(G, whh_f, whh_r, out, gates, csave, Bc, T, ND);
+    if (tiny) lstm_rec_f32<128, 4, 32><<<dim3(ceil_div(Bc, 2 * 4), ND), REC_THREADS, 0, st>>>(G, whh_f, whh_r, out, gates, csave, Bc, T, ND);
+    else if (small) lstm_rec_f32<128, 8, 32><<<dim3(ceil_div(Bc, 2 * 8), ND), REC_THREADS, 0, st>>>(G, whh_f, whh_r, out, gates, csave, Bc, T, ND);
     else lstm_rec_f32<128, 16><<<dim3(ceil_div(Bc, 2 * 16), ND), REC_THREADS, 0, st>>>(G, whh_f, whh_r, out, gates, csave, Bc, T, ND);
   } else {
-    if (small) lstm_rec_f32<256, 8><<<dim3(ceil_div(Bc, 8), ND), REC_THREADS, 0, st>>>(G, whh_f, whh_r, out, gates, csave, Bc, T, ND);
+    if (tiny) lstm_rec_f32<256, 4, 32><<<dim3(ceil_div(Bc, 4), ND), REC_THREADS, 0, st>>>(G, whh_f, whh_r, out, gates, csave, Bc, T, ND);
+    else if (small) lstm_rec_f32<256, 8, 32><<<dim3(ceil_div(Bc, 8), ND), REC_THREADS, 0, st>>>(G, whh_f, whh_r, out, gates, csave, Bc, T, ND);
     else lstm_rec_f32<256, 16><<<dim3(ceil_div(Bc, 16), ND), REC_THREADS, 0, st>>>(G, whh_f, whh_r, out, gates, csave, Bc, T, ND);
   }
   BCI_LAUNCH_OK();
@@ -231,6 +237,16 @@ __global__ void pack_gates_t_kernel(const float* __restrict__ src, float* __rest
   const int row = (int)(i / K), k = (int)(i - (long long)row * K);
   const int gate = row / H, unit = row - gate * H;
   dst[(long long)k * ld + col0 + unit * 4 + gate] = src[i];
+}
+
+// W_hh (4H, H) gate-major rows -> dst [unit][j][gate]: one float4 = the four gate rows of `unit` at input column j (BPTT reads
+// dh_{t-1}[j] = sum_n dG[n] W_hh[n][j] with coalesced 16-byte loads over j)
+__global__ void pack_whh_b4_kernel(const float* __restrict__ src, float* __restrict__ dst, int H) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)4 * H * H) return;
+  const int row = (int)(i / H), j = (int)(i - (long long)row * H);
+  const int gate = row / H, unit = row - gate * H;
+  dst[((long long)unit * H + j) * 4 + gate] = src[i];
 }
 
 // src (4H, K) gate-major rows -> dst [row0 + unit*4 + gate][K]
@@ -274,7 +290,7 @@ int lstm_pack_f32(bci_lstm_s* h, cudaStream_t st) {
       pack_gates_t_kernel<<<nblk((long long)4 * H * H), 256, 0, st>>>(w.w_hh[l][d], p.whh_t[l][d], H, H, 4 * H, 0);
       pack_bias_kernel<<<nblk(4 * H), 256, 0, st>>>(w.b_ih[l][d], w.b_hh[l][d], p.bias[l], H, d * 4 * H);
       pack_gates_rows_kernel<<<nblk((long long)4 * H * K), 256, 0, st>>>(w.w_ih[l][d], p.wih_b[l], H, K, d * 4 * H);
-      pack_gates_rows_kernel<<<nblk((long long)4 * H * H), 256, 0, st>>>(w.w_hh[l][d], p.whh_b[l][d], H, H, 0);
+      pack_whh_b4_kernel<<<nblk((long long)4 * H * H), 256, 0, st>>>(w.w_hh[l][d], p.whh_b[l][d], H);
     }
   }
   if (c.use_layer_norm) {

@@ -18,7 +18,7 @@ struct PackedF32 {
   float* whh_t[BCI_MAX_LAYERS][2];  // [H][4H]     per direction, gate-interleaved
   // row-major copies with gate-interleaved ROWS (n = dir*4H + unit*4 + gate), used by the backward pass:
   float* wih_b[BCI_MAX_LAYERS];     // [ND*4H][K_l] din = dG . wih_b
-  float* whh_b[BCI_MAX_LAYERS][2];  // [4H][H]     dh_{t-1} = dG_t . whh_b
+  float* whh_b[BCI_MAX_LAYERS][2];  // [H unit][H j][4 gates]  dh_{t-1}[j] = sum_(unit,gate) dG_t . whh_b
   float* lnw;    // [D]         D = ND*H
   float* lnb;    // [D]
   float* aw1t;   // [D][D/2]    attention.0.weight^T

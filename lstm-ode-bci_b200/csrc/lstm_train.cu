@@ -596,7 +596,7 @@ __global__ void __launch_bounds__(BP_THREADS, 1)
 lstm_bptt_f32(const float* __restrict__ dout,    // [T][Bc][ND*H]  grad wrt the layer output
               const float* __restrict__ gates,   // [T][Bc][ND][H][4] post-activation i,f,g,o
               const float* __restrict__ csave,   // [T][Bc][ND][H]
-              const float* __restrict__ whh_bf,  // [4H][H] gate-interleaved rows, forward direction
+              const float* __restrict__ whh_bf,  // [unit][j][4 gates] (float4 per (unit, j)), forward direction
               const float* __restrict__ whh_br,  // reverse direction
               float* __restrict__ dG,            // [T][Bc][ND][H][4]
               int Bc, int T, int ND) {
@@ -605,7 +605,7 @@ lstm_bptt_f32(const float* __restrict__ dout,    // [T][Bc][ND*H]  grad wrt the 
   const int tid = threadIdx.x, j = tid % H, grp = tid / H;
   const int dir = blockIdx.y;
   const int b_base = blockIdx.x * MT + grp * BP_WPT;
-  const float* __restrict__ W = dir ? whh_br : whh_bf;
+  const float4* __restrict__ W = reinterpret_cast<const float4*>(dir ? whh_br : whh_bf);
   float dh_rec[BP_WPT], dc[BP_WPT];
 #pragma unroll
   for (int w = 0; w < BP_WPT; ++w) { dh_rec[w] = 0.f; dc[w] = 0.f; }
@@ -641,21 +641,27 @@ lstm_bptt_f32(const float* __restrict__ dout,    // [T][Bc][ND*H]  grad wrt the 
 #pragma unroll
     for (int w = 0; w < BP_WPT; ++w) acc[w] = 0.f;
     const float* gsrc = bp_smem + grp * BP_WPT;
-    // 16 independent weight loads in flight per thread (see lstm_rec_f32: the L2 round trip must not be paid per row)
-    for (int n0 = 0; n0 < 4 * H; n0 += 16) {
-      float wv[16];
+    // 32 independent 16-byte weight loads (= 128 rows of W_hh) in flight per thread: with training batches the machine is not
+    // full and the L2 round trips of this stream ARE the step time (the first version had 16 four-byte loads in flight:
+    // 32 round trips per step, 31 us; this one pays H/32 round trips)
+    for (int u0 = 0; u0 < H; u0 += 32) {
+      float4 wv[32];
 #pragma unroll
-      for (int nn = 0; nn < 16; ++nn) wv[nn] = __ldg(W + (long long)(n0 + nn) * H + j);
+      for (int uu = 0; uu < 32; ++uu) wv[uu] = __ldg(W + (long long)(u0 + uu) * H + j);
 #pragma unroll
-      for (int nn = 0; nn < 16; ++nn) {
-        const float4* gp = reinterpret_cast<const float4*>(gsrc + (n0 + nn) * GS);
+      for (int uu = 0; uu < 32; ++uu) {
+        const float wg[4] = {wv[uu].x, wv[uu].y, wv[uu].z, wv[uu].w};
 #pragma unroll
-        for (int q = 0; q < BP_WPT / 4; ++q) {
-          const float4 g4 = gp[q];
-          acc[q * 4 + 0] = fmaf(g4.x, wv[nn], acc[q * 4 + 0]);
-          acc[q * 4 + 1] = fmaf(g4.y, wv[nn], acc[q * 4 + 1]);
-          acc[q * 4 + 2] = fmaf(g4.z, wv[nn], acc[q * 4 + 2]);
-          acc[q * 4 + 3] = fmaf(g4.w, wv[nn], acc[q * 4 + 3]);
+        for (int gsel = 0; gsel < 4; ++gsel) {
+          const float4* gp = reinterpret_cast<const float4*>(gsrc + ((u0 + uu) * 4 + gsel) * GS);
+#pragma unroll
+          for (int q = 0; q < BP_WPT / 4; ++q) {
+            const float4 g4 = gp[q];
+            acc[q * 4 + 0] = fmaf(g4.x, wg[gsel], acc[q * 4 + 0]);
+            acc[q * 4 + 1] = fmaf(g4.y, wg[gsel], acc[q * 4 + 1]);
+            acc[q * 4 + 2] = fmaf(g4.z, wg[gsel], acc[q * 4 + 2]);
+            acc[q * 4 + 3] = fmaf(g4.w, wg[gsel], acc[q * 4 + 3]);
+          }
         }
       }
     }
@@ -841,12 +847,15 @@ static int backward_t(bci_lstm_s* h, const float* dlogits, int B, int T, float p
   // ---- LSTM layers, top down ----
   // 16 windows per thread unless that leaves most SMs idle (typical training batches): then 8
   const bool small = ND * ceil_div(B, (BP_THREADS / H) * 16) < sm_count();
-  const int MT = (BP_THREADS / H) * (small ? 8 : 16);
+  const bool tiny = ND * ceil_div(B, (BP_THREADS / H) * 8) < sm_count();
+  const int MT = (BP_THREADS / H) * (tiny ? 4 : small ? 8 : 16);
   const size_t bp_smem = (size_t)4 * H * (MT + 4) * sizeof(float);
   static bool attr = false;
   if (!attr) {
     BCI_CUDA_OK(cudaFuncSetAttribute(lstm_bptt_f32<H, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)((size_t)4 * H * ((BP_THREADS / H) * 16 + 4) * sizeof(float))));
+    BCI_CUDA_OK(cudaFuncSetAttribute(lstm_bptt_f32<H, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)((size_t)4 * H * ((BP_THREADS / H) * 4 + 4) * sizeof(float))));
     BCI_CUDA_OK(cudaFuncSetAttribute(lstm_bptt_f32<H, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)((size_t)4 * H * ((BP_THREADS / H) * 8 + 4) * sizeof(float))));
     attr = true;
@@ -854,7 +863,9 @@ static int backward_t(bci_lstm_s* h, const float* dlogits, int B, int T, float p
   for (int l = L - 1; l >= 0; --l) {
     const int K = layer_in_width(c, l);
     const float* in = (l == 0) ? w.z : w.outd[l - 1];
-    if (small)
+    if (tiny)
+      lstm_bptt_f32<H, 4><<<dim3(ceil_div(B, MT), ND), BP_THREADS, bp_smem, st>>>(dcur, w.gates[l], w.cst[l], p.whh_b[l][0], p.whh_b[l][1], w.G, B, T, ND);
+    else if (small)
       lstm_bptt_f32<H, 8><<<dim3(ceil_div(B, MT), ND), BP_THREADS, bp_smem, st>>>(dcur, w.gates[l], w.cst[l], p.whh_b[l][0], p.whh_b[l][1], w.G, B, T, ND);
     else
       lstm_bptt_f32<H, 16><<<dim3(ceil_div(B, MT), ND), BP_THREADS, bp_smem, st>>>(dcur, w.gates[l], w.cst[l], p.whh_b[l][0], p.whh_b[l][1], w.G, B, T, ND);
