@@ -109,6 +109,10 @@ extern "C" int bci_lstm_destroy(bci_lstm_t h) {
   if (!h) return BCI_OK;
   if (h->store) cudaFree(h->store);
   if (h->prof.created) for (int i = 0; i < Profiler::MAX_EV; ++i) cudaEventDestroy(h->prof.ev[i]);
+  if (h->side_ready) {
+    cudaStreamDestroy(h->side);
+    cudaEventDestroy(h->ev_dg); cudaEventDestroy(h->ev_side[0]); cudaEventDestroy(h->ev_side[1]); cudaEventDestroy(h->ev_join);
+  }
   delete h;
   return BCI_OK;
 }

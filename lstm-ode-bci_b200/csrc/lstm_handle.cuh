@@ -91,6 +91,10 @@ struct bci_lstm_s {
   // raw (unpacked) weight pointers of the last load_weights (caller-owned; used by backward)
   bci_lstm_weights raw;
   bci::Profiler prof;
+  // side stream of the backward pass (weight-gradient GEMMs of layer l overlap the BPTT recurrence of layer l-1)
+  cudaStream_t side;
+  cudaEvent_t ev_dg, ev_side[2], ev_join;
+  bool side_ready;
 };
 
 namespace bci {

@@ -706,7 +706,10 @@ __global__ void untranspose_x_kernel(const float* __restrict__ src, float* __res
 struct TrainWs {
   float *xT, *xhat0, *rstd0, *z;
   float *gates[BCI_MAX_LAYERS], *cst[BCI_MAX_LAYERS], *out[BCI_MAX_LAYERS], *outd[BCI_MAX_LAYERS];
-  float *G;                 // forward: projected inputs; backward: dG
+  float *G;                 // forward: projected inputs; backward: dG of layers l = L-1, L-3, ...
+  float *G2;                // backward: dG of layers L-2, L-4, ... (the weight-gradient GEMMs of layer l read dG(l) on a side stream
+                            // while BPTT of layer l-1 writes the other buffer)
+  float *tmpW2;             // scratch of the side stream
   float *xhatF, *rstdF, *Y, *PRE, *attn, *ctx, *pre1, *h1d, *pre2, *h2d;
   float *dA, *dB;           // [M][2H] gradient ping-pong
   float *dctx, *dpre1, *dpre2, *tmpW, *hdr;
@@ -725,12 +728,14 @@ static void carve_train(const bci_lstm_config& c, int B, int T, float p_drop, ch
     w.outd[l] = (p_drop > 0.f && l < c.num_layers - 1) ? take(M * D) : w.out[l];
   }
   w.G = take(M * 4 * D);
+  w.G2 = take(M * 4 * D);
   w.xhatF = take(M * D); w.rstdF = take(M); w.Y = take(M * D); w.PRE = take(M * (D / 2));
   w.attn = take((size_t)B * T); w.ctx = take(B * D); w.pre1 = take(B * H); w.h1d = take(B * H);
   w.pre2 = take(B * (H / 2)); w.h2d = take(B * (H / 2));
   w.dA = take(M * D); w.dB = take(M * D);
   w.dctx = take(B * D); w.dpre1 = take(B * H); w.dpre2 = take(B * (H / 2));
   w.tmpW = take(4 * D * (D > H ? D : H) + 1024);
+  w.tmpW2 = take(4 * D * (D > H ? D : H) + 1024);
   w.total = off;
 }
 
@@ -809,6 +814,7 @@ static int backward_t(bci_lstm_s* h, const float* dlogits, int B, int T, float p
   const long long M = (long long)B * T;
   const int rb = (int)((M + 7) / 8 < 4096 ? (M + 7) / 8 : 4096);
   auto zero = [&](float* ptr, size_t n) { return cudaMemsetAsync(ptr, 0, n * sizeof(float), st); };
+  auto zero_on = [&](cudaStream_t s2, float* ptr, size_t n) { return cudaMemsetAsync(ptr, 0, n * sizeof(float), s2); };
   int rc;
   // ---- head ----
   head_train_bwd<H><<<B, H, 0, st>>>(dlogits, cls, w.pre1, w.pre2, raw.cls_w6, raw.cls_w3, raw.cls_w0, w.dpre1, w.dpre2, w.dctx,
@@ -860,42 +866,61 @@ static int backward_t(bci_lstm_s* h, const float* dlogits, int B, int T, float p
                                      (int)((size_t)4 * H * ((BP_THREADS / H) * 8 + 4) * sizeof(float))));
     attr = true;
   }
+  // side stream: everything that only produces weight gradients of layer l (it needs dG(l), the layer's input and output, all
+  // final by then) runs beside the BPTT recurrence of layer l-1, which at training batch sizes leaves most of the machine idle
+  if (!h->side_ready) {
+    BCI_CUDA_OK(cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking));
+    BCI_CUDA_OK(cudaEventCreateWithFlags(&h->ev_dg, cudaEventDisableTiming));
+    BCI_CUDA_OK(cudaEventCreateWithFlags(&h->ev_side[0], cudaEventDisableTiming));
+    BCI_CUDA_OK(cudaEventCreateWithFlags(&h->ev_side[1], cudaEventDisableTiming));
+    BCI_CUDA_OK(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
+    h->side_ready = true;
+  }
+  cudaStream_t sd = h->side;
+  int used[2] = {0, 0};
   for (int l = L - 1; l >= 0; --l) {
     const int K = layer_in_width(c, l);
     const float* in = (l == 0) ? w.z : w.outd[l - 1];
+    const int gb = (L - 1 - l) & 1;
+    float* dGl = gb ? w.G2 : w.G;
+    if (used[gb]) BCI_CUDA_OK(cudaStreamWaitEvent(st, h->ev_side[gb], 0));  // the side stream has finished reading this buffer
     if (tiny)
-      lstm_bptt_f32<H, 4><<<dim3(ceil_div(B, MT), ND), BP_THREADS, bp_smem, st>>>(dcur, w.gates[l], w.cst[l], p.whh_b[l][0], p.whh_b[l][1], w.G, B, T, ND);
+      lstm_bptt_f32<H, 4><<<dim3(ceil_div(B, MT), ND), BP_THREADS, bp_smem, st>>>(dcur, w.gates[l], w.cst[l], p.whh_b[l][0], p.whh_b[l][1], dGl, B, T, ND);
     else if (small)
-      lstm_bptt_f32<H, 8><<<dim3(ceil_div(B, MT), ND), BP_THREADS, bp_smem, st>>>(dcur, w.gates[l], w.cst[l], p.whh_b[l][0], p.whh_b[l][1], w.G, B, T, ND);
+      lstm_bptt_f32<H, 8><<<dim3(ceil_div(B, MT), ND), BP_THREADS, bp_smem, st>>>(dcur, w.gates[l], w.cst[l], p.whh_b[l][0], p.whh_b[l][1], dGl, B, T, ND);
     else
-      lstm_bptt_f32<H, 16><<<dim3(ceil_div(B, MT), ND), BP_THREADS, bp_smem, st>>>(dcur, w.gates[l], w.cst[l], p.whh_b[l][0], p.whh_b[l][1], w.G, B, T, ND);
+      lstm_bptt_f32<H, 16><<<dim3(ceil_div(B, MT), ND), BP_THREADS, bp_smem, st>>>(dcur, w.gates[l], w.cst[l], p.whh_b[l][0], p.whh_b[l][1], dGl, B, T, ND);
     BCI_LAUNCH_OK();
+    BCI_CUDA_OK(cudaEventRecord(h->ev_dg, st));
+    BCI_CUDA_OK(cudaStreamWaitEvent(sd, h->ev_dg, 0));
     // dW_ih (all directions at once, interleaved rows) = dG^T . in
-    BCI_CUDA_OK(zero(w.tmpW, (size_t)G4 * K));
-    if ((rc = gemm_tn(w.G, G4, in, K, w.tmpW, K, M, G4, K, st))) return rc;
+    BCI_CUDA_OK(zero_on(sd, w.tmpW2, (size_t)G4 * K));
+    if ((rc = gemm_tn(dGl, G4, in, K, w.tmpW2, K, M, G4, K, sd))) return rc;
     for (int d = 0; d < ND; ++d) {
-      unpack_gate_rows_kernel<<<(unsigned)ceil_div64((long long)4 * H * K, 256), 256, 0, st>>>(w.tmpW, g->w_ih[l][d], H, K, d * 4 * H);
+      unpack_gate_rows_kernel<<<(unsigned)ceil_div64((long long)4 * H * K, 256), 256, 0, sd>>>(w.tmpW2, g->w_ih[l][d], H, K, d * 4 * H);
       BCI_LAUNCH_OK();
     }
     // dW_hh[d] = dG[:, d]^T . h_prev, h_prev(t) = out[t-1] (forward) / out[t+1] (reverse): a row shift by Bc rows
     for (int d = 0; d < ND; ++d) {
-      BCI_CUDA_OK(zero(w.tmpW, (size_t)4 * H * H));
+      BCI_CUDA_OK(zero_on(sd, w.tmpW2, (size_t)4 * H * H));
       const long long R = M - B;
-      const float* Ad = w.G + d * 4 * H + (d == 0 ? (long long)B * G4 : 0);
+      const float* Ad = dGl + d * 4 * H + (d == 0 ? (long long)B * G4 : 0);
       const float* Bd = w.out[l] + d * H + (d == 0 ? 0 : (long long)B * D);
-      if ((rc = gemm_tn(Ad, G4, Bd, D, w.tmpW, H, R, 4 * H, H, st))) return rc;
-      unpack_gate_rows_kernel<<<(unsigned)ceil_div64((long long)4 * H * H, 256), 256, 0, st>>>(w.tmpW, g->w_hh[l][d], H, H, 0);
+      if ((rc = gemm_tn(Ad, G4, Bd, D, w.tmpW2, H, R, 4 * H, H, sd))) return rc;
+      unpack_gate_rows_kernel<<<(unsigned)ceil_div64((long long)4 * H * H, 256), 256, 0, sd>>>(w.tmpW2, g->w_hh[l][d], H, H, 0);
       BCI_LAUNCH_OK();
     }
     // biases
-    BCI_CUDA_OK(zero(w.tmpW, (size_t)G4));
-    if ((rc = colsum(w.G, G4, M, G4, w.tmpW, st))) return rc;
+    BCI_CUDA_OK(zero_on(sd, w.tmpW2, (size_t)G4));
+    if ((rc = colsum(dGl, G4, M, G4, w.tmpW2, sd))) return rc;
     for (int d = 0; d < ND; ++d) {
-      unpack_bias_kernel<<<ceil_div(4 * H, 256), 256, 0, st>>>(w.tmpW, g->b_ih[l][d], g->b_hh[l][d], H, d * 4 * H);
+      unpack_bias_kernel<<<ceil_div(4 * H, 256), 256, 0, sd>>>(w.tmpW2, g->b_ih[l][d], g->b_hh[l][d], H, d * 4 * H);
       BCI_LAUNCH_OK();
     }
+    BCI_CUDA_OK(cudaEventRecord(h->ev_side[gb], sd));
+    used[gb] = 1;
     // grad wrt the layer input: dnext [M][K] = dG . wih_b
-    if ((rc = gemm_nn(w.G, G4, p.wih_b[l], K, dnext, K, (int)M, K, G4, nullptr, 0, st))) return rc;
+    if ((rc = gemm_nn(dGl, G4, p.wih_b[l], K, dnext, K, (int)M, K, G4, nullptr, 0, st))) return rc;
     if (l > 0 && w.outd[l - 1] != w.out[l - 1]) {
       scale_mask_kernel<<<(unsigned)ceil_div64(M * K, 256), 256, 0, st>>>(dnext, dnext, M * K, p_drop, seed, 16 + (l - 1));
       BCI_LAUNCH_OK();
@@ -916,6 +941,9 @@ static int backward_t(bci_lstm_s* h, const float* dlogits, int B, int T, float p
     untranspose_x_kernel<<<(unsigned)ceil_div64(M * C, 256), 256, 0, st>>>(dcur, dx, B, T, C);
     BCI_LAUNCH_OK();
   }
+  // the caller's stream owns every gradient again
+  BCI_CUDA_OK(cudaEventRecord(h->ev_join, sd));
+  BCI_CUDA_OK(cudaStreamWaitEvent(st, h->ev_join, 0));
   return BCI_OK;
 }
 
