@@ -7,6 +7,7 @@ import ctypes as C
 import os
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
+ABI_VERSION = 2   # include/bci_b200.h: BCI_ABI_VERSION
 LIB_PATH = os.path.join(_PKG, "lib", "libbci_b200.so")
 
 BCI_MAX_LAYERS = 4
@@ -128,7 +129,7 @@ def lib():
             fn = getattr(l, name)
             fn.restype = res
             fn.argtypes = args
-        if l.bci_abi_version() != 2:
+        if l.bci_abi_version() != ABI_VERSION:
             raise BciError(-1, "ABI version mismatch")
         _lib = l
     return _lib

@@ -34,9 +34,16 @@ def test_ctypes_mirror_matches_header(libpath):
     from lstm_ode_bci_b200 import _native
     assert sorted(_native.SIGNATURES) == _declared()
     lib = _native.lib()
-    assert lib.bci_abi_version() == 2
+    hdr = open(os.path.join(ROOT, "include", "bci_b200.h")).read()
+    assert lib.bci_abi_version() == _native.ABI_VERSION == int(re.search(r"#define BCI_ABI_VERSION (\d+)", hdr).group(1))
     for name in _native.SIGNATURES:
         assert getattr(lib, name) is not None
+
+
+def test_graft_entry_build(libpath):
+    """The driver's build hook: compiles (or finds current) the library, imports the package, checks the ABI version."""
+    import __graft_entry__ as g
+    assert g.build() == libpath
 
 
 def test_library_is_sm100a_only(libpath):
