@@ -229,6 +229,27 @@ typedef struct {
  * CognitiveStateODE.solve / predict_trajectory themselves: one launch, one thread per trajectory. */
 int bci_ode_solve(const bci_ode_args* args, void* stream);
 
+/* replaces CognitiveStateODE.solve_with_modulation (05_ode_model.py:171-196): rates that vary with time.  The reference
+ * calls a Python `modulation_func(t, params)` from inside LSODA; here the caller samples it once at the stage times of a
+ * fixed-step RK4 -- node m at t0 + m*h/2, h = t_span / (n_points-1) / substeps, M = 2*substeps*(n_points-1) + 1 nodes,
+ * rate order k_ap,k_af,k_pa,k_pf,k_fa,k_fp -- and N trajectories integrate in one launch (fp64).
+ *   rate_nodes  (M,6) fp64 shared by all trajectories, or (M,6,N) when per_trajectory != 0
+ *   y0          (3,N) fp64 SoA;  style REF06: y0 /= sum, max(0,.) clamp, clip + renormalise (05:184-194); REF08: raw
+ *   traj        optional (N,n_points,3) fp64;  final_state optional (N,3) fp64 */
+typedef struct {
+  int64_t n;
+  int32_t style;
+  int32_t n_points;
+  int32_t substeps;
+  int32_t per_trajectory;
+  double t_span;
+  const double* rate_nodes;
+  const double* y0;
+  double* traj;
+  double* final_state;
+} bci_ode_mod_args;
+int bci_ode_solve_modulated(const bci_ode_mod_args* args, void* stream);
+
 /* replaces the read-outs that follow the solve:
  *   pred06[i]  = traj_last[i].F > 0.5                          (06:396-401)
  *   cls10[i]   = 2 if F > .5 else 0 if A > .5 else 1           (10:282-288)

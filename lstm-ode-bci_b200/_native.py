@@ -60,6 +60,12 @@ class OdeArgs(C.Structure):
                 ("traj", _FP), ("final_state", _FP), ("n_steps", _FP)]
 
 
+class OdeModArgs(C.Structure):
+    _fields_ = [("n", C.c_int64), ("style", C.c_int32), ("n_points", C.c_int32), ("substeps", C.c_int32),
+                ("per_trajectory", C.c_int32), ("t_span", C.c_double), ("rate_nodes", _FP), ("y0", _FP),
+                ("traj", _FP), ("final_state", _FP)]
+
+
 class PreprocArgs(C.Structure):
     _fields_ = [("n_recordings", C.c_int32), ("n_channels", C.c_int32), ("n_samples", C.c_int64), ("in_dtype", C.c_int32),
                 ("order", C.c_int32), ("b_host", C.POINTER(C.c_double)), ("a_host", C.POINTER(C.c_double)),
@@ -96,6 +102,7 @@ SIGNATURES = {
     "bci_preprocess_workspace_bytes": (C.c_int, [C.POINTER(PreprocArgs), C.POINTER(C.c_size_t)]),
     "bci_preprocess": (C.c_int, [C.POINTER(PreprocArgs), _FP, _FP, _FP, _FP, _FP, _FP, C.c_size_t, C.c_void_p]),
     "bci_ode_solve": (C.c_int, [C.POINTER(OdeArgs), C.c_void_p]),
+    "bci_ode_solve_modulated": (C.c_int, [C.POINTER(OdeModArgs), C.c_void_p]),
     "bci_ode_classify": (C.c_int, [_FP, C.c_int64, _FP, _FP, C.c_void_p]),
     "bci_ode_forecast_readout": (C.c_int, [_FP, C.c_int64, C.c_int32, C.POINTER(C.c_int32), C.c_int32, _FP, C.c_void_p]),
     "bci_selftest_proj_gemm_bf16": (C.c_int, [_FP, _FP, _FP, _FP, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),

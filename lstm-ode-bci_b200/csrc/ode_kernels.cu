@@ -403,6 +403,75 @@ ode_rk45_kernel(const OdeParams P) {
   if (P.n_steps) P.n_steps[i] = steps;
 }
 
+// ---- RK4 with time-varying rates (fp64) -----------------------------------------------------
+// CognitiveStateODE.solve_with_modulation (05_ode_model.py:171-196): the reference lets LSODA call a Python
+// `modulation_func(t, params)` at every right-hand-side evaluation.  Here the host samples that callback ONCE at the
+// stage times of a fixed-step RK4 -- node m sits at t0 + m*h/2, M = 2*S*(n_points-1) + 1 nodes -- so the stages read the
+// rates at exactly t, t + h/2 and t + h (no interpolation), and the ensemble integrates in one launch.  The node table is
+// either shared by all trajectories ((M,6), every lane reads the same address: a broadcast) or per trajectory ((M,6,N)
+// structure-of-arrays, coalesced).  fp64 throughout: this is an analysis path, its cost is the host callback.
+struct OdeModParams {
+  long long n;
+  int n_points, substeps, per_trajectory;
+  double t_span;
+  const double* nodes;
+  const double* y0;
+  double* traj;
+  double* final_state;
+};
+
+__device__ __forceinline__ void load_node(const OdeModParams& P, long long i, long long m, double k[6]) {
+#pragma unroll
+  for (int r = 0; r < 6; ++r)
+    k[r] = P.per_trajectory ? __ldg(P.nodes + (m * 6 + r) * P.n + i) : __ldg(P.nodes + m * 6 + r);
+}
+
+template <bool CLAMP>
+__global__ void __launch_bounds__(ODE_BLOCK) ode_rk4_modulated_kernel(OdeModParams P) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= P.n) return;
+  double A = __ldg(P.y0 + i), Pq = __ldg(P.y0 + P.n + i), F = __ldg(P.y0 + 2 * P.n + i);
+  if (CLAMP) {  // 05:184  initial_state / sum(initial_state)
+    const double s = (A + Pq) + F;
+    A /= s; Pq /= s; F /= s;
+  }
+  auto emit = [&](int j) {
+    double a = A, p = Pq, f = F;
+    if (CLAMP) post06<double>(a, p, f);  // 05:193-194
+    if (P.traj) {
+      double* o = P.traj + (i * P.n_points + j) * 3;
+      o[0] = a; o[1] = p; o[2] = f;
+    }
+    if (P.final_state && j == P.n_points - 1) {
+      double* o = P.final_state + i * 3;
+      o[0] = a; o[1] = p; o[2] = f;
+    }
+  };
+  emit(0);
+  const double h = P.t_span / (double)(P.n_points - 1) / (double)P.substeps;
+  const double hh = 0.5 * h, h6 = h / 6.0;
+  double k0[6], k1[6], k2[6], d1[3], d2[3], d3[3], d4[3];
+  long long m = 0;
+  load_node(P, i, 0, k0);
+  for (int j = 1; j < P.n_points; ++j) {
+    for (int s = 0; s < P.substeps; ++s) {
+      load_node(P, i, m + 1, k1);
+      load_node(P, i, m + 2, k2);
+      rhs64<CLAMP>(k0, A, Pq, F, d1);
+      rhs64<CLAMP>(k1, A + hh * d1[0], Pq + hh * d1[1], F + hh * d1[2], d2);
+      rhs64<CLAMP>(k1, A + hh * d2[0], Pq + hh * d2[1], F + hh * d2[2], d3);
+      rhs64<CLAMP>(k2, A + h * d3[0], Pq + h * d3[1], F + h * d3[2], d4);
+      A += h6 * ((d1[0] + d4[0]) + 2.0 * (d2[0] + d3[0]));
+      Pq += h6 * ((d1[1] + d4[1]) + 2.0 * (d2[1] + d3[1]));
+      F += h6 * ((d1[2] + d4[2]) + 2.0 * (d2[2] + d3[2]));
+#pragma unroll
+      for (int r = 0; r < 6; ++r) k0[r] = k2[r];
+      m += 2;
+    }
+    emit(j);
+  }
+}
+
 // ---- read-outs ------------------------------------------------------------------------------
 __global__ void ode_classify_kernel(const float* __restrict__ fs, long long n, int* pred06, int* cls10) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -485,6 +554,26 @@ extern "C" int bci_ode_solve(const bci_ode_args* a, void* stream) {
   const bool clamp = a->style == BCI_ODE_STYLE_REF06;
   if (a->out_dtype == BCI_OUT_F32) return clamp ? launch_ode<true, float>(P, a->mode, st) : launch_ode<false, float>(P, a->mode, st);
   return clamp ? launch_ode<true, double>(P, a->mode, st) : launch_ode<false, double>(P, a->mode, st);
+}
+
+extern "C" int bci_ode_solve_modulated(const bci_ode_mod_args* a, void* stream) {
+  BCI_REQUIRE(a != nullptr, BCI_EINVAL, "bci_ode_solve_modulated: args is NULL");
+  BCI_REQUIRE(a->style == BCI_ODE_STYLE_REF06 || a->style == BCI_ODE_STYLE_REF08, BCI_EINVAL, "bci_ode_solve_modulated: bad style %d", a->style);
+  BCI_REQUIRE(a->n >= 0, BCI_EINVAL, "bci_ode_solve_modulated: negative n");
+  BCI_REQUIRE(a->n_points >= 2, BCI_EINVAL, "bci_ode_solve_modulated: n_points must be >= 2 (got %d)", a->n_points);
+  BCI_REQUIRE(a->substeps >= 1, BCI_EINVAL, "bci_ode_solve_modulated: substeps must be >= 1");
+  BCI_REQUIRE(a->t_span > 0.0, BCI_EINVAL, "bci_ode_solve_modulated: t_span must be > 0");
+  if (a->n == 0) return BCI_OK;
+  BCI_REQUIRE(a->rate_nodes && a->y0, BCI_EINVAL, "bci_ode_solve_modulated: rate_nodes and y0 are required");
+  BCI_REQUIRE(a->traj || a->final_state, BCI_EINVAL, "bci_ode_solve_modulated: no output requested");
+  OdeModParams P;
+  P.n = a->n; P.n_points = a->n_points; P.substeps = a->substeps; P.per_trajectory = a->per_trajectory ? 1 : 0;
+  P.t_span = a->t_span; P.nodes = a->rate_nodes; P.y0 = a->y0; P.traj = a->traj; P.final_state = a->final_state;
+  const unsigned grid = (unsigned)ceil_div64(P.n, ODE_BLOCK);
+  if (a->style == BCI_ODE_STYLE_REF06) ode_rk4_modulated_kernel<true><<<grid, ODE_BLOCK, 0, (cudaStream_t)stream>>>(P);
+  else ode_rk4_modulated_kernel<false><<<grid, ODE_BLOCK, 0, (cudaStream_t)stream>>>(P);
+  BCI_LAUNCH_OK();
+  return BCI_OK;
 }
 
 extern "C" int bci_ode_classify(const float* fs, int64_t n, int32_t* pred06, int32_t* cls10, void* stream) {

@@ -58,6 +58,43 @@ def solve_ensemble(n, *, p_open=None, p_closed=None, rates=None, base_rates=None
                             bool(want_traj), bool(want_steps), bool(f64), dev.index)
 
 
+def modulation_nodes(t0, t1, n_points, substeps):
+    """Times at which a fixed-step RK4 with `substeps` steps per output interval evaluates its stages:
+    node m at t0 + m*h/2, M = 2*substeps*(n_points-1) + 1 (include/bci_b200.h: bci_ode_solve_modulated)."""
+    m = 2 * int(substeps) * (int(n_points) - 1) + 1
+    return np.linspace(float(t0), float(t1), m)
+
+
+def solve_modulated_ensemble(y0, rate_nodes, t_span, n_points, substeps, style="ref06", want_traj=True, device=None):
+    """N trajectories with time-varying rates in one launch (fp64; 05_ode_model.py:171-196 batched).
+
+    y0          (3,N) initial states
+    rate_nodes  (M,6) shared schedule or (M,6,N) per-trajectory schedules sampled at modulation_nodes(...)
+    Returns (traj (N,n_points,3) float64 or empty, final_state (N,3) float64) CUDA tensors."""
+    import ctypes as C
+    dev = _dev(device)
+    y0 = torch.as_tensor(y0, dtype=torch.float64).to(dev).contiguous()
+    nodes = torch.as_tensor(rate_nodes, dtype=torch.float64).to(dev).contiguous()
+    n = int(y0.shape[1])
+    m = 2 * int(substeps) * (int(n_points) - 1) + 1
+    if y0.shape[0] != 3 or nodes.shape[0] != m or nodes.shape[1] != 6 or (nodes.dim() == 3 and nodes.shape[2] != n) \
+            or nodes.dim() not in (2, 3):
+        raise N.BciError(-1, "solve_modulated_ensemble: y0 must be (3,N) and rate_nodes (%d,6[,N]); got %s and %s"
+                         % (m, tuple(y0.shape), tuple(nodes.shape)))
+    a = N.OdeModArgs()
+    a.n, a.n_points, a.substeps, a.per_trajectory = n, int(n_points), int(substeps), int(nodes.dim() == 3)
+    a.style = {"ref06": N.STYLE_REF06, "ref08": N.STYLE_REF08}[style]
+    a.t_span = float(t_span[1]) - float(t_span[0])
+    traj = torch.empty((n, n_points, 3) if want_traj else (0,), device=dev, dtype=torch.float64)
+    final = torch.empty((n, 3), device=dev, dtype=torch.float64)
+    a.rate_nodes, a.y0 = nodes.data_ptr(), y0.data_ptr()
+    a.traj = traj.data_ptr() if want_traj else None
+    a.final_state = final.data_ptr()
+    with torch.cuda.device(dev):
+        N.check(N.lib().bci_ode_solve_modulated(C.byref(a), torch.cuda.current_stream().cuda_stream))
+    return traj, final
+
+
 class CognitiveStateODE:
     """Drop-in for the reference class (05_ode_model.py:58; 06:146; 10:117)."""
 
@@ -87,6 +124,29 @@ class CognitiveStateODE:
         traj, _, _ = solve_ensemble(1, base_rates=self.params, y0=y0, y0_mode="given", coupling=False, style="ref06",
                                     mode=mode, t_end=t1 - t0, n_points=n_points, substeps=self.substeps,
                                     f64=True, device=self.device)
+        return t, traj[0].cpu().numpy()
+
+    def solve_with_modulation(self, initial_state, t_span, modulation_func, n_points=100, substeps=None):
+        """05:171-196: rates vary with time through `modulation_func(t, params) -> params`.  The reference lets LSODA call it
+        at every right-hand-side evaluation; here it is sampled once at the stage times of a fixed-step RK4 (so the stages see
+        the exact rates at t, t+h/2, t+h) and the integration is one GPU launch.  `substeps` per output interval: default
+        chosen from the sampled rates so that h*lambda <= 0.05 (truncation ~1e-8 for modulations that are smooth on that scale;
+        pass a larger value for faster-varying ones).  Returns (t, solution[n_points,3]) float64 like the reference."""
+        t0, t1 = float(t_span[0]), float(t_span[1])
+        t = np.linspace(t0, t1, n_points)
+
+        def sample(S):
+            tn = modulation_nodes(t0, t1, n_points, S)
+            return np.array([[float(modulation_func(float(tt), self.params.copy())[k]) for k in RATE_ORDER] for tt in tn])
+
+        if substeps is None:
+            coarse = sample(1)
+            lam = max(float((coarse[:, 0] + coarse[:, 1]).max()), float((coarse[:, 2] + coarse[:, 3]).max()),
+                      float((coarse[:, 4] + coarse[:, 5]).max()), 1e-12)
+            substeps = int(min(256, max(2, np.ceil((t1 - t0) / (n_points - 1) * lam / 0.05))))
+        nodes = sample(substeps)
+        y0 = np.asarray(initial_state, dtype=np.float64).reshape(3, 1)
+        traj, _ = solve_modulated_ensemble(y0, nodes, (t0, t1), n_points, substeps, style="ref06", device=self.device)
         return t, traj[0].cpu().numpy()
 
     FIT_BOUNDS = [(0.01, 0.5), (0.001, 0.2), (0.02, 0.5), (0.01, 0.3), (0.01, 0.3), (0.02, 0.4)]   # 05:287-294

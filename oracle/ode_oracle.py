@@ -332,3 +332,70 @@ def reference_style_loop(p_open, p_closed, base_params, alpha, forecast_steps=20
         sol = np.clip(sol, 0, 1)
         trajs[i] = sol / sol.sum(axis=1, keepdims=True)
     return trajs
+
+
+# ---- time-varying rates (05_ode_model.py:171-196) ------------------------------------------
+def solve_with_modulation(params, initial_state, t_span, modulation_func, n_points=100):
+    """Restatement of CognitiveStateODE.solve_with_modulation: LSODA (scipy.odeint defaults) on a right-hand side that
+    asks `modulation_func(t, params.copy())` for the rate dict at every evaluation (05:188-190), then clip + renormalise
+    (05:193-194).  Returns (t, solution[n_points,3])."""
+    from scipy.integrate import odeint
+    t = np.linspace(t_span[0], t_span[1], n_points)                    # 05:183
+    y0 = np.array(initial_state, dtype=np.float64) / np.sum(initial_state)   # 05:184
+
+    def f(y, tt):
+        p = modulation_func(tt, dict(params))
+        k = np.array([[p[name]] for name in RATE_ORDER], dtype=np.float64)
+        return rhs(np.asarray(y, dtype=np.float64).reshape(1, 3), k, True)[0]
+
+    return t, post_process_06(odeint(f, y0, t))
+
+
+def rk4_modulated(style, y0, nodes, t_span, n_points, substeps):
+    """Fixed-step RK4 reading the rates from a node table sampled at t0 + m*h/2 (what bci_ode_solve_modulated
+    integrates): y0 (N,3), nodes (M,6) or (M,6,N), M = 2*substeps*(n_points-1)+1.  Returns (N,n_points,3)."""
+    y = np.asarray(y0, dtype=np.float64).reshape(-1, 3)
+    clamp = style == STYLE_REF06
+    if clamp:
+        y = y / y.sum(axis=1, keepdims=True)
+    nodes = np.asarray(nodes, dtype=np.float64)
+    if nodes.ndim == 2:
+        nodes = np.broadcast_to(nodes[:, :, None], nodes.shape + (y.shape[0],))
+    assert nodes.shape[0] == 2 * substeps * (n_points - 1) + 1
+    out = np.empty((y.shape[0], n_points, 3), dtype=np.float64)
+    out[:, 0] = y
+    h = (t_span[1] - t_span[0]) / (n_points - 1) / substeps
+    m = 0
+    for i in range(1, n_points):
+        for _ in range(substeps):
+            k1 = rhs(y, nodes[m], clamp)
+            k2 = rhs(y + 0.5 * h * k1, nodes[m + 1], clamp)
+            k3 = rhs(y + 0.5 * h * k2, nodes[m + 1], clamp)
+            k4 = rhs(y + h * k3, nodes[m + 2], clamp)
+            y = y + (h / 6.0) * ((k1 + k4) + 2.0 * (k2 + k3))
+            m += 2
+        out[:, i] = y
+    return post_process_06(out) if clamp else out
+
+
+def modulation_cases():
+    """Named modulation functions shared by tests/golden/make_golden_modulation.py (run against the live reference) and the
+    parity tests: (name, modulation_func, initial_state, t_span, n_points)."""
+    def lstm_coupling(t, p):        # time-varying P(closed) driving the 06-style coupling (06:249-262), alpha = 0.5
+        pc = 0.5 + 0.4 * np.sin(0.35 * t)
+        po = 1.0 - pc
+        p["k_af"] *= 1 + 0.5 * pc; p["k_pf"] *= 1 + 0.5 * pc
+        p["k_fa"] *= 1 + 0.5 * po; p["k_pa"] *= 1 + 0.5 * po
+        return {k: max(RATE_FLOOR, v) for k, v in p.items()}
+
+    def fatigue_ramp(t, p):         # time-on-task: fatigue inflow grows, recovery decays
+        p["k_af"] *= 1.0 + 0.08 * t
+        p["k_fa"] *= np.exp(-0.05 * t)
+        return p
+
+    def identity(t, p):
+        return p
+
+    return [("lstm_coupling", lstm_coupling, [0.6, 0.2, 0.2], (0.0, 20.0), 100),
+            ("fatigue_ramp", fatigue_ramp, [0.33, 0.34, 0.33], (0.0, 50.0), 60),
+            ("identity", identity, [0.2, 0.2, 0.6], (5.0, 25.0), 20)]

@@ -102,6 +102,43 @@ def test_cognitive_state_ode_object_contract(golden):
     assert np.abs(pi @ Q).max() < 1e-6 and abs(pi.sum() - 1) < 1e-6
 
 
+def test_solve_with_modulation_matches_reference_05(golden):
+    """05:171-196 through the drop-in object (host samples the callback at the RK4 stage times, one launch integrates)."""
+    g = golden("ode_ref05_modulation.npz")
+    for name, fn, y0, t_span, n_points in oo.modulation_cases():
+        m = ode.CognitiveStateODE()
+        t, sol = m.solve_with_modulation(y0, t_span, fn, n_points=n_points)
+        assert sol.shape == (n_points, 3) and sol.dtype == np.float64
+        assert np.array_equal(t, g[name + "_t"])
+        assert np.abs(sol - g[name + "_sol"]).max() <= 1e-6, (name, np.abs(sol - g[name + "_sol"]).max())
+        assert np.abs(sol.sum(axis=1) - 1).max() <= 1e-15
+    # identity modulation == plain solve
+    t, a = ode.CognitiveStateODE().solve_with_modulation([0.2, 0.2, 0.6], (5.0, 25.0), lambda t, p: p, n_points=20)
+    _, b = ode.CognitiveStateODE().solve([0.2, 0.2, 0.6], (5.0, 25.0), 20)
+    assert np.abs(a - b).max() <= 1e-6
+
+
+def test_modulated_ensemble_matches_oracle_same_method():
+    """bci_ode_solve_modulated against the fp64 numpy restatement of the same node-table RK4: shared and per-trajectory
+    schedules, both styles, ragged N."""
+    rng = np.random.default_rng(5)
+    n, n_points, S, t_span = 333, 20, 4, (0.0, 20.0)
+    tn = ode.modulation_nodes(*t_span, n_points, S)
+    base = np.array([synth.DEFAULT_RATES[k] for k in synth.RATE_ORDER])
+    y0 = rng.dirichlet([2, 2, 2], size=n)
+    shared = base[None, :] * (1.0 + 0.5 * np.sin(0.3 * tn)[:, None] * np.array([0, 1, 0, 1, -1, 0])[None, :])
+    per = shared[:, :, None] * rng.uniform(0.5, 1.5, size=(1, 6, n))
+    for nodes in (shared, per):
+        for style, st in (("ref06", oo.STYLE_REF06), ("ref08", oo.STYLE_REF08)):
+            traj, fin = ode.solve_modulated_ensemble(y0.T.copy(), nodes, t_span, n_points, S, style=style)
+            want = oo.rk4_modulated(st, y0, nodes, t_span, n_points, S)
+            got = traj.cpu().numpy()
+            assert np.abs(got - want).max() <= 1e-13
+            assert np.array_equal(fin.cpu().numpy(), got[:, -1])
+    with pytest.raises(Exception):
+        ode.solve_modulated_ensemble(y0.T.copy(), shared[:-1], t_span, n_points, S)
+
+
 @pytest.mark.parametrize("n", [1, 127, 128, 129, 10_000])
 def test_sweep_matches_oracle_and_invariants(n):
     sw = synth.make_ode_sweep(42, n)

@@ -96,6 +96,23 @@ def test_exact_and_rk4_match_reference_lsoda(golden):
         assert (e <= 0.0105 * (20.0 / 19 / s * lam) ** 4 + 1e-12).all()
 
 
+def test_modulated_solve_matches_reference_05(golden):
+    """CognitiveStateODE.solve_with_modulation (05:171-196): the LSODA restatement and the node-table RK4 (what the CUDA
+    kernel integrates) against the live reference's outputs."""
+    g = golden("ode_ref05_modulation.npz")
+    base = dict(synth.DEFAULT_RATES)
+    for name, fn, y0, t_span, n_points in ode_oracle.modulation_cases():
+        t, sol = ode_oracle.solve_with_modulation(base, y0, t_span, fn, n_points)
+        assert np.array_equal(t, g[name + "_t"])
+        assert np.abs(sol - g[name + "_sol"]).max() < 1e-12, name        # same LSODA, same right-hand side
+        S = 8
+        tn = np.linspace(t_span[0], t_span[1], 2 * S * (n_points - 1) + 1)
+        nodes = np.array([[fn(tt, dict(base))[k] for k in ode_oracle.RATE_ORDER] for tt in tn])
+        r = ode_oracle.rk4_modulated(ode_oracle.STYLE_REF06, [y0], nodes, t_span, n_points, S)[0]
+        assert np.abs(r - g[name + "_sol"]).max() < 2e-7, name           # LSODA's own error is ~4e-8
+        assert np.abs(r.sum(axis=1) - 1).max() < 1e-15
+
+
 def test_rk45_restatement_matches_reference_solve_ivp(golden):
     g = golden("ode_ref05.npz")
     out, stats = ode_oracle.rk45_scipy(ode_oracle.STYLE_REF06, g["y0"], g["rates"], 20.0, 20, return_stats=True)
