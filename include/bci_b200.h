@@ -319,6 +319,13 @@ int bci_selftest_rec256_bf16(const void* G, const void* whh, void* out, int32_t 
 int bci_selftest_fused_rec_bf16(const void* in, const void* wih, const void* whh_f, const void* whh_r, const float* bias,
                                 void* out, void* stats, int32_t Bc, int32_t T, int32_t Kin, void* stream);
 
+/* split-precision (3 x TF32) tcgen05 GEMMs of the fp32 path (csrc/gemm_tf32x3.cu), fp32 in / fp32 out:
+ *   mode 0 (NT): C[M][N] = A[M][K] . B[N][K]^T + bias[N] (bias optional)
+ *   mode 1 (TN): C[M][N] = A[K][M]^T . B[K][N]            (split-K, partial tiles reduce-added)
+ * explicit_hi != 0: the tf32-rounded high parts are separate arrays instead of the raw operands. */
+int bci_selftest_gemm_tf32x3(int32_t mode, const float* A, const float* B, const float* bias, float* C, int32_t M, int32_t N,
+                             int64_t K, int32_t explicit_hi, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,399 @@
+// Split-precision (3 x TF32) tcgen05 GEMMs for the fp32 parity path.
+//
+// The fp32 mode must stay within 1e-5 of the reference's fp32 CPU arithmetic (04_lstm_model.py:181-188 through torch's
+// CPU kernels), which plain TF32 (10-bit mantissa) cannot do.  Every fp32 operand x is therefore written as
+//     x = hi + lo,   hi = tf32(x) (the tensor core reads the upper 19 bits),  lo = tf32(x - hi)
+// and the product is accumulated in fp32 in TMEM as  A.B ~= A_lo.B_hi + A_hi.B_lo + A_hi.B_hi  (the dropped lo.lo term is
+// 2^-22 relative): three kind::tf32 MMAs per product instead of CUDA-core FFMAs -- ~370 TFLOP/s of fp32-grade math per
+// GPU against 71.6 TFLOP/s on the FMA pipe.  The lo parts are produced by one elementwise pass (split_tf32_kernel; weights:
+// once per load_weights) so that the GEMM itself is a pure TMA -> tcgen05 pipeline.
+//
+//   NT  C[M][N] (=|+=) A[M][K] . W[N][K]^T (+ bias)      time-parallel projections G = in . W_ih^T (forward) and data
+//                                                        gradients d_in = dG . W_ih (backward, W given as [Kin][8H])
+//   TN  C[P][Q]  =     sum_r A[r][P] . B[r][Q]           weight gradients dW = dG^T . in over the R = T*Bc rows; operands
+//                                                        are read as MN-major UMMA tiles straight from the row-major
+//                                                        activations (no transpose pass), split-K over CTAs, partial
+//                                                        tiles combined in L2 by the TMA reduce-add store
+//
+// Kernel shape (both): persistent CTAs, warp 0 = TMA producer (3-stage ring of {A_hi, A_lo, B_hi, B_lo} 128x32 fp32 tiles,
+// SWIZZLE_128B), warp 1 = MMA issuer (M128 x N128 x K8; two accumulators per tile -- hi.hi and the
+// correction terms -- double-buffered: all 512 TMEM columns), warps 2-5 = epilogue
+// (tcgen05.ld -> +bias -> swizzled staging -> TMA store / reduce-add, one 32x32 box per warp).
+#include "lstm_handle.cuh"
+#include "sm100_prims.cuh"
+#include "tmap.cuh"
+#include <cstdlib>
+
+namespace bci {
+using namespace sm100;
+
+constexpr int TX_BM = 128, TX_BN = 128, TX_BK = 32, TX_STAGES = 3;
+constexpr int TX_THREADS = 192;
+constexpr uint32_t TX_TILE = TX_BM * TX_BK * 4;     // 16 KB: one operand tile
+constexpr uint32_t TX_STAGE = 4 * TX_TILE;          // A_hi, A_lo, B_hi, B_lo
+constexpr uint32_t TX_CSTAGE = 4 * 32 * 128;        // per epilogue warp: 32 rows x 128 B
+constexpr size_t TX_SMEM = 1024 + (size_t)TX_STAGES * TX_STAGE + TX_CSTAGE + 128 * sizeof(float) + 256;
+
+// x -> lo (and optionally hi).  hi == nullptr: the tensor core is trusted to ignore the low 13 bits of the raw operand,
+// so lo is the remainder after truncation; otherwise hi is the round-to-nearest tf32 value and lo its remainder.
+__global__ void split_tf32_kernel(const float4* __restrict__ x, float4* __restrict__ hi, float4* __restrict__ lo, long long n4) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  const float4 v = __ldg(x + i);
+  float in[4] = {v.x, v.y, v.z, v.w}, h[4], l[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    uint32_t hb;
+    if (hi) asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(in[j]));
+    else hb = __float_as_uint(in[j]) & 0xFFFFE000u;
+    h[j] = __uint_as_float(hb);
+    uint32_t lb;
+    const float rem = in[j] - h[j];  // exact
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lb) : "f"(rem));
+    l[j] = __uint_as_float(lb);
+  }
+  if (hi) hi[i] = make_float4(h[0], h[1], h[2], h[3]);
+  lo[i] = make_float4(l[0], l[1], l[2], l[3]);
+}
+
+int split_tf32(const float* x, float* hi, float* lo, long long n, cudaStream_t st) {
+  BCI_REQUIRE(n % 4 == 0 && ((uintptr_t)x & 15) == 0 && ((uintptr_t)lo & 15) == 0 && ((uintptr_t)hi & 15) == 0, BCI_EINVAL,
+              "split_tf32: 16-byte aligned arrays with n %% 4 == 0 required");
+  if (n == 0) return BCI_OK;
+  split_tf32_kernel<<<(unsigned)ceil_div64(n / 4, 256), 256, 0, st>>>(reinterpret_cast<const float4*>(x), reinterpret_cast<float4*>(hi),
+                                                                       reinterpret_cast<float4*>(lo), n / 4);
+  BCI_LAUNCH_OK();
+  return BCI_OK;
+}
+
+// Instruction descriptor, kind::tf32: D fp32, A/B tf32 (format 2); bit 15 / 16 = A / B is MN-major.
+__host__ __device__ constexpr uint32_t umma_idesc_tf32(int M, int N, int mn_major) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(mn_major ? 1 : 0) << 15) | ((uint32_t)(mn_major ? 1 : 0) << 16) |
+         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+// MN-major operand tile: [MN group of 32 floats][k row][128 B].  32-bit MN-major operands exist only in the
+// "128-byte swizzle with a 32-byte base" layout (UMMA layout type 1 = TMA CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B: the 32-byte
+// chunk index of a row is XORed with the row index mod 4; plain SWIZZLE_128B is silently read as zeros): atoms of 4 k-rows
+// (512 B, SBO), MN groups 4096 B apart (LBO); one K = 8 MMA spans two atoms = 1024 B
+__device__ __forceinline__ uint64_t umma_desc_sw128_mn(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)(4096 >> 4) << 16;
+  d |= (uint64_t)(512 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)1 << 61;
+  return d;
+}
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tma_reduce_add_2d(const void* tmap, uint32_t src_smem, int c0, int c1) {
+  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(tmap), "r"(src_smem), "r"(c0), "r"(c1) : "memory");
+}
+
+struct TxMaps { CUtensorMap a_hi, a_lo, b_hi, b_lo, c; };
+
+// TN = false: tile (mb, nb) of C[M][N], K loop over [0, K) (k_splits == 1) -- operands K-major, 2-D maps {k, row}
+// TN = true : tile (mb, nb) of C[P=M][Q=N], K loop over the R rows in k_splits ranges -- operands MN-major (four {32 floats, 32 rows}
+//             boxes per tile); partial tiles are reduce-added
+template <bool TN>
+__global__ void __launch_bounds__(TX_THREADS, 1)
+gemm_tf32x3_kernel(const __grid_constant__ TxMaps maps, const float* __restrict__ bias, int M, int N, long long K, int k_splits,
+                   int reduce_add) {
+  extern __shared__ uint8_t tx_smem_raw[];
+  const uint32_t raw = smem_u32(tx_smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* gen = tx_smem_raw + (base - raw);
+  const uint32_t sRing = base, sC = base + TX_STAGES * TX_STAGE;
+  uint8_t* genC = gen + TX_STAGES * TX_STAGE;
+  float* bias_s = reinterpret_cast<float*>(genC + TX_CSTAGE);
+  uint8_t* ctl = genC + TX_CSTAGE + 128 * sizeof(float);
+  const uint32_t bar0 = smem_u32(ctl);
+  auto full_bar = [&](int s) { return bar0 + 8u * s; };
+  auto empty_bar = [&](int s) { return bar0 + 8u * (TX_STAGES + s); };
+  auto tfull_bar = [&](int a) { return bar0 + 8u * (2 * TX_STAGES + a); };
+  auto tempty_bar = [&](int a) { return bar0 + 8u * (2 * TX_STAGES + 2 + a); };
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ctl + 8 * (2 * TX_STAGES + 4));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m_blocks = (M + TX_BM - 1) / TX_BM, n_blocks = (N + TX_BN - 1) / TX_BN;
+  const long long kb_total = (K + TX_BK - 1) / TX_BK;
+  const long long kb_per = (kb_total + k_splits - 1) / k_splits;
+  const long long tiles = (long long)m_blocks * n_blocks * k_splits;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&maps.a_hi); tma_prefetch_desc(&maps.a_lo);
+    tma_prefetch_desc(&maps.b_hi); tma_prefetch_desc(&maps.b_lo);
+    tma_prefetch_desc(&maps.c);
+    for (int s = 0; s < TX_STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 128); }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(smem_u32(tmem_slot), 4 * TX_BN);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (long long t = blockIdx.x; t < tiles; t += gridDim.x) {
+        const int nb = (int)(t % n_blocks);
+        const int mb = (int)((t / n_blocks) % m_blocks);
+        const int ks = (int)(t / ((long long)n_blocks * m_blocks));
+        const long long kb0 = ks * kb_per, kb1 = (kb0 + kb_per < kb_total) ? kb0 + kb_per : kb_total;
+        for (long long kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          mbar_arrive_expect_tx(full_bar(stage), TX_STAGE);
+          const uint32_t s0 = sRing + stage * TX_STAGE;
+          if (TN) {
+            // MN-major tile = four {32 floats, 32 rows} boxes side by side: [group][k row][128 B]
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              tma_load_2d(s0 + g * 4096, &maps.a_hi, mb * TX_BM + g * 32, (int)(kb * TX_BK), full_bar(stage));
+              tma_load_2d(s0 + TX_TILE + g * 4096, &maps.a_lo, mb * TX_BM + g * 32, (int)(kb * TX_BK), full_bar(stage));
+              tma_load_2d(s0 + 2 * TX_TILE + g * 4096, &maps.b_hi, nb * TX_BN + g * 32, (int)(kb * TX_BK), full_bar(stage));
+              tma_load_2d(s0 + 3 * TX_TILE + g * 4096, &maps.b_lo, nb * TX_BN + g * 32, (int)(kb * TX_BK), full_bar(stage));
+            }
+          } else {
+            tma_load_2d(s0, &maps.a_hi, (int)(kb * TX_BK), mb * TX_BM, full_bar(stage));
+            tma_load_2d(s0 + TX_TILE, &maps.a_lo, (int)(kb * TX_BK), mb * TX_BM, full_bar(stage));
+            tma_load_2d(s0 + 2 * TX_TILE, &maps.b_hi, (int)(kb * TX_BK), nb * TX_BN, full_bar(stage));
+            tma_load_2d(s0 + 3 * TX_TILE, &maps.b_lo, (int)(kb * TX_BK), nb * TX_BN, full_bar(stage));
+          }
+          if (++stage == TX_STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_tf32(TX_BM, TX_BN, TN ? 1 : 0);
+      constexpr uint32_t KSTEP = TN ? 1024u : 32u;  // 8 k-rows of an MN-major tile / 8 floats inside a K-major row
+      int stage = 0; uint32_t phase = 0; int acc = 0; uint32_t acc_phase = 0;
+      for (long long t = blockIdx.x; t < tiles; t += gridDim.x) {
+        const int ks = (int)(t / ((long long)n_blocks * m_blocks));
+        const long long kb0 = ks * kb_per, kb1 = (kb0 + kb_per < kb_total) ? kb0 + kb_per : kb_total;
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+        tc_fence_after();
+        // two accumulators per tile: the tensor core adds into TMEM with truncation, an error that grows with the number of
+        // accumulation steps times the accumulator's magnitude -- the small correction terms are summed apart from the
+        // hi.hi products (a third of the steps on the big accumulator) and the epilogue adds the two in fp32 registers
+        const uint32_t d_tmem = tmem_base + (uint32_t)acc * (2 * TX_BN), d_lo = d_tmem + TX_BN;
+        for (long long kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t s0 = sRing + stage * TX_STAGE;
+#pragma unroll
+          for (int kk = 0; kk < TX_BK / 8; ++kk) {
+            const uint32_t o = kk * KSTEP;
+            const uint64_t ah = TN ? umma_desc_sw128_mn(s0 + o) : umma_desc_sw128(s0 + o);
+            const uint64_t al = TN ? umma_desc_sw128_mn(s0 + TX_TILE + o) : umma_desc_sw128(s0 + TX_TILE + o);
+            const uint64_t bh = TN ? umma_desc_sw128_mn(s0 + 2 * TX_TILE + o) : umma_desc_sw128(s0 + 2 * TX_TILE + o);
+            const uint64_t bl = TN ? umma_desc_sw128_mn(s0 + 3 * TX_TILE + o) : umma_desc_sw128(s0 + 3 * TX_TILE + o);
+            const uint32_t first = (kb != kb0 || kk != 0) ? 1u : 0u;
+            umma_tf32(d_lo, al, bh, idesc, first);
+            umma_tf32(d_lo, ah, bl, idesc, 1u);
+            umma_tf32(d_tmem, ah, bh, idesc, first);
+          }
+          umma_commit(empty_bar(stage));
+          if (++stage == TX_STAGES) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit(tfull_bar(acc));
+        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      }
+    }
+  } else {
+    // epilogue warp w: TMEM lanes / tile rows [32 (w % 4), +32); four 32-column slabs, each staged as a swizzled 32 x 128 B box
+    const int quarter = warp & 3;
+    uint8_t* cst = genC + quarter * 4096;
+    const uint32_t cst_s = sC + quarter * 4096;
+    const int et = (warp - 2) * 32 + lane;
+    int acc = 0; uint32_t acc_phase = 0;
+    for (long long t = blockIdx.x; t < tiles; t += gridDim.x) {
+      const int nb = (int)(t % n_blocks);
+      const int mb = (int)((t / n_blocks) % m_blocks);
+      const int ks = (int)(t / ((long long)n_blocks * m_blocks));
+      const bool add_bias = bias != nullptr && ks == 0;
+      // all four epilogue warps: previous tile's bias reads are done before it is overwritten
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      bias_s[et] = (add_bias && nb * TX_BN + et < N) ? __ldg(bias + nb * TX_BN + et) : 0.f;
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)acc * (2 * TX_BN);
+#pragma unroll 1
+      for (int slab = 0; slab < TX_BN / 32; ++slab) {
+        uint32_t r[32], rl[32];
+        tmem_ld32(taddr + slab * 32, r);
+        tmem_ld32(taddr + TX_BN + slab * 32, rl);
+        if (lane == 0) tma_store_wait_read();  // the staging box has been drained by the previous store
+        __syncwarp();
+        tmem_ld_wait();
+        if (slab == TX_BN / 32 - 1) {  // all TMEM reads of this accumulator by this thread are done
+          tc_fence_before();
+          mbar_arrive(tempty_bar(acc));
+        }
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          float4 v;
+          v.x = (__uint_as_float(r[4 * q + 0]) + __uint_as_float(rl[4 * q + 0])) + bias_s[slab * 32 + 4 * q + 0];
+          v.y = (__uint_as_float(r[4 * q + 1]) + __uint_as_float(rl[4 * q + 1])) + bias_s[slab * 32 + 4 * q + 1];
+          v.z = (__uint_as_float(r[4 * q + 2]) + __uint_as_float(rl[4 * q + 2])) + bias_s[slab * 32 + 4 * q + 2];
+          v.w = (__uint_as_float(r[4 * q + 3]) + __uint_as_float(rl[4 * q + 3])) + bias_s[slab * 32 + 4 * q + 3];
+          *reinterpret_cast<float4*>(cst + sw128_chunk_off((uint32_t)lane, (uint32_t)q)) = v;
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          const int c0 = nb * TX_BN + slab * 32, c1 = mb * TX_BM + quarter * 32;
+          if (c0 < N && c1 < M) {
+            if (reduce_add) tma_reduce_add_2d(&maps.c, cst_s, c0, c1);
+            else tma_store_2d(&maps.c, cst_s, c0, c1);
+          }
+          tma_store_commit();
+        }
+      }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+    }
+    if (lane == 0) tma_store_wait_all();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 4 * TX_BN);
+}
+
+static int make_tmap_f32_2d(CUtensorMap* tm, const float* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_cols,
+                            uint32_t box_rows, CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
+  EncodeTiledFn enc = get_encode_fn();
+  BCI_REQUIRE(enc, BCI_ECUDA, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {ld * 4};
+  cuuint32_t box[2] = {box_cols, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  BCI_REQUIRE(r == CUDA_SUCCESS, BCI_ECUDA, "cuTensorMapEncodeTiled(f32 2D) failed with CUresult %d", (int)r);
+  return BCI_OK;
+}
+static int tx_prepare() {
+  static bool done = false;
+  if (!done) {
+    BCI_CUDA_OK(cudaFuncSetAttribute(gemm_tf32x3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TX_SMEM));
+    BCI_CUDA_OK(cudaFuncSetAttribute(gemm_tf32x3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TX_SMEM));
+    done = true;
+  }
+  return BCI_OK;
+}
+
+bool tf32x3_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("BCI_FP32_GEMM");  // "simt": CUDA-core GEMMs (the first version of the fp32 path)
+    v = (e && e[0] == 's') ? 0 : 1;
+  }
+  return v != 0;
+}
+bool tf32x3_nt_ok(const void* A, int lda, const void* W, int ldw, const void* C, int ldc, int M, int N, int K) {
+  return tf32x3_enabled() && M >= 128 && N % 32 == 0 && K % 4 == 0 && lda % 4 == 0 && ldw % 4 == 0 && ldc % 4 == 0 &&
+         ((uintptr_t)A & 15) == 0 && ((uintptr_t)W & 15) == 0 && ((uintptr_t)C & 15) == 0;
+}
+bool tf32x3_tn_ok(const void* A, int lda, const void* B, int ldb, const void* C, int ldc, long long R, int P, int Q) {
+  return tf32x3_enabled() && R >= 1024 && R < (1ll << 31) && P % 128 == 0 && Q % 128 == 0 && lda % 4 == 0 && ldb % 4 == 0 &&
+         ldc % 4 == 0 && ((uintptr_t)A & 15) == 0 && ((uintptr_t)B & 15) == 0 && ((uintptr_t)C & 15) == 0;
+}
+
+// C[M][N] (ldc) (=|+=) A[M][K] (lda) . W[N][K]^T (ldw) + bias[N];  *_lo from split_tf32 (hi = the raw array, or the rounded copy)
+int gemm_tf32x3_nt(const float* A_hi, const float* A_lo, int lda, const float* W_hi, const float* W_lo, int ldw, const float* bias,
+                   float* C, int ldc, int M, int N, int K, int accumulate, cudaStream_t st) {
+  int rc = tx_prepare();
+  if (rc) return rc;
+  TxMaps maps;
+  if ((rc = make_tmap_f32_2d(&maps.a_hi, A_hi, M, K, lda, TX_BK, TX_BM))) return rc;
+  if ((rc = make_tmap_f32_2d(&maps.a_lo, A_lo, M, K, lda, TX_BK, TX_BM))) return rc;
+  if ((rc = make_tmap_f32_2d(&maps.b_hi, W_hi, N, K, ldw, TX_BK, TX_BN))) return rc;
+  if ((rc = make_tmap_f32_2d(&maps.b_lo, W_lo, N, K, ldw, TX_BK, TX_BN))) return rc;
+  if ((rc = make_tmap_f32_2d(&maps.c, C, M, N, ldc, 32, 32))) return rc;
+  const long long tiles = (long long)ceil_div(M, TX_BM) * ceil_div(N, TX_BN);
+  const int grid = (int)(tiles < sm_count() ? tiles : sm_count());
+  gemm_tf32x3_kernel<false><<<grid, TX_THREADS, TX_SMEM, st>>>(maps, bias, M, N, (long long)K, 1, accumulate);
+  BCI_LAUNCH_OK();
+  return BCI_OK;
+}
+
+// C[P][Q] (ldc) = sum over r < R of A[r][P] (lda) . B[r][Q] (ldb)   (C is overwritten)
+int gemm_tf32x3_tn(const float* A_hi, const float* A_lo, int lda, const float* B_hi, const float* B_lo, int ldb, float* C, int ldc,
+                   long long R, int P, int Q, cudaStream_t st, int force_splits) {
+  int rc = tx_prepare();
+  if (rc) return rc;
+  TxMaps maps;
+  if ((rc = make_tmap_f32_2d(&maps.a_hi, A_hi, R, P, lda, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))) return rc;
+  if ((rc = make_tmap_f32_2d(&maps.a_lo, A_lo, R, P, lda, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))) return rc;
+  if ((rc = make_tmap_f32_2d(&maps.b_hi, B_hi, R, Q, ldb, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))) return rc;
+  if ((rc = make_tmap_f32_2d(&maps.b_lo, B_lo, R, Q, ldb, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))) return rc;
+  if ((rc = make_tmap_f32_2d(&maps.c, C, P, Q, ldc, 32, 32))) return rc;
+  const int out_tiles = (P / TX_BM) * (Q / TX_BN);
+  const long long kb_total = (R + TX_BK - 1) / TX_BK;
+  // K ranges of at most 1024 rows per accumulator (the TMEM accumulation error grows with the range: 3e-5 relative at 4096
+  // rows in one accumulator, 2e-6 when the same sum is split four ways and combined by the fp32 reduce-add), and enough
+  // of them to fill the machine
+  long long splits = (sm_count() + out_tiles - 1) / out_tiles;
+  if (splits > kb_total / 8) splits = kb_total / 8;
+  if (splits < (kb_total + 31) / 32) splits = (kb_total + 31) / 32;
+  if (splits < 1) splits = 1;
+  if (force_splits > 0) splits = force_splits;
+  const long long per = (kb_total + splits - 1) / splits;
+  splits = (kb_total + per - 1) / per;  // every split owns at least one k block
+  if (splits > 1) BCI_CUDA_OK(cudaMemset2DAsync(C, (size_t)ldc * 4, 0, (size_t)Q * 4, P, st));
+  const long long tiles = out_tiles * splits;
+  const int grid = (int)(tiles < sm_count() ? tiles : sm_count());
+  gemm_tf32x3_kernel<true><<<grid, TX_THREADS, TX_SMEM, st>>>(maps, nullptr, P, Q, R, (int)splits, splits > 1 ? 1 : 0);
+  BCI_LAUNCH_OK();
+  return BCI_OK;
+}
+
+}  // namespace bci
+
+// Diagnostic entry point: mode 0  C[M][N] = A[M][K] . B[N][K]^T + bias;  mode 1  C[M][N] = A[K][M]^T . B[K][N].
+// explicit_hi != 0 rounds hi into a separate array instead of passing the raw operand.  Scratch is allocated here (test only).
+extern "C" int bci_selftest_gemm_tf32x3(int32_t mode, const float* A, const float* B, const float* bias, float* C, int32_t M, int32_t N,
+                                        int64_t K, int32_t explicit_hi, void* stream) {
+  using namespace bci;
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long na = (long long)M * K, nb = (long long)N * K;
+  // modes 2 / 3: diagnostics -- NT accumulating into the caller's C (reduce-add epilogue) / TN without split-K (plain store)
+  const bool nt_acc = mode == 2, tn_single = mode == 3;
+  if (nt_acc) mode = 0;
+  if (tn_single) mode = 1;
+  BCI_REQUIRE(mode == 0 || mode == 1, BCI_EINVAL, "bci_selftest_gemm_tf32x3: mode must be 0 (NT) or 1 (TN)");
+  BCI_REQUIRE(na % 4 == 0 && nb % 4 == 0, BCI_EINVAL, "bci_selftest_gemm_tf32x3: operand sizes must be multiples of 4");
+  float* scratch = nullptr;
+  BCI_CUDA_OK(cudaMalloc(&scratch, (size_t)(na + nb) * 8));
+  float *alo = scratch, *blo = scratch + na, *ahi = blo + nb, *bhi = ahi + na;
+  int rc = split_tf32(A, explicit_hi ? ahi : nullptr, alo, na, st);
+  if (!rc) rc = split_tf32(B, explicit_hi ? bhi : nullptr, blo, nb, st);
+  const float* Ah = explicit_hi ? ahi : A;
+  const float* Bh = explicit_hi ? bhi : B;
+  if (!rc) {
+    if (mode == 0) {
+      rc = tf32x3_nt_ok(A, (int)K, B, (int)K, C, N, M, N, (int)K)
+               ? gemm_tf32x3_nt(Ah, alo, (int)K, Bh, blo, (int)K, bias, C, N, M, N, (int)K, nt_acc ? 1 : 0, st) : BCI_EINVAL;
+    } else {
+      rc = tf32x3_tn_ok(A, M, B, N, C, N, K, M, N) ? gemm_tf32x3_tn(Ah, alo, M, Bh, blo, N, C, N, K, M, N, st, tn_single ? 1 : 0) : BCI_EINVAL;
+    }
+    if (rc == BCI_EINVAL) set_error("bci_selftest_gemm_tf32x3: shape not supported by the tcgen05 path");
+  }
+  const cudaError_t se = cudaStreamSynchronize(st);
+  cudaFree(scratch);
+  BCI_REQUIRE(se == cudaSuccess, BCI_ECUDA, "bci_selftest_gemm_tf32x3: %s", cudaGetErrorString(se));
+  return rc;
+}

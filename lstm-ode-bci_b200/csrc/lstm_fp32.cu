@@ -292,6 +292,9 @@ int lstm_pack_f32(bci_lstm_s* h, cudaStream_t st) {
       pack_gates_rows_kernel<<<nblk((long long)4 * H * K), 256, 0, st>>>(w.w_ih[l][d], p.wih_b[l], H, K, d * 4 * H);
       pack_whh_b4_kernel<<<nblk((long long)4 * H * H), 256, 0, st>>>(w.w_hh[l][d], p.whh_b[l][d], H);
     }
+    int rc = split_tf32(p.wih_b[l], nullptr, p.wih_b_lo[l], (long long)ND * 4 * H * K, st);
+    if (!rc) rc = split_tf32(p.wih_t[l], nullptr, p.wih_t_lo[l], (long long)ND * 4 * H * K, st);
+    if (rc) return rc;
   }
   if (c.use_layer_norm) {
     copy_kernel<<<nblk(D), 256, 0, st>>>(w.ln_w, p.lnw, D);
@@ -316,7 +319,7 @@ int lstm_pack_f32(bci_lstm_s* h, cudaStream_t st) {
 size_t lstm_store_bytes_f32(const bci_lstm_config& c) {
   const size_t H = c.hidden_size, C = c.input_size, D = 2 * H;
   size_t n = C * H + 3 * H;
-  for (int l = 0; l < c.num_layers; ++l) n += 2 * ((size_t)layer_in_width(c, l) * 8 * H + 2 * H * 4 * H) + 8 * H;
+  for (int l = 0; l < c.num_layers; ++l) n += 4 * ((size_t)layer_in_width(c, l) * 8 * H) + 2 * (2 * H * 4 * H) + 8 * H;
   n += 2 * D + D * H + H + H + 4 + D * H + H + H * (H / 2) + H / 2 + (size_t)c.num_classes * (H / 2) + c.num_classes + 64;
   return align_up(n * sizeof(float) + 256 * 64, 256);
 }
@@ -336,6 +339,8 @@ void lstm_carve_f32(bci_lstm_s* h, char* base) {
     p.wih_b[l] = take((size_t)layer_in_width(c, l) * 8 * H);
     p.whh_b[l][0] = take(H * 4 * H);
     p.whh_b[l][1] = take(H * 4 * H);
+    p.wih_b_lo[l] = take((size_t)layer_in_width(c, l) * 8 * H);
+    p.wih_t_lo[l] = take((size_t)layer_in_width(c, l) * 8 * H);
   }
   p.lnw = take(D); p.lnb = take(D); p.aw1t = take(D * H); p.ab1 = take(H); p.aw2 = take(H); p.ab2 = take(4);
   p.c0t = take(D * H); p.cb0 = take(H); p.c3t = take(H * (H / 2)); p.cb3 = take(H / 2);
@@ -347,7 +352,7 @@ void lstm_carve_f32(bci_lstm_s* h, char* base) {
 // ---------------------------------------------------------------------------------------------
 static size_t chunk_bytes_f32(const bci_lstm_config& c, int Bc, int T) {
   const size_t H = c.hidden_size, D = feat_width(c), rows = (size_t)Bc * T;
-  return align_up(rows * H * 4, 256) + align_up(rows * 4 * D * 4, 256) + 2 * align_up(rows * D * 4, 256) +
+  return align_up(rows * H * 4, 256) + align_up(rows * 4 * D * 4, 256) + 3 * align_up(rows * D * 4, 256) +
          align_up((size_t)Bc * T * 4, 256);
 }
 
@@ -369,6 +374,7 @@ static int forward_chunk_f32(bci_lstm_s* h, const float* x, int Bc, int T, float
   float* o0 = reinterpret_cast<float*>(take(rows * D * 4));
   float* o1 = reinterpret_cast<float*>(take(rows * D * 4));
   float* scores = reinterpret_cast<float*>(take(rows * 4));
+  float* in_lo = reinterpret_cast<float*>(take(rows * D * 4));  // tf32 remainder of the layer input (split-precision GEMM)
   h->prof.mark(-1, st);
   int rc = launch_input_proj<H, float>(h, x, Bc, T, z, st);
   if (rc) return rc;
@@ -379,9 +385,15 @@ static int forward_chunk_f32(bci_lstm_s* h, const float* x, int Bc, int T, float
   for (int l = 0; l < c.num_layers; ++l) {
     const int K = layer_in_width(c, l);
     const int M = (int)rows, N = 4 * D;
-    dim3 gg(N / GN, ceil_div(M, GM));
-    proj_gemm_f32<<<gg, GEMM_THREADS, 0, st>>>(in, h->f32.wih_t[l], h->f32.bias[l], g, M, N, K, 0);
-    BCI_LAUNCH_OK();
+    if (tf32x3_nt_ok(in, K, h->f32.wih_b[l], K, g, N, M, N, K)) {
+      // G = in . W_ih^T on the tensor cores in split precision (3 x TF32, fp32-grade)
+      if ((rc = split_tf32(in, nullptr, in_lo, (long long)M * K, st))) return rc;
+      if ((rc = gemm_tf32x3_nt(in, in_lo, K, h->f32.wih_b[l], h->f32.wih_b_lo[l], K, h->f32.bias[l], g, N, M, N, K, 0, st))) return rc;
+    } else {
+      dim3 gg(N / GN, ceil_div(M, GM));
+      proj_gemm_f32<<<gg, GEMM_THREADS, 0, st>>>(in, h->f32.wih_t[l], h->f32.bias[l], g, M, N, K, 0);
+      BCI_LAUNCH_OK();
+    }
     h->prof.mark(1, st);
     float* o = outs[l & 1];
     dim3 gr(ceil_div(Bc, MT), ND);

@@ -19,6 +19,9 @@ struct PackedF32 {
   // row-major copies with gate-interleaved ROWS (n = dir*4H + unit*4 + gate), used by the backward pass:
   float* wih_b[BCI_MAX_LAYERS];     // [ND*4H][K_l] din = dG . wih_b
   float* whh_b[BCI_MAX_LAYERS][2];  // [H unit][H j][4 gates]  dh_{t-1}[j] = sum_(unit,gate) dG_t . whh_b
+  // tf32 remainders (x - tf32(x)) of wih_b / wih_t: second operand of the split-precision tcgen05 GEMMs (gemm_tf32x3.cu)
+  float* wih_b_lo[BCI_MAX_LAYERS];
+  float* wih_t_lo[BCI_MAX_LAYERS];
   float* lnw;    // [D]         D = ND*H
   float* lnb;    // [D]
   float* aw1t;   // [D][D/2]    attention.0.weight^T
@@ -130,6 +133,15 @@ int launch_proj_gemm_f32(const float* A, const float* Bt, const float* bias, flo
                          int accumulate = 0);
 int launch_rec_f32(int H, int ND, const float* G, const float* whh_f, const float* whh_r, float* out, float* gates, float* csave,
                    int Bc, int T, cudaStream_t st);
+// split-precision tcgen05 GEMMs of the fp32 path (gemm_tf32x3.cu)
+bool tf32x3_enabled();
+bool tf32x3_nt_ok(const void* A, int lda, const void* W, int ldw, const void* C, int ldc, int M, int N, int K);
+bool tf32x3_tn_ok(const void* A, int lda, const void* B, int ldb, const void* C, int ldc, long long R, int P, int Q);
+int split_tf32(const float* x, float* hi, float* lo, long long n, cudaStream_t st);
+int gemm_tf32x3_nt(const float* A_hi, const float* A_lo, int lda, const float* W_hi, const float* W_lo, int ldw, const float* bias,
+                   float* C, int ldc, int M, int N, int K, int accumulate, cudaStream_t st);
+int gemm_tf32x3_tn(const float* A_hi, const float* A_lo, int lda, const float* B_hi, const float* B_lo, int ldb, float* C, int ldc,
+                   long long R, int P, int Q, cudaStream_t st, int force_splits = 0);
 // bf16 / tcgen05 forward (lstm_bf16.cu)
 int lstm_forward_bf16(bci_lstm_s* h, const float* x, int batch, int T, float* logits, float* probs, float* attn,
                       void* ws, size_t ws_bytes, cudaStream_t st);

@@ -713,6 +713,9 @@ struct TrainWs {
   float *xhatF, *rstdF, *Y, *PRE, *attn, *ctx, *pre1, *h1d, *pre2, *h2d;
   float *dA, *dB;           // [M][2H] gradient ping-pong
   float *dctx, *dpre1, *dpre2, *tmpW, *hdr;
+  // tf32 remainders for the split-precision tcgen05 GEMMs: layer input (main stream), dG (one per dG buffer), and the side
+  // stream's copies of the layer input / output
+  float *lo_in, *lo_G, *lo_G2, *lo_in2, *lo_out2;
   size_t total;
 };
 struct TrainHeader { float dropout; uint32_t valid; uint64_t seed; int batch, T; };
@@ -736,6 +739,11 @@ static void carve_train(const bci_lstm_config& c, int B, int T, float p_drop, ch
   w.dctx = take(B * D); w.dpre1 = take(B * H); w.dpre2 = take(B * (H / 2));
   w.tmpW = take(4 * D * (D > H ? D : H) + 1024);
   w.tmpW2 = take(4 * D * (D > H ? D : H) + 1024);
+  if (tf32x3_enabled()) {
+    w.lo_in = take(M * D); w.lo_G = take(M * 4 * D); w.lo_G2 = take(M * 4 * D); w.lo_in2 = take(M * D); w.lo_out2 = take(M * D);
+  } else {
+    w.lo_in = w.lo_G = w.lo_G2 = w.lo_in2 = w.lo_out2 = nullptr;
+  }
   w.total = off;
 }
 
@@ -758,7 +766,14 @@ static int forward_train_t(bci_lstm_s* h, const float* x, int B, int T, float p_
   BCI_LAUNCH_OK();
   const float* in = w.z;
   for (int l = 0; l < c.num_layers; ++l) {
-    int rc = launch_proj_gemm_f32(in, p.wih_t[l], p.bias[l], w.G, (int)M, 4 * D, layer_in_width(c, l), st);
+    const int K = layer_in_width(c, l);
+    int rc;
+    if (tf32x3_nt_ok(in, K, p.wih_b[l], K, w.G, 4 * D, (int)M, 4 * D, K)) {
+      if ((rc = split_tf32(in, nullptr, w.lo_in, M * K, st))) return rc;
+      rc = gemm_tf32x3_nt(in, w.lo_in, K, p.wih_b[l], p.wih_b_lo[l], K, p.bias[l], w.G, 4 * D, (int)M, 4 * D, K, 0, st);
+    } else {
+      rc = launch_proj_gemm_f32(in, p.wih_t[l], p.bias[l], w.G, (int)M, 4 * D, K, st);
+    }
     if (rc) return rc;
     rc = launch_rec_f32(H, ND, w.G, p.whh_t[l][0], p.whh_t[l][1], w.out[l], w.gates[l], w.cst[l], B, T, st);
     if (rc) return rc;
@@ -891,22 +906,38 @@ static int backward_t(bci_lstm_s* h, const float* dlogits, int B, int T, float p
     else
       lstm_bptt_f32<H, 16><<<dim3(ceil_div(B, MT), ND), BP_THREADS, bp_smem, st>>>(dcur, w.gates[l], w.cst[l], p.whh_b[l][0], p.whh_b[l][1], dGl, B, T, ND);
     BCI_LAUNCH_OK();
+    // split-precision tensor-core GEMMs for this layer's gradients when the shapes allow (training batches do)
+    float* dGl_lo = gb ? w.lo_G2 : w.lo_G;
+    const bool tc = tf32x3_tn_ok(dGl, G4, in, K, w.tmpW2, K, M, G4, K) && tf32x3_tn_ok(dGl, G4, w.out[l], D, w.tmpW2, H, M - B, 4 * H, H) &&
+                    tf32x3_nt_ok(dGl, G4, p.wih_t[l], G4, dnext, K, (int)M, K, G4);
+    if (tc && (rc = split_tf32(dGl, nullptr, dGl_lo, M * G4, st))) return rc;
     BCI_CUDA_OK(cudaEventRecord(h->ev_dg, st));
     BCI_CUDA_OK(cudaStreamWaitEvent(sd, h->ev_dg, 0));
     // dW_ih (all directions at once, interleaved rows) = dG^T . in
-    BCI_CUDA_OK(zero_on(sd, w.tmpW2, (size_t)G4 * K));
-    if ((rc = gemm_tn(dGl, G4, in, K, w.tmpW2, K, M, G4, K, sd))) return rc;
+    if (tc) {
+      if ((rc = split_tf32(in, nullptr, w.lo_in2, M * K, sd))) return rc;
+      if ((rc = gemm_tf32x3_tn(dGl, dGl_lo, G4, in, w.lo_in2, K, w.tmpW2, K, M, G4, K, sd))) return rc;
+      if ((rc = split_tf32(w.out[l], nullptr, w.lo_out2, M * D, sd))) return rc;
+    } else {
+      BCI_CUDA_OK(zero_on(sd, w.tmpW2, (size_t)G4 * K));
+      if ((rc = gemm_tn(dGl, G4, in, K, w.tmpW2, K, M, G4, K, sd))) return rc;
+    }
     for (int d = 0; d < ND; ++d) {
       unpack_gate_rows_kernel<<<(unsigned)ceil_div64((long long)4 * H * K, 256), 256, 0, sd>>>(w.tmpW2, g->w_ih[l][d], H, K, d * 4 * H);
       BCI_LAUNCH_OK();
     }
     // dW_hh[d] = dG[:, d]^T . h_prev, h_prev(t) = out[t-1] (forward) / out[t+1] (reverse): a row shift by Bc rows
     for (int d = 0; d < ND; ++d) {
-      BCI_CUDA_OK(zero_on(sd, w.tmpW2, (size_t)4 * H * H));
       const long long R = M - B;
-      const float* Ad = dGl + d * 4 * H + (d == 0 ? (long long)B * G4 : 0);
-      const float* Bd = w.out[l] + d * H + (d == 0 ? 0 : (long long)B * D);
-      if ((rc = gemm_tn(Ad, G4, Bd, D, w.tmpW2, H, R, 4 * H, H, sd))) return rc;
+      const long long offA = d * 4 * H + (d == 0 ? (long long)B * G4 : 0), offB = d * H + (d == 0 ? 0 : (long long)B * D);
+      const float* Ad = dGl + offA;
+      const float* Bd = w.out[l] + offB;
+      if (tc) {
+        if ((rc = gemm_tf32x3_tn(Ad, dGl_lo + offA, G4, Bd, w.lo_out2 + offB, D, w.tmpW2, H, R, 4 * H, H, sd))) return rc;
+      } else {
+        BCI_CUDA_OK(zero_on(sd, w.tmpW2, (size_t)4 * H * H));
+        if ((rc = gemm_tn(Ad, G4, Bd, D, w.tmpW2, H, R, 4 * H, H, sd))) return rc;
+      }
       unpack_gate_rows_kernel<<<(unsigned)ceil_div64((long long)4 * H * H, 256), 256, 0, sd>>>(w.tmpW2, g->w_hh[l][d], H, H, 0);
       BCI_LAUNCH_OK();
     }
@@ -920,7 +951,11 @@ static int backward_t(bci_lstm_s* h, const float* dlogits, int B, int T, float p
     BCI_CUDA_OK(cudaEventRecord(h->ev_side[gb], sd));
     used[gb] = 1;
     // grad wrt the layer input: dnext [M][K] = dG . wih_b
-    if ((rc = gemm_nn(dGl, G4, p.wih_b[l], K, dnext, K, (int)M, K, G4, nullptr, 0, st))) return rc;
+    if (tc) {
+      if ((rc = gemm_tf32x3_nt(dGl, dGl_lo, G4, p.wih_t[l], p.wih_t_lo[l], G4, nullptr, dnext, K, (int)M, K, G4, 0, st))) return rc;
+    } else if ((rc = gemm_nn(dGl, G4, p.wih_b[l], K, dnext, K, (int)M, K, G4, nullptr, 0, st))) {
+      return rc;
+    }
     if (l > 0 && w.outd[l - 1] != w.out[l - 1]) {
       scale_mask_kernel<<<(unsigned)ceil_div64(M * K, 256), 256, 0, st>>>(dnext, dnext, M * K, p_drop, seed, 16 + (l - 1));
       BCI_LAUNCH_OK();

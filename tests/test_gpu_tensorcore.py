@@ -284,3 +284,44 @@ def test_recurrence_h256_cluster_matches_stepwise(Bc, T):
     got = out.float()
     assert torch.isfinite(got).all()
     assert float((got - want).abs().max()) <= 1.5e-2
+
+
+def _tf32x3(mode, A, B, bias, M, Nn, K):
+    C_ = torch.full((M, Nn), float("nan"), device="cuda")
+    N.check(N.lib().bci_selftest_gemm_tf32x3(mode, A.data_ptr(), B.data_ptr(), bias.data_ptr() if bias is not None else None,
+                                             C_.data_ptr(), M, Nn, K, 0, torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    return C_
+
+
+@pytest.mark.parametrize("M,Nn,K", [(128, 128, 32), (1000, 256, 128), (4097, 1024, 256), (3000, 128, 1024), (640, 160, 36)])
+def test_gemm_tf32x3_nt_is_fp32_grade(M, Nn, K):
+    """Split-precision tcgen05 GEMM of the fp32 path (projections, data gradients): C = A . B^T + bias against fp64;
+    tolerance 4e-6 of max|C| (a cuBLAS fp32 GEMM measures 0.2-1.4e-6 on the same inputs, plain TF32 ~5e-4); ragged M,
+    K tails and partial N blocks are handled by the tensor maps."""
+    g = torch.Generator(device="cuda").manual_seed(M + K)
+    A = torch.randn(M, K, device="cuda", generator=g)
+    B = torch.randn(Nn, K, device="cuda", generator=g) * 0.1
+    bias = torch.randn(Nn, device="cuda", generator=g)
+    ref = A.double() @ B.double().T + bias.double()
+    got = _tf32x3(0, A, B, bias, M, Nn, K)
+    assert not torch.isnan(got).any()
+    assert float((got.double() - ref).abs().max() / ref.abs().max()) <= 4e-6
+
+
+@pytest.mark.parametrize("P,Q,R", [(128, 128, 1024), (512, 128, 4000), (1024, 256, 16384)])
+def test_gemm_tf32x3_tn_is_fp32_grade(P, Q, R):
+    """Weight-gradient shape: C[P][Q] = sum_r A[r][P] B[r][Q] with MN-major operand tiles read straight from the row-major
+    activations, split-K partial tiles combined by the TMA reduce-add (order-nondeterministic fp32 adds)."""
+    g = torch.Generator(device="cuda").manual_seed(P + R)
+    A = torch.randn(R, P, device="cuda", generator=g)
+    B = torch.randn(R, Q, device="cuda", generator=g) * 0.1
+    ref = A.double().T @ B.double()
+    got = _tf32x3(1, A, B, None, P, Q, R)
+    assert not torch.isnan(got).any()
+    assert float((got.double() - ref).abs().max() / ref.abs().max()) <= 6e-6
+    # one-hot operands: exact products land in exactly the right cells (layout / swizzle check)
+    A0 = torch.zeros(R, P, device="cuda"); B0 = torch.zeros(R, Q, device="cuda")
+    A0[9, 70] = 1.0; B0[9, 33] = 3.0; A0[R - 1, 1] = 1.0; B0[R - 1, Q - 2] = 5.0
+    got = _tf32x3(1, A0, B0, None, P, Q, R)
+    assert got.nonzero().tolist() == [[1, Q - 2], [70, 33]] and float(got[1, Q - 2]) == 5.0 and float(got[70, 33]) == 3.0
