@@ -106,7 +106,12 @@ constexpr int REC_WPT = 16;  // windows per thread (inference tiles); small trai
 // PF = W_hh rows (float4 each) in flight per thread.  Large batches run two CTAs per SM and are FMA-bound: PF = 8 (128-register
 // budget).  Small (training) batches cannot fill the machine: there the L2 round trips of the weight stream are the step time,
 // so the <.., 8, 32> variant runs one CTA per SM with 32 loads in flight (4 round trips per step instead of 16).
-template <int H, int REC_WPT = 16, int PF = 8>
+//
+// RES_K > 0 (training batches, H = 128): the first RES_K rows of W_hh^T (96 of 128 = 192 KB) are copied into shared memory
+// once and stay there for the whole sequence; only the remaining rows stream from L2, prefetched into registers at the top
+// of the step.  With 512 windows the kernel was bound by exactly that stream (128 CTAs x 256 KB per step = 33 MB through
+// L2 per step, ~10 us); the resident copy cuts it to a quarter.
+template <int H, int REC_WPT = 16, int PF = 8, int RES_K = 0>
 __global__ void __launch_bounds__(REC_THREADS, PF > 8 ? 1 : 2)
 lstm_rec_f32(const float* __restrict__ G,      // [T][Bc][ND][H][4]
              const float* __restrict__ whh_f,  // [H][H][4] forward direction
@@ -125,6 +130,9 @@ lstm_rec_f32(const float* __restrict__ G,      // [T][Bc][ND][H][4]
   const int b_base = blockIdx.x * MT + grp * REC_WPT;
   const float4* __restrict__ W = reinterpret_cast<const float4*>(dir ? whh_r : whh_f);
 
+  extern __shared__ __align__(16) float4 rec_wres[];  // [RES_K][H] (RES_K > 0 only)
+  if (RES_K > 0)
+    for (int i = tid; i < RES_K * H; i += REC_THREADS) rec_wres[i] = __ldg(W + i);
   for (int i = tid; i < 2 * H * HS; i += REC_THREADS) (&hs[0][0][0])[i] = 0.f;
   float c[REC_WPT];
 #pragma unroll
@@ -136,35 +144,56 @@ lstm_rec_f32(const float* __restrict__ G,      // [T][Bc][ND][H][4]
     const int t = dir ? (T - 1 - s) : s;
     float4 acc[REC_WPT];
     const float4* Gt = reinterpret_cast<const float4*>(G) + (((long long)t * Bc) * ND + dir) * H + j;
+    // latency-bound variant (RES_K > 0): the projected inputs are added AFTER the recurrent product, so their loads are in
+    // flight during the whole k loop instead of heading the dependent FMA chains (~1 us of exposed latency per step)
+    constexpr bool LATE_G = RES_K > 0;
+    float4 gin[LATE_G ? REC_WPT : 1];
 #pragma unroll
     for (int w = 0; w < REC_WPT; ++w) {
       const int b = b_base + w;
-      acc[w] = (b < Bc) ? __ldg(Gt + (long long)b * ND * H) : make_float4(0.f, 0.f, 0.f, 0.f);
+      const float4 gv = (b < Bc) ? __ldg(Gt + (long long)b * ND * H) : make_float4(0.f, 0.f, 0.f, 0.f);
+      if (LATE_G) { gin[w] = gv; acc[w] = make_float4(0.f, 0.f, 0.f, 0.f); }
+      else acc[w] = gv;
     }
     const float* hcur = &hs[cur][0][grp * REC_WPT];
     // W_hh^T streams from L2 (it does not fit beside h in one SM's smem in fp32): 8 independent 16-byte loads are issued
     // per thread before they are consumed, otherwise each k iteration exposes a full L2 round trip (the first version,
     // unrolled by 2, spent ~36 k cycles per step on exactly that).
-    for (int k0 = 0; k0 < H; k0 += PF) {
-      float4 w8[PF];
+    auto fma_row = [&](int k, const float4 w4) {
+      const float4* hp = reinterpret_cast<const float4*>(hcur + k * HS);
 #pragma unroll
-      for (int kk = 0; kk < PF; ++kk) w8[kk] = __ldg(W + (long long)(k0 + kk) * H + j);
+      for (int q = 0; q < REC_WPT / 4; ++q) {
+        const float4 h4 = hp[q];
+        const float hv[4] = {h4.x, h4.y, h4.z, h4.w};
 #pragma unroll
-      for (int kk = 0; kk < PF; ++kk) {
-        const float4 w4 = w8[kk];
-        const float4* hp = reinterpret_cast<const float4*>(hcur + (k0 + kk) * HS);
-#pragma unroll
-        for (int q = 0; q < REC_WPT / 4; ++q) {
-          const float4 h4 = hp[q];
-          const float hv[4] = {h4.x, h4.y, h4.z, h4.w};
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            float4& a = acc[q * 4 + e];
-            a.x = fmaf(hv[e], w4.x, a.x); a.y = fmaf(hv[e], w4.y, a.y);
-            a.z = fmaf(hv[e], w4.z, a.z); a.w = fmaf(hv[e], w4.w, a.w);
-          }
+        for (int e = 0; e < 4; ++e) {
+          float4& a = acc[q * 4 + e];
+          a.x = fmaf(hv[e], w4.x, a.x); a.y = fmaf(hv[e], w4.y, a.y);
+          a.z = fmaf(hv[e], w4.z, a.z); a.w = fmaf(hv[e], w4.w, a.w);
         }
       }
+    };
+    if (RES_K > 0) {
+      constexpr int TAIL = H - RES_K;
+      float4 wt[TAIL > 0 ? TAIL : 1];
+#pragma unroll
+      for (int kk = 0; kk < TAIL; ++kk) wt[kk] = __ldg(W + (long long)(RES_K + kk) * H + j);  // in flight during the resident part
+#pragma unroll 8
+      for (int k = 0; k < RES_K; ++k) fma_row(k, rec_wres[k * H + j]);
+#pragma unroll
+      for (int kk = 0; kk < TAIL; ++kk) fma_row(RES_K + kk, wt[kk]);
+    } else {
+      for (int k0 = 0; k0 < H; k0 += PF) {
+        float4 w8[PF];
+#pragma unroll
+        for (int kk = 0; kk < PF; ++kk) w8[kk] = __ldg(W + (long long)(k0 + kk) * H + j);
+#pragma unroll
+        for (int kk = 0; kk < PF; ++kk) fma_row(k0 + kk, w8[kk]);
+      }
+    }
+    if (LATE_G) {
+#pragma unroll
+      for (int w = 0; w < REC_WPT; ++w) { acc[w].x += gin[w].x; acc[w].y += gin[w].y; acc[w].z += gin[w].z; acc[w].w += gin[w].w; }
     }
     float4* hnext = reinterpret_cast<float4*>(&hs[cur ^ 1][j][grp * REC_WPT]);
     float hq[4];
@@ -207,7 +236,16 @@ int launch_rec_f32(int H, int ND, const float* G, const float* whh_f, const floa
   const bool small = ND * ceil_div(Bc, groups * 16) < sm_count();
   const bool tiny = ND * ceil_div(Bc, groups * 8) < sm_count();  // even 8-window groups leave SMs idle (training: 512 windows)
   if (H == 128) {
-    if (tiny) lstm_rec_f32<128, 4, 32><<<dim3(ceil_div(Bc, 2 * 4), ND), REC_THREADS, 0, st>>>(G, whh_f, whh_r, out, gates, csave, Bc, T, ND);
+    if (tiny) {
+      constexpr int RES = 96;
+      constexpr size_t res_bytes = (size_t)RES * 128 * sizeof(float4);
+      static bool attr = false;
+      if (!attr) {
+        BCI_CUDA_OK(cudaFuncSetAttribute(lstm_rec_f32<128, 4, 32, RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)res_bytes));
+        attr = true;
+      }
+      lstm_rec_f32<128, 4, 32, RES><<<dim3(ceil_div(Bc, 2 * 4), ND), REC_THREADS, res_bytes, st>>>(G, whh_f, whh_r, out, gates, csave, Bc, T, ND);
+    }
     else if (small) lstm_rec_f32<128, 8, 32><<<dim3(ceil_div(Bc, 2 * 8), ND), REC_THREADS, 0, st>>>(G, whh_f, whh_r, out, gates, csave, Bc, T, ND);
     else lstm_rec_f32<128, 16><<<dim3(ceil_div(Bc, 2 * 16), ND), REC_THREADS, 0, st>>>(G, whh_f, whh_r, out, gates, csave, Bc, T, ND);
   } else {

@@ -591,7 +591,8 @@ head_train_bwd(const float* __restrict__ dlogits, int classes, const float* __re
 // input GEMMs and, transposed, to shared memory for dh_{t-1} = dG_t . W_hh.
 constexpr int BP_THREADS = 256;
 
-template <int H, int BP_WPT>
+// RES_U > 0: the first RES_U unit rows of the packed W_hh stay in shared memory behind the dG tile (see lstm_rec_f32's RES_K).
+template <int H, int BP_WPT, int RES_U = 0>
 __global__ void __launch_bounds__(BP_THREADS, 1)
 lstm_bptt_f32(const float* __restrict__ dout,    // [T][Bc][ND*H]  grad wrt the layer output
               const float* __restrict__ gates,   // [T][Bc][ND][H][4] post-activation i,f,g,o
@@ -609,21 +610,52 @@ lstm_bptt_f32(const float* __restrict__ dout,    // [T][Bc][ND*H]  grad wrt the 
   float dh_rec[BP_WPT], dc[BP_WPT];
 #pragma unroll
   for (int w = 0; w < BP_WPT; ++w) { dh_rec[w] = 0.f; dc[w] = 0.f; }
+  float4* wres = reinterpret_cast<float4*>(bp_smem + 4 * H * GS);  // [RES_U][H]
+  if (RES_U > 0)
+    for (int i = tid; i < RES_U * H; i += BP_THREADS) wres[i] = __ldg(W + i);
 
+  // latency-bound variant (RES_U > 0): the saved activations of step s-1 are requested while the recurrent product of step s
+  // runs (the elementwise part at the top of a step otherwise waits ~1 us for them); c(s-1) is step s's cprev, already here
+  constexpr bool PRE = RES_U > 0;
+  float4 pg[PRE ? BP_WPT : 1];
+  float pc[PRE ? BP_WPT : 1], pcp[PRE ? BP_WPT : 1], pdo[PRE ? BP_WPT : 1];
+  auto fetch = [&](int s, float4* g4, float* cc, float* cp, float* dd) {
+    const int t = dir ? (T - 1 - s) : s;
+    const int tp = dir ? (t + 1) : (t - 1);
+#pragma unroll
+    for (int w = 0; w < BP_WPT; ++w) {
+      const int b = b_base + w;
+      if (b < Bc) {
+        const long long row = (long long)t * Bc + b;
+        g4[w] = __ldg(reinterpret_cast<const float4*>(gates) + (row * ND + dir) * H + j);
+        if (cc) cc[w] = __ldg(csave + (row * ND + dir) * H + j);
+        cp[w] = (s > 0) ? __ldg(csave + (((long long)tp * Bc + b) * ND + dir) * H + j) : 0.f;
+        dd[w] = __ldg(dout + row * (ND * H) + dir * H + j);
+      }
+    }
+  };
+  if (PRE) fetch(T - 1, pg, pc, pcp, pdo);
   for (int s = T - 1; s >= 0; --s) {
     const int t = dir ? (T - 1 - s) : s;               // time index of forward step s
     const int tp = dir ? (t + 1) : (t - 1);            // time index of forward step s-1 (previous state)
     float* dgs = bp_smem + (j * 4) * GS + grp * BP_WPT;
+    // rows that are not resident: requested now, consumed after the resident part of the product
+    constexpr int TAIL_U = RES_U > 0 ? H - RES_U : 1;
+    float4 wt[TAIL_U];
+    if (RES_U > 0) {
+#pragma unroll
+      for (int uu = 0; uu < TAIL_U; ++uu) wt[uu] = __ldg(W + (long long)(RES_U + uu) * H + j);
+    }
 #pragma unroll
     for (int w = 0; w < BP_WPT; ++w) {
       const int b = b_base + w;
       float4 dg = make_float4(0.f, 0.f, 0.f, 0.f);
       if (b < Bc) {
         const long long row = (long long)t * Bc + b;
-        const float4 g = reinterpret_cast<const float4*>(gates)[(row * ND + dir) * H + j];
-        const float c = csave[(row * ND + dir) * H + j];
-        const float cprev = (s > 0) ? csave[(((long long)tp * Bc + b) * ND + dir) * H + j] : 0.f;
-        const float dh = dout[row * (ND * H) + dir * H + j] + dh_rec[w];
+        const float4 g = PRE ? pg[w] : reinterpret_cast<const float4*>(gates)[(row * ND + dir) * H + j];
+        const float c = PRE ? pc[w] : csave[(row * ND + dir) * H + j];
+        const float cprev = PRE ? pcp[w] : ((s > 0) ? csave[(((long long)tp * Bc + b) * ND + dir) * H + j] : 0.f);
+        const float dh = (PRE ? pdo[w] : dout[row * (ND * H) + dir * H + j]) + dh_rec[w];
         const float tc = tanhf(c);
         const float dct = fmaf(dh * g.w, 1.0f - tc * tc, dc[w]);
         dg.x = dct * g.z * g.x * (1.0f - g.x);          // d pre_i
@@ -636,6 +668,9 @@ lstm_bptt_f32(const float* __restrict__ dout,    // [T][Bc][ND*H]  grad wrt the 
       dgs[0 * GS + w] = dg.x; dgs[1 * GS + w] = dg.y; dgs[2 * GS + w] = dg.z; dgs[3 * GS + w] = dg.w;
     }
     __syncthreads();
+    float4 ng[PRE ? BP_WPT : 1];
+    float ncp[PRE ? BP_WPT : 1], ndo[PRE ? BP_WPT : 1];
+    if (PRE && s > 0) fetch(s - 1, ng, nullptr, ncp, ndo);
     // dh_rec[w] (unit j) = sum_n dG[w][n] * W_hh_b[n][j]
     float acc[BP_WPT];
 #pragma unroll
@@ -644,29 +679,41 @@ lstm_bptt_f32(const float* __restrict__ dout,    // [T][Bc][ND*H]  grad wrt the 
     // 32 independent 16-byte weight loads (= 128 rows of W_hh) in flight per thread: with training batches the machine is not
     // full and the L2 round trips of this stream ARE the step time (the first version had 16 four-byte loads in flight:
     // 32 round trips per step, 31 us; this one pays H/32 round trips)
-    for (int u0 = 0; u0 < H; u0 += 32) {
-      float4 wv[32];
+    auto fma_unit = [&](int u, const float4 w4) {
+      const float wg[4] = {w4.x, w4.y, w4.z, w4.w};
 #pragma unroll
-      for (int uu = 0; uu < 32; ++uu) wv[uu] = __ldg(W + (long long)(u0 + uu) * H + j);
+      for (int gsel = 0; gsel < 4; ++gsel) {
+        const float4* gp = reinterpret_cast<const float4*>(gsrc + (u * 4 + gsel) * GS);
 #pragma unroll
-      for (int uu = 0; uu < 32; ++uu) {
-        const float wg[4] = {wv[uu].x, wv[uu].y, wv[uu].z, wv[uu].w};
-#pragma unroll
-        for (int gsel = 0; gsel < 4; ++gsel) {
-          const float4* gp = reinterpret_cast<const float4*>(gsrc + ((u0 + uu) * 4 + gsel) * GS);
-#pragma unroll
-          for (int q = 0; q < BP_WPT / 4; ++q) {
-            const float4 g4 = gp[q];
-            acc[q * 4 + 0] = fmaf(g4.x, wg[gsel], acc[q * 4 + 0]);
-            acc[q * 4 + 1] = fmaf(g4.y, wg[gsel], acc[q * 4 + 1]);
-            acc[q * 4 + 2] = fmaf(g4.z, wg[gsel], acc[q * 4 + 2]);
-            acc[q * 4 + 3] = fmaf(g4.w, wg[gsel], acc[q * 4 + 3]);
-          }
+        for (int q = 0; q < BP_WPT / 4; ++q) {
+          const float4 g4 = gp[q];
+          acc[q * 4 + 0] = fmaf(g4.x, wg[gsel], acc[q * 4 + 0]);
+          acc[q * 4 + 1] = fmaf(g4.y, wg[gsel], acc[q * 4 + 1]);
+          acc[q * 4 + 2] = fmaf(g4.z, wg[gsel], acc[q * 4 + 2]);
+          acc[q * 4 + 3] = fmaf(g4.w, wg[gsel], acc[q * 4 + 3]);
         }
+      }
+    };
+    if (RES_U > 0) {
+#pragma unroll 8
+      for (int u = 0; u < RES_U; ++u) fma_unit(u, wres[u * H + j]);
+#pragma unroll
+      for (int uu = 0; uu < TAIL_U; ++uu) fma_unit(RES_U + uu, wt[uu]);
+    } else {
+      for (int u0 = 0; u0 < H; u0 += 32) {
+        float4 wv[32];
+#pragma unroll
+        for (int uu = 0; uu < 32; ++uu) wv[uu] = __ldg(W + (long long)(u0 + uu) * H + j);
+#pragma unroll
+        for (int uu = 0; uu < 32; ++uu) fma_unit(u0 + uu, wv[uu]);
       }
     }
 #pragma unroll
     for (int w = 0; w < BP_WPT; ++w) dh_rec[w] = acc[w];
+    if (PRE && s > 0) {
+#pragma unroll
+      for (int w = 0; w < BP_WPT; ++w) { pc[w] = pcp[w]; pg[w] = ng[w]; pcp[w] = ncp[w]; pdo[w] = ndo[w]; }
+    }
     __syncthreads();
   }
 }
@@ -871,8 +918,14 @@ static int backward_t(bci_lstm_s* h, const float* dlogits, int B, int T, float p
   const bool tiny = ND * ceil_div(B, (BP_THREADS / H) * 8) < sm_count();
   const int MT = (BP_THREADS / H) * (tiny ? 4 : small ? 8 : 16);
   const size_t bp_smem = (size_t)4 * H * (MT + 4) * sizeof(float);
+  // training batches at H = 128: 96 of the 128 unit rows of W_hh resident in shared memory behind the dG tile
+  constexpr int BP_RES = H == 128 ? 96 : 0;
+  constexpr size_t bp_res_bytes = (size_t)BP_RES * H * sizeof(float4);
   static bool attr = false;
   if (!attr) {
+    if (H == 128)
+      BCI_CUDA_OK(cudaFuncSetAttribute(lstm_bptt_f32<H, 4, BP_RES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)((size_t)4 * H * ((BP_THREADS / H) * 4 + 4) * sizeof(float) + bp_res_bytes)));
     BCI_CUDA_OK(cudaFuncSetAttribute(lstm_bptt_f32<H, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)((size_t)4 * H * ((BP_THREADS / H) * 16 + 4) * sizeof(float))));
     BCI_CUDA_OK(cudaFuncSetAttribute(lstm_bptt_f32<H, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -899,7 +952,9 @@ static int backward_t(bci_lstm_s* h, const float* dlogits, int B, int T, float p
     const int gb = (L - 1 - l) & 1;
     float* dGl = gb ? w.G2 : w.G;
     if (used[gb]) BCI_CUDA_OK(cudaStreamWaitEvent(st, h->ev_side[gb], 0));  // the side stream has finished reading this buffer
-    if (tiny)
+    if (tiny && H == 128)
+      lstm_bptt_f32<H, 4, BP_RES><<<dim3(ceil_div(B, MT), ND), BP_THREADS, bp_smem + bp_res_bytes, st>>>(dcur, w.gates[l], w.cst[l], p.whh_b[l][0], p.whh_b[l][1], dGl, B, T, ND);
+    else if (tiny)
       lstm_bptt_f32<H, 4><<<dim3(ceil_div(B, MT), ND), BP_THREADS, bp_smem, st>>>(dcur, w.gates[l], w.cst[l], p.whh_b[l][0], p.whh_b[l][1], dGl, B, T, ND);
     else if (small)
       lstm_bptt_f32<H, 8><<<dim3(ceil_div(B, MT), ND), BP_THREADS, bp_smem, st>>>(dcur, w.gates[l], w.cst[l], p.whh_b[l][0], p.whh_b[l][1], dGl, B, T, ND);
