@@ -377,7 +377,7 @@ def main():
         barrier()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
-        tsteps = 3
+        tsteps = 5
         for i in range(tsteps):
             loss_t, norm_t = trainer.step(xt, yt, seed=10 + i)
         b.record()
@@ -385,12 +385,32 @@ def main():
         tms = max_over_ranks(a.elapsed_time(b)) / tsteps
         line["train_step"] = {"metric": "train_windows_per_s", "value": world * tb / (tms * 1e-3), "unit": "windows/s",
                               "ms_per_step": tms, "windows_per_gpu": tb, "precision": "fp32", "dropout": 0.4,
+                              "gemms": "split-precision 3xTF32 tcgen05 (gemm_tf32x3.cu)" if os.environ.get("BCI_FP32_GEMM", "")[:1] != "s"
+                              else "CUDA-core FFMA (BCI_FP32_GEMM=simt)",
                               "optimizer": "AdamW(3e-4, wd 1e-4) + clip 1.0 with the gradient all-reduce fused into the optimizer kernels "
                                            "over NVLink peer memory (bci_fused_step)" if world > 1
                               else "AdamW(3e-4, wd 1e-4) + clip 1.0, fused",
                               "flop_per_window": 3 * FLOP_PER_WINDOW, "achieved_tflops_per_gpu": tb * 3 * FLOP_PER_WINDOW / (tms * 1e-3) / 1e12,
                               "loss": float(loss_t), "grad_norm": float(norm_t)}
-        del trainer, tmodel
+        del trainer
+        # fp32 parity mode of the inference forward (BASELINE configs[1] lists fp32 next to bf16): 2048 windows, one chunk
+        tmodel.eval()
+        xf = x[:2048]
+        with torch.no_grad():
+            for _ in range(2):
+                tmodel.predict_proba(xf)
+            barrier()
+            a.record()
+            for _ in range(3):
+                tmodel.predict_proba(xf)
+            b.record()
+        barrier()
+        fms = max_over_ranks(a.elapsed_time(b)) / 3
+        line["fp32_mode"] = {"metric": "windows_per_s", "value": world * int(xf.shape[0]) / (fms * 1e-3), "unit": "windows/s", "ms": fms,
+                             "windows_per_gpu": int(xf.shape[0]),
+                             "tflops_per_gpu": int(xf.shape[0]) * FLOP_PER_WINDOW / (fms * 1e-3) / 1e12,
+                             "tolerance": "logits/probabilities <= 1e-5, attention <= 1e-6 vs the reference's fp32 CPU path"}
+        del tmodel
 
     # ---- SURVEY §8 f rows 3-4: preprocessing of raw recordings and one ablation variant (measured, not part of `value`) ----
     if not args.no_extras:

@@ -340,6 +340,10 @@ int lstm_pack_f32(bci_lstm_s* h, cudaStream_t st) {
   }
   if (c.use_attention) {
     transpose_kernel<<<nblk((long long)AH * D), 256, 0, st>>>(w.attn_w1, p.aw1t, AH, D);
+    copy_kernel<<<nblk(AH * D), 256, 0, st>>>(w.attn_w1, p.aw1, AH * D);
+    int rc = split_tf32(p.aw1, nullptr, p.aw1_lo, (long long)AH * D, st);
+    if (!rc) rc = split_tf32(p.aw1t, nullptr, p.aw1t_lo, (long long)AH * D, st);
+    if (rc) return rc;
     copy_kernel<<<nblk(AH), 256, 0, st>>>(w.attn_b1, p.ab1, AH);
     copy_kernel<<<nblk(AH), 256, 0, st>>>(w.attn_w2, p.aw2, AH);
     copy_kernel<<<1, 256, 0, st>>>(w.attn_b2, p.ab2, 1);
@@ -358,7 +362,7 @@ size_t lstm_store_bytes_f32(const bci_lstm_config& c) {
   const size_t H = c.hidden_size, C = c.input_size, D = 2 * H;
   size_t n = C * H + 3 * H;
   for (int l = 0; l < c.num_layers; ++l) n += 4 * ((size_t)layer_in_width(c, l) * 8 * H) + 2 * (2 * H * 4 * H) + 8 * H;
-  n += 2 * D + D * H + H + H + 4 + D * H + H + H * (H / 2) + H / 2 + (size_t)c.num_classes * (H / 2) + c.num_classes + 64;
+  n += 2 * D + 4 * D * H + H + H + 4 + D * H + H + H * (H / 2) + H / 2 + (size_t)c.num_classes * (H / 2) + c.num_classes + 64;
   return align_up(n * sizeof(float) + 256 * 64, 256);
 }
 
@@ -381,6 +385,7 @@ void lstm_carve_f32(bci_lstm_s* h, char* base) {
     p.wih_t_lo[l] = take((size_t)layer_in_width(c, l) * 8 * H);
   }
   p.lnw = take(D); p.lnb = take(D); p.aw1t = take(D * H); p.ab1 = take(H); p.aw2 = take(H); p.ab2 = take(4);
+  p.aw1 = take(D * H); p.aw1_lo = take(D * H); p.aw1t_lo = take(D * H);
   p.c0t = take(D * H); p.cb0 = take(H); p.c3t = take(H * (H / 2)); p.cb3 = take(H / 2);
   p.c6 = take((size_t)c.num_classes * (H / 2)); p.cb6 = take(c.num_classes);
 }

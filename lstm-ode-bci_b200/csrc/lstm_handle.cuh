@@ -22,6 +22,9 @@ struct PackedF32 {
   // tf32 remainders (x - tf32(x)) of wih_b / wih_t: second operand of the split-precision tcgen05 GEMMs (gemm_tf32x3.cu)
   float* wih_b_lo[BCI_MAX_LAYERS];
   float* wih_t_lo[BCI_MAX_LAYERS];
+  float* aw1;      // [D/2][D]    attention.0.weight (own copy: the split pair below must describe the same bits)
+  float* aw1_lo;   // remainder of aw1
+  float* aw1t_lo;  // remainder of aw1t
   float* lnw;    // [D]         D = ND*H
   float* lnb;    // [D]
   float* aw1t;   // [D][D/2]    attention.0.weight^T

@@ -835,7 +835,12 @@ static int forward_train_t(bci_lstm_s* h, const float* x, int B, int T, float p_
   BCI_LAUNCH_OK();
   int rc = BCI_OK;
   if (c.use_attention) {
-    rc = gemm_nn(w.Y, D, p.aw1t, AH, w.PRE, AH, (int)M, AH, D, p.ab1, 0, st);
+    if (tf32x3_nt_ok(w.Y, D, p.aw1, D, w.PRE, AH, (int)M, AH, D)) {
+      if ((rc = split_tf32(w.Y, nullptr, w.lo_in, M * D, st))) return rc;
+      rc = gemm_tf32x3_nt(w.Y, w.lo_in, D, p.aw1, p.aw1_lo, D, p.ab1, w.PRE, AH, (int)M, AH, D, 0, st);
+    } else {
+      rc = gemm_nn(w.Y, D, p.aw1t, AH, w.PRE, AH, (int)M, AH, D, p.ab1, 0, st);
+    }
     if (rc) return rc;
   }
   attn_train_fwd<<<B, 256, T * sizeof(float), st>>>(c.use_attention ? w.PRE : nullptr, w.Y, B, T, D, AH, p.aw2, p.ab2, w.attn, w.ctx);
@@ -903,8 +908,16 @@ static int backward_t(bci_lstm_s* h, const float* dlogits, int B, int T, float p
   BCI_LAUNCH_OK();
   if (c.use_attention) {
     // dY += dPRE . W1 ; dW1 = dPRE^T Y ; db1 = colsum(dPRE)
-    if ((rc = gemm_nn(dPRE, AH, raw.attn_w1, D, w.dA, D, (int)M, D, AH, nullptr, 1, st))) return rc;
-    if ((rc = gemm_tn(dPRE, AH, w.Y, D, g->attn_w1, D, M, AH, D, st))) return rc;
+    if (tf32x3_nt_ok(dPRE, AH, p.aw1t, AH, w.dA, D, (int)M, D, AH) && tf32x3_tn_ok(dPRE, AH, w.Y, D, g->attn_w1, D, M, AH, D)) {
+      // lo_in / lo_out2 are free here: the forward is over and the side stream starts after the top layer's BPTT
+      if ((rc = split_tf32(dPRE, nullptr, w.lo_in, M * AH, st))) return rc;
+      if ((rc = split_tf32(w.Y, nullptr, w.lo_out2, M * D, st))) return rc;
+      if ((rc = gemm_tf32x3_nt(dPRE, w.lo_in, AH, p.aw1t, p.aw1t_lo, AH, nullptr, w.dA, D, (int)M, D, AH, 1, st))) return rc;
+      if ((rc = gemm_tf32x3_tn(dPRE, w.lo_in, AH, w.Y, w.lo_out2, D, g->attn_w1, D, M, AH, D, st))) return rc;
+    } else {
+      if ((rc = gemm_nn(dPRE, AH, raw.attn_w1, D, w.dA, D, (int)M, D, AH, nullptr, 1, st))) return rc;
+      if ((rc = gemm_tn(dPRE, AH, w.Y, D, g->attn_w1, D, M, AH, D, st))) return rc;
+    }
     if ((rc = colsum(dPRE, AH, M, AH, g->attn_b1, st))) return rc;
   }
   // final LayerNorm backward: dA (dY) -> dB (grad wrt the last LSTM layer's output)

@@ -49,7 +49,14 @@ def main():
     m.eval()
     for B in (512, 4096, 16896):
         x = torch.randn(B, 256, 61, device=dev)
-        for tag, ctx in (("fp32", torch.autocast("cuda", enabled=False)), ("autocast_fp16", torch.autocast("cuda", dtype=torch.float16))):
+        for tag, ctx in (("fp32", torch.autocast("cuda", enabled=False)), ("fp32_strict", torch.autocast("cuda", enabled=False)),
+                         ("autocast_fp16", torch.autocast("cuda", dtype=torch.float16))):
+            # "fp32" = torch defaults (cuDNN RNN may use TF32); "fp32_strict" = TF32 disabled everywhere (an fp32-parity mode)
+            torch.backends.cudnn.allow_tf32 = tag != "fp32_strict"
+            torch.backends.cuda.matmul.allow_tf32 = False
+            if B > 4096 and tag == "fp32_strict":
+                continue
+
             def f():
                 with torch.no_grad(), ctx:
                     return torch.softmax(m(x), 1)
@@ -65,10 +72,12 @@ def main():
     x = torch.randn(512, 256, 61, device=dev); y = torch.arange(512, device=dev) % 2
     w = torch.tensor([0.8, 1.2], device=dev)
     scaler = torch.amp.GradScaler("cuda")
-    for tag in ("fp32", "autocast_fp16"):
+    for tag in ("fp32", "fp32_strict", "autocast_fp16"):
+        torch.backends.cudnn.allow_tf32 = tag != "fp32_strict"
+
         def step():
             opt.zero_grad(set_to_none=True)
-            if tag == "fp32":
+            if tag != "autocast_fp16":
                 loss = nn.functional.cross_entropy(m(x), y, weight=w)
                 loss.backward()
                 torch.nn.utils.clip_grad_norm_(m.parameters(), 1.0)
