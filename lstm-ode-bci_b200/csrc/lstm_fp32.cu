@@ -8,6 +8,7 @@
 //                       gates = G_t + h W_hh^T, sigma/tanh, cell update, h -> smem for step t+1
 // Reference: nn.LSTM inside EnhancedLSTMModel (04_lstm_model.py:181-188,211).
 #include "lstm_shared_kernels.cuh"
+#include <cstdlib>
 
 namespace bci {
 
@@ -229,12 +230,29 @@ int launch_proj_gemm_f32(const float* A, const float* Bt, const float* bias, flo
   return BCI_OK;
 }
 
+// Windows per thread of the small-batch recurrences (shared with BPTT): the smallest tile that still leaves SMs idle wins.
+// BCI_REC_WPT=4|8|16 overrides it (experiment, 512-window training step: H = 128 16.8 / 32.9 ms with 4 / 8 windows per thread;
+// H = 256 54.7 / 60.8 / 102 ms with 4 / 8 / 16 -- even where 4-window tiles need 1.7 waves and stream 1 MB of W_hh per CTA and
+// step, the smaller tile is faster: the step is latency-bound, not L2-bandwidth-bound).
+void small_batch_policy(int H, int ND, int Bc, int groups, bool& small, bool& tiny) {
+  static int forced = -1;
+  if (forced < 0) {
+    const char* e = getenv("BCI_REC_WPT");
+    forced = e ? atoi(e) : 0;
+  }
+  if (forced == 4) { small = true; tiny = true; return; }
+  if (forced == 8) { small = true; tiny = false; return; }
+  if (forced == 16) { small = false; tiny = false; return; }
+  (void)H; (void)ND; (void)Bc; (void)groups;
+}
+
 int launch_rec_f32(int H, int ND, const float* G, const float* whh_f, const float* whh_r, float* out, float* gates, float* csave,
                    int Bc, int T, cudaStream_t st) {
   // tiles of 16 windows per thread unless that leaves most SMs idle (training batches): then 8
   const int groups = REC_THREADS / H;
-  const bool small = ND * ceil_div(Bc, groups * 16) < sm_count();
-  const bool tiny = ND * ceil_div(Bc, groups * 8) < sm_count();  // even 8-window groups leave SMs idle (training: 512 windows)
+  bool small = ND * ceil_div(Bc, groups * 16) < sm_count();
+  bool tiny = ND * ceil_div(Bc, groups * 8) < sm_count();  // even 8-window groups leave SMs idle (training: 512 windows)
+  small_batch_policy(H, ND, Bc, groups, small, tiny);
   if (H == 128) {
     if (tiny) {
       constexpr int RES = 96;

@@ -136,6 +136,7 @@ int launch_proj_gemm_f32(const float* A, const float* Bt, const float* bias, flo
                          int accumulate = 0);
 int launch_rec_f32(int H, int ND, const float* G, const float* whh_f, const float* whh_r, float* out, float* gates, float* csave,
                    int Bc, int T, cudaStream_t st);
+void small_batch_policy(int H, int ND, int Bc, int groups, bool& small, bool& tiny);
 // split-precision tcgen05 GEMMs of the fp32 path (gemm_tf32x3.cu)
 bool tf32x3_enabled();
 bool tf32x3_nt_ok(const void* A, int lda, const void* W, int ldw, const void* C, int ldc, int M, int N, int K);

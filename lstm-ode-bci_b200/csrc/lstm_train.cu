@@ -927,8 +927,9 @@ static int backward_t(bci_lstm_s* h, const float* dlogits, int B, int T, float p
   float* dnext = w.dA;  // scratch for grad wrt the layer input
   // ---- LSTM layers, top down ----
   // 16 windows per thread unless that leaves most SMs idle (typical training batches): then 8
-  const bool small = ND * ceil_div(B, (BP_THREADS / H) * 16) < sm_count();
-  const bool tiny = ND * ceil_div(B, (BP_THREADS / H) * 8) < sm_count();
+  bool small = ND * ceil_div(B, (BP_THREADS / H) * 16) < sm_count();
+  bool tiny = ND * ceil_div(B, (BP_THREADS / H) * 8) < sm_count();
+  small_batch_policy(H, ND, B, BP_THREADS / H, small, tiny);
   const int MT = (BP_THREADS / H) * (tiny ? 4 : small ? 8 : 16);
   const size_t bp_smem = (size_t)4 * H * (MT + 4) * sizeof(float);
   // training batches at H = 128: 96 of the 128 unit rows of W_hh resident in shared memory behind the dG tile
