@@ -734,7 +734,9 @@ static int forward_chunk_bf16(bci_lstm_s* h, const float* x, int Bc, int T, floa
     h->prof.mark(2, st);
     in = o;
   }
-  rc = launch_pool_bf16(h, in, stats, scores, Bc, T, logits, probs, attn, st);
+  // single pass over the sequence when the batch fills the machine (the score buffer then holds the pooled context)
+  rc = pool_stream_ok(h, Bc, T) ? launch_pool_stream_bf16(h, in, stats, scores, Bc, T, logits, probs, attn, st)
+                                : launch_pool_bf16(h, in, stats, scores, Bc, T, logits, probs, attn, st);
   h->prof.mark(3, st);
   return rc;
 }

@@ -43,6 +43,14 @@ int pack_pool_bf16(bci_lstm_s* h, cudaStream_t st) {
   pack_attn_w1_kernel<<<ceil_div(H * D, 256), 256, 0, st>>>(w.attn_w1, w.ln_w, h->bf16.aw1_bf, H, D);
   pack_attn_par_kernel<<<ceil_div(H, 128), 128, 0, st>>>(w.attn_w1, h->bf16.aw1_bf, w.ln_b, w.attn_b1, w.attn_w2, h->bf16.apar, H, D);
   BCI_LAUNCH_OK();
+  // weight-only bound on |score| = |sum_j w2_j tanh(.)| for the single-pass pooling kernel (host value: one small copy per
+  // load_weights of a bf16 handle)
+  float w2h[256];
+  BCI_CUDA_OK(cudaMemcpyAsync(w2h, w.attn_w2, (size_t)H * sizeof(float), cudaMemcpyDeviceToHost, st));
+  BCI_CUDA_OK(cudaStreamSynchronize(st));
+  float smax = 0.f;
+  for (int j = 0; j < H; ++j) smax += fabsf(w2h[j]);
+  h->bf16.pool_smax = (smax == smax) ? fmaxf(smax, 1e-6f) : 0.f;  // NaN weights: keep the two-kernel path
   return BCI_OK;
 }
 

@@ -1,0 +1,400 @@
+// bf16 mode of K4/K5, single-pass version: LayerNorm + additive-attention pooling (04_lstm_model.py:112-128,192-193,212-215)
+// with the sequence read from HBM exactly ONCE.
+//
+// The two-kernel version (lstm_bf16_pool.cu) computes all scores, then streams the sequence a second time for the
+// softmax-weighted sum: 2 x 128 KB per window, 1.13 ms per 16 896 windows against 7.8 ms for the three LSTM layers.  Here one CTA
+// owns 128 windows and walks the T time steps of the time-major sequence [T][Bc][256]:
+//
+//   TMA        tile X_t = rows (t, 128 windows) x 256 features, 4 SWIZZLE_128B k-blocks of 16 KB, two tiles in flight
+//   MMA 1      S_t = X_t . W1'^T  (M128 x N128 x K256, W1' = W1 diag(ln_w) resident)          -> TMEM columns [0,128)
+//   epilogue   thread = window: score_t = sum_j w2_j tanh(rstd (S_tj - mean s_j) + c_j)  (LayerNorm folded in, row statistics
+//              from the last recurrence layer's epilogue), e_t = exp(score_t - S_max) with the weight-only bound
+//              S_max = sum_j |w2_j| >= |score| (no running maximum, so nothing accumulated ever needs rescaling),
+//              beta_t = bf16(e_t rstd_t), l += e_t, gamma += beta_t mean_t; beta_t is written onto the diagonal of a 128 x 128
+//              bf16 tile in shared memory
+//   MMA 2      CTX += diag(beta_t) . X_t  (M128 x N256 x K128; the SAME shared-memory tile is read a second time, now as the
+//              MN-major B operand: rows = K = windows, 64-feature groups 16 KB apart)         -> TMEM columns [256,512)
+//
+// so the softmax-weighted sum over time is accumulated by the tensor core in fp32 TMEM and the tile never leaves the SM.
+// After the last step: ctx = ln_w (CTX - gamma) / l + ln_b, written as fp32 [Bc][256] for the classifier kernel below.
+// Attention weights (optional output): e_t is stored as it is produced and divided by l at the end.
+#include "lstm_shared_kernels.cuh"
+#include "sm100_prims.cuh"
+#include "tmap.cuh"
+#include <cstdlib>
+
+namespace bci {
+using namespace sm100;
+
+constexpr int PS_THREADS = 320;  // warp 0 TMA, warp 1 MMA + TMEM, warps 2-9 epilogue: two threads per window (64 of the 128 score terms each)
+constexpr uint32_t PS_KB_BYTES = 128 * 64 * 2;        // one 128-row x 64-column bf16 k-block (16 KB)
+constexpr uint32_t PS_B_BYTES = 4 * PS_KB_BYTES;      // W1' [128][256]
+constexpr uint32_t PS_RING = 8;                       // two tiles of four k-blocks
+constexpr uint32_t PS_D_BYTES = 2 * PS_KB_BYTES;      // diag(beta) [128][128]
+constexpr uint32_t PS_PAR_BYTES = 128 * 12;            // {s_j, c_j} float2 + w2_j float (2 KB of float4 would not fit)
+constexpr uint32_t PS_NEEDED = PS_B_BYTES + PS_RING * PS_KB_BYTES + PS_D_BYTES + PS_PAR_BYTES + 512 + 256;  // + partial scores + barriers
+// 512 bytes of alignment slack instead of 1024 (the budget is 227 KB to the byte): dynamic shared memory starts 1 KB-aligned on
+// this architecture when the kernel has no static shared memory; the kernel traps if that ever fails to hold
+constexpr size_t PS_SMEM = 512 + PS_NEEDED;
+
+// MN-major bf16 operand inside a K-major-loaded tile: rows (= K index) of 128 B, 8-row groups 1024 B apart (SBO), 64-element
+// groups of N one k-block (16 KB) apart (LBO); SWIZZLE_128B
+__device__ __forceinline__ uint64_t umma_desc_sw128_mn16(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)(PS_KB_BYTES >> 4) << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+__device__ __forceinline__ float tanh_mufu_ps(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+__global__ void __launch_bounds__(PS_THREADS, 1)
+attn_pool_stream_bf16(const __grid_constant__ CUtensorMap tmA,   // seq [T*Bc][256] bf16, box 64 x 128
+                      const __grid_constant__ CUtensorMap tmB,   // W1' [128][256] bf16, box 64 x 128
+                      const float4* __restrict__ par,            // [128] {s_j, c_j, w2_j, 0}
+                      const float2* __restrict__ stats,          // [T][8][Bc] partial (sum, sumsq) over 32 features each
+                      const float* __restrict__ lnw, const float* __restrict__ lnb,
+                      float smax, float* __restrict__ ctx_out,   // [Bc][256]
+                      float* __restrict__ attn,                  // optional [Bc][T]
+                      int Bc, int T) {
+  extern __shared__ uint8_t ps_smem_raw[];
+  const uint32_t raw = smem_u32(ps_smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* gen = ps_smem_raw + (base - raw);
+  const uint32_t sB = base, sA = sB + PS_B_BYTES, sD = sA + PS_RING * PS_KB_BYTES;
+  uint8_t* genD = gen + PS_B_BYTES + PS_RING * PS_KB_BYTES;
+  float2* par_sc = reinterpret_cast<float2*>(genD + PS_D_BYTES);   // [128] {s_j, c_j}
+  float* par_w2 = reinterpret_cast<float*>(par_sc + 128);          // [128]
+  float* part_s = par_w2 + 128;                                    // [128] partial scores of the second column half
+  uint8_t* ctl = genD + PS_D_BYTES + PS_PAR_BYTES + 512;
+  const uint32_t bar0 = smem_u32(ctl);
+  if ((base - raw) + PS_NEEDED > PS_SMEM) __trap();
+  auto full_bar = [&](int s) { return bar0 + 8u * s; };
+  auto empty_bar = [&](int s) { return bar0 + 8u * (PS_RING + s); };
+  auto tfull_bar = [&](uint32_t b) { return bar0 + 8u * (2 * PS_RING + b); };       // score accumulator b holds S_t
+  auto tempty_bar = [&](uint32_t b) { return bar0 + 8u * (2 * PS_RING + 2 + b); };  // ... has been read by the epilogue
+  const uint32_t bfull_bar = bar0 + 8u * (2 * PS_RING + 4);
+  const uint32_t dready_bar = bfull_bar + 8, dfree_bar = bfull_bar + 16, cdone_bar = bfull_bar + 24, cfree_bar = bfull_bar + 32;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ctl + 8 * (2 * PS_RING + 9));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int wblocks = (Bc + 127) / 128;
+
+  // diag(beta) starts as zeros; only its diagonal is ever written
+  for (uint32_t i = threadIdx.x; i < PS_D_BYTES / 16; i += PS_THREADS) reinterpret_cast<uint4*>(genD)[i] = make_uint4(0, 0, 0, 0);
+  fence_proxy_async_smem();
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (uint32_t s = 0; s < PS_RING; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (uint32_t b = 0; b < 2; ++b) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), 256); }
+    mbar_init(bfull_bar, 1);
+    mbar_init(dready_bar, 128); mbar_init(dfree_bar, 1); mbar_init(cdone_bar, 1); mbar_init(cfree_bar, 128);
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(smem_u32(tmem_slot), 512);
+    tmem_relinquish();
+  }
+  if (warp >= 2 && warp < 6) {
+    const int j = (warp - 2) * 32 + lane;
+    const float4 p = __ldg(par + j);
+    par_sc[j] = make_float2(p.x, p.y);
+    par_w2[j] = p.z;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_arrive_expect_tx(bfull_bar, PS_B_BYTES);
+      for (int kb = 0; kb < 4; ++kb) tma_load_2d(sB + kb * PS_KB_BYTES, &tmB, kb * 64, 0, bfull_bar);
+      uint32_t stage = 0, phase = 0;
+      for (int wb = blockIdx.x; wb < wblocks; wb += gridDim.x) {
+        for (int t = 0; t < T; ++t) {
+          for (int kb = 0; kb < 4; ++kb) {
+            mbar_wait(empty_bar(stage), phase ^ 1u);
+            mbar_arrive_expect_tx(full_bar(stage), PS_KB_BYTES);
+            tma_load_2d(sA + stage * PS_KB_BYTES, &tmA, kb * 64, t * Bc + wb * 128, full_bar(stage));
+            if (++stage == PS_RING) { stage = 0; phase ^= 1u; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc1 = umma_idesc_bf16(128, 128);
+      constexpr uint32_t idesc2 = umma_idesc_bf16(128, 64) | (1u << 16);  // B is MN-major, one 64-feature group per instruction
+      uint32_t stage = 0, phase = 0, it = 0, nwb = 0;
+      mbar_wait(bfull_bar, 0);
+      // S_t = X_t . W1'^T into score accumulator (tile counter & 1); consumes the tile's four ring stages.  `block` = false:
+      // returns false without issuing anything if the tile has not landed yet
+      auto issue_scores = [&](uint32_t tile_it, bool block) -> bool {
+        const uint32_t b = tile_it & 1u;
+        if (!block) {
+          if (!mbar_try_wait(tempty_bar(b), ((tile_it >> 1) & 1u) ^ 1u)) return false;
+          // the four k-blocks of a tile are requested back to back: the last one landing is the test
+          if (!mbar_try_wait(full_bar(stage + 3), phase)) return false;
+        }
+        mbar_wait(tempty_bar(b), ((tile_it >> 1) & 1u) ^ 1u);  // the epilogue has read this accumulator's previous tile
+        tc_fence_after();
+        for (int kb = 0; kb < 4; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk)
+            umma_bf16(tmem_base + b * 128, umma_desc_sw128(sA + stage * PS_KB_BYTES + kk * 32),
+                      umma_desc_sw128(sB + kb * PS_KB_BYTES + kk * 32), idesc1, (kb | kk) != 0 ? 1u : 0u);
+          if (++stage == PS_RING) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit(tfull_bar(b));
+        return true;
+      };
+      for (int wb = blockIdx.x; wb < wblocks; wb += gridDim.x, ++nwb) {
+        if (nwb > 0) { mbar_wait(cfree_bar, (nwb - 1) & 1u); tc_fence_after(); }  // the epilogue has read the previous CTX
+        issue_scores(it, true);
+        for (int t = 0; t < T; ++t, ++it) {
+          const uint32_t stage0 = (it & 1u) * 4;  // ring half of tile t
+          // Two things to issue, in whichever order they become possible: the next tile's scores (as soon as it has landed: its
+          // epilogue then overlaps this tile's context MMAs) and this tile's context MMAs (as soon as beta_t is on the diagonal:
+          // their completion frees the ring half the tile after next is loaded into -- waiting for the next tile first would put
+          // a full load latency between consecutive context MMAs)
+          bool need_scores = t + 1 < T, need_ctx = true;
+          while (need_scores || need_ctx) {
+            if (need_scores && issue_scores(it + 1, false)) need_scores = false;
+            if (need_ctx && mbar_try_wait(dready_bar, it & 1u)) {
+              tc_fence_after();
+              // one 64-feature group (= one k-block of the ring) at a time, so each k-block is released as soon as it is done
+#pragma unroll
+              for (int g = 0; g < 4; ++g) {
+#pragma unroll
+                for (int ks = 0; ks < 8; ++ks)  // K = 16 windows per instruction
+                  umma_bf16(tmem_base + 256 + g * 64, umma_desc_sw128(sD + (ks >> 2) * PS_KB_BYTES + (ks & 3) * 32),
+                            umma_desc_sw128_mn16(sA + (stage0 + g) * PS_KB_BYTES + ks * 2048), idesc2, (t | ks) != 0 ? 1u : 0u);
+                umma_commit(empty_bar(stage0 + g));
+              }
+              umma_commit(dfree_bar);
+              need_ctx = false;
+            }
+          }
+        }
+        umma_commit(cdone_bar);
+      }
+    }
+  } else {
+    const int quarter = warp & 3;
+    const int half = (warp - 2) >> 2;   // column half of the score accumulator this thread reduces (0: also owns the window's state)
+    const int r = quarter * 32 + lane;  // row of the tile = TMEM lane = window inside the block
+    const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
+    __nv_bfloat16* dslot = reinterpret_cast<__nv_bfloat16*>(genD + (r >> 6) * PS_KB_BYTES + sw128_chunk_off((uint32_t)r, (uint32_t)((r & 63) >> 3))) + (r & 7);
+    uint32_t it = 0, nwb = 0;
+    for (int wb = blockIdx.x; wb < wblocks; wb += gridDim.x, ++nwb) {
+      const int w = wb * 128 + r;
+      const bool valid = w < Bc;
+      float l = 0.f, gamma = 0.f;
+      // row statistics of step t are requested one step ahead (8 x 8-byte loads from a 277 MB array: ~1 us from HBM)
+      float2 sv[8];
+      auto fetch_stats = [&](int t) {
+        if (valid) {
+          const float2* sp = stats + ((long long)t * 8) * Bc + w;
+#pragma unroll
+          for (int k = 0; k < 8; ++k) sv[k] = __ldg(sp + (long long)k * Bc);
+        }
+      };
+      fetch_stats(0);
+      for (int t = 0; t < T; ++t, ++it) {
+        const uint32_t b = it & 1u;
+        mbar_wait(tfull_bar(b), (it >> 1) & 1u);
+        tc_fence_after();
+        float rs = 0.f, mean = 0.f;
+        if (valid) {
+          float sum = 0.f, sq = 0.f;
+#pragma unroll
+          for (int k = 0; k < 8; ++k) { sum += sv[k].x; sq += sv[k].y; }
+          mean = sum * (1.0f / 256.0f);
+          rs = 1.0f / sqrtf(fmaxf(sq * (1.0f / 256.0f) - mean * mean, 0.f) + 1e-5f);
+        }
+        if (t + 1 < T) fetch_stats(t + 1);
+        const float mp = -rs * mean;
+        uint32_t rg[2][32];
+        const uint32_t tcol = tmem_base + lane_off + b * 128 + half * 64;
+        tmem_ld32(tcol, rg[0]);
+        float score = 0.f;
+#pragma unroll
+        for (int ch = 0; ch < 2; ++ch) {
+          tmem_ld_wait();
+          if (ch + 1 < 2) tmem_ld32(tcol + 32, rg[1]);
+          const uint32_t* rc = rg[ch];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float2 sc = par_sc[half * 64 + ch * 32 + j];
+            score = fmaf(par_w2[half * 64 + ch * 32 + j], tanh_mufu_ps(fmaf(rs, __uint_as_float(rc[j]), fmaf(mp, sc.x, sc.y))), score);
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(tempty_bar(b));
+        // the two halves of a row meet in shared memory (pairs of warps with the same TMEM lane quarter)
+        if (half == 1) part_s[r] = score;
+        asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");
+        if (half == 1) {
+          asm volatile("bar.sync %0, 64;" ::"r"(5 + quarter) : "memory");  // part_s[r] has been consumed
+          continue;
+        }
+        score += part_s[r];
+        asm volatile("bar.sync %0, 64;" ::"r"(5 + quarter) : "memory");
+        const float e = valid ? __expf(score - smax) : 0.f;
+        const __nv_bfloat16 bb = __float2bfloat16_rn(e * rs);
+        l += e;
+        gamma = fmaf(__bfloat162float(bb), mean, gamma);
+        mbar_wait(dfree_bar, (it & 1u) ^ 1u);  // MMA 2 of the previous step has read the diagonal
+        *dslot = bb;
+        fence_proxy_async_smem();
+        mbar_arrive(dready_bar);
+        if (attn && valid) attn[(long long)w * T + t] = e;
+      }
+      if (half == 1) continue;  // the window's state (l, gamma) lives in the first thread of the pair
+      // context of this window: TMEM columns [256,512) of its lane
+      mbar_wait(cdone_bar, nwb & 1u);
+      tc_fence_after();
+      const float inv_l = valid ? 1.0f / l : 0.f;
+#pragma unroll 1
+      for (int ch = 0; ch < 8; ++ch) {
+        uint32_t rc[32];
+        tmem_ld32(tmem_base + lane_off + 256 + ch * 32, rc);
+        tmem_ld_wait();
+        if (valid) {
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            float4 o;
+            const int c = ch * 32 + q * 4;
+            o.x = fmaf(__ldg(lnw + c + 0), (__uint_as_float(rc[q * 4 + 0]) - gamma) * inv_l, __ldg(lnb + c + 0));
+            o.y = fmaf(__ldg(lnw + c + 1), (__uint_as_float(rc[q * 4 + 1]) - gamma) * inv_l, __ldg(lnb + c + 1));
+            o.z = fmaf(__ldg(lnw + c + 2), (__uint_as_float(rc[q * 4 + 2]) - gamma) * inv_l, __ldg(lnb + c + 2));
+            o.w = fmaf(__ldg(lnw + c + 3), (__uint_as_float(rc[q * 4 + 3]) - gamma) * inv_l, __ldg(lnb + c + 3));
+            *reinterpret_cast<float4*>(ctx_out + (long long)w * 256 + c) = o;
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(cfree_bar);
+      if (attn && valid)
+        for (int t = 0; t < T; ++t) attn[(long long)w * T + t] *= inv_l;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ---- classifier on the pooled context: Linear(2H,H) GELU Linear(H,H/2) GELU Linear(H/2,classes); softmax (04:196-204,218) ----
+constexpr int HM_WPC = 16;  // windows per CTA: the 160 KB of fp32 classifier weights are read once per 16 windows
+template <int H>
+__global__ void __launch_bounds__(H)
+head_mlp_kernel(const float* __restrict__ ctx, int Bc, int classes, const float* __restrict__ c0t, const float* __restrict__ cb0,
+                const float* __restrict__ c3t, const float* __restrict__ cb3, const float* __restrict__ c6, const float* __restrict__ cb6,
+                float* __restrict__ logits, float* __restrict__ probs) {
+  constexpr int D = 2 * H;
+  __shared__ __align__(16) float ctx_s[HM_WPC][D];
+  __shared__ float h1_s[HM_WPC][H], h2_s[HM_WPC][H / 2], lg_s[HM_WPC][8];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int b_first = blockIdx.x * HM_WPC;
+  const int nwin = (Bc - b_first) < HM_WPC ? (Bc - b_first) : HM_WPC;
+  for (int i = tid; i < HM_WPC * D / 4; i += H) {
+    const int w = i / (D / 4);
+    reinterpret_cast<float4*>(&ctx_s[0][0])[i] =
+        w < nwin ? __ldg(reinterpret_cast<const float4*>(ctx + (long long)b_first * D) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  __syncthreads();
+  {
+    float a[HM_WPC];
+#pragma unroll
+    for (int w = 0; w < HM_WPC; ++w) a[w] = cb0[tid];
+    for (int d = 0; d < D; ++d) {
+      const float wt = __ldg(c0t + (long long)d * H + tid);
+#pragma unroll
+      for (int w = 0; w < HM_WPC; ++w) a[w] = fmaf(ctx_s[w][d], wt, a[w]);
+    }
+#pragma unroll
+    for (int w = 0; w < HM_WPC; ++w) h1_s[w][tid] = gelu_erf(a[w]);
+  }
+  __syncthreads();
+  if (tid < H / 2) {
+    float a[HM_WPC];
+#pragma unroll
+    for (int w = 0; w < HM_WPC; ++w) a[w] = cb3[tid];
+    for (int k = 0; k < H; ++k) {
+      const float wt = __ldg(c3t + k * (H / 2) + tid);
+#pragma unroll
+      for (int w = 0; w < HM_WPC; ++w) a[w] = fmaf(h1_s[w][k], wt, a[w]);
+    }
+#pragma unroll
+    for (int w = 0; w < HM_WPC; ++w) h2_s[w][tid] = gelu_erf(a[w]);
+  }
+  __syncthreads();
+  for (int i = warp; i < nwin * classes; i += H / 32) {
+    const int w = i / classes, c = i - w * classes;
+    float a = 0.f;
+    for (int k = lane; k < H / 2; k += 32) a = fmaf(h2_s[w][k], __ldg(c6 + c * (H / 2) + k), a);
+    a = warp_sum(a) + cb6[c];
+    if (lane == 0) { logits[(long long)(b_first + w) * classes + c] = a; lg_s[w][c] = a; }
+  }
+  if (probs) {
+    __syncthreads();
+    if (tid < nwin) {
+      float mx = -INFINITY;
+      for (int c = 0; c < classes; ++c) mx = fmaxf(mx, lg_s[tid][c]);
+      float den = 0.f;
+      for (int c = 0; c < classes; ++c) den += expf(lg_s[tid][c] - mx);
+      for (int c = 0; c < classes; ++c) probs[(long long)(b_first + tid) * classes + c] = expf(lg_s[tid][c] - mx) / den;
+    }
+  }
+}
+
+// Is the single-pass kernel applicable?  It needs enough 128-window blocks to occupy the machine (each CTA streams its block's
+// whole sequence), seq_len >= 256 (the context buffer reuses the score workspace), at most 8 classes, and a score bound
+// small enough that exp(score - S_max) cannot underflow for the largest weights (2 S_max < 80).
+bool pool_stream_ok(const bci_lstm_s* h, int Bc, int T) {
+  static int off = -1;
+  if (off < 0) {
+    const char* e = getenv("BCI_BF16_POOL");  // "two": the two-kernel version
+    off = (e && e[0] == 't') ? 1 : 0;
+  }
+  return !off && h->cfg.hidden_size == 128 && Bc >= 4096 && T >= 256 && h->cfg.num_classes <= 8 && h->bf16.pool_smax > 0.f &&
+         h->bf16.pool_smax <= 30.f;
+}
+
+// seq [T][Bc][256] bf16 -> logits / probs / attention; ctx_ws = Bc x 256 floats of workspace
+int launch_pool_stream_bf16(bci_lstm_s* h, const __nv_bfloat16* seq, const float2* stats, float* ctx_ws, int Bc, int T, float* logits,
+                            float* probs, float* attn, cudaStream_t st) {
+  CUtensorMap tmA, tmB;
+  int rc = make_tmap_bf16(&tmA, seq, (uint64_t)Bc * T, 256, 64, 128);
+  if (rc) return rc;
+  rc = make_tmap_bf16(&tmB, h->bf16.aw1_bf, 128, 256, 64, 128);
+  if (rc) return rc;
+  static bool attr = false;
+  if (!attr) {
+    BCI_CUDA_OK(cudaFuncSetAttribute(attn_pool_stream_bf16, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PS_SMEM));
+    attr = true;
+  }
+  const PackedF32& p = h->f32;
+  const int wblocks = ceil_div(Bc, 128);
+  const int grid = wblocks < sm_count() ? wblocks : sm_count();
+  attn_pool_stream_bf16<<<grid, PS_THREADS, PS_SMEM, st>>>(tmA, tmB, h->bf16.apar, stats, p.lnw, p.lnb, h->bf16.pool_smax, ctx_ws, attn, Bc, T);
+  BCI_LAUNCH_OK();
+  head_mlp_kernel<128><<<ceil_div(Bc, HM_WPC), 128, 0, st>>>(ctx_ws, Bc, h->cfg.num_classes, p.c0t, p.cb0, p.c3t, p.cb3, p.c6, p.cb6, logits, probs);
+  BCI_LAUNCH_OK();
+  return BCI_OK;
+}
+
+}  // namespace bci

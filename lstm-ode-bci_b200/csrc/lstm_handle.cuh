@@ -60,6 +60,7 @@ struct PackedBF16 {
   //   aw1_bf [H][2H] = bf16(W1[j][d] * ln_w[d]);  apar[j] = {s_j = sum_d aw1_bf[j][d], c_j = b1_j + sum_d ln_b[d] W1[j][d], w2_j, 0}
   __nv_bfloat16* aw1_bf;
   float4* apar;
+  float pool_smax;  // HOST value: sum_j |attention.2.weight_j| >= |score| (bound used by the single-pass pooling kernel)
   // input projection on tensor cores (lstm_bf16_inproj.cu): w0_bf [H][64] = bf16(input_proj.0.weight), K zero-padded
   // from C to 64; par0[j] = {b0_j, ln_w_j, ln_b_j, 0}
   __nv_bfloat16* w0_bf;
@@ -158,6 +159,10 @@ int pack_inproj_bf16(bci_lstm_s* h, cudaStream_t st);
 int launch_input_proj_bf16(bci_lstm_s* h, const float* x, int Bc, int T, __nv_bfloat16* z, cudaStream_t st);
 int launch_pool_bf16(bci_lstm_s* h, const __nv_bfloat16* seq, float2* stats, float* scores, int Bc, int T, float* logits,
                      float* probs, float* attn, cudaStream_t st);
+// single-pass pooling (lstm_bf16_pool_stream.cu)
+bool pool_stream_ok(const bci_lstm_s* h, int Bc, int T);
+int launch_pool_stream_bf16(bci_lstm_s* h, const __nv_bfloat16* seq, const float2* stats, float* ctx_ws, int Bc, int T, float* logits,
+                            float* probs, float* attn, cudaStream_t st);
 int launch_fused_rec_bf16(const __nv_bfloat16* in, const __nv_bfloat16* wih, const __nv_bfloat16* whh_f, const __nv_bfloat16* whh_r,
                           const float* bias, __nv_bfloat16* out, float2* stats, int Bc, int T, int Kin, cudaStream_t st);
 int fused_max_clusters();  // co-resident 4-CTA clusters of the fused kernel on this device (0 if it cannot run)

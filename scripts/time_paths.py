@@ -1,5 +1,6 @@
 """Device-resident timing of the bf16 forward for a given batch (BCI_BF16_PATH=split|fused picks the recurrence path)."""
-import sys, time
+import os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 from lstm_ode_bci_b200 import lstm, synth, ops
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 16896
@@ -27,3 +28,10 @@ m32 = lstm.from_params(params, precision="fp32")
 with torch.no_grad():
     p32 = m32.predict_proba(x[:256]).cpu().numpy()
 print("dprob vs fp32 path", float(np.abs(p[:256].cpu().numpy() - p32).max()))
+# attention and the tail of the batch (partial last block when B % 128 != 0)
+with torch.no_grad():
+    pb, ab = m.predict_proba(x, return_attention=True)
+    p32t, a32t = m32.predict_proba(x[-200:], return_attention=True)
+print("tail: dprob %.3e dattn %.3e  attn row sums %.6f..%.6f  nan %d" % (
+    float((pb[-200:] - p32t).abs().max()), float((ab[-200:] - a32t).abs().max()), float(ab.sum(1).min()), float(ab.sum(1).max()),
+    int(torch.isnan(pb).sum() + torch.isnan(ab).sum())))

@@ -325,3 +325,24 @@ def test_gemm_tf32x3_tn_is_fp32_grade(P, Q, R):
     A0[9, 70] = 1.0; B0[9, 33] = 3.0; A0[R - 1, 1] = 1.0; B0[R - 1, Q - 2] = 5.0
     got = _tf32x3(1, A0, B0, None, P, Q, R)
     assert got.nonzero().tolist() == [[1, Q - 2], [70, 33]] and float(got[1, Q - 2]) == 5.0 and float(got[70, 33]) == 3.0
+
+
+def test_bf16_single_pass_pooling_large_batch():
+    """Batches of >= 4096 windows pool with the single-pass kernel (lstm_bf16_pool_stream.cu: score GEMM, softmax weights on the
+    diagonal of a bf16 tile, context accumulated by a second MMA in TMEM).  4100 windows = 32 full 128-window blocks + a partial
+    one; reference = the fp32 CUDA path (itself <= 1e-5 from the oracle) on the head, the tail and a middle slice."""
+    B, T = 4100, 256
+    params = synth.make_lstm_params(42, 61, 128, 3, logit_gain=12.0)
+    x = torch.from_numpy(synth.make_windows(11, B, T, 61, structured=True)).cuda()
+    mb = lstm.from_params(params, precision="bf16")
+    m32 = lstm.from_params(params, precision="fp32")
+    with torch.no_grad():
+        pb, ab = mb.predict_proba(x, return_attention=True)
+        pb2 = mb.predict_proba(x)
+    assert torch.isfinite(pb).all() and torch.isfinite(ab).all()
+    assert torch.equal(pb, pb2)                                   # attention output on/off does not change the probabilities
+    assert float((ab.sum(dim=1) - 1).abs().max()) <= 1e-5         # softmax over T
+    for sl in (slice(0, 96), slice(2000, 2064), slice(B - 100, B)):
+        with torch.no_grad():
+            p32, a32 = m32.predict_proba(x[sl], return_attention=True)
+        assert float((pb[sl] - p32).abs().max()) <= 1e-2 and float((ab[sl] - a32).abs().max()) <= 2e-3
