@@ -45,11 +45,15 @@ int pack_pool_bf16(bci_lstm_s* h, cudaStream_t st) {
   BCI_LAUNCH_OK();
   // weight-only bound on |score| = |sum_j w2_j tanh(.)| for the single-pass pooling kernel (host value: one small copy per
   // load_weights of a bf16 handle)
-  float w2h[256];
-  BCI_CUDA_OK(cudaMemcpyAsync(w2h, w.attn_w2, (size_t)H * sizeof(float), cudaMemcpyDeviceToHost, st));
+  float4 parh[128];
+  BCI_REQUIRE(H == 128, BCI_EINVAL, "pack_pool_bf16: hidden_size 128 expected");
+  BCI_CUDA_OK(cudaMemcpyAsync(parh, h->bf16.apar, (size_t)H * sizeof(float4), cudaMemcpyDeviceToHost, st));
   BCI_CUDA_OK(cudaStreamSynchronize(st));
   float smax = 0.f;
-  for (int j = 0; j < H; ++j) smax += fabsf(w2h[j]);
+  for (int j = 0; j < H; ++j) {
+    smax += fabsf(parh[j].z);
+    h->bf16.pool_par[0][j] = parh[j].x; h->bf16.pool_par[1][j] = parh[j].y; h->bf16.pool_par[2][j] = parh[j].z;
+  }
   h->bf16.pool_smax = (smax == smax) ? fmaxf(smax, 1e-6f) : 0.f;  // NaN weights: keep the two-kernel path
   return BCI_OK;
 }

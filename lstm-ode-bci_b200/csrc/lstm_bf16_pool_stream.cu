@@ -31,8 +31,7 @@ constexpr uint32_t PS_KB_BYTES = 128 * 64 * 2;        // one 128-row x 64-column
 constexpr uint32_t PS_B_BYTES = 4 * PS_KB_BYTES;      // W1' [128][256]
 constexpr uint32_t PS_RING = 8;                       // two tiles of four k-blocks
 constexpr uint32_t PS_D_BYTES = 2 * PS_KB_BYTES;      // diag(beta) [128][128]
-constexpr uint32_t PS_PAR_BYTES = 128 * 12;            // {s_j, c_j} float2 + w2_j float (2 KB of float4 would not fit)
-constexpr uint32_t PS_NEEDED = PS_B_BYTES + PS_RING * PS_KB_BYTES + PS_D_BYTES + PS_PAR_BYTES + 512 + 256;  // + partial scores + barriers
+constexpr uint32_t PS_NEEDED = PS_B_BYTES + PS_RING * PS_KB_BYTES + PS_D_BYTES + 512 + 256;  // + partial scores + barriers
 // 512 bytes of alignment slack instead of 1024 (the budget is 227 KB to the byte): dynamic shared memory starts 1 KB-aligned on
 // this architecture when the kernel has no static shared memory; the kernel traps if that ever fails to hold
 constexpr size_t PS_SMEM = 512 + PS_NEEDED;
@@ -54,10 +53,36 @@ __device__ __forceinline__ float tanh_mufu_ps(float x) {
   return y;
 }
 
+struct PoolPar { float s[128], c[128], w2[128]; };
+
+// 64 of the 128 terms of one row's score: sum_j w2_j tanh(rstd (S_j - mean s_j) + c_j); HALF is a compile-time constant so every
+// parameter is a constant-bank operand at a fixed offset
+template <int HALF>
+__device__ __forceinline__ float score_half(const PoolPar& pp, uint32_t tcol, float rs, float mp) {
+  uint32_t rg[2][32];
+  tmem_ld32(tcol, rg[0]);
+  float score = 0.f;
+#pragma unroll
+  for (int ch = 0; ch < 2; ++ch) {
+    tmem_ld_wait();
+    if (ch + 1 < 2) tmem_ld32(tcol + 32, rg[1]);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const int jj = HALF * 64 + ch * 32 + j;
+      float y;
+      asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(fmaf(rs, __uint_as_float(rg[ch][j]), fmaf(mp, pp.s[jj], pp.c[jj]))));
+      score = fmaf(pp.w2[jj], y, score);
+    }
+  }
+  return score;
+}
+
 __global__ void __launch_bounds__(PS_THREADS, 1)
 attn_pool_stream_bf16(const __grid_constant__ CUtensorMap tmA,   // seq [T*Bc][256] bf16, box 64 x 128
                       const __grid_constant__ CUtensorMap tmB,   // W1' [128][256] bf16, box 64 x 128
-                      const float4* __restrict__ par,            // [128] {s_j, c_j, w2_j, 0}
+                      const __grid_constant__ PoolPar pp,        // per score column j: s_j, c_j, w2_j -- read through the constant
+                                                                 // bank as FMA operands: the shared-memory pipe is what bounds this
+                                                                 // kernel (operand fetch of both MMAs), so the epilogue stays off it
                       const float2* __restrict__ stats,          // [T][8][Bc] partial (sum, sumsq) over 32 features each
                       const float* __restrict__ lnw, const float* __restrict__ lnb,
                       float smax, float* __restrict__ ctx_out,   // [Bc][256]
@@ -69,10 +94,8 @@ attn_pool_stream_bf16(const __grid_constant__ CUtensorMap tmA,   // seq [T*Bc][2
   uint8_t* gen = ps_smem_raw + (base - raw);
   const uint32_t sB = base, sA = sB + PS_B_BYTES, sD = sA + PS_RING * PS_KB_BYTES;
   uint8_t* genD = gen + PS_B_BYTES + PS_RING * PS_KB_BYTES;
-  float2* par_sc = reinterpret_cast<float2*>(genD + PS_D_BYTES);   // [128] {s_j, c_j}
-  float* par_w2 = reinterpret_cast<float*>(par_sc + 128);          // [128]
-  float* part_s = par_w2 + 128;                                    // [128] partial scores of the second column half
-  uint8_t* ctl = genD + PS_D_BYTES + PS_PAR_BYTES + 512;
+  float* part_s = reinterpret_cast<float*>(genD + PS_D_BYTES);     // [128] partial scores of the second column half
+  uint8_t* ctl = genD + PS_D_BYTES + 512;
   const uint32_t bar0 = smem_u32(ctl);
   if ((base - raw) + PS_NEEDED > PS_SMEM) __trap();
   auto full_bar = [&](int s) { return bar0 + 8u * s; };
@@ -93,20 +116,14 @@ attn_pool_stream_bf16(const __grid_constant__ CUtensorMap tmA,   // seq [T*Bc][2
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     for (uint32_t s = 0; s < PS_RING; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (uint32_t b = 0; b < 2; ++b) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), 256); }
+    for (uint32_t b = 0; b < 2; ++b) { mbar_init(tfull_bar(b), 1); mbar_init(tempty_bar(b), 8); }  // one elected arrive per epilogue warp
     mbar_init(bfull_bar, 1);
-    mbar_init(dready_bar, 128); mbar_init(dfree_bar, 1); mbar_init(cdone_bar, 1); mbar_init(cfree_bar, 128);
+    mbar_init(dready_bar, 4); mbar_init(dfree_bar, 1); mbar_init(cdone_bar, 1); mbar_init(cfree_bar, 128);
     fence_mbar_init();
   }
   if (warp == 1) {
     tmem_alloc(smem_u32(tmem_slot), 512);
     tmem_relinquish();
-  }
-  if (warp >= 2 && warp < 6) {
-    const int j = (warp - 2) * 32 + lane;
-    const float4 p = __ldg(par + j);
-    par_sc[j] = make_float2(p.x, p.y);
-    par_w2[j] = p.z;
   }
   tc_fence_before();
   __syncthreads();
@@ -119,7 +136,14 @@ attn_pool_stream_bf16(const __grid_constant__ CUtensorMap tmA,   // seq [T*Bc][2
       for (int kb = 0; kb < 4; ++kb) tma_load_2d(sB + kb * PS_KB_BYTES, &tmB, kb * 64, 0, bfull_bar);
       uint32_t stage = 0, phase = 0;
       for (int wb = blockIdx.x; wb < wblocks; wb += gridDim.x) {
+        // The ring holds two tiles and a tile's life (load -> scores -> epilogue -> context MMAs) is ~4 us, so a load is only
+        // requested one tile period before it is needed: an L2 prefetch two tiles further ahead turns that load into an L2 hit
+        constexpr int PD = 2;
+        for (int t = 0; t < PD && t < T; ++t)
+          for (int kb = 0; kb < 4; ++kb) tma_prefetch_l2_2d(&tmA, kb * 64, t * Bc + wb * 128);
         for (int t = 0; t < T; ++t) {
+          if (t + PD < T)
+            for (int kb = 0; kb < 4; ++kb) tma_prefetch_l2_2d(&tmA, kb * 64, (t + PD) * Bc + wb * 128);
           for (int kb = 0; kb < 4; ++kb) {
             mbar_wait(empty_bar(stage), phase ^ 1u);
             mbar_arrive_expect_tx(full_bar(stage), PS_KB_BYTES);
@@ -132,7 +156,7 @@ attn_pool_stream_bf16(const __grid_constant__ CUtensorMap tmA,   // seq [T*Bc][2
   } else if (warp == 1) {
     if (lane == 0) {
       constexpr uint32_t idesc1 = umma_idesc_bf16(128, 128);
-      constexpr uint32_t idesc2 = umma_idesc_bf16(128, 64) | (1u << 16);  // B is MN-major, one 64-feature group per instruction
+      constexpr uint32_t idesc2 = umma_idesc_bf16(128, 256) | (1u << 16);  // B is MN-major
       uint32_t stage = 0, phase = 0, it = 0, nwb = 0;
       mbar_wait(bfull_bar, 0);
       // S_t = X_t . W1'^T into score accumulator (tile counter & 1); consumes the tile's four ring stages.  `block` = false:
@@ -172,15 +196,15 @@ attn_pool_stream_bf16(const __grid_constant__ CUtensorMap tmA,   // seq [T*Bc][2
             if (need_scores && issue_scores(it + 1, false)) need_scores = false;
             if (need_ctx && mbar_try_wait(dready_bar, it & 1u)) {
               tc_fence_after();
-              // one 64-feature group (= one k-block of the ring) at a time, so each k-block is released as soon as it is done
+              // 8 instructions of N = 256 (the single issuing thread needs ~40 cycles per tcgen05.mma: 32 instructions of N = 64,
+              // one per k-block for an earlier release, cost more on this strictly serial diagonal -> MMA -> diagonal chain than
+              // the earlier release gained)
 #pragma unroll
-              for (int g = 0; g < 4; ++g) {
+              for (int ks = 0; ks < 8; ++ks)  // K = 16 windows per instruction
+                umma_bf16(tmem_base + 256, umma_desc_sw128(sD + (ks >> 2) * PS_KB_BYTES + (ks & 3) * 32),
+                          umma_desc_sw128_mn16(sA + stage0 * PS_KB_BYTES + ks * 2048), idesc2, (t | ks) != 0 ? 1u : 0u);
 #pragma unroll
-                for (int ks = 0; ks < 8; ++ks)  // K = 16 windows per instruction
-                  umma_bf16(tmem_base + 256 + g * 64, umma_desc_sw128(sD + (ks >> 2) * PS_KB_BYTES + (ks & 3) * 32),
-                            umma_desc_sw128_mn16(sA + (stage0 + g) * PS_KB_BYTES + ks * 2048), idesc2, (t | ks) != 0 ? 1u : 0u);
-                umma_commit(empty_bar(stage0 + g));
-              }
+              for (int g = 0; g < 4; ++g) umma_commit(empty_bar(stage0 + g));
               umma_commit(dfree_bar);
               need_ctx = false;
             }
@@ -224,23 +248,11 @@ attn_pool_stream_bf16(const __grid_constant__ CUtensorMap tmA,   // seq [T*Bc][2
         }
         if (t + 1 < T) fetch_stats(t + 1);
         const float mp = -rs * mean;
-        uint32_t rg[2][32];
         const uint32_t tcol = tmem_base + lane_off + b * 128 + half * 64;
-        tmem_ld32(tcol, rg[0]);
-        float score = 0.f;
-#pragma unroll
-        for (int ch = 0; ch < 2; ++ch) {
-          tmem_ld_wait();
-          if (ch + 1 < 2) tmem_ld32(tcol + 32, rg[1]);
-          const uint32_t* rc = rg[ch];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const float2 sc = par_sc[half * 64 + ch * 32 + j];
-            score = fmaf(par_w2[half * 64 + ch * 32 + j], tanh_mufu_ps(fmaf(rs, __uint_as_float(rc[j]), fmaf(mp, sc.x, sc.y))), score);
-          }
-        }
+        float score = half ? score_half<1>(pp, tcol, rs, mp) : score_half<0>(pp, tcol, rs, mp);
         tc_fence_before();
-        mbar_arrive(tempty_bar(b));
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty_bar(b));  // 256 arrivals on one mbarrier would serialise on the step's critical chain
         // the two halves of a row meet in shared memory (pairs of warps with the same TMEM lane quarter)
         if (half == 1) part_s[r] = score;
         asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");
@@ -257,7 +269,8 @@ attn_pool_stream_bf16(const __grid_constant__ CUtensorMap tmA,   // seq [T*Bc][2
         mbar_wait(dfree_bar, (it & 1u) ^ 1u);  // MMA 2 of the previous step has read the diagonal
         *dslot = bb;
         fence_proxy_async_smem();
-        mbar_arrive(dready_bar);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(dready_bar);
         if (attn && valid) attn[(long long)w * T + t] = e;
       }
       if (half == 1) continue;  // the window's state (l, gamma) lives in the first thread of the pair
@@ -388,9 +401,11 @@ int launch_pool_stream_bf16(bci_lstm_s* h, const __nv_bfloat16* seq, const float
     attr = true;
   }
   const PackedF32& p = h->f32;
+  PoolPar pp;
+  for (int j = 0; j < 128; ++j) { pp.s[j] = h->bf16.pool_par[0][j]; pp.c[j] = h->bf16.pool_par[1][j]; pp.w2[j] = h->bf16.pool_par[2][j]; }
   const int wblocks = ceil_div(Bc, 128);
   const int grid = wblocks < sm_count() ? wblocks : sm_count();
-  attn_pool_stream_bf16<<<grid, PS_THREADS, PS_SMEM, st>>>(tmA, tmB, h->bf16.apar, stats, p.lnw, p.lnb, h->bf16.pool_smax, ctx_ws, attn, Bc, T);
+  attn_pool_stream_bf16<<<grid, PS_THREADS, PS_SMEM, st>>>(tmA, tmB, pp, stats, p.lnw, p.lnb, h->bf16.pool_smax, ctx_ws, attn, Bc, T);
   BCI_LAUNCH_OK();
   head_mlp_kernel<128><<<ceil_div(Bc, HM_WPC), 128, 0, st>>>(ctx_ws, Bc, h->cfg.num_classes, p.c0t, p.cb0, p.c3t, p.cb3, p.c6, p.cb6, logits, probs);
   BCI_LAUNCH_OK();

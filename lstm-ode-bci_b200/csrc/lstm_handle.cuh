@@ -61,6 +61,7 @@ struct PackedBF16 {
   __nv_bfloat16* aw1_bf;
   float4* apar;
   float pool_smax;  // HOST value: sum_j |attention.2.weight_j| >= |score| (bound used by the single-pass pooling kernel)
+  float pool_par[3][128];  // HOST copies of apar's {s_j}, {c_j}, {w2_j}: passed to that kernel as a constant-bank argument
   // input projection on tensor cores (lstm_bf16_inproj.cu): w0_bf [H][64] = bf16(input_proj.0.weight), K zero-padded
   // from C to 64; par0[j] = {b0_j, ln_w_j, ln_b_j, 0}
   __nv_bfloat16* w0_bf;
