@@ -29,6 +29,7 @@
 #include "lstm_shared_kernels.cuh"
 #include "sm100_prims.cuh"
 #include "tmap.cuh"
+#include <cstdlib>
 
 namespace bci {
 using namespace sm100;
@@ -421,6 +422,12 @@ static int fused_setup(int* max_clusters_out) {
     cfg.attrs = la; cfg.numAttrs = 1;
     BCI_CUDA_OK(cudaOccupancyMaxActiveClusters(&max_clusters, lstm_fused_bf16<false>, &cfg));
     BCI_REQUIRE(max_clusters > 0, BCI_ECUDA, "fused recurrence: no 4-CTA cluster fits on this device");
+    // BCI_FUSED_CLUSTERS=n caps the co-resident clusters used (experiment: on a 148-SM B200 32 clusters x 512 windows were 2 % faster per
+    // window than 33 x 512 in one 5-step sweep and 4 % slower in a sustained bench run on another box: within run-to-run variation, so
+    // the occupancy limit stays the default)
+    const int occ = max_clusters;
+    const char* e = getenv("BCI_FUSED_CLUSTERS");
+    if (e && atoi(e) > 0) max_clusters = atoi(e) < occ ? atoi(e) : occ;
     state = 1;
   }
   if (max_clusters_out) *max_clusters_out = max_clusters;
