@@ -55,11 +55,12 @@ class ClockSampler:
 
     def __init__(self, index):
         self.index, self.rows, self.proc = index, [], None
+        self.t_begin, self.t_end = 0.0, float("inf")
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
@@ -68,17 +69,21 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
 
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.25)
+        time.sleep(0.1)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
+        # samples taken while the timed region ran (a line is stamped when it is read: up to one period after it was taken);
+        # if the region was shorter than the sampling period, fall back to the nearest samples around it
+        inside = [r for ts, r in self.rows if self.t_begin <= ts <= self.t_end + 0.06]
+        self.rows = inside if inside else [r for ts, r in self.rows if ts >= self.t_begin - 0.1][:2]
         sm = sorted(float(r[1]) for r in self.rows if len(r) >= 8 and r[1].replace(".", "").isdigit())
         mx = [float(r[2]) for r in self.rows if len(r) >= 8 and r[2].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
@@ -235,13 +240,17 @@ def main():
     x = torch.randn((B, 256, 61), device="cuda", generator=gen)           # N(0,1): z-scored EEG (02:134-152)
 
     # ---- device-resident throughput (value) --------------------------------------------------
+    # the clock sampler starts before the warm-up so that nvidia-smi is already reporting when the timed region begins (a K-step
+    # region lasts a few hundred ms); samples are stamped and only those taken inside the region are kept
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
     for _ in range(W):
         model.predict_proba(x)
     ops.lstm_set_profiling(hid, True)
     ops.lstm_get_profile(hid)
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
+    torch.cuda.synchronize()
+    sampler.t_begin = time.time()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     l0 = ops.launch_count()
@@ -250,6 +259,7 @@ def main():
         probs = model.predict_proba(x)
     e1.record()
     barrier()
+    sampler.t_end = time.time()
     launches = ops.launch_count() - l0
     ms = max_over_ranks(e0.elapsed_time(e1))
     prof = ops.lstm_get_profile(hid)

@@ -600,6 +600,7 @@ lstm_bptt_f32(const float* __restrict__ dout,    // [T][Bc][ND*H]  grad wrt the 
               const float* __restrict__ whh_bf,  // [unit][j][4 gates] (float4 per (unit, j)), forward direction
               const float* __restrict__ whh_br,  // reverse direction
               float* __restrict__ dG,            // [T][Bc][ND][H][4]
+              float* __restrict__ dG_lo,         // optional: tf32 remainder of dG for the split-precision GEMMs (gemm_tf32x3.cu)
               int Bc, int T, int ND) {
   constexpr int GROUPS = BP_THREADS / H, MT = GROUPS * BP_WPT, GS = MT + 4;
   extern __shared__ __align__(16) float bp_smem[];  // [4H][GS]
@@ -664,6 +665,15 @@ lstm_bptt_f32(const float* __restrict__ dout,    // [T][Bc][ND*H]  grad wrt the 
         dg.w = dh * tc * g.w * (1.0f - g.w);            // d pre_o
         dc[w] = dct * g.y;
         reinterpret_cast<float4*>(dG)[(row * ND + dir) * H + j] = dg;
+        if (dG_lo) {  // x - trunc_tf32(x), rounded to tf32: what split_tf32_kernel would produce in a separate pass over dG
+          auto lo = [](float x) {
+            const float rem = x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
+            uint32_t r;
+            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(rem));
+            return __uint_as_float(r);
+          };
+          reinterpret_cast<float4*>(dG_lo)[(row * ND + dir) * H + j] = make_float4(lo(dg.x), lo(dg.y), lo(dg.z), lo(dg.w));
+        }
       }
       dgs[0 * GS + w] = dg.x; dgs[1 * GS + w] = dg.y; dgs[2 * GS + w] = dg.z; dgs[3 * GS + w] = dg.w;
     }
@@ -719,9 +729,19 @@ lstm_bptt_f32(const float* __restrict__ dout,    // [T][Bc][ND*H]  grad wrt the 
 }
 
 // ---- small elementwise helpers ---------------------------------------------------------------------------------
-__global__ void scale_mask_kernel(const float* __restrict__ src, float* __restrict__ dst, long long n, float p, uint64_t seed, uint32_t site) {
+// dst = dropout(src); lo (optional) = tf32 remainder of dst for the split-precision GEMM that consumes it next
+__global__ void scale_mask_kernel(const float* __restrict__ src, float* __restrict__ dst, long long n, float p, uint64_t seed, uint32_t site,
+                                  float* __restrict__ lo = nullptr) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) dst[i] = src[i] * drop_scale(seed, site, (uint64_t)i, p);
+  if (i >= n) return;
+  const float v = src[i] * drop_scale(seed, site, (uint64_t)i, p);
+  dst[i] = v;
+  if (lo) {
+    const float rem = v - __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(rem));
+    lo[i] = __uint_as_float(r);
+  }
 }
 // interleaved rows (n = unit*4 + gate, optionally + dir*4H) -> reference gate-major rows; dst (4H, K)
 __global__ void unpack_gate_rows_kernel(const float* __restrict__ src, float* __restrict__ dst, int H, int K, int row0) {
@@ -812,11 +832,12 @@ static int forward_train_t(bci_lstm_s* h, const float* x, int B, int T, float p_
   inproj_train_fwd<H><<<rb, 256, 0, st>>>(x, B, T, C, p.w0t, p.b0, p.ln0w, p.ln0b, w.xT, w.xhat0, w.rstd0, w.z, p_drop * 0.5f, seed, use_ln);
   BCI_LAUNCH_OK();
   const float* in = w.z;
+  bool lo_ready = false;  // w.lo_in already holds the remainder of `in` (written by the dropout kernel of the layer below)
   for (int l = 0; l < c.num_layers; ++l) {
     const int K = layer_in_width(c, l);
     int rc;
     if (tf32x3_nt_ok(in, K, p.wih_b[l], K, w.G, 4 * D, (int)M, 4 * D, K)) {
-      if ((rc = split_tf32(in, nullptr, w.lo_in, M * K, st))) return rc;
+      if (!lo_ready && (rc = split_tf32(in, nullptr, w.lo_in, M * K, st))) return rc;
       rc = gemm_tf32x3_nt(in, w.lo_in, K, p.wih_b[l], p.wih_b_lo[l], K, p.bias[l], w.G, 4 * D, (int)M, 4 * D, K, 0, st);
     } else {
       rc = launch_proj_gemm_f32(in, p.wih_t[l], p.bias[l], w.G, (int)M, 4 * D, K, st);
@@ -824,9 +845,11 @@ static int forward_train_t(bci_lstm_s* h, const float* x, int B, int T, float p_
     if (rc) return rc;
     rc = launch_rec_f32(H, ND, w.G, p.whh_t[l][0], p.whh_t[l][1], w.out[l], w.gates[l], w.cst[l], B, T, st);
     if (rc) return rc;
+    lo_ready = false;
     if (w.outd[l] != w.out[l]) {
-      scale_mask_kernel<<<(unsigned)ceil_div64(M * D, 256), 256, 0, st>>>(w.out[l], w.outd[l], M * D, p_drop, seed, 16 + l);
+      scale_mask_kernel<<<(unsigned)ceil_div64(M * D, 256), 256, 0, st>>>(w.out[l], w.outd[l], M * D, p_drop, seed, 16 + l, w.lo_in);
       BCI_LAUNCH_OK();
+      lo_ready = w.lo_in != nullptr;
     }
     in = w.outd[l];
   }
@@ -966,20 +989,20 @@ static int backward_t(bci_lstm_s* h, const float* dlogits, int B, int T, float p
     const int gb = (L - 1 - l) & 1;
     float* dGl = gb ? w.G2 : w.G;
     if (used[gb]) BCI_CUDA_OK(cudaStreamWaitEvent(st, h->ev_side[gb], 0));  // the side stream has finished reading this buffer
-    if (tiny && H == 128)
-      lstm_bptt_f32<H, 4, BP_RES><<<dim3(ceil_div(B, MT), ND), BP_THREADS, bp_smem + bp_res_bytes, st>>>(dcur, w.gates[l], w.cst[l], p.whh_b[l][0], p.whh_b[l][1], dGl, B, T, ND);
-    else if (tiny)
-      lstm_bptt_f32<H, 4><<<dim3(ceil_div(B, MT), ND), BP_THREADS, bp_smem, st>>>(dcur, w.gates[l], w.cst[l], p.whh_b[l][0], p.whh_b[l][1], dGl, B, T, ND);
-    else if (small)
-      lstm_bptt_f32<H, 8><<<dim3(ceil_div(B, MT), ND), BP_THREADS, bp_smem, st>>>(dcur, w.gates[l], w.cst[l], p.whh_b[l][0], p.whh_b[l][1], dGl, B, T, ND);
-    else
-      lstm_bptt_f32<H, 16><<<dim3(ceil_div(B, MT), ND), BP_THREADS, bp_smem, st>>>(dcur, w.gates[l], w.cst[l], p.whh_b[l][0], p.whh_b[l][1], dGl, B, T, ND);
-    BCI_LAUNCH_OK();
-    // split-precision tensor-core GEMMs for this layer's gradients when the shapes allow (training batches do)
+    // split-precision tensor-core GEMMs for this layer's gradients when the shapes allow (training batches do); BPTT then also
+    // writes the tf32 remainder of dG (no separate pass over the 0.5 GB array)
     float* dGl_lo = gb ? w.lo_G2 : w.lo_G;
     const bool tc = tf32x3_tn_ok(dGl, G4, in, K, w.tmpW2, K, M, G4, K) && tf32x3_tn_ok(dGl, G4, w.out[l], D, w.tmpW2, H, M - B, 4 * H, H) &&
                     tf32x3_nt_ok(dGl, G4, p.wih_t[l], G4, dnext, K, (int)M, K, G4);
-    if (tc && (rc = split_tf32(dGl, nullptr, dGl_lo, M * G4, st))) return rc;
+    if (tiny && H == 128)
+      lstm_bptt_f32<H, 4, BP_RES><<<dim3(ceil_div(B, MT), ND), BP_THREADS, bp_smem + bp_res_bytes, st>>>(dcur, w.gates[l], w.cst[l], p.whh_b[l][0], p.whh_b[l][1], dGl, tc ? dGl_lo : nullptr, B, T, ND);
+    else if (tiny)
+      lstm_bptt_f32<H, 4><<<dim3(ceil_div(B, MT), ND), BP_THREADS, bp_smem, st>>>(dcur, w.gates[l], w.cst[l], p.whh_b[l][0], p.whh_b[l][1], dGl, tc ? dGl_lo : nullptr, B, T, ND);
+    else if (small)
+      lstm_bptt_f32<H, 8><<<dim3(ceil_div(B, MT), ND), BP_THREADS, bp_smem, st>>>(dcur, w.gates[l], w.cst[l], p.whh_b[l][0], p.whh_b[l][1], dGl, tc ? dGl_lo : nullptr, B, T, ND);
+    else
+      lstm_bptt_f32<H, 16><<<dim3(ceil_div(B, MT), ND), BP_THREADS, bp_smem, st>>>(dcur, w.gates[l], w.cst[l], p.whh_b[l][0], p.whh_b[l][1], dGl, tc ? dGl_lo : nullptr, B, T, ND);
+    BCI_LAUNCH_OK();
     BCI_CUDA_OK(cudaEventRecord(h->ev_dg, st));
     BCI_CUDA_OK(cudaStreamWaitEvent(sd, h->ev_dg, 0));
     // dW_ih (all directions at once, interleaved rows) = dG^T . in
