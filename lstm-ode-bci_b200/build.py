@@ -21,6 +21,8 @@ OBJ_DIR = os.path.join(ROOT, "build", "obj")
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--threads", "2"]
+# extra -D switches for experiments (e.g. BCI_NVCC_DEFINES="-DBCI_REC_ACCURATE_ACT"); changing them needs --force
+NVCC_FLAGS += os.environ.get("BCI_NVCC_DEFINES", "").split()
 
 
 def _nvcc():

@@ -1,4 +1,4 @@
-// fp32 (parity) mode of the BiLSTM forward: CUDA-core FMA everywhere, accurate expf/tanhf, so
+// fp32 (parity) mode of the BiLSTM forward: fp32 arithmetic everywhere (see rec_sigmoid / rec_tanh for the gate activations), so
 // logits/probabilities match the reference's fp32 path to <= 1e-5 (north_star).  Tensor cores
 // (10-bit TF32 / 8-bit bf16 mantissas) cannot meet that bound over 3 x 256 dependent steps; the
 // tcgen05 path lives in lstm_bf16.cu.
@@ -200,10 +200,10 @@ lstm_rec_f32(const float* __restrict__ G,      // [T][Bc][ND][H][4]
     float hq[4];
 #pragma unroll
     for (int w = 0; w < REC_WPT; ++w) {
-      const float ig = sigmoid_acc(acc[w].x), fg = sigmoid_acc(acc[w].y);
-      const float gg = tanhf(acc[w].z), og = sigmoid_acc(acc[w].w);
+      const float ig = rec_sigmoid(acc[w].x), fg = rec_sigmoid(acc[w].y);
+      const float gg = rec_tanh(acc[w].z), og = rec_sigmoid(acc[w].w);
       c[w] = fmaf(fg, c[w], ig * gg);
-      const float hv = og * tanhf(c[w]);
+      const float hv = og * rec_tanh(c[w]);
       hq[w & 3] = hv;
       if ((w & 3) == 3) hnext[w >> 2] = make_float4(hq[0], hq[1], hq[2], hq[3]);
       const int b = b_base + w;

@@ -657,7 +657,7 @@ lstm_bptt_f32(const float* __restrict__ dout,    // [T][Bc][ND*H]  grad wrt the 
         const float c = PRE ? pc[w] : csave[(row * ND + dir) * H + j];
         const float cprev = PRE ? pcp[w] : ((s > 0) ? csave[(((long long)tp * Bc + b) * ND + dir) * H + j] : 0.f);
         const float dh = (PRE ? pdo[w] : dout[row * (ND * H) + dir * H + j]) + dh_rec[w];
-        const float tc = tanhf(c);
+        const float tc = rec_tanh(c);  // the forward's own tanh(c) (h = o tanh(c))
         const float dct = fmaf(dh * g.w, 1.0f - tc * tc, dc[w]);
         dg.x = dct * g.z * g.x * (1.0f - g.x);          // d pre_i
         dg.y = dct * cprev * g.y * (1.0f - g.y);        // d pre_f
