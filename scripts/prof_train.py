@@ -3,7 +3,8 @@ import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from lstm_ode_bci_b200 import lstm, synth, train
-m = lstm.from_params(synth.make_lstm_params(42, 61, 128, 3), precision="fp32", dropout=0.4).train()
+H = int(sys.argv[1]) if len(sys.argv) > 1 else 128
+m = lstm.from_params(synth.make_lstm_params(42, 61, H, 3), precision="fp32", dropout=0.4).train()
 tr = train.FusedTrainer(m, class_weight=[0.8, 1.2])
 x = torch.randn(512, 256, 61, device="cuda"); y = torch.arange(512, device="cuda") % 2
 for i in range(2):
