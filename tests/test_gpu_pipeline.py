@@ -64,3 +64,28 @@ def test_config5_pipeline_single_rank_matches_unsharded_mirrors():
     assert (b, e) == (0, len(x) - 20)
     for j, h in enumerate((5, 10, 20)):
         assert np.abs(got[:, j] - fc[h]["predictions"]).max() <= 1e-6
+
+
+def test_empty_and_single_window_inputs():
+    """Edge cases of the caller contracts: N = 0 (the reference's loops simply do not run, 06:339,372) and N = 1."""
+    import numpy as np
+    import torch
+    from lstm_ode_bci_b200 import integration, lstm, ode, synth
+    params = synth.make_lstm_params(42, 61, 128, 3, logit_gain=12.0)
+    for precision in ("fp32", "bf16"):
+        m = lstm.from_params(params, precision=precision)
+        integ = integration.LSTMODEIntegration(m, ode.CognitiveStateODE(), coupling_strength=0.5)
+        traj, probs, preds = integ.predict_batch(np.zeros((0, 256, 61), dtype=np.float32), forecast_steps=20, show_progress=False)
+        assert traj.shape == (0, 20, 3) and probs.shape == (0, 2) and preds.shape == (0,)
+        with torch.no_grad():
+            lg, at = m(torch.zeros((0, 256, 61), device="cuda"), return_attention=True)
+        assert lg.shape == (0, 2) and at.shape == (0, 256)
+        x1 = synth.make_windows(3, 1, 256, 61, structured=True)
+        traj, probs, preds = integ.predict_batch(x1, forecast_steps=20, show_progress=False)
+        assert traj.shape == (1, 20, 3) and abs(float(probs.sum()) - 1.0) < 1e-5 and preds.shape == (1,)
+        assert np.abs(traj.sum(axis=2) - 1).max() <= 2e-7
+    lp, ts, cls = integration.get_three_state_probabilities(m, ode.CognitiveStateODE(), np.zeros((0, 256, 61), dtype=np.float32))
+    assert lp.shape == (0, 2) and ts.shape == (0, 3) and cls.shape == (0,)
+    t, f = ode.solve_modulated_ensemble(np.zeros((3, 0)), np.tile(np.array([0.1, 0.02, 0.15, 0.08, 0.05, 0.1]), (2 * 2 * 4 + 1, 1)),
+                                        (0.0, 4.0), 5, 2)
+    assert t.shape == (0, 5, 3) and f.shape == (0, 3)
