@@ -614,6 +614,21 @@ lstm_bptt_f32(const float* __restrict__ dout,    // [T][Bc][ND*H]  grad wrt the 
   float4* wres = reinterpret_cast<float4*>(bp_smem + 4 * H * GS);  // [RES_U][H]
   if (RES_U > 0)
     for (int i = tid; i < RES_U * H; i += BP_THREADS) wres[i] = __ldg(W + i);
+  // USPLIT (the training-size variant): the two thread groups of a CTA do not split the tile's 8 windows but the 128 unit rows of
+  // the product dh[j][w] = sum_u dG[u][.][w] W[u][.][j] -- each thread covers all 8 windows for half of the rows (16-row blocks
+  // alternate between the groups, so both have 48 resident and 16 streamed rows) and the halves are exchanged through 4 KB of
+  // shared memory.  Per thread and step that is 64 weight reads + 512 broadcast dG reads instead of 128 + 512, a quarter fewer
+  // shared-memory wavefronts on a kernel ncu showed at 79 % of that pipe.
+  constexpr bool USPLIT = RES_U > 0 && GROUPS == 2 && BP_WPT == 4;
+  static_assert(!USPLIT || RES_U == 96, "the u-split variant is written for 96 resident rows of 128");
+  float4* xch = reinterpret_cast<float4*>(wres + RES_U * H);  // [2 destination groups][H]: partial dh of the other group's windows
+  float own[BP_WPT];
+  if (USPLIT) {
+#pragma unroll
+    for (int w = 0; w < BP_WPT; ++w) own[w] = 0.f;
+    xch[tid] = make_float4(0.f, 0.f, 0.f, 0.f);
+    __syncthreads();
+  }
 
   // latency-bound variant (RES_U > 0): the saved activations of step s-1 are requested while the recurrent product of step s
   // runs (the elementwise part at the top of a step otherwise waits ~1 us for them); c(s-1) is step s's cprev, already here
@@ -640,12 +655,16 @@ lstm_bptt_f32(const float* __restrict__ dout,    // [T][Bc][ND*H]  grad wrt the 
     const int t = dir ? (T - 1 - s) : s;               // time index of forward step s
     const int tp = dir ? (t + 1) : (t - 1);            // time index of forward step s-1 (previous state)
     float* dgs = bp_smem + (j * 4) * GS + grp * BP_WPT;
+    if (USPLIT) {  // this group's windows: own half of the unit rows + the other group's half (written before the last barrier)
+      const float4 o = xch[grp * H + j];
+      dh_rec[0] = own[0] + o.x; dh_rec[1] = own[1] + o.y; dh_rec[2] = own[2] + o.z; dh_rec[3] = own[3] + o.w;
+    }
     // rows that are not resident: requested now, consumed after the resident part of the product
-    constexpr int TAIL_U = RES_U > 0 ? H - RES_U : 1;
+    constexpr int TAIL_U = RES_U > 0 ? (USPLIT ? 16 : H - RES_U) : 1;
     float4 wt[TAIL_U];
     if (RES_U > 0) {
 #pragma unroll
-      for (int uu = 0; uu < TAIL_U; ++uu) wt[uu] = __ldg(W + (long long)(RES_U + uu) * H + j);
+      for (int uu = 0; uu < TAIL_U; ++uu) wt[uu] = __ldg(W + (long long)(RES_U + (USPLIT ? grp * 16 : 0) + uu) * H + j);
     }
 #pragma unroll
     for (int w = 0; w < BP_WPT; ++w) {
@@ -704,7 +723,39 @@ lstm_bptt_f32(const float* __restrict__ dout,    // [T][Bc][ND*H]  grad wrt the 
         }
       }
     };
-    if (RES_U > 0) {
+    if (USPLIT) {
+      float a8[8];
+#pragma unroll
+      for (int w = 0; w < 8; ++w) a8[w] = 0.f;
+      auto fma8 = [&](int u, const float4 w4) {
+        const float wg[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+        for (int gsel = 0; gsel < 4; ++gsel) {
+          const float4* gp = reinterpret_cast<const float4*>(bp_smem + (u * 4 + gsel) * GS);  // all 8 windows of the tile
+          const float4 g0 = gp[0], g1 = gp[1];
+          a8[0] = fmaf(g0.x, wg[gsel], a8[0]); a8[1] = fmaf(g0.y, wg[gsel], a8[1]);
+          a8[2] = fmaf(g0.z, wg[gsel], a8[2]); a8[3] = fmaf(g0.w, wg[gsel], a8[3]);
+          a8[4] = fmaf(g1.x, wg[gsel], a8[4]); a8[5] = fmaf(g1.y, wg[gsel], a8[5]);
+          a8[6] = fmaf(g1.z, wg[gsel], a8[6]); a8[7] = fmaf(g1.w, wg[gsel], a8[7]);
+        }
+      };
+#pragma unroll
+      for (int blk = 0; blk < 3; ++blk) {  // resident 16-row blocks 2 blk + grp (< 6)
+        const int u0 = (2 * blk + grp) * 16;
+#pragma unroll 8
+        for (int i = 0; i < 16; ++i) fma8(u0 + i, wres[(u0 + i) * H + j]);
+      }
+#pragma unroll
+      for (int uu = 0; uu < 16; ++uu) fma8(RES_U + grp * 16 + uu, wt[uu]);  // streamed block 6 + grp
+      // the other group's windows go to shared memory, this group's stay in registers until the halves meet after the barrier
+      if (grp == 0) {
+        own[0] = a8[0]; own[1] = a8[1]; own[2] = a8[2]; own[3] = a8[3];
+        xch[1 * H + j] = make_float4(a8[4], a8[5], a8[6], a8[7]);
+      } else {
+        own[0] = a8[4]; own[1] = a8[5]; own[2] = a8[6]; own[3] = a8[7];
+        xch[0 * H + j] = make_float4(a8[0], a8[1], a8[2], a8[3]);
+      }
+    } else if (RES_U > 0) {
 #pragma unroll 8
       for (int u = 0; u < RES_U; ++u) fma_unit(u, wres[u * H + j]);
 #pragma unroll
@@ -718,8 +769,10 @@ lstm_bptt_f32(const float* __restrict__ dout,    // [T][Bc][ND*H]  grad wrt the 
         for (int uu = 0; uu < 32; ++uu) fma_unit(u0 + uu, wv[uu]);
       }
     }
+    if (!USPLIT) {
 #pragma unroll
-    for (int w = 0; w < BP_WPT; ++w) dh_rec[w] = acc[w];
+      for (int w = 0; w < BP_WPT; ++w) dh_rec[w] = acc[w];
+    }
     if (PRE && s > 0) {
 #pragma unroll
       for (int w = 0; w < BP_WPT; ++w) { pc[w] = pcp[w]; pg[w] = ng[w]; pcp[w] = ncp[w]; pdo[w] = ndo[w]; }
@@ -957,7 +1010,7 @@ static int backward_t(bci_lstm_s* h, const float* dlogits, int B, int T, float p
   const size_t bp_smem = (size_t)4 * H * (MT + 4) * sizeof(float);
   // training batches at H = 128: 96 of the 128 unit rows of W_hh resident in shared memory behind the dG tile
   constexpr int BP_RES = H == 128 ? 96 : 0;
-  constexpr size_t bp_res_bytes = (size_t)BP_RES * H * sizeof(float4);
+  constexpr size_t bp_res_bytes = (size_t)(BP_RES + 2) * H * sizeof(float4);  // resident rows + the u-split exchange buffer
   static bool attr = false;
   if (!attr) {
     if (H == 128)
