@@ -577,8 +577,9 @@ extern "C" int bci_ode_solve_modulated(const bci_ode_mod_args* a, void* stream) 
 }
 
 extern "C" int bci_ode_classify(const float* fs, int64_t n, int32_t* pred06, int32_t* cls10, void* stream) {
-  BCI_REQUIRE(fs && n >= 0, BCI_EINVAL, "bci_ode_classify: bad arguments");
-  if (n == 0) return BCI_OK;
+  BCI_REQUIRE(n >= 0, BCI_EINVAL, "bci_ode_classify: negative n");
+  if (n == 0) return BCI_OK;  // empty ensemble: nothing to read or write (pointers of empty tensors may be NULL)
+  BCI_REQUIRE(fs != nullptr, BCI_EINVAL, "bci_ode_classify: final_state is NULL");
   ode_classify_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, (cudaStream_t)stream>>>(fs, n, pred06, cls10);
   BCI_LAUNCH_OK();
   return BCI_OK;
@@ -586,7 +587,8 @@ extern "C" int bci_ode_classify(const float* fs, int64_t n, int32_t* pred06, int
 
 extern "C" int bci_ode_forecast_readout(const float* traj, int64_t n, int32_t n_points, const int32_t* hz, int32_t n_h,
                                         float* out, void* stream) {
-  BCI_REQUIRE(traj && out && hz && n >= 0, BCI_EINVAL, "bci_ode_forecast_readout: bad arguments");
+  BCI_REQUIRE(hz && n >= 0, BCI_EINVAL, "bci_ode_forecast_readout: bad arguments");
+  BCI_REQUIRE(n == 0 || (traj && out), BCI_EINVAL, "bci_ode_forecast_readout: traj / out is NULL");
   BCI_REQUIRE(n_h >= 1 && n_h <= 16, BCI_EINVAL, "bci_ode_forecast_readout: 1..16 horizons supported");
   Horizons H;
   H.n = n_h;
