@@ -318,15 +318,17 @@ head_mlp_kernel(const float* __restrict__ ctx, int Bc, int classes, const float*
                 const float* __restrict__ c3t, const float* __restrict__ cb3, const float* __restrict__ c6, const float* __restrict__ cb6,
                 float* __restrict__ logits, float* __restrict__ probs) {
   constexpr int D = 2 * H;
-  __shared__ __align__(16) float ctx_s[HM_WPC][D];
-  __shared__ float h1_s[HM_WPC][H], h2_s[HM_WPC][H / 2], lg_s[HM_WPC][8];
+  // activations are kept feature-major ([feature][window]) so that one 16-byte shared-memory read feeds four windows' FMAs
+  __shared__ __align__(16) float ctx_s[D][HM_WPC];
+  __shared__ __align__(16) float h1_s[H][HM_WPC];
+  __shared__ __align__(16) float h2_s[H / 2][HM_WPC];
+  __shared__ float lg_s[HM_WPC][8];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int b_first = blockIdx.x * HM_WPC;
   const int nwin = (Bc - b_first) < HM_WPC ? (Bc - b_first) : HM_WPC;
-  for (int i = tid; i < HM_WPC * D / 4; i += H) {
-    const int w = i / (D / 4);
-    reinterpret_cast<float4*>(&ctx_s[0][0])[i] =
-        w < nwin ? __ldg(reinterpret_cast<const float4*>(ctx + (long long)b_first * D) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int i = tid; i < HM_WPC * D; i += H) {
+    const int w = i / D, d = i - w * D;  // coalesced over d
+    ctx_s[d][w] = w < nwin ? __ldg(ctx + (long long)(b_first + w) * D + d) : 0.f;
   }
   __syncthreads();
   {
@@ -336,10 +338,14 @@ head_mlp_kernel(const float* __restrict__ ctx, int Bc, int classes, const float*
     for (int d = 0; d < D; ++d) {
       const float wt = __ldg(c0t + (long long)d * H + tid);
 #pragma unroll
-      for (int w = 0; w < HM_WPC; ++w) a[w] = fmaf(ctx_s[w][d], wt, a[w]);
+      for (int q = 0; q < HM_WPC / 4; ++q) {
+        const float4 c4 = *reinterpret_cast<const float4*>(&ctx_s[d][q * 4]);
+        a[q * 4 + 0] = fmaf(c4.x, wt, a[q * 4 + 0]); a[q * 4 + 1] = fmaf(c4.y, wt, a[q * 4 + 1]);
+        a[q * 4 + 2] = fmaf(c4.z, wt, a[q * 4 + 2]); a[q * 4 + 3] = fmaf(c4.w, wt, a[q * 4 + 3]);
+      }
     }
 #pragma unroll
-    for (int w = 0; w < HM_WPC; ++w) h1_s[w][tid] = gelu_erf(a[w]);
+    for (int w = 0; w < HM_WPC; ++w) h1_s[tid][w] = gelu_erf(a[w]);
   }
   __syncthreads();
   if (tid < H / 2) {
@@ -349,16 +355,20 @@ head_mlp_kernel(const float* __restrict__ ctx, int Bc, int classes, const float*
     for (int k = 0; k < H; ++k) {
       const float wt = __ldg(c3t + k * (H / 2) + tid);
 #pragma unroll
-      for (int w = 0; w < HM_WPC; ++w) a[w] = fmaf(h1_s[w][k], wt, a[w]);
+      for (int q = 0; q < HM_WPC / 4; ++q) {
+        const float4 c4 = *reinterpret_cast<const float4*>(&h1_s[k][q * 4]);
+        a[q * 4 + 0] = fmaf(c4.x, wt, a[q * 4 + 0]); a[q * 4 + 1] = fmaf(c4.y, wt, a[q * 4 + 1]);
+        a[q * 4 + 2] = fmaf(c4.z, wt, a[q * 4 + 2]); a[q * 4 + 3] = fmaf(c4.w, wt, a[q * 4 + 3]);
+      }
     }
 #pragma unroll
-    for (int w = 0; w < HM_WPC; ++w) h2_s[w][tid] = gelu_erf(a[w]);
+    for (int w = 0; w < HM_WPC; ++w) h2_s[tid][w] = gelu_erf(a[w]);
   }
   __syncthreads();
   for (int i = warp; i < nwin * classes; i += H / 32) {
     const int w = i / classes, c = i - w * classes;
     float a = 0.f;
-    for (int k = lane; k < H / 2; k += 32) a = fmaf(h2_s[w][k], __ldg(c6 + c * (H / 2) + k), a);
+    for (int k = lane; k < H / 2; k += 32) a = fmaf(h2_s[k][w], __ldg(c6 + c * (H / 2) + k), a);
     a = warp_sum(a) + cb6[c];
     if (lane == 0) { logits[(long long)(b_first + w) * classes + c] = a; lg_s[w][c] = a; }
   }
