@@ -4,10 +4,12 @@
 // train loop (04_lstm_model.py:482-507; plain variant 09_sensitivity_analysis.py:297-303) and the
 // backward-to-input used by the attribution script (07_explainability.py:242-258).
 //
-// Structure: every dense contraction is one of two generic fp32 GEMMs over the flattened row space
-// M = T*Bc (NN: data gradients / projections, TN with split-K + atomics: weight gradients); the serial
-// parts are lstm_rec_f32 (forward, saving gate activations and cell states) and lstm_bptt_f32 (its
-// mirror: dh_{t-1} = dG_t . W_hh with the same thread = (hidden unit, 16 windows) mapping); everything
+// Structure: every large dense contraction over the flattened row space M = T*Bc runs on the tensor cores in split
+// precision (gemm_tf32x3.cu: NT for projections / data gradients, TN with split-K + TMA reduce-add for weight gradients;
+// shapes it does not cover -- the 61-channel input projection, the classifier heads, tiny test batches -- fall back to
+// the two generic CUDA-core GEMMs below); the serial parts are lstm_rec_f32 (forward, saving gate activations and cell
+// states) and lstm_bptt_f32 (its mirror: dh_{t-1} = dG_t . W_hh; training-size batches keep 96 of the 128 W_hh rows in
+// shared memory and split the unit rows of the product between the CTA's two thread groups); everything
 // row-local (LayerNorm, GELU, softmax over T, head MLP) is small fused kernels.  Dropout (four sites,
 // 04:177,186,199,202) uses a stateless hash of (seed, site, element index) so the backward pass
 // regenerates the masks instead of storing them.
