@@ -1,9 +1,11 @@
 // fp32 (parity) mode of the BiLSTM forward: fp32 arithmetic everywhere (see rec_sigmoid / rec_tanh for the gate activations), so
-// logits/probabilities match the reference's fp32 path to <= 1e-5 (north_star).  Tensor cores
-// (10-bit TF32 / 8-bit bf16 mantissas) cannot meet that bound over 3 x 256 dependent steps; the
-// tcgen05 path lives in lstm_bf16.cu.
+// logits/probabilities match the reference's fp32 path to <= 1e-5 (north_star).  Plain TF32 / bf16 tensor-core math
+// (10- / 8-bit mantissas) cannot meet that bound over 3 x 256 dependent steps: the recurrence stays on the FMA pipe and the
+// time-parallel GEMMs use TF32 in split precision; the bf16 tcgen05 path lives in lstm_bf16*.cu.
 //
-//   K2  proj_gemm_f32 : G[T*Bc][8H] = in[T*Bc][K] . W_ih^T (both directions) + (b_ih + b_hh)
+//   K2  G[T*Bc][8H] = in[T*Bc][K] . W_ih^T (both directions) + (b_ih + b_hh): the split-precision tcgen05 GEMM of
+//       gemm_tf32x3.cu (three TF32 MMAs per product, fp32-grade); proj_gemm_f32 below is the CUDA-core version it
+//       replaced (BCI_FP32_GEMM=simt, and shapes with fewer than 128 rows)
 //   K3  lstm_rec_f32  : persistent over the whole sequence per (window tile, direction):
 //                       gates = G_t + h W_hh^T, sigma/tanh, cell update, h -> smem for step t+1
 // Reference: nn.LSTM inside EnhancedLSTMModel (04_lstm_model.py:181-188,211).
