@@ -9,6 +9,8 @@ Same names, arguments, return shapes/dtypes; but the per-sample host loops of th
 (06:372-401, 10:245-273, 08:264-282) become ONE ODE-ensemble launch, and the LSTM
 probabilities never leave the device between the two stages.
 """
+import os
+
 import numpy as np
 import torch
 
@@ -16,6 +18,27 @@ from . import _native as N
 from . import ops
 from .ode import CognitiveStateODE, solve_ensemble, _dev
 from .synth import RATE_ORDER
+
+
+_STAGING_POOL = None
+
+
+def _staging_copy(dst, src):
+    """pageable -> pinned staging copy on several host threads (Tensor.copy_ releases the GIL; one thread moves ~15 GB/s, a third of
+    what the PCIe link then takes from the pinned buffer)."""
+    global _STAGING_POOL
+    n = src.shape[0]
+    workers = min(8, os.cpu_count() or 1)
+    if workers <= 1 or src.numel() < (1 << 22):
+        dst.copy_(src)
+        return
+    if _STAGING_POOL is None:
+        from concurrent.futures import ThreadPoolExecutor
+        _STAGING_POOL = ThreadPoolExecutor(max_workers=workers, thread_name_prefix="bci-staging")
+    step = (n + workers - 1) // workers
+    futs = [_STAGING_POOL.submit(dst[a:a + step].copy_, src[a:a + step]) for a in range(0, n, step)]
+    for f in futs:
+        f.result()
 
 
 def stream_lstm_probs(lstm_model, host_batches, device=None, chunk=None, want_attn=False):
@@ -54,7 +77,7 @@ def stream_lstm_probs(lstm_model, host_batches, device=None, chunk=None, want_at
             m = min(chunk, n - i)
             src = xh[i:i + m]
             if not direct:
-                sl["pin"][i:i + m].copy_(src)
+                _staging_copy(sl["pin"][i:i + m], src)
                 src = sl["pin"][i:i + m]
             with torch.cuda.stream(copy_stream):
                 sl["buf"][i:i + m].copy_(src, non_blocking=True)
@@ -99,18 +122,27 @@ def stream_lstm_probs(lstm_model, host_batches, device=None, chunk=None, want_at
 
 
 def _lstm_probs_device(lstm_model, X, batch_size, want_attn, device):
-    """All-window inference returning device tensors; X numpy/CPU tensor (pipelined H2D) or CUDA tensor."""
+    """All-window inference returning device tensors; X numpy/CPU tensor (pipelined H2D) or CUDA tensor.
+
+    `batch_size` is the reference callers' argument (512 in predict_batch 06:308, 256 in 08:198, 512 in 10:204).  There it only
+    bounds the reference's own memory use; windows are independent, so the result does not depend on it.  Here it is a LOWER
+    bound on the pass size: a pass is at least one full wave of the recurrence kernel (`bci_lstm_chunk_windows`, 16 896 windows
+    for the bf16 path on a 148-SM B200) -- a drop-in caller that keeps the reference's 512 would otherwise run the GPU at a
+    tenth of its rate."""
     dev = _dev(device)
     lstm_model.eval()
     n = len(X)
-    if batch_size is None:  # one full wave of the recurrence kernel (the reference's 512, 06:308, only bounds ITS memory use)
-        batch_size = ops.lstm_chunk_windows(lstm_model._engine(lstm_model._precision_now()))
+    wave = ops.lstm_chunk_windows(lstm_model._engine(lstm_model._precision_now()))
+    piece = max(int(batch_size or 0), int(wave), 1)
+    if n == 0:
+        return (torch.empty((0, lstm_model.num_classes), device=dev),
+                torch.empty((0, 0), device=dev) if want_attn else None)
     if isinstance(X, torch.Tensor) and X.is_cuda:
         probs = torch.empty((n, lstm_model.num_classes), device=dev, dtype=torch.float32)
         attn = None
         with torch.no_grad():
-            for i in range(0, n, batch_size):
-                xb = X[i:i + batch_size]
+            for i in range(0, n, piece):
+                xb = X[i:i + piece]
                 if want_attn:
                     p, a = lstm_model.predict_proba(xb, return_attention=True)
                     if attn is None:
@@ -120,10 +152,13 @@ def _lstm_probs_device(lstm_model, X, batch_size, want_attn, device):
                     p = lstm_model.predict_proba(xb)
                 probs[i:i + len(xb)] = p
         return probs, attn
-    if n == 0:
-        return (torch.empty((0, lstm_model.num_classes), device=dev),
-                torch.empty((0, 0), device=dev) if want_attn else None)
-    (probs, attn), = list(stream_lstm_probs(lstm_model, [X], dev, chunk=max(int(batch_size), 1), want_attn=want_attn))
+    # host input: one pass-sized piece at a time through the double-buffered H2D pipeline (device and pinned staging memory stay
+    # bounded by two pieces however long X is)
+    outs = list(stream_lstm_probs(lstm_model, (X[i:i + piece] for i in range(0, n, piece)), dev, chunk=piece, want_attn=want_attn))
+    probs = outs[0][0] if len(outs) == 1 else torch.cat([o[0] for o in outs])
+    attn = None
+    if want_attn:
+        attn = outs[0][1] if len(outs) == 1 else torch.cat([o[1] for o in outs])
     return probs, attn
 
 
