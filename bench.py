@@ -486,6 +486,24 @@ def main():
         line["ablation_minimal"] = {"metric": "windows_per_s", "value": world * 2048 / (ams * 1e-3), "unit": "windows/s", "ms": ams,
                                     "config": "09:342-349 'Minimal': H=256, 1 layer, unidirectional, mean pooling, fp32", "windows_per_gpu": 2048}
         del abl
+        # the reference's own call, unmodified: LSTMODEIntegration.predict_batch(X_numpy, forecast_steps=20, batch_size=512)
+        # (06_lstm_ode_integration.py:801-806) -- pageable numpy in, numpy out, LSTM + coupling + ODE + classification.  Rank 0 only.
+        if rank == 0:
+            import numpy as np
+            integ = integration.LSTMODEIntegration(model, ode.CognitiveStateODE(), coupling_strength=0.5, device=f"cuda:{local}")
+            nd = 2 * B
+            xd = np.random.default_rng(0).standard_normal((nd, 256, 61), dtype=np.float32)
+            integ.predict_batch(xd, forecast_steps=20, batch_size=512, show_progress=False)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            trj, _pp, _pd = integ.predict_batch(xd, forecast_steps=20, batch_size=512, show_progress=False)
+            dsec = time.perf_counter() - t0
+            line["dropin_predict_batch"] = {"metric": "windows_per_s", "value": nd / dsec, "unit": "windows/s", "windows": nd, "seconds": dsec,
+                                            "api": "LSTMODEIntegration.predict_batch(X: pageable numpy (N,256,61), forecast_steps=20, batch_size=512) "
+                                                   "-> (trajectories (N,20,3) f64, probs (N,2), predictions (N,)) as numpy; one process, one GPU",
+                                            "h2d_bytes": int(xd.nbytes), "d2h_bytes": int(trj.nbytes + _pp.nbytes + _pd.nbytes)}
+            del xd, trj, integ
+        barrier()
 
     if rank == 0 and not args.no_cpu_baseline and world == 1:
         line["cpu_baseline"] = cpu_lstm_baseline()
