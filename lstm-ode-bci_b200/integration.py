@@ -28,7 +28,7 @@ def _staging_copy(dst, src):
     what the PCIe link then takes from the pinned buffer)."""
     global _STAGING_POOL
     n = src.shape[0]
-    workers = min(8, os.cpu_count() or 1)
+    workers = min(int(os.environ.get("BCI_STAGING_THREADS", "8")), os.cpu_count() or 1)
     if workers <= 1 or src.numel() < (1 << 22):
         dst.copy_(src)
         return
@@ -69,18 +69,25 @@ def stream_lstm_probs(lstm_model, host_batches, device=None, chunk=None, want_at
         direct = xh.is_pinned() and xh.is_contiguous()
         if not direct:
             if sl["pin"] is None or sl["pin"].shape[0] < n or sl["pin"].shape[1:] != xh.shape[1:]:
-                sl["pin"] = torch.empty(tuple(xh.shape), dtype=torch.float32).pin_memory()
+                sl["pin"] = torch.empty(tuple(xh.shape), dtype=torch.float32, pin_memory=True)   # (.pin_memory() would copy a pageable tensor first)
             if sl["free"] is not None:
                 sl["free"].synchronize()
         events = []
+        # pageable input: staged and copied in eighths of a pass, so the DMA of one eighth overlaps the staging of the next (the
+        # compute still runs per pass, after the pass's last eighth has landed)
+        sub = chunk if direct else max((chunk + 7) // 8, 1)
         for i in range(0, n, chunk):
             m = min(chunk, n - i)
-            src = xh[i:i + m]
-            if not direct:
-                _staging_copy(sl["pin"][i:i + m], src)
-                src = sl["pin"][i:i + m]
+            ev = None
+            for j in range(i, i + m, sub):
+                mj = min(sub, i + m - j)
+                src = xh[j:j + mj]
+                if not direct:
+                    _staging_copy(sl["pin"][j:j + mj], src)
+                    src = sl["pin"][j:j + mj]
+                with torch.cuda.stream(copy_stream):
+                    sl["buf"][j:j + mj].copy_(src, non_blocking=True)
             with torch.cuda.stream(copy_stream):
-                sl["buf"][i:i + m].copy_(src, non_blocking=True)
                 ev = torch.cuda.Event()
                 ev.record(copy_stream)
             events.append((i, m, ev))
