@@ -45,3 +45,23 @@ def _worker(rank, world, port, n):
 def test_gather_and_reduce_over_gloo(n):
     port = 29600 + n
     mp.spawn(_worker, args=(2, port, n), nprocs=2, join=True)
+
+
+def test_host_side_helpers_cpu():
+    """Host logic that needs no GPU: the multi-threaded staging copy and the RK4 stage-time grid of solve_with_modulation."""
+    import numpy as np
+    import torch
+    from lstm_ode_bci_b200 import integration, ode
+    src = torch.from_numpy(np.random.default_rng(1).standard_normal((4099, 64, 17), dtype=np.float32))   # > 4 Mi elements: threaded path
+    dst = torch.empty_like(src)
+    integration._staging_copy(dst, src)
+    assert torch.equal(dst, src)
+    small = torch.arange(12, dtype=torch.float32).reshape(3, 4)
+    out = torch.empty_like(small)
+    integration._staging_copy(out, small)
+    assert torch.equal(out, small)
+    tn = ode.modulation_nodes(5.0, 25.0, 20, 4)
+    assert len(tn) == 2 * 4 * 19 + 1 and tn[0] == 5.0 and tn[-1] == 25.0
+    h = (25.0 - 5.0) / 19 / 4
+    assert np.allclose(np.diff(tn), h / 2)
+    assert np.allclose(tn[::8], np.linspace(5.0, 25.0, 20))       # every 2*substeps-th node is an output time
