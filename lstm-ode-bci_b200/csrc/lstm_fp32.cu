@@ -154,9 +154,10 @@ lstm_rec_f32(const float* __restrict__ G,      // [T][Bc][ND][H][4]
 #pragma unroll
     for (int w = 0; w < REC_WPT; ++w) {
       const int b = b_base + w;
-      const float4 gv = (b < Bc) ? __ldg(Gt + (long long)b * ND * H) : make_float4(0.f, 0.f, 0.f, 0.f);
-      if (LATE_G) { gin[w] = gv; acc[w] = make_float4(0.f, 0.f, 0.f, 0.f); }
-      else acc[w] = gv;
+      acc[w] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (LATE_G) gin[w] = (b < Bc) ? __ldg(Gt + (long long)b * ND * H) : make_float4(0.f, 0.f, 0.f, 0.f);
+      else if (b < Bc) asm volatile("prefetch.global.L1 [%0];" ::"l"(Gt + (long long)b * ND * H));  // no registers to park it in: the
+                                                                                             // load after the k loop then hits L1
     }
     const float* hcur = &hs[cur][0][grp * REC_WPT];
     // W_hh^T streams from L2 (it does not fit beside h in one SM's smem in fp32): 8 independent 16-byte loads are issued
@@ -194,9 +195,13 @@ lstm_rec_f32(const float* __restrict__ G,      // [T][Bc][ND][H][4]
         for (int kk = 0; kk < PF; ++kk) fma_row(k0 + kk, w8[kk]);
       }
     }
-    if (LATE_G) {
+    // every variant adds the projected input AFTER the recurrent sum (same k order everywhere), so a window's result does not depend on
+    // which variant -- i.e. which batch size -- computed it; the throughput variants load it here (the other CTA of the SM covers the latency)
 #pragma unroll
-      for (int w = 0; w < REC_WPT; ++w) { acc[w].x += gin[w].x; acc[w].y += gin[w].y; acc[w].z += gin[w].z; acc[w].w += gin[w].w; }
+    for (int w = 0; w < REC_WPT; ++w) {
+      const int b = b_base + w;
+      const float4 gv = LATE_G ? gin[w] : ((b < Bc) ? __ldg(Gt + (long long)b * ND * H) : make_float4(0.f, 0.f, 0.f, 0.f));
+      acc[w].x += gv.x; acc[w].y += gv.y; acc[w].z += gv.z; acc[w].w += gv.w;
     }
     float4* hnext = reinterpret_cast<float4*>(&hs[cur ^ 1][j][grp * REC_WPT]);
     float hq[4];
@@ -444,7 +449,6 @@ static int forward_chunk_f32(bci_lstm_s* h, const float* x, int Bc, int T, float
   h->prof.mark(0, st);
   const float* in = z;
   float* outs[2] = {o0, o1};
-  constexpr int MT = (REC_THREADS / H) * REC_WPT;
   for (int l = 0; l < c.num_layers; ++l) {
     const int K = layer_in_width(c, l);
     const int M = (int)rows, N = 4 * D;
@@ -459,9 +463,9 @@ static int forward_chunk_f32(bci_lstm_s* h, const float* x, int Bc, int T, float
     }
     h->prof.mark(1, st);
     float* o = outs[l & 1];
-    dim3 gr(ceil_div(Bc, MT), ND);
-    lstm_rec_f32<H, REC_WPT><<<gr, REC_THREADS, 0, st>>>(g, h->f32.whh_t[l][0], h->f32.whh_t[l][1], o, nullptr, nullptr, Bc, T, ND);
-    BCI_LAUNCH_OK();
+    // the tile size follows the batch (launch_rec_f32): small batches -- single windows of predict_trajectory, the reference's 256 /
+    // 512-window passes -- use the latency-oriented variants with W_hh resident in shared memory instead of leaving most SMs idle
+    if ((rc = launch_rec_f32(H, ND, g, h->f32.whh_t[l][0], h->f32.whh_t[l][1], o, nullptr, nullptr, Bc, T, st))) return rc;
     h->prof.mark(2, st);
     in = o;
   }
