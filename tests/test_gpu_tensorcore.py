@@ -346,3 +346,24 @@ def test_bf16_single_pass_pooling_large_batch():
         with torch.no_grad():
             p32, a32 = m32.predict_proba(x[sl], return_attention=True)
         assert float((pb[sl] - p32).abs().max()) <= 1e-2 and float((ab[sl] - a32).abs().max()) <= 2e-3
+
+
+def test_bf16_full_wave_properties():
+    """Size-independent properties at the benchmark's full size (one full wave of the fused kernel, BASELINE configs[1]):
+    windows are independent, so reversing their order reverses the outputs BIT FOR BIT (any cross-window leak in the cluster
+    kernel's h exchange, the diag(beta) context MMA or the tile bookkeeping breaks this); probabilities and attention are
+    normalised; a slice computed alone (other kernels: small-batch pooling) agrees within the bf16 tolerance."""
+    params = synth.make_lstm_params(42, 61, 128, 3, logit_gain=12.0)
+    m = lstm.from_params(params, precision="bf16")
+    from lstm_ode_bci_b200 import ops
+    B = ops.lstm_chunk_windows(m._engine("bf16"))
+    g = torch.Generator(device="cuda").manual_seed(3)
+    x = torch.randn((B, 256, 61), device="cuda", generator=g)
+    with torch.no_grad():
+        p, a = m.predict_proba(x, return_attention=True)
+        pr, ar = m.predict_proba(x.flip(0).contiguous(), return_attention=True)
+        ps = m.predict_proba(x[1000:1100].contiguous())
+    assert torch.isfinite(p).all() and torch.isfinite(a).all()
+    assert torch.equal(pr.flip(0), p) and torch.equal(ar.flip(0), a)
+    assert float((p.sum(1) - 1).abs().max()) <= 1e-6 and float((a.sum(1) - 1).abs().max()) <= 1e-5
+    assert float((ps - p[1000:1100]).abs().max()) <= 2e-3
