@@ -91,3 +91,36 @@ def test_state_dict_roundtrip_with_port():
         want = port.eval()(torch.from_numpy(x))
         got = m(torch.from_numpy(x).cuda())
     assert np.abs(got.cpu().numpy() - want.numpy()).max() <= 1e-5
+
+
+def test_environment_switches_select_equivalent_paths(tmp_path):
+    """BCI_FP32_GEMM=simt (CUDA-core GEMMs) and BCI_BF16_POOL=two (two-kernel pooling) are read once per process: each is run
+    in a subprocess on the same seeded inputs and compared with this process's default path."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    prog = (
+        "import sys, numpy as np, torch\n"
+        "sys.path.insert(0, %r)\n"
+        "from lstm_ode_bci_b200 import lstm, synth\n"
+        "prec, B, out = sys.argv[1], int(sys.argv[2]), sys.argv[3]\n"
+        "m = lstm.from_params(synth.make_lstm_params(42, 61, 128, 3, logit_gain=12.0), precision=prec)\n"
+        "x = torch.from_numpy(synth.make_windows(5, B, 256, 61, structured=True)).cuda()\n"
+        "with torch.no_grad():\n"
+        "    p = m.predict_proba(x)\n"
+        "np.save(out, p.cpu().numpy())\n" % root)
+    script = tmp_path / "run.py"
+    script.write_text(prog)
+
+    def run(prec, B, env):
+        out = str(tmp_path / ("%s_%d_%s.npy" % (prec, B, "_".join(env) or "default")))
+        e = dict(os.environ)
+        e.update(env)
+        subprocess.run([sys.executable, str(script), prec, str(B), out], check=True, env=e, timeout=300)
+        return np.load(out)
+
+    a, b = run("fp32", 8, {}), run("fp32", 8, {"BCI_FP32_GEMM": "simt"})      # 2048 rows: the tcgen05 GEMMs are used by default
+    assert np.abs(a - b).max() <= 1e-5
+    c, d = run("bf16", 4224, {}), run("bf16", 4224, {"BCI_BF16_POOL": "two"})
+    assert np.abs(c - d).max() <= 2e-3
