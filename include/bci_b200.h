@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define BCI_ABI_VERSION 2
+#define BCI_ABI_VERSION 3
 #define BCI_MAX_LAYERS 4
 
 enum {
@@ -131,6 +131,31 @@ int bci_lstm_forward(bci_lstm_t h, const float* x, int32_t batch, int32_t seq_le
                      float dropout, uint64_t seed, float* logits, float* probs, float* attn,
                      void* workspace, size_t workspace_bytes, void* stream);
 
+/* Where the windows of an inference forward live.  The reference materialises every window: X (N,256,61) float32 written by
+ * create_sequences (02_preprocessing.py:157-180) and read back by 04/06/08/10.  Those windows overlap by 50 % (step 128 of 256
+ * samples, 02:50-51,170), so the same samples cross PCIe and HBM twice.  A view lets the forward read the windows IN PLACE from
+ * (samples, C) recordings -- window w of a run starts `window_stride` elements after window w-1 and is seq_len*C contiguous
+ * elements long -- and in bf16 as well as fp32 (the bf16 tensor-core mode rounds x to bf16 on load, so bf16 storage changes no
+ * result bit there and halves the bytes again).
+ *   packed windows, the reference's X:            windows_per_run = 0, window_stride = seq_len*C
+ *   R recordings of S samples, (R,S,C) row-major: windows_per_run = (S - seq_len)/step + 1, window_stride = step*C, run_stride = S*C */
+enum { BCI_IN_F32 = 0, BCI_IN_BF16 = 1 };
+typedef struct {
+  const void* data;         /* DEVICE pointer to the first element of window 0                         */
+  int32_t dtype;            /* BCI_IN_F32 | BCI_IN_BF16                                                */
+  int32_t windows_per_run;  /* windows cut from one run (recording); 0 = all windows form a single run */
+  int64_t window_stride;    /* ELEMENTS between the starts of consecutive windows of a run             */
+  int64_t run_stride;       /* ELEMENTS between the starts of consecutive runs (ignored for a single run) */
+  int64_t first_window;     /* index (in the run/window numbering above) of the call's window 0: lets a caller walk a resident
+                               buffer in pass-sized pieces that cross run boundaries                   */
+} bci_lstm_input;
+/* bci_lstm_forward (train = 0) over a view: window b reads elements [off(b), off(b) + seq_len*C) with
+ * off(b) = (w / windows_per_run) * run_stride + (w % windows_per_run) * window_stride, w = first_window + b.  Same outputs, workspace and precision
+ * modes as bci_lstm_forward; every window start should be 16-byte aligned for the TMA-fed input projection (otherwise the
+ * CUDA-core projection kernel runs). */
+int bci_lstm_forward_view(bci_lstm_t h, const bci_lstm_input* in, int32_t batch, int32_t seq_len, float* logits, float* probs,
+                          float* attn, void* workspace, size_t workspace_bytes, void* stream);
+
 /* Gradient pointers, same layout/shape as bci_lstm_weights; every pointer of a module the configuration has
  * must be non-NULL.  Gradients are OVERWRITTEN (not accumulated). */
 typedef struct {
@@ -147,6 +172,16 @@ typedef struct {
 int bci_lstm_backward(bci_lstm_t h, const float* x, const float* dlogits, int32_t batch, int32_t seq_len,
                       float* dx, const bci_lstm_grads* grads, void* workspace, size_t workspace_bytes,
                       void* stream);
+
+/* replaces criterion(outputs, y) / accumulation_steps and its backward to the logits (04:456-458,486-494: CrossEntropyLoss with
+ * class weights, mean reduction = sum_i w[y_i] nll_i / sum_i w[y_i]):
+ *   logits (B,classes) fp32, labels (B) int64, class_weight (classes) fp32 or NULL (all ones),
+ *   loss_scale multiplies both outputs (1/accumulation_steps; a GradScaler scale would go here too),
+ *   loss_out (1) fp32 receives the scaled loss, dlogits (B,classes) fp32 its gradient.  One block, fixed-order reductions. */
+int bci_ce_loss_grad(const float* logits, const int64_t* labels, const float* class_weight, int32_t batch, int32_t classes,
+                     float loss_scale, float* loss_out, float* dlogits, void* stream);
+/* gradient accumulation over micro-batches (04:489,497: accumulation_steps = 4): acc = (first ? 0 : acc) + g over n floats */
+int bci_grad_accumulate(float* acc, const float* g, int64_t n, int32_t first, void* stream);
 
 /* replaces clip_grad_norm_ + AdamW.step on a flat fp32 bucket (04:497-507, 04:438): p, g, m, v
  * are flat arrays of n floats; `grad_scale` multiplies g first (1/world_size after an NCCL

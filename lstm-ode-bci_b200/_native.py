@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-ABI_VERSION = 2   # include/bci_b200.h: BCI_ABI_VERSION
+ABI_VERSION = 3   # include/bci_b200.h: BCI_ABI_VERSION
 LIB_PATH = os.path.join(_PKG, "lib", "libbci_b200.so")
 
 BCI_MAX_LAYERS = 4
@@ -16,6 +16,7 @@ ODE_RK4, ODE_RK45 = 0, 1
 STYLE_REF06, STYLE_REF08 = 0, 1
 Y0_GIVEN, Y0_FROM_PROBS_06, Y0_FROM_PCLOSED_08 = 0, 1, 2
 OUT_F32, OUT_F64 = 0, 1
+IN_F32, IN_BF16 = 0, 1
 COMM_HANDLE_BYTES = 128
 
 _ERR_NAMES = {-1: "BCI_EINVAL", -2: "BCI_ECUDA", -3: "BCI_ENOMEM", -4: "BCI_ESTATE", -5: "BCI_EUNSUPPORTED"}
@@ -49,6 +50,11 @@ class LstmWeights(C.Structure):
 
 class LstmGrads(C.Structure):
     _fields_ = _WEIGHT_FIELDS
+
+
+class LstmInput(C.Structure):
+    _fields_ = [("data", _FP), ("dtype", C.c_int32), ("windows_per_run", C.c_int32), ("window_stride", C.c_int64),
+                ("run_stride", C.c_int64), ("first_window", C.c_int64)]
 
 
 class OdeArgs(C.Structure):
@@ -88,6 +94,10 @@ SIGNATURES = {
     "bci_lstm_workspace_bytes": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_size_t)]),
     "bci_lstm_forward": (C.c_int, [C.c_void_p, _FP, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_uint64,
                                    _FP, _FP, _FP, _FP, C.c_size_t, C.c_void_p]),
+    "bci_lstm_forward_view": (C.c_int, [C.c_void_p, C.POINTER(LstmInput), C.c_int32, C.c_int32, _FP, _FP, _FP, _FP, C.c_size_t,
+                                        C.c_void_p]),
+    "bci_ce_loss_grad": (C.c_int, [_FP, _FP, _FP, C.c_int32, C.c_int32, C.c_float, _FP, _FP, C.c_void_p]),
+    "bci_grad_accumulate": (C.c_int, [_FP, _FP, C.c_int64, C.c_int32, C.c_void_p]),
     "bci_lstm_backward": (C.c_int, [C.c_void_p, _FP, _FP, C.c_int32, C.c_int32, _FP, C.POINTER(LstmGrads),
                                     _FP, C.c_size_t, C.c_void_p]),
     "bci_adamw_step": (C.c_int, [_FP, _FP, _FP, _FP, C.c_int64, C.c_float, C.c_float, C.c_float, C.c_float,

@@ -3,7 +3,7 @@
     python -m lstm_ode_bci_b200.build [--force]
 
 The shared library lands in lstm-ode-bci_b200/lib/ (git-ignored, but it travels to the GPU box
-with the gpurun snapshot).  Objects are cached under build/ keyed by source mtime.
+with the gpurun snapshot).  Objects are cached under build/ keyed by source mtime and a hash of the nvcc flags.
 """
 import concurrent.futures as cf
 import glob
@@ -21,7 +21,7 @@ OBJ_DIR = os.path.join(ROOT, "build", "obj")
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--threads", "2"]
-# extra -D switches for experiments (e.g. BCI_NVCC_DEFINES="-DBCI_REC_ACCURATE_ACT"); changing them needs --force
+# extra -D switches for experiments (e.g. BCI_NVCC_DEFINES="-DBCI_REC_ACCURATE_ACT -DBCI_DEBUG_SWITCHES")
 NVCC_FLAGS += os.environ.get("BCI_NVCC_DEFINES", "").split()
 
 
@@ -41,8 +41,14 @@ def _headers_mtime():
     return max(os.path.getmtime(h) for h in hs)
 
 
+def _flags_tag():
+    """Objects are cached per flag set: changing BCI_NVCC_DEFINES (or NVCC_FLAGS) never reuses objects built with other flags."""
+    import hashlib
+    return hashlib.sha1(" ".join(NVCC_FLAGS).encode()).hexdigest()[:10]
+
+
 def _compile(src, verbose):
-    obj = os.path.join(OBJ_DIR, os.path.basename(src)[:-3] + ".o")
+    obj = os.path.join(OBJ_DIR, "%s.%s.o" % (os.path.basename(src)[:-3], _flags_tag()))
     newest = max(os.path.getmtime(src), _headers_mtime())
     if os.path.exists(obj) and os.path.getmtime(obj) >= newest:
         return obj, ""
@@ -67,11 +73,14 @@ def build(force=False, verbose=False):
         for _, log in results:
             if log:
                 print(log)
-    if (not os.path.exists(LIB)) or any(os.path.getmtime(o) > os.path.getmtime(LIB) for o in objs):
+    tag_file = os.path.join(OBJ_DIR, "linked.tag")
+    linked_tag = open(tag_file).read() if os.path.exists(tag_file) else ""
+    if (not os.path.exists(LIB)) or linked_tag != _flags_tag() or any(os.path.getmtime(o) > os.path.getmtime(LIB) for o in objs):
         cmd = [_nvcc(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError("link failed:\n%s\n%s" % (r.stdout, r.stderr))
+        open(tag_file, "w").write(_flags_tag())
     return LIB
 
 

@@ -27,6 +27,25 @@ size_t lstm_workspace_train(const bci_lstm_config& c, int batch, int T);
 int lstm_backward_impl(bci_lstm_s* h, const float* x, const float* dlogits, int batch, int T, float* dx,
                        const bci_lstm_grads* grads, void* ws, size_t ws_bytes, cudaStream_t st);
 
+// Makes the handle's device current for the duration of an entry point (a caller driving several GPUs from one process may have
+// another one current); restores the previous device on exit.
+struct DeviceGuard {
+  int prev = -1;
+  bool ok = true;
+  explicit DeviceGuard(int dev) {
+    int cur = 0;
+    if (cudaGetDevice(&cur) != cudaSuccess) { ok = false; return; }
+    if (cur != dev) {
+      ok = cudaSetDevice(dev) == cudaSuccess;
+      if (ok) prev = cur;
+    }
+  }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+#define BCI_ON_DEVICE_OF(h)                                                                             \
+  DeviceGuard _guard((h)->device);                                                                      \
+  BCI_REQUIRE(_guard.ok, BCI_ECUDA, "cannot make device %d (the handle's) current", (h)->device)
+
 }  // namespace bci
 
 using namespace bci;
@@ -45,6 +64,7 @@ extern "C" int bci_lstm_set_profiling(bci_lstm_t h, int32_t enable) {
 
 extern "C" int bci_lstm_get_profile(bci_lstm_t h, float ms[BCI_PROF_PHASES], int32_t launches[BCI_PROF_PHASES]) {
   BCI_REQUIRE(h && ms && launches, BCI_EINVAL, "bci_lstm_get_profile: NULL argument");
+  BCI_ON_DEVICE_OF(h);
   for (int i = 0; i < BCI_PROF_PHASES; ++i) { ms[i] = 0.f; launches[i] = 0; }
   Profiler& p = h->prof;
   if (p.n > 0) BCI_CUDA_OK(cudaEventSynchronize(p.ev[p.n - 1]));
@@ -107,6 +127,7 @@ extern "C" int bci_lstm_create(const bci_lstm_config* cfg, bci_lstm_t* out) {
 
 extern "C" int bci_lstm_destroy(bci_lstm_t h) {
   if (!h) return BCI_OK;
+  DeviceGuard _guard(h->device);
   if (h->store) cudaFree(h->store);
   if (h->prof.created) for (int i = 0; i < Profiler::MAX_EV; ++i) cudaEventDestroy(h->prof.ev[i]);
   if (h->side_ready) {
@@ -119,6 +140,7 @@ extern "C" int bci_lstm_destroy(bci_lstm_t h) {
 
 extern "C" int bci_lstm_load_weights(bci_lstm_t h, const bci_lstm_weights* w, void* stream) {
   BCI_REQUIRE(h && w, BCI_EINVAL, "bci_lstm_load_weights: NULL argument");
+  BCI_ON_DEVICE_OF(h);
   const bci_lstm_config& c = h->cfg;
   const void* must[] = {w->input_proj_w, w->input_proj_b, w->cls_w0, w->cls_b0, w->cls_w3, w->cls_b3, w->cls_w6, w->cls_b6};
   for (const void* p : must) BCI_REQUIRE(p, BCI_EINVAL, "bci_lstm_load_weights: a required weight pointer is NULL");
@@ -157,6 +179,12 @@ extern "C" int bci_lstm_workspace_bytes(bci_lstm_t h, int32_t batch, int32_t seq
   return BCI_OK;
 }
 
+static int forward_infer(bci_lstm_t h, const InputView& v, int batch, int T, float* logits, float* probs, float* attn, void* ws,
+                         size_t ws_bytes, cudaStream_t st) {
+  if (h->cfg.precision == BCI_PRECISION_BF16) return lstm_forward_bf16(h, v, batch, T, logits, probs, attn, ws, ws_bytes, st);
+  return lstm_forward_fp32(h, v, batch, T, logits, probs, attn, ws, ws_bytes, st);
+}
+
 extern "C" int bci_lstm_forward(bci_lstm_t h, const float* x, int32_t batch, int32_t seq_len, int32_t train, float dropout,
                                 uint64_t seed, float* logits, float* probs, float* attn, void* workspace,
                                 size_t workspace_bytes, void* stream) {
@@ -167,16 +195,34 @@ extern "C" int bci_lstm_forward(bci_lstm_t h, const float* x, int32_t batch, int
   BCI_REQUIRE(x && logits, BCI_EINVAL, "bci_lstm_forward: x and logits are required");
   BCI_REQUIRE(workspace, BCI_ENOMEM, "bci_lstm_forward: workspace is NULL");
   BCI_REQUIRE(dropout >= 0.f && dropout < 1.f, BCI_EINVAL, "bci_lstm_forward: dropout must be in [0,1)");
+  BCI_ON_DEVICE_OF(h);
   cudaStream_t st = (cudaStream_t)stream;
   if (train) return lstm_forward_train(h, x, batch, seq_len, dropout, seed, logits, probs, attn, workspace, workspace_bytes, st);
-  if (h->cfg.precision == BCI_PRECISION_BF16)
-    return lstm_forward_bf16(h, x, batch, seq_len, logits, probs, attn, workspace, workspace_bytes, st);
-  return lstm_forward_fp32(h, x, batch, seq_len, logits, probs, attn, workspace, workspace_bytes, st);
+  return forward_infer(h, packed_view(x, seq_len, h->cfg.input_size), batch, seq_len, logits, probs, attn, workspace, workspace_bytes, st);
+}
+
+extern "C" int bci_lstm_forward_view(bci_lstm_t h, const bci_lstm_input* in, int32_t batch, int32_t seq_len, float* logits,
+                                     float* probs, float* attn, void* workspace, size_t workspace_bytes, void* stream) {
+  BCI_REQUIRE(h && in, BCI_EINVAL, "bci_lstm_forward_view: NULL argument");
+  BCI_REQUIRE(h->loaded, BCI_ESTATE, "bci_lstm_forward_view: call bci_lstm_load_weights first");
+  BCI_REQUIRE(batch >= 0 && seq_len >= 1 && seq_len <= 65536, BCI_EINVAL, "bci_lstm_forward_view: bad shape (%d,%d)", batch, seq_len);
+  if (batch == 0) return BCI_OK;
+  BCI_REQUIRE(in->data && logits, BCI_EINVAL, "bci_lstm_forward_view: data and logits are required");
+  BCI_REQUIRE(workspace, BCI_ENOMEM, "bci_lstm_forward_view: workspace is NULL");
+  BCI_REQUIRE(in->dtype == BCI_IN_F32 || in->dtype == BCI_IN_BF16, BCI_EINVAL, "bci_lstm_forward_view: dtype must be BCI_IN_F32 or BCI_IN_BF16");
+  BCI_REQUIRE(in->window_stride >= 1 && in->windows_per_run >= 0 && (in->windows_per_run == 0 || in->run_stride >= 0), BCI_EINVAL,
+              "bci_lstm_forward_view: window_stride must be >= 1, windows_per_run and run_stride >= 0");
+  BCI_ON_DEVICE_OF(h);
+  BCI_REQUIRE(in->first_window >= 0, BCI_EINVAL, "bci_lstm_forward_view: first_window must be >= 0");
+  const InputView v{in->data, in->dtype, in->windows_per_run, in->window_stride, in->windows_per_run ? in->run_stride : 0,
+                    in->first_window};
+  return forward_infer(h, v, batch, seq_len, logits, probs, attn, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
 extern "C" int bci_lstm_backward(bci_lstm_t h, const float* x, const float* dlogits, int32_t batch, int32_t seq_len, float* dx,
                                  const bci_lstm_grads* grads, void* workspace, size_t workspace_bytes, void* stream) {
   BCI_REQUIRE(h && x && dlogits && grads && workspace, BCI_EINVAL, "bci_lstm_backward: NULL argument");
   BCI_REQUIRE(h->loaded, BCI_ESTATE, "bci_lstm_backward: call bci_lstm_load_weights first");
+  BCI_ON_DEVICE_OF(h);
   return lstm_backward_impl(h, x, dlogits, batch, seq_len, dx, grads, workspace, workspace_bytes, (cudaStream_t)stream);
 }

@@ -39,12 +39,27 @@ void note_launch();  // counts kernel launches (bci_launch_count)
     ::bci::note_launch();                                                              \
   } while (0)
 
+// Per-device state: one process may drive several GPUs (the tests and torch allow it), and kernel attributes
+// (cudaFuncSetAttribute), occupancy results and the SM count belong to the device that is current at the call.
+constexpr int BCI_MAX_DEVICES = 64;
+inline int current_device() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return dev & (BCI_MAX_DEVICES - 1);
+}
+struct PerDeviceFlag {
+  bool v[BCI_MAX_DEVICES] = {};
+  bool& cur() { return v[current_device()]; }
+};
+struct PerDeviceInt {
+  int v[BCI_MAX_DEVICES] = {};
+  int& cur() { return v[current_device()]; }
+};
 inline int sm_count() {
-  static int n = 0;
+  static PerDeviceInt n_pd;
+  int& n = n_pd.cur();
   if (n == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, current_device());
     if (n <= 0) n = 148;
   }
   return n;

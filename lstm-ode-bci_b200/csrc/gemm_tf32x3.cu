@@ -286,7 +286,8 @@ static int make_tmap_f32_2d(CUtensorMap* tm, const float* ptr, uint64_t rows, ui
   return BCI_OK;
 }
 static int tx_prepare() {
-  static bool done = false;
+  static PerDeviceFlag done_pd;
+  bool& done = done_pd.cur();
   if (!done) {
     BCI_CUDA_OK(cudaFuncSetAttribute(gemm_tf32x3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TX_SMEM));
     BCI_CUDA_OK(cudaFuncSetAttribute(gemm_tf32x3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TX_SMEM));

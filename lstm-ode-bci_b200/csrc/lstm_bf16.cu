@@ -76,7 +76,7 @@ int bf16_chunk_windows() {
 }
 
 size_t lstm_workspace_h256(const bci_lstm_config& c, int batch, int T);
-int lstm_forward_h256(bci_lstm_s* h, const float* x, int batch, int T, float* logits, float* probs, float* attn, void* ws,
+int lstm_forward_h256(bci_lstm_s* h, const InputView& x, int batch, int T, float* logits, float* probs, float* attn, void* ws,
                       size_t ws_bytes, cudaStream_t st);
 
 size_t lstm_store_bytes_bf16(const bci_lstm_config& c) {
@@ -354,7 +354,8 @@ static int launch_proj_gemm_bn(const __nv_bfloat16* A, const __nv_bfloat16* W, c
   if (rc) return rc;
   rc = make_tmap_bf16(&tmB, W, (uint64_t)N, (uint64_t)K, 64, BN);
   if (rc) return rc;
-  static bool attr = false;
+  static PerDeviceFlag attr_pd;
+  bool& attr = attr_pd.cur();
   if (!attr) {
     BCI_CUDA_OK(cudaFuncSetAttribute(proj_gemm_bf16<false, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gb_smem(GbCfg<BN>::MAX_K, BN)));
     BCI_CUDA_OK(cudaFuncSetAttribute(proj_gemm_bf16<true, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gb_smem(GbCfg<BN>::MAX_K, BN)));
@@ -648,14 +649,19 @@ static int rec_act_mode() {
   return mode;
 }
 static int rec_dbg() {  // timing experiments only (results are wrong when set): 1 = no G traffic, 2 = no h TMA store, 4 = no MMA
+#ifdef BCI_DEBUG_SWITCHES  // compiled out of the shipped library: a stray environment variable must not corrupt inference
   static int v = -1;
   if (v < 0) { const char* e = getenv("BCI_REC_DBG"); v = e ? atoi(e) : 0; }
   return v;
+#else
+  return 0;
+#endif
 }
 
 int launch_rec_bf16(const __nv_bfloat16* G, const __nv_bfloat16* whh_f, const __nv_bfloat16* whh_r, __nv_bfloat16* out,
                     float2* stats, int Bc, int T, cudaStream_t st) {
-  static bool attr = false;
+  static PerDeviceFlag attr_pd;
+  bool& attr = attr_pd.cur();
   if (!attr) {
     BCI_CUDA_OK(cudaFuncSetAttribute(lstm_rec_bf16<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RB_SMEM));
     BCI_CUDA_OK(cudaFuncSetAttribute(lstm_rec_bf16<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RB_SMEM));
@@ -695,7 +701,7 @@ size_t lstm_workspace_bf16(const bci_lstm_config& c, int batch, int T) {
   return chunk_bytes_bf16(c, Bc > 0 ? Bc : 1, T) + 1024;  // + slack: the TMA-addressed buffers are aligned to 1 KB internally
 }
 
-static int forward_chunk_bf16(bci_lstm_s* h, const float* x, int Bc, int T, float* logits, float* probs, float* attn, char* ws,
+static int forward_chunk_bf16(bci_lstm_s* h, const InputView& x, int Bc, int T, float* logits, float* probs, float* attn, char* ws,
                               cudaStream_t st) {
   constexpr int H = 128;
   const bci_lstm_config& c = h->cfg;
@@ -711,7 +717,7 @@ static int forward_chunk_bf16(bci_lstm_s* h, const float* x, int Bc, int T, floa
   float2* stats = reinterpret_cast<float2*>(take(rows * 8 * sizeof(float2)));
   h->prof.mark(-1, st);
   // tensor-core input projection needs whole 128-row tiles inside one window; other lengths use the CUDA-core kernel
-  int rc = (T % 128 == 0) ? launch_input_proj_bf16(h, x, Bc, T, z, st) : launch_input_proj<H, __nv_bfloat16>(h, x, Bc, T, z, st);
+  int rc = input_proj_bf16_ok(h, x, T) ? launch_input_proj_bf16(h, x, Bc, T, z, st) : launch_input_proj<H, __nv_bfloat16>(h, x, Bc, T, z, st);
   if (rc) return rc;
   h->prof.mark(0, st);
   const __nv_bfloat16* in = z;
@@ -741,7 +747,7 @@ static int forward_chunk_bf16(bci_lstm_s* h, const float* x, int Bc, int T, floa
   return rc;
 }
 
-int lstm_forward_bf16(bci_lstm_s* h, const float* x, int batch, int T, float* logits, float* probs, float* attn, void* ws,
+int lstm_forward_bf16(bci_lstm_s* h, const InputView& x, int batch, int T, float* logits, float* probs, float* attn, void* ws,
                       size_t ws_bytes, cudaStream_t st) {
   const bci_lstm_config& c = h->cfg;
   if (c.hidden_size == 256) return lstm_forward_h256(h, x, batch, T, logits, probs, attn, ws, ws_bytes, st);
@@ -752,7 +758,7 @@ int lstm_forward_bf16(bci_lstm_s* h, const float* x, int batch, int T, float* lo
               "bci_lstm_forward: workspace %zu < %zu bytes", ws_bytes, chunk_bytes_bf16(c, chunk, T) + 1024);
   for (int b0 = 0; b0 < batch; b0 += chunk) {
     const int Bc = (batch - b0) < chunk ? (batch - b0) : chunk;
-    int rc = forward_chunk_bf16(h, x + (size_t)b0 * T * c.input_size, Bc, T, logits + (size_t)b0 * c.num_classes,
+    int rc = forward_chunk_bf16(h, chunk_view(x, b0), Bc, T, logits + (size_t)b0 * c.num_classes,
                                 probs ? probs + (size_t)b0 * c.num_classes : nullptr, attn ? attn + (size_t)b0 * T : nullptr,
                                 ws_al, st);
     if (rc) return rc;

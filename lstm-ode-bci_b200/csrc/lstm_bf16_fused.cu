@@ -407,7 +407,9 @@ lstm_fused_bf16(const __grid_constant__ CUtensorMap tmIn,   // in  [T][Bc][Kin] 
 }
 
 static int fused_setup(int* max_clusters_out) {
-  static int state = 0, max_clusters = 0;  // 0 = not tried, 1 = ok, -1 = unavailable
+  static PerDeviceInt state_pd, max_pd;  // state: 0 = not tried, 1 = ok, -1 = unavailable
+  int& state = state_pd.cur();
+  int& max_clusters = max_pd.cur();
   if (state == 0) {
     state = -1;
     BCI_CUDA_OK(cudaFuncSetAttribute(lstm_fused_bf16<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FR_SMEM));
@@ -453,7 +455,11 @@ int launch_fused_rec_bf16(const __nv_bfloat16* in, const __nv_bfloat16* wih, con
   const int tiles = ceil_div(Bc, FR_M), tile_quads = (tiles + 3) / 4;
   int clusters = 2 * tile_quads < max_clusters ? 2 * tile_quads : max_clusters;
   // BCI_FUSED_TIMELINE=<path>: clock64 stamps of the first 64 steps of cluster 0 / rank 0 are written to <path> (debug only)
+#ifdef BCI_DEBUG_SWITCHES
   static const char* tl_path = getenv("BCI_FUSED_TIMELINE");
+#else
+  static const char* tl_path = nullptr;
+#endif
   static long long* tl_dev = nullptr;
   if (tl_path && !tl_dev) { BCI_CUDA_OK(cudaMalloc(&tl_dev, 4 * 64 * 8 * sizeof(long long))); }
   if (tl_dev) BCI_CUDA_OK(cudaMemsetAsync(tl_dev, 0, 4 * 64 * 8 * sizeof(long long), st));

@@ -323,7 +323,9 @@ lstm_rec256_bf16(const __nv_bfloat16* __restrict__ G,        // blocked: [row/12
 }
 
 static int h256_setup(int* max_clusters_out) {
-  static int state = 0, max_clusters = 0;
+  static PerDeviceInt state_pd, max_pd;  // state: 0 = not tried, 1 = ok, -1 = unavailable
+  int& state = state_pd.cur();
+  int& max_clusters = max_pd.cur();
   if (state == 0) {
     state = -1;
     BCI_CUDA_OK(cudaFuncSetAttribute(lstm_rec256_bf16, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HR_SMEM));
@@ -364,7 +366,7 @@ int launch_rec256_bf16(const __nv_bfloat16* G, const __nv_bfloat16* whh, __nv_bf
 }
 
 // ---- K1 for H = 256: x (B,T,C) fp32 -> bf16 rows [T][Bc][64] -> tcgen05 GEMM (+ b0) -> LayerNorm + GELU row kernel ----------------
-__global__ void x_to_bf16_rows(const float* __restrict__ x, int Bc, int T, int C, __nv_bfloat16* __restrict__ xr) {
+__global__ void x_to_bf16_rows(const InputView x, int Bc, int T, int C, __nv_bfloat16* __restrict__ xr) {
   // one thread per (row, pair of channels); rows are time-major r = t*Bc + b, K padded from C to 64 with zeros
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long rows = (long long)Bc * T;
@@ -372,8 +374,8 @@ __global__ void x_to_bf16_rows(const float* __restrict__ x, int Bc, int T, int C
   const long long r = i >> 5;
   const int k = (int)(i & 31) * 2;
   const int t = (int)(r / Bc), b = (int)(r - (long long)t * Bc);
-  const float* src = x + ((long long)b * T + t) * C;
-  const float v0 = k < C ? src[k] : 0.f, v1 = (k + 1) < C ? src[k + 1] : 0.f;
+  const long long src = x.elem_off(b) + (long long)t * C;
+  const float v0 = k < C ? view_load(x, src + k) : 0.f, v1 = (k + 1) < C ? view_load(x, src + k + 1) : 0.f;
   reinterpret_cast<__nv_bfloat162*>(xr)[i] = __floats2bfloat162_rn(v0, v1);
 }
 
@@ -428,7 +430,7 @@ __global__ void pack_w0_256(const float* __restrict__ w0, __nv_bfloat16* __restr
   dst[i] = __float2bfloat16_rn(k < C ? w0[j * C + k] : 0.f);
 }
 
-static int launch_input_proj256(bci_lstm_s* h, const float* x, int Bc, int T, __nv_bfloat16* xr, __nv_bfloat16* z, cudaStream_t st) {
+static int launch_input_proj256(bci_lstm_s* h, const InputView& x, int Bc, int T, __nv_bfloat16* xr, __nv_bfloat16* z, cudaStream_t st) {
   const long long rows = (long long)Bc * T;
   x_to_bf16_rows<<<(unsigned)ceil_div64(rows * 32, 256), 256, 0, st>>>(x, Bc, T, h->cfg.input_size, xr);
   BCI_LAUNCH_OK();
@@ -470,7 +472,7 @@ size_t lstm_workspace_h256(const bci_lstm_config& c, int batch, int T) {
 }
 
 // every contraction runs on tensor cores: K1 = bf16 row conversion + proj_gemm_bf16 (K = 64) + LayerNorm/GELU row kernel
-int lstm_forward_h256(bci_lstm_s* h, const float* x, int batch, int T, float* logits, float* probs, float* attn, void* ws,
+int lstm_forward_h256(bci_lstm_s* h, const InputView& x, int batch, int T, float* logits, float* probs, float* attn, void* ws,
                       size_t ws_bytes, cudaStream_t st) {
   const bci_lstm_config& c = h->cfg;
   const int chunk = batch < max_chunk(c, 0) ? batch : max_chunk(c, 0);
@@ -490,7 +492,7 @@ int lstm_forward_h256(bci_lstm_s* h, const float* x, int batch, int T, float* lo
     float2* rowstat = reinterpret_cast<float2*>(take(rows * 8));
     h->prof.mark(-1, st);
     // (x as bf16 rows is staged in the second output buffer, which is not written before layer 1)
-    int rc = launch_input_proj256(h, x + (size_t)b0 * T * c.input_size, Bc, T, o1, z, st);
+    int rc = launch_input_proj256(h, chunk_view(x, b0), Bc, T, o1, z, st);
     if (rc) return rc;
     h->prof.mark(0, st);
     const __nv_bfloat16* in = z;

@@ -2,8 +2,12 @@
 //
 // x is fp32 (B,T,C) with C = 61 channels: rows are 244 bytes, which no TMA tensor map can describe
 // (strides must be multiples of 16 B).  But a tile of 128 consecutive (b,t) rows is one CONTIGUOUS block of
-// 128*C*4 bytes, so it is fetched with a 1-D bulk copy (cp.async.bulk, mbarrier-completed) into a raw fp32
-// staging buffer; four converter warps then turn it into the bf16 K-major SWIZZLE_128B A operand (K zero-padded
+// 128*C*4 bytes, so it is fetched with a 1-D bulk copy (cp.async.bulk, mbarrier-completed) into a raw
+// staging buffer.  The windows need not be packed: an InputView (lstm_handle.cuh) gives the element offset of
+// every window, so the 50 %-overlapping windows of a (samples, C) recording (02_preprocessing.py:157-180) are
+// read in place -- half the HBM and host->device bytes of materialised windows -- and the elements may already
+// be bf16 (the converter warps round fp32 input to bf16 anyway, so bf16 input gives bit-identical results at
+// half the bytes again); four converter warps then turn it into the bf16 K-major SWIZZLE_128B A operand (K zero-padded
 // 61 -> 64), one thread issues 4 tcgen05.mma (M128 x N128 x K16), and four epilogue warps apply bias +
 // LayerNorm + GELU thread-locally (one thread owns one row's 128 accumulator columns in TMEM) and write
 // the bf16 tile back time-major with TMA stores.  Every stage is double-buffered.
@@ -63,8 +67,9 @@ __device__ __forceinline__ void bulk_copy_g2s(uint32_t dst_smem, const void* src
                ::"r"(dst_smem), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
 
+template <typename InT>
 __global__ void __launch_bounds__(IP_THREADS, 1)
-input_proj_bf16(const float* __restrict__ x,              // (Bc,T,C) fp32
+input_proj_bf16(const InputView x,                         // windows of T x C elements of InT (fp32 or bf16)
                 const __grid_constant__ CUtensorMap tmB,   // W0 bf16 [128][64], box 64 x 128
                 const __grid_constant__ CUtensorMap tmZ,   // z [T][Bc][128] bf16 (3D), box 64 x 1 x 128
                 const float4* __restrict__ par,            // [128] {b0, ln_w, ln_b, 0}
@@ -77,7 +82,7 @@ input_proj_bf16(const float* __restrict__ x,              // (Bc,T,C) fp32
   const uint32_t sA = base, sB = sA + 2 * IP_A_BYTES, sO = sB + IP_B_BYTES, sR = sO + IP_OUT_BYTES;
   uint8_t* genA = gen;
   uint8_t* genO = gen + 2 * IP_A_BYTES + IP_B_BYTES;
-  const float* genR = reinterpret_cast<const float*>(genO + IP_OUT_BYTES);
+  const InT* genR = reinterpret_cast<const InT*>(genO + IP_OUT_BYTES);
   float4* par_s = reinterpret_cast<float4*>(gen + 2 * IP_A_BYTES + IP_B_BYTES + IP_OUT_BYTES + 2 * IP_RAW_MAX);
   float2* part_s = reinterpret_cast<float2*>(par_s + IP_N);  // [2 column halves][128 rows] partial (sum, sumsq)
   uint8_t* ctl = reinterpret_cast<uint8_t*>(part_s + 2 * IP_M);
@@ -94,7 +99,7 @@ input_proj_bf16(const float* __restrict__ x,              // (Bc,T,C) fp32
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tiles_per_win = T / IP_M;
   const int tiles = Bc * tiles_per_win;
-  const uint32_t tile_bytes = (uint32_t)IP_M * C * 4;
+  const uint32_t tile_bytes = (uint32_t)IP_M * C * (uint32_t)sizeof(InT);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmB);
@@ -127,7 +132,9 @@ input_proj_bf16(const float* __restrict__ x,              // (Bc,T,C) fp32
         const int s = it & 1;
         mbar_wait(raw_empty(s), ((it >> 1) & 1u) ^ 1u);
         mbar_arrive_expect_tx(raw_full(s), tile_bytes);
-        bulk_copy_g2s(sR + s * IP_RAW_MAX, reinterpret_cast<const uint8_t*>(x) + (size_t)tile * tile_bytes, tile_bytes, raw_full(s));
+        const int b = tile / tiles_per_win, part = tile - b * tiles_per_win;
+        const InT* src = reinterpret_cast<const InT*>(x.data) + x.elem_off(b) + (long long)part * IP_M * C;
+        bulk_copy_g2s(sR + s * IP_RAW_MAX, src, tile_bytes, raw_full(s));
       }
     }
   } else if (warp == 1) {
@@ -159,7 +166,7 @@ input_proj_bf16(const float* __restrict__ x,              // (Bc,T,C) fp32
       const uint32_t ph = (it >> 1) & 1u;
       mbar_wait(raw_full(s), ph);
       mbar_wait(a_empty(s), ph ^ 1u);
-      const float* row = genR + s * (IP_RAW_MAX / 4) + r * C;
+      const InT* row = genR + s * (IP_RAW_MAX / (int)sizeof(InT)) + r * C;
       uint8_t* arow = genA + s * IP_A_BYTES;
 #pragma unroll
       for (int c = 0; c < 8; ++c) {
@@ -167,8 +174,8 @@ input_proj_bf16(const float* __restrict__ x,              // (Bc,T,C) fp32
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const int k = c * 8 + 2 * j;
-          const float v0 = k < C ? row[k] : 0.f;
-          const float v1 = (k + 1) < C ? row[k + 1] : 0.f;
+          const float v0 = k < C ? to_f32<InT>(row[k]) : 0.f;
+          const float v1 = (k + 1) < C ? to_f32<InT>(row[k + 1]) : 0.f;
           __nv_bfloat162 p = __floats2bfloat162_rn(v0, v1);
           w[j] = *reinterpret_cast<uint32_t*>(&p);
         }
@@ -264,23 +271,32 @@ static int make_tmap_z(CUtensorMap* tm, const void* z, uint64_t T, uint64_t Bc) 
   return BCI_OK;
 }
 
-int launch_input_proj_bf16(bci_lstm_s* h, const float* x, int Bc, int T, __nv_bfloat16* z, cudaStream_t st) {
+// whole 128-row tiles inside one window, and every tile start 16-byte aligned (bulk-copy source); anything else runs the CUDA-core K1
+bool input_proj_bf16_ok(const bci_lstm_s* h, const InputView& x, int T) {
+  const long long es = x.esize();
+  return T % IP_M == 0 && h->cfg.input_size <= 64 && h->cfg.hidden_size == 128 && ((uintptr_t)x.data & 15) == 0 &&
+         (x.wstride * es) % 16 == 0 && (x.rstride * es) % 16 == 0 && ((long long)IP_M * h->cfg.input_size * es) % 16 == 0;
+}
+
+int launch_input_proj_bf16(bci_lstm_s* h, const InputView& x, int Bc, int T, __nv_bfloat16* z, cudaStream_t st) {
   const int C = h->cfg.input_size;
-  BCI_REQUIRE(T % IP_M == 0 && C <= 64 && h->cfg.hidden_size == 128, BCI_EINVAL, "input_proj_bf16: unsupported shape");
-  BCI_REQUIRE(((uintptr_t)x & 15) == 0, BCI_EINVAL, "bci_lstm_forward: x must be 16-byte aligned");
+  BCI_REQUIRE(input_proj_bf16_ok(h, x, T), BCI_EINVAL, "input_proj_bf16: unsupported shape or alignment");
   CUtensorMap tmB, tmZ;
   int rc = make_tmap_bf16(&tmB, h->bf16.w0_bf, 128, 64, 64, IP_N);
   if (rc) return rc;
   rc = make_tmap_z(&tmZ, z, (uint64_t)T, (uint64_t)Bc);
   if (rc) return rc;
-  static bool attr = false;
+  static PerDeviceFlag attr_pd;
+  bool& attr = attr_pd.cur();
   if (!attr) {
-    BCI_CUDA_OK(cudaFuncSetAttribute(input_proj_bf16, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)IP_SMEM));
+    BCI_CUDA_OK(cudaFuncSetAttribute(input_proj_bf16<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)IP_SMEM));
+    BCI_CUDA_OK(cudaFuncSetAttribute(input_proj_bf16<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)IP_SMEM));
     attr = true;
   }
   const int tiles = Bc * (T / IP_M);
   const int grid = tiles < sm_count() ? tiles : sm_count();
-  input_proj_bf16<<<grid, IP_THREADS, IP_SMEM, st>>>(x, tmB, tmZ, h->bf16.par0, Bc, T, C);
+  if (x.dtype == BCI_IN_BF16) input_proj_bf16<__nv_bfloat16><<<grid, IP_THREADS, IP_SMEM, st>>>(x, tmB, tmZ, h->bf16.par0, Bc, T, C);
+  else input_proj_bf16<float><<<grid, IP_THREADS, IP_SMEM, st>>>(x, tmB, tmZ, h->bf16.par0, Bc, T, C);
   BCI_LAUNCH_OK();
   return BCI_OK;
 }

@@ -453,7 +453,8 @@ int launch_pool_bf16(bci_lstm_s* h, const __nv_bfloat16* seq, float2* stats, flo
   if (rc) return rc;
   rc = make_tmap_bf16(&tmB, h->bf16.aw1_bf, 128, 256, 64, SC_N);
   if (rc) return rc;
-  static bool attr = false;
+  static PerDeviceFlag attr_pd;
+  bool& attr = attr_pd.cur();
   if (!attr) {
     BCI_CUDA_OK(cudaFuncSetAttribute(attn_score_bf16, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SC_SMEM));
     attr = true;

@@ -405,7 +405,8 @@ int launch_pool_stream_bf16(bci_lstm_s* h, const __nv_bfloat16* seq, const float
   if (rc) return rc;
   rc = make_tmap_bf16(&tmB, h->bf16.aw1_bf, 128, 256, 64, 128);
   if (rc) return rc;
-  static bool attr = false;
+  static PerDeviceFlag attr_pd;
+  bool& attr = attr_pd.cur();
   if (!attr) {
     BCI_CUDA_OK(cudaFuncSetAttribute(attn_pool_stream_bf16, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PS_SMEM));
     attr = true;

@@ -264,7 +264,8 @@ int launch_rec_f32(int H, int ND, const float* G, const float* whh_f, const floa
     if (tiny) {
       constexpr int RES = 96;
       constexpr size_t res_bytes = (size_t)RES * 128 * sizeof(float4);
-      static bool attr = false;
+      static PerDeviceFlag attr_pd;
+  bool& attr = attr_pd.cur();
       if (!attr) {
         BCI_CUDA_OK(cudaFuncSetAttribute(lstm_rec_f32<128, 4, 32, RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)res_bytes));
         attr = true;
@@ -430,7 +431,7 @@ size_t lstm_workspace_fp32(const bci_lstm_config& c, int batch, int T) {
 }
 
 template <int H, int ND>
-static int forward_chunk_f32(bci_lstm_s* h, const float* x, int Bc, int T, float* logits, float* probs, float* attn,
+static int forward_chunk_f32(bci_lstm_s* h, const InputView& x, int Bc, int T, float* logits, float* probs, float* attn,
                              char* ws, cudaStream_t st) {
   const bci_lstm_config& c = h->cfg;
   const size_t rows = (size_t)Bc * T;
@@ -474,7 +475,7 @@ static int forward_chunk_f32(bci_lstm_s* h, const float* x, int Bc, int T, float
   return rc;
 }
 
-int lstm_forward_fp32(bci_lstm_s* h, const float* x, int batch, int T, float* logits, float* probs, float* attn,
+int lstm_forward_fp32(bci_lstm_s* h, const InputView& x, int batch, int T, float* logits, float* probs, float* attn,
                       void* ws, size_t ws_bytes, cudaStream_t st) {
   const bci_lstm_config& c = h->cfg;
   const int chunk = batch < max_chunk(c, 0) ? batch : max_chunk(c, 0);
@@ -482,7 +483,7 @@ int lstm_forward_fp32(bci_lstm_s* h, const float* x, int batch, int T, float* lo
               chunk_bytes_f32(c, chunk, T));
   for (int b0 = 0; b0 < batch; b0 += chunk) {
     const int Bc = (batch - b0) < chunk ? (batch - b0) : chunk;
-    const float* xb = x + (size_t)b0 * T * c.input_size;
+    const InputView xb = chunk_view(x, b0);
     float* lg = logits + (size_t)b0 * c.num_classes;
     float* pr = probs ? probs + (size_t)b0 * c.num_classes : nullptr;
     float* at = attn ? attn + (size_t)b0 * T : nullptr;

@@ -103,9 +103,40 @@ struct bci_lstm_s {
   cudaStream_t side;
   cudaEvent_t ev_dg, ev_side[2], ev_join;
   bool side_ready;
+  // the last train=1 forward (workspace + header): a backward on the same workspace needs no device->host read of the header
+  void* last_train_ws;
+  float last_dropout;
+  uint64_t last_seed;
+  int last_batch, last_T;
 };
 
 namespace bci {
+
+// Where the windows of a forward come from (bci_lstm_input of the C ABI + the index of the chunk's first window).  Window w starts at
+// element  (w / wpr) * rstride + (w % wpr) * wstride  (wpr == 0: w * wstride) and is seq_len x C contiguous elements from there:
+// packed (B,T,C) windows have wstride = T*C; overlapping windows of a (samples, C) recording have wstride = step*C (02:157-180).
+struct InputView {
+  const void* data;
+  int dtype;              // BCI_IN_F32 | BCI_IN_BF16
+  int wpr;                // windows per run (recording); 0 = one run
+  long long wstride;      // elements
+  long long rstride;      // elements
+  long long first;        // global index of window 0 of this chunk
+  __host__ __device__ long long elem_off(long long b) const {
+    const long long w = first + b;
+    if (wpr > 0) { const long long r = w / wpr; return r * rstride + (w - r * wpr) * wstride; }
+    return w * wstride;
+  }
+  __host__ __device__ int esize() const { return dtype == BCI_IN_BF16 ? 2 : 4; }
+};
+inline InputView packed_view(const float* x, int T, int C) { return InputView{x, BCI_IN_F32, 0, (long long)T * C, 0, 0}; }
+inline InputView chunk_view(InputView v, long long b0) { v.first += b0; return v; }
+#ifdef __CUDACC__
+__device__ __forceinline__ float view_load(const InputView& v, long long e) {
+  return v.dtype == BCI_IN_BF16 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(v.data)[e])
+                                : reinterpret_cast<const float*>(v.data)[e];
+}
+#endif
 
 inline int num_dirs(const bci_lstm_config& c) { return c.bidirectional ? 2 : 1; }
 inline int feat_width(const bci_lstm_config& c) { return num_dirs(c) * c.hidden_size; }          // D: LSTM output width
@@ -131,7 +162,7 @@ struct FwdWorkspace {
 };
 
 // fp32 forward entry points (lstm_fp32.cu)
-int lstm_forward_fp32(bci_lstm_s* h, const float* x, int batch, int T, float* logits, float* probs, float* attn,
+int lstm_forward_fp32(bci_lstm_s* h, const InputView& x, int batch, int T, float* logits, float* probs, float* attn,
                       void* ws, size_t ws_bytes, cudaStream_t st);
 size_t lstm_workspace_fp32(const bci_lstm_config& c, int batch, int T);
 int launch_proj_gemm_f32(const float* A, const float* Bt, const float* bias, float* C, int M, int N, int K, cudaStream_t st,
@@ -149,7 +180,7 @@ int gemm_tf32x3_nt(const float* A_hi, const float* A_lo, int lda, const float* W
 int gemm_tf32x3_tn(const float* A_hi, const float* A_lo, int lda, const float* B_hi, const float* B_lo, int ldb, float* C, int ldc,
                    long long R, int P, int Q, cudaStream_t st, int force_splits = 0);
 // bf16 / tcgen05 forward (lstm_bf16.cu)
-int lstm_forward_bf16(bci_lstm_s* h, const float* x, int batch, int T, float* logits, float* probs, float* attn,
+int lstm_forward_bf16(bci_lstm_s* h, const InputView& x, int batch, int T, float* logits, float* probs, float* attn,
                       void* ws, size_t ws_bytes, cudaStream_t st);
 size_t lstm_workspace_bf16(const bci_lstm_config& c, int batch, int T);
 int lstm_pack_bf16(bci_lstm_s* h, cudaStream_t st);
@@ -157,7 +188,8 @@ size_t lstm_store_bytes_bf16(const bci_lstm_config& c);
 void lstm_carve_bf16(bci_lstm_s* h, char* base);
 int pack_pool_bf16(bci_lstm_s* h, cudaStream_t st);
 int pack_inproj_bf16(bci_lstm_s* h, cudaStream_t st);
-int launch_input_proj_bf16(bci_lstm_s* h, const float* x, int Bc, int T, __nv_bfloat16* z, cudaStream_t st);
+bool input_proj_bf16_ok(const bci_lstm_s* h, const InputView& x, int T);
+int launch_input_proj_bf16(bci_lstm_s* h, const InputView& x, int Bc, int T, __nv_bfloat16* z, cudaStream_t st);
 int launch_pool_bf16(bci_lstm_s* h, const __nv_bfloat16* seq, float2* stats, float* scores, int Bc, int T, float* logits,
                      float* probs, float* attn, cudaStream_t st);
 // single-pass pooling (lstm_bf16_pool_stream.cu)

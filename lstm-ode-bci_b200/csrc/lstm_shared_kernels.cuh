@@ -23,7 +23,7 @@ constexpr int K1_THREADS = 256;
 
 template <int H, typename OutT>
 __global__ void __launch_bounds__(K1_THREADS)
-input_proj_kernel(const float* __restrict__ x, int Bc, int T, int C, const float* __restrict__ w0t,
+input_proj_kernel(const InputView x, int Bc, int T, int C, const float* __restrict__ w0t,
                   const float* __restrict__ b0, const float* __restrict__ lnw, const float* __restrict__ lnb,
                   OutT* __restrict__ z, int use_ln) {
   extern __shared__ __align__(16) float k1_smem[];  // [C][H]
@@ -45,9 +45,9 @@ input_proj_kernel(const float* __restrict__ x, int Bc, int T, int C, const float
     }
   for (long long r = (long long)blockIdx.x * (K1_THREADS / 32) + warp; r < rows; r += wstride) {
     const int b = (int)(r / T), t = (int)(r - (long long)b * T);
-    const float* xr = x + r * C;
-    float xa = lane < C ? xr[lane] : 0.f;
-    float xb = (32 + lane) < C ? xr[32 + lane] : 0.f;
+    const long long xr = x.elem_off(b) + (long long)t * C;   // first element of the row (windows may overlap / be bf16: InputView)
+    float xa = lane < C ? view_load(x, xr + lane) : 0.f;
+    float xb = (32 + lane) < C ? view_load(x, xr + 32 + lane) : 0.f;
     float acc[NV];
 #pragma unroll
     for (int v = 0; v < NV; ++v) acc[v] = bias[v];
@@ -279,7 +279,8 @@ inline int launch_pool_head(const bci_lstm_s* h, const InT* seq, int Bc, int T, 
                             float* scores_ws, cudaStream_t st) {
   using Cfg = PoolCfg<H, ND>;
   const size_t smem = Cfg::SMEM_FLOATS * sizeof(float);
-  static bool attr_set = false;
+  static PerDeviceFlag attr_pd;
+  bool& attr_set = attr_pd.cur();
   if (!attr_set) {
     BCI_CUDA_OK(cudaFuncSetAttribute(attn_pool_head_kernel<H, ND, InT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;
@@ -294,10 +295,11 @@ inline int launch_pool_head(const bci_lstm_s* h, const InT* seq, int Bc, int T, 
 }
 
 template <int H, typename OutT>
-inline int launch_input_proj(const bci_lstm_s* h, const float* x, int Bc, int T, OutT* z, cudaStream_t st) {
+inline int launch_input_proj(const bci_lstm_s* h, const InputView& x, int Bc, int T, OutT* z, cudaStream_t st) {
   const int C = h->cfg.input_size;
   const size_t smem = (size_t)C * H * sizeof(float);
-  static bool attr_set = false;
+  static PerDeviceFlag attr_pd;
+  bool& attr_set = attr_pd.cur();
   if (!attr_set) {
     BCI_CUDA_OK(cudaFuncSetAttribute(input_proj_kernel<H, OutT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;

@@ -941,6 +941,7 @@ int lstm_forward_train(bci_lstm_s* h, const float* x, int batch, int T, float dr
   BCI_REQUIRE(T * sizeof(float) + 2 * c.hidden_size * sizeof(float) <= 40 * 1024, BCI_EINVAL, "training supports seq_len <= 8192");
   TrainHeader hd{dropout, 0xB200C0DEu, seed, batch, T};
   BCI_CUDA_OK(cudaMemcpyAsync(w.hdr, &hd, sizeof(hd), cudaMemcpyHostToDevice, st));
+  h->last_train_ws = ws; h->last_dropout = dropout; h->last_seed = seed; h->last_batch = batch; h->last_T = T;
   if (c.bidirectional)
     return c.hidden_size == 128 ? forward_train_t<128, 2>(h, x, batch, T, dropout, seed, logits, probs, attn, w, st)
                                 : forward_train_t<256, 2>(h, x, batch, T, dropout, seed, logits, probs, attn, w, st);
@@ -1013,7 +1014,8 @@ static int backward_t(bci_lstm_s* h, const float* dlogits, int B, int T, float p
   // training batches at H = 128: 96 of the 128 unit rows of W_hh resident in shared memory behind the dG tile
   constexpr int BP_RES = H == 128 ? 96 : 0;
   constexpr size_t bp_res_bytes = (size_t)(BP_RES + 2) * H * sizeof(float4);  // resident rows + the u-split exchange buffer
-  static bool attr = false;
+  static PerDeviceFlag attr_pd;
+  bool& attr = attr_pd.cur();
   if (!attr) {
     if (H == 128)
       BCI_CUDA_OK(cudaFuncSetAttribute(lstm_bptt_f32<H, 4, BP_RES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -1135,8 +1137,13 @@ int lstm_backward_impl(bci_lstm_s* h, const float* x, const float* dlogits, int 
   const bci_lstm_config& c = h->cfg;
   // the forward left its configuration in the workspace header
   TrainHeader hd;
-  BCI_CUDA_OK(cudaMemcpyAsync(&hd, ws, sizeof(hd), cudaMemcpyDeviceToHost, st));
-  BCI_CUDA_OK(cudaStreamSynchronize(st));
+  if (ws == h->last_train_ws && batch == h->last_batch && T == h->last_T) {
+    // the usual case -- backward right after its forward: no stream synchronisation inside the training step
+    hd = TrainHeader{h->last_dropout, 0xB200C0DEu, h->last_seed, batch, T};
+  } else {  // an older forward's workspace (07:252 keeps several alive): read what that forward left there
+    BCI_CUDA_OK(cudaMemcpyAsync(&hd, ws, sizeof(hd), cudaMemcpyDeviceToHost, st));
+    BCI_CUDA_OK(cudaStreamSynchronize(st));
+  }
   BCI_REQUIRE(hd.valid == 0xB200C0DEu && hd.batch == batch && hd.T == T, BCI_ESTATE,
               "bci_lstm_backward: workspace does not hold a train=1 forward of this shape");
   TrainWs w;
@@ -1195,7 +1202,73 @@ __global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g,
   }
 }
 
+// weighted cross-entropy (mean over the batch's class weights) and its gradient wrt the logits: one block, every reduction in a
+// fixed order (the loss is bit-reproducible from run to run); B is a training batch (hundreds of windows), classes <= 8
+__global__ void __launch_bounds__(256)
+ce_loss_grad_kernel(const float* __restrict__ logits, const long long* __restrict__ labels, const float* __restrict__ cw, int B, int classes,
+                    float loss_scale, float* __restrict__ loss_out, float* __restrict__ dlogits) {
+  __shared__ float red_w[8], red_l[8];
+  __shared__ float tot_w;
+  float sw = 0.f, sl = 0.f;
+  for (int i = threadIdx.x; i < B; i += blockDim.x) {
+    const int y = (int)labels[i];
+    float mx = -INFINITY;
+    for (int c = 0; c < classes; ++c) mx = fmaxf(mx, logits[(long long)i * classes + c]);
+    float den = 0.f;
+    for (int c = 0; c < classes; ++c) den += expf(logits[(long long)i * classes + c] - mx);
+    const float w = cw ? cw[y] : 1.f;
+    sw += w;
+    sl += w * (logf(den) + mx - logits[(long long)i * classes + y]);
+  }
+  sw = warp_sum(sw); sl = warp_sum(sl);
+  if ((threadIdx.x & 31) == 0) { red_w[threadIdx.x >> 5] = sw; red_l[threadIdx.x >> 5] = sl; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float a = 0.f, b = 0.f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { a += red_w[w]; b += red_l[w]; }
+    tot_w = a;
+    if (loss_out) *loss_out = loss_scale * b / a;
+  }
+  __syncthreads();
+  const float inv = loss_scale / tot_w;
+  for (int i = threadIdx.x; i < B; i += blockDim.x) {
+    const int y = (int)labels[i];
+    float mx = -INFINITY;
+    for (int c = 0; c < classes; ++c) mx = fmaxf(mx, logits[(long long)i * classes + c]);
+    float den = 0.f;
+    for (int c = 0; c < classes; ++c) den += expf(logits[(long long)i * classes + c] - mx);
+    const float w = (cw ? cw[y] : 1.f) * inv;
+    for (int c = 0; c < classes; ++c)
+      dlogits[(long long)i * classes + c] = w * (expf(logits[(long long)i * classes + c] - mx) / den - (c == y ? 1.f : 0.f));
+  }
+}
+
+__global__ void grad_accumulate_kernel(float* __restrict__ acc, const float* __restrict__ g, long long n, int first) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    acc[i] = first ? g[i] : acc[i] + g[i];
+}
+
 }  // namespace bci
+
+extern "C" int bci_ce_loss_grad(const float* logits, const int64_t* labels, const float* class_weight, int32_t batch, int32_t classes,
+                                float loss_scale, float* loss_out, float* dlogits, void* stream) {
+  using namespace bci;
+  BCI_REQUIRE(logits && labels && dlogits && batch >= 1 && classes >= 1 && classes <= 8, BCI_EINVAL, "bci_ce_loss_grad: bad arguments");
+  ce_loss_grad_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(logits, reinterpret_cast<const long long*>(labels), class_weight, batch, classes,
+                                                         loss_scale, loss_out, dlogits);
+  BCI_LAUNCH_OK();
+  return BCI_OK;
+}
+
+extern "C" int bci_grad_accumulate(float* acc, const float* g, int64_t n, int32_t first, void* stream) {
+  using namespace bci;
+  BCI_REQUIRE(acc && g && n >= 0, BCI_EINVAL, "bci_grad_accumulate: bad arguments");
+  if (n == 0) return BCI_OK;
+  const int blocks = (int)((n + 1023) / 1024 < 4 * sm_count() ? (n + 1023) / 1024 : 4 * sm_count());
+  grad_accumulate_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(acc, g, n, first);
+  BCI_LAUNCH_OK();
+  return BCI_OK;
+}
 
 extern "C" int bci_adamw_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
                               float weight_decay, int32_t step, float grad_scale, float max_norm, float* norm_scratch, void* stream) {

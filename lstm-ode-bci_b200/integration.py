@@ -64,6 +64,9 @@ def stream_lstm_probs(lstm_model, host_batches, device=None, chunk=None, want_at
         n = xh.shape[0]
         if sl["buf"] is None or sl["buf"].shape[0] < n or sl["buf"].shape[1:] != xh.shape[1:]:
             sl["buf"] = torch.empty(tuple(xh.shape), dtype=torch.float32, device=dev)
+            # the block may have just been freed by main-stream work that is still in flight (the caching allocator hands it
+            # out in main-stream order): the copy stream must not write into it before that work has finished
+            copy_stream.wait_stream(main)
         if sl["free"] is not None:
             copy_stream.wait_event(sl["free"])           # kernels of the batch that last used this buffer are done
         direct = xh.is_pinned() and xh.is_contiguous()
@@ -128,7 +131,138 @@ def stream_lstm_probs(lstm_model, host_batches, device=None, chunk=None, want_at
         k += 1
 
 
-def _lstm_probs_device(lstm_model, X, batch_size, want_attn, device):
+class _H2DRing:
+    """Two device buffers fed by a copy stream: the H2D copy of batch k+1 overlaps the kernels of batch k (main stream).
+    Pinned contiguous host tensors are DMA-ed in place; pageable ones go through a pinned staging buffer per slot."""
+
+    def __init__(self, dev):
+        self.dev = dev
+        self.copy_stream = torch.cuda.Stream(device=dev)
+        self.main = torch.cuda.current_stream(dev)
+        self.slots = [dict(buf=None, free=None, pin=None) for _ in range(2)]
+
+    def submit(self, k, host):
+        sl = self.slots[k & 1]
+        if sl["buf"] is None or sl["buf"].shape != host.shape or sl["buf"].dtype != host.dtype:
+            sl["buf"] = torch.empty(tuple(host.shape), dtype=host.dtype, device=self.dev)
+            # a block the caching allocator just recycled may still be in use by main-stream work in flight
+            self.copy_stream.wait_stream(self.main)
+        if sl["free"] is not None:
+            self.copy_stream.wait_event(sl["free"])          # kernels of the batch that last used this buffer are done
+        src = host
+        if not (host.is_pinned() and host.is_contiguous()):
+            if sl["pin"] is None or sl["pin"].shape != host.shape or sl["pin"].dtype != host.dtype:
+                sl["pin"] = torch.empty(tuple(host.shape), dtype=host.dtype, pin_memory=True)
+            if sl["free"] is not None:
+                sl["free"].synchronize()
+            _staging_copy(sl["pin"], host)
+            src = sl["pin"]
+        with torch.cuda.stream(self.copy_stream):
+            sl["buf"].copy_(src, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(self.copy_stream)
+        return sl, ev
+
+    def acquire(self, token):
+        sl, ev = token
+        self.main.wait_event(ev)
+        return sl["buf"]
+
+    def release(self, token):
+        sl, _ = token
+        sl["free"] = torch.cuda.Event()
+        sl["free"].record(self.main)
+
+    def run(self, host_batches, prepare, compute):
+        it = iter(host_batches)
+        k = 0
+        try:
+            pending = self.submit(k, prepare(next(it)))
+        except StopIteration:
+            return
+        while pending is not None:
+            try:
+                nxt = self.submit(k + 1, prepare(next(it)))   # queue the next batch's copy before computing this one
+            except StopIteration:
+                nxt = None
+            out = compute(self.acquire(pending))
+            self.release(pending)
+            yield out
+            pending = nxt
+            k += 1
+
+
+def stream_recordings(lstm_model, host_batches, seq_len=256, step=128, device=None, want_attn=False):
+    """Pipelined inference straight from normalised RECORDINGS on the host: the windows are never materialised.
+
+    The reference writes every window to disk and host memory (create_sequences, 02_preprocessing.py:157-180: 50 % overlap, so
+    each sample is stored twice) and copies fp32 windows to the GPU (06:346: 62 464 B per window).  Here the host keeps what 02
+    has just before that step -- the band-passed, z-scored recording, sample-major (S, C) -- and the input projection cuts the
+    windows out of it on the device (`bci_lstm_forward_view`): 31 232 B per window in float32, 15 616 B in bfloat16 (the bf16
+    tensor-core mode rounds x to bf16 on load anyway: same result bits, a quarter of the reference's bytes).
+
+    host_batches: iterable of CPU tensors / numpy arrays (R_i, S, C), float32 or torch.bfloat16.  Yields, in order,
+    (probs (R_i * n_seq, 2), attention-or-None) as CUDA tensors enqueued on the current stream; n_seq = (S - seq_len) // step + 1,
+    windows ordered recording by recording as create_sequences emits them."""
+    dev = _dev(device)
+    lstm_model.eval()
+
+    def prepare(rb):
+        rh = torch.as_tensor(rb)
+        if rh.dtype not in (torch.float32, torch.bfloat16):
+            rh = rh.float()
+        if rh.dim() != 3:
+            raise N.BciError(-1, "a recording batch must be (R, S, C), got %s" % (tuple(rh.shape),))
+        return rh
+
+    def compute(buf):
+        out = lstm_model.predict_proba_recordings(buf, seq_len=seq_len, step=step, return_attention=want_attn)
+        return out if want_attn else (out, None)
+
+    yield from _H2DRing(dev).run(host_batches, prepare, compute)
+
+
+def stream_raw_recordings(lstm_model, host_batches, lowcut=1.0, highcut=45.0, fs=500, order=4, seq_len=256, overlap=0.5,
+                          normalization_params=None, device=None):
+    """Pipelined inference from RAW recordings on the host (what mne's raw.get_data() returns, 02_preprocessing.py:200):
+    H2D of (R_i, C, n) float32/float64 batches on a copy stream -> band-pass filtfilt + per-channel z-score + 50 %-overlap
+    windowing on the device (`bci_preprocess`, 02:114-180) -> BiLSTM forward.  31 232 B per window cross PCIe in float32
+    instead of the 62 464 B of materialised fp32 windows, and the filter runs at GPU rate.  Yields (probs (R_i * n_seq, 2),
+    dict(mean, std)) per batch, CUDA tensors on the current stream."""
+    from . import preprocessing as pp
+    dev = _dev(device)
+    lstm_model.eval()
+    b, a, zi, padlen = pp.design_bandpass(lowcut, highcut, fs, order)
+    mean = std = None
+    if normalization_params:
+        mean, std = normalization_params["mean"], normalization_params["std"]
+
+    def prepare(rb):
+        rh = torch.as_tensor(rb)
+        if rh.dtype not in (torch.float32, torch.float64):
+            rh = rh.double()
+        if rh.dim() == 2:
+            rh = rh[None]
+        return rh
+
+    def compute(buf):
+        out = pp.preprocess_recordings(buf, b, a, zi, padlen, seq_len, overlap, mean, std)
+        return lstm_model.predict_proba(out["X"]), {"mean": out["mean"], "std": out["std"]}
+
+    yield from _H2DRing(dev).run(host_batches, prepare, compute)
+
+
+def _lstm_probs_device(lstm_model, X, batch_size, want_attn, device, autocast=False):
+    """`autocast=True`: run where the reference enters `with autocast():` (06_lstm_ode_integration.py:348-351) -- a model built with
+    precision="auto" then takes its reduced-precision (bf16 tensor-core) engine exactly there, and its fp32 engine in the callers
+    that do not autocast (06:216-234, 08:203-208, 10:226-231).  An explicit precision= on the model always wins."""
+    if autocast:
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            return _lstm_probs_device_impl(lstm_model, X, batch_size, want_attn, device)
+    return _lstm_probs_device_impl(lstm_model, X, batch_size, want_attn, device)
+
+
+def _lstm_probs_device_impl(lstm_model, X, batch_size, want_attn, device):
     """All-window inference returning device tensors; X numpy/CPU tensor (pipelined H2D) or CUDA tensor.
 
     `batch_size` is the reference callers' argument (512 in predict_batch 06:308, 256 in 08:198, 512 in 10:204).  There it only
@@ -219,14 +353,14 @@ class LSTMODEIntegration:
 
     def predict_batch(self, X_batch, forecast_steps=20, batch_size=512, show_progress=True):
         """(trajectories (N,steps,3) f64, probs (N,2) f32, predictions (N,) int) -- 06:308-406."""
-        probs, _ = _lstm_probs_device(self.lstm_model, X_batch, batch_size, False, self.device)
+        probs, _ = _lstm_probs_device(self.lstm_model, X_batch, batch_size, False, self.device, autocast=True)   # 06:348-351
         traj, final, _ = self._solve(probs, forecast_steps)
         pred, _ = ops.ode_classify(final, True, False)
         return traj.double().cpu().numpy(), probs.cpu().numpy(), pred.cpu().numpy().astype(np.int64)
 
     def predict_batch_device(self, X_dev, forecast_steps=20, batch_size=None, want_traj=True):
         """Same computation with every tensor left on the device (used by the sharded pipeline)."""
-        probs, _ = _lstm_probs_device(self.lstm_model, X_dev, batch_size, False, self.device)
+        probs, _ = _lstm_probs_device(self.lstm_model, X_dev, batch_size, False, self.device, autocast=True)
         n = probs.shape[0]
         traj, final, _ = solve_ensemble(n, p_open=probs[:, 0].contiguous(), p_closed=probs[:, 1].contiguous(),
                                         base_rates=self.base_params, alpha=self.coupling_strength, y0_mode="probs06",

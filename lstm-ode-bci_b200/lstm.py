@@ -50,8 +50,9 @@ class EnhancedLSTMModel(nn.Module):
         self.classifier = nn.Sequential(nn.Linear(d, hidden_size), nn.GELU(), nn.Dropout(dropout),
                                         nn.Linear(hidden_size, hidden_size // 2), nn.GELU(), nn.Dropout(dropout),
                                         nn.Linear(hidden_size // 2, num_classes))
-        self._engines = {}       # precision -> handle id
-        self._loaded = {}        # precision -> tuple of parameter versions/ptrs at last load
+        self._engines = {}       # precision -> handle id (owned by THIS object; never shared with copies)
+        self._loaded = {}        # precision -> signature of the parameters at the last load
+        self._weights_gen = 0    # bumped by whoever rewrites parameters through raw pointers (train.FusedTrainer)
 
     @property
     def is_full_model(self):
@@ -64,21 +65,52 @@ class EnhancedLSTMModel(nn.Module):
         return self.precision
 
     def _signature(self):
-        return tuple((p.data_ptr(), p._version) for p in self.parameters())
+        return (self._weights_gen,) + tuple((p.data_ptr(), p._version) for p in self.parameters())
+
+    def mark_weights_changed(self):
+        """Call after parameters were rewritten behind torch's back (raw-pointer optimizer kernels): `data_ptr`/`_version` do not
+        change then, so the packed engine copies would otherwise stay one step behind (fp32) or frozen (bf16)."""
+        self._weights_gen += 1
+
+    # engine handles are raw library objects: a copy (copy.deepcopy for a best-model snapshot / EMA, pickling) starts without
+    # any and packs its own on first use, instead of sharing -- and later double-freeing -- the original's
+    def __deepcopy__(self, memo):
+        import copy
+        new = self.__class__.__new__(self.__class__)
+        memo[id(self)] = new
+        for k, v in self.__dict__.items():
+            new.__dict__[k] = {} if k in ("_engines", "_loaded") else copy.deepcopy(v, memo)
+        return new
+
+    def __getstate__(self):
+        st = dict(self.__dict__)
+        st["_engines"], st["_loaded"] = {}, {}
+        return st
+
+    def _device_of(self, x):
+        dev = self.input_proj[0].weight.device
+        if x.device != dev:
+            raise N.BciError(-1, "input is on %s but the model's parameters are on %s" % (x.device, dev))
+        return dev
 
     def _engine(self, prec):
         if prec not in ("fp32", "bf16"):
             raise N.BciError(-1, "precision must be fp32, bf16 or auto")
-        hid = self._engines.get(prec)
-        if hid is None:
-            hid = ops.lstm_create(self.input_size, self.hidden_size, self.num_layers, self.num_classes,
-                                  N.PRECISION_BF16 if prec == "bf16" else N.PRECISION_FP32, self.bidirectional,
-                                  self.use_attention, self.use_layer_norm)
-            self._engines[prec] = hid
-        sig = self._signature()
-        if self._loaded.get(prec) != sig:
-            ops.lstm_load_weights(hid, {k: v for k, v in self.state_dict().items()})
-            self._loaded[prec] = sig
+        dev = self.input_proj[0].weight.device
+        if dev.type != "cuda":
+            raise N.BciError(-1, "the model's parameters are on %s; move it with .to('cuda') -- there is no CPU fallback" % dev)
+        key = (prec, dev.index if dev.index is not None else torch.cuda.current_device())
+        with torch.cuda.device(dev):        # the handle's packed store lives on the parameters' device
+            hid = self._engines.get(key)
+            if hid is None:
+                hid = ops.lstm_create(self.input_size, self.hidden_size, self.num_layers, self.num_classes,
+                                      N.PRECISION_BF16 if prec == "bf16" else N.PRECISION_FP32, self.bidirectional,
+                                      self.use_attention, self.use_layer_norm)
+                self._engines[key] = hid
+            sig = self._signature()
+            if self._loaded.get(key) != sig:
+                ops.lstm_load_weights(hid, {k: v for k, v in self.state_dict().items()})
+                self._loaded[key] = sig
         return hid
 
     def __del__(self):
@@ -97,15 +129,45 @@ class EnhancedLSTMModel(nn.Module):
         if torch.is_grad_enabled() and (x.requires_grad or (self.training and any(p.requires_grad for p in self.parameters()))):
             from .train import lstm_attn_autograd
             return lstm_attn_autograd(self, x, return_attention)
-        hid = self._engine(self._precision_now())
-        logits, _probs, attn = ops.lstm_attn_forward(x, hid, bool(return_attention))
+        with torch.cuda.device(self._device_of(x)):       # kernels, packed weights and the stream belong to x's device
+            hid = self._engine(self._precision_now())
+            logits, _probs, attn = ops.lstm_attn_forward(x, hid, bool(return_attention))
         return (logits, attn) if return_attention else logits
 
     @torch.no_grad()
     def predict_proba(self, x, return_attention=False):
         """logits -> softmax fused in the head kernel: columns [P(open), P(closed)] (06:223,232)."""
-        hid = self._engine(self._precision_now())
-        _logits, probs, attn = ops.lstm_attn_forward(x.float(), hid, bool(return_attention))
+        if not x.is_cuda:
+            raise N.BciError(-1, "predict_proba runs on CUDA tensors only (there is no CPU fallback)")
+        with torch.cuda.device(self._device_of(x)):
+            hid = self._engine(self._precision_now())
+            _logits, probs, attn = ops.lstm_attn_forward(x.float(), hid, bool(return_attention))
+        return (probs, attn) if return_attention else probs
+
+
+    @torch.no_grad()
+    def predict_proba_recordings(self, recordings, seq_len=256, step=128, first_window=0, n_windows=None, return_attention=False):
+        """Probabilities of the overlapping windows of normalised recordings read IN PLACE (`bci::lstm_attn_forward_view`).
+
+        recordings: (R, S, C) CUDA tensor, float32 or bfloat16, sample-major -- 02_preprocessing.py's normalised signal
+        transposed to (samples, channels).  Window w = r * n_seq + i (n_seq = (S - seq_len) // step + 1, 02:169) is samples
+        [i*step, i*step + seq_len) of recording r: the order create_sequences (02:157-180) emits them in, recording after
+        recording.  Returns probabilities of windows [first_window, first_window + n_windows) -- default: all of them."""
+        if not recordings.is_cuda or recordings.dim() != 3 or recordings.shape[2] != self.input_size:
+            raise N.BciError(-1, "recordings must be a CUDA tensor (R, S, %d)" % self.input_size)
+        R, S, Cc = (int(v) for v in recordings.shape)
+        if S < seq_len:
+            raise N.BciError(-1, "recordings of %d samples are shorter than one window (%d)" % (S, seq_len))
+        n_seq = (S - seq_len) // step + 1
+        total = R * n_seq
+        n = total - first_window if n_windows is None else int(n_windows)
+        if first_window < 0 or n < 0 or first_window + n > total:
+            raise N.BciError(-1, "windows [%d, %d) are outside the %d windows of these recordings" % (first_window, first_window + n, total))
+        data = recordings.contiguous()
+        with torch.cuda.device(self._device_of(data)):
+            hid = self._engine(self._precision_now())
+            _logits, probs, attn = ops.lstm_attn_forward_view(data.view(-1), hid, n, int(seq_len), n_seq, int(step) * Cc, S * Cc,
+                                                             int(first_window), bool(return_attention))
         return (probs, attn) if return_attention else probs
 
 

@@ -16,8 +16,8 @@ _handles_lock = threading.Lock()
 _next_handle = [1]
 
 
-def _stream():
-    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+def _stream(device=None):
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 
 def _ptr(t):
@@ -40,7 +40,9 @@ class _Handle:
         self.cfg = cfg
         self.ptr = C.c_void_p(0)
         N.check(N.lib().bci_lstm_create(C.byref(cfg), C.byref(self.ptr)))
+        self.device = torch.cuda.current_device()      # the library allocates the packed store on the current device
         self.keepalive = None
+        self.layout = []
 
     def close(self):
         if self.ptr:
@@ -101,6 +103,10 @@ def lstm_load_weights(hid, state):
     w = fill_pointer_struct(N.LstmWeights(), tensors, h.cfg.num_layers)
     N.check(N.lib().bci_lstm_load_weights(h.ptr, C.byref(w), _stream()))
     h.keepalive = tensors  # backward reads the raw weights; keep them alive with the handle
+    off, h.layout = 0, []
+    for k, v in state.items():
+        h.layout.append((k, off, v.numel(), tuple(v.shape)))
+        off += v.numel()
 
 
 PHASES = ("input_proj", "proj_gemm", "recurrence", "pool_head")
@@ -144,6 +150,7 @@ def lstm_attn_forward(x: torch.Tensor, handle: int, want_attn: bool) -> tuple[to
     x = _need_cuda(x, "x")
     if x.dim() != 3 or x.shape[2] != h.cfg.input_size:
         raise N.BciError(-1, "x must be (B,T,%d), got %s" % (h.cfg.input_size, tuple(x.shape)))
+    _same_device(h, x, "x")
     B, T = int(x.shape[0]), int(x.shape[1])
     logits = torch.empty((B, h.cfg.num_classes), device=x.device, dtype=torch.float32)
     probs = torch.empty_like(logits)
@@ -153,7 +160,7 @@ def lstm_attn_forward(x: torch.Tensor, handle: int, want_attn: bool) -> tuple[to
     nbytes = lstm_workspace_bytes(handle, B, T, 0)
     ws = torch.empty((nbytes,), device=x.device, dtype=torch.uint8)
     N.check(N.lib().bci_lstm_forward(h.ptr, _ptr(x), B, T, 0, 0.0, 0, _ptr(logits), _ptr(probs),
-                                     _ptr(attn) if want_attn else C.c_void_p(0), _ptr(ws), nbytes, _stream()))
+                                     _ptr(attn) if want_attn else C.c_void_p(0), _ptr(ws), nbytes, _stream(x.device)))
     return logits, probs, attn
 
 
@@ -163,6 +170,132 @@ def _(x, handle, want_attn):
     B, T = x.shape[0], x.shape[1]
     lg = x.new_empty((B, h.cfg.num_classes))
     return lg, x.new_empty((B, h.cfg.num_classes)), x.new_empty((B, T) if want_attn else (0,))
+
+
+def _same_device(h, t, name):
+    if t.device.index != h.device:
+        raise N.BciError(-1, "%s is on cuda:%s but the engine was built on cuda:%d" % (name, t.device.index, h.device))
+
+
+@torch.library.custom_op("bci::lstm_attn_forward_view", mutates_args=())
+def lstm_attn_forward_view(data: torch.Tensor, handle: int, batch: int, seq_len: int, windows_per_run: int, window_stride: int,
+                           run_stride: int, first_window: int, want_attn: bool) -> tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """The same forward over windows read IN PLACE from `data` (bci_lstm_forward_view): a flat fp32 or bf16 CUDA tensor holding
+    e.g. (R, S, C) recordings whose 50 %-overlapping windows (02_preprocessing.py:157-180) start every `window_stride` elements.
+    Window b covers elements [off, off + seq_len*C), off = (w // windows_per_run) * run_stride + (w % windows_per_run) * window_stride
+    with w = first_window + b (windows_per_run = 0: w * window_stride)."""
+    h = _handles[handle]
+    if not (isinstance(data, torch.Tensor) and data.is_cuda and data.is_contiguous()):
+        raise N.BciError(-1, "data must be a contiguous CUDA tensor (there is no CPU fallback)")
+    if data.dtype not in (torch.float32, torch.bfloat16):
+        raise N.BciError(-1, "data must be float32 or bfloat16, got %s" % data.dtype)
+    _same_device(h, data, "data")
+    B, T, Cc = int(batch), int(seq_len), h.cfg.input_size
+    if B > 0:
+        last = first_window + B - 1
+        off = (last // windows_per_run) * run_stride + (last % windows_per_run) * window_stride if windows_per_run > 0 \
+            else last * window_stride
+        if window_stride < 1 or first_window < 0 or off + T * Cc > data.numel():
+            raise N.BciError(-1, "view of %d windows x %d x %d reaches element %d of a %d-element tensor"
+                             % (B, T, Cc, off + T * Cc, data.numel()))
+    logits = torch.empty((B, h.cfg.num_classes), device=data.device, dtype=torch.float32)
+    probs = torch.empty_like(logits)
+    attn = torch.empty((B, T) if want_attn else (0,), device=data.device, dtype=torch.float32)
+    if B == 0:
+        return logits, probs, attn
+    nbytes = lstm_workspace_bytes(handle, B, T, 0)
+    ws = torch.empty((nbytes,), device=data.device, dtype=torch.uint8)
+    view = N.LstmInput(data.data_ptr(), N.IN_BF16 if data.dtype == torch.bfloat16 else N.IN_F32, int(windows_per_run),
+                       int(window_stride), int(run_stride), int(first_window))
+    N.check(N.lib().bci_lstm_forward_view(h.ptr, C.byref(view), B, T, _ptr(logits), _ptr(probs),
+                                          _ptr(attn) if want_attn else C.c_void_p(0), _ptr(ws), nbytes, _stream(data.device)))
+    return logits, probs, attn
+
+
+@lstm_attn_forward_view.register_fake
+def _(data, handle, batch, seq_len, windows_per_run, window_stride, run_stride, first_window, want_attn):
+    h = _handles[handle]
+    lg = data.new_empty((batch, h.cfg.num_classes), dtype=torch.float32)
+    return lg, torch.empty_like(lg), data.new_empty((batch, seq_len) if want_attn else (0,), dtype=torch.float32)
+
+
+# ------------------------------------------------------------------------------------------
+# training step: forward with saved activations, BPTT (the autograd bridge in train.py calls these two ops)
+# ------------------------------------------------------------------------------------------
+@torch.library.custom_op("bci::lstm_attn_forward_train", mutates_args=())
+def lstm_attn_forward_train(x: torch.Tensor, handle: int, dropout: float, seed: int) -> tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """EnhancedLSTMModel.forward in .train() mode (04_lstm_model.py:206-222 with the dropout sites of 04:177,186,199,202):
+    x (B,T,C) fp32 -> logits (B,classes), attention (B,T), and the opaque workspace holding the activations BPTT needs."""
+    h = _handles[handle]
+    x = _need_cuda(x, "x")
+    _same_device(h, x, "x")
+    B, T = int(x.shape[0]), int(x.shape[1])
+    logits = torch.empty((B, h.cfg.num_classes), device=x.device, dtype=torch.float32)
+    attn = torch.empty((B, T), device=x.device, dtype=torch.float32)
+    nbytes = lstm_workspace_bytes(handle, B, T, 1)
+    ws = torch.empty((nbytes,), device=x.device, dtype=torch.uint8)
+    N.check(N.lib().bci_lstm_forward(h.ptr, _ptr(x), B, T, 1, float(dropout), int(seed), _ptr(logits), C.c_void_p(0), _ptr(attn),
+                                     _ptr(ws), nbytes, _stream(x.device)))
+    return logits, attn, ws
+
+
+@lstm_attn_forward_train.register_fake
+def _(x, handle, dropout, seed):
+    h = _handles[handle]
+    B, T = x.shape[0], x.shape[1]
+    return (x.new_empty((B, h.cfg.num_classes)), x.new_empty((B, T)),
+            x.new_empty((lstm_workspace_bytes(handle, int(B), int(T), 1),), dtype=torch.uint8))
+
+
+@torch.library.custom_op("bci::lstm_attn_backward", mutates_args=("workspace",))
+def lstm_attn_backward(x: torch.Tensor, dlogits: torch.Tensor, workspace: torch.Tensor, handle: int,
+                       need_dx: bool) -> tuple[torch.Tensor, torch.Tensor]:
+    """loss.backward() through the model (04_lstm_model.py:490-494; 07_explainability.py:242-258 for dx): BPTT from
+    dlogits (B,classes) on the workspace of a `bci::lstm_attn_forward_train` call.  Returns (dx (B,T,C) or empty,
+    flat fp32 gradient bucket in state-dict order: `param_layout(handle)` gives each parameter's (key, offset, numel, shape))."""
+    h = _handles[handle]
+    x = _need_cuda(x, "x")
+    _same_device(h, x, "x")
+    B, T = int(x.shape[0]), int(x.shape[1])
+    lay = param_layout(handle)
+    flat = torch.empty((lay[-1][1] + lay[-1][2],), device=x.device, dtype=torch.float32)
+    grads = {k: flat[o:o + n] for k, o, n, _ in lay}
+    gs = fill_pointer_struct(N.LstmGrads(), grads, h.cfg.num_layers)
+    dx = torch.empty_like(x) if need_dx else torch.empty((0,), device=x.device, dtype=torch.float32)
+    dl = _need_cuda(dlogits.float(), "dlogits")
+    N.check(N.lib().bci_lstm_backward(h.ptr, _ptr(x), _ptr(dl), B, T, _ptr(dx) if need_dx else C.c_void_p(0), C.byref(gs),
+                                      _ptr(workspace), workspace.numel(), _stream(x.device)))
+    return dx, flat
+
+
+@lstm_attn_backward.register_fake
+def _(x, dlogits, workspace, handle, need_dx):
+    lay = param_layout(handle)
+    return (torch.empty_like(x) if need_dx else x.new_empty((0,))), x.new_empty((lay[-1][1] + lay[-1][2],))
+
+
+def param_layout(hid):
+    """[(state-dict key, offset, numel, shape)] of the parameters last loaded into the handle, in state-dict order."""
+    lay = _handles[hid].layout
+    if not lay:
+        raise N.BciError(-4, "no weights loaded into this engine yet")
+    return lay
+
+
+def ce_loss_grad(logits, labels, class_weight=None, loss_scale=1.0):
+    """criterion(outputs, y) * loss_scale and its gradient wrt the logits (04:456-458,486-494): (loss (1,), dlogits (B,classes))."""
+    lg = _need_cuda(logits, "logits")
+    y = _need_cuda(labels, "labels", torch.int64)
+    cw = _need_cuda(class_weight, "class_weight") if class_weight is not None else None
+    loss = torch.empty((1,), device=lg.device, dtype=torch.float32)
+    dl = torch.empty_like(lg)
+    N.check(N.lib().bci_ce_loss_grad(_ptr(lg), _ptr(y), _ptr(cw), int(lg.shape[0]), int(lg.shape[1]), float(loss_scale), _ptr(loss),
+                                     _ptr(dl), _stream(lg.device)))
+    return loss, dl
+
+
+def grad_accumulate(acc, g, first):
+    N.check(N.lib().bci_grad_accumulate(_ptr(acc), _ptr(g), acc.numel(), int(bool(first)), _stream(acc.device)))
 
 
 # ------------------------------------------------------------------------------------------

@@ -38,24 +38,58 @@ def max_over_ranks(value, device, group=None):
     return float(t.item())
 
 
-def forecast_pipeline_sharded(integration, X_local, n_total, horizons=(5, 10, 20), ode_params=None, group=None):
-    """Config 5: each rank classifies its contiguous window shard and integrates its coupled trajectories;
-    the 08-style forecast needs probs[i+h] across shard edges, so the (N,2) probabilities are gathered first
-    (3.4 MB for 421 200 windows) and the forecast ODE stage is sharded again.  Returns rank-local tensors plus the
-    gathered probabilities."""
+def _ode_and_forecast(integration, probs, n_total, horizons, ode_params, group, want_traj=True):
+    """Stages 2-4 of config 5 on this rank's probabilities: coupled ODE (06 path), gather of the (N,2) probabilities, 08-style
+    forecast of this rank's share of the N - max(h) forecast origins."""
     from . import ops
     from .integration import _forecast_device
+    from .ode import solve_ensemble
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     world = dist.get_world_size(group) if dist.is_initialized() else 1
-    traj, probs, final, pred, cls = integration.predict_batch_device(X_local)
+    n = probs.shape[0]
+    traj, final, _ = solve_ensemble(n, p_open=probs[:, 0].contiguous(), p_closed=probs[:, 1].contiguous(),
+                                    base_rates=integration.base_params, alpha=integration.coupling_strength, y0_mode="probs06",
+                                    coupling=True, style="ref06", mode="rk4", t_end=20.0, n_points=20,
+                                    substeps=integration.substeps, want_traj=want_traj, device=probs.device)
+    pred, cls = ops.ode_classify(final, True, True)
     all_probs = gather_shards(probs, n_total, group)
     m = n_total - max(horizons)
     b, e = shard_range(max(m, 0), rank, world)
     fc = None
     if e > b:
         prm = ode_params if ode_params is not None else integration.base_params
-        fc = _forecast_device(all_probs[b:e, 1].contiguous(), prm, max(horizons), list(horizons), X_local.device, integration.substeps)
+        fc = _forecast_device(all_probs[b:e, 1].contiguous(), prm, max(horizons), list(horizons), probs.device, integration.substeps)
     return {"traj": traj, "final": final, "pred": pred, "cls": cls, "probs": all_probs, "forecast": fc, "forecast_range": (b, e)}
+
+
+def forecast_pipeline_sharded(integration, X_local, n_total, horizons=(5, 10, 20), ode_params=None, group=None):
+    """Config 5: each rank classifies its contiguous window shard and integrates its coupled trajectories;
+    the 08-style forecast needs probs[i+h] across shard edges, so the (N,2) probabilities are gathered first
+    (3.4 MB for 421 200 windows) and the forecast ODE stage is sharded again.  Returns rank-local tensors plus the
+    gathered probabilities."""
+    from .integration import _lstm_probs_device
+    probs, _ = _lstm_probs_device(integration.lstm_model, X_local, None, False, X_local.device, autocast=True)
+    return _ode_and_forecast(integration, probs, n_total, tuple(horizons), ode_params, group)
+
+
+def forecast_pipeline_from_recordings(integration, host_recording_batches, n_total, horizons=(5, 10, 20), ode_params=None,
+                                      group=None, raw=True, want_traj=True, **stream_kw):
+    """Config 5 end to end FROM THE HOST: this rank's recordings are streamed to its GPU (copy stream, double-buffered) and the
+    windows are cut on the device -- raw=True: raw (R, C, n) recordings -> band-pass + z-score + windowing (`bci_preprocess`,
+    02_preprocessing.py:114-180) -> BiLSTM; raw=False: normalised sample-major (R, S, C) recordings (fp32 or bf16) read in
+    place by the input projection -- then coupling + ODE, the probability gather and the 08-style forecast as in
+    `forecast_pipeline_sharded`.  `n_total` = windows over all ranks (ranks own contiguous recording ranges, so window order is
+    rank order)."""
+    import torch
+    from .integration import stream_raw_recordings, stream_recordings
+    model = integration.lstm_model
+    with torch.autocast("cuda", dtype=torch.bfloat16):           # where the reference's predict_batch autocasts (06:348-351)
+        if raw:
+            parts = [p for p, _ in stream_raw_recordings(model, host_recording_batches, device=integration.device, **stream_kw)]
+        else:
+            parts = [p for p, _ in stream_recordings(model, host_recording_batches, device=integration.device, **stream_kw)]
+    probs = parts[0] if len(parts) == 1 else torch.cat(parts)
+    return _ode_and_forecast(integration, probs, n_total, tuple(horizons), ode_params, group, want_traj=want_traj)
 
 
 class _DevArray:
@@ -101,8 +135,15 @@ class P2PComm:
                                        int(step), max_norm, _ptr(norm_out), _stream()))
 
     def close(self):
+        """Frees the bucket: every tensor view of it (`.bucket`, a trainer's gradient views) is invalid afterwards."""
         if self.ptr:
             torch.cuda.synchronize(self.device)
             self.bucket = None
             self._N.lib().bci_comm_destroy(self.ptr)
             self.ptr = C.c_void_p(0)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -6,6 +6,9 @@ whatever the module calls `EnhancedLSTMModel`, `CognitiveStateODE`, `LSTMODEInte
 `predict_trajectory`, `prob_to_ode_state`, `multistep_forecast`, `rolling_forecast_evaluation`,
 `get_lstm_probabilities`, `get_three_state_probabilities` is replaced when present.
 """
+import functools
+import inspect
+
 from . import integration, lstm, ode, preprocessing
 
 _REPLACEMENTS = {
@@ -23,17 +26,50 @@ _REPLACEMENTS = {
 }
 
 
+def _with_reference_defaults(new_obj, ref_obj):
+    """The reference redeclares its classes per script with DIFFERENT defaults (EnhancedLSTMModel: input_size 14 / hidden 128 in
+    04/07/08, 64 / 256 in 06/10): the replacement installed into a script takes that script's defaults."""
+    new_fn = new_obj.__init__ if inspect.isclass(new_obj) else new_obj
+    ref_fn = ref_obj.__init__ if inspect.isclass(ref_obj) else ref_obj
+    try:
+        ref_sig, new_sig = inspect.signature(ref_fn), inspect.signature(new_fn)
+    except (TypeError, ValueError):
+        return new_obj
+    over = {n: p.default for n, p in ref_sig.parameters.items()
+            if p.default is not inspect._empty and n in new_sig.parameters and new_sig.parameters[n].default != p.default}
+    if not over:
+        return new_obj
+    sig = new_sig.replace(parameters=[p.replace(default=over[n]) if n in over else p for n, p in new_sig.parameters.items()])
+
+    def fill(args, kwargs, skip_self):
+        given = new_sig.bind_partial(*(((None,) if skip_self else ()) + tuple(args)), **kwargs).arguments
+        return dict(kwargs, **{n: v for n, v in over.items() if n not in given})
+
+    if inspect.isclass(new_obj):
+        def __init__(self, *args, **kwargs):
+            new_obj.__init__(self, *args, **fill(args, kwargs, True))
+        __init__.__signature__ = sig
+        return type(new_obj.__name__, (new_obj,), {"__init__": __init__, "__module__": new_obj.__module__,
+                                                   "__doc__": new_obj.__doc__, "__qualname__": new_obj.__qualname__})
+
+    @functools.wraps(new_obj)
+    def wrapper(*args, **kwargs):
+        return new_obj(*args, **fill(args, kwargs, False))
+    wrapper.__signature__ = sig
+    return wrapper
+
+
 def patch_reference(module):
     """Returns the list of names replaced.  08's module-level predict_trajectory/get_lstm_probabilities
     are only replaced when the module has no LSTMODEIntegration (i.e. it is 08, not 06)."""
     done = []
     for name, repl in _REPLACEMENTS.items():
         if hasattr(module, name):
-            setattr(module, name, repl)
+            setattr(module, name, _with_reference_defaults(repl, getattr(module, name)))
             done.append(name)
     if not hasattr(module, "LSTMODEIntegration"):
         for name in ("predict_trajectory", "get_lstm_probabilities"):
             if hasattr(module, name):
-                setattr(module, name, getattr(integration, name))
+                setattr(module, name, _with_reference_defaults(getattr(integration, name), getattr(module, name)))
                 done.append(name)
     return done

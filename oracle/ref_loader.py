@@ -67,9 +67,10 @@ def _install_plot_stubs():
 _cache = {}
 
 
-def load(name):
-    """name in {ref02, ref04, ref05, ref06, ref08, ref09, ref10}; returns the imported module."""
-    if name in _cache:
+def load(name, fresh=False):
+    """name in {ref02, ref04, ref05, ref06, ref08, ref09, ref10}; returns the imported module (fresh=True: a new, uncached
+    module object -- for tests that monkey-patch it)."""
+    if name in _cache and not fresh:
         return _cache[name]
     if not reference_available():
         raise FileNotFoundError("reference tree not present at %s" % REFERENCE_ROOT)
@@ -87,5 +88,6 @@ def load(name):
             spec.loader.exec_module(mod)
     finally:
         pathlib.Path.mkdir = real_mkdir
-    _cache[name] = mod
+    if not fresh:
+        _cache[name] = mod
     return mod

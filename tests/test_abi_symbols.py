@@ -57,18 +57,18 @@ def test_struct_layouts_match_c(libpath, tmp_path):
     import ctypes as C
     from lstm_ode_bci_b200 import _native as N
     prog = tmp_path / "sz.c"
-    prog.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "bci_b200.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n",'
+    prog.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "bci_b200.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n",'
                     "sizeof(bci_lstm_config),sizeof(bci_lstm_weights),sizeof(bci_lstm_grads),sizeof(bci_ode_args),"
                     "offsetof(bci_ode_args,rates),offsetof(bci_ode_args,t_end),offsetof(bci_ode_args,traj),"
                     "sizeof(bci_ode_mod_args),offsetof(bci_ode_mod_args,t_span),offsetof(bci_ode_mod_args,final_state),"
-                    "sizeof(bci_preproc_args),offsetof(bci_preproc_args,std_in));return 0;}\n")
+                    "sizeof(bci_preproc_args),offsetof(bci_preproc_args,std_in),sizeof(bci_lstm_input),offsetof(bci_lstm_input,window_stride));return 0;}\n")
     exe = tmp_path / "sz"
     subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(prog), "-o", str(exe)], check=True)
     got = [int(v) for v in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
     want = [C.sizeof(N.LstmConfig), C.sizeof(N.LstmWeights), C.sizeof(N.LstmGrads), C.sizeof(N.OdeArgs),
             N.OdeArgs.rates.offset, N.OdeArgs.t_end.offset, N.OdeArgs.traj.offset,
             C.sizeof(N.OdeModArgs), N.OdeModArgs.t_span.offset, N.OdeModArgs.final_state.offset,
-            C.sizeof(N.PreprocArgs), N.PreprocArgs.std_in.offset]
+            C.sizeof(N.PreprocArgs), N.PreprocArgs.std_in.offset, C.sizeof(N.LstmInput), N.LstmInput.window_stride.offset]
     assert got == want
 
 

@@ -59,3 +59,18 @@ def test_population_loss_and_fit_recover_known_rates():
     assert loss <= floor + 1e-6
     t, sol = ode.CognitiveStateODE(fitted).solve(obs[0], (0, 40), 41)
     assert np.abs(sol - obs).max() <= 2e-2                    # the 1e-3 |k|^2 regulariser trades a little data fit for smaller rates
+
+
+def test_fit_matches_reference_seeded_fit(golden):
+    """The reference's own seeded fit (05_ode_model.py:296-303: differential_evolution(seed=42, maxiter=1000, tol=1e-7,
+    polish=True)), run by the live reference (tests/golden/make_golden_fit.py): the GPU objective reproduces the reference's
+    final loss at the reference's fitted rates, and the GPU fit converges to the same loss within 1e-6."""
+    g = golden("ode_ref05_fit.npz")
+    obs, tp = g["observed"], g["time_points"]
+    model = ode.CognitiveStateODE()
+    at_ref = model.population_loss(g["fitted"].reshape(6, 1), obs, tp)[0]
+    assert abs(at_ref - float(g["loss"])) <= 1e-7, (at_ref, float(g["loss"]))
+    fitted, loss = model.fit_to_data(obs, tp)
+    print("GPU fit loss %.10f, reference %.10f" % (loss, float(g["loss"])))
+    assert abs(loss - float(g["loss"])) <= 1e-6
+    assert all(lo - 1e-12 <= fitted[k] <= hi + 1e-12 for k, (lo, hi) in zip(ode.RATE_ORDER, ode.CognitiveStateODE.FIT_BOUNDS))

@@ -89,3 +89,30 @@ def test_empty_and_single_window_inputs():
     t, f = ode.solve_modulated_ensemble(np.zeros((3, 0)), np.tile(np.array([0.1, 0.02, 0.15, 0.08, 0.05, 0.1]), (2 * 2 * 4 + 1, 1)),
                                         (0.0, 4.0), 5, 2)
     assert t.shape == (0, 5, 3) and f.shape == (0, 3)
+
+
+def test_auto_precision_follows_the_reference_autocast():
+    """06_lstm_ode_integration.py:348-351 enters autocast inside predict_batch; 06:216-234, 08:203-208, 10:226-231 do not."""
+    m = lstm.EnhancedLSTMModel(61, 128, 3, 2, precision="auto")
+    assert m._precision_now() == "fp32"
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        assert m._precision_now() == "bf16"
+    assert lstm.EnhancedLSTMModel(61, 128, 3, 2, precision="fp32")._precision_now() == "fp32"
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        assert lstm.EnhancedLSTMModel(61, 128, 3, 2, precision="fp32")._precision_now() == "fp32"     # explicit wins
+        assert lstm.AblationLSTMModel(61, 256, 1, bidirectional=False, precision="auto")._precision_now() == "fp32"
+
+
+def test_predict_batch_takes_the_bf16_engine_where_the_reference_autocasts():
+    """precision="auto": LSTMODEIntegration.predict_batch == the explicit bf16 model bit for bit (the reference's autocast site,
+    06:348-351), get_lstm_probabilities == the explicit fp32 model (no autocast there, 06:216-234)."""
+    params = synth.make_lstm_params(42, 61, 128, 3, logit_gain=12.0)
+    x = synth.make_windows(7, 40, 256, 61, structured=True)
+    outs = {}
+    for prec in ("auto", "bf16", "fp32"):
+        m = lstm.from_params(params, precision=prec)
+        integ = integration.LSTMODEIntegration(m, ode.CognitiveStateODE(), coupling_strength=0.5)
+        outs[prec] = (integ.predict_batch(x, forecast_steps=20, batch_size=512, show_progress=False)[1], integ.get_lstm_probabilities(x)[0])
+    assert np.array_equal(outs["auto"][0], outs["bf16"][0]) and not np.array_equal(outs["auto"][0], outs["fp32"][0])
+    assert np.array_equal(outs["auto"][1], outs["fp32"][1])
+    assert np.abs(outs["auto"][0] - outs["fp32"][0]).max() <= 1.2e-3

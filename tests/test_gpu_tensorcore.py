@@ -105,6 +105,10 @@ def test_recurrence_tcgen05_matches_stepwise(Bc, T):
     assert float((got - want).abs().max()) <= 1.5e-2      # bf16 output rounding (4e-3) + tanh.approx, compounding over T
 
 
+# bf16 tensor-core mode vs the fp32 oracle at logit gain 12: 3x the measured errors (see the test below)
+BF16_TOL = {"logits": 6e-3, "probs": 1.2e-3, "attn": 1.2e-4}
+
+
 @pytest.mark.parametrize("B,T", [(8, 256), (130, 64), (37, 128)])
 def test_bf16_forward_close_to_fp32_oracle(B, T):
     params = synth.make_lstm_params(42, 61, 128, 3, logit_gain=12.0)
@@ -121,7 +125,9 @@ def test_bf16_forward_close_to_fp32_oracle(B, T):
     dp = np.abs(probs.cpu().numpy() - want_probs).max()
     da = np.abs(attn.cpu().numpy() - want_attn.numpy()).max()
     print(f"bf16 vs fp32 oracle: dlogit {dl:.3e} dprob {dp:.3e} dattn {da:.3e}")
-    assert dl <= 12.0 * 3e-2 and dp <= 1e-2 and da <= 2e-3
+    # stated bf16-mode tolerance = 3x the errors measured on this configuration (logit gain 12: logits 1.1-2.0e-3,
+    # probabilities 1.5-3.9e-4, attention 1-4e-5): a regression of the recurrence's accuracy fails here
+    assert dl <= BF16_TOL["logits"] and dp <= BF16_TOL["probs"] and da <= BF16_TOL["attn"], (dl, dp, da)
     # fp32 mode on the same inputs for reference of scale
     m32 = lstm.from_params(params, precision="fp32")
     with torch.no_grad():
@@ -147,7 +153,8 @@ def test_bf16_h256_forward_close_to_fp32_oracle(B, T):
     dp = np.abs(probs.cpu().numpy() - want_probs).max()
     da = np.abs(attn.cpu().numpy() - want_attn.numpy()).max()
     print(f"bf16 H=256 vs fp32 oracle: dlogit {dl:.3e} dprob {dp:.3e} dattn {da:.3e}")
-    assert dl <= 12.0 * 3e-2 and dp <= 1e-2 and da <= 2e-3
+    # measured at H = 256: logits 1.0-1.8e-3, probabilities 1.8-5.1e-4, attention 1-6e-5; asserted at 3x
+    assert dl <= BF16_TOL["logits"] and dp <= 1.5e-3 and da <= 2e-4, (dl, dp, da)
 
 
 def test_bf16_rejects_ablation_variants_and_other_sizes():
@@ -345,7 +352,7 @@ def test_bf16_single_pass_pooling_large_batch():
     for sl in (slice(0, 96), slice(2000, 2064), slice(B - 100, B)):
         with torch.no_grad():
             p32, a32 = m32.predict_proba(x[sl], return_attention=True)
-        assert float((pb[sl] - p32).abs().max()) <= 1e-2 and float((ab[sl] - a32).abs().max()) <= 2e-3
+        assert float((pb[sl] - p32).abs().max()) <= BF16_TOL["probs"] and float((ab[sl] - a32).abs().max()) <= BF16_TOL["attn"]
 
 
 def test_bf16_full_wave_properties():
@@ -366,4 +373,43 @@ def test_bf16_full_wave_properties():
     assert torch.isfinite(p).all() and torch.isfinite(a).all()
     assert torch.equal(pr.flip(0), p) and torch.equal(ar.flip(0), a)
     assert float((p.sum(1) - 1).abs().max()) <= 1e-6 and float((a.sum(1) - 1).abs().max()) <= 1e-5
-    assert float((ps - p[1000:1100]).abs().max()) <= 2e-3
+    assert float((ps - p[1000:1100]).abs().max()) <= BF16_TOL["probs"]
+    # ... and against the ORACLE (torch CPU port of the reference module) on three 32-window slices of this very wave: the first
+    # tile, a middle one that the persistent loop reaches as a later work item, and the last (the wave's final cluster)
+    port = torch_port.build_port(params).eval()
+    xc = x.cpu()
+    for lo in (0, B // 2 - 16, B - 32):
+        with torch.no_grad():
+            wl, wa = port(xc[lo:lo + 32], return_attention=True)
+            wp = torch.softmax(wl, 1)
+        dp = float((p[lo:lo + 32].cpu() - wp).abs().max())
+        da = float((a[lo:lo + 32].cpu() - wa).abs().max())
+        print(f"full wave vs oracle, windows {lo}..{lo + 32}: dprob {dp:.3e} dattn {da:.3e}")
+        assert dp <= BF16_TOL["probs"] and da <= BF16_TOL["attn"], (lo, dp, da)
+
+
+def test_bf16_view_input_equals_packed_windows():
+    """bci_lstm_forward_view: windows read in place from (R, S, C) recordings with 50 % overlap (02_preprocessing.py:157-180), in
+    fp32 and in bf16, against the same windows materialised as the reference does -- BIT-identical in the bf16 mode (its input
+    projection rounds x to bf16 on load, so storing bf16 loses nothing), and a pass that starts in the middle of a recording and
+    crosses into the next one (first_window) returns the matching rows."""
+    params = synth.make_lstm_params(42, 61, 128, 3, logit_gain=12.0)
+    m = lstm.from_params(params, precision="bf16")
+    R, S, C_, T, step = 3, 2000, 61, 256, 128
+    g = torch.Generator(device="cuda").manual_seed(5)
+    rec = torch.randn((R, S, C_), device="cuda", generator=g)
+    n_seq = (S - T) // step + 1
+    X = torch.stack([rec[r, i * step:i * step + T] for r in range(R) for i in range(n_seq)]).contiguous()
+    with torch.no_grad():
+        want, want_a = m.predict_proba(X, return_attention=True)
+        got32, got32_a = m.predict_proba_recordings(rec, T, step, return_attention=True)
+        got16 = m.predict_proba_recordings(rec.to(torch.bfloat16), T, step)
+        part = m.predict_proba_recordings(rec.to(torch.bfloat16), T, step, first_window=n_seq - 3, n_windows=7)
+    assert want.shape[0] == R * n_seq
+    assert torch.equal(got32, want) and torch.equal(got32_a, want_a)
+    assert torch.equal(got16, want)
+    assert torch.equal(part, want[n_seq - 3:n_seq + 4])
+    # fp32 parity mode through the same view (CUDA-core input projection): equal to its packed-window result as well
+    m32 = lstm.from_params(params, precision="fp32")
+    with torch.no_grad():
+        assert torch.equal(m32.predict_proba_recordings(rec, T, step), m32.predict_proba(X))

@@ -19,7 +19,9 @@ def _setup(H, B, T, seed_w=45, seed_x=10, gain=4.0):
     return params, x, y
 
 
-@pytest.mark.parametrize("H,B,T", [(128, 6, 64), (128, 37, 19), (256, 5, 24)])
+# (128, 8, 256) and (128, 64, 128): B*T >= 1024 rows, so the weight gradients run as split-K TN tcgen05 GEMMs with the TMA
+# reduce-add and the side-stream dG double buffer (gemm_tf32x3.cu: tf32x3_tn_ok) -- the path config 3 takes
+@pytest.mark.parametrize("H,B,T", [(128, 6, 64), (128, 37, 19), (256, 5, 24), (128, 8, 256), (128, 64, 128), (256, 16, 128)])
 def test_gradients_match_autograd_of_reference_port(H, B, T):
     params, x, y = _setup(H, B, T)
     cw = np.array([0.7, 1.3], dtype=np.float32)
@@ -38,6 +40,110 @@ def test_gradients_match_autograd_of_reference_port(H, B, T):
         assert np.abs(got - want).max() <= tol, (k, np.abs(got - want).max(), tol)
     tol = 2e-4 * np.abs(dx_ref).max() + 1e-8
     assert np.abs(xc.grad.cpu().numpy() - dx_ref).max() <= tol
+
+
+def test_config3_shape_step_matches_reference_port():
+    """BASELINE configs[2] at its own shape -- 512 windows x 256 steps per GPU, H = 128, class weights, clip 1.0 -- one full
+    step against torch autograd + clip_grad_norm_ on the CPU port: loss, pre-clip gradient norm, every gradient tensor."""
+    H, B, T = 128, 512, 256
+    params, x, y = _setup(H, B, T, seed_w=46, seed_x=12, gain=4.0)
+    cw = np.array([0.8, 1.2], dtype=np.float32)
+    port = torch_port.build_port(params, dropout=0.0)
+    loss_ref, g_ref, _dx, _lg = torch_port.loss_and_grads(port, x, y, cw)
+    norm_ref = float(np.sqrt(sum(float((g.astype(np.float64) ** 2).sum()) for g in g_ref.values())))
+    m = lstm.from_params(params, precision="fp32", dropout=0.0).train()
+    tr = train.FusedTrainer(m, lr=3e-4, weight_decay=1e-4, max_norm=1.0, class_weight=cw)
+    loss, norm = tr.step(torch.from_numpy(x).cuda(), torch.from_numpy(y).cuda())
+    assert abs(float(loss) - loss_ref) <= 1e-5, (float(loss), loss_ref)
+    assert abs(float(norm) - norm_ref) <= 3e-4 * norm_ref, (float(norm), norm_ref)
+    worst = 0.0
+    for k, _ in m.named_parameters():
+        got, want = tr.grad_views[k].cpu().numpy(), g_ref[k]
+        rel = np.abs(got - want).max() / (np.abs(want).max() + 1e-12)
+        worst = max(worst, rel)
+        assert np.abs(got - want).max() <= 2e-4 * np.abs(want).max() + 1e-7, (k, rel)
+    print(f"config-3 shape: loss {float(loss):.6f} vs {loss_ref:.6f}, norm {float(norm):.6e} vs {norm_ref:.6e}, worst grad rel {worst:.2e}")
+
+
+def test_inference_after_trainer_step_sees_updated_weights():
+    """model.eval()(x) after FusedTrainer.step must run the UPDATED weights in both engines (the optimizer kernels rewrite the
+    parameters through raw pointers: data_ptr/_version do not change)."""
+    H, B, T = 128, 8, 64
+    params, x, y = _setup(H, B, T, gain=8.0)
+    m = lstm.from_params(params, precision="auto", dropout=0.0).train()
+    tr = train.FusedTrainer(m, lr=2e-3, weight_decay=0.0, max_norm=0.0)
+    xc, yc = torch.from_numpy(x).cuda(), torch.from_numpy(y).cuda()
+    m.eval()
+    with torch.no_grad():
+        before32 = m(xc).clone()
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            before16 = m(xc).clone()          # packs the bf16 engine with the initial weights
+    m.train()
+    for i in range(2):
+        tr.step(xc, yc)
+    m.eval()
+    port = torch_port.build_port({k: v.detach().cpu().numpy() for k, v in m.state_dict().items()}).eval()
+    with torch.no_grad():
+        want = port(torch.from_numpy(x)).numpy()
+        got32 = m(xc).cpu().numpy()
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            got16 = m(xc).cpu().numpy()
+    moved = np.abs(want - before32.cpu().numpy()).max()
+    assert moved > 1e-2, moved                                  # two AdamW steps of 2e-3 per weight really moved the logits
+    assert np.abs(got32 - want).max() <= 1e-5 * max(1.0, np.abs(want).max())
+    assert np.abs(got16 - want).max() <= 2e-2 * max(1.0, np.abs(want).max()) and np.abs(got16 - before16.cpu().numpy()).max() > 1e-2
+
+
+def test_gradient_accumulation_matches_reference_loop():
+    """04_lstm_model.py:489,497-507: loss / accumulation_steps per micro-batch, one clip + AdamW step every 4 micro-batches."""
+    H, B, T, A = 128, 6, 32, 4
+    params, x, y = _setup(H, B * A, T, gain=8.0)
+    cw = np.array([0.6, 1.4], dtype=np.float32)
+    port = torch_port.build_port(params, dropout=0.0).train()
+    opt = torch.optim.AdamW(port.parameters(), lr=3e-3, weight_decay=1e-2)
+    m = lstm.from_params(params, precision="fp32", dropout=0.0).train()
+    tr = train.FusedTrainer(m, lr=3e-3, weight_decay=1e-2, max_norm=0.05, class_weight=cw, accumulation_steps=A)
+    xt, yt = torch.from_numpy(x), torch.from_numpy(y)
+    opt.zero_grad()
+    for a in range(A):
+        sl = slice(a * B, (a + 1) * B)
+        loss_ref = torch.nn.functional.cross_entropy(port(xt[sl]), yt[sl], weight=torch.from_numpy(cw))
+        (loss_ref / A).backward()
+        loss, norm = tr.step(xt[sl].cuda(), yt[sl].cuda())
+        assert abs(float(loss) - float(loss_ref)) <= 1e-5, a
+        assert tr.step_count == (1 if a == A - 1 else 0)
+    norm_ref = torch.nn.utils.clip_grad_norm_(port.parameters(), 0.05)
+    opt.step()
+    assert abs(float(norm) - float(norm_ref)) <= 3e-4 * float(norm_ref)
+    ref_sd = port.state_dict()
+    for k, p in m.state_dict().items():
+        if k == "attention.attention.2.bias":
+            continue                                            # see test_fused_trainer_matches_torch_adamw_and_clip
+        assert np.abs(p.cpu().numpy() - ref_sd[k].numpy()).max() <= 3e-4, k
+
+
+def test_deepcopy_gets_its_own_engines():
+    import copy
+    params, x, _ = _setup(128, 4, 32)
+    m = lstm.from_params(params, precision="fp32")
+    xc = torch.from_numpy(x).cuda()
+    with torch.no_grad():
+        a = m(xc).clone()
+        snap = copy.deepcopy(m)                                 # best-model snapshot
+        assert snap._engines == {} and m._engines               # the copy starts without handles
+        for p in m.parameters():
+            p.mul_(1.5)
+        b = m(xc)
+        c = snap(xc)
+    assert torch.equal(a, c) and not torch.equal(a, b)
+    del snap
+    with torch.no_grad():
+        assert torch.equal(m(xc), b)                            # the original's handle survived the copy's destruction
+
+
+def test_registered_train_ops_exist():
+    assert hasattr(torch.ops.bci, "lstm_attn_forward_train") and hasattr(torch.ops.bci, "lstm_attn_backward")
+    assert hasattr(torch.ops.bci, "lstm_attn_forward_view")
 
 
 def test_gradients_match_reference_golden(golden):

@@ -220,3 +220,22 @@ def test_ablation_oracles_match_reference_golden(golden, tag):
     for k, gr in grads.items():
         assert abs(np.linalg.norm(gr.astype(np.float64)) - float(g[tag + ":gnorm:" + k])) <= 1e-5 * max(float(g[tag + ":gnorm:" + k]), 1e-3), k
     assert abs(np.linalg.norm(dx.astype(np.float64)) - float(g[tag + ":dx_norm"])) <= 1e-5 * float(g[tag + ":dx_norm"])
+
+
+def test_fit_objective_matches_reference_seeded_fit(golden):
+    """Pins the oracle's restatement of fit_to_data's objective (05_ode_model.py:259-283: MSE + 1e-3 |k|^2 over the clipped,
+    renormalised solution) on the reference's own seeded fit result: objective(reference's fitted rates) == reference's loss."""
+    from oracle import ode_oracle as oo
+    g = golden("ode_ref05_fit.npz")
+    obs, tp, k = g["observed"], g["time_points"], g["fitted"]
+    sol = oo.exact_solution(oo.STYLE_REF06, obs[:1], k[:, None], float(tp[-1] - tp[0]), len(tp))[0]
+    loss = float(np.mean((sol - obs) ** 2) + 0.001 * np.sum(k ** 2))
+    assert abs(loss - float(g["loss"])) <= 1e-9, (loss, float(g["loss"]))
+    # and the fit really is a (bound-constrained) minimum of it: nudging any rate inside its bounds does not lower the loss
+    bounds = [(0.01, 0.5), (0.001, 0.2), (0.02, 0.5), (0.01, 0.3), (0.01, 0.3), (0.02, 0.4)]      # 05:287-294
+    for i, (lo, hi) in enumerate(bounds):
+        for d in (-1e-3, 1e-3):
+            kk = k.copy()
+            kk[i] = min(max(kk[i] + d, lo), hi)
+            s2 = oo.exact_solution(oo.STYLE_REF06, obs[:1], kk[:, None], float(tp[-1] - tp[0]), len(tp))[0]
+            assert float(np.mean((s2 - obs) ** 2) + 0.001 * np.sum(kk ** 2)) >= loss - 1e-9
