@@ -672,9 +672,16 @@ def main():
     # ---- CPU baselines: rank 0, at every N (the other ranks wait at the barrier).  They run in a child process that starts
     # with the affinity this process had BEFORE it bound itself to the GPU's NUMA node (threads created since inherit the
     # binding), so the reference's CPU path gets every host core ----
+    # The other ranks must SLEEP meanwhile (a wait on the rendezvous store), not spin in an NCCL barrier / cudaDeviceSynchronize:
+    # OpenMP's active-wait barriers degrade by an order of magnitude when spinning threads of other processes hold cores
+    # (measured: 68 instead of 1058 windows/s on the 2-GPU box with rank 1 parked in dist.barrier()).
     cpu = None
+    barrier()
+    store = dist.distributed_c10d._get_default_store() if world > 1 else None
     if rank == 0 and not args.no_cpu_baseline:
-        env = dict(os.environ, BCI_BENCH_CPUS=",".join(str(c) for c in (all_cpus or [])))
+        ncpu = len(all_cpus) if all_cpus else (os.cpu_count() or 1)
+        env = dict(os.environ, BCI_BENCH_CPUS=",".join(str(c) for c in (all_cpus or [])), OMP_NUM_THREADS=str(ncpu))
+        env.pop("MKL_NUM_THREADS", None)
         legs = ["lstm"] + ([] if args.no_ode else ["ode"]) + ([] if args.no_train else ["train:%d" % args.train_batch])
         r = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "cpu_legs", "--cpu-legs", ",".join(legs)],
                            env=env, capture_output=True, text=True, timeout=600)
@@ -686,6 +693,12 @@ def main():
             tail["train_cpu_baseline"] = got["train"]
         if "error" in got:
             tail["cpu_baseline_error"] = got["error"]
+    if store is not None:
+        if rank == 0:
+            store.set("bci_bench_cpu_legs_done", "1")
+        else:
+            import datetime
+            store.wait(["bci_bench_cpu_legs_done"], datetime.timedelta(seconds=1200))
     barrier()
     line["e2e"] = e2e
     line["cpu_baseline"] = cpu
