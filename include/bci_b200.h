@@ -361,6 +361,16 @@ int bci_selftest_fused_rec_bf16(const void* in, const void* wih, const void* whh
 int bci_selftest_gemm_tf32x3(int32_t mode, const float* A, const float* B, const float* bias, float* C, int32_t M, int32_t N,
                              int64_t K, int32_t explicit_hi, void* stream);
 
+/* the same NT product with both operands split into FP16 (hi, lo) pairs (kind::f16, twice the MMA rate; forward projections of the
+ * fp32 inference path): C[M][N] = A[M][K] . B[N][K]^T + bias, fp32 in / fp32 out */
+int bci_selftest_gemm_f16x3(const float* A, const float* B, const float* bias, float* C, int32_t M, int32_t N, int32_t K, void* stream);
+
+/* fp32-grade recurrence on the tensor cores (csrc/lstm_fp32_tc.cu: h . W_hh^T as three fp16 tcgen05 MMA chains on a CTA pair):
+ *   G [T*Bc][ND*512] fp32, column dir*512 + unit*4 + gate (bias included); w_hh [ND][512][128] fp32 in the PyTorch layout
+ *   (gate-major rows i,f,g,o); packed: [ND][2][512][128] fp16 scratch (filled here); out [T][Bc][ND*128] fp32 */
+int bci_selftest_rec_f16x3(const float* G, const float* w_hh, void* packed, float* out, int32_t Bc, int32_t T, int32_t ND,
+                           void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -15,6 +15,13 @@
 //                                                        activations (no transpose pass), split-K over CTAs, partial
 //                                                        tiles combined in L2 by the TMA reduce-add store
 //
+// F16 = true (NT only): the same pipeline with every operand split into two FP16 numbers instead of two TF32 numbers
+// (x = hi + lo, hi = fp16(x), lo = fp16(x - hi): 22 significant bits as long as lo stays out of fp16's subnormals -- activations
+// of the LSTM are O(1), the weights are pre-scaled by 16 and the epilogue multiplies by 1/16).  kind::f16 runs at twice the rate
+// of kind::tf32 and the operand tiles hold 64 instead of 32 K values in the same 16 KB, so the forward projections of the fp32
+// inference path (G = in . W_ih^T) cost about half; fp16 x fp16 products are exact in the fp32 accumulator.  Not used for
+// gradients (their magnitudes leave fp16's range).
+//
 // Kernel shape (both): persistent CTAs, warp 0 = TMA producer (3-stage ring of {A_hi, A_lo, B_hi, B_lo} 128x32 fp32 tiles,
 // SWIZZLE_128B), warp 1 = MMA issuer (M128 x N128 x K8; two accumulators per tile -- hi.hi and the
 // correction terms -- double-buffered: all 512 TMEM columns), warps 2-5 = epilogue
@@ -101,10 +108,24 @@ struct TxMaps { CUtensorMap a_hi, a_lo, b_hi, b_lo, c; };
 // TN = false: tile (mb, nb) of C[M][N], K loop over [0, K) (k_splits == 1) -- operands K-major, 2-D maps {k, row}
 // TN = true : tile (mb, nb) of C[P=M][Q=N], K loop over the R rows in k_splits ranges -- operands MN-major (four {32 floats, 32 rows}
 //             boxes per tile); partial tiles are reduce-added
-template <bool TN>
+__device__ __forceinline__ void umma_f16_1sm(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// kind::f16 with FP16 inputs (a_format = b_format = 0), fp32 accumulate, both operands K-major
+__host__ __device__ constexpr uint32_t umma_idesc_f16_k(int M, int N) {
+  return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+template <bool TN, bool F16>
 __global__ void __launch_bounds__(TX_THREADS, 1)
 gemm_tf32x3_kernel(const __grid_constant__ TxMaps maps, const float* __restrict__ bias, int M, int N, long long K, int k_splits,
-                   int reduce_add) {
+                   int reduce_add, float out_scale) {
+  static_assert(!(TN && F16), "the fp16 split is built for the NT projections only");
+  constexpr int BK = F16 ? 2 * TX_BK : TX_BK;   // K values per stage: 128-byte rows of fp16 / fp32
   extern __shared__ uint8_t tx_smem_raw[];
   const uint32_t raw = smem_u32(tx_smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
@@ -122,7 +143,7 @@ gemm_tf32x3_kernel(const __grid_constant__ TxMaps maps, const float* __restrict_
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m_blocks = (M + TX_BM - 1) / TX_BM, n_blocks = (N + TX_BN - 1) / TX_BN;
-  const long long kb_total = (K + TX_BK - 1) / TX_BK;
+  const long long kb_total = (K + BK - 1) / BK;
   const long long kb_per = (kb_total + k_splits - 1) / k_splits;
   const long long tiles = (long long)m_blocks * n_blocks * k_splits;
 
@@ -165,10 +186,10 @@ gemm_tf32x3_kernel(const __grid_constant__ TxMaps maps, const float* __restrict_
               tma_load_2d(s0 + 3 * TX_TILE + g * 4096, &maps.b_lo, nb * TX_BN + g * 32, (int)(kb * TX_BK), full_bar(stage));
             }
           } else {
-            tma_load_2d(s0, &maps.a_hi, (int)(kb * TX_BK), mb * TX_BM, full_bar(stage));
-            tma_load_2d(s0 + TX_TILE, &maps.a_lo, (int)(kb * TX_BK), mb * TX_BM, full_bar(stage));
-            tma_load_2d(s0 + 2 * TX_TILE, &maps.b_hi, (int)(kb * TX_BK), nb * TX_BN, full_bar(stage));
-            tma_load_2d(s0 + 3 * TX_TILE, &maps.b_lo, (int)(kb * TX_BK), nb * TX_BN, full_bar(stage));
+            tma_load_2d(s0, &maps.a_hi, (int)(kb * BK), mb * TX_BM, full_bar(stage));
+            tma_load_2d(s0 + TX_TILE, &maps.a_lo, (int)(kb * BK), mb * TX_BM, full_bar(stage));
+            tma_load_2d(s0 + 2 * TX_TILE, &maps.b_hi, (int)(kb * BK), nb * TX_BN, full_bar(stage));
+            tma_load_2d(s0 + 3 * TX_TILE, &maps.b_lo, (int)(kb * BK), nb * TX_BN, full_bar(stage));
           }
           if (++stage == TX_STAGES) { stage = 0; phase ^= 1u; }
         }
@@ -176,7 +197,7 @@ gemm_tf32x3_kernel(const __grid_constant__ TxMaps maps, const float* __restrict_
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_tf32(TX_BM, TX_BN, TN ? 1 : 0);
+      constexpr uint32_t idesc = F16 ? umma_idesc_f16_k(TX_BM, TX_BN) : umma_idesc_tf32(TX_BM, TX_BN, TN ? 1 : 0);
       constexpr uint32_t KSTEP = TN ? 1024u : 32u;  // 8 k-rows of an MN-major tile / 8 floats inside a K-major row
       int stage = 0; uint32_t phase = 0; int acc = 0; uint32_t acc_phase = 0;
       for (long long t = blockIdx.x; t < tiles; t += gridDim.x) {
@@ -200,9 +221,15 @@ gemm_tf32x3_kernel(const __grid_constant__ TxMaps maps, const float* __restrict_
             const uint64_t bh = TN ? umma_desc_sw128_mn(s0 + 2 * TX_TILE + o) : umma_desc_sw128(s0 + 2 * TX_TILE + o);
             const uint64_t bl = TN ? umma_desc_sw128_mn(s0 + 3 * TX_TILE + o) : umma_desc_sw128(s0 + 3 * TX_TILE + o);
             const uint32_t first = (kb != kb0 || kk != 0) ? 1u : 0u;
-            umma_tf32(d_lo, al, bh, idesc, first);
-            umma_tf32(d_lo, ah, bl, idesc, 1u);
-            umma_tf32(d_tmem, ah, bh, idesc, first);
+            if (F16) {
+              umma_f16_1sm(d_lo, al, bh, idesc, first);
+              umma_f16_1sm(d_lo, ah, bl, idesc, 1u);
+              umma_f16_1sm(d_tmem, ah, bh, idesc, first);
+            } else {
+              umma_tf32(d_lo, al, bh, idesc, first);
+              umma_tf32(d_lo, ah, bl, idesc, 1u);
+              umma_tf32(d_tmem, ah, bh, idesc, first);
+            }
           }
           umma_commit(empty_bar(stage));
           if (++stage == TX_STAGES) { stage = 0; phase ^= 1u; }
@@ -245,10 +272,10 @@ gemm_tf32x3_kernel(const __grid_constant__ TxMaps maps, const float* __restrict_
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
           float4 v;
-          v.x = (__uint_as_float(r[4 * q + 0]) + __uint_as_float(rl[4 * q + 0])) + bias_s[slab * 32 + 4 * q + 0];
-          v.y = (__uint_as_float(r[4 * q + 1]) + __uint_as_float(rl[4 * q + 1])) + bias_s[slab * 32 + 4 * q + 1];
-          v.z = (__uint_as_float(r[4 * q + 2]) + __uint_as_float(rl[4 * q + 2])) + bias_s[slab * 32 + 4 * q + 2];
-          v.w = (__uint_as_float(r[4 * q + 3]) + __uint_as_float(rl[4 * q + 3])) + bias_s[slab * 32 + 4 * q + 3];
+          v.x = fmaf(__uint_as_float(r[4 * q + 0]) + __uint_as_float(rl[4 * q + 0]), out_scale, bias_s[slab * 32 + 4 * q + 0]);
+          v.y = fmaf(__uint_as_float(r[4 * q + 1]) + __uint_as_float(rl[4 * q + 1]), out_scale, bias_s[slab * 32 + 4 * q + 1]);
+          v.z = fmaf(__uint_as_float(r[4 * q + 2]) + __uint_as_float(rl[4 * q + 2]), out_scale, bias_s[slab * 32 + 4 * q + 2]);
+          v.w = fmaf(__uint_as_float(r[4 * q + 3]) + __uint_as_float(rl[4 * q + 3]), out_scale, bias_s[slab * 32 + 4 * q + 3]);
           *reinterpret_cast<float4*>(cst + sw128_chunk_off((uint32_t)lane, (uint32_t)q)) = v;
         }
         fence_proxy_async_smem();
@@ -289,8 +316,9 @@ static int tx_prepare() {
   static PerDeviceFlag done_pd;
   bool& done = done_pd.cur();
   if (!done) {
-    BCI_CUDA_OK(cudaFuncSetAttribute(gemm_tf32x3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TX_SMEM));
-    BCI_CUDA_OK(cudaFuncSetAttribute(gemm_tf32x3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TX_SMEM));
+    BCI_CUDA_OK(cudaFuncSetAttribute(gemm_tf32x3_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TX_SMEM));
+    BCI_CUDA_OK(cudaFuncSetAttribute(gemm_tf32x3_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TX_SMEM));
+    BCI_CUDA_OK(cudaFuncSetAttribute(gemm_tf32x3_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TX_SMEM));
     done = true;
   }
   return BCI_OK;
@@ -326,7 +354,7 @@ int gemm_tf32x3_nt(const float* A_hi, const float* A_lo, int lda, const float* W
   if ((rc = make_tmap_f32_2d(&maps.c, C, M, N, ldc, 32, 32))) return rc;
   const long long tiles = (long long)ceil_div(M, TX_BM) * ceil_div(N, TX_BN);
   const int grid = (int)(tiles < sm_count() ? tiles : sm_count());
-  gemm_tf32x3_kernel<false><<<grid, TX_THREADS, TX_SMEM, st>>>(maps, bias, M, N, (long long)K, 1, accumulate);
+  gemm_tf32x3_kernel<false, false><<<grid, TX_THREADS, TX_SMEM, st>>>(maps, bias, M, N, (long long)K, 1, accumulate, 1.0f);
   BCI_LAUNCH_OK();
   return BCI_OK;
 }
@@ -357,7 +385,72 @@ int gemm_tf32x3_tn(const float* A_hi, const float* A_lo, int lda, const float* B
   if (splits > 1) BCI_CUDA_OK(cudaMemset2DAsync(C, (size_t)ldc * 4, 0, (size_t)Q * 4, P, st));
   const long long tiles = out_tiles * splits;
   const int grid = (int)(tiles < sm_count() ? tiles : sm_count());
-  gemm_tf32x3_kernel<true><<<grid, TX_THREADS, TX_SMEM, st>>>(maps, nullptr, P, Q, R, (int)splits, splits > 1 ? 1 : 0);
+  gemm_tf32x3_kernel<true, false><<<grid, TX_THREADS, TX_SMEM, st>>>(maps, nullptr, P, Q, R, (int)splits, splits > 1 ? 1 : 0, 1.0f);
+  BCI_LAUNCH_OK();
+  return BCI_OK;
+}
+
+// ---- fp16-split variant (NT): x -> (hi, lo) fp16 pair, optionally pre-scaled -------------------------------------------------
+__global__ void split_f16_kernel(const float4* __restrict__ x, uint2* __restrict__ hi, uint2* __restrict__ lo, long long n4, float scale) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  const float4 v = __ldg(x + i);
+  const float in[4] = {v.x * scale, v.y * scale, v.z * scale, v.w * scale};
+  __half2 h[2], l[2];
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    h[j] = __floats2half2_rn(in[2 * j], in[2 * j + 1]);
+    const float2 back = __half22float2(h[j]);
+    l[j] = __floats2half2_rn(in[2 * j] - back.x, in[2 * j + 1] - back.y);
+  }
+  hi[i] = make_uint2(*reinterpret_cast<const uint32_t*>(&h[0]), *reinterpret_cast<const uint32_t*>(&h[1]));
+  lo[i] = make_uint2(*reinterpret_cast<const uint32_t*>(&l[0]), *reinterpret_cast<const uint32_t*>(&l[1]));
+}
+
+int split_f16(const float* x, __half* hi, __half* lo, long long n, float scale, cudaStream_t st) {
+  BCI_REQUIRE(n % 4 == 0 && ((uintptr_t)x & 15) == 0 && ((uintptr_t)hi & 7) == 0 && ((uintptr_t)lo & 7) == 0, BCI_EINVAL,
+              "split_f16: aligned arrays with n %% 4 == 0 required");
+  if (n == 0) return BCI_OK;
+  split_f16_kernel<<<(unsigned)ceil_div64(n / 4, 256), 256, 0, st>>>(reinterpret_cast<const float4*>(x), reinterpret_cast<uint2*>(hi),
+                                                                      reinterpret_cast<uint2*>(lo), n / 4, scale);
+  BCI_LAUNCH_OK();
+  return BCI_OK;
+}
+
+static int make_tmap_f16_2d(CUtensorMap* tm, const __half* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_cols,
+                            uint32_t box_rows) {
+  EncodeTiledFn enc = get_encode_fn();
+  BCI_REQUIRE(enc, BCI_ECUDA, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {ld * 2};
+  cuuint32_t box[2] = {box_cols, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<__half*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  BCI_REQUIRE(r == CUDA_SUCCESS, BCI_ECUDA, "cuTensorMapEncodeTiled(f16 2D) failed with CUresult %d", (int)r);
+  return BCI_OK;
+}
+
+bool f16x3_nt_ok(const void* A_hi, int lda, const void* W_hi, int ldw, const void* C, int ldc, int M, int N, int K) {
+  return tf32x3_enabled() && M >= 128 && N % 32 == 0 && K % 8 == 0 && lda % 8 == 0 && ldw % 8 == 0 && ldc % 4 == 0 &&
+         ((uintptr_t)A_hi & 15) == 0 && ((uintptr_t)W_hi & 15) == 0 && ((uintptr_t)C & 15) == 0;
+}
+
+// C[M][N] (ldc, fp32) = out_scale * (A[M][K] . W[N][K]^T) + bias[N], operands as fp16 (hi, lo) pairs
+int gemm_f16x3_nt(const __half* A_hi, const __half* A_lo, int lda, const __half* W_hi, const __half* W_lo, int ldw, const float* bias,
+                  float* C, int ldc, int M, int N, int K, float out_scale, cudaStream_t st) {
+  int rc = tx_prepare();
+  if (rc) return rc;
+  TxMaps maps;
+  if ((rc = make_tmap_f16_2d(&maps.a_hi, A_hi, M, K, lda, 2 * TX_BK, TX_BM))) return rc;
+  if ((rc = make_tmap_f16_2d(&maps.a_lo, A_lo, M, K, lda, 2 * TX_BK, TX_BM))) return rc;
+  if ((rc = make_tmap_f16_2d(&maps.b_hi, W_hi, N, K, ldw, 2 * TX_BK, TX_BN))) return rc;
+  if ((rc = make_tmap_f16_2d(&maps.b_lo, W_lo, N, K, ldw, 2 * TX_BK, TX_BN))) return rc;
+  if ((rc = make_tmap_f32_2d(&maps.c, C, M, N, ldc, 32, 32))) return rc;
+  const long long tiles = (long long)ceil_div(M, TX_BM) * ceil_div(N, TX_BN);
+  const int grid = (int)(tiles < sm_count() ? tiles : sm_count());
+  gemm_tf32x3_kernel<false, true><<<grid, TX_THREADS, TX_SMEM, st>>>(maps, bias, M, N, (long long)K, 1, 0, out_scale);
   BCI_LAUNCH_OK();
   return BCI_OK;
 }
@@ -396,5 +489,29 @@ extern "C" int bci_selftest_gemm_tf32x3(int32_t mode, const float* A, const floa
   const cudaError_t se = cudaStreamSynchronize(st);
   cudaFree(scratch);
   BCI_REQUIRE(se == cudaSuccess, BCI_ECUDA, "bci_selftest_gemm_tf32x3: %s", cudaGetErrorString(se));
+  return rc;
+}
+
+
+// Diagnostic entry point of the fp16-split form: C[M][N] = A[M][K] . B[N][K]^T + bias, A split as is, B scaled by 16 as the packed
+// weights are.  Scratch is allocated here (test only).
+extern "C" int bci_selftest_gemm_f16x3(const float* A, const float* B, const float* bias, float* C, int32_t M, int32_t N, int32_t K,
+                                       void* stream) {
+  using namespace bci;
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long na = (long long)M * K, nb = (long long)N * K;
+  BCI_REQUIRE(na % 4 == 0 && nb % 4 == 0, BCI_EINVAL, "bci_selftest_gemm_f16x3: operand sizes must be multiples of 4");
+  __half* scratch = nullptr;
+  BCI_CUDA_OK(cudaMalloc(&scratch, (size_t)(na + nb) * 4));
+  __half *ahi = scratch, *alo = ahi + na, *bhi = alo + na, *blo = bhi + nb;
+  int rc = split_f16(A, ahi, alo, na, 1.0f, st);
+  if (!rc) rc = split_f16(B, bhi, blo, nb, F16X3_WSCALE, st);
+  if (!rc) {
+    if (f16x3_nt_ok(ahi, K, bhi, K, C, N, M, N, K)) rc = gemm_f16x3_nt(ahi, alo, K, bhi, blo, K, bias, C, N, M, N, K, 1.0f / F16X3_WSCALE, st);
+    else { set_error("bci_selftest_gemm_f16x3: shape not supported"); rc = BCI_EINVAL; }
+  }
+  const cudaError_t se = cudaStreamSynchronize(st);
+  cudaFree(scratch);
+  BCI_REQUIRE(se == cudaSuccess, BCI_ECUDA, "bci_selftest_gemm_f16x3: %s", cudaGetErrorString(se));
   return rc;
 }

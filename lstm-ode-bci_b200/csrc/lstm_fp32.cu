@@ -355,8 +355,14 @@ int lstm_pack_f32(bci_lstm_s* h, cudaStream_t st) {
       pack_bias_kernel<<<nblk(4 * H), 256, 0, st>>>(w.b_ih[l][d], w.b_hh[l][d], p.bias[l], H, d * 4 * H);
       pack_gates_rows_kernel<<<nblk((long long)4 * H * K), 256, 0, st>>>(w.w_ih[l][d], p.wih_b[l], H, K, d * 4 * H);
       pack_whh_b4_kernel<<<nblk((long long)4 * H * H), 256, 0, st>>>(w.w_hh[l][d], p.whh_b[l][d], H);
+      if (H == 128) {
+        int rc16 = pack_whh_f16x3(w.w_hh[l][d], p.whh16[l] + (size_t)d * 2 * 4 * H * H, H, st);
+        if (rc16) return rc16;
+      }
     }
-    int rc = split_tf32(p.wih_b[l], nullptr, p.wih_b_lo[l], (long long)ND * 4 * H * K, st);
+    int rc = H == 128 ? split_f16(p.wih_b[l], p.wih16[l], p.wih16[l] + (size_t)ND * 4 * H * K, (long long)ND * 4 * H * K, F16X3_WSCALE, st) : 0;
+    if (rc) return rc;
+    rc = split_tf32(p.wih_b[l], nullptr, p.wih_b_lo[l], (long long)ND * 4 * H * K, st);
     if (!rc) rc = split_tf32(p.wih_t[l], nullptr, p.wih_t_lo[l], (long long)ND * 4 * H * K, st);
     if (rc) return rc;
   }
@@ -387,7 +393,7 @@ int lstm_pack_f32(bci_lstm_s* h, cudaStream_t st) {
 size_t lstm_store_bytes_f32(const bci_lstm_config& c) {
   const size_t H = c.hidden_size, C = c.input_size, D = 2 * H;
   size_t n = C * H + 3 * H;
-  for (int l = 0; l < c.num_layers; ++l) n += 4 * ((size_t)layer_in_width(c, l) * 8 * H) + 2 * (2 * H * 4 * H) + 8 * H;
+  for (int l = 0; l < c.num_layers; ++l) n += 4 * ((size_t)layer_in_width(c, l) * 8 * H) + 2 * (2 * H * 4 * H) + 8 * H + 2 * 4 * H * H + (size_t)layer_in_width(c, l) * 8 * H;
   n += 2 * D + 4 * D * H + H + H + 4 + D * H + H + H * (H / 2) + H / 2 + (size_t)c.num_classes * (H / 2) + c.num_classes + 64;
   return align_up(n * sizeof(float) + 256 * 64, 256);
 }
@@ -409,6 +415,8 @@ void lstm_carve_f32(bci_lstm_s* h, char* base) {
     p.whh_b[l][1] = take(H * 4 * H);
     p.wih_b_lo[l] = take((size_t)layer_in_width(c, l) * 8 * H);
     p.wih_t_lo[l] = take((size_t)layer_in_width(c, l) * 8 * H);
+    p.whh16[l] = reinterpret_cast<__half*>(take(2 * 4 * H * H));   // 2 directions x 2 parts x 4H x H halves
+    p.wih16[l] = reinterpret_cast<__half*>(take((size_t)layer_in_width(c, l) * 8 * H));   // 2 parts x 8H x K_l halves
   }
   p.lnw = take(D); p.lnb = take(D); p.aw1t = take(D * H); p.ab1 = take(H); p.aw2 = take(H); p.ab2 = take(4);
   p.aw1 = take(D * H); p.aw1_lo = take(D * H); p.aw1t_lo = take(D * H);
@@ -450,9 +458,32 @@ static int forward_chunk_f32(bci_lstm_s* h, const InputView& x, int Bc, int T, f
   h->prof.mark(0, st);
   const float* in = z;
   float* outs[2] = {o0, o1};
+  // Large batches (H = 128): the whole LSTM stack on the tensor cores in split FP16 precision -- projections as three fp16 MMA
+  // chains per product (gemm_f16x3_nt: twice the rate of the 3 x TF32 form), recurrences on CTA pairs (lstm_fp32_tc.cu).  The layer
+  // input travels as an fp16 (hi, lo) pair: z is split once, and every recurrence writes h_t directly in that form for the next
+  // layer's projection (the pair it computes for its own MMA operand), so there is no split pass between layers; only the last
+  // layer writes fp32 for the pooling kernel.  The pair buffers reuse the space of the tf32 remainder array.
+  __half* in_hi16 = reinterpret_cast<__half*>(in_lo);
+  __half* in_lo16 = in_hi16 + rows * D;
+  const bool tc = tc_rec_ok(H, ND, Bc, g, 4 * D, o0, D) && f16x3_nt_ok(in_hi16, H, h->f32.wih16[0], H, g, 4 * D, (int)rows, 4 * D, H);
+  if (tc && (rc = split_f16(z, in_hi16, in_lo16, (long long)rows * H, 1.0f, st))) return rc;
   for (int l = 0; l < c.num_layers; ++l) {
     const int K = layer_in_width(c, l);
     const int M = (int)rows, N = 4 * D;
+    if (tc) {
+      const bool last = l == c.num_layers - 1;
+      const __half* w16 = h->f32.wih16[l];
+      if ((rc = gemm_f16x3_nt(in_hi16, in_lo16, K, w16, w16 + (size_t)N * K, K, h->f32.bias[l], g, N, M, N, K, 1.0f / F16X3_WSCALE, st)))
+        return rc;
+      h->prof.mark(1, st);
+      float* o = outs[l & 1];
+      if ((rc = launch_rec_f16x3(ND, g, N, h->f32.whh16[l], last ? o : nullptr, last ? nullptr : in_hi16, last ? nullptr : in_lo16,
+                                 nullptr, nullptr, D, Bc, T, st)))
+        return rc;
+      h->prof.mark(2, st);
+      in = o;
+      continue;
+    }
     if (tf32x3_nt_ok(in, K, h->f32.wih_b[l], K, g, N, M, N, K)) {
       // G = in . W_ih^T on the tensor cores in split precision (3 x TF32, fp32-grade)
       if ((rc = split_tf32(in, nullptr, in_lo, (long long)M * K, st))) return rc;

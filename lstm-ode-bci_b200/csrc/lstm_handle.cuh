@@ -2,6 +2,7 @@
 #pragma once
 #include "common.cuh"
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 namespace bci {
 
@@ -19,6 +20,11 @@ struct PackedF32 {
   // row-major copies with gate-interleaved ROWS (n = dir*4H + unit*4 + gate), used by the backward pass:
   float* wih_b[BCI_MAX_LAYERS];     // [ND*4H][K_l] din = dG . wih_b
   float* whh_b[BCI_MAX_LAYERS][2];  // [H unit][H j][4 gates]  dh_{t-1}[j] = sum_(unit,gate) dG_t . whh_b
+  // split-precision fp16 operand of the tensor-core recurrence (lstm_fp32_tc.cu, H = 128): [ND][part hi/lo][n' = unit*4 + gate][k],
+  // values scaled by 16
+  __half* whh16[BCI_MAX_LAYERS];
+  // ... and of the projection GEMM in its fp16-split form (gemm_tf32x3.cu, F16): [part hi/lo][ND*4H gate-interleaved rows][K_l], x 16
+  __half* wih16[BCI_MAX_LAYERS];
   // tf32 remainders (x - tf32(x)) of wih_b / wih_t: second operand of the split-precision tcgen05 GEMMs (gemm_tf32x3.cu)
   float* wih_b_lo[BCI_MAX_LAYERS];
   float* wih_t_lo[BCI_MAX_LAYERS];
@@ -146,10 +152,16 @@ inline int layer_in_width(const bci_lstm_config& c, int l) { return l == 0 ? c.h
 // chunking policy: windows processed per internal pass (bounds the workspace)
 int bf16_chunk_windows();  // lstm_bf16.cu: depends on the recurrence path in use (split K2+K3 or fused cluster kernel)
 int h256_max_clusters();   // lstm_bf16_h256.cu: co-resident 4-CTA clusters of the H = 256 recurrence
+int tc_max_clusters();     // lstm_fp32_tc.cu: co-resident CTA pairs of the fp32 tensor-core recurrence
 inline int max_chunk(const bci_lstm_config& c, int train) {
   if (c.precision == BCI_PRECISION_BF16)
     return train ? 2048 : (c.hidden_size == 256 ? h256_max_clusters() * 2 * 128 : bf16_chunk_windows());
   const int base = train ? 512 : 2048;
+  if (!train && c.hidden_size == 128 && tc_max_clusters() > 0) {
+    // fp32 inference, H = 128: one full wave of the pair recurrence (lstm_fp32_tc.cu): clusters x 256 windows / 2 directions
+    const int wave = tc_max_clusters() * 128;
+    return wave > base ? wave : base;
+  }
   return c.hidden_size > 128 ? base / 2 : base;
 }
 
@@ -170,6 +182,17 @@ int launch_proj_gemm_f32(const float* A, const float* Bt, const float* bias, flo
 int launch_rec_f32(int H, int ND, const float* G, const float* whh_f, const float* whh_r, float* out, float* gates, float* csave,
                    int Bc, int T, cudaStream_t st);
 void small_batch_policy(int H, int ND, int Bc, int groups, bool& small, bool& tiny);
+// fp32-grade recurrence on the tensor cores (lstm_fp32_tc.cu)
+int pack_whh_f16x3(const float* w_hh, __half* dst, int H, cudaStream_t st);
+bool tc_rec_ok(int H, int ND, int Bc, const void* G, int ldg, const void* out, int D);
+int tc_max_clusters();
+int launch_rec_f16x3(int ND, const float* G, int ldg, const __half* whh16, float* out, __half* out_hi16, __half* out_lo16, float* gates,
+                     float* csave, int D, int Bc, int T, cudaStream_t st);
+constexpr float F16X3_WSCALE = 16.0f;   // weights of the fp16-split paths are stored x 16 (keeps their lo parts out of fp16's subnormals)
+int split_f16(const float* x, __half* hi, __half* lo, long long n, float scale, cudaStream_t st);
+bool f16x3_nt_ok(const void* A_hi, int lda, const void* W_hi, int ldw, const void* C, int ldc, int M, int N, int K);
+int gemm_f16x3_nt(const __half* A_hi, const __half* A_lo, int lda, const __half* W_hi, const __half* W_lo, int ldw, const float* bias,
+                  float* C, int ldc, int M, int N, int K, float out_scale, cudaStream_t st);
 // split-precision tcgen05 GEMMs of the fp32 path (gemm_tf32x3.cu)
 bool tf32x3_enabled();
 bool tf32x3_nt_ok(const void* A, int lda, const void* W, int ldw, const void* C, int ldc, int M, int N, int K);

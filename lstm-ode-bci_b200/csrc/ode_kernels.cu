@@ -18,6 +18,7 @@
 // accept/reject decisions are discontinuous, so the whole controller runs in fp64 per thread.
 #include "common.cuh"
 #include <math_constants.h>
+#include <cstdlib>
 
 namespace bci {
 
@@ -238,6 +239,150 @@ ode_rk4_kernel(const OdeParams P) {
     if (P.final_state) {
       float oa = A, op = Pp, of = F;
       if (CLAMP) post06_rcp(oa, op, of);  // same arithmetic as the trajectory rows: final_state == traj[:, -1] bit for bit
+      OutT* fs = reinterpret_cast<OutT*>(P.final_state) + i * 3;
+      fs[0] = (OutT)oa; fs[1] = (OutT)op; fs[2] = (OutT)of;
+    }
+    if (P.n_steps) P.n_steps[i] = S * (P.n_points - 1);
+  }
+}
+
+// ---- RK4, fp32, TWO trajectories per thread on the packed FP32 instructions -------------------------------------------------
+// ncu on ode_rk4_kernel (profiles/r1_ode_rk4.md): issue slots 88 % busy, FMA pipe 62 % -- the kernel is bound by instruction
+// ISSUE, not by the FP32 lanes.  Blackwell's FFMA2 / FMUL2 / FADD2 (`fma.rn.f32x2`) do two independent fp32 operations per
+// issued instruction, so a thread that integrates two trajectories side by side -- A, P, F, the nine step-scaled coefficients
+// and the Kahan terms each held as a float2, lane x = trajectory r, lane y = trajectory r + 64 of the block -- issues half the
+// floating-point instructions per trajectory (66 + 24 FMNMX + loop per PAIR of steps instead of 66 + 12 + loop per step) and
+// leaves the FP32 pipe, not the scheduler, as the limit.  Every lane performs exactly the operation sequence of the scalar
+// kernel (an FSUB a - b is written fma(b, -1, a): the same correctly rounded result), so the two kernels agree BIT FOR BIT
+// (tests/test_gpu_ode.py).  Used for a uniform step count (substeps > 0); per-trajectory step counts keep the scalar kernel.
+constexpr int ODE_X2_THREADS = ODE_BLOCK / 2;
+struct HQ2 { float2 aa, ap, af, pa, pp, pf, fa, fp, ff; };
+
+__device__ __forceinline__ float2 f2(float a, float b) { return make_float2(a, b); }
+__device__ __forceinline__ float2 sub2(float2 a, float2 b) { return __ffma2_rn(b, make_float2(-1.f, -1.f), a); }  // a - b, exact FSUB semantics
+
+template <bool CLAMP>
+__device__ __forceinline__ void rhs_h2(const HQ2& q, float2 A, float2 P, float2 F, float2& dA, float2& dP, float2& dF) {
+  if (CLAMP) {
+    A.x = fmaxf(A.x, 0.f); A.y = fmaxf(A.y, 0.f); P.x = fmaxf(P.x, 0.f); P.y = fmaxf(P.y, 0.f);
+    F.x = fmaxf(F.x, 0.f); F.y = fmaxf(F.y, 0.f);
+  }
+  dA = __ffma2_rn(q.af, F, __ffma2_rn(q.ap, P, __fmul2_rn(q.aa, A)));
+  dP = __ffma2_rn(q.pf, F, __ffma2_rn(q.pa, A, __fmul2_rn(q.pp, P)));
+  dF = __ffma2_rn(q.fp, P, __ffma2_rn(q.fa, A, __fmul2_rn(q.ff, F)));
+}
+
+template <bool CLAMP, typename OutT>
+__global__ void __launch_bounds__(ODE_X2_THREADS)
+ode_rk4x2_kernel(const OdeParams P) {
+  extern __shared__ float stage[];  // [ODE_BLOCK][row_stride]
+  const int tid = threadIdx.x;
+  const long long base_i = (long long)blockIdx.x * ODE_BLOCK;
+  const int n3 = P.n_points * 3;
+  const int chunk_pts = P.n_points < ODE_CHUNK_POINTS ? P.n_points : ODE_CHUNK_POINTS;
+  const int row_stride = (chunk_pts * 3) | 1;
+  const bool want_traj = P.traj != nullptr;
+  const int rows_here = (int)((P.n - base_i) < ODE_BLOCK ? (P.n - base_i) : ODE_BLOCK);
+  const int S = P.substeps;
+  const double dt_out = P.t_end / (double)(P.n_points - 1);
+  const float h = (float)(dt_out / (double)S);
+
+  // lane e of every float2 = trajectory base_i + tid + e * 64 (two coalesced halves of the block's 128 trajectories)
+  float kk[2][6], y0[2][3];
+  bool live[2];
+#pragma unroll
+  for (int e = 0; e < 2; ++e) {
+    const long long i = base_i + tid + e * ODE_X2_THREADS;
+    live[e] = i < P.n;
+#pragma unroll
+    for (int r = 0; r < 6; ++r) kk[e][r] = 0.f;
+    y0[e][0] = y0[e][1] = y0[e][2] = 0.f;
+    if (live[e]) {
+      float po, pc;
+      load_rates(P, i, kk[e], po, pc);
+      double y[3];
+      initial_state(P, i, po, pc, y);
+      y0[e][0] = (float)y[0]; y0[e][1] = (float)y[1]; y0[e][2] = (float)y[2];
+    }
+  }
+  HQ2 q;
+  q.aa = f2(-h * (kk[0][0] + kk[0][1]), -h * (kk[1][0] + kk[1][1])); q.ap = f2(h * kk[0][2], h * kk[1][2]); q.af = f2(h * kk[0][4], h * kk[1][4]);
+  q.pa = f2(h * kk[0][0], h * kk[1][0]); q.pp = f2(-h * (kk[0][2] + kk[0][3]), -h * (kk[1][2] + kk[1][3])); q.pf = f2(h * kk[0][5], h * kk[1][5]);
+  q.fa = f2(h * kk[0][1], h * kk[1][1]); q.fp = f2(h * kk[0][3], h * kk[1][3]); q.ff = f2(-h * (kk[0][4] + kk[0][5]), -h * (kk[1][4] + kk[1][5]));
+  float2 A = f2(y0[0][0], y0[1][0]), Pp = f2(y0[0][1], y0[1][1]), F = f2(y0[0][2], y0[1][2]);
+  float2 cA = f2(0.f, 0.f), cP = cA, cF = cA;  // Kahan compensation of the state
+  const float2 half = f2(0.5f, 0.5f), two = f2(2.f, 2.f), sixth = f2(1.0f / 6.0f, 1.0f / 6.0f);
+
+  int pt = 0;
+  while (pt < P.n_points) {
+    const int pts = (P.n_points - pt) < chunk_pts ? (P.n_points - pt) : chunk_pts;
+    for (int qq = 0; qq < pts; ++qq, ++pt) {
+      if (pt > 0) {
+#pragma unroll 2
+        for (int s = 0; s < S; ++s) {
+          float2 a1, p1, f1, a2, p2, f2_, a3, p3, f3, a4, p4, f4;  // h * k_i
+          rhs_h2<CLAMP>(q, A, Pp, F, a1, p1, f1);
+          rhs_h2<CLAMP>(q, __ffma2_rn(half, a1, A), __ffma2_rn(half, p1, Pp), __ffma2_rn(half, f1, F), a2, p2, f2_);
+          rhs_h2<CLAMP>(q, __ffma2_rn(half, a2, A), __ffma2_rn(half, p2, Pp), __ffma2_rn(half, f2_, F), a3, p3, f3);
+          rhs_h2<CLAMP>(q, __fadd2_rn(A, a3), __fadd2_rn(Pp, p3), __fadd2_rn(F, f3), a4, p4, f4);
+          // y += (k1 + 2 k2 + 2 k3 + k4) / 6, compensated: fma(fma(2, k2 + k3, k1 + k4), 1/6, -c) as in the scalar kernel
+          const float2 dAa = __ffma2_rn(__ffma2_rn(two, __fadd2_rn(a2, a3), __fadd2_rn(a1, a4)), sixth, f2(-cA.x, -cA.y));
+          const float2 dPp = __ffma2_rn(__ffma2_rn(two, __fadd2_rn(p2, p3), __fadd2_rn(p1, p4)), sixth, f2(-cP.x, -cP.y));
+          const float2 dFf = __ffma2_rn(__ffma2_rn(two, __fadd2_rn(f2_, f3), __fadd2_rn(f1, f4)), sixth, f2(-cF.x, -cF.y));
+          const float2 nA = __fadd2_rn(A, dAa), nP = __fadd2_rn(Pp, dPp), nF = __fadd2_rn(F, dFf);
+          cA = sub2(sub2(nA, A), dAa); cP = sub2(sub2(nP, Pp), dPp); cF = sub2(sub2(nF, F), dFf);
+          A = nA; Pp = nP; F = nF;
+        }
+      }
+      if (want_traj) {
+        float oa = A.x, op = Pp.x, of = F.x;
+        if (CLAMP) post06_rcp(oa, op, of);
+        float* row = stage + tid * row_stride + qq * 3;
+        row[0] = oa; row[1] = op; row[2] = of;
+        oa = A.y; op = Pp.y; of = F.y;
+        if (CLAMP) post06_rcp(oa, op, of);
+        row = stage + (tid + ODE_X2_THREADS) * row_stride + qq * 3;
+        row[0] = oa; row[1] = op; row[2] = of;
+      }
+    }
+    if (want_traj) {
+      __syncthreads();
+      const int w = pts * 3;
+      const int col0 = (pt - pts) * 3;
+      OutT* out = reinterpret_cast<OutT*>(P.traj);
+      const int total = rows_here * w;
+      if (w == n3) {  // whole rows staged: one contiguous range, fully coalesced
+        OutT* dst = out + base_i * n3;
+        if (sizeof(OutT) == 4 && (w & 3) == 0 && rows_here == ODE_BLOCK) {
+          float4* dst4 = reinterpret_cast<float4*>(dst);
+          for (int e4 = tid; e4 < total / 4; e4 += ODE_X2_THREADS) {
+            const int e = e4 * 4;
+            const int r = e / w, c = e - r * w;
+            const float* sp = stage + r * row_stride + c;
+            dst4[e4] = make_float4(sp[0], sp[1], sp[2], sp[3]);
+          }
+        } else {
+          for (int e = tid; e < total; e += ODE_X2_THREADS) {
+            const int r = e / w, c = e - r * w;
+            dst[e] = (OutT)stage[r * row_stride + c];
+          }
+        }
+      } else {
+        for (int e = tid; e < total; e += ODE_X2_THREADS) {
+          const int r = e / w, c = e - r * w;
+          out[(base_i + r) * n3 + col0 + c] = (OutT)stage[r * row_stride + c];
+        }
+      }
+      __syncthreads();
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < 2; ++e) {
+    if (!live[e]) continue;
+    const long long i = base_i + tid + e * ODE_X2_THREADS;
+    if (P.final_state) {
+      float oa = e ? A.y : A.x, op = e ? Pp.y : Pp.x, of = e ? F.y : F.x;
+      if (CLAMP) post06_rcp(oa, op, of);
       OutT* fs = reinterpret_cast<OutT*>(P.final_state) + i * 3;
       fs[0] = (OutT)oa; fs[1] = (OutT)op; fs[2] = (OutT)of;
     }
@@ -518,7 +663,11 @@ static int launch_ode(const OdeParams& P, int mode, cudaStream_t st) {
   if (mode == BCI_ODE_RK4) {
     const int chunk_pts = P.n_points < ODE_CHUNK_POINTS ? P.n_points : ODE_CHUNK_POINTS;
     const size_t smem = P.traj ? (size_t)ODE_BLOCK * ((chunk_pts * 3) | 1) * sizeof(float) : 0;
-    ode_rk4_kernel<CLAMP, OutT><<<grid, ODE_BLOCK, smem, st>>>(P);
+    // uniform step count: two trajectories per thread on the packed fp32 instructions (bit-identical results); BCI_ODE_RK4=scalar
+    // keeps the one-trajectory-per-thread kernel for comparison
+    static const bool scalar_only = [] { const char* e = getenv("BCI_ODE_RK4"); return e && e[0] == 's'; }();
+    if (P.substeps > 0 && !scalar_only) ode_rk4x2_kernel<CLAMP, OutT><<<grid, ODE_X2_THREADS, smem, st>>>(P);
+    else ode_rk4_kernel<CLAMP, OutT><<<grid, ODE_BLOCK, smem, st>>>(P);
   } else {
     ode_rk45_kernel<CLAMP, OutT><<<grid, ODE_BLOCK, 0, st>>>(P);
   }

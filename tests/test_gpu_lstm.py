@@ -57,16 +57,47 @@ def test_fp32_forward_matches_oracle(H, B, T):
 
 
 def test_fp32_chunked_batch_equals_unchunked():
-    """batch larger than the internal chunk (2048 windows) == concatenation of smaller calls; windows are
-    independent (SURVEY.md §8 e)."""
+    """a batch == the concatenation of smaller calls; windows are independent (SURVEY.md §8 e).  Within one recurrence kernel a
+    window's result is BIT-identical whatever batch it arrives in: the tensor-core pair recurrence (>= 16 work items of 256
+    windows x direction, lstm_fp32_tc.cu) and the CUDA-core recurrence (smaller batches); across the two the results agree to
+    fp32 rounding (both are <= 1e-5 from the reference)."""
     params = synth.make_lstm_params(5, 61, 128, 3, logit_gain=6.0)
     m = lstm.from_params(params, precision="fp32")
-    x = torch.from_numpy(synth.make_windows(6, 2100, 16, 61)).cuda()
+    x = torch.from_numpy(synth.make_windows(6, 4200, 16, 61)).cuda()
     with torch.no_grad():
         full = m(x)
-        parts = torch.cat([m(x[:1000]), m(x[1000:])])
+        parts = torch.cat([m(x[:2100]), m(x[2100:])])           # tensor-core recurrence in all three calls
+        small = torch.cat([m(x[:1000]), m(x[1000:1500])])       # CUDA-core recurrence
+        small2 = torch.cat([m(x[:700]), m(x[700:1500])])
     assert torch.equal(full, parts)
+    assert torch.equal(small, small2)
+    assert float((full[:1500] - small).abs().max()) <= 2e-6
     assert m(x[:0]).shape == (0, 2)
+
+
+def test_fp32_tensorcore_recurrence_matches_oracle():
+    """fp32 parity mode at a batch that runs the recurrence on the tensor cores (lstm_fp32_tc.cu: split fp16 MMAs on CTA pairs;
+    2304 windows = 9 pairs x 2 directions = 18 work items), full sequence length (3 x 256 dependent steps), logit gain 12: the
+    north_star tolerances against the ORACLE (torch CPU port of the reference module) on three 32-window slices, one of them in
+    the ragged last pair."""
+    B, T = 2304 + 40, 256
+    params = synth.make_lstm_params(42, 61, 128, 3, logit_gain=12.0)
+    x = synth.make_windows(21, B, T, 61, structured=True)
+    m = lstm.from_params(params, precision="fp32")
+    xc = torch.from_numpy(x).cuda()
+    with torch.no_grad():
+        logits, attn = m(xc, return_attention=True)
+        probs = m.predict_proba(xc)
+    port = torch_port.build_port(params).eval()
+    for lo in (0, 1100, B - 32):
+        with torch.no_grad():
+            wl, wa = port(torch.from_numpy(x[lo:lo + 32]), return_attention=True)
+            wp = torch.softmax(wl, 1)
+        dl = float((logits[lo:lo + 32].cpu() - wl).abs().max())
+        dp = float((probs[lo:lo + 32].cpu() - wp).abs().max())
+        da = float((attn[lo:lo + 32].cpu() - wa).abs().max())
+        print(f"fp32 tensor-core recurrence vs oracle, windows {lo}..{lo + 32}: dlogit {dl:.2e} dprob {dp:.2e} dattn {da:.2e}")
+        assert dl <= 1e-5 and dp <= 1e-5 and da <= 1e-6, (lo, dl, dp, da)
 
 
 def test_weights_reload_after_update():

@@ -199,3 +199,37 @@ def test_edge_cases_and_errors():
         ode.solve_ensemble(4, y0_mode="probs06", coupling=True)        # missing probabilities
     with pytest.raises(_native.BciError):
         ode.solve_ensemble(4, y0=torch.zeros(3, 4), n_points=1)
+
+
+def test_packed_two_trajectory_kernel_is_bit_identical_to_scalar(tmp_path):
+    """ode_rk4x2_kernel (two trajectories per thread on FFMA2/FMUL2/FADD2) performs, per lane, exactly the scalar kernel's
+    operation sequence: trajectories, final states and both styles agree BIT FOR BIT, including a ragged last block (odd n:
+    the last thread's second lane is dead) and the final-state-only launch."""
+    import os, subprocess, sys
+    code = (
+        "import sys, numpy as np, torch\n"
+        "from lstm_ode_bci_b200 import ode, synth\n"
+        "out = {}\n"
+        "for n in (1, 129, 100003):\n"
+        "    sw = synth.make_ode_sweep(7, n)\n"
+        "    dev = {k: torch.from_numpy(v).cuda() for k, v in sw.items()}\n"
+        "    for style, y0m in (('ref06', 'probs06'), ('ref08', 'pclosed08')):\n"
+        "        for S in (1, 8):\n"
+        "            t, f, _ = ode.solve_ensemble(n, p_open=dev['p_open'], p_closed=dev['p_closed'], rates=dev['rates'], alpha_arr=dev['alpha'],\n"
+        "                                         y0_mode=y0m, coupling=True, style=style, mode='rk4', t_end=20.0, n_points=20, substeps=S)\n"
+        "            _, f2, _ = ode.solve_ensemble(n, p_open=dev['p_open'], p_closed=dev['p_closed'], rates=dev['rates'], alpha_arr=dev['alpha'],\n"
+        "                                          y0_mode=y0m, coupling=True, style=style, mode='rk4', t_end=20.0, n_points=20, substeps=S, want_traj=False)\n"
+        "            assert torch.equal(f, f2) and torch.equal(t[:, -1], f)\n"
+        "            out['%d_%s_%d' % (n, style, S)] = t.cpu().numpy()\n"
+        "np.savez(sys.argv[1], **out)\n")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = {}
+    for tag, env in (("packed", {}), ("scalar", {"BCI_ODE_RK4": "scalar"})):
+        path = str(tmp_path / (tag + ".npz"))
+        r = subprocess.run([sys.executable, "-c", code, path], env=dict(os.environ, PYTHONPATH=root, **env), capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stderr[-2000:]
+        res[tag] = dict(np.load(path))
+    assert set(res["packed"]) == set(res["scalar"]) and len(res["packed"]) == 12
+    for k in res["packed"]:
+        assert np.array_equal(res["packed"][k], res["scalar"][k]), k
+        assert np.isfinite(res["packed"][k]).all()

@@ -413,3 +413,58 @@ def test_bf16_view_input_equals_packed_windows():
     m32 = lstm.from_params(params, precision="fp32")
     with torch.no_grad():
         assert torch.equal(m32.predict_proba_recordings(rec, T, step), m32.predict_proba(X))
+
+
+
+@pytest.mark.parametrize("Bc,T,ND", [(256, 8, 2), (300, 33, 2), (5, 40, 1), (4300, 6, 2), (129, 64, 2)])
+def test_recurrence_f16x3_is_fp32_grade(Bc, T, ND):
+    """lstm_rec_f16x3 (CTA pair, cta_group::2, h . W_hh^T as three fp16 MMA chains: lo.hi + hi.lo + hi.hi) against a float64
+    step-by-step recurrence: fp32-grade (the bf16 recurrence kernels are asserted at 1.5e-2 on the same quantity).  Covers a
+    single pair, ragged tiles (300, 129: the pair's second CTA mostly / entirely dead), one direction, and more work items than
+    resident clusters (4300 windows x 2 directions = 34 items)."""
+    H = 128
+    g = torch.Generator(device="cuda").manual_seed(Bc * 13 + T + ND)
+    whh = (torch.rand(ND, 4 * H, H, device="cuda", generator=g) * 2 - 1) / np.sqrt(H) * 1.5
+    G = (torch.randn(T * Bc, ND * 4 * H, device="cuda", generator=g) * 1.2).contiguous()     # column dir*512 + unit*4 + gate
+    packed = torch.empty(ND * 2 * 4 * H * H, device="cuda", dtype=torch.float16)
+    out = torch.full((T, Bc, ND * H), float("nan"), device="cuda")
+    N.check(N.lib().bci_selftest_rec_f16x3(_p(G), _p(whh.contiguous()), _p(packed), _p(out), Bc, T, ND, _stream()))
+    torch.cuda.synchronize()
+    want = torch.empty(T, Bc, ND * H, device="cuda", dtype=torch.float64)
+    G4 = G.double().reshape(T, Bc, ND, H, 4)                  # (unit, gate) interleaved
+    for d in range(ND):
+        w = whh[d].double()                                   # rows gate*H + unit
+        h = torch.zeros(Bc, H, device="cuda", dtype=torch.float64)
+        c = torch.zeros_like(h)
+        for s in range(T):
+            t = T - 1 - s if d else s
+            rec = (h @ w.T).reshape(Bc, 4, H)                 # (gate, unit)
+            pre = G4[t, :, d] + rec.permute(0, 2, 1)          # (unit, gate)
+            i, f, gg, o = pre[..., 0].sigmoid(), pre[..., 1].sigmoid(), pre[..., 2].tanh(), pre[..., 3].sigmoid()
+            c = f * c + i * gg
+            h = o * c.tanh()
+            want[t, :, d * H:(d + 1) * H] = h
+    assert torch.isfinite(out).all()
+    err = float((out.double() - want).abs().max())
+    print(f"f16x3 recurrence vs float64: max abs err {err:.3e} (Bc={Bc}, T={T}, ND={ND})")
+    assert err <= 3e-6
+
+
+
+@pytest.mark.parametrize("M,Nn,K", [(128, 128, 64), (1000, 256, 128), (4097, 1024, 256), (640, 160, 72)])
+def test_gemm_f16x3_nt_is_fp32_grade(M, Nn, K):
+    """fp16-split form of the projection GEMM (A and B as fp16 (hi, lo) pairs, three kind::f16 MMA chains, B pre-scaled by 16):
+    C = A . B^T + bias against fp64 on LSTM-like operands (activations O(1), weights ~1/sqrt(K)); same 4e-6-of-max|C| bound as
+    the 3 x TF32 form; ragged M, a K tail and a partial N block."""
+    g = torch.Generator(device="cuda").manual_seed(M + K + 1)
+    A = torch.randn(M, K, device="cuda", generator=g) * 0.7
+    B = (torch.rand(Nn, K, device="cuda", generator=g) * 2 - 1) / np.sqrt(K) * 1.5
+    bias = torch.randn(Nn, device="cuda", generator=g)
+    ref = A.double() @ B.double().T + bias.double()
+    C_ = torch.full((M, Nn), float("nan"), device="cuda")
+    N.check(N.lib().bci_selftest_gemm_f16x3(_p(A), _p(B), _p(bias), _p(C_), M, Nn, K, _stream()))
+    torch.cuda.synchronize()
+    assert not torch.isnan(C_).any()
+    err = float((C_.double() - ref).abs().max() / ref.abs().max())
+    print(f"f16x3 GEMM rel err {err:.2e} (M={M}, N={Nn}, K={K})")
+    assert err <= 4e-6
