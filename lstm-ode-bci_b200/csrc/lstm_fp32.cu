@@ -336,12 +336,24 @@ __global__ void copy_kernel(const float* __restrict__ src, float* __restrict__ d
 
 static inline unsigned nblk(long long n) { return (unsigned)ceil_div64(n, 256); }
 
+// input_proj.0.weight (H, C) -> [part][H][64] fp16 pair x 16, K zero-padded
+__global__ void pack_w0_f16_kernel(const float* __restrict__ w0, __half* __restrict__ dst, int H, int C) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= H * 64) return;
+  const int j = i >> 6, k = i & 63;
+  const float v = k < C ? w0[j * C + k] * F16X3_WSCALE : 0.f;
+  const __half hi = __float2half_rn(v);
+  dst[i] = hi;
+  dst[H * 64 + i] = __float2half_rn(v - __half2float(hi));
+}
+
 int lstm_pack_f32(bci_lstm_s* h, cudaStream_t st) {
   const bci_lstm_config& c = h->cfg;
   const bci_lstm_weights& w = h->raw;
   PackedF32& p = h->f32;
   const int H = c.hidden_size, C = c.input_size, ND = num_dirs(c), D = ND * H, AH = D / 2;
   transpose_kernel<<<nblk((long long)H * C), 256, 0, st>>>(w.input_proj_w, p.w0t, H, C);
+  pack_w0_f16_kernel<<<nblk((long long)H * 64), 256, 0, st>>>(w.input_proj_w, p.w0_16, H, C);
   copy_kernel<<<nblk(H), 256, 0, st>>>(w.input_proj_b, p.b0, H);
   if (c.use_layer_norm) {
     copy_kernel<<<nblk(H), 256, 0, st>>>(w.input_ln_w, p.ln0w, H);
@@ -375,6 +387,7 @@ int lstm_pack_f32(bci_lstm_s* h, cudaStream_t st) {
     copy_kernel<<<nblk(AH * D), 256, 0, st>>>(w.attn_w1, p.aw1, AH * D);
     int rc = split_tf32(p.aw1, nullptr, p.aw1_lo, (long long)AH * D, st);
     if (!rc) rc = split_tf32(p.aw1t, nullptr, p.aw1t_lo, (long long)AH * D, st);
+    if (!rc) rc = split_f16(p.aw1, p.aw1_16, p.aw1_16 + (size_t)AH * D, (long long)AH * D, F16X3_WSCALE, st);
     if (rc) return rc;
     copy_kernel<<<nblk(AH), 256, 0, st>>>(w.attn_b1, p.ab1, AH);
     copy_kernel<<<nblk(AH), 256, 0, st>>>(w.attn_w2, p.aw2, AH);
@@ -394,7 +407,7 @@ size_t lstm_store_bytes_f32(const bci_lstm_config& c) {
   const size_t H = c.hidden_size, C = c.input_size, D = 2 * H;
   size_t n = C * H + 3 * H;
   for (int l = 0; l < c.num_layers; ++l) n += 4 * ((size_t)layer_in_width(c, l) * 8 * H) + 2 * (2 * H * 4 * H) + 8 * H + 2 * 4 * H * H + (size_t)layer_in_width(c, l) * 8 * H;
-  n += 2 * D + 4 * D * H + H + H + 4 + D * H + H + H * (H / 2) + H / 2 + (size_t)c.num_classes * (H / 2) + c.num_classes + 64;
+  n += 2 * D + 5 * D * H + 64 * H + H + H + 4 + D * H + H + H * (H / 2) + H / 2 + (size_t)c.num_classes * (H / 2) + c.num_classes + 64;
   return align_up(n * sizeof(float) + 256 * 64, 256);
 }
 
@@ -420,6 +433,8 @@ void lstm_carve_f32(bci_lstm_s* h, char* base) {
   }
   p.lnw = take(D); p.lnb = take(D); p.aw1t = take(D * H); p.ab1 = take(H); p.aw2 = take(H); p.ab2 = take(4);
   p.aw1 = take(D * H); p.aw1_lo = take(D * H); p.aw1t_lo = take(D * H);
+  p.aw1_16 = reinterpret_cast<__half*>(take(D * H));   // 2 parts x (D/2) x D halves
+  p.w0_16 = reinterpret_cast<__half*>(take(64 * H));   // 2 parts x H x 64 halves
   p.c0t = take(D * H); p.cb0 = take(H); p.c3t = take(H * (H / 2)); p.cb3 = take(H / 2);
   p.c6 = take((size_t)c.num_classes * (H / 2)); p.cb6 = take(c.num_classes);
 }
@@ -453,9 +468,7 @@ static int forward_chunk_f32(bci_lstm_s* h, const InputView& x, int Bc, int T, f
   float* scores = reinterpret_cast<float*>(take(rows * 4));
   float* in_lo = reinterpret_cast<float*>(take(rows * D * 4));  // tf32 remainder of the layer input (split-precision GEMM)
   h->prof.mark(-1, st);
-  int rc = launch_input_proj<H, float>(h, x, Bc, T, z, st);
-  if (rc) return rc;
-  h->prof.mark(0, st);
+  int rc = 0;
   const float* in = z;
   float* outs[2] = {o0, o1};
   // Large batches (H = 128): the whole LSTM stack on the tensor cores in split FP16 precision -- projections as three fp16 MMA
@@ -465,8 +478,25 @@ static int forward_chunk_f32(bci_lstm_s* h, const InputView& x, int Bc, int T, f
   // layer writes fp32 for the pooling kernel.  The pair buffers reuse the space of the tf32 remainder array.
   __half* in_hi16 = reinterpret_cast<__half*>(in_lo);
   __half* in_lo16 = in_hi16 + rows * D;
-  const bool tc = tc_rec_ok(H, ND, Bc, g, 4 * D, o0, D) && f16x3_nt_ok(in_hi16, H, h->f32.wih16[0], H, g, 4 * D, (int)rows, 4 * D, H);
-  if (tc && (rc = split_f16(z, in_hi16, in_lo16, (long long)rows * H, 1.0f, st))) return rc;
+  const bool tc = H == 128 && tc_rec_ok(H, ND, Bc, g, 4 * D, o0, D) && c.input_size <= 64 &&
+                  f16x3_nt_ok(in_hi16, H, h->f32.wih16[0], H, g, 4 * D, (int)rows, 4 * D, H);
+  if (tc) {
+    // K1 on the tensor cores too: x -> fp16 pair rows (K padded to 64, in the z buffer) -> split-fp16 GEMM (+ b0, into the G
+    // buffer) -> LayerNorm + erf-GELU row kernel that writes z directly as the pair the first projection reads
+    __half* x_hi = reinterpret_cast<__half*>(z);
+    __half* x_lo = x_hi + rows * 64;
+    x_pair_rows_kernel<<<(unsigned)ceil_div64((long long)rows * 32, 256), 256, 0, st>>>(x, Bc, T, c.input_size, x_hi, x_lo);
+    BCI_LAUNCH_OK();
+    if ((rc = gemm_f16x3_nt(x_hi, x_lo, 64, h->f32.w0_16, h->f32.w0_16 + (size_t)H * 64, 64, h->f32.b0, g, H, (int)rows, H, 64,
+                            1.0f / F16X3_WSCALE, st)))
+      return rc;
+    ln_gelu_pair_rows128_kernel<<<(unsigned)(rows / 8 < 4096 ? (rows + 7) / 8 : 4096), 256, 0, st>>>(
+        g, (long long)rows, h->f32.ln0w, h->f32.ln0b, c.use_layer_norm, in_hi16, in_lo16);
+    BCI_LAUNCH_OK();
+  } else {
+    if ((rc = launch_input_proj<H, float>(h, x, Bc, T, z, st))) return rc;
+  }
+  h->prof.mark(0, st);
   for (int l = 0; l < c.num_layers; ++l) {
     const int K = layer_in_width(c, l);
     const int M = (int)rows, N = 4 * D;
@@ -501,7 +531,20 @@ static int forward_chunk_f32(bci_lstm_s* h, const InputView& x, int Bc, int T, f
     h->prof.mark(2, st);
     in = o;
   }
-  rc = launch_pool_head<H, ND, float>(h, in, Bc, T, logits, probs, attn, scores, st);
+  if (tc && ND == 2 && c.use_layer_norm && c.use_attention && f16x3_nt_ok(in_hi16, D, h->f32.aw1_16, D, g, D / 2, (int)rows, D / 2, D)) {
+    // attention scores on the tensor cores as well: y = LN(out) as an fp16 pair (the pair buffers are free again), then
+    // pre = y . W1^T + b1 by the split-fp16 GEMM into the (now dead) G buffer; the pooling kernel reads pre instead of running
+    // its CUDA-core score product (7.1 -> ~3 ms per 9472 windows)
+    ln_pair_rows256_kernel<<<(unsigned)(rows / 8 < 4096 ? (rows + 7) / 8 : 4096), 256, 0, st>>>(in, (long long)rows, h->f32.lnw, h->f32.lnb,
+                                                                                              in_hi16, in_lo16);
+    BCI_LAUNCH_OK();
+    if ((rc = gemm_f16x3_nt(in_hi16, in_lo16, D, h->f32.aw1_16, h->f32.aw1_16 + (size_t)(D / 2) * D, D, h->f32.ab1, g, D / 2, (int)rows,
+                            D / 2, D, 1.0f / F16X3_WSCALE, st)))
+      return rc;
+    rc = launch_pool_head<H, ND, float>(h, in, Bc, T, logits, probs, attn, scores, st, g);
+  } else {
+    rc = launch_pool_head<H, ND, float>(h, in, Bc, T, logits, probs, attn, scores, st);
+  }
   h->prof.mark(3, st);
   return rc;
 }

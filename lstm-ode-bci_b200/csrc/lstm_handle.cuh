@@ -25,6 +25,8 @@ struct PackedF32 {
   __half* whh16[BCI_MAX_LAYERS];
   // ... and of the projection GEMM in its fp16-split form (gemm_tf32x3.cu, F16): [part hi/lo][ND*4H gate-interleaved rows][K_l], x 16
   __half* wih16[BCI_MAX_LAYERS];
+  __half* w0_16;   // input_proj.0.weight (H, C) zero-padded to K = 64, fp16 (hi, lo) pair x 16
+  __half* aw1_16;  // attention.0.weight (D/2, D) as an fp16 (hi, lo) pair x 16: B operand of the score GEMM (fp32 large-batch path)
   // tf32 remainders (x - tf32(x)) of wih_b / wih_t: second operand of the split-precision tcgen05 GEMMs (gemm_tf32x3.cu)
   float* wih_b_lo[BCI_MAX_LAYERS];
   float* wih_t_lo[BCI_MAX_LAYERS];

@@ -120,7 +120,8 @@ attn_pool_head_kernel(const InT* __restrict__ seq,  // [T][Bc][2H]
                       float* __restrict__ probs,    // [Bc][classes] or null
                       float* __restrict__ attn,     // [Bc][T] or null
                       float* __restrict__ scores_ws, // [Bc][T] scratch for raw scores (needed iff attn)
-                      int use_ln, int use_attn) {
+                      int use_ln, int use_attn,
+                      const float* __restrict__ pre = nullptr) {  // optional [T][Bc][AH]: W1 LN(seq) + b1 already computed (tensor cores)
   using Cfg = PoolCfg<H, ND>;
   constexpr int D = Cfg::D, AH = Cfg::AH, TC = Cfg::TC, RPT = Cfg::RPT, YS = Cfg::YS_STRIDE, WPG = Cfg::WARPS_PER_GROUP;
   extern __shared__ __align__(16) float k4_smem[];
@@ -177,7 +178,14 @@ attn_pool_head_kernel(const InT* __restrict__ seq,  // [T][Bc][2H]
 #pragma unroll
     for (int r = 0; r < RPT; ++r) acc[r] = b1;
     const float* yrow = ys_t + grp * RPT;
-    if (use_attn) {
+    if (pre) {
+      // the score pre-activations come from the split-fp16 tensor-core GEMM (fp32 large-batch path): one coalesced row read each
+#pragma unroll
+      for (int r = 0; r < RPT; ++r) {
+        const int t = t0 + grp * RPT + r;
+        acc[r] = t < T ? __ldg(pre + ((long long)t * Bc + b) * AH + j) : 0.f;
+      }
+    } else if (use_attn) {
 #pragma unroll 4
     for (int d = 0; d < D; ++d) {
       const float w = __ldg(aw1t + (long long)d * AH + j);
@@ -276,7 +284,7 @@ attn_pool_head_kernel(const InT* __restrict__ seq,  // [T][Bc][2H]
 
 template <int H, int ND, typename InT>
 inline int launch_pool_head(const bci_lstm_s* h, const InT* seq, int Bc, int T, float* logits, float* probs, float* attn,
-                            float* scores_ws, cudaStream_t st) {
+                            float* scores_ws, cudaStream_t st, const float* pre = nullptr) {
   using Cfg = PoolCfg<H, ND>;
   const size_t smem = Cfg::SMEM_FLOATS * sizeof(float);
   static PerDeviceFlag attr_pd;
@@ -289,9 +297,98 @@ inline int launch_pool_head(const bci_lstm_s* h, const InT* seq, int Bc, int T, 
   attn_pool_head_kernel<H, ND, InT><<<Bc, K4_THREADS, smem, st>>>(seq, Bc, T, h->cfg.num_classes, p.lnw, p.lnb, p.aw1t, p.ab1,
                                                                    p.aw2, p.ab2, p.c0t, p.cb0, p.c3t, p.cb3, p.c6, p.cb6,
                                                                    logits, probs, attn, scores_ws, h->cfg.use_layer_norm,
-                                                                   h->cfg.use_attention);
+                                                                   h->cfg.use_attention, pre);
   BCI_LAUNCH_OK();
   return BCI_OK;
+}
+
+// x (any InputView) -> fp16 (hi, lo) pair rows [T][Bc][64] (time-major, K padded from C to 64 with zeros): A operand of the input
+// projection in its split-fp16 GEMM form (fp32 large-batch path).  One thread per (row, pair of channels).
+static __global__ void x_pair_rows_kernel(const InputView x, int Bc, int T, int C, __half* __restrict__ x_hi, __half* __restrict__ x_lo) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long rows = (long long)Bc * T;
+  if (i >= rows * 32) return;
+  const long long r = i >> 5;
+  const int k = (int)(i & 31) * 2;
+  const int t = (int)(r / Bc), b = (int)(r - (long long)t * Bc);
+  const long long src = x.elem_off(b) + (long long)t * C;
+  const float v0 = k < C ? view_load(x, src + k) : 0.f, v1 = (k + 1) < C ? view_load(x, src + k + 1) : 0.f;
+  const __half2 h2 = __floats2half2_rn(v0, v1);
+  const float2 back = __half22float2(h2);
+  reinterpret_cast<__half2*>(x_hi)[i] = h2;
+  reinterpret_cast<__half2*>(x_lo)[i] = __floats2half2_rn(v0 - back.x, v1 - back.y);
+}
+
+// z = GELU_erf(LayerNorm(pre row)) -> fp16 (hi, lo) pair: rows of 128, one warp per row, 4 consecutive features per lane
+static __global__ void __launch_bounds__(256)
+ln_gelu_pair_rows128_kernel(const float* __restrict__ pre, long long rows, const float* __restrict__ lnw, const float* __restrict__ lnb,
+                            int use_ln, __half* __restrict__ z_hi, __half* __restrict__ z_lo) {
+  const int lane = threadIdx.x & 31;
+  float gw[4], gb[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { gw[i] = use_ln ? lnw[lane * 4 + i] : 1.f; gb[i] = use_ln ? lnb[lane * 4 + i] : 0.f; }
+  const long long wstride = (long long)gridDim.x * 8;
+  for (long long r = (long long)blockIdx.x * 8 + (threadIdx.x >> 5); r < rows; r += wstride) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(pre + r * 128) + lane);
+    const float v[4] = {a.x, a.y, a.z, a.w};
+    float mean = warp_sum((v[0] + v[1]) + (v[2] + v[3])) * (1.0f / 128);
+    float q2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { const float dd = v[i] - mean; q2 = fmaf(dd, dd, q2); }
+    float rstd = 1.0f / sqrtf(warp_sum(q2) * (1.0f / 128) + 1e-5f);
+    if (!use_ln) { mean = 0.f; rstd = 1.f; }
+    uint32_t hi[2], lo[2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const float y0 = gelu_erf(use_ln ? (v[2 * i] - mean) * rstd * gw[2 * i] + gb[2 * i] : v[2 * i]);
+      const float y1 = gelu_erf(use_ln ? (v[2 * i + 1] - mean) * rstd * gw[2 * i + 1] + gb[2 * i + 1] : v[2 * i + 1]);
+      const __half2 h2 = __floats2half2_rn(y0, y1);
+      const float2 back = __half22float2(h2);
+      const __half2 l2 = __floats2half2_rn(y0 - back.x, y1 - back.y);
+      hi[i] = *reinterpret_cast<const uint32_t*>(&h2);
+      lo[i] = *reinterpret_cast<const uint32_t*>(&l2);
+    }
+    *reinterpret_cast<uint2*>(z_hi + r * 128 + lane * 4) = make_uint2(hi[0], hi[1]);
+    *reinterpret_cast<uint2*>(z_lo + r * 128 + lane * 4) = make_uint2(lo[0], lo[1]);
+  }
+}
+
+// y = LayerNorm(seq row) -> fp16 (hi, lo) pair, the A operand of the score GEMM in its split-fp16 form.  One warp per row,
+// 8 consecutive features per lane (D = 256): 1 KB coalesced in, 2 x 512 B coalesced out.
+static __global__ void __launch_bounds__(256)
+ln_pair_rows256_kernel(const float* __restrict__ seq, long long rows, const float* __restrict__ lnw, const float* __restrict__ lnb,
+                       __half* __restrict__ y_hi, __half* __restrict__ y_lo) {
+  const int lane = threadIdx.x & 31;
+  float gw[8], gb[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { gw[i] = lnw[lane * 8 + i]; gb[i] = lnb[lane * 8 + i]; }
+  const long long wstride = (long long)gridDim.x * 8;
+  for (long long r = (long long)blockIdx.x * 8 + (threadIdx.x >> 5); r < rows; r += wstride) {
+    const float4* p = reinterpret_cast<const float4*>(seq + r * 256) + lane * 2;
+    const float4 a = __ldg(p), b = __ldg(p + 1);
+    float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += v[i];
+    const float mean = warp_sum(s) * (1.0f / 256);
+    float q2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { const float dd = v[i] - mean; q2 = fmaf(dd, dd, q2); }
+    const float rstd = 1.0f / sqrtf(warp_sum(q2) * (1.0f / 256) + 1e-5f);
+    uint32_t hi[4], lo[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float y0 = (v[2 * i] - mean) * rstd * gw[2 * i] + gb[2 * i];
+      const float y1 = (v[2 * i + 1] - mean) * rstd * gw[2 * i + 1] + gb[2 * i + 1];
+      const __half2 h2 = __floats2half2_rn(y0, y1);
+      const float2 back = __half22float2(h2);
+      const __half2 l2 = __floats2half2_rn(y0 - back.x, y1 - back.y);
+      hi[i] = *reinterpret_cast<const uint32_t*>(&h2);
+      lo[i] = *reinterpret_cast<const uint32_t*>(&l2);
+    }
+    *reinterpret_cast<uint4*>(y_hi + r * 256 + lane * 8) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    *reinterpret_cast<uint4*>(y_lo + r * 256 + lane * 8) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+  }
 }
 
 template <int H, typename OutT>
