@@ -347,13 +347,32 @@ __global__ void pack_w0_f16_kernel(const float* __restrict__ w0, __half* __restr
   dst[H * 64 + i] = __float2half_rn(v - __half2float(hi));
 }
 
+// the fp16-split operand copies of the large-batch inference path, from the fp32 layouts packed by lstm_pack_f32 (same stream)
+static int pack_f16_operands(bci_lstm_s* h, cudaStream_t st) {
+  const bci_lstm_config& c = h->cfg;
+  const bci_lstm_weights& w = h->raw;
+  PackedF32& p = h->f32;
+  const int H = c.hidden_size, C = c.input_size, ND = num_dirs(c), D = ND * H, AH = D / 2;
+  int rc = 0;
+  pack_w0_f16_kernel<<<ceil_div(H * 64, 256), 256, 0, st>>>(w.input_proj_w, p.w0_16, H, C);
+  BCI_LAUNCH_OK();
+  for (int l = 0; l < c.num_layers && !rc; ++l) {
+    const int K = layer_in_width(c, l);
+    for (int d = 0; d < ND && !rc; ++d) rc = pack_whh_f16x3(w.w_hh[l][d], p.whh16[l] + (size_t)d * 2 * 4 * H * H, H, st);
+    if (!rc) rc = split_f16(p.wih_b[l], p.wih16[l], p.wih16[l] + (size_t)ND * 4 * H * K, (long long)ND * 4 * H * K, F16X3_WSCALE, st);
+  }
+  if (!rc && c.use_attention) rc = split_f16(p.aw1, p.aw1_16, p.aw1_16 + (size_t)AH * D, (long long)AH * D, F16X3_WSCALE, st);
+  if (!rc) h->f16_stale = false;
+  return rc;
+}
+
 int lstm_pack_f32(bci_lstm_s* h, cudaStream_t st) {
   const bci_lstm_config& c = h->cfg;
   const bci_lstm_weights& w = h->raw;
   PackedF32& p = h->f32;
   const int H = c.hidden_size, C = c.input_size, ND = num_dirs(c), D = ND * H, AH = D / 2;
   transpose_kernel<<<nblk((long long)H * C), 256, 0, st>>>(w.input_proj_w, p.w0t, H, C);
-  pack_w0_f16_kernel<<<nblk((long long)H * 64), 256, 0, st>>>(w.input_proj_w, p.w0_16, H, C);
+  h->f16_stale = true;
   copy_kernel<<<nblk(H), 256, 0, st>>>(w.input_proj_b, p.b0, H);
   if (c.use_layer_norm) {
     copy_kernel<<<nblk(H), 256, 0, st>>>(w.input_ln_w, p.ln0w, H);
@@ -367,14 +386,8 @@ int lstm_pack_f32(bci_lstm_s* h, cudaStream_t st) {
       pack_bias_kernel<<<nblk(4 * H), 256, 0, st>>>(w.b_ih[l][d], w.b_hh[l][d], p.bias[l], H, d * 4 * H);
       pack_gates_rows_kernel<<<nblk((long long)4 * H * K), 256, 0, st>>>(w.w_ih[l][d], p.wih_b[l], H, K, d * 4 * H);
       pack_whh_b4_kernel<<<nblk((long long)4 * H * H), 256, 0, st>>>(w.w_hh[l][d], p.whh_b[l][d], H);
-      if (H == 128) {
-        int rc16 = pack_whh_f16x3(w.w_hh[l][d], p.whh16[l] + (size_t)d * 2 * 4 * H * H, H, st);
-        if (rc16) return rc16;
-      }
     }
-    int rc = H == 128 ? split_f16(p.wih_b[l], p.wih16[l], p.wih16[l] + (size_t)ND * 4 * H * K, (long long)ND * 4 * H * K, F16X3_WSCALE, st) : 0;
-    if (rc) return rc;
-    rc = split_tf32(p.wih_b[l], nullptr, p.wih_b_lo[l], (long long)ND * 4 * H * K, st);
+    int rc = split_tf32(p.wih_b[l], nullptr, p.wih_b_lo[l], (long long)ND * 4 * H * K, st);
     if (!rc) rc = split_tf32(p.wih_t[l], nullptr, p.wih_t_lo[l], (long long)ND * 4 * H * K, st);
     if (rc) return rc;
   }
@@ -387,7 +400,6 @@ int lstm_pack_f32(bci_lstm_s* h, cudaStream_t st) {
     copy_kernel<<<nblk(AH * D), 256, 0, st>>>(w.attn_w1, p.aw1, AH * D);
     int rc = split_tf32(p.aw1, nullptr, p.aw1_lo, (long long)AH * D, st);
     if (!rc) rc = split_tf32(p.aw1t, nullptr, p.aw1t_lo, (long long)AH * D, st);
-    if (!rc) rc = split_f16(p.aw1, p.aw1_16, p.aw1_16 + (size_t)AH * D, (long long)AH * D, F16X3_WSCALE, st);
     if (rc) return rc;
     copy_kernel<<<nblk(AH), 256, 0, st>>>(w.attn_b1, p.ab1, AH);
     copy_kernel<<<nblk(AH), 256, 0, st>>>(w.attn_w2, p.aw2, AH);
@@ -480,6 +492,7 @@ static int forward_chunk_f32(bci_lstm_s* h, const InputView& x, int Bc, int T, f
   __half* in_lo16 = in_hi16 + rows * D;
   const bool tc = H == 128 && tc_rec_ok(H, ND, Bc, g, 4 * D, o0, D) && c.input_size <= 64 &&
                   f16x3_nt_ok(in_hi16, H, h->f32.wih16[0], H, g, 4 * D, (int)rows, 4 * D, H);
+  if (tc && h->f16_stale && (rc = pack_f16_operands(h, st))) return rc;
   if (tc) {
     // K1 on the tensor cores too: x -> fp16 pair rows (K padded to 64, in the z buffer) -> split-fp16 GEMM (+ b0, into the G
     // buffer) -> LayerNorm + erf-GELU row kernel that writes z directly as the pair the first projection reads

@@ -98,8 +98,17 @@ lstm_rec_f16x3(const float* __restrict__ G,        // [T*Bc][ldg] fp32: column d
                __half* __restrict__ out_lo16,      //   reads its A operand in this form (gemm_f16x3_nt) -- no separate split pass
                float* __restrict__ gates,          // SAVE: [T*Bc][ldg] gate ACTIVATIONS (i,f,g,o), same layout as G
                float* __restrict__ csave,          // SAVE: [T*Bc][D] cell states
-               int D, int Bc, int T, int n_pairs, int ND, int pf_mode) {
+               int D, int Bc, int T, int n_pairs, int ND, int pf_mode, int jitter) {  // jitter: 0 or a power of two (max sleep, ns)
   extern __shared__ uint8_t tc_smem_raw[];
+  // BCI_FUSED_JITTER (tests only): every thread sleeps a pseudo-random time at its synchronisation points, to shake out ordering
+  // assumptions of the pair protocol that only hold at the natural timing (compute-sanitizer is not available on the GPU pool)
+  uint32_t jit_state = jitter ? (uint32_t)(blockIdx.x * 7919u + threadIdx.x * 104729u + 12345u) : 0u;
+  auto jit = [&]() {
+    if (jitter) {
+      jit_state = jit_state * 1664525u + 1013904223u;
+      __nanosleep((jit_state >> 20) & (uint32_t)(jitter - 1));
+    }
+  };
   const uint32_t raw = smem_u32(tc_smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t* gen = tc_smem_raw + (base - raw);
@@ -214,6 +223,8 @@ lstm_rec_f16x3(const float* __restrict__ G,        // [T*Bc][ldg] fp32: column d
         cp_async_commit();
       };
       copy_slab(0);
+      if (lane == 0) jit();
+      __syncwarp();
       mbar_wait(acc_full, (uint32_t)(g & 1));
       tc_fence_after();
       uint32_t acc[32];
@@ -300,8 +311,9 @@ lstm_rec_f16x3(const float* __restrict__ G,        // [T*Bc][ldg] fp32: column d
       fence_proxy_async_smem();  // generic-proxy stores of h -> visible to the next step's tcgen05.mma
       tc_fence_before();         // order this thread's TMEM reads before the arrive
       __syncwarp();
-      if (lane == 0) mbar_arrive(h_local);
+      if (lane == 0) { jit(); mbar_arrive(h_local); }
       if (tid == 0) {
+        jit();
         // issuer / relay duty: both CTAs hold h_t and have drained their accumulators -> next step's MMAs.  The peer's arrive is
         // RELAXED: its data sits in ITS shared memory, written by its epilogue warps who fenced generic -> async before arriving
         // on its h_local (same protocol as the relay of lstm_bf16_fused.cu, where a release arrive measured 640 ns per step)
@@ -384,8 +396,9 @@ int launch_rec_f16x3(int ND, const float* G, int ldg, const __half* whh16, float
   // L2 prefetch of the next step's rows (BCI_TC_PF = 1 bulk per thread, 2 rolling per slab) measured no gain and doubled the DRAM
   // reads (ncu: 17.8 GB against 9.9 GB of G, L2 hit rate 14 %): off by default
   static const int pf_mode = [] { const char* e = getenv("BCI_TC_PF"); return e ? atoi(e) : 0; }();
-  if (gates) lstm_rec_f16x3<true><<<2 * clusters, TC_THREADS, TC_SMEM, st>>>(G, ldg, whh16, out, out_hi16, out_lo16, gates, csave, D, Bc, T, n_pairs, ND, pf_mode);
-  else lstm_rec_f16x3<false><<<2 * clusters, TC_THREADS, TC_SMEM, st>>>(G, ldg, whh16, out, out_hi16, out_lo16, nullptr, nullptr, D, Bc, T, n_pairs, ND, pf_mode);
+  static const int jitter = [] { const char* e = getenv("BCI_FUSED_JITTER"); int v = e ? atoi(e) : 0; return (v > 0 && (v & (v - 1)) == 0) ? v : 0; }();
+  if (gates) lstm_rec_f16x3<true><<<2 * clusters, TC_THREADS, TC_SMEM, st>>>(G, ldg, whh16, out, out_hi16, out_lo16, gates, csave, D, Bc, T, n_pairs, ND, pf_mode, jitter);
+  else lstm_rec_f16x3<false><<<2 * clusters, TC_THREADS, TC_SMEM, st>>>(G, ldg, whh16, out, out_hi16, out_lo16, nullptr, nullptr, D, Bc, T, n_pairs, ND, pf_mode, jitter);
   BCI_LAUNCH_OK();
   return BCI_OK;
 }

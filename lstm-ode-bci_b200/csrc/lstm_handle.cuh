@@ -111,6 +111,9 @@ struct bci_lstm_s {
   cudaStream_t side;
   cudaEvent_t ev_dg, ev_side[2], ev_join;
   bool side_ready;
+  // the fp16-split operand copies (whh16 / wih16 / aw1_16 / w0_16) serve the large-batch fp32 INFERENCE path only: they are packed on
+  // its first use after a load, so a training loop that reloads the weights every step does not pay for them
+  bool f16_stale;
   // the last train=1 forward (workspace + header): a backward on the same workspace needs no device->host read of the header
   void* last_train_ws;
   float last_dropout;

@@ -222,7 +222,8 @@ def test_fused_cluster_recurrence_matches_stepwise(Bc, T, Kin):
 def test_fused_kernel_is_robust_to_timing_jitter():
     """The cluster kernel's cross-CTA protocol (mbarriers, DSMEM copies, relays) must not depend on the natural timing:
     with BCI_FUSED_JITTER every role sleeps a pseudo-random time (up to 4 us) at its synchronisation points.  An earlier
-    version re-armed an mbarrier too early and only failed (launch failure) under such perturbation or under ncu."""
+    version re-armed an mbarrier too early and only failed (launch failure) under such perturbation or under ncu.  The same
+    perturbation is applied to the CTA-pair recurrence of the fp32 path (lstm_rec_f16x3: commit multicast, h_local, peer relay)."""
     import os, subprocess, sys
     code = (
         "import numpy as np, torch\n"
@@ -232,6 +233,11 @@ def test_fused_kernel_is_robust_to_timing_jitter():
         "a = lstm.from_params(p, precision='bf16').predict_proba(x).cpu().numpy()\n"
         "b = lstm.from_params(p, precision='fp32').predict_proba(x[:64]).cpu().numpy()\n"
         "assert np.isfinite(a).all() and np.abs(a[:64] - b).max() <= 1e-2, np.abs(a[:64] - b).max()\n"
+        "xf = torch.from_numpy(synth.make_windows(8, 2100, 24, 61, structured=True)).cuda()\n"   # 18 work items: the fp32 pair recurrence
+        "m32 = lstm.from_params(p, precision='fp32')\n"
+        "c = m32.predict_proba(xf).cpu().numpy()\n"
+        "d = torch.cat([m32.predict_proba(xf[:1000]), m32.predict_proba(xf[1000:2000])]).cpu().numpy()\n"   # CUDA-core recurrence
+        "assert np.isfinite(c).all() and np.abs(c[:2000] - d).max() <= 2e-6, np.abs(c[:2000] - d).max()\n"
         "print('jitter ok')\n")
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     env = dict(os.environ, BCI_FUSED_JITTER="4096", PYTHONPATH=root)
