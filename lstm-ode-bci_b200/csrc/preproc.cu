@@ -53,6 +53,8 @@ __device__ __forceinline__ double df2t_step(const FiltCoef& c, double (&z)[ORD],
 // e^-39: the chunked result equals the serial one to rounding (1e-16 of the signal), far inside the 1e-9 parity bound, while
 // a batch of R recordings exposes R x 61 x n/PP_CHUNK threads instead of R x 61 (the fp64 pipe issues one warp instruction per
 // 8 cycles per SM sub-partition on B200; a single warp per 32 rows left 130 of 148 SMs idle).
+// (Round 2 tried 4096-sample chunks with 6144 of warm-up -- 4x the threads for 1.67x the arithmetic: 14 recordings per call ran 6 %
+// faster, 36 recordings 34 % slower (15.3 instead of 11.4 ms): from ~80 k threads on the kernel is no longer latency-bound.  Kept as is.)
 constexpr int PP_CHUNK = 16384, PP_WARM = 8192;
 
 // pass = 0: forward over the odd-extended input -> yf (rows x m);  pass = 1: backward over yf -> yb (rows x m), plus per-chunk

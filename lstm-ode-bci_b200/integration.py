@@ -245,6 +245,9 @@ def stream_raw_recordings(lstm_model, host_batches, lowcut=1.0, highcut=45.0, fs
             rh = rh[None]
         return rh
 
+    # (Tried: preprocessing of batch k+1 on its own stream beside the BiLSTM of batch k -- the filter is a latency-bound fp64 recursion
+    # with few threads.  Its blocks delay the 4-CTA cluster launches of the LSTM: config 5 ran at 0.76 M instead of 1.05 M windows/s.
+    # The stages of one batch therefore run back to back; only the H2D copy of the next batch overlaps them.)
     def compute(buf):
         out = pp.preprocess_recordings(buf, b, a, zi, padlen, seq_len, overlap, mean, std)
         return lstm_model.predict_proba(out["X"]), {"mean": out["mean"], "std": out["std"]}

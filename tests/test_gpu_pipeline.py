@@ -116,3 +116,58 @@ def test_predict_batch_takes_the_bf16_engine_where_the_reference_autocasts():
     assert np.array_equal(outs["auto"][0], outs["bf16"][0]) and not np.array_equal(outs["auto"][0], outs["fp32"][0])
     assert np.array_equal(outs["auto"][1], outs["fp32"][1])
     assert np.abs(outs["auto"][0] - outs["fp32"][0]).max() <= 1.2e-3
+
+
+def test_stream_recordings_equals_materialised_windows():
+    """integration.stream_recordings (host recordings -> H2D ring -> windows cut in place) == predict_proba on the windows
+    create_sequences (02:157-180) would materialise; pinned and pageable host batches, fp32 and bf16 storage, fp32 and bf16 engines."""
+    params = synth.make_lstm_params(42, 61, 128, 3, logit_gain=12.0)
+    R, S, T, step = 3, 1504, 256, 128      # S % 8 == 0: every window start of the bf16 copy is 16-byte aligned (TMA-fed projection)
+    n_seq = (S - T) // step + 1
+    rng = np.random.default_rng(3)
+    recs = [rng.standard_normal((R, S, 61), dtype=np.float32) for _ in range(3)]
+    for prec in ("bf16", "fp32"):
+        m = lstm.from_params(params, precision=prec)
+        want = []
+        for rec in recs:
+            X = np.stack([rec[r, i * step:i * step + T] for r in range(R) for i in range(n_seq)])
+            with torch.no_grad():
+                want.append(m.predict_proba(torch.from_numpy(X).cuda()))
+        want = torch.cat(want)
+        batches = [torch.from_numpy(recs[0]).pin_memory(), recs[1], torch.from_numpy(recs[2])]      # pinned, numpy, pageable tensor
+        got = torch.cat([p for p, _ in integration.stream_recordings(m, batches, seq_len=T, step=step)])
+        assert got.shape == (3 * R * n_seq, 2) and torch.equal(got, want), prec
+        if prec == "bf16":       # bf16 storage changes no bit in the bf16 engine
+            got16 = torch.cat([p for p, _ in integration.stream_recordings(m, [torch.from_numpy(r).to(torch.bfloat16) for r in recs], T, step)])
+            assert torch.equal(got16, want)
+    assert list(integration.stream_recordings(m, [])) == []
+
+
+def test_stream_raw_recordings_equals_preprocess_then_predict():
+    """integration.stream_raw_recordings (H2D of the next batch beside filtfilt + z-score + windowing + BiLSTM of this one) == the
+    same stages run one after the other; config 5 from host recordings through parallel.forecast_pipeline_from_recordings == the
+    mirrors run back to back on the same windows."""
+    from lstm_ode_bci_b200 import parallel, preprocessing as pp
+    params = synth.make_lstm_params(3, 61, 128, 3, logit_gain=20.0)
+    m = lstm.from_params(params, precision="fp32")
+    rng = np.random.default_rng(5)
+    raws = [(rng.standard_normal((2, 61, 4000)) * 1e-5 + 1e-4).astype(np.float32) for _ in range(4)]
+    b, a, zi, padlen = pp.design_bandpass()
+    want, Xs = [], []
+    for raw in raws:
+        out = pp.preprocess_recordings(torch.from_numpy(raw).cuda(), b, a, zi, padlen)
+        Xs.append(out["X"])
+        with torch.no_grad():
+            want.append(m.predict_proba(out["X"]))
+    want = torch.cat(want)
+    got = torch.cat([p for p, _ in integration.stream_raw_recordings(m, raws)])
+    assert torch.equal(got, want)
+    integ = integration.LSTMODEIntegration(m, ode.CognitiveStateODE(), coupling_strength=0.5)
+    n_total = want.shape[0]
+    res = parallel.forecast_pipeline_from_recordings(integ, raws, n_total, raw=True)
+    assert torch.equal(res["probs"], want)
+    traj, probs, preds = integ.predict_batch(torch.cat(Xs).cpu().numpy(), forecast_steps=20, batch_size=32, show_progress=False)
+    assert np.abs(res["traj"].cpu().numpy() - traj).max() <= 1e-6 and np.array_equal(res["pred"].cpu().numpy(), preds)
+    fc = integration.multistep_forecast(probs, integ.base_params, horizons=[5, 10, 20])
+    for j, h in enumerate((5, 10, 20)):
+        assert np.abs(res["forecast"].cpu().numpy()[:, j] - fc[h]["predictions"]).max() <= 1e-6
