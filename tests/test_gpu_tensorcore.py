@@ -474,3 +474,33 @@ def test_gemm_f16x3_nt_is_fp32_grade(M, Nn, K):
     err = float((C_.double() - ref).abs().max() / ref.abs().max())
     print(f"f16x3 GEMM rel err {err:.2e} (M={M}, N={Nn}, K={K})")
     assert err <= 4e-6
+
+
+def test_bf16_recording_view_at_the_reference_recording_shape_matches_oracle():
+    """The end-to-end path of the bench at the reference's own recording shape: one 300 s x 500 Hz recording (150 000 samples x 61
+    channels, 01:51-52) stored as bf16, its 1 170 overlapping windows (02:49-51,169) read in place by the input projection, against
+    the ORACLE (torch CPU port of the reference module, fed the fp32 windows create_sequences would cut) on the first, a middle and
+    the last 16 windows; stated bf16-mode tolerance."""
+    S, C_, T, step = 150_000, 61, 256, 128
+    n_seq = (S - T) // step + 1
+    assert n_seq == 1170
+    params = synth.make_lstm_params(42, 61, 128, 3, logit_gain=12.0)
+    g = torch.Generator().manual_seed(11)
+    t = torch.arange(S, dtype=torch.float32)[:, None] / 500.0
+    freqs = torch.rand(1, C_, generator=g) * 40 + 2
+    rec = (torch.sin(2 * np.pi * freqs * t + torch.rand(1, C_, generator=g) * 6.28) + 0.5 * torch.randn(S, C_, generator=g))
+    rec = ((rec - rec.mean(0)) / rec.std(0))[None].contiguous()                  # z-scored per channel (02:134-154), (1, S, C)
+    m = lstm.from_params(params, precision="bf16")
+    with torch.no_grad():
+        probs, attn = m.predict_proba_recordings(rec.to(torch.bfloat16).cuda(), T, step, return_attention=True)
+    assert probs.shape == (n_seq, 2) and torch.isfinite(probs).all()
+    port = torch_port.build_port(params).eval()
+    for lo in (0, 577, n_seq - 16):
+        X = torch.stack([rec[0, (lo + i) * step:(lo + i) * step + T] for i in range(16)])
+        with torch.no_grad():
+            wl, wa = port(X, return_attention=True)
+            wp = torch.softmax(wl, 1)
+        dp = float((probs[lo:lo + 16].cpu() - wp).abs().max())
+        da = float((attn[lo:lo + 16].cpu() - wa).abs().max())
+        print(f"recording view vs oracle, windows {lo}..{lo + 16}: dprob {dp:.3e} dattn {da:.3e}")
+        assert dp <= BF16_TOL["probs"] and da <= BF16_TOL["attn"], (lo, dp, da)
