@@ -1,5 +1,5 @@
 """BASELINE configs[1]: inference sweep, batch 256 ... 65536 windows on one B200, fp32 parity mode and bf16 tensor-core mode.
-Device-resident inputs, CUDA-event timing, >= 3 warm-ups, best of 5 and median; writes a JSON table (profiles/r1_sweep_config2.json)."""
+Device-resident inputs, CUDA-event timing, >= 3 warm-ups, best of 5 and median; writes a JSON table (profiles/r1_sweep_config2.json, r2_sweep_config2.json)."""
 import json, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
@@ -12,7 +12,7 @@ gen = torch.Generator(device="cuda").manual_seed(42)
 xmax = torch.randn((65536, 256, 61), device="cuda", generator=gen)
 for prec in ("bf16", "fp32"):
     m = lstm.from_params(params, precision=prec)
-    for B in (256, 1024, 4096, 16384, 16896, 65536):
+    for B in (256, 1024, 4096, 9472, 16384, 16896, 65536):
         x = xmax[:B]
         reps = 5 if (prec == "bf16" or B <= 16896) else 2
         for _ in range(3 if B <= 16896 else 1):
