@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define BCI_ABI_VERSION 3
+#define BCI_ABI_VERSION 4
 #define BCI_MAX_LAYERS 4
 
 enum {
@@ -98,6 +98,16 @@ int bci_lstm_destroy(bci_lstm_t h);
  * kernels' layouts (transposed fp32 copies; bf16 swizzle-ready copies in BF16 precision).
  * Re-callable after every optimizer step. */
 int bci_lstm_load_weights(bci_lstm_t h, const bci_lstm_weights* w, void* stream);
+
+/* Precision of the TRAINING step (bci_lstm_forward(train=1) + bci_lstm_backward), independent of the handle's inference precision.
+ *   BCI_TRAIN_FP32  (default) fp32-parity step: gradients within 2e-4 of each tensor's max-abs of torch autograd on the reference
+ *                   module in fp32 (04:482-507 without autocast).
+ *   BCI_TRAIN_MIXED the analogue of the reference's own GPU training mode, autocast + GradScaler (04:486-490, 499-503): the two
+ *                   recurrences of every layer run on the tensor cores with 16-bit operands (forward fp16, BPTT bf16 -- bf16 has
+ *                   fp32's exponent range, so no loss scaling is needed) and the large GEMMs in single-pass TF32; accumulators,
+ *                   gates, cell states, LayerNorm, softmax, loss and the optimizer stay fp32.  hidden_size 128 only. */
+enum { BCI_TRAIN_FP32 = 0, BCI_TRAIN_MIXED = 1 };
+int bci_lstm_set_train_mode(bci_lstm_t h, int32_t mode);
 
 /* Optional per-phase device timing for bench.py's roofline (SURVEY.md §8 d).  When enabled, forward
  * records CUDA events on the caller's stream between its phases; bci_lstm_get_profile synchronises
@@ -370,6 +380,16 @@ int bci_selftest_gemm_f16x3(const float* A, const float* B, const float* bias, f
  *   (gate-major rows i,f,g,o); packed: [ND][2][512][128] fp16 scratch (filled here); out [T][Bc][ND*128] fp32 */
 int bci_selftest_rec_f16x3(const float* G, const float* w_hh, void* packed, float* out, int32_t Bc, int32_t T, int32_t ND,
                            void* stream);
+
+/* swapped (weights-as-A-operand) tensor-core recurrences of the mixed-precision training step (csrc/lstm_rec_swap.cu), in isolation:
+ *   G / gates / dG [T*Bc][ND*512] fp32, column dir*512 + unit*4 + gate; out / csave / dout [T][Bc][ND*128] fp32; w_hh [ND][512][128]
+ *   fp32 in the PyTorch layout; packed: 2 x ND x 512 x 128 16-bit values of scratch (filled here) */
+int bci_selftest_rec_swap_fwd(const float* G, const float* w_hh, void* packed, float* out, float* gates, float* csave, int32_t Bc,
+                              int32_t T, int32_t ND, void* stream);
+int bci_selftest_bptt_swap(const float* dout, const float* gates, const float* csave, const float* w_hh, void* packed, float* dG,
+                           int32_t Bc, int32_t T, int32_t ND, void* stream);
+/* layout probe: one M128 x N16 x K16 tcgen05.mma whose A operand is read from tensor memory; out [128][16] fp32 */
+int bci_selftest_tmem_a_probe(float* out, void* stream);
 
 #ifdef __cplusplus
 }

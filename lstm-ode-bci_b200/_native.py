@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-ABI_VERSION = 3   # include/bci_b200.h: BCI_ABI_VERSION
+ABI_VERSION = 4   # include/bci_b200.h: BCI_ABI_VERSION
 LIB_PATH = os.path.join(_PKG, "lib", "libbci_b200.so")
 
 BCI_MAX_LAYERS = 4
@@ -122,6 +122,10 @@ SIGNATURES = {
     "bci_selftest_gemm_tf32x3": (C.c_int, [C.c_int32, _FP, _FP, _FP, _FP, C.c_int32, C.c_int32, C.c_int64, C.c_int32, C.c_void_p]),
     "bci_selftest_gemm_f16x3": (C.c_int, [_FP, _FP, _FP, _FP, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     "bci_selftest_rec_f16x3": (C.c_int, [_FP, _FP, _FP, _FP, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
+    "bci_selftest_rec_swap_fwd": (C.c_int, [_FP, _FP, _FP, _FP, _FP, _FP, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
+    "bci_selftest_bptt_swap": (C.c_int, [_FP, _FP, _FP, _FP, _FP, _FP, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
+    "bci_selftest_tmem_a_probe": (C.c_int, [_FP, C.c_void_p]),
+    "bci_lstm_set_train_mode": (C.c_int, [C.c_void_p, C.c_int32]),
     "bci_fp32_peak_probe": (C.c_int, [C.POINTER(C.c_double), C.c_void_p]),
     "bci_fp64_peak_probe": (C.c_int, [C.POINTER(C.c_double), C.c_void_p]),
 }

@@ -23,6 +23,10 @@ struct PackedF32 {
   // split-precision fp16 operand of the tensor-core recurrence (lstm_fp32_tc.cu, H = 128): [ND][part hi/lo][n' = unit*4 + gate][k],
   // values scaled by 16
   __half* whh16[BCI_MAX_LAYERS];
+  // operands of the swapped tensor-core recurrences of the mixed-precision training step (lstm_rec_swap.cu, H = 128):
+  // whh_sw_f [ND][4H][H] fp16 (PyTorch row order), whh_sw_b [ND][H j][4H k = gate*H + unit] bf16 (the transpose)
+  __half* whh_sw_f[BCI_MAX_LAYERS];
+  __nv_bfloat16* whh_sw_b[BCI_MAX_LAYERS];
   // ... and of the projection GEMM in its fp16-split form (gemm_tf32x3.cu, F16): [part hi/lo][ND*4H gate-interleaved rows][K_l], x 16
   __half* wih16[BCI_MAX_LAYERS];
   __half* w0_16;   // input_proj.0.weight (H, C) zero-padded to K = 64, fp16 (hi, lo) pair x 16
@@ -114,6 +118,10 @@ struct bci_lstm_s {
   // the fp16-split operand copies (whh16 / wih16 / aw1_16 / w0_16) serve the large-batch fp32 INFERENCE path only: they are packed on
   // its first use after a load, so a training loop that reloads the weights every step does not pay for them
   bool f16_stale;
+  // training precision (bci_lstm_set_train_mode): BCI_TRAIN_FP32 (parity) or BCI_TRAIN_MIXED; the mixed step's 16-bit recurrent
+  // operands are packed on its first forward after a load
+  int train_mode;
+  bool sw_stale;
   // the last train=1 forward (workspace + header): a backward on the same workspace needs no device->host read of the header
   void* last_train_ws;
   float last_dropout;
@@ -193,6 +201,13 @@ bool tc_rec_ok(int H, int ND, int Bc, const void* G, int ldg, const void* out, i
 int tc_max_clusters();
 int launch_rec_f16x3(int ND, const float* G, int ldg, const __half* whh16, float* out, __half* out_hi16, __half* out_lo16, float* gates,
                      float* csave, int D, int Bc, int T, cudaStream_t st);
+// swapped (weights-as-A) tensor-core recurrences of the mixed-precision training step (lstm_rec_swap.cu)
+int pack_whh_swap(const float* w_hh, __half* fwd, __nv_bfloat16* bwd, int H, cudaStream_t st);
+bool rec_swap_ok(int H, const void* G, int ldg);
+int launch_rec_swap_fwd(int ND, const float* G, int ldg, const __half* whh, float* out, float* gates, float* csave, int D, int Bc, int T,
+                        cudaStream_t st);
+int launch_bptt_swap(int ND, const float* dout, const float* gates, const float* csave, const __nv_bfloat16* whhT, float* dG, float* dG_lo,
+                     int ldg, int D, int Bc, int T, cudaStream_t st);
 constexpr float F16X3_WSCALE = 16.0f;   // weights of the fp16-split paths are stored x 16 (keeps their lo parts out of fp16's subnormals)
 int split_f16(const float* x, __half* hi, __half* lo, long long n, float scale, cudaStream_t st);
 bool f16x3_nt_ok(const void* A_hi, int lda, const void* W_hi, int ldw, const void* C, int ldc, int M, int N, int K);

@@ -884,6 +884,16 @@ static int forward_train_t(bci_lstm_s* h, const float* x, int B, int T, float p_
   const int C = c.input_size, use_ln = c.use_layer_norm;
   const long long M = (long long)B * T;
   const int rb = (int)((M + 7) / 8 < 4096 ? (M + 7) / 8 : 4096);
+  // mixed-precision step: the recurrences run on the tensor cores with 16-bit operands (lstm_rec_swap.cu)
+  const bool mixed = h->train_mode == BCI_TRAIN_MIXED && rec_swap_ok(H, w.G, 4 * D);
+  if (mixed && h->sw_stale) {
+    for (int l = 0; l < c.num_layers; ++l)
+      for (int d = 0; d < ND; ++d) {
+        int rc = pack_whh_swap(h->raw.w_hh[l][d], p.whh_sw_f[l] + (size_t)d * 4 * H * H, p.whh_sw_b[l] + (size_t)d * 4 * H * H, H, st);
+        if (rc) return rc;
+      }
+    h->sw_stale = false;
+  }
   inproj_train_fwd<H><<<rb, 256, 0, st>>>(x, B, T, C, p.w0t, p.b0, p.ln0w, p.ln0b, w.xT, w.xhat0, w.rstd0, w.z, p_drop * 0.5f, seed, use_ln);
   BCI_LAUNCH_OK();
   const float* in = w.z;
@@ -898,7 +908,8 @@ static int forward_train_t(bci_lstm_s* h, const float* x, int B, int T, float p_
       rc = launch_proj_gemm_f32(in, p.wih_t[l], p.bias[l], w.G, (int)M, 4 * D, K, st);
     }
     if (rc) return rc;
-    rc = launch_rec_f32(H, ND, w.G, p.whh_t[l][0], p.whh_t[l][1], w.out[l], w.gates[l], w.cst[l], B, T, st);
+    if (mixed) rc = launch_rec_swap_fwd(ND, w.G, 4 * D, p.whh_sw_f[l], w.out[l], w.gates[l], w.cst[l], D, B, T, st);
+    else rc = launch_rec_f32(H, ND, w.G, p.whh_t[l][0], p.whh_t[l][1], w.out[l], w.gates[l], w.cst[l], B, T, st);
     if (rc) return rc;
     lo_ready = false;
     if (w.outd[l] != w.out[l]) {
@@ -1051,7 +1062,9 @@ static int backward_t(bci_lstm_s* h, const float* dlogits, int B, int T, float p
     float* dGl_lo = gb ? w.lo_G2 : w.lo_G;
     const bool tc = tf32x3_tn_ok(dGl, G4, in, K, w.tmpW2, K, M, G4, K) && tf32x3_tn_ok(dGl, G4, w.out[l], D, w.tmpW2, H, M - B, 4 * H, H) &&
                     tf32x3_nt_ok(dGl, G4, p.wih_t[l], G4, dnext, K, (int)M, K, G4);
-    if (tiny && H == 128)
+    if (h->train_mode == BCI_TRAIN_MIXED && rec_swap_ok(H, dGl, G4) && !h->sw_stale) {
+      if ((rc = launch_bptt_swap(ND, dcur, w.gates[l], w.cst[l], p.whh_sw_b[l], dGl, tc ? dGl_lo : nullptr, G4, D, B, T, st))) return rc;
+    } else if (tiny && H == 128)
       lstm_bptt_f32<H, 4, BP_RES><<<dim3(ceil_div(B, MT), ND), BP_THREADS, bp_smem + bp_res_bytes, st>>>(dcur, w.gates[l], w.cst[l], p.whh_b[l][0], p.whh_b[l][1], dGl, tc ? dGl_lo : nullptr, B, T, ND);
     else if (tiny)
       lstm_bptt_f32<H, 4><<<dim3(ceil_div(B, MT), ND), BP_THREADS, bp_smem, st>>>(dcur, w.gates[l], w.cst[l], p.whh_b[l][0], p.whh_b[l][1], dGl, tc ? dGl_lo : nullptr, B, T, ND);

@@ -39,6 +39,9 @@ class EnhancedLSTMModel(nn.Module):
         self.num_directions = 2 if bidirectional else 1
         self.input_size, self.num_classes, self.dropout_p = input_size, num_classes, dropout
         self.precision = precision
+        # training step: "fp32" (parity), "mixed" (tensor-core recurrences with 16-bit operands) or "auto" = mixed exactly where the
+        # reference trains in reduced precision, i.e. inside torch.autocast (04:486-490), fp32 elsewhere
+        self.train_precision = "auto"
         d = self.num_directions * hidden_size
         self.input_proj = nn.Sequential(nn.Linear(input_size, hidden_size),
                                         nn.LayerNorm(hidden_size) if use_layer_norm else nn.Identity(),
@@ -63,6 +66,11 @@ class EnhancedLSTMModel(nn.Module):
         if self.precision == "auto":
             return "bf16" if (torch.is_autocast_enabled("cuda") and self.is_full_model and self.hidden_size in (128, 256)) else "fp32"
         return self.precision
+
+    def _train_precision_now(self):
+        if self.train_precision == "auto":
+            return "mixed" if (torch.is_autocast_enabled("cuda") and self.hidden_size == 128) else "fp32"
+        return self.train_precision
 
     def _signature(self):
         return (self._weights_gen,) + tuple((p.data_ptr(), p._version) for p in self.parameters())

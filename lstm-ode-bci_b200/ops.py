@@ -112,6 +112,17 @@ def lstm_load_weights(hid, state):
 PHASES = ("input_proj", "proj_gemm", "recurrence", "pool_head")
 
 
+TRAIN_MODES = {"fp32": 0, "mixed": 1}   # include/bci_b200.h: BCI_TRAIN_FP32 / BCI_TRAIN_MIXED
+
+
+def lstm_set_train_mode(hid, mode):
+    """Precision of the training step of this handle: "fp32" (parity) or "mixed" (16-bit tensor-core recurrences, single-pass TF32
+    GEMMs -- the analogue of the reference's autocast training, 04_lstm_model.py:486-490)."""
+    if mode not in TRAIN_MODES:
+        raise N.BciError(-1, "train precision must be fp32 or mixed")
+    N.check(N.lib().bci_lstm_set_train_mode(_handles[hid].ptr, TRAIN_MODES[mode]))
+
+
 def lstm_set_profiling(hid, enable):
     N.check(N.lib().bci_lstm_set_profiling(_handles[hid].ptr, int(bool(enable))))
 

@@ -28,9 +28,10 @@ class _LstmAttnFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, model, x, want_attn, dropout, seed, *params):
-        hid = model._engine("fp32")          # training runs the fp32 path
+        hid = model._engine("fp32")          # the training step lives on the fp32 engine (fp32 master weights and layouts)
         xc = x.contiguous()
         with torch.cuda.device(xc.device):
+            ops.lstm_set_train_mode(hid, model._train_precision_now())
             logits, attn, ws = ops.lstm_attn_forward_train(xc, hid, float(dropout), int(seed))
         ctx.hid, ctx.ws, ctx.x = hid, ws, xc
         ctx.names = [k for k, _ in model.named_parameters()]
@@ -69,8 +70,14 @@ class FusedTrainer:
     (mark_weights_changed), so a following model.eval()(x) -- fp32 or bf16 engine -- re-packs and sees the new weights."""
 
     def __init__(self, model, lr=3e-4, weight_decay=1e-4, betas=(0.9, 0.999), eps=1e-8, max_norm=1.0, class_weight=None,
-                 process_group=None, collective="auto", accumulation_steps=1):
+                 process_group=None, collective="auto", accumulation_steps=1, precision="fp32"):
+        """precision: "fp32" (parity step) or "mixed" -- the reduced-precision step corresponding to the reference's autocast +
+        GradScaler training (04:486-490,499-503): 16-bit tensor-core recurrences and single-pass TF32 GEMMs, fp32 master weights,
+        loss and optimizer; bf16 carries the gradients through time, so there is no loss scale to maintain."""
         self.model = model
+        if precision not in ops.TRAIN_MODES:
+            raise N.BciError(-1, "precision must be fp32 or mixed")
+        self.precision = precision
         self.lr, self.wd, self.betas, self.eps, self.max_norm = lr, weight_decay, betas, eps, max_norm
         self.pg = process_group
         self.step_count = 0          # optimizer steps taken
@@ -123,6 +130,7 @@ class FusedTrainer:
         with torch.cuda.device(x.device):
             self.hid = model._engine("fp32")          # re-packs the kernel layouts iff the parameters changed since the last pack
             h = ops._handles[self.hid]
+            ops.lstm_set_train_mode(self.hid, self.precision)
             B, T = int(x.shape[0]), int(x.shape[1])
             p_drop = float(model.dropout_p) if model.training else 0.0
             logits = torch.empty((B, model.num_classes), device=x.device, dtype=torch.float32)

@@ -1,0 +1,164 @@
+"""GPU checks of the mixed-precision training step (BCI_TRAIN_MIXED): the swapped tensor-core recurrences of
+csrc/lstm_rec_swap.cu in isolation against float64 recurrences / torch autograd, and the whole step against the fp32-parity step
+and the CPU port of the reference module (oracle/torch_port.py).
+
+Stated tolerances of the mixed mode (forward operands fp16, BPTT operands bf16, single-pass TF32 GEMMs; the reference's own GPU
+training runs under autocast fp16, 04_lstm_model.py:486-490): h_t within 2e-3 of float64; dG within 2 % of max|dG|; loss within
+2e-3 of the fp32 reference; every gradient tensor at cosine >= 0.999 and within 5 % of its max-abs."""
+import numpy as np
+import pytest
+import torch
+
+from lstm_ode_bci_b200 import _native as N
+from lstm_ode_bci_b200 import lstm, synth, train
+from oracle import torch_port
+
+pytestmark = pytest.mark.gpu
+
+
+def _p(t):
+    return t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ref_forward64(G, whh, Bc, T, ND, H=128):
+    """float64 step-by-step recurrence; G [T*Bc][ND*4H] (column dir*4H + unit*4 + gate), whh [ND][4H][H] PyTorch rows.
+    Returns out [T][Bc][ND*H], gates [T][Bc][ND][H][4], c [T][Bc][ND][H] (differentiable wrt G if G requires grad)."""
+    G4 = G.reshape(T, Bc, ND, H, 4)
+    outs = [[None] * ND for _ in range(T)]
+    gates = [[None] * ND for _ in range(T)]
+    cs = [[None] * ND for _ in range(T)]
+    for d in range(ND):
+        w = whh[d]
+        h = torch.zeros(Bc, H, device=G.device, dtype=G.dtype)
+        c = torch.zeros_like(h)
+        for s in range(T):
+            t = T - 1 - s if d else s
+            rec = (h @ w.T).reshape(Bc, 4, H)
+            pre = G4[t, :, d] + rec.permute(0, 2, 1)
+            i, f, gg, o = pre[..., 0].sigmoid(), pre[..., 1].sigmoid(), pre[..., 2].tanh(), pre[..., 3].sigmoid()
+            c = f * c + i * gg
+            h = o * c.tanh()
+            outs[t][d], cs[t][d] = h, c
+            gates[t][d] = torch.stack([i, f, gg, o], dim=-1)
+    out = torch.stack([torch.cat(r, dim=1) for r in outs])
+    gt = torch.stack([torch.stack(r, dim=1) for r in gates])
+    ct = torch.stack([torch.stack(r, dim=1) for r in cs])
+    return out, gt, ct
+
+
+def test_tmem_a_operand_layout_probe():
+    """tcgen05.mma with its A operand in tensor memory: lane = row, 32-bit column c = (K element 2c | K element 2c+1 << 16)."""
+    out = torch.full((128, 16), float("nan"), device="cuda")
+    N.check(N.lib().bci_selftest_tmem_a_probe(_p(out), _stream()))
+    torch.cuda.synchronize()
+    got = out.cpu().numpy()
+    print("TMEM-A probe rows 0, 5, 127:", got[0], got[5], got[127])
+    want = np.tile(np.arange(1, 17, dtype=np.float32), (128, 1))
+    want[5, 0::2] += 100.0
+    assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("Bc,T,ND", [(8, 8, 2), (512, 24, 2), (13, 40, 1), (300, 9, 2)])
+def test_rec_swap_forward_matches_float64(Bc, T, ND):
+    H = 128
+    g = torch.Generator(device="cuda").manual_seed(Bc * 7 + T + ND)
+    whh = ((torch.rand(ND, 4 * H, H, device="cuda", generator=g) * 2 - 1) / np.sqrt(H) * 1.5).contiguous()
+    G = (torch.randn(T * Bc, ND * 4 * H, device="cuda", generator=g) * 1.2).contiguous()
+    packed = torch.empty(2 * ND * 4 * H * H, device="cuda", dtype=torch.float16)
+    out = torch.full((T, Bc, ND * H), float("nan"), device="cuda")
+    gates = torch.full((T * Bc, ND * 4 * H), float("nan"), device="cuda")
+    cs = torch.full((T, Bc, ND * H), float("nan"), device="cuda")
+    N.check(N.lib().bci_selftest_rec_swap_fwd(_p(G), _p(whh), _p(packed), _p(out), _p(gates), _p(cs), Bc, T, ND, _stream()))
+    torch.cuda.synchronize()
+    want, wg, wc = _ref_forward64(G.double(), whh.double(), Bc, T, ND)
+    assert torch.isfinite(out).all() and torch.isfinite(gates).all() and torch.isfinite(cs).all()
+    e_h = float((out.double() - want).abs().max())
+    e_g = float((gates.double().reshape(T, Bc, ND, H, 4) - wg).abs().max())
+    e_c = float((cs.double().reshape(T, Bc, ND, H) - wc).abs().max())
+    print(f"swap forward vs float64: h {e_h:.2e}, gates {e_g:.2e}, c {e_c:.2e} (Bc={Bc}, T={T}, ND={ND})")
+    assert e_h <= 2e-3 and e_g <= 2e-3 and e_c <= 6e-3
+
+
+@pytest.mark.parametrize("Bc,T,ND", [(8, 6, 2), (512, 16, 2), (13, 30, 1)])
+def test_bptt_swap_matches_autograd(Bc, T, ND):
+    H = 128
+    g = torch.Generator(device="cuda").manual_seed(Bc * 3 + T + ND)
+    whh = ((torch.rand(ND, 4 * H, H, device="cuda", generator=g) * 2 - 1) / np.sqrt(H) * 1.5).contiguous()
+    G = (torch.randn(T * Bc, ND * 4 * H, device="cuda", generator=g) * 1.2).contiguous()
+    dout = (torch.randn(T, Bc, ND * H, device="cuda", generator=g) * 1e-3).contiguous()
+    G64 = G.double().requires_grad_(True)
+    out, wg, wc = _ref_forward64(G64, whh.double(), Bc, T, ND)
+    (out * dout.double()).sum().backward()
+    want = G64.grad
+    gates = wg.detach().float().reshape(T * Bc, ND * 4 * H).contiguous()
+    cs = wc.detach().float().reshape(T, Bc, ND * H).contiguous()
+    packed = torch.empty(2 * ND * 4 * H * H, device="cuda", dtype=torch.float16)
+    dG = torch.full((T * Bc, ND * 4 * H), float("nan"), device="cuda")
+    N.check(N.lib().bci_selftest_bptt_swap(_p(dout), _p(gates), _p(cs), _p(whh), _p(packed), _p(dG), Bc, T, ND, _stream()))
+    torch.cuda.synchronize()
+    assert torch.isfinite(dG).all()
+    err = float((dG.double() - want).abs().max() / want.abs().max())
+    cos = float((dG.double() * want).sum() / (dG.double().norm() * want.norm()))
+    print(f"swap BPTT vs autograd: rel-to-max err {err:.2e}, cosine {cos:.6f} (Bc={Bc}, T={T}, ND={ND})")
+    assert err <= 2e-2 and cos >= 0.9995
+
+
+@pytest.mark.parametrize("B,T", [(16, 64), (512, 256)])
+def test_mixed_step_gradients_against_fp32_reference(B, T):
+    """One training step in the mixed mode against torch autograd on the CPU port of the reference module (fp32)."""
+    H = 128
+    params = synth.make_lstm_params(46, 61, H, 3, logit_gain=4.0)
+    x = synth.make_windows(12, B, T, 61)
+    y = (np.arange(B) % 2).astype(np.int64)
+    cw = np.array([0.8, 1.2], dtype=np.float32)
+    port = torch_port.build_port(params, dropout=0.0)
+    loss_ref, g_ref, _dx, _lg = torch_port.loss_and_grads(port, x, y, cw)
+    m = lstm.from_params(params, precision="fp32", dropout=0.0).train()
+    tr = train.FusedTrainer(m, lr=3e-4, weight_decay=1e-4, max_norm=1.0, class_weight=cw, precision="mixed")
+    loss, norm = tr.step(torch.from_numpy(x).cuda(), torch.from_numpy(y).cuda())
+    assert abs(float(loss) - loss_ref) <= 2e-3, (float(loss), loss_ref)
+    worst_cos, worst_rel = 1.0, 0.0
+    for k, _ in m.named_parameters():
+        got, want = tr.grad_views[k].cpu().numpy().astype(np.float64).ravel(), g_ref[k].astype(np.float64).ravel()
+        if k == "attention.attention.2.bias":     # softmax is shift-invariant: this gradient is exactly zero
+            continue
+        cos = float(got @ want / (np.linalg.norm(got) * np.linalg.norm(want) + 1e-300))
+        rel = float(np.abs(got - want).max() / (np.abs(want).max() + 1e-300))
+        worst_cos, worst_rel = min(worst_cos, cos), max(worst_rel, rel)
+        assert cos >= 0.999 and rel <= 5e-2, (k, cos, rel)
+    print(f"mixed step B={B} T={T}: loss {float(loss):.6f} vs {loss_ref:.6f}; worst cosine {worst_cos:.6f}, worst rel-to-max {worst_rel:.2e}")
+
+
+def test_mixed_mode_through_autocast_autograd_bridge():
+    """train_precision='auto': the reference's own loop under torch.autocast (04:486-490) takes the mixed step, without autocast the
+    fp32-parity step; both produce gradients for every parameter."""
+    H, B, T = 128, 8, 32
+    params = synth.make_lstm_params(45, 61, H, 3, logit_gain=4.0)
+    x = torch.from_numpy(synth.make_windows(10, B, T, 61)).cuda()
+    y = (torch.arange(B) % 2).cuda()
+    m = lstm.from_params(params, precision="auto", dropout=0.0).train()
+    grads = {}
+    for mode in ("fp32", "mixed"):
+        m.zero_grad()
+        if mode == "mixed":
+            with torch.autocast("cuda", dtype=torch.float16):
+                assert m._train_precision_now() == "mixed"
+                loss = torch.nn.functional.cross_entropy(m(x).float(), y)
+        else:
+            assert m._train_precision_now() == "fp32"
+            loss = torch.nn.functional.cross_entropy(m(x), y)
+        loss.backward()
+        grads[mode] = {k: p.grad.clone() for k, p in m.named_parameters()}
+    diff = 0.0
+    for k in grads["fp32"]:
+        a, b = grads["fp32"][k].double().ravel(), grads["mixed"][k].double().ravel()
+        if k == "attention.attention.2.bias":
+            continue
+        cos = float(a @ b / (a.norm() * b.norm() + 1e-300))
+        assert cos >= 0.999, (k, cos)
+        diff = max(diff, float((a - b).abs().max()))
+    assert diff > 0.0     # the two modes really are different code paths
