@@ -123,7 +123,7 @@ __host__ __device__ constexpr uint32_t umma_idesc_f16_k(int M, int N) {
 template <bool TN, bool F16>
 __global__ void __launch_bounds__(TX_THREADS, 1)
 gemm_tf32x3_kernel(const __grid_constant__ TxMaps maps, const float* __restrict__ bias, int M, int N, long long K, int k_splits,
-                   int reduce_add, float out_scale) {
+                   int reduce_add, float out_scale, int single) {   // single: plain one-pass product of the hi operands (mixed training mode)
   static_assert(!(TN && F16), "the fp16 split is built for the NT projections only");
   constexpr int BK = F16 ? 2 * TX_BK : TX_BK;   // K values per stage: 128-byte rows of fp16 / fp32
   extern __shared__ uint8_t tx_smem_raw[];
@@ -174,9 +174,20 @@ gemm_tf32x3_kernel(const __grid_constant__ TxMaps maps, const float* __restrict_
         const long long kb0 = ks * kb_per, kb1 = (kb0 + kb_per < kb_total) ? kb0 + kb_per : kb_total;
         for (long long kb = kb0; kb < kb1; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
-          mbar_arrive_expect_tx(full_bar(stage), TX_STAGE);
+          mbar_arrive_expect_tx(full_bar(stage), single ? TX_STAGE / 2 : TX_STAGE);
           const uint32_t s0 = sRing + stage * TX_STAGE;
-          if (TN) {
+          if (single) {
+            if (TN) {
+#pragma unroll
+              for (int g = 0; g < 4; ++g) {
+                tma_load_2d(s0 + g * 4096, &maps.a_hi, mb * TX_BM + g * 32, (int)(kb * TX_BK), full_bar(stage));
+                tma_load_2d(s0 + 2 * TX_TILE + g * 4096, &maps.b_hi, nb * TX_BN + g * 32, (int)(kb * TX_BK), full_bar(stage));
+              }
+            } else {
+              tma_load_2d(s0, &maps.a_hi, (int)(kb * BK), mb * TX_BM, full_bar(stage));
+              tma_load_2d(s0 + 2 * TX_TILE, &maps.b_hi, (int)(kb * BK), nb * TX_BN, full_bar(stage));
+            }
+          } else if (TN) {
             // MN-major tile = four {32 floats, 32 rows} boxes side by side: [group][k row][128 B]
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
@@ -221,7 +232,10 @@ gemm_tf32x3_kernel(const __grid_constant__ TxMaps maps, const float* __restrict_
             const uint64_t bh = TN ? umma_desc_sw128_mn(s0 + 2 * TX_TILE + o) : umma_desc_sw128(s0 + 2 * TX_TILE + o);
             const uint64_t bl = TN ? umma_desc_sw128_mn(s0 + 3 * TX_TILE + o) : umma_desc_sw128(s0 + 3 * TX_TILE + o);
             const uint32_t first = (kb != kb0 || kk != 0) ? 1u : 0u;
-            if (F16) {
+            if (single) {
+              if (F16) umma_f16_1sm(d_tmem, ah, bh, idesc, first);
+              else umma_tf32(d_tmem, ah, bh, idesc, first);
+            } else if (F16) {
               umma_f16_1sm(d_lo, al, bh, idesc, first);
               umma_f16_1sm(d_lo, ah, bl, idesc, 1u);
               umma_f16_1sm(d_tmem, ah, bh, idesc, first);
@@ -261,7 +275,12 @@ gemm_tf32x3_kernel(const __grid_constant__ TxMaps maps, const float* __restrict_
       for (int slab = 0; slab < TX_BN / 32; ++slab) {
         uint32_t r[32], rl[32];
         tmem_ld32(taddr + slab * 32, r);
-        tmem_ld32(taddr + TX_BN + slab * 32, rl);
+        if (single) {
+#pragma unroll
+          for (int q = 0; q < 32; ++q) rl[q] = 0u;
+        } else {
+          tmem_ld32(taddr + TX_BN + slab * 32, rl);
+        }
         if (lane == 0) tma_store_wait_read();  // the staging box has been drained by the previous store
         __syncwarp();
         tmem_ld_wait();
@@ -347,6 +366,10 @@ int gemm_tf32x3_nt(const float* A_hi, const float* A_lo, int lda, const float* W
   int rc = tx_prepare();
   if (rc) return rc;
   TxMaps maps;
+  // A_lo == W_lo == nullptr: single-pass TF32 product (the mixed-precision training step)
+  const int single = (A_lo == nullptr && W_lo == nullptr) ? 1 : 0;
+  BCI_REQUIRE(single || (A_lo && W_lo), BCI_EINVAL, "gemm_tf32x3_nt: both remainders or neither");
+  if (single) { A_lo = A_hi; W_lo = W_hi; }
   if ((rc = make_tmap_f32_2d(&maps.a_hi, A_hi, M, K, lda, TX_BK, TX_BM))) return rc;
   if ((rc = make_tmap_f32_2d(&maps.a_lo, A_lo, M, K, lda, TX_BK, TX_BM))) return rc;
   if ((rc = make_tmap_f32_2d(&maps.b_hi, W_hi, N, K, ldw, TX_BK, TX_BN))) return rc;
@@ -354,7 +377,7 @@ int gemm_tf32x3_nt(const float* A_hi, const float* A_lo, int lda, const float* W
   if ((rc = make_tmap_f32_2d(&maps.c, C, M, N, ldc, 32, 32))) return rc;
   const long long tiles = (long long)ceil_div(M, TX_BM) * ceil_div(N, TX_BN);
   const int grid = (int)(tiles < sm_count() ? tiles : sm_count());
-  gemm_tf32x3_kernel<false, false><<<grid, TX_THREADS, TX_SMEM, st>>>(maps, bias, M, N, (long long)K, 1, accumulate, 1.0f);
+  gemm_tf32x3_kernel<false, false><<<grid, TX_THREADS, TX_SMEM, st>>>(maps, bias, M, N, (long long)K, 1, accumulate, 1.0f, single);
   BCI_LAUNCH_OK();
   return BCI_OK;
 }
@@ -365,6 +388,9 @@ int gemm_tf32x3_tn(const float* A_hi, const float* A_lo, int lda, const float* B
   int rc = tx_prepare();
   if (rc) return rc;
   TxMaps maps;
+  const int single = (A_lo == nullptr && B_lo == nullptr) ? 1 : 0;
+  BCI_REQUIRE(single || (A_lo && B_lo), BCI_EINVAL, "gemm_tf32x3_tn: both remainders or neither");
+  if (single) { A_lo = A_hi; B_lo = B_hi; }
   if ((rc = make_tmap_f32_2d(&maps.a_hi, A_hi, R, P, lda, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))) return rc;
   if ((rc = make_tmap_f32_2d(&maps.a_lo, A_lo, R, P, lda, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))) return rc;
   if ((rc = make_tmap_f32_2d(&maps.b_hi, B_hi, R, Q, ldb, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))) return rc;
@@ -385,7 +411,7 @@ int gemm_tf32x3_tn(const float* A_hi, const float* A_lo, int lda, const float* B
   if (splits > 1) BCI_CUDA_OK(cudaMemset2DAsync(C, (size_t)ldc * 4, 0, (size_t)Q * 4, P, st));
   const long long tiles = out_tiles * splits;
   const int grid = (int)(tiles < sm_count() ? tiles : sm_count());
-  gemm_tf32x3_kernel<true, false><<<grid, TX_THREADS, TX_SMEM, st>>>(maps, nullptr, P, Q, R, (int)splits, splits > 1 ? 1 : 0, 1.0f);
+  gemm_tf32x3_kernel<true, false><<<grid, TX_THREADS, TX_SMEM, st>>>(maps, nullptr, P, Q, R, (int)splits, splits > 1 ? 1 : 0, 1.0f, single);
   BCI_LAUNCH_OK();
   return BCI_OK;
 }
@@ -450,7 +476,7 @@ int gemm_f16x3_nt(const __half* A_hi, const __half* A_lo, int lda, const __half*
   if ((rc = make_tmap_f32_2d(&maps.c, C, M, N, ldc, 32, 32))) return rc;
   const long long tiles = (long long)ceil_div(M, TX_BM) * ceil_div(N, TX_BN);
   const int grid = (int)(tiles < sm_count() ? tiles : sm_count());
-  gemm_tf32x3_kernel<false, true><<<grid, TX_THREADS, TX_SMEM, st>>>(maps, bias, M, N, (long long)K, 1, 0, out_scale);
+  gemm_tf32x3_kernel<false, true><<<grid, TX_THREADS, TX_SMEM, st>>>(maps, bias, M, N, (long long)K, 1, 0, out_scale, 0);
   BCI_LAUNCH_OK();
   return BCI_OK;
 }

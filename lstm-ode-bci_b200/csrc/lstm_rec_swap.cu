@@ -32,13 +32,10 @@ namespace bci {
 using namespace sm100;
 
 constexpr int SW_NW = 8;                     // windows per CTA
-constexpr int SW_THREADS = 128;              // thread = hidden unit
-constexpr uint32_t SW_AATOM = 128 * 128;     // A atom: 128 rows x 64 halves
 constexpr uint32_t SW_BATOM = 16 * 128;      // B atom: 16 rows x 64 halves (rows 8-15 zero)
-constexpr uint32_t SW_A_BYTES = 8 * SW_AATOM;             // forward: [gate 4][K atom 2]; BPTT: [K atom 8]
 constexpr uint32_t SW_FWD_B = 2 * SW_BATOM, SW_BWD_B = 8 * SW_BATOM;
-constexpr size_t SW_FWD_SMEM = 1024 + SW_A_BYTES + SW_FWD_B + 64;
-constexpr size_t SW_BWD_SMEM = 1024 + SW_A_BYTES + SW_BWD_B + 64;
+constexpr size_t SW_FWD_SMEM = 1024 + SW_FWD_B + 64;
+constexpr size_t SW_BWD_SMEM = 1024 + SW_BWD_B + 64;
 
 __host__ __device__ constexpr uint32_t sw_idesc(int M, int N, bool bf16) {
   return (1u << 4) | (bf16 ? ((1u << 7) | (1u << 10)) : 0u) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
@@ -49,6 +46,25 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
                : "r"(taddr) : "memory");
 }
+
+// 32 lanes x 16 consecutive 32-bit columns, registers -> tensor memory
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+               ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+                 "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]) : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// D[tmem] (+)= A[TENSOR MEMORY] * B[smem]^T: A is 128 lanes (rows) x 8 columns per K = 16 slice, column c of a slice = the 16-bit
+// K elements (2c | 2c+1 << 16) (tests/test_gpu_rec_swap.py::test_tmem_a_operand_layout_probe).  Read at TMEM bandwidth: an
+// M128 x N16 x K16 product costs ~8 tensor cycles instead of the 32 its 4 KB A tile needs on the shared-memory port.
+__device__ __forceinline__ void umma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+constexpr uint32_t SW_WCOL = 64;   // first TMEM column of the resident weights (accumulators sit in columns [0, 64))
 
 // ---- operand packing --------------------------------------------------------------------------------------------------------
 // w_hh (4H, H) fp32 -> fp16, same order
@@ -71,141 +87,214 @@ int pack_whh_swap(const float* w_hh, __half* fwd, __nv_bfloat16* bwd, int H, cud
   return BCI_OK;
 }
 
-// common prologue: 1024-aligned dynamic shared memory, one mbarrier, TMEM columns
+// one elected lane of a converged warp (the branch on it is warp-uniform for the compiler: tcgen05 instructions inside are issued
+// back to back instead of inside a per-instruction election loop)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ void tmem_ld2(uint32_t taddr, uint32_t (&r)[2]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void sw_prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+__device__ __forceinline__ float tanh_mufu(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// gate activations of the mixed mode: one MUFU each (sigma(x) = 1/2 + 1/2 tanh(x/2)); ~5e-4 absolute, the size of the fp16
+// operand rounding.  The saved activations are the values actually used, so BPTT differentiates the computed function.
+__device__ __forceinline__ float sw_sigmoid(float x) { return fmaf(tanh_mufu(0.5f * x), 0.5f, 0.5f); }
+
+// Block layout: 16 epilogue warps (thread = hidden unit u = tid % 128, window pair tid / 128: with ONE warp per scheduler the
+// per-step elementwise chain ran at its full dependent latency -- 2 400 cycles for 8 windows -- instead of its issue rate)
+// + one MMA warp.  The two sides meet on two mbarriers only: acc_full (tcgen05.commit) and op_ready (one arrive per epilogue warp).
+constexpr int SW_EPI = 512;
+constexpr int SW_BLOCK = SW_EPI + 32;
+constexpr int SW_WPT = SW_NW / (SW_EPI / 128);   // windows per thread: 2
+
 struct SwCtx {
-  uint32_t base, sA, sB, bar, tmem;
-  uint8_t* gen;
+  uint32_t sB, acc_full, op_ready, tmem;
+  uint8_t* genB;
 };
-template <uint32_t B_BYTES, uint32_t TMEM_COLS>
-__device__ __forceinline__ SwCtx sw_prologue(uint8_t* raw_ptr, const uint4* __restrict__ wsrc, int chunks_per_row) {
+// prologue: barriers, TMEM (512 columns: accumulators at [0, 64), weights at [SW_WCOL, SW_WCOL + 256)), zeroed B tile, and the
+// weights: thread (u, q) stores 64 columns = 128 sixteen-bit K elements of row u: rows are `row_stride` 16-byte chunks apart in
+// global memory and quarter q of the columns starts `q_stride` chunks into ... (forward: q = gate block, rows q*128 + u of
+// [512][16 chunks]; BPTT: q = K quarter of row u of [128][64 chunks])
+template <uint32_t B_BYTES>
+__device__ __forceinline__ SwCtx sw_prologue(uint8_t* raw_ptr, const uint4* __restrict__ wrow) {
   SwCtx c;
   const uint32_t raw = smem_u32(raw_ptr);
-  c.base = (raw + 1023u) & ~1023u;
-  c.gen = raw_ptr + (c.base - raw);
-  c.sA = c.base;
-  c.sB = c.base + SW_A_BYTES;
-  uint8_t* ctl = c.gen + SW_A_BYTES + B_BYTES;
-  c.bar = smem_u32(ctl);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  c.genB = raw_ptr + (base - raw);
+  c.sB = base;
+  uint8_t* ctl = c.genB + B_BYTES;
+  c.acc_full = smem_u32(ctl);
+  c.op_ready = c.acc_full + 8;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ctl + 16);
   const int tid = threadIdx.x;
   if (tid == 0) {
-    mbar_init(c.bar, 1);
+    mbar_init(c.acc_full, 1);
+    mbar_init(c.op_ready, SW_EPI / 32);
     fence_mbar_init();
   }
-  if (tid < 32) {
-    tmem_alloc(smem_u32(tmem_slot), TMEM_COLS);
+  if (tid >= SW_EPI) {
+    tmem_alloc(smem_u32(tmem_slot), 512);
     tmem_relinquish();
   }
-  // weights: global row-major [block][128 rows][chunks_per_row x 8 halves] (128 KB) -> atoms [block][K atom][row][64], SW128
-  const int katoms = chunks_per_row >> 3;
-  for (int i = tid; i < (int)(SW_A_BYTES / 16); i += SW_THREADS) {
-    const int row_g = i / chunks_per_row, cc = i - row_g * chunks_per_row;
-    const int blk = row_g >> 7, row = row_g & 127;
-    const uint4 v = __ldg(wsrc + i);
-    *reinterpret_cast<uint4*>(c.gen + (uint32_t)(blk * katoms + (cc >> 3)) * SW_AATOM + sw128_chunk_off((uint32_t)row, (uint32_t)(cc & 7))) = v;
-  }
-  for (int i = tid; i < (int)(B_BYTES / 16); i += SW_THREADS) reinterpret_cast<uint4*>(c.gen + SW_A_BYTES)[i] = make_uint4(0, 0, 0, 0);
+  for (int i = tid; i < (int)(B_BYTES / 16); i += SW_BLOCK) reinterpret_cast<uint4*>(c.genB)[i] = make_uint4(0, 0, 0, 0);
   fence_proxy_async_smem();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   c.tmem = *tmem_slot;
+  if (tid < SW_EPI) {
+    const int u = tid & 127, q = tid >> 7;
+    const uint32_t dst = c.tmem + ((uint32_t)((u >> 5) * 32) << 16) + SW_WCOL + (uint32_t)q * 64u;
+#pragma unroll 1
+    for (int k = 0; k < 4; ++k) {
+      uint32_t r[16];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const uint4 v = __ldg(wrow + k * 4 + i);
+        r[4 * i] = v.x; r[4 * i + 1] = v.y; r[4 * i + 2] = v.z; r[4 * i + 3] = v.w;
+      }
+      tmem_st16(dst + (uint32_t)k * 16u, r);
+    }
+    tmem_st_wait();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
   return c;
 }
 
+#define SW_STAMP(cond, i) do { if (dbg && st >= 100 && st < 104 && (cond) && blockIdx.x == 0 && blockIdx.y == 0) dbg[(st - 100) * 8 + (i)] = clock64(); } while (0)
+
 // ---- forward --------------------------------------------------------------------------------------------------------------------
 // grid = (ceil(Bc / 8), ND)
-__global__ void __launch_bounds__(SW_THREADS, 1)
+__global__ void __launch_bounds__(SW_BLOCK, 1)
 lstm_rec_swap_fwd(const float* __restrict__ G,        // [T*Bc][ldg] fp32: column dir*512 + unit*4 + gate, bias included
                   int ldg,
                   const __half* __restrict__ whh,     // [ND][512][128] fp16, PyTorch row order
                   float* __restrict__ out,            // [T][Bc][D]: h_t at column dir*128 + unit
                   float* __restrict__ gates,          // optional [T*Bc][ldg] gate ACTIVATIONS, same layout as G
                   float* __restrict__ csave,          // optional [T*Bc][D] cell states
-                  int D, int Bc, int T) {
+                  int D, int Bc, int T, long long* __restrict__ dbg) {
   extern __shared__ uint8_t sw_smem_raw[];
-  const int tid = threadIdx.x, warp = tid >> 5, u = tid;
+  const int tid = threadIdx.x, u = tid & 127, wq = (tid >> 7) & 3;
+  const int warp_u = __shfl_sync(0xffffffffu, tid >> 5, 0);   // warp-uniform for the compiler
   const int dir = blockIdx.y, b0 = blockIdx.x * SW_NW;
-  const SwCtx cx = sw_prologue<SW_FWD_B, 64>(sw_smem_raw, reinterpret_cast<const uint4*>(whh + (size_t)dir * 512 * 128), 16);
-  const uint32_t taddr = cx.tmem + ((uint32_t)(warp * 32) << 16);
+  const SwCtx cx = sw_prologue<SW_FWD_B>(sw_smem_raw, reinterpret_cast<const uint4*>(whh + ((size_t)dir * 512 + wq * 128 + u) * 128));
 
-  // this thread's element of row n of the B tile: k = u
-  uint32_t hoff[SW_NW];
+  if (warp_u == SW_EPI / 32) {
+    // ---- MMA warp: 4 gate blocks x 8 K slices per step, A = resident weights in tensor memory, B = h_{t-1}
+    for (int st = 0; st < T; ++st) {
+      if (st > 0) mbar_wait(cx.op_ready, (uint32_t)((st - 1) & 1));
+      tc_fence_after();
+      if (elect_one()) {
+        SW_STAMP(true, 6);
+        constexpr uint32_t idesc = sw_idesc(128, 16, false);
 #pragma unroll
-  for (int n = 0; n < SW_NW; ++n)
-    hoff[n] = (uint32_t)(u >> 6) * SW_BATOM + (uint32_t)n * 128u + (((uint32_t)((u & 63) >> 3) ^ (uint32_t)n) << 4) + (uint32_t)(u & 7) * 2u;
-  uint8_t* genB = cx.gen + SW_A_BYTES;
-  int brow[SW_NW];
+        for (int g = 0; g < 4; ++g) {
 #pragma unroll
-  for (int n = 0; n < SW_NW; ++n) brow[n] = b0 + n < Bc ? b0 + n : Bc - 1;   // dead windows read a valid row and store nothing
-  const int colg = dir * 512 + u * 4, colh = dir * 128 + u;
-
-  float c[SW_NW];
-  float4 gq[SW_NW];
+          for (int k = 0; k < 8; ++k) {
+            const uint64_t db = umma_desc_sw128(cx.sB + (uint32_t)(k >> 2) * SW_BATOM + (uint32_t)(k & 3) * 32u);
+            umma_f16_ts(cx.tmem + g * 16, cx.tmem + SW_WCOL + g * 64 + k * 8, db, idesc, k != 0 ? 1u : 0u);
+          }
+        }
+        umma_commit(cx.acc_full);
+        SW_STAMP(true, 7);
+      }
+      __syncwarp();
+    }
+  } else {
+    // ---- epilogue warps
+    const uint32_t taddr = cx.tmem + ((uint32_t)((u >> 5) * 32) << 16) + (uint32_t)(wq * SW_WPT);
+    uint32_t hoff[SW_WPT];
+    int brow[SW_WPT];
 #pragma unroll
-  for (int n = 0; n < SW_NW; ++n) c[n] = 0.f;
-  {
-    const int t0 = dir ? T - 1 : 0;
+    for (int i = 0; i < SW_WPT; ++i) {
+      const int n = wq * SW_WPT + i;
+      hoff[i] = (uint32_t)(u >> 6) * SW_BATOM + (uint32_t)n * 128u + (((uint32_t)((u & 63) >> 3) ^ (uint32_t)n) << 4) + (uint32_t)(u & 7) * 2u;
+      brow[i] = b0 + n < Bc ? b0 + n : Bc - 1;   // dead windows read a valid row and store nothing
+    }
+    const int colg = dir * 512 + u * 4, colh = dir * 128 + u;
+    float c[SW_WPT];
+    float4 gq[SW_WPT];
 #pragma unroll
-    for (int n = 0; n < SW_NW; ++n) gq[n] = __ldg(reinterpret_cast<const float4*>(G + ((long long)t0 * Bc + brow[n]) * ldg + colg));
-  }
-  for (int st = 0; st < T; ++st) {
-    const int t = dir ? (T - 1 - st) : st;
-    if (tid == 0) {
-      constexpr uint32_t idesc = sw_idesc(128, 16, false);
+    for (int i = 0; i < SW_WPT; ++i) {
+      c[i] = 0.f;
+      gq[i] = __ldg(reinterpret_cast<const float4*>(G + ((long long)(dir ? T - 1 : 0) * Bc + brow[i]) * ldg + colg));
+    }
+    for (int st = 0; st < T; ++st) {
+      const int t = dir ? (T - 1 - st) : st;
+      SW_STAMP(tid == 0, 0);
+      float4 gc[SW_WPT];
 #pragma unroll
-      for (int g = 0; g < 4; ++g) {
+      for (int i = 0; i < SW_WPT; ++i) gc[i] = gq[i];
+      if (st + 1 < T) {
+        const int tn = dir ? (T - 2 - st) : st + 1;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          const uint64_t da = umma_desc_sw128(cx.sA + (uint32_t)(g * 2 + (k >> 2)) * SW_AATOM + (uint32_t)(k & 3) * 32u);
-          const uint64_t db = umma_desc_sw128(cx.sB + (uint32_t)(k >> 2) * SW_BATOM + (uint32_t)(k & 3) * 32u);
-          umma_bf16(cx.tmem + g * 16, da, db, idesc, k != 0 ? 1u : 0u);
+        for (int i = 0; i < SW_WPT; ++i) gq[i] = __ldg(reinterpret_cast<const float4*>(G + ((long long)tn * Bc + brow[i]) * ldg + colg));
+      }
+      // the register prefetch above covers one step (~1.2 us): not always a DRAM round trip under load.  Pull the rows of
+      // step st + 4 into L2 now (one request per 128-byte line)
+      if (st + 4 < T && (tid & 7) == 0) {
+        const int t4 = dir ? (T - 5 - st) : st + 4;
+#pragma unroll
+        for (int i = 0; i < SW_WPT; ++i) sw_prefetch_l2(G + ((long long)t4 * Bc + brow[i]) * ldg + colg);
+      }
+      SW_STAMP(tid == 0, 1);
+      mbar_wait(cx.acc_full, (uint32_t)(st & 1));
+      tc_fence_after();
+      SW_STAMP(tid == 0, 2);
+      uint32_t a[4][SW_WPT];
+#pragma unroll
+      for (int g = 0; g < 4; ++g) tmem_ld2(taddr + g * 16, a[g]);
+      tmem_ld_wait();
+      SW_STAMP(tid == 0, 3);
+#pragma unroll
+      for (int i = 0; i < SW_WPT; ++i) {
+        const float ig = sw_sigmoid(__uint_as_float(a[0][i]) + gc[i].x);
+        const float fg = sw_sigmoid(__uint_as_float(a[1][i]) + gc[i].y);
+        const float gg = tanh_mufu(__uint_as_float(a[2][i]) + gc[i].z);
+        const float og = sw_sigmoid(__uint_as_float(a[3][i]) + gc[i].w);
+        c[i] = fmaf(fg, c[i], ig * gg);
+        const float hv = og * tanh_mufu(c[i]);
+        *reinterpret_cast<__half*>(cx.genB + hoff[i]) = __float2half_rn(hv);
+        if (b0 + wq * SW_WPT + i < Bc) {
+          const long long row = (long long)t * Bc + b0 + wq * SW_WPT + i;
+          out[row * D + colh] = hv;
+          if (gates) *reinterpret_cast<float4*>(gates + row * ldg + colg) = make_float4(ig, fg, gg, og);
+          if (csave) csave[row * D + colh] = c[i];
         }
       }
-      umma_commit(cx.bar);
+      SW_STAMP(tid == 0, 4);
+      fence_proxy_async_smem();  // h_t (generic-proxy stores) -> visible to the next step's tcgen05.mma
+      tc_fence_before();         // this thread's TMEM reads are ordered before the arrive
+      __syncwarp();
+      if ((tid & 31) == 0) mbar_arrive(cx.op_ready);
+      SW_STAMP(tid == 0, 5);
     }
-    float4 gc[SW_NW];
-#pragma unroll
-    for (int n = 0; n < SW_NW; ++n) gc[n] = gq[n];
-    if (st + 1 < T) {
-      const int tn = dir ? (T - 2 - st) : st + 1;
-#pragma unroll
-      for (int n = 0; n < SW_NW; ++n) gq[n] = __ldg(reinterpret_cast<const float4*>(G + ((long long)tn * Bc + brow[n]) * ldg + colg));
-    }
-    mbar_wait(cx.bar, (uint32_t)(st & 1));
-    tc_fence_after();
-    uint32_t a[4][8];
-#pragma unroll
-    for (int g = 0; g < 4; ++g) tmem_ld8(taddr + g * 16, a[g]);
-    tmem_ld_wait();
-#pragma unroll
-    for (int n = 0; n < SW_NW; ++n) {
-      const float ig = rec_sigmoid(__uint_as_float(a[0][n]) + gc[n].x);
-      const float fg = rec_sigmoid(__uint_as_float(a[1][n]) + gc[n].y);
-      const float gg = rec_tanh(__uint_as_float(a[2][n]) + gc[n].z);
-      const float og = rec_sigmoid(__uint_as_float(a[3][n]) + gc[n].w);
-      c[n] = fmaf(fg, c[n], ig * gg);
-      const float hv = og * rec_tanh(c[n]);
-      if (b0 + n < Bc) {
-        const long long row = (long long)t * Bc + b0 + n;
-        out[row * D + colh] = hv;
-        if (gates) *reinterpret_cast<float4*>(gates + row * ldg + colg) = make_float4(ig, fg, gg, og);
-        if (csave) csave[row * D + colh] = c[n];
-      }
-      *reinterpret_cast<__half*>(genB + hoff[n]) = __float2half_rn(hv);
-    }
-    fence_proxy_async_smem();  // h_t (generic-proxy stores) -> visible to the next step's tcgen05.mma
-    tc_fence_before();         // this thread's TMEM reads are ordered before the barrier
-    __syncthreads();
-    tc_fence_after();
   }
-  if (tid < 32) tmem_dealloc(cx.tmem, 64);
+  tc_fence_before();
+  __syncthreads();
+  if (warp_u == SW_EPI / 32) {
+    tc_fence_after();
+    tmem_dealloc(cx.tmem, 512);
+  }
 }
 
 // ---- BPTT -----------------------------------------------------------------------------------------------------------------------
 // The mirror of lstm_bptt_f32 (lstm_train.cu): walks the direction's time order backwards, dG_t to global (fp32, + optional tf32
 // remainder for the split-precision GEMMs) and, as bf16, into the B tile of  dh_{t-1}[j] = sum_k dG_t[k] W_hh[k][j].
-__global__ void __launch_bounds__(SW_THREADS, 1)
+__global__ void __launch_bounds__(SW_BLOCK, 1)
 lstm_bptt_swap(const float* __restrict__ dout,           // [T][Bc][D]
                const float* __restrict__ gates,          // [T*Bc][ldg]: i,f,g,o of (dir, unit) at column dir*512 + unit*4
                const float* __restrict__ csave,          // [T*Bc][D]
@@ -214,118 +303,130 @@ lstm_bptt_swap(const float* __restrict__ dout,           // [T][Bc][D]
                float* __restrict__ dG_lo,                // optional
                int ldg, int D, int Bc, int T) {
   extern __shared__ uint8_t sw_smem_raw[];
-  const int tid = threadIdx.x, warp = tid >> 5, u = tid;
+  const int tid = threadIdx.x, u = tid & 127, wq = (tid >> 7) & 3;
+  const int warp_u = __shfl_sync(0xffffffffu, tid >> 5, 0);
   const int dir = blockIdx.y, b0 = blockIdx.x * SW_NW;
-  const SwCtx cx = sw_prologue<SW_BWD_B, 32>(sw_smem_raw, reinterpret_cast<const uint4*>(whhT + (size_t)dir * 512 * 128), 64);
-  const uint32_t taddr = cx.tmem + ((uint32_t)(warp * 32) << 16);
-  uint8_t* genB = cx.gen + SW_A_BYTES;
-  // element (row n, k = gate*128 + u) of the B tile: atom gate*2 + u/64
-  uint32_t boff[SW_NW];
-#pragma unroll
-  for (int n = 0; n < SW_NW; ++n)
-    boff[n] = (uint32_t)(u >> 6) * SW_BATOM + (uint32_t)n * 128u + (((uint32_t)((u & 63) >> 3) ^ (uint32_t)n) << 4) + (uint32_t)(u & 7) * 2u;
-  int brow[SW_NW];
-#pragma unroll
-  for (int n = 0; n < SW_NW; ++n) brow[n] = b0 + n < Bc ? b0 + n : Bc - 1;
-  const int colg = dir * 512 + u * 4, colh = dir * 128 + u;
+  const SwCtx cx = sw_prologue<SW_BWD_B>(sw_smem_raw, reinterpret_cast<const uint4*>(whhT + ((size_t)dir * 128 + u) * 512 + wq * 128));
 
-  float dh_rec[SW_NW], dc[SW_NW];
+  if (warp_u == SW_EPI / 32) {
+    for (int s = T - 1; s > 0; --s) {
+      mbar_wait(cx.op_ready, (uint32_t)((T - 1 - s) & 1));
+      tc_fence_after();
+      if (elect_one()) {
+        constexpr uint32_t idesc = sw_idesc(128, 16, true);
 #pragma unroll
-  for (int n = 0; n < SW_NW; ++n) { dh_rec[n] = 0.f; dc[n] = 0.f; }
-  float4 pg[SW_NW];
-  float pc[SW_NW], pcp[SW_NW], pdo[SW_NW];
-  auto fetch = [&](int s, float4* g4, float* cc, float* cp, float* dd) {
-    const int t = dir ? (T - 1 - s) : s;
-    const int tp = dir ? (t + 1) : (t - 1);
-#pragma unroll
-    for (int n = 0; n < SW_NW; ++n) {
-      const long long row = (long long)t * Bc + brow[n];
-      g4[n] = __ldg(reinterpret_cast<const float4*>(gates + row * ldg + colg));
-      if (cc) cc[n] = __ldg(csave + row * D + colh);
-      cp[n] = (s > 0) ? __ldg(csave + ((long long)tp * Bc + brow[n]) * D + colh) : 0.f;
-      dd[n] = __ldg(dout + row * D + colh);
+        for (int k = 0; k < 32; ++k) {
+          const uint64_t db = umma_desc_sw128(cx.sB + (uint32_t)(k >> 2) * SW_BATOM + (uint32_t)(k & 3) * 32u);
+          umma_f16_ts(cx.tmem, cx.tmem + SW_WCOL + k * 8, db, idesc, k != 0 ? 1u : 0u);
+        }
+        umma_commit(cx.acc_full);
+      }
+      __syncwarp();
     }
-  };
-  fetch(T - 1, pg, pc, pcp, pdo);
-  for (int s = T - 1; s >= 0; --s) {
-    const int t = dir ? (T - 1 - s) : s;
+  } else {
+    const uint32_t taddr = cx.tmem + ((uint32_t)((u >> 5) * 32) << 16) + (uint32_t)(wq * SW_WPT);
+    // element (row n, k = gate*128 + u) of the B tile: atom gate*2 + u/64
+    uint32_t boff[SW_WPT];
+    int brow[SW_WPT];
 #pragma unroll
-    for (int n = 0; n < SW_NW; ++n) {
-      float4 dg = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (b0 + n < Bc) {
-        const float4 g = pg[n];
-        const float dh = pdo[n] + dh_rec[n];
-        const float tc = rec_tanh(pc[n]);  // the forward's own tanh(c)
-        const float dct = fmaf(dh * g.w, 1.0f - tc * tc, dc[n]);
-        dg.x = dct * g.z * g.x * (1.0f - g.x);
-        dg.y = dct * pcp[n] * g.y * (1.0f - g.y);
-        dg.z = dct * g.x * (1.0f - g.z * g.z);
-        dg.w = dh * tc * g.w * (1.0f - g.w);
-        dc[n] = dct * g.y;
-        const long long row = (long long)t * Bc + b0 + n;
-        *reinterpret_cast<float4*>(dG + row * ldg + colg) = dg;
-        if (dG_lo) {
-          auto lo = [](float x) {
-            const float rem = x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
-            uint32_t r;
-            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(rem));
-            return __uint_as_float(r);
-          };
-          *reinterpret_cast<float4*>(dG_lo + row * ldg + colg) = make_float4(lo(dg.x), lo(dg.y), lo(dg.z), lo(dg.w));
+    for (int i = 0; i < SW_WPT; ++i) {
+      const int n = wq * SW_WPT + i;
+      boff[i] = (uint32_t)(u >> 6) * SW_BATOM + (uint32_t)n * 128u + (((uint32_t)((u & 63) >> 3) ^ (uint32_t)n) << 4) + (uint32_t)(u & 7) * 2u;
+      brow[i] = b0 + n < Bc ? b0 + n : Bc - 1;
+    }
+    const int colg = dir * 512 + u * 4, colh = dir * 128 + u;
+    float dh_rec[SW_WPT], dc[SW_WPT];
+    float4 pg[SW_WPT];
+    float pc[SW_WPT], pcp[SW_WPT], pdo[SW_WPT];
+#pragma unroll
+    for (int i = 0; i < SW_WPT; ++i) { dh_rec[i] = 0.f; dc[i] = 0.f; }
+    auto fetch = [&](int s, float4* g4, float* cc, float* cp, float* dd) {
+      const int t = dir ? (T - 1 - s) : s;
+      const int tp = dir ? (t + 1) : (t - 1);
+#pragma unroll
+      for (int i = 0; i < SW_WPT; ++i) {
+        const long long row = (long long)t * Bc + brow[i];
+        g4[i] = __ldg(reinterpret_cast<const float4*>(gates + row * ldg + colg));
+        if (cc) cc[i] = __ldg(csave + row * D + colh);
+        cp[i] = (s > 0) ? __ldg(csave + ((long long)tp * Bc + brow[i]) * D + colh) : 0.f;
+        dd[i] = __ldg(dout + row * D + colh);
+      }
+    };
+    fetch(T - 1, pg, pc, pcp, pdo);
+    for (int s = T - 1; s >= 0; --s) {
+      const int t = dir ? (T - 1 - s) : s;
+#pragma unroll
+      for (int i = 0; i < SW_WPT; ++i) {
+        float4 dg = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (b0 + wq * SW_WPT + i < Bc) {
+          const float4 g = pg[i];
+          const float dh = pdo[i] + dh_rec[i];
+          const float tc = tanh_mufu(pc[i]);  // the forward's own tanh(c)
+          const float dct = fmaf(dh * g.w, 1.0f - tc * tc, dc[i]);
+          dg.x = dct * g.z * g.x * (1.0f - g.x);
+          dg.y = dct * pcp[i] * g.y * (1.0f - g.y);
+          dg.z = dct * g.x * (1.0f - g.z * g.z);
+          dg.w = dh * tc * g.w * (1.0f - g.w);
+          dc[i] = dct * g.y;
+          const long long row = (long long)t * Bc + b0 + wq * SW_WPT + i;
+          *reinterpret_cast<float4*>(dG + row * ldg + colg) = dg;
+          if (dG_lo) {
+            auto lo = [](float x) {
+              const float rem = x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
+              uint32_t r;
+              asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(rem));
+              return __uint_as_float(r);
+            };
+            *reinterpret_cast<float4*>(dG_lo + row * ldg + colg) = make_float4(lo(dg.x), lo(dg.y), lo(dg.z), lo(dg.w));
+          }
+        }
+        if (s > 0) {
+          *reinterpret_cast<__nv_bfloat16*>(cx.genB + 0 * 2 * SW_BATOM + boff[i]) = __float2bfloat16_rn(dg.x);
+          *reinterpret_cast<__nv_bfloat16*>(cx.genB + 1 * 2 * SW_BATOM + boff[i]) = __float2bfloat16_rn(dg.y);
+          *reinterpret_cast<__nv_bfloat16*>(cx.genB + 2 * 2 * SW_BATOM + boff[i]) = __float2bfloat16_rn(dg.z);
+          *reinterpret_cast<__nv_bfloat16*>(cx.genB + 3 * 2 * SW_BATOM + boff[i]) = __float2bfloat16_rn(dg.w);
         }
       }
-      if (s > 0) {
-        *reinterpret_cast<__nv_bfloat16*>(genB + 0 * 2 * SW_BATOM + boff[n]) = __float2bfloat16_rn(dg.x);
-        *reinterpret_cast<__nv_bfloat16*>(genB + 1 * 2 * SW_BATOM + boff[n]) = __float2bfloat16_rn(dg.y);
-        *reinterpret_cast<__nv_bfloat16*>(genB + 2 * 2 * SW_BATOM + boff[n]) = __float2bfloat16_rn(dg.z);
-        *reinterpret_cast<__nv_bfloat16*>(genB + 3 * 2 * SW_BATOM + boff[n]) = __float2bfloat16_rn(dg.w);
-      }
-    }
-    if (s == 0) break;
-    fence_proxy_async_smem();
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    if (tid == 0) {
-      constexpr uint32_t idesc = sw_idesc(128, 16, true);
+      if (s == 0) break;
+      fence_proxy_async_smem();
+      tc_fence_before();
+      __syncwarp();
+      if ((tid & 31) == 0) mbar_arrive(cx.op_ready);
+      // step s-1's saved activations are requested while the product runs; c(s-1) is this step's cprev
+      float4 ng[SW_WPT];
+      float ncp[SW_WPT], ndo[SW_WPT];
+      fetch(s - 1, ng, nullptr, ncp, ndo);
+      if (s >= 4) {   // rows of step s - 4 -> L2
+        const int t4 = dir ? (T - 1 - (s - 4)) : s - 4;
 #pragma unroll
-      for (int k = 0; k < 32; ++k) {
-        const uint64_t da = umma_desc_sw128(cx.sA + (uint32_t)(k >> 2) * SW_AATOM + (uint32_t)(k & 3) * 32u);
-        const uint64_t db = umma_desc_sw128(cx.sB + (uint32_t)(k >> 2) * SW_BATOM + (uint32_t)(k & 3) * 32u);
-        umma_bf16(cx.tmem, da, db, idesc, k != 0 ? 1u : 0u);
+        for (int i = 0; i < SW_WPT; ++i) {
+          const long long row = (long long)t4 * Bc + brow[i];
+          if ((tid & 7) == 0) sw_prefetch_l2(gates + row * ldg + colg);
+          if ((tid & 31) == 0) { sw_prefetch_l2(csave + row * D + colh); sw_prefetch_l2(dout + row * D + colh); }
+        }
       }
-      umma_commit(cx.bar);
-    }
-    // step s-1's saved activations are requested while the product runs; c(s-1) is this step's cprev
-    float4 ng[SW_NW];
-    float ncp[SW_NW], ndo[SW_NW];
-    fetch(s - 1, ng, nullptr, ncp, ndo);
-    mbar_wait(cx.bar, (uint32_t)((T - 1 - s) & 1));
-    tc_fence_after();
-    uint32_t a[8];
-    tmem_ld8(taddr, a);
-    tmem_ld_wait();
+      mbar_wait(cx.acc_full, (uint32_t)((T - 1 - s) & 1));
+      tc_fence_after();
+      uint32_t a[SW_WPT];
+      tmem_ld2(taddr, a);
+      tmem_ld_wait();
 #pragma unroll
-    for (int n = 0; n < SW_NW; ++n) {
-      dh_rec[n] = __uint_as_float(a[n]);
-      pc[n] = pcp[n]; pg[n] = ng[n]; pcp[n] = ncp[n]; pdo[n] = ndo[n];
+      for (int i = 0; i < SW_WPT; ++i) {
+        dh_rec[i] = __uint_as_float(a[i]);
+        pc[i] = pcp[i]; pg[i] = ng[i]; pcp[i] = ncp[i]; pdo[i] = ndo[i];
+      }
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (tid < 32) tmem_dealloc(cx.tmem, 32);
+  if (warp_u == SW_EPI / 32) {
+    tc_fence_after();
+    tmem_dealloc(cx.tmem, 512);
+  }
 }
 
-static int sw_setup() {
-  static PerDeviceFlag done_pd;
-  bool& done = done_pd.cur();
-  if (!done) {
-    BCI_CUDA_OK(cudaFuncSetAttribute(lstm_rec_swap_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SW_FWD_SMEM));
-    BCI_CUDA_OK(cudaFuncSetAttribute(lstm_bptt_swap, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SW_BWD_SMEM));
-    done = true;
-  }
-  return BCI_OK;
-}
+static int sw_setup() { return BCI_OK; }
+static long long* g_sw_dbg = nullptr;   // selftest only: clock stamps of CTA (0, 0)
 
 bool rec_swap_ok(int H, const void* G, int ldg) { return H == 128 && ((uintptr_t)G & 15) == 0 && (ldg & 3) == 0; }
 
@@ -333,7 +434,7 @@ int launch_rec_swap_fwd(int ND, const float* G, int ldg, const __half* whh, floa
                         cudaStream_t st) {
   int rc = sw_setup();
   if (rc) return rc;
-  lstm_rec_swap_fwd<<<dim3(ceil_div(Bc, SW_NW), ND), SW_THREADS, SW_FWD_SMEM, st>>>(G, ldg, whh, out, gates, csave, D, Bc, T);
+  lstm_rec_swap_fwd<<<dim3(ceil_div(Bc, SW_NW), ND), SW_BLOCK, SW_FWD_SMEM, st>>>(G, ldg, whh, out, gates, csave, D, Bc, T, g_sw_dbg);
   BCI_LAUNCH_OK();
   return BCI_OK;
 }
@@ -342,7 +443,7 @@ int launch_bptt_swap(int ND, const float* dout, const float* gates, const float*
                      int ldg, int D, int Bc, int T, cudaStream_t st) {
   int rc = sw_setup();
   if (rc) return rc;
-  lstm_bptt_swap<<<dim3(ceil_div(Bc, SW_NW), ND), SW_THREADS, SW_BWD_SMEM, st>>>(dout, gates, csave, whhT, dG, dG_lo, ldg, D, Bc, T);
+  lstm_bptt_swap<<<dim3(ceil_div(Bc, SW_NW), ND), SW_BLOCK, SW_BWD_SMEM, st>>>(dout, gates, csave, whhT, dG, dG_lo, ldg, D, Bc, T);
   BCI_LAUNCH_OK();
   return BCI_OK;
 }
@@ -436,6 +537,11 @@ extern "C" int bci_selftest_bptt_swap(const float* dout, const float* gates, con
     if (rc) return rc;
   }
   return launch_bptt_swap(ND, dout, gates, csave, b, dG, nullptr, ND * 512, ND * 128, Bc, T, st);
+}
+/* selftest only: clock64 stamps (8 per step, steps 100-103) of CTA (0,0) of the next forward launches; NULL switches them off */
+extern "C" int bci_selftest_swap_set_debug(long long* stamps) {
+  bci::g_sw_dbg = stamps;
+  return BCI_OK;
 }
 extern "C" int bci_selftest_tmem_a_probe(float* out, void* stream) {
   using namespace bci;

@@ -902,8 +902,10 @@ static int forward_train_t(bci_lstm_s* h, const float* x, int B, int T, float p_
     const int K = layer_in_width(c, l);
     int rc;
     if (tf32x3_nt_ok(in, K, p.wih_b[l], K, w.G, 4 * D, (int)M, 4 * D, K)) {
-      if (!lo_ready && (rc = split_tf32(in, nullptr, w.lo_in, M * K, st))) return rc;
-      rc = gemm_tf32x3_nt(in, w.lo_in, K, p.wih_b[l], p.wih_b_lo[l], K, p.bias[l], w.G, 4 * D, (int)M, 4 * D, K, 0, st);
+      // mixed mode: one TF32 pass over the raw operands, no remainders
+      if (!mixed && !lo_ready && (rc = split_tf32(in, nullptr, w.lo_in, M * K, st))) return rc;
+      rc = gemm_tf32x3_nt(in, mixed ? nullptr : w.lo_in, K, p.wih_b[l], mixed ? nullptr : p.wih_b_lo[l], K, p.bias[l], w.G, 4 * D, (int)M,
+                          4 * D, K, 0, st);
     } else {
       rc = launch_proj_gemm_f32(in, p.wih_t[l], p.bias[l], w.G, (int)M, 4 * D, K, st);
     }
@@ -913,9 +915,10 @@ static int forward_train_t(bci_lstm_s* h, const float* x, int B, int T, float p_
     if (rc) return rc;
     lo_ready = false;
     if (w.outd[l] != w.out[l]) {
-      scale_mask_kernel<<<(unsigned)ceil_div64(M * D, 256), 256, 0, st>>>(w.out[l], w.outd[l], M * D, p_drop, seed, 16 + l, w.lo_in);
+      scale_mask_kernel<<<(unsigned)ceil_div64(M * D, 256), 256, 0, st>>>(w.out[l], w.outd[l], M * D, p_drop, seed, 16 + l,
+                                                                          mixed ? nullptr : w.lo_in);
       BCI_LAUNCH_OK();
-      lo_ready = w.lo_in != nullptr;
+      lo_ready = w.lo_in != nullptr && !mixed;
     }
     in = w.outd[l];
   }
@@ -925,8 +928,8 @@ static int forward_train_t(bci_lstm_s* h, const float* x, int B, int T, float p_
   int rc = BCI_OK;
   if (c.use_attention) {
     if (tf32x3_nt_ok(w.Y, D, p.aw1, D, w.PRE, AH, (int)M, AH, D)) {
-      if ((rc = split_tf32(w.Y, nullptr, w.lo_in, M * D, st))) return rc;
-      rc = gemm_tf32x3_nt(w.Y, w.lo_in, D, p.aw1, p.aw1_lo, D, p.ab1, w.PRE, AH, (int)M, AH, D, 0, st);
+      if (!mixed && (rc = split_tf32(w.Y, nullptr, w.lo_in, M * D, st))) return rc;
+      rc = gemm_tf32x3_nt(w.Y, mixed ? nullptr : w.lo_in, D, p.aw1, mixed ? nullptr : p.aw1_lo, D, p.ab1, w.PRE, AH, (int)M, AH, D, 0, st);
     } else {
       rc = gemm_nn(w.Y, D, p.aw1t, AH, w.PRE, AH, (int)M, AH, D, p.ab1, 0, st);
     }
@@ -973,6 +976,7 @@ static int backward_t(bci_lstm_s* h, const float* dlogits, int B, int T, float p
   auto zero = [&](float* ptr, size_t n) { return cudaMemsetAsync(ptr, 0, n * sizeof(float), st); };
   auto zero_on = [&](cudaStream_t s2, float* ptr, size_t n) { return cudaMemsetAsync(ptr, 0, n * sizeof(float), s2); };
   int rc;
+  const bool mixed = h->train_mode == BCI_TRAIN_MIXED && rec_swap_ok(H, w.G, G4) && !h->sw_stale;
   // ---- head ----
   head_train_bwd<H><<<B, H, 0, st>>>(dlogits, cls, w.pre1, w.pre2, raw.cls_w6, raw.cls_w3, raw.cls_w0, w.dpre1, w.dpre2, w.dctx,
                                        p_drop, seed, D);
@@ -1000,10 +1004,10 @@ static int backward_t(bci_lstm_s* h, const float* dlogits, int B, int T, float p
     // dY += dPRE . W1 ; dW1 = dPRE^T Y ; db1 = colsum(dPRE)
     if (tf32x3_nt_ok(dPRE, AH, p.aw1t, AH, w.dA, D, (int)M, D, AH) && tf32x3_tn_ok(dPRE, AH, w.Y, D, g->attn_w1, D, M, AH, D)) {
       // lo_in / lo_out2 are free here: the forward is over and the side stream starts after the top layer's BPTT
-      if ((rc = split_tf32(dPRE, nullptr, w.lo_in, M * AH, st))) return rc;
-      if ((rc = split_tf32(w.Y, nullptr, w.lo_out2, M * D, st))) return rc;
-      if ((rc = gemm_tf32x3_nt(dPRE, w.lo_in, AH, p.aw1t, p.aw1t_lo, AH, nullptr, w.dA, D, (int)M, D, AH, 1, st))) return rc;
-      if ((rc = gemm_tf32x3_tn(dPRE, w.lo_in, AH, w.Y, w.lo_out2, D, g->attn_w1, D, M, AH, D, st))) return rc;
+      if (!mixed && (rc = split_tf32(dPRE, nullptr, w.lo_in, M * AH, st))) return rc;
+      if (!mixed && (rc = split_tf32(w.Y, nullptr, w.lo_out2, M * D, st))) return rc;
+      if ((rc = gemm_tf32x3_nt(dPRE, mixed ? nullptr : w.lo_in, AH, p.aw1t, mixed ? nullptr : p.aw1t_lo, AH, nullptr, w.dA, D, (int)M, D, AH, 1, st))) return rc;
+      if ((rc = gemm_tf32x3_tn(dPRE, mixed ? nullptr : w.lo_in, AH, w.Y, mixed ? nullptr : w.lo_out2, D, g->attn_w1, D, M, AH, D, st))) return rc;
     } else {
       if ((rc = gemm_nn(dPRE, AH, raw.attn_w1, D, w.dA, D, (int)M, D, AH, nullptr, 1, st))) return rc;
       if ((rc = gemm_tn(dPRE, AH, w.Y, D, g->attn_w1, D, M, AH, D, st))) return rc;
@@ -1062,8 +1066,8 @@ static int backward_t(bci_lstm_s* h, const float* dlogits, int B, int T, float p
     float* dGl_lo = gb ? w.lo_G2 : w.lo_G;
     const bool tc = tf32x3_tn_ok(dGl, G4, in, K, w.tmpW2, K, M, G4, K) && tf32x3_tn_ok(dGl, G4, w.out[l], D, w.tmpW2, H, M - B, 4 * H, H) &&
                     tf32x3_nt_ok(dGl, G4, p.wih_t[l], G4, dnext, K, (int)M, K, G4);
-    if (h->train_mode == BCI_TRAIN_MIXED && rec_swap_ok(H, dGl, G4) && !h->sw_stale) {
-      if ((rc = launch_bptt_swap(ND, dcur, w.gates[l], w.cst[l], p.whh_sw_b[l], dGl, tc ? dGl_lo : nullptr, G4, D, B, T, st))) return rc;
+    if (mixed) {
+      if ((rc = launch_bptt_swap(ND, dcur, w.gates[l], w.cst[l], p.whh_sw_b[l], dGl, nullptr, G4, D, B, T, st))) return rc;
     } else if (tiny && H == 128)
       lstm_bptt_f32<H, 4, BP_RES><<<dim3(ceil_div(B, MT), ND), BP_THREADS, bp_smem + bp_res_bytes, st>>>(dcur, w.gates[l], w.cst[l], p.whh_b[l][0], p.whh_b[l][1], dGl, tc ? dGl_lo : nullptr, B, T, ND);
     else if (tiny)
@@ -1077,9 +1081,9 @@ static int backward_t(bci_lstm_s* h, const float* dlogits, int B, int T, float p
     BCI_CUDA_OK(cudaStreamWaitEvent(sd, h->ev_dg, 0));
     // dW_ih (all directions at once, interleaved rows) = dG^T . in
     if (tc) {
-      if ((rc = split_tf32(in, nullptr, w.lo_in2, M * K, sd))) return rc;
-      if ((rc = gemm_tf32x3_tn(dGl, dGl_lo, G4, in, w.lo_in2, K, w.tmpW2, K, M, G4, K, sd))) return rc;
-      if ((rc = split_tf32(w.out[l], nullptr, w.lo_out2, M * D, sd))) return rc;
+      if (!mixed && (rc = split_tf32(in, nullptr, w.lo_in2, M * K, sd))) return rc;
+      if ((rc = gemm_tf32x3_tn(dGl, mixed ? nullptr : dGl_lo, G4, in, mixed ? nullptr : w.lo_in2, K, w.tmpW2, K, M, G4, K, sd))) return rc;
+      if (!mixed && (rc = split_tf32(w.out[l], nullptr, w.lo_out2, M * D, sd))) return rc;
     } else {
       BCI_CUDA_OK(zero_on(sd, w.tmpW2, (size_t)G4 * K));
       if ((rc = gemm_tn(dGl, G4, in, K, w.tmpW2, K, M, G4, K, sd))) return rc;
@@ -1095,7 +1099,7 @@ static int backward_t(bci_lstm_s* h, const float* dlogits, int B, int T, float p
       const float* Ad = dGl + offA;
       const float* Bd = w.out[l] + offB;
       if (tc) {
-        if ((rc = gemm_tf32x3_tn(Ad, dGl_lo + offA, G4, Bd, w.lo_out2 + offB, D, w.tmpW2, H, R, 4 * H, H, sd))) return rc;
+        if ((rc = gemm_tf32x3_tn(Ad, mixed ? nullptr : dGl_lo + offA, G4, Bd, mixed ? nullptr : w.lo_out2 + offB, D, w.tmpW2, H, R, 4 * H, H, sd))) return rc;
       } else {
         BCI_CUDA_OK(zero_on(sd, w.tmpW2, (size_t)4 * H * H));
         if ((rc = gemm_tn(Ad, G4, Bd, D, w.tmpW2, H, R, 4 * H, H, sd))) return rc;
@@ -1114,7 +1118,7 @@ static int backward_t(bci_lstm_s* h, const float* dlogits, int B, int T, float p
     used[gb] = 1;
     // grad wrt the layer input: dnext [M][K] = dG . wih_b
     if (tc) {
-      if ((rc = gemm_tf32x3_nt(dGl, dGl_lo, G4, p.wih_t[l], p.wih_t_lo[l], G4, nullptr, dnext, K, (int)M, K, G4, 0, st))) return rc;
+      if ((rc = gemm_tf32x3_nt(dGl, mixed ? nullptr : dGl_lo, G4, p.wih_t[l], mixed ? nullptr : p.wih_t_lo[l], G4, nullptr, dnext, K, (int)M, K, G4, 0, st))) return rc;
     } else if ((rc = gemm_nn(dGl, G4, p.wih_b[l], K, dnext, K, (int)M, K, G4, nullptr, 0, st))) {
       return rc;
     }

@@ -45,6 +45,17 @@ def main():
     dG = torch.empty_like(gates)
     st = torch.cuda.current_stream().cuda_stream
     lib = N.lib()
+    stamps = torch.zeros(32, dtype=torch.int64, device="cuda")
+    lib.bci_selftest_swap_set_debug(stamps.data_ptr())
+    N.check(lib.bci_selftest_rec_swap_fwd(G.data_ptr(), whh.data_ptr(), packed.data_ptr(), out.data_ptr(), gates.data_ptr(), cs.data_ptr(), B, T, ND, st))
+    torch.cuda.synchronize()
+    lib.bci_selftest_swap_set_debug(None)
+    sv = stamps.cpu().numpy().reshape(4, 8)
+    print("forward timeline of CTA (0,0), SM cycles per phase [G prefetch, acc wait, tmem ld, epilogue, fence+arrive | (6,7) = MMA warp issue start, after commit] and step:")
+    for r in range(4):
+        d = np.diff(sv[r])
+        nxt = (sv[r + 1][0] - sv[r][0]) if r < 3 else 0
+        print("   ", d.tolist(), "step", int(nxt))
     ms = timed(lambda: N.check(lib.bci_selftest_rec_swap_fwd(G.data_ptr(), whh.data_ptr(), packed.data_ptr(), out.data_ptr(), gates.data_ptr(), cs.data_ptr(), B, T, ND, st)), steps)
     print(f"swap forward recurrence (incl. 4 pack launches): {ms:.3f} ms per layer = {ms * 1e3 / T:.2f} us per step")
     dout = torch.randn_like(out) * 1e-3
