@@ -496,9 +496,10 @@ def main():
         xt = x[:tb].contiguous()
         yt = (torch.arange(tb, device="cuda") % 2)
 
-        def make_trainer(collective):
+        def make_trainer(collective, precision="fp32"):
             tm = lstm.from_params(params, precision="fp32", device=f"cuda:{local}", dropout=0.4).train()
-            return tm, train.FusedTrainer(tm, lr=3e-4, weight_decay=1e-4, max_norm=1.0, class_weight=[0.8, 1.2], collective=collective)
+            return tm, train.FusedTrainer(tm, lr=3e-4, weight_decay=1e-4, max_norm=1.0, class_weight=[0.8, 1.2], collective=collective,
+                                          precision=precision)
         tmodel, trainer = make_trainer("auto")          # p2p fused step when world > 1
         seeds = iter(range(10_000))
         tms = timed(lambda: trainer.step(xt, yt, seed=next(seeds)), 5, 2)
@@ -553,6 +554,24 @@ def main():
         else:
             trainer.close()
         del trainer
+        # the same step in the mixed mode (BCI_TRAIN_MIXED: the reference's own GPU training runs under autocast + GradScaler,
+        # 04:486-490): 16-bit tensor-core recurrences with W_hh resident in tensor memory, single-pass TF32 GEMMs
+        barrier()
+        mmodel, mtrainer = make_trainer("auto", "mixed")
+        mms = timed(lambda: mtrainer.step(xt, yt, seed=next(seeds)), 5, 2)
+        loss_m, norm_m = mtrainer.step(xt, yt, seed=next(seeds))
+        line["train_step_mixed"] = {"value": world * tb / (mms * 1e-3), "unit": "windows/s", "ms_per_step": mms, "windows_per_gpu": tb,
+                                    "precision": "mixed (fp16 / bf16 recurrence operands, TF32 GEMMs, fp32 accumulation and state)",
+                                    "tflops_per_gpu": tb * 3 * FLOP_PER_WINDOW / (mms * 1e-3) / 1e12,
+                                    "loss": float(loss_m), "grad_norm": float(norm_m)}
+        tail["train_mixed_ms_per_step"] = round(mms, 3)
+        tail["train_mixed_windows_s"] = round(world * tb / (mms * 1e-3), 1)
+        if world > 1:
+            hs = all_ranks(float(mtrainer.flat.view(torch.int32).to(torch.int64).sum() % (1 << 40)))
+            checks["mixed_replicas_bit_identical"] = bool(len(set(hs)) == 1)
+            barrier()
+        mtrainer.close()
+        del mtrainer, mmodel
         # fp32 parity mode of the inference forward (BASELINE configs[1] lists fp32 next to bf16): one full pass of its pair recurrence
         # (bci_lstm_chunk_windows: 9472 windows on 148 SMs); the whole LSTM stack runs on the tensor cores in split fp16 precision
         tmodel.eval()

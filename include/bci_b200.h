@@ -383,9 +383,10 @@ int bci_selftest_rec_f16x3(const float* G, const float* w_hh, void* packed, floa
 
 /* swapped (weights-as-A-operand) tensor-core recurrences of the mixed-precision training step (csrc/lstm_rec_swap.cu), in isolation:
  *   G / gates / dG [T*Bc][ND*512] fp32, column dir*512 + unit*4 + gate; out / csave / dout [T][Bc][ND*128] fp32; w_hh [ND][512][128]
- *   fp32 in the PyTorch layout; packed: 2 x ND x 512 x 128 16-bit values of scratch (filled here) */
+ *   fp32 in the PyTorch layout; packed: 5 x ND x 512 x 128 16-bit values of scratch (filled here); split != 0: the fp32-parity form
+ *   of the forward (three fp16 product chains, accurate gate activations) */
 int bci_selftest_rec_swap_fwd(const float* G, const float* w_hh, void* packed, float* out, float* gates, float* csave, int32_t Bc,
-                              int32_t T, int32_t ND, void* stream);
+                              int32_t T, int32_t ND, int32_t split, void* stream);
 int bci_selftest_bptt_swap(const float* dout, const float* gates, const float* csave, const float* w_hh, void* packed, float* dG,
                            int32_t Bc, int32_t T, int32_t ND, void* stream);
 /* selftest only: clock64 stamps (8 per step, steps 100-103; int64[32]) of CTA (0,0) of the following swapped forward launches */

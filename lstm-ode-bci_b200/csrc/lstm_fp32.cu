@@ -419,7 +419,7 @@ int lstm_pack_f32(bci_lstm_s* h, cudaStream_t st) {
 size_t lstm_store_bytes_f32(const bci_lstm_config& c) {
   const size_t H = c.hidden_size, C = c.input_size, D = 2 * H;
   size_t n = C * H + 3 * H;
-  for (int l = 0; l < c.num_layers; ++l) n += 4 * ((size_t)layer_in_width(c, l) * 8 * H) + 2 * (2 * H * 4 * H) + 8 * H + 2 * 4 * H * H + (size_t)layer_in_width(c, l) * 8 * H + 2 * (4 * H * H);
+  for (int l = 0; l < c.num_layers; ++l) n += 4 * ((size_t)layer_in_width(c, l) * 8 * H) + 2 * (2 * H * 4 * H) + 8 * H + 2 * 4 * H * H + (size_t)layer_in_width(c, l) * 8 * H + 5 * (4 * H * H);
   n += 2 * D + 5 * D * H + 64 * H + H + H + 4 + D * H + H + H * (H / 2) + H / 2 + (size_t)c.num_classes * (H / 2) + c.num_classes + 64;
   return align_up(n * sizeof(float) + 256 * 80, 256);
 }
@@ -443,8 +443,9 @@ void lstm_carve_f32(bci_lstm_s* h, char* base) {
     p.wih_t_lo[l] = take((size_t)layer_in_width(c, l) * 8 * H);
     p.whh16[l] = reinterpret_cast<__half*>(take(2 * 4 * H * H));   // 2 directions x 2 parts x 4H x H halves
     p.wih16[l] = reinterpret_cast<__half*>(take((size_t)layer_in_width(c, l) * 8 * H));   // 2 parts x 8H x K_l halves
-    p.whh_sw_f[l] = reinterpret_cast<__half*>(take(4 * H * H));          // 2 directions x 4H x H halves
+    p.whh_sw_f[l] = reinterpret_cast<__half*>(take(2 * 4 * H * H));      // 2 directions x 2 parts x 4H x H halves
     p.whh_sw_b[l] = reinterpret_cast<__nv_bfloat16*>(take(4 * H * H));   // 2 directions x H x 4H bf16
+    p.whh_sw_b16[l] = reinterpret_cast<__half*>(take(2 * 4 * H * H));    // 2 directions x 2 parts x H x 4H halves
   }
   p.lnw = take(D); p.lnb = take(D); p.aw1t = take(D * H); p.ab1 = take(H); p.aw2 = take(H); p.ab2 = take(4);
   p.aw1 = take(D * H); p.aw1_lo = take(D * H); p.aw1t_lo = take(D * H);

@@ -24,9 +24,11 @@ struct PackedF32 {
   // values scaled by 16
   __half* whh16[BCI_MAX_LAYERS];
   // operands of the swapped tensor-core recurrences of the mixed-precision training step (lstm_rec_swap.cu, H = 128):
-  // whh_sw_f [ND][4H][H] fp16 (PyTorch row order), whh_sw_b [ND][H j][4H k = gate*H + unit] bf16 (the transpose)
+  // whh_sw_f [ND][part hi/lo][4H][H] fp16 of 16 w (PyTorch row order); the transpose [H j][4H k = gate*H + unit] as bf16
+  // (whh_sw_b [ND][H][4H]) and as an fp16 pair of 16 w (whh_sw_b16 [ND][part][H][4H])
   __half* whh_sw_f[BCI_MAX_LAYERS];
   __nv_bfloat16* whh_sw_b[BCI_MAX_LAYERS];
+  __half* whh_sw_b16[BCI_MAX_LAYERS];
   // ... and of the projection GEMM in its fp16-split form (gemm_tf32x3.cu, F16): [part hi/lo][ND*4H gate-interleaved rows][K_l], x 16
   __half* wih16[BCI_MAX_LAYERS];
   __half* w0_16;   // input_proj.0.weight (H, C) zero-padded to K = 64, fp16 (hi, lo) pair x 16
@@ -202,10 +204,10 @@ int tc_max_clusters();
 int launch_rec_f16x3(int ND, const float* G, int ldg, const __half* whh16, float* out, __half* out_hi16, __half* out_lo16, float* gates,
                      float* csave, int D, int Bc, int T, cudaStream_t st);
 // swapped (weights-as-A) tensor-core recurrences of the mixed-precision training step (lstm_rec_swap.cu)
-int pack_whh_swap(const float* w_hh, __half* fwd, __nv_bfloat16* bwd, int H, cudaStream_t st);
+int pack_whh_swap(const float* w_hh, __half* fwd, __nv_bfloat16* bwd, __half* bwd16, int H, cudaStream_t st);
 bool rec_swap_ok(int H, const void* G, int ldg);
 int launch_rec_swap_fwd(int ND, const float* G, int ldg, const __half* whh, float* out, float* gates, float* csave, int D, int Bc, int T,
-                        cudaStream_t st);
+                        bool split, cudaStream_t st);
 int launch_bptt_swap(int ND, const float* dout, const float* gates, const float* csave, const __nv_bfloat16* whhT, float* dG, float* dG_lo,
                      int ldg, int D, int Bc, int T, cudaStream_t st);
 constexpr float F16X3_WSCALE = 16.0f;   // weights of the fp16-split paths are stored x 16 (keeps their lo parts out of fp16's subnormals)

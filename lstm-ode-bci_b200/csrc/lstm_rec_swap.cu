@@ -34,8 +34,11 @@ using namespace sm100;
 constexpr int SW_NW = 8;                     // windows per CTA
 constexpr uint32_t SW_BATOM = 16 * 128;      // B atom: 16 rows x 64 halves (rows 8-15 zero)
 constexpr uint32_t SW_FWD_B = 2 * SW_BATOM, SW_BWD_B = 8 * SW_BATOM;
-constexpr size_t SW_FWD_SMEM = 1024 + SW_FWD_B + 64;
-constexpr size_t SW_BWD_SMEM = 1024 + SW_BWD_B + 64;
+constexpr uint32_t SW_AATOM = 128 * 128;     // A atom in shared memory (split mode: the weights' lo parts): 128 rows x 64 halves
+constexpr uint32_t SW_ALO_BYTES = 8 * SW_AATOM;   // forward: [gate 4][K atom 2]; BPTT: [K atom 8]
+constexpr float SW_WSCALE = 16.0f;           // weights are stored x 16 (keeps the lo parts out of fp16's subnormals)
+// SPLIT (fp32-parity step): weights hi in tensor memory, weights lo in shared memory, B tile as an fp16 (hi, lo) pair
+constexpr size_t sw_smem_bytes(uint32_t b_bytes, bool split) { return 1024 + (split ? SW_ALO_BYTES + 2 * b_bytes : b_bytes) + 64; }
 
 __host__ __device__ constexpr uint32_t sw_idesc(int M, int N, bool bf16) {
   return (1u << 4) | (bf16 ? ((1u << 7) | (1u << 10)) : 0u) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
@@ -67,22 +70,31 @@ __device__ __forceinline__ void umma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, ui
 constexpr uint32_t SW_WCOL = 64;   // first TMEM column of the resident weights (accumulators sit in columns [0, 64))
 
 // ---- operand packing --------------------------------------------------------------------------------------------------------
-// w_hh (4H, H) fp32 -> fp16, same order
+// w_hh (4H, H) fp32 -> [part hi/lo][4H][H] fp16 of 16 w, same row order
 __global__ void pack_whh_swap_fwd_kernel(const float* __restrict__ w, __half* __restrict__ dst, int n) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) dst[i] = __float2half_rn(w[i]);
+  if (i >= n) return;
+  const float v = w[i] * SW_WSCALE;
+  const __half hi = __float2half_rn(v);
+  dst[i] = hi;
+  dst[n + i] = __float2half_rn(v - __half2float(hi));
 }
-// w_hh (4H, H) fp32 -> dst [j][k = gate*H + unit] bf16 = w_hh[k][j]
-__global__ void pack_whh_swap_bwd_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ dst, int H) {
+// w_hh (4H, H) fp32 -> the transpose [j][k = gate*H + unit] = w_hh[k][j]: bf16 (mixed BPTT) and an fp16 (hi, lo) pair of 16 w
+__global__ void pack_whh_swap_bwd_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ dst, __half* __restrict__ dst16, int H) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= 4 * H * H) return;
   const int j = i / (4 * H), k = i - j * 4 * H;
-  dst[i] = __float2bfloat16_rn(w[(size_t)k * H + j]);
+  const float v = w[(size_t)k * H + j];
+  dst[i] = __float2bfloat16_rn(v);
+  const __half hi = __float2half_rn(v * SW_WSCALE);
+  dst16[i] = hi;
+  dst16[4 * H * H + i] = __float2half_rn(v * SW_WSCALE - __half2float(hi));
 }
-int pack_whh_swap(const float* w_hh, __half* fwd, __nv_bfloat16* bwd, int H, cudaStream_t st) {
+// fwd [2][4H][H] fp16, bwd [H][4H] bf16, bwd16 [2][H][4H] fp16
+int pack_whh_swap(const float* w_hh, __half* fwd, __nv_bfloat16* bwd, __half* bwd16, int H, cudaStream_t st) {
   pack_whh_swap_fwd_kernel<<<ceil_div(4 * H * H, 256), 256, 0, st>>>(w_hh, fwd, 4 * H * H);
   BCI_LAUNCH_OK();
-  pack_whh_swap_bwd_kernel<<<ceil_div(4 * H * H, 256), 256, 0, st>>>(w_hh, bwd, H);
+  pack_whh_swap_bwd_kernel<<<ceil_div(4 * H * H, 256), 256, 0, st>>>(w_hh, bwd, bwd16, H);
   BCI_LAUNCH_OK();
   return BCI_OK;
 }
@@ -119,21 +131,34 @@ constexpr int SW_BLOCK = SW_EPI + 32;
 constexpr int SW_WPT = SW_NW / (SW_EPI / 128);   // windows per thread: 2
 
 struct SwCtx {
-  uint32_t sB, acc_full, op_ready, tmem;
+  uint32_t sA, sB, acc_full, op_ready, tmem;
   uint8_t* genB;
 };
 // prologue: barriers, TMEM (512 columns: accumulators at [0, 64), weights at [SW_WCOL, SW_WCOL + 256)), zeroed B tile, and the
 // weights: thread (u, q) stores 64 columns = 128 sixteen-bit K elements of row u: rows are `row_stride` 16-byte chunks apart in
 // global memory and quarter q of the columns starts `q_stride` chunks into ... (forward: q = gate block, rows q*128 + u of
 // [512][16 chunks]; BPTT: q = K quarter of row u of [128][64 chunks])
-template <uint32_t B_BYTES>
-__device__ __forceinline__ SwCtx sw_prologue(uint8_t* raw_ptr, const uint4* __restrict__ wrow) {
+// SPLIT: `wlo` (global, row-major [block][128 rows][chunks_per_row x 8 halves], 128 KB) additionally goes to shared memory as K-major
+// SWIZZLE_128B atoms [block][K atom][row][64 halves] in front of the B tiles (hi tile, then lo tile)
+template <uint32_t B_BYTES, bool SPLIT>
+__device__ __forceinline__ SwCtx sw_prologue(uint8_t* raw_ptr, const uint4* __restrict__ wrow, const uint4* __restrict__ wlo, int chunks_per_row) {
+  constexpr uint32_t B_ALL = SPLIT ? 2 * B_BYTES : B_BYTES;
   SwCtx c;
   const uint32_t raw = smem_u32(raw_ptr);
   const uint32_t base = (raw + 1023u) & ~1023u;
-  c.genB = raw_ptr + (base - raw);
-  c.sB = base;
-  uint8_t* ctl = c.genB + B_BYTES;
+  uint8_t* genA = raw_ptr + (base - raw);
+  c.sA = base;
+  c.genB = genA + (SPLIT ? SW_ALO_BYTES : 0u);
+  c.sB = base + (SPLIT ? SW_ALO_BYTES : 0u);
+  uint8_t* ctl = c.genB + B_ALL;
+  if (SPLIT) {
+    const int katoms = chunks_per_row >> 3;
+    for (int i = threadIdx.x; i < (int)(SW_ALO_BYTES / 16); i += SW_BLOCK) {
+      const int row_g = i / chunks_per_row, cc = i - row_g * chunks_per_row;
+      const int blk = row_g >> 7, row = row_g & 127;
+      *reinterpret_cast<uint4*>(genA + (uint32_t)(blk * katoms + (cc >> 3)) * SW_AATOM + sw128_chunk_off((uint32_t)row, (uint32_t)(cc & 7))) = __ldg(wlo + i);
+    }
+  }
   c.acc_full = smem_u32(ctl);
   c.op_ready = c.acc_full + 8;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ctl + 16);
@@ -147,7 +172,7 @@ __device__ __forceinline__ SwCtx sw_prologue(uint8_t* raw_ptr, const uint4* __re
     tmem_alloc(smem_u32(tmem_slot), 512);
     tmem_relinquish();
   }
-  for (int i = tid; i < (int)(B_BYTES / 16); i += SW_BLOCK) reinterpret_cast<uint4*>(c.genB)[i] = make_uint4(0, 0, 0, 0);
+  for (int i = tid; i < (int)(B_ALL / 16); i += SW_BLOCK) reinterpret_cast<uint4*>(c.genB)[i] = make_uint4(0, 0, 0, 0);
   fence_proxy_async_smem();
   tc_fence_before();
   __syncthreads();
@@ -177,11 +202,14 @@ __device__ __forceinline__ SwCtx sw_prologue(uint8_t* raw_ptr, const uint4* __re
 #define SW_STAMP(cond, i) do { if (dbg && st >= 100 && st < 104 && (cond) && blockIdx.x == 0 && blockIdx.y == 0) dbg[(st - 100) * 8 + (i)] = clock64(); } while (0)
 
 // ---- forward --------------------------------------------------------------------------------------------------------------------
-// grid = (ceil(Bc / 8), ND)
+// grid = (ceil(Bc / 8), ND).  SPLIT = the fp32-parity form: h . W_hh^T as three fp16 product chains  lo.hi + hi.lo + hi.hi  (the small
+// terms first: the tensor core adds into TMEM with truncation), accurate (ex2-based) gate activations -- the arithmetic of
+// lstm_fp32_tc.cu's pair kernel; W_hi lives in tensor memory, W_lo (128 KB) in shared memory.
+template <bool SPLIT>
 __global__ void __launch_bounds__(SW_BLOCK, 1)
 lstm_rec_swap_fwd(const float* __restrict__ G,        // [T*Bc][ldg] fp32: column dir*512 + unit*4 + gate, bias included
                   int ldg,
-                  const __half* __restrict__ whh,     // [ND][512][128] fp16, PyTorch row order
+                  const __half* __restrict__ whh,     // [ND][2 parts][512][128] fp16 of 16 w, PyTorch row order
                   float* __restrict__ out,            // [T][Bc][D]: h_t at column dir*128 + unit
                   float* __restrict__ gates,          // optional [T*Bc][ldg] gate ACTIVATIONS, same layout as G
                   float* __restrict__ csave,          // optional [T*Bc][D] cell states
@@ -190,7 +218,9 @@ lstm_rec_swap_fwd(const float* __restrict__ G,        // [T*Bc][ldg] fp32: colum
   const int tid = threadIdx.x, u = tid & 127, wq = (tid >> 7) & 3;
   const int warp_u = __shfl_sync(0xffffffffu, tid >> 5, 0);   // warp-uniform for the compiler
   const int dir = blockIdx.y, b0 = blockIdx.x * SW_NW;
-  const SwCtx cx = sw_prologue<SW_FWD_B>(sw_smem_raw, reinterpret_cast<const uint4*>(whh + ((size_t)dir * 512 + wq * 128 + u) * 128));
+  const __half* wdir = whh + (size_t)dir * 2 * 512 * 128;
+  const SwCtx cx = sw_prologue<SW_FWD_B, SPLIT>(sw_smem_raw, reinterpret_cast<const uint4*>(wdir + ((size_t)wq * 128 + u) * 128),
+                                                reinterpret_cast<const uint4*>(wdir + 512 * 128), 16);
 
   if (warp_u == SW_EPI / 32) {
     // ---- MMA warp: 4 gate blocks x 8 K slices per step, A = resident weights in tensor memory, B = h_{t-1}
@@ -202,10 +232,23 @@ lstm_rec_swap_fwd(const float* __restrict__ G,        // [T*Bc][ldg] fp32: colum
         constexpr uint32_t idesc = sw_idesc(128, 16, false);
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
+          if (SPLIT) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {   // W_lo (shared memory) . h_hi
+              const uint64_t da = umma_desc_sw128(cx.sA + (uint32_t)(g * 2 + (k >> 2)) * SW_AATOM + (uint32_t)(k & 3) * 32u);
+              const uint64_t db = umma_desc_sw128(cx.sB + (uint32_t)(k >> 2) * SW_BATOM + (uint32_t)(k & 3) * 32u);
+              umma_bf16(cx.tmem + g * 16, da, db, idesc, k != 0 ? 1u : 0u);
+            }
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {   // W_hi (tensor memory) . h_lo
+              const uint64_t db = umma_desc_sw128(cx.sB + SW_FWD_B + (uint32_t)(k >> 2) * SW_BATOM + (uint32_t)(k & 3) * 32u);
+              umma_f16_ts(cx.tmem + g * 16, cx.tmem + SW_WCOL + g * 64 + k * 8, db, idesc, 1u);
+            }
+          }
 #pragma unroll
           for (int k = 0; k < 8; ++k) {
             const uint64_t db = umma_desc_sw128(cx.sB + (uint32_t)(k >> 2) * SW_BATOM + (uint32_t)(k & 3) * 32u);
-            umma_f16_ts(cx.tmem + g * 16, cx.tmem + SW_WCOL + g * 64 + k * 8, db, idesc, k != 0 ? 1u : 0u);
+            umma_f16_ts(cx.tmem + g * 16, cx.tmem + SW_WCOL + g * 64 + k * 8, db, idesc, (SPLIT || k != 0) ? 1u : 0u);
           }
         }
         umma_commit(cx.acc_full);
@@ -261,13 +304,17 @@ lstm_rec_swap_fwd(const float* __restrict__ G,        // [T*Bc][ldg] fp32: colum
       SW_STAMP(tid == 0, 3);
 #pragma unroll
       for (int i = 0; i < SW_WPT; ++i) {
-        const float ig = sw_sigmoid(__uint_as_float(a[0][i]) + gc[i].x);
-        const float fg = sw_sigmoid(__uint_as_float(a[1][i]) + gc[i].y);
-        const float gg = tanh_mufu(__uint_as_float(a[2][i]) + gc[i].z);
-        const float og = sw_sigmoid(__uint_as_float(a[3][i]) + gc[i].w);
+        const float pi = fmaf(__uint_as_float(a[0][i]), 1.0f / SW_WSCALE, gc[i].x), pf = fmaf(__uint_as_float(a[1][i]), 1.0f / SW_WSCALE, gc[i].y);
+        const float pg = fmaf(__uint_as_float(a[2][i]), 1.0f / SW_WSCALE, gc[i].z), po = fmaf(__uint_as_float(a[3][i]), 1.0f / SW_WSCALE, gc[i].w);
+        const float ig = SPLIT ? rec_sigmoid(pi) : sw_sigmoid(pi);
+        const float fg = SPLIT ? rec_sigmoid(pf) : sw_sigmoid(pf);
+        const float gg = SPLIT ? rec_tanh(pg) : tanh_mufu(pg);
+        const float og = SPLIT ? rec_sigmoid(po) : sw_sigmoid(po);
         c[i] = fmaf(fg, c[i], ig * gg);
-        const float hv = og * tanh_mufu(c[i]);
-        *reinterpret_cast<__half*>(cx.genB + hoff[i]) = __float2half_rn(hv);
+        const float hv = og * (SPLIT ? rec_tanh(c[i]) : tanh_mufu(c[i]));
+        const __half hh = __float2half_rn(hv);
+        *reinterpret_cast<__half*>(cx.genB + hoff[i]) = hh;
+        if (SPLIT) *reinterpret_cast<__half*>(cx.genB + SW_FWD_B + hoff[i]) = __float2half_rn(hv - __half2float(hh));
         if (b0 + wq * SW_WPT + i < Bc) {
           const long long row = (long long)t * Bc + b0 + wq * SW_WPT + i;
           out[row * D + colh] = hv;
@@ -306,7 +353,7 @@ lstm_bptt_swap(const float* __restrict__ dout,           // [T][Bc][D]
   const int tid = threadIdx.x, u = tid & 127, wq = (tid >> 7) & 3;
   const int warp_u = __shfl_sync(0xffffffffu, tid >> 5, 0);
   const int dir = blockIdx.y, b0 = blockIdx.x * SW_NW;
-  const SwCtx cx = sw_prologue<SW_BWD_B>(sw_smem_raw, reinterpret_cast<const uint4*>(whhT + ((size_t)dir * 128 + u) * 512 + wq * 128));
+  const SwCtx cx = sw_prologue<SW_BWD_B, false>(sw_smem_raw, reinterpret_cast<const uint4*>(whhT + ((size_t)dir * 128 + u) * 512 + wq * 128), nullptr, 64);
 
   if (warp_u == SW_EPI / 32) {
     for (int s = T - 1; s > 0; --s) {
@@ -425,16 +472,26 @@ lstm_bptt_swap(const float* __restrict__ dout,           // [T][Bc][D]
   }
 }
 
-static int sw_setup() { return BCI_OK; }
+static int sw_setup() {
+  static PerDeviceFlag done_pd;
+  bool& done = done_pd.cur();
+  if (!done) {
+    BCI_CUDA_OK(cudaFuncSetAttribute(lstm_rec_swap_fwd<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sw_smem_bytes(SW_FWD_B, true)));
+    done = true;
+  }
+  return BCI_OK;
+}
 static long long* g_sw_dbg = nullptr;   // selftest only: clock stamps of CTA (0, 0)
 
 bool rec_swap_ok(int H, const void* G, int ldg) { return H == 128 && ((uintptr_t)G & 15) == 0 && (ldg & 3) == 0; }
 
 int launch_rec_swap_fwd(int ND, const float* G, int ldg, const __half* whh, float* out, float* gates, float* csave, int D, int Bc, int T,
-                        cudaStream_t st) {
+                        bool split, cudaStream_t st) {
   int rc = sw_setup();
   if (rc) return rc;
-  lstm_rec_swap_fwd<<<dim3(ceil_div(Bc, SW_NW), ND), SW_BLOCK, SW_FWD_SMEM, st>>>(G, ldg, whh, out, gates, csave, D, Bc, T, g_sw_dbg);
+  const dim3 grid(ceil_div(Bc, SW_NW), ND);
+  if (split) lstm_rec_swap_fwd<true><<<grid, SW_BLOCK, sw_smem_bytes(SW_FWD_B, true), st>>>(G, ldg, whh, out, gates, csave, D, Bc, T, g_sw_dbg);
+  else lstm_rec_swap_fwd<false><<<grid, SW_BLOCK, sw_smem_bytes(SW_FWD_B, false), st>>>(G, ldg, whh, out, gates, csave, D, Bc, T, g_sw_dbg);
   BCI_LAUNCH_OK();
   return BCI_OK;
 }
@@ -443,7 +500,7 @@ int launch_bptt_swap(int ND, const float* dout, const float* gates, const float*
                      int ldg, int D, int Bc, int T, cudaStream_t st) {
   int rc = sw_setup();
   if (rc) return rc;
-  lstm_bptt_swap<<<dim3(ceil_div(Bc, SW_NW), ND), SW_BLOCK, SW_BWD_SMEM, st>>>(dout, gates, csave, whhT, dG, dG_lo, ldg, D, Bc, T);
+  lstm_bptt_swap<<<dim3(ceil_div(Bc, SW_NW), ND), SW_BLOCK, sw_smem_bytes(SW_BWD_B, false), st>>>(dout, gates, csave, whhT, dG, dG_lo, ldg, D, Bc, T);
   BCI_LAUNCH_OK();
   return BCI_OK;
 }
@@ -511,18 +568,29 @@ __global__ void __launch_bounds__(128, 1) tmem_a_probe_kernel(float* __restrict_
 }  // namespace bci
 
 // diagnostics (tests/test_gpu_rec_swap.py): the swapped recurrences in isolation, fp32 weights in the PyTorch layout
+// scratch layout: fwd [ND][2][512][128] fp16 | bwd [ND][128][512] bf16 | bwd16 [ND][2][128][512] fp16  = 5 ND 65 536 sixteen-bit values
+static int sw_selftest_pack(const float* w_hh, void* packed, int ND, __half** f, __nv_bfloat16** b, __half** b16, cudaStream_t st) {
+  using namespace bci;
+  const size_t W = 512 * 128;
+  *f = reinterpret_cast<__half*>(packed);
+  *b = reinterpret_cast<__nv_bfloat16*>(*f + (size_t)ND * 2 * W);
+  *b16 = reinterpret_cast<__half*>(*b + (size_t)ND * W);
+  for (int d = 0; d < ND; ++d) {
+    int rc = pack_whh_swap(w_hh + d * W, *f + d * 2 * W, *b + d * W, *b16 + d * 2 * W, 128, st);
+    if (rc) return rc;
+  }
+  return BCI_OK;
+}
 extern "C" int bci_selftest_rec_swap_fwd(const float* G, const float* w_hh, void* packed, float* out, float* gates, float* csave, int32_t Bc,
-                                         int32_t T, int32_t ND, void* stream) {
+                                         int32_t T, int32_t ND, int32_t split, void* stream) {
   using namespace bci;
   BCI_REQUIRE(G && w_hh && packed && out && Bc >= 1 && T >= 1 && (ND == 1 || ND == 2), BCI_EINVAL, "bci_selftest_rec_swap_fwd: bad arguments");
   cudaStream_t st = (cudaStream_t)stream;
-  __half* f = reinterpret_cast<__half*>(packed);
-  __nv_bfloat16* b = reinterpret_cast<__nv_bfloat16*>(f + (size_t)ND * 512 * 128);
-  for (int d = 0; d < ND; ++d) {
-    int rc = pack_whh_swap(w_hh + (size_t)d * 512 * 128, f + (size_t)d * 512 * 128, b + (size_t)d * 512 * 128, 128, st);
-    if (rc) return rc;
-  }
-  return launch_rec_swap_fwd(ND, G, ND * 512, f, out, gates, csave, ND * 128, Bc, T, st);
+  __half *f, *b16;
+  __nv_bfloat16* b;
+  int rc = sw_selftest_pack(w_hh, packed, ND, &f, &b, &b16, st);
+  if (rc) return rc;
+  return launch_rec_swap_fwd(ND, G, ND * 512, f, out, gates, csave, ND * 128, Bc, T, split != 0, st);
 }
 extern "C" int bci_selftest_bptt_swap(const float* dout, const float* gates, const float* csave, const float* w_hh, void* packed, float* dG,
                                       int32_t Bc, int32_t T, int32_t ND, void* stream) {
@@ -530,12 +598,10 @@ extern "C" int bci_selftest_bptt_swap(const float* dout, const float* gates, con
   BCI_REQUIRE(dout && gates && csave && w_hh && packed && dG && Bc >= 1 && T >= 1 && (ND == 1 || ND == 2), BCI_EINVAL,
               "bci_selftest_bptt_swap: bad arguments");
   cudaStream_t st = (cudaStream_t)stream;
-  __half* f = reinterpret_cast<__half*>(packed);
-  __nv_bfloat16* b = reinterpret_cast<__nv_bfloat16*>(f + (size_t)ND * 512 * 128);
-  for (int d = 0; d < ND; ++d) {
-    int rc = pack_whh_swap(w_hh + (size_t)d * 512 * 128, f + (size_t)d * 512 * 128, b + (size_t)d * 512 * 128, 128, st);
-    if (rc) return rc;
-  }
+  __half *f, *b16;
+  __nv_bfloat16* b;
+  int rc = sw_selftest_pack(w_hh, packed, ND, &f, &b, &b16, st);
+  if (rc) return rc;
   return launch_bptt_swap(ND, dout, gates, csave, b, dG, nullptr, ND * 512, ND * 128, Bc, T, st);
 }
 /* selftest only: clock64 stamps (8 per step, steps 100-103) of CTA (0,0) of the next forward launches; NULL switches them off */

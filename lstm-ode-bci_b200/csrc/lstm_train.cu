@@ -875,6 +875,15 @@ size_t lstm_workspace_train(const bci_lstm_config& c, int batch, int T) {
   return w.total;
 }
 
+static bool train_rec_tc() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("BCI_TRAIN_REC");
+    v = (e && e[0] == 's') ? 0 : 1;
+  }
+  return v != 0;
+}
+
 template <int H, int ND>
 static int forward_train_t(bci_lstm_s* h, const float* x, int B, int T, float p_drop, uint64_t seed, float* logits, float* probs,
                            float* attn, TrainWs& w, cudaStream_t st) {
@@ -886,10 +895,14 @@ static int forward_train_t(bci_lstm_s* h, const float* x, int B, int T, float p_
   const int rb = (int)((M + 7) / 8 < 4096 ? (M + 7) / 8 : 4096);
   // mixed-precision step: the recurrences run on the tensor cores with 16-bit operands (lstm_rec_swap.cu)
   const bool mixed = h->train_mode == BCI_TRAIN_MIXED && rec_swap_ok(H, w.G, 4 * D);
-  if (mixed && h->sw_stale) {
+  // fp32-parity step: the same kernel in its split-precision form (three fp16 product chains, fp32-grade); BCI_TRAIN_REC=simt keeps
+  // the CUDA-core recurrence of round 1
+  const bool split_fwd = !mixed && train_rec_tc() && rec_swap_ok(H, w.G, 4 * D);
+  if ((mixed || split_fwd) && h->sw_stale) {
     for (int l = 0; l < c.num_layers; ++l)
       for (int d = 0; d < ND; ++d) {
-        int rc = pack_whh_swap(h->raw.w_hh[l][d], p.whh_sw_f[l] + (size_t)d * 4 * H * H, p.whh_sw_b[l] + (size_t)d * 4 * H * H, H, st);
+        int rc = pack_whh_swap(h->raw.w_hh[l][d], p.whh_sw_f[l] + (size_t)d * 2 * 4 * H * H, p.whh_sw_b[l] + (size_t)d * 4 * H * H,
+                               p.whh_sw_b16[l] + (size_t)d * 2 * 4 * H * H, H, st);
         if (rc) return rc;
       }
     h->sw_stale = false;
@@ -910,7 +923,7 @@ static int forward_train_t(bci_lstm_s* h, const float* x, int B, int T, float p_
       rc = launch_proj_gemm_f32(in, p.wih_t[l], p.bias[l], w.G, (int)M, 4 * D, K, st);
     }
     if (rc) return rc;
-    if (mixed) rc = launch_rec_swap_fwd(ND, w.G, 4 * D, p.whh_sw_f[l], w.out[l], w.gates[l], w.cst[l], D, B, T, st);
+    if (mixed || split_fwd) rc = launch_rec_swap_fwd(ND, w.G, 4 * D, p.whh_sw_f[l], w.out[l], w.gates[l], w.cst[l], D, B, T, split_fwd, st);
     else rc = launch_rec_f32(H, ND, w.G, p.whh_t[l][0], p.whh_t[l][1], w.out[l], w.gates[l], w.cst[l], B, T, st);
     if (rc) return rc;
     lo_ready = false;

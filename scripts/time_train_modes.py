@@ -38,7 +38,7 @@ def main():
     g = torch.Generator(device="cuda").manual_seed(1)
     whh = ((torch.rand(ND, 4 * H, H, device="cuda", generator=g) * 2 - 1) / np.sqrt(H)).contiguous()
     G = torch.randn(T * B, ND * 4 * H, device="cuda", generator=g).contiguous()
-    packed = torch.empty(2 * ND * 4 * H * H, device="cuda", dtype=torch.float16)
+    packed = torch.empty(5 * ND * 4 * H * H, device="cuda", dtype=torch.float16)
     out = torch.empty((T, B, ND * H), device="cuda")
     gates = torch.empty((T * B, ND * 4 * H), device="cuda")
     cs = torch.empty((T, B, ND * H), device="cuda")
@@ -47,7 +47,7 @@ def main():
     lib = N.lib()
     stamps = torch.zeros(32, dtype=torch.int64, device="cuda")
     lib.bci_selftest_swap_set_debug(stamps.data_ptr())
-    N.check(lib.bci_selftest_rec_swap_fwd(G.data_ptr(), whh.data_ptr(), packed.data_ptr(), out.data_ptr(), gates.data_ptr(), cs.data_ptr(), B, T, ND, st))
+    N.check(lib.bci_selftest_rec_swap_fwd(G.data_ptr(), whh.data_ptr(), packed.data_ptr(), out.data_ptr(), gates.data_ptr(), cs.data_ptr(), B, T, ND, 0, st))
     torch.cuda.synchronize()
     lib.bci_selftest_swap_set_debug(None)
     sv = stamps.cpu().numpy().reshape(4, 8)
@@ -56,8 +56,9 @@ def main():
         d = np.diff(sv[r])
         nxt = (sv[r + 1][0] - sv[r][0]) if r < 3 else 0
         print("   ", d.tolist(), "step", int(nxt))
-    ms = timed(lambda: N.check(lib.bci_selftest_rec_swap_fwd(G.data_ptr(), whh.data_ptr(), packed.data_ptr(), out.data_ptr(), gates.data_ptr(), cs.data_ptr(), B, T, ND, st)), steps)
-    print(f"swap forward recurrence (incl. 4 pack launches): {ms:.3f} ms per layer = {ms * 1e3 / T:.2f} us per step")
+    for split in (0, 1):
+        ms = timed(lambda: N.check(lib.bci_selftest_rec_swap_fwd(G.data_ptr(), whh.data_ptr(), packed.data_ptr(), out.data_ptr(), gates.data_ptr(), cs.data_ptr(), B, T, ND, split, st)), steps)
+        print(f"swap forward recurrence split={split} (incl. 4 pack launches): {ms:.3f} ms per layer = {ms * 1e3 / T:.2f} us per step")
     dout = torch.randn_like(out) * 1e-3
     ms = timed(lambda: N.check(lib.bci_selftest_bptt_swap(dout.data_ptr(), gates.data_ptr(), cs.data_ptr(), whh.data_ptr(), packed.data_ptr(), dG.data_ptr(), B, T, ND, st)), steps)
     print(f"swap BPTT recurrence (incl. 4 pack launches): {ms:.3f} ms per layer = {ms * 1e3 / T:.2f} us per step")

@@ -62,25 +62,31 @@ def test_tmem_a_operand_layout_probe():
     assert np.array_equal(got, want)
 
 
-@pytest.mark.parametrize("Bc,T,ND", [(8, 8, 2), (512, 24, 2), (13, 40, 1), (300, 9, 2)])
-def test_rec_swap_forward_matches_float64(Bc, T, ND):
+@pytest.mark.parametrize("split", [0, 1])
+@pytest.mark.parametrize("Bc,T,ND", [(8, 8, 2), (512, 24, 2), (13, 40, 1), (300, 9, 2), (64, 256, 2)])
+def test_rec_swap_forward_matches_float64(Bc, T, ND, split):
+    """split=0: the mixed mode's fp16 product (one chain, tanh.approx gates); split=1: the fp32-parity form (three chains: lo.hi +
+    hi.lo + hi.hi, ex2-based gates) -- fp32-grade like lstm_rec_f16x3."""
     H = 128
     g = torch.Generator(device="cuda").manual_seed(Bc * 7 + T + ND)
     whh = ((torch.rand(ND, 4 * H, H, device="cuda", generator=g) * 2 - 1) / np.sqrt(H) * 1.5).contiguous()
     G = (torch.randn(T * Bc, ND * 4 * H, device="cuda", generator=g) * 1.2).contiguous()
-    packed = torch.empty(2 * ND * 4 * H * H, device="cuda", dtype=torch.float16)
+    packed = torch.empty(5 * ND * 4 * H * H, device="cuda", dtype=torch.float16)
     out = torch.full((T, Bc, ND * H), float("nan"), device="cuda")
     gates = torch.full((T * Bc, ND * 4 * H), float("nan"), device="cuda")
     cs = torch.full((T, Bc, ND * H), float("nan"), device="cuda")
-    N.check(N.lib().bci_selftest_rec_swap_fwd(_p(G), _p(whh), _p(packed), _p(out), _p(gates), _p(cs), Bc, T, ND, _stream()))
+    N.check(N.lib().bci_selftest_rec_swap_fwd(_p(G), _p(whh), _p(packed), _p(out), _p(gates), _p(cs), Bc, T, ND, split, _stream()))
     torch.cuda.synchronize()
     want, wg, wc = _ref_forward64(G.double(), whh.double(), Bc, T, ND)
     assert torch.isfinite(out).all() and torch.isfinite(gates).all() and torch.isfinite(cs).all()
     e_h = float((out.double() - want).abs().max())
     e_g = float((gates.double().reshape(T, Bc, ND, H, 4) - wg).abs().max())
     e_c = float((cs.double().reshape(T, Bc, ND, H) - wc).abs().max())
-    print(f"swap forward vs float64: h {e_h:.2e}, gates {e_g:.2e}, c {e_c:.2e} (Bc={Bc}, T={T}, ND={ND})")
-    assert e_h <= 2e-3 and e_g <= 2e-3 and e_c <= 6e-3
+    print(f"swap forward vs float64: h {e_h:.2e}, gates {e_g:.2e}, c {e_c:.2e} (Bc={Bc}, T={T}, ND={ND}, split={split})")
+    if split:
+        assert e_h <= 3e-6 and e_g <= 3e-6 and e_c <= 1e-5
+    else:
+        assert e_h <= 4e-3 and e_g <= 4e-3 and e_c <= 1.2e-2
 
 
 @pytest.mark.parametrize("Bc,T,ND", [(8, 6, 2), (512, 16, 2), (13, 30, 1)])
@@ -96,7 +102,7 @@ def test_bptt_swap_matches_autograd(Bc, T, ND):
     want = G64.grad
     gates = wg.detach().float().reshape(T * Bc, ND * 4 * H).contiguous()
     cs = wc.detach().float().reshape(T, Bc, ND * H).contiguous()
-    packed = torch.empty(2 * ND * 4 * H * H, device="cuda", dtype=torch.float16)
+    packed = torch.empty(5 * ND * 4 * H * H, device="cuda", dtype=torch.float16)
     dG = torch.full((T * Bc, ND * 4 * H), float("nan"), device="cuda")
     N.check(N.lib().bci_selftest_bptt_swap(_p(dout), _p(gates), _p(cs), _p(whh), _p(packed), _p(dG), Bc, T, ND, _stream()))
     torch.cuda.synchronize()
