@@ -388,7 +388,7 @@ int bci_selftest_rec_f16x3(const float* G, const float* w_hh, void* packed, floa
 int bci_selftest_rec_swap_fwd(const float* G, const float* w_hh, void* packed, float* out, float* gates, float* csave, int32_t Bc,
                               int32_t T, int32_t ND, int32_t split, void* stream);
 int bci_selftest_bptt_swap(const float* dout, const float* gates, const float* csave, const float* w_hh, void* packed, float* dG,
-                           int32_t Bc, int32_t T, int32_t ND, void* stream);
+                           int32_t Bc, int32_t T, int32_t ND, int32_t split, void* stream);
 /* selftest only: clock64 stamps (8 per step, steps 100-103; int64[32]) of CTA (0,0) of the following swapped forward launches */
 int bci_selftest_swap_set_debug(long long* stamps);
 /* layout probe: one M128 x N16 x K16 tcgen05.mma whose A operand is read from tensor memory; out [128][16] fp32 */

@@ -341,11 +341,24 @@ lstm_rec_swap_fwd(const float* __restrict__ G,        // [T*Bc][ldg] fp32: colum
 // ---- BPTT -----------------------------------------------------------------------------------------------------------------------
 // The mirror of lstm_bptt_f32 (lstm_train.cu): walks the direction's time order backwards, dG_t to global (fp32, + optional tf32
 // remainder for the split-precision GEMMs) and, as bf16, into the B tile of  dh_{t-1}[j] = sum_k dG_t[k] W_hh[k][j].
+//
+// SPLIT = the fp32-parity form.  Gradients do not fit fp16's range as they come, so every step's dG tile is multiplied by a power
+// of two S before it is split into an fp16 (hi, lo) pair: S puts the PREVIOUS step's largest |dG| of this CTA at 2^8 (the maximum
+// is collected with one shared-memory atomicMax per warp and read a step later -- no extra barrier; three rotating slots), which
+// leaves a factor 128 of growth per step before the saturating conversion clips, 22 significant bits for every element within 2^-10
+// of the tile's maximum and an absolute error of 2^-33 of that maximum below.  dh = D / (16 S) is exact.  Three product chains as in
+// the forward: W_lo (shared memory) . dG_hi, W_hi (tensor memory) . dG_lo, W_hi . dG_hi.
+__device__ __forceinline__ uint16_t f2h_sat(float x) {
+  uint16_t r;
+  asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(r) : "f"(x));
+  return r;
+}
+template <bool SPLIT>
 __global__ void __launch_bounds__(SW_BLOCK, 1)
 lstm_bptt_swap(const float* __restrict__ dout,           // [T][Bc][D]
                const float* __restrict__ gates,          // [T*Bc][ldg]: i,f,g,o of (dir, unit) at column dir*512 + unit*4
                const float* __restrict__ csave,          // [T*Bc][D]
-               const __nv_bfloat16* __restrict__ whhT,   // [ND][128 j][512 k = gate*128 + unit] bf16
+               const void* __restrict__ whhT_v,          // mixed: [ND][128 j][512 k = gate*128 + unit] bf16; SPLIT: [ND][2][128][512] fp16 of 16 w
                float* __restrict__ dG,                   // [T*Bc][ldg]
                float* __restrict__ dG_lo,                // optional
                int ldg, int D, int Bc, int T) {
@@ -353,18 +366,36 @@ lstm_bptt_swap(const float* __restrict__ dout,           // [T][Bc][D]
   const int tid = threadIdx.x, u = tid & 127, wq = (tid >> 7) & 3;
   const int warp_u = __shfl_sync(0xffffffffu, tid >> 5, 0);
   const int dir = blockIdx.y, b0 = blockIdx.x * SW_NW;
-  const SwCtx cx = sw_prologue<SW_BWD_B, false>(sw_smem_raw, reinterpret_cast<const uint4*>(whhT + ((size_t)dir * 128 + u) * 512 + wq * 128), nullptr, 64);
+  const uint16_t* whhT = reinterpret_cast<const uint16_t*>(whhT_v) + (size_t)dir * (SPLIT ? 2 : 1) * 128 * 512;
+  const SwCtx cx = sw_prologue<SW_BWD_B, SPLIT>(sw_smem_raw, reinterpret_cast<const uint4*>(whhT + (size_t)u * 512 + wq * 128),
+                                                reinterpret_cast<const uint4*>(whhT + 128 * 512), 64);
+  uint32_t* mx = reinterpret_cast<uint32_t*>(cx.genB + (SPLIT ? 2 : 1) * SW_BWD_B + 32);   // three slots behind the barriers / TMEM slot
+  if (SPLIT && tid < 3) mx[tid] = 0u;
+  if (SPLIT) __syncthreads();
 
   if (warp_u == SW_EPI / 32) {
     for (int s = T - 1; s > 0; --s) {
       mbar_wait(cx.op_ready, (uint32_t)((T - 1 - s) & 1));
       tc_fence_after();
       if (elect_one()) {
-        constexpr uint32_t idesc = sw_idesc(128, 16, true);
+        constexpr uint32_t idesc = sw_idesc(128, 16, !SPLIT);
+        if (SPLIT) {
+#pragma unroll
+          for (int k = 0; k < 32; ++k) {   // W_lo (shared memory) . dG_hi
+            const uint64_t da = umma_desc_sw128(cx.sA + (uint32_t)(k >> 2) * SW_AATOM + (uint32_t)(k & 3) * 32u);
+            const uint64_t db = umma_desc_sw128(cx.sB + (uint32_t)(k >> 2) * SW_BATOM + (uint32_t)(k & 3) * 32u);
+            umma_bf16(cx.tmem, da, db, idesc, k != 0 ? 1u : 0u);
+          }
+#pragma unroll
+          for (int k = 0; k < 32; ++k) {   // W_hi (tensor memory) . dG_lo
+            const uint64_t db = umma_desc_sw128(cx.sB + SW_BWD_B + (uint32_t)(k >> 2) * SW_BATOM + (uint32_t)(k & 3) * 32u);
+            umma_f16_ts(cx.tmem, cx.tmem + SW_WCOL + k * 8, db, idesc, 1u);
+          }
+        }
 #pragma unroll
         for (int k = 0; k < 32; ++k) {
           const uint64_t db = umma_desc_sw128(cx.sB + (uint32_t)(k >> 2) * SW_BATOM + (uint32_t)(k & 3) * 32u);
-          umma_f16_ts(cx.tmem, cx.tmem + SW_WCOL + k * 8, db, idesc, k != 0 ? 1u : 0u);
+          umma_f16_ts(cx.tmem, cx.tmem + SW_WCOL + k * 8, db, idesc, (SPLIT || k != 0) ? 1u : 0u);
         }
         umma_commit(cx.acc_full);
       }
@@ -402,13 +433,16 @@ lstm_bptt_swap(const float* __restrict__ dout,           // [T][Bc][D]
     fetch(T - 1, pg, pc, pcp, pdo);
     for (int s = T - 1; s >= 0; --s) {
       const int t = dir ? (T - 1 - s) : s;
+      const int it = T - 1 - s;
+      float4 dgs[SW_WPT];
+      float lmax = 0.f;
 #pragma unroll
       for (int i = 0; i < SW_WPT; ++i) {
         float4 dg = make_float4(0.f, 0.f, 0.f, 0.f);
         if (b0 + wq * SW_WPT + i < Bc) {
           const float4 g = pg[i];
           const float dh = pdo[i] + dh_rec[i];
-          const float tc = tanh_mufu(pc[i]);  // the forward's own tanh(c)
+          const float tc = SPLIT ? rec_tanh(pc[i]) : tanh_mufu(pc[i]);  // the forward's own tanh(c)
           const float dct = fmaf(dh * g.w, 1.0f - tc * tc, dc[i]);
           dg.x = dct * g.z * g.x * (1.0f - g.x);
           dg.y = dct * pcp[i] * g.y * (1.0f - g.y);
@@ -427,14 +461,42 @@ lstm_bptt_swap(const float* __restrict__ dout,           // [T][Bc][D]
             *reinterpret_cast<float4*>(dG_lo + row * ldg + colg) = make_float4(lo(dg.x), lo(dg.y), lo(dg.z), lo(dg.w));
           }
         }
-        if (s > 0) {
+        if (!SPLIT && s > 0) {
           *reinterpret_cast<__nv_bfloat16*>(cx.genB + 0 * 2 * SW_BATOM + boff[i]) = __float2bfloat16_rn(dg.x);
           *reinterpret_cast<__nv_bfloat16*>(cx.genB + 1 * 2 * SW_BATOM + boff[i]) = __float2bfloat16_rn(dg.y);
           *reinterpret_cast<__nv_bfloat16*>(cx.genB + 2 * 2 * SW_BATOM + boff[i]) = __float2bfloat16_rn(dg.z);
           *reinterpret_cast<__nv_bfloat16*>(cx.genB + 3 * 2 * SW_BATOM + boff[i]) = __float2bfloat16_rn(dg.w);
         }
+        if (SPLIT) {
+          dgs[i] = dg;
+          lmax = fmaxf(lmax, fmaxf(fmaxf(fabsf(dg.x), fabsf(dg.y)), fmaxf(fabsf(dg.z), fabsf(dg.w))));
+        }
       }
       if (s == 0) break;
+      float inv_scale = 1.0f;
+      if (SPLIT) {
+        // this CTA's largest |dG| of this step -> slot it % 3 (read by step it + 1); slot (it + 1) % 3 was last read in step it - 1
+        lmax = warp_max(lmax);
+        if ((tid & 31) == 0) atomicMax(&mx[it % 3], __float_as_uint(lmax));
+        if (tid == 0) mx[(it + 1) % 3] = 0u;
+        if (it == 0) asm volatile("bar.sync 1, %0;" ::"n"(SW_EPI) : "memory");   // first step: its own maximum
+        const uint32_t pm = *reinterpret_cast<volatile uint32_t*>(&mx[it == 0 ? 0 : (it - 1) % 3]);
+        int se = 262 - (int)((pm >> 23) & 0xffu);     // biased exponent of S: largest |dG| . S in [2^8, 2^9)
+        se = se > 187 ? 187 : (se < 40 ? 40 : se);    // an all-zero tile (exponent field 0) or absurd magnitudes: clamp S to [2^-87, 2^60]
+        const float S = __uint_as_float((uint32_t)se << 23);
+        inv_scale = __uint_as_float((uint32_t)(254 - se) << 23) * (1.0f / SW_WSCALE);
+#pragma unroll
+        for (int i = 0; i < SW_WPT; ++i) {
+          const float v[4] = {dgs[i].x * S, dgs[i].y * S, dgs[i].z * S, dgs[i].w * S};
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const uint16_t hi = f2h_sat(v[g]);
+            const uint16_t lo = f2h_sat(v[g] - __half2float(__ushort_as_half(hi)));
+            *reinterpret_cast<uint16_t*>(cx.genB + g * 2 * SW_BATOM + boff[i]) = hi;
+            *reinterpret_cast<uint16_t*>(cx.genB + SW_BWD_B + g * 2 * SW_BATOM + boff[i]) = lo;
+          }
+        }
+      }
       fence_proxy_async_smem();
       tc_fence_before();
       __syncwarp();
@@ -459,7 +521,7 @@ lstm_bptt_swap(const float* __restrict__ dout,           // [T][Bc][D]
       tmem_ld_wait();
 #pragma unroll
       for (int i = 0; i < SW_WPT; ++i) {
-        dh_rec[i] = __uint_as_float(a[i]);
+        dh_rec[i] = SPLIT ? __uint_as_float(a[i]) * inv_scale : __uint_as_float(a[i]);
         pc[i] = pcp[i]; pg[i] = ng[i]; pcp[i] = ncp[i]; pdo[i] = ndo[i];
       }
     }
@@ -477,6 +539,7 @@ static int sw_setup() {
   bool& done = done_pd.cur();
   if (!done) {
     BCI_CUDA_OK(cudaFuncSetAttribute(lstm_rec_swap_fwd<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sw_smem_bytes(SW_FWD_B, true)));
+    BCI_CUDA_OK(cudaFuncSetAttribute(lstm_bptt_swap<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sw_smem_bytes(SW_BWD_B, true)));
     done = true;
   }
   return BCI_OK;
@@ -496,11 +559,14 @@ int launch_rec_swap_fwd(int ND, const float* G, int ldg, const __half* whh, floa
   return BCI_OK;
 }
 
-int launch_bptt_swap(int ND, const float* dout, const float* gates, const float* csave, const __nv_bfloat16* whhT, float* dG, float* dG_lo,
-                     int ldg, int D, int Bc, int T, cudaStream_t st) {
+// whhT: split ? the fp16 (hi, lo) pair [ND][2][128][512] : bf16 [ND][128][512]
+int launch_bptt_swap(int ND, const float* dout, const float* gates, const float* csave, const void* whhT, float* dG, float* dG_lo,
+                     int ldg, int D, int Bc, int T, bool split, cudaStream_t st) {
   int rc = sw_setup();
   if (rc) return rc;
-  lstm_bptt_swap<<<dim3(ceil_div(Bc, SW_NW), ND), SW_BLOCK, sw_smem_bytes(SW_BWD_B, false), st>>>(dout, gates, csave, whhT, dG, dG_lo, ldg, D, Bc, T);
+  const dim3 grid(ceil_div(Bc, SW_NW), ND);
+  if (split) lstm_bptt_swap<true><<<grid, SW_BLOCK, sw_smem_bytes(SW_BWD_B, true), st>>>(dout, gates, csave, whhT, dG, dG_lo, ldg, D, Bc, T);
+  else lstm_bptt_swap<false><<<grid, SW_BLOCK, sw_smem_bytes(SW_BWD_B, false), st>>>(dout, gates, csave, whhT, dG, dG_lo, ldg, D, Bc, T);
   BCI_LAUNCH_OK();
   return BCI_OK;
 }
@@ -593,7 +659,7 @@ extern "C" int bci_selftest_rec_swap_fwd(const float* G, const float* w_hh, void
   return launch_rec_swap_fwd(ND, G, ND * 512, f, out, gates, csave, ND * 128, Bc, T, split != 0, st);
 }
 extern "C" int bci_selftest_bptt_swap(const float* dout, const float* gates, const float* csave, const float* w_hh, void* packed, float* dG,
-                                      int32_t Bc, int32_t T, int32_t ND, void* stream) {
+                                      int32_t Bc, int32_t T, int32_t ND, int32_t split, void* stream) {
   using namespace bci;
   BCI_REQUIRE(dout && gates && csave && w_hh && packed && dG && Bc >= 1 && T >= 1 && (ND == 1 || ND == 2), BCI_EINVAL,
               "bci_selftest_bptt_swap: bad arguments");
@@ -602,7 +668,7 @@ extern "C" int bci_selftest_bptt_swap(const float* dout, const float* gates, con
   __nv_bfloat16* b;
   int rc = sw_selftest_pack(w_hh, packed, ND, &f, &b, &b16, st);
   if (rc) return rc;
-  return launch_bptt_swap(ND, dout, gates, csave, b, dG, nullptr, ND * 512, ND * 128, Bc, T, st);
+  return launch_bptt_swap(ND, dout, gates, csave, split ? (const void*)b16 : (const void*)b, dG, nullptr, ND * 512, ND * 128, Bc, T, split != 0, st);
 }
 /* selftest only: clock64 stamps (8 per step, steps 100-103) of CTA (0,0) of the next forward launches; NULL switches them off */
 extern "C" int bci_selftest_swap_set_debug(long long* stamps) {

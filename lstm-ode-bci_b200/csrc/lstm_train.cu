@@ -990,6 +990,7 @@ static int backward_t(bci_lstm_s* h, const float* dlogits, int B, int T, float p
   auto zero_on = [&](cudaStream_t s2, float* ptr, size_t n) { return cudaMemsetAsync(ptr, 0, n * sizeof(float), s2); };
   int rc;
   const bool mixed = h->train_mode == BCI_TRAIN_MIXED && rec_swap_ok(H, w.G, G4) && !h->sw_stale;
+  const bool split_bwd = !mixed && train_rec_tc() && rec_swap_ok(H, w.G, G4) && !h->sw_stale;   // fp32-parity BPTT on the tensor cores
   // ---- head ----
   head_train_bwd<H><<<B, H, 0, st>>>(dlogits, cls, w.pre1, w.pre2, raw.cls_w6, raw.cls_w3, raw.cls_w0, w.dpre1, w.dpre2, w.dctx,
                                        p_drop, seed, D);
@@ -1080,7 +1081,9 @@ static int backward_t(bci_lstm_s* h, const float* dlogits, int B, int T, float p
     const bool tc = tf32x3_tn_ok(dGl, G4, in, K, w.tmpW2, K, M, G4, K) && tf32x3_tn_ok(dGl, G4, w.out[l], D, w.tmpW2, H, M - B, 4 * H, H) &&
                     tf32x3_nt_ok(dGl, G4, p.wih_t[l], G4, dnext, K, (int)M, K, G4);
     if (mixed) {
-      if ((rc = launch_bptt_swap(ND, dcur, w.gates[l], w.cst[l], p.whh_sw_b[l], dGl, nullptr, G4, D, B, T, st))) return rc;
+      if ((rc = launch_bptt_swap(ND, dcur, w.gates[l], w.cst[l], p.whh_sw_b[l], dGl, nullptr, G4, D, B, T, false, st))) return rc;
+    } else if (split_bwd) {
+      if ((rc = launch_bptt_swap(ND, dcur, w.gates[l], w.cst[l], p.whh_sw_b16[l], dGl, tc ? dGl_lo : nullptr, G4, D, B, T, true, st))) return rc;
     } else if (tiny && H == 128)
       lstm_bptt_f32<H, 4, BP_RES><<<dim3(ceil_div(B, MT), ND), BP_THREADS, bp_smem + bp_res_bytes, st>>>(dcur, w.gates[l], w.cst[l], p.whh_b[l][0], p.whh_b[l][1], dGl, tc ? dGl_lo : nullptr, B, T, ND);
     else if (tiny)

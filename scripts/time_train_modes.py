@@ -60,8 +60,9 @@ def main():
         ms = timed(lambda: N.check(lib.bci_selftest_rec_swap_fwd(G.data_ptr(), whh.data_ptr(), packed.data_ptr(), out.data_ptr(), gates.data_ptr(), cs.data_ptr(), B, T, ND, split, st)), steps)
         print(f"swap forward recurrence split={split} (incl. 4 pack launches): {ms:.3f} ms per layer = {ms * 1e3 / T:.2f} us per step")
     dout = torch.randn_like(out) * 1e-3
-    ms = timed(lambda: N.check(lib.bci_selftest_bptt_swap(dout.data_ptr(), gates.data_ptr(), cs.data_ptr(), whh.data_ptr(), packed.data_ptr(), dG.data_ptr(), B, T, ND, st)), steps)
-    print(f"swap BPTT recurrence (incl. 4 pack launches): {ms:.3f} ms per layer = {ms * 1e3 / T:.2f} us per step")
+    for split in (0, 1):
+        ms = timed(lambda: N.check(lib.bci_selftest_bptt_swap(dout.data_ptr(), gates.data_ptr(), cs.data_ptr(), whh.data_ptr(), packed.data_ptr(), dG.data_ptr(), B, T, ND, split, st)), steps)
+        print(f"swap BPTT recurrence split={split} (incl. 4 pack launches): {ms:.3f} ms per layer = {ms * 1e3 / T:.2f} us per step")
 
 
 if __name__ == "__main__":
