@@ -209,7 +209,7 @@ bool rec_swap_ok(int H, const void* G, int ldg);
 int launch_rec_swap_fwd(int ND, const float* G, int ldg, const __half* whh, float* out, float* gates, float* csave, int D, int Bc, int T,
                         bool split, cudaStream_t st);
 int launch_bptt_swap(int ND, const float* dout, const float* gates, const float* csave, const void* whhT, float* dG, float* dG_lo,
-                     int ldg, int D, int Bc, int T, bool split, cudaStream_t st);
+                     float* dbias, int ldg, int D, int Bc, int T, bool split, cudaStream_t st);
 constexpr float F16X3_WSCALE = 16.0f;   // weights of the fp16-split paths are stored x 16 (keeps their lo parts out of fp16's subnormals)
 int split_f16(const float* x, __half* hi, __half* lo, long long n, float scale, cudaStream_t st);
 bool f16x3_nt_ok(const void* A_hi, int lda, const void* W_hi, int ldw, const void* C, int ldc, int M, int N, int K);

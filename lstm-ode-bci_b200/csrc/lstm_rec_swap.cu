@@ -1,4 +1,4 @@
-// Training-size recurrences on the tensor cores: the "swapped" form  pre^T = W_hh . h^T  with W_hh RESIDENT as the MMA's A operand.
+// Training-size recurrences on the tensor cores: the "swapped" form  pre^T = W_hh . h^T  with W_hh RESIDENT IN TENSOR MEMORY.
 //
 // A 512-window training batch is 4 tiles of 128 windows: the tile-per-CTA tensor-core recurrences of the inference paths
 // (lstm_bf16_fused.cu, lstm_fp32_tc.cu) would keep 8 SMs busy, which is why the training step of round 1 ran its recurrences on
@@ -8,20 +8,32 @@
 //   forward   D_g[u][n] = sum_k W_hh[g*128 + u][k] . h_{t-1}[n][k]      four M128 x N16 x K128 products (one per gate) -> 64 TMEM columns
 //   BPTT      D[j][n]   = sum_k W_hh^T[j][k] . dG_t[n][k],  k = (gate, unit)    one M128 x N16 x K512 product            -> 16 TMEM columns
 //
-//   A = the weights, 128 KB of 16-bit values, K-major SWIZZLE_128B atoms, loaded ONCE per CTA (the PyTorch (4H, H) row order is
-//       already "gate block g, row u": the forward operand is a plain fp16 cast; BPTT's is the transpose in bf16)
-//   B = h_{t-1} (4 KB) / dG_t (16 KB): rows = windows, written by the epilogue threads of the previous step
-//   D = TMEM lane u (hidden unit) x column n (window): thread u of the CTA owns unit u for the CTA's 8 windows, reads its four
-//       gate pre-activations with four tcgen05.ld.32x32b.x8 -- the whole cell update is thread-local, no exchange of any kind.
+//   A = the weights: 128 KB of 16-bit values per direction = 256 of the SM's 512 tensor-memory columns (lane = row, column c of a
+//       K = 16 slice = elements 2c | 2c+1 << 16), written once per CTA with tcgen05.st and read by tcgen05.mma as its A operand:
+//       an M128 x N16 x K16 product then costs 8 tensor cycles, against 32 for a 4 KB A tile on the shared-memory port
+//   B = h_{t-1} (4 KB) / dG_t (16 KB) in shared memory: rows = windows, written by the epilogue threads of the previous step
+//   D = TMEM lane u (hidden unit) x column n (window): a thread owns unit u for two of the CTA's 8 windows and reads its four gate
+//       pre-activations with four tcgen05.ld.32x32b.x2 -- the whole cell update is thread-local, no exchange of any kind.
 //
-// One CTA = 8 windows x one direction (N = 16 is the smallest legal N at M = 128; rows 8-15 of B stay zero), 128 threads, one CTA
-// per SM: 512 windows x 2 directions = 128 CTAs.  Per step: thread 0 issues 32 MMAs (4 KB of A each: the product is bound by the
-// shared-memory read of the weights, ~1 000 cycles) and commits to an mbarrier; everybody prefetches the next step's G_t / saved
-// activations (coalesced: consecutive threads = consecutive units) while the product runs.
+// One CTA = 8 windows x one direction (N = 16 is the smallest legal N at M = 128; rows 8-15 of B stay zero), one CTA per SM:
+// 512 windows x 2 directions = 128 CTAs.  16 epilogue warps + one MMA warp, coupled by two mbarriers only (acc_full: tcgen05.commit;
+// op_ready: one arrive per epilogue warp).  Three things took the forward step from 2.44 to 0.93 us (clock64 timelines, CTA 0):
+//   * the MMAs are issued by ONE ELECTED LANE OF A CONVERGED WARP whose index the compiler knows to be warp-uniform
+//     (__shfl_sync(tid / 32) + elect.sync): ptxas then emits the 32 UTCHMMA back to back (260 cycles); issued under `if (tid == 0)`
+//     every one of them sat in its own election loop (ELECT / BRA.U.ANY) and cost 47 cycles -- 1 500 per step, more than the math
+//   * 16 epilogue warps instead of 4: with one warp per scheduler the per-window dependent chain (tcgen05.ld -> 5 activations ->
+//     cell update -> stores) ran at its full latency, 2 400 cycles for 8 windows; four warps per scheduler overlap it: 650
+//   * next step's G_t / saved activations requested into registers before the accumulator wait, and the rows of four steps
+//     ahead pulled into L2 (a single step of lookahead is shorter than a DRAM round trip under load: step times jittered 1.5-2.5 k)
 //
-// Precision ("mixed" training mode, the analogue of the reference's autocast training, 04_lstm_model.py:486-490): forward operands
-// fp16 (h in [-1, 1], 11 significant bits), BPTT operands bf16 (gradients need the exponent range, not the bits), accumulation,
-// gates, cell state, dG in fp32.  The fp32-parity training step keeps the CUDA-core recurrences.
+// Two precisions:
+//   mixed (BCI_TRAIN_MIXED; the analogue of the reference's autocast training, 04_lstm_model.py:486-490): one product chain, forward
+//       operands fp16 (h in [-1, 1], 11 significant bits), BPTT operands bf16 (gradients need the exponent range, not the bits),
+//       gates from tanh.approx (one MUFU each); accumulation, gates, cell state, dG in fp32.
+//   split (the fp32-parity step): every operand as an fp16 (hi, lo) pair and three chains  lo.hi + hi.lo + hi.hi  (small terms
+//       first; the arithmetic of lstm_fp32_tc.cu): W_hi in tensor memory, W_lo (128 KB) in shared memory; BPTT scales each step's
+//       dG tile by a power of two that follows the gradient's magnitude (see lstm_bptt_swap).  3e-7 from float64 on h, 2e-7 of
+//       autograd on dG; forward 0.50 ms and BPTT 0.67 ms per layer against 1.25 / 1.8 ms on the CUDA cores.
 #include "lstm_shared_kernels.cuh"
 #include "sm100_prims.cuh"
 #include <cuda_bf16.h>
@@ -361,6 +373,7 @@ lstm_bptt_swap(const float* __restrict__ dout,           // [T][Bc][D]
                const void* __restrict__ whhT_v,          // mixed: [ND][128 j][512 k = gate*128 + unit] bf16; SPLIT: [ND][2][128][512] fp16 of 16 w
                float* __restrict__ dG,                   // [T*Bc][ldg]
                float* __restrict__ dG_lo,                // optional
+               float* __restrict__ dbias,                // optional [ldg]: += sum over rows of dG (the bias gradient, b_ih = b_hh)
                int ldg, int D, int Bc, int T) {
   extern __shared__ uint8_t sw_smem_raw[];
   const int tid = threadIdx.x, u = tid & 127, wq = (tid >> 7) & 3;
@@ -431,6 +444,7 @@ lstm_bptt_swap(const float* __restrict__ dout,           // [T][Bc][D]
       }
     };
     fetch(T - 1, pg, pc, pcp, pdo);
+    float4 bsum = make_float4(0.f, 0.f, 0.f, 0.f);   // this thread's share of the bias gradient: its windows, all steps
     for (int s = T - 1; s >= 0; --s) {
       const int t = dir ? (T - 1 - s) : s;
       const int it = T - 1 - s;
@@ -449,6 +463,7 @@ lstm_bptt_swap(const float* __restrict__ dout,           // [T][Bc][D]
           dg.z = dct * g.x * (1.0f - g.z * g.z);
           dg.w = dh * tc * g.w * (1.0f - g.w);
           dc[i] = dct * g.y;
+          bsum.x += dg.x; bsum.y += dg.y; bsum.z += dg.z; bsum.w += dg.w;
           const long long row = (long long)t * Bc + b0 + wq * SW_WPT + i;
           *reinterpret_cast<float4*>(dG + row * ldg + colg) = dg;
           if (dG_lo) {
@@ -472,7 +487,13 @@ lstm_bptt_swap(const float* __restrict__ dout,           // [T][Bc][D]
           lmax = fmaxf(lmax, fmaxf(fmaxf(fabsf(dg.x), fabsf(dg.y)), fmaxf(fabsf(dg.z), fabsf(dg.w))));
         }
       }
-      if (s == 0) break;
+      if (s == 0) {
+        if (dbias) {
+          atomicAdd(dbias + colg + 0, bsum.x); atomicAdd(dbias + colg + 1, bsum.y);
+          atomicAdd(dbias + colg + 2, bsum.z); atomicAdd(dbias + colg + 3, bsum.w);
+        }
+        break;
+      }
       float inv_scale = 1.0f;
       if (SPLIT) {
         // this CTA's largest |dG| of this step -> slot it % 3 (read by step it + 1); slot (it + 1) % 3 was last read in step it - 1
@@ -561,12 +582,12 @@ int launch_rec_swap_fwd(int ND, const float* G, int ldg, const __half* whh, floa
 
 // whhT: split ? the fp16 (hi, lo) pair [ND][2][128][512] : bf16 [ND][128][512]
 int launch_bptt_swap(int ND, const float* dout, const float* gates, const float* csave, const void* whhT, float* dG, float* dG_lo,
-                     int ldg, int D, int Bc, int T, bool split, cudaStream_t st) {
+                     float* dbias, int ldg, int D, int Bc, int T, bool split, cudaStream_t st) {
   int rc = sw_setup();
   if (rc) return rc;
   const dim3 grid(ceil_div(Bc, SW_NW), ND);
-  if (split) lstm_bptt_swap<true><<<grid, SW_BLOCK, sw_smem_bytes(SW_BWD_B, true), st>>>(dout, gates, csave, whhT, dG, dG_lo, ldg, D, Bc, T);
-  else lstm_bptt_swap<false><<<grid, SW_BLOCK, sw_smem_bytes(SW_BWD_B, false), st>>>(dout, gates, csave, whhT, dG, dG_lo, ldg, D, Bc, T);
+  if (split) lstm_bptt_swap<true><<<grid, SW_BLOCK, sw_smem_bytes(SW_BWD_B, true), st>>>(dout, gates, csave, whhT, dG, dG_lo, dbias, ldg, D, Bc, T);
+  else lstm_bptt_swap<false><<<grid, SW_BLOCK, sw_smem_bytes(SW_BWD_B, false), st>>>(dout, gates, csave, whhT, dG, dG_lo, dbias, ldg, D, Bc, T);
   BCI_LAUNCH_OK();
   return BCI_OK;
 }
@@ -668,7 +689,7 @@ extern "C" int bci_selftest_bptt_swap(const float* dout, const float* gates, con
   __nv_bfloat16* b;
   int rc = sw_selftest_pack(w_hh, packed, ND, &f, &b, &b16, st);
   if (rc) return rc;
-  return launch_bptt_swap(ND, dout, gates, csave, split ? (const void*)b16 : (const void*)b, dG, nullptr, ND * 512, ND * 128, Bc, T, split != 0, st);
+  return launch_bptt_swap(ND, dout, gates, csave, split ? (const void*)b16 : (const void*)b, dG, nullptr, nullptr, ND * 512, ND * 128, Bc, T, split != 0, st);
 }
 /* selftest only: clock64 stamps (8 per step, steps 100-103) of CTA (0,0) of the next forward launches; NULL switches them off */
 extern "C" int bci_selftest_swap_set_debug(long long* stamps) {

@@ -833,6 +833,7 @@ struct TrainWs {
                             // while BPTT of layer l-1 writes the other buffer)
   float *tmpW2;             // scratch of the side stream
   float *xhatF, *rstdF, *Y, *PRE, *attn, *ctx, *pre1, *h1d, *pre2, *h2d;
+  float *dbias[2];          // bias gradients of the tensor-core BPTT (summed inside the kernel), one per dG buffer
   float *dA, *dB;           // [M][2H] gradient ping-pong
   float *dctx, *dpre1, *dpre2, *tmpW, *hdr;
   // tf32 remainders for the split-precision tcgen05 GEMMs: layer input (main stream), dG (one per dG buffer), and the side
@@ -854,6 +855,7 @@ static void carve_train(const bci_lstm_config& c, int B, int T, float p_drop, ch
   }
   w.G = take(M * 4 * D);
   w.G2 = take(M * 4 * D);
+  w.dbias[0] = take(4 * D); w.dbias[1] = take(4 * D);
   w.xhatF = take(M * D); w.rstdF = take(M); w.Y = take(M * D); w.PRE = take(M * (D / 2));
   w.attn = take((size_t)B * T); w.ctx = take(B * D); w.pre1 = take(B * H); w.h1d = take(B * H);
   w.pre2 = take(B * (H / 2)); w.h2d = take(B * (H / 2));
@@ -1080,10 +1082,11 @@ static int backward_t(bci_lstm_s* h, const float* dlogits, int B, int T, float p
     float* dGl_lo = gb ? w.lo_G2 : w.lo_G;
     const bool tc = tf32x3_tn_ok(dGl, G4, in, K, w.tmpW2, K, M, G4, K) && tf32x3_tn_ok(dGl, G4, w.out[l], D, w.tmpW2, H, M - B, 4 * H, H) &&
                     tf32x3_nt_ok(dGl, G4, p.wih_t[l], G4, dnext, K, (int)M, K, G4);
+    if (mixed || split_bwd) BCI_CUDA_OK(zero(w.dbias[gb], (size_t)G4));
     if (mixed) {
-      if ((rc = launch_bptt_swap(ND, dcur, w.gates[l], w.cst[l], p.whh_sw_b[l], dGl, nullptr, G4, D, B, T, false, st))) return rc;
+      if ((rc = launch_bptt_swap(ND, dcur, w.gates[l], w.cst[l], p.whh_sw_b[l], dGl, nullptr, w.dbias[gb], G4, D, B, T, false, st))) return rc;
     } else if (split_bwd) {
-      if ((rc = launch_bptt_swap(ND, dcur, w.gates[l], w.cst[l], p.whh_sw_b16[l], dGl, tc ? dGl_lo : nullptr, G4, D, B, T, true, st))) return rc;
+      if ((rc = launch_bptt_swap(ND, dcur, w.gates[l], w.cst[l], p.whh_sw_b16[l], dGl, tc ? dGl_lo : nullptr, w.dbias[gb], G4, D, B, T, true, st))) return rc;
     } else if (tiny && H == 128)
       lstm_bptt_f32<H, 4, BP_RES><<<dim3(ceil_div(B, MT), ND), BP_THREADS, bp_smem + bp_res_bytes, st>>>(dcur, w.gates[l], w.cst[l], p.whh_b[l][0], p.whh_b[l][1], dGl, tc ? dGl_lo : nullptr, B, T, ND);
     else if (tiny)
@@ -1124,10 +1127,15 @@ static int backward_t(bci_lstm_s* h, const float* dlogits, int B, int T, float p
       BCI_LAUNCH_OK();
     }
     // biases
-    BCI_CUDA_OK(zero_on(sd, w.tmpW2, (size_t)G4));
-    if ((rc = colsum(dGl, G4, M, G4, w.tmpW2, sd))) return rc;
+    const float* bsrc = w.tmpW2;
+    if (mixed || split_bwd) {
+      bsrc = w.dbias[gb];   // summed by the BPTT kernel itself: no pass over dG
+    } else {
+      BCI_CUDA_OK(zero_on(sd, w.tmpW2, (size_t)G4));
+      if ((rc = colsum(dGl, G4, M, G4, w.tmpW2, sd))) return rc;
+    }
     for (int d = 0; d < ND; ++d) {
-      unpack_bias_kernel<<<ceil_div(4 * H, 256), 256, 0, sd>>>(w.tmpW2, g->b_ih[l][d], g->b_hh[l][d], H, d * 4 * H);
+      unpack_bias_kernel<<<ceil_div(4 * H, 256), 256, 0, sd>>>(bsrc, g->b_ih[l][d], g->b_hh[l][d], H, d * 4 * H);
       BCI_LAUNCH_OK();
     }
     BCI_CUDA_OK(cudaEventRecord(h->ev_side[gb], sd));
