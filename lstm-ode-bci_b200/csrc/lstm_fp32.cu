@@ -544,7 +544,14 @@ static int forward_chunk_f32(bci_lstm_s* h, const InputView& x, int Bc, int T, f
     float* o = outs[l & 1];
     // the tile size follows the batch (launch_rec_f32): small batches -- single windows of predict_trajectory, the reference's 256 /
     // 512-window passes -- use the latency-oriented variants with W_hh resident in shared memory instead of leaving most SMs idle
-    if ((rc = launch_rec_f32(H, ND, g, h->f32.whh_t[l][0], h->f32.whh_t[l][1], o, nullptr, nullptr, Bc, T, st))) return rc;
+    // H = 128: the swapped tensor-core recurrence in its split (fp32-grade) form -- W_hh resident in tensor memory, 8 windows per
+    // CTA (lstm_rec_swap.cu; 1.96 us per step against 4.9 on the CUDA cores at 512 windows)
+    if (H == 128 && swap_rec_enabled() && rec_swap_ok(H, g, N)) {
+      if ((rc = pack_swap_operands(h, st))) return rc;
+      if ((rc = launch_rec_swap_fwd(ND, g, N, h->f32.whh_sw_f[l], o, nullptr, nullptr, D, Bc, T, true, st))) return rc;
+    } else if ((rc = launch_rec_f32(H, ND, g, h->f32.whh_t[l][0], h->f32.whh_t[l][1], o, nullptr, nullptr, Bc, T, st))) {
+      return rc;
+    }
     h->prof.mark(2, st);
     in = o;
   }

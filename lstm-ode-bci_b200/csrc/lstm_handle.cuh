@@ -206,6 +206,8 @@ int launch_rec_f16x3(int ND, const float* G, int ldg, const __half* whh16, float
 // swapped (weights-as-A) tensor-core recurrences of the mixed-precision training step (lstm_rec_swap.cu)
 int pack_whh_swap(const float* w_hh, __half* fwd, __nv_bfloat16* bwd, __half* bwd16, int H, cudaStream_t st);
 bool rec_swap_ok(int H, const void* G, int ldg);
+bool swap_rec_enabled();
+int pack_swap_operands(bci_lstm_s* h, cudaStream_t st);
 int launch_rec_swap_fwd(int ND, const float* G, int ldg, const __half* whh, float* out, float* gates, float* csave, int D, int Bc, int T,
                         bool split, cudaStream_t st);
 int launch_bptt_swap(int ND, const float* dout, const float* gates, const float* csave, const void* whhT, float* dG, float* dG_lo,

@@ -569,6 +569,30 @@ static long long* g_sw_dbg = nullptr;   // selftest only: clock stamps of CTA (0
 
 bool rec_swap_ok(int H, const void* G, int ldg) { return H == 128 && ((uintptr_t)G & 15) == 0 && (ldg & 3) == 0; }
 
+// BCI_TRAIN_REC=simt keeps the CUDA-core recurrences of round 1 in the fp32-parity training step and the small-batch fp32 forward
+bool swap_rec_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("BCI_TRAIN_REC");
+    v = (e && e[0] == 's') ? 0 : 1;
+  }
+  return v != 0;
+}
+
+// the 16-bit recurrent operands of every layer and direction, from the raw weights of the last load (no-op until the next load)
+int pack_swap_operands(bci_lstm_s* h, cudaStream_t st) {
+  if (!h->sw_stale) return BCI_OK;
+  const int H = h->cfg.hidden_size, ND = num_dirs(h->cfg);
+  for (int l = 0; l < h->cfg.num_layers; ++l)
+    for (int d = 0; d < ND; ++d) {
+      int rc = pack_whh_swap(h->raw.w_hh[l][d], h->f32.whh_sw_f[l] + (size_t)d * 2 * 4 * H * H, h->f32.whh_sw_b[l] + (size_t)d * 4 * H * H,
+                             h->f32.whh_sw_b16[l] + (size_t)d * 2 * 4 * H * H, H, st);
+      if (rc) return rc;
+    }
+  h->sw_stale = false;
+  return BCI_OK;
+}
+
 int launch_rec_swap_fwd(int ND, const float* G, int ldg, const __half* whh, float* out, float* gates, float* csave, int D, int Bc, int T,
                         bool split, cudaStream_t st) {
   int rc = sw_setup();

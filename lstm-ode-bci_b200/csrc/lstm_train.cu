@@ -877,15 +877,6 @@ size_t lstm_workspace_train(const bci_lstm_config& c, int batch, int T) {
   return w.total;
 }
 
-static bool train_rec_tc() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("BCI_TRAIN_REC");
-    v = (e && e[0] == 's') ? 0 : 1;
-  }
-  return v != 0;
-}
-
 template <int H, int ND>
 static int forward_train_t(bci_lstm_s* h, const float* x, int B, int T, float p_drop, uint64_t seed, float* logits, float* probs,
                            float* attn, TrainWs& w, cudaStream_t st) {
@@ -899,15 +890,10 @@ static int forward_train_t(bci_lstm_s* h, const float* x, int B, int T, float p_
   const bool mixed = h->train_mode == BCI_TRAIN_MIXED && rec_swap_ok(H, w.G, 4 * D);
   // fp32-parity step: the same kernel in its split-precision form (three fp16 product chains, fp32-grade); BCI_TRAIN_REC=simt keeps
   // the CUDA-core recurrence of round 1
-  const bool split_fwd = !mixed && train_rec_tc() && rec_swap_ok(H, w.G, 4 * D);
-  if ((mixed || split_fwd) && h->sw_stale) {
-    for (int l = 0; l < c.num_layers; ++l)
-      for (int d = 0; d < ND; ++d) {
-        int rc = pack_whh_swap(h->raw.w_hh[l][d], p.whh_sw_f[l] + (size_t)d * 2 * 4 * H * H, p.whh_sw_b[l] + (size_t)d * 4 * H * H,
-                               p.whh_sw_b16[l] + (size_t)d * 2 * 4 * H * H, H, st);
-        if (rc) return rc;
-      }
-    h->sw_stale = false;
+  const bool split_fwd = !mixed && swap_rec_enabled() && rec_swap_ok(H, w.G, 4 * D);
+  if (mixed || split_fwd) {
+    int rc = pack_swap_operands(h, st);
+    if (rc) return rc;
   }
   inproj_train_fwd<H><<<rb, 256, 0, st>>>(x, B, T, C, p.w0t, p.b0, p.ln0w, p.ln0b, w.xT, w.xhat0, w.rstd0, w.z, p_drop * 0.5f, seed, use_ln);
   BCI_LAUNCH_OK();
@@ -992,7 +978,7 @@ static int backward_t(bci_lstm_s* h, const float* dlogits, int B, int T, float p
   auto zero_on = [&](cudaStream_t s2, float* ptr, size_t n) { return cudaMemsetAsync(ptr, 0, n * sizeof(float), s2); };
   int rc;
   const bool mixed = h->train_mode == BCI_TRAIN_MIXED && rec_swap_ok(H, w.G, G4) && !h->sw_stale;
-  const bool split_bwd = !mixed && train_rec_tc() && rec_swap_ok(H, w.G, G4) && !h->sw_stale;   // fp32-parity BPTT on the tensor cores
+  const bool split_bwd = !mixed && swap_rec_enabled() && rec_swap_ok(H, w.G, G4) && !h->sw_stale;   // fp32-parity BPTT on the tensor cores
   // ---- head ----
   head_train_bwd<H><<<B, H, 0, st>>>(dlogits, cls, w.pre1, w.pre2, raw.cls_w6, raw.cls_w3, raw.cls_w0, w.dpre1, w.dpre2, w.dctx,
                                        p_drop, seed, D);
