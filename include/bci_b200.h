@@ -105,7 +105,8 @@ int bci_lstm_load_weights(bci_lstm_t h, const bci_lstm_weights* w, void* stream)
  *   BCI_TRAIN_MIXED the analogue of the reference's own GPU training mode, autocast + GradScaler (04:486-490, 499-503): the two
  *                   recurrences of every layer run on the tensor cores with 16-bit operands (forward fp16, BPTT bf16 -- bf16 has
  *                   fp32's exponent range, so no loss scaling is needed) and the large GEMMs in single-pass TF32; accumulators,
- *                   gates, cell states, LayerNorm, softmax, loss and the optimizer stay fp32.  hidden_size 128 only. */
+ *                   gates, cell states, LayerNorm, softmax, loss and the optimizer stay fp32.  Full-width variants only
+ *                   (hidden_size 128: one CTA per 8 windows; 256: CTA pairs). */
 enum { BCI_TRAIN_FP32 = 0, BCI_TRAIN_MIXED = 1 };
 int bci_lstm_set_train_mode(bci_lstm_t h, int32_t mode);
 
@@ -389,6 +390,12 @@ int bci_selftest_rec_swap_fwd(const float* G, const float* w_hh, void* packed, f
                               int32_t T, int32_t ND, int32_t split, void* stream);
 int bci_selftest_bptt_swap(const float* dout, const float* gates, const float* csave, const float* w_hh, void* packed, float* dG,
                            int32_t Bc, int32_t T, int32_t ND, int32_t split, void* stream);
+/* the hidden-size-256 pair kernels (mixed precision): G / gates / dG [T*Bc][ND*1024] (column dir*1024 + unit*4 + gate), out / csave /
+ * dout [T][Bc][ND*256], w_hh [ND][1024][256] fp32; packed: 5 x ND x 1024 x 256 sixteen-bit values of scratch */
+int bci_selftest_rec_swap256_fwd(const float* G, const float* w_hh, void* packed, float* out, float* gates, float* csave, int32_t Bc,
+                                 int32_t T, int32_t ND, void* stream);
+int bci_selftest_bptt_swap256(const float* dout, const float* gates, const float* csave, const float* w_hh, void* packed, float* dG,
+                              int32_t Bc, int32_t T, int32_t ND, void* stream);
 /* selftest only: clock64 stamps (8 per step, steps 100-103; int64[32]) of CTA (0,0) of the following swapped forward launches */
 int bci_selftest_swap_set_debug(long long* stamps);
 /* layout probe: one M128 x N16 x K16 tcgen05.mma whose A operand is read from tensor memory; out [128][16] fp32 */

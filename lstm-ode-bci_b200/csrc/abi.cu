@@ -167,8 +167,6 @@ extern "C" int bci_lstm_load_weights(bci_lstm_t h, const bci_lstm_weights* w, vo
 extern "C" int bci_lstm_set_train_mode(bci_lstm_t h, int32_t mode) {
   BCI_REQUIRE(h, BCI_EINVAL, "bci_lstm_set_train_mode: NULL handle");
   BCI_REQUIRE(mode == BCI_TRAIN_FP32 || mode == BCI_TRAIN_MIXED, BCI_EINVAL, "bci_lstm_set_train_mode: mode must be BCI_TRAIN_FP32 or BCI_TRAIN_MIXED");
-  BCI_REQUIRE(mode == BCI_TRAIN_FP32 || h->cfg.hidden_size == 128, BCI_EINVAL,
-              "bci_lstm_set_train_mode: the mixed-precision training step is built for hidden_size 128 (got %d)", h->cfg.hidden_size);
   h->train_mode = mode;
   return BCI_OK;
 }

@@ -207,6 +207,12 @@ int launch_rec_f16x3(int ND, const float* G, int ldg, const __half* whh16, float
 int pack_whh_swap(const float* w_hh, __half* fwd, __nv_bfloat16* bwd, __half* bwd16, int H, cudaStream_t st);
 bool rec_swap_ok(int H, const void* G, int ldg);
 bool swap_rec_enabled();
+// hidden_size 256, mixed precision: the same recurrences on CTA pairs (each CTA owns 128 units; h / dG halves exchanged through DSMEM)
+bool rec_swap256_ok(int H, const void* G, int ldg);
+int launch_rec_swap256_fwd(int ND, const float* G, int ldg, const __half* whh, float* out, float* gates, float* csave, int D, int Bc, int T,
+                           cudaStream_t st);
+int launch_bptt_swap256(int ND, const float* dout, const float* gates, const float* csave, const __nv_bfloat16* whhT, float* dG, float* dbias,
+                        int ldg, int D, int Bc, int T, cudaStream_t st);
 int pack_swap_operands(bci_lstm_s* h, cudaStream_t st);
 int launch_rec_swap_fwd(int ND, const float* G, int ldg, const __half* whh, float* out, float* gates, float* csave, int D, int Bc, int T,
                         bool split, cudaStream_t st);

@@ -616,6 +616,404 @@ int launch_bptt_swap(int ND, const float* dout, const float* gates, const float*
   return BCI_OK;
 }
 
+
+// =====================================================================================================================================
+// hidden_size 256 (the reference's trained checkpoint, 04_lstm_model.py:876-877), mixed precision: the same swapped recurrences on a
+// CTA PAIR.  W_hh is 512 KB in 16 bits -- neither one SM's tensor memory (256 KB, of which the accumulators need a share) nor its
+// shared memory holds it, so the 256 hidden units are split between the two CTAs of a cluster: each owns 128 units, i.e. 128 rows of
+// every gate block (forward) / 128 rows j of W_hh^T (BPTT), for the SAME 16 windows.  Per CTA that is 256 KB of weights: three
+// quarters live in tensor memory (384 columns), the fourth (64 KB) in shared memory as the classic K-major SW128 A operand.
+//
+//   forward  per gate g:  D_g[u][n] = sum_{k < 256} W_hh[g*256 + 128 r + u][k] . h_{t-1}[n][k]     gates i, f, g~ from TMEM, o from smem
+//   BPTT                  D[j][n]   = sum_{k < 1024} W_hh^T[128 r + j][k] . dG_t[n][k]             K quarters 0-2 from TMEM, 3 from smem
+//
+// The cell update / gate backward stay thread-local (a thread owns one unit and four of the 16 windows).  What the pair must exchange
+// every step is the B operand: each CTA produces h_t (forward, 4 KB) / dG_t (BPTT, 16 KB) of ITS 128 units and needs the other
+// half.  The producer's MMA warp pushes its half into the same place of the peer's B tile with cp.async.bulk shared::cta ->
+// shared::cluster, counted on the peer's mbarrier x_in; B tiles and x_in are double-buffered by step parity, so there is no
+// "receive buffer free" handshake (a CTA can only be one step ahead of its peer: it needs the peer's half of every step), and
+// x_in[b] is re-armed by its single waiter right after each completed phase (lstm_bf16_fused.cu's protocol).
+constexpr int S2_NW = 16, S2_WPT = 4;
+constexpr uint32_t S2_FB = 4 * SW_BATOM;      // forward B tile: 16 windows x K 256 = 8 KB
+constexpr uint32_t S2_BB = 16 * SW_BATOM;     // BPTT B tile:    16 windows x K 1024 = 32 KB
+constexpr uint32_t S2_WSM = 4 * SW_AATOM;     // the weight quarter kept in shared memory: 128 rows x K 256 = 64 KB
+constexpr size_t s2_smem_bytes(uint32_t b_bytes) { return 1024 + S2_WSM + 2 * b_bytes + 128; }
+
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, uint32_t (&r)[4]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(taddr) : "memory");
+}
+
+struct S2Ctx {
+  uint32_t sA, sB, acc_full, op_ready, x_in, tmem, rank;
+  uint8_t* genB;
+};
+// wsm: this CTA's 128 rows of the shared-memory quarter, row-major [128][32 chunks of 8 halves] with row stride `wsm_stride` chunks;
+// wrow: this thread's row of the tensor-memory quarters (quarter q, this thread's 64-element slice at wrow + q * q_stride chunks)
+template <uint32_t B_BYTES, uint32_t D_COLS>
+__device__ __forceinline__ S2Ctx s2_prologue(uint8_t* raw_ptr, const uint4* __restrict__ wsm, int wsm_stride, const uint4* __restrict__ wrow,
+                                             int q_stride, uint32_t tx_bytes) {
+  S2Ctx c;
+  const uint32_t raw = smem_u32(raw_ptr);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* genA = raw_ptr + (base - raw);
+  c.sA = base;
+  c.genB = genA + S2_WSM;
+  c.sB = base + S2_WSM;
+  uint8_t* ctl = c.genB + 2 * B_BYTES;
+  c.acc_full = smem_u32(ctl);
+  c.op_ready = c.acc_full + 8;
+  c.x_in = c.acc_full + 16;   // two barriers
+  c.rank = cluster_ctarank();
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ctl + 32);
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+    mbar_init(c.acc_full, 1);
+    mbar_init(c.op_ready, SW_EPI / 32);
+    mbar_init(c.x_in, 1);
+    mbar_init(c.x_in + 8, 1);
+    fence_mbar_init();
+    mbar_arrive_expect_tx(c.x_in, tx_bytes);
+    mbar_arrive_expect_tx(c.x_in + 8, tx_bytes);
+  }
+  if (tid >= SW_EPI) {
+    tmem_alloc(smem_u32(tmem_slot), 512);
+    tmem_relinquish();
+  }
+  for (int i = tid; i < 128 * 32; i += SW_BLOCK) {
+    const int row = i >> 5, cc = i & 31;
+    *reinterpret_cast<uint4*>(genA + (uint32_t)(cc >> 3) * SW_AATOM + sw128_chunk_off((uint32_t)row, (uint32_t)(cc & 7))) =
+        __ldg(wsm + (size_t)row * wsm_stride + cc);
+  }
+  for (int i = tid; i < (int)(2 * B_BYTES / 16); i += SW_BLOCK) reinterpret_cast<uint4*>(c.genB)[i] = make_uint4(0, 0, 0, 0);
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  c.tmem = *tmem_slot;
+  if (tid < SW_EPI) {
+    const int u = tid & 127, wq = tid >> 7;
+    const uint32_t dst = c.tmem + ((uint32_t)((u >> 5) * 32) << 16) + D_COLS + (uint32_t)wq * 32u;
+#pragma unroll 1
+    for (int q = 0; q < 3; ++q) {
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        uint32_t r[16];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const uint4 v = __ldg(wrow + (size_t)q * q_stride + k * 4 + i);
+          r[4 * i] = v.x; r[4 * i + 1] = v.y; r[4 * i + 2] = v.z; r[4 * i + 3] = v.w;
+        }
+        tmem_st16(dst + (uint32_t)q * 128u + (uint32_t)k * 16u, r);
+      }
+    }
+    tmem_st_wait();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  cluster_sync_all();   // the peer's barriers are initialised and armed before anything is pushed to it
+  return c;
+}
+
+// grid = (2 * ceil(Bc / 16), ND), cluster (2, 1, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(SW_BLOCK, 1)
+lstm_rec_swap256_fwd(const float* __restrict__ G,        // [T*Bc][ldg] fp32: column dir*1024 + unit*4 + gate, bias included
+                     int ldg,
+                     const __half* __restrict__ whh,     // [ND][2 parts][1024][256] fp16 of 16 w (the hi part is used)
+                     float* __restrict__ out,            // [T][Bc][D]: column dir*256 + unit
+                     float* __restrict__ gates, float* __restrict__ csave, int D, int Bc, int T) {
+  extern __shared__ uint8_t sw_smem_raw[];
+  const int tid = threadIdx.x, u = tid & 127, wq = (tid >> 7) & 3;
+  const int warp_u = __shfl_sync(0xffffffffu, tid >> 5, 0);
+  const int dir = blockIdx.y, b0 = (int)(blockIdx.x >> 1) * S2_NW;
+  const uint32_t rank = cluster_ctarank(), peer = rank ^ 1u;
+  const __half* wdir = whh + (size_t)dir * 2 * 1024 * 256;
+  // shared-memory quarter = the o gate's rows of this CTA; tensor-memory quarters q = gates i, f, g~ (row q*256 + 128 r + u)
+  const S2Ctx cx = s2_prologue<S2_FB, 64>(sw_smem_raw, reinterpret_cast<const uint4*>(wdir + ((size_t)3 * 256 + 128 * rank) * 256), 32,
+                                          reinterpret_cast<const uint4*>(wdir + ((size_t)128 * rank + u) * 256 + wq * 64), 256 * 32, 4096u);
+
+  if (warp_u == SW_EPI / 32) {
+    for (int st = 0; st < T; ++st) {
+      const uint32_t buf = (uint32_t)(st & 1), sBb = cx.sB + buf * S2_FB, xin = cx.x_in + 8u * buf;
+      if (st > 0) {
+        mbar_wait(cx.op_ready, (uint32_t)((st - 1) & 1));   // this CTA's half of h_{st-1} is in B[buf]
+        if (elect_one()) {
+          const uint32_t mine = sBb + 2u * rank * SW_BATOM;
+          bulk_copy_s2s_cluster(mapa_u32(mine, peer), mine, 4096u, mapa_u32(xin, peer));
+        }
+        mbar_wait(xin, (uint32_t)(((st - 1) >> 1) & 1));    // the peer's half has landed
+        if (elect_one()) mbar_arrive_expect_tx(xin, 4096u);  // re-arm for step st + 2
+      }
+      tc_fence_after();
+      if (elect_one()) {
+        constexpr uint32_t idesc = sw_idesc(128, 16, false);
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+#pragma unroll
+          for (int k = 0; k < 16; ++k) {
+            const uint64_t db = umma_desc_sw128(sBb + (uint32_t)(k >> 2) * SW_BATOM + (uint32_t)(k & 3) * 32u);
+            if (g < 3) {
+              umma_f16_ts(cx.tmem + g * 16, cx.tmem + 64 + g * 128 + k * 8, db, idesc, k != 0 ? 1u : 0u);
+            } else {
+              const uint64_t da = umma_desc_sw128(cx.sA + (uint32_t)(k >> 2) * SW_AATOM + (uint32_t)(k & 3) * 32u);
+              umma_bf16(cx.tmem + g * 16, da, db, idesc, k != 0 ? 1u : 0u);
+            }
+          }
+        }
+        umma_commit(cx.acc_full);
+      }
+      __syncwarp();
+    }
+  } else {
+    const uint32_t taddr = cx.tmem + ((uint32_t)((u >> 5) * 32) << 16) + (uint32_t)(wq * S2_WPT);
+    const int unit = 128 * (int)rank + u;
+    uint32_t hoff[S2_WPT];
+    int brow[S2_WPT];
+#pragma unroll
+    for (int i = 0; i < S2_WPT; ++i) {
+      const int n = wq * S2_WPT + i;
+      hoff[i] = (uint32_t)(2 * rank + (u >> 6)) * SW_BATOM + (uint32_t)n * 128u + (((uint32_t)((u & 63) >> 3) ^ (uint32_t)(n & 7)) << 4) + (uint32_t)(u & 7) * 2u;
+      brow[i] = b0 + n < Bc ? b0 + n : Bc - 1;
+    }
+    const int colg = dir * 1024 + unit * 4, colh = dir * 256 + unit;
+    float c[S2_WPT];
+    float4 gq[S2_WPT];
+#pragma unroll
+    for (int i = 0; i < S2_WPT; ++i) {
+      c[i] = 0.f;
+      gq[i] = __ldg(reinterpret_cast<const float4*>(G + ((long long)(dir ? T - 1 : 0) * Bc + brow[i]) * ldg + colg));
+    }
+    for (int st = 0; st < T; ++st) {
+      const int t = dir ? (T - 1 - st) : st;
+      uint8_t* Bn = cx.genB + (uint32_t)((st + 1) & 1) * S2_FB;   // h_t is the B operand of step st + 1
+      float4 gc[S2_WPT];
+#pragma unroll
+      for (int i = 0; i < S2_WPT; ++i) gc[i] = gq[i];
+      if (st + 1 < T) {
+        const int tn = dir ? (T - 2 - st) : st + 1;
+#pragma unroll
+        for (int i = 0; i < S2_WPT; ++i) gq[i] = __ldg(reinterpret_cast<const float4*>(G + ((long long)tn * Bc + brow[i]) * ldg + colg));
+      }
+      if (st + 4 < T && (tid & 7) == 0) {
+        const int t4 = dir ? (T - 5 - st) : st + 4;
+#pragma unroll
+        for (int i = 0; i < S2_WPT; ++i) sw_prefetch_l2(G + ((long long)t4 * Bc + brow[i]) * ldg + colg);
+      }
+      mbar_wait(cx.acc_full, (uint32_t)(st & 1));
+      tc_fence_after();
+      uint32_t a[4][S2_WPT];
+#pragma unroll
+      for (int g = 0; g < 4; ++g) tmem_ld4(taddr + g * 16, a[g]);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < S2_WPT; ++i) {
+        const float ig = sw_sigmoid(fmaf(__uint_as_float(a[0][i]), 1.0f / SW_WSCALE, gc[i].x));
+        const float fg = sw_sigmoid(fmaf(__uint_as_float(a[1][i]), 1.0f / SW_WSCALE, gc[i].y));
+        const float gg = tanh_mufu(fmaf(__uint_as_float(a[2][i]), 1.0f / SW_WSCALE, gc[i].z));
+        const float og = sw_sigmoid(fmaf(__uint_as_float(a[3][i]), 1.0f / SW_WSCALE, gc[i].w));
+        c[i] = fmaf(fg, c[i], ig * gg);
+        const float hv = og * tanh_mufu(c[i]);
+        *reinterpret_cast<__half*>(Bn + hoff[i]) = __float2half_rn(hv);
+        if (b0 + wq * S2_WPT + i < Bc) {
+          const long long row = (long long)t * Bc + b0 + wq * S2_WPT + i;
+          out[row * D + colh] = hv;
+          if (gates) *reinterpret_cast<float4*>(gates + row * ldg + colg) = make_float4(ig, fg, gg, og);
+          if (csave) csave[row * D + colh] = c[i];
+        }
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      __syncwarp();
+      if ((tid & 31) == 0) mbar_arrive(cx.op_ready);
+    }
+  }
+  tc_fence_before();
+  cluster_sync_all();   // nobody leaves while the peer may still push into / wait on this CTA
+  if (warp_u == SW_EPI / 32) {
+    tc_fence_after();
+    tmem_dealloc(cx.tmem, 512);
+  }
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(SW_BLOCK, 1)
+lstm_bptt_swap256(const float* __restrict__ dout,           // [T][Bc][D]
+                  const float* __restrict__ gates,          // [T*Bc][ldg]: column dir*1024 + unit*4
+                  const float* __restrict__ csave,          // [T*Bc][D]
+                  const __nv_bfloat16* __restrict__ whhT,   // [ND][256 j][1024 k = gate*256 + unit] bf16
+                  float* __restrict__ dG, float* __restrict__ dbias, int ldg, int D, int Bc, int T) {
+  extern __shared__ uint8_t sw_smem_raw[];
+  const int tid = threadIdx.x, u = tid & 127, wq = (tid >> 7) & 3;
+  const int warp_u = __shfl_sync(0xffffffffu, tid >> 5, 0);
+  const int dir = blockIdx.y, b0 = (int)(blockIdx.x >> 1) * S2_NW;
+  const uint32_t rank = cluster_ctarank(), peer = rank ^ 1u;
+  const __nv_bfloat16* wdir = whhT + (size_t)dir * 256 * 1024;
+  // this CTA's rows j = 128 r + u; K quarters 0-2 in tensor memory, quarter 3 (k in [768, 1024): the o gate) in shared memory
+  const S2Ctx cx = s2_prologue<S2_BB, 32>(sw_smem_raw, reinterpret_cast<const uint4*>(wdir + ((size_t)128 * rank) * 1024 + 768), 128,
+                                          reinterpret_cast<const uint4*>(wdir + ((size_t)128 * rank + u) * 1024 + wq * 64), 32, 16384u);
+
+  if (warp_u == SW_EPI / 32) {
+    for (int it = 0; it + 1 < T; ++it) {
+      const uint32_t buf = (uint32_t)(it & 1), sBb = cx.sB + buf * S2_BB, xin = cx.x_in + 8u * buf;
+      mbar_wait(cx.op_ready, (uint32_t)(it & 1));   // this CTA's half of dG is in B[buf]
+      if (elect_one()) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {   // gate g: atoms 4 g + 2 r, + 1
+          const uint32_t mine = sBb + (uint32_t)(4 * g + 2 * rank) * SW_BATOM;
+          bulk_copy_s2s_cluster(mapa_u32(mine, peer), mine, 4096u, mapa_u32(xin, peer));
+        }
+      }
+      mbar_wait(xin, (uint32_t)((it >> 1) & 1));
+      if (elect_one()) mbar_arrive_expect_tx(xin, 16384u);
+      tc_fence_after();
+      if (elect_one()) {
+        constexpr uint32_t idesc = sw_idesc(128, 16, true);
+#pragma unroll
+        for (int k = 0; k < 64; ++k) {
+          const uint64_t db = umma_desc_sw128(sBb + (uint32_t)(k >> 2) * SW_BATOM + (uint32_t)(k & 3) * 32u);
+          if (k < 48) {
+            umma_f16_ts(cx.tmem, cx.tmem + 32 + k * 8, db, idesc, k != 0 ? 1u : 0u);
+          } else {
+            const uint64_t da = umma_desc_sw128(cx.sA + (uint32_t)((k - 48) >> 2) * SW_AATOM + (uint32_t)(k & 3) * 32u);
+            umma_bf16(cx.tmem, da, db, idesc, 1u);
+          }
+        }
+        umma_commit(cx.acc_full);
+      }
+      __syncwarp();
+    }
+  } else {
+    const uint32_t taddr = cx.tmem + ((uint32_t)((u >> 5) * 32) << 16) + (uint32_t)(wq * S2_WPT);
+    const int unit = 128 * (int)rank + u;
+    uint32_t boff[S2_WPT];
+    int brow[S2_WPT];
+#pragma unroll
+    for (int i = 0; i < S2_WPT; ++i) {
+      const int n = wq * S2_WPT + i;
+      boff[i] = (uint32_t)(2 * rank + (u >> 6)) * SW_BATOM + (uint32_t)n * 128u + (((uint32_t)((u & 63) >> 3) ^ (uint32_t)(n & 7)) << 4) + (uint32_t)(u & 7) * 2u;
+      brow[i] = b0 + n < Bc ? b0 + n : Bc - 1;
+    }
+    const int colg = dir * 1024 + unit * 4, colh = dir * 256 + unit;
+    float dh_rec[S2_WPT], dc[S2_WPT];
+    float4 pg[S2_WPT];
+    float pc[S2_WPT], pcp[S2_WPT], pdo[S2_WPT];
+#pragma unroll
+    for (int i = 0; i < S2_WPT; ++i) { dh_rec[i] = 0.f; dc[i] = 0.f; }
+    auto fetch = [&](int s, float4* g4, float* cc, float* cp, float* dd) {
+      const int t = dir ? (T - 1 - s) : s;
+      const int tp = dir ? (t + 1) : (t - 1);
+#pragma unroll
+      for (int i = 0; i < S2_WPT; ++i) {
+        const long long row = (long long)t * Bc + brow[i];
+        g4[i] = __ldg(reinterpret_cast<const float4*>(gates + row * ldg + colg));
+        if (cc) cc[i] = __ldg(csave + row * D + colh);
+        cp[i] = (s > 0) ? __ldg(csave + ((long long)tp * Bc + brow[i]) * D + colh) : 0.f;
+        dd[i] = __ldg(dout + row * D + colh);
+      }
+    };
+    fetch(T - 1, pg, pc, pcp, pdo);
+    float4 bsum = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int s = T - 1; s >= 0; --s) {
+      const int t = dir ? (T - 1 - s) : s;
+      const int it = T - 1 - s;
+      uint8_t* Bn = cx.genB + (uint32_t)(it & 1) * S2_BB;
+#pragma unroll
+      for (int i = 0; i < S2_WPT; ++i) {
+        float4 dg = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (b0 + wq * S2_WPT + i < Bc) {
+          const float4 g = pg[i];
+          const float dh = pdo[i] + dh_rec[i];
+          const float tc = tanh_mufu(pc[i]);
+          const float dct = fmaf(dh * g.w, 1.0f - tc * tc, dc[i]);
+          dg.x = dct * g.z * g.x * (1.0f - g.x);
+          dg.y = dct * pcp[i] * g.y * (1.0f - g.y);
+          dg.z = dct * g.x * (1.0f - g.z * g.z);
+          dg.w = dh * tc * g.w * (1.0f - g.w);
+          dc[i] = dct * g.y;
+          bsum.x += dg.x; bsum.y += dg.y; bsum.z += dg.z; bsum.w += dg.w;
+          const long long row = (long long)t * Bc + b0 + wq * S2_WPT + i;
+          *reinterpret_cast<float4*>(dG + row * ldg + colg) = dg;
+        }
+        if (s > 0) {   // k = gate*256 + unit: atom 4 gate + 2 r + u / 64
+          *reinterpret_cast<__nv_bfloat16*>(Bn + 0 * 4 * SW_BATOM + boff[i]) = __float2bfloat16_rn(dg.x);
+          *reinterpret_cast<__nv_bfloat16*>(Bn + 1 * 4 * SW_BATOM + boff[i]) = __float2bfloat16_rn(dg.y);
+          *reinterpret_cast<__nv_bfloat16*>(Bn + 2 * 4 * SW_BATOM + boff[i]) = __float2bfloat16_rn(dg.z);
+          *reinterpret_cast<__nv_bfloat16*>(Bn + 3 * 4 * SW_BATOM + boff[i]) = __float2bfloat16_rn(dg.w);
+        }
+      }
+      if (s == 0) {
+        if (dbias) {
+          atomicAdd(dbias + colg + 0, bsum.x); atomicAdd(dbias + colg + 1, bsum.y);
+          atomicAdd(dbias + colg + 2, bsum.z); atomicAdd(dbias + colg + 3, bsum.w);
+        }
+        break;
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      __syncwarp();
+      if ((tid & 31) == 0) mbar_arrive(cx.op_ready);
+      float4 ng[S2_WPT];
+      float ncp[S2_WPT], ndo[S2_WPT];
+      fetch(s - 1, ng, nullptr, ncp, ndo);
+      if (s >= 4) {
+        const int t4 = dir ? (T - 1 - (s - 4)) : s - 4;
+#pragma unroll
+        for (int i = 0; i < S2_WPT; ++i) {
+          const long long row = (long long)t4 * Bc + brow[i];
+          if ((tid & 7) == 0) sw_prefetch_l2(gates + row * ldg + colg);
+          if ((tid & 31) == 0) { sw_prefetch_l2(csave + row * D + colh); sw_prefetch_l2(dout + row * D + colh); }
+        }
+      }
+      mbar_wait(cx.acc_full, (uint32_t)(it & 1));
+      tc_fence_after();
+      uint32_t a[S2_WPT];
+      tmem_ld4(taddr, a);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < S2_WPT; ++i) {
+        dh_rec[i] = __uint_as_float(a[i]);
+        pc[i] = pcp[i]; pg[i] = ng[i]; pcp[i] = ncp[i]; pdo[i] = ndo[i];
+      }
+    }
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp_u == SW_EPI / 32) {
+    tc_fence_after();
+    tmem_dealloc(cx.tmem, 512);
+  }
+}
+
+static int s2_setup() {
+  static PerDeviceFlag done_pd;
+  bool& done = done_pd.cur();
+  if (!done) {
+    BCI_CUDA_OK(cudaFuncSetAttribute(lstm_rec_swap256_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s2_smem_bytes(S2_FB)));
+    BCI_CUDA_OK(cudaFuncSetAttribute(lstm_bptt_swap256, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s2_smem_bytes(S2_BB)));
+    done = true;
+  }
+  return BCI_OK;
+}
+
+bool rec_swap256_ok(int H, const void* G, int ldg) { return H == 256 && ((uintptr_t)G & 15) == 0 && (ldg & 3) == 0; }
+
+int launch_rec_swap256_fwd(int ND, const float* G, int ldg, const __half* whh, float* out, float* gates, float* csave, int D, int Bc, int T,
+                           cudaStream_t st) {
+  int rc = s2_setup();
+  if (rc) return rc;
+  lstm_rec_swap256_fwd<<<dim3(2 * ceil_div(Bc, S2_NW), ND), SW_BLOCK, s2_smem_bytes(S2_FB), st>>>(G, ldg, whh, out, gates, csave, D, Bc, T);
+  BCI_LAUNCH_OK();
+  return BCI_OK;
+}
+
+int launch_bptt_swap256(int ND, const float* dout, const float* gates, const float* csave, const __nv_bfloat16* whhT, float* dG, float* dbias,
+                        int ldg, int D, int Bc, int T, cudaStream_t st) {
+  int rc = s2_setup();
+  if (rc) return rc;
+  lstm_bptt_swap256<<<dim3(2 * ceil_div(Bc, S2_NW), ND), SW_BLOCK, s2_smem_bytes(S2_BB), st>>>(dout, gates, csave, whhT, dG, dbias, ldg, D, Bc, T);
+  BCI_LAUNCH_OK();
+  return BCI_OK;
+}
+
 // ---- probe: the A operand of tcgen05.mma read from TENSOR MEMORY ---------------------------------------------------------------
 // One M128 x N16 x K16 product whose B is the 16 x 16 identity: D[m][n] = A[m][n] as the tensor core sees it.  A is written with
 // tcgen05.st.32x32b.x8 (lane = row m): column c of the 8 carries the two halves value(c, 0) | value(c, 1) << 16 with
@@ -714,6 +1112,43 @@ extern "C" int bci_selftest_bptt_swap(const float* dout, const float* gates, con
   int rc = sw_selftest_pack(w_hh, packed, ND, &f, &b, &b16, st);
   if (rc) return rc;
   return launch_bptt_swap(ND, dout, gates, csave, split ? (const void*)b16 : (const void*)b, dG, nullptr, nullptr, ND * 512, ND * 128, Bc, T, split != 0, st);
+}
+// H = 256 pair kernels in isolation: G / gates / dG [T*Bc][ND*1024], out / csave / dout [T][Bc][ND*256], w_hh [ND][1024][256] fp32;
+// packed: 5 x ND x 1024 x 256 sixteen-bit values of scratch
+static int s2_selftest_pack(const float* w_hh, void* packed, int ND, __half** f, __nv_bfloat16** b, cudaStream_t st) {
+  using namespace bci;
+  const size_t W = 1024 * 256;
+  *f = reinterpret_cast<__half*>(packed);
+  *b = reinterpret_cast<__nv_bfloat16*>(*f + (size_t)ND * 2 * W);
+  __half* b16 = reinterpret_cast<__half*>(*b + (size_t)ND * W);
+  for (int d = 0; d < ND; ++d) {
+    int rc = pack_whh_swap(w_hh + d * W, *f + d * 2 * W, *b + d * W, b16 + d * 2 * W, 256, st);
+    if (rc) return rc;
+  }
+  return BCI_OK;
+}
+extern "C" int bci_selftest_rec_swap256_fwd(const float* G, const float* w_hh, void* packed, float* out, float* gates, float* csave,
+                                            int32_t Bc, int32_t T, int32_t ND, void* stream) {
+  using namespace bci;
+  BCI_REQUIRE(G && w_hh && packed && out && Bc >= 1 && T >= 1 && (ND == 1 || ND == 2), BCI_EINVAL, "bci_selftest_rec_swap256_fwd: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  __half* f;
+  __nv_bfloat16* b;
+  int rc = s2_selftest_pack(w_hh, packed, ND, &f, &b, st);
+  if (rc) return rc;
+  return launch_rec_swap256_fwd(ND, G, ND * 1024, f, out, gates, csave, ND * 256, Bc, T, st);
+}
+extern "C" int bci_selftest_bptt_swap256(const float* dout, const float* gates, const float* csave, const float* w_hh, void* packed,
+                                         float* dG, int32_t Bc, int32_t T, int32_t ND, void* stream) {
+  using namespace bci;
+  BCI_REQUIRE(dout && gates && csave && w_hh && packed && dG && Bc >= 1 && T >= 1 && (ND == 1 || ND == 2), BCI_EINVAL,
+              "bci_selftest_bptt_swap256: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  __half* f;
+  __nv_bfloat16* b;
+  int rc = s2_selftest_pack(w_hh, packed, ND, &f, &b, st);
+  if (rc) return rc;
+  return launch_bptt_swap256(ND, dout, gates, csave, b, dG, nullptr, ND * 1024, ND * 256, Bc, T, st);
 }
 /* selftest only: clock64 stamps (8 per step, steps 100-103) of CTA (0,0) of the next forward launches; NULL switches them off */
 extern "C" int bci_selftest_swap_set_debug(long long* stamps) {

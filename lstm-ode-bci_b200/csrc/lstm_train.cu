@@ -887,7 +887,7 @@ static int forward_train_t(bci_lstm_s* h, const float* x, int B, int T, float p_
   const long long M = (long long)B * T;
   const int rb = (int)((M + 7) / 8 < 4096 ? (M + 7) / 8 : 4096);
   // mixed-precision step: the recurrences run on the tensor cores with 16-bit operands (lstm_rec_swap.cu)
-  const bool mixed = h->train_mode == BCI_TRAIN_MIXED && rec_swap_ok(H, w.G, 4 * D);
+  const bool mixed = h->train_mode == BCI_TRAIN_MIXED && (rec_swap_ok(H, w.G, 4 * D) || rec_swap256_ok(H, w.G, 4 * D));
   // fp32-parity step: the same kernel in its split-precision form (three fp16 product chains, fp32-grade); BCI_TRAIN_REC=simt keeps
   // the CUDA-core recurrence of round 1
   const bool split_fwd = !mixed && swap_rec_enabled() && rec_swap_ok(H, w.G, 4 * D);
@@ -911,7 +911,8 @@ static int forward_train_t(bci_lstm_s* h, const float* x, int B, int T, float p_
       rc = launch_proj_gemm_f32(in, p.wih_t[l], p.bias[l], w.G, (int)M, 4 * D, K, st);
     }
     if (rc) return rc;
-    if (mixed || split_fwd) rc = launch_rec_swap_fwd(ND, w.G, 4 * D, p.whh_sw_f[l], w.out[l], w.gates[l], w.cst[l], D, B, T, split_fwd, st);
+    if (mixed && H == 256) rc = launch_rec_swap256_fwd(ND, w.G, 4 * D, p.whh_sw_f[l], w.out[l], w.gates[l], w.cst[l], D, B, T, st);
+    else if (mixed || split_fwd) rc = launch_rec_swap_fwd(ND, w.G, 4 * D, p.whh_sw_f[l], w.out[l], w.gates[l], w.cst[l], D, B, T, split_fwd, st);
     else rc = launch_rec_f32(H, ND, w.G, p.whh_t[l][0], p.whh_t[l][1], w.out[l], w.gates[l], w.cst[l], B, T, st);
     if (rc) return rc;
     lo_ready = false;
@@ -977,7 +978,7 @@ static int backward_t(bci_lstm_s* h, const float* dlogits, int B, int T, float p
   auto zero = [&](float* ptr, size_t n) { return cudaMemsetAsync(ptr, 0, n * sizeof(float), st); };
   auto zero_on = [&](cudaStream_t s2, float* ptr, size_t n) { return cudaMemsetAsync(ptr, 0, n * sizeof(float), s2); };
   int rc;
-  const bool mixed = h->train_mode == BCI_TRAIN_MIXED && rec_swap_ok(H, w.G, G4) && !h->sw_stale;
+  const bool mixed = h->train_mode == BCI_TRAIN_MIXED && (rec_swap_ok(H, w.G, G4) || rec_swap256_ok(H, w.G, G4)) && !h->sw_stale;
   const bool split_bwd = !mixed && swap_rec_enabled() && rec_swap_ok(H, w.G, G4) && !h->sw_stale;   // fp32-parity BPTT on the tensor cores
   // ---- head ----
   head_train_bwd<H><<<B, H, 0, st>>>(dlogits, cls, w.pre1, w.pre2, raw.cls_w6, raw.cls_w3, raw.cls_w0, w.dpre1, w.dpre2, w.dctx,
@@ -1069,7 +1070,9 @@ static int backward_t(bci_lstm_s* h, const float* dlogits, int B, int T, float p
     const bool tc = tf32x3_tn_ok(dGl, G4, in, K, w.tmpW2, K, M, G4, K) && tf32x3_tn_ok(dGl, G4, w.out[l], D, w.tmpW2, H, M - B, 4 * H, H) &&
                     tf32x3_nt_ok(dGl, G4, p.wih_t[l], G4, dnext, K, (int)M, K, G4);
     if (mixed || split_bwd) BCI_CUDA_OK(zero(w.dbias[gb], (size_t)G4));
-    if (mixed) {
+    if (mixed && H == 256) {
+      if ((rc = launch_bptt_swap256(ND, dcur, w.gates[l], w.cst[l], p.whh_sw_b[l], dGl, w.dbias[gb], G4, D, B, T, st))) return rc;
+    } else if (mixed) {
       if ((rc = launch_bptt_swap(ND, dcur, w.gates[l], w.cst[l], p.whh_sw_b[l], dGl, nullptr, w.dbias[gb], G4, D, B, T, false, st))) return rc;
     } else if (split_bwd) {
       if ((rc = launch_bptt_swap(ND, dcur, w.gates[l], w.cst[l], p.whh_sw_b16[l], dGl, tc ? dGl_lo : nullptr, w.dbias[gb], G4, D, B, T, true, st))) return rc;

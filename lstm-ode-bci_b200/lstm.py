@@ -69,7 +69,7 @@ class EnhancedLSTMModel(nn.Module):
 
     def _train_precision_now(self):
         if self.train_precision == "auto":
-            return "mixed" if (torch.is_autocast_enabled("cuda") and self.hidden_size == 128) else "fp32"
+            return "mixed" if (torch.is_autocast_enabled("cuda") and self.hidden_size in (128, 256)) else "fp32"
         return self.train_precision
 
     def _signature(self):

@@ -24,6 +24,16 @@ def timed(fn, n):
 
 def main():
     steps = int(sys.argv[1]) if len(sys.argv) > 1 else 10
+    H, B, T = 256, 512, 256
+    params = synth.make_lstm_params(42, 61, H, 3, logit_gain=4.0)
+    x = torch.from_numpy(synth.make_windows(3, B, T, 61)).cuda()
+    y = (torch.arange(B) % 2).cuda()
+    for mode in ("fp32", "mixed"):
+        m = lstm.from_params(params, precision="fp32", dropout=0.4).train()
+        tr = train.FusedTrainer(m, precision=mode)
+        ms = timed(lambda: tr.step(x, y, seed=1), max(3, steps // 2))
+        print(f"H=256 train step {mode}: {ms:.3f} ms  ({B / ms:.1f} k windows/s)")
+        del tr, m
     H, B, T = 128, 512, 256
     params = synth.make_lstm_params(42, 61, H, 3, logit_gain=4.0)
     x = torch.from_numpy(synth.make_windows(3, B, T, 61)).cuda()

@@ -125,10 +125,56 @@ def test_bptt_swap_matches_autograd(Bc, T, ND, decay, split):
         assert err <= 2e-2 and cos >= 0.9995
 
 
-@pytest.mark.parametrize("B,T", [(16, 64), (512, 256)])
-def test_mixed_step_gradients_against_fp32_reference(B, T):
+@pytest.mark.parametrize("Bc,T,ND", [(16, 8, 2), (512, 12, 2), (21, 40, 1), (100, 64, 2)])
+def test_rec_swap256_forward_matches_float64(Bc, T, ND):
+    """hidden_size 256: the CTA-pair form (each CTA owns 128 units, h halves pushed through DSMEM every step)."""
+    H = 256
+    g = torch.Generator(device="cuda").manual_seed(Bc * 7 + T + ND)
+    whh = ((torch.rand(ND, 4 * H, H, device="cuda", generator=g) * 2 - 1) / np.sqrt(H) * 1.5).contiguous()
+    G = (torch.randn(T * Bc, ND * 4 * H, device="cuda", generator=g) * 1.2).contiguous()
+    packed = torch.empty(5 * ND * 4 * H * H, device="cuda", dtype=torch.float16)
+    out = torch.full((T, Bc, ND * H), float("nan"), device="cuda")
+    gates = torch.full((T * Bc, ND * 4 * H), float("nan"), device="cuda")
+    cs = torch.full((T, Bc, ND * H), float("nan"), device="cuda")
+    N.check(N.lib().bci_selftest_rec_swap256_fwd(_p(G), _p(whh), _p(packed), _p(out), _p(gates), _p(cs), Bc, T, ND, _stream()))
+    torch.cuda.synchronize()
+    want, wg, wc = _ref_forward64(G.double(), whh.double(), Bc, T, ND, H)
+    assert torch.isfinite(out).all() and torch.isfinite(gates).all() and torch.isfinite(cs).all()
+    e_h = float((out.double() - want).abs().max())
+    e_g = float((gates.double().reshape(T, Bc, ND, H, 4) - wg).abs().max())
+    e_c = float((cs.double().reshape(T, Bc, ND, H) - wc).abs().max())
+    print(f"swap256 forward vs float64: h {e_h:.2e}, gates {e_g:.2e}, c {e_c:.2e} (Bc={Bc}, T={T}, ND={ND})")
+    assert e_h <= 4e-3 and e_g <= 4e-3 and e_c <= 1.2e-2
+
+
+@pytest.mark.parametrize("Bc,T,ND", [(16, 6, 2), (512, 10, 2), (21, 30, 1)])
+def test_bptt_swap256_matches_autograd(Bc, T, ND):
+    H = 256
+    g = torch.Generator(device="cuda").manual_seed(Bc * 3 + T + ND)
+    whh = ((torch.rand(ND, 4 * H, H, device="cuda", generator=g) * 2 - 1) / np.sqrt(H) * 1.5).contiguous()
+    G = (torch.randn(T * Bc, ND * 4 * H, device="cuda", generator=g) * 1.2).contiguous()
+    dout = (torch.randn(T, Bc, ND * H, device="cuda", generator=g) * 1e-3).contiguous()
+    G64 = G.double().requires_grad_(True)
+    out, wg, wc = _ref_forward64(G64, whh.double(), Bc, T, ND, H)
+    (out * dout.double()).sum().backward()
+    want = G64.grad
+    gates = wg.detach().float().reshape(T * Bc, ND * 4 * H).contiguous()
+    cs = wc.detach().float().reshape(T, Bc, ND * H).contiguous()
+    packed = torch.empty(5 * ND * 4 * H * H, device="cuda", dtype=torch.float16)
+    dG = torch.full((T * Bc, ND * 4 * H), float("nan"), device="cuda")
+    N.check(N.lib().bci_selftest_bptt_swap256(_p(dout), _p(gates), _p(cs), _p(whh), _p(packed), _p(dG), Bc, T, ND, _stream()))
+    torch.cuda.synchronize()
+    assert torch.isfinite(dG).all()
+    d3, w3 = dG.double().reshape(T, -1), want.reshape(T, -1)
+    err = float(((d3 - w3).abs().max(dim=1).values / w3.abs().max(dim=1).values).max())
+    cos = float((dG.double() * want).sum() / (dG.double().norm() * want.norm()))
+    print(f"swap256 BPTT vs autograd: worst per-step rel-to-max err {err:.2e}, cosine {cos:.8f} (Bc={Bc}, T={T}, ND={ND})")
+    assert err <= 2e-2 and cos >= 0.9995
+
+
+@pytest.mark.parametrize("H,B,T", [(128, 16, 64), (128, 512, 256), (256, 24, 48), (256, 512, 64)])
+def test_mixed_step_gradients_against_fp32_reference(H, B, T):
     """One training step in the mixed mode against torch autograd on the CPU port of the reference module (fp32)."""
-    H = 128
     params = synth.make_lstm_params(46, 61, H, 3, logit_gain=4.0)
     x = synth.make_windows(12, B, T, 61)
     y = (np.arange(B) % 2).astype(np.int64)
