@@ -670,6 +670,20 @@ def main():
                              "windows_per_gpu": int(x256.shape[0]), "tflops_per_gpu": int(x256.shape[0]) * 2.223047168e9 / (hms * 1e-3) / 1e12}
         tail["h256_bf16_windows_s"] = round(world * int(x256.shape[0]) / (hms * 1e-3), 1)
         del m256
+        # ... and its training step in the mixed mode (CTA-pair tensor-core recurrences, lstm_rec_swap.cu), 512 windows per GPU, no collective
+        if not args.no_train:
+            from lstm_ode_bci_b200 import train as _train
+            t256 = lstm.from_params(synth.make_lstm_params(44, 61, 256, 3), precision="fp32", device=f"cuda:{local}", dropout=0.4).train()
+            tr256 = _train.FusedTrainer(t256, lr=3e-4, weight_decay=1e-4, max_norm=1.0, class_weight=[0.8, 1.2], collective="none",
+                                        precision="mixed")
+            xt256, yt256 = x[:args.train_batch].contiguous(), (torch.arange(args.train_batch, device="cuda") % 2)
+            h256ms = timed(lambda: tr256.step(xt256, yt256, seed=7), 3, 2)
+            line["h256_train_mixed"] = {"ms_per_step": h256ms, "windows_per_gpu": args.train_batch, "value": world * args.train_batch / (h256ms * 1e-3),
+                                        "unit": "windows/s", "library_bar_ms": {"cudnn_autocast_fp16": 38.9, "cudnn_tf32": 40.0,
+                                                                                 "source": "profiles/r1_library_bar_torch_cuda.json"}}
+            tail["h256_train_mixed_ms_per_step"] = round(h256ms, 3)
+            tr256.close()
+            del tr256, t256
         # the reference's own call, unmodified: LSTMODEIntegration.predict_batch(X_numpy, forecast_steps=20, batch_size=512)
         # (06:801-806) -- pageable fp32 numpy windows in, numpy out, LSTM + coupling + ODE + classification; a model built
         # with precision="auto" runs its bf16 engine there because that is where the reference autocasts (06:348-351).  Rank 0 only.
