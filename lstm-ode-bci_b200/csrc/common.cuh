@@ -98,4 +98,15 @@ __device__ __forceinline__ float rec_tanh(float x) { return tanhf(x); }
 #endif
 
 
+// stateless dropout of the training step: the mask is a hash of (seed, site, element index) and is regenerated instead of stored
+__device__ __forceinline__ float drop_scale(uint64_t seed, uint32_t site, uint64_t idx, float p) {
+  if (p <= 0.f) return 1.f;
+  uint64_t z = seed + 0x9E3779B97F4A7C15ull * (idx + 1) + ((uint64_t)site << 56);
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z ^= z >> 31;
+  const float u = (float)(uint32_t)(z >> 40) * (1.0f / 16777216.0f);
+  return u < p ? 0.f : 1.0f / (1.0f - p);
+}
+
 }  // namespace bci

@@ -204,20 +204,29 @@ int tc_max_clusters();
 int launch_rec_f16x3(int ND, const float* G, int ldg, const __half* whh16, float* out, __half* out_hi16, __half* out_lo16, float* gates,
                      float* csave, int D, int Bc, int T, cudaStream_t st);
 // swapped (weights-as-A) tensor-core recurrences of the mixed-precision training step (lstm_rec_swap.cu)
+// dropout between LSTM layers folded into the recurrence kernels (forward: dropped copy of h_t written next to h_t; BPTT: the same
+// mask applied to the incoming gradient)
+struct SwapDropout {
+  float* outd;
+  float* outd_lo;
+  float p;
+  uint64_t seed;
+  uint32_t site;
+};
 int pack_whh_swap(const float* w_hh, __half* fwd, __nv_bfloat16* bwd, __half* bwd16, int H, cudaStream_t st);
 bool rec_swap_ok(int H, const void* G, int ldg);
 bool swap_rec_enabled();
 // hidden_size 256, mixed precision: the same recurrences on CTA pairs (each CTA owns 128 units; h / dG halves exchanged through DSMEM)
 bool rec_swap256_ok(int H, const void* G, int ldg);
 int launch_rec_swap256_fwd(int ND, const float* G, int ldg, const __half* whh, float* out, float* gates, float* csave, int D, int Bc, int T,
-                           cudaStream_t st);
+                           cudaStream_t st, const SwapDropout* drop = nullptr);
 int launch_bptt_swap256(int ND, const float* dout, const float* gates, const float* csave, const __nv_bfloat16* whhT, float* dG, float* dbias,
-                        int ldg, int D, int Bc, int T, cudaStream_t st);
+                        int ldg, int D, int Bc, int T, cudaStream_t st, const SwapDropout* drop = nullptr);
 int pack_swap_operands(bci_lstm_s* h, cudaStream_t st);
 int launch_rec_swap_fwd(int ND, const float* G, int ldg, const __half* whh, float* out, float* gates, float* csave, int D, int Bc, int T,
-                        bool split, cudaStream_t st);
+                        bool split, cudaStream_t st, const SwapDropout* drop = nullptr);
 int launch_bptt_swap(int ND, const float* dout, const float* gates, const float* csave, const void* whhT, float* dG, float* dG_lo,
-                     float* dbias, int ldg, int D, int Bc, int T, bool split, cudaStream_t st);
+                     float* dbias, int ldg, int D, int Bc, int T, bool split, cudaStream_t st, const SwapDropout* drop = nullptr);
 constexpr float F16X3_WSCALE = 16.0f;   // weights of the fp16-split paths are stored x 16 (keeps their lo parts out of fp16's subnormals)
 int split_f16(const float* x, __half* hi, __half* lo, long long n, float scale, cudaStream_t st);
 bool f16x3_nt_ok(const void* A_hi, int lda, const void* W_hi, int ldw, const void* C, int ldc, int M, int N, int K);

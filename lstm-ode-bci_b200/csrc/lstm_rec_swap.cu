@@ -211,6 +211,22 @@ __device__ __forceinline__ SwCtx sw_prologue(uint8_t* raw_ptr, const uint4* __re
   return c;
 }
 
+// dropout between LSTM layers (nn.LSTM(dropout=p), 04:181-188) folded into the recurrence kernels: the forward writes the dropped
+// copy of h_t next to h_t (it was a separate pass over the layer output), BPTT multiplies the incoming gradient by the same mask
+struct SwDrop {
+  float* outd;       // forward: dropped copy of out (nullptr: none)
+  float* outd_lo;    // forward: its tf32 remainder for the split-precision GEMM that reads it next (nullptr: not needed)
+  float p;           // BPTT: p > 0 applies the mask of `site` to dout
+  uint64_t seed;
+  uint32_t site;
+};
+__device__ __forceinline__ float tf32_lo(float x) {   // x - trunc_tf32(x), rounded to tf32 (what split_tf32_kernel produces)
+  const float rem = x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(rem));
+  return __uint_as_float(r);
+}
+
 #define SW_STAMP(cond, i) do { if (dbg && st >= 100 && st < 104 && (cond) && blockIdx.x == 0 && blockIdx.y == 0) dbg[(st - 100) * 8 + (i)] = clock64(); } while (0)
 
 // ---- forward --------------------------------------------------------------------------------------------------------------------
@@ -225,6 +241,7 @@ lstm_rec_swap_fwd(const float* __restrict__ G,        // [T*Bc][ldg] fp32: colum
                   float* __restrict__ out,            // [T][Bc][D]: h_t at column dir*128 + unit
                   float* __restrict__ gates,          // optional [T*Bc][ldg] gate ACTIVATIONS, same layout as G
                   float* __restrict__ csave,          // optional [T*Bc][D] cell states
+                  SwDrop dr,                          // optional dropped copy of h_t (the next layer's input), written here
                   int D, int Bc, int T, long long* __restrict__ dbg) {
   extern __shared__ uint8_t sw_smem_raw[];
   const int tid = threadIdx.x, u = tid & 127, wq = (tid >> 7) & 3;
@@ -305,6 +322,11 @@ lstm_rec_swap_fwd(const float* __restrict__ G,        // [T*Bc][ldg] fp32: colum
 #pragma unroll
         for (int i = 0; i < SW_WPT; ++i) sw_prefetch_l2(G + ((long long)t4 * Bc + brow[i]) * ldg + colg);
       }
+      float dsc[SW_WPT];   // dropout factors of this step's outputs: index arithmetic only, done while the product runs
+      if (dr.outd) {
+#pragma unroll
+        for (int i = 0; i < SW_WPT; ++i) dsc[i] = drop_scale(dr.seed, dr.site, (uint64_t)(((long long)t * Bc + brow[i]) * D + colh), dr.p);
+      }
       SW_STAMP(tid == 0, 1);
       mbar_wait(cx.acc_full, (uint32_t)(st & 1));
       tc_fence_after();
@@ -332,6 +354,11 @@ lstm_rec_swap_fwd(const float* __restrict__ G,        // [T*Bc][ldg] fp32: colum
           out[row * D + colh] = hv;
           if (gates) *reinterpret_cast<float4*>(gates + row * ldg + colg) = make_float4(ig, fg, gg, og);
           if (csave) csave[row * D + colh] = c[i];
+          if (dr.outd) {
+            const float hd = hv * dsc[i];
+            dr.outd[row * D + colh] = hd;
+            if (dr.outd_lo) dr.outd_lo[row * D + colh] = tf32_lo(hd);
+          }
         }
       }
       SW_STAMP(tid == 0, 4);
@@ -374,6 +401,7 @@ lstm_bptt_swap(const float* __restrict__ dout,           // [T][Bc][D]
                float* __restrict__ dG,                   // [T*Bc][ldg]
                float* __restrict__ dG_lo,                // optional
                float* __restrict__ dbias,                // optional [ldg]: += sum over rows of dG (the bias gradient, b_ih = b_hh)
+               SwDrop dr,                                // dr.p > 0: dout is the gradient wrt the DROPPED layer output (mask of dr.site)
                int ldg, int D, int Bc, int T) {
   extern __shared__ uint8_t sw_smem_raw[];
   const int tid = threadIdx.x, u = tid & 127, wq = (tid >> 7) & 3;
@@ -441,6 +469,7 @@ lstm_bptt_swap(const float* __restrict__ dout,           // [T][Bc][D]
         if (cc) cc[i] = __ldg(csave + row * D + colh);
         cp[i] = (s > 0) ? __ldg(csave + ((long long)tp * Bc + brow[i]) * D + colh) : 0.f;
         dd[i] = __ldg(dout + row * D + colh);
+        if (dr.p > 0.f) dd[i] *= drop_scale(dr.seed, dr.site, (uint64_t)(row * D + colh), dr.p);
       }
     };
     fetch(T - 1, pg, pc, pcp, pdo);
@@ -594,24 +623,26 @@ int pack_swap_operands(bci_lstm_s* h, cudaStream_t st) {
 }
 
 int launch_rec_swap_fwd(int ND, const float* G, int ldg, const __half* whh, float* out, float* gates, float* csave, int D, int Bc, int T,
-                        bool split, cudaStream_t st) {
+                        bool split, cudaStream_t st, const SwapDropout* drop) {
   int rc = sw_setup();
   if (rc) return rc;
   const dim3 grid(ceil_div(Bc, SW_NW), ND);
-  if (split) lstm_rec_swap_fwd<true><<<grid, SW_BLOCK, sw_smem_bytes(SW_FWD_B, true), st>>>(G, ldg, whh, out, gates, csave, D, Bc, T, g_sw_dbg);
-  else lstm_rec_swap_fwd<false><<<grid, SW_BLOCK, sw_smem_bytes(SW_FWD_B, false), st>>>(G, ldg, whh, out, gates, csave, D, Bc, T, g_sw_dbg);
+  const SwDrop dr = drop ? SwDrop{drop->outd, drop->outd_lo, drop->p, drop->seed, drop->site} : SwDrop{nullptr, nullptr, 0.f, 0, 0};
+  if (split) lstm_rec_swap_fwd<true><<<grid, SW_BLOCK, sw_smem_bytes(SW_FWD_B, true), st>>>(G, ldg, whh, out, gates, csave, dr, D, Bc, T, g_sw_dbg);
+  else lstm_rec_swap_fwd<false><<<grid, SW_BLOCK, sw_smem_bytes(SW_FWD_B, false), st>>>(G, ldg, whh, out, gates, csave, dr, D, Bc, T, g_sw_dbg);
   BCI_LAUNCH_OK();
   return BCI_OK;
 }
 
 // whhT: split ? the fp16 (hi, lo) pair [ND][2][128][512] : bf16 [ND][128][512]
 int launch_bptt_swap(int ND, const float* dout, const float* gates, const float* csave, const void* whhT, float* dG, float* dG_lo,
-                     float* dbias, int ldg, int D, int Bc, int T, bool split, cudaStream_t st) {
+                     float* dbias, int ldg, int D, int Bc, int T, bool split, cudaStream_t st, const SwapDropout* drop) {
   int rc = sw_setup();
   if (rc) return rc;
   const dim3 grid(ceil_div(Bc, SW_NW), ND);
-  if (split) lstm_bptt_swap<true><<<grid, SW_BLOCK, sw_smem_bytes(SW_BWD_B, true), st>>>(dout, gates, csave, whhT, dG, dG_lo, dbias, ldg, D, Bc, T);
-  else lstm_bptt_swap<false><<<grid, SW_BLOCK, sw_smem_bytes(SW_BWD_B, false), st>>>(dout, gates, csave, whhT, dG, dG_lo, dbias, ldg, D, Bc, T);
+  const SwDrop dr = drop ? SwDrop{nullptr, nullptr, drop->p, drop->seed, drop->site} : SwDrop{nullptr, nullptr, 0.f, 0, 0};
+  if (split) lstm_bptt_swap<true><<<grid, SW_BLOCK, sw_smem_bytes(SW_BWD_B, true), st>>>(dout, gates, csave, whhT, dG, dG_lo, dbias, dr, ldg, D, Bc, T);
+  else lstm_bptt_swap<false><<<grid, SW_BLOCK, sw_smem_bytes(SW_BWD_B, false), st>>>(dout, gates, csave, whhT, dG, dG_lo, dbias, dr, ldg, D, Bc, T);
   BCI_LAUNCH_OK();
   return BCI_OK;
 }
@@ -721,7 +752,7 @@ lstm_rec_swap256_fwd(const float* __restrict__ G,        // [T*Bc][ldg] fp32: co
                      int ldg,
                      const __half* __restrict__ whh,     // [ND][2 parts][1024][256] fp16 of 16 w (the hi part is used)
                      float* __restrict__ out,            // [T][Bc][D]: column dir*256 + unit
-                     float* __restrict__ gates, float* __restrict__ csave, int D, int Bc, int T) {
+                     float* __restrict__ gates, float* __restrict__ csave, SwDrop dr, int D, int Bc, int T) {
   extern __shared__ uint8_t sw_smem_raw[];
   const int tid = threadIdx.x, u = tid & 127, wq = (tid >> 7) & 3;
   const int warp_u = __shfl_sync(0xffffffffu, tid >> 5, 0);
@@ -799,6 +830,11 @@ lstm_rec_swap256_fwd(const float* __restrict__ G,        // [T*Bc][ldg] fp32: co
 #pragma unroll
         for (int i = 0; i < S2_WPT; ++i) sw_prefetch_l2(G + ((long long)t4 * Bc + brow[i]) * ldg + colg);
       }
+      float dsc[S2_WPT];
+      if (dr.outd) {
+#pragma unroll
+        for (int i = 0; i < S2_WPT; ++i) dsc[i] = drop_scale(dr.seed, dr.site, (uint64_t)(((long long)t * Bc + brow[i]) * D + colh), dr.p);
+      }
       mbar_wait(cx.acc_full, (uint32_t)(st & 1));
       tc_fence_after();
       uint32_t a[4][S2_WPT];
@@ -819,6 +855,7 @@ lstm_rec_swap256_fwd(const float* __restrict__ G,        // [T*Bc][ldg] fp32: co
           out[row * D + colh] = hv;
           if (gates) *reinterpret_cast<float4*>(gates + row * ldg + colg) = make_float4(ig, fg, gg, og);
           if (csave) csave[row * D + colh] = c[i];
+          if (dr.outd) dr.outd[row * D + colh] = hv * dsc[i];
         }
       }
       fence_proxy_async_smem();
@@ -840,7 +877,7 @@ lstm_bptt_swap256(const float* __restrict__ dout,           // [T][Bc][D]
                   const float* __restrict__ gates,          // [T*Bc][ldg]: column dir*1024 + unit*4
                   const float* __restrict__ csave,          // [T*Bc][D]
                   const __nv_bfloat16* __restrict__ whhT,   // [ND][256 j][1024 k = gate*256 + unit] bf16
-                  float* __restrict__ dG, float* __restrict__ dbias, int ldg, int D, int Bc, int T) {
+                  float* __restrict__ dG, float* __restrict__ dbias, SwDrop dr, int ldg, int D, int Bc, int T) {
   extern __shared__ uint8_t sw_smem_raw[];
   const int tid = threadIdx.x, u = tid & 127, wq = (tid >> 7) & 3;
   const int warp_u = __shfl_sync(0xffffffffu, tid >> 5, 0);
@@ -908,6 +945,7 @@ lstm_bptt_swap256(const float* __restrict__ dout,           // [T][Bc][D]
         if (cc) cc[i] = __ldg(csave + row * D + colh);
         cp[i] = (s > 0) ? __ldg(csave + ((long long)tp * Bc + brow[i]) * D + colh) : 0.f;
         dd[i] = __ldg(dout + row * D + colh);
+        if (dr.p > 0.f) dd[i] *= drop_scale(dr.seed, dr.site, (uint64_t)(row * D + colh), dr.p);
       }
     };
     fetch(T - 1, pg, pc, pcp, pdo);
@@ -997,19 +1035,21 @@ static int s2_setup() {
 bool rec_swap256_ok(int H, const void* G, int ldg) { return H == 256 && ((uintptr_t)G & 15) == 0 && (ldg & 3) == 0; }
 
 int launch_rec_swap256_fwd(int ND, const float* G, int ldg, const __half* whh, float* out, float* gates, float* csave, int D, int Bc, int T,
-                           cudaStream_t st) {
+                           cudaStream_t st, const SwapDropout* drop) {
   int rc = s2_setup();
   if (rc) return rc;
-  lstm_rec_swap256_fwd<<<dim3(2 * ceil_div(Bc, S2_NW), ND), SW_BLOCK, s2_smem_bytes(S2_FB), st>>>(G, ldg, whh, out, gates, csave, D, Bc, T);
+  const SwDrop dr = drop ? SwDrop{drop->outd, drop->outd_lo, drop->p, drop->seed, drop->site} : SwDrop{nullptr, nullptr, 0.f, 0, 0};
+  lstm_rec_swap256_fwd<<<dim3(2 * ceil_div(Bc, S2_NW), ND), SW_BLOCK, s2_smem_bytes(S2_FB), st>>>(G, ldg, whh, out, gates, csave, dr, D, Bc, T);
   BCI_LAUNCH_OK();
   return BCI_OK;
 }
 
 int launch_bptt_swap256(int ND, const float* dout, const float* gates, const float* csave, const __nv_bfloat16* whhT, float* dG, float* dbias,
-                        int ldg, int D, int Bc, int T, cudaStream_t st) {
+                        int ldg, int D, int Bc, int T, cudaStream_t st, const SwapDropout* drop) {
   int rc = s2_setup();
   if (rc) return rc;
-  lstm_bptt_swap256<<<dim3(2 * ceil_div(Bc, S2_NW), ND), SW_BLOCK, s2_smem_bytes(S2_BB), st>>>(dout, gates, csave, whhT, dG, dbias, ldg, D, Bc, T);
+  const SwDrop dr = drop ? SwDrop{nullptr, nullptr, drop->p, drop->seed, drop->site} : SwDrop{nullptr, nullptr, 0.f, 0, 0};
+  lstm_bptt_swap256<<<dim3(2 * ceil_div(Bc, S2_NW), ND), SW_BLOCK, s2_smem_bytes(S2_BB), st>>>(dout, gates, csave, whhT, dG, dbias, dr, ldg, D, Bc, T);
   BCI_LAUNCH_OK();
   return BCI_OK;
 }

@@ -17,16 +17,6 @@
 
 namespace bci {
 
-// ---- stateless dropout -------------------------------------------------------------------------
-__device__ __forceinline__ float drop_scale(uint64_t seed, uint32_t site, uint64_t idx, float p) {
-  if (p <= 0.f) return 1.f;
-  uint64_t z = seed + 0x9E3779B97F4A7C15ull * (idx + 1) + ((uint64_t)site << 56);
-  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
-  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-  z ^= z >> 31;
-  const float u = (float)(uint32_t)(z >> 40) * (1.0f / 16777216.0f);
-  return u < p ? 0.f : 1.0f / (1.0f - p);
-}
 __device__ __forceinline__ float gelu_grad(float x) {
   // d/dx [0.5 x (1 + erf(x/sqrt2))] = Phi(x) + x phi(x)
   const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
@@ -911,12 +901,15 @@ static int forward_train_t(bci_lstm_s* h, const float* x, int B, int T, float p_
       rc = launch_proj_gemm_f32(in, p.wih_t[l], p.bias[l], w.G, (int)M, 4 * D, K, st);
     }
     if (rc) return rc;
-    if (mixed && H == 256) rc = launch_rec_swap256_fwd(ND, w.G, 4 * D, p.whh_sw_f[l], w.out[l], w.gates[l], w.cst[l], D, B, T, st);
-    else if (mixed || split_fwd) rc = launch_rec_swap_fwd(ND, w.G, 4 * D, p.whh_sw_f[l], w.out[l], w.gates[l], w.cst[l], D, B, T, split_fwd, st);
+    // tensor-core recurrences write the dropped copy of the layer output themselves (no separate pass)
+    const bool fused_drop = (mixed || split_fwd) && w.outd[l] != w.out[l];
+    const SwapDropout fdrop{w.outd[l], mixed ? nullptr : w.lo_in, p_drop, seed, (uint32_t)(16 + l)};
+    if (mixed && H == 256) rc = launch_rec_swap256_fwd(ND, w.G, 4 * D, p.whh_sw_f[l], w.out[l], w.gates[l], w.cst[l], D, B, T, st, fused_drop ? &fdrop : nullptr);
+    else if (mixed || split_fwd) rc = launch_rec_swap_fwd(ND, w.G, 4 * D, p.whh_sw_f[l], w.out[l], w.gates[l], w.cst[l], D, B, T, split_fwd, st, fused_drop ? &fdrop : nullptr);
     else rc = launch_rec_f32(H, ND, w.G, p.whh_t[l][0], p.whh_t[l][1], w.out[l], w.gates[l], w.cst[l], B, T, st);
     if (rc) return rc;
-    lo_ready = false;
-    if (w.outd[l] != w.out[l]) {
+    lo_ready = fused_drop && !mixed && w.lo_in != nullptr;
+    if (w.outd[l] != w.out[l] && !fused_drop) {
       scale_mask_kernel<<<(unsigned)ceil_div64(M * D, 256), 256, 0, st>>>(w.out[l], w.outd[l], M * D, p_drop, seed, 16 + l,
                                                                           mixed ? nullptr : w.lo_in);
       BCI_LAUNCH_OK();
@@ -1070,12 +1063,15 @@ static int backward_t(bci_lstm_s* h, const float* dlogits, int B, int T, float p
     const bool tc = tf32x3_tn_ok(dGl, G4, in, K, w.tmpW2, K, M, G4, K) && tf32x3_tn_ok(dGl, G4, w.out[l], D, w.tmpW2, H, M - B, 4 * H, H) &&
                     tf32x3_nt_ok(dGl, G4, p.wih_t[l], G4, dnext, K, (int)M, K, G4);
     if (mixed || split_bwd) BCI_CUDA_OK(zero(w.dbias[gb], (size_t)G4));
+    // dcur is the gradient wrt this layer's DROPPED output when a dropout site follows it: the tensor-core BPTT kernels apply the mask
+    const bool drop_here = (mixed || split_bwd) && l < L - 1 && w.outd[l] != w.out[l];
+    const SwapDropout bdrop{nullptr, nullptr, drop_here ? p_drop : 0.f, seed, (uint32_t)(16 + l)};
     if (mixed && H == 256) {
-      if ((rc = launch_bptt_swap256(ND, dcur, w.gates[l], w.cst[l], p.whh_sw_b[l], dGl, w.dbias[gb], G4, D, B, T, st))) return rc;
+      if ((rc = launch_bptt_swap256(ND, dcur, w.gates[l], w.cst[l], p.whh_sw_b[l], dGl, w.dbias[gb], G4, D, B, T, st, &bdrop))) return rc;
     } else if (mixed) {
-      if ((rc = launch_bptt_swap(ND, dcur, w.gates[l], w.cst[l], p.whh_sw_b[l], dGl, nullptr, w.dbias[gb], G4, D, B, T, false, st))) return rc;
+      if ((rc = launch_bptt_swap(ND, dcur, w.gates[l], w.cst[l], p.whh_sw_b[l], dGl, nullptr, w.dbias[gb], G4, D, B, T, false, st, &bdrop))) return rc;
     } else if (split_bwd) {
-      if ((rc = launch_bptt_swap(ND, dcur, w.gates[l], w.cst[l], p.whh_sw_b16[l], dGl, tc ? dGl_lo : nullptr, w.dbias[gb], G4, D, B, T, true, st))) return rc;
+      if ((rc = launch_bptt_swap(ND, dcur, w.gates[l], w.cst[l], p.whh_sw_b16[l], dGl, tc ? dGl_lo : nullptr, w.dbias[gb], G4, D, B, T, true, st, &bdrop))) return rc;
     } else if (tiny && H == 128)
       lstm_bptt_f32<H, 4, BP_RES><<<dim3(ceil_div(B, MT), ND), BP_THREADS, bp_smem + bp_res_bytes, st>>>(dcur, w.gates[l], w.cst[l], p.whh_b[l][0], p.whh_b[l][1], dGl, tc ? dGl_lo : nullptr, B, T, ND);
     else if (tiny)
@@ -1135,7 +1131,7 @@ static int backward_t(bci_lstm_s* h, const float* dlogits, int B, int T, float p
     } else if ((rc = gemm_nn(dGl, G4, p.wih_b[l], K, dnext, K, (int)M, K, G4, nullptr, 0, st))) {
       return rc;
     }
-    if (l > 0 && w.outd[l - 1] != w.out[l - 1]) {
+    if (l > 0 && w.outd[l - 1] != w.out[l - 1] && !(mixed || split_bwd)) {   // (the tensor-core BPTT of layer l-1 applies this mask itself)
       scale_mask_kernel<<<(unsigned)ceil_div64(M * K, 256), 256, 0, st>>>(dnext, dnext, M * K, p_drop, seed, 16 + (l - 1));
       BCI_LAUNCH_OK();
     }

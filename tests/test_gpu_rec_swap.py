@@ -226,3 +226,29 @@ def test_mixed_mode_through_autocast_autograd_bridge():
         assert cos >= 0.999, (k, cos)
         diff = max(diff, float((a - b).abs().max()))
     assert diff > 0.0     # the two modes really are different code paths
+
+
+@pytest.mark.parametrize("H,B,T", [(128, 24, 48), (256, 24, 48)])
+def test_mixed_step_with_dropout_matches_fp32_step(H, B, T):
+    """dropout 0.4, same seed => same masks in both modes (the mask is a hash of seed / site / element index).  The tensor-core
+    recurrences apply the inter-layer masks themselves (forward: dropped copy written next to h_t; BPTT: mask on the incoming
+    gradient); at H = 256 the fp32-parity step still uses the separate mask passes of round 1, so this also cross-checks the two
+    implementations of the same dropout."""
+    params = synth.make_lstm_params(47, 61, H, 3, logit_gain=4.0)
+    x = torch.from_numpy(synth.make_windows(13, B, T, 61)).cuda()
+    y = (torch.arange(B) % 2).cuda()
+    grads, losses = {}, {}
+    for mode in ("fp32", "mixed"):
+        m = lstm.from_params(params, precision="fp32", dropout=0.4).train()
+        tr = train.FusedTrainer(m, lr=0.0, weight_decay=0.0, max_norm=0.0, precision=mode)
+        loss, _ = tr.step(x, y, seed=99)
+        losses[mode] = float(loss)
+        grads[mode] = {k: v.clone() for k, v in tr.grad_views.items()}
+        tr.close()
+    assert abs(losses["fp32"] - losses["mixed"]) <= 2e-3, losses
+    for k in grads["fp32"]:
+        if k == "attention.attention.2.bias":
+            continue
+        a, b = grads["fp32"][k].double().ravel(), grads["mixed"][k].double().ravel()
+        cos = float(a @ b / (a.norm() * b.norm() + 1e-300))
+        assert cos >= 0.999, (k, cos)
