@@ -695,10 +695,30 @@ static size_t chunk_bytes_bf16(const bci_lstm_config& c, int Bc, int T) {
          align_up(rows * 4, 1024) + align_up(rows * 8 * sizeof(float2), 1024);
 }
 
+// Batches up to this many windows do not fill one wave of the tile-per-CTA tcgen05 kernels (128 windows per CTA): they run the
+// swapped recurrence (8 windows per CTA, W_hh in tensor memory: lstm_rec_swap.cu) in its one-chain fp16 form, fed by single-pass
+// TF32 projections, through the fp32 path's small-batch code.  BCI_BF16_SMALL=off keeps the tile kernels for them.
+// (measured: 256 windows 3.10 -> 1.21 ms, 512 windows 3.12 -> 1.78 ms, single window 3.04 -> 0.72 ms; from one wave of the swapped
+// kernel -- 148 CTAs x 8 windows / 2 directions -- upwards the 3.1 ms latency of the fused cluster kernel is the shorter one)
+constexpr int BF16_SMALL_BATCH = 592;
+static bool bf16_small_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("BCI_BF16_SMALL");
+    v = (e && e[0] == 'o') ? 0 : 1;
+  }
+  return v != 0 && swap_rec_enabled();
+}
+
 size_t lstm_workspace_bf16(const bci_lstm_config& c, int batch, int T) {
   if (c.hidden_size == 256) return lstm_workspace_h256(c, batch, T);
   const int Bc = batch < max_chunk(c, 0) ? batch : max_chunk(c, 0);
-  return chunk_bytes_bf16(c, Bc > 0 ? Bc : 1, T) + 1024;  // + slack: the TMA-addressed buffers are aligned to 1 KB internally
+  size_t n = chunk_bytes_bf16(c, Bc > 0 ? Bc : 1, T) + 1024;  // + slack: the TMA-addressed buffers are aligned to 1 KB internally
+  if (batch <= BF16_SMALL_BATCH && bf16_small_enabled()) {
+    const size_t m = lstm_chunk_bytes_f32(c, batch > 0 ? batch : 1, T);
+    if (m > n) n = m;
+  }
+  return n;
 }
 
 static int forward_chunk_bf16(bci_lstm_s* h, const InputView& x, int Bc, int T, float* logits, float* probs, float* attn, char* ws,
@@ -752,6 +772,12 @@ int lstm_forward_bf16(bci_lstm_s* h, const InputView& x, int batch, int T, float
   const bci_lstm_config& c = h->cfg;
   if (c.hidden_size == 256) return lstm_forward_h256(h, x, batch, T, logits, probs, attn, ws, ws_bytes, st);
   BCI_REQUIRE(c.hidden_size == 128, BCI_EINVAL, "bf16 mode supports hidden_size 128 and 256");
+  if (batch <= BF16_SMALL_BATCH && bf16_small_enabled()) {
+    h->infer_fast = true;
+    const int rc = lstm_forward_fp32(h, x, batch, T, logits, probs, attn, ws, ws_bytes, st);
+    h->infer_fast = false;
+    return rc;
+  }
   const int chunk = batch < max_chunk(c, 0) ? batch : max_chunk(c, 0);
   char* ws_al = reinterpret_cast<char*>(((uintptr_t)ws + 1023) & ~(uintptr_t)1023);
   BCI_REQUIRE(ws_bytes >= chunk_bytes_bf16(c, chunk, T) + (size_t)(ws_al - (char*)ws), BCI_ENOMEM,

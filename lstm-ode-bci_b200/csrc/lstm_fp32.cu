@@ -464,6 +464,8 @@ static size_t chunk_bytes_f32(const bci_lstm_config& c, int Bc, int T) {
          align_up((size_t)Bc * T * 4, 256);
 }
 
+size_t lstm_chunk_bytes_f32(const bci_lstm_config& c, int Bc, int T) { return chunk_bytes_f32(c, Bc, T); }
+
 size_t lstm_workspace_fp32(const bci_lstm_config& c, int batch, int T) {
   const int Bc = batch < max_chunk(c, 0) ? batch : max_chunk(c, 0);
   return chunk_bytes_f32(c, Bc > 0 ? Bc : 1, T);
@@ -494,7 +496,8 @@ static int forward_chunk_f32(bci_lstm_s* h, const InputView& x, int Bc, int T, f
   // layer writes fp32 for the pooling kernel.  The pair buffers reuse the space of the tf32 remainder array.
   __half* in_hi16 = reinterpret_cast<__half*>(in_lo);
   __half* in_lo16 = in_hi16 + rows * D;
-  const bool tc = H == 128 && tc_rec_ok(H, ND, Bc, g, 4 * D, o0, D) && c.input_size <= 64 &&
+  const bool fast = h->infer_fast;   // small batch of the bf16 engine: reduced-precision forms of the same kernels
+  const bool tc = !fast && H == 128 && tc_rec_ok(H, ND, Bc, g, 4 * D, o0, D) && c.input_size <= 64 &&
                   f16x3_nt_ok(in_hi16, H, h->f32.wih16[0], H, g, 4 * D, (int)rows, 4 * D, H);
   if (tc && h->f16_stale && (rc = pack_f16_operands(h, st))) return rc;
   if (tc) {
@@ -511,7 +514,7 @@ static int forward_chunk_f32(bci_lstm_s* h, const InputView& x, int Bc, int T, f
         g, (long long)rows, h->f32.ln0w, h->f32.ln0b, c.use_layer_norm, in_hi16, in_lo16);
     BCI_LAUNCH_OK();
   } else {
-    if ((rc = launch_input_proj<H, float>(h, x, Bc, T, z, st))) return rc;
+    if ((rc = launch_input_proj<H, float>(h, x, Bc, T, z, st, fast))) return rc;
   }
   h->prof.mark(0, st);
   for (int l = 0; l < c.num_layers; ++l) {
@@ -533,8 +536,10 @@ static int forward_chunk_f32(bci_lstm_s* h, const InputView& x, int Bc, int T, f
     }
     if (tf32x3_nt_ok(in, K, h->f32.wih_b[l], K, g, N, M, N, K)) {
       // G = in . W_ih^T on the tensor cores in split precision (3 x TF32, fp32-grade)
-      if ((rc = split_tf32(in, nullptr, in_lo, (long long)M * K, st))) return rc;
-      if ((rc = gemm_tf32x3_nt(in, in_lo, K, h->f32.wih_b[l], h->f32.wih_b_lo[l], K, h->f32.bias[l], g, N, M, N, K, 0, st))) return rc;
+      if (!fast && (rc = split_tf32(in, nullptr, in_lo, (long long)M * K, st))) return rc;
+      if ((rc = gemm_tf32x3_nt(in, fast ? nullptr : in_lo, K, h->f32.wih_b[l], fast ? nullptr : h->f32.wih_b_lo[l], K, h->f32.bias[l], g, N,
+                               M, N, K, 0, st)))
+        return rc;
     } else {
       dim3 gg(N / GN, ceil_div(M, GM));
       proj_gemm_f32<<<gg, GEMM_THREADS, 0, st>>>(in, h->f32.wih_t[l], h->f32.bias[l], g, M, N, K, 0);
@@ -548,7 +553,7 @@ static int forward_chunk_f32(bci_lstm_s* h, const InputView& x, int Bc, int T, f
     // CTA (lstm_rec_swap.cu; 1.96 us per step against 4.9 on the CUDA cores at 512 windows)
     if (H == 128 && swap_rec_enabled() && rec_swap_ok(H, g, N)) {
       if ((rc = pack_swap_operands(h, st))) return rc;
-      if ((rc = launch_rec_swap_fwd(ND, g, N, h->f32.whh_sw_f[l], o, nullptr, nullptr, D, Bc, T, true, st))) return rc;
+      if ((rc = launch_rec_swap_fwd(ND, g, N, h->f32.whh_sw_f[l], o, nullptr, nullptr, D, Bc, T, !fast, st))) return rc;
     } else if ((rc = launch_rec_f32(H, ND, g, h->f32.whh_t[l][0], h->f32.whh_t[l][1], o, nullptr, nullptr, Bc, T, st))) {
       return rc;
     }

@@ -124,6 +124,9 @@ struct bci_lstm_s {
   // operands are packed on its first forward after a load
   int train_mode;
   bool sw_stale;
+  // set by the bf16 engine around a small-batch forward it hands to the fp32 path's small-batch code in its fast form (one fp16
+  // product chain in the swapped recurrence, single-pass TF32 projections): see lstm_forward_bf16
+  bool infer_fast;
   // the last train=1 forward (workspace + header): a backward on the same workspace needs no device->host read of the header
   void* last_train_ws;
   float last_dropout;
@@ -192,6 +195,7 @@ struct FwdWorkspace {
 int lstm_forward_fp32(bci_lstm_s* h, const InputView& x, int batch, int T, float* logits, float* probs, float* attn,
                       void* ws, size_t ws_bytes, cudaStream_t st);
 size_t lstm_workspace_fp32(const bci_lstm_config& c, int batch, int T);
+size_t lstm_chunk_bytes_f32(const bci_lstm_config& c, int Bc, int T);
 int launch_proj_gemm_f32(const float* A, const float* Bt, const float* bias, float* C, int M, int N, int K, cudaStream_t st,
                          int accumulate = 0);
 int launch_rec_f32(int H, int ND, const float* G, const float* whh_f, const float* whh_r, float* out, float* gates, float* csave,

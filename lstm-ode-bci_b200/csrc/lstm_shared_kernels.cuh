@@ -25,7 +25,9 @@ template <int H, typename OutT>
 __global__ void __launch_bounds__(K1_THREADS)
 input_proj_kernel(const InputView x, int Bc, int T, int C, const float* __restrict__ w0t,
                   const float* __restrict__ b0, const float* __restrict__ lnw, const float* __restrict__ lnb,
-                  OutT* __restrict__ z, int use_ln) {
+                  OutT* __restrict__ z, int flags) {   // flags: bit 0 = LayerNorm present, bit 1 = round x to bf16 on load
+  const int use_ln = flags & 1;
+  const bool round_x = (flags & 2) != 0;   // the bf16 engine's contract: bf16 storage of the input changes no result bit
   extern __shared__ __align__(16) float k1_smem[];  // [C][H]
   constexpr int NV = H / 32;          // outputs per lane (4 or 8)
   constexpr int NQ = NV / 4;          // float4 groups per lane
@@ -48,6 +50,7 @@ input_proj_kernel(const InputView x, int Bc, int T, int C, const float* __restri
     const long long xr = x.elem_off(b) + (long long)t * C;   // first element of the row (windows may overlap / be bf16: InputView)
     float xa = lane < C ? view_load(x, xr + lane) : 0.f;
     float xb = (32 + lane) < C ? view_load(x, xr + 32 + lane) : 0.f;
+    if (round_x) { xa = __bfloat162float(__float2bfloat16_rn(xa)); xb = __bfloat162float(__float2bfloat16_rn(xb)); }
     float acc[NV];
 #pragma unroll
     for (int v = 0; v < NV; ++v) acc[v] = bias[v];
@@ -392,7 +395,7 @@ ln_pair_rows256_kernel(const float* __restrict__ seq, long long rows, const floa
 }
 
 template <int H, typename OutT>
-inline int launch_input_proj(const bci_lstm_s* h, const InputView& x, int Bc, int T, OutT* z, cudaStream_t st) {
+inline int launch_input_proj(const bci_lstm_s* h, const InputView& x, int Bc, int T, OutT* z, cudaStream_t st, bool round_x_bf16 = false) {
   const int C = h->cfg.input_size;
   const size_t smem = (size_t)C * H * sizeof(float);
   static PerDeviceFlag attr_pd;
@@ -407,7 +410,7 @@ inline int launch_input_proj(const bci_lstm_s* h, const InputView& x, int Bc, in
   if (blocks > cap) blocks = cap;
   const PackedF32& p = h->f32;
   input_proj_kernel<H, OutT><<<(unsigned)blocks, K1_THREADS, smem, st>>>(x, Bc, T, C, p.w0t, p.b0, p.ln0w, p.ln0b, z,
-                                                                         h->cfg.use_layer_norm);
+                                                                         (h->cfg.use_layer_norm ? 1 : 0) | (round_x_bf16 ? 2 : 0));
   BCI_LAUNCH_OK();
   return BCI_OK;
 }
