@@ -12,7 +12,7 @@ gen = torch.Generator(device="cuda").manual_seed(42)
 xmax = torch.randn((65536, 256, 61), device="cuda", generator=gen)
 for prec in ("bf16", "fp32"):
     m = lstm.from_params(params, precision=prec)
-    for B in (256, 1024, 4096, 9472, 16384, 16896, 65536):
+    for B in (1, 256, 512, 1024, 4096, 9472, 16384, 16896, 65536):
         x = xmax[:B]
         reps = 5 if (prec == "bf16" or B <= 16896) else 2
         for _ in range(3 if B <= 16896 else 1):

@@ -114,3 +114,12 @@ def test_host_scalar_helpers_match_golden(golden):
         integ = integration.LSTMODEIntegration(None, ode.CognitiveStateODE(dict(base)), float(g6["alpha"][i]))
         mod = integ.modulate_ode_rates(g6["p_closed"][i], g6["p_open"][i])
         assert [mod[k] for k in synth.RATE_ORDER] == list(g6["rates"][:, i])
+
+
+def test_train_mode_constants_match_header():
+    """ops.TRAIN_MODES mirrors the BCI_TRAIN_* enum of include/bci_b200.h; bci_lstm_set_train_mode is exported."""
+    from lstm_ode_bci_b200 import _native, ops
+    hdr = open(os.path.join(ROOT, "include", "bci_b200.h")).read()
+    m = re.search(r"enum \{ BCI_TRAIN_FP32 = (\d+), BCI_TRAIN_MIXED = (\d+) \}", hdr)
+    assert m and ops.TRAIN_MODES == {"fp32": int(m.group(1)), "mixed": int(m.group(2))}
+    assert hasattr(_native.lib(), "bci_lstm_set_train_mode")

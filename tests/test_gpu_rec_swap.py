@@ -252,3 +252,31 @@ def test_mixed_step_with_dropout_matches_fp32_step(H, B, T):
         a, b = grads["fp32"][k].double().ravel(), grads["mixed"][k].double().ravel()
         cos = float(a @ b / (a.norm() * b.norm() + 1e-300))
         assert cos >= 0.999, (k, cos)
+
+
+@pytest.mark.parametrize("kw", [dict(hidden_size=128, bidirectional=False, use_attention=False, num_layers=1),
+                                dict(hidden_size=256, bidirectional=True, use_attention=False, use_layer_norm=False, num_layers=2),
+                                dict(hidden_size=256, bidirectional=False, use_attention=True, num_layers=3)])
+def test_mixed_mode_on_ablation_variants(kw):
+    """The ablation switches of 09_sensitivity_analysis.py:176-240 (unidirectional, mean pooling, no LayerNorm, fewer layers) under the
+    mixed training mode: gradients against the fp32-parity step of the same variant."""
+    torch.manual_seed(3)
+    m = lstm.AblationLSTMModel(input_size=61, dropout=0.0, **kw).cuda().train()
+    B, T = 20, 40
+    x = torch.from_numpy(synth.make_windows(14, B, T, 61)).cuda()
+    y = (torch.arange(B) % 2).cuda()
+    grads = {}
+    for mode in ("fp32", "mixed"):
+        m.train_precision = mode
+        m.zero_grad()
+        torch.nn.functional.cross_entropy(m(x), y).backward()
+        grads[mode] = {k: p.grad.clone() for k, p in m.named_parameters()}
+    moved = 0.0
+    for k in grads["fp32"]:
+        a, b = grads["fp32"][k].double().ravel(), grads["mixed"][k].double().ravel()
+        if float(a.norm()) < 1e-12 or k == "attention.attention.2.bias":   # softmax is shift-invariant: that gradient is rounding noise
+            continue
+        cos = float(a @ b / (a.norm() * b.norm() + 1e-300))
+        assert cos >= 0.999, (k, cos)
+        moved = max(moved, float((a - b).abs().max()))
+    assert moved > 0.0
