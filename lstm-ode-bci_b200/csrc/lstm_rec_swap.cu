@@ -227,6 +227,25 @@ __device__ __forceinline__ float tf32_lo(float x) {   // x - trunc_tf32(x), roun
   return __uint_as_float(r);
 }
 
+// BCI_FUSED_JITTER (tests only; a power of two = the longest sleep in ns): every role sleeps a pseudo-random time at its
+// synchronisation points, to shake out ordering assumptions that only hold at the natural timing (compute-sanitizer is not available
+// on the GPU pool; lstm_bf16_fused.cu's first protocol bug only showed under such perturbation)
+struct SwJitter {
+  uint32_t state;
+  int max_ns;
+  __device__ __forceinline__ SwJitter(int m) : state((uint32_t)(blockIdx.x * 7919u + blockIdx.y * 131u + threadIdx.x * 104729u + 12345u)), max_ns(m) {}
+  __device__ __forceinline__ void operator()() {
+    if (max_ns) {
+      state = state * 1664525u + 1013904223u;
+      __nanosleep((state >> 20) & (uint32_t)(max_ns - 1));
+    }
+  }
+};
+static int sw_jitter() {
+  static const int v = [] { const char* e = getenv("BCI_FUSED_JITTER"); int j = e ? atoi(e) : 0; return (j > 0 && (j & (j - 1)) == 0) ? j : 0; }();
+  return v;
+}
+
 #define SW_STAMP(cond, i) do { if (dbg && st >= 100 && st < 104 && (cond) && blockIdx.x == 0 && blockIdx.y == 0) dbg[(st - 100) * 8 + (i)] = clock64(); } while (0)
 
 // ---- forward --------------------------------------------------------------------------------------------------------------------
@@ -242,7 +261,8 @@ lstm_rec_swap_fwd(const float* __restrict__ G,        // [T*Bc][ldg] fp32: colum
                   float* __restrict__ gates,          // optional [T*Bc][ldg] gate ACTIVATIONS, same layout as G
                   float* __restrict__ csave,          // optional [T*Bc][D] cell states
                   SwDrop dr,                          // optional dropped copy of h_t (the next layer's input), written here
-                  int D, int Bc, int T, long long* __restrict__ dbg) {
+                  int D, int Bc, int T, long long* __restrict__ dbg, int jitter) {
+  SwJitter jit(jitter);
   extern __shared__ uint8_t sw_smem_raw[];
   const int tid = threadIdx.x, u = tid & 127, wq = (tid >> 7) & 3;
   const int warp_u = __shfl_sync(0xffffffffu, tid >> 5, 0);   // warp-uniform for the compiler
@@ -254,6 +274,7 @@ lstm_rec_swap_fwd(const float* __restrict__ G,        // [T*Bc][ldg] fp32: colum
   if (warp_u == SW_EPI / 32) {
     // ---- MMA warp: 4 gate blocks x 8 K slices per step, A = resident weights in tensor memory, B = h_{t-1}
     for (int st = 0; st < T; ++st) {
+      jit();
       if (st > 0) mbar_wait(cx.op_ready, (uint32_t)((st - 1) & 1));
       tc_fence_after();
       if (elect_one()) {
@@ -328,6 +349,7 @@ lstm_rec_swap_fwd(const float* __restrict__ G,        // [T*Bc][ldg] fp32: colum
         for (int i = 0; i < SW_WPT; ++i) dsc[i] = drop_scale(dr.seed, dr.site, (uint64_t)(((long long)t * Bc + brow[i]) * D + colh), dr.p);
       }
       SW_STAMP(tid == 0, 1);
+      jit();
       mbar_wait(cx.acc_full, (uint32_t)(st & 1));
       tc_fence_after();
       SW_STAMP(tid == 0, 2);
@@ -365,7 +387,7 @@ lstm_rec_swap_fwd(const float* __restrict__ G,        // [T*Bc][ldg] fp32: colum
       fence_proxy_async_smem();  // h_t (generic-proxy stores) -> visible to the next step's tcgen05.mma
       tc_fence_before();         // this thread's TMEM reads are ordered before the arrive
       __syncwarp();
-      if ((tid & 31) == 0) mbar_arrive(cx.op_ready);
+      if ((tid & 31) == 0) { jit(); mbar_arrive(cx.op_ready); }
       SW_STAMP(tid == 0, 5);
     }
   }
@@ -402,7 +424,8 @@ lstm_bptt_swap(const float* __restrict__ dout,           // [T][Bc][D]
                float* __restrict__ dG_lo,                // optional
                float* __restrict__ dbias,                // optional [ldg]: += sum over rows of dG (the bias gradient, b_ih = b_hh)
                SwDrop dr,                                // dr.p > 0: dout is the gradient wrt the DROPPED layer output (mask of dr.site)
-               int ldg, int D, int Bc, int T) {
+               int ldg, int D, int Bc, int T, int jitter) {
+  SwJitter jit(jitter);
   extern __shared__ uint8_t sw_smem_raw[];
   const int tid = threadIdx.x, u = tid & 127, wq = (tid >> 7) & 3;
   const int warp_u = __shfl_sync(0xffffffffu, tid >> 5, 0);
@@ -416,6 +439,7 @@ lstm_bptt_swap(const float* __restrict__ dout,           // [T][Bc][D]
 
   if (warp_u == SW_EPI / 32) {
     for (int s = T - 1; s > 0; --s) {
+      jit();
       mbar_wait(cx.op_ready, (uint32_t)((T - 1 - s) & 1));
       tc_fence_after();
       if (elect_one()) {
@@ -550,7 +574,7 @@ lstm_bptt_swap(const float* __restrict__ dout,           // [T][Bc][D]
       fence_proxy_async_smem();
       tc_fence_before();
       __syncwarp();
-      if ((tid & 31) == 0) mbar_arrive(cx.op_ready);
+      if ((tid & 31) == 0) { jit(); mbar_arrive(cx.op_ready); }
       // step s-1's saved activations are requested while the product runs; c(s-1) is this step's cprev
       float4 ng[SW_WPT];
       float ncp[SW_WPT], ndo[SW_WPT];
@@ -628,8 +652,8 @@ int launch_rec_swap_fwd(int ND, const float* G, int ldg, const __half* whh, floa
   if (rc) return rc;
   const dim3 grid(ceil_div(Bc, SW_NW), ND);
   const SwDrop dr = drop ? SwDrop{drop->outd, drop->outd_lo, drop->p, drop->seed, drop->site} : SwDrop{nullptr, nullptr, 0.f, 0, 0};
-  if (split) lstm_rec_swap_fwd<true><<<grid, SW_BLOCK, sw_smem_bytes(SW_FWD_B, true), st>>>(G, ldg, whh, out, gates, csave, dr, D, Bc, T, g_sw_dbg);
-  else lstm_rec_swap_fwd<false><<<grid, SW_BLOCK, sw_smem_bytes(SW_FWD_B, false), st>>>(G, ldg, whh, out, gates, csave, dr, D, Bc, T, g_sw_dbg);
+  if (split) lstm_rec_swap_fwd<true><<<grid, SW_BLOCK, sw_smem_bytes(SW_FWD_B, true), st>>>(G, ldg, whh, out, gates, csave, dr, D, Bc, T, g_sw_dbg, sw_jitter());
+  else lstm_rec_swap_fwd<false><<<grid, SW_BLOCK, sw_smem_bytes(SW_FWD_B, false), st>>>(G, ldg, whh, out, gates, csave, dr, D, Bc, T, g_sw_dbg, sw_jitter());
   BCI_LAUNCH_OK();
   return BCI_OK;
 }
@@ -641,8 +665,8 @@ int launch_bptt_swap(int ND, const float* dout, const float* gates, const float*
   if (rc) return rc;
   const dim3 grid(ceil_div(Bc, SW_NW), ND);
   const SwDrop dr = drop ? SwDrop{nullptr, nullptr, drop->p, drop->seed, drop->site} : SwDrop{nullptr, nullptr, 0.f, 0, 0};
-  if (split) lstm_bptt_swap<true><<<grid, SW_BLOCK, sw_smem_bytes(SW_BWD_B, true), st>>>(dout, gates, csave, whhT, dG, dG_lo, dbias, dr, ldg, D, Bc, T);
-  else lstm_bptt_swap<false><<<grid, SW_BLOCK, sw_smem_bytes(SW_BWD_B, false), st>>>(dout, gates, csave, whhT, dG, dG_lo, dbias, dr, ldg, D, Bc, T);
+  if (split) lstm_bptt_swap<true><<<grid, SW_BLOCK, sw_smem_bytes(SW_BWD_B, true), st>>>(dout, gates, csave, whhT, dG, dG_lo, dbias, dr, ldg, D, Bc, T, sw_jitter());
+  else lstm_bptt_swap<false><<<grid, SW_BLOCK, sw_smem_bytes(SW_BWD_B, false), st>>>(dout, gates, csave, whhT, dG, dG_lo, dbias, dr, ldg, D, Bc, T, sw_jitter());
   BCI_LAUNCH_OK();
   return BCI_OK;
 }
@@ -752,7 +776,8 @@ lstm_rec_swap256_fwd(const float* __restrict__ G,        // [T*Bc][ldg] fp32: co
                      int ldg,
                      const __half* __restrict__ whh,     // [ND][2 parts][1024][256] fp16 of 16 w (the hi part is used)
                      float* __restrict__ out,            // [T][Bc][D]: column dir*256 + unit
-                     float* __restrict__ gates, float* __restrict__ csave, SwDrop dr, int D, int Bc, int T) {
+                     float* __restrict__ gates, float* __restrict__ csave, SwDrop dr, int D, int Bc, int T, int jitter) {
+  SwJitter jit(jitter);
   extern __shared__ uint8_t sw_smem_raw[];
   const int tid = threadIdx.x, u = tid & 127, wq = (tid >> 7) & 3;
   const int warp_u = __shfl_sync(0xffffffffu, tid >> 5, 0);
@@ -767,12 +792,16 @@ lstm_rec_swap256_fwd(const float* __restrict__ G,        // [T*Bc][ldg] fp32: co
     for (int st = 0; st < T; ++st) {
       const uint32_t buf = (uint32_t)(st & 1), sBb = cx.sB + buf * S2_FB, xin = cx.x_in + 8u * buf;
       if (st > 0) {
+        jit();
         mbar_wait(cx.op_ready, (uint32_t)((st - 1) & 1));   // this CTA's half of h_{st-1} is in B[buf]
+        jit();
         if (elect_one()) {
           const uint32_t mine = sBb + 2u * rank * SW_BATOM;
           bulk_copy_s2s_cluster(mapa_u32(mine, peer), mine, 4096u, mapa_u32(xin, peer));
         }
+        jit();
         mbar_wait(xin, (uint32_t)(((st - 1) >> 1) & 1));    // the peer's half has landed
+        jit();
         if (elect_one()) mbar_arrive_expect_tx(xin, 4096u);  // re-arm for step st + 2
       }
       tc_fence_after();
@@ -835,6 +864,7 @@ lstm_rec_swap256_fwd(const float* __restrict__ G,        // [T*Bc][ldg] fp32: co
 #pragma unroll
         for (int i = 0; i < S2_WPT; ++i) dsc[i] = drop_scale(dr.seed, dr.site, (uint64_t)(((long long)t * Bc + brow[i]) * D + colh), dr.p);
       }
+      jit();
       mbar_wait(cx.acc_full, (uint32_t)(st & 1));
       tc_fence_after();
       uint32_t a[4][S2_WPT];
@@ -861,7 +891,7 @@ lstm_rec_swap256_fwd(const float* __restrict__ G,        // [T*Bc][ldg] fp32: co
       fence_proxy_async_smem();
       tc_fence_before();
       __syncwarp();
-      if ((tid & 31) == 0) mbar_arrive(cx.op_ready);
+      if ((tid & 31) == 0) { jit(); mbar_arrive(cx.op_ready); }
     }
   }
   tc_fence_before();
@@ -877,7 +907,8 @@ lstm_bptt_swap256(const float* __restrict__ dout,           // [T][Bc][D]
                   const float* __restrict__ gates,          // [T*Bc][ldg]: column dir*1024 + unit*4
                   const float* __restrict__ csave,          // [T*Bc][D]
                   const __nv_bfloat16* __restrict__ whhT,   // [ND][256 j][1024 k = gate*256 + unit] bf16
-                  float* __restrict__ dG, float* __restrict__ dbias, SwDrop dr, int ldg, int D, int Bc, int T) {
+                  float* __restrict__ dG, float* __restrict__ dbias, SwDrop dr, int ldg, int D, int Bc, int T, int jitter) {
+  SwJitter jit(jitter);
   extern __shared__ uint8_t sw_smem_raw[];
   const int tid = threadIdx.x, u = tid & 127, wq = (tid >> 7) & 3;
   const int warp_u = __shfl_sync(0xffffffffu, tid >> 5, 0);
@@ -891,7 +922,9 @@ lstm_bptt_swap256(const float* __restrict__ dout,           // [T][Bc][D]
   if (warp_u == SW_EPI / 32) {
     for (int it = 0; it + 1 < T; ++it) {
       const uint32_t buf = (uint32_t)(it & 1), sBb = cx.sB + buf * S2_BB, xin = cx.x_in + 8u * buf;
+      jit();
       mbar_wait(cx.op_ready, (uint32_t)(it & 1));   // this CTA's half of dG is in B[buf]
+      jit();
       if (elect_one()) {
 #pragma unroll
         for (int g = 0; g < 4; ++g) {   // gate g: atoms 4 g + 2 r, + 1
@@ -899,7 +932,9 @@ lstm_bptt_swap256(const float* __restrict__ dout,           // [T][Bc][D]
           bulk_copy_s2s_cluster(mapa_u32(mine, peer), mine, 4096u, mapa_u32(xin, peer));
         }
       }
+      jit();
       mbar_wait(xin, (uint32_t)((it >> 1) & 1));
+      jit();
       if (elect_one()) mbar_arrive_expect_tx(xin, 16384u);
       tc_fence_after();
       if (elect_one()) {
@@ -988,7 +1023,7 @@ lstm_bptt_swap256(const float* __restrict__ dout,           // [T][Bc][D]
       fence_proxy_async_smem();
       tc_fence_before();
       __syncwarp();
-      if ((tid & 31) == 0) mbar_arrive(cx.op_ready);
+      if ((tid & 31) == 0) { jit(); mbar_arrive(cx.op_ready); }
       float4 ng[S2_WPT];
       float ncp[S2_WPT], ndo[S2_WPT];
       fetch(s - 1, ng, nullptr, ncp, ndo);
@@ -1039,7 +1074,7 @@ int launch_rec_swap256_fwd(int ND, const float* G, int ldg, const __half* whh, f
   int rc = s2_setup();
   if (rc) return rc;
   const SwDrop dr = drop ? SwDrop{drop->outd, drop->outd_lo, drop->p, drop->seed, drop->site} : SwDrop{nullptr, nullptr, 0.f, 0, 0};
-  lstm_rec_swap256_fwd<<<dim3(2 * ceil_div(Bc, S2_NW), ND), SW_BLOCK, s2_smem_bytes(S2_FB), st>>>(G, ldg, whh, out, gates, csave, dr, D, Bc, T);
+  lstm_rec_swap256_fwd<<<dim3(2 * ceil_div(Bc, S2_NW), ND), SW_BLOCK, s2_smem_bytes(S2_FB), st>>>(G, ldg, whh, out, gates, csave, dr, D, Bc, T, sw_jitter());
   BCI_LAUNCH_OK();
   return BCI_OK;
 }
@@ -1049,7 +1084,7 @@ int launch_bptt_swap256(int ND, const float* dout, const float* gates, const flo
   int rc = s2_setup();
   if (rc) return rc;
   const SwDrop dr = drop ? SwDrop{nullptr, nullptr, drop->p, drop->seed, drop->site} : SwDrop{nullptr, nullptr, 0.f, 0, 0};
-  lstm_bptt_swap256<<<dim3(2 * ceil_div(Bc, S2_NW), ND), SW_BLOCK, s2_smem_bytes(S2_BB), st>>>(dout, gates, csave, whhT, dG, dbias, dr, ldg, D, Bc, T);
+  lstm_bptt_swap256<<<dim3(2 * ceil_div(Bc, S2_NW), ND), SW_BLOCK, s2_smem_bytes(S2_BB), st>>>(dout, gates, csave, whhT, dG, dbias, dr, ldg, D, Bc, T, sw_jitter());
   BCI_LAUNCH_OK();
   return BCI_OK;
 }

@@ -280,3 +280,41 @@ def test_mixed_mode_on_ablation_variants(kw):
         assert cos >= 0.999, (k, cos)
         moved = max(moved, float((a - b).abs().max()))
     assert moved > 0.0
+
+
+_JITTER_CODE = """
+import numpy as np, torch
+from lstm_ode_bci_b200 import lstm, synth, train
+out = []
+for H, mode in ((128, "fp32"), (128, "mixed"), (256, "mixed")):
+    params = synth.make_lstm_params(48, 61, H, 3, logit_gain=4.0)
+    x = torch.from_numpy(synth.make_windows(15, 40, 96, 61)).cuda()
+    y = (torch.arange(40) % 2).cuda()
+    m = lstm.from_params(params, precision="fp32", dropout=0.3).train()
+    tr = train.FusedTrainer(m, lr=0.0, weight_decay=0.0, max_norm=0.0, precision=mode)
+    loss, _ = tr.step(x, y, seed=5)
+    g = tr.grad.double()
+    out += [float(loss), float(g.norm()), float(g.abs().max())]
+    tr.close()
+m32 = lstm.from_params(synth.make_lstm_params(48, 61, 128, 3, logit_gain=4.0), precision="bf16")
+out.append(float(m32.predict_proba(torch.from_numpy(synth.make_windows(16, 100, 64, 61)).cuda()).double().sum()))
+print("RESULT", " ".join("%.12e" % v for v in out))
+"""
+
+
+def test_swapped_recurrences_are_robust_to_timing_jitter():
+    """BCI_FUSED_JITTER on the swapped recurrences: every MMA warp and epilogue warp sleeps a pseudo-random time (up to 4 us) before
+    its waits, arrives and DSMEM pushes -- single-CTA kernels (two mbarriers) and the H = 256 CTA pairs (double-buffered B tiles and
+    x_in barriers, re-armed by the waiter).  Results must be those of the unperturbed run (up to the summation order of the
+    bias-gradient atomics)."""
+    import os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    vals = {}
+    for tag, extra in (("plain", {}), ("jitter", {"BCI_FUSED_JITTER": "4096"})):
+        env = dict(os.environ, PYTHONPATH=root, **extra)
+        r = subprocess.run([sys.executable, "-c", _JITTER_CODE], env=env, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0 and "RESULT" in r.stdout, r.stderr[-2000:]
+        vals[tag] = np.array([float(v) for v in r.stdout.split("RESULT")[1].split()])
+    assert np.isfinite(vals["jitter"]).all()
+    rel = np.abs(vals["jitter"] - vals["plain"]) / (np.abs(vals["plain"]) + 1e-30)
+    assert rel.max() <= 1e-5, (rel, vals)
