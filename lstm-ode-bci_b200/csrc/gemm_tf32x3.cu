@@ -24,7 +24,7 @@
 //
 // Kernel shape (both): persistent CTAs, warp 0 = TMA producer (3-stage ring of {A_hi, A_lo, B_hi, B_lo} 128x32 fp32 tiles,
 // SWIZZLE_128B), warp 1 = MMA issuer (M128 x N128 x K8; two accumulators per tile -- hi.hi and the
-// correction terms -- double-buffered: all 512 TMEM columns), warps 2-5 = epilogue
+// correction terms -- double-buffered: all 512 TMEM columns), warps 2-9 = epilogue (two per TMEM lane quarter, two 32-column slabs each)
 // (tcgen05.ld -> +bias -> swizzled staging -> TMA store / reduce-add, one 32x32 box per warp).
 #include "lstm_handle.cuh"
 #include "sm100_prims.cuh"
@@ -35,10 +35,10 @@ namespace bci {
 using namespace sm100;
 
 constexpr int TX_BM = 128, TX_BN = 128, TX_BK = 32, TX_STAGES = 3;
-constexpr int TX_THREADS = 192;
+constexpr int TX_THREADS = 320;                     // TMA warp, MMA warp, 8 epilogue warps
 constexpr uint32_t TX_TILE = TX_BM * TX_BK * 4;     // 16 KB: one operand tile
 constexpr uint32_t TX_STAGE = 4 * TX_TILE;          // A_hi, A_lo, B_hi, B_lo
-constexpr uint32_t TX_CSTAGE = 4 * 32 * 128;        // per epilogue warp: 32 rows x 128 B
+constexpr uint32_t TX_CSTAGE = 8 * 32 * 128;        // per epilogue warp: 32 rows x 128 B
 constexpr size_t TX_SMEM = 1024 + (size_t)TX_STAGES * TX_STAGE + TX_CSTAGE + 128 * sizeof(float) + 256;
 
 // x -> lo (and optionally hi).  hi == nullptr: the tensor core is trusted to ignore the low 13 bits of the raw operand,
@@ -136,10 +136,16 @@ gemm_tf32x3_kernel(const __grid_constant__ TxMaps maps, const float* __restrict_
   uint8_t* ctl = genC + TX_CSTAGE + 128 * sizeof(float);
   const uint32_t bar0 = smem_u32(ctl);
   auto full_bar = [&](int s) { return bar0 + 8u * s; };
-  auto empty_bar = [&](int s) { return bar0 + 8u * (TX_STAGES + s); };
-  auto tfull_bar = [&](int a) { return bar0 + 8u * (2 * TX_STAGES + a); };
-  auto tempty_bar = [&](int a) { return bar0 + 8u * (2 * TX_STAGES + 2 + a); };
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ctl + 8 * (2 * TX_STAGES + 4));
+  // single-pass mode loads two tiles per k-block instead of four: every ring stage then holds TWO k-blocks (A in the hi / lo slot of
+  // the A pair, B likewise), i.e. a ring of 6.  With 4 MMAs (256 tensor cycles) per k-block, three slots covered 770 cycles of load
+  // latency -- less than an L2-miss TMA round trip: the mainloop waited on loads
+  const int nslots = single ? 2 * TX_STAGES : TX_STAGES;
+  auto empty_bar = [&](int s) { return bar0 + 8u * (2 * TX_STAGES + s); };
+  auto tfull_bar = [&](int a) { return bar0 + 8u * (4 * TX_STAGES + a); };
+  auto tempty_bar = [&](int a) { return bar0 + 8u * (4 * TX_STAGES + 2 + a); };
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ctl + 8 * (4 * TX_STAGES + 4));
+  // slot -> shared-memory offset of its A tile (its B tile is 2 * TX_TILE further)
+  auto slot_base = [&](int s) { return single ? (uint32_t)(s >> 1) * TX_STAGE + (uint32_t)(s & 1) * TX_TILE : (uint32_t)s * TX_STAGE; };
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m_blocks = (M + TX_BM - 1) / TX_BM, n_blocks = (N + TX_BN - 1) / TX_BN;
@@ -151,8 +157,8 @@ gemm_tf32x3_kernel(const __grid_constant__ TxMaps maps, const float* __restrict_
     tma_prefetch_desc(&maps.a_hi); tma_prefetch_desc(&maps.a_lo);
     tma_prefetch_desc(&maps.b_hi); tma_prefetch_desc(&maps.b_lo);
     tma_prefetch_desc(&maps.c);
-    for (int s = 0; s < TX_STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 128); }
+    for (int s = 0; s < 2 * TX_STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 256); }
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -175,7 +181,7 @@ gemm_tf32x3_kernel(const __grid_constant__ TxMaps maps, const float* __restrict_
         for (long long kb = kb0; kb < kb1; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
           mbar_arrive_expect_tx(full_bar(stage), single ? TX_STAGE / 2 : TX_STAGE);
-          const uint32_t s0 = sRing + stage * TX_STAGE;
+          const uint32_t s0 = sRing + slot_base(stage);
           if (single) {
             if (TN) {
 #pragma unroll
@@ -202,7 +208,7 @@ gemm_tf32x3_kernel(const __grid_constant__ TxMaps maps, const float* __restrict_
             tma_load_2d(s0 + 2 * TX_TILE, &maps.b_hi, (int)(kb * BK), nb * TX_BN, full_bar(stage));
             tma_load_2d(s0 + 3 * TX_TILE, &maps.b_lo, (int)(kb * BK), nb * TX_BN, full_bar(stage));
           }
-          if (++stage == TX_STAGES) { stage = 0; phase ^= 1u; }
+          if (++stage == nslots) { stage = 0; phase ^= 1u; }
         }
       }
     }
@@ -223,7 +229,7 @@ gemm_tf32x3_kernel(const __grid_constant__ TxMaps maps, const float* __restrict_
         for (long long kb = kb0; kb < kb1; ++kb) {
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
-          const uint32_t s0 = sRing + stage * TX_STAGE;
+          const uint32_t s0 = sRing + slot_base(stage);
 #pragma unroll
           for (int kk = 0; kk < TX_BK / 8; ++kk) {
             const uint32_t o = kk * KSTEP;
@@ -246,17 +252,20 @@ gemm_tf32x3_kernel(const __grid_constant__ TxMaps maps, const float* __restrict_
             }
           }
           umma_commit(empty_bar(stage));
-          if (++stage == TX_STAGES) { stage = 0; phase ^= 1u; }
+          if (++stage == nslots) { stage = 0; phase ^= 1u; }
         }
         umma_commit(tfull_bar(acc));
         if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
       }
     }
   } else {
-    // epilogue warp w: TMEM lanes / tile rows [32 (w % 4), +32); four 32-column slabs, each staged as a swizzled 32 x 128 B box
+    // epilogue warp w: TMEM lanes / tile rows [32 (w % 4), +32), two of the four 32-column slabs (two warps per lane quarter: with
+    // four warps the single-pass products were bound by this epilogue -- ~7 000 cycles per tile against 2 048 of MMA time), each slab
+    // staged as a swizzled 32 x 128 B box
     const int quarter = warp & 3;
-    uint8_t* cst = genC + quarter * 4096;
-    const uint32_t cst_s = sC + quarter * 4096;
+    const int ehalf = (warp - 2) >> 2;
+    uint8_t* cst = genC + (warp - 2) * 4096;
+    const uint32_t cst_s = sC + (warp - 2) * 4096;
     const int et = (warp - 2) * 32 + lane;
     int acc = 0; uint32_t acc_phase = 0;
     for (long long t = blockIdx.x; t < tiles; t += gridDim.x) {
@@ -264,15 +273,15 @@ gemm_tf32x3_kernel(const __grid_constant__ TxMaps maps, const float* __restrict_
       const int mb = (int)((t / n_blocks) % m_blocks);
       const int ks = (int)(t / ((long long)n_blocks * m_blocks));
       const bool add_bias = bias != nullptr && ks == 0;
-      // all four epilogue warps: previous tile's bias reads are done before it is overwritten
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      bias_s[et] = (add_bias && nb * TX_BN + et < N) ? __ldg(bias + nb * TX_BN + et) : 0.f;
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      // all eight epilogue warps: previous tile's bias reads are done before it is overwritten
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (et < TX_BN) bias_s[et] = (add_bias && nb * TX_BN + et < N) ? __ldg(bias + nb * TX_BN + et) : 0.f;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)acc * (2 * TX_BN);
 #pragma unroll 1
-      for (int slab = 0; slab < TX_BN / 32; ++slab) {
+      for (int slab = 2 * ehalf; slab < 2 * ehalf + 2; ++slab) {
         uint32_t r[32], rl[32];
         tmem_ld32(taddr + slab * 32, r);
         if (single) {
@@ -284,7 +293,7 @@ gemm_tf32x3_kernel(const __grid_constant__ TxMaps maps, const float* __restrict_
         if (lane == 0) tma_store_wait_read();  // the staging box has been drained by the previous store
         __syncwarp();
         tmem_ld_wait();
-        if (slab == TX_BN / 32 - 1) {  // all TMEM reads of this accumulator by this thread are done
+        if (slab == 2 * ehalf + 1) {  // all TMEM reads of this accumulator by this thread are done
           tc_fence_before();
           mbar_arrive(tempty_bar(acc));
         }
