@@ -372,6 +372,11 @@ int bci_selftest_fused_rec_bf16(const void* in, const void* wih, const void* whh
 int bci_selftest_gemm_tf32x3(int32_t mode, const float* A, const float* B, const float* bias, float* C, int32_t M, int32_t N,
                              int64_t K, int32_t explicit_hi, void* stream);
 
+/* single-pass TF32 form of the NT product (mixed training step): C[M][N] (=|+=) A[M][K] . B[N][K]^T + bias; M >= 512 and N >= 256 run on
+ * CTA pairs (cta_group::2, 256 x 256 tiles) */
+int bci_selftest_gemm_tf32_single(const float* A, const float* B, const float* bias, float* C, int32_t M, int32_t N, int32_t K,
+                                  int32_t accumulate, void* stream);
+
 /* the same NT product with both operands split into FP16 (hi, lo) pairs (kind::f16, twice the MMA rate; forward projections of the
  * fp32 inference path): C[M][N] = A[M][K] . B[N][K]^T + bias, fp32 in / fp32 out */
 int bci_selftest_gemm_f16x3(const float* A, const float* B, const float* bias, float* C, int32_t M, int32_t N, int32_t K, void* stream);

@@ -369,6 +369,11 @@ bool tf32x3_tn_ok(const void* A, int lda, const void* B, int ldb, const void* C,
          ldc % 4 == 0 && ((uintptr_t)A & 15) == 0 && ((uintptr_t)B & 15) == 0 && ((uintptr_t)C & 15) == 0;
 }
 
+static bool tf32_pair_enabled();
+static int tf32_pair_max_clusters();
+static int gemm_tf32_pair_nt(const float* A, int lda, const float* W, int ldw, const float* bias, float* C, int ldc, int M, int N, int K,
+                             int accumulate, cudaStream_t st);
+
 // C[M][N] (ldc) (=|+=) A[M][K] (lda) . W[N][K]^T (ldw) + bias[N];  *_lo from split_tf32 (hi = the raw array, or the rounded copy)
 int gemm_tf32x3_nt(const float* A_hi, const float* A_lo, int lda, const float* W_hi, const float* W_lo, int ldw, const float* bias,
                    float* C, int ldc, int M, int N, int K, int accumulate, cudaStream_t st) {
@@ -378,6 +383,8 @@ int gemm_tf32x3_nt(const float* A_hi, const float* A_lo, int lda, const float* W
   // A_lo == W_lo == nullptr: single-pass TF32 product (the mixed-precision training step)
   const int single = (A_lo == nullptr && W_lo == nullptr) ? 1 : 0;
   BCI_REQUIRE(single || (A_lo && W_lo), BCI_EINVAL, "gemm_tf32x3_nt: both remainders or neither");
+  if (single && M >= 512 && N >= 256 && tf32_pair_enabled() && tf32_pair_max_clusters() > 0)
+    return gemm_tf32_pair_nt(A_hi, lda, W_hi, ldw, bias, C, ldc, M, N, K, accumulate, st);
   if (single) { A_lo = A_hi; W_lo = W_hi; }
   if ((rc = make_tmap_f32_2d(&maps.a_hi, A_hi, M, K, lda, TX_BK, TX_BM))) return rc;
   if ((rc = make_tmap_f32_2d(&maps.a_lo, A_lo, M, K, lda, TX_BK, TX_BM))) return rc;
@@ -387,6 +394,245 @@ int gemm_tf32x3_nt(const float* A_hi, const float* A_lo, int lda, const float* W
   const long long tiles = (long long)ceil_div(M, TX_BM) * ceil_div(N, TX_BN);
   const int grid = (int)(tiles < sm_count() ? tiles : sm_count());
   gemm_tf32x3_kernel<false, false><<<grid, TX_THREADS, TX_SMEM, st>>>(maps, bias, M, N, (long long)K, 1, accumulate, 1.0f, single);
+  BCI_LAUNCH_OK();
+  return BCI_OK;
+}
+
+// ---- single-pass TF32 NT product on CTA PAIRS (cta_group::2): 256 x 256 output tiles ------------------------------------------
+// The single-pass products of the mixed training step (one TF32 MMA per product, fp32 operands) are bound by the L2 -> shared
+// memory operand stream, not by the tensor pipe: a 128 x 128 tile moves 32 KB per 32 K values = 32 FLOP per byte, and the step's
+// GEMMs sat at ~320 TFLOP/s = 11 TB/s of L2 reads with the ring six deep and the epilogue on eight warps.  A CTA pair computes a
+// 256 x 256 tile with ONE tcgen05.mma.cta_group::2 (M 256 x N 256 x K 8) per K slice: each CTA loads its own 128 rows of A and HALF
+// of the 256 rows of W (the pair's MMA reads both halves), i.e. the same 32 KB per k-block per CTA for twice the FLOPs.
+// Roles per CTA: warp 0 = TMA producer (its loads are counted on the LEADER's full barrier), warp 1 = MMA issuer (leader) /
+// accumulator-drained relay (peer), warps 2-9 = epilogue of the CTA's own 128 rows x 256 columns (TMEM lanes = rows).
+constexpr int TP_STAGES = 5;
+constexpr uint32_t TP_STAGE = 2 * TX_TILE;   // A (this CTA's 128 rows) + B (this CTA's 128 of the tile's 256 W rows), 32 K values each
+constexpr size_t TP_SMEM = 1024 + (size_t)TP_STAGES * TP_STAGE + TX_CSTAGE + 256 * sizeof(float) + 256;
+
+__device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst_smem, const void* tmap, int c0, int c1, uint32_t bar) {
+  const uint32_t lead_bar = bar & 0xFEFFFFFFu;   // the same offset in the pair's leader CTA (as tma_load_3d_2sm)
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst_smem), "l"(tmap), "r"(lead_bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void umma_tf32_2sm(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ bool tp_elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
+struct TpMaps { CUtensorMap a, b, c; };
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TX_THREADS, 1)
+gemm_tf32_pair_kernel(const __grid_constant__ TpMaps maps, const float* __restrict__ bias, int M, int N, int K, int reduce_add) {
+  extern __shared__ uint8_t tx_smem_raw[];
+  const uint32_t raw = smem_u32(tx_smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* gen = tx_smem_raw + (base - raw);
+  const uint32_t sRing = base, sC = base + TP_STAGES * TP_STAGE;
+  uint8_t* genC = gen + TP_STAGES * TP_STAGE;
+  float* bias_s = reinterpret_cast<float*>(genC + TX_CSTAGE);
+  uint8_t* ctl = genC + TX_CSTAGE + 256 * sizeof(float);
+  const uint32_t bar0 = smem_u32(ctl);
+  auto full_bar = [&](int s) { return bar0 + 8u * s; };                            // leader: both CTAs' tiles of the stage have landed
+  auto empty_bar = [&](int s) { return bar0 + 8u * (TP_STAGES + s); };             // every CTA: the pair's MMAs have read the stage
+  auto tfull_bar = [&](int a) { return bar0 + 8u * (2 * TP_STAGES + a); };         // every CTA: accumulator a is complete
+  auto tempty_bar = [&](int a) { return bar0 + 8u * (2 * TP_STAGES + 2 + a); };    // every CTA: its epilogue has drained accumulator a
+  auto peer_tempty_bar = [&](int a) { return bar0 + 8u * (2 * TP_STAGES + 4 + a); };  // leader: relay of the peer's tempty
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ctl + 8 * (2 * TP_STAGES + 6));
+
+  const int lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int m_blocks = (M + 255) / 256, n_blocks = (N + 255) / 256;
+  const int kb_total = (K + TX_BK - 1) / TX_BK;
+  const long long tiles = (long long)m_blocks * n_blocks;
+  const int n_clusters = (int)cluster_nclusters_x(), cid = (int)cluster_id_x();
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&maps.a); tma_prefetch_desc(&maps.b); tma_prefetch_desc(&maps.c);
+    for (int s = 0; s < TP_STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 256); mbar_init(peer_tempty_bar(a), 1); }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc_2sm(smem_u32(tmem_slot), 512);
+    tmem_relinquish_2sm();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  cluster_sync_all();   // both CTAs' barriers exist before anything is signalled across the pair
+
+  if (warp == 0) {
+    // ---- TMA producer: this CTA's A rows and its half of the W rows; bytes are counted on the leader's full barrier
+    int stage = 0; uint32_t phase = 0;
+    for (long long t = cid; t < tiles; t += n_clusters) {
+      const int nb = (int)(t % n_blocks), mb = (int)(t / n_blocks);
+      for (int kb = 0; kb < kb_total; ++kb) {
+        mbar_wait(empty_bar(stage), phase ^ 1u);
+        if (tp_elect_one()) {
+          if (leader) mbar_arrive_expect_tx(full_bar(stage), 2 * TP_STAGE);
+          const uint32_t s0 = sRing + stage * TP_STAGE;
+          tma_load_2d_2sm(s0, &maps.a, kb * TX_BK, mb * 256 + (int)rank * 128, full_bar(stage));
+          tma_load_2d_2sm(s0 + TX_TILE, &maps.b, kb * TX_BK, nb * 256 + (int)rank * 128, full_bar(stage));
+        }
+        __syncwarp();
+        if (++stage == TP_STAGES) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else if (warp == 1) {
+    if (leader) {
+      // ---- MMA issuer
+      constexpr uint32_t idesc = umma_idesc_tf32(256, 256, 0);
+      int stage = 0; uint32_t phase = 0; int acc = 0; uint32_t acc_phase = 0;
+      for (long long t = cid; t < tiles; t += n_clusters) {
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+        mbar_wait_cluster(peer_tempty_bar(acc), acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)acc * 256u;
+        for (int kb = 0; kb < kb_total; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          if (tp_elect_one()) {
+            const uint32_t s0 = sRing + stage * TP_STAGE;
+#pragma unroll
+            for (int kk = 0; kk < TX_BK / 8; ++kk)
+              umma_tf32_2sm(d_tmem, umma_desc_sw128(s0 + kk * 32), umma_desc_sw128(s0 + TX_TILE + kk * 32), idesc, (kb | kk) != 0 ? 1u : 0u);
+            umma_commit_2sm_mc(empty_bar(stage), (uint16_t)3);
+            if (kb == kb_total - 1) umma_commit_2sm_mc(tfull_bar(acc), (uint16_t)3);
+          }
+          __syncwarp();
+          if (++stage == TP_STAGES) { stage = 0; phase ^= 1u; }
+        }
+        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      }
+    } else {
+      // ---- peer: tells the leader when this CTA's epilogue has drained an accumulator (relaxed: it publishes no data)
+      int acc = 0; uint32_t acc_phase = 0;
+      const uint32_t remote0 = mapa_u32(peer_tempty_bar(0), 0);
+      for (long long t = cid; t < tiles; t += n_clusters) {
+        // phase k of tempty completes after the epilogue of this accumulator's k-th tile; the leader waits for "previous tile drained"
+        // before tile t, i.e. nothing for an accumulator's first use: mirror that by signalling after each drain
+        mbar_wait(tempty_bar(acc), acc_phase);
+        if (tp_elect_one()) mbar_arrive_cluster_relaxed(remote0 + 8u * (uint32_t)acc);
+        __syncwarp();
+        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      }
+    }
+  } else {
+    // ---- epilogue: this CTA's 128 rows (TMEM lanes) x 256 columns; warp w: lane quarter w % 4, slabs [4 (w-2)/4, +4)
+    const int quarter = warp & 3;
+    const int ehalf = (warp - 2) >> 2;
+    uint8_t* cst = genC + (warp - 2) * 4096;
+    const uint32_t cst_s = sC + (warp - 2) * 4096;
+    const int et = (warp - 2) * 32 + lane;
+    int acc = 0; uint32_t acc_phase = 0;
+    for (long long t = cid; t < tiles; t += n_clusters) {
+      const int nb = (int)(t % n_blocks), mb = (int)(t / n_blocks);
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      bias_s[et] = (bias != nullptr && nb * 256 + et < N) ? __ldg(bias + nb * 256 + et) : 0.f;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)acc * 256u;
+#pragma unroll 1
+      for (int slab = 4 * ehalf; slab < 4 * ehalf + 4; ++slab) {
+        uint32_t r[32];
+        tmem_ld32(taddr + slab * 32, r);
+        if (lane == 0) tma_store_wait_read();
+        __syncwarp();
+        tmem_ld_wait();
+        if (slab == 4 * ehalf + 3) {
+          tc_fence_before();
+          mbar_arrive(tempty_bar(acc));
+        }
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          float4 v;
+          v.x = __uint_as_float(r[4 * q + 0]) + bias_s[slab * 32 + 4 * q + 0];
+          v.y = __uint_as_float(r[4 * q + 1]) + bias_s[slab * 32 + 4 * q + 1];
+          v.z = __uint_as_float(r[4 * q + 2]) + bias_s[slab * 32 + 4 * q + 2];
+          v.w = __uint_as_float(r[4 * q + 3]) + bias_s[slab * 32 + 4 * q + 3];
+          *reinterpret_cast<float4*>(cst + sw128_chunk_off((uint32_t)lane, (uint32_t)q)) = v;
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          const int c0 = nb * 256 + slab * 32, c1 = mb * 256 + (int)rank * 128 + quarter * 32;
+          if (c0 < N && c1 < M) {
+            if (reduce_add) tma_reduce_add_2d(&maps.c, cst_s, c0, c1);
+            else tma_store_2d(&maps.c, cst_s, c0, c1);
+          }
+          tma_store_commit();
+        }
+      }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+    }
+    if (lane == 0) tma_store_wait_all();
+  }
+  tc_fence_before();
+  cluster_sync_all();   // no CTA leaves while the pair's MMAs may still read its shared memory or signal its barriers
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_2sm(tmem_base, 512);
+  }
+}
+
+// BCI_GEMM_PAIR=off keeps the one-CTA kernel for the single-pass products
+static bool tf32_pair_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("BCI_GEMM_PAIR");
+    v = (e && e[0] == 'o') ? 0 : 1;
+  }
+  return v != 0;
+}
+static int tf32_pair_max_clusters() {
+  static PerDeviceInt state_pd, max_pd;   // state: 0 = not tried, 1 = ok, -1 = unavailable
+  int& state = state_pd.cur();
+  int& mx = max_pd.cur();
+  if (state == 0) {
+    state = -1;
+    if (cudaFuncSetAttribute(gemm_tf32_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TP_SMEM) != cudaSuccess) return 0;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * sm_count(), 1, 1);
+    cfg.blockDim = dim3(TX_THREADS, 1, 1);
+    cfg.dynamicSmemBytes = TP_SMEM;
+    cudaLaunchAttribute la[1];
+    la[0].id = cudaLaunchAttributeClusterDimension;
+    la[0].val.clusterDim.x = 2; la[0].val.clusterDim.y = 1; la[0].val.clusterDim.z = 1;
+    cfg.attrs = la; cfg.numAttrs = 1;
+    if (cudaOccupancyMaxActiveClusters(&mx, gemm_tf32_pair_kernel, &cfg) != cudaSuccess || mx <= 0) { mx = 0; return 0; }
+    state = 1;
+  }
+  return state == 1 ? mx : 0;
+}
+static int gemm_tf32_pair_nt(const float* A, int lda, const float* W, int ldw, const float* bias, float* C, int ldc, int M, int N, int K,
+                             int accumulate, cudaStream_t st) {
+  TpMaps maps;
+  int rc;
+  if ((rc = make_tmap_f32_2d(&maps.a, A, M, K, lda, TX_BK, 128))) return rc;
+  if ((rc = make_tmap_f32_2d(&maps.b, W, N, K, ldw, TX_BK, 128))) return rc;
+  if ((rc = make_tmap_f32_2d(&maps.c, C, M, N, ldc, 32, 32))) return rc;
+  const long long tiles = (long long)ceil_div(M, 256) * ceil_div(N, 256);
+  const int mx = tf32_pair_max_clusters();
+  const int clusters = (int)(tiles < mx ? tiles : mx);
+  gemm_tf32_pair_kernel<<<2 * clusters, TX_THREADS, TP_SMEM, st>>>(maps, bias, M, N, K, accumulate);
   BCI_LAUNCH_OK();
   return BCI_OK;
 }
@@ -550,3 +796,14 @@ extern "C" int bci_selftest_gemm_f16x3(const float* A, const float* B, const flo
   BCI_REQUIRE(se == cudaSuccess, BCI_ECUDA, "bci_selftest_gemm_f16x3: %s", cudaGetErrorString(se));
   return rc;
 }
+
+// single-pass TF32 NT product (the mixed training step's GEMM form): C[M][N] = A[M][K] . B[N][K]^T + bias, accumulate != 0: C += ...
+// M >= 512 and N >= 256 run on CTA pairs (gemm_tf32_pair_kernel), smaller shapes on the one-CTA kernel
+extern "C" int bci_selftest_gemm_tf32_single(const float* A, const float* B, const float* bias, float* C, int32_t M, int32_t N, int32_t K,
+                                             int32_t accumulate, void* stream) {
+  using namespace bci;
+  BCI_REQUIRE(A && B && C && M >= 1 && N >= 1 && K >= 1, BCI_EINVAL, "bci_selftest_gemm_tf32_single: bad arguments");
+  BCI_REQUIRE(tf32x3_nt_ok(A, K, B, K, C, N, M, N, K), BCI_EINVAL, "bci_selftest_gemm_tf32_single: shape not supported by the tensor-core path");
+  return gemm_tf32x3_nt(A, nullptr, K, B, nullptr, K, bias, C, N, M, N, K, accumulate, (cudaStream_t)stream);
+}
+

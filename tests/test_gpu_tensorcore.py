@@ -504,3 +504,24 @@ def test_bf16_recording_view_at_the_reference_recording_shape_matches_oracle():
         da = float((attn[lo:lo + 16].cpu() - wa).abs().max())
         print(f"recording view vs oracle, windows {lo}..{lo + 16}: dprob {dp:.3e} dattn {da:.3e}")
         assert dp <= BF16_TOL["probs"] and da <= BF16_TOL["attn"], (lo, dp, da)
+
+
+@pytest.mark.parametrize("M,Nn,K,acc", [(512, 256, 64, 0), (1000, 1024, 256, 0), (4097, 512, 72, 0), (2048, 384, 128, 1), (131072, 1024, 128, 0),
+                                        (300, 128, 64, 0)])
+def test_gemm_tf32_single_pass_pair_kernel(M, Nn, K, acc):
+    """Single-pass TF32 NT product of the mixed training step.  M >= 512 and N >= 256 run on CTA pairs (cta_group::2, one
+    M256 x N256 x K8 MMA per K slice, each CTA loading its own A rows and half of the W rows); ragged M, a K tail, a partial N
+    block, accumulation into C and the one-CTA fallback shape.  TF32 tolerance: 2e-3 of max|C| (10-bit mantissas, truncated operands)."""
+    g = torch.Generator(device="cuda").manual_seed(M + K + Nn)
+    A = torch.randn(M, K, device="cuda", generator=g) * 0.7
+    B = (torch.rand(Nn, K, device="cuda", generator=g) * 2 - 1) / np.sqrt(K) * 1.5
+    bias = torch.randn(Nn, device="cuda", generator=g)
+    C0 = torch.randn(M, Nn, device="cuda", generator=g) if acc else None
+    C_ = C0.clone() if acc else torch.full((M, Nn), float("nan"), device="cuda")
+    ref = A.double() @ B.double().T + bias.double() + (C0.double() if acc else 0.0)
+    N.check(N.lib().bci_selftest_gemm_tf32_single(_p(A), _p(B), _p(bias), _p(C_), M, Nn, K, acc, _stream()))
+    torch.cuda.synchronize()
+    assert not torch.isnan(C_).any()
+    err = float((C_.double() - ref).abs().max() / ref.abs().max())
+    print(f"single-pass TF32 GEMM rel err {err:.2e} (M={M}, N={Nn}, K={K}, accumulate={acc})")
+    assert err <= 2e-3
