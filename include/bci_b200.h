@@ -373,9 +373,11 @@ int bci_selftest_gemm_tf32x3(int32_t mode, const float* A, const float* B, const
                              int64_t K, int32_t explicit_hi, void* stream);
 
 /* single-pass TF32 form of the NT product (mixed training step): C[M][N] (=|+=) A[M][K] . B[N][K]^T + bias; M >= 512 and N >= 256 run on
- * CTA pairs (cta_group::2, 256 x 256 tiles) */
+ * CTA pairs (cta_group::2, 256 x 256 tiles); _tn: C[M][N] = A[K][M]^T . B[K][N] (weight gradients; pairs when M % 256 == 0, N % 128 == 0) */
 int bci_selftest_gemm_tf32_single(const float* A, const float* B, const float* bias, float* C, int32_t M, int32_t N, int32_t K,
                                   int32_t accumulate, void* stream);
+
+int bci_selftest_gemm_tf32_single_tn(const float* A, const float* B, float* C, int32_t M, int32_t N, int64_t K, void* stream);
 
 /* the same NT product with both operands split into FP16 (hi, lo) pairs (kind::f16, twice the MMA rate; forward projections of the
  * fp32 inference path): C[M][N] = A[M][K] . B[N][K]^T + bias, fp32 in / fp32 out */

@@ -121,6 +121,7 @@ SIGNATURES = {
     "bci_selftest_fused_rec_bf16": (C.c_int, [_FP, _FP, _FP, _FP, _FP, _FP, _FP, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     "bci_selftest_gemm_tf32x3": (C.c_int, [C.c_int32, _FP, _FP, _FP, _FP, C.c_int32, C.c_int32, C.c_int64, C.c_int32, C.c_void_p]),
     "bci_selftest_gemm_tf32_single": (C.c_int, [_FP, _FP, _FP, _FP, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
+    "bci_selftest_gemm_tf32_single_tn": (C.c_int, [_FP, _FP, _FP, C.c_int32, C.c_int32, C.c_int64, C.c_void_p]),
     "bci_selftest_gemm_f16x3": (C.c_int, [_FP, _FP, _FP, _FP, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     "bci_selftest_rec_f16x3": (C.c_int, [_FP, _FP, _FP, _FP, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     "bci_selftest_rec_swap_fwd": (C.c_int, [_FP, _FP, _FP, _FP, _FP, _FP, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),

@@ -373,6 +373,8 @@ static bool tf32_pair_enabled();
 static int tf32_pair_max_clusters();
 static int gemm_tf32_pair_nt(const float* A, int lda, const float* W, int ldw, const float* bias, float* C, int ldc, int M, int N, int K,
                              int accumulate, cudaStream_t st);
+static int gemm_tf32_pair_tn(const float* A, int lda, const float* B, int ldb, float* C, int ldc, long long R, int P, int Q, cudaStream_t st,
+                             int force_splits);
 
 // C[M][N] (ldc) (=|+=) A[M][K] (lda) . W[N][K]^T (ldw) + bias[N];  *_lo from split_tf32 (hi = the raw array, or the rounded copy)
 int gemm_tf32x3_nt(const float* A_hi, const float* A_lo, int lda, const float* W_hi, const float* W_lo, int ldw, const float* bias,
@@ -435,8 +437,13 @@ __device__ __forceinline__ bool tp_elect_one() {
 
 struct TpMaps { CUtensorMap a, b, c; };
 
+// TN = false: C[M][N] (=|+=) A[M][K] . W[N][K]^T + bias, K-major operands, 256 x 256 tiles
+// TN = true : C[P=M][Q=N] += sum_r A[r][P] . B[r][Q] over the R = K rows in k_splits ranges (MN-major operands, boxes of {32 floats, 32
+//             rows}, partial tiles reduce-added); 256 x (2 nhalf) tiles, nhalf = 128 or 64 columns of B per CTA
+template <bool TN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TX_THREADS, 1)
-gemm_tf32_pair_kernel(const __grid_constant__ TpMaps maps, const float* __restrict__ bias, int M, int N, int K, int reduce_add) {
+gemm_tf32_pair_kernel(const __grid_constant__ TpMaps maps, const float* __restrict__ bias, int M, int N, long long K, int k_splits,
+                      int reduce_add, int nhalf) {
   extern __shared__ uint8_t tx_smem_raw[];
   const uint32_t raw = smem_u32(tx_smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
@@ -457,10 +464,20 @@ gemm_tf32_pair_kernel(const __grid_constant__ TpMaps maps, const float* __restri
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   const uint32_t rank = cluster_ctarank();
   const bool leader = rank == 0;
-  const int m_blocks = (M + 255) / 256, n_blocks = (N + 255) / 256;
-  const int kb_total = (K + TX_BK - 1) / TX_BK;
-  const long long tiles = (long long)m_blocks * n_blocks;
+  const int ntile = 2 * nhalf;                      // tile width
+  const int m_blocks = (M + 255) / 256, n_blocks = (N + ntile - 1) / ntile;
+  const long long kb_total = (K + TX_BK - 1) / TX_BK;
+  const long long kb_per = (kb_total + k_splits - 1) / k_splits;
+  const long long tiles = (long long)m_blocks * n_blocks * k_splits;
   const int n_clusters = (int)cluster_nclusters_x(), cid = (int)cluster_id_x();
+  const uint32_t stage_bytes = TX_TILE + (uint32_t)nhalf * TX_BK * 4u;   // A tile + this CTA's part of the B tile
+  auto decode = [&](long long t, int& nb, int& mb, long long& kb0, long long& kb1) {
+    nb = (int)(t % n_blocks);
+    mb = (int)((t / n_blocks) % m_blocks);
+    const int ks = (int)(t / ((long long)n_blocks * m_blocks));
+    kb0 = ks * kb_per;
+    kb1 = (kb0 + kb_per < kb_total) ? kb0 + kb_per : kb_total;
+  };
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&maps.a); tma_prefetch_desc(&maps.b); tma_prefetch_desc(&maps.c);
@@ -479,17 +496,25 @@ gemm_tf32_pair_kernel(const __grid_constant__ TpMaps maps, const float* __restri
   cluster_sync_all();   // both CTAs' barriers exist before anything is signalled across the pair
 
   if (warp == 0) {
-    // ---- TMA producer: this CTA's A rows and its half of the W rows; bytes are counted on the leader's full barrier
+    // ---- TMA producer: this CTA's A rows / columns and its half of the B operand; bytes are counted on the leader's full barrier
     int stage = 0; uint32_t phase = 0;
     for (long long t = cid; t < tiles; t += n_clusters) {
-      const int nb = (int)(t % n_blocks), mb = (int)(t / n_blocks);
-      for (int kb = 0; kb < kb_total; ++kb) {
+      int nb, mb; long long kb0, kb1;
+      decode(t, nb, mb, kb0, kb1);
+      for (long long kb = kb0; kb < kb1; ++kb) {
         mbar_wait(empty_bar(stage), phase ^ 1u);
         if (tp_elect_one()) {
-          if (leader) mbar_arrive_expect_tx(full_bar(stage), 2 * TP_STAGE);
+          if (leader) mbar_arrive_expect_tx(full_bar(stage), 2 * stage_bytes);
           const uint32_t s0 = sRing + stage * TP_STAGE;
-          tma_load_2d_2sm(s0, &maps.a, kb * TX_BK, mb * 256 + (int)rank * 128, full_bar(stage));
-          tma_load_2d_2sm(s0 + TX_TILE, &maps.b, kb * TX_BK, nb * 256 + (int)rank * 128, full_bar(stage));
+          if (TN) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) tma_load_2d_2sm(s0 + g * 4096, &maps.a, mb * 256 + (int)rank * 128 + g * 32, (int)(kb * TX_BK), full_bar(stage));
+            for (int g = 0; g < nhalf / 32; ++g)
+              tma_load_2d_2sm(s0 + TX_TILE + g * 4096, &maps.b, nb * ntile + (int)rank * nhalf + g * 32, (int)(kb * TX_BK), full_bar(stage));
+          } else {
+            tma_load_2d_2sm(s0, &maps.a, (int)(kb * TX_BK), mb * 256 + (int)rank * 128, full_bar(stage));
+            tma_load_2d_2sm(s0 + TX_TILE, &maps.b, (int)(kb * TX_BK), nb * 256 + (int)rank * 128, full_bar(stage));
+          }
         }
         __syncwarp();
         if (++stage == TP_STAGES) { stage = 0; phase ^= 1u; }
@@ -498,23 +523,29 @@ gemm_tf32_pair_kernel(const __grid_constant__ TpMaps maps, const float* __restri
   } else if (warp == 1) {
     if (leader) {
       // ---- MMA issuer
-      constexpr uint32_t idesc = umma_idesc_tf32(256, 256, 0);
+      const uint32_t idesc = umma_idesc_tf32(256, ntile, TN ? 1 : 0);
+      constexpr uint32_t KSTEP = TN ? 1024u : 32u;
       int stage = 0; uint32_t phase = 0; int acc = 0; uint32_t acc_phase = 0;
       for (long long t = cid; t < tiles; t += n_clusters) {
+        int nb, mb; long long kb0, kb1;
+        decode(t, nb, mb, kb0, kb1);
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
         mbar_wait_cluster(peer_tempty_bar(acc), acc_phase ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)acc * 256u;
-        for (int kb = 0; kb < kb_total; ++kb) {
+        for (long long kb = kb0; kb < kb1; ++kb) {
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
           if (tp_elect_one()) {
             const uint32_t s0 = sRing + stage * TP_STAGE;
 #pragma unroll
-            for (int kk = 0; kk < TX_BK / 8; ++kk)
-              umma_tf32_2sm(d_tmem, umma_desc_sw128(s0 + kk * 32), umma_desc_sw128(s0 + TX_TILE + kk * 32), idesc, (kb | kk) != 0 ? 1u : 0u);
+            for (int kk = 0; kk < TX_BK / 8; ++kk) {
+              const uint64_t da = TN ? umma_desc_sw128_mn(s0 + kk * KSTEP) : umma_desc_sw128(s0 + kk * KSTEP);
+              const uint64_t db = TN ? umma_desc_sw128_mn(s0 + TX_TILE + kk * KSTEP) : umma_desc_sw128(s0 + TX_TILE + kk * KSTEP);
+              umma_tf32_2sm(d_tmem, da, db, idesc, (kb != kb0 || kk != 0) ? 1u : 0u);
+            }
             umma_commit_2sm_mc(empty_bar(stage), (uint16_t)3);
-            if (kb == kb_total - 1) umma_commit_2sm_mc(tfull_bar(acc), (uint16_t)3);
+            if (kb == kb1 - 1) umma_commit_2sm_mc(tfull_bar(acc), (uint16_t)3);
           }
           __syncwarp();
           if (++stage == TP_STAGES) { stage = 0; phase ^= 1u; }
@@ -526,8 +557,6 @@ gemm_tf32_pair_kernel(const __grid_constant__ TpMaps maps, const float* __restri
       int acc = 0; uint32_t acc_phase = 0;
       const uint32_t remote0 = mapa_u32(peer_tempty_bar(0), 0);
       for (long long t = cid; t < tiles; t += n_clusters) {
-        // phase k of tempty completes after the epilogue of this accumulator's k-th tile; the leader waits for "previous tile drained"
-        // before tile t, i.e. nothing for an accumulator's first use: mirror that by signalling after each drain
         mbar_wait(tempty_bar(acc), acc_phase);
         if (tp_elect_one()) mbar_arrive_cluster_relaxed(remote0 + 8u * (uint32_t)acc);
         __syncwarp();
@@ -535,29 +564,31 @@ gemm_tf32_pair_kernel(const __grid_constant__ TpMaps maps, const float* __restri
       }
     }
   } else {
-    // ---- epilogue: this CTA's 128 rows (TMEM lanes) x 256 columns; warp w: lane quarter w % 4, slabs [4 (w-2)/4, +4)
+    // ---- epilogue: this CTA's 128 rows (TMEM lanes) x ntile columns; warp w: lane quarter w % 4, half of the 32-column slabs
     const int quarter = warp & 3;
     const int ehalf = (warp - 2) >> 2;
+    const int spw = ntile / 64;   // slabs per warp: 4 (256 columns) or 2 (128)
     uint8_t* cst = genC + (warp - 2) * 4096;
     const uint32_t cst_s = sC + (warp - 2) * 4096;
     const int et = (warp - 2) * 32 + lane;
     int acc = 0; uint32_t acc_phase = 0;
     for (long long t = cid; t < tiles; t += n_clusters) {
-      const int nb = (int)(t % n_blocks), mb = (int)(t / n_blocks);
+      int nb, mb; long long kb0, kb1;
+      decode(t, nb, mb, kb0, kb1);
       asm volatile("bar.sync 1, 256;" ::: "memory");
-      bias_s[et] = (bias != nullptr && nb * 256 + et < N) ? __ldg(bias + nb * 256 + et) : 0.f;
+      bias_s[et] = (bias != nullptr && kb0 == 0 && nb * ntile + et < N) ? __ldg(bias + nb * ntile + et) : 0.f;
       asm volatile("bar.sync 1, 256;" ::: "memory");
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)acc * 256u;
 #pragma unroll 1
-      for (int slab = 4 * ehalf; slab < 4 * ehalf + 4; ++slab) {
+      for (int slab = spw * ehalf; slab < spw * ehalf + spw; ++slab) {
         uint32_t r[32];
         tmem_ld32(taddr + slab * 32, r);
         if (lane == 0) tma_store_wait_read();
         __syncwarp();
         tmem_ld_wait();
-        if (slab == 4 * ehalf + 3) {
+        if (slab == spw * ehalf + spw - 1) {
           tc_fence_before();
           mbar_arrive(tempty_bar(acc));
         }
@@ -573,7 +604,7 @@ gemm_tf32_pair_kernel(const __grid_constant__ TpMaps maps, const float* __restri
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) {
-          const int c0 = nb * 256 + slab * 32, c1 = mb * 256 + (int)rank * 128 + quarter * 32;
+          const int c0 = nb * ntile + slab * 32, c1 = mb * 256 + (int)rank * 128 + quarter * 32;
           if (c0 < N && c1 < M) {
             if (reduce_add) tma_reduce_add_2d(&maps.c, cst_s, c0, c1);
             else tma_store_2d(&maps.c, cst_s, c0, c1);
@@ -608,7 +639,8 @@ static int tf32_pair_max_clusters() {
   int& mx = max_pd.cur();
   if (state == 0) {
     state = -1;
-    if (cudaFuncSetAttribute(gemm_tf32_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TP_SMEM) != cudaSuccess) return 0;
+    if (cudaFuncSetAttribute(gemm_tf32_pair_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TP_SMEM) != cudaSuccess) return 0;
+    if (cudaFuncSetAttribute(gemm_tf32_pair_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TP_SMEM) != cudaSuccess) return 0;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(2 * sm_count(), 1, 1);
     cfg.blockDim = dim3(TX_THREADS, 1, 1);
@@ -617,7 +649,7 @@ static int tf32_pair_max_clusters() {
     la[0].id = cudaLaunchAttributeClusterDimension;
     la[0].val.clusterDim.x = 2; la[0].val.clusterDim.y = 1; la[0].val.clusterDim.z = 1;
     cfg.attrs = la; cfg.numAttrs = 1;
-    if (cudaOccupancyMaxActiveClusters(&mx, gemm_tf32_pair_kernel, &cfg) != cudaSuccess || mx <= 0) { mx = 0; return 0; }
+    if (cudaOccupancyMaxActiveClusters(&mx, gemm_tf32_pair_kernel<false>, &cfg) != cudaSuccess || mx <= 0) { mx = 0; return 0; }
     state = 1;
   }
   return state == 1 ? mx : 0;
@@ -632,7 +664,32 @@ static int gemm_tf32_pair_nt(const float* A, int lda, const float* W, int ldw, c
   const long long tiles = (long long)ceil_div(M, 256) * ceil_div(N, 256);
   const int mx = tf32_pair_max_clusters();
   const int clusters = (int)(tiles < mx ? tiles : mx);
-  gemm_tf32_pair_kernel<<<2 * clusters, TX_THREADS, TP_SMEM, st>>>(maps, bias, M, N, K, accumulate);
+  gemm_tf32_pair_kernel<false><<<2 * clusters, TX_THREADS, TP_SMEM, st>>>(maps, bias, M, N, (long long)K, 1, accumulate, 128);
+  BCI_LAUNCH_OK();
+  return BCI_OK;
+}
+// C[P][Q] = sum_r A[r][P] . B[r][Q] on CTA pairs: P % 256 == 0, Q % 128 == 0
+static int gemm_tf32_pair_tn(const float* A, int lda, const float* B, int ldb, float* C, int ldc, long long R, int P, int Q, cudaStream_t st,
+                             int force_splits) {
+  TpMaps maps;
+  int rc;
+  if ((rc = make_tmap_f32_2d(&maps.a, A, R, P, lda, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))) return rc;
+  if ((rc = make_tmap_f32_2d(&maps.b, B, R, Q, ldb, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))) return rc;
+  if ((rc = make_tmap_f32_2d(&maps.c, C, P, Q, ldc, 32, 32))) return rc;
+  const int nhalf = (Q % 256 == 0) ? 128 : 64;
+  const int out_tiles = (P / 256) * (Q / (2 * nhalf));
+  const int mx = tf32_pair_max_clusters();
+  const long long kb_total = (R + TX_BK - 1) / TX_BK;
+  long long splits = (mx + out_tiles - 1) / out_tiles;
+  if (splits > kb_total / 8) splits = kb_total / 8;
+  if (splits < 1) splits = 1;
+  if (force_splits > 0) splits = force_splits;
+  const long long per = (kb_total + splits - 1) / splits;
+  splits = (kb_total + per - 1) / per;
+  if (splits > 1) BCI_CUDA_OK(cudaMemset2DAsync(C, (size_t)ldc * 4, 0, (size_t)Q * 4, P, st));
+  const long long tiles = out_tiles * splits;
+  const int clusters = (int)(tiles < mx ? tiles : mx);
+  gemm_tf32_pair_kernel<true><<<2 * clusters, TX_THREADS, TP_SMEM, st>>>(maps, nullptr, P, Q, R, (int)splits, splits > 1 ? 1 : 0, nhalf);
   BCI_LAUNCH_OK();
   return BCI_OK;
 }
@@ -645,6 +702,8 @@ int gemm_tf32x3_tn(const float* A_hi, const float* A_lo, int lda, const float* B
   TxMaps maps;
   const int single = (A_lo == nullptr && B_lo == nullptr) ? 1 : 0;
   BCI_REQUIRE(single || (A_lo && B_lo), BCI_EINVAL, "gemm_tf32x3_tn: both remainders or neither");
+  if (single && P % 256 == 0 && Q % 128 == 0 && tf32_pair_enabled() && tf32_pair_max_clusters() > 0)
+    return gemm_tf32_pair_tn(A_hi, lda, B_hi, ldb, C, ldc, R, P, Q, st, force_splits);
   if (single) { A_lo = A_hi; B_lo = B_hi; }
   if ((rc = make_tmap_f32_2d(&maps.a_hi, A_hi, R, P, lda, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))) return rc;
   if ((rc = make_tmap_f32_2d(&maps.a_lo, A_lo, R, P, lda, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))) return rc;
@@ -805,5 +864,12 @@ extern "C" int bci_selftest_gemm_tf32_single(const float* A, const float* B, con
   BCI_REQUIRE(A && B && C && M >= 1 && N >= 1 && K >= 1, BCI_EINVAL, "bci_selftest_gemm_tf32_single: bad arguments");
   BCI_REQUIRE(tf32x3_nt_ok(A, K, B, K, C, N, M, N, K), BCI_EINVAL, "bci_selftest_gemm_tf32_single: shape not supported by the tensor-core path");
   return gemm_tf32x3_nt(A, nullptr, K, B, nullptr, K, bias, C, N, M, N, K, accumulate, (cudaStream_t)stream);
+}
+// ... and of the TN product (weight gradients): C[M][N] = A[K][M]^T . B[K][N]; M % 256 == 0 and N % 128 == 0 run on CTA pairs
+extern "C" int bci_selftest_gemm_tf32_single_tn(const float* A, const float* B, float* C, int32_t M, int32_t N, int64_t K, void* stream) {
+  using namespace bci;
+  BCI_REQUIRE(A && B && C && M >= 1 && N >= 1 && K >= 1, BCI_EINVAL, "bci_selftest_gemm_tf32_single_tn: bad arguments");
+  BCI_REQUIRE(tf32x3_tn_ok(A, M, B, N, C, N, K, M, N), BCI_EINVAL, "bci_selftest_gemm_tf32_single_tn: shape not supported by the tensor-core path");
+  return gemm_tf32x3_tn(A, nullptr, M, B, nullptr, N, C, N, K, M, N, (cudaStream_t)stream, 0);
 }
 

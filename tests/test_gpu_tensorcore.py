@@ -525,3 +525,21 @@ def test_gemm_tf32_single_pass_pair_kernel(M, Nn, K, acc):
     err = float((C_.double() - ref).abs().max() / ref.abs().max())
     print(f"single-pass TF32 GEMM rel err {err:.2e} (M={M}, N={Nn}, K={K}, accumulate={acc})")
     assert err <= 2e-3
+
+
+@pytest.mark.parametrize("M,Nn,K", [(256, 128, 1024), (1024, 256, 131072), (512, 128, 130560), (1024, 128, 5000), (128, 256, 4096)])
+def test_gemm_tf32_single_pass_tn_pair_kernel(M, Nn, K):
+    """Single-pass TF32 TN product (weight gradients of the mixed step): C[M][N] = A[K][M]^T . B[K][N], MN-major operands read
+    straight from the row-major activations, split-K with reduce-add.  M % 256 == 0 runs on CTA pairs (N = 256: 256 x 256 tiles,
+    N = 128: 256 x 128); K with a tail block; the last shape is the one-CTA fallback."""
+    g = torch.Generator(device="cuda").manual_seed(M + K + Nn)
+    A = torch.randn(K, M, device="cuda", generator=g) * 0.5
+    B = torch.randn(K, Nn, device="cuda", generator=g) * 0.5
+    C_ = torch.full((M, Nn), float("nan"), device="cuda")
+    N.check(N.lib().bci_selftest_gemm_tf32_single_tn(_p(A), _p(B), _p(C_), M, Nn, K, _stream()))
+    torch.cuda.synchronize()
+    ref = A.double().T @ B.double()
+    assert not torch.isnan(C_).any()
+    err = float((C_.double() - ref).abs().max() / ref.abs().max())
+    print(f"single-pass TF32 TN GEMM rel err {err:.2e} (M={M}, N={Nn}, K={K})")
+    assert err <= 3e-3
