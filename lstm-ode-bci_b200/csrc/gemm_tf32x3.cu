@@ -371,10 +371,10 @@ bool tf32x3_tn_ok(const void* A, int lda, const void* B, int ldb, const void* C,
 
 static bool tf32_pair_enabled();
 static int tf32_pair_max_clusters();
-static int gemm_tf32_pair_nt(const float* A, int lda, const float* W, int ldw, const float* bias, float* C, int ldc, int M, int N, int K,
-                             int accumulate, cudaStream_t st);
-static int gemm_tf32_pair_tn(const float* A, int lda, const float* B, int ldb, float* C, int ldc, long long R, int P, int Q, cudaStream_t st,
-                             int force_splits);
+static int gemm_tf32_pair_nt(const float* A, const float* A_lo, int lda, const float* W, const float* W_lo, int ldw, const float* bias,
+                             float* C, int ldc, int M, int N, int K, int accumulate, cudaStream_t st);
+static int gemm_tf32_pair_tn(const float* A, const float* A_lo, int lda, const float* B, const float* B_lo, int ldb, float* C, int ldc,
+                             long long R, int P, int Q, cudaStream_t st, int force_splits);
 
 // C[M][N] (ldc) (=|+=) A[M][K] (lda) . W[N][K]^T (ldw) + bias[N];  *_lo from split_tf32 (hi = the raw array, or the rounded copy)
 int gemm_tf32x3_nt(const float* A_hi, const float* A_lo, int lda, const float* W_hi, const float* W_lo, int ldw, const float* bias,
@@ -385,8 +385,8 @@ int gemm_tf32x3_nt(const float* A_hi, const float* A_lo, int lda, const float* W
   // A_lo == W_lo == nullptr: single-pass TF32 product (the mixed-precision training step)
   const int single = (A_lo == nullptr && W_lo == nullptr) ? 1 : 0;
   BCI_REQUIRE(single || (A_lo && W_lo), BCI_EINVAL, "gemm_tf32x3_nt: both remainders or neither");
-  if (single && M >= 512 && N >= 256 && tf32_pair_enabled() && tf32_pair_max_clusters() > 0)
-    return gemm_tf32_pair_nt(A_hi, lda, W_hi, ldw, bias, C, ldc, M, N, K, accumulate, st);
+  if (M >= 512 && N >= (single ? 256 : 128) && tf32_pair_enabled() && tf32_pair_max_clusters() > 0)
+    return gemm_tf32_pair_nt(A_hi, single ? nullptr : A_lo, lda, W_hi, single ? nullptr : W_lo, ldw, bias, C, ldc, M, N, K, accumulate, st);
   if (single) { A_lo = A_hi; W_lo = W_hi; }
   if ((rc = make_tmap_f32_2d(&maps.a_hi, A_hi, M, K, lda, TX_BK, TX_BM))) return rc;
   if ((rc = make_tmap_f32_2d(&maps.a_lo, A_lo, M, K, lda, TX_BK, TX_BM))) return rc;
@@ -435,7 +435,7 @@ __device__ __forceinline__ bool tp_elect_one() {
   return pred != 0;
 }
 
-struct TpMaps { CUtensorMap a, b, c; };
+struct TpMaps { CUtensorMap a, b, c, a_lo, b_lo; };
 
 // TN = false: C[M][N] (=|+=) A[M][K] . W[N][K]^T + bias, K-major operands, 256 x 256 tiles
 // TN = true : C[P=M][Q=N] += sum_r A[r][P] . B[r][Q] over the R = K rows in k_splits ranges (MN-major operands, boxes of {32 floats, 32
@@ -443,7 +443,7 @@ struct TpMaps { CUtensorMap a, b, c; };
 template <bool TN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TX_THREADS, 1)
 gemm_tf32_pair_kernel(const __grid_constant__ TpMaps maps, const float* __restrict__ bias, int M, int N, long long K, int k_splits,
-                      int reduce_add, int nhalf) {
+                      int reduce_add, int nhalf, int terms) {   // terms = 3: split precision (hi / lo operand pairs, nhalf = 64)
   extern __shared__ uint8_t tx_smem_raw[];
   const uint32_t raw = smem_u32(tx_smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
@@ -470,7 +470,12 @@ gemm_tf32_pair_kernel(const __grid_constant__ TpMaps maps, const float* __restri
   const long long kb_per = (kb_total + k_splits - 1) / k_splits;
   const long long tiles = (long long)m_blocks * n_blocks * k_splits;
   const int n_clusters = (int)cluster_nclusters_x(), cid = (int)cluster_id_x();
-  const uint32_t stage_bytes = TX_TILE + (uint32_t)nhalf * TX_BK * 4u;   // A tile + this CTA's part of the B tile
+  // a stage: A (this CTA's 128 rows) [, its remainder], this CTA's nhalf rows / columns of B [, their remainder]
+  const uint32_t b_bytes = (uint32_t)nhalf * TX_BK * 4u;
+  const uint32_t stage_bytes = terms == 3 ? 2 * TX_TILE + 2 * b_bytes : TX_TILE + b_bytes;
+  const uint32_t stage_stride = terms == 3 ? 3 * TX_TILE : TP_STAGE;       // 48 KB x 3 stages or 32 KB x 5
+  const int nstages = terms == 3 ? 3 : TP_STAGES;
+  const uint32_t off_b = terms == 3 ? 2 * TX_TILE : TX_TILE;
   auto decode = [&](long long t, int& nb, int& mb, long long& kb0, long long& kb1) {
     nb = (int)(t % n_blocks);
     mb = (int)((t / n_blocks) % m_blocks);
@@ -505,19 +510,30 @@ gemm_tf32_pair_kernel(const __grid_constant__ TpMaps maps, const float* __restri
         mbar_wait(empty_bar(stage), phase ^ 1u);
         if (tp_elect_one()) {
           if (leader) mbar_arrive_expect_tx(full_bar(stage), 2 * stage_bytes);
-          const uint32_t s0 = sRing + stage * TP_STAGE;
+          const uint32_t s0 = sRing + stage * stage_stride;
           if (TN) {
 #pragma unroll
             for (int g = 0; g < 4; ++g) tma_load_2d_2sm(s0 + g * 4096, &maps.a, mb * 256 + (int)rank * 128 + g * 32, (int)(kb * TX_BK), full_bar(stage));
             for (int g = 0; g < nhalf / 32; ++g)
-              tma_load_2d_2sm(s0 + TX_TILE + g * 4096, &maps.b, nb * ntile + (int)rank * nhalf + g * 32, (int)(kb * TX_BK), full_bar(stage));
+              tma_load_2d_2sm(s0 + off_b + g * 4096, &maps.b, nb * ntile + (int)rank * nhalf + g * 32, (int)(kb * TX_BK), full_bar(stage));
+            if (terms == 3) {
+#pragma unroll
+              for (int g = 0; g < 4; ++g)
+                tma_load_2d_2sm(s0 + TX_TILE + g * 4096, &maps.a_lo, mb * 256 + (int)rank * 128 + g * 32, (int)(kb * TX_BK), full_bar(stage));
+              for (int g = 0; g < nhalf / 32; ++g)
+                tma_load_2d_2sm(s0 + off_b + b_bytes + g * 4096, &maps.b_lo, nb * ntile + (int)rank * nhalf + g * 32, (int)(kb * TX_BK), full_bar(stage));
+            }
           } else {
             tma_load_2d_2sm(s0, &maps.a, (int)(kb * TX_BK), mb * 256 + (int)rank * 128, full_bar(stage));
-            tma_load_2d_2sm(s0 + TX_TILE, &maps.b, (int)(kb * TX_BK), nb * 256 + (int)rank * 128, full_bar(stage));
+            tma_load_2d_2sm(s0 + off_b, &maps.b, (int)(kb * TX_BK), nb * ntile + (int)rank * nhalf, full_bar(stage));
+            if (terms == 3) {
+              tma_load_2d_2sm(s0 + TX_TILE, &maps.a_lo, (int)(kb * TX_BK), mb * 256 + (int)rank * 128, full_bar(stage));
+              tma_load_2d_2sm(s0 + off_b + b_bytes, &maps.b_lo, (int)(kb * TX_BK), nb * ntile + (int)rank * nhalf, full_bar(stage));
+            }
           }
         }
         __syncwarp();
-        if (++stage == TP_STAGES) { stage = 0; phase ^= 1u; }
+        if (++stage == nstages) { stage = 0; phase ^= 1u; }
       }
     }
   } else if (warp == 1) {
@@ -532,23 +548,31 @@ gemm_tf32_pair_kernel(const __grid_constant__ TpMaps maps, const float* __restri
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
         mbar_wait_cluster(peer_tempty_bar(acc), acc_phase ^ 1u);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)acc * 256u;
+        const uint32_t d_tmem = tmem_base + (uint32_t)acc * 256u, d_lo = d_tmem + 128u;   // split precision: second accumulator (ntile = 128)
         for (long long kb = kb0; kb < kb1; ++kb) {
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
           if (tp_elect_one()) {
-            const uint32_t s0 = sRing + stage * TP_STAGE;
+            const uint32_t s0 = sRing + stage * stage_stride;
 #pragma unroll
             for (int kk = 0; kk < TX_BK / 8; ++kk) {
-              const uint64_t da = TN ? umma_desc_sw128_mn(s0 + kk * KSTEP) : umma_desc_sw128(s0 + kk * KSTEP);
-              const uint64_t db = TN ? umma_desc_sw128_mn(s0 + TX_TILE + kk * KSTEP) : umma_desc_sw128(s0 + TX_TILE + kk * KSTEP);
-              umma_tf32_2sm(d_tmem, da, db, idesc, (kb != kb0 || kk != 0) ? 1u : 0u);
+              const uint32_t o = kk * KSTEP;
+              const uint64_t ah = TN ? umma_desc_sw128_mn(s0 + o) : umma_desc_sw128(s0 + o);
+              const uint64_t bh = TN ? umma_desc_sw128_mn(s0 + off_b + o) : umma_desc_sw128(s0 + off_b + o);
+              const uint32_t first = (kb != kb0 || kk != 0) ? 1u : 0u;
+              if (terms == 3) {
+                const uint64_t al = TN ? umma_desc_sw128_mn(s0 + TX_TILE + o) : umma_desc_sw128(s0 + TX_TILE + o);
+                const uint64_t bl = TN ? umma_desc_sw128_mn(s0 + off_b + b_bytes + o) : umma_desc_sw128(s0 + off_b + b_bytes + o);
+                umma_tf32_2sm(d_lo, al, bh, idesc, first);
+                umma_tf32_2sm(d_lo, ah, bl, idesc, 1u);
+              }
+              umma_tf32_2sm(d_tmem, ah, bh, idesc, first);
             }
             umma_commit_2sm_mc(empty_bar(stage), (uint16_t)3);
             if (kb == kb1 - 1) umma_commit_2sm_mc(tfull_bar(acc), (uint16_t)3);
           }
           __syncwarp();
-          if (++stage == TP_STAGES) { stage = 0; phase ^= 1u; }
+          if (++stage == nstages) { stage = 0; phase ^= 1u; }
         }
         if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
       }
@@ -583,8 +607,14 @@ gemm_tf32_pair_kernel(const __grid_constant__ TpMaps maps, const float* __restri
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)acc * 256u;
 #pragma unroll 1
       for (int slab = spw * ehalf; slab < spw * ehalf + spw; ++slab) {
-        uint32_t r[32];
+        uint32_t r[32], rl[32];
         tmem_ld32(taddr + slab * 32, r);
+        if (terms == 3) {
+          tmem_ld32(taddr + 128 + slab * 32, rl);
+        } else {
+#pragma unroll
+          for (int q = 0; q < 32; ++q) rl[q] = 0u;
+        }
         if (lane == 0) tma_store_wait_read();
         __syncwarp();
         tmem_ld_wait();
@@ -595,10 +625,10 @@ gemm_tf32_pair_kernel(const __grid_constant__ TpMaps maps, const float* __restri
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
           float4 v;
-          v.x = __uint_as_float(r[4 * q + 0]) + bias_s[slab * 32 + 4 * q + 0];
-          v.y = __uint_as_float(r[4 * q + 1]) + bias_s[slab * 32 + 4 * q + 1];
-          v.z = __uint_as_float(r[4 * q + 2]) + bias_s[slab * 32 + 4 * q + 2];
-          v.w = __uint_as_float(r[4 * q + 3]) + bias_s[slab * 32 + 4 * q + 3];
+          v.x = __uint_as_float(r[4 * q + 0]) + __uint_as_float(rl[4 * q + 0]) + bias_s[slab * 32 + 4 * q + 0];
+          v.y = __uint_as_float(r[4 * q + 1]) + __uint_as_float(rl[4 * q + 1]) + bias_s[slab * 32 + 4 * q + 1];
+          v.z = __uint_as_float(r[4 * q + 2]) + __uint_as_float(rl[4 * q + 2]) + bias_s[slab * 32 + 4 * q + 2];
+          v.w = __uint_as_float(r[4 * q + 3]) + __uint_as_float(rl[4 * q + 3]) + bias_s[slab * 32 + 4 * q + 3];
           *reinterpret_cast<float4*>(cst + sw128_chunk_off((uint32_t)lane, (uint32_t)q)) = v;
         }
         fence_proxy_async_smem();
@@ -654,34 +684,43 @@ static int tf32_pair_max_clusters() {
   }
   return state == 1 ? mx : 0;
 }
-static int gemm_tf32_pair_nt(const float* A, int lda, const float* W, int ldw, const float* bias, float* C, int ldc, int M, int N, int K,
-                             int accumulate, cudaStream_t st) {
+static int gemm_tf32_pair_nt(const float* A, const float* A_lo, int lda, const float* W, const float* W_lo, int ldw, const float* bias,
+                             float* C, int ldc, int M, int N, int K, int accumulate, cudaStream_t st) {
   TpMaps maps;
   int rc;
+  const int terms = A_lo ? 3 : 1;
+  const int nhalf = terms == 3 ? 64 : 128;   // split precision keeps two accumulators per tile: 256 x 128 tiles
   if ((rc = make_tmap_f32_2d(&maps.a, A, M, K, lda, TX_BK, 128))) return rc;
-  if ((rc = make_tmap_f32_2d(&maps.b, W, N, K, ldw, TX_BK, 128))) return rc;
+  if ((rc = make_tmap_f32_2d(&maps.b, W, N, K, ldw, TX_BK, nhalf))) return rc;
+  if ((rc = make_tmap_f32_2d(&maps.a_lo, A_lo ? A_lo : A, M, K, lda, TX_BK, 128))) return rc;
+  if ((rc = make_tmap_f32_2d(&maps.b_lo, W_lo ? W_lo : W, N, K, ldw, TX_BK, nhalf))) return rc;
   if ((rc = make_tmap_f32_2d(&maps.c, C, M, N, ldc, 32, 32))) return rc;
-  const long long tiles = (long long)ceil_div(M, 256) * ceil_div(N, 256);
+  const long long tiles = (long long)ceil_div(M, 256) * ceil_div(N, 2 * nhalf);
   const int mx = tf32_pair_max_clusters();
   const int clusters = (int)(tiles < mx ? tiles : mx);
-  gemm_tf32_pair_kernel<false><<<2 * clusters, TX_THREADS, TP_SMEM, st>>>(maps, bias, M, N, (long long)K, 1, accumulate, 128);
+  gemm_tf32_pair_kernel<false><<<2 * clusters, TX_THREADS, TP_SMEM, st>>>(maps, bias, M, N, (long long)K, 1, accumulate, nhalf, terms);
   BCI_LAUNCH_OK();
   return BCI_OK;
 }
 // C[P][Q] = sum_r A[r][P] . B[r][Q] on CTA pairs: P % 256 == 0, Q % 128 == 0
-static int gemm_tf32_pair_tn(const float* A, int lda, const float* B, int ldb, float* C, int ldc, long long R, int P, int Q, cudaStream_t st,
-                             int force_splits) {
+static int gemm_tf32_pair_tn(const float* A, const float* A_lo, int lda, const float* B, const float* B_lo, int ldb, float* C, int ldc,
+                             long long R, int P, int Q, cudaStream_t st, int force_splits) {
   TpMaps maps;
   int rc;
+  const int terms = A_lo ? 3 : 1;
   if ((rc = make_tmap_f32_2d(&maps.a, A, R, P, lda, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))) return rc;
   if ((rc = make_tmap_f32_2d(&maps.b, B, R, Q, ldb, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))) return rc;
+  if ((rc = make_tmap_f32_2d(&maps.a_lo, A_lo ? A_lo : A, R, P, lda, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))) return rc;
+  if ((rc = make_tmap_f32_2d(&maps.b_lo, B_lo ? B_lo : B, R, Q, ldb, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))) return rc;
   if ((rc = make_tmap_f32_2d(&maps.c, C, P, Q, ldc, 32, 32))) return rc;
-  const int nhalf = (Q % 256 == 0) ? 128 : 64;
+  const int nhalf = (terms == 1 && Q % 256 == 0) ? 128 : 64;
   const int out_tiles = (P / 256) * (Q / (2 * nhalf));
   const int mx = tf32_pair_max_clusters();
   const long long kb_total = (R + TX_BK - 1) / TX_BK;
   long long splits = (mx + out_tiles - 1) / out_tiles;
   if (splits > kb_total / 8) splits = kb_total / 8;
+  // split precision: at most 1024 rows per accumulator (the TMEM accumulation error grows with the range, see gemm_tf32x3_tn)
+  if (terms == 3 && splits < (kb_total + 31) / 32) splits = (kb_total + 31) / 32;
   if (splits < 1) splits = 1;
   if (force_splits > 0) splits = force_splits;
   const long long per = (kb_total + splits - 1) / splits;
@@ -689,7 +728,7 @@ static int gemm_tf32_pair_tn(const float* A, int lda, const float* B, int ldb, f
   if (splits > 1) BCI_CUDA_OK(cudaMemset2DAsync(C, (size_t)ldc * 4, 0, (size_t)Q * 4, P, st));
   const long long tiles = out_tiles * splits;
   const int clusters = (int)(tiles < mx ? tiles : mx);
-  gemm_tf32_pair_kernel<true><<<2 * clusters, TX_THREADS, TP_SMEM, st>>>(maps, nullptr, P, Q, R, (int)splits, splits > 1 ? 1 : 0, nhalf);
+  gemm_tf32_pair_kernel<true><<<2 * clusters, TX_THREADS, TP_SMEM, st>>>(maps, nullptr, P, Q, R, (int)splits, splits > 1 ? 1 : 0, nhalf, terms);
   BCI_LAUNCH_OK();
   return BCI_OK;
 }
@@ -702,8 +741,8 @@ int gemm_tf32x3_tn(const float* A_hi, const float* A_lo, int lda, const float* B
   TxMaps maps;
   const int single = (A_lo == nullptr && B_lo == nullptr) ? 1 : 0;
   BCI_REQUIRE(single || (A_lo && B_lo), BCI_EINVAL, "gemm_tf32x3_tn: both remainders or neither");
-  if (single && P % 256 == 0 && Q % 128 == 0 && tf32_pair_enabled() && tf32_pair_max_clusters() > 0)
-    return gemm_tf32_pair_tn(A_hi, lda, B_hi, ldb, C, ldc, R, P, Q, st, force_splits);
+  if (P % 256 == 0 && Q % 128 == 0 && tf32_pair_enabled() && tf32_pair_max_clusters() > 0)
+    return gemm_tf32_pair_tn(A_hi, single ? nullptr : A_lo, lda, B_hi, single ? nullptr : B_lo, ldb, C, ldc, R, P, Q, st, force_splits);
   if (single) { A_lo = A_hi; B_lo = B_hi; }
   if ((rc = make_tmap_f32_2d(&maps.a_hi, A_hi, R, P, lda, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))) return rc;
   if ((rc = make_tmap_f32_2d(&maps.a_lo, A_lo, R, P, lda, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))) return rc;
