@@ -47,7 +47,7 @@ constexpr int SW_NW = 8;                     // windows per CTA
 constexpr uint32_t SW_BATOM = 16 * 128;      // B atom: 16 rows x 64 halves (rows 8-15 zero)
 constexpr uint32_t SW_FWD_B = 2 * SW_BATOM, SW_BWD_B = 8 * SW_BATOM;
 constexpr uint32_t SW_AATOM = 128 * 128;     // A atom in shared memory (split mode: the weights' lo parts): 128 rows x 64 halves
-constexpr uint32_t SW_ALO_BYTES = 8 * SW_AATOM;   // forward: [gate 4][K atom 2]; BPTT: [K atom 8]
+constexpr uint32_t SW_ALO_BYTES = 2 * SW_AATOM;   // split mode: the fourth quarter of W_lo (forward: gate o, BPTT: K 384-511), two atoms
 constexpr float SW_WSCALE = 16.0f;           // weights are stored x 16 (keeps the lo parts out of fp16's subnormals)
 // SPLIT (fp32-parity step): weights hi in tensor memory, weights lo in shared memory, B tile as an fp16 (hi, lo) pair
 constexpr size_t sw_smem_bytes(uint32_t b_bytes, bool split) { return 1024 + (split ? SW_ALO_BYTES + 2 * b_bytes : b_bytes) + 64; }
@@ -146,14 +146,17 @@ struct SwCtx {
   uint32_t sA, sB, acc_full, op_ready, tmem;
   uint8_t* genB;
 };
-// prologue: barriers, TMEM (512 columns: accumulators at [0, 64), weights at [SW_WCOL, SW_WCOL + 256)), zeroed B tile, and the
-// weights: thread (u, q) stores 64 columns = 128 sixteen-bit K elements of row u: rows are `row_stride` 16-byte chunks apart in
-// global memory and quarter q of the columns starts `q_stride` chunks into ... (forward: q = gate block, rows q*128 + u of
-// [512][16 chunks]; BPTT: q = K quarter of row u of [128][64 chunks])
-// SPLIT: `wlo` (global, row-major [block][128 rows][chunks_per_row x 8 halves], 128 KB) additionally goes to shared memory as K-major
-// SWIZZLE_128B atoms [block][K atom][row][64 halves] in front of the B tiles (hi tile, then lo tile)
+// prologue: barriers, TMEM (512 columns: accumulators at [0, 64), weights hi at [SW_WCOL, SW_WCOL + 256)), zeroed B tile, and the
+// weights: thread (u, q) stores 64 columns = 128 sixteen-bit K elements of row u at `wrow` (forward: q = gate block, row q*128 + u
+// of [512][128]; BPTT: q = K quarter of row u of [128][512]).
+// SPLIT: the lo parts follow the same way for q < 3 at columns [SW_WLO, SW_WLO + 192) -- with the 64 accumulator columns that is
+// all 512 -- and only the fourth quarter (`wsm`: 128 rows x 16 chunks of 8 halves, rows `wsm_stride` chunks apart) goes to shared
+// memory as two K-major SWIZZLE_128B atoms in front of the B tiles (hi tile, then lo tile): 8 of the 32 W_lo MMAs of a step read
+// their A operand through the shared-memory port (32 cycles each) instead of all 32
+constexpr uint32_t SW_WLO = SW_WCOL + 256;
 template <uint32_t B_BYTES, bool SPLIT>
-__device__ __forceinline__ SwCtx sw_prologue(uint8_t* raw_ptr, const uint4* __restrict__ wrow, const uint4* __restrict__ wlo, int chunks_per_row) {
+__device__ __forceinline__ SwCtx sw_prologue(uint8_t* raw_ptr, const uint4* __restrict__ wrow, const uint4* __restrict__ wrow_lo,
+                                             const uint4* __restrict__ wsm, int wsm_stride) {
   constexpr uint32_t B_ALL = SPLIT ? 2 * B_BYTES : B_BYTES;
   SwCtx c;
   const uint32_t raw = smem_u32(raw_ptr);
@@ -164,11 +167,10 @@ __device__ __forceinline__ SwCtx sw_prologue(uint8_t* raw_ptr, const uint4* __re
   c.sB = base + (SPLIT ? SW_ALO_BYTES : 0u);
   uint8_t* ctl = c.genB + B_ALL;
   if (SPLIT) {
-    const int katoms = chunks_per_row >> 3;
-    for (int i = threadIdx.x; i < (int)(SW_ALO_BYTES / 16); i += SW_BLOCK) {
-      const int row_g = i / chunks_per_row, cc = i - row_g * chunks_per_row;
-      const int blk = row_g >> 7, row = row_g & 127;
-      *reinterpret_cast<uint4*>(genA + (uint32_t)(blk * katoms + (cc >> 3)) * SW_AATOM + sw128_chunk_off((uint32_t)row, (uint32_t)(cc & 7))) = __ldg(wlo + i);
+    for (int i = threadIdx.x; i < 128 * 16; i += SW_BLOCK) {
+      const int row = i >> 4, cc = i & 15;
+      *reinterpret_cast<uint4*>(genA + (uint32_t)(cc >> 3) * SW_AATOM + sw128_chunk_off((uint32_t)row, (uint32_t)(cc & 7))) =
+          __ldg(wsm + (size_t)row * wsm_stride + cc);
     }
   }
   c.acc_full = smem_u32(ctl);
@@ -192,16 +194,22 @@ __device__ __forceinline__ SwCtx sw_prologue(uint8_t* raw_ptr, const uint4* __re
   c.tmem = *tmem_slot;
   if (tid < SW_EPI) {
     const int u = tid & 127, q = tid >> 7;
-    const uint32_t dst = c.tmem + ((uint32_t)((u >> 5) * 32) << 16) + SW_WCOL + (uint32_t)q * 64u;
+    const uint32_t lane_base = c.tmem + ((uint32_t)((u >> 5) * 32) << 16);
 #pragma unroll 1
-    for (int k = 0; k < 4; ++k) {
-      uint32_t r[16];
+    for (int part = 0; part < (SPLIT ? 2 : 1); ++part) {
+      if (part == 1 && q == 3) break;   // the fourth lo quarter lives in shared memory
+      const uint4* src = part ? wrow_lo : wrow;
+      const uint32_t dst = lane_base + (part ? SW_WLO : SW_WCOL) + (uint32_t)q * 64u;
+#pragma unroll 1
+      for (int k = 0; k < 4; ++k) {
+        uint32_t r[16];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const uint4 v = __ldg(wrow + k * 4 + i);
-        r[4 * i] = v.x; r[4 * i + 1] = v.y; r[4 * i + 2] = v.z; r[4 * i + 3] = v.w;
+        for (int i = 0; i < 4; ++i) {
+          const uint4 v = __ldg(src + k * 4 + i);
+          r[4 * i] = v.x; r[4 * i + 1] = v.y; r[4 * i + 2] = v.z; r[4 * i + 3] = v.w;
+        }
+        tmem_st16(dst + (uint32_t)k * 16u, r);
       }
-      tmem_st16(dst + (uint32_t)k * 16u, r);
     }
     tmem_st_wait();
   }
@@ -268,8 +276,10 @@ lstm_rec_swap_fwd(const float* __restrict__ G,        // [T*Bc][ldg] fp32: colum
   const int warp_u = __shfl_sync(0xffffffffu, tid >> 5, 0);   // warp-uniform for the compiler
   const int dir = blockIdx.y, b0 = blockIdx.x * SW_NW;
   const __half* wdir = whh + (size_t)dir * 2 * 512 * 128;
+  const __half* wlo = wdir + 512 * 128;
   const SwCtx cx = sw_prologue<SW_FWD_B, SPLIT>(sw_smem_raw, reinterpret_cast<const uint4*>(wdir + ((size_t)wq * 128 + u) * 128),
-                                                reinterpret_cast<const uint4*>(wdir + 512 * 128), 16);
+                                                reinterpret_cast<const uint4*>(wlo + ((size_t)wq * 128 + u) * 128),
+                                                reinterpret_cast<const uint4*>(wlo + (size_t)3 * 128 * 128), 16);
 
   if (warp_u == SW_EPI / 32) {
     // ---- MMA warp: 4 gate blocks x 8 K slices per step, A = resident weights in tensor memory, B = h_{t-1}
@@ -284,10 +294,14 @@ lstm_rec_swap_fwd(const float* __restrict__ G,        // [T*Bc][ldg] fp32: colum
         for (int g = 0; g < 4; ++g) {
           if (SPLIT) {
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {   // W_lo (shared memory) . h_hi
-              const uint64_t da = umma_desc_sw128(cx.sA + (uint32_t)(g * 2 + (k >> 2)) * SW_AATOM + (uint32_t)(k & 3) * 32u);
+            for (int k = 0; k < 8; ++k) {   // W_lo . h_hi: gates i, f, g~ from tensor memory, o from shared memory
               const uint64_t db = umma_desc_sw128(cx.sB + (uint32_t)(k >> 2) * SW_BATOM + (uint32_t)(k & 3) * 32u);
-              umma_bf16(cx.tmem + g * 16, da, db, idesc, k != 0 ? 1u : 0u);
+              if (g < 3) {
+                umma_f16_ts(cx.tmem + g * 16, cx.tmem + SW_WLO + g * 64 + k * 8, db, idesc, k != 0 ? 1u : 0u);
+              } else {
+                const uint64_t da = umma_desc_sw128(cx.sA + (uint32_t)(k >> 2) * SW_AATOM + (uint32_t)(k & 3) * 32u);
+                umma_bf16(cx.tmem + g * 16, da, db, idesc, k != 0 ? 1u : 0u);
+              }
             }
 #pragma unroll
             for (int k = 0; k < 8; ++k) {   // W_hi (tensor memory) . h_lo
@@ -432,7 +446,8 @@ lstm_bptt_swap(const float* __restrict__ dout,           // [T][Bc][D]
   const int dir = blockIdx.y, b0 = blockIdx.x * SW_NW;
   const uint16_t* whhT = reinterpret_cast<const uint16_t*>(whhT_v) + (size_t)dir * (SPLIT ? 2 : 1) * 128 * 512;
   const SwCtx cx = sw_prologue<SW_BWD_B, SPLIT>(sw_smem_raw, reinterpret_cast<const uint4*>(whhT + (size_t)u * 512 + wq * 128),
-                                                reinterpret_cast<const uint4*>(whhT + 128 * 512), 64);
+                                                reinterpret_cast<const uint4*>(whhT + 128 * 512 + (size_t)u * 512 + wq * 128),
+                                                reinterpret_cast<const uint4*>(whhT + 128 * 512 + 384), 64);
   uint32_t* mx = reinterpret_cast<uint32_t*>(cx.genB + (SPLIT ? 2 : 1) * SW_BWD_B + 32);   // three slots behind the barriers / TMEM slot
   if (SPLIT && tid < 3) mx[tid] = 0u;
   if (SPLIT) __syncthreads();
@@ -446,10 +461,14 @@ lstm_bptt_swap(const float* __restrict__ dout,           // [T][Bc][D]
         constexpr uint32_t idesc = sw_idesc(128, 16, !SPLIT);
         if (SPLIT) {
 #pragma unroll
-          for (int k = 0; k < 32; ++k) {   // W_lo (shared memory) . dG_hi
-            const uint64_t da = umma_desc_sw128(cx.sA + (uint32_t)(k >> 2) * SW_AATOM + (uint32_t)(k & 3) * 32u);
+          for (int k = 0; k < 32; ++k) {   // W_lo . dG_hi: K quarters 0-2 from tensor memory, quarter 3 from shared memory
             const uint64_t db = umma_desc_sw128(cx.sB + (uint32_t)(k >> 2) * SW_BATOM + (uint32_t)(k & 3) * 32u);
-            umma_bf16(cx.tmem, da, db, idesc, k != 0 ? 1u : 0u);
+            if (k < 24) {
+              umma_f16_ts(cx.tmem, cx.tmem + SW_WLO + k * 8, db, idesc, k != 0 ? 1u : 0u);
+            } else {
+              const uint64_t da = umma_desc_sw128(cx.sA + (uint32_t)((k - 24) >> 2) * SW_AATOM + (uint32_t)(k & 3) * 32u);
+              umma_bf16(cx.tmem, da, db, idesc, 1u);
+            }
           }
 #pragma unroll
           for (int k = 0; k < 32; ++k) {   // W_hi (tensor memory) . dG_lo
