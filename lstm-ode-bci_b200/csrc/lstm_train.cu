@@ -187,9 +187,13 @@ __global__ void colsum_kernel(const float* __restrict__ A, int lda, long long R,
   if (n >= N) return;
   const long long per = (R + gridDim.y - 1) / gridDim.y;
   const long long r0 = per * blockIdx.y, r1 = (r0 + per < R) ? r0 + per : R;
-  float s = 0.f;
-  for (long long r = r0; r < r1; ++r) s += A[r * lda + n];
-  atomicAdd(out + n, s);
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  long long r = r0;
+  for (; r + 3 < r1; r += 4) {   // four independent loads in flight per thread
+    s0 += A[r * lda + n]; s1 += A[(r + 1) * lda + n]; s2 += A[(r + 2) * lda + n]; s3 += A[(r + 3) * lda + n];
+  }
+  for (; r < r1; ++r) s0 += A[r * lda + n];
+  atomicAdd(out + n, (s0 + s1) + (s2 + s3));
 }
 
 static int gemm_nn(const float* A, int lda, const float* Bt, int ldb, float* C, int ldc, int M, int N, int K, const float* bias,
@@ -225,8 +229,11 @@ static int gemm_tn(const float* A, int lda, const float* B, int ldb, float* C, i
   return BCI_OK;
 }
 static int colsum(const float* A, int lda, long long R, int N, float* out, cudaStream_t st) {
-  int ys = (int)((R + 1023) / 1024);
-  if (ys > 1024) ys = 1024;
+  // enough row ranges to fill the machine whatever N is (N = 128: one column block; 1024-row ranges left it at 128 CTAs)
+  const int xb = ceil_div(N, 128);
+  long long want = (8LL * sm_count() + xb - 1) / xb;
+  int ys = (int)((R + 63) / 64 < want ? (R + 63) / 64 : want);
+  if (ys > 4096) ys = 4096;
   if (ys < 1) ys = 1;
   colsum_kernel<<<dim3(ceil_div(N, 128), ys), 128, 0, st>>>(A, lda, R, N, out);
   BCI_LAUNCH_OK();
@@ -278,6 +285,25 @@ inproj_train_fwd(const float* __restrict__ x, int Bc, int T, int C, const float*
   }
 }
 
+// per-warp partial sums of NV columns per lane (column e*32 + lane) -> one atomicAdd per column and BLOCK: every warp adding its own
+// partials put 32 768 warps x 512 atomics on 512 addresses (ln_rows_bwd spent 300 us of the step there)
+template <int NV>
+__device__ __forceinline__ void block_col_atomic_add(float* __restrict__ dst_w, float* __restrict__ dst_b, const float (&gw)[NV],
+                                                     const float (&gb)[NV]) {
+  __shared__ float red[2][8][NV * 32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int e = 0; e < NV; ++e) { red[0][warp][e * 32 + lane] = gw[e]; red[1][warp][e * 32 + lane] = gb[e]; }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * NV * 32; i += 256) {
+    const int which = i / (NV * 32), col = i - which * NV * 32;
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) s += red[which][w][col];
+    atomicAdd((which ? dst_b : dst_w) + col, s);
+  }
+}
+
 // dv = LayerNorm-backward(dz * mask * gelu'(y)); accumulates dlnw/dlnb.  One warp per row.
 template <int H>
 __global__ void __launch_bounds__(256)
@@ -321,11 +347,7 @@ inproj_bwd_rows(const float* __restrict__ dz, const float* __restrict__ xhat, co
       dv[r * H + j] = rstd * (dy[v] * lnw[j] - s1 - xh[v] * s2);
     }
   }
-#pragma unroll
-  for (int v = 0; v < NV; ++v) {
-    atomicAdd(dlnw + v * 32 + lane, gw[v]);
-    atomicAdd(dlnb + v * 32 + lane, gb[v]);
-  }
+  block_col_atomic_add<NV>(dlnw, dlnb, gw, gb);
 }
 
 // final LayerNorm forward over rows of width D: xhat, rstd, Y = xhat*w + b
@@ -395,11 +417,7 @@ ln_rows_bwd(const float* __restrict__ dy, const float* __restrict__ xhat, const 
       dx[r * D + d] = rstd * (g[e] * w[d] - s1 - xh[e] * s2);
     }
   }
-#pragma unroll
-  for (int e = 0; e < NV; ++e) {
-    atomicAdd(dw + e * 32 + lane, gw[e]);
-    atomicAdd(db + e * 32 + lane, gb[e]);
-  }
+  block_col_atomic_add<NV>(dw, db, gw, gb);
 }
 
 // ---- attention pooling (train): one CTA per window -------------------------------------------------
@@ -967,7 +985,7 @@ static int backward_t(bci_lstm_s* h, const float* dlogits, int B, int T, float p
   constexpr int D = ND * H, AH = D / 2, G4 = 4 * D;  // G4: gate columns of all directions
   const int C = c.input_size, L = c.num_layers, cls = c.num_classes, use_ln = c.use_layer_norm;
   const long long M = (long long)B * T;
-  const int rb = (int)((M + 7) / 8 < 4096 ? (M + 7) / 8 : 4096);
+  const int rb = (int)((M + 7) / 8 < 8LL * sm_count() ? (M + 7) / 8 : 8LL * sm_count());   // row kernels that end in column atomics: few, long blocks
   auto zero = [&](float* ptr, size_t n) { return cudaMemsetAsync(ptr, 0, n * sizeof(float), st); };
   auto zero_on = [&](cudaStream_t s2, float* ptr, size_t n) { return cudaMemsetAsync(ptr, 0, n * sizeof(float), s2); };
   int rc;
