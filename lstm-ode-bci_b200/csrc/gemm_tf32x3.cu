@@ -374,7 +374,7 @@ static int tf32_pair_max_clusters();
 static int gemm_tf32_pair_nt(const float* A, const float* A_lo, int lda, const float* W, const float* W_lo, int ldw, const float* bias,
                              float* C, int ldc, int M, int N, int K, int accumulate, cudaStream_t st);
 static int gemm_tf32_pair_tn(const float* A, const float* A_lo, int lda, const float* B, const float* B_lo, int ldb, float* C, int ldc,
-                             long long R, int P, int Q, cudaStream_t st, int force_splits);
+                             long long R, int P, int Q, cudaStream_t st, int force_splits, int qcols);
 
 // C[M][N] (ldc) (=|+=) A[M][K] (lda) . W[N][K]^T (ldw) + bias[N];  *_lo from split_tf32 (hi = the raw array, or the rounded copy)
 int gemm_tf32x3_nt(const float* A_hi, const float* A_lo, int lda, const float* W_hi, const float* W_lo, int ldw, const float* bias,
@@ -704,14 +704,14 @@ static int gemm_tf32_pair_nt(const float* A, const float* A_lo, int lda, const f
 }
 // C[P][Q] = sum_r A[r][P] . B[r][Q] on CTA pairs: P % 256 == 0, Q % 128 == 0
 static int gemm_tf32_pair_tn(const float* A, const float* A_lo, int lda, const float* B, const float* B_lo, int ldb, float* C, int ldc,
-                             long long R, int P, int Q, cudaStream_t st, int force_splits) {
+                             long long R, int P, int Q, cudaStream_t st, int force_splits, int qcols) {
   TpMaps maps;
   int rc;
   const int terms = A_lo ? 3 : 1;
   if ((rc = make_tmap_f32_2d(&maps.a, A, R, P, lda, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))) return rc;
-  if ((rc = make_tmap_f32_2d(&maps.b, B, R, Q, ldb, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))) return rc;
+  if ((rc = make_tmap_f32_2d(&maps.b, B, R, qcols, ldb, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))) return rc;
   if ((rc = make_tmap_f32_2d(&maps.a_lo, A_lo ? A_lo : A, R, P, lda, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))) return rc;
-  if ((rc = make_tmap_f32_2d(&maps.b_lo, B_lo ? B_lo : B, R, Q, ldb, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))) return rc;
+  if ((rc = make_tmap_f32_2d(&maps.b_lo, B_lo ? B_lo : B, R, qcols, ldb, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))) return rc;
   if ((rc = make_tmap_f32_2d(&maps.c, C, P, Q, ldc, 32, 32))) return rc;
   const int nhalf = (terms == 1 && Q % 256 == 0) ? 128 : 64;
   const int out_tiles = (P / 256) * (Q / (2 * nhalf));
@@ -734,20 +734,22 @@ static int gemm_tf32_pair_tn(const float* A, const float* A_lo, int lda, const f
 }
 
 // C[P][Q] (ldc) = sum over r < R of A[r][P] (lda) . B[r][Q] (ldb)   (C is overwritten)
+// q_valid > 0: B has only q_valid (< Q) columns in memory (row stride ldb); the rest of the tile is zero-filled by the TMA unit
 int gemm_tf32x3_tn(const float* A_hi, const float* A_lo, int lda, const float* B_hi, const float* B_lo, int ldb, float* C, int ldc,
-                   long long R, int P, int Q, cudaStream_t st, int force_splits) {
+                   long long R, int P, int Q, cudaStream_t st, int force_splits, int q_valid) {
   int rc = tx_prepare();
   if (rc) return rc;
   TxMaps maps;
   const int single = (A_lo == nullptr && B_lo == nullptr) ? 1 : 0;
   BCI_REQUIRE(single || (A_lo && B_lo), BCI_EINVAL, "gemm_tf32x3_tn: both remainders or neither");
+  const int qcols = q_valid > 0 ? q_valid : Q;
   if (P % 256 == 0 && Q % 128 == 0 && tf32_pair_enabled() && tf32_pair_max_clusters() > 0)
-    return gemm_tf32_pair_tn(A_hi, single ? nullptr : A_lo, lda, B_hi, single ? nullptr : B_lo, ldb, C, ldc, R, P, Q, st, force_splits);
+    return gemm_tf32_pair_tn(A_hi, single ? nullptr : A_lo, lda, B_hi, single ? nullptr : B_lo, ldb, C, ldc, R, P, Q, st, force_splits, qcols);
   if (single) { A_lo = A_hi; B_lo = B_hi; }
   if ((rc = make_tmap_f32_2d(&maps.a_hi, A_hi, R, P, lda, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))) return rc;
   if ((rc = make_tmap_f32_2d(&maps.a_lo, A_lo, R, P, lda, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))) return rc;
-  if ((rc = make_tmap_f32_2d(&maps.b_hi, B_hi, R, Q, ldb, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))) return rc;
-  if ((rc = make_tmap_f32_2d(&maps.b_lo, B_lo, R, Q, ldb, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))) return rc;
+  if ((rc = make_tmap_f32_2d(&maps.b_hi, B_hi, R, qcols, ldb, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))) return rc;
+  if ((rc = make_tmap_f32_2d(&maps.b_lo, B_lo, R, qcols, ldb, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))) return rc;
   if ((rc = make_tmap_f32_2d(&maps.c, C, P, Q, ldc, 32, 32))) return rc;
   const int out_tiles = (P / TX_BM) * (Q / TX_BN);
   const long long kb_total = (R + TX_BK - 1) / TX_BK;

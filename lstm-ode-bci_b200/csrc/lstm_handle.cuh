@@ -244,7 +244,7 @@ int split_tf32(const float* x, float* hi, float* lo, long long n, cudaStream_t s
 int gemm_tf32x3_nt(const float* A_hi, const float* A_lo, int lda, const float* W_hi, const float* W_lo, int ldw, const float* bias,
                    float* C, int ldc, int M, int N, int K, int accumulate, cudaStream_t st);
 int gemm_tf32x3_tn(const float* A_hi, const float* A_lo, int lda, const float* B_hi, const float* B_lo, int ldb, float* C, int ldc,
-                   long long R, int P, int Q, cudaStream_t st, int force_splits = 0);
+                   long long R, int P, int Q, cudaStream_t st, int force_splits = 0, int q_valid = 0);
 // bf16 / tcgen05 forward (lstm_bf16.cu)
 int lstm_forward_bf16(bci_lstm_s* h, const InputView& x, int batch, int T, float* logits, float* probs, float* attn,
                       void* ws, size_t ws_bytes, cudaStream_t st);

@@ -219,7 +219,9 @@ static int gemm_tn(const float* A, int lda, const float* B, int ldb, float* C, i
   }
   const int tiles = ceil_div(P, TG) * ceil_div(Q, TG);
   int splits = (4 * sm_count() + tiles - 1) / tiles;
-  const long long max_splits = (R + 255) / 256;
+  // row ranges of at least 32 rows: the classifier gradients reduce over the batch only (R = 512), where 256-row ranges left a
+  // handful of CTAs each walking 16 dependent k-steps (48 us per launch for a few MFLOP)
+  const long long max_splits = (R + 31) / 32;
   if (splits > max_splits) splits = (int)max_splits;
   if (splits < 1) splits = 1;
   if (splits > 65535) splits = 65535;
@@ -241,46 +243,97 @@ static int colsum(const float* A, int lda, long long R, int N, float* out, cudaS
 }
 
 // ---- row-local forward kernels -----------------------------------------------------------------
-// K1 (train): one warp per (t,b) row.  Saves xT (time-major copy of x), xhat0 (normalised pre-activation), rstd0 and
-// z = dropout(GELU(LN(.))).  x (Bc,T,C) batch-first.
+// K1 (train): one warp per FOUR (t,b) rows.  Saves xT (time-major copy of x, rows padded to 64 floats so that the weight-gradient
+// GEMM can read it through a tensor map), xhat0 (normalised pre-activation), rstd0 and z = dropout(GELU(LN(.))).  x (Bc,T,C)
+// batch-first.  W0^T sits in shared memory; a lane owns output columns q*128 + 4 lane .. + 3, so one 16-byte shared-memory read per
+// input channel feeds 16 FMAs (four rows) -- the first version (one row per warp, weights from global memory, the row copy written
+// by lane 0 element by element) took 261 us per 131 072 rows.
+constexpr int K1T_ROWS = 4, K1T_XS = 64;
 template <int H>
 __global__ void __launch_bounds__(256)
 inproj_train_fwd(const float* __restrict__ x, int Bc, int T, int C, const float* __restrict__ w0t, const float* __restrict__ b0,
                  const float* __restrict__ lnw, const float* __restrict__ lnb, float* __restrict__ xT, float* __restrict__ xhat,
                  float* __restrict__ rstd_out, float* __restrict__ z, float p_drop, uint64_t seed, int use_ln) {
-  constexpr int NV = H / 32;
+  extern __shared__ __align__(16) float k1t_w[];   // [C][H]
+  constexpr int NQ = H / 128;
+  for (int i = threadIdx.x; i < C * H; i += 256) k1t_w[i] = w0t[i];
+  __syncthreads();
   const int lane = threadIdx.x & 31;
   const long long rows = (long long)Bc * T;
+  const long long groups = (rows + K1T_ROWS - 1) / K1T_ROWS;
   const long long wstride = (long long)gridDim.x * 8;
-  for (long long r = (long long)blockIdx.x * 8 + (threadIdx.x >> 5); r < rows; r += wstride) {
-    const int t = (int)(r / Bc), b = (int)(r - (long long)t * Bc);  // r is the TIME-MAJOR row index
-    const float* xr = x + ((long long)b * T + t) * C;
-    float acc[NV];
+  float4 bias[NQ], gw[NQ], gb[NQ];
 #pragma unroll
-    for (int v = 0; v < NV; ++v) acc[v] = b0[v * 32 + lane];
-    for (int c = 0; c < C; ++c) {
-      const float xv = xr[c];
-      if (lane == 0) xT[r * C + c] = xv;
+  for (int q = 0; q < NQ; ++q) {
+    const int j = q * 128 + lane * 4;
+    bias[q] = *reinterpret_cast<const float4*>(b0 + j);
+    gw[q] = use_ln ? *reinterpret_cast<const float4*>(lnw + j) : make_float4(1.f, 1.f, 1.f, 1.f);
+    gb[q] = use_ln ? *reinterpret_cast<const float4*>(lnb + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  for (long long grp = (long long)blockIdx.x * 8 + (threadIdx.x >> 5); grp < groups; grp += wstride) {
+    float xa[K1T_ROWS], xb[K1T_ROWS];
+    float4 acc[K1T_ROWS][NQ];
 #pragma unroll
-      for (int v = 0; v < NV; ++v) acc[v] = fmaf(xv, w0t[c * H + v * 32 + lane], acc[v]);
+    for (int i = 0; i < K1T_ROWS; ++i) {
+      const long long r = grp * K1T_ROWS + i;   // TIME-MAJOR row index
+      xa[i] = xb[i] = 0.f;
+      if (r < rows) {
+        const int t = (int)(r / Bc), b = (int)(r - (long long)t * Bc);
+        const float* xr = x + ((long long)b * T + t) * C;
+        if (lane < C) xa[i] = xr[lane];
+        if (32 + lane < C) xb[i] = xr[32 + lane];
+        xT[r * K1T_XS + lane] = xa[i];
+        xT[r * K1T_XS + 32 + lane] = xb[i];
+      }
+#pragma unroll
+      for (int q = 0; q < NQ; ++q) acc[i][q] = bias[q];
     }
-    float s = 0.f;
+    for (int c = 0; c < C; ++c) {
+      float xv[K1T_ROWS];
 #pragma unroll
-    for (int v = 0; v < NV; ++v) s += acc[v];
-    const float mean = warp_sum(s) * (1.0f / H);
-    float q2 = 0.f;
+      for (int i = 0; i < K1T_ROWS; ++i) xv[i] = __shfl_sync(0xffffffffu, c < 32 ? xa[i] : xb[i], c & 31);
 #pragma unroll
-    for (int v = 0; v < NV; ++v) { const float d = acc[v] - mean; q2 = fmaf(d, d, q2); }
-    const float rstd = 1.0f / sqrtf(warp_sum(q2) * (1.0f / H) + 1e-5f);
-    if (lane == 0) rstd_out[r] = rstd;
+      for (int q = 0; q < NQ; ++q) {
+        const float4 w = *reinterpret_cast<const float4*>(k1t_w + c * H + q * 128 + lane * 4);
 #pragma unroll
-    for (int v = 0; v < NV; ++v) {
-      const int j = v * 32 + lane;
-      // without LayerNorm (09:191) xhat holds the raw pre-activation and y = xhat
-      const float xh = use_ln ? (acc[v] - mean) * rstd : acc[v];
-      xhat[r * H + j] = xh;
-      const float y = use_ln ? fmaf(xh, lnw[j], lnb[j]) : xh;
-      z[r * H + j] = gelu_erf(y) * drop_scale(seed, 0, (uint64_t)r * H + j, p_drop);
+        for (int i = 0; i < K1T_ROWS; ++i) {
+          acc[i][q].x = fmaf(xv[i], w.x, acc[i][q].x); acc[i][q].y = fmaf(xv[i], w.y, acc[i][q].y);
+          acc[i][q].z = fmaf(xv[i], w.z, acc[i][q].z); acc[i][q].w = fmaf(xv[i], w.w, acc[i][q].w);
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < K1T_ROWS; ++i) {
+      const long long r = grp * K1T_ROWS + i;
+      float s = 0.f;
+#pragma unroll
+      for (int q = 0; q < NQ; ++q) s += (acc[i][q].x + acc[i][q].y) + (acc[i][q].z + acc[i][q].w);
+      const float mean = warp_sum(s) * (1.0f / H);
+      float q2 = 0.f;
+#pragma unroll
+      for (int q = 0; q < NQ; ++q) {
+        const float d0 = acc[i][q].x - mean, d1 = acc[i][q].y - mean, d2 = acc[i][q].z - mean, d3 = acc[i][q].w - mean;
+        q2 = fmaf(d0, d0, q2); q2 = fmaf(d1, d1, q2); q2 = fmaf(d2, d2, q2); q2 = fmaf(d3, d3, q2);
+      }
+      const float rstd = 1.0f / sqrtf(warp_sum(q2) * (1.0f / H) + 1e-5f);
+      if (r >= rows) continue;
+      if (lane == 0) rstd_out[r] = rstd;
+#pragma unroll
+      for (int q = 0; q < NQ; ++q) {
+        const int j = q * 128 + lane * 4;
+        const float a4[4] = {acc[i][q].x, acc[i][q].y, acc[i][q].z, acc[i][q].w};
+        const float w4[4] = {gw[q].x, gw[q].y, gw[q].z, gw[q].w}, b4[4] = {gb[q].x, gb[q].y, gb[q].z, gb[q].w};
+        float xh4[4], z4[4];
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+          // without LayerNorm (09:191) xhat holds the raw pre-activation and y = xhat
+          xh4[v] = use_ln ? (a4[v] - mean) * rstd : a4[v];
+          const float y = use_ln ? fmaf(xh4[v], w4[v], b4[v]) : xh4[v];
+          z4[v] = gelu_erf(y) * drop_scale(seed, 0, (uint64_t)r * H + j + v, p_drop);
+        }
+        *reinterpret_cast<float4*>(xhat + r * H + j) = make_float4(xh4[0], xh4[1], xh4[2], xh4[3]);
+        *reinterpret_cast<float4*>(z + r * H + j) = make_float4(z4[0], z4[1], z4[2], z4[3]);
+      }
     }
   }
 }
@@ -429,14 +482,27 @@ attn_train_fwd(const float* __restrict__ pre, const float* __restrict__ y, int B
   extern __shared__ float at_smem[];  // [T] scores -> weights
   __shared__ float red[8];
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  for (int t = warp; t < T; t += 8) {
-    float s = 0.f;
-    if (pre) {
-      const float* pr = pre + ((long long)t * Bc + b) * AH;
-      for (int j = lane; j < AH; j += 32) s = fmaf(w2[j], tanhf(pr[j]), s);
-      s = warp_sum(s) + b2[0];
+  // four time steps per warp iteration, all their loads issued before the first tanh: the rows of one window are 512 KB apart, and
+  // one dependent load per step made this loop (and the context sum below) pure DRAM latency
+  const int nq = AH / 32;   // <= 8
+  float w2r[8];
+#pragma unroll
+  for (int q = 0; q < 8; ++q) w2r[q] = (pre && q < nq) ? w2[lane + 32 * q] : 0.f;
+  for (int t0 = warp * 4; t0 < T; t0 += 32) {
+    float v[4][8];
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+      for (int q = 0; q < 8; ++q)
+        v[u][q] = (pre && t0 + u < T && q < nq) ? pre[((long long)(t0 + u) * Bc + b) * AH + lane + 32 * q] : 0.f;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      float s = 0.f;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) s = fmaf(w2r[q], tanhf(v[u][q]), s);
+      s = warp_sum(s) + (pre ? b2[0] : 0.f);
+      if (lane == 0 && t0 + u < T) at_smem[t0 + u] = pre ? s : 0.f;
     }
-    if (lane == 0) at_smem[t] = s;
   }
   __syncthreads();
   float m = -INFINITY;
@@ -459,7 +525,15 @@ attn_train_fwd(const float* __restrict__ pre, const float* __restrict__ y, int B
   __syncthreads();
   for (int d = tid; d < D; d += 256) {
     float c = 0.f;
-    for (int t = 0; t < T; ++t) c = fmaf(at_smem[t], y[((long long)t * Bc + b) * D + d], c);
+    int t = 0;
+    for (; t + 8 <= T; t += 8) {
+      float yv[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) yv[u] = y[((long long)(t + u) * Bc + b) * D + d];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) c = fmaf(at_smem[t + u], yv[u], c);
+    }
+    for (; t < T; ++t) c = fmaf(at_smem[t], y[((long long)t * Bc + b) * D + d], c);
     ctx[(long long)b * D + d] = c;
   }
 }
@@ -477,16 +551,30 @@ attn_train_bwd(const float* __restrict__ pre, float* __restrict__ dpre, const fl
   for (int d = tid; d < D; d += 256) dc[d] = dctx[(long long)b * D + d];
   __syncthreads();
   // da_t = dctx . Y_t ; dY_t = a_t * dctx
-  for (int t = warp; t < T; t += 8) {
-    const long long row = (long long)t * Bc + b;
-    const float a = attn[(long long)b * T + t];
-    float s = 0.f;
-    for (int d = lane; d < D; d += 32) {
-      s = fmaf(dc[d], y[row * D + d], s);
-      dY[row * D + d] = a * dc[d];
+  const int nd = D / 32;   // <= 16
+  for (int t0 = warp * 2; t0 < T; t0 += 16) {   // two time steps per warp iteration, loads first
+    float yv[2][16];
+#pragma unroll
+    for (int u = 0; u < 2; ++u)
+#pragma unroll
+      for (int q = 0; q < 16; ++q) yv[u][q] = (t0 + u < T && q < nd) ? y[((long long)(t0 + u) * Bc + b) * D + lane + 32 * q] : 0.f;
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      if (t0 + u >= T) break;
+      const long long row = (long long)(t0 + u) * Bc + b;
+      const float a = attn[(long long)b * T + t0 + u];
+      float s = 0.f;
+#pragma unroll
+      for (int q = 0; q < 16; ++q) {
+        if (q < nd) {
+          const float dcv = dc[lane + 32 * q];
+          s = fmaf(dcv, yv[u][q], s);
+          dY[row * D + lane + 32 * q] = a * dcv;
+        }
+      }
+      s = warp_sum(s);
+      if (lane == 0) ds[t0 + u] = s;
     }
-    s = warp_sum(s);
-    if (lane == 0) ds[t] = s;
   }
   if (!pre) return;  // mean pooling: a_t = 1/T is a constant, dY = dctx / T is all there is
   __syncthreads();
@@ -504,16 +592,43 @@ attn_train_bwd(const float* __restrict__ pre, float* __restrict__ dpre, const fl
   if (lane == 0) red[warp] = sb2;
   __syncthreads();
   if (tid == 0) { float s = 0.f; for (int w = 0; w < 8; ++w) s += red[w]; atomicAdd(db2, s); }
-  // dPRE[t][j] = ds_t w2_j (1 - u^2), u = tanh(pre);  dw2_j += sum_t ds_t u
-  for (int j = tid; j < AH; j += 256) {
-    const float w = w2[j];
-    float g = 0.f;
-    for (int t = 0; t < T; ++t) {
-      const long long o = ((long long)t * Bc + b) * AH + j;
-      const float u = tanhf(pre[o]);
-      g = fmaf(ds[t], u, g);
-      dpre[o] = ds[t] * w * (1.0f - u * u);
+  __syncthreads();   // ds is final
+  // dPRE[t][j] = ds_t w2_j (1 - u^2), u = tanh(pre);  dw2_j += sum_t ds_t u.  A warp per time step (two in flight), a lane per 32-strided
+  // column: the first version gave every column j to ONE thread that walked the 256 steps with dependent loads 512 KB apart
+  const int nq = AH / 32;   // <= 8
+  float gacc[8], w2r[8];
+#pragma unroll
+  for (int q = 0; q < 8; ++q) { gacc[q] = 0.f; w2r[q] = q < nq ? w2[lane + 32 * q] : 0.f; }
+  for (int t0 = warp * 2; t0 < T; t0 += 16) {
+    float pv[2][8];
+#pragma unroll
+    for (int u = 0; u < 2; ++u)
+#pragma unroll
+      for (int q = 0; q < 8; ++q) pv[u][q] = (t0 + u < T && q < nq) ? pre[((long long)(t0 + u) * Bc + b) * AH + lane + 32 * q] : 0.f;
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      if (t0 + u >= T) break;
+      const float dst = ds[t0 + u];
+      const long long o = ((long long)(t0 + u) * Bc + b) * AH;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        if (q < nq) {
+          const float uu = tanhf(pv[u][q]);
+          gacc[q] = fmaf(dst, uu, gacc[q]);
+          dpre[o + lane + 32 * q] = dst * w2r[q] * (1.0f - uu * uu);
+        }
+      }
     }
+  }
+  float* gred = ab_smem + T + D;   // [8 warps][AH]
+#pragma unroll
+  for (int q = 0; q < 8; ++q)
+    if (q < nq) gred[warp * AH + lane + 32 * q] = gacc[q];
+  __syncthreads();
+  for (int j = tid; j < AH; j += 256) {
+    float g = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) g += gred[w * AH + j];
     atomicAdd(dw2 + j, g);
   }
 }
@@ -822,6 +937,13 @@ __global__ void unpack_bias_kernel(const float* __restrict__ src, float* __restr
   d_ih[i] = v;
   d_hh[i] = v;
 }
+// dst[r][c] = src[r][c] for c < cols (row strides lds / ldd)
+__global__ void copy_cols_kernel(const float* __restrict__ src, int lds, float* __restrict__ dst, int ldd, int rows, int cols) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * cols) return;
+  const int r = i / cols, c = i - r * cols;
+  dst[r * ldd + c] = src[r * lds + c];
+}
 // dxT [T][Bc][C] -> dx (Bc,T,C)
 __global__ void untranspose_x_kernel(const float* __restrict__ src, float* __restrict__ dst, int Bc, int T, int C) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -856,7 +978,7 @@ static void carve_train(const bci_lstm_config& c, int B, int T, float p_drop, ch
   size_t off = 0;
   auto take = [&](size_t n) { float* p = reinterpret_cast<float*>(base + off); off += align_up(n * sizeof(float), 256); return p; };
   w.hdr = take(64);
-  w.xT = take(M * C); w.xhat0 = take(M * H); w.rstd0 = take(M); w.z = take(M * H);
+  w.xT = take(M * K1T_XS); w.xhat0 = take(M * H); w.rstd0 = take(M); w.z = take(M * H);
   for (int l = 0; l < c.num_layers; ++l) {
     w.gates[l] = take(M * 4 * D); w.cst[l] = take(M * D); w.out[l] = take(M * D);
     w.outd[l] = (p_drop > 0.f && l < c.num_layers - 1) ? take(M * D) : w.out[l];
@@ -903,7 +1025,16 @@ static int forward_train_t(bci_lstm_s* h, const float* x, int B, int T, float p_
     int rc = pack_swap_operands(h, st);
     if (rc) return rc;
   }
-  inproj_train_fwd<H><<<rb, 256, 0, st>>>(x, B, T, C, p.w0t, p.b0, p.ln0w, p.ln0b, w.xT, w.xhat0, w.rstd0, w.z, p_drop * 0.5f, seed, use_ln);
+  {
+    static PerDeviceFlag k1_attr_pd;
+    bool& k1_attr = k1_attr_pd.cur();
+    if (!k1_attr) {
+      BCI_CUDA_OK(cudaFuncSetAttribute(inproj_train_fwd<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * H * (int)sizeof(float)));
+      k1_attr = true;
+    }
+  }
+  const int k1_blocks = (int)((M + 31) / 32 < 4LL * sm_count() ? (M + 31) / 32 : 4LL * sm_count());
+  inproj_train_fwd<H><<<k1_blocks, 256, (size_t)C * H * sizeof(float), st>>>(x, B, T, C, p.w0t, p.b0, p.ln0w, p.ln0b, w.xT, w.xhat0, w.rstd0, w.z, p_drop * 0.5f, seed, use_ln);
   BCI_LAUNCH_OK();
   const float* in = w.z;
   bool lo_ready = false;  // w.lo_in already holds the remainder of `in` (written by the dropout kernel of the layer below)
@@ -1011,7 +1142,7 @@ static int backward_t(bci_lstm_s* h, const float* dlogits, int B, int T, float p
     BCI_CUDA_OK(zero(g->attn_w1, (size_t)AH * D)); BCI_CUDA_OK(zero(g->attn_b1, AH));
   }
   if (use_ln) { BCI_CUDA_OK(zero(g->ln_w, D)); BCI_CUDA_OK(zero(g->ln_b, D)); }
-  attn_train_bwd<<<B, 256, (T + D) * sizeof(float), st>>>(c.use_attention ? w.PRE : nullptr, dPRE, w.Y, w.attn, w.dctx, B, T, D, AH, p.aw2,
+  attn_train_bwd<<<B, 256, (T + D + 8 * AH) * sizeof(float), st>>>(c.use_attention ? w.PRE : nullptr, dPRE, w.Y, w.attn, w.dctx, B, T, D, AH, p.aw2,
                                                           w.dA /*dY*/, g->attn_w2, g->attn_b2);
   BCI_LAUNCH_OK();
   if (c.use_attention) {
@@ -1161,7 +1292,21 @@ static int backward_t(bci_lstm_s* h, const float* dlogits, int B, int T, float p
   inproj_bwd_rows<H><<<rb, 256, 0, st>>>(dcur, w.xhat0, w.rstd0, p.ln0w, p.ln0b, M, dnext /*dv*/, g->input_ln_w, g->input_ln_b,
                                          p_drop * 0.5f, seed, use_ln);
   BCI_LAUNCH_OK();
-  if ((rc = gemm_tn(dnext, H, w.xT, C, g->input_proj_w, C, M, H, C, st))) return rc;
+  // dW0 (H, C) = dv^T . xT: on the tensor cores as a 128-column product -- xT rows are 64 floats (C <= 64, zero-padded), the TMA unit
+  // zero-fills the rest of the tile -- into scratch, then the C valid columns are copied out (the gradient's rows are C floats apart:
+  // no tensor map can describe them)
+  if (tf32x3_tn_ok(dnext, H, w.xT, K1T_XS, w.tmpW, 128, M, H, 128)) {
+    const bool sp = !mixed;
+    // remainders into buffers the main stream owns and no longer needs (the final LayerNorm's xhat and output: the side stream may
+    // still be reading the dG remainders)
+    if (sp && (rc = split_tf32(dnext, nullptr, w.xhatF, M * H, st))) return rc;
+    if (sp && (rc = split_tf32(w.xT, nullptr, w.Y, M * K1T_XS, st))) return rc;
+    if ((rc = gemm_tf32x3_tn(dnext, sp ? w.xhatF : nullptr, H, w.xT, sp ? w.Y : nullptr, K1T_XS, w.tmpW, 128, M, H, 128, st, 0, K1T_XS))) return rc;
+    copy_cols_kernel<<<ceil_div(H * C, 256), 256, 0, st>>>(w.tmpW, 128, g->input_proj_w, C, H, C);
+    BCI_LAUNCH_OK();
+  } else if ((rc = gemm_tn(dnext, H, w.xT, K1T_XS, g->input_proj_w, C, M, H, C, st))) {
+    return rc;
+  }
   if ((rc = colsum(dnext, H, M, H, g->input_proj_b, st))) return rc;
   if (dx) {
     // dxT [M][C] = dv . W0 (H x C); reuse dcur as scratch
