@@ -403,6 +403,8 @@ int bci_selftest_rec_swap256_fwd(const float* G, const float* w_hh, void* packed
                                  int32_t T, int32_t ND, void* stream);
 int bci_selftest_bptt_swap256(const float* dout, const float* gates, const float* csave, const float* w_hh, void* packed, float* dG,
                               int32_t Bc, int32_t T, int32_t ND, void* stream);
+/* the stateless dropout mask of the training step (a hash of seed / site / element index): out[i] = 0 or 1/(1-p) for i < n */
+int bci_selftest_dropout_mask(float* out, int64_t n, float p, uint64_t seed, uint32_t site, void* stream);
 /* selftest only: clock64 stamps (8 per step, steps 100-103; int64[32]) of CTA (0,0) of the following swapped forward launches */
 int bci_selftest_swap_set_debug(long long* stamps);
 /* layout probe: one M128 x N16 x K16 tcgen05.mma whose A operand is read from tensor memory; out [128][16] fp32 */

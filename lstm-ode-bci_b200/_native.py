@@ -128,6 +128,7 @@ SIGNATURES = {
     "bci_selftest_bptt_swap": (C.c_int, [_FP, _FP, _FP, _FP, _FP, _FP, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     "bci_selftest_rec_swap256_fwd": (C.c_int, [_FP, _FP, _FP, _FP, _FP, _FP, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     "bci_selftest_bptt_swap256": (C.c_int, [_FP, _FP, _FP, _FP, _FP, _FP, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
+    "bci_selftest_dropout_mask": (C.c_int, [_FP, C.c_int64, C.c_float, C.c_uint64, C.c_uint32, C.c_void_p]),
     "bci_selftest_swap_set_debug": (C.c_int, [_FP]),
     "bci_selftest_tmem_a_probe": (C.c_int, [_FP, C.c_void_p]),
     "bci_lstm_set_train_mode": (C.c_int, [C.c_void_p, C.c_int32]),

@@ -101,11 +101,15 @@ __device__ __forceinline__ float rec_tanh(float x) { return tanhf(x); }
 // stateless dropout of the training step: the mask is a hash of (seed, site, element index) and is regenerated instead of stored
 __device__ __forceinline__ float drop_scale(uint64_t seed, uint32_t site, uint64_t idx, float p) {
   if (p <= 0.f) return 1.f;
-  uint64_t z = seed + 0x9E3779B97F4A7C15ull * (idx + 1) + ((uint64_t)site << 56);
-  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
-  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-  z ^= z >> 31;
-  const float u = (float)(uint32_t)(z >> 40) * (1.0f / 16777216.0f);
+  // 32-bit avalanche hash (two multiply-xorshift rounds) of the element index keyed by (seed, site): ~10 integer instructions per
+  // element -- the masks are evaluated inside the recurrence epilogues, where the 64-bit splitmix of the first version (six 64-bit
+  // multiplies' worth of 32-bit IMADs) cost 50 us per layer.  The key part is loop-invariant.
+  const uint32_t key = ((uint32_t)seed * 0x9E3779B1u) ^ ((uint32_t)(seed >> 32) * 0x85EBCA77u) ^ (site * 0xC2B2AE3Du) ^ 0x27D4EB2Fu;
+  uint32_t h = ((uint32_t)idx * 0x9E3779B1u) ^ ((uint32_t)(idx >> 32) * 0x85EBCA77u) ^ key;
+  h ^= h >> 16; h *= 0x7FEB352Du;
+  h ^= h >> 15; h *= 0x846CA68Bu;
+  h ^= h >> 16;
+  const float u = (float)(h >> 8) * (1.0f / 16777216.0f);
   return u < p ? 0.f : 1.0f / (1.0f - p);
 }
 

@@ -1474,3 +1474,18 @@ extern "C" int bci_adamw_step(float* p, const float* g, float* m, float* v, int6
   BCI_LAUNCH_OK();
   return BCI_OK;
 }
+
+// diagnostics: the stateless dropout mask (common.cuh: drop_scale) of elements [0, n) of one site, as the kernels evaluate it
+__global__ void dropout_mask_kernel(float* __restrict__ out, long long n, float p, uint64_t seed, uint32_t site) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = bci::drop_scale(seed, site, (uint64_t)i, p);
+}
+extern "C" int bci_selftest_dropout_mask(float* out, int64_t n, float p, uint64_t seed, uint32_t site, void* stream) {
+  using namespace bci;
+  BCI_REQUIRE(out && n >= 0 && p >= 0.f && p < 1.f, BCI_EINVAL, "bci_selftest_dropout_mask: bad arguments");
+  if (n == 0) return BCI_OK;
+  dropout_mask_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, (cudaStream_t)stream>>>(out, n, p, seed, site);
+  BCI_LAUNCH_OK();
+  return BCI_OK;
+}
+

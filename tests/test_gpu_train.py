@@ -224,3 +224,28 @@ def test_dropout_is_reproducible_and_consistent():
         w[5, 9] += eps
     fd = (lp - lm) / (2 * eps)
     assert abs(fd - g) <= 0.1 * abs(g) + 2e-5, (fd, g)
+
+
+def test_dropout_mask_statistics():
+    """The stateless mask (hash of seed / site / element index): drop rate within 4 sigma of p, kept elements scaled by 1/(1-p),
+    no visible correlation between neighbouring elements, between sites or between seeds."""
+    from lstm_ode_bci_b200 import _native as N
+    n, p = 1 << 22, 0.4
+    masks = {}
+    for seed, site in ((7, 16), (7, 17), (8, 16), ((1 << 40) + 7, 16)):
+        out = torch.empty(n, device="cuda")
+        N.check(N.lib().bci_selftest_dropout_mask(out.data_ptr(), n, p, seed, site, torch.cuda.current_stream().cuda_stream))
+        vals = torch.unique(out)
+        assert vals.numel() == 2 and float(vals[0]) == 0.0 and abs(float(vals[1]) - 1.0 / (1.0 - p)) <= 1e-6
+        keep = (out > 0).double()
+        rate = 1.0 - float(keep.mean())
+        assert abs(rate - p) <= 4 * np.sqrt(p * (1 - p) / n), rate
+        for lag in (1, 2, 32, 128, 256):     # neighbours along a row and along the time-major layout
+            c = float(((keep[:-lag] - keep.mean()) * (keep[lag:] - keep.mean())).mean() / keep.var())
+            assert abs(c) <= 5 / np.sqrt(n), (lag, c)
+        masks[(seed, site)] = keep
+    base = masks[(7, 16)]
+    for k, m in masks.items():
+        if k != (7, 16):
+            c = float(((base - base.mean()) * (m - m.mean())).mean() / base.var())
+            assert abs(c) <= 5 / np.sqrt(n), (k, c)
