@@ -131,7 +131,7 @@ struct bci_lstm_s {
   void* last_train_ws;
   float last_dropout;
   uint64_t last_seed;
-  int last_batch, last_T;
+  int last_batch, last_T, last_mode;
 };
 
 namespace bci {

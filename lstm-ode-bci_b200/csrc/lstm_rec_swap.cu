@@ -388,7 +388,15 @@ lstm_rec_swap_fwd(const float* __restrict__ G,        // [T*Bc][ldg] fp32: colum
         if (b0 + wq * SW_WPT + i < Bc) {
           const long long row = (long long)t * Bc + b0 + wq * SW_WPT + i;
           out[row * D + colh] = hv;
-          if (gates) *reinterpret_cast<float4*>(gates + row * ldg + colg) = make_float4(ig, fg, gg, og);
+          if (gates) {
+            if (SPLIT) {
+              *reinterpret_cast<float4*>(gates + row * ldg + colg) = make_float4(ig, fg, gg, og);
+            } else {   // mixed mode: the saved activations are fp16 (values in [-1, 1]; half the bytes of an HBM-bound kernel)
+              const __half2 lo2 = __floats2half2_rn(ig, fg), hi2 = __floats2half2_rn(gg, og);
+              *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(gates) + row * ldg + colg) =
+                  make_uint2(*reinterpret_cast<const uint32_t*>(&lo2), *reinterpret_cast<const uint32_t*>(&hi2));
+            }
+          }
           if (csave) csave[row * D + colh] = c[i];
           if (dr.outd) {
             const float hd = hv * dsc[i];
@@ -508,7 +516,13 @@ lstm_bptt_swap(const float* __restrict__ dout,           // [T][Bc][D]
 #pragma unroll
       for (int i = 0; i < SW_WPT; ++i) {
         const long long row = (long long)t * Bc + brow[i];
-        g4[i] = __ldg(reinterpret_cast<const float4*>(gates + row * ldg + colg));
+        if (SPLIT) {
+          g4[i] = __ldg(reinterpret_cast<const float4*>(gates + row * ldg + colg));
+        } else {   // mixed mode: fp16 activations
+          const uint2 gv = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const __half*>(gates) + row * ldg + colg));
+          const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&gv.x)), b = __half22float2(*reinterpret_cast<const __half2*>(&gv.y));
+          g4[i] = make_float4(a.x, a.y, b.x, b.y);
+        }
         if (cc) cc[i] = __ldg(csave + row * D + colh);
         cp[i] = (s > 0) ? __ldg(csave + ((long long)tp * Bc + brow[i]) * D + colh) : 0.f;
         dd[i] = __ldg(dout + row * D + colh);
@@ -603,7 +617,8 @@ lstm_bptt_swap(const float* __restrict__ dout,           // [T][Bc][D]
 #pragma unroll
         for (int i = 0; i < SW_WPT; ++i) {
           const long long row = (long long)t4 * Bc + brow[i];
-          if ((tid & 7) == 0) sw_prefetch_l2(gates + row * ldg + colg);
+          if (SPLIT) { if ((tid & 7) == 0) sw_prefetch_l2(gates + row * ldg + colg); }
+          else if ((tid & 15) == 0) sw_prefetch_l2(reinterpret_cast<const __half*>(gates) + row * ldg + colg);
           if ((tid & 31) == 0) { sw_prefetch_l2(csave + row * D + colh); sw_prefetch_l2(dout + row * D + colh); }
         }
       }
@@ -902,7 +917,11 @@ lstm_rec_swap256_fwd(const float* __restrict__ G,        // [T*Bc][ldg] fp32: co
         if (b0 + wq * S2_WPT + i < Bc) {
           const long long row = (long long)t * Bc + b0 + wq * S2_WPT + i;
           out[row * D + colh] = hv;
-          if (gates) *reinterpret_cast<float4*>(gates + row * ldg + colg) = make_float4(ig, fg, gg, og);
+          if (gates) {   // fp16, as in the H = 128 mixed kernel
+            const __half2 lo2 = __floats2half2_rn(ig, fg), hi2 = __floats2half2_rn(gg, og);
+            *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(gates) + row * ldg + colg) =
+                make_uint2(*reinterpret_cast<const uint32_t*>(&lo2), *reinterpret_cast<const uint32_t*>(&hi2));
+          }
           if (csave) csave[row * D + colh] = c[i];
           if (dr.outd) dr.outd[row * D + colh] = hv * dsc[i];
         }
@@ -995,7 +1014,11 @@ lstm_bptt_swap256(const float* __restrict__ dout,           // [T][Bc][D]
 #pragma unroll
       for (int i = 0; i < S2_WPT; ++i) {
         const long long row = (long long)t * Bc + brow[i];
-        g4[i] = __ldg(reinterpret_cast<const float4*>(gates + row * ldg + colg));
+        {
+          const uint2 gv = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const __half*>(gates) + row * ldg + colg));
+          const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&gv.x)), b = __half22float2(*reinterpret_cast<const __half2*>(&gv.y));
+          g4[i] = make_float4(a.x, a.y, b.x, b.y);
+        }
         if (cc) cc[i] = __ldg(csave + row * D + colh);
         cp[i] = (s > 0) ? __ldg(csave + ((long long)tp * Bc + brow[i]) * D + colh) : 0.f;
         dd[i] = __ldg(dout + row * D + colh);
@@ -1051,7 +1074,7 @@ lstm_bptt_swap256(const float* __restrict__ dout,           // [T][Bc][D]
 #pragma unroll
         for (int i = 0; i < S2_WPT; ++i) {
           const long long row = (long long)t4 * Bc + brow[i];
-          if ((tid & 7) == 0) sw_prefetch_l2(gates + row * ldg + colg);
+          if ((tid & 15) == 0) sw_prefetch_l2(reinterpret_cast<const __half*>(gates) + row * ldg + colg);
           if ((tid & 31) == 0) { sw_prefetch_l2(csave + row * D + colh); sw_prefetch_l2(dout + row * D + colh); }
         }
       }

@@ -971,7 +971,8 @@ struct TrainWs {
   float *lo_in, *lo_G, *lo_G2, *lo_in2, *lo_out2;
   size_t total;
 };
-struct TrainHeader { float dropout; uint32_t valid; uint64_t seed; int batch, T; };
+// mode: 1 = the forward ran the mixed step (its saved gate activations are fp16: the backward must be the mixed one too), 0 = fp32-parity
+struct TrainHeader { float dropout; uint32_t valid; uint64_t seed; int batch, T, mode; };
 
 static void carve_train(const bci_lstm_config& c, int B, int T, float p_drop, char* base, TrainWs& w) {
   const size_t H = c.hidden_size, D = feat_width(c), C = c.input_size, M = (size_t)B * T;
@@ -1017,7 +1018,7 @@ static int forward_train_t(bci_lstm_s* h, const float* x, int B, int T, float p_
   const long long M = (long long)B * T;
   const int rb = (int)((M + 7) / 8 < 4096 ? (M + 7) / 8 : 4096);
   // mixed-precision step: the recurrences run on the tensor cores with 16-bit operands (lstm_rec_swap.cu)
-  const bool mixed = h->train_mode == BCI_TRAIN_MIXED && (rec_swap_ok(H, w.G, 4 * D) || rec_swap256_ok(H, w.G, 4 * D));
+  const bool mixed = h->last_mode == 1;   // decided by lstm_forward_train (recorded in the workspace header for the backward)
   // fp32-parity step: the same kernel in its split-precision form (three fp16 product chains, fp32-grade); BCI_TRAIN_REC=simt keeps
   // the CUDA-core recurrence of round 1
   const bool split_fwd = !mixed && swap_rec_enabled() && rec_swap_ok(H, w.G, 4 * D);
@@ -1097,9 +1098,11 @@ int lstm_forward_train(bci_lstm_s* h, const float* x, int batch, int T, float dr
   carve_train(c, batch, T, dropout, (char*)ws, w);
   BCI_REQUIRE(ws_bytes >= w.total, BCI_ENOMEM, "bci_lstm_forward(train=1): workspace %zu < %zu bytes", ws_bytes, w.total);
   BCI_REQUIRE(T * sizeof(float) + 2 * c.hidden_size * sizeof(float) <= 40 * 1024, BCI_EINVAL, "training supports seq_len <= 8192");
-  TrainHeader hd{dropout, 0xB200C0DEu, seed, batch, T};
+  const int G4 = 4 * feat_width(c);
+  const int mode = (h->train_mode == BCI_TRAIN_MIXED && (rec_swap_ok(c.hidden_size, w.G, G4) || rec_swap256_ok(c.hidden_size, w.G, G4))) ? 1 : 0;
+  TrainHeader hd{dropout, 0xB200C0DEu, seed, batch, T, mode};
   BCI_CUDA_OK(cudaMemcpyAsync(w.hdr, &hd, sizeof(hd), cudaMemcpyHostToDevice, st));
-  h->last_train_ws = ws; h->last_dropout = dropout; h->last_seed = seed; h->last_batch = batch; h->last_T = T;
+  h->last_train_ws = ws; h->last_dropout = dropout; h->last_seed = seed; h->last_batch = batch; h->last_T = T; h->last_mode = mode;
   if (c.bidirectional)
     return c.hidden_size == 128 ? forward_train_t<128, 2>(h, x, batch, T, dropout, seed, logits, probs, attn, w, st)
                                 : forward_train_t<256, 2>(h, x, batch, T, dropout, seed, logits, probs, attn, w, st);
@@ -1108,8 +1111,8 @@ int lstm_forward_train(bci_lstm_s* h, const float* x, int batch, int T, float dr
 }
 
 template <int H, int ND>
-static int backward_t(bci_lstm_s* h, const float* dlogits, int B, int T, float p_drop, uint64_t seed, float* dx, const bci_lstm_grads* g,
-                      TrainWs& w, cudaStream_t st) {
+static int backward_t(bci_lstm_s* h, const float* dlogits, int B, int T, float p_drop, uint64_t seed, int fwd_mode, float* dx,
+                      const bci_lstm_grads* g, TrainWs& w, cudaStream_t st) {
   const bci_lstm_config& c = h->cfg;
   const PackedF32& p = h->f32;
   const bci_lstm_weights& raw = h->raw;
@@ -1120,7 +1123,9 @@ static int backward_t(bci_lstm_s* h, const float* dlogits, int B, int T, float p
   auto zero = [&](float* ptr, size_t n) { return cudaMemsetAsync(ptr, 0, n * sizeof(float), st); };
   auto zero_on = [&](cudaStream_t s2, float* ptr, size_t n) { return cudaMemsetAsync(ptr, 0, n * sizeof(float), s2); };
   int rc;
-  const bool mixed = h->train_mode == BCI_TRAIN_MIXED && (rec_swap_ok(H, w.G, G4) || rec_swap256_ok(H, w.G, G4)) && !h->sw_stale;
+  // the mode of the forward that filled this workspace (its saved gate activations are fp16 in the mixed mode)
+  const bool mixed = fwd_mode == 1;
+  if (mixed && (rc = pack_swap_operands(h, st))) return rc;   // (no-op unless the weights were reloaded since the forward)
   const bool split_bwd = !mixed && swap_rec_enabled() && rec_swap_ok(H, w.G, G4) && !h->sw_stale;   // fp32-parity BPTT on the tensor cores
   // ---- head ----
   head_train_bwd<H><<<B, H, 0, st>>>(dlogits, cls, w.pre1, w.pre2, raw.cls_w6, raw.cls_w3, raw.cls_w0, w.dpre1, w.dpre2, w.dctx,
@@ -1328,7 +1333,7 @@ int lstm_backward_impl(bci_lstm_s* h, const float* x, const float* dlogits, int 
   TrainHeader hd;
   if (ws == h->last_train_ws && batch == h->last_batch && T == h->last_T) {
     // the usual case -- backward right after its forward: no stream synchronisation inside the training step
-    hd = TrainHeader{h->last_dropout, 0xB200C0DEu, h->last_seed, batch, T};
+    hd = TrainHeader{h->last_dropout, 0xB200C0DEu, h->last_seed, batch, T, h->last_mode};
   } else {  // an older forward's workspace (07:252 keeps several alive): read what that forward left there
     BCI_CUDA_OK(cudaMemcpyAsync(&hd, ws, sizeof(hd), cudaMemcpyDeviceToHost, st));
     BCI_CUDA_OK(cudaStreamSynchronize(st));
@@ -1350,10 +1355,10 @@ int lstm_backward_impl(bci_lstm_s* h, const float* x, const float* dlogits, int 
       BCI_REQUIRE(g->w_ih[l][d] && g->w_hh[l][d] && g->b_ih[l][d] && g->b_hh[l][d], BCI_EINVAL,
                   "bci_lstm_backward: LSTM gradient pointer NULL (layer %d dir %d)", l, d);
   if (c.bidirectional)
-    return c.hidden_size == 128 ? backward_t<128, 2>(h, dlogits, batch, T, hd.dropout, hd.seed, dx, g, w, st)
-                                : backward_t<256, 2>(h, dlogits, batch, T, hd.dropout, hd.seed, dx, g, w, st);
-  return c.hidden_size == 128 ? backward_t<128, 1>(h, dlogits, batch, T, hd.dropout, hd.seed, dx, g, w, st)
-                              : backward_t<256, 1>(h, dlogits, batch, T, hd.dropout, hd.seed, dx, g, w, st);
+    return c.hidden_size == 128 ? backward_t<128, 2>(h, dlogits, batch, T, hd.dropout, hd.seed, hd.mode, dx, g, w, st)
+                                : backward_t<256, 2>(h, dlogits, batch, T, hd.dropout, hd.seed, hd.mode, dx, g, w, st);
+  return c.hidden_size == 128 ? backward_t<128, 1>(h, dlogits, batch, T, hd.dropout, hd.seed, hd.mode, dx, g, w, st)
+                              : backward_t<256, 1>(h, dlogits, batch, T, hd.dropout, hd.seed, hd.mode, dx, g, w, st);
 }
 
 // ---- fused clip + AdamW ---------------------------------------------------------------------------------------------

@@ -52,7 +52,7 @@ def main():
     out = torch.empty((T, B, ND * H), device="cuda")
     gates = torch.empty((T * B, ND * 4 * H), device="cuda")
     cs = torch.empty((T, B, ND * H), device="cuda")
-    dG = torch.empty_like(gates)
+    dG = torch.empty((T * B, ND * 4 * H), device="cuda")
     st = torch.cuda.current_stream().cuda_stream
     lib = N.lib()
     stamps = torch.zeros(32, dtype=torch.int64, device="cuda")

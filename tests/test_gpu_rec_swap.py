@@ -73,7 +73,8 @@ def test_rec_swap_forward_matches_float64(Bc, T, ND, split):
     G = (torch.randn(T * Bc, ND * 4 * H, device="cuda", generator=g) * 1.2).contiguous()
     packed = torch.empty(5 * ND * 4 * H * H, device="cuda", dtype=torch.float16)
     out = torch.full((T, Bc, ND * H), float("nan"), device="cuda")
-    gates = torch.full((T * Bc, ND * 4 * H), float("nan"), device="cuda")
+    # the mixed form saves its gate activations as fp16, the fp32-parity form as fp32
+    gates = torch.full((T * Bc, ND * 4 * H), float("nan"), device="cuda", dtype=torch.float32 if split else torch.float16)
     cs = torch.full((T, Bc, ND * H), float("nan"), device="cuda")
     N.check(N.lib().bci_selftest_rec_swap_fwd(_p(G), _p(whh), _p(packed), _p(out), _p(gates), _p(cs), Bc, T, ND, split, _stream()))
     torch.cuda.synchronize()
@@ -107,7 +108,7 @@ def test_bptt_swap_matches_autograd(Bc, T, ND, decay, split):
     out, wg, wc = _ref_forward64(G64, whh.double(), Bc, T, ND)
     (out * dout.double()).sum().backward()
     want = G64.grad
-    gates = wg.detach().float().reshape(T * Bc, ND * 4 * H).contiguous()
+    gates = wg.detach().to(torch.float32 if split else torch.float16).reshape(T * Bc, ND * 4 * H).contiguous()
     cs = wc.detach().float().reshape(T, Bc, ND * H).contiguous()
     packed = torch.empty(5 * ND * 4 * H * H, device="cuda", dtype=torch.float16)
     dG = torch.full((T * Bc, ND * 4 * H), float("nan"), device="cuda")
@@ -134,7 +135,7 @@ def test_rec_swap256_forward_matches_float64(Bc, T, ND):
     G = (torch.randn(T * Bc, ND * 4 * H, device="cuda", generator=g) * 1.2).contiguous()
     packed = torch.empty(5 * ND * 4 * H * H, device="cuda", dtype=torch.float16)
     out = torch.full((T, Bc, ND * H), float("nan"), device="cuda")
-    gates = torch.full((T * Bc, ND * 4 * H), float("nan"), device="cuda")
+    gates = torch.full((T * Bc, ND * 4 * H), float("nan"), device="cuda", dtype=torch.float16)
     cs = torch.full((T, Bc, ND * H), float("nan"), device="cuda")
     N.check(N.lib().bci_selftest_rec_swap256_fwd(_p(G), _p(whh), _p(packed), _p(out), _p(gates), _p(cs), Bc, T, ND, _stream()))
     torch.cuda.synchronize()
@@ -158,7 +159,7 @@ def test_bptt_swap256_matches_autograd(Bc, T, ND):
     out, wg, wc = _ref_forward64(G64, whh.double(), Bc, T, ND, H)
     (out * dout.double()).sum().backward()
     want = G64.grad
-    gates = wg.detach().float().reshape(T * Bc, ND * 4 * H).contiguous()
+    gates = wg.detach().to(torch.float16).reshape(T * Bc, ND * 4 * H).contiguous()
     cs = wc.detach().float().reshape(T, Bc, ND * H).contiguous()
     packed = torch.empty(5 * ND * 4 * H * H, device="cuda", dtype=torch.float16)
     dG = torch.full((T * Bc, ND * 4 * H), float("nan"), device="cuda")
