@@ -443,7 +443,8 @@ struct TpMaps { CUtensorMap a, b, c, a_lo, b_lo; };
 template <bool TN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TX_THREADS, 1)
 gemm_tf32_pair_kernel(const __grid_constant__ TpMaps maps, const float* __restrict__ bias, int M, int N, long long K, int k_splits,
-                      int reduce_add, int nhalf, int terms) {   // terms = 3: split precision (hi / lo operand pairs, nhalf = 64)
+                      int reduce_add, int nhalf, int terms, int c_half) {   // terms = 3: split precision (hi / lo operand pairs, nhalf = 64)
+  // c_half: C is fp16 (the mixed step's G): 64-column TMA boxes, two accumulator slabs per store
   extern __shared__ uint8_t tx_smem_raw[];
   const uint32_t raw = smem_u32(tx_smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
@@ -605,6 +606,43 @@ gemm_tf32_pair_kernel(const __grid_constant__ TpMaps maps, const float* __restri
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)acc * 256u;
+      if (c_half) {
+#pragma unroll 1
+        for (int sp = 0; sp < spw / 2; ++sp) {
+          const int slab = spw * ehalf + 2 * sp;
+          uint32_t r[32], r2[32];
+          tmem_ld32(taddr + slab * 32, r);
+          tmem_ld32(taddr + slab * 32 + 32, r2);
+          if (lane == 0) tma_store_wait_read();
+          __syncwarp();
+          tmem_ld_wait();
+          if (sp == spw / 2 - 1) {
+            tc_fence_before();
+            mbar_arrive(tempty_bar(acc));
+          }
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {   // chunk q = columns [8 q, 8 q + 8) of the 64-column box
+            const uint32_t* src = q < 4 ? r + 8 * q : r2 + 8 * (q - 4);
+            const float* bs = bias_s + slab * 32 + 8 * q;
+            uint32_t pk[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const __half2 h2 = __floats2half2_rn(__uint_as_float(src[2 * e]) + bs[2 * e], __uint_as_float(src[2 * e + 1]) + bs[2 * e + 1]);
+              pk[e] = *reinterpret_cast<const uint32_t*>(&h2);
+            }
+            *reinterpret_cast<uint4*>(cst + sw128_chunk_off((uint32_t)lane, (uint32_t)q)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            const int c0 = nb * ntile + slab * 32, c1 = mb * 256 + (int)rank * 128 + quarter * 32;
+            if (c0 < N && c1 < M) tma_store_2d(&maps.c, cst_s, c0, c1);
+            tma_store_commit();
+          }
+        }
+        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+        continue;
+      }
 #pragma unroll 1
       for (int slab = spw * ehalf; slab < spw * ehalf + spw; ++slab) {
         uint32_t r[32], rl[32];
@@ -654,6 +692,8 @@ gemm_tf32_pair_kernel(const __grid_constant__ TpMaps maps, const float* __restri
   }
 }
 
+static int make_tmap_f16_2d(CUtensorMap* tm, const __half* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_cols,
+                            uint32_t box_rows);
 // BCI_GEMM_PAIR=off keeps the one-CTA kernel for the single-pass products
 static bool tf32_pair_enabled() {
   static int v = -1;
@@ -698,7 +738,29 @@ static int gemm_tf32_pair_nt(const float* A, const float* A_lo, int lda, const f
   const long long tiles = (long long)ceil_div(M, 256) * ceil_div(N, 2 * nhalf);
   const int mx = tf32_pair_max_clusters();
   const int clusters = (int)(tiles < mx ? tiles : mx);
-  gemm_tf32_pair_kernel<false><<<2 * clusters, TX_THREADS, TP_SMEM, st>>>(maps, bias, M, N, (long long)K, 1, accumulate, nhalf, terms);
+  gemm_tf32_pair_kernel<false><<<2 * clusters, TX_THREADS, TP_SMEM, st>>>(maps, bias, M, N, (long long)K, 1, accumulate, nhalf, terms, 0);
+  BCI_LAUNCH_OK();
+  return BCI_OK;
+}
+// single-pass NT product with an fp16 result (the mixed step's projected inputs G): C16[M][N] = fp16(A . W^T + bias).  Needs the pair
+// kernel (M >= 512, N >= 256, N % 64 == 0, ldc % 8 == 0); callers check gemm_tf32_half_ok first
+bool gemm_tf32_half_ok(const void* A, int lda, const void* W, int ldw, const void* C, int ldc, int M, int N, int K) {
+  return tf32x3_enabled() && tf32_pair_enabled() && M >= 512 && N >= 256 && N % 64 == 0 && K % 4 == 0 && lda % 4 == 0 && ldw % 4 == 0 &&
+         ldc % 8 == 0 && ((uintptr_t)A & 15) == 0 && ((uintptr_t)W & 15) == 0 && ((uintptr_t)C & 15) == 0 && tf32_pair_max_clusters() > 0;
+}
+int gemm_tf32_nt_half(const float* A, int lda, const float* W, int ldw, const float* bias, __half* C, int ldc, int M, int N, int K,
+                      cudaStream_t st) {
+  TpMaps maps;
+  int rc;
+  if ((rc = make_tmap_f32_2d(&maps.a, A, M, K, lda, TX_BK, 128))) return rc;
+  if ((rc = make_tmap_f32_2d(&maps.b, W, N, K, ldw, TX_BK, 128))) return rc;
+  if ((rc = make_tmap_f32_2d(&maps.a_lo, A, M, K, lda, TX_BK, 128))) return rc;
+  if ((rc = make_tmap_f32_2d(&maps.b_lo, W, N, K, ldw, TX_BK, 128))) return rc;
+  if ((rc = make_tmap_f16_2d(&maps.c, C, M, N, ldc, 64, 32))) return rc;
+  const long long tiles = (long long)ceil_div(M, 256) * ceil_div(N, 256);
+  const int mx = tf32_pair_max_clusters();
+  const int clusters = (int)(tiles < mx ? tiles : mx);
+  gemm_tf32_pair_kernel<false><<<2 * clusters, TX_THREADS, TP_SMEM, st>>>(maps, bias, M, N, (long long)K, 1, 0, 128, 1, 1);
   BCI_LAUNCH_OK();
   return BCI_OK;
 }
@@ -728,7 +790,7 @@ static int gemm_tf32_pair_tn(const float* A, const float* A_lo, int lda, const f
   if (splits > 1) BCI_CUDA_OK(cudaMemset2DAsync(C, (size_t)ldc * 4, 0, (size_t)Q * 4, P, st));
   const long long tiles = out_tiles * splits;
   const int clusters = (int)(tiles < mx ? tiles : mx);
-  gemm_tf32_pair_kernel<true><<<2 * clusters, TX_THREADS, TP_SMEM, st>>>(maps, nullptr, P, Q, R, (int)splits, splits > 1 ? 1 : 0, nhalf, terms);
+  gemm_tf32_pair_kernel<true><<<2 * clusters, TX_THREADS, TP_SMEM, st>>>(maps, nullptr, P, Q, R, (int)splits, splits > 1 ? 1 : 0, nhalf, terms, 0);
   BCI_LAUNCH_OK();
   return BCI_OK;
 }

@@ -223,12 +223,12 @@ bool swap_rec_enabled();
 // hidden_size 256, mixed precision: the same recurrences on CTA pairs (each CTA owns 128 units; h / dG halves exchanged through DSMEM)
 bool rec_swap256_ok(int H, const void* G, int ldg);
 int launch_rec_swap256_fwd(int ND, const float* G, int ldg, const __half* whh, float* out, float* gates, float* csave, int D, int Bc, int T,
-                           cudaStream_t st, const SwapDropout* drop = nullptr);
+                           cudaStream_t st, const SwapDropout* drop = nullptr, bool g_half = false);
 int launch_bptt_swap256(int ND, const float* dout, const float* gates, const float* csave, const __nv_bfloat16* whhT, float* dG, float* dbias,
                         int ldg, int D, int Bc, int T, cudaStream_t st, const SwapDropout* drop = nullptr);
 int pack_swap_operands(bci_lstm_s* h, cudaStream_t st);
 int launch_rec_swap_fwd(int ND, const float* G, int ldg, const __half* whh, float* out, float* gates, float* csave, int D, int Bc, int T,
-                        bool split, cudaStream_t st, const SwapDropout* drop = nullptr);
+                        bool split, cudaStream_t st, const SwapDropout* drop = nullptr, bool g_half = false);
 int launch_bptt_swap(int ND, const float* dout, const float* gates, const float* csave, const void* whhT, float* dG, float* dG_lo,
                      float* dbias, int ldg, int D, int Bc, int T, bool split, cudaStream_t st, const SwapDropout* drop = nullptr);
 constexpr float F16X3_WSCALE = 16.0f;   // weights of the fp16-split paths are stored x 16 (keeps their lo parts out of fp16's subnormals)
@@ -243,6 +243,9 @@ bool tf32x3_tn_ok(const void* A, int lda, const void* B, int ldb, const void* C,
 int split_tf32(const float* x, float* hi, float* lo, long long n, cudaStream_t st);
 int gemm_tf32x3_nt(const float* A_hi, const float* A_lo, int lda, const float* W_hi, const float* W_lo, int ldw, const float* bias,
                    float* C, int ldc, int M, int N, int K, int accumulate, cudaStream_t st);
+bool gemm_tf32_half_ok(const void* A, int lda, const void* W, int ldw, const void* C, int ldc, int M, int N, int K);
+int gemm_tf32_nt_half(const float* A, int lda, const float* W, int ldw, const float* bias, __half* C, int ldc, int M, int N, int K,
+                      cudaStream_t st);
 int gemm_tf32x3_tn(const float* A_hi, const float* A_lo, int lda, const float* B_hi, const float* B_lo, int ldb, float* C, int ldc,
                    long long R, int P, int Q, cudaStream_t st, int force_splits = 0, int q_valid = 0);
 // bf16 / tcgen05 forward (lstm_bf16.cu)

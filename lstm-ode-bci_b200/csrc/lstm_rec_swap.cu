@@ -269,7 +269,7 @@ lstm_rec_swap_fwd(const float* __restrict__ G,        // [T*Bc][ldg] fp32: colum
                   float* __restrict__ gates,          // optional [T*Bc][ldg] gate ACTIVATIONS, same layout as G
                   float* __restrict__ csave,          // optional [T*Bc][D] cell states
                   SwDrop dr,                          // optional dropped copy of h_t (the next layer's input), written here
-                  int D, int Bc, int T, long long* __restrict__ dbg, int jitter) {
+                  int D, int Bc, int T, long long* __restrict__ dbg, int jitter, int g_half) {   // g_half: G is fp16 (mixed step)
   SwJitter jit(jitter);
   extern __shared__ uint8_t sw_smem_raw[];
   const int tid = threadIdx.x, u = tid & 127, wq = (tid >> 7) & 3;
@@ -333,29 +333,45 @@ lstm_rec_swap_fwd(const float* __restrict__ G,        // [T*Bc][ldg] fp32: colum
     }
     const int colg = dir * 512 + u * 4, colh = dir * 128 + u;
     float c[SW_WPT];
-    float4 gq[SW_WPT];
+    uint4 gq[SW_WPT];
 #pragma unroll
+    // the next step's G row is requested RAW into registers (fp32: 16 bytes, fp16: 8) and converted when it is used a step later:
+    // converting at the load would stall on the DRAM round trip right here, in front of the accumulator wait
+    auto load_g = [&](int tt, int i) -> uint4 {
+      const long long e = ((long long)tt * Bc + brow[i]) * ldg + colg;
+      if (!g_half) return __ldg(reinterpret_cast<const uint4*>(G + e));
+      const uint2 gv = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const __half*>(G) + e));
+      return make_uint4(gv.x, gv.y, 0u, 0u);
+    };
+    auto cvt_g = [&](const uint4& r) -> float4 {
+      if (!g_half) return make_float4(__uint_as_float(r.x), __uint_as_float(r.y), __uint_as_float(r.z), __uint_as_float(r.w));
+      const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&r.x)), b = __half22float2(*reinterpret_cast<const __half2*>(&r.y));
+      return make_float4(a.x, a.y, b.x, b.y);
+    };
     for (int i = 0; i < SW_WPT; ++i) {
       c[i] = 0.f;
-      gq[i] = __ldg(reinterpret_cast<const float4*>(G + ((long long)(dir ? T - 1 : 0) * Bc + brow[i]) * ldg + colg));
+      gq[i] = load_g(dir ? T - 1 : 0, i);
     }
     for (int st = 0; st < T; ++st) {
       const int t = dir ? (T - 1 - st) : st;
       SW_STAMP(tid == 0, 0);
       float4 gc[SW_WPT];
 #pragma unroll
-      for (int i = 0; i < SW_WPT; ++i) gc[i] = gq[i];
+      for (int i = 0; i < SW_WPT; ++i) gc[i] = cvt_g(gq[i]);
       if (st + 1 < T) {
         const int tn = dir ? (T - 2 - st) : st + 1;
 #pragma unroll
-        for (int i = 0; i < SW_WPT; ++i) gq[i] = __ldg(reinterpret_cast<const float4*>(G + ((long long)tn * Bc + brow[i]) * ldg + colg));
+        for (int i = 0; i < SW_WPT; ++i) gq[i] = load_g(tn, i);
       }
       // the register prefetch above covers one step (~1.2 us): not always a DRAM round trip under load.  Pull the rows of
       // step st + 4 into L2 now (one request per 128-byte line)
-      if (st + 4 < T && (tid & 7) == 0) {
+      if (st + 4 < T && (tid & (g_half ? 15 : 7)) == 0) {
         const int t4 = dir ? (T - 5 - st) : st + 4;
 #pragma unroll
-        for (int i = 0; i < SW_WPT; ++i) sw_prefetch_l2(G + ((long long)t4 * Bc + brow[i]) * ldg + colg);
+        for (int i = 0; i < SW_WPT; ++i) {
+          const long long e = ((long long)t4 * Bc + brow[i]) * ldg + colg;
+          if (g_half) sw_prefetch_l2(reinterpret_cast<const __half*>(G) + e); else sw_prefetch_l2(G + e);
+        }
       }
       float dsc[SW_WPT];   // dropout factors of this step's outputs: index arithmetic only, done while the product runs
       if (dr.outd) {
@@ -510,7 +526,10 @@ lstm_bptt_swap(const float* __restrict__ dout,           // [T][Bc][D]
     float pc[SW_WPT], pcp[SW_WPT], pdo[SW_WPT];
 #pragma unroll
     for (int i = 0; i < SW_WPT; ++i) { dh_rec[i] = 0.f; dc[i] = 0.f; }
-    auto fetch = [&](int s, float4* g4, float* cc, float* cp, float* dd) {
+    // everything fetch() requests is left RAW in registers (fp16 gate bits unconverted, dout unscaled: the dropout factor goes to
+    // sc[]): any arithmetic on a loaded value here would stall on its DRAM round trip in front of the accumulator wait
+    float pds[SW_WPT];
+    auto fetch = [&](int s, float4* g4, float* cc, float* cp, float* dd, float* sc) {
       const int t = dir ? (T - 1 - s) : s;
       const int tp = dir ? (t + 1) : (t - 1);
 #pragma unroll
@@ -518,18 +537,23 @@ lstm_bptt_swap(const float* __restrict__ dout,           // [T][Bc][D]
         const long long row = (long long)t * Bc + brow[i];
         if (SPLIT) {
           g4[i] = __ldg(reinterpret_cast<const float4*>(gates + row * ldg + colg));
-        } else {   // mixed mode: fp16 activations
+        } else {   // mixed mode: fp16 activations (bits in .x / .y)
           const uint2 gv = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const __half*>(gates) + row * ldg + colg));
-          const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&gv.x)), b = __half22float2(*reinterpret_cast<const __half2*>(&gv.y));
-          g4[i] = make_float4(a.x, a.y, b.x, b.y);
+          g4[i] = make_float4(__uint_as_float(gv.x), __uint_as_float(gv.y), 0.f, 0.f);
         }
         if (cc) cc[i] = __ldg(csave + row * D + colh);
         cp[i] = (s > 0) ? __ldg(csave + ((long long)tp * Bc + brow[i]) * D + colh) : 0.f;
         dd[i] = __ldg(dout + row * D + colh);
-        if (dr.p > 0.f) dd[i] *= drop_scale(dr.seed, dr.site, (uint64_t)(row * D + colh), dr.p);
+        sc[i] = dr.p > 0.f ? drop_scale(dr.seed, dr.site, (uint64_t)(row * D + colh), dr.p) : 1.0f;
       }
     };
-    fetch(T - 1, pg, pc, pcp, pdo);
+    auto gate_vals = [&](const float4& r) -> float4 {
+      if (SPLIT) return r;
+      const uint32_t x = __float_as_uint(r.x), y = __float_as_uint(r.y);
+      const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&x)), b = __half22float2(*reinterpret_cast<const __half2*>(&y));
+      return make_float4(a.x, a.y, b.x, b.y);
+    };
+    fetch(T - 1, pg, pc, pcp, pdo, pds);
     float4 bsum = make_float4(0.f, 0.f, 0.f, 0.f);   // this thread's share of the bias gradient: its windows, all steps
     for (int s = T - 1; s >= 0; --s) {
       const int t = dir ? (T - 1 - s) : s;
@@ -540,8 +564,8 @@ lstm_bptt_swap(const float* __restrict__ dout,           // [T][Bc][D]
       for (int i = 0; i < SW_WPT; ++i) {
         float4 dg = make_float4(0.f, 0.f, 0.f, 0.f);
         if (b0 + wq * SW_WPT + i < Bc) {
-          const float4 g = pg[i];
-          const float dh = pdo[i] + dh_rec[i];
+          const float4 g = gate_vals(pg[i]);
+          const float dh = fmaf(pdo[i], pds[i], dh_rec[i]);
           const float tc = SPLIT ? rec_tanh(pc[i]) : tanh_mufu(pc[i]);  // the forward's own tanh(c)
           const float dct = fmaf(dh * g.w, 1.0f - tc * tc, dc[i]);
           dg.x = dct * g.z * g.x * (1.0f - g.x);
@@ -610,8 +634,8 @@ lstm_bptt_swap(const float* __restrict__ dout,           // [T][Bc][D]
       if ((tid & 31) == 0) { jit(); mbar_arrive(cx.op_ready); }
       // step s-1's saved activations are requested while the product runs; c(s-1) is this step's cprev
       float4 ng[SW_WPT];
-      float ncp[SW_WPT], ndo[SW_WPT];
-      fetch(s - 1, ng, nullptr, ncp, ndo);
+      float ncp[SW_WPT], ndo[SW_WPT], nds[SW_WPT];
+      fetch(s - 1, ng, nullptr, ncp, ndo, nds);
       if (s >= 4) {   // rows of step s - 4 -> L2
         const int t4 = dir ? (T - 1 - (s - 4)) : s - 4;
 #pragma unroll
@@ -630,7 +654,7 @@ lstm_bptt_swap(const float* __restrict__ dout,           // [T][Bc][D]
 #pragma unroll
       for (int i = 0; i < SW_WPT; ++i) {
         dh_rec[i] = SPLIT ? __uint_as_float(a[i]) * inv_scale : __uint_as_float(a[i]);
-        pc[i] = pcp[i]; pg[i] = ng[i]; pcp[i] = ncp[i]; pdo[i] = ndo[i];
+        pc[i] = pcp[i]; pg[i] = ng[i]; pcp[i] = ncp[i]; pdo[i] = ndo[i]; pds[i] = nds[i];
       }
     }
   }
@@ -681,13 +705,13 @@ int pack_swap_operands(bci_lstm_s* h, cudaStream_t st) {
 }
 
 int launch_rec_swap_fwd(int ND, const float* G, int ldg, const __half* whh, float* out, float* gates, float* csave, int D, int Bc, int T,
-                        bool split, cudaStream_t st, const SwapDropout* drop) {
+                        bool split, cudaStream_t st, const SwapDropout* drop, bool g_half) {
   int rc = sw_setup();
   if (rc) return rc;
   const dim3 grid(ceil_div(Bc, SW_NW), ND);
   const SwDrop dr = drop ? SwDrop{drop->outd, drop->outd_lo, drop->p, drop->seed, drop->site} : SwDrop{nullptr, nullptr, 0.f, 0, 0};
-  if (split) lstm_rec_swap_fwd<true><<<grid, SW_BLOCK, sw_smem_bytes(SW_FWD_B, true), st>>>(G, ldg, whh, out, gates, csave, dr, D, Bc, T, g_sw_dbg, sw_jitter());
-  else lstm_rec_swap_fwd<false><<<grid, SW_BLOCK, sw_smem_bytes(SW_FWD_B, false), st>>>(G, ldg, whh, out, gates, csave, dr, D, Bc, T, g_sw_dbg, sw_jitter());
+  if (split) lstm_rec_swap_fwd<true><<<grid, SW_BLOCK, sw_smem_bytes(SW_FWD_B, true), st>>>(G, ldg, whh, out, gates, csave, dr, D, Bc, T, g_sw_dbg, sw_jitter(), 0);
+  else lstm_rec_swap_fwd<false><<<grid, SW_BLOCK, sw_smem_bytes(SW_FWD_B, false), st>>>(G, ldg, whh, out, gates, csave, dr, D, Bc, T, g_sw_dbg, sw_jitter(), g_half ? 1 : 0);
   BCI_LAUNCH_OK();
   return BCI_OK;
 }
@@ -810,7 +834,7 @@ lstm_rec_swap256_fwd(const float* __restrict__ G,        // [T*Bc][ldg] fp32: co
                      int ldg,
                      const __half* __restrict__ whh,     // [ND][2 parts][1024][256] fp16 of 16 w (the hi part is used)
                      float* __restrict__ out,            // [T][Bc][D]: column dir*256 + unit
-                     float* __restrict__ gates, float* __restrict__ csave, SwDrop dr, int D, int Bc, int T, int jitter) {
+                     float* __restrict__ gates, float* __restrict__ csave, SwDrop dr, int D, int Bc, int T, int jitter, int g_half) {
   SwJitter jit(jitter);
   extern __shared__ uint8_t sw_smem_raw[];
   const int tid = threadIdx.x, u = tid & 127, wq = (tid >> 7) & 3;
@@ -871,27 +895,43 @@ lstm_rec_swap256_fwd(const float* __restrict__ G,        // [T*Bc][ldg] fp32: co
     }
     const int colg = dir * 1024 + unit * 4, colh = dir * 256 + unit;
     float c[S2_WPT];
-    float4 gq[S2_WPT];
+    uint4 gq[S2_WPT];
 #pragma unroll
+    // the next step's G row is requested RAW into registers (fp32: 16 bytes, fp16: 8) and converted when it is used a step later:
+    // converting at the load would stall on the DRAM round trip right here, in front of the accumulator wait
+    auto load_g = [&](int tt, int i) -> uint4 {
+      const long long e = ((long long)tt * Bc + brow[i]) * ldg + colg;
+      if (!g_half) return __ldg(reinterpret_cast<const uint4*>(G + e));
+      const uint2 gv = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const __half*>(G) + e));
+      return make_uint4(gv.x, gv.y, 0u, 0u);
+    };
+    auto cvt_g = [&](const uint4& r) -> float4 {
+      if (!g_half) return make_float4(__uint_as_float(r.x), __uint_as_float(r.y), __uint_as_float(r.z), __uint_as_float(r.w));
+      const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&r.x)), b = __half22float2(*reinterpret_cast<const __half2*>(&r.y));
+      return make_float4(a.x, a.y, b.x, b.y);
+    };
     for (int i = 0; i < S2_WPT; ++i) {
       c[i] = 0.f;
-      gq[i] = __ldg(reinterpret_cast<const float4*>(G + ((long long)(dir ? T - 1 : 0) * Bc + brow[i]) * ldg + colg));
+      gq[i] = load_g(dir ? T - 1 : 0, i);
     }
     for (int st = 0; st < T; ++st) {
       const int t = dir ? (T - 1 - st) : st;
       uint8_t* Bn = cx.genB + (uint32_t)((st + 1) & 1) * S2_FB;   // h_t is the B operand of step st + 1
       float4 gc[S2_WPT];
 #pragma unroll
-      for (int i = 0; i < S2_WPT; ++i) gc[i] = gq[i];
+      for (int i = 0; i < S2_WPT; ++i) gc[i] = cvt_g(gq[i]);
       if (st + 1 < T) {
         const int tn = dir ? (T - 2 - st) : st + 1;
 #pragma unroll
-        for (int i = 0; i < S2_WPT; ++i) gq[i] = __ldg(reinterpret_cast<const float4*>(G + ((long long)tn * Bc + brow[i]) * ldg + colg));
+        for (int i = 0; i < S2_WPT; ++i) gq[i] = load_g(tn, i);
       }
-      if (st + 4 < T && (tid & 7) == 0) {
+      if (st + 4 < T && (tid & (g_half ? 15 : 7)) == 0) {
         const int t4 = dir ? (T - 5 - st) : st + 4;
 #pragma unroll
-        for (int i = 0; i < S2_WPT; ++i) sw_prefetch_l2(G + ((long long)t4 * Bc + brow[i]) * ldg + colg);
+        for (int i = 0; i < S2_WPT; ++i) {
+          const long long e = ((long long)t4 * Bc + brow[i]) * ldg + colg;
+          if (g_half) sw_prefetch_l2(reinterpret_cast<const __half*>(G) + e); else sw_prefetch_l2(G + e);
+        }
       }
       float dsc[S2_WPT];
       if (dr.outd) {
@@ -1008,24 +1048,27 @@ lstm_bptt_swap256(const float* __restrict__ dout,           // [T][Bc][D]
     float pc[S2_WPT], pcp[S2_WPT], pdo[S2_WPT];
 #pragma unroll
     for (int i = 0; i < S2_WPT; ++i) { dh_rec[i] = 0.f; dc[i] = 0.f; }
-    auto fetch = [&](int s, float4* g4, float* cc, float* cp, float* dd) {
+    float pds[S2_WPT];
+    auto fetch = [&](int s, float4* g4, float* cc, float* cp, float* dd, float* sc) {   // raw, as in lstm_bptt_swap
       const int t = dir ? (T - 1 - s) : s;
       const int tp = dir ? (t + 1) : (t - 1);
 #pragma unroll
       for (int i = 0; i < S2_WPT; ++i) {
         const long long row = (long long)t * Bc + brow[i];
-        {
-          const uint2 gv = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const __half*>(gates) + row * ldg + colg));
-          const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&gv.x)), b = __half22float2(*reinterpret_cast<const __half2*>(&gv.y));
-          g4[i] = make_float4(a.x, a.y, b.x, b.y);
-        }
+        const uint2 gv = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const __half*>(gates) + row * ldg + colg));
+        g4[i] = make_float4(__uint_as_float(gv.x), __uint_as_float(gv.y), 0.f, 0.f);
         if (cc) cc[i] = __ldg(csave + row * D + colh);
         cp[i] = (s > 0) ? __ldg(csave + ((long long)tp * Bc + brow[i]) * D + colh) : 0.f;
         dd[i] = __ldg(dout + row * D + colh);
-        if (dr.p > 0.f) dd[i] *= drop_scale(dr.seed, dr.site, (uint64_t)(row * D + colh), dr.p);
+        sc[i] = dr.p > 0.f ? drop_scale(dr.seed, dr.site, (uint64_t)(row * D + colh), dr.p) : 1.0f;
       }
     };
-    fetch(T - 1, pg, pc, pcp, pdo);
+    auto gate_vals = [&](const float4& r) -> float4 {
+      const uint32_t x = __float_as_uint(r.x), y = __float_as_uint(r.y);
+      const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&x)), b = __half22float2(*reinterpret_cast<const __half2*>(&y));
+      return make_float4(a.x, a.y, b.x, b.y);
+    };
+    fetch(T - 1, pg, pc, pcp, pdo, pds);
     float4 bsum = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int s = T - 1; s >= 0; --s) {
       const int t = dir ? (T - 1 - s) : s;
@@ -1035,8 +1078,8 @@ lstm_bptt_swap256(const float* __restrict__ dout,           // [T][Bc][D]
       for (int i = 0; i < S2_WPT; ++i) {
         float4 dg = make_float4(0.f, 0.f, 0.f, 0.f);
         if (b0 + wq * S2_WPT + i < Bc) {
-          const float4 g = pg[i];
-          const float dh = pdo[i] + dh_rec[i];
+          const float4 g = gate_vals(pg[i]);
+          const float dh = fmaf(pdo[i], pds[i], dh_rec[i]);
           const float tc = tanh_mufu(pc[i]);
           const float dct = fmaf(dh * g.w, 1.0f - tc * tc, dc[i]);
           dg.x = dct * g.z * g.x * (1.0f - g.x);
@@ -1067,8 +1110,8 @@ lstm_bptt_swap256(const float* __restrict__ dout,           // [T][Bc][D]
       __syncwarp();
       if ((tid & 31) == 0) { jit(); mbar_arrive(cx.op_ready); }
       float4 ng[S2_WPT];
-      float ncp[S2_WPT], ndo[S2_WPT];
-      fetch(s - 1, ng, nullptr, ncp, ndo);
+      float ncp[S2_WPT], ndo[S2_WPT], nds[S2_WPT];
+      fetch(s - 1, ng, nullptr, ncp, ndo, nds);
       if (s >= 4) {
         const int t4 = dir ? (T - 1 - (s - 4)) : s - 4;
 #pragma unroll
@@ -1086,7 +1129,7 @@ lstm_bptt_swap256(const float* __restrict__ dout,           // [T][Bc][D]
 #pragma unroll
       for (int i = 0; i < S2_WPT; ++i) {
         dh_rec[i] = __uint_as_float(a[i]);
-        pc[i] = pcp[i]; pg[i] = ng[i]; pcp[i] = ncp[i]; pdo[i] = ndo[i];
+        pc[i] = pcp[i]; pg[i] = ng[i]; pcp[i] = ncp[i]; pdo[i] = ndo[i]; pds[i] = nds[i];
       }
     }
   }
@@ -1112,11 +1155,11 @@ static int s2_setup() {
 bool rec_swap256_ok(int H, const void* G, int ldg) { return H == 256 && ((uintptr_t)G & 15) == 0 && (ldg & 3) == 0; }
 
 int launch_rec_swap256_fwd(int ND, const float* G, int ldg, const __half* whh, float* out, float* gates, float* csave, int D, int Bc, int T,
-                           cudaStream_t st, const SwapDropout* drop) {
+                           cudaStream_t st, const SwapDropout* drop, bool g_half) {
   int rc = s2_setup();
   if (rc) return rc;
   const SwDrop dr = drop ? SwDrop{drop->outd, drop->outd_lo, drop->p, drop->seed, drop->site} : SwDrop{nullptr, nullptr, 0.f, 0, 0};
-  lstm_rec_swap256_fwd<<<dim3(2 * ceil_div(Bc, S2_NW), ND), SW_BLOCK, s2_smem_bytes(S2_FB), st>>>(G, ldg, whh, out, gates, csave, dr, D, Bc, T, sw_jitter());
+  lstm_rec_swap256_fwd<<<dim3(2 * ceil_div(Bc, S2_NW), ND), SW_BLOCK, s2_smem_bytes(S2_FB), st>>>(G, ldg, whh, out, gates, csave, dr, D, Bc, T, sw_jitter(), g_half ? 1 : 0);
   BCI_LAUNCH_OK();
   return BCI_OK;
 }

@@ -1042,11 +1042,17 @@ static int forward_train_t(bci_lstm_s* h, const float* x, int B, int T, float p_
   for (int l = 0; l < c.num_layers; ++l) {
     const int K = layer_in_width(c, l);
     int rc;
+    bool g_half = false;
     if (tf32x3_nt_ok(in, K, p.wih_b[l], K, w.G, 4 * D, (int)M, 4 * D, K)) {
-      // mixed mode: one TF32 pass over the raw operands, no remainders
+      // mixed mode: one TF32 pass over the raw operands, no remainders, and G written as fp16 (the recurrence that reads it is
+      // HBM-bound) when the CTA-pair kernel takes the shape
+      g_half = mixed && gemm_tf32_half_ok(in, K, p.wih_b[l], K, w.G, 4 * D, (int)M, 4 * D, K);
       if (!mixed && !lo_ready && (rc = split_tf32(in, nullptr, w.lo_in, M * K, st))) return rc;
-      rc = gemm_tf32x3_nt(in, mixed ? nullptr : w.lo_in, K, p.wih_b[l], mixed ? nullptr : p.wih_b_lo[l], K, p.bias[l], w.G, 4 * D, (int)M,
-                          4 * D, K, 0, st);
+      if (g_half)
+        rc = gemm_tf32_nt_half(in, K, p.wih_b[l], K, p.bias[l], reinterpret_cast<__half*>(w.G), 4 * D, (int)M, 4 * D, K, st);
+      else
+        rc = gemm_tf32x3_nt(in, mixed ? nullptr : w.lo_in, K, p.wih_b[l], mixed ? nullptr : p.wih_b_lo[l], K, p.bias[l], w.G, 4 * D, (int)M,
+                            4 * D, K, 0, st);
     } else {
       rc = launch_proj_gemm_f32(in, p.wih_t[l], p.bias[l], w.G, (int)M, 4 * D, K, st);
     }
@@ -1054,8 +1060,8 @@ static int forward_train_t(bci_lstm_s* h, const float* x, int B, int T, float p_
     // tensor-core recurrences write the dropped copy of the layer output themselves (no separate pass)
     const bool fused_drop = (mixed || split_fwd) && w.outd[l] != w.out[l];
     const SwapDropout fdrop{w.outd[l], mixed ? nullptr : w.lo_in, p_drop, seed, (uint32_t)(16 + l)};
-    if (mixed && H == 256) rc = launch_rec_swap256_fwd(ND, w.G, 4 * D, p.whh_sw_f[l], w.out[l], w.gates[l], w.cst[l], D, B, T, st, fused_drop ? &fdrop : nullptr);
-    else if (mixed || split_fwd) rc = launch_rec_swap_fwd(ND, w.G, 4 * D, p.whh_sw_f[l], w.out[l], w.gates[l], w.cst[l], D, B, T, split_fwd, st, fused_drop ? &fdrop : nullptr);
+    if (mixed && H == 256) rc = launch_rec_swap256_fwd(ND, w.G, 4 * D, p.whh_sw_f[l], w.out[l], w.gates[l], w.cst[l], D, B, T, st, fused_drop ? &fdrop : nullptr, g_half);
+    else if (mixed || split_fwd) rc = launch_rec_swap_fwd(ND, w.G, 4 * D, p.whh_sw_f[l], w.out[l], w.gates[l], w.cst[l], D, B, T, split_fwd, st, fused_drop ? &fdrop : nullptr, g_half);
     else rc = launch_rec_f32(H, ND, w.G, p.whh_t[l][0], p.whh_t[l][1], w.out[l], w.gates[l], w.cst[l], B, T, st);
     if (rc) return rc;
     lo_ready = fused_drop && !mixed && w.lo_in != nullptr;
