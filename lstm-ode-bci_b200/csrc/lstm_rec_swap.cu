@@ -26,6 +26,12 @@
 //   * next step's G_t / saved activations requested into registers before the accumulator wait, and the rows of four steps
 //     ahead pulled into L2 (a single step of lookahead is shorter than a DRAM round trip under load: step times jittered 1.5-2.5 k)
 //
+// Tried and rejected: two independent window groups per CTA (4 windows each, own B tile / accumulator columns / barrier pair) so that
+// one group's product runs under the other group's epilogue.  Correct, but slower (forward 0.95 -> 1.03 us, BPTT 1.00 -> 1.22 us per
+// step, the split forms 25 % slower): after the fixes above a step is no longer "MMA latency + epilogue" but the epilogue warps' own
+// instruction stream (~170 instructions per thread and step on 16 warps: issue slots 59 % busy) -- there is no idle time left for a
+// second group to fill, and the N = 16 minimum doubles the tensor work.
+//
 // Two precisions:
 //   mixed (BCI_TRAIN_MIXED; the analogue of the reference's autocast training, 04_lstm_model.py:486-490): one product chain, forward
 //       operands fp16 (h in [-1, 1], 11 significant bits), BPTT operands bf16 (gradients need the exponent range, not the bits),
@@ -334,7 +340,6 @@ lstm_rec_swap_fwd(const float* __restrict__ G,        // [T*Bc][ldg] fp32: colum
     const int colg = dir * 512 + u * 4, colh = dir * 128 + u;
     float c[SW_WPT];
     uint4 gq[SW_WPT];
-#pragma unroll
     // the next step's G row is requested RAW into registers (fp32: 16 bytes, fp16: 8) and converted when it is used a step later:
     // converting at the load would stall on the DRAM round trip right here, in front of the accumulator wait
     auto load_g = [&](int tt, int i) -> uint4 {
