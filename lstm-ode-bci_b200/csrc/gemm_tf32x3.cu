@@ -443,7 +443,9 @@ struct TpMaps { CUtensorMap a, b, c, a_lo, b_lo; };
 template <bool TN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TX_THREADS, 1)
 gemm_tf32_pair_kernel(const __grid_constant__ TpMaps maps, const float* __restrict__ bias, int M, int N, long long K, int k_splits,
-                      int reduce_add, int nhalf, int terms, int c_half) {   // terms = 3: split precision (hi / lo operand pairs, nhalf = 64)
+                      int reduce_add, int nhalf, int terms, int c_half, int f16, float out_scale) {   // terms = 3: split precision (nhalf = 64)
+  // f16 (NT only): operands are fp16 (hi, lo) pairs -- 64 K values per 128-byte tile row, kind::f16 MMAs (twice the TF32 rate),
+  // C = out_scale * acc + bias (the weights of that form are stored x 16)
   // c_half: C is fp16 (the mixed step's G): 64-column TMA boxes, two accumulator slabs per store
   extern __shared__ uint8_t tx_smem_raw[];
   const uint32_t raw = smem_u32(tx_smem_raw);
@@ -467,7 +469,8 @@ gemm_tf32_pair_kernel(const __grid_constant__ TpMaps maps, const float* __restri
   const bool leader = rank == 0;
   const int ntile = 2 * nhalf;                      // tile width
   const int m_blocks = (M + 255) / 256, n_blocks = (N + ntile - 1) / ntile;
-  const long long kb_total = (K + TX_BK - 1) / TX_BK;
+  const int bk = f16 ? 2 * TX_BK : TX_BK;   // K values per k-block
+  const long long kb_total = (K + bk - 1) / bk;
   const long long kb_per = (kb_total + k_splits - 1) / k_splits;
   const long long tiles = (long long)m_blocks * n_blocks * k_splits;
   const int n_clusters = (int)cluster_nclusters_x(), cid = (int)cluster_id_x();
@@ -525,11 +528,11 @@ gemm_tf32_pair_kernel(const __grid_constant__ TpMaps maps, const float* __restri
                 tma_load_2d_2sm(s0 + off_b + b_bytes + g * 4096, &maps.b_lo, nb * ntile + (int)rank * nhalf + g * 32, (int)(kb * TX_BK), full_bar(stage));
             }
           } else {
-            tma_load_2d_2sm(s0, &maps.a, (int)(kb * TX_BK), mb * 256 + (int)rank * 128, full_bar(stage));
-            tma_load_2d_2sm(s0 + off_b, &maps.b, (int)(kb * TX_BK), nb * ntile + (int)rank * nhalf, full_bar(stage));
+            tma_load_2d_2sm(s0, &maps.a, (int)(kb * bk), mb * 256 + (int)rank * 128, full_bar(stage));
+            tma_load_2d_2sm(s0 + off_b, &maps.b, (int)(kb * bk), nb * ntile + (int)rank * nhalf, full_bar(stage));
             if (terms == 3) {
-              tma_load_2d_2sm(s0 + TX_TILE, &maps.a_lo, (int)(kb * TX_BK), mb * 256 + (int)rank * 128, full_bar(stage));
-              tma_load_2d_2sm(s0 + off_b + b_bytes, &maps.b_lo, (int)(kb * TX_BK), nb * ntile + (int)rank * nhalf, full_bar(stage));
+              tma_load_2d_2sm(s0 + TX_TILE, &maps.a_lo, (int)(kb * bk), mb * 256 + (int)rank * 128, full_bar(stage));
+              tma_load_2d_2sm(s0 + off_b + b_bytes, &maps.b_lo, (int)(kb * bk), nb * ntile + (int)rank * nhalf, full_bar(stage));
             }
           }
         }
@@ -540,7 +543,7 @@ gemm_tf32_pair_kernel(const __grid_constant__ TpMaps maps, const float* __restri
   } else if (warp == 1) {
     if (leader) {
       // ---- MMA issuer
-      const uint32_t idesc = umma_idesc_tf32(256, ntile, TN ? 1 : 0);
+      const uint32_t idesc = f16 ? umma_idesc_f16_k(256, ntile) : umma_idesc_tf32(256, ntile, TN ? 1 : 0);
       constexpr uint32_t KSTEP = TN ? 1024u : 32u;
       int stage = 0; uint32_t phase = 0; int acc = 0; uint32_t acc_phase = 0;
       for (long long t = cid; t < tiles; t += n_clusters) {
@@ -564,10 +567,11 @@ gemm_tf32_pair_kernel(const __grid_constant__ TpMaps maps, const float* __restri
               if (terms == 3) {
                 const uint64_t al = TN ? umma_desc_sw128_mn(s0 + TX_TILE + o) : umma_desc_sw128(s0 + TX_TILE + o);
                 const uint64_t bl = TN ? umma_desc_sw128_mn(s0 + off_b + b_bytes + o) : umma_desc_sw128(s0 + off_b + b_bytes + o);
-                umma_tf32_2sm(d_lo, al, bh, idesc, first);
-                umma_tf32_2sm(d_lo, ah, bl, idesc, 1u);
+                if (f16) { umma_bf16_2sm(d_lo, al, bh, idesc, first); umma_bf16_2sm(d_lo, ah, bl, idesc, 1u); }
+                else { umma_tf32_2sm(d_lo, al, bh, idesc, first); umma_tf32_2sm(d_lo, ah, bl, idesc, 1u); }
               }
-              umma_tf32_2sm(d_tmem, ah, bh, idesc, first);
+              if (f16) umma_bf16_2sm(d_tmem, ah, bh, idesc, first);
+              else umma_tf32_2sm(d_tmem, ah, bh, idesc, first);
             }
             umma_commit_2sm_mc(empty_bar(stage), (uint16_t)3);
             if (kb == kb1 - 1) umma_commit_2sm_mc(tfull_bar(acc), (uint16_t)3);
@@ -663,10 +667,10 @@ gemm_tf32_pair_kernel(const __grid_constant__ TpMaps maps, const float* __restri
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
           float4 v;
-          v.x = __uint_as_float(r[4 * q + 0]) + __uint_as_float(rl[4 * q + 0]) + bias_s[slab * 32 + 4 * q + 0];
-          v.y = __uint_as_float(r[4 * q + 1]) + __uint_as_float(rl[4 * q + 1]) + bias_s[slab * 32 + 4 * q + 1];
-          v.z = __uint_as_float(r[4 * q + 2]) + __uint_as_float(rl[4 * q + 2]) + bias_s[slab * 32 + 4 * q + 2];
-          v.w = __uint_as_float(r[4 * q + 3]) + __uint_as_float(rl[4 * q + 3]) + bias_s[slab * 32 + 4 * q + 3];
+          v.x = fmaf(__uint_as_float(r[4 * q + 0]) + __uint_as_float(rl[4 * q + 0]), out_scale, bias_s[slab * 32 + 4 * q + 0]);
+          v.y = fmaf(__uint_as_float(r[4 * q + 1]) + __uint_as_float(rl[4 * q + 1]), out_scale, bias_s[slab * 32 + 4 * q + 1]);
+          v.z = fmaf(__uint_as_float(r[4 * q + 2]) + __uint_as_float(rl[4 * q + 2]), out_scale, bias_s[slab * 32 + 4 * q + 2]);
+          v.w = fmaf(__uint_as_float(r[4 * q + 3]) + __uint_as_float(rl[4 * q + 3]), out_scale, bias_s[slab * 32 + 4 * q + 3]);
           *reinterpret_cast<float4*>(cst + sw128_chunk_off((uint32_t)lane, (uint32_t)q)) = v;
         }
         fence_proxy_async_smem();
@@ -738,7 +742,7 @@ static int gemm_tf32_pair_nt(const float* A, const float* A_lo, int lda, const f
   const long long tiles = (long long)ceil_div(M, 256) * ceil_div(N, 2 * nhalf);
   const int mx = tf32_pair_max_clusters();
   const int clusters = (int)(tiles < mx ? tiles : mx);
-  gemm_tf32_pair_kernel<false><<<2 * clusters, TX_THREADS, TP_SMEM, st>>>(maps, bias, M, N, (long long)K, 1, accumulate, nhalf, terms, 0);
+  gemm_tf32_pair_kernel<false><<<2 * clusters, TX_THREADS, TP_SMEM, st>>>(maps, bias, M, N, (long long)K, 1, accumulate, nhalf, terms, 0, 0, 1.0f);
   BCI_LAUNCH_OK();
   return BCI_OK;
 }
@@ -760,7 +764,7 @@ int gemm_tf32_nt_half(const float* A, int lda, const float* W, int ldw, const fl
   const long long tiles = (long long)ceil_div(M, 256) * ceil_div(N, 256);
   const int mx = tf32_pair_max_clusters();
   const int clusters = (int)(tiles < mx ? tiles : mx);
-  gemm_tf32_pair_kernel<false><<<2 * clusters, TX_THREADS, TP_SMEM, st>>>(maps, bias, M, N, (long long)K, 1, 0, 128, 1, 1);
+  gemm_tf32_pair_kernel<false><<<2 * clusters, TX_THREADS, TP_SMEM, st>>>(maps, bias, M, N, (long long)K, 1, 0, 128, 1, 1, 0, 1.0f);
   BCI_LAUNCH_OK();
   return BCI_OK;
 }
@@ -790,7 +794,7 @@ static int gemm_tf32_pair_tn(const float* A, const float* A_lo, int lda, const f
   if (splits > 1) BCI_CUDA_OK(cudaMemset2DAsync(C, (size_t)ldc * 4, 0, (size_t)Q * 4, P, st));
   const long long tiles = out_tiles * splits;
   const int clusters = (int)(tiles < mx ? tiles : mx);
-  gemm_tf32_pair_kernel<true><<<2 * clusters, TX_THREADS, TP_SMEM, st>>>(maps, nullptr, P, Q, R, (int)splits, splits > 1 ? 1 : 0, nhalf, terms, 0);
+  gemm_tf32_pair_kernel<true><<<2 * clusters, TX_THREADS, TP_SMEM, st>>>(maps, nullptr, P, Q, R, (int)splits, splits > 1 ? 1 : 0, nhalf, terms, 0, 0, 1.0f);
   BCI_LAUNCH_OK();
   return BCI_OK;
 }
@@ -885,6 +889,21 @@ int gemm_f16x3_nt(const __half* A_hi, const __half* A_lo, int lda, const __half*
                   float* C, int ldc, int M, int N, int K, float out_scale, cudaStream_t st) {
   int rc = tx_prepare();
   if (rc) return rc;
+  if (M >= 512 && N >= 128 && tf32_pair_enabled() && tf32_pair_max_clusters() > 0) {
+    // CTA pairs, 256 x 128 tiles (two accumulators per tile): each CTA loads its own 128 rows of A (hi, lo) and 64 of the 128 W rows
+    TpMaps pm;
+    if ((rc = make_tmap_f16_2d(&pm.a, A_hi, M, K, lda, 2 * TX_BK, 128))) return rc;
+    if ((rc = make_tmap_f16_2d(&pm.a_lo, A_lo, M, K, lda, 2 * TX_BK, 128))) return rc;
+    if ((rc = make_tmap_f16_2d(&pm.b, W_hi, N, K, ldw, 2 * TX_BK, 64))) return rc;
+    if ((rc = make_tmap_f16_2d(&pm.b_lo, W_lo, N, K, ldw, 2 * TX_BK, 64))) return rc;
+    if ((rc = make_tmap_f32_2d(&pm.c, C, M, N, ldc, 32, 32))) return rc;
+    const long long ptiles = (long long)ceil_div(M, 256) * ceil_div(N, 128);
+    const int mx = tf32_pair_max_clusters();
+    const int clusters = (int)(ptiles < mx ? ptiles : mx);
+    gemm_tf32_pair_kernel<false><<<2 * clusters, TX_THREADS, TP_SMEM, st>>>(pm, bias, M, N, (long long)K, 1, 0, 64, 3, 0, 1, out_scale);
+    BCI_LAUNCH_OK();
+    return BCI_OK;
+  }
   TxMaps maps;
   if ((rc = make_tmap_f16_2d(&maps.a_hi, A_hi, M, K, lda, 2 * TX_BK, TX_BM))) return rc;
   if ((rc = make_tmap_f16_2d(&maps.a_lo, A_lo, M, K, lda, 2 * TX_BK, TX_BM))) return rc;
