@@ -334,6 +334,13 @@ int bci_preprocess_workspace_bytes(const bci_preproc_args* a, size_t* bytes);
 int bci_preprocess(const bci_preproc_args* a, const void* raw, float* windows, double* mean_out, double* std_out,
                    double* filtered, void* workspace, size_t workspace_bytes, void* stream);
 
+/* Host-side staging copy of the drop-in callers (06_lstm_ode_integration.py:346 `torch.FloatTensor(X[i:i+bs]).to(device)`: a
+ * synchronous pageable copy per batch).  Copies n fp32 values from pageable `src` into the pinned staging buffer `dst` on `threads`
+ * host threads with streaming stores; to_bf16 = 1 narrows to bf16 on the way (round to nearest even, bit-identical to the
+ * conversion the input projection does on load, so the bf16 engine's results do not change while the PCIe bytes halve).
+ * Pure host code: no CUDA call, no stream. */
+int bci_host_stage(void* dst, const float* src, int64_t n, int32_t to_bf16, int32_t threads);
+
 /* Micro-benchmark used by bench.py for the FP32 roofline denominator (SURVEY.md §8 d: the FP32
  * FMA peak is not in MEASURED_PEAKS.json): launches a dependent-FMA kernel, returns TFLOP/s. */
 int bci_fp32_peak_probe(double* tflops, void* stream);

@@ -20,25 +20,29 @@ from .ode import CognitiveStateODE, solve_ensemble, _dev
 from .synth import RATE_ORDER
 
 
-_STAGING_POOL = None
+def _staging_threads():
+    """BCI_STAGING_THREADS, else this rank's share of the host cores (a core streams ~7 GB/s whatever the instruction mix: the
+    copy scales with threads until the memory controllers saturate), at most 32."""
+    env = os.environ.get("BCI_STAGING_THREADS")
+    if env:
+        return max(int(env), 1)
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except (AttributeError, OSError):
+        cores = os.cpu_count() or 1
+    local_world = max(int(os.environ.get("LOCAL_WORLD_SIZE", "1") or 1), 1)
+    return max(1, min(32, cores // local_world))
 
 
 def _staging_copy(dst, src):
-    """pageable -> pinned staging copy on several host threads (Tensor.copy_ releases the GIL; one thread moves ~15 GB/s, a third of
-    what the PCIe link then takes from the pinned buffer)."""
-    global _STAGING_POOL
-    n = src.shape[0]
-    workers = min(int(os.environ.get("BCI_STAGING_THREADS", "8")), os.cpu_count() or 1)
-    if workers <= 1 or src.numel() < (1 << 22):
-        dst.copy_(src)
+    """pageable -> pinned staging copy on several host threads (`bci_host_stage`: streaming stores, optional fp32 -> bf16 narrowing;
+    ctypes releases the GIL).  One thread moves ~7 GB/s, the PCIe link takes ~53 GB/s from the pinned buffer: this leg bounds the
+    drop-in callers, which is why it is native."""
+    workers = _staging_threads()
+    if not (src.is_contiguous() and dst.is_contiguous() and src.dtype == torch.float32 and dst.dtype in (torch.float32, torch.bfloat16)):
+        dst.copy_(src)          # strided or non-fp32 host input: torch's own copy (still host -> pinned staging, same data path)
         return
-    if _STAGING_POOL is None:
-        from concurrent.futures import ThreadPoolExecutor
-        _STAGING_POOL = ThreadPoolExecutor(max_workers=workers, thread_name_prefix="bci-staging")
-    step = (n + workers - 1) // workers
-    futs = [_STAGING_POOL.submit(dst[a:a + step].copy_, src[a:a + step]) for a in range(0, n, step)]
-    for f in futs:
-        f.result()
+    N.check(N.lib().bci_host_stage(dst.data_ptr(), src.data_ptr(), src.numel(), 1 if dst.dtype == torch.bfloat16 else 0, max(workers, 1)))
 
 
 def stream_lstm_probs(lstm_model, host_batches, device=None, chunk=None, want_attn=False):
@@ -55,6 +59,9 @@ def stream_lstm_probs(lstm_model, host_batches, device=None, chunk=None, want_at
     copy_stream = torch.cuda.Stream(device=dev)
     main = torch.cuda.current_stream(dev)
     slots = [dict(buf=None, free=None, pin=None) for _ in range(2)]
+    # bf16 engine + pageable input: the staging copy narrows to bf16 (the rounding the input projection applies on load anyway, so
+    # no result bit changes) and the link carries half the bytes; the windows are then read as one "recording" with step = seq_len
+    narrow_ok = lstm_model._precision_now() == "bf16" and os.environ.get("BCI_STAGING_BF16", "1") != "0"
 
     def submit(k, xb):
         sl = slots[k & 1]
@@ -62,17 +69,18 @@ def stream_lstm_probs(lstm_model, host_batches, device=None, chunk=None, want_at
         if xh.dtype != torch.float32:
             xh = xh.float()
         n = xh.shape[0]
-        if sl["buf"] is None or sl["buf"].shape[0] < n or sl["buf"].shape[1:] != xh.shape[1:]:
-            sl["buf"] = torch.empty(tuple(xh.shape), dtype=torch.float32, device=dev)
+        direct = xh.is_pinned() and xh.is_contiguous()
+        dt = torch.bfloat16 if (narrow_ok and not direct and xh.dim() == 3) else torch.float32
+        if sl["buf"] is None or sl["buf"].shape[0] < n or sl["buf"].shape[1:] != xh.shape[1:] or sl["buf"].dtype != dt:
+            sl["buf"] = torch.empty(tuple(xh.shape), dtype=dt, device=dev)
             # the block may have just been freed by main-stream work that is still in flight (the caching allocator hands it
             # out in main-stream order): the copy stream must not write into it before that work has finished
             copy_stream.wait_stream(main)
         if sl["free"] is not None:
             copy_stream.wait_event(sl["free"])           # kernels of the batch that last used this buffer are done
-        direct = xh.is_pinned() and xh.is_contiguous()
         if not direct:
-            if sl["pin"] is None or sl["pin"].shape[0] < n or sl["pin"].shape[1:] != xh.shape[1:]:
-                sl["pin"] = torch.empty(tuple(xh.shape), dtype=torch.float32, pin_memory=True)   # (.pin_memory() would copy a pageable tensor first)
+            if sl["pin"] is None or sl["pin"].shape[0] < n or sl["pin"].shape[1:] != xh.shape[1:] or sl["pin"].dtype != dt:
+                sl["pin"] = torch.empty(tuple(xh.shape), dtype=dt, pin_memory=True)   # (.pin_memory() would copy a pageable tensor first)
             if sl["free"] is not None:
                 sl["free"].synchronize()
         events = []
@@ -103,13 +111,16 @@ def stream_lstm_probs(lstm_model, host_batches, device=None, chunk=None, want_at
             for i, m, ev in events:
                 main.wait_event(ev)
                 xb = sl["buf"][i:i + m]
+                if xb.dtype == torch.bfloat16:
+                    T = xb.shape[1]
+                    p = lstm_model.predict_proba_recordings(xb.view(1, m * T, xb.shape[2]), T, T, return_attention=want_attn)
+                else:
+                    p = lstm_model.predict_proba(xb, return_attention=want_attn)
                 if want_attn:
-                    p, a = lstm_model.predict_proba(xb, return_attention=True)
+                    p, a = p
                     if attn is None:
                         attn = torch.empty((n, a.shape[1]), device=dev, dtype=torch.float32)
                     attn[i:i + m] = a
-                else:
-                    p = lstm_model.predict_proba(xb)
                 probs[i:i + m] = p
         sl["free"] = torch.cuda.Event()
         sl["free"].record(main)
@@ -122,11 +133,12 @@ def stream_lstm_probs(lstm_model, host_batches, device=None, chunk=None, want_at
     except StopIteration:
         return
     while pending is not None:
+        out = compute(*pending)                           # batch k's kernels are queued (they wait on its copy events) ...
         try:
-            nxt = submit(k + 1, next(it))                 # queue the next batch's copies before computing this one
+            nxt = submit(k + 1, next(it))                 # ... and run while the host stages batch k + 1 and queues its copies
         except StopIteration:
             nxt = None
-        yield compute(*pending)
+        yield out
         pending = nxt
         k += 1
 
@@ -181,12 +193,12 @@ class _H2DRing:
         except StopIteration:
             return
         while pending is not None:
+            out = compute(self.acquire(pending))              # batch k's kernels are queued ...
+            self.release(pending)
             try:
-                nxt = self.submit(k + 1, prepare(next(it)))   # queue the next batch's copy before computing this one
+                nxt = self.submit(k + 1, prepare(next(it)))   # ... and run while the host stages batch k + 1 / its copy is queued
             except StopIteration:
                 nxt = None
-            out = compute(self.acquire(pending))
-            self.release(pending)
             yield out
             pending = nxt
             k += 1

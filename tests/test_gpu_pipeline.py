@@ -118,6 +118,34 @@ def test_predict_batch_takes_the_bf16_engine_where_the_reference_autocasts():
     assert np.abs(outs["auto"][0] - outs["fp32"][0]).max() <= 1.2e-3
 
 
+def test_pageable_windows_staged_as_bf16_change_no_bit():
+    """Drop-in callers hand pageable fp32 numpy windows (06:346).  With the bf16 engine the native staging copy (`bci_host_stage`)
+    narrows them to bf16 on the host -- the rounding the input projection applies on load anyway: probabilities and attention are
+    bit-identical to the fp32-staged path and to the device-resident call; several passes, a ragged tail, attention on and off."""
+    import os
+    params = synth.make_lstm_params(42, 61, 128, 3, logit_gain=12.0)
+    m = lstm.from_params(params, precision="bf16")
+    x = synth.make_windows(11, 75, 256, 61, structured=True)
+    with torch.no_grad():
+        want_p, want_a = m.predict_proba(torch.from_numpy(x).cuda(), return_attention=True)
+    batches = [x[:32], x[32:64], x[64:]]
+    for flag in ("1", "0"):
+        os.environ["BCI_STAGING_BF16"] = flag
+        try:
+            outs = list(integration.stream_lstm_probs(m, batches, chunk=20, want_attn=True))
+            outs2 = list(integration.stream_lstm_probs(m, batches, chunk=20, want_attn=False))
+        finally:
+            os.environ.pop("BCI_STAGING_BF16", None)
+        assert torch.equal(torch.cat([o[0] for o in outs]), want_p), flag
+        assert torch.equal(torch.cat([o[1] for o in outs]), want_a), flag
+        assert torch.equal(torch.cat([o[0] for o in outs2]), want_p) and all(o[1] is None for o in outs2)
+    # the fp32 engine never sees narrowed input
+    mf = lstm.from_params(params, precision="fp32")
+    with torch.no_grad():
+        want_f = mf.predict_proba(torch.from_numpy(x).cuda())
+    assert torch.equal(torch.cat([o[0] for o in integration.stream_lstm_probs(mf, batches, chunk=20)]), want_f)
+
+
 def test_stream_recordings_equals_materialised_windows():
     """integration.stream_recordings (host recordings -> H2D ring -> windows cut in place) == predict_proba on the windows
     create_sequences (02:157-180) would materialise; pinned and pageable host batches, fp32 and bf16 storage, fp32 and bf16 engines."""

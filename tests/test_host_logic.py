@@ -44,3 +44,27 @@ def test_view_offsets_enumerate_create_sequences_order():
     for w in (0, 1, n_seq - 1, n_seq, 2 * n_seq + 3):
         off = (w // n_seq) * (S * C) + (w % n_seq) * (step * C)
         assert np.array_equal(flat[off:off + T * C].reshape(T, C), want[w])
+
+
+def test_host_stage_is_bit_exact_round_to_nearest_even():
+    """bci_host_stage (pure host code of the library: pageable -> pinned staging of the drop-in callers): the fp32 copy is exact, the
+    bf16 narrowing equals round-to-nearest-even on the bit pattern (what cvt.rn.bf16.f32 does on the device), for every alignment of
+    the destination, thread counts that do not divide the length, ties, denormals, infinities and signed zeros."""
+    from lstm_ode_bci_b200 import _native as N
+    rng = np.random.default_rng(5)
+    n = (1 << 20) + 37
+    src = rng.standard_normal(n).astype(np.float32)
+    src[:10] = np.array([0.0, -0.0, 1e-40, -1e-39, np.inf, -np.inf, 3.3895314e38, 1.00390625, 1.01171875, -1.00390625], np.float32)
+    u = src.view(np.uint32).astype(np.uint64)
+    want = ((u + 0x7FFF + ((u >> 16) & 1)) >> 16).astype(np.uint16)
+    assert want[7] == 0x3F80 and want[8] == 0x3F82            # the two ties go to the even neighbour
+    for off in (0, 1, 5, 16):
+        for threads in (1, 3, 8):
+            d16 = np.zeros(n + off, np.uint16)
+            N.check(N.lib().bci_host_stage(d16[off:].ctypes.data, src.ctypes.data, n, 1, threads))
+            assert np.array_equal(d16[off:], want) and not d16[:off].any()
+            d32 = np.zeros(n + off, np.float32)
+            N.check(N.lib().bci_host_stage(d32[off:].ctypes.data, src.ctypes.data, n, 0, threads))
+            assert np.array_equal(d32[off:].view(np.uint32), src.view(np.uint32)) and not d32[:off].any()
+    assert N.lib().bci_host_stage(None, src.ctypes.data, 4, 1, 1) != 0
+    N.check(N.lib().bci_host_stage(None, None, 0, 1, 4))
