@@ -359,6 +359,8 @@ int bci_fp64_peak_probe(double* tflops, void* stream);
  * ---------------------------------------------------------------------------------------- */
 int bci_selftest_proj_gemm_bf16(const void* A, const void* W, const float* bias, void* C, int32_t M, int32_t N,
                                 int32_t K, void* stream);
+int bci_selftest_proj_gemm_bf16_blocked(const void* A, const void* W, const float* bias, void* C, int32_t M, int32_t N,
+                                        int32_t K, void* stream);
 int bci_selftest_rec_bf16(const void* G, const void* whh_f, const void* whh_r, void* out, int32_t Bc, int32_t T,
                           void* stream);
 /* fused projection + recurrence of one layer on a 4-CTA cluster (csrc/lstm_bf16_fused.cu):

@@ -116,6 +116,7 @@ SIGNATURES = {
     "bci_ode_classify": (C.c_int, [_FP, C.c_int64, _FP, _FP, C.c_void_p]),
     "bci_ode_forecast_readout": (C.c_int, [_FP, C.c_int64, C.c_int32, C.POINTER(C.c_int32), C.c_int32, _FP, C.c_void_p]),
     "bci_selftest_proj_gemm_bf16": (C.c_int, [_FP, _FP, _FP, _FP, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
+    "bci_selftest_proj_gemm_bf16_blocked": (C.c_int, [_FP, _FP, _FP, _FP, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     "bci_selftest_rec_bf16": (C.c_int, [_FP, _FP, _FP, _FP, C.c_int32, C.c_int32, C.c_void_p]),
     "bci_selftest_rec256_bf16": (C.c_int, [_FP, _FP, _FP, C.c_int32, C.c_int32, C.c_void_p]),
     "bci_selftest_fused_rec_bf16": (C.c_int, [_FP, _FP, _FP, _FP, _FP, _FP, _FP, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),

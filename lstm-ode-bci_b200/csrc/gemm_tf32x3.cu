@@ -412,12 +412,6 @@ constexpr int TP_STAGES = 5;
 constexpr uint32_t TP_STAGE = 2 * TX_TILE;   // A (this CTA's 128 rows) + B (this CTA's 128 of the tile's 256 W rows), 32 K values each
 constexpr size_t TP_SMEM = 1024 + (size_t)TP_STAGES * TP_STAGE + TX_CSTAGE + 256 * sizeof(float) + 256;
 
-__device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst_smem, const void* tmap, int c0, int c1, uint32_t bar) {
-  const uint32_t lead_bar = bar & 0xFEFFFFFFu;   // the same offset in the pair's leader CTA (as tma_load_3d_2sm)
-  asm volatile(
-      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(dst_smem), "l"(tmap), "r"(lead_bar), "r"(c0), "r"(c1) : "memory");
-}
 __device__ __forceinline__ void umma_tf32_2sm(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
@@ -425,16 +419,6 @@ __device__ __forceinline__ void umma_tf32_2sm(uint32_t d_tmem, uint64_t a_desc, 
       "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
       ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
 }
-__device__ __forceinline__ bool tp_elect_one() {
-  uint32_t pred = 0;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "elect.sync _|p, 0xffffffff;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(pred));
-  return pred != 0;
-}
-
 struct TpMaps { CUtensorMap a, b, c, a_lo, b_lo; };
 
 // TN = false: C[M][N] (=|+=) A[M][K] . W[N][K]^T + bias, K-major operands, 256 x 256 tiles

@@ -373,6 +373,9 @@ static int launch_proj_gemm_bn(const __nv_bfloat16* A, const __nv_bfloat16* W, c
 
 int launch_proj_gemm_bf16(const __nv_bfloat16* A, const __nv_bfloat16* W, const float* bias, __nv_bfloat16* C, int M, int N,
                           int K, bool blocked, cudaStream_t st) {
+  // large products: CTA pairs, 256 x 256 tiles (lstm_bf16_gemm_pair.cu) -- half the L2 -> SM operand bytes per flop
+  const int rc_pair = launch_proj_gemm_bf16_pair(A, W, bias, C, M, N, K, blocked, st);
+  if (rc_pair != 1) return rc_pair;
   if (K <= 256 && N % 256 == 0) return launch_proj_gemm_bn<256>(A, W, bias, C, M, N, K, blocked, st);
   return launch_proj_gemm_bn<128>(A, W, bias, C, M, N, K, blocked, st);
 }
@@ -798,6 +801,12 @@ int lstm_forward_bf16(bci_lstm_s* h, const InputView& x, int batch, int T, float
 extern "C" int bci_selftest_proj_gemm_bf16(const void* A, const void* W, const float* bias, void* C, int32_t M, int32_t N,
                                            int32_t K, void* stream) {
   return bci::launch_proj_gemm_bf16((const __nv_bfloat16*)A, (const __nv_bfloat16*)W, bias, (__nv_bfloat16*)C, M, N, K, false,
+                                    (cudaStream_t)stream);
+}
+// the same product written in the recurrence's blocked streaming layout [row / 128][n / 8][row % 128][8] (C holds ceil(M / 128) row blocks)
+extern "C" int bci_selftest_proj_gemm_bf16_blocked(const void* A, const void* W, const float* bias, void* C, int32_t M, int32_t N,
+                                                   int32_t K, void* stream) {
+  return bci::launch_proj_gemm_bf16((const __nv_bfloat16*)A, (const __nv_bfloat16*)W, bias, (__nv_bfloat16*)C, M, N, K, true,
                                     (cudaStream_t)stream);
 }
 extern "C" int bci_selftest_rec_bf16(const void* G, const void* whh_f, const void* whh_r, void* out, int32_t Bc, int32_t T,

@@ -274,6 +274,9 @@ int pack_h256_bf16(bci_lstm_s* h, cudaStream_t st);
 int pack_pool256_bf16(bci_lstm_s* h, cudaStream_t st);
 int launch_pool256_bf16(bci_lstm_s* h, const __nv_bfloat16* seq, __nv_bfloat16* pre, float2* rowstat, float* scores, int Bc, int T,
                         float* logits, float* probs, float* attn, cudaStream_t st);
+// CTA-pair form (lstm_bf16_gemm_pair.cu); returns 1 when the shape is not for it
+int launch_proj_gemm_bf16_pair(const __nv_bfloat16* A, const __nv_bfloat16* W, const float* bias, __nv_bfloat16* C, int M, int N, int K,
+                               bool blocked, cudaStream_t st);
 int launch_proj_gemm_bf16(const __nv_bfloat16* A, const __nv_bfloat16* W, const float* bias, __nv_bfloat16* C, int M, int N, int K,
                           bool blocked, cudaStream_t st);
 

@@ -208,6 +208,24 @@ __device__ __forceinline__ void tma_load_3d_2sm(uint32_t dst_smem, const void* t
       ::"r"(dst_smem), "l"(tmap), "r"(lead_bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
 
+// 2D tile load of a CTA pair (see tma_load_3d_2sm)
+__device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst_smem, const void* tmap, int c0, int c1, uint32_t bar) {
+  const uint32_t lead_bar = bar & 0xFEFFFFFFu;   // the same offset in the pair's leader CTA (as tma_load_3d_2sm)
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst_smem), "l"(tmap), "r"(lead_bar), "r"(c0), "r"(c1) : "memory");
+}
+// one lane of a converged warp
+__device__ __forceinline__ bool tp_elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // ---- descriptors ---------------------------------------------------------------------------
 // K-major operand tile in the canonical SWIZZLE_128B layout: rows of 64 bf16 (128 B) at 128 B pitch,
 // 16-byte chunk c of row r stored at chunk (c ^ (r & 7)); 8-row groups 1024 B apart (SBO).

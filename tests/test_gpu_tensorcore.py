@@ -29,7 +29,10 @@ def _p(t):
 
 # K = 512 / N % 256 != 0 select the 128-column W-block variant (H = 256 layers 1-2)
 @pytest.mark.parametrize("M,Nn,K", [(128, 256, 64), (128, 256, 128), (1000, 1024, 128), (4173, 1024, 256), (77, 512, 256), (300, 2048, 64),
-                                    (300, 2048, 512), (1000, 1024, 384), (129, 128, 256), (2500, 2048, 256)])
+                                    (300, 2048, 512), (1000, 1024, 384), (129, 128, 256), (2500, 2048, 256),
+                                    # M >= 512, N % 256 == 0: the CTA-pair kernel (lstm_bf16_gemm_pair.cu); odd / even numbers of
+                                    # 128-row blocks, ragged last block, K = 64 ... 512, more tiles than clusters
+                                    (4100, 2048, 512), (777, 256, 512), (512, 256, 64), (70000, 2048, 512), (33000, 256, 448)])
 def test_proj_gemm_tcgen05_matches_matmul(M, Nn, K):
     g = torch.Generator(device="cuda").manual_seed(M + K)
     A = (torch.randn(M, K, device="cuda", generator=g) * 0.7).to(torch.bfloat16)
@@ -44,6 +47,29 @@ def test_proj_gemm_tcgen05_matches_matmul(M, Nn, K):
     err = (got - want).abs()
     tol = 2.0 ** -8 * want.abs() + 1e-3          # one bf16 rounding of the fp32 result
     assert bool((err <= tol).all()), float((err - tol).max())
+
+
+@pytest.mark.parametrize("M,Nn,K", [(300, 1024, 128), (1000, 2048, 512), (4173, 2048, 256), (640, 256, 512), (70000, 2048, 512)])
+def test_proj_gemm_blocked_layout_matches_matmul(M, Nn, K):
+    """The same GEMMs writing the recurrence's streaming layout [row / 128][n / 8][row % 128][8] (one-CTA kernel below 512 rows,
+    CTA pairs from there on): un-blocked on the host side and compared with the plain product."""
+    g = torch.Generator(device="cuda").manual_seed(M + K + 1)
+    A = (torch.randn(M, K, device="cuda", generator=g) * 0.7).to(torch.bfloat16)
+    W = (torch.randn(Nn, K, device="cuda", generator=g) * 0.2).to(torch.bfloat16)
+    bias = torch.randn(Nn, device="cuda", generator=g)
+    mb = (M + 127) // 128
+    Cb = torch.full((mb, Nn // 8, 128, 8), float("nan"), device="cuda", dtype=torch.bfloat16)
+    N.check(N.lib().bci_selftest_proj_gemm_bf16_blocked(_p(A), _p(W), _p(bias), _p(Cb), M, Nn, K, _stream()))
+    torch.cuda.synchronize()
+    got = Cb.permute(0, 2, 1, 3).reshape(mb * 128, Nn)[:M].float()
+    want = A.float() @ W.float().T + bias
+    assert torch.isfinite(got).all()
+    err = (got - want).abs()
+    tol = 2.0 ** -8 * want.abs() + 1e-3
+    assert bool((err <= tol).all()), float((err - tol).max())
+    if M % 128:      # rows past M inside the last block hold bias only (zero-filled operand rows), never garbage from another tile
+        pad = Cb.permute(0, 2, 1, 3).reshape(mb * 128, Nn)[M:].float()
+        assert bool((pad - bias.to(torch.bfloat16).float()).abs().max() <= 1e-6)
 
 
 def _perm(H=128, order="T"):
