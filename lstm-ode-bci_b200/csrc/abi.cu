@@ -228,6 +228,7 @@ extern "C" int bci_lstm_forward_view(bci_lstm_t h, const bci_lstm_input* in, int
 
 extern "C" int bci_lstm_backward(bci_lstm_t h, const float* x, const float* dlogits, int32_t batch, int32_t seq_len, float* dx,
                                  const bci_lstm_grads* grads, void* workspace, size_t workspace_bytes, void* stream) {
+  bci::NvtxRange nvtx_range("bci_lstm_backward");
   BCI_REQUIRE(h && x && dlogits && grads && workspace, BCI_EINVAL, "bci_lstm_backward: NULL argument");
   BCI_REQUIRE(h->loaded, BCI_ESTATE, "bci_lstm_backward: call bci_lstm_load_weights first");
   BCI_ON_DEVICE_OF(h);

@@ -233,6 +233,7 @@ extern "C" int bci_comm_destroy(bci_comm_t c) {
 
 extern "C" int bci_fused_step(bci_comm_t c, float* p, float* m, float* v, float lr, float beta1, float beta2, float eps,
                               float weight_decay, int32_t step, float max_norm, float* norm_out, void* stream) {
+  bci::NvtxRange nvtx_range("bci_fused_step");
   BCI_REQUIRE(c && p && m && v && step >= 1, BCI_EINVAL, "bci_fused_step: bad arguments");
   BCI_REQUIRE(c->connected, BCI_ESTATE, "bci_fused_step: call bci_comm_connect first");
   cudaStream_t st = (cudaStream_t)stream;

@@ -4,6 +4,8 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstdarg>
+#include <cstdlib>
+#include <nvtx3/nvToolsExt.h>
 
 #include "../../include/bci_b200.h"
 
@@ -41,6 +43,17 @@ void note_launch();  // counts kernel launches (bci_launch_count)
 
 // Per-device state: one process may drive several GPUs (the tests and torch allow it), and kernel attributes
 // (cudaFuncSetAttribute), occupancy results and the SM count belong to the device that is current at the call.
+// BCI_NVTX=1: NVTX ranges around the library's entry points (no-ops without an attached tool; nvtx3 is header-only)
+inline bool nvtx_on() {
+  static const bool on = [] { const char* e = getenv("BCI_NVTX"); return e && e[0] == '1'; }();
+  return on;
+}
+struct NvtxRange {
+  bool on;
+  explicit NvtxRange(const char* name) : on(nvtx_on()) { if (on) nvtxRangePushA(name); }
+  ~NvtxRange() { if (on) nvtxRangePop(); }
+};
+
 constexpr int BCI_MAX_DEVICES = 64;
 inline int current_device() {
   int dev = 0;

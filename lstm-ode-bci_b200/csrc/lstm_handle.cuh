@@ -85,6 +85,18 @@ struct PackedBF16 {
 }  // namespace bci
 
 namespace bci {
+// BCI_NVTX=1: an NVTX range per forward ("bci_lstm_forward") with a mark at the end of each phase, for `ncu --nvtx --nvtx-include`
+// / timeline tools (tracing).  nvtx3 is header-only; without an attached tool the calls are no-ops.
+inline void nvtx_phase(int ph) {
+  if (!nvtx_on()) return;
+  static const char* const names[4] = {"end input_proj", "end proj_gemm", "end recurrence", "end pool_head"};
+  if (ph < 0) {
+    nvtxRangePushA("bci_lstm_forward");
+  } else {
+    nvtxMarkA(names[ph & 3]);
+    if (ph == 3) nvtxRangePop();
+  }
+}
 struct Profiler {
   static constexpr int MAX_EV = 2048;
   bool enabled = false;
@@ -94,6 +106,7 @@ struct Profiler {
   bool created = false;
   // record the end of `ph` (or the start marker with ph = -1)
   void mark(int ph, cudaStream_t st) {
+    nvtx_phase(ph);
     if (!enabled || n >= MAX_EV) return;
     if (!created) { for (int i = 0; i < MAX_EV; ++i) cudaEventCreate(&ev[i]); created = true; }
     cudaEventRecord(ev[n], st);

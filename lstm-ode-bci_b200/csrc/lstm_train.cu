@@ -1472,6 +1472,7 @@ extern "C" int bci_grad_accumulate(float* acc, const float* g, int64_t n, int32_
 
 extern "C" int bci_adamw_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
                               float weight_decay, int32_t step, float grad_scale, float max_norm, float* norm_scratch, void* stream) {
+  bci::NvtxRange nvtx_range("bci_adamw_step");
   using namespace bci;
   BCI_REQUIRE(p && g && m && v && norm_scratch && n >= 0 && step >= 1, BCI_EINVAL, "bci_adamw_step: bad arguments");
   if (n == 0) return BCI_OK;

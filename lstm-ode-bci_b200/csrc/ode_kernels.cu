@@ -676,6 +676,7 @@ static int launch_ode(const OdeParams& P, int mode, cudaStream_t st) {
 }
 
 extern "C" int bci_ode_solve(const bci_ode_args* a, void* stream) {
+  bci::NvtxRange nvtx_range("bci_ode_solve");
   BCI_REQUIRE(a != nullptr, BCI_EINVAL, "bci_ode_solve: args is NULL");
   BCI_REQUIRE(a->mode == BCI_ODE_RK4 || a->mode == BCI_ODE_RK45, BCI_EINVAL, "bci_ode_solve: bad mode %d", a->mode);
   BCI_REQUIRE(a->style == BCI_ODE_STYLE_REF06 || a->style == BCI_ODE_STYLE_REF08, BCI_EINVAL, "bci_ode_solve: bad style %d", a->style);
@@ -706,6 +707,7 @@ extern "C" int bci_ode_solve(const bci_ode_args* a, void* stream) {
 }
 
 extern "C" int bci_ode_solve_modulated(const bci_ode_mod_args* a, void* stream) {
+  bci::NvtxRange nvtx_range("bci_ode_solve_modulated");
   BCI_REQUIRE(a != nullptr, BCI_EINVAL, "bci_ode_solve_modulated: args is NULL");
   BCI_REQUIRE(a->style == BCI_ODE_STYLE_REF06 || a->style == BCI_ODE_STYLE_REF08, BCI_EINVAL, "bci_ode_solve_modulated: bad style %d", a->style);
   BCI_REQUIRE(a->n >= 0, BCI_EINVAL, "bci_ode_solve_modulated: negative n");

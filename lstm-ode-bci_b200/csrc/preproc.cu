@@ -284,6 +284,7 @@ extern "C" int bci_preprocess_workspace_bytes(const bci_preproc_args* a, size_t*
 
 extern "C" int bci_preprocess(const bci_preproc_args* a, const void* raw, float* windows, double* mean_out, double* std_out,
                               double* filtered, void* workspace, size_t workspace_bytes, void* stream) {
+  bci::NvtxRange nvtx_range("bci_preprocess");
   BCI_REQUIRE(a && raw && windows && mean_out && std_out && workspace, BCI_EINVAL, "bci_preprocess: NULL argument");
   BCI_REQUIRE(a->n_channels >= 1 && a->n_channels <= 256 && a->n_recordings >= 1, BCI_EINVAL, "bci_preprocess: bad channel/recording count");
   BCI_REQUIRE(a->order >= 1 && a->order <= PP_MAX_ORDER && a->b_host && a->a_host && a->zi_host, BCI_EINVAL, "bci_preprocess: bad filter");
