@@ -338,6 +338,296 @@ lstm_rec_f16x3(const float* __restrict__ G,        // [T*Bc][ldg] fp32: column d
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Pipelined form (inference): the step above is  MMA (48 instructions, ~3 us) -> epilogue (MUFU-bound, ~4 us) -> MMA ...  with the
+// tensor pipe idle during the epilogue and the epilogue warps idle during the product (ncu: tensor 22 %, XU 29 %).  Here the two
+// column blocks of the accumulator (units 0-63 / 64-127) are STAGGERED: all eight epilogue warps work on block 0, then on block 1
+// (thread = window x 32 units of the current block), and a ninth warp issues the MMAs in four groups (column block, K atom):
+//
+//     b0a0(t+1)  as soon as phase 0 of step t is done: it needs K atom 0 of h_t (units 0-63: written by phase 0) and accumulator
+//                block 0 drained (read by phase 0) -- it runs on the tensor pipe while the warps evaluate block 1 of step t
+//     after phase 1 of step t:  b0a1(t+1), commit acc_full[0];  b1a0(t+1), commit a0_free;  b1a1(t+1), commit acc_full[1]
+//                the warps start on block 0 of step t+1 after ONE quarter of the product, and the rest runs under that phase
+//
+// Who may overwrite h: phase nb of step t+1 replaces K atom nb of h_t by h_{t+1}.  Atom 1 is read by b0a1 and b1a1, both in front
+// of the commit phase 1 waits for.  Atom 0 is read by b0a0 and by b1a0 -- the latter is issued AFTER acc_full[0], so phase 0 waits
+// for a third commit (a0_free) right before its first store into the atom (one slab of gate math later: b1a0 is done by then).
+// Every group runs [lo.hi, hi.lo, hi.hi] over its own K atom (small terms first within the group).  Barriers per CTA: acc_full[2],
+// a0_free (multicast commits), h_local[2] (one arrive per epilogue warp and phase), and on the leader peer_local[2] (the peer's
+// ninth warp relays its CTA's h_local with a relaxed remote arrive, as above).
+constexpr int TCP_THREADS = 384;   // 8 epilogue warps + a control warpgroup: warp 8 = MMA issuer (leader) / relay (peer), warps 9-11 idle
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TCP_THREADS, 1)
+lstm_rec_f16x3_pipe(const float* __restrict__ G, int ldg, const __half* __restrict__ whh16, float* __restrict__ out,
+                    __half* __restrict__ out_hi16, __half* __restrict__ out_lo16, int D, int Bc, int T, int n_pairs, int ND, int jitter) {
+  extern __shared__ uint8_t tc_smem_raw[];
+  uint32_t jit_state = jitter ? (uint32_t)(blockIdx.x * 7919u + threadIdx.x * 104729u + 12345u) : 0u;
+  auto jit = [&]() {
+    if (jitter) {
+      jit_state = jit_state * 1664525u + 1013904223u;
+      __nanosleep((jit_state >> 20) & (uint32_t)(jitter - 1));
+    }
+  };
+  const uint32_t raw = smem_u32(tc_smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* gen = tc_smem_raw + (base - raw);
+  const uint32_t sW = base, sH = base + TC_OFF_H;
+  uint8_t* genH = gen + TC_OFF_H;
+  uint8_t* ctl = gen + TC_OFF_CTL;
+  const uint32_t bar0 = smem_u32(ctl);
+  auto acc_full = [&](int nb) { return bar0 + 8u * nb; };          // every CTA: multicast commit -- column block nb is complete
+  auto h_local = [&](int nb) { return bar0 + 16u + 8u * nb; };     // every CTA: its 8 warps wrote K atom nb of h_t and drained block nb
+  auto peer_local = [&](int nb) { return bar0 + 32u + 8u * nb; };  // leader: relay of the peer's h_local[nb]
+  const uint32_t a0_free = bar0 + 48u;                             // every CTA: multicast commit -- no MMA reads K atom 0 of h_{t-1} any more
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ctl + 56);
+
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+
+  if (tid == 0) {
+    for (int nb = 0; nb < 2; ++nb) { mbar_init(acc_full(nb), 1); mbar_init(h_local(nb), 8); mbar_init(peer_local(nb), 1); }
+    mbar_init(a0_free, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc_2sm(smem_u32(tmem_slot), 512);
+    tmem_relinquish_2sm();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  cluster_sync_all();
+
+  constexpr uint32_t idesc = umma_idesc_f16(256, 256);
+  // one (column block, K atom) group in the order lo.hi, hi.lo, hi.hi; `first` clears the accumulator
+  auto issue_group = [&](int nb, int atom, bool first) {
+#pragma unroll
+    for (int term = 0; term < 3; ++term) {
+      const uint32_t ap = term == 0 ? 1u : 0u, bp = term == 1 ? 1u : 0u;
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {
+        const uint64_t da = umma_desc_sw128(sH + (ap * 2 + atom) * TC_ATOM + kk * 32);
+        const uint64_t db = umma_desc_sw128(sW + ((nb * 2 + bp) * 2 + atom) * TC_ATOM + kk * 32);
+        umma_bf16_2sm(tmem_base + nb * 256, da, db, idesc, (first && term == 0 && kk == 0) ? 0u : 1u);
+      }
+    }
+  };
+  // everything of a step that follows its first group
+  auto issue_rest = [&]() {
+    issue_group(0, 1, false);
+    umma_commit_2sm_mc(acc_full(0), (uint16_t)3);
+    issue_group(1, 0, true);
+    umma_commit_2sm_mc(a0_free, (uint16_t)3);
+    issue_group(1, 1, false);
+    umma_commit_2sm_mc(acc_full(1), (uint16_t)3);
+  };
+
+  const int n_work = ND * n_pairs;
+  const int n_clusters = (int)cluster_nclusters_x();
+  const int quarter = warp & 3, wq = (warp >> 2) & 1;
+  const int r = quarter * 32 + lane;   // window row of the tile == TMEM lane
+  const uint32_t peer0_on_leader = mapa_u32(peer_local(0), 0);
+
+  // Register budget: a CTA's registers are a pool fixed at launch (threads x the compiled count, in whole groups of four warps:
+  // 384 x 168 = 64 512), and `setmaxnreg` only moves registers between warpgroups through that pool -- a ninth warp alone cannot
+  // give the eight epilogue warps the ~210 registers they need (a first version asked for them without a matching release and
+  // spun in USETMAXREG.TRY_ALLOC forever).  So the CTA has a whole control warpgroup (warp 8 issues / relays, warps 9-11 only keep
+  // the barriers company) that shrinks to 64 registers per thread, and the two epilogue warpgroups grow to 216:
+  // 128 x 64 + 256 x 216 = 63 488.  The roles split ONCE, in front of the work loop, so each side is compiled against its budget.
+  if (warp >= 8) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 64;" ::: "memory");
+    int g0 = 0;
+    for (int w = (int)cluster_id_x(); w < n_work; w += n_clusters, g0 += T) {
+      const int dir = w / n_pairs, tp = w - dir * n_pairs;
+      const int b0 = (2 * tp + (int)rank) * TC_M;
+      if (g0 > 0) cluster_sync_all();
+      {
+        const uint4* src = reinterpret_cast<const uint4*>(whh16 + (size_t)dir * 2 * 512 * 128);
+        for (int i = tid; i < 4 * 128 * 16; i += TCP_THREADS) {
+          const int blk = i >> 11, rem = i & 2047, row = rem >> 4, cc = rem & 15;   // blk = nb*2 + part
+          const int nb = blk >> 1, part = blk & 1;
+          const uint4 v = __ldg(src + ((size_t)part * 512 + nb * 256 + rank * 128 + row) * 16 + cc);
+          *reinterpret_cast<uint4*>(gen + (blk * 2 + (cc >> 3)) * TC_ATOM + sw128_chunk_off((uint32_t)row, (uint32_t)(cc & 7))) = v;
+        }
+        for (int i = tid; i < (int)(4 * TC_ATOM / 16); i += TCP_THREADS) reinterpret_cast<uint4*>(genH)[i] = make_uint4(0, 0, 0, 0);
+      }
+      fence_proxy_async_all();
+      __syncthreads();
+      cluster_sync_all();
+
+      // ---------------- MMA issuer (leader) / relay (peer) ----------------
+      if (warp != 8) {
+        // idle members of the control warpgroup
+      } else if (leader) {
+        if (tp_elect_one()) {   // step 0: h_{-1} = 0
+          issue_group(0, 0, true);
+          issue_rest();
+        }
+        __syncwarp();
+        for (int st = 0; st < T; ++st) {
+          const uint32_t par = (uint32_t)((g0 + st) & 1);
+          const bool more = st + 1 < T;
+          mbar_wait(h_local(0), par);
+          mbar_wait_cluster(peer_local(0), par);
+          tc_fence_after();
+          if (more && tp_elect_one()) issue_group(0, 0, true);
+          __syncwarp();
+          mbar_wait(h_local(1), par);
+          mbar_wait_cluster(peer_local(1), par);
+          tc_fence_after();
+          if (more && tp_elect_one()) issue_rest();
+          __syncwarp();
+        }
+      } else {
+        for (int st = 0; st < T; ++st) {
+          const uint32_t par = (uint32_t)((g0 + st) & 1);
+#pragma unroll
+          for (int nb = 0; nb < 2; ++nb) {
+            mbar_wait(h_local(nb), par);
+            if (tp_elect_one()) mbar_arrive_cluster_relaxed(peer0_on_leader + 8u * (uint32_t)nb);
+            __syncwarp();
+          }
+        }
+      }
+
+      __syncthreads();
+    }
+  } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 216;" ::: "memory");
+    int g0 = 0;
+    for (int w = (int)cluster_id_x(); w < n_work; w += n_clusters, g0 += T) {
+      const int dir = w / n_pairs, tp = w - dir * n_pairs;
+      const int b0 = (2 * tp + (int)rank) * TC_M;
+      if (g0 > 0) cluster_sync_all();
+      {
+        const uint4* src = reinterpret_cast<const uint4*>(whh16 + (size_t)dir * 2 * 512 * 128);
+        for (int i = tid; i < 4 * 128 * 16; i += TCP_THREADS) {
+          const int blk = i >> 11, rem = i & 2047, row = rem >> 4, cc = rem & 15;   // blk = nb*2 + part
+          const int nb = blk >> 1, part = blk & 1;
+          const uint4 v = __ldg(src + ((size_t)part * 512 + nb * 256 + rank * 128 + row) * 16 + cc);
+          *reinterpret_cast<uint4*>(gen + (blk * 2 + (cc >> 3)) * TC_ATOM + sw128_chunk_off((uint32_t)row, (uint32_t)(cc & 7))) = v;
+        }
+        for (int i = tid; i < (int)(4 * TC_ATOM / 16); i += TCP_THREADS) reinterpret_cast<uint4*>(genH)[i] = make_uint4(0, 0, 0, 0);
+      }
+      fence_proxy_async_all();
+      __syncthreads();
+      cluster_sync_all();
+
+      // ---------------- epilogue: thread = (window r, 32 units of the current column block) ----------------
+      const bool live = b0 + r < Bc;
+      const int brow = live ? b0 + r : Bc - 1;   // dead rows read a valid row and store nothing
+      uint32_t goff[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int rr = b0 + quarter * 32 + 4 * j + (lane >> 3);
+        goff[j] = (uint32_t)(rr < Bc ? rr : Bc - 1) * (uint32_t)ldg + (uint32_t)(lane & 7) * 4u;
+      }
+      uint8_t* stg = gen + TC_OFF_STAGE + warp * 4096;
+      const uint32_t stg_s = base + TC_OFF_STAGE + warp * 4096;
+      float c[64];   // [block][32 units]
+#pragma unroll
+      for (int i = 0; i < 64; ++i) c[i] = 0.f;
+
+      for (int st = 0; st < T; ++st) {
+        const int g = g0 + st;
+        const int t = dir ? (T - 1 - st) : st;
+        const long long row = (long long)t * Bc + brow;
+#pragma unroll
+        for (int nb = 0; nb < 2; ++nb) {
+          const int col0 = nb * 256 + wq * 128;                     // this thread's 128 accumulator columns = 32 units x 4 gates
+          const float* gstep = G + (long long)t * Bc * ldg + dir * 512 + col0;
+          auto copy_slab = [&](int sl) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const uint32_t rr = 4 * j + (lane >> 3);
+              cp_async16(stg_s + rr * 128 + ((((uint32_t)lane & 7u) ^ (rr & 7u)) << 4), gstep + goff[j] + sl * 32);
+            }
+            cp_async_commit();
+          };
+          copy_slab(0);
+          if (lane == 0) jit();
+          __syncwarp();
+          mbar_wait(acc_full(nb), (uint32_t)(g & 1));
+          tc_fence_after();
+          const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)col0;
+          uint32_t acc[32];
+          tmem_ld32(taddr, acc);
+          const int unit0 = nb * 64 + wq * 32;                       // first hidden unit of this thread in this phase
+          float* orow = out + row * D + dir * 128 + unit0;
+#pragma unroll
+          for (int sl = 0; sl < 4; ++sl) {
+            cp_async_wait_all();
+            __syncwarp();
+            tmem_ld_wait();
+            float pre[32];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const uint4 gv = *reinterpret_cast<const uint4*>(stg + lane * 128 + (((uint32_t)i ^ ((uint32_t)lane & 7u)) << 4));
+              pre[4 * i + 0] = fmaf(__uint_as_float(acc[4 * i + 0]), 1.0f / TC_WSCALE, __uint_as_float(gv.x));
+              pre[4 * i + 1] = fmaf(__uint_as_float(acc[4 * i + 1]), 1.0f / TC_WSCALE, __uint_as_float(gv.y));
+              pre[4 * i + 2] = fmaf(__uint_as_float(acc[4 * i + 2]), 1.0f / TC_WSCALE, __uint_as_float(gv.z));
+              pre[4 * i + 3] = fmaf(__uint_as_float(acc[4 * i + 3]), 1.0f / TC_WSCALE, __uint_as_float(gv.w));
+            }
+            __syncwarp();
+            if (sl + 1 < 4) {
+              copy_slab(sl + 1);
+              tmem_ld32(taddr + (sl + 1) * 32, acc);
+            }
+            float hv[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+              float& cc = c[nb * 32 + sl * 8 + u];
+              const float a_i = __expf(-fmaxf(pre[4 * u + 0], -30.f));
+              const float b_g = __expf(2.0f * fminf(fmaxf(pre[4 * u + 2], -15.f), 15.f));
+              const float ig_gg = __fdividef(b_g - 1.0f, (1.0f + a_i) * (b_g + 1.0f));
+              const float fg = rec_sigmoid(pre[4 * u + 1]);
+              cc = fmaf(fg, cc, ig_gg);
+              const float a_o = __expf(-fmaxf(pre[4 * u + 3], -30.f));
+              const float b_c = __expf(2.0f * fminf(fmaxf(cc, -15.f), 15.f));
+              hv[u] = __fdividef(b_c - 1.0f, (1.0f + a_o) * (b_c + 1.0f));
+            }
+            if (live && out) stg256(orow + sl * 8, hv);
+            uint32_t hi[4], lo[4];
+#pragma unroll
+            for (int u2 = 0; u2 < 4; ++u2) {
+              const __half2 h2 = __floats2half2_rn(hv[2 * u2], hv[2 * u2 + 1]);
+              const float2 back = __half22float2(h2);
+              const __half2 l2 = __floats2half2_rn(hv[2 * u2] - back.x, hv[2 * u2 + 1] - back.y);
+              hi[u2] = *reinterpret_cast<const uint32_t*>(&h2);
+              lo[u2] = *reinterpret_cast<const uint32_t*>(&l2);
+            }
+            if (out_hi16 && live) {
+              const long long eo = row * D + dir * 128 + unit0 + sl * 8;
+              *reinterpret_cast<uint4*>(out_hi16 + eo) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+              *reinterpret_cast<uint4*>(out_lo16 + eo) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+            }
+            // K atom nb of h_t, 16-byte chunk wq*4 + sl of this row (see "who may overwrite h" above)
+            if (nb == 0 && sl == 0) mbar_wait(a0_free, (uint32_t)(g & 1));
+            const uint32_t off = sw128_chunk_off((uint32_t)r, (uint32_t)(wq * 4 + sl));
+            *reinterpret_cast<uint4*>(genH + (0 * 2 + nb) * TC_ATOM + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+            *reinterpret_cast<uint4*>(genH + (1 * 2 + nb) * TC_ATOM + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+          }
+          fence_proxy_async_smem();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) { jit(); mbar_arrive(h_local(nb)); }
+        }
+      }
+
+      __syncthreads();
+    }
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_2sm(tmem_base, 512);
+  }
+}
+
 static int tc_setup(int* max_clusters_out) {
   static PerDeviceInt state_pd, max_pd;  // state: 0 = not tried, 1 = ok, -1 = unavailable
   int& state = state_pd.cur();
@@ -397,6 +687,19 @@ int launch_rec_f16x3(int ND, const float* G, int ldg, const __half* whh16, float
   // reads (ncu: 17.8 GB against 9.9 GB of G, L2 hit rate 14 %): off by default
   static const int pf_mode = [] { const char* e = getenv("BCI_TC_PF"); return e ? atoi(e) : 0; }();
   static const int jitter = [] { const char* e = getenv("BCI_FUSED_JITTER"); int v = e ? atoi(e) : 0; return (v > 0 && (v & (v - 1)) == 0) ? v : 0; }();
+  // BCI_TC_PIPE=0 keeps the plain (unstaggered) kernel for inference as well
+  static const bool pipe = [] { const char* e = getenv("BCI_TC_PIPE"); return !(e && e[0] == '0'); }();
+  if (!gates && pipe) {
+    static PerDeviceFlag attr_pd;
+    bool& attr = attr_pd.cur();
+    if (!attr) {
+      BCI_CUDA_OK(cudaFuncSetAttribute(lstm_rec_f16x3_pipe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM));
+      attr = true;
+    }
+    lstm_rec_f16x3_pipe<<<2 * clusters, TCP_THREADS, TC_SMEM, st>>>(G, ldg, whh16, out, out_hi16, out_lo16, D, Bc, T, n_pairs, ND, jitter);
+    BCI_LAUNCH_OK();
+    return BCI_OK;
+  }
   if (gates) lstm_rec_f16x3<true><<<2 * clusters, TC_THREADS, TC_SMEM, st>>>(G, ldg, whh16, out, out_hi16, out_lo16, gates, csave, D, Bc, T, n_pairs, ND, pf_mode, jitter);
   else lstm_rec_f16x3<false><<<2 * clusters, TC_THREADS, TC_SMEM, st>>>(G, ldg, whh16, out, out_hi16, out_lo16, nullptr, nullptr, D, Bc, T, n_pairs, ND, pf_mode, jitter);
   BCI_LAUNCH_OK();
