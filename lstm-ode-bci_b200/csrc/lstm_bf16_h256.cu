@@ -23,6 +23,7 @@
 #include "lstm_shared_kernels.cuh"
 #include "sm100_prims.cuh"
 #include "tmap.cuh"
+#include <cstdlib>
 
 namespace bci {
 using namespace sm100;
@@ -322,6 +323,322 @@ lstm_rec256_bf16(const __nv_bfloat16* __restrict__ G,        // blocked: [row/12
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Staggered form of the recurrence above.  There a step is  MMA block 0 -> MMA block 1 -> both 4-warp epilogue halves side by side ->
+// exchange -> next MMA: ~8 us, with the tensor pipe idle during the gates and one warp per scheduler in each half.  Here (as in
+// lstm_rec_f16x3_pipe, lstm_fp32_tc.cu) all eight epilogue warps evaluate accumulator block 0 (units 128 p + 0..63), then block 1,
+// and the next step's MMAs are issued in (block, K atom) groups as soon as their operands exist:
+//
+//     own atom nb  (units 128 p + 64 nb ..)  is written by phase nb of both CTAs of the pair        -> h_local[nb] (+ relay)
+//     partner atom nb                         arrives by DSMEM bulk copy from CTA (1 - p, s)          -> h_in[nb]   (+ relay)
+//     step t+1:  b0.own0 | b0.par0 | b0.own1 | b0.par1, commit acc_full[0] | b1.own0, commit a0_free | b1.par0, b1.own1, b1.par1,
+//                commit acc_full[1]      (each group waits only for its own atom; block 1 runs under phase 0 of step t+1)
+//
+// Who may overwrite what: phase nb replaces own atom nb (h_t by h_{t+1}) after (i) every MMA that reads it has retired -- atom 1:
+// all in front of acc_full[1]; atom 0: b1.own0 follows acc_full[0], hence the extra commit a0_free -- and (ii) its TMA store and
+// its copy to the partner have finished reading it (st_free[nb], copy_done[nb] = the receiver's ack).  The partner's copy of
+// step t+1 may land in this CTA's partner atoms once this pair's MMAs of step t+1 have all retired: the h-store warp forwards
+// acc_full[1] to the partner as recv_ready.  h_in[nb] are transaction barriers re-armed by their single waiter.
+// Register budget (see lstm_rec_f16x3_pipe): control warpgroup (warp 8 MMA / relay, 9 h store, 10 L2 prefetch, 11 idle) at 96
+// registers, the two epilogue warpgroups at 200: 128 x 96 + 256 x 200 = 63 488 of the CTA's 384 x 168.
+constexpr int HP_THREADS = 384;
+
+__global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(HP_THREADS, 1)
+lstm_rec256_bf16_pipe(const __nv_bfloat16* __restrict__ G, const __grid_constant__ CUtensorMap tmOut,
+                      const __nv_bfloat16* __restrict__ whh, int Bc, int T, int tile_pairs, int jitter) {
+  extern __shared__ uint8_t hr_smem_raw[];
+  uint32_t jit_state = jitter ? (uint32_t)(blockIdx.x * 7919u + threadIdx.x * 104729u + 12345u) : 0u;
+  auto jit = [&]() {
+    if (jitter) {
+      jit_state = jit_state * 1664525u + 1013904223u;
+      __nanosleep((jit_state >> 20) & (uint32_t)(jitter - 1));
+    }
+  };
+  const uint32_t raw = smem_u32(hr_smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* gen = hr_smem_raw + (base - raw);
+  const uint32_t sW = base, sH = base + HR_OFF_H;
+  uint8_t* genH = gen + HR_OFF_H;
+  uint8_t* ctl = gen + HR_OFF_CTL;
+  const uint32_t bar0 = smem_u32(ctl);
+  // every barrier completes once per step g: parity g & 1
+  auto acc_full = [&](int nb) { return bar0 + 8u * nb; };
+  const uint32_t a0_free = bar0 + 16u;
+  auto h_local = [&](int nb) { return bar0 + 24u + 8u * nb; };
+  auto h_in = [&](int nb) { return bar0 + 40u + 8u * nb; };
+  auto st_free = [&](int nb) { return bar0 + 56u + 8u * nb; };
+  auto copy_done = [&](int nb) { return bar0 + 72u + 8u * nb; };
+  const uint32_t recv_ready = bar0 + 88u;
+  auto peer_local = [&](int nb) { return bar0 + 96u + 8u * nb; };
+  auto peer_in = [&](int nb) { return bar0 + 112u + 8u * nb; };
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ctl + 128);
+
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+  const uint32_t rank = cluster_ctarank();
+  const int p = (int)(rank >> 1), s = (int)(rank & 1);
+  const bool leader = (s == 0);
+  const uint32_t partner = (uint32_t)(2 * (1 - p) + s);
+
+  if (tid == 0) {
+    for (int nb = 0; nb < 2; ++nb) {
+      mbar_init(acc_full(nb), 1);
+      mbar_init(h_local(nb), HR_EPI_WARPS);
+      mbar_init(h_in(nb), 1);
+      mbar_init(st_free(nb), 1);
+      mbar_init(copy_done(nb), 1);
+      mbar_init(peer_local(nb), 1);
+      mbar_init(peer_in(nb), 1);
+    }
+    mbar_init(a0_free, 1);
+    mbar_init(recv_ready, 1);
+    fence_mbar_init();
+    mbar_arrive_expect_tx(h_in(0), HR_ATOM);   // armed for the first step; re-armed by their single waiter afterwards
+    mbar_arrive_expect_tx(h_in(1), HR_ATOM);
+    tma_prefetch_desc(&tmOut);
+  }
+  if (warp == HR_EPI_WARPS) {
+    tmem_alloc_2sm(smem_u32(tmem_slot), 512);
+    tmem_relinquish_2sm();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  cluster_sync_all();
+
+  const int n_work = 2 * tile_pairs;
+  const int n_clusters = (int)cluster_nclusters_x();
+  // start of a work item, executed by every thread: this CTA's W_hh rows (for N block nb, rows [p*512 + nb*256 + 128 s, +128)), h_{-1} = 0
+  auto item_begin = [&](int dir, bool first) {
+    if (!first) cluster_sync_all();
+    for (int i = tid; i < 2 * 128 * 32; i += HP_THREADS) {
+      const uint32_t nb = i >> 12, rem = i & 4095, row = rem >> 5, cc = rem & 31, atom = cc >> 3, c = cc & 7;
+      const uint4* src = reinterpret_cast<const uint4*>(whh + ((size_t)dir * 1024 + p * 512 + nb * 256 + 128 * s + row) * 256);
+      *reinterpret_cast<uint4*>(gen + (nb * 4 + atom) * HR_ATOM + sw128_chunk_off(row, c)) = __ldg(src + cc);
+    }
+    for (int i = tid; i < (int)(4 * HR_ATOM / 16); i += HP_THREADS) reinterpret_cast<uint4*>(genH)[i] = make_uint4(0, 0, 0, 0);
+    fence_proxy_async_all();
+    __syncthreads();
+    cluster_sync_all();
+  };
+  // chunk 0 of a row's 128-row block in the blocked G layout: 256 chunks of 2 KB per block
+  auto g_block = [&](long long row) { return reinterpret_cast<const uint8_t*>(G) + (row >> 7) * (256ll * 2048); };
+
+  if (warp >= HR_EPI_WARPS) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 96;" ::: "memory");
+    int g0 = 0;
+    for (int w = (int)cluster_id_x(); w < n_work; w += n_clusters, g0 += T) {
+      const int dir = w / tile_pairs, tp = w - dir * tile_pairs;
+      const int b0 = (2 * tp + s) * HR_M;
+      item_begin(dir, g0 == 0);
+      if (warp == HR_EPI_WARPS + 2) {
+        // ---------------- L2 prefetcher: this CTA's part of the NEXT step's G block (64 chunks of 2 KB = 128 KB) ----------------
+        const long long n_blocks = ((long long)T * Bc + 127) >> 7;
+        for (int st = 0; st + 1 < T && b0 < Bc; ++st) {
+          const int sn = st + 1;
+          const long long row0 = (long long)(dir ? (T - 1 - sn) : sn) * Bc + b0;
+          const uint8_t* blk = g_block(row0) + (long long)(dir * 128 + p * 64) * 2048;
+          if (lane < 8) bulk_prefetch_l2(blk + lane * 16384, 16384u);
+          if ((row0 & 127) != 0 && (row0 >> 7) + 1 < n_blocks && lane >= 8 && lane < 16)
+            bulk_prefetch_l2(blk + 256ll * 2048 + (lane - 8) * 16384, 16384u);
+          // pace: nothing depends on this warp, so it may fall behind and see the barrier two phases later (same parity):
+          // bounded polling instead of a wait that could then never return
+          for (int polls = 0; polls < 50000 && !mbar_try_wait(h_local(1), (uint32_t)((g0 + st) & 1)); ++polls) { }
+        }
+      } else if (warp == HR_EPI_WARPS + 1) {
+        // ---------------- h store warp: this CTA's two K-atoms of h_t -> partner CTA (DSMEM) and -> out[t] ----------------
+        if (lane == 0) {
+          const uint32_t atoms = sH + 2 * p * HR_ATOM;
+          const uint32_t rr = mapa_u32(recv_ready, partner);
+          for (int st = 0; st < T; ++st) {
+            const uint32_t par = (uint32_t)((g0 + st) & 1);
+            const int t = dir ? (T - 1 - st) : st;
+            jit();
+            mbar_wait(acc_full(1), par);              // this pair's MMAs of the step have all retired:
+            mbar_arrive_cluster_relaxed(rr);          // the partner may replace its atoms in this CTA
+            mbar_wait(h_local(0), par);
+            mbar_wait_cluster(recv_ready, par);       // ... and this CTA its atoms in the partner
+            bulk_copy_s2s_cluster(mapa_u32(atoms, partner), atoms, HR_ATOM, mapa_u32(h_in(0), partner));
+            tma_store_3d(&tmOut, atoms, dir * 256 + 128 * p, b0, t);
+            tma_store_commit();
+            mbar_wait(h_local(1), par);
+            bulk_copy_s2s_cluster(mapa_u32(atoms + HR_ATOM, partner), atoms + HR_ATOM, HR_ATOM, mapa_u32(h_in(1), partner));
+            tma_store_3d(&tmOut, atoms + HR_ATOM, dir * 256 + 128 * p + 64, b0, t);
+            tma_store_commit();
+            asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+            mbar_arrive(st_free(0));
+            tma_store_wait_read();
+            mbar_arrive(st_free(1));
+          }
+          tma_store_wait_all();
+        }
+      } else if (warp == HR_EPI_WARPS) {
+        // ---------------- MMA issuer (pair leader) / relay (its peer) ----------------
+        constexpr uint32_t idesc = umma_idesc_bf16(256, 256);
+        const uint16_t pair_mask = (uint16_t)(3u << (2 * p));
+        const uint32_t own = (uint32_t)(2 * p), par_atom = (uint32_t)(2 * (1 - p));
+        auto issue4 = [&](int nb, uint32_t atom, bool first) {
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) {
+            const uint64_t da = umma_desc_sw128(sH + atom * HR_ATOM + kk * 32);
+            const uint64_t db = umma_desc_sw128(sW + (nb * 4 + atom) * HR_ATOM + kk * 32);
+            umma_bf16_2sm(tmem_base + nb * 256, da, db, idesc, (first && kk == 0) ? 0u : 1u);
+          }
+        };
+        auto issue_tail = [&]() {   // everything of a step behind b0.own0, b0.par0, b0.own1
+          issue4(0, par_atom + 1, false);
+          umma_commit_2sm_mc(acc_full(0), pair_mask);
+          issue4(1, own, true);
+          umma_commit_2sm_mc(a0_free, pair_mask);
+          issue4(1, par_atom, false);
+          issue4(1, own + 1, false);
+          issue4(1, par_atom + 1, false);
+          umma_commit_2sm_mc(acc_full(1), pair_mask);
+        };
+        const uint32_t lead = rank & ~1u;
+        const uint32_t ack0 = mapa_u32(copy_done(0), partner);
+        const uint32_t pl0 = mapa_u32(peer_local(0), lead), pi0 = mapa_u32(peer_in(0), lead);
+        if (leader) {
+          if (tp_elect_one()) {   // step 0: h_{-1} = 0
+            issue4(0, own, true);
+            issue4(0, par_atom, false);
+            issue4(0, own + 1, false);
+            issue_tail();
+          }
+          __syncwarp();
+        }
+        for (int st = 0; st < T; ++st) {
+          const uint32_t par = (uint32_t)((g0 + st) & 1);
+          const bool more = st + 1 < T;
+#pragma unroll
+          for (int nb = 0; nb < 2; ++nb) {
+            if (lane == 0) jit();
+            __syncwarp();
+            // own atom nb of h_t (and accumulator block nb drained)
+            mbar_wait(h_local(nb), par);
+            if (leader) {
+              mbar_wait_cluster(peer_local(nb), par);
+              tc_fence_after();
+              if (more && tp_elect_one()) issue4(0, own + nb, nb == 0);
+            } else {
+              if (tp_elect_one()) mbar_arrive_cluster_relaxed(pl0 + 8u * (uint32_t)nb);
+            }
+            __syncwarp();
+            // the partner's atom nb of h_t
+            mbar_wait(h_in(nb), par);
+            if (tp_elect_one()) {
+              mbar_arrive_expect_tx(h_in(nb), HR_ATOM);
+              mbar_arrive_cluster_relaxed(ack0 + 8u * (uint32_t)nb);
+              if (!leader) mbar_arrive_cluster_relaxed(pi0 + 8u * (uint32_t)nb);
+            }
+            __syncwarp();
+            if (leader) {
+              mbar_wait_cluster(peer_in(nb), par);
+              tc_fence_after();
+              if (more && tp_elect_one()) {
+                if (nb == 0) issue4(0, par_atom, false);
+                else issue_tail();
+              }
+              __syncwarp();
+            }
+          }
+        }
+      }
+      __syncthreads();
+    }
+  } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 200;" ::: "memory");
+    // ---------------- epilogue: thread = (window row, 32 of the current block's 64 hidden units) ----------------
+    const int quarter = warp & 3, wq = warp >> 2;
+    const int r = quarter * 32 + lane;
+    int g0 = 0;
+    for (int w = (int)cluster_id_x(); w < n_work; w += n_clusters, g0 += T) {
+      const int dir = w / tile_pairs, tp = w - dir * tile_pairs;
+      const int b0 = (2 * tp + s) * HR_M;
+      item_begin(dir, g0 == 0);
+      const bool live = b0 + r < Bc;
+      float c[64];   // [block][32 units]
+#pragma unroll
+      for (int i = 0; i < 64; ++i) c[i] = 0.f;
+      for (int st = 0; st < T; ++st) {
+        const int g = g0 + st;
+        const int t = dir ? (T - 1 - st) : st;
+        // rows of windows beyond the batch (partial or absent tiles) read a valid row instead; their results are never stored
+        const long long row = (long long)t * Bc + (live ? b0 + r : (b0 < Bc ? b0 : 0));
+#pragma unroll
+        for (int nb = 0; nb < 2; ++nb) {
+          // chunks (slab*4 + gate) of units 128 p + 64 nb + 8 slab .. +7, this thread's slabs wq*4 .. wq*4 + 3
+          const uint8_t* gp = g_block(row) + (long long)(dir * 128 + p * 64 + nb * 32 + wq * 16) * 2048 + (row & 127) * 16ll;
+          uint4 gbuf[3][4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) gbuf[0][q] = ldg_stream_v4(gp + q * 2048);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) gbuf[1][q] = ldg_stream_v4(gp + (4 + q) * 2048);
+          if (lane == 0) jit();
+          __syncwarp();
+          mbar_wait(acc_full(nb), (uint32_t)(g & 1));
+          tc_fence_after();
+          const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(nb * 256 + wq * 128);
+          uint8_t* hrow = genH + (2 * p + nb) * HR_ATOM;   // own atom nb
+#pragma unroll
+          for (int sl = 0; sl < 4; ++sl) {
+            uint32_t acc[32];
+            tmem_ld32(taddr + sl * 32, acc);
+            if (sl < 2) {
+#pragma unroll
+              for (int q = 0; q < 4; ++q) gbuf[(sl + 2) % 3][q] = ldg_stream_v4(gp + ((sl + 2) * 4 + q) * 2048);
+            }
+            tmem_ld_wait();
+            const uint32_t* gw = reinterpret_cast<const uint32_t*>(gbuf[sl % 3]);
+            auto gval = [&](int gate, int u) {
+              const uint32_t wv = gw[gate * 4 + (u >> 1)];
+              return __uint_as_float((u & 1) ? (wv & 0xFFFF0000u) : (wv << 16));
+            };
+            uint32_t hp[4];
+#pragma unroll
+            for (int u2 = 0; u2 < 4; ++u2) {
+              float hv[2];
+#pragma unroll
+              for (int e = 0; e < 2; ++e) {
+                const int u = u2 * 2 + e;
+                const float ig = fmaf(0.5f, hr_tanh(__uint_as_float(acc[0 * 8 + u]) + gval(0, u)), 0.5f);
+                const float fg = fmaf(0.5f, hr_tanh(__uint_as_float(acc[1 * 8 + u]) + gval(1, u)), 0.5f);
+                const float gg = hr_tanh(__uint_as_float(acc[2 * 8 + u]) + gval(2, u));
+                const float og = fmaf(0.5f, hr_tanh(__uint_as_float(acc[3 * 8 + u]) + gval(3, u)), 0.5f);
+                float& cc = c[nb * 32 + sl * 8 + u];
+                cc = fmaf(fg, cc, ig * gg);
+                hv[e] = og * hr_tanh(cc);
+              }
+              __nv_bfloat162 pk = __floats2bfloat162_rn(hv[0], hv[1]);
+              hp[u2] = *reinterpret_cast<uint32_t*>(&pk);
+            }
+            if (sl == 0) {   // own atom nb still holds h_{g-1}: see "who may overwrite what"
+              if (g > 0) {
+                mbar_wait(st_free(nb), (uint32_t)((g - 1) & 1));
+                mbar_wait_cluster(copy_done(nb), (uint32_t)((g - 1) & 1));
+              }
+              if (nb == 0) mbar_wait(a0_free, (uint32_t)(g & 1));
+            }
+            *reinterpret_cast<uint4*>(hrow + sw128_chunk_off((uint32_t)r, (uint32_t)(wq * 4 + sl))) = make_uint4(hp[0], hp[1], hp[2], hp[3]);
+          }
+          fence_proxy_async_smem();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(h_local(nb));
+        }
+      }
+      __syncthreads();
+    }
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == HR_EPI_WARPS) {
+    tc_fence_after();
+    tmem_dealloc_2sm(tmem_base, 512);
+  }
+}
+
 static int h256_setup(int* max_clusters_out) {
   static PerDeviceInt state_pd, max_pd;  // state: 0 = not tried, 1 = ok, -1 = unavailable
   int& state = state_pd.cur();
@@ -360,6 +677,19 @@ int launch_rec256_bf16(const __nv_bfloat16* G, const __nv_bfloat16* whh, __nv_bf
   const int tiles = ceil_div(Bc, HR_M), tile_pairs = (tiles + 1) / 2;
   const int clusters = 2 * tile_pairs < max_clusters ? 2 * tile_pairs : max_clusters;
   static const int jitter = [] { const char* e = getenv("BCI_FUSED_JITTER"); int v = e ? atoi(e) : 0; return (v > 0 && (v & (v - 1)) == 0) ? v : 0; }();
+  // BCI_H256_PIPE=0 keeps the unstaggered kernel
+  static const bool pipe = [] { const char* e = getenv("BCI_H256_PIPE"); return !(e && e[0] == '0'); }();
+  if (pipe) {
+    static PerDeviceFlag attr_pd;
+    bool& attr = attr_pd.cur();
+    if (!attr) {
+      BCI_CUDA_OK(cudaFuncSetAttribute(lstm_rec256_bf16_pipe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HR_SMEM));
+      attr = true;
+    }
+    lstm_rec256_bf16_pipe<<<4 * clusters, HP_THREADS, HR_SMEM, st>>>(G, tmOut, whh, Bc, T, tile_pairs, jitter);
+    BCI_LAUNCH_OK();
+    return BCI_OK;
+  }
   lstm_rec256_bf16<<<4 * clusters, HR_THREADS, HR_SMEM, st>>>(G, tmOut, whh, Bc, T, tile_pairs, jitter);
   BCI_LAUNCH_OK();
   return BCI_OK;
