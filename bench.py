@@ -692,6 +692,13 @@ def main():
             integ = integration.LSTMODEIntegration(auto, ode.CognitiveStateODE(), coupling_strength=0.5, device=f"cuda:{local}")
             nd = 4 * B      # four passes of the recurrence wave: the call is a pipeline (stage k+1 on the host | kernels of k), fill included
             xd = np.concatenate([np.random.default_rng(0).standard_normal((B, 256, 61), dtype=np.float32)] * 4)
+            # this leg runs on rank 0 alone (the other ranks wait at the barrier, one core each): the staging copy may use the rest
+            # of the host cores instead of rank 0's 1/world share
+            if world > 1 and not os.environ.get("BCI_STAGING_THREADS"):
+                os.environ["BCI_STAGING_THREADS"] = str(max(1, min(32, (len(all_cpus) if all_cpus else (os.cpu_count() or 1)) - (world - 1))))
+                staging_env_set = True
+            else:
+                staging_env_set = False
             integ.predict_batch(xd, forecast_steps=20, batch_size=512, show_progress=False)
             torch.cuda.synchronize()
             t0 = time.perf_counter()
@@ -704,6 +711,8 @@ def main():
                                             # input projection applies on load): half the bytes cross the link, no result bit changes
                                             "h2d_bytes": int(xd.nbytes) // 2, "d2h_bytes": int(trj.nbytes + _pp.nbytes + _pd.nbytes)}
             tail["dropin_predict_batch_windows_s"] = round(nd / dsec, 1)
+            if staging_env_set:
+                os.environ.pop("BCI_STAGING_THREADS", None)
             del xd, trj, integ, auto
         barrier()
 

@@ -100,6 +100,34 @@ def test_fp32_tensorcore_recurrence_matches_oracle():
         assert dl <= 1e-5 and dp <= 1e-5 and da <= 1e-6, (lo, dl, dp, da)
 
 
+def test_fp32_full_pass_matches_oracle_and_is_order_independent():
+    """The fp32 parity mode at the bench's own pass size (`bci_lstm_chunk_windows`: 9 472 windows on a 148-SM B200 = 148 work items on 74
+    CTA pairs, two per pair -- the staggered recurrence lstm_rec_f16x3_pipe with its per-item reload of the weights and barrier
+    parities carried across items): windows are independent, so reversing their order reverses the outputs BIT FOR BIT; three
+    32-window slices (first pair, a second-round item, the last pair) against the ORACLE within the north_star tolerances."""
+    from lstm_ode_bci_b200 import ops
+    params = synth.make_lstm_params(42, 61, 128, 3, logit_gain=12.0)
+    m = lstm.from_params(params, precision="fp32")
+    B = ops.lstm_chunk_windows(m._engine("fp32"))
+    g = torch.Generator(device="cuda").manual_seed(17)
+    x = torch.randn((B, 256, 61), device="cuda", generator=g)
+    with torch.no_grad():
+        p, a = m.predict_proba(x, return_attention=True)
+        pr, ar = m.predict_proba(x.flip(0).contiguous(), return_attention=True)
+    assert torch.isfinite(p).all() and torch.isfinite(a).all()
+    assert torch.equal(pr.flip(0), p) and torch.equal(ar.flip(0), a)
+    port = torch_port.build_port(params).eval()
+    xc = x.cpu()
+    for lo in (0, (3 * B) // 4 - 16, B - 32):
+        with torch.no_grad():
+            wl, wa = port(xc[lo:lo + 32], return_attention=True)
+            wp = torch.softmax(wl, 1)
+        dp = float((p[lo:lo + 32].cpu() - wp).abs().max())
+        da = float((a[lo:lo + 32].cpu() - wa).abs().max())
+        print(f"fp32 full pass vs oracle, windows {lo}..{lo + 32}: dprob {dp:.2e} dattn {da:.2e}")
+        assert dp <= 1e-5 and da <= 1e-6, (lo, dp, da)
+
+
 def test_weights_reload_after_update():
     params = synth.make_lstm_params(9, 61, 128, 3)
     m = lstm.from_params(params, precision="fp32")

@@ -183,6 +183,35 @@ def test_bf16_h256_forward_close_to_fp32_oracle(B, T):
     assert dl <= BF16_TOL["logits"] and dp <= 1.5e-3 and da <= 2e-4, (dl, dp, da)
 
 
+def test_bf16_h256_full_chunk_matches_oracle_and_is_order_independent():
+    """H = 256 bf16 at its own chunk size (`bci_lstm_chunk_windows`: 8 448 windows = 33 clusters x 256, two work items -- the two
+    directions -- per cluster: the CTA-pair projection GEMM over 2.2 M rows and the staggered recurrence with barrier parities carried
+    across items): reversing the window order reverses the outputs BIT FOR BIT, and three 16-window slices agree with the ORACLE
+    (torch CPU port of the reference module at its checkpoint size) within the stated bf16 tolerance."""
+    from lstm_ode_bci_b200 import ops
+    params = synth.make_lstm_params(44, 61, 256, 3, logit_gain=12.0)
+    m = lstm.from_params(params, precision="bf16")
+    B = ops.lstm_chunk_windows(m._engine("bf16"))
+    g = torch.Generator(device="cuda").manual_seed(23)
+    x = torch.randn((B, 256, 61), device="cuda", generator=g)
+    with torch.no_grad():
+        p, a = m.predict_proba(x, return_attention=True)
+        pr, ar = m.predict_proba(x.flip(0).contiguous(), return_attention=True)
+    assert torch.isfinite(p).all() and torch.isfinite(a).all()
+    assert torch.equal(pr.flip(0), p) and torch.equal(ar.flip(0), a)
+    assert float((p.sum(1) - 1).abs().max()) <= 1e-6 and float((a.sum(1) - 1).abs().max()) <= 1e-5
+    port = torch_port.build_port(params).eval()
+    xc = x.cpu()
+    for lo in (0, B // 2 - 8, B - 16):
+        with torch.no_grad():
+            wl, wa = port(xc[lo:lo + 16], return_attention=True)
+            wp = torch.softmax(wl, 1)
+        dp = float((p[lo:lo + 16].cpu() - wp).abs().max())
+        da = float((a[lo:lo + 16].cpu() - wa).abs().max())
+        print(f"H=256 full chunk vs oracle, windows {lo}..{lo + 16}: dprob {dp:.3e} dattn {da:.3e}")
+        assert dp <= 1.5e-3 and da <= 2e-4, (lo, dp, da)
+
+
 def test_bf16_rejects_ablation_variants_and_other_sizes():
     params = synth.make_lstm_params(1, 61, 128, 2, bidirectional=False)
     m = lstm.from_params(params, precision="bf16")
@@ -269,6 +298,34 @@ def test_fused_kernel_is_robust_to_timing_jitter():
     env = dict(os.environ, BCI_FUSED_JITTER="4096", PYTHONPATH=root)
     r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "jitter ok" in r.stdout, r.stderr[-2000:]
+
+
+def test_staggered_h256_recurrence_is_robust_to_timing_jitter(tmp_path):
+    """lstm_rec256_bf16_pipe exchanges K atoms between CTA pairs per phase (h_in / copy_done / st_free / recv_ready / a0_free per atom):
+    under BCI_FUSED_JITTER (every role sleeps up to 4 us at its synchronisation points) the H = 256 bf16 forward must return the very bits
+    of the unperturbed run -- 700 windows (three tile pairs per direction: several work items per cluster generation) x 40 steps."""
+    import os, subprocess, sys
+    code = (
+        "import sys, numpy as np, torch\n"
+        "from lstm_ode_bci_b200 import lstm, synth\n"
+        "p = synth.make_lstm_params(44, 61, 256, 3, logit_gain=12.0)\n"
+        "x = torch.from_numpy(synth.make_windows(9, 700, 40, 61, structured=True)).cuda()\n"
+        "pr, at = lstm.from_params(p, precision='bf16').predict_proba(x, return_attention=True)\n"
+        "assert torch.isfinite(pr).all() and torch.isfinite(at).all()\n"
+        "np.savez(sys.argv[1], probs=pr.cpu().numpy(), attn=at.cpu().numpy())\n"
+        "print('run ok')\n")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    outs = []
+    for tag, jitter in (("plain", None), ("jitter", "4096")):
+        env = dict(os.environ, PYTHONPATH=root)
+        env.pop("BCI_FUSED_JITTER", None)
+        if jitter:
+            env["BCI_FUSED_JITTER"] = jitter
+        f = str(tmp_path / (tag + ".npz"))
+        r = subprocess.run([sys.executable, "-c", code, f], env=env, capture_output=True, text=True, timeout=240)
+        assert r.returncode == 0 and "run ok" in r.stdout, r.stderr[-2000:]
+        outs.append(np.load(f))
+    assert np.array_equal(outs[0]["probs"], outs[1]["probs"]) and np.array_equal(outs[0]["attn"], outs[1]["attn"])
 
 
 def _perm256():
