@@ -684,6 +684,25 @@ def main():
             tail["h256_train_mixed_ms_per_step"] = round(h256ms, 3)
             tr256.close()
             del tr256, t256
+        # 07_explainability.py:287-361 at its own defaults (1 000 test windows, 61 channels x 5 permutations + the baseline = 306
+        # sweeps): the subset stays resident, bci_permute_channels gathers the variants, the bf16 forward runs them in full passes
+        from lstm_ode_bci_b200 import explain
+        n_pi, reps_pi = 1000, 5
+        ch_pi = [-1] + [c for c in range(61) for _ in range(reps_pi)]
+        rng_pi = np.random.default_rng(3)
+        perms_pi = np.stack([rng_pi.permutation(n_pi) for _ in ch_pi])
+        y_pi = rng_pi.integers(0, 2, n_pi)
+        x_pi = x[:n_pi]
+        explain.permuted_channel_accuracy(model, x_pi, y_pi, ch_pi[:40], perms_pi[:40])
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        explain.permuted_channel_accuracy(model, x_pi, y_pi, ch_pi, perms_pi)
+        torch.cuda.synchronize()
+        sec_pi = time.perf_counter() - t0
+        line["permutation_importance"] = {"value": world * len(ch_pi) * n_pi / sec_pi, "unit": "windows/s", "seconds": sec_pi,
+                                          "sweeps": len(ch_pi), "windows_per_sweep": n_pi, "precision": "bf16",
+                                          "config": "07:287 defaults: n_samples=1000, n_permutations=5, 61 channels"}
+        tail["permutation_importance_windows_s"] = round(world * len(ch_pi) * n_pi / sec_pi, 1)
         # the reference's own call, unmodified: LSTMODEIntegration.predict_batch(X_numpy, forecast_steps=20, batch_size=512)
         # (06:801-806) -- pageable fp32 numpy windows in, numpy out, LSTM + coupling + ODE + classification; a model built
         # with precision="auto" runs its bf16 engine there because that is where the reference autocasts (06:348-351).  Rank 0 only.

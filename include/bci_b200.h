@@ -341,6 +341,16 @@ int bci_preprocess(const bci_preproc_args* a, const void* raw, float* windows, d
  * Pure host code: no CUDA call, no stream. */
 int bci_host_stage(void* dst, const float* src, int64_t n, int32_t to_bf16, int32_t threads);
 
+/* Permutation-importance inputs (SURVEY.md §8 f rank 1; replaces the host-side `X_permuted = X_subset.copy();
+ * X_permuted[:, :, ch] = X_subset[perm_idx, :, ch]` + per-batch upload of 07_explainability.py:336-339,312-322).  The test subset
+ * x (n, seq_len, channels) fp32 stays on the DEVICE; rows [row0, row0 + rows) of the V x n stack of variants are written in the
+ * forward's input layout:   out[r][t][c] = x[c == channel[v] ? perm[g] : i][t][c],   g = row0 + r, v = g / n, i = g % n
+ *   perm     (V*n) int32 DEVICE: numpy's np.random.permutation(n) of each variant, concatenated (07:338)
+ *   channel  (V)   int32 DEVICE: the permuted channel of each variant; < 0 = unpermuted copy (the baseline sweep, 07:325)
+ *   out      (rows, seq_len, channels) fp32 (BCI_IN_F32) or bf16 (BCI_IN_BF16: rounded exactly as the bf16 engine rounds x on load) */
+int bci_permute_channels(const float* x, int32_t n, int32_t seq_len, int32_t channels, const int32_t* perm,
+                         const int32_t* channel, int64_t row0, int64_t rows, int32_t out_dtype, void* out, void* stream);
+
 /* Micro-benchmark used by bench.py for the FP32 roofline denominator (SURVEY.md §8 d: the FP32
  * FMA peak is not in MEASURED_PEAKS.json): launches a dependent-FMA kernel, returns TFLOP/s. */
 int bci_fp32_peak_probe(double* tflops, void* stream);

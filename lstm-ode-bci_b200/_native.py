@@ -134,6 +134,8 @@ SIGNATURES = {
     "bci_selftest_tmem_a_probe": (C.c_int, [_FP, C.c_void_p]),
     "bci_lstm_set_train_mode": (C.c_int, [C.c_void_p, C.c_int32]),
     "bci_host_stage": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32]),
+    "bci_permute_channels": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64,
+                             C.c_int32, C.c_void_p, C.c_void_p]),
     "bci_fp32_peak_probe": (C.c_int, [C.POINTER(C.c_double), C.c_void_p]),
     "bci_fp64_peak_probe": (C.c_int, [C.POINTER(C.c_double), C.c_void_p]),
 }

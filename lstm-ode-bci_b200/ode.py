@@ -202,3 +202,45 @@ class CognitiveStateODE:
         return {"Active": sol[-1][0], "Passive": sol[-1][1], "Fatigued": sol[-1][2]}
 
 
+
+
+def steady_state_ensemble(param_matrix, device=None, substeps=2):
+    """get_steady_state (05:198-221: solve from [.33,.33,.34] to t = 1000 over 1000 points, keep the last state) for S parameter sets
+    in ONE launch: param_matrix (6,S) in RATE_ORDER -> (S,3) float64 numpy.
+
+    Integrated in fp64 by the node-table RK4 kernel (`bci_ode_solve_modulated` with a constant schedule per trajectory) rather than
+    by the fp32 ensemble kernel: callers difference these states (sensitivity_analysis divides a +-20 % difference by 0.4 k, i.e.
+    amplifies errors up to 125x), and the fixed point of an RK4 map of a linear system is the exact null vector of Q, so the
+    converged fp64 state carries no truncation error at all.  Only the final state is written."""
+    pm = np.ascontiguousarray(np.asarray(param_matrix, dtype=np.float64).reshape(6, -1))
+    S = pm.shape[1]
+    n_points = 1000
+    m = 2 * int(substeps) * (n_points - 1) + 1
+    nodes = np.broadcast_to(pm[None], (m, 6, S))
+    y0 = np.repeat(np.array([[0.33], [0.33], [0.34]], dtype=np.float64), S, axis=1)
+    _, final = solve_modulated_ensemble(y0, np.ascontiguousarray(nodes), (0.0, 1000.0), n_points, substeps, style="ref06",
+                                        want_traj=False, device=device)
+    return final.cpu().numpy()
+
+
+def sensitivity_analysis(ode_model, output_path=None):
+    """05_ode_model.py:687-750 (SURVEY.md §8 f rank 2): central-difference sensitivity of the steady state to each rate,
+    +-20 % perturbations -> [{'parameter', 'sens_Active', 'sens_Passive', 'sens_Fatigued'}, ...] in the order of
+    `ode_model.params`.  The reference builds 12 models and integrates each to t = 1000 with odeint, one after the other; here the 12
+    perturbed parameter sets are one ODE-ensemble launch.  `output_path` is accepted for signature compatibility: the heat-map
+    figure (05:721-745) is plotting, outside this library."""
+    base_params = dict(ode_model.params)
+    param_names = list(base_params.keys())
+    perturbation = 0.2
+    columns = []
+    for param in param_names:
+        for factor in (1 - perturbation, 1 + perturbation):
+            test_params = dict(base_params)
+            test_params[param] = base_params[param] * factor
+            columns.append([float(test_params[k]) for k in RATE_ORDER])
+    steady = steady_state_ensemble(np.array(columns, dtype=np.float64).T, device=getattr(ode_model, "device", None))
+    results = []
+    for j, param in enumerate(param_names):
+        delta = (steady[2 * j + 1] - steady[2 * j]) / (2 * perturbation * base_params[param])
+        results.append({"parameter": param, "sens_Active": delta[0], "sens_Passive": delta[1], "sens_Fatigued": delta[2]})
+    return results

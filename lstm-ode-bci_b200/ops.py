@@ -385,6 +385,23 @@ def ode_forecast_readout(traj, horizons):
     return out
 
 
+def permute_channels(x, perm, channel, row0, rows, bf16_out=False):
+    """Rows [row0, row0 + rows) of the V x n stack of channel-permuted copies of x (n,T,C) fp32 (bci_permute_channels;
+    07_explainability.py:336-339): perm (V*n) int32, channel (V) int32 (< 0: unpermuted copy).  -> (rows,T,C) fp32 / bf16."""
+    x = _need_cuda(x, "x")
+    perm = _need_cuda(perm, "perm", torch.int32)
+    channel = _need_cuda(channel, "channel", torch.int32)
+    n, T, Cc = (int(v) for v in x.shape)
+    if perm.numel() != channel.numel() * n or row0 < 0 or row0 + rows > perm.numel():
+        raise N.BciError(-1, "permute_channels: perm must hold %d x %d indices and rows [%d, %d) must lie inside them"
+                         % (channel.numel(), n, row0, row0 + rows))
+    out = torch.empty((int(rows), T, Cc), device=x.device, dtype=torch.bfloat16 if bf16_out else torch.float32)
+    with torch.cuda.device(x.device):
+        N.check(N.lib().bci_permute_channels(_ptr(x), n, T, Cc, _ptr(perm), _ptr(channel), int(row0), int(rows),
+                                             N.IN_BF16 if bf16_out else N.IN_F32, _ptr(out), _stream(x.device)))
+    return out
+
+
 def fp32_peak_probe():
     v = C.c_double(0.0)
     N.check(N.lib().bci_fp32_peak_probe(C.byref(v), _stream()))

@@ -1,15 +1,16 @@
 """patch_reference(module): swap the hot-path callables of an imported reference script
-(02/04/06/08/09/10) for the B200 implementations, so its own main()/pipeline code runs unmodified.
+(02/04/05/06/07/08/09/10) for the B200 implementations, so its own main()/pipeline code runs unmodified.
 
 The reference redeclares its classes in every script, so we patch by structure:
 whatever the module calls `EnhancedLSTMModel`, `CognitiveStateODE`, `LSTMODEIntegration`,
 `predict_trajectory`, `prob_to_ode_state`, `multistep_forecast`, `rolling_forecast_evaluation`,
-`get_lstm_probabilities`, `get_three_state_probabilities` is replaced when present.
+`get_lstm_probabilities`, `get_three_state_probabilities`, 05's `sensitivity_analysis`, 07's `compute_channel_importance` /
+`compute_permutation_importance` is replaced when present.
 """
 import functools
 import inspect
 
-from . import integration, lstm, ode, preprocessing
+from . import explain, integration, lstm, ode, preprocessing
 
 _REPLACEMENTS = {
     "EnhancedLSTMModel": lstm.EnhancedLSTMModel,
@@ -23,6 +24,12 @@ _REPLACEMENTS = {
     "multistep_forecast": integration.multistep_forecast,
     "rolling_forecast_evaluation": integration.rolling_forecast_evaluation,
     "prob_to_ode_state": integration.prob_to_ode_state,
+    "sensitivity_analysis": ode.sensitivity_analysis,       # 05_ode_model.py:687-750 (12 steady states in one launch)
+}
+# 07_explainability.py:203-361: the attribution sweeps; they label channels with the script's own EEG_CHANNELS (07:63-71,222-225)
+_EXPLAIN = {
+    "compute_channel_importance": explain.compute_channel_importance,
+    "compute_permutation_importance": explain.compute_permutation_importance,
 }
 
 
@@ -59,6 +66,14 @@ def _with_reference_defaults(new_obj, ref_obj):
     return wrapper
 
 
+def _with_channel_names(fn, names):
+    @functools.wraps(fn)
+    def wrapper(*args, **kwargs):
+        kwargs.setdefault("channel_names", names)
+        return fn(*args, **kwargs)
+    return wrapper
+
+
 def patch_reference(module):
     """Returns the list of names replaced.  08's module-level predict_trajectory/get_lstm_probabilities
     are only replaced when the module has no LSTMODEIntegration (i.e. it is 08, not 06)."""
@@ -66,6 +81,14 @@ def patch_reference(module):
     for name, repl in _REPLACEMENTS.items():
         if hasattr(module, name):
             setattr(module, name, _with_reference_defaults(repl, getattr(module, name)))
+            done.append(name)
+    for name, repl in _EXPLAIN.items():
+        if hasattr(module, name):
+            fn = _with_reference_defaults(repl, getattr(module, name))
+            names = getattr(module, "EEG_CHANNELS", None)
+            if names is not None:
+                fn = _with_channel_names(fn, list(names))
+            setattr(module, name, fn)
             done.append(name)
     if not hasattr(module, "LSTMODEIntegration"):
         for name in ("predict_trajectory", "get_lstm_probabilities"):

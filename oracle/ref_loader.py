@@ -25,6 +25,7 @@ _FILES = {
     "ref04": "04_lstm_model.py",
     "ref05": "05_ode_model.py",
     "ref06": "06_lstm_ode_integration.py",
+    "ref07": "07_explainability.py",
     "ref08": "08_forecasting.py",
     "ref10": "10_three_state_probabilities.py",
 }
@@ -55,6 +56,9 @@ def _install_plot_stubs():
         plt.style = types.SimpleNamespace(use=lambda *a, **k: None)
     if not hasattr(plt, "rcParams"):
         plt.rcParams = {}
+    gs = sys.modules["matplotlib.gridspec"]
+    if not hasattr(gs, "GridSpec"):                 # 07_explainability.py:33 `from matplotlib.gridspec import GridSpec`
+        gs.GridSpec = type("GridSpec", (), {})
     mne = sys.modules["mne"]
     if not hasattr(mne, "set_log_level"):
         mne.set_log_level = lambda *a, **k: None
@@ -68,7 +72,7 @@ _cache = {}
 
 
 def load(name, fresh=False):
-    """name in {ref02, ref04, ref05, ref06, ref08, ref09, ref10}; returns the imported module (fresh=True: a new, uncached
+    """name in {ref02, ref04, ref05, ref06, ref07, ref08, ref09, ref10}; returns the imported module (fresh=True: a new, uncached
     module object -- for tests that monkey-patch it)."""
     if name in _cache and not fresh:
         return _cache[name]

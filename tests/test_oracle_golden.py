@@ -239,3 +239,58 @@ def test_fit_objective_matches_reference_seeded_fit(golden):
             kk[i] = min(max(kk[i] + d, lo), hi)
             s2 = oo.exact_solution(oo.STYLE_REF06, obs[:1], kk[:, None], float(tp[-1] - tp[0]), len(tp))[0]
             assert float(np.mean((s2 - obs) ** 2) + 0.001 * np.sum(kk ** 2)) >= loss - 1e-9
+
+
+def explain_case_inputs(g):
+    """Model parameters, test windows and labels of tests/golden/explain_ref07.npz, regenerated from its stored seeds
+    (tests/golden/make_golden_explain.py: perm_case_params)."""
+    params = synth.make_lstm_params(int(g["param_seed"]), 61, 128, 3, logit_gain=float(g["logit_gain"]))
+    params["input_proj.0.weight"][:, g["boosted_channels"]] *= np.float32(g["boost"])
+    params["classifier.6.bias"] = g["final_bias"].astype(np.float32)
+    X = synth.make_windows(int(g["x_seed"]), int(g["n_test"]), 256, 61, structured=True)
+    return params, X, g["labels"]
+
+
+def test_permutation_importance_oracle_matches_reference_07(golden):
+    """oracle/explain_oracle.py (07:287-361 restated around the torch port) against the live reference's own run, seeded the same
+    way: same subset, same permutations, same predictions -> the same importance per channel, exactly."""
+    import torch
+    from oracle import explain_oracle
+    g = golden("explain_ref07.npz")
+    params, X, y = explain_case_inputs(g)
+    port = torch_port.build_port(params, dropout=0.0).eval()
+    with torch.no_grad():
+        assert np.abs(port(torch.from_numpy(X)).numpy() - g["logits"]).max() <= 1e-4      # gain-200 logits of O(10)
+
+    def predict(Xb):
+        with torch.no_grad():
+            return port(torch.from_numpy(np.ascontiguousarray(Xb))).argmax(dim=1).numpy()
+
+    np.random.seed(int(g["numpy_seed"]))
+    imp, base = explain_oracle.permutation_importance(predict, X, y, int(g["n_permutations"]), int(g["n_samples"]))
+    assert np.array_equal(imp, g["importance"])
+    assert imp.max() > 0.1 and (imp != 0).sum() > 20            # the case discriminates channels
+    order = np.argsort(-imp, kind="stable")
+    assert set(order[:3]) == set(g["sorted_order"][:3])
+
+
+def test_sensitivity_oracle_matches_reference_05(golden):
+    """05:687-719 restated around the exact steady state (null vector of the generator matrix) against the live reference's
+    sensitivity_analysis / get_steady_state (LSODA to t = 1000): 1e-7 on the state, 2e-5 on the finite differences (the
+    reference's own integration error, amplified by 1 / (0.4 k))."""
+    from oracle import explain_oracle
+    g = golden("ode_ref05_sensitivity.npz")
+
+    def steady(p):
+        Q = ode_oracle.generator_matrix(ode_oracle.rates_to_array(p))      # dy/dt = Q^T y (05:236-240): pi spans null(Q^T)
+        w, v = np.linalg.eig(Q.T)
+        pi = np.real(v[:, np.argmin(np.abs(w))])
+        return pi / pi.sum()
+
+    for j in (0, 1):
+        base = {k: float(g["params_%d" % j][i]) for i, k in enumerate(synth.RATE_ORDER)}
+        ss = steady(base)
+        assert np.abs(ss - g["steady_%d" % j]).max() <= 1e-7
+        assert list(g["names_%d" % j]) == list(base)
+        sens = explain_oracle.sensitivity(base, steady)
+        assert np.abs(sens - g["sens_%d" % j]).max() <= 2e-5, np.abs(sens - g["sens_%d" % j]).max()
