@@ -322,6 +322,9 @@ lstm_fused_bf16(const __grid_constant__ CUtensorMap tmIn,   // in  [T][Bc][Kin] 
       for (int q = 0; q < 2; ++q)
 #pragma unroll
         for (int i = 0; i < 32; ++i) c[q][i] = 0.f;
+      float4 bq[8];  // bias of the next slab's 32 columns: warp-uniform 16-byte shared-memory loads (the same four slabs every tile-step)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) bq[i] = bias4[i];
 
       for (int st = 0; st < T; ++st) {
         const int g = g0 + st;
@@ -349,13 +352,20 @@ lstm_fused_bf16(const __grid_constant__ CUtensorMap tmIn,   // in  [T][Bc][Kin] 
               if (lane == 0) mbar_arrive(acc_free(q));
             }
             const uint32_t* a = acc[sl & 1];
-            float4 bq[8];  // bias of the slab's 32 columns (gate*8 + u): warp-uniform 16-byte loads
+            // pre-activations = accumulator + bias; bq holds the slab's 32 bias values (gate*8 + u), loaded one slab AHEAD: ncu
+            // (profiles/r5_fused_epilogue_stalls.md) showed the first FADDs of every slab waiting on their just-issued LDS (short
+            // scoreboard, 12 % of the epilogue warps' samples), so the next slab's values are requested as soon as these adds have
+            // consumed the current ones and arrive under the slab's MUFU work
+            float pre[32];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) bq[i] = bias4[sl * 8 + i];
-            auto bval = [&](int gate, int u) {
-              const float4& v = bq[gate * 2 + (u >> 2)];
-              return (u & 3) == 0 ? v.x : (u & 3) == 1 ? v.y : (u & 3) == 2 ? v.z : v.w;
-            };
+            for (int i = 0; i < 8; ++i) {
+              pre[i * 4 + 0] = __uint_as_float(a[i * 4 + 0]) + bq[i].x;
+              pre[i * 4 + 1] = __uint_as_float(a[i * 4 + 1]) + bq[i].y;
+              pre[i * 4 + 2] = __uint_as_float(a[i * 4 + 2]) + bq[i].z;
+              pre[i * 4 + 3] = __uint_as_float(a[i * 4 + 3]) + bq[i].w;
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) bq[i] = bias4[((sl + 1) & 3) * 8 + i];
             uint32_t hp[4];
 #pragma unroll
             for (int u2 = 0; u2 < 4; ++u2) {
@@ -363,10 +373,10 @@ lstm_fused_bf16(const __grid_constant__ CUtensorMap tmIn,   // in  [T][Bc][Kin] 
 #pragma unroll
               for (int e = 0; e < 2; ++e) {
                 const int u = u2 * 2 + e;
-                const float ig = fmaf(0.5f, fr_tanh(__uint_as_float(a[0 * 8 + u]) + bval(0, u)), 0.5f);
-                const float fg = fmaf(0.5f, fr_tanh(__uint_as_float(a[1 * 8 + u]) + bval(1, u)), 0.5f);
-                const float gg = fr_tanh(__uint_as_float(a[2 * 8 + u]) + bval(2, u));
-                const float og = fmaf(0.5f, fr_tanh(__uint_as_float(a[3 * 8 + u]) + bval(3, u)), 0.5f);
+                const float ig = fmaf(0.5f, fr_tanh(pre[0 * 8 + u]), 0.5f);
+                const float fg = fmaf(0.5f, fr_tanh(pre[1 * 8 + u]), 0.5f);
+                const float gg = fr_tanh(pre[2 * 8 + u]);
+                const float og = fmaf(0.5f, fr_tanh(pre[3 * 8 + u]), 0.5f);
                 float& cc = c[q][sl * 8 + u];
                 cc = fmaf(fg, cc, ig * gg);
                 hv[e] = og * fr_tanh(cc);
