@@ -317,11 +317,11 @@ lstm_fused_bf16(const __grid_constant__ CUtensorMap tmIn,   // in  [T][Bc][Kin] 
       const int r = quarter * 32 + lane;
       const uint32_t taddr0 = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)ch * 128;
       const float4* bias4 = reinterpret_cast<const float4*>(bias_s) + ch * 32;
-      float c[2][32];
+      float2 c[2][16];  // fp32 cell state of the thread's 32 units per tile, as (even, odd) unit pairs
 #pragma unroll
       for (int q = 0; q < 2; ++q)
 #pragma unroll
-        for (int i = 0; i < 32; ++i) c[q][i] = 0.f;
+        for (int i = 0; i < 16; ++i) c[q][i] = make_float2(0.f, 0.f);
       float4 bq[8];  // bias of the next slab's 32 columns: warp-uniform 16-byte shared-memory loads (the same four slabs every tile-step)
 #pragma unroll
       for (int i = 0; i < 8; ++i) bq[i] = bias4[i];
@@ -356,33 +356,31 @@ lstm_fused_bf16(const __grid_constant__ CUtensorMap tmIn,   // in  [T][Bc][Kin] 
             // (profiles/r5_fused_epilogue_stalls.md) showed the first FADDs of every slab waiting on their just-issued LDS (short
             // scoreboard, 12 % of the epilogue warps' samples), so the next slab's values are requested as soon as these adds have
             // consumed the current ones and arrive under the slab's MUFU work
-            float pre[32];
+            // Packed fp32 (FADD2 / FFMA2 / FMUL2: two independent IEEE operations per issued instruction, so every lane computes
+            // exactly what the scalar form did): units are handled in (even, odd) pairs -- the accumulator registers of a
+            // 32-column tcgen05.ld and the .xy / .zw halves of the bias float4s are already aligned register pairs.
+            float2 pre[16];
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-              pre[i * 4 + 0] = __uint_as_float(a[i * 4 + 0]) + bq[i].x;
-              pre[i * 4 + 1] = __uint_as_float(a[i * 4 + 1]) + bq[i].y;
-              pre[i * 4 + 2] = __uint_as_float(a[i * 4 + 2]) + bq[i].z;
-              pre[i * 4 + 3] = __uint_as_float(a[i * 4 + 3]) + bq[i].w;
+              pre[i * 2 + 0] = __fadd2_rn(make_float2(__uint_as_float(a[i * 4 + 0]), __uint_as_float(a[i * 4 + 1])), make_float2(bq[i].x, bq[i].y));
+              pre[i * 2 + 1] = __fadd2_rn(make_float2(__uint_as_float(a[i * 4 + 2]), __uint_as_float(a[i * 4 + 3])), make_float2(bq[i].z, bq[i].w));
             }
 #pragma unroll
             for (int i = 0; i < 8; ++i) bq[i] = bias4[((sl + 1) & 3) * 8 + i];
+            const float2 half2v = make_float2(0.5f, 0.5f);
             uint32_t hp[4];
 #pragma unroll
-            for (int u2 = 0; u2 < 4; ++u2) {
-              float hv[2];
-#pragma unroll
-              for (int e = 0; e < 2; ++e) {
-                const int u = u2 * 2 + e;
-                const float ig = fmaf(0.5f, fr_tanh(pre[0 * 8 + u]), 0.5f);
-                const float fg = fmaf(0.5f, fr_tanh(pre[1 * 8 + u]), 0.5f);
-                const float gg = fr_tanh(pre[2 * 8 + u]);
-                const float og = fmaf(0.5f, fr_tanh(pre[3 * 8 + u]), 0.5f);
-                float& cc = c[q][sl * 8 + u];
-                cc = fmaf(fg, cc, ig * gg);
-                hv[e] = og * fr_tanh(cc);
-                if (STATS) { ssum += hv[e]; ssq = fmaf(hv[e], hv[e], ssq); }
-              }
-              __nv_bfloat162 pk = __floats2bfloat162_rn(hv[0], hv[1]);
+            for (int u2 = 0; u2 < 4; ++u2) {   // units 2*u2, 2*u2 + 1 of the slab: pre[gate * 4 + u2]
+              const float2 pi = pre[0 * 4 + u2], pf = pre[1 * 4 + u2], pg = pre[2 * 4 + u2], po = pre[3 * 4 + u2];
+              const float2 ig = __ffma2_rn(half2v, make_float2(fr_tanh(pi.x), fr_tanh(pi.y)), half2v);
+              const float2 fg = __ffma2_rn(half2v, make_float2(fr_tanh(pf.x), fr_tanh(pf.y)), half2v);
+              const float2 gg = make_float2(fr_tanh(pg.x), fr_tanh(pg.y));
+              const float2 og = __ffma2_rn(half2v, make_float2(fr_tanh(po.x), fr_tanh(po.y)), half2v);
+              float2& cc = c[q][sl * 4 + u2];
+              cc = __ffma2_rn(fg, cc, __fmul2_rn(ig, gg));
+              const float2 hv = __fmul2_rn(og, make_float2(fr_tanh(cc.x), fr_tanh(cc.y)));
+              if (STATS) { ssum += hv.x; ssq = fmaf(hv.x, hv.x, ssq); ssum += hv.y; ssq = fmaf(hv.y, hv.y, ssq); }
+              __nv_bfloat162 pk = __floats2bfloat162_rn(hv.x, hv.y);
               hp[u2] = *reinterpret_cast<uint32_t*>(&pk);
             }
             const uint4 hvec = make_uint4(hp[0], hp[1], hp[2], hp[3]);
