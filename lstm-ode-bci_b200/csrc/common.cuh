@@ -102,9 +102,28 @@ __device__ __forceinline__ float sigmoid_acc(float x) { return 1.0f / (1.0f + ex
 // fp32 forward 91.5 k -> 99.7 k windows/s, training step 16.3 -> 15.3 ms.  Absolute error ~1e-7 per gate; measured against the
 // reference's CPU path at logit gain 12: logits 7.2e-7 (H = 128) / 2.1e-6 (H = 256), attention <= 8e-9 -- inside the 1e-5 / 1e-6
 // parity tolerances with 5-14x to spare (3e-7 / 1e-6 with libm).  -DBCI_REC_ACCURATE_ACT (BCI_NVCC_DEFINES, build.py) restores libm.
+// fast_expf / fast_divf: the flush-to-zero forms `ex2.approx.ftz.f32` / `rcp.approx.ftz.f32` = ONE MUFU each.  CUDA's __expf / __fdividef
+// are the non-ftz approximations, which ptxas wraps in denormal range handling -- FSETP + two predicated FMULs around every MUFU.EX2,
+// FSETP + scaling FMULs around every MUFU.RCP: in the SASS of lstm_rec_f16x3_pipe that was 7 FSETP and ~14 of the 25 FMULs per hidden
+// unit (64 instructions per unit in all).  Inside the fast path both forms are the same MUFU instruction, so results only differ where a
+// value is below 2^-126 (flushed to 0) or a divisor above 2^126 (quotient flushed to 0): for the gate forms below that is sigma -> 0 / 1
+// and tanh -> -1 / 1 at |x| > 87, their correctly rounded limits.
+__device__ __forceinline__ float fast_ex2f(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float fast_expf(float x) { return fast_ex2f(x * 1.4426950408889634f); }
+__device__ __forceinline__ float fast_rcpf(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float fast_divf(float a, float b) { return a * fast_rcpf(b); }
+
 #ifndef BCI_REC_ACCURATE_ACT
-__device__ __forceinline__ float rec_sigmoid(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
-__device__ __forceinline__ float rec_tanh(float x) { return 1.0f - __fdividef(2.0f, 1.0f + __expf(2.0f * x)); }
+__device__ __forceinline__ float rec_sigmoid(float x) { return fast_rcpf(1.0f + fast_expf(-x)); }
+__device__ __forceinline__ float rec_tanh(float x) { return 1.0f - 2.0f * fast_rcpf(1.0f + fast_expf(2.0f * x)); }
 #else
 __device__ __forceinline__ float rec_sigmoid(float x) { return sigmoid_acc(x); }
 __device__ __forceinline__ float rec_tanh(float x) { return tanhf(x); }

@@ -262,7 +262,7 @@ attn_pool_stream_bf16(const __grid_constant__ CUtensorMap tmA,   // seq [T*Bc][2
         }
         score += part_s[r];
         asm volatile("bar.sync %0, 64;" ::"r"(5 + quarter) : "memory");
-        const float e = valid ? __expf(score - smax) : 0.f;
+        const float e = valid ? fast_expf(score - smax) : 0.f;
         const __nv_bfloat16 bb = __float2bfloat16_rn(e * rs);
         l += e;
         gamma = fmaf(__bfloat162float(bb), mean, gamma);

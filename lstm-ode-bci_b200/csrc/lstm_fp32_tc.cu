@@ -267,14 +267,14 @@ lstm_rec_f16x3(const float* __restrict__ G,        // [T*Bc][ldg] fp32: column d
             // one reciprocal each -- (b - 1) / ((1 + a)(b + 1)), a = e^-i, b = e^2g -- 8 MUFU operations per unit instead of 10.
             // Arguments are clamped where the functions are saturated to fp32 precision (|tanh| = 1 beyond 15, sigma(-30) =
             // 9e-14), so no product of exponentials overflows.
-            const float a_i = __expf(-fmaxf(pre[4 * u + 0], -30.f));
-            const float b_g = __expf(2.0f * fminf(fmaxf(pre[4 * u + 2], -15.f), 15.f));
-            const float ig_gg = __fdividef(b_g - 1.0f, (1.0f + a_i) * (b_g + 1.0f));
+            const float a_i = fast_expf(-fmaxf(pre[4 * u + 0], -30.f));
+            const float b_g = fast_expf(2.0f * fminf(fmaxf(pre[4 * u + 2], -15.f), 15.f));
+            const float ig_gg = fast_divf(b_g - 1.0f, (1.0f + a_i) * (b_g + 1.0f));
             const float fg = rec_sigmoid(pre[4 * u + 1]);
             cc = fmaf(fg, cc, ig_gg);
-            const float a_o = __expf(-fmaxf(pre[4 * u + 3], -30.f));
-            const float b_c = __expf(2.0f * fminf(fmaxf(cc, -15.f), 15.f));
-            hv[u] = __fdividef(b_c - 1.0f, (1.0f + a_o) * (b_c + 1.0f));
+            const float a_o = fast_expf(-fmaxf(pre[4 * u + 3], -30.f));
+            const float b_c = fast_expf(2.0f * fminf(fmaxf(cc, -15.f), 15.f));
+            hv[u] = fast_divf(b_c - 1.0f, (1.0f + a_o) * (b_c + 1.0f));
           }
         }
         if (live) {
@@ -580,14 +580,14 @@ lstm_rec_f16x3_pipe(const float* __restrict__ G, int ldg, const __half* __restri
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
               float& cc = c[nb * 32 + sl * 8 + u];
-              const float a_i = __expf(-fmaxf(pre[4 * u + 0], -30.f));
-              const float b_g = __expf(2.0f * fminf(fmaxf(pre[4 * u + 2], -15.f), 15.f));
-              const float ig_gg = __fdividef(b_g - 1.0f, (1.0f + a_i) * (b_g + 1.0f));
+              const float a_i = fast_expf(-fmaxf(pre[4 * u + 0], -30.f));
+              const float b_g = fast_expf(2.0f * fminf(fmaxf(pre[4 * u + 2], -15.f), 15.f));
+              const float ig_gg = fast_divf(b_g - 1.0f, (1.0f + a_i) * (b_g + 1.0f));
               const float fg = rec_sigmoid(pre[4 * u + 1]);
               cc = fmaf(fg, cc, ig_gg);
-              const float a_o = __expf(-fmaxf(pre[4 * u + 3], -30.f));
-              const float b_c = __expf(2.0f * fminf(fmaxf(cc, -15.f), 15.f));
-              hv[u] = __fdividef(b_c - 1.0f, (1.0f + a_o) * (b_c + 1.0f));
+              const float a_o = fast_expf(-fmaxf(pre[4 * u + 3], -30.f));
+              const float b_c = fast_expf(2.0f * fminf(fmaxf(cc, -15.f), 15.f));
+              hv[u] = fast_divf(b_c - 1.0f, (1.0f + a_o) * (b_c + 1.0f));
             }
             if (live && out) stg256(orow + sl * 8, hv);
             uint32_t hi[4], lo[4];
