@@ -56,6 +56,10 @@ __device__ __forceinline__ double df2t_step(const FiltCoef& c, double (&z)[ORD],
 // (Round 2 tried 4096-sample chunks with 6144 of warm-up -- 4x the threads for 1.67x the arithmetic: 14 recordings per call ran 6 %
 // faster, 36 recordings 34 % slower (15.3 instead of 11.4 ms): from ~80 k threads on the kernel is no longer latency-bound.  Kept as is.)
 constexpr int PP_CHUNK = 16384, PP_WARM = 8192;
+// (Session 5, ncu source view: 60 % of the forward pass's samples sit on the use of the batch loaded one batch earlier, 64 % in the
+// backward pass -- the 32 lanes of a warp walk 32 rows 0.6-1.2 MB apart and the passes stream 6.5 GB in all, so a load costs more than
+// the ~600 cycles of recursion it is hidden behind.  An L2 prefetch 96 samples ahead made both passes SLOWER (4.0 -> 4.5, 4.5 -> 6.3 ms):
+// the fetch itself is not what the warps wait for.  Left as measured.)
 
 // pass = 0: forward over the odd-extended input -> yf (rows x m);  pass = 1: backward over yf -> yb (rows x m), plus per-chunk
 // (sum, sumsq) of the kept samples [p, p+n)
@@ -66,6 +70,7 @@ filtfilt_chunk_kernel(const InT* __restrict__ raw, long long n, int rows, int p,
   const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (gid >= (long long)rows * chunks) return;
   // consecutive threads = consecutive rows of the same chunk index: the 32 lanes of a warp walk 32 different rows in step
+  // (the other mapping -- a warp = the chunks of 3-4 rows, i.e. 4-8 pages per warp access instead of 32 -- measured 9 % slower)
   const int ck = (int)(gid / rows), row = (int)(gid - (long long)ck * rows);
   const long long m = n + 2 * (long long)p;
   const InT* x = raw + (long long)row * n;
@@ -188,39 +193,49 @@ __global__ void rowstats_kernel(const double* __restrict__ partial, int chunks, 
 constexpr int WIN_TILE = 128;
 
 // grid = (sample tiles, recordings).  ybuf rows are (recording, channel) of length m = n + 2p, valid part at offset p.
+// ncu on the first version (profiles/r5_preproc.md): issue slots 79 % busy at 23 % of DRAM peak -- ~240 instructions per sample, most
+// of them 64-bit and runtime-divisor integer divisions of the index arithmetic.  Here the load phase indexes with shifts (a warp =
+// 32 consecutive samples of one channel: coalesced fp64 reads, mean / std broadcast), the store phase maps lanes to channels
+// (c = tid % 64, four samples per pass: no division by C), and the window range of a sample costs two 32-bit divisions.
 __global__ void __launch_bounds__(256)
-zscore_window_kernel(const double* __restrict__ ybuf, long long n, int p, int C, int seq_len, int step, long long n_seq,
+zscore_window_kernel(const double* __restrict__ ybuf, int n, int p, int C, int seq_len, int step, int n_seq,
                      const double* __restrict__ mean, const double* __restrict__ stdv, float* __restrict__ X /* (R*n_seq, seq_len, C) */,
                      double* __restrict__ filtered /* optional (R, C, n) */) {
-  extern __shared__ float win_tile[];  // [WIN_TILE][C + 1]
+  extern __shared__ float win_tile[];  // [WIN_TILE][CS], CS odd (<= C + 1): the transposing writes of a warp hit 32 different banks
+  __shared__ int w_first[WIN_TILE], w_last[WIN_TILE];   // windows containing sample k0 + k (two 32-bit divisions per SAMPLE, not per element)
   const int r = blockIdx.y;
-  const long long k0 = (long long)blockIdx.x * WIN_TILE;
-  const long long m = n + 2 * (long long)p;
-  const int CS = C + 1;
+  const int k0 = blockIdx.x * WIN_TILE;
+  const long long m = (long long)n + 2 * (long long)p;
+  const int CS = C | 1;
+  if (threadIdx.x < WIN_TILE) {
+    const int g = k0 + threadIdx.x;
+    // windows w with w*step <= g < w*step + seq_len and w < n_seq
+    int w_hi = g / step;
+    if (w_hi >= n_seq) w_hi = n_seq - 1;
+    w_first[threadIdx.x] = g < seq_len ? 0 : (g - seq_len + step) / step;   // ceil((g - seq_len + 1) / step)
+    w_last[threadIdx.x] = w_hi;
+  }
   for (int e = threadIdx.x; e < C * WIN_TILE; e += blockDim.x) {
-    const int c = e / WIN_TILE, k = e - c * WIN_TILE;
-    const long long g = k0 + k;
+    const int c = e >> 7, k = e & (WIN_TILE - 1);   // a warp = 32 consecutive samples of one channel: coalesced reads, mean / std broadcast
+    const int g = k0 + k;
     if (g < n) {
       const long long row = (long long)r * C + c;
       const double v = ybuf[row * m + p + g];
-      if (filtered) filtered[row * n + g] = v;
+      if (filtered) filtered[row * (long long)n + g] = v;
       win_tile[k * CS + c] = (float)((v - mean[row]) / stdv[row]);
     }
   }
   __syncthreads();
-  for (int e = threadIdx.x; e < C * WIN_TILE; e += blockDim.x) {
-    const int k = e / C, c = e - k * C;
-    const long long g = k0 + k;
+  const int c0 = threadIdx.x & 63;
+  for (int k = threadIdx.x >> 6; k < WIN_TILE; k += 4) {
+    const int g = k0 + k;
     if (g >= n) break;
-    const float v = win_tile[k * CS + c];
-    // windows w with w*step <= g < w*step + seq_len and w < n_seq
-    long long w_hi = g / step;
-    if (w_hi >= n_seq) w_hi = n_seq - 1;
-    long long w_lo = (g - seq_len + step) / step;  // ceil((g - seq_len + 1) / step) for g - seq_len + 1 > 0
-    if (g < seq_len) w_lo = 0;
-    for (long long w = w_lo; w <= w_hi; ++w) {
-      const long long t = g - w * step;
-      if (t >= 0 && t < seq_len) X[(((long long)r * n_seq + w) * seq_len + t) * C + c] = v;
+    const int w_hi = w_last[k];
+    for (int w = w_first[k]; w <= w_hi; ++w) {
+      const int t = g - w * step;
+      if (t < 0 || t >= seq_len) continue;
+      float* dst = X + (((long long)r * n_seq + w) * seq_len + t) * C;
+      for (int c = c0; c < C; c += 64) dst[c] = win_tile[k * CS + c];
     }
   }
 }
@@ -316,6 +331,7 @@ extern "C" int bci_preprocess(const bci_preproc_args* a, const void* raw, float*
   if (rc) return rc;
   rowstats_kernel<<<ceil_div(rows, 128), 128, 0, st>>>(sums, chunks, n, rows, a->mean_in, a->std_in, a->n_channels, mean_out, std_out);
   BCI_LAUNCH_OK();
+  BCI_REQUIRE(m < (1ll << 31) - WIN_TILE, BCI_EINVAL, "bci_preprocess: recordings of more than 2^31 samples are not supported");
   const long long n_seq = (n - a->seq_len) / a->step + 1;
   const size_t smem = (size_t)WIN_TILE * (a->n_channels + 1) * sizeof(float);
   static size_t smem_set = 0;
@@ -324,7 +340,7 @@ extern "C" int bci_preprocess(const bci_preproc_args* a, const void* raw, float*
     smem_set = smem;
   }
   dim3 grid((unsigned)ceil_div64(n, WIN_TILE), (unsigned)a->n_recordings);
-  zscore_window_kernel<<<grid, 256, smem, st>>>(ybuf, n, a->padlen, a->n_channels, a->seq_len, a->step, n_seq, mean_out, std_out,
+  zscore_window_kernel<<<grid, 256, smem, st>>>(ybuf, (int)n, a->padlen, a->n_channels, a->seq_len, a->step, (int)n_seq, mean_out, std_out,
                                                 windows, filtered);
   BCI_LAUNCH_OK();
   return BCI_OK;
