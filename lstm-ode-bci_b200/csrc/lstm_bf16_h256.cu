@@ -558,9 +558,9 @@ lstm_rec256_bf16_pipe(const __nv_bfloat16* __restrict__ G, const __grid_constant
       const int b0 = (2 * tp + s) * HR_M;
       item_begin(dir, g0 == 0);
       const bool live = b0 + r < Bc;
-      float c[64];   // [block][32 units]
+      float2 c[32];   // [block][16 (even, odd) unit pairs]: fp32 cell state
 #pragma unroll
-      for (int i = 0; i < 64; ++i) c[i] = 0.f;
+      for (int i = 0; i < 32; ++i) c[i] = make_float2(0.f, 0.f);
       for (int st = 0; st < T; ++st) {
         const int g = g0 + st;
         const int t = dir ? (T - 1 - st) : st;
@@ -591,26 +591,26 @@ lstm_rec256_bf16_pipe(const __nv_bfloat16* __restrict__ G, const __grid_constant
             }
             tmem_ld_wait();
             const uint32_t* gw = reinterpret_cast<const uint32_t*>(gbuf[sl % 3]);
-            auto gval = [&](int gate, int u) {
-              const uint32_t wv = gw[gate * 4 + (u >> 1)];
-              return __uint_as_float((u & 1) ? (wv & 0xFFFF0000u) : (wv << 16));
+            // packed fp32 (FADD2 / FFMA2 / FMUL2, bit-identical to the scalar form): units in (even, odd) pairs -- one 32-bit word of
+            // G holds the bf16 pre-activations of such a pair, the accumulator registers of the pair are adjacent
+            auto pre2 = [&](int gate, int u2) {
+              const uint32_t wv = gw[gate * 4 + u2];
+              return __fadd2_rn(make_float2(__uint_as_float(acc[gate * 8 + 2 * u2]), __uint_as_float(acc[gate * 8 + 2 * u2 + 1])),
+                                make_float2(__uint_as_float(wv << 16), __uint_as_float(wv & 0xFFFF0000u)));
             };
+            const float2 half2v = make_float2(0.5f, 0.5f);
             uint32_t hp[4];
 #pragma unroll
             for (int u2 = 0; u2 < 4; ++u2) {
-              float hv[2];
-#pragma unroll
-              for (int e = 0; e < 2; ++e) {
-                const int u = u2 * 2 + e;
-                const float ig = fmaf(0.5f, hr_tanh(__uint_as_float(acc[0 * 8 + u]) + gval(0, u)), 0.5f);
-                const float fg = fmaf(0.5f, hr_tanh(__uint_as_float(acc[1 * 8 + u]) + gval(1, u)), 0.5f);
-                const float gg = hr_tanh(__uint_as_float(acc[2 * 8 + u]) + gval(2, u));
-                const float og = fmaf(0.5f, hr_tanh(__uint_as_float(acc[3 * 8 + u]) + gval(3, u)), 0.5f);
-                float& cc = c[nb * 32 + sl * 8 + u];
-                cc = fmaf(fg, cc, ig * gg);
-                hv[e] = og * hr_tanh(cc);
-              }
-              __nv_bfloat162 pk = __floats2bfloat162_rn(hv[0], hv[1]);
+              const float2 pi = pre2(0, u2), pf = pre2(1, u2), pg = pre2(2, u2), po = pre2(3, u2);
+              const float2 ig = __ffma2_rn(half2v, make_float2(hr_tanh(pi.x), hr_tanh(pi.y)), half2v);
+              const float2 fg = __ffma2_rn(half2v, make_float2(hr_tanh(pf.x), hr_tanh(pf.y)), half2v);
+              const float2 gg = make_float2(hr_tanh(pg.x), hr_tanh(pg.y));
+              const float2 og = __ffma2_rn(half2v, make_float2(hr_tanh(po.x), hr_tanh(po.y)), half2v);
+              float2& cc = c[nb * 16 + sl * 4 + u2];
+              cc = __ffma2_rn(fg, cc, __fmul2_rn(ig, gg));
+              const float2 hv = __fmul2_rn(og, make_float2(hr_tanh(cc.x), hr_tanh(cc.y)));
+              __nv_bfloat162 pk = __floats2bfloat162_rn(hv.x, hv.y);
               hp[u2] = *reinterpret_cast<uint32_t*>(&pk);
             }
             if (sl == 0) {   // own atom nb still holds h_{g-1}: see "who may overwrite what"
