@@ -62,6 +62,16 @@ __device__ __forceinline__ float gelu_tanh_fast(float y) {
   return fmaf(hy, t, hy);
 }
 
+// the same on a pair of values (two scalar MUFUs, everything else packed)
+__device__ __forceinline__ float2 gelu_tanh_fast2(float2 y) {
+  const float2 u = __fmul2_rn(y, __ffma2_rn(make_float2(0.0356774081f, 0.0356774081f), __fmul2_rn(y, y), make_float2(0.7978845608f, 0.7978845608f)));
+  float2 t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t.x) : "f"(u.x));
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t.y) : "f"(u.y));
+  const float2 hy = __fmul2_rn(make_float2(0.5f, 0.5f), y);
+  return __ffma2_rn(hy, t, hy);
+}
+
 __device__ __forceinline__ void bulk_copy_g2s(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(dst_smem), "l"(src), "r"(bytes), "r"(bar) : "memory");
@@ -116,7 +126,13 @@ input_proj_bf16(const InputView x,                         // windows of T x C e
     tmem_alloc(smem_u32(tmem_slot), 256);
     tmem_relinquish();
   }
-  if (warp >= 6 && warp < 10) par_s[(warp - 6) * 32 + lane] = __ldg(par + (warp - 6) * 32 + lane);
+  // parameters of column pair j = (2j, 2j+1), the unit of the packed-fp32 epilogue: par_s[2j] = {b0, b1, gamma0, gamma1}, par_s[2j+1] = {beta0, beta1, -, -}
+  if (warp >= 6 && warp < 10) {
+    const int col = (warp - 6) * 32 + lane;
+    const float4 pc = __ldg(par + col);   // {bias, LN weight, LN bias, -} of one column
+    float* pf = reinterpret_cast<float*>(par_s) + (col >> 1) * 8 + (col & 1);
+    pf[0] = pc.x; pf[2] = pc.y; pf[4] = pc.z;
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -205,16 +221,20 @@ input_proj_bf16(const InputView x,                         // windows of T x C e
       tmem_ld_wait();
       tc_fence_before();
       mbar_arrive(t_empty(s));               // TMEM accumulator free again
-      float sum = 0.f, sq = 0.f;
+      // packed fp32 (FADD2 / FFMA2 / FMUL2) on column pairs: the accumulator registers of a pair are adjacent
+      float2 sum2 = make_float2(0.f, 0.f), sq2 = make_float2(0.f, 0.f);
 #pragma unroll
       for (int ch = 0; ch < 2; ++ch)
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const float v = __uint_as_float(a[ch][j]) + par_s[grp * 64 + ch * 32 + j].x;
-          a[ch][j] = __float_as_uint(v);
-          sum += v;
-          sq = fmaf(v, v, sq);
+        for (int j = 0; j < 16; ++j) {
+          const float4 pa = par_s[(grp * 32 + ch * 16 + j) * 2];
+          const float2 v = __fadd2_rn(make_float2(__uint_as_float(a[ch][2 * j]), __uint_as_float(a[ch][2 * j + 1])), make_float2(pa.x, pa.y));
+          a[ch][2 * j] = __float_as_uint(v.x);
+          a[ch][2 * j + 1] = __float_as_uint(v.y);
+          sum2 = __fadd2_rn(sum2, v);
+          sq2 = __ffma2_rn(v, v, sq2);
         }
+      const float sum = sum2.x + sum2.y, sq = sq2.x + sq2.y;
       part_s[grp * IP_M + r] = make_float2(sum, sq);
       // staging atom free? (this group's previous TMA store has finished reading it)
       if (issuer) tma_store_wait_read();
@@ -222,15 +242,17 @@ input_proj_bf16(const InputView x,                         // windows of T x C e
       const float2 other = part_s[(grp ^ 1) * IP_M + r];
       const float mean = (sum + other.x) * (1.0f / IP_N);
       const float rstd = 1.0f / sqrtf(fmaxf((sq + other.y) * (1.0f / IP_N) - mean * mean, 0.f) + 1e-5f);
+      const float2 nmean2 = make_float2(-mean, -mean), rstd2 = make_float2(rstd, rstd);
 #pragma unroll
       for (int ch = 0; ch < 2; ++ch) {
         uint32_t o[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
-          const float4 p0 = par_s[grp * 64 + ch * 32 + 2 * j], p1 = par_s[grp * 64 + ch * 32 + 2 * j + 1];
-          const float y0 = fmaf((__uint_as_float(a[ch][2 * j]) - mean) * rstd, p0.y, p0.z);
-          const float y1 = fmaf((__uint_as_float(a[ch][2 * j + 1]) - mean) * rstd, p1.y, p1.z);
-          __nv_bfloat162 pk = __floats2bfloat162_rn(gelu_tanh_fast(y0), gelu_tanh_fast(y1));
+          const float4 pa = par_s[(grp * 32 + ch * 16 + j) * 2], pb = par_s[(grp * 32 + ch * 16 + j) * 2 + 1];
+          const float2 v = make_float2(__uint_as_float(a[ch][2 * j]), __uint_as_float(a[ch][2 * j + 1]));
+          const float2 y = __ffma2_rn(__fmul2_rn(__fadd2_rn(v, nmean2), rstd2), make_float2(pa.z, pa.w), make_float2(pb.x, pb.y));
+          const float2 g = gelu_tanh_fast2(y);
+          __nv_bfloat162 pk = __floats2bfloat162_rn(g.x, g.y);
           o[j] = *reinterpret_cast<uint32_t*>(&pk);
         }
 #pragma unroll
