@@ -9,8 +9,8 @@
 // initial state zi * ext[0] (zi = lfilter_zi(b, a): the steady state of a unit step), runs it again over the reversed
 // output with zi * y[-1], reverses and trims the padding.
 //
-// Layout: one thread per (recording, channel, chunk of 16 384 samples) walks its samples serially in fp64 with 8 192 samples of
-// warm-up (see filtfilt_chunk_kernel); the forward pass writes the extended signal to the workspace, the backward pass reads
+// Layout: one thread per (recording, channel, chunk of 8 192 samples) walks its samples serially in fp64 with 8 192 samples of
+// warm-up (see filtfilt_tile_kernel, the warp-cooperative default, and filtfilt_chunk_kernel, the first form); the forward pass writes the extended signal to the workspace, the backward pass reads
 // it and writes a second buffer plus per-chunk sum / sum of squares; a last kernel normalises, transposes through shared
 // memory and writes every sample into all windows that contain it (coalesced 4-byte stores, C contiguous floats per step).
 // Bound: the FP64 pipe (33 unfused operations per sample and pass); bci_fp64_peak_probe measures its peak.
@@ -55,7 +55,13 @@ __device__ __forceinline__ double df2t_step(const FiltCoef& c, double (&z)[ORD],
 // 8 cycles per SM sub-partition on B200; a single warp per 32 rows left 130 of 148 SMs idle).
 // (Round 2 tried 4096-sample chunks with 6144 of warm-up -- 4x the threads for 1.67x the arithmetic: 14 recordings per call ran 6 %
 // faster, 36 recordings 34 % slower (15.3 instead of 11.4 ms): from ~80 k threads on the kernel is no longer latency-bound.  Kept as is.)
-constexpr int PP_CHUNK = 16384, PP_WARM = 8192;
+// (Session 5: with the warp-cooperative kernel below the passes are no longer bound by their scattered memory requests, and more, shorter
+// chunks now pay: 8192-sample chunks -- 2x the warps for 1.33x the arithmetic -- take 7.30 instead of 7.62 ms for 36 recordings and 3.65
+// instead of 5.30 ms for the 14-recording batches of the config-5 pipeline; 4096-sample chunks 8.31 / 3.68 ms.)
+#ifndef BCI_PP_CHUNK
+#define BCI_PP_CHUNK 8192
+#endif
+constexpr int PP_CHUNK = BCI_PP_CHUNK, PP_WARM = 8192;
 // (Session 5, ncu source view: 60 % of the forward pass's samples sit on the use of the batch loaded one batch earlier, 64 % in the
 // backward pass -- the 32 lanes of a warp walk 32 rows 0.6-1.2 MB apart and the passes stream 6.5 GB in all, so a load costs more than
 // the ~600 cycles of recursion it is hidden behind.  An L2 prefetch 96 samples ahead made both passes SLOWER (4.0 -> 4.5, 4.5 -> 6.3 ms):
@@ -168,6 +174,150 @@ filtfilt_chunk_kernel(const InT* __restrict__ raw, long long n, int rows, int p,
   }
 }
 
+// Warp-cooperative form of the same passes (session 5; the default).  ncu on filtfilt_chunk_kernel (profiles/r5_preproc.md): every
+// load / store instruction of a warp touches 32 sectors in 32 different rows; the warps wait on those requests (long scoreboard 3.8 of
+// 6.0 cycles per issued instruction), and putting MORE of them in flight (L2 prefetch, a third register batch) made the passes slower --
+// the memory pipeline is bound by the number of scattered requests, not by latency or bytes.  Here the 32 lanes of a warp still own 32
+// rows for the serial recursion, but global memory is only touched a TILE at a time: 32 consecutive samples of each of the 32 rows,
+// loaded with lane = sample (one contiguous 128- / 256-byte request per row), transposed through shared memory (row stride 33), consumed
+// and overwritten in place by the owning lane, and written back the same way.  The next tile's loads are issued before the current tile
+// is computed (~5 000 cycles of recursion).  Arithmetic per row is unchanged (same operations, same order): results are bit-identical.
+constexpr int PP_TILE = 32;
+constexpr int PP_TW = 4;   // warps per block
+
+template <typename InT, int ORD, int PASS>
+__global__ void __launch_bounds__(PP_TW * 32)
+filtfilt_tile_kernel(const InT* __restrict__ raw, long long n, int rows, int p, const FiltCoef c, const double* __restrict__ yf,
+                     double* __restrict__ yout, int chunks, double* __restrict__ partial /* rows x chunks x 2 */) {
+  __shared__ double tile_s[PP_TW][PP_TILE][PP_TILE + 1];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int warps_per_ck = (rows + 31) / 32;
+  const long long wg = (long long)blockIdx.x * PP_TW + wib;
+  if (wg >= (long long)warps_per_ck * chunks) return;   // warp-uniform
+  const int ck = (int)(wg / warps_per_ck), row0 = (int)(wg - (long long)ck * warps_per_ck) * 32;
+  const int row = row0 + lane;
+  const bool valid = row < rows;
+  const int rowc = valid ? row : rows - 1;               // lanes past the last row shadow it and store nothing
+  const long long m = n + 2 * (long long)p;
+  const InT* x = raw + (long long)rowc * n;
+  const double* src = yf + (long long)rowc * m;
+  double* dst = yout + (long long)rowc * m;
+  double (*tl)[PP_TILE + 1] = tile_s[wib];
+  double z[ORD];
+  auto row_of = [&](int rr) { const int r2 = row0 + rr; return r2 < rows ? r2 : rows - 1; };
+
+  if (PASS == 0) {
+    const long long s0 = (long long)ck * PP_CHUNK, e0 = (s0 + PP_CHUNK < m) ? s0 + PP_CHUNK : m;
+    long long i = s0 - PP_WARM;
+    if (i <= 0) {
+      i = 0;
+      const double x0 = ext_sample(x, n, p, 0);
+#pragma unroll
+      for (int j = 0; j < ORD; ++j) z[j] = __dmul_rn(c.zi[j], x0);
+    } else {
+#pragma unroll
+      for (int j = 0; j < ORD; ++j) z[j] = 0.0;
+    }
+    const long long in_end = (e0 < p + n) ? e0 : p + n;
+    InT nxt[PP_TILE];
+    auto load_tile = [&](long long kt) {     // lane = sample kt + lane of row rr
+#pragma unroll
+      for (int rr = 0; rr < PP_TILE; ++rr) nxt[rr] = raw[(long long)row_of(rr) * n + (kt - p) + lane];
+    };
+    auto stage_tile = [&]() {
+#pragma unroll
+      for (int rr = 0; rr < PP_TILE; ++rr) tl[rr][lane] = (double)nxt[rr];
+    };
+    bool have = false;
+    for (long long k = i; k < e0; k += PP_TILE) {
+      const bool keep = k >= s0;
+      const bool interior = k >= p && k + PP_TILE <= in_end;
+      if (!interior) {   // the odd-extended edges and the last partial tile: per-lane, sample by sample
+        const long long kb = (k + PP_TILE < e0) ? k + PP_TILE : e0;
+        for (long long kk = k; kk < kb; ++kk) {
+          const double o = df2t_step<ORD>(c, z, ext_sample(x, n, p, kk));
+          if (keep && valid) dst[kk] = o;
+        }
+        have = false;
+        continue;
+      }
+      if (!have) { load_tile(k); stage_tile(); __syncwarp(); }
+      const bool next_interior = k + PP_TILE >= p && k + 2 * PP_TILE <= in_end && k + PP_TILE < e0;
+      if (next_interior) load_tile(k + PP_TILE);
+#pragma unroll 8
+      for (int j = 0; j < PP_TILE; ++j) tl[lane][j] = df2t_step<ORD>(c, z, tl[lane][j]);
+      __syncwarp();
+      if (keep) {
+#pragma unroll 8
+        for (int rr = 0; rr < PP_TILE; ++rr)
+          if (row0 + rr < rows) yout[(long long)(row0 + rr) * m + k + lane] = tl[rr][lane];
+      }
+      __syncwarp();
+      if (next_interior) { stage_tile(); __syncwarp(); }
+      have = next_interior;
+    }
+  } else {
+    // backward: chunk ck covers [lo, hi) counted from the END of the extended signal; descending tiles [k - 31, k]
+    const long long hi = m - (long long)ck * PP_CHUNK;              // exclusive upper index
+    const long long lo = (hi - PP_CHUNK > 0) ? hi - PP_CHUNK : 0;   // inclusive lower index
+    long long i = hi - 1 + PP_WARM;
+    if (i >= m - 1) {
+      i = m - 1;
+      const double yl = src[m - 1];
+#pragma unroll
+      for (int j = 0; j < ORD; ++j) z[j] = __dmul_rn(c.zi[j], yl);
+    } else {
+#pragma unroll
+      for (int j = 0; j < ORD; ++j) z[j] = 0.0;
+    }
+    double sm = 0.0, ss = 0.0;
+    double nxt[PP_TILE];
+    auto load_tile = [&](long long kt) {     // tile [kt - 31, kt]: lane = sample kt - 31 + lane of row rr
+#pragma unroll
+      for (int rr = 0; rr < PP_TILE; ++rr) nxt[rr] = yf[(long long)row_of(rr) * m + (kt - (PP_TILE - 1)) + lane];
+    };
+    auto stage_tile = [&]() {
+#pragma unroll
+      for (int rr = 0; rr < PP_TILE; ++rr) tl[rr][lane] = nxt[rr];
+    };
+    bool have = false;
+    for (long long k = i; k >= lo; k -= PP_TILE) {
+      const bool keep = k <= hi - 1;
+      const bool full = k - (PP_TILE - 1) >= lo;
+      if (!full) {
+        for (long long kk = k; kk >= lo; --kk) {
+          const double o = df2t_step<ORD>(c, z, src[kk]);
+          if (keep) { if (valid) dst[kk] = o; if (kk >= p && kk < p + n) { sm += o; ss = fma(o, o, ss); } }
+        }
+        break;
+      }
+      if (!have) { load_tile(k); stage_tile(); __syncwarp(); }
+      const bool next_full = k - (2 * PP_TILE - 1) >= lo;
+      if (next_full) load_tile(k - PP_TILE);
+#pragma unroll 8
+      for (int j = PP_TILE - 1; j >= 0; --j) {
+        const double o = df2t_step<ORD>(c, z, tl[lane][j]);
+        tl[lane][j] = o;
+        const long long kk = k - (PP_TILE - 1) + j;
+        if (keep && kk >= p && kk < p + n) { sm += o; ss = fma(o, o, ss); }
+      }
+      __syncwarp();
+      if (keep) {
+#pragma unroll 8
+        for (int rr = 0; rr < PP_TILE; ++rr)
+          if (row0 + rr < rows) yout[(long long)(row0 + rr) * m + (k - (PP_TILE - 1)) + lane] = tl[rr][lane];
+      }
+      __syncwarp();
+      if (next_full) { stage_tile(); __syncwarp(); }
+      have = next_full;
+    }
+    if (valid) {
+      partial[((long long)row * chunks + ck) * 2] = sm;
+      partial[((long long)row * chunks + ck) * 2 + 1] = ss;
+    }
+  }
+}
+
 // mean / std per row from the sums (np.mean, np.std ddof=0, std floored at 1e-10: 02:145-151) unless given
 __global__ void rowstats_kernel(const double* __restrict__ partial, int chunks, long long n, int rows, const double* __restrict__ mean_in,
                                 const double* __restrict__ std_in, int C, double* __restrict__ mean_out, double* __restrict__ std_out) {
@@ -243,11 +393,21 @@ zscore_window_kernel(const double* __restrict__ ybuf, int n, int p, int C, int s
 template <typename InT, int ORD>
 static int launch_filtfilt_ord(const InT* raw, long long n, int rows, int p, const FiltCoef& c, double* yf, double* yb, int chunks,
                                double* partial, cudaStream_t st) {
-  const long long threads = (long long)rows * chunks;
-  const unsigned blocks = (unsigned)ceil_div64(threads, 128);
-  filtfilt_chunk_kernel<InT, ORD, 0><<<blocks, 128, 0, st>>>(raw, n, rows, p, c, nullptr, yf, chunks, partial);
+  static const bool lanes_form = [] { const char* e = getenv("BCI_PP_FILTER"); return e && e[0] == 'l'; }();   // BCI_PP_FILTER=lanes: the first form
+  if (lanes_form) {
+    const long long threads = (long long)rows * chunks;
+    const unsigned blocks = (unsigned)ceil_div64(threads, 128);
+    filtfilt_chunk_kernel<InT, ORD, 0><<<blocks, 128, 0, st>>>(raw, n, rows, p, c, nullptr, yf, chunks, partial);
+    BCI_LAUNCH_OK();
+    filtfilt_chunk_kernel<InT, ORD, 1><<<blocks, 128, 0, st>>>(raw, n, rows, p, c, yf, yb, chunks, partial);
+    BCI_LAUNCH_OK();
+    return BCI_OK;
+  }
+  const long long warps = (long long)((rows + 31) / 32) * chunks;
+  const unsigned blocks = (unsigned)ceil_div64(warps, PP_TW);
+  filtfilt_tile_kernel<InT, ORD, 0><<<blocks, PP_TW * 32, 0, st>>>(raw, n, rows, p, c, nullptr, yf, chunks, partial);
   BCI_LAUNCH_OK();
-  filtfilt_chunk_kernel<InT, ORD, 1><<<blocks, 128, 0, st>>>(raw, n, rows, p, c, yf, yb, chunks, partial);
+  filtfilt_tile_kernel<InT, ORD, 1><<<blocks, PP_TW * 32, 0, st>>>(raw, n, rows, p, c, yf, yb, chunks, partial);
   BCI_LAUNCH_OK();
   return BCI_OK;
 }
