@@ -720,10 +720,12 @@ def main():
                 staging_env_set = False
             integ.predict_batch(xd, forecast_steps=20, batch_size=512, show_progress=False)
             torch.cuda.synchronize()
-            t0 = time.perf_counter()
-            trj, _pp, _pd = integ.predict_batch(xd, forecast_steps=20, batch_size=512, show_progress=False)
-            dsec = time.perf_counter() - t0
-            line["dropin_predict_batch"] = {"value": nd / dsec, "unit": "windows/s", "windows": nd, "seconds": dsec,
+            dsec = float("inf")
+            for _ in range(3):   # host-bound leg on a shared VM: best of three calls (0.1-0.2 s each)
+                t0 = time.perf_counter()
+                trj, _pp, _pd = integ.predict_batch(xd, forecast_steps=20, batch_size=512, show_progress=False)
+                dsec = min(dsec, time.perf_counter() - t0)
+            line["dropin_predict_batch"] = {"value": nd / dsec, "unit": "windows/s", "windows": nd, "seconds": dsec, "timing": "best of 3 calls",
                                             "precision": "auto -> bf16 under the method's own autocast",
                                             "host_bytes_in": int(xd.nbytes), "staging_threads": integration._staging_threads(),
                                             # the native staging copy narrows the pageable fp32 windows to bf16 (the rounding the
