@@ -68,3 +68,27 @@ def test_host_stage_is_bit_exact_round_to_nearest_even():
             assert np.array_equal(d32[off:].view(np.uint32), src.view(np.uint32)) and not d32[:off].any()
     assert N.lib().bci_host_stage(None, src.ctypes.data, 4, 1, 1) != 0
     N.check(N.lib().bci_host_stage(None, None, 0, 1, 4))
+
+
+def test_permutation_importance_host_side_contract():
+    """explain.compute_permutation_importance without a GPU: a CPU model is refused loudly (no CPU fallback), and the oracle's
+    host-side gather -- what bci_permute_channels replaces -- is the reference's `X_permuted[:, :, ch] = X_subset[perm, :, ch]`."""
+    import pytest
+    from lstm_ode_bci_b200 import _native as N
+    from lstm_ode_bci_b200 import explain
+    from oracle import explain_oracle
+    m = lstm.EnhancedLSTMModel(5, 128, 1, 2)
+    X = np.random.default_rng(0).standard_normal((6, 8, 5)).astype(np.float32)
+    y = np.zeros(6, dtype=np.int64)
+    np.random.seed(0)
+    with pytest.raises(N.BciError):
+        explain.compute_permutation_importance(m, X, y, n_permutations=1, n_samples=4)
+    perm = np.array([3, 0, 5, 1, 2, 4])
+    Xp = explain_oracle.permuted_copy(X, perm, 2)
+    assert np.array_equal(Xp[:, :, 2], X[perm][:, :, 2]) and np.array_equal(np.delete(Xp, 2, axis=2), np.delete(X, 2, axis=2))
+    assert not np.shares_memory(Xp, X)
+    # the oracle's importance of a classifier that looks at channel 2 only: every other channel scores exactly 0
+    yy = (X[:, :, 2].sum(axis=1) > 0).astype(np.int64)
+    np.random.seed(1)
+    imp, base = explain_oracle.permutation_importance(lambda Z: (Z[:, :, 2].sum(axis=1) > 0).astype(np.int64), X, yy, 3, 100)
+    assert base == 1.0 and np.all(np.delete(imp, 2) == 0.0) and imp[2] >= 0.0
