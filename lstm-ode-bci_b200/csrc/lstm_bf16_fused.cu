@@ -24,6 +24,9 @@
 //   buffers                       W 6 atoms (96 KB) + h 2 tiles x 2 atoms (64 KB, single-buffered: the ping-pong schedule separates
 //                                 readers and writers) + 4-slot TMA ring for in_t (64 KB) + bias; TMEM 2 tiles x 256 columns.
 //   h_t -> HBM                    each CTA TMA-stores its own 64-unit atom of h_t.
+//   epilogue arithmetic           (session 5, profiles/r5_fused_epilogue_stalls.md) the bias of slab s+1 is requested from shared memory while
+//                                 slab s is evaluated, and the fp32 operations run in packed form (FADD2 / FFMA2 / FMUL2 on (even, odd)
+//                                 unit pairs): per thread-step 320 MUFU.TANH + 320 packed FP instructions instead of 640 scalar ones.
 //
 // Reference semantics: nn.LSTM inside EnhancedLSTMModel (04_lstm_model.py:181-188,211).
 #include "lstm_shared_kernels.cuh"
