@@ -50,7 +50,9 @@ __device__ __forceinline__ double df2t_step(const FiltCoef& c, double (&z)[ORD],
 // first runs PP_WARM samples of warm-up from a zero state (outputs discarded), except where the chunk reaches the start of the
 // pass, which begins exactly as scipy does (state zi * first sample).  The filter's slowest pole (Butterworth band-pass, 1 Hz
 // corner at 500 Hz) has |p| = 0.9952 per sample, so after 8192 samples the influence of the unknown state has decayed by
-// e^-39: the chunked result equals the serial one to rounding (1e-16 of the signal), far inside the 1e-9 parity bound, while
+// e^-39.  What a chunked evaluation cannot reproduce is scipy's ROUNDING: this direct-form recursion amplifies rounding differences to
+// ~2e-7 of the output scale (scipy's own lfilter moves by 2.5e-7 under a 1e-15 perturbation of its initial state), so rows of one chunk
+// are bit-identical to scipy and longer rows agree to 1.5-2.1e-7 of the scale (tests/test_gpu_preproc.py), while
 // a batch of R recordings exposes R x 61 x n/PP_CHUNK threads instead of R x 61 (the fp64 pipe issues one warp instruction per
 // 8 cycles per SM sub-partition on B200; a single warp per 32 rows left 130 of 148 SMs idle).
 // (Round 2 tried 4096-sample chunks with 6144 of warm-up -- 4x the threads for 1.67x the arithmetic: 14 recordings per call ran 6 %

@@ -30,20 +30,41 @@ def test_matches_reference_golden(golden):
     assert np.abs(X2.cpu().numpy()[::3, :, ::9] - g["X2"]).max() <= 2e-6
 
 
-@pytest.mark.parametrize("R,C,n,dtype", [(3, 61, 5000, np.float64), (2, 7, 1301, np.float32), (1, 64, 256, np.float64)])
+# the last two cases span several 8192-sample chunks of the time-parallel filter (warm-up, chunk joins, a partial last tile and chunk)
+@pytest.mark.parametrize("R,C,n,dtype", [(3, 61, 5000, np.float64), (2, 7, 1301, np.float32), (1, 64, 256, np.float64),
+                                         (2, 5, 20011, np.float32), (1, 35, 41000, np.float64)])
 def test_batch_matches_oracle(R, C, n, dtype):
+    """Against the oracle (scipy filtfilt + the reference's normalisation / windowing).  Rows that fit one chunk of the time-parallel
+    filter start from scipy's own initial state and repeat its operation sequence: <= 1e-9 of the signal's scale.  Longer rows are
+    cut into chunks that warm up from a zero state; the warm-up error itself is e^-39, but this 8th-order direct-form band-pass
+    (poles at |z| = 0.9954) amplifies ROUNDING differences to ~2e-7 of the output scale -- scipy's own output moves by that much when
+    its initial state is perturbed by 1e-15 (oracle check below) -- so no chunked evaluation can agree with it more closely: the
+    bound there is 5e-7 of the scale, i.e. the recursion's rounding-noise floor, and 3e-6 on the z-scored fp32 windows."""
     raw = synth.make_raw_eeg(11, R, C, n, dtype=dtype)
     b, a, zi, padlen = pp.design_bandpass()
     out = pp.preprocess_recordings(torch.from_numpy(raw).cuda(), b, a, zi, padlen, want_filtered=True)
     n_seq = (n - 256) // 128 + 1
     assert out["n_seq"] == n_seq and tuple(out["X"].shape) == (R * n_seq, 256, C)
     X = out["X"].cpu().numpy()
+    multi = n + 2 * padlen > 8192
+    tol_f, tol_s, tol_x = (5e-7, 1e-6, 3e-6) if multi else (1e-9, 1e-9, 2e-6)
+    worst = [0.0, 0.0, 0.0]
     for r in range(R):
         filt = po.bandpass_filter(raw[r].astype(np.float64), 1.0, 45.0, 500, 4)
-        assert np.abs(out["filtered"][r].cpu().numpy() - filt).max() <= 1e-9 * np.abs(filt).max()
         Xr, _, prm = po.preprocess_recording(raw[r].astype(np.float64), 0)
-        assert np.abs(out["std"][r].cpu().numpy() / np.asarray(prm["std"]) - 1).max() <= 1e-9
-        assert np.abs(X[r * n_seq:(r + 1) * n_seq] - Xr.astype(np.float32)).max() <= 2e-6
+        worst[0] = max(worst[0], np.abs(out["filtered"][r].cpu().numpy() - filt).max() / np.abs(filt).max())
+        worst[1] = max(worst[1], np.abs(out["std"][r].cpu().numpy() / np.asarray(prm["std"]) - 1).max())
+        worst[2] = max(worst[2], np.abs(X[r * n_seq:(r + 1) * n_seq] - Xr.astype(np.float32)).max())
+    print("preprocess R=%d C=%d n=%d: filtered %.2e of scale, std %.2e, windows %.2e" % (R, C, n, *worst))
+    assert worst[0] <= tol_f and worst[1] <= tol_s and worst[2] <= tol_x, worst
+    if multi:   # the noise floor claimed above, measured on the oracle itself: scipy's recursion under a 1e-15 initial-state perturbation
+        from scipy.signal import lfilter
+        x0 = raw[0, 0].astype(np.float64)
+        y0, _ = lfilter(b, a, x0, zi=np.asarray(zi) * x0[0])
+        y1, _ = lfilter(b, a, x0, zi=np.asarray(zi) * x0[0] * (1 + 1e-15))
+        floor = np.abs(y1 - y0).max() / np.abs(y0).max()
+        print("  scipy lfilter under a 1e-15 state perturbation moves by %.2e of its scale" % floor)
+        assert floor >= 1e-8 and worst[0] <= 10 * floor
 
 
 def test_reference_function_mirrors_and_window_geometry():
