@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define BCI_ABI_VERSION 4
+#define BCI_ABI_VERSION 5   /* 5: + bci_permute_channels (additive) */
 #define BCI_MAX_LAYERS 4
 
 enum {

@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-ABI_VERSION = 4   # include/bci_b200.h: BCI_ABI_VERSION
+ABI_VERSION = 5   # include/bci_b200.h: BCI_ABI_VERSION
 LIB_PATH = os.path.join(_PKG, "lib", "libbci_b200.so")
 
 BCI_MAX_LAYERS = 4
